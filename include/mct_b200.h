@@ -1,0 +1,219 @@
+/*
+ * mct_b200.h -- C-ABI of the B200-native appearance-scoring path (libmct_b200.so).
+ *
+ * The reference (santhosh-kumar/MultiCameraTracking) has no plugin/FFI ABI: its seam is a set of
+ * C++ virtual interfaces.  Each entry point below names the reference interface it
+ * replaces (file:line under /root/reference/src).  The C++ host mirror in
+ * multicameratracking_b200/host/ keeps the reference's class names and forwards to these calls.
+ *
+ * Conventions
+ *   - every call returns 0 (MCT_OK) or a negative MCT_E_* code; it never exits or throws
+ *     (the reference's abortError() calls exit(0), Public.h:288-308).  mct_last_error() gives text.
+ *   - one mct_ctx per camera == per GPU, bound to one CUDA stream; calls on a ctx are stream-ordered
+ *     and not thread-safe; distinct ctxs are independent.
+ *   - plain pointers + sizes only.  "host" pointers are ordinary (ideally pinned) host memory;
+ *     pointers documented "dev" are CUDA device pointers on the ctx's device.
+ *   - there is NO CPU fallback: without a CUDA device every compute call returns MCT_E_CUDA.
+ *   - feature matrices are feature-major [F][ld] f32 exactly like SampleSet::m_featureMatrix
+ *     (SampleSet.h:41-43, 92-93).
+ */
+#ifndef MCT_B200_H
+#define MCT_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCT_OK            0
+#define MCT_E_ARG        -1   /* invalid argument */
+#define MCT_E_CUDA       -2   /* CUDA runtime error / no device */
+#define MCT_E_STATE      -3   /* call out of order (e.g. no frame set) */
+#define MCT_E_EMPTY      -4   /* no valid test sample (reference: ASSERT abort, ParticleFilterTracker.cpp:513) */
+#define MCT_E_NOMEM      -5
+#define MCT_E_UNSUPPORTED -6
+
+#define MCT_MAX_RECTS 6       /* DefaultParameters.h:14-15 */
+
+/* Features::FeatureType (FeatureParameters.h:12-16) */
+enum { MCT_FEAT_HAAR = 0, MCT_FEAT_CCH = 1, MCT_FEAT_MDCH = 2, MCT_FEAT_HAAR_MDCH = 3 };
+/* Classifier::WeakClassifierType (WeakClassifierBase.h:13-16) */
+enum { MCT_WEAK_STUMP = 0, MCT_WEAK_WSTUMP = 1, MCT_WEAK_PERCEPTRON = 2 };
+/* Classifier::StrongClassifierType (ClassifierParameters.h:11-18) */
+enum { MCT_STRONG_MILBOOST = 2, MCT_STRONG_MILANYBOOST = 4 };
+/* ParticleFilter::State (ParticleFilter.h:33-37) */
+enum { MCT_PF_UNINIT = 0, MCT_PF_INIT = 1, MCT_PF_PREDICTED = 2, MCT_PF_RESAMPLED = 3 };
+
+typedef struct mct_ctx mct_ctx;
+typedef struct mct_clf mct_clf;
+typedef struct mct_pf  mct_pf;
+
+/* ---------------------------------------------------------------- context ---------------- */
+/* cuda_stream: a cudaStream_t to run on (e.g. torch's current stream) or NULL to create one. */
+int  mct_ctx_create(int device, void* cuda_stream, mct_ctx** out);
+int  mct_ctx_destroy(mct_ctx* ctx);
+int  mct_sync(mct_ctx* ctx);
+const char* mct_last_error(mct_ctx* ctx);           /* ctx may be NULL: last global error */
+const char* mct_version(void);
+/* number of kernels this library has launched on the ctx since creation (bench: gpu_launches) */
+long long mct_launch_count(mct_ctx* ctx);
+void* mct_ctx_stream(mct_ctx* ctx);
+
+/* ---------------------------------------------------------------- frame ------------------ */
+/* Replaces Matrixu planes + Matrixu::initII()/FreeII() per frame (Matrix.cpp:33-47, Camera.cpp:491,389).
+ * gray is required; c0,c1,c2 are the colour planes the MDCH/CCH features read (R,G,B in that order,
+ * Matrix.cpp:92-94, or H,S,V) and may be NULL when only Haar features are used.
+ * is_device = 0: host pointers, copied H2D asynchronously on the ctx stream;
+ * is_device = 1: device pointers adopted without a copy (must stay valid until the next frame_set).
+ * Computes the (H+1)x(W+1) f32 integral image of gray: exact u32 prefix sums rounded once to f32. */
+int mct_frame_set(mct_ctx* ctx, const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2,
+                  int W, int H, int pitch, int is_device);
+/* dense (H+1)*(W+1) host copy of the integral image (tests) */
+int mct_frame_get_integral(mct_ctx* ctx, float* out_host);
+/* Matrixu::sumRect (Matrix.cpp:49-67): n rects {x,y,w,h} -> ((br+tl)-tr)-bl in f32.  Host in/out. */
+int mct_sum_rects(mct_ctx* ctx, const int* rects_xywh, int n, float* out_host);
+
+/* ---------------------------------------------------------------- boxes == SampleSet ------ */
+/* Sample.h:41-51 as SoA; all boxes refer to the ctx's current frame (the reference stores raw
+ * Matrixu* in every Sample).  host arrays. */
+typedef struct {
+    int n;
+    const int*   col;   /* m_col  (left) */
+    const int*   row;   /* m_row  (top)  */
+    const float* sx;    /* m_scaleX */
+    const float* sy;    /* m_scaleY */
+} mct_boxes;
+
+/* ---------------------------------------------------------------- strong classifier ------- */
+/* ClassifierParameters.h:38-65 + FeatureParameters.h */
+typedef struct {
+    int   feature_type;      /* MCT_FEAT_* */
+    int   n_haar;            /* Tracker_Feature_Parameter (ignored for colour-only types) */
+    int   n_bins;            /* Color_Number_Of_Bins (8) */
+    int   w0, h0;            /* m_width, m_height of the object blob at scale 1 */
+    int   weak_type;         /* MCT_WEAK_* */
+    int   strong_type;       /* MCT_STRONG_* */
+    int   n_selected;        /* K; clamped to F/2 when out of range (StrongClassifierBase.cpp:20-23) */
+    float learning_rate;     /* 0.85 (DefaultParameters.h:18); 0 for the appearance fuser */
+    int   cch_mode;          /* 0 = reference_exact, 1 = intended */
+    int   max_train;         /* capacity for P + Nn training boxes (0 -> 4096) */
+    int   max_test;          /* capacity for test boxes per classify call (0 -> 65536) */
+} mct_clf_params;
+
+/* Haar table generated on the host with the reference RNG order (HaarFeature.cpp:25-69). */
+typedef struct {
+    int n_features;
+    const int*   nrect;      /* [F] 2..6 */
+    const int*   rects;      /* [F][6][4] x,y,w,h in the w0 x h0 frame */
+    const float* weights;    /* [F][6] */
+} mct_haar_table;
+
+/* StrongClassifierFactory::CreateAndInitializeClassifier (StrongClassifierFactory.cpp:14-43) +
+ * StrongClassifierBase ctor (StrongClassifierBase.cpp:8-129). */
+int mct_classifier_create(mct_ctx* ctx, const mct_clf_params* p, const mct_haar_table* haar, mct_clf** out);
+int mct_classifier_destroy(mct_clf* clf);
+/* StrongClassifierBase::GetNumberOfFeatures (StrongClassifierBase.h:47-51) */
+int mct_classifier_num_features(mct_clf* clf);
+/* FeatureVector::Compute (FeatureVector.h:40; HaarFeatureVector.cpp:48-79,
+ * MultiDimensionalColorHistogramFeatureVector.cpp:52-90, CultureColorHistogramFeatureVector.cpp:48-81,
+ * HaarAndColorHistogramFeatureVector.cpp:33-44): out_host is [F][boxes->n]. */
+int mct_features_compute(mct_clf* clf, const mct_boxes* boxes, float* out_host);
+/* StrongClassifierBase::Update(pos, neg) (MILBoostClassifier.cpp:15-157, MILAnyBoostClassifier.cpp:14-254).
+ * wpos/wneg: WeightedStumps sample weights, NULL => uniform 1.0. */
+int mct_classifier_update(mct_clf* clf, const mct_boxes* pos, const mct_boxes* neg,
+                          const float* wpos, const float* wneg);
+/* Same from already-computed feature rows [F][P], [F][Nn] (host) -- the appearance fuser's pooled
+ * sample sets arrive as feature rows after the cross-camera allgather. */
+int mct_classifier_update_from_features(mct_clf* clf, const float* fpos, int P, const float* fneg, int Nn,
+                                        const float* wpos, const float* wneg);
+/* StrongClassifierBase::Classify(set, isLogRatioEnabled) (MILBoostClassifier.cpp:339-374). */
+int mct_classifier_classify(mct_clf* clf, const mct_boxes* boxes, int log_ratio, float* out_host);
+int mct_classifier_classify_from_features(mct_clf* clf, const float* feat, int n, int log_ratio, float* out_host);
+/* m_selectorList (StrongClassifierBase.h:63) */
+int mct_classifier_get_selectors(mct_clf* clf, int* idx_host, int* n);
+/* weak-classifier state, 8 rows x F: mu0,mu1,sig0,sig1,n0,n1,e0,e1 (OnlineStumpsWeakClassifier.h:33-40);
+ * perceptron: rows 0,1 = m_weightList[0], [1] */
+int mct_classifier_get_weak_state(mct_clf* clf, float* out8xF_host);
+/* last Update's weak predictions [F][P+Nn] (positives first) -- parity tests */
+int mct_classifier_get_predictions(mct_clf* clf, float* out_host, int* P, int* Nn);
+/* cluster width used by the MIL selection kernel (0 = auto) */
+int mct_classifier_set_cluster(mct_clf* clf, int cluster_size);
+
+/* ---------------------------------------------------------------- particle filter --------- */
+/* ParticleFilter (ParticleFilter.h:28-156).  Device state is SoA cx,cy,sx,sy,w; host views are the
+ * reference's row-major [N][5] (ParticleFilter.h:139). */
+int mct_pf_create(mct_ctx* ctx, int n_particles, float image_w, float image_h, mct_pf** out);
+int mct_pf_destroy(mct_pf* pf);
+/* ParticleFilter::Initialize (ParticleFilter.cpp:15-75) */
+int mct_pf_initialize(mct_pf* pf, float cx, float cy, float sx, float sy,
+                      float max_scale_change, float max_scale, float min_scale);
+/* ParticleFilter::PredictWithBrownianMotion (ParticleFilter.cpp:236-341).  noise4xN (host, or dev when
+ * noise_is_device) holds the four cv::randn(1xN,0,sigma) rows (x, y, scaleX, scaleY): the host owns the
+ * Gaussian stream.  w0/h0 feed CheckForParticleRefinement (:328). */
+int mct_pf_predict(mct_pf* pf, const float* noise4xN, int noise_is_device, float w0, float h0);
+/* ParticleFilter::UpdateAllParticlesWeight (ParticleFilter.cpp:680-717): prob is the compacted list
+ * for the particles with non-zero weight.  u01 = the randfloat() the reference would draw inside
+ * ResampleParticles (:936); *resampled tells the host whether that draw was consumed. */
+int mct_pf_update_all_weights(mct_pf* pf, const float* prob_host, int n_prob, int only_nonzero,
+                              int force_reset, int resample, float u01, int* resampled);
+/* ParticleFilter::ResampleParticles(force) (ParticleFilter.cpp:920-978) */
+int mct_pf_resample(mct_pf* pf, int force_state_change, float u01);
+/* m_particlesStateMatrix / m_particlesResampledMatrix / m_resampleIndexList */
+int mct_pf_get_state(mct_pf* pf, float* out_Nx5_host);
+int mct_pf_set_state(mct_pf* pf, const float* in_Nx5_host, int filter_state);
+int mct_pf_get_resampled(mct_pf* pf, float* out_Nx5_host);
+int mct_pf_get_resample_indices(mct_pf* pf, int* out_N_host);
+
+/* Read-out used by StoreObjectState / GenerateTrainingSampleSet (ParticleFilterTracker.cpp:286-393,
+ * 647-688), computed on the device so only this struct crosses PCIe per object per frame. */
+typedef struct {
+    int   n_valid;          /* test samples scored this frame */
+    int   resampled;        /* 1 if ResampleIfRequired fired (the u01 draw was consumed) */
+    int   filter_state;     /* MCT_PF_* after the call */
+    int   n_unique;         /* rows of m_particlesOrderedUniqueMatrix */
+    float neff_inv;         /* sum w^2 after normalisation (ParticleFilter.cpp:860-875) */
+    float max_response;     /* max H over the test set (return value of TrackObjectOnTheGivenFrame) */
+    float average[4];       /* GetAverageofAllParticles (ParticleFilter.cpp:601-633) */
+    float ordered_first[5]; /* GetOrderedUniqueParticles(0) (ParticleFilter.cpp:507-522, 728-815) */
+    float highest_close[5]; /* GetHighestOrderedUniqueParticleCloseToTheGivenState (:557-593) */
+} mct_pf_summary;
+int mct_pf_get_summary(mct_pf* pf, mct_pf_summary* out_host);
+
+/* ---------------------------------------------------------------- fused per-frame path ---- */
+/* One call = TrackObjectOnTheGivenFrame (ParticleFilterTracker.cpp:468-639) for n_obj objects of this
+ * camera in a handful of batched launches: predict -> GenerateTestSampleSet (:1247-1305) -> Classify
+ * (selected features only; identical result to the reference, which computes all F and reads K) ->
+ * likelihood map ((H-min)/range)^exponent (:541-566) -> UpdateAllParticlesWeight -> Normalize ->
+ * ResampleIfRequired -> read-out.  noise: [n_obj][4][N] (host or dev); u01: [n_obj] host.
+ * summaries: [n_obj] host, valid after the call returns (the call synchronises the stream). */
+typedef struct {
+    float w0, h0;           /* m_currentStateList[2], [3] */
+    int   exponent;         /* 20 (:556); 1 for the re-score variant (:1407) */
+    int   force_reset;      /* shouldForceReset */
+    int   resample;         /* shouldResample */
+} mct_track_params;
+int mct_track_score(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, mct_clf* const* clfs,
+                    const mct_track_params* params /* [n_obj] */,
+                    const float* noise, int noise_is_device, const float* u01,
+                    mct_pf_summary* summaries);
+/* asynchronous variant: no stream sync, summaries land in the ctx's pinned buffer; collect with
+ * mct_track_collect (which synchronises). */
+int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, mct_clf* const* clfs,
+                          const mct_track_params* params, const float* noise, int noise_is_device,
+                          const float* u01);
+int mct_track_collect(mct_ctx* ctx, int n_obj, mct_pf_summary* summaries);
+/* UpdateClassifier (ParticleFilterTracker.cpp:1013-1032) for n_obj objects, batched, asynchronous. */
+int mct_track_update(mct_ctx* ctx, int n_obj, mct_clf* const* clfs,
+                     const mct_boxes* pos /* [n_obj] */, const mct_boxes* neg /* [n_obj] */);
+/* per-object H (log-ratio response) of the last mct_track_score, dense over particles (tests) */
+int mct_pf_get_last_response(mct_pf* pf, float* out_N_host, int* valid_N_host);
+
+/* ---------------------------------------------------------------- cross-camera exchange --- */
+/* Packs the per-object payload the fusers exchange: foot point of the highest-weight
+ * particle (cx, cy + sy*h0/2) (ParticleFilterTracker.cpp:1223-1238) into dev_out[n_obj][2] (dev),
+ * ready for an NCCL allgather on the same stream. */
+int mct_fuser_pack_foot_points(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, const float* h0, float* dev_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCT_B200_H */

@@ -1,0 +1,324 @@
+// k_milselect.cu -- greedy weak-learner selection (hot loop D).
+//
+// k_milboost_select: MILBoostClassifier::Update selection loop (MILBoostClassifier.cpp:61-131).
+//   K sequential rounds, each scoring all F candidates over the P positives / Nn negatives:
+//       Lp  = prod_i (1 - sigmoid(Hp_i + pp[f][i]))                       f32 product, in order
+//       nll = (float)-log(1 - Lp + 1e-5)/P + sum_j (float)-logf(1e-5f + 1 - sigmoid(Hn_j + pn[f][j]))/Nn
+//   then argmin over the not-yet-selected valid candidates, stop when the NLL stops improving.
+//   The whole loop runs inside ONE kernel on a thread-block cluster (one cluster per classifier):
+//   the candidates are partitioned over the CTAs of the cluster; per round every CTA
+//     phase 1  evaluates the sigmoid/log terms for its candidates on all threads (coalesced over the
+//              samples) into a transposed shared-memory tile,
+//     phase 2  lets one thread per candidate run the product / sum chains *in reference order* (so the
+//              bag likelihood is bit-identical to a sequential evaluation given the same terms),
+//     then publishes its best candidate into every peer's shared memory (DSMEM), one cluster.sync()
+//     later every CTA holds all candidates' bests and takes the same argmin (ties -> lowest index,
+//     the stable-sort order; the reference's std::sort tie order is unspecified, Public.h:223).
+//   SFU/latency bound (exp, rcp, log per term), not a bandwidth kernel; the prediction matrix
+//   [F][P+Nn] (a few hundred KB) stays L2 resident.
+//
+// k_anyboost_select: MILAnyBoostClassifier::Update selection loop (MILAnyBoostClassifier.cpp:78-222),
+//   one CTA per classifier (one sigmoid pass + F dot products per round).
+#include "mct_internal.cuh"
+#include <cooperative_groups.h>
+#include <math_constants.h>
+namespace cg = cooperative_groups;
+
+#define SEL_THREADS 256
+#define SEL_MAX_CLUSTER 16
+
+struct SelSlot { float nll; int f; };
+
+__device__ __forceinline__ bool better_min(float v, int f, float bv, int bf)
+{
+    return (v < bv) || (v == bv && f < bf);
+}
+
+__global__ void __launch_bounds__(SEL_THREADS)
+k_milboost_select(const float* __restrict__ pred, int ld, int F, int P, int Nn, int K,
+                  const float* __restrict__ weak, int weak_type, int* __restrict__ sel, int* __restrict__ nsel,
+                  int FC)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int M = P + Nn;
+    const int FCP = FC + 1;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    float* Hs = (float*)smraw;                               // [M]
+    float* scratch = Hs + M;                                 // [M][FC+1]
+    unsigned char* selflag = (unsigned char*)(scratch + (size_t)M * FCP);   // [F]
+    __shared__ SelSlot slots[2][SEL_MAX_CLUSTER];
+    __shared__ SelSlot s_best[SEL_THREADS / 32];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int FL = (F + C - 1) / C;
+    const int f_begin = rank * FL;
+    const int f_end = min(F, f_begin + FL);
+
+    for (int i = tid; i < M; i += blockDim.x) Hs[i] = 0.0f;
+    for (int f = tid; f < F; f += blockDim.x) selflag[f] = 0;
+    __syncthreads();
+
+    double prev = 1000000.0;
+    int n_sel = 0;
+    for (int s = 0; s < K; s++) {
+        float bv = CUDART_INF_F; int bf = 0x7fffffff;
+        for (int fc = f_begin; fc < f_end; fc += FC) {
+            const int nfc = min(FC, f_end - fc);
+            // phase 1: terms, coalesced over samples, transposed into scratch[i][fl]
+            for (int fl = warp; fl < nfc; fl += nwarps) {
+                const float* pr = pred + (size_t)(fc + fl) * ld;
+                for (int i = lane; i < M; i += 32) {
+                    const float sg = sigmoid_dev(__fadd_rn(Hs[i], pr[i]));
+                    float t;
+                    if (i < P) t = __fsub_rn(1.0f, sg);
+                    else t = -logf(__fsub_rn(__fadd_rn(1e-5f, 1.0f), sg));
+                    scratch[(size_t)i * FCP + fl] = t;
+                }
+            }
+            __syncthreads();
+            // phase 2: ordered chains, one thread per candidate
+            if (tid < nfc) {
+                const int f = fc + tid;
+                float like = 1.0f;
+                for (int i = 0; i < P; i++) like = __fmul_rn(like, scratch[(size_t)i * FCP + tid]);
+                const float posl = (float)(-log((double)__fsub_rn(1.0f, like) + 1e-5));
+                float sn = 0.0f;
+                for (int j = P; j < M; j++) sn = __fadd_rn(sn, scratch[(size_t)j * FCP + tid]);
+                const float nll = __fadd_rn(__fdiv_rn(posl, (float)P), __fdiv_rn(sn, (float)Nn));
+                bool ok = !selflag[f];
+                if (ok && weak_type != MCT_WEAK_PERCEPTRON)
+                    ok = weak[0 * (size_t)F + f] != weak[1 * (size_t)F + f];      // IsValidWeakClassifier: mu0 != mu1
+                if (ok && better_min(nll, f, bv, bf)) { bv = nll; bf = f; }
+            }
+            __syncthreads();
+        }
+        // CTA argmin
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            int of = __shfl_xor_sync(0xffffffffu, bf, o);
+            if (better_min(ov, of, bv, bf)) { bv = ov; bf = of; }
+        }
+        if (lane == 0) { s_best[warp].nll = bv; s_best[warp].f = bf; }
+        __syncthreads();
+        const int par = s & 1;
+        if (tid < C) {
+            float v = s_best[0].nll; int f = s_best[0].f;
+            for (int w = 1; w < nwarps; w++)
+                if (better_min(s_best[w].nll, s_best[w].f, v, f)) { v = s_best[w].nll; f = s_best[w].f; }
+            // publish into peer `tid`'s slot table (distributed shared memory)
+            SelSlot* remote = cluster.map_shared_rank(&slots[0][0], tid);
+            remote[par * SEL_MAX_CLUSTER + rank].nll = v;
+            remote[par * SEL_MAX_CLUSTER + rank].f = f;
+        }
+        cluster.sync();
+        float gv = slots[par][0].nll; int gf = slots[par][0].f;
+        for (int q = 1; q < C; q++)
+            if (better_min(slots[par][q].nll, slots[par][q].f, gv, gf)) { gv = slots[par][q].nll; gf = slots[par][q].f; }
+        if (gf == 0x7fffffff) break;                               // nothing eligible (reference: UB read)
+        if ((prev - (double)gv) < 1e-100) break;                   // :108-112 no improvement -> pop & stop
+        prev = (double)gv;
+        if (rank == 0 && tid == 0) sel[n_sel] = gf;
+        n_sel++;
+        const float* pb = pred + (size_t)gf * ld;
+        for (int i = tid; i < M; i += blockDim.x) Hs[i] = __fadd_rn(Hs[i], pb[i]);
+        if (tid == 0) selflag[gf] = 1;
+        __syncthreads();
+    }
+    if (rank == 0 && tid == 0) *nsel = n_sel;
+    cluster.sync();          // no CTA may exit while a peer can still write its slots
+}
+
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool better_max(float v, int f, float bv, int bf)
+{
+    return (v > bv) || (v == bv && f < bf);
+}
+// block argmax over (value desc, index asc); returns through shared
+__device__ void block_argmax(float v, int f, float* out_v, int* out_f, SelSlot* sh)
+{
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        int of = __shfl_xor_sync(0xffffffffu, f, o);
+        if (better_max(ov, of, v, f)) { v = ov; f = of; }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) { sh[warp].nll = v; sh[warp].f = f; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++)
+            if (better_max(sh[w].nll, sh[w].f, sh[0].nll, sh[0].f)) sh[0] = sh[w];
+    }
+    __syncthreads();
+    *out_v = sh[0].nll; *out_f = sh[0].f;
+    __syncthreads();
+}
+
+#define ANY_THREADS 1024
+__global__ void __launch_bounds__(ANY_THREADS)
+k_anyboost_select(const float* __restrict__ pred, int ld, int F, int P, int Nn, int K,
+                  int* __restrict__ sel, int* __restrict__ nsel)
+{
+    const int M = P + Nn;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    float* Hs = (float*)smraw;              // [M]  hypothesis
+    float* pi = Hs + M;                     // [M]  instance probabilities
+    float* tq = pi + M;                     // [M]  chain terms, later instance weights
+    float* obj = tq + M;                    // [F]  last objective values
+    unsigned char* selflag = (unsigned char*)(obj + F);
+    __shared__ SelSlot sh[ANY_THREADS / 32];
+    __shared__ float s_pbag, s_nll;
+    __shared__ int s_action;                // 0 continue normally, 1 special retry, 2 pop & stop
+    const int tid = threadIdx.x, nt = blockDim.x;
+
+    for (int i = tid; i < M; i += nt) Hs[i] = 0.0f;
+    for (int f = tid; f < F; f += nt) { selflag[f] = 0; obj[f] = 0.0f; }
+    __syncthreads();
+    double prev = 1000000.0;
+    int n_sel = 0;
+    float cur_v = 0.0f; int cur_f = -1;     // position k in the last sorted order
+    int have_order = 0;
+    int last_sel = -1;                      // m_selectorList.back()
+    // `s` mirrors selectedFeatureIndex; the retry branch re-enters the same round
+    for (int s = 0; s < K; s++) {
+        for (int i = tid; i < M; i += nt) {
+            const float p = sigmoid_dev(Hs[i]);
+            pi[i] = p;
+            if (i < P) tq[i] = __fsub_rn(1.0f, p);
+            else tq[i] = __fdiv_rn(-logf(__fsub_rn(__fadd_rn(1e-5f, 1.0f), p)), (float)Nn);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float like = 1.0f;
+            for (int i = 0; i < P; i++) like = __fmul_rn(like, tq[i]);
+            const float y = __fdiv_rn(1.0f, (float)P);
+            const float pbag = __fsub_rn(1.0f, (float)pow((double)like, (double)y));   // 1 - powf(like, 1/(float)P)
+            float nll = -logf(__fadd_rn(pbag, 1e-5f));
+            for (int j = P; j < M; j++) nll = __fadd_rn(nll, tq[j]);
+            s_pbag = pbag; s_nll = nll;
+            int action = 0;
+            if ((prev - (double)nll) < 1e-100) action = (n_sel <= 2) ? 1 : 2;
+            s_action = action;
+        }
+        __syncthreads();
+        const int action = s_action;
+        const float pbag = s_pbag;
+        if (action == 2) { n_sel--; break; }
+        if (action == 1) {
+            // :104-150 special retry: drop the last pick, take the next one in the previous order
+            if (n_sel == 0 || !have_order) break;
+            const float* pl = pred + (size_t)last_sel * ld;
+            for (int i = tid; i < M; i += nt) Hs[i] = __fsub_rn(Hs[i], pl[i]);
+            if (tid == 0) selflag[last_sel] = 0;
+            __syncthreads();
+            n_sel--;
+            float bv = -CUDART_INF_F; int bf = 0x7fffffff;
+            for (int f = tid; f < F; f += nt) {
+                const float v = obj[f];
+                const bool after = (v < cur_v) || (v == cur_v && f > cur_f);
+                if (after && !selflag[f] && better_max(v, f, bv, bf)) { bv = v; bf = f; }
+            }
+            float gv; int gf;
+            block_argmax(bv, bf, &gv, &gf, sh);
+            if (gf == 0x7fffffff) break;                          // reference: abortError
+            if (tid == 0) { sel[n_sel] = gf; selflag[gf] = 1; }
+            n_sel++;
+            last_sel = gf; cur_v = gv; cur_f = gf;
+            const float* pb = pred + (size_t)gf * ld;
+            __syncthreads();
+            for (int i = tid; i < M; i += nt) Hs[i] = __fadd_rn(Hs[i], pb[i]);
+            __syncthreads();
+            s = n_sel - 1;                                        // selectedFeatureIndex-- ; continue -> ++
+            continue;
+        }
+        prev = (double)s_nll;
+        // instance weights (:163-173)
+        const float invP = __fdiv_rn(1.0f, (float)P), invN = __fdiv_rn(1.0f, (float)Nn);
+        __syncthreads();
+        for (int i = tid; i < M; i += nt) {
+            if (i < P) tq[i] = __fdiv_rn(__fmul_rn(__fmul_rn(invP, __fsub_rn(1.0f, pbag)), pi[i]), pbag);
+            else tq[i] = __fmul_rn(-invN, pi[i]);
+        }
+        __syncthreads();
+        // objective: ordered f32 chain per candidate (:176-189)
+        float bv = -CUDART_INF_F; int bf = 0x7fffffff;
+        for (int f = tid; f < F; f += nt) {
+            const float* pr = pred + (size_t)f * ld;
+            float o = 0.0f;
+            for (int i = 0; i < M; i++) o = __fadd_rn(o, __fmul_rn(tq[i], pr[i]));
+            obj[f] = o;
+            if (!selflag[f] && better_max(o, f, bv, bf)) { bv = o; bf = f; }
+        }
+        have_order = 1;
+        float gv; int gf;
+        block_argmax(bv, bf, &gv, &gf, sh);
+        if (gf == 0x7fffffff) break;                              // all selected (:203-207)
+        if (tid == 0) { sel[n_sel] = gf; selflag[gf] = 1; }
+        n_sel++;
+        last_sel = gf; cur_v = gv; cur_f = gf;
+        const float* pb = pred + (size_t)gf * ld;
+        __syncthreads();
+        for (int i = tid; i < M; i += nt) Hs[i] = __fadd_rn(Hs[i], pb[i]);
+        __syncthreads();
+    }
+    if (tid == 0) *nsel = n_sel < 0 ? 0 : n_sel;
+}
+
+// ------------------------------------------------------------------------------------------
+int launch_mil_select(mct_clf* clf, int P, int Nn)
+{
+    mct_ctx* ctx = clf->ctx;
+    const int F = clf->F, M = P + Nn;
+    if (clf->p.strong_type == MCT_STRONG_MILANYBOOST) {
+        size_t smem = (size_t)(3 * M + F) * sizeof(float) + (size_t)F;
+        if (smem > 200 * 1024) return mct_fail(ctx, MCT_E_UNSUPPORTED, "training set too large for the AnyBoost kernel%s (M=%d)", "", M);
+        static size_t s_attr = 32 * 1024;
+        if (smem > s_attr) {
+            MCT_CUDA(ctx, cudaFuncSetAttribute(k_anyboost_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            s_attr = smem;
+        }
+        k_anyboost_select<<<1, ANY_THREADS, smem, ctx->stream>>>(clf->d_pred, clf->ldT, F, P, Nn, clf->K, clf->d_sel, clf->d_nsel);
+        MCT_KERNEL_CHECK(ctx);
+        return MCT_OK;
+    }
+    // cluster width: enough CTAs that each owns <= ~48 candidates, capped at 16 (non-portable size)
+    int C = clf->cluster;
+    if (C <= 0) { C = 1; while (C < SEL_MAX_CLUSTER && ceil_div(F, C) > 48) C <<= 1; }
+    if (C > SEL_MAX_CLUSTER) C = SEL_MAX_CLUSTER;
+    const int FL = ceil_div(F, C);
+    // candidates per chunk: the transposed tile [M][FC+1] must fit beside H[M] and the flags
+    const size_t budget = 180 * 1024;
+    long fc_max = ((long)budget - (long)M * 4 - F) / ((long)M * 4) - 1;
+    if (fc_max < 1) return mct_fail(ctx, MCT_E_UNSUPPORTED, "training set too large for the MIL selection kernel%s (M=%d)", "", M);
+    int FC = FL < (int)fc_max ? FL : (int)fc_max;
+    if (FC > SEL_THREADS) FC = SEL_THREADS;
+    size_t smem = (size_t)M * 4 + (size_t)M * (FC + 1) * 4 + (size_t)F;
+    smem = (smem + 15) & ~(size_t)15;
+    static size_t s_attr = 0;
+    static int s_np = 0;
+    if (smem > s_attr) {
+        MCT_CUDA(ctx, cudaFuncSetAttribute(k_milboost_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        s_attr = smem;
+    }
+    if (C > 8 && !s_np) {
+        MCT_CUDA(ctx, cudaFuncSetAttribute(k_milboost_select, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        s_np = 1;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(C, 1, 1);
+    cfg.blockDim = dim3(SEL_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const float* pred = clf->d_pred; const float* weak = clf->d_weak;
+    int ld = clf->ldT, K = clf->K, wt = clf->p.weak_type;
+    int* sel = clf->d_sel; int* nsel = clf->d_nsel;
+    MCT_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_milboost_select, pred, ld, F, P, Nn, K, weak, wt, sel, nsel, FC));
+    MCT_KERNEL_CHECK(ctx);
+    return MCT_OK;
+}

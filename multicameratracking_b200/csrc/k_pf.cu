@@ -1,0 +1,514 @@
+// k_pf.cu -- ParticleFilter device path (ParticleFilter.cpp) + GenerateTestSampleSet
+// (ParticleFilterTracker.cpp:1247-1305) + likelihood map (:541-566).
+//
+// Bit-exactness contract (north_star: resampling indices bit-exact given identical weights):
+//   NormalizeParticleWeights (:987-1011) and the CDF (:927-933) are *sequential f32 add chains* in the
+//   reference; a parallel scan reassociates and can flip an index by one ulp.  k_pf_update therefore
+//   stages the weights in shared memory and lets one lane run the N-long chains in reference order
+//   (4 cycles per dependent FADD, ~4 us for N = 2000), while everything elementwise (likelihood map,
+//   weight products, divisions, the threshold search) runs on the whole CTA.  The N_eff test (:860-875)
+//   is decided from an f64 block reduction; the serial f32/f64 chain is only run when the reduction
+//   lands within the chain's rounding band of the threshold, so the decision always equals the chain's.
+#include "mct_internal.cuh"
+#include <math_constants.h>
+
+#define PF_THREADS 1024
+
+__device__ __forceinline__ float block_reduce_minmax(float v, bool is_max, float* sh)
+{
+    for (int o = 16; o > 0; o >>= 1) {
+        float t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_max ? fmaxf(v, t) : fminf(v, t);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = (lane < (blockDim.x >> 5)) ? sh[lane] : (is_max ? -CUDART_INF_F : CUDART_INF_F);
+        for (int o = 16; o > 0; o >>= 1) {
+            float t = __shfl_xor_sync(0xffffffffu, v, o);
+            v = is_max ? fmaxf(v, t) : fminf(v, t);
+        }
+        if (lane == 0) sh[0] = v;
+    }
+    __syncthreads();
+    return sh[0];
+}
+__device__ __forceinline__ double block_reduce_sum_d(double v, double* sh)
+{
+    v = warp_sum_d(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = (lane < (blockDim.x >> 5)) ? sh[lane] : 0.0;
+        v = warp_sum_d(v);
+        if (lane == 0) sh[0] = v;
+    }
+    __syncthreads();
+    return sh[0];
+}
+__device__ __forceinline__ int block_reduce_sum_i(int v, int* sh)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = (lane < (blockDim.x >> 5)) ? sh[lane] : 0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sh[0] = v;
+    }
+    __syncthreads();
+    return sh[0];
+}
+
+// ParticleFilter::UpdateParticleWeight scale-ratio clamp (ParticleFilter.cpp:658-665): 1.2 and 0.9 are
+// double literals, so the comparison and the product are evaluated in double.
+__device__ __forceinline__ void scale_ratio_clamp(float& sx, float& sy)
+{
+    if ((double)__fdiv_rn(sx, sy) > 1.2) sy = (float)(0.9 * (double)sx);
+    else if ((double)__fdiv_rn(sy, sx) > 1.2) sx = (float)(0.9 * (double)sy);
+}
+
+// ------------------------------------------------------------------------------------------
+// PredictWithBrownianMotion (ParticleFilter.cpp:236-341).  x and y use the scale *before* its update.
+__device__ __forceinline__ float scale_step_dev(float s, float n, float msc, float maxs, float mins)
+{
+    if (msc > fabsf(n)) s = __fadd_rn(s, n);
+    else if (n < 0) s = __fsub_rn(s, msc);
+    else s = __fadd_rn(s, msc);
+    if (s > maxs) s = maxs;
+    if (s < mins) s = mins;
+    return s;
+}
+__global__ void __launch_bounds__(256) k_pf_predict(const ObjDesc* __restrict__ descs)
+{
+    const ObjDesc& d = descs[blockIdx.y];
+    const int N = d.N;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { d.st->filter_state = MCT_PF_PREDICTED; d.st->time_index += 1; }
+    if (i >= N) return;
+    const float* nz = d.noise;
+    float sx = d.sx[i], sy = d.sy[i];
+    d.cx[i] = (float)__float2int_rn(__fadd_rn(d.cx[i], __fmul_rn(sx, nz[i])));
+    d.cy[i] = (float)__float2int_rn(__fadd_rn(d.cy[i], __fmul_rn(sy, nz[(size_t)N + i])));
+    d.sx[i] = scale_step_dev(sx, nz[(size_t)2 * N + i], d.msc, d.maxs, d.mins);
+    d.sy[i] = scale_step_dev(sy, nz[(size_t)3 * N + i], d.msc, d.maxs, d.mins);
+}
+int launch_pf_predict(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max)
+{
+    dim3 g(ceil_div(n_max, 256), n_obj);
+    k_pf_predict<<<g, 256, 0, ctx->stream>>>(d_desc);
+    MCT_KERNEL_CHECK(ctx);
+    return MCT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// GenerateTestSampleSet (ParticleFilterTracker.cpp:1247-1305): box per particle; out-of-frame particles
+// get UpdateParticleWeight(p, 0) (weight *= 0 and the scale-ratio clamp); in-frame particles with a
+// non-zero weight form the test set (dense mask instead of the reference's compaction).
+__global__ void __launch_bounds__(256) k_pf_testset(const ObjDesc* __restrict__ descs, int fw, int fh)
+{
+    const ObjDesc& d = descs[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.N) return;
+    float sx = d.sx[i], sy = d.sy[i];
+    const float wf = __fmul_rn(sx, d.w0), hf = __fmul_rn(sy, d.h0);
+    const float left = (float)__float2int_rn(__fsub_rn(d.cx[i], __fdiv_rn(wf, 2.0f)));
+    const float top = (float)__float2int_rn(__fsub_rn(d.cy[i], __fdiv_rn(hf, 2.0f)));
+    const float width = (float)__float2int_rn(wf), height = (float)__float2int_rn(hf);
+    int v = 0;
+    if (left <= 0 || __fadd_rn(left, width) >= (float)(fw - 1) || top <= 0 || __fadd_rn(top, height) >= (float)(fh - 1)) {
+        d.w[i] = __fmul_rn(0.0f, d.w[i]);
+        scale_ratio_clamp(sx, sy);
+        d.sx[i] = sx; d.sy[i] = sy;
+    } else if (d.w[i] != 0) {
+        v = 1;
+    }
+    d.col[i] = (int)left; d.row[i] = (int)top;
+    d.valid[i] = v;
+}
+int launch_pf_testset(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max)
+{
+    dim3 g(ceil_div(n_max, 256), n_obj);
+    k_pf_testset<<<g, 256, 0, ctx->stream>>>(d_desc, ctx->W, ctx->H);
+    MCT_KERNEL_CHECK(ctx);
+    return MCT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// ResampleParticles body (ParticleFilter.cpp:920-978).  sw = weights after the first normalisation
+// (shared or global), cdf = scratch of the same length.
+__device__ void resample_body(const ObjDesc& d, float* sw, float* cdf, int force, float* sh_f)
+{
+    const int N = d.N, tid = threadIdx.x, nt = blockDim.x;
+    // NormalizeParticleWeights again (:924)
+    if (tid == 0) {
+        float total = 0.0f;
+        for (int i = 0; i < N; i++) total = __fadd_rn(total, sw[i]);
+        sh_f[0] = total;
+    }
+    __syncthreads();
+    const float total = sh_f[0];
+    for (int i = tid; i < N; i += nt) sw[i] = (total != 0) ? __fdiv_rn(sw[i], total) : 1e-2f;
+    __syncthreads();
+    // cdf[0] = 0 (w[0] excluded -- reference quirk), cdf[i] = cdf[i-1] + w[i]
+    if (tid == 0) {
+        float c = 0.0f;
+        cdf[0] = 0.0f;
+        for (int i = 1; i < N; i++) { c = __fadd_rn(c, sw[i]); cdf[i] = c; }
+    }
+    __syncthreads();
+    const float invN = __fdiv_rn(1.0f, (float)N);
+    const float seed = __fmul_rn(invN, d.u01);
+    for (int i = tid; i < N; i += nt) {
+        const float thr = __fadd_rn(seed, __fmul_rn(invN, (float)i));
+        // idx = min(N-1, #{j : cdf[j] < thr})  == the reference's monotone walk
+        int lo = 0, hi = N;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (cdf[mid] < thr) lo = mid + 1; else hi = mid;
+        }
+        const int idx = lo < N - 1 ? lo : N - 1;
+        d.residx[i] = idx;
+        d.rcx[i] = d.cx[idx]; d.rcy[i] = d.cy[idx]; d.rsx[i] = d.sx[idx]; d.rsy[i] = d.sy[idx];
+        d.rw[i] = 1.0f;
+    }
+    __syncthreads();
+    if (force) {
+        for (int i = tid; i < N; i += nt) {
+            d.cx[i] = d.rcx[i]; d.cy[i] = d.rcy[i]; d.sx[i] = d.rsx[i]; d.sy[i] = d.rsy[i]; d.w[i] = 1.0f;
+        }
+        if (tid == 0) d.st->filter_state = MCT_PF_RESAMPLED;
+    } else {
+        for (int i = tid; i < N; i += nt) d.w[i] = sw[i];
+    }
+}
+
+// mode 0: d.H holds the classifier response; build the likelihood map ((H-min)/range)^exponent over the
+//         valid particles (ParticleFilterTracker.cpp:541-566) and use it as prob.
+// mode 1: d.H already holds prob, dense by particle (mask d.valid).
+// Then UpdateAllParticlesWeight (:680-717): w <- p*w (or p), scale clamp, Normalize, ResampleIfRequired.
+__global__ void __launch_bounds__(PF_THREADS) k_pf_update(const ObjDesc* __restrict__ descs, int mode, int smem_floats)
+{
+    extern __shared__ float smf[];
+    __shared__ float sh_f[32];
+    __shared__ double sh_d[32];
+    __shared__ int sh_i[32];
+    __shared__ int s_decide;
+    const ObjDesc& d = descs[blockIdx.x];
+    const int N = d.N, tid = threadIdx.x, nt = blockDim.x;
+    float* sw = (2 * N <= smem_floats) ? smf : d.scratch;
+    float* cdf = (2 * N <= smem_floats) ? smf + N : d.scratch + d.ld;
+
+    // 0. valid count, min / max of H over the test set
+    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+    int cnt = 0;
+    for (int i = tid; i < N; i += nt)
+        if (d.valid[i]) { float h = d.H[i]; mn = fminf(mn, h); mx = fmaxf(mx, h); cnt++; }
+    cnt = block_reduce_sum_i(cnt, sh_i);
+    if (mode == 0) {
+        mn = block_reduce_minmax(mn, false, sh_f);
+        mx = block_reduce_minmax(mx, true, sh_f);
+    }
+    if (tid == 0) {
+        d.st->n_valid = cnt; d.st->resampled = 0;
+        if (mode == 0) d.st->max_response = cnt > 0 ? mx : 0.0f;
+    }
+    if (mode == 0 && cnt == 0) return;        // reference: ASSERT abort (ParticleFilterTracker.cpp:513)
+    const double dmn = (double)mn, range = (double)mx - (double)mn;
+
+    // 1. weight update
+    for (int i = tid; i < N; i += nt) {
+        float w = d.w[i];
+        if (d.valid[i]) {
+            float p;
+            if (mode == 0) p = (range != 0) ? (float)pow(((double)d.H[i] - dmn) / range, (double)d.exponent) : 1.0f;
+            else p = d.H[i];
+            w = d.force_reset ? p : __fmul_rn(p, w);
+            float sx = d.sx[i], sy = d.sy[i];
+            scale_ratio_clamp(sx, sy);
+            d.sx[i] = sx; d.sy[i] = sy;
+        }
+        sw[i] = w;
+    }
+    __syncthreads();
+    // 2. NormalizeParticleWeights: sequential f32 total (:991-995)
+    if (tid == 0) {
+        float total = 0.0f;
+        for (int i = 0; i < N; i++) total = __fadd_rn(total, sw[i]);
+        sh_f[0] = total;
+    }
+    __syncthreads();
+    const float total = sh_f[0];
+    __syncthreads();
+    double s2 = 0.0;
+    for (int i = tid; i < N; i += nt) {
+        float w = (total != 0) ? __fdiv_rn(sw[i], total) : 1e-2f;
+        sw[i] = w;
+        s2 += (double)w * (double)w;
+    }
+    s2 = block_reduce_sum_d(s2, sh_d);
+    // 3. ResampleIfRequired, WEIGHT_BASED (:845-910)
+    if (tid == 0) {
+        int decide = 0;
+        float neff_inv = (float)s2;
+        if (d.resample && s2 != 0.0) {
+            const double thr = (double)(float)((double)N * 0.01);
+            const double m = (double)N * 1.2e-7 + 1e-6;           // rounding band of the sequential chain
+            const double hi = 1.0 / (s2 * (1.0 - m)), lo = 1.0 / (s2 * (1.0 + m));
+            if (hi < thr) decide = 1;
+            else if (lo >= thr) decide = 0;
+            else {
+                float e = 0.0f;                                    // exact reference chain
+                for (int i = 0; i < N; i++) e = (float)((double)e + (double)sw[i] * (double)sw[i]);
+                neff_inv = e;
+                decide = (e != 0) && (__fdiv_rn(1.0f, e) < (float)thr);
+            }
+        }
+        d.st->neff_inv = neff_inv;
+        s_decide = decide;
+    }
+    __syncthreads();
+    if (s_decide) {
+        resample_body(d, sw, cdf, 1, sh_f);
+        if (tid == 0) d.st->resampled = 1;
+    } else {
+        for (int i = tid; i < N; i += nt) d.w[i] = sw[i];
+    }
+}
+
+static int pf_update_smem(mct_ctx* ctx, int n_max, int* smem_floats, size_t* smem_bytes)
+{
+    // both chains' operands in shared memory when 2*N floats fit in 200 KB, else global scratch
+    size_t want = (size_t)2 * n_max * sizeof(float);
+    if (want > 200 * 1024) want = 0;
+    *smem_bytes = want;
+    *smem_floats = (int)(want / sizeof(float));
+    (void)ctx;
+    return MCT_OK;
+}
+
+int launch_pf_update(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int use_H)
+{
+    int sf; size_t sb;
+    pf_update_smem(ctx, n_max, &sf, &sb);
+    static size_t s_attr = 32 * 1024;
+    if (sb > s_attr) {
+        MCT_CUDA(ctx, cudaFuncSetAttribute(k_pf_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
+        s_attr = sb;
+    }
+    k_pf_update<<<n_obj, PF_THREADS, sb, ctx->stream>>>(d_desc, use_H ? 0 : 1, sf);
+    MCT_KERNEL_CHECK(ctx);
+    return MCT_OK;
+}
+
+// ResampleParticles(force) on its own (ParticleFilter.cpp:920-978)
+__global__ void __launch_bounds__(PF_THREADS) k_pf_resample(const ObjDesc* __restrict__ descs, int force, int smem_floats)
+{
+    extern __shared__ float smf[];
+    __shared__ float sh_f[32];
+    const ObjDesc& d = descs[blockIdx.x];
+    const int N = d.N;
+    float* sw = (2 * N <= smem_floats) ? smf : d.scratch;
+    float* cdf = (2 * N <= smem_floats) ? smf + N : d.scratch + d.ld;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) sw[i] = d.w[i];
+    __syncthreads();
+    resample_body(d, sw, cdf, force, sh_f);
+}
+int launch_pf_resample_only(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int force)
+{
+    int sf; size_t sb;
+    pf_update_smem(ctx, n_max, &sf, &sb);
+    static size_t s_attr = 32 * 1024;
+    if (sb > s_attr) {
+        MCT_CUDA(ctx, cudaFuncSetAttribute(k_pf_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
+        s_attr = sb;
+    }
+    k_pf_resample<<<n_obj, PF_THREADS, sb, ctx->stream>>>(d_desc, force, sf);
+    MCT_KERNEL_CHECK(ctx);
+    return MCT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// UpdateAllParticlesWeight takes a *compacted* prob list (ParticleFilter.cpp:696-704): the p2-th entry
+// belongs to the p2-th particle whose weight is non-zero.  Expand it to a dense array + mask.
+__global__ void __launch_bounds__(PF_THREADS) k_pf_expand_prob(const ObjDesc* __restrict__ descs,
+                                                               const float* __restrict__ prob, int n_prob, int only_nonzero)
+{
+    __shared__ int sh_i[32];
+    __shared__ int s_base;
+    const ObjDesc& d = descs[0];
+    const int N = d.N, tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < N; i0 += nt) {
+        const int i = i0 + tid;
+        int nz = 0;
+        if (i < N) nz = only_nonzero ? (d.w[i] != 0) : 1;
+        // block exclusive scan of nz
+        int v = nz;
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+        if (lane == 31) sh_i[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            int t = sh_i[lane];
+            int s = t;
+            for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += u; }
+            sh_i[lane] = s - t;        // exclusive warp offsets
+        }
+        __syncthreads();
+        const int excl = s_base + sh_i[warp] + v - nz;
+        if (i < N) {
+            const int ok = nz && excl < n_prob;
+            d.valid[i] = ok;
+            d.H[i] = ok ? prob[excl] : 0.0f;
+        }
+        __syncthreads();
+        if (tid == nt - 1) s_base = excl + nz;
+        __syncthreads();
+    }
+}
+int launch_pf_expand_prob(mct_ctx* ctx, const ObjDesc* d_desc, const float* d_prob_compact, int n_prob, int only_nonzero)
+{
+    k_pf_expand_prob<<<1, PF_THREADS, 0, ctx->stream>>>(d_desc, d_prob_compact, n_prob, only_nonzero);
+    MCT_KERNEL_CHECK(ctx);
+    return MCT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Read-out (StoreObjectState / GenerateTrainingSampleSet inputs):
+//   average        GetAverageofAllParticles (:601-633)  (f64 tree instead of the f32 chain; 1e-6 rel)
+//   ordered_first  GetOrderedUniqueParticles(0): FindOrderedUniqueParticles (:728-815)
+//   highest_close  GetHighestOrderedUniqueParticleCloseToTheGivenState (:557-593): closestDistance is
+//                  never updated, so the *last* row tied with the top weight wins.
+// PREDICTED: rows = particles sorted by weight (descending, ties by index).
+// RESAMPLED: the resample index list is non-decreasing, so sorting it is the identity; unique runs are
+//            contiguous; run weights are summed in order; the reference then pairs the states in *index*
+//            order with the weights in *sorted* order (:799-806) -- kept.
+__global__ void __launch_bounds__(PF_THREADS) k_pf_summary(const ObjDesc* __restrict__ descs)
+{
+    __shared__ float sh_f[32];
+    __shared__ double sh_d[32];
+    __shared__ int sh_i[32];
+    __shared__ int s_first, s_last;
+    const ObjDesc& d = descs[blockIdx.x];
+    const int N = d.N, tid = threadIdx.x, nt = blockDim.x;
+    mct_pf_summary* out = d.summ;
+    const int fs = d.st->filter_state;
+
+    double acc[5] = {0, 0, 0, 0, 0};
+    for (int i = tid; i < N; i += nt) {
+        const float w = d.w[i];
+        acc[0] += (double)__fmul_rn(d.cx[i], w); acc[1] += (double)__fmul_rn(d.cy[i], w);
+        acc[2] += (double)__fmul_rn(d.sx[i], w); acc[3] += (double)__fmul_rn(d.sy[i], w);
+        acc[4] += (double)w;
+    }
+    for (int q = 0; q < 5; q++) acc[q] = block_reduce_sum_d(acc[q], sh_d);
+    if (tid == 0) {
+        for (int q = 0; q < 4; q++) out->average[q] = (float)(acc[q] / acc[4]);
+        out->n_valid = d.st->n_valid; out->resampled = d.st->resampled; out->filter_state = fs;
+        out->neff_inv = d.st->neff_inv; out->max_response = d.st->max_response;
+    }
+    if (fs == MCT_PF_PREDICTED) {
+        float mx = -CUDART_INF_F;
+        for (int i = tid; i < N; i += nt) mx = fmaxf(mx, d.w[i]);
+        mx = block_reduce_minmax(mx, true, sh_f);
+        if (tid == 0) { s_first = N; s_last = -1; }
+        __syncthreads();
+        int lf = N, ll = -1;
+        for (int i = tid; i < N; i += nt) if (d.w[i] == mx) { lf = min(lf, i); ll = max(ll, i); }
+        if (lf < N) atomicMin(&s_first, lf);
+        if (ll >= 0) atomicMax(&s_last, ll);
+        __syncthreads();
+        if (tid == 0) {
+            int a = s_first < N ? s_first : 0, b = s_last >= 0 ? s_last : 0;
+            out->ordered_first[0] = d.cx[a]; out->ordered_first[1] = d.cy[a]; out->ordered_first[2] = d.sx[a];
+            out->ordered_first[3] = d.sy[a]; out->ordered_first[4] = d.w[a];
+            out->highest_close[0] = d.cx[b]; out->highest_close[1] = d.cy[b]; out->highest_close[2] = d.sx[b];
+            out->highest_close[3] = d.sy[b]; out->highest_close[4] = d.w[b];
+            out->n_unique = N;
+        }
+    } else if (fs == MCT_PF_RESAMPLED) {
+        // run weights: the run-start thread sums its run in order
+        float mx = -CUDART_INF_F;
+        int nruns = 0;
+        for (int i = tid; i < N; i += nt) {
+            const bool start = (i == 0) || (d.residx[i] != d.residx[i - 1]);
+            float rw = 0.0f;
+            if (start) {
+                nruns++;
+                rw = d.w[i];
+                for (int j = i + 1; j < N && d.residx[j] == d.residx[i]; j++) rw = __fadd_rn(rw, d.w[j]);
+                mx = fmaxf(mx, rw);
+            }
+            d.rw[i] = start ? rw : -1.0f;          // resampled-weight column doubles as run-weight scratch
+        }
+        mx = block_reduce_minmax(mx, true, sh_f);
+        nruns = block_reduce_sum_i(nruns, sh_i);
+        int ties = 0;
+        for (int i = tid; i < N; i += nt) if (d.rw[i] == mx) ties++;
+        ties = block_reduce_sum_i(ties, sh_i);
+        if (tid == 0) {
+            // row (ties-1) of the ordered-unique matrix = state of the (ties-1)-th run in index order
+            int want = ties - 1, ord = -1, b = 0;
+            if (want > 0) {
+                for (int i = 0; i < N; i++) if (d.rw[i] >= 0.0f) { ord++; if (ord == want) { b = i; break; } }
+            }
+            out->ordered_first[0] = d.cx[0]; out->ordered_first[1] = d.cy[0]; out->ordered_first[2] = d.sx[0];
+            out->ordered_first[3] = d.sy[0]; out->ordered_first[4] = mx;
+            out->highest_close[0] = d.cx[b]; out->highest_close[1] = d.cy[b]; out->highest_close[2] = d.sx[b];
+            out->highest_close[3] = d.sy[b]; out->highest_close[4] = mx;
+            out->n_unique = nruns;
+        }
+        __syncthreads();
+        for (int i = tid; i < N; i += nt) d.rw[i] = 1.0f;       // restore m_particlesResampledMatrix weights
+    } else if (tid == 0) {
+        for (int q = 0; q < 5; q++) { out->ordered_first[q] = 0; out->highest_close[q] = 0; }
+        out->n_unique = 0;
+    }
+}
+int launch_pf_summary(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max)
+{
+    (void)n_max;
+    k_pf_summary<<<n_obj, PF_THREADS, 0, ctx->stream>>>(d_desc);
+    MCT_KERNEL_CHECK(ctx);
+    return MCT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Foot point of the highest-weight particle (GetAverageParticleOnGroundMatrix,
+// ParticleFilterTracker.cpp:1223-1238; GetHighestWeightParticle :529-549 = first maximum).
+__global__ void __launch_bounds__(256) k_foot_points(const ObjDesc* __restrict__ descs, const float* __restrict__ h0,
+                                                     float* __restrict__ out)
+{
+    __shared__ float sh_f[32];
+    __shared__ int s_first;
+    const ObjDesc& d = descs[blockIdx.x];
+    const int N = d.N, tid = threadIdx.x, nt = blockDim.x;
+    float mx = -CUDART_INF_F;
+    for (int i = tid; i < N; i += nt) mx = fmaxf(mx, d.w[i]);
+    mx = block_reduce_minmax(mx, true, sh_f);
+    if (tid == 0) s_first = N;
+    __syncthreads();
+    int lf = N;
+    for (int i = tid; i < N; i += nt) if (d.w[i] == mx) lf = min(lf, i);
+    if (lf < N) atomicMin(&s_first, lf);
+    __syncthreads();
+    if (tid == 0) {
+        int a = s_first < N ? s_first : 0;
+        out[2 * blockIdx.x + 0] = d.cx[a];
+        out[2 * blockIdx.x + 1] = __fadd_rn(d.cy[a], __fdiv_rn(__fmul_rn(d.sy[a], h0[blockIdx.x]), 2.0f));
+    }
+}
+int launch_foot_points(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, const float* d_h0, float* d_out)
+{
+    k_foot_points<<<n_obj, 256, 0, ctx->stream>>>(d_desc, d_h0, d_out);
+    MCT_KERNEL_CHECK(ctx);
+    return MCT_OK;
+}

@@ -1,0 +1,771 @@
+// mct_api.cu -- C-ABI entry points (include/mct_b200.h): context, frame, classifier, particle filter and
+// the fused per-frame path.  Host logic only; every compute step is a CUDA kernel in k_*.cu.
+// There is no CPU fallback anywhere in this library.
+#include "mct_internal.cuh"
+#include <new>
+#include <vector>
+
+char g_mct_err[512] = "";
+
+#define DESC_RING 32
+#define DESC_MAX_OBJ 64
+
+struct DescRing {
+    ObjDesc* h;            // pinned [DESC_RING][DESC_MAX_OBJ]
+    ObjDesc* d;            // device [DESC_RING][DESC_MAX_OBJ]
+    cudaEvent_t ev[DESC_RING];
+    int next;
+};
+
+static DescRing* ring_of(mct_ctx* ctx) { return (DescRing*)ctx->h_desc; }
+
+// Reserve a descriptor slot: returns host pointer to fill; call desc_commit afterwards.
+static int desc_acquire(mct_ctx* ctx, ObjDesc** h, ObjDesc** d, int* slot)
+{
+    DescRing* r = ring_of(ctx);
+    int s = r->next;
+    r->next = (r->next + 1) % DESC_RING;
+    MCT_CUDA(ctx, cudaEventSynchronize(r->ev[s]));
+    *h = r->h + (size_t)s * DESC_MAX_OBJ;
+    *d = r->d + (size_t)s * DESC_MAX_OBJ;
+    *slot = s;
+    return MCT_OK;
+}
+static int desc_commit(mct_ctx* ctx, int slot, int n)
+{
+    DescRing* r = ring_of(ctx);
+    MCT_CUDA(ctx, cudaMemcpyAsync(r->d + (size_t)slot * DESC_MAX_OBJ, r->h + (size_t)slot * DESC_MAX_OBJ,
+                                  (size_t)n * sizeof(ObjDesc), cudaMemcpyHostToDevice, ctx->stream));
+    MCT_CUDA(ctx, cudaEventRecord(r->ev[slot], ctx->stream));
+    return MCT_OK;
+}
+
+// ------------------------------------------------------------------------------------------ context
+extern "C" const char* mct_version(void) { return "mct-b200 0.1 (sm_100a)"; }
+extern "C" const char* mct_last_error(mct_ctx* ctx) { return ctx ? ctx->err : g_mct_err; }
+extern "C" long long mct_launch_count(mct_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void* mct_ctx_stream(mct_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+extern "C" int mct_ctx_create(int device, void* cuda_stream, mct_ctx** out)
+{
+    if (!out) return mct_fail(nullptr, MCT_E_ARG, "mct_ctx_create: out is NULL%s");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return mct_fail(nullptr, MCT_E_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                        cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return mct_fail(nullptr, MCT_E_ARG, "device index out of range%s (%d)", "", device);
+    MCT_CUDA(nullptr, cudaSetDevice(device));
+    mct_ctx* ctx = new (std::nothrow) mct_ctx();
+    if (!ctx) return mct_fail(nullptr, MCT_E_NOMEM, "out of host memory%s");
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->device = device;
+    ctx->binimg_frame = -1;
+    if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false; }
+    else { MCT_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    DescRing* r = new (std::nothrow) DescRing();
+    if (!r) return mct_fail(nullptr, MCT_E_NOMEM, "out of host memory%s");
+    MCT_CUDA(nullptr, cudaMallocHost(&r->h, sizeof(ObjDesc) * DESC_RING * DESC_MAX_OBJ));
+    MCT_CUDA(nullptr, cudaMalloc(&r->d, sizeof(ObjDesc) * DESC_RING * DESC_MAX_OBJ));
+    for (int i = 0; i < DESC_RING; i++) MCT_CUDA(nullptr, cudaEventCreateWithFlags(&r->ev[i], cudaEventDisableTiming));
+    r->next = 0;
+    ctx->h_desc = r;
+    ctx->summ_cap = DESC_MAX_OBJ;
+    MCT_CUDA(nullptr, cudaMallocHost(&ctx->h_summ, sizeof(mct_pf_summary) * DESC_MAX_OBJ));
+    *out = ctx;
+    return MCT_OK;
+}
+
+extern "C" int mct_ctx_destroy(mct_ctx* ctx)
+{
+    if (!ctx) return MCT_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 4; i++) if (ctx->own_planes[i]) cudaFree(ctx->own_planes[i]);
+    if (ctx->ii_base) cudaFree(ctx->ii_base);
+    if (ctx->bandsum) cudaFree(ctx->bandsum);
+    if (ctx->binimg) cudaFree(ctx->binimg);
+    if (ctx->d_tmp) cudaFree(ctx->d_tmp);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    if (ctx->h_summ) cudaFreeHost(ctx->h_summ);
+    DescRing* r = ring_of(ctx);
+    if (r) {
+        for (int i = 0; i < DESC_RING; i++) cudaEventDestroy(r->ev[i]);
+        cudaFreeHost(r->h); cudaFree(r->d);
+        delete r;
+    }
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return MCT_OK;
+}
+
+extern "C" int mct_sync(mct_ctx* ctx)
+{
+    if (!ctx) return MCT_E_ARG;
+    MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MCT_OK;
+}
+
+static int ensure_tmp(mct_ctx* ctx, size_t bytes)
+{
+    if (bytes <= ctx->tmp_cap) return MCT_OK;
+    if (ctx->d_tmp) { MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_tmp); }
+    MCT_CUDA(ctx, cudaMalloc(&ctx->d_tmp, bytes));
+    ctx->tmp_cap = bytes;
+    return MCT_OK;
+}
+
+// ------------------------------------------------------------------------------------------ frame
+extern "C" int mct_frame_set(mct_ctx* ctx, const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2,
+                             int W, int H, int pitch, int is_device)
+{
+    if (!ctx) return MCT_E_ARG;
+    if (!gray || W < 4 || H < 4 || pitch < W) return mct_fail(ctx, MCT_E_ARG, "mct_frame_set: bad frame geometry%s");
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint8_t* src[4] = {gray, c0, c1, c2};
+    if (is_device) {
+        ctx->gray = gray; ctx->c0 = c0; ctx->c1 = c1; ctx->c2 = c2;
+        ctx->pitch = pitch;
+    } else {
+        int dp = round_up(W, 16);
+        size_t need = (size_t)dp * H;
+        if (need > ctx->own_plane_cap) {
+            MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            for (int i = 0; i < 4; i++) {
+                if (ctx->own_planes[i]) cudaFree(ctx->own_planes[i]);
+                MCT_CUDA(ctx, cudaMalloc(&ctx->own_planes[i], need));
+            }
+            ctx->own_plane_cap = need;
+        }
+        for (int i = 0; i < 4; i++)
+            if (src[i])
+                MCT_CUDA(ctx, cudaMemcpy2DAsync(ctx->own_planes[i], dp, src[i], pitch, W, H, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->gray = ctx->own_planes[0];
+        ctx->c0 = c0 ? ctx->own_planes[1] : nullptr;
+        ctx->c1 = c1 ? ctx->own_planes[2] : nullptr;
+        ctx->c2 = c2 ? ctx->own_planes[3] : nullptr;
+        ctx->pitch = dp;
+    }
+    ctx->W = W; ctx->H = H;
+    int iip = round_up(W + 1, 4);
+    size_t need = (size_t)MCT_II_LEAD + (size_t)(H + 1) * iip + 4;
+    if (need > ctx->ii_cap || iip != ctx->ii_pitch) {
+        if (need > ctx->ii_cap) {
+            if (ctx->ii_base) { MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->ii_base); }
+            MCT_CUDA(ctx, cudaMalloc(&ctx->ii_base, need * sizeof(float)));
+            ctx->ii_cap = need;
+        }
+        ctx->ii_pitch = iip;
+    }
+    ctx->frame_id++;
+    return launch_integral(ctx);
+}
+
+extern "C" int mct_frame_get_integral(mct_ctx* ctx, float* out_host)
+{
+    if (!ctx || !out_host) return MCT_E_ARG;
+    if (!ctx->ii_base || ctx->frame_id == 0) return mct_fail(ctx, MCT_E_STATE, "no frame set%s");
+    MCT_CUDA(ctx, cudaMemcpy2DAsync(out_host, (size_t)(ctx->W + 1) * sizeof(float), ctx->ii_base + MCT_II_LEAD,
+                                    (size_t)ctx->ii_pitch * sizeof(float), (size_t)(ctx->W + 1) * sizeof(float),
+                                    ctx->H + 1, cudaMemcpyDeviceToHost, ctx->stream));
+    return mct_sync(ctx);
+}
+
+extern "C" int mct_sum_rects(mct_ctx* ctx, const int* rects, int n, float* out_host)
+{
+    if (!ctx || (n > 0 && (!rects || !out_host))) return MCT_E_ARG;
+    if (!ctx->ii_base || ctx->frame_id == 0) return mct_fail(ctx, MCT_E_STATE, "no frame set%s");
+    if (n <= 0) return MCT_OK;
+    int rc = ensure_tmp(ctx, (size_t)n * 5 * sizeof(float));
+    if (rc) return rc;
+    int* d_r = (int*)ctx->d_tmp;
+    float* d_o = ctx->d_tmp + (size_t)4 * n;
+    MCT_CUDA(ctx, cudaMemcpyAsync(d_r, rects, (size_t)n * 4 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = launch_sum_rects(ctx, d_r, n, d_o))) return rc;
+    MCT_CUDA(ctx, cudaMemcpyAsync(out_host, d_o, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    return mct_sync(ctx);
+}
+
+// ------------------------------------------------------------------------------------------ classifier
+static int clf_ensure_test(mct_clf* clf, int n, int rows)
+{
+    mct_ctx* ctx = clf->ctx;
+    if (n > clf->test_cap) {
+        MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        int cap = round_up(n, 256);
+        if (clf->d_col) { cudaFree(clf->d_col); cudaFree(clf->d_row); cudaFree(clf->d_sx); cudaFree(clf->d_sy); cudaFree(clf->d_H); }
+        MCT_CUDA(ctx, cudaMalloc(&clf->d_col, (size_t)cap * 4)); MCT_CUDA(ctx, cudaMalloc(&clf->d_row, (size_t)cap * 4));
+        MCT_CUDA(ctx, cudaMalloc(&clf->d_sx, (size_t)cap * 4)); MCT_CUDA(ctx, cudaMalloc(&clf->d_sy, (size_t)cap * 4));
+        MCT_CUDA(ctx, cudaMalloc(&clf->d_H, (size_t)cap * 4));
+        clf->test_cap = cap;
+    }
+    int ldN = round_up(n > 0 ? n : 1, 32);
+    size_t need = (size_t)(rows > 0 ? rows : 1) * ldN;
+    if (need > clf->featN_cap) {
+        MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (clf->d_featN) cudaFree(clf->d_featN);
+        MCT_CUDA(ctx, cudaMalloc(&clf->d_featN, need * sizeof(float)));
+        clf->featN_cap = need;
+    }
+    clf->ldN = ldN;
+    return MCT_OK;
+}
+
+static int upload_boxes(mct_ctx* ctx, const mct_boxes* b, int* d_col, int* d_row, float* d_sx, float* d_sy, int off)
+{
+    if (b->n <= 0) return MCT_OK;
+    if (!b->col || !b->row || !b->sx || !b->sy) return mct_fail(ctx, MCT_E_ARG, "box arrays are NULL%s");
+    size_t bytes = (size_t)b->n * 4;
+    MCT_CUDA(ctx, cudaMemcpyAsync(d_col + off, b->col, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    MCT_CUDA(ctx, cudaMemcpyAsync(d_row + off, b->row, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    MCT_CUDA(ctx, cudaMemcpyAsync(d_sx + off, b->sx, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    MCT_CUDA(ctx, cudaMemcpyAsync(d_sy + off, b->sy, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return MCT_OK;
+}
+
+extern "C" int mct_classifier_create(mct_ctx* ctx, const mct_clf_params* p, const mct_haar_table* haar, mct_clf** out)
+{
+    if (!ctx || !p || !out) return MCT_E_ARG;
+    *out = nullptr;
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    int ncol = p->n_bins * p->n_bins * p->n_bins;
+    int n_haar = 0, n_color = 0;
+    switch (p->feature_type) {
+        case MCT_FEAT_HAAR: n_haar = p->n_haar; break;
+        case MCT_FEAT_CCH: n_color = 11; break;
+        case MCT_FEAT_MDCH: n_color = ncol; break;
+        case MCT_FEAT_HAAR_MDCH: n_haar = p->n_haar; n_color = ncol; break;
+        default: return mct_fail(ctx, MCT_E_ARG, "unknown feature type%s (%d)", "", p->feature_type);
+    }
+    if ((p->feature_type == MCT_FEAT_MDCH || p->feature_type == MCT_FEAT_HAAR_MDCH) &&
+        (p->n_bins < 1 || p->n_bins > 8 || 256 % p->n_bins != 0))
+        return mct_fail(ctx, MCT_E_UNSUPPORTED, "Color_Number_Of_Bins must divide 256 and be <= 8%s (%d)", "", p->n_bins);
+    if (p->weak_type < 0 || p->weak_type > 2) return mct_fail(ctx, MCT_E_ARG, "unknown weak classifier type%s (%d)", "", p->weak_type);
+    if (p->strong_type != MCT_STRONG_MILBOOST && p->strong_type != MCT_STRONG_MILANYBOOST)
+        return mct_fail(ctx, MCT_E_UNSUPPORTED, "strong classifier type not on the hot path%s (%d)", "", p->strong_type);
+    if (n_haar > 0 && (!haar || haar->n_features != n_haar || !haar->nrect || !haar->rects || !haar->weights))
+        return mct_fail(ctx, MCT_E_ARG, "Haar table missing or of the wrong size%s");
+    if (p->w0 < 4 || p->h0 < 4) return mct_fail(ctx, MCT_E_ARG, "object blob too small%s");
+    int F = n_haar + n_color;
+    if (F < 1) return mct_fail(ctx, MCT_E_ARG, "classifier has no features%s");
+    mct_clf* c = new (std::nothrow) mct_clf();
+    if (!c) return mct_fail(ctx, MCT_E_NOMEM, "out of host memory%s");
+    memset(c, 0, sizeof(*c));
+    c->ctx = ctx; c->p = *p; c->F = F; c->n_haar = n_haar; c->n_color = n_color;
+    int K = p->n_selected;
+    if (K > F || K < 1) K = F / 2;                       // StrongClassifierBase.cpp:20-23
+    if (K < 1) K = 1;
+    c->K = K;
+    c->max_train = p->max_train > 0 ? p->max_train : 4096;
+    c->ldT = round_up(c->max_train, 32);
+    if (n_haar > 0) {
+        std::vector<int4> r((size_t)n_haar * MCT_MAX_RECTS);
+        for (int f = 0; f < n_haar; f++) {
+            if (haar->nrect[f] < 1 || haar->nrect[f] > MCT_MAX_RECTS) { delete c; return mct_fail(ctx, MCT_E_ARG, "Haar feature with a bad rect count%s (%d)", "", f); }
+            for (int k = 0; k < MCT_MAX_RECTS; k++) {
+                const int* s = haar->rects + ((size_t)f * MCT_MAX_RECTS + k) * 4;
+                r[(size_t)f * MCT_MAX_RECTS + k] = make_int4(s[0], s[1], s[2], s[3]);
+            }
+        }
+        MCT_CUDA(ctx, cudaMalloc(&c->d_rects, r.size() * sizeof(int4)));
+        MCT_CUDA(ctx, cudaMalloc(&c->d_wts, (size_t)n_haar * MCT_MAX_RECTS * 4));
+        MCT_CUDA(ctx, cudaMalloc(&c->d_nrect, (size_t)n_haar * 4));
+        MCT_CUDA(ctx, cudaMemcpy(c->d_rects, r.data(), r.size() * sizeof(int4), cudaMemcpyHostToDevice));
+        MCT_CUDA(ctx, cudaMemcpy(c->d_wts, haar->weights, (size_t)n_haar * MCT_MAX_RECTS * 4, cudaMemcpyHostToDevice));
+        MCT_CUDA(ctx, cudaMemcpy(c->d_nrect, haar->nrect, (size_t)n_haar * 4, cudaMemcpyHostToDevice));
+    }
+    // weak state: mu = 0, sig = 1 (OnlineStumpsWeakClassifier.cpp:53-60); derived rows filled by the first Update
+    std::vector<float> w((size_t)8 * F, 0.0f);
+    for (int f = 0; f < F; f++) { w[(size_t)2 * F + f] = 1.0f; w[(size_t)3 * F + f] = 1.0f; }
+    MCT_CUDA(ctx, cudaMalloc(&c->d_weak, w.size() * 4));
+    MCT_CUDA(ctx, cudaMemcpy(c->d_weak, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+    MCT_CUDA(ctx, cudaMalloc(&c->d_trained, (size_t)F * 4));
+    MCT_CUDA(ctx, cudaMemset(c->d_trained, 0, (size_t)F * 4));
+    MCT_CUDA(ctx, cudaMalloc(&c->d_sel, (size_t)F * 4));
+    MCT_CUDA(ctx, cudaMemset(c->d_sel, 0, (size_t)F * 4));
+    MCT_CUDA(ctx, cudaMalloc(&c->d_nsel, 4));
+    MCT_CUDA(ctx, cudaMemset(c->d_nsel, 0, 4));
+    MCT_CUDA(ctx, cudaMalloc(&c->d_tcol, (size_t)c->ldT * 4)); MCT_CUDA(ctx, cudaMalloc(&c->d_trow, (size_t)c->ldT * 4));
+    MCT_CUDA(ctx, cudaMalloc(&c->d_tsx, (size_t)c->ldT * 4)); MCT_CUDA(ctx, cudaMalloc(&c->d_tsy, (size_t)c->ldT * 4));
+    MCT_CUDA(ctx, cudaMalloc(&c->d_tw, (size_t)c->ldT * 4));
+    MCT_CUDA(ctx, cudaMalloc(&c->d_featT, (size_t)F * c->ldT * 4));
+    MCT_CUDA(ctx, cudaMalloc(&c->d_pred, (size_t)F * c->ldT * 4));
+    if (n_color > 0) {
+        std::vector<int> id(n_color);
+        for (int i = 0; i < n_color; i++) id[i] = i;
+        MCT_CUDA(ctx, cudaMalloc(&c->d_colorrow, (size_t)n_color * 4));
+        MCT_CUDA(ctx, cudaMemcpy(c->d_colorrow, id.data(), (size_t)n_color * 4, cudaMemcpyHostToDevice));
+    }
+    *out = c;
+    return MCT_OK;
+}
+
+extern "C" int mct_classifier_destroy(mct_clf* c)
+{
+    if (!c) return MCT_OK;
+    cudaSetDevice(c->ctx->device);
+    cudaStreamSynchronize(c->ctx->stream);
+    void* ptrs[] = {c->d_rects, c->d_wts, c->d_nrect, c->d_weak, c->d_trained, c->d_sel, c->d_nsel, c->d_tcol, c->d_trow,
+                    c->d_tsx, c->d_tsy, c->d_tw, c->d_featT, c->d_pred, c->d_col, c->d_row, c->d_sx, c->d_sy, c->d_featN,
+                    c->d_H, c->d_outbins, c->d_colorrow};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    delete c;
+    return MCT_OK;
+}
+
+extern "C" int mct_classifier_num_features(mct_clf* c) { return c ? c->F : MCT_E_ARG; }
+extern "C" int mct_classifier_set_cluster(mct_clf* c, int cluster)
+{
+    if (!c || cluster < 0 || cluster > 16 || (cluster & (cluster - 1))) return MCT_E_ARG;
+    c->cluster = cluster;
+    return MCT_OK;
+}
+
+static int need_frame(mct_clf* c)
+{
+    mct_ctx* ctx = c->ctx;
+    if (ctx->frame_id == 0) return mct_fail(ctx, MCT_E_STATE, "no frame set%s");
+    if (c->n_color > 0 && c->p.feature_type != MCT_FEAT_CCH && (!ctx->c0 || !ctx->c1 || !ctx->c2))
+        return mct_fail(ctx, MCT_E_STATE, "colour planes not set for a colour-histogram classifier%s");
+    if (c->p.feature_type == MCT_FEAT_CCH && !ctx->c0) return mct_fail(ctx, MCT_E_STATE, "hue plane not set%s");
+    return MCT_OK;
+}
+
+extern "C" int mct_features_compute(mct_clf* c, const mct_boxes* boxes, float* out_host)
+{
+    if (!c || !boxes || (boxes->n > 0 && !out_host)) return MCT_E_ARG;
+    mct_ctx* ctx = c->ctx;
+    int rc = need_frame(c);
+    if (rc) return rc;
+    const int n = boxes->n;
+    if (n <= 0) return MCT_OK;
+    if ((rc = clf_ensure_test(c, n, c->F))) return rc;
+    if ((rc = upload_boxes(ctx, boxes, c->d_col, c->d_row, c->d_sx, c->d_sy, 0))) return rc;
+    if ((rc = mct_feature_matrix_full(c, c->d_col, c->d_row, c->d_sx, c->d_sy, n, c->d_featN, c->ldN))) return rc;
+    MCT_CUDA(ctx, cudaMemcpy2DAsync(out_host, (size_t)n * 4, c->d_featN, (size_t)c->ldN * 4, (size_t)n * 4, c->F,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+    return mct_sync(ctx);
+}
+
+static int clf_train_common(mct_clf* c, int P, int Nn, const float* wpos, const float* wneg)
+{
+    mct_ctx* ctx = c->ctx;
+    int has_w = (wpos && wneg) ? 1 : 0;
+    if (has_w) {
+        MCT_CUDA(ctx, cudaMemcpyAsync(c->d_tw, wpos, (size_t)P * 4, cudaMemcpyHostToDevice, ctx->stream));
+        MCT_CUDA(ctx, cudaMemcpyAsync(c->d_tw + P, wneg, (size_t)Nn * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    int rc;
+    if ((rc = launch_weak_update(c, P, Nn, has_w))) return rc;
+    if ((rc = launch_mil_select(c, P, Nn))) return rc;
+    c->lastP = P; c->lastNn = Nn;
+    return MCT_OK;
+}
+
+extern "C" int mct_classifier_update(mct_clf* c, const mct_boxes* pos, const mct_boxes* neg, const float* wpos, const float* wneg)
+{
+    if (!c || !pos || !neg) return MCT_E_ARG;
+    mct_ctx* ctx = c->ctx;
+    int rc = need_frame(c);
+    if (rc) return rc;
+    const int P = pos->n, Nn = neg->n;
+    if (P < 1 || Nn < 1) return mct_fail(ctx, MCT_E_ARG, "Update needs at least one positive and one negative sample%s");
+    if (P + Nn > c->max_train) return mct_fail(ctx, MCT_E_ARG, "training set exceeds max_train%s (%d)", "", P + Nn);
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if ((rc = upload_boxes(ctx, pos, c->d_tcol, c->d_trow, c->d_tsx, c->d_tsy, 0))) return rc;
+    if ((rc = upload_boxes(ctx, neg, c->d_tcol, c->d_trow, c->d_tsx, c->d_tsy, P))) return rc;
+    if ((rc = mct_feature_matrix_full(c, c->d_tcol, c->d_trow, c->d_tsx, c->d_tsy, P + Nn, c->d_featT, c->ldT))) return rc;
+    return clf_train_common(c, P, Nn, wpos, wneg);
+}
+
+extern "C" int mct_classifier_update_from_features(mct_clf* c, const float* fpos, int P, const float* fneg, int Nn,
+                                                   const float* wpos, const float* wneg)
+{
+    if (!c || !fpos || !fneg) return MCT_E_ARG;
+    mct_ctx* ctx = c->ctx;
+    if (P < 1 || Nn < 1) return mct_fail(ctx, MCT_E_ARG, "Update needs at least one positive and one negative sample%s");
+    if (P + Nn > c->max_train) return mct_fail(ctx, MCT_E_ARG, "training set exceeds max_train%s (%d)", "", P + Nn);
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    MCT_CUDA(ctx, cudaMemcpy2DAsync(c->d_featT, (size_t)c->ldT * 4, fpos, (size_t)P * 4, (size_t)P * 4, c->F,
+                                    cudaMemcpyHostToDevice, ctx->stream));
+    MCT_CUDA(ctx, cudaMemcpy2DAsync(c->d_featT + P, (size_t)c->ldT * 4, fneg, (size_t)Nn * 4, (size_t)Nn * 4, c->F,
+                                    cudaMemcpyHostToDevice, ctx->stream));
+    return clf_train_common(c, P, Nn, wpos, wneg);
+}
+
+static void fill_clf_desc(ObjDesc* d, mct_clf* c)
+{
+    d->rects = c->d_rects; d->wts = c->d_wts; d->nrect = c->d_nrect;
+    d->weak = c->d_weak; d->sel = c->d_sel; d->nsel = c->d_nsel;
+    d->featN = c->d_featN; d->ldN = c->ldN; d->n_color_rows = c->n_color;
+    d->colorrow = c->d_colorrow; d->outbins = nullptr;
+    d->F = c->F; d->n_haar = c->n_haar; d->nb = c->p.n_bins; d->weak_type = c->p.weak_type;
+    d->feature_type = c->p.feature_type; d->cch_mode = c->p.cch_mode; d->K = c->K;
+}
+
+static int classify_boxes_on_device(mct_clf* c, int n, int from_matrix, int log_ratio)
+{
+    mct_ctx* ctx = c->ctx;
+    ObjDesc *h, *d; int slot, rc;
+    if ((rc = desc_acquire(ctx, &h, &d, &slot))) return rc;
+    memset(h, 0, sizeof(ObjDesc));
+    fill_clf_desc(h, c);
+    h->N = n; h->ld = c->ldN;
+    h->col = c->d_col; h->row = c->d_row; h->sx = c->d_sx; h->sy = c->d_sy; h->valid = nullptr; h->H = c->d_H;
+    if ((rc = desc_commit(ctx, slot, 1))) return rc;
+    return launch_classify(ctx, d, 1, n, c->K, from_matrix, log_ratio);
+}
+
+extern "C" int mct_classifier_classify(mct_clf* c, const mct_boxes* boxes, int log_ratio, float* out_host)
+{
+    if (!c || !boxes || (boxes->n > 0 && !out_host)) return MCT_E_ARG;
+    mct_ctx* ctx = c->ctx;
+    int rc = need_frame(c);
+    if (rc) return rc;
+    const int n = boxes->n;
+    if (n <= 0) return MCT_OK;
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if ((rc = clf_ensure_test(c, n, c->n_color))) return rc;
+    if ((rc = upload_boxes(ctx, boxes, c->d_col, c->d_row, c->d_sx, c->d_sy, 0))) return rc;
+    if (c->n_color > 0 &&
+        (rc = mct_feature_color_rows(c, c->d_col, c->d_row, c->d_sx, c->d_sy, nullptr, n, nullptr, c->n_color, c->d_featN, c->ldN)))
+        return rc;
+    if ((rc = classify_boxes_on_device(c, n, 0, log_ratio))) return rc;
+    MCT_CUDA(ctx, cudaMemcpyAsync(out_host, c->d_H, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return mct_sync(ctx);
+}
+
+extern "C" int mct_classifier_classify_from_features(mct_clf* c, const float* feat, int n, int log_ratio, float* out_host)
+{
+    if (!c || !feat || n < 0 || (n > 0 && !out_host)) return MCT_E_ARG;
+    mct_ctx* ctx = c->ctx;
+    if (n == 0) return MCT_OK;
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = clf_ensure_test(c, n, c->F))) return rc;
+    MCT_CUDA(ctx, cudaMemcpy2DAsync(c->d_featN, (size_t)c->ldN * 4, feat, (size_t)n * 4, (size_t)n * 4, c->F,
+                                    cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = classify_boxes_on_device(c, n, 1, log_ratio))) return rc;
+    MCT_CUDA(ctx, cudaMemcpyAsync(out_host, c->d_H, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return mct_sync(ctx);
+}
+
+extern "C" int mct_classifier_get_selectors(mct_clf* c, int* idx_host, int* n)
+{
+    if (!c || !idx_host || !n) return MCT_E_ARG;
+    mct_ctx* ctx = c->ctx;
+    MCT_CUDA(ctx, cudaMemcpyAsync(n, c->d_nsel, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    int rc = mct_sync(ctx);
+    if (rc) return rc;
+    if (*n > 0) {
+        MCT_CUDA(ctx, cudaMemcpyAsync(idx_host, c->d_sel, (size_t)(*n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        return mct_sync(ctx);
+    }
+    return MCT_OK;
+}
+extern "C" int mct_classifier_get_weak_state(mct_clf* c, float* out)
+{
+    if (!c || !out) return MCT_E_ARG;
+    mct_ctx* ctx = c->ctx;
+    MCT_CUDA(ctx, cudaMemcpyAsync(out, c->d_weak, (size_t)8 * c->F * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return mct_sync(ctx);
+}
+extern "C" int mct_classifier_get_predictions(mct_clf* c, float* out, int* P, int* Nn)
+{
+    if (!c || !out || !P || !Nn) return MCT_E_ARG;
+    mct_ctx* ctx = c->ctx;
+    *P = c->lastP; *Nn = c->lastNn;
+    int M = c->lastP + c->lastNn;
+    if (M <= 0) return MCT_OK;
+    MCT_CUDA(ctx, cudaMemcpy2DAsync(out, (size_t)M * 4, c->d_pred, (size_t)c->ldT * 4, (size_t)M * 4, c->F,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+    return mct_sync(ctx);
+}
+
+// ------------------------------------------------------------------------------------------ particle filter
+extern "C" int mct_pf_create(mct_ctx* ctx, int N, float image_w, float image_h, mct_pf** out)
+{
+    if (!ctx || !out || N < 1) return MCT_E_ARG;
+    *out = nullptr;
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    mct_pf* p = new (std::nothrow) mct_pf();
+    if (!p) return mct_fail(ctx, MCT_E_NOMEM, "out of host memory%s");
+    memset(p, 0, sizeof(*p));
+    p->ctx = ctx; p->N = N; p->ld = round_up(N, 32); p->img_w = image_w; p->img_h = image_h;
+    size_t ld = p->ld;
+    MCT_CUDA(ctx, cudaMalloc(&p->d_state, 5 * ld * 4)); MCT_CUDA(ctx, cudaMalloc(&p->d_res, 5 * ld * 4));
+    MCT_CUDA(ctx, cudaMalloc(&p->d_residx, ld * 4));
+    MCT_CUDA(ctx, cudaMalloc(&p->d_col, ld * 4)); MCT_CUDA(ctx, cudaMalloc(&p->d_row, ld * 4));
+    MCT_CUDA(ctx, cudaMalloc(&p->d_valid, ld * 4)); MCT_CUDA(ctx, cudaMalloc(&p->d_H, ld * 4));
+    MCT_CUDA(ctx, cudaMalloc(&p->d_noise, 4 * ld * 4)); MCT_CUDA(ctx, cudaMalloc(&p->d_prob, ld * 4));
+    MCT_CUDA(ctx, cudaMalloc(&p->d_scratch, 2 * ld * 4));
+    MCT_CUDA(ctx, cudaMalloc(&p->d_st, sizeof(PfDev))); MCT_CUDA(ctx, cudaMemset(p->d_st, 0, sizeof(PfDev)));
+    MCT_CUDA(ctx, cudaMalloc(&p->d_summ, sizeof(mct_pf_summary)));
+    MCT_CUDA(ctx, cudaMemset(p->d_summ, 0, sizeof(mct_pf_summary)));
+    MCT_CUDA(ctx, cudaMemset(p->d_state, 0, 5 * ld * 4)); MCT_CUDA(ctx, cudaMemset(p->d_res, 0, 5 * ld * 4));
+    MCT_CUDA(ctx, cudaMemset(p->d_residx, 0, ld * 4)); MCT_CUDA(ctx, cudaMemset(p->d_valid, 0, ld * 4));
+    MCT_CUDA(ctx, cudaMemset(p->d_H, 0, ld * 4));
+    *out = p;
+    return MCT_OK;
+}
+extern "C" int mct_pf_destroy(mct_pf* p)
+{
+    if (!p) return MCT_OK;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    void* ptrs[] = {p->d_state, p->d_res, p->d_residx, p->d_col, p->d_row, p->d_valid, p->d_H, p->d_noise, p->d_prob,
+                    p->d_scratch, p->d_st, p->d_summ};
+    for (void* q : ptrs) if (q) cudaFree(q);
+    delete p;
+    return MCT_OK;
+}
+
+static void fill_pf_desc(ObjDesc* d, mct_pf* p)
+{
+    size_t ld = p->ld;
+    d->cx = p->d_state; d->cy = p->d_state + ld; d->sx = p->d_state + 2 * ld; d->sy = p->d_state + 3 * ld; d->w = p->d_state + 4 * ld;
+    d->rcx = p->d_res; d->rcy = p->d_res + ld; d->rsx = p->d_res + 2 * ld; d->rsy = p->d_res + 3 * ld; d->rw = p->d_res + 4 * ld;
+    d->residx = p->d_residx; d->col = p->d_col; d->row = p->d_row; d->valid = p->d_valid;
+    d->H = p->d_H; d->noise = p->d_noise; d->scratch = p->d_scratch; d->st = p->d_st; d->summ = p->d_summ;
+    d->N = p->N; d->ld = p->ld;
+    d->img_w = p->img_w; d->img_h = p->img_h; d->msc = p->msc; d->maxs = p->maxs; d->mins = p->mins;
+    d->exponent = 20; d->force_reset = 0; d->resample = 1;
+}
+
+// host staging of an [N][5] row-major matrix <-> device SoA
+static int pf_upload_matrix(mct_pf* p, float* d_dst, const float* src_Nx5)
+{
+    mct_ctx* ctx = p->ctx;
+    std::vector<float> soa((size_t)5 * p->ld, 0.0f);
+    for (int i = 0; i < p->N; i++)
+        for (int j = 0; j < 5; j++) soa[(size_t)j * p->ld + i] = src_Nx5[(size_t)i * 5 + j];
+    MCT_CUDA(ctx, cudaMemcpyAsync(d_dst, soa.data(), soa.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    return mct_sync(ctx);
+}
+static int pf_download_matrix(mct_pf* p, const float* d_src, float* dst_Nx5)
+{
+    mct_ctx* ctx = p->ctx;
+    std::vector<float> soa((size_t)5 * p->ld);
+    MCT_CUDA(ctx, cudaMemcpyAsync(soa.data(), d_src, soa.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    int rc = mct_sync(ctx);
+    if (rc) return rc;
+    for (int i = 0; i < p->N; i++)
+        for (int j = 0; j < 5; j++) dst_Nx5[(size_t)i * 5 + j] = soa[(size_t)j * p->ld + i];
+    return MCT_OK;
+}
+
+extern "C" int mct_pf_initialize(mct_pf* p, float cx, float cy, float sx, float sy, float msc, float maxs, float mins)
+{
+    if (!p) return MCT_E_ARG;
+    mct_ctx* ctx = p->ctx;
+    if (msc < 0 || !(maxs > 0 && maxs > sx && maxs > sy) || !(mins > 0 && mins < sx && mins < sy))
+        return mct_fail(ctx, MCT_E_ARG, "ParticleFilter::Initialize: scale limits violated%s");
+    p->msc = msc; p->maxs = maxs; p->mins = mins;
+    std::vector<float> m((size_t)p->N * 5);
+    for (int i = 0; i < p->N; i++) { m[i * 5 + 0] = cx; m[i * 5 + 1] = cy; m[i * 5 + 2] = sx; m[i * 5 + 3] = sy; m[i * 5 + 4] = 1.0f; }
+    int rc;
+    if ((rc = pf_upload_matrix(p, p->d_res, m.data()))) return rc;
+    if ((rc = pf_upload_matrix(p, p->d_state, m.data()))) return rc;
+    PfDev st; memset(&st, 0, sizeof(st)); st.filter_state = MCT_PF_INIT;
+    MCT_CUDA(ctx, cudaMemcpyAsync(p->d_st, &st, sizeof(st), cudaMemcpyHostToDevice, ctx->stream));
+    p->initialized = 1;
+    return mct_sync(ctx);
+}
+
+extern "C" int mct_pf_get_state(mct_pf* p, float* out) { return (!p || !out) ? MCT_E_ARG : pf_download_matrix(p, p->d_state, out); }
+extern "C" int mct_pf_get_resampled(mct_pf* p, float* out) { return (!p || !out) ? MCT_E_ARG : pf_download_matrix(p, p->d_res, out); }
+extern "C" int mct_pf_set_state(mct_pf* p, const float* in, int filter_state)
+{
+    if (!p || !in) return MCT_E_ARG;
+    mct_ctx* ctx = p->ctx;
+    int rc = pf_upload_matrix(p, p->d_state, in);
+    if (rc) return rc;
+    MCT_CUDA(ctx, cudaMemcpyAsync(&p->d_st->filter_state, &filter_state, 4, cudaMemcpyHostToDevice, ctx->stream));
+    return mct_sync(ctx);
+}
+extern "C" int mct_pf_get_resample_indices(mct_pf* p, int* out)
+{
+    if (!p || !out) return MCT_E_ARG;
+    mct_ctx* ctx = p->ctx;
+    MCT_CUDA(ctx, cudaMemcpyAsync(out, p->d_residx, (size_t)p->N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return mct_sync(ctx);
+}
+
+static int pf_single_desc(mct_pf* p, ObjDesc** d_out, float w0, float h0, int force_reset, int resample, float u01)
+{
+    mct_ctx* ctx = p->ctx;
+    ObjDesc *h, *d; int slot, rc;
+    if ((rc = desc_acquire(ctx, &h, &d, &slot))) return rc;
+    memset(h, 0, sizeof(ObjDesc));
+    fill_pf_desc(h, p);
+    h->w0 = w0; h->h0 = h0; h->force_reset = force_reset; h->resample = resample; h->u01 = u01;
+    if ((rc = desc_commit(ctx, slot, 1))) return rc;
+    *d_out = d;
+    return MCT_OK;
+}
+
+extern "C" int mct_pf_predict(mct_pf* p, const float* noise, int noise_is_device, float w0, float h0)
+{
+    if (!p || !noise) return MCT_E_ARG;
+    mct_ctx* ctx = p->ctx;
+    if (!p->initialized) return mct_fail(ctx, MCT_E_STATE, "particle filter not initialised%s");
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    MCT_CUDA(ctx, cudaMemcpyAsync(p->d_noise, noise, (size_t)4 * p->N * 4,
+                                  noise_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    ObjDesc* d; int rc;
+    if ((rc = pf_single_desc(p, &d, w0, h0, 0, 1, 0.0f))) return rc;
+    if ((rc = launch_pf_predict(ctx, d, 1, p->N))) return rc;
+    return mct_sync(ctx);     // the host noise buffer may be reused by the caller
+}
+
+extern "C" int mct_pf_update_all_weights(mct_pf* p, const float* prob, int n_prob, int only_nonzero, int force_reset,
+                                         int resample, float u01, int* resampled)
+{
+    if (!p || (n_prob > 0 && !prob)) return MCT_E_ARG;
+    mct_ctx* ctx = p->ctx;
+    if (!p->initialized) return mct_fail(ctx, MCT_E_STATE, "particle filter not initialised%s");
+    if (n_prob > p->N) return mct_fail(ctx, MCT_E_ARG, "more probabilities than particles%s");
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_prob > 0) MCT_CUDA(ctx, cudaMemcpyAsync(p->d_prob, prob, (size_t)n_prob * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ObjDesc* d; int rc;
+    if ((rc = pf_single_desc(p, &d, 0, 0, force_reset, resample, u01))) return rc;
+    if ((rc = launch_pf_expand_prob(ctx, d, p->d_prob, n_prob, only_nonzero))) return rc;
+    if ((rc = launch_pf_update(ctx, d, 1, p->N, 0))) return rc;
+    PfDev st;
+    MCT_CUDA(ctx, cudaMemcpyAsync(&st, p->d_st, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = mct_sync(ctx))) return rc;
+    if (resampled) *resampled = st.resampled;
+    return MCT_OK;
+}
+
+extern "C" int mct_pf_resample(mct_pf* p, int force, float u01)
+{
+    if (!p) return MCT_E_ARG;
+    mct_ctx* ctx = p->ctx;
+    if (!p->initialized) return mct_fail(ctx, MCT_E_STATE, "particle filter not initialised%s");
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    ObjDesc* d; int rc;
+    if ((rc = pf_single_desc(p, &d, 0, 0, 0, 1, u01))) return rc;
+    if ((rc = launch_pf_resample_only(ctx, d, 1, p->N, force))) return rc;
+    return mct_sync(ctx);
+}
+
+extern "C" int mct_pf_get_summary(mct_pf* p, mct_pf_summary* out)
+{
+    if (!p || !out) return MCT_E_ARG;
+    mct_ctx* ctx = p->ctx;
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    ObjDesc* d; int rc;
+    if ((rc = pf_single_desc(p, &d, 0, 0, 0, 1, 0.0f))) return rc;
+    if ((rc = launch_pf_summary(ctx, d, 1, p->N))) return rc;
+    MCT_CUDA(ctx, cudaMemcpyAsync(out, p->d_summ, sizeof(*out), cudaMemcpyDeviceToHost, ctx->stream));
+    return mct_sync(ctx);
+}
+
+extern "C" int mct_pf_get_last_response(mct_pf* p, float* out, int* valid)
+{
+    if (!p || !out) return MCT_E_ARG;
+    mct_ctx* ctx = p->ctx;
+    MCT_CUDA(ctx, cudaMemcpyAsync(out, p->d_H, (size_t)p->N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (valid) MCT_CUDA(ctx, cudaMemcpyAsync(valid, p->d_valid, (size_t)p->N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return mct_sync(ctx);
+}
+
+// ------------------------------------------------------------------------------------------ fused path
+extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, mct_clf* const* clfs,
+                                     const mct_track_params* params, const float* noise, int noise_is_device,
+                                     const float* u01)
+{
+    if (!ctx || n_obj < 1 || n_obj > DESC_MAX_OBJ || !pfs || !clfs || !params || !noise || !u01) return MCT_E_ARG;
+    if (ctx->frame_id == 0) return mct_fail(ctx, MCT_E_STATE, "no frame set%s");
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc, n_max = 0, K_max = 1;
+    size_t noff = 0;
+    for (int o = 0; o < n_obj; o++) {
+        mct_pf* p = pfs[o]; mct_clf* c = clfs[o];
+        if (!p || !c || p->ctx != ctx || c->ctx != ctx) return mct_fail(ctx, MCT_E_ARG, "object handle belongs to another ctx%s");
+        if (!p->initialized) return mct_fail(ctx, MCT_E_STATE, "particle filter not initialised%s");
+        if ((rc = need_frame(c))) return rc;
+        if ((rc = clf_ensure_test(c, p->N, c->n_color))) return rc;
+        MCT_CUDA(ctx, cudaMemcpyAsync(p->d_noise, noise + noff, (size_t)4 * p->N * 4,
+                                      noise_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+        noff += (size_t)4 * p->N;
+        if (p->N > n_max) n_max = p->N;
+        if (c->K > K_max) K_max = c->K;
+    }
+    ObjDesc *h, *d; int slot;
+    if ((rc = desc_acquire(ctx, &h, &d, &slot))) return rc;
+    for (int o = 0; o < n_obj; o++) {
+        memset(&h[o], 0, sizeof(ObjDesc));
+        fill_pf_desc(&h[o], pfs[o]);
+        fill_clf_desc(&h[o], clfs[o]);
+        h[o].w0 = params[o].w0; h[o].h0 = params[o].h0; h[o].exponent = params[o].exponent;
+        h[o].force_reset = params[o].force_reset; h[o].resample = params[o].resample; h[o].u01 = u01[o];
+    }
+    if ((rc = desc_commit(ctx, slot, n_obj))) return rc;
+    if ((rc = launch_pf_predict(ctx, d, n_obj, n_max))) return rc;
+    if ((rc = launch_pf_testset(ctx, d, n_obj, n_max))) return rc;
+    for (int o = 0; o < n_obj; o++) {
+        mct_clf* c = clfs[o]; mct_pf* p = pfs[o];
+        if (c->n_color > 0) {
+            float* sx = p->d_state + 2 * (size_t)p->ld; float* sy = p->d_state + 3 * (size_t)p->ld;
+            if ((rc = mct_feature_color_rows(c, p->d_col, p->d_row, sx, sy, p->d_valid, p->N, nullptr, c->n_color,
+                                             c->d_featN, c->ldN)))
+                return rc;
+        }
+    }
+    if ((rc = launch_classify(ctx, d, n_obj, n_max, K_max, 0, 1))) return rc;
+    if ((rc = launch_pf_update(ctx, d, n_obj, n_max, 1))) return rc;
+    if ((rc = launch_pf_summary(ctx, d, n_obj, n_max))) return rc;
+    for (int o = 0; o < n_obj; o++)
+        MCT_CUDA(ctx, cudaMemcpyAsync(&ctx->h_summ[o], pfs[o]->d_summ, sizeof(mct_pf_summary), cudaMemcpyDeviceToHost, ctx->stream));
+    return MCT_OK;
+}
+
+extern "C" int mct_track_collect(mct_ctx* ctx, int n_obj, mct_pf_summary* summaries)
+{
+    if (!ctx || n_obj < 1 || n_obj > DESC_MAX_OBJ || !summaries) return MCT_E_ARG;
+    int rc = mct_sync(ctx);
+    if (rc) return rc;
+    memcpy(summaries, ctx->h_summ, sizeof(mct_pf_summary) * n_obj);
+    for (int o = 0; o < n_obj; o++)
+        if (summaries[o].n_valid == 0)
+            return mct_fail(ctx, MCT_E_EMPTY, "object %s%d has no valid test sample (all particles out of frame)", "", o);
+    return MCT_OK;
+}
+
+extern "C" int mct_track_score(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, mct_clf* const* clfs,
+                               const mct_track_params* params, const float* noise, int noise_is_device, const float* u01,
+                               mct_pf_summary* summaries)
+{
+    int rc = mct_track_score_async(ctx, n_obj, pfs, clfs, params, noise, noise_is_device, u01);
+    if (rc) return rc;
+    return mct_track_collect(ctx, n_obj, summaries);
+}
+
+extern "C" int mct_track_update(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, const mct_boxes* pos, const mct_boxes* neg)
+{
+    if (!ctx || n_obj < 1 || !clfs || !pos || !neg) return MCT_E_ARG;
+    for (int o = 0; o < n_obj; o++) {
+        if (!clfs[o] || clfs[o]->ctx != ctx) return mct_fail(ctx, MCT_E_ARG, "classifier handle belongs to another ctx%s");
+        int rc = mct_classifier_update(clfs[o], &pos[o], &neg[o], nullptr, nullptr);
+        if (rc) return rc;
+    }
+    return MCT_OK;
+}
+
+extern "C" int mct_fuser_pack_foot_points(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, const float* h0, float* dev_out)
+{
+    if (!ctx || n_obj < 1 || n_obj > DESC_MAX_OBJ || !pfs || !h0 || !dev_out) return MCT_E_ARG;
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = ensure_tmp(ctx, (size_t)n_obj * 4);
+    if (rc) return rc;
+    MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tmp, h0, (size_t)n_obj * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ObjDesc *h, *d; int slot;
+    if ((rc = desc_acquire(ctx, &h, &d, &slot))) return rc;
+    for (int o = 0; o < n_obj; o++) { memset(&h[o], 0, sizeof(ObjDesc)); fill_pf_desc(&h[o], pfs[o]); }
+    if ((rc = desc_commit(ctx, slot, n_obj))) return rc;
+    if ((rc = launch_foot_points(ctx, d, n_obj, ctx->d_tmp, dev_out))) return rc;
+    return mct_sync(ctx);
+}

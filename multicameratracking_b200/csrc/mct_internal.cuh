@@ -1,0 +1,220 @@
+// mct_internal.cuh -- shared host structs, launch helpers and device arithmetic helpers.
+// Compiled for sm_100a only, with -fmad=false so every f32 result follows the reference's
+// operation order (no FMA contraction); see DESIGN.md "Arithmetic contract".
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/mct_b200.h"
+
+#define MCT_II_LEAD 3          // integral rows start 3 floats into a 16B-aligned row so that column 1 is 16B aligned
+#define MCT_FIX_SHIFT_MAX 20   // MDCH fixed-point histogram scale 2^20
+#define MCT_MDCH_SEG_PIX 4096  // pixels per fixed-point segment (u32 cannot overflow: 4096 * 2^20 = 2^32 excluded by weight <= 1 and shift rule)
+
+// ------------------------------------------------------------------ per-object device status
+struct PfDev {
+    int   filter_state;
+    int   n_valid;
+    int   resampled;
+    int   n_unique;
+    float neff_inv;
+    float max_response;
+    int   time_index;
+    int   pad;
+};
+
+// ------------------------------------------------------------------ host-side objects
+struct mct_ctx {
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    int W, H, pitch;                       // current frame geometry (u8 planes)
+    const uint8_t* gray; const uint8_t* c0; const uint8_t* c1; const uint8_t* c2;   // device planes in use
+    uint8_t* own_planes[4]; size_t own_plane_cap;
+    float* ii_base; int ii_pitch; size_t ii_cap;       // integral image storage; element (y,x) at ii_base[MCT_II_LEAD + y*ii_pitch + x]
+    uint32_t* bandsum; size_t bandsum_cap;
+    uint16_t* binimg; size_t binimg_cap; int binimg_nb; long long binimg_frame;   // MDCH joint-bin image of the colour planes
+    long long frame_id;
+    void* d_desc; void* h_desc; size_t desc_cap;       // batched object descriptors (device + pinned host)
+    mct_pf_summary* h_summ; int summ_cap;              // pinned read-out buffer
+    float* d_tmp; size_t tmp_cap;                      // scratch (sum_rects etc.)
+    float* h_pin; size_t pin_cap;                      // pinned staging for small host arrays
+    long long launches;
+    char err[512];
+};
+
+struct mct_clf {
+    mct_ctx* ctx;
+    mct_clf_params p;
+    int F, K, n_haar, n_color;
+    // Haar table
+    int4* d_rects; float* d_wts; int* d_nrect;
+    // weak state [8][F], trained flags
+    float* d_weak; int* d_trained;
+    // selection
+    int* d_sel; int* d_nsel;
+    int cluster;                                       // requested cluster width (0 auto)
+    // training buffers
+    int max_train, ldT;
+    int* d_tcol; int* d_trow; float* d_tsx; float* d_tsy;   // P then Nn boxes
+    float* d_tw;                                        // sample weights (P then Nn)
+    float* d_featT;                                     // [F][ldT]
+    float* d_pred;                                      // [F][ldT]
+    int lastP, lastNn;
+    // test buffers (grow-only)
+    int test_cap, ldN;
+    int* d_col; int* d_row; float* d_sx; float* d_sy;
+    float* d_featN; size_t featN_cap;                   // [rows][ldN]
+    float* d_H;
+    // selected colour rows map for classify
+    int* d_outbins; int* d_colorrow;                    // [n_color]: bins to write / feature -> row in featN
+};
+
+struct mct_pf {
+    mct_ctx* ctx;
+    int N, ld;
+    float img_w, img_h, msc, maxs, mins;
+    float* d_state;      // 5*ld : cx,cy,sx,sy,w
+    float* d_res;        // 5*ld
+    int*   d_residx;
+    int*   d_col; int* d_row; int* d_valid;
+    float* d_H;
+    float* d_noise;      // 4*ld
+    float* d_prob;       // ld
+    float* d_scratch;    // 2*ld (cdf / weights when N too large for smem)
+    PfDev* d_st;
+    mct_pf_summary* d_summ;
+    int initialized;
+};
+
+// ------------------------------------------------------------------ batched object descriptor
+struct ObjDesc {
+    // particle filter
+    float* cx; float* cy; float* sx; float* sy; float* w;
+    float* rcx; float* rcy; float* rsx; float* rsy; float* rw;
+    int* residx; int* col; int* row; int* valid;
+    float* H; const float* noise; float* scratch;
+    PfDev* st; mct_pf_summary* summ;
+    int N, ld;
+    float img_w, img_h, msc, maxs, mins;
+    float w0, h0, u01;
+    int exponent, force_reset, resample, pad0;
+    // classifier
+    const int4* rects; const float* wts; const int* nrect;
+    const float* weak; const int* sel; const int* nsel;
+    float* featN; int ldN; int n_color_rows;
+    const int* colorrow; const int* outbins;
+    int F, n_haar, nb, weak_type, feature_type, cch_mode, K, pad1;
+};
+
+// ------------------------------------------------------------------ error helpers
+extern char g_mct_err[512];
+static inline int mct_fail(mct_ctx* ctx, int code, const char* fmt, const char* a = "", int b = 0)
+{
+    char* dst = ctx ? ctx->err : g_mct_err;
+    snprintf(dst, 512, fmt, a, b);
+    if (ctx) snprintf(g_mct_err, 512, "%s", dst);
+    return code;
+}
+#define MCT_CUDA(ctx, call)                                                                 \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return mct_fail((ctx), MCT_E_CUDA, "CUDA error: %s (line %d)", cudaGetErrorString(e__), __LINE__); \
+    } while (0)
+#define MCT_KERNEL_CHECK(ctx)                                                                \
+    do {                                                                                     \
+        (ctx)->launches++;                                                                   \
+        cudaError_t e__ = cudaGetLastError();                                                \
+        if (e__ != cudaSuccess)                                                              \
+            return mct_fail((ctx), MCT_E_CUDA, "kernel launch failed: %s (line %d)", cudaGetErrorString(e__), __LINE__); \
+    } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+// ------------------------------------------------------------------ kernel launchers (defined per .cu)
+int launch_integral(mct_ctx* ctx);
+int launch_bin_image(mct_ctx* ctx, int nb);
+int launch_sum_rects(mct_ctx* ctx, const int* d_rects, int n, float* d_out);
+// full [F][ld] feature matrix of one box list (FeatureVector::Compute)
+int mct_feature_matrix_full(mct_clf* clf, const int* d_col, const int* d_row, const float* d_sx, const float* d_sy,
+                            int n, float* d_out, int ld);
+// colour rows needed by Classify: the selected bins only (MDCH) / all 11 (CCH)
+int mct_feature_color_rows(mct_clf* clf, const int* d_col, const int* d_row, const float* d_sx, const float* d_sy,
+                           const int* d_valid, int n, const int* d_outbins, int n_out, float* d_out, int ld);
+int launch_classify(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int K_max, int from_matrix, int log_ratio);
+int launch_pf_predict(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max);
+int launch_pf_testset(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max);
+int launch_pf_update(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int use_H);
+int launch_pf_resample_only(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int force);
+int launch_pf_summary(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max);
+int launch_pf_expand_prob(mct_ctx* ctx, const ObjDesc* d_desc, const float* d_prob_compact, int n_prob, int only_nonzero);
+int launch_weak_update(mct_clf* clf, int P, int Nn, int has_weights);
+int launch_mil_select(mct_clf* clf, int P, int Nn);
+int launch_foot_points(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, const float* d_h0, float* d_out);
+
+// ------------------------------------------------------------------ device helpers
+#ifdef __CUDACC__
+// OnlineStumps/WeightedStumps::ClassifyF (OnlineStumpsWeakClassifier.cpp:83-90): p_c in f32 via expf,
+// then f64 logs, result rounded to f32.  Perceptron::ClassifyF (PerceptronWeakClassifier.cpp:78-89).
+__device__ __forceinline__ float weak_classify_dev(int weak_type, float x, float mu0, float mu1,
+                                                   float n0, float n1, float e0, float e1)
+{
+    if (weak_type == MCT_WEAK_PERCEPTRON) {
+        // rows 0,1 of the state hold m_weightList[0], [1]
+        double fv = (double)x;
+        return (fv * (double)mu0 > (double)mu1) ? 1.0f : -1.0f;
+    }
+    float d0 = __fsub_rn(x, mu0), d1 = __fsub_rn(x, mu1);
+    float a0 = __fmul_rn(__fmul_rn(d0, d0), e0);
+    float a1 = __fmul_rn(__fmul_rn(d1, d1), e1);
+    double p0 = (double)__fmul_rn(expf(a0), n0);
+    double p1 = (double)__fmul_rn(expf(a1), n1);
+    return (float)(log(1e-5 + p1) - log(1e-5 + p0));
+}
+// Public.h:169-172
+__device__ __forceinline__ float sigmoid_dev(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// Matrixu::sumRect (Matrix.cpp:49-67) on the padded integral image; coordinates are clamped to the
+// table so that an out-of-frame rect (reference: debug assert / UB) cannot fault.
+__device__ __forceinline__ float sum_rect_dev(const float* __restrict__ ii, int iip, int W, int H, int x, int y, int w, int h)
+{
+    int x0 = clampi(x, 0, W), x1 = clampi(x + w, 0, W);
+    int y0 = clampi(y, 0, H), y1 = clampi(y + h, 0, H);
+    const float* r0 = ii + (size_t)y0 * iip;
+    const float* r1 = ii + (size_t)y1 * iip;
+    float tl = __ldg(r0 + x0), tr = __ldg(r0 + x1), br = __ldg(r1 + x1), bl = __ldg(r1 + x0);
+    return __fsub_rn(__fsub_rn(__fadd_rn(br, tl), tr), bl);
+}
+// HaarFeature::Compute (HaarFeature.cpp:111-141)
+__device__ __forceinline__ float haar_eval_dev(const float* __restrict__ ii, int iip, int W, int H,
+                                               const int4* rects, const float* wts, int nrect,
+                                               int col, int row, float sx, float sy)
+{
+    float sum = 0.0f;
+    for (int k = 0; k < nrect; k++) {
+        int4 r = rects[k];
+        int x = __float2int_rn(__fmul_rn((float)r.x, sx)) + col;
+        int y = __float2int_rn(__fmul_rn((float)r.y, sy)) + row;
+        int h = __float2int_rn(__fmul_rn((float)r.w, sy));     // .w = height
+        int w = __float2int_rn(__fmul_rn((float)r.z, sx));     // .z = width
+        sum = __fadd_rn(sum, __fmul_rn(wts[k], sum_rect_dev(ii, iip, W, H, x, y, w, h)));
+    }
+    return __fdiv_rn(sum, __fmul_rn(sx, sy));
+}
+
+__device__ __forceinline__ float warp_sum_f(float v)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#endif

@@ -1,0 +1,60 @@
+"""Synthetic camera sequences: smooth low-frequency background + uniform noise, plus one
+textured rectangle per object with a distinct mean colour moving along x(t) = x0 + v t + A sin(w t).
+Planes are R, G, B (Matrix.cpp:92-94) and gray = (R*4899 + G*9617 + B*1868 + 8192) >> 14 (cv BGR2GRAY).
+"""
+import numpy as np
+
+OBJ_WH = {(640, 480): (40, 80), (1280, 720): (60, 120), (1920, 1080): (90, 180)}
+
+
+def gray_from_rgb(r, g, b):
+    return ((r.astype(np.int32) * 4899 + g.astype(np.int32) * 9617 + b.astype(np.int32) * 1868 + 8192) >> 14).astype(np.uint8)
+
+
+class Sequence:
+    def __init__(self, W=640, H=480, n_objects=1, camera=0, n_frames=100, obj_wh=None):
+        self.W, self.H, self.n_objects, self.n_frames = W, H, n_objects, n_frames
+        self.w0, self.h0 = obj_wh if obj_wh else OBJ_WH.get((W, H), (40, 80))
+        rng = np.random.default_rng(1000 + camera)
+        yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+        bg = []
+        for _ in range(3):
+            a = rng.uniform(60, 160); fx, fy = rng.uniform(0.004, 0.02, 2); ph = rng.uniform(0, 6.28, 2)
+            bg.append(a + 40 * np.sin(fx * xx + ph[0]) * np.cos(fy * yy + ph[1]))
+        self.bg = np.stack(bg)
+        self.colors = rng.uniform(30, 225, (n_objects, 3)).astype(np.float32)
+        self.tex = rng.uniform(-25, 25, (n_objects, 3, self.h0, self.w0)).astype(np.float32)
+        m = 2 * 20 + 8
+        self.x0 = rng.uniform(m, W - self.w0 - m, n_objects)
+        self.y0 = rng.uniform(m, H - self.h0 - m, n_objects)
+        self.v = rng.uniform(-1.5, 1.5, (n_objects, 2))
+        self.A = rng.uniform(2, 10, (n_objects, 2))
+        self.om = rng.uniform(0.05, 0.2, (n_objects, 2))
+        self.camera = camera
+
+    def box(self, t, o):
+        m = 2 * 20 + 8
+        x = self.x0[o] + self.v[o, 0] * t + self.A[o, 0] * np.sin(self.om[o, 0] * t)
+        y = self.y0[o] + self.v[o, 1] * t + self.A[o, 1] * np.sin(self.om[o, 1] * t)
+        x = float(np.clip(x, m, self.W - self.w0 - m)); y = float(np.clip(y, m, self.H - self.h0 - m))
+        return int(round(x)), int(round(y)), self.w0, self.h0
+
+    def frame(self, t):
+        """returns gray, r, g, b (uint8 [H][W])"""
+        rng = np.random.default_rng(100000 * (self.camera + 1) + t)
+        img = self.bg + rng.uniform(-8, 8, self.bg.shape).astype(np.float32)
+        for o in range(self.n_objects):
+            x, y, w, h = self.box(t, o)
+            img[:, y:y + h, x:x + w] = self.colors[o][:, None, None] + self.tex[o]
+        img = np.clip(img, 0, 255).astype(np.uint8)
+        r, g, b = img[0], img[1], img[2]
+        return gray_from_rgb(r, g, b), np.ascontiguousarray(r), np.ascontiguousarray(g), np.ascontiguousarray(b)
+
+
+def noise(n_particles, sd, camera=0, obj=0, t=0):
+    """The four cv::randn(1xN, 0, sigma) rows of PredictWithBrownianMotion (x, y, scaleX, scaleY)."""
+    rng = np.random.default_rng(2000 + camera * 64 + obj + 7919 * t)
+    out = np.empty((4, n_particles), np.float32)
+    for k in range(4):
+        out[k] = (rng.standard_normal(n_particles) * sd[k]).astype(np.float32)
+    return out
