@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- particles scored/s (and tracked frames/s per camera) of the appearance-scoring path.
+
+Workload (BASELINE.json configs[1]): one camera per GPU, 8 objects, HaarAndColorHistogram features
+(250 Haar + 512 MDCH -> 152 selected), WeightedStumps + MILBoost, 2000 particles/object, 640x480 synthetic frames.
+
+  step   = one frame of the SCORE PATH for all 8 objects: integral image + MDCH bin image + predict + test set +
+           colour-histogram rows + fused Haar/stump response + likelihood map + weight update + normalise +
+           N_eff + systematic resample + read-out  (SURVEY.md 8d "particles scored/s").
+  value  = whole-job particles scored / s with frames and prediction noise already resident in HBM
+           (frame pool larger than L2 is cycled), timed with CUDA events on the launching stream.
+  e2e    = the same metric through the reference-facing C++ host API (ParticleFilterTracker::TrackCameraObjects)
+           with HOST buffers: per step the H2D copy of the 4 frame planes + noise from pinned memory and the D2H
+           read-out of the per-object summaries are inside the timed region.
+  extra  = tracked_frames_per_sec_per_camera: full frames (score path + UpdateClassifier) through the host API.
+
+`--impl reference` times the CPU restatement of the reference (oracle/, all host threads via the reference's own
+omp pragmas) on the same config and metric.  Multi-GPU: one process per GPU (torchrun), one camera per rank,
+no data-path collective (configs[1] has no fuser) -> weak scaling.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 640, 480
+N_OBJ, N_PART = 8, 2000
+N_HAAR, N_BINS, PCT = 250, 8, 20
+FEAT, WEAK, STRONG = 3, 1, 2          # HAAR_COLOR_HISTOGRAM, WEIGHTED_STUMP, MILBoost
+SD = (20.0, 20.0, 1e-7, 1e-7)
+POOL = 128                            # frames in the resident pool: 128 * 4 planes * 300 KB = 157 MB > 126 MB L2
+METRIC = "particles_scored_per_sec"
+CONFIG = {"workload": "configs[1]: 1 camera/GPU, 8 objects, Haar(250)+MDCH(512) -> 152 selected, WeightedStumps+MILBoost, "
+                      "2000 particles/object, 640x480 synthetic",
+          "frame": [W, H], "objects_per_camera": N_OBJ, "particles_per_object": N_PART, "features": N_HAAR + N_BINS ** 3,
+          "selected": int((N_HAAR + N_BINS ** 3) * PCT / 100),
+          "l2_policy": "inputs larger than L2: %d-frame device-resident pool (157 MB) cycled" % POOL}
+
+
+def pingpong(i, n):
+    """frame index sequence 1,2,..,n-1,n-2,..,1,2.. so that object motion stays continuous"""
+    period = 2 * (n - 2)
+    k = i % period
+    return 1 + (k if k < n - 1 else period - k)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = max(int(s[1]) for s in self.samples if s[1].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(s) > 2 + k and s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.samples)}
+
+
+def make_sequence(camera):
+    from multicameratracking_b200 import synth
+    seq = synth.Sequence(W, H, N_OBJ, camera=camera, n_frames=POOL)
+    frames = [seq.frame(t) for t in range(POOL)]
+    return seq, frames
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def oracle_setup(orc, seq, frames):
+    from oracle import oracle_py
+    f0 = orc.frame(*frames[0])
+    F = N_HAAR + N_BINS ** 3
+    K = int(F * PCT / 100)
+    trackers = []
+    for o in range(N_OBJ):
+        rng = orc.rng(o + 1)
+        t = orc.haar_generate(rng, N_HAAR, seq.w0, seq.h0)
+        clf = orc.clf_create(FEAT, N_HAAR, N_BINS, seq.w0, seq.h0, WEAK, STRONG, K, 0.85, t)
+        tp = oracle_py.TrackerParams(N_PART, SD[0], SD[1], SD[2], SD[3], 10.0, 7.0, 30, 30, 100000, 20, 0, 0, 0, 30)
+        init = np.array(seq.box(0, o), np.float32)
+        trk = orc.lib.orc_tracker_create(C.byref(tp), clf, C.byref(f0), init.ctypes.data_as(C.POINTER(C.c_float)), C.byref(rng))
+        trackers.append((trk, clf, rng))
+    return trackers
+
+
+def oracle_score_frame(orc, trackers, frames, t, objs, phases=1):
+    """one frame of the score path (incl. the integral image) for `objs` objects; returns particles scored"""
+    from multicameratracking_b200 import synth
+    g, r, gg, b = frames[t]
+    of = orc.frame(g, r, gg, b)               # computes the integral image (Matrixu::initII)
+    box = np.zeros(4, np.int32)
+    scored = 0
+    for o in objs:
+        nz = synth.noise(N_PART, SD, obj=o, t=t)
+        orc.lib.orc_tracker_track(trackers[o][0], C.byref(of), nz.ctypes.data_as(C.POINTER(C.c_float)),
+                                  box.ctypes.data_as(C.POINTER(C.c_int)), phases)
+        scored += orc.lib.orc_tracker_last_valid(trackers[o][0])
+    return scored
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.oracle_py import Oracle
+    cores = os.cpu_count() or 1
+    try:
+        orc = Oracle(omp=True)
+        orc.lib.orc_clf_set_threads(cores)
+        kind_threads = cores
+    except OSError:
+        orc = Oracle(omp=False)
+        kind_threads = 1
+    seq, frames = make_sequence(0)
+    trackers = oracle_setup(orc, seq, frames)
+    objs = list(range(N_OBJ))
+    # bounded sample: shrink the number of objects per step if a full frame would blow the time budget
+    t0 = time.perf_counter()
+    oracle_score_frame(orc, trackers, frames, 1, objs[:1])
+    per_obj = time.perf_counter() - t0
+    budget = 150.0
+    n_o = max(1, min(N_OBJ, int(budget / max(per_obj * (args.steps + args.warmup), 1e-9))))
+    objs = objs[:n_o]
+    for i in range(args.warmup):
+        oracle_score_frame(orc, trackers, frames, pingpong(i, POOL), objs)
+    scored = 0
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        scored += oracle_score_frame(orc, trackers, frames, pingpong(args.warmup + i, POOL), objs)
+    dt = time.perf_counter() - t0
+    val = scored / dt
+    sample = "%d steps x %d of %d objects x %d particles (score path incl. integral image)" % (args.steps, n_o, N_OBJ, N_PART)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "particles/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
+        "cpu_baseline": {"value": val, "unit": "particles/s", "cores": kind_threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def cpu_baseline_leg():
+    """oracle (single thread, as the reference ships) on a bounded sample: a few frames of 2 objects"""
+    from oracle.oracle_py import Oracle
+    orc = Oracle(omp=False)
+    seq, frames = make_sequence(0)
+    trackers = oracle_setup(orc, seq, frames)
+    objs = [0, 1]
+    oracle_score_frame(orc, trackers, frames, 1, objs)
+    scored, t0, n = 0, time.perf_counter(), 0
+    while time.perf_counter() - t0 < 12.0 and n < 40:
+        scored += oracle_score_frame(orc, trackers, frames, pingpong(n + 1, POOL), objs)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": scored / dt, "unit": "particles/s", "cores": 1, "kind": "port",
+            "sample": "%d frames x 2 of %d objects x %d particles, single thread (reference builds compile omp out)" % (n, N_OBJ, N_PART)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from multicameratracking_b200 import capi, synth
+    from multicameratracking_b200 import host as mhost
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream(dev)
+
+    seq, frames = make_sequence(rank)
+    cam = mhost.Camera(local, n_frames=POOL + 8, stream=stream.cuda_stream)
+    L = capi.load()
+    ctx_h = C.c_void_p(cam.L.mcth_camera_ctx(cam.h))
+    cam.set_frame(*frames[0])
+    for o in range(N_OBJ):
+        cam.add_object(seq.box(0, o), feature_type=FEAT, n_haar=N_HAAR, n_bins=N_BINS, weak_type=WEAK, strong_type=STRONG,
+                       percent_selected=PCT, n_particles=N_PART, sd_x=SD[0], sd_y=SD[1], sd_sx=SD[2], sd_sy=SD[3], rng_seed=o + 1)
+    cam.init_trackers()
+    cam.sync()
+
+    total = args.steps + args.warmup
+    # resident inputs: frame pool + per-step noise on the device; pinned copies for the e2e leg
+    planes_dev = [[torch.from_numpy(p).to(dev) for p in fr] for fr in frames]
+    planes_pin = [[torch.from_numpy(p).pin_memory() for p in fr] for fr in frames]
+    noise_np = [np.stack([synth.noise(N_PART, SD, camera=rank, obj=o, t=i) for o in range(N_OBJ)]) for i in range(total)]
+    noise_dev = [torch.from_numpy(n).to(dev) for n in noise_np]
+    noise_pin = [torch.from_numpy(n).pin_memory() for n in noise_np]
+    torch.cuda.synchronize()
+
+    vp = C.c_void_p
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(i):
+        t = pingpong(i, POOL)
+        g, r, gg, b = planes_dev[t]
+        cam.set_frame_device(W, H, W, g.data_ptr(), r.data_ptr(), gg.data_ptr(), b.data_ptr())
+        nz = noise_dev[i]
+        rc = cam.L.mcth_camera_track_resident(cam.h, t, vp(nz.data_ptr()))
+        if rc:
+            cam._chk(rc)
+
+    def step_e2e(i, phases):
+        t = pingpong(i, POOL)
+        g, r, gg, b = planes_pin[t]
+        cam._chk(cam.L.mcth_camera_set_frame(cam.h, vp(g.data_ptr()), vp(r.data_ptr()), vp(gg.data_ptr()), vp(b.data_ptr()), W, H, W, 0))
+        out = np.zeros((N_OBJ, 4), np.int32)
+        cam._chk(cam.L.mcth_camera_track(cam.h, t, vp(noise_pin[i].data_ptr()), phases, out.ctypes.data_as(C.POINTER(C.c_int))))
+        return out
+
+    def timed(fn, n_warm, n_steps, offset=0):
+        for i in range(n_warm):
+            fn(offset + i)
+        barrier()
+        capi.scored_particles(L, ctx_h, reset=True)
+        l0 = cam.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(n_steps):
+            fn(offset + n_warm + i)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        return ms, capi.scored_particles(L, ctx_h), cam.launches - l0
+
+    # ---- 1. resident-input throughput (value) ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, scored, launches = timed(step_resident, args.warmup, args.steps)
+    sampler.stop_flag = True
+    # ---- 2. per-kernel CUDA-event timing of the same steps (roofline of the dominant kernel) ----
+    L.mct_profile_enable(ctx_h, 1)
+    for i in range(args.steps):
+        step_resident(args.warmup + i)
+    prof = capi.profile_read(L, ctx_h)
+    L.mct_profile_enable(ctx_h, 0)
+    # ---- 3. end to end through the host API, host buffers ----
+    ms_e2e, scored_e2e, _ = timed(lambda i: step_e2e(i, 1), args.warmup, args.steps)
+    # ---- 4. full frames (score + UpdateClassifier) through the host API ----
+    ms_full, _, _ = timed(lambda i: step_e2e(i, 3), args.warmup, args.steps)
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    ms_max, ms_e2e_max, ms_full_max = allmax(ms), allmax(ms_e2e), allmax(ms_full)
+    scored_all, scored_e2e_all = allsum(scored), allsum(scored_e2e)
+    launches_all = allsum(launches)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        # dominant kernel by total event time over the profiled steps
+        tot = sum(v[0] for v in prof.values()) or 1.0
+        dom = max(prof.items(), key=lambda kv: kv[1][0])
+        dom_name, (dom_ms, dom_n) = dom
+        avg_us = 1e3 * dom_ms / max(dom_n, 1)
+        rows, cols = seq.h0, seq.w0
+        alg = {   # ALGORITHMIC bytes per launch, see DESIGN.md
+            "k_mdch": N_PART * rows * cols * 3 + N_PART * (N_BINS ** 3) * 4,
+            "k_classify": N_OBJ * N_PART * (50 * 4 * 16 + (CONFIG["selected"] - 50) * 4 + 4),
+            "k_integral_band": W * H + (W + 1) * (H + 1) * 4,
+            "k_pf_update": N_OBJ * N_PART * 44,
+        }.get(dom_name, 0)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(dom_name)
+        except Exception:
+            pass
+        achieved = alg / (avg_us * 1e-6) / 1e9 if avg_us > 0 else 0.0
+        shares = {k: round(v[0] / tot, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+        out = {
+            "metric": METRIC, "value": scored_all / (ms_max * 1e-3), "unit": "particles/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
+            "e2e": {"value": scored_e2e_all / (ms_e2e_max * 1e-3), "unit": "particles/s",
+                    "h2d_bytes_per_step": 4 * W * H + N_OBJ * 4 * N_PART * 4, "d2h_bytes_per_step": N_OBJ * C.sizeof(capi.PfSummary),
+                    "ms_per_step": ms_e2e_max / args.steps},
+            "tracked_frames_per_sec_per_camera": args.steps / (ms_full_max * 1e-3),
+            "gpu_launches": int(launches_all),
+            "roofline": {"kernel": dom_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
+                         "avg_launch_us": avg_us, "algorithmic_bytes_per_launch": alg, "kernel_time_shares": shares},
+            "clocks": sampler.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline_leg()
+        print(json.dumps(out))
+    cam.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -57,6 +57,12 @@ const char* mct_version(void);
 /* number of kernels this library has launched on the ctx since creation (bench: gpu_launches) */
 long long mct_launch_count(mct_ctx* ctx);
 void* mct_ctx_stream(mct_ctx* ctx);
+/* measurement hooks (bench.py): per-kernel CUDA-event timing on the ctx stream, and the number of test
+ * samples scored since the last reset (sum of n_valid over mct_track_score calls, counted on the device).
+ * names: [max_kernels][48] chars. */
+int mct_profile_enable(mct_ctx* ctx, int on);
+int mct_profile_read(mct_ctx* ctx, int max_kernels, char* names, float* total_ms, int* launches, int* n_out);
+int mct_scored_particles(mct_ctx* ctx, unsigned long long* out, int reset);
 
 /* ---------------------------------------------------------------- frame ------------------ */
 /* Replaces Matrixu planes + Matrixu::initII()/FreeII() per frame (Matrix.cpp:33-47, Camera.cpp:491,389).

@@ -24,7 +24,7 @@ PF_UNINIT, PF_INIT, PF_PREDICTED, PF_RESAMPLED = 0, 1, 2, 3
 # every symbol include/mct_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "mct_ctx_create", "mct_ctx_destroy", "mct_sync", "mct_last_error", "mct_version", "mct_launch_count",
-    "mct_ctx_stream", "mct_frame_set", "mct_frame_get_integral", "mct_sum_rects", "mct_classifier_create",
+    "mct_ctx_stream", "mct_profile_enable", "mct_profile_read", "mct_scored_particles", "mct_frame_set", "mct_frame_get_integral", "mct_sum_rects", "mct_classifier_create",
     "mct_classifier_destroy", "mct_classifier_num_features", "mct_features_compute", "mct_classifier_update",
     "mct_classifier_update_from_features", "mct_classifier_classify", "mct_classifier_classify_from_features",
     "mct_classifier_get_selectors", "mct_classifier_get_weak_state", "mct_classifier_get_predictions",
@@ -88,6 +88,9 @@ def load():
     L.mct_version.restype = C.c_char_p
     L.mct_launch_count.argtypes = [vp]; L.mct_launch_count.restype = C.c_longlong
     L.mct_ctx_stream.argtypes = [vp]; L.mct_ctx_stream.restype = vp
+    L.mct_profile_enable.argtypes = [vp, C.c_int]
+    L.mct_profile_read.argtypes = [vp, C.c_int, C.c_char_p, _c_float_p, _c_int_p, _c_int_p]
+    L.mct_scored_particles.argtypes = [vp, C.POINTER(C.c_ulonglong), C.c_int]
     L.mct_frame_set.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
     L.mct_frame_get_integral.argtypes = [vp, _c_float_p]
     L.mct_sum_rects.argtypes = [vp, _c_int_p, C.c_int, _c_float_p]
@@ -142,6 +145,32 @@ def make_boxes(col, row, sx, sy):
     b = Boxes(len(col), _ip(col), _ip(row), _fp(sx), _fp(sy))
     b._keep = (col, row, sx, sy)
     return b
+
+
+def profile_enable(L, h, on):
+    L.mct_profile_enable(h, int(on))
+
+
+def profile_read(L, h, max_kernels=64):
+    """-> {kernel name: (total_ms, launches)} since the last read (synchronises the stream)"""
+    names = C.create_string_buffer(48 * max_kernels)
+    ms = np.zeros(max_kernels, np.float32); cnt = np.zeros(max_kernels, np.int32); n = C.c_int(0)
+    rc = L.mct_profile_read(h, max_kernels, names, _fp(ms), _ip(cnt), C.byref(n))
+    if rc:
+        raise MctError(rc, "mct_profile_read")
+    out = {}
+    for i in range(n.value):
+        nm = names.raw[48 * i:48 * (i + 1)].split(b"\0")[0].decode()
+        out[nm] = (float(ms[i]), int(cnt[i]))
+    return out
+
+
+def scored_particles(L, h, reset=False):
+    v = C.c_ulonglong(0)
+    rc = L.mct_scored_particles(h, C.byref(v), int(reset))
+    if rc:
+        raise MctError(rc, "mct_scored_particles")
+    return int(v.value)
 
 
 class Context:

@@ -73,8 +73,7 @@ int launch_classify(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, i
         s_attr = smem;
     }
     dim3 g(ceil_div(n_max, 256), n_obj);
-    k_classify<<<g, 256, smem, ctx->stream>>>(d_desc, ctx->ii_base ? ctx->ii_base + MCT_II_LEAD : nullptr, ctx->ii_pitch,
-                                              ctx->W, ctx->H, from_matrix, log_ratio);
-    MCT_KERNEL_CHECK(ctx);
+    MCT_LAUNCH(ctx, "k_classify", k_classify<<<g, 256, smem, ctx->stream>>>(d_desc, ctx->ii_base ? ctx->ii_base + MCT_II_LEAD : nullptr, ctx->ii_pitch,
+                                              ctx->W, ctx->H, from_matrix, log_ratio));
     return MCT_OK;
 }

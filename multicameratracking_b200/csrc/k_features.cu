@@ -182,9 +182,8 @@ static int launch_haar_rows(mct_clf* clf, const int* d_col, const int* d_row, co
 {
     mct_ctx* ctx = clf->ctx;
     dim3 g(ceil_div(n, 256), ceil_div(clf->n_haar, HAAR_FT));
-    k_haar_matrix<<<g, 256, 0, ctx->stream>>>(ctx->ii_base + MCT_II_LEAD, ctx->ii_pitch, ctx->W, ctx->H, clf->d_rects,
-                                              clf->d_wts, clf->d_nrect, clf->n_haar, d_col, d_row, d_sx, d_sy, n, d_out, ld);
-    MCT_KERNEL_CHECK(ctx);
+    MCT_LAUNCH(ctx, "k_haar_matrix", k_haar_matrix<<<g, 256, 0, ctx->stream>>>(ctx->ii_base + MCT_II_LEAD, ctx->ii_pitch, ctx->W, ctx->H, clf->d_rects,
+                                              clf->d_wts, clf->d_nrect, clf->n_haar, d_col, d_row, d_sx, d_sy, n, d_out, ld));
     return MCT_OK;
 }
 
@@ -207,10 +206,9 @@ static int launch_mdch_rows(mct_clf* clf, const int* d_col, const int* d_row, co
         MCT_CUDA(ctx, cudaFuncSetAttribute(k_mdch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         s_attr = smem;
     }
-    k_mdch<<<ceil_div(n, MDCH_TILE), MDCH_WARPS * 32, smem, ctx->stream>>>(
+    MCT_LAUNCH(ctx, "k_mdch", k_mdch<<<ceil_div(n, MDCH_TILE), MDCH_WARPS * 32, smem, ctx->stream>>>(
         ctx->binimg, ctx->W, ctx->H, clf->p.n_bins, clf->p.w0, clf->p.h0, d_col, d_row, d_sx, d_sy, d_valid, n,
-        d_outbins, n_out, d_out, ld);
-    MCT_KERNEL_CHECK(ctx);
+        d_outbins, n_out, d_out, ld));
     return MCT_OK;
 }
 
@@ -228,9 +226,8 @@ int mct_feature_matrix_full(mct_clf* clf, const int* d_col, const int* d_row, co
         if (rc) return rc;
     } else if (clf->p.feature_type == MCT_FEAT_CCH) {
         if (!ctx->c0) return mct_fail(ctx, MCT_E_STATE, "hue plane not set%s", "");
-        k_cch<<<ceil_div(n, 8), 256, 0, ctx->stream>>>(ctx->c0, ctx->pitch, ctx->W, ctx->H, clf->p.w0, clf->p.h0, d_col,
-                                                       d_row, d_sx, d_sy, nullptr, n, clf->p.cch_mode, d_out, ld);
-        MCT_KERNEL_CHECK(ctx);
+        MCT_LAUNCH(ctx, "k_cch", k_cch<<<ceil_div(n, 8), 256, 0, ctx->stream>>>(ctx->c0, ctx->pitch, ctx->W, ctx->H, clf->p.w0, clf->p.h0, d_col,
+                                                       d_row, d_sx, d_sy, nullptr, n, clf->p.cch_mode, d_out, ld));
     }
     return MCT_OK;
 }
@@ -245,9 +242,8 @@ int mct_feature_color_rows(mct_clf* clf, const int* d_col, const int* d_row, con
         return launch_mdch_rows(clf, d_col, d_row, d_sx, d_sy, d_valid, n, d_outbins, n_out, d_out, ld);
     if (clf->p.feature_type == MCT_FEAT_CCH) {
         if (!ctx->c0) return mct_fail(ctx, MCT_E_STATE, "hue plane not set%s", "");
-        k_cch<<<ceil_div(n, 8), 256, 0, ctx->stream>>>(ctx->c0, ctx->pitch, ctx->W, ctx->H, clf->p.w0, clf->p.h0, d_col,
-                                                       d_row, d_sx, d_sy, d_valid, n, clf->p.cch_mode, d_out, ld);
-        MCT_KERNEL_CHECK(ctx);
+        MCT_LAUNCH(ctx, "k_cch", k_cch<<<ceil_div(n, 8), 256, 0, ctx->stream>>>(ctx->c0, ctx->pitch, ctx->W, ctx->H, clf->p.w0, clf->p.h0, d_col,
+                                                       d_row, d_sx, d_sy, d_valid, n, clf->p.cch_mode, d_out, ld));
     }
     return MCT_OK;
 }

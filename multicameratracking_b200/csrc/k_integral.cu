@@ -119,8 +119,7 @@ int launch_integral(mct_ctx* ctx)
         ctx->bandsum_cap = need;
     }
     dim3 g1(ceil_div(W, 128), nb);
-    k_band_colsum<<<g1, 128, 0, ctx->stream>>>(ctx->gray, W, H, ctx->pitch, BH, ctx->bandsum);
-    MCT_KERNEL_CHECK(ctx);
+    MCT_LAUNCH(ctx, "k_band_colsum", k_band_colsum<<<g1, 128, 0, ctx->stream>>>(ctx->gray, W, H, ctx->pitch, BH, ctx->bandsum));
     size_t smem = (size_t)(BH + 1) * W * sizeof(uint32_t);
     static size_t s_attr = 0;
     if (smem > s_attr) {
@@ -129,9 +128,8 @@ int launch_integral(mct_ctx* ctx)
     }
     int nt = W >= 1024 ? 1024 : round_up(W, 32);
     if (nt < 128) nt = 128;
-    k_integral_band<<<nb, nt, smem, ctx->stream>>>(ctx->gray, W, H, ctx->pitch, BH, ctx->bandsum,
-                                                  ctx->ii_base + MCT_II_LEAD, ctx->ii_pitch);
-    MCT_KERNEL_CHECK(ctx);
+    MCT_LAUNCH(ctx, "k_integral_band", k_integral_band<<<nb, nt, smem, ctx->stream>>>(ctx->gray, W, H, ctx->pitch, BH, ctx->bandsum,
+                                                  ctx->ii_base + MCT_II_LEAD, ctx->ii_pitch));
     return MCT_OK;
 }
 
@@ -146,9 +144,8 @@ __global__ void k_sum_rects(const float* __restrict__ ii, int iip, int W, int H,
 int launch_sum_rects(mct_ctx* ctx, const int* d_rects, int n, float* d_out)
 {
     if (n <= 0) return MCT_OK;
-    k_sum_rects<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(ctx->ii_base + MCT_II_LEAD, ctx->ii_pitch, ctx->W, ctx->H,
-                                                          d_rects, n, d_out);
-    MCT_KERNEL_CHECK(ctx);
+    MCT_LAUNCH(ctx, "k_sum_rects", k_sum_rects<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(ctx->ii_base + MCT_II_LEAD, ctx->ii_pitch, ctx->W, ctx->H,
+                                                          d_rects, n, d_out));
     return MCT_OK;
 }
 
@@ -179,9 +176,8 @@ int launch_bin_image(mct_ctx* ctx, int nb)
         ctx->binimg_cap = need;
     }
     dim3 g(ceil_div(ctx->W, 256), ctx->H);
-    k_bin_image<<<g, 256, 0, ctx->stream>>>(ctx->c0, ctx->c1, ctx->c2, ctx->W, ctx->H, ctx->pitch, nb,
-                                            (float)(256 / nb), ctx->binimg);
-    MCT_KERNEL_CHECK(ctx);
+    MCT_LAUNCH(ctx, "k_bin_image", k_bin_image<<<g, 256, 0, ctx->stream>>>(ctx->c0, ctx->c1, ctx->c2, ctx->W, ctx->H, ctx->pitch, nb,
+                                            (float)(256 / nb), ctx->binimg));
     ctx->binimg_nb = nb;
     ctx->binimg_frame = ctx->frame_id;
     return MCT_OK;

@@ -279,8 +279,7 @@ int launch_mil_select(mct_clf* clf, int P, int Nn)
             MCT_CUDA(ctx, cudaFuncSetAttribute(k_anyboost_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             s_attr = smem;
         }
-        k_anyboost_select<<<1, ANY_THREADS, smem, ctx->stream>>>(clf->d_pred, clf->ldT, F, P, Nn, clf->K, clf->d_sel, clf->d_nsel);
-        MCT_KERNEL_CHECK(ctx);
+        MCT_LAUNCH(ctx, "k_anyboost_select", k_anyboost_select<<<1, ANY_THREADS, smem, ctx->stream>>>(clf->d_pred, clf->ldT, F, P, Nn, clf->K, clf->d_sel, clf->d_nsel));
         return MCT_OK;
     }
     // cluster width: enough CTAs that each owns <= ~48 candidates, capped at 16 (non-portable size)
@@ -318,7 +317,9 @@ int launch_mil_select(mct_clf* clf, int P, int Nn)
     const float* pred = clf->d_pred; const float* weak = clf->d_weak;
     int ld = clf->ldT, K = clf->K, wt = clf->p.weak_type;
     int* sel = clf->d_sel; int* nsel = clf->d_nsel;
+    mct_prof_begin(ctx, "k_milboost_select");
     MCT_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_milboost_select, pred, ld, F, P, Nn, K, weak, wt, sel, nsel, FC));
+    mct_prof_end(ctx);
     MCT_KERNEL_CHECK(ctx);
     return MCT_OK;
 }

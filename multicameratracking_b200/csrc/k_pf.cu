@@ -102,8 +102,7 @@ __global__ void __launch_bounds__(256) k_pf_predict(const ObjDesc* __restrict__ 
 int launch_pf_predict(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max)
 {
     dim3 g(ceil_div(n_max, 256), n_obj);
-    k_pf_predict<<<g, 256, 0, ctx->stream>>>(d_desc);
-    MCT_KERNEL_CHECK(ctx);
+    MCT_LAUNCH(ctx, "k_pf_predict", k_pf_predict<<<g, 256, 0, ctx->stream>>>(d_desc));
     return MCT_OK;
 }
 
@@ -135,8 +134,7 @@ __global__ void __launch_bounds__(256) k_pf_testset(const ObjDesc* __restrict__ 
 int launch_pf_testset(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max)
 {
     dim3 g(ceil_div(n_max, 256), n_obj);
-    k_pf_testset<<<g, 256, 0, ctx->stream>>>(d_desc, ctx->W, ctx->H);
-    MCT_KERNEL_CHECK(ctx);
+    MCT_LAUNCH(ctx, "k_pf_testset", k_pf_testset<<<g, 256, 0, ctx->stream>>>(d_desc, ctx->W, ctx->H));
     return MCT_OK;
 }
 
@@ -217,7 +215,10 @@ __global__ void __launch_bounds__(PF_THREADS) k_pf_update(const ObjDesc* __restr
     }
     if (tid == 0) {
         d.st->n_valid = cnt; d.st->resampled = 0;
-        if (mode == 0) d.st->max_response = cnt > 0 ? mx : 0.0f;
+        if (mode == 0) {
+            d.st->max_response = cnt > 0 ? mx : 0.0f;
+            if (d.scored) atomicAdd(d.scored, (unsigned long long)cnt);
+        }
     }
     if (mode == 0 && cnt == 0) return;        // reference: ASSERT abort (ParticleFilterTracker.cpp:513)
     const double dmn = (double)mn, range = (double)mx - (double)mn;
@@ -302,8 +303,7 @@ int launch_pf_update(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, 
         MCT_CUDA(ctx, cudaFuncSetAttribute(k_pf_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
         s_attr = sb;
     }
-    k_pf_update<<<n_obj, PF_THREADS, sb, ctx->stream>>>(d_desc, use_H ? 0 : 1, sf);
-    MCT_KERNEL_CHECK(ctx);
+    MCT_LAUNCH(ctx, "k_pf_update", k_pf_update<<<n_obj, PF_THREADS, sb, ctx->stream>>>(d_desc, use_H ? 0 : 1, sf));
     return MCT_OK;
 }
 
@@ -329,8 +329,7 @@ int launch_pf_resample_only(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int 
         MCT_CUDA(ctx, cudaFuncSetAttribute(k_pf_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
         s_attr = sb;
     }
-    k_pf_resample<<<n_obj, PF_THREADS, sb, ctx->stream>>>(d_desc, force, sf);
-    MCT_KERNEL_CHECK(ctx);
+    MCT_LAUNCH(ctx, "k_pf_resample", k_pf_resample<<<n_obj, PF_THREADS, sb, ctx->stream>>>(d_desc, force, sf));
     return MCT_OK;
 }
 
@@ -376,8 +375,7 @@ __global__ void __launch_bounds__(PF_THREADS) k_pf_expand_prob(const ObjDesc* __
 }
 int launch_pf_expand_prob(mct_ctx* ctx, const ObjDesc* d_desc, const float* d_prob_compact, int n_prob, int only_nonzero)
 {
-    k_pf_expand_prob<<<1, PF_THREADS, 0, ctx->stream>>>(d_desc, d_prob_compact, n_prob, only_nonzero);
-    MCT_KERNEL_CHECK(ctx);
+    MCT_LAUNCH(ctx, "k_pf_expand_prob", k_pf_expand_prob<<<1, PF_THREADS, 0, ctx->stream>>>(d_desc, d_prob_compact, n_prob, only_nonzero));
     return MCT_OK;
 }
 
@@ -476,8 +474,7 @@ __global__ void __launch_bounds__(PF_THREADS) k_pf_summary(const ObjDesc* __rest
 int launch_pf_summary(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max)
 {
     (void)n_max;
-    k_pf_summary<<<n_obj, PF_THREADS, 0, ctx->stream>>>(d_desc);
-    MCT_KERNEL_CHECK(ctx);
+    MCT_LAUNCH(ctx, "k_pf_summary", k_pf_summary<<<n_obj, PF_THREADS, 0, ctx->stream>>>(d_desc));
     return MCT_OK;
 }
 
@@ -508,7 +505,6 @@ __global__ void __launch_bounds__(256) k_foot_points(const ObjDesc* __restrict__
 }
 int launch_foot_points(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, const float* d_h0, float* d_out)
 {
-    k_foot_points<<<n_obj, 256, 0, ctx->stream>>>(d_desc, d_h0, d_out);
-    MCT_KERNEL_CHECK(ctx);
+    MCT_LAUNCH(ctx, "k_foot_points", k_foot_points<<<n_obj, 256, 0, ctx->stream>>>(d_desc, d_h0, d_out));
     return MCT_OK;
 }

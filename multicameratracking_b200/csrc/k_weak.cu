@@ -159,9 +159,8 @@ k_weak_update(const float* __restrict__ feat, int ld, int F, int P, int Nn, int 
 int launch_weak_update(mct_clf* clf, int P, int Nn, int has_weights)
 {
     mct_ctx* ctx = clf->ctx;
-    k_weak_update<<<ceil_div(clf->F, 8), 256, 0, ctx->stream>>>(clf->d_featT, clf->ldT, clf->F, P, Nn, clf->p.weak_type,
+    MCT_LAUNCH(ctx, "k_weak_update", k_weak_update<<<ceil_div(clf->F, 8), 256, 0, ctx->stream>>>(clf->d_featT, clf->ldT, clf->F, P, Nn, clf->p.weak_type,
                                                                clf->p.learning_rate, has_weights ? clf->d_tw : nullptr,
-                                                               clf->d_weak, clf->d_trained, clf->d_pred);
-    MCT_KERNEL_CHECK(ctx);
+                                                               clf->d_weak, clf->d_trained, clf->d_pred));
     return MCT_OK;
 }

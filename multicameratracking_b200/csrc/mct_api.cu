@@ -17,6 +17,37 @@ struct DescRing {
     int next;
 };
 
+// ---- optional per-kernel timing: CUDA events recorded on the launching stream around every launch ----
+struct ProfEntry { const char* name; cudaEvent_t a, b; };
+struct ProfState {
+    bool on;
+    std::vector<ProfEntry> entries;      // recorded launches since the last read
+    std::vector<cudaEvent_t> pool;       // reusable events
+    const char* cur;
+    cudaEvent_t cur_a;
+};
+static cudaEvent_t prof_event(ProfState* ps)
+{
+    if (!ps->pool.empty()) { cudaEvent_t e = ps->pool.back(); ps->pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void mct_prof_begin(mct_ctx* ctx, const char* name)
+{
+    ProfState* ps = (ProfState*)ctx->prof;
+    if (!ps || !ps->on) return;
+    ps->cur = name; ps->cur_a = prof_event(ps);
+    cudaEventRecord(ps->cur_a, ctx->stream);
+}
+void mct_prof_end(mct_ctx* ctx)
+{
+    ProfState* ps = (ProfState*)ctx->prof;
+    if (!ps || !ps->on || !ps->cur) return;
+    cudaEvent_t b = prof_event(ps);
+    cudaEventRecord(b, ctx->stream);
+    ps->entries.push_back({ps->cur, ps->cur_a, b});
+    ps->cur = nullptr;
+}
+
 static DescRing* ring_of(mct_ctx* ctx) { return (DescRing*)ctx->h_desc; }
 
 // Reserve a descriptor slot: returns host pointer to fill; call desc_commit afterwards.
@@ -73,7 +104,46 @@ extern "C" int mct_ctx_create(int device, void* cuda_stream, mct_ctx** out)
     ctx->h_desc = r;
     ctx->summ_cap = DESC_MAX_OBJ;
     MCT_CUDA(nullptr, cudaMallocHost(&ctx->h_summ, sizeof(mct_pf_summary) * DESC_MAX_OBJ));
+    MCT_CUDA(nullptr, cudaMalloc(&ctx->d_scored, sizeof(unsigned long long)));
+    MCT_CUDA(nullptr, cudaMemset(ctx->d_scored, 0, sizeof(unsigned long long)));
     *out = ctx;
+    return MCT_OK;
+}
+
+extern "C" int mct_profile_enable(mct_ctx* ctx, int on)
+{
+    if (!ctx) return MCT_E_ARG;
+    if (!ctx->prof) { ProfState* ps = new (std::nothrow) ProfState(); if (!ps) return MCT_E_NOMEM; ps->on = false; ps->cur = nullptr; ctx->prof = ps; }
+    ((ProfState*)ctx->prof)->on = on != 0;
+    return MCT_OK;
+}
+extern "C" int mct_profile_read(mct_ctx* ctx, int max_kernels, char* names, float* total_ms, int* launches, int* n_out)
+{
+    if (!ctx || !names || !total_ms || !launches || !n_out) return MCT_E_ARG;
+    *n_out = 0;
+    ProfState* ps = (ProfState*)ctx->prof;
+    if (!ps) return MCT_OK;
+    MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int n = 0;
+    for (ProfEntry& e : ps->entries) {
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, e.a, e.b);
+        int k = -1;
+        for (int i = 0; i < n; i++) if (!strncmp(names + (size_t)i * 48, e.name, 47)) { k = i; break; }
+        if (k < 0 && n < max_kernels) { k = n++; snprintf(names + (size_t)k * 48, 48, "%s", e.name); total_ms[k] = 0; launches[k] = 0; }
+        if (k >= 0) { total_ms[k] += ms; launches[k] += 1; }
+        ps->pool.push_back(e.a); ps->pool.push_back(e.b);
+    }
+    ps->entries.clear();
+    *n_out = n;
+    return MCT_OK;
+}
+extern "C" int mct_scored_particles(mct_ctx* ctx, unsigned long long* out, int reset)
+{
+    if (!ctx || !out) return MCT_E_ARG;
+    MCT_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_scored, sizeof(*out), cudaMemcpyDeviceToHost, ctx->stream));
+    MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (reset) MCT_CUDA(ctx, cudaMemsetAsync(ctx->d_scored, 0, sizeof(*out), ctx->stream));
     return MCT_OK;
 }
 
@@ -82,6 +152,13 @@ extern "C" int mct_ctx_destroy(mct_ctx* ctx)
     if (!ctx) return MCT_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->d_scored) cudaFree(ctx->d_scored);
+    if (ctx->prof) {
+        ProfState* ps = (ProfState*)ctx->prof;
+        for (ProfEntry& e : ps->entries) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+        for (cudaEvent_t e : ps->pool) cudaEventDestroy(e);
+        delete ps;
+    }
     for (int i = 0; i < 4; i++) if (ctx->own_planes[i]) cudaFree(ctx->own_planes[i]);
     if (ctx->ii_base) cudaFree(ctx->ii_base);
     if (ctx->bandsum) cudaFree(ctx->bandsum);
@@ -528,6 +605,7 @@ static void fill_pf_desc(ObjDesc* d, mct_pf* p)
     d->rcx = p->d_res; d->rcy = p->d_res + ld; d->rsx = p->d_res + 2 * ld; d->rsy = p->d_res + 3 * ld; d->rw = p->d_res + 4 * ld;
     d->residx = p->d_residx; d->col = p->d_col; d->row = p->d_row; d->valid = p->d_valid;
     d->H = p->d_H; d->noise = p->d_noise; d->scratch = p->d_scratch; d->st = p->d_st; d->summ = p->d_summ;
+    d->scored = p->ctx->d_scored;
     d->N = p->N; d->ld = p->ld;
     d->img_w = p->img_w; d->img_h = p->img_h; d->msc = p->msc; d->maxs = p->maxs; d->mins = p->mins;
     d->exponent = 20; d->force_reset = 0; d->resample = 1;

@@ -41,6 +41,8 @@ struct mct_ctx {
     float* d_tmp; size_t tmp_cap;                      // scratch (sum_rects etc.)
     float* h_pin; size_t pin_cap;                      // pinned staging for small host arrays
     long long launches;
+    unsigned long long* d_scored;                      // device counter: test samples scored (sum of n_valid)
+    void* prof;                                        // per-kernel event timing state (NULL = off)
     char err[512];
 };
 
@@ -95,7 +97,7 @@ struct ObjDesc {
     float* rcx; float* rcy; float* rsx; float* rsy; float* rw;
     int* residx; int* col; int* row; int* valid;
     float* H; const float* noise; float* scratch;
-    PfDev* st; mct_pf_summary* summ;
+    PfDev* st; mct_pf_summary* summ; unsigned long long* scored;
     int N, ld;
     float img_w, img_h, msc, maxs, mins;
     float w0, h0, u01;
@@ -129,6 +131,17 @@ static inline int mct_fail(mct_ctx* ctx, int code, const char* fmt, const char* 
         cudaError_t e__ = cudaGetLastError();                                                \
         if (e__ != cudaSuccess)                                                              \
             return mct_fail((ctx), MCT_E_CUDA, "kernel launch failed: %s (line %d)", cudaGetErrorString(e__), __LINE__); \
+    } while (0)
+
+// optional per-kernel CUDA-event timing on the launching stream (bench.py roofline); see mct_api.cu
+void mct_prof_begin(mct_ctx* ctx, const char* name);
+void mct_prof_end(mct_ctx* ctx);
+#define MCT_LAUNCH(ctx, name, ...)                                                           \
+    do {                                                                                     \
+        mct_prof_begin((ctx), (name));                                                       \
+        __VA_ARGS__;                                                                         \
+        mct_prof_end((ctx));                                                                 \
+        MCT_KERNEL_CHECK(ctx);                                                               \
     } while (0)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

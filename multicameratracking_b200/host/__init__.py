@@ -1,0 +1,143 @@
+"""ctypes binding of libmct_host.so: the C++ host mirror of the reference's Tracker / StrongClassifierFactory /
+FeatureVector / SampleSet / ParticleFilter interfaces (mct_host.h), driven per camera."""
+import ctypes as C
+
+import numpy as np
+
+from . import build_host
+
+_lib = None
+
+
+class ObjectParams(C.Structure):
+    _fields_ = [("feature_type", C.c_int), ("n_haar", C.c_int), ("n_bins", C.c_int), ("weak_type", C.c_int),
+                ("strong_type", C.c_int), ("percent_selected", C.c_int), ("n_particles", C.c_int),
+                ("sd_x", C.c_float), ("sd_y", C.c_float), ("sd_sx", C.c_float), ("sd_sy", C.c_float),
+                ("pos_radius_train", C.c_float), ("init_pos_radius_train", C.c_float),
+                ("n_neg_train", C.c_int), ("init_n_neg_train", C.c_int), ("search_win", C.c_int),
+                ("trajectory_option", C.c_int), ("rng_seed", C.c_int64), ("init_xywh", C.c_float * 4)]
+
+
+def load():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build_host.build())
+        vp = C.c_void_p
+        L.mcth_last_error.argtypes = [vp]; L.mcth_last_error.restype = C.c_char_p
+        L.mcth_camera_create.argtypes = [C.c_int, vp, C.c_int, C.POINTER(vp)]
+        L.mcth_camera_destroy.argtypes = [vp]
+        L.mcth_camera_ctx.argtypes = [vp]; L.mcth_camera_ctx.restype = vp
+        L.mcth_camera_set_frame.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.mcth_camera_add_object.argtypes = [vp, C.POINTER(ObjectParams)]
+        L.mcth_camera_init_trackers.argtypes = [vp]
+        L.mcth_camera_track.argtypes = [vp, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]
+        L.mcth_camera_track_resident.argtypes = [vp, C.c_int, vp]
+        L.mcth_camera_sync.argtypes = [vp]
+        L.mcth_camera_launches.argtypes = [vp]; L.mcth_camera_launches.restype = C.c_longlong
+        L.mcth_object_selectors.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
+        L.mcth_object_state.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
+        L.mcth_object_particles.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
+        L.mcth_object_last_train.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]
+        L.mcth_object_rng_state.argtypes = [vp, C.c_int]; L.mcth_object_rng_state.restype = C.c_uint64
+        _lib = L
+    return _lib
+
+
+class HostError(RuntimeError):
+    pass
+
+
+# config.cfg values
+DEFAULTS = dict(feature_type=0, n_haar=250, n_bins=8, weak_type=0, strong_type=2, percent_selected=20, n_particles=1000,
+                sd_x=20.0, sd_y=20.0, sd_sx=1e-7, sd_sy=1e-7, pos_radius_train=10.0, init_pos_radius_train=7.0,
+                n_neg_train=30, init_n_neg_train=30, search_win=20, trajectory_option=0, rng_seed=1)
+
+
+class Camera:
+    """One camera on one GPU: frame + the ParticleFilterTrackers of its objects."""
+
+    def __init__(self, device=0, n_frames=100, stream=None):
+        self.L = load()
+        h = C.c_void_p()
+        rc = self.L.mcth_camera_create(device, C.c_void_p(stream) if stream else None, n_frames, C.byref(h))
+        if rc:
+            raise HostError("mcth_camera_create failed (%d): no CUDA device? (there is no CPU fallback)" % rc)
+        self.h = h
+        self.n_obj = 0
+        self.N = []
+        self._keep = None
+
+    def _chk(self, rc):
+        if rc:
+            raise HostError("host error %d: %s" % (rc, self.L.mcth_last_error(self.h).decode()))
+
+    def close(self):
+        if self.h:
+            self.L.mcth_camera_destroy(self.h)
+            self.h = None
+
+    def add_object(self, init_xywh, **kw):
+        p = dict(DEFAULTS); p.update(kw)
+        op = ObjectParams()
+        for k, v in p.items():
+            setattr(op, k, v)
+        op.init_xywh = (C.c_float * 4)(*[float(x) for x in init_xywh])
+        self._chk(self.L.mcth_camera_add_object(self.h, C.byref(op)))
+        self.n_obj += 1
+        self.N.append(p["n_particles"])
+
+    def set_frame(self, gray, c0=None, c1=None, c2=None):
+        gray = np.ascontiguousarray(gray, np.uint8)
+        H, W = gray.shape
+        pl = [None if p is None else np.ascontiguousarray(p, np.uint8) for p in (c0, c1, c2)]
+        self._keep = (gray, pl)
+        ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        self._chk(self.L.mcth_camera_set_frame(self.h, ptr(gray), ptr(pl[0]), ptr(pl[1]), ptr(pl[2]), W, H, W, 0))
+
+    def set_frame_device(self, W, H, pitch, gray_ptr, c0_ptr=0, c1_ptr=0, c2_ptr=0):
+        vp = lambda p: C.c_void_p(p) if p else None
+        self._chk(self.L.mcth_camera_set_frame(self.h, vp(gray_ptr), vp(c0_ptr), vp(c1_ptr), vp(c2_ptr), W, H, pitch, 1))
+
+    def init_trackers(self):
+        self._chk(self.L.mcth_camera_init_trackers(self.h))
+
+    def track(self, frameind, noise, phases=3):
+        """noise: [n_obj][4][N] float32.  Returns [n_obj][4] boxes (x, y, w, h) when phases & 1."""
+        nz = np.ascontiguousarray(noise, np.float32)
+        out = np.zeros((self.n_obj, 4), np.int32)
+        self._chk(self.L.mcth_camera_track(self.h, frameind, nz.ctypes.data_as(C.c_void_p), phases,
+                                           out.ctypes.data_as(C.POINTER(C.c_int))))
+        return out
+
+    def sync(self):
+        self._chk(self.L.mcth_camera_sync(self.h))
+
+    @property
+    def launches(self):
+        return int(self.L.mcth_camera_launches(self.h))
+
+    def selectors(self, o):
+        idx = np.zeros(4096, np.int32)
+        n = self.L.mcth_object_selectors(self.h, o, idx.ctypes.data_as(C.POINTER(C.c_int)))
+        if n < 0:
+            self._chk(n)
+        return idx[:n].copy()
+
+    def state(self, o):
+        s = np.zeros(6, np.float32)
+        self.L.mcth_object_state(self.h, o, s.ctypes.data_as(C.POINTER(C.c_float)))
+        return s
+
+    def particles(self, o):
+        m = np.zeros((self.N[o], 5), np.float32)
+        self._chk(self.L.mcth_object_particles(self.h, o, m.ctypes.data_as(C.POINTER(C.c_float))))
+        return m
+
+    def last_train(self, o, which):
+        col = np.zeros(16384, np.int32); row = np.zeros(16384, np.int32)
+        n = self.L.mcth_object_last_train(self.h, o, which, col.ctypes.data_as(C.POINTER(C.c_int)),
+                                          row.ctypes.data_as(C.POINTER(C.c_int)), 16384)
+        return col[:n].copy(), row[:n].copy()
+
+    def rng_state(self, o):
+        return int(self.L.mcth_object_rng_state(self.h, o))

@@ -1,0 +1,522 @@
+// mct_host.cpp -- host-side orchestration behind the reference's interface names (see mct_host.h).
+// Everything numeric on the scoring path is delegated to libmct_b200.so; what stays here is the RNG-order
+// sensitive host logic the reference also runs on the host: Haar table generation (HaarFeature.cpp:25-69),
+// training-box enumeration + Bernoulli thinning (SampleSet.cpp:82-361) and the tracker's per-frame
+// sequencing (ParticleFilterTracker.cpp).
+#include "mct_host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+static void chk(mct_ctx* ctx, int rc)
+{
+    if (rc != MCT_OK) throw MctHostError(rc, std::string(mct_last_error(ctx)));
+}
+
+// ================================================================================ Public
+namespace Public {
+static RngStream g_default(1);              // static CvRNG rng_state = cvRNG(1)   (Public.h:156)
+static RngStream* g_cur = &g_default;
+
+uint32_t RngStream::Next()
+{
+    uint64_t t = state;
+    t = (uint64_t)(uint32_t)t * 4164903690U + (t >> 32);
+    state = t;
+    return (uint32_t)t;
+}
+uint32_t RngStream::Peek() const
+{
+    uint64_t t = (uint64_t)(uint32_t)state * 4164903690U + (state >> 32);
+    return (uint32_t)t;
+}
+void SetCurrentRng(RngStream* s) { g_cur = s ? s : &g_default; }
+RngStream* CurrentRng() { return g_cur; }
+void randinitalize(const int init) { g_cur->Seed(init); }
+int randint(const int mn, const int mx) { return (int)(g_cur->Next() % (unsigned)(mx - mn + 1) + (unsigned)mn); }
+float randfloat() { return (float)(g_cur->Next() * 2.3283064365386962890625e-10); }
+float peekfloat() { return (float)(g_cur->Peek() * 2.3283064365386962890625e-10); }
+int cvRound(double v) { return (int)std::lrint(v); }
+}  // namespace Public
+using Public::cvRound;
+
+// ================================================================================ Matrixu
+void Matrixu::SetFrame(const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2, int cols, int rows,
+                       int pitch, bool deviceResident)
+{
+    chk(m_ctx, mct_frame_set(m_ctx, gray, c0, c1, c2, cols, rows, pitch, deviceResident ? 1 : 0));
+    m_rows = rows; m_cols = cols; m_iiInit = true;
+}
+float Matrixu::sumRect(int x, int y, int w, int h) const
+{
+    int r[4] = {x, y, w, h};
+    float out = 0;
+    chk(m_ctx, mct_sum_rects(m_ctx, r, 1, &out));
+    return out;
+}
+
+// ================================================================================ SampleSet
+namespace Classifier {
+void SampleSet::PushBackSample(Matrixu* gray, int x, int y, int width, int height, float weight, Matrixu* rgb,
+                               Matrixu* hsv, float scaleX, float scaleY)
+{
+    Sample s;
+    s.m_pImgGray = gray; s.m_pImgColor = rgb; s.m_pImgHSV = hsv;
+    s.m_row = y; s.m_col = x; s.m_width = width; s.m_height = height;
+    s.m_weight = weight; s.m_scaleX = scaleX; s.m_scaleY = scaleY;
+    m_sampleList.push_back(s);
+}
+
+static void frame_limits(Matrixu* gray, Matrixu* rgb, Matrixu* hsv, int width, int height, float sx, float sy,
+                         int& numberOfRows, int& numberOfColumns)
+{
+    Matrixu* m = gray ? gray : (rgb ? rgb : hsv);
+    if (!m) throw MctHostError(MCT_E_ARG, "SampleImage: no image given");
+    int scaledWidth = cvRound((double)((float)width * sx));
+    int scaledHeight = cvRound((double)((float)height * sy));
+    numberOfRows = m->rows() - scaledHeight - 1;
+    numberOfColumns = m->cols() - scaledWidth - 1;
+}
+
+void SampleSet::SampleImage(Matrixu* gray, int x, int y, int width, int height, float outerCircleRadius,
+                            float innerCircleRadius, int maximumNumberOfSamples, Matrixu* rgb, Matrixu* hsv,
+                            float scaleX, float scaleY)
+{
+    if (!(outerCircleRadius > innerCircleRadius)) throw MctHostError(MCT_E_ARG, "SampleImage: outer radius <= inner radius");
+    int nrows, ncols;
+    frame_limits(gray, rgb, hsv, width, height, scaleX, scaleY, nrows, ncols);
+    const float outerSq = outerCircleRadius * outerCircleRadius, innerSq = innerCircleRadius * innerCircleRadius;
+    const int minrow = std::max(0, y - (int)outerCircleRadius), maxrow = std::min(nrows - 1, y + (int)outerCircleRadius);
+    const int mincol = std::max(0, x - (int)outerCircleRadius), maxcol = std::min(ncols - 1, x + (int)outerCircleRadius);
+    m_sampleList.clear();
+    for (int r = minrow; r <= maxrow; r++)
+        for (int c = mincol; c <= maxcol; c++) {
+            const int dist = (y - r) * (y - r) + (x - c) * (x - c);
+            if ((float)dist < outerSq && (float)dist >= innerSq)
+                PushBackSample(gray, c, r, width, height, 1.0f, rgb, hsv, scaleX, scaleY);
+        }
+    SelectSamplesUniformlyFromLargerSet(maximumNumberOfSamples);
+}
+
+void SampleSet::SampleImage(Matrixu* gray, int x, int y, int width, int height, float maximumDistanceX,
+                            float maximumDistanceY, float minimumDistanceX, float minimumDistanceY,
+                            int maximumNumberOfSamples, Matrixu* rgb, Matrixu* hsv, float scaleX, float scaleY)
+{
+    if (!(maximumDistanceY > minimumDistanceY) || !(maximumDistanceX > minimumDistanceX))
+        throw MctHostError(MCT_E_ARG, "SampleImage: max distance <= min distance");
+    int nrows, ncols;
+    frame_limits(gray, rgb, hsv, width, height, scaleX, scaleY, nrows, ncols);
+    const int minrow = std::max(0, y - (int)maximumDistanceY), maxrow = std::min(nrows - 1, y + (int)maximumDistanceY);
+    const int mincol = std::max(0, x - (int)maximumDistanceX), maxcol = std::min(ncols - 1, x + (int)maximumDistanceX);
+    m_sampleList.clear();
+    for (int r = minrow; r <= maxrow; r++)
+        for (int c = mincol; c <= maxcol; c++) {
+            const int dx = std::abs(x - c), dy = std::abs(y - r);
+            if ((float)dx >= minimumDistanceX || (float)dy >= minimumDistanceY)
+                PushBackSample(gray, c, r, width, height, 1.0f, rgb, hsv, scaleX, scaleY);
+        }
+    SelectSamplesUniformlyFromLargerSet(maximumNumberOfSamples);
+}
+
+void SampleSet::SampleImage(Matrixu* gray, uint numberOfSamples, int w, int h, Matrixu* rgb, Matrixu* hsv, float scaleX,
+                            float scaleY)
+{
+    int nrows, ncols;
+    frame_limits(gray, rgb, hsv, w, h, scaleX, scaleY, nrows, ncols);
+    m_sampleList.clear();
+    for (uint i = 0; i < numberOfSamples; i++) {
+        const int c = Public::randint(0, ncols);
+        const int r = Public::randint(0, nrows);
+        PushBackSample(gray, c, r, w, h, 1.0f, rgb, hsv, scaleX, scaleY);
+    }
+}
+
+void SampleSet::SelectSamplesUniformlyFromLargerSet(int maximumNumberOfSamples)
+{
+    const uint numberOfSamples = (uint)Size();
+    const float probability = ((float)(maximumNumberOfSamples + 1)) / (float)numberOfSamples;
+    if (probability < 1) {
+        // one draw per candidate, in order; survivors keep their relative order
+        size_t kept = 0;
+        for (size_t i = 0; i < m_sampleList.size(); i++)
+            if (!(Public::randfloat() > probability)) m_sampleList[kept++] = m_sampleList[i];
+        m_sampleList.resize(std::min(kept, (size_t)maximumNumberOfSamples));
+    }
+}
+
+void SampleSet::ResizeFeatures(size_t numFeatures)
+{
+    m_numFeatures = numFeatures;
+    m_featureMatrix.assign(numFeatures * Size(), 0.0f);
+}
+
+void SampleSet::ToBoxes(vectori& col, vectori& row, vectorf& sx, vectorf& sy) const
+{
+    const size_t n = Size();
+    col.resize(n); row.resize(n); sx.resize(n); sy.resize(n);
+    for (size_t i = 0; i < n; i++) {
+        col[i] = m_sampleList[i].m_col; row[i] = m_sampleList[i].m_row;
+        sx[i] = m_sampleList[i].m_scaleX; sy[i] = m_sampleList[i].m_scaleY;
+    }
+}
+}  // namespace Classifier
+
+// ================================================================================ Features
+namespace Features {
+void HaarFeature::Generate(const FeatureParameters& p)
+{
+    const int n = Public::randint((int)p.m_minimumNumberOfRectangles, (int)p.m_maximumNumberOfRectangles);
+    m_rects.resize((size_t)n * 4);
+    m_weights.resize(n);
+    for (int k = 0; k < n; k++) {
+        m_weights[k] = Public::randfloat() * 2 - 1;
+        const int x = Public::randint(0, (int)(p.m_width - 3));
+        const int y = Public::randint(0, (int)(p.m_height - 3));
+        const int w = Public::randint(1, (int)(p.m_width - x - 2));
+        const int h = Public::randint(1, (int)(p.m_height - y - 2));
+        m_rects[4 * k + 0] = x; m_rects[4 * k + 1] = y; m_rects[4 * k + 2] = w; m_rects[4 * k + 3] = h;
+    }
+    // one more draw selects the channel among the single enabled one (HaarFeature.cpp:68)
+    m_channel = (uint)Public::randint(0, 0);
+}
+
+void FeatureVector::Generate(FeatureParametersPtr p)
+{
+    m_params = p;
+    m_haar.clear();
+    const uint nh = p->GetHaarFeatureDimension();
+    m_haar.resize(nh);
+    for (uint f = 0; f < nh; f++) m_haar[f].Generate(*p);
+}
+
+void FeatureVector::Compute(Classifier::SampleSet& set, bool shouldResizeFeatureMatrix)
+{
+    if (!m_clf) throw MctHostError(MCT_E_STATE, "FeatureVector::Compute: not bound to a classifier");
+    if (set.Size() == 0) return;
+    if (shouldResizeFeatureMatrix || set.NumFeatures() != GetNumberOfFeatures()) set.ResizeFeatures(GetNumberOfFeatures());
+    vectori col, row; vectorf sx, sy;
+    set.ToBoxes(col, row, sx, sy);
+    mct_boxes b = {(int)set.Size(), col.data(), row.data(), sx.data(), sy.data()};
+    int rc = mct_features_compute(m_clf, &b, set.FeatureData());
+    if (rc) throw MctHostError(rc, "mct_features_compute failed");
+}
+}  // namespace Features
+
+// ================================================================================ strong classifier
+namespace Classifier {
+StrongClassifierBase::StrongClassifierBase(mct_ctx* ctx, StrongClassifierParametersBasePtr p)
+    : m_ctx(ctx), m_clf(nullptr), m_strongClassifierParametersBasePtr(p)
+{
+    if (!p || !p->m_featureParametersPtr) throw MctHostError(MCT_E_ARG, "classifier parameters missing");
+    // K clamp (StrongClassifierBase.cpp:20-23)
+    if (p->m_numberOfSelectedWeakClassifiers > p->m_totalNumberOfWeakClassifiers || p->m_numberOfSelectedWeakClassifiers < 1)
+        p->m_numberOfSelectedWeakClassifiers = p->m_totalNumberOfWeakClassifiers / 2;
+    // InitializeFeatureVector: Generate consumes the RNG exactly like the reference
+    m_featureVectorPtr = Features::FeatureVectorPtr(new Features::FeatureVector());
+    m_featureVectorPtr->Generate(p->m_featureParametersPtr);
+    const Features::FeatureParameters& fp = *p->m_featureParametersPtr;
+    mct_clf_params cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.feature_type = (int)fp.type; cp.n_haar = (int)fp.GetHaarFeatureDimension(); cp.n_bins = (int)fp.m_numberOfBins;
+    cp.w0 = (int)fp.m_width; cp.h0 = (int)fp.m_height;
+    cp.weak_type = (int)p->m_weakClassifierType;
+    cp.strong_type = (int)p->GetClassifierType();
+    cp.n_selected = p->m_numberOfSelectedWeakClassifiers;
+    cp.learning_rate = p->m_learningRate;
+    cp.cch_mode = fp.m_cultureColorMode;
+    const auto& hf = m_featureVectorPtr->HaarFeatures();
+    std::vector<int> nrect(hf.size()), rects(hf.size() * MCT_MAX_RECTS * 4, 0);
+    std::vector<float> wts(hf.size() * MCT_MAX_RECTS, 0.0f);
+    for (size_t f = 0; f < hf.size(); f++) {
+        nrect[f] = (int)hf[f].m_weights.size();
+        for (int k = 0; k < nrect[f]; k++) {
+            for (int q = 0; q < 4; q++) rects[(f * MCT_MAX_RECTS + k) * 4 + q] = hf[f].m_rects[4 * k + q];
+            wts[f * MCT_MAX_RECTS + k] = hf[f].m_weights[k];
+        }
+    }
+    mct_haar_table ht = {(int)hf.size(), nrect.data(), rects.data(), wts.data()};
+    chk(ctx, mct_classifier_create(ctx, &cp, hf.empty() ? nullptr : &ht, &m_clf));
+    m_featureVectorPtr->Bind(m_clf);
+}
+StrongClassifierBase::~StrongClassifierBase() { if (m_clf) mct_classifier_destroy(m_clf); }
+
+void StrongClassifierBase::Update(SampleSet& pos, SampleSet& neg)
+{
+    vectori pc, pr, nc, nr; vectorf psx, psy, nsx, nsy;
+    pos.ToBoxes(pc, pr, psx, psy); neg.ToBoxes(nc, nr, nsx, nsy);
+    mct_boxes pb = {(int)pos.Size(), pc.data(), pr.data(), psx.data(), psy.data()};
+    mct_boxes nb = {(int)neg.Size(), nc.data(), nr.data(), nsx.data(), nsy.data()};
+    chk(m_ctx, mct_classifier_update(m_clf, &pb, &nb, nullptr, nullptr));
+}
+vectorf StrongClassifierBase::Classify(SampleSet& set, bool isLogRatioEnabled)
+{
+    vectorf out(set.Size());
+    if (set.Size() == 0) return out;
+    vectori col, row; vectorf sx, sy;
+    set.ToBoxes(col, row, sx, sy);
+    mct_boxes b = {(int)set.Size(), col.data(), row.data(), sx.data(), sy.data()};
+    chk(m_ctx, mct_classifier_classify(m_clf, &b, isLogRatioEnabled ? 1 : 0, out.data()));
+    return out;
+}
+vectori StrongClassifierBase::GetSelectorList()
+{
+    vectori s(GetNumberOfFeatures());
+    int n = 0;
+    chk(m_ctx, mct_classifier_get_selectors(m_clf, s.data(), &n));
+    s.resize(n);
+    return s;
+}
+
+StrongClassifierBasePtr StrongClassifierFactory::CreateAndInitializeClassifier(StrongClassifierParametersBasePtr p, mct_ctx* ctx)
+{
+    if (!p) throw MctHostError(MCT_E_ARG, "CreateAndInitializeClassifier: NULL parameters");
+    switch (p->GetClassifierType()) {
+        case ONLINE_STOCHASTIC_BOOST_MIL: return StrongClassifierBasePtr(new MILBoostClassifier(ctx, p));
+        case ONLINE_ANY_BOOST_MIL: return StrongClassifierBasePtr(new MILAnyBoostClassifier(ctx, p));
+        default: throw MctHostError(MCT_E_UNSUPPORTED, "strong classifier type is outside the B200 hot path (AdaBoost / MILEnsemble)");
+    }
+}
+}  // namespace Classifier
+
+// ================================================================================ ParticleFilter
+namespace MultipleCameraTracking {
+ParticleFilter::ParticleFilter(mct_ctx* ctx, float imageWidth, float imageHeight)
+    : m_ctx(ctx), m_pf(nullptr), m_imageWidth(imageWidth), m_imageHeight(imageHeight), m_maxScale(10), m_numberOfParticles(0),
+      m_summaryValid(false), m_hostStateValid(false)
+{
+    memset(&m_summary, 0, sizeof(m_summary));
+}
+ParticleFilter::~ParticleFilter() { if (m_pf) mct_pf_destroy(m_pf); }
+
+void ParticleFilter::Initialize(int numberOfParticles, float centerX, float centerY, float scaleX, float scaleY,
+                                float maximumScaleChangeBetweenFrame, float maxScale, float minScale)
+{
+    if (m_pf) throw MctHostError(MCT_E_STATE, "ParticleFilter::Initialize called twice");
+    m_numberOfParticles = numberOfParticles; m_maxScale = maxScale;
+    chk(m_ctx, mct_pf_create(m_ctx, numberOfParticles, m_imageWidth, m_imageHeight, &m_pf));
+    chk(m_ctx, mct_pf_initialize(m_pf, centerX, centerY, scaleX, scaleY, maximumScaleChangeBetweenFrame, maxScale, minScale));
+}
+void ParticleFilter::PredictWithBrownianMotion(const float* noise4xN, float width, float height)
+{
+    chk(m_ctx, mct_pf_predict(m_pf, noise4xN, 0, width, height));
+    m_summaryValid = false; m_hostStateValid = false;
+}
+void ParticleFilter::UpdateAllParticlesWeight(vectorf& probability, bool onlyNonZero, bool forceReset, bool shouldResample)
+{
+    int resampled = 0;
+    const float u01 = Public::peekfloat();
+    chk(m_ctx, mct_pf_update_all_weights(m_pf, probability.data(), (int)probability.size(), onlyNonZero, forceReset,
+                                         shouldResample, u01, &resampled));
+    if (resampled) (void)Public::randfloat();       // the draw ResampleParticles consumed (ParticleFilter.cpp:936)
+    m_summaryValid = false; m_hostStateValid = false;
+}
+void ParticleFilter::ResampleParticles(bool force)
+{
+    chk(m_ctx, mct_pf_resample(m_pf, force ? 1 : 0, Public::randfloat()));
+    m_summaryValid = false; m_hostStateValid = false;
+}
+const mct_pf_summary& ParticleFilter::Summary()
+{
+    if (!m_summaryValid) { chk(m_ctx, mct_pf_get_summary(m_pf, &m_summary)); m_summaryValid = true; }
+    return m_summary;
+}
+void ParticleFilter::FetchState()
+{
+    if (m_hostStateValid) return;
+    m_hostState.resize((size_t)m_numberOfParticles * 5); m_hostResampled.resize((size_t)m_numberOfParticles * 5);
+    chk(m_ctx, mct_pf_get_state(m_pf, m_hostState.data()));
+    chk(m_ctx, mct_pf_get_resampled(m_pf, m_hostResampled.data()));
+    m_hostStateValid = true;
+}
+void ParticleFilter::GetParticle(int index, vectorf& particle)
+{
+    FetchState();
+    particle.assign(m_hostState.begin() + (size_t)index * 5, m_hostState.begin() + (size_t)index * 5 + 5);
+}
+void ParticleFilter::GetResampledParticle(int index, vectorf& particle)
+{
+    FetchState();
+    particle.assign(m_hostResampled.begin() + (size_t)index * 5, m_hostResampled.begin() + (size_t)index * 5 + 5);
+}
+void ParticleFilter::GetOrderedUniqueParticles(int index, vectorf& particle)
+{
+    if (index != 0) throw MctHostError(MCT_E_UNSUPPORTED, "GetOrderedUniqueParticles: only row 0 is read on the hot path");
+    const mct_pf_summary& s = Summary();
+    particle.assign(s.ordered_first, s.ordered_first + 5);
+}
+void ParticleFilter::GetHighestOrderedUniqueParticleCloseToTheGivenState(vectorf& particle, vectorf&)
+{
+    const mct_pf_summary& s = Summary();
+    particle.assign(s.highest_close, s.highest_close + 5);
+}
+void ParticleFilter::GetAverageofAllParticles(vectorf& particle)
+{
+    const mct_pf_summary& s = Summary();
+    particle.assign(s.average, s.average + 4);
+}
+int ParticleFilter::GetNumberOfOrderedUniqueParticles() { return Summary().n_unique; }
+
+// ================================================================================ ParticleFilterTracker
+ParticleFilterTracker::ParticleFilterTracker(mct_ctx* ctx, int64_t rngSeed)
+    : m_ctx(ctx), m_rng(rngSeed), m_currentStateList(6, 0.0f), m_noise(nullptr), m_isInitialized(false)
+{
+}
+
+// InitializeTracker (ParticleFilterTracker.cpp:101-231)
+void ParticleFilterTracker::InitializeTrackerWithParameters(Matrixu* pColor, Matrixu* pGray, int, uint videoLength,
+                                                            TrackerParametersPtr tp,
+                                                            Classifier::StrongClassifierParametersBasePtr cp, Matrixu* pHSV)
+{
+    Public::SetCurrentRng(&m_rng);
+    m_params = tp;
+    m_states.assign((size_t)videoLength * 4, 0);
+    m_strongClassifierBasePtr = Classifier::StrongClassifierFactory::CreateAndInitializeClassifier(cp, m_ctx);
+    for (int i = 0; i < 4; i++) m_currentStateList[i] = tp->m_initState[i];
+    m_currentStateList[4] = 1; m_currentStateList[5] = 1;
+    m_positiveSampleSet.SampleImage(pGray, (int)(uint)m_currentStateList[0], (int)(uint)m_currentStateList[1],
+                                    (int)(uint)m_currentStateList[2], (int)(uint)m_currentStateList[3],
+                                    tp->m_init_posTrainRadius, 0, 1000000, pColor, pHSV);
+    m_negativeSampleSet.SampleImage(pGray, (int)(uint)m_currentStateList[0], (int)(uint)m_currentStateList[1],
+                                    (int)(uint)m_currentStateList[2], (int)(uint)m_currentStateList[3],
+                                    2.0f * tp->m_searchWindSize, 1.5f * tp->m_init_posTrainRadius, (int)tp->m_init_negNumTrain,
+                                    pColor, pHSV);
+    if (m_positiveSampleSet.Size() < 1 || m_negativeSampleSet.Size() < 1)
+        throw MctHostError(MCT_E_EMPTY, "InitializeTracker: empty initial training set");
+    m_strongClassifierBasePtr->Update(m_positiveSampleSet, m_negativeSampleSet);
+    m_positiveSampleSet.Clear(); m_negativeSampleSet.Clear();
+    Matrixu* fr = pGray ? pGray : pColor;
+    m_particleFilterPtr = ParticleFilterPtr(new ParticleFilter(m_ctx, (float)fr->cols(), (float)fr->rows()));
+    m_particleFilterPtr->Initialize(tp->m_numberOfParticles, m_currentStateList[0] + m_currentStateList[2] / 2,
+                                    m_currentStateList[1] + m_currentStateList[3] / 2, m_currentStateList[4],
+                                    m_currentStateList[5]);
+    m_isInitialized = true;
+}
+
+// StoreObjectState (ParticleFilterTracker.cpp:286-393)
+void ParticleFilterTracker::StoreObjectState(int frameind)
+{
+    vectorf a;
+    if (m_params->m_outputTrajectoryOption == PARTICLE_HIGHEST_WEIGHT) {
+        vectorf prev(2);
+        prev[0] = m_currentStateList[0] + m_currentStateList[2] * m_currentStateList[4] / 2;
+        prev[1] = m_currentStateList[1] + m_currentStateList[3] * m_currentStateList[5] / 2;
+        m_particleFilterPtr->GetHighestOrderedUniqueParticleCloseToTheGivenState(a, prev);
+    } else {
+        m_particleFilterPtr->GetAverageofAllParticles(a);
+    }
+    m_currentStateList[0] = a[0] - m_currentStateList[2] * a[2] / 2;
+    m_currentStateList[1] = a[1] - m_currentStateList[3] * a[3] / 2;
+    m_currentStateList[4] = a[2]; m_currentStateList[5] = a[3];
+    if ((size_t)frameind * 4 + 3 < m_states.size()) {
+        m_states[(size_t)frameind * 4 + 0] = cvRound((double)m_currentStateList[0]);
+        m_states[(size_t)frameind * 4 + 1] = cvRound((double)m_currentStateList[1]);
+        m_states[(size_t)frameind * 4 + 2] = cvRound((double)(m_currentStateList[2] * m_currentStateList[4]));
+        m_states[(size_t)frameind * 4 + 3] = cvRound((double)(m_currentStateList[3] * m_currentStateList[5]));
+    }
+}
+
+// GenerateTrainingSampleSet (ParticleFilterTracker.cpp:647-688), strategies SAMPLE_POS/NEG_SIMPLETRACKER (:723-736, :921-937)
+void ParticleFilterTracker::GenerateTrainingSampleSet(Matrixu* pColor, Matrixu* pGray, Matrixu* pHSV)
+{
+    Public::SetCurrentRng(&m_rng);
+    if (m_params->m_positiveSampleStrategy != 0 || m_params->m_negativeSampleStrategy != 0)
+        throw MctHostError(MCT_E_UNSUPPORTED, "only the SIMPLETRACKER training-sample strategies are on the hot path");
+    vectorf a;
+    if (m_params->m_outputTrajectoryOption == PARTICLE_HIGHEST_WEIGHT) m_particleFilterPtr->GetOrderedUniqueParticles(0, a);
+    else m_particleFilterPtr->GetAverageofAllParticles(a);
+    const float widthFloat = a[2] * m_currentStateList[2], heightFloat = a[3] * m_currentStateList[3];
+    m_currentStateList[0] = std::max(a[0] - widthFloat / 2, 0.0f);
+    m_currentStateList[1] = std::max(a[1] - heightFloat / 2, 0.0f);
+    m_currentStateList[4] = a[2]; m_currentStateList[5] = a[3];
+    m_positiveSampleSet.Clear();
+    m_positiveSampleSet.SampleImage(pGray, (int)m_currentStateList[0], (int)m_currentStateList[1], (int)m_currentStateList[2],
+                                    (int)m_currentStateList[3], m_params->m_posRadiusTrain, 0,
+                                    (int)m_params->m_maximumNumberOfPositiveTrainingSamples, pColor, pHSV,
+                                    m_currentStateList[4], m_currentStateList[5]);
+    const float maxs = m_particleFilterPtr->GetMaxScale();
+    m_negativeSampleSet.Clear();
+    m_negativeSampleSet.SampleImage(pGray, cvRound((double)m_currentStateList[0]), cvRound((double)m_currentStateList[1]),
+                                    cvRound((double)m_currentStateList[2]), cvRound((double)m_currentStateList[3]),
+                                    1.5f * m_params->m_searchWindSize, m_params->m_posRadiusTrain + 15,
+                                    (int)m_params->m_numberOfNegativeTrainingSamples, pColor, pHSV,
+                                    std::min(m_currentStateList[4], maxs), std::min(m_currentStateList[5], maxs));
+    if (m_positiveSampleSet.Size() < 1 || m_negativeSampleSet.Size() < 1)
+        throw MctHostError(MCT_E_EMPTY, "GenerateTrainingSampleSet: empty training set");
+}
+
+// UpdateClassifier (ParticleFilterTracker.cpp:1013-1032)
+void ParticleFilterTracker::UpdateClassifier(Matrixu* pColor, Matrixu* pGray, Matrixu* pHSV)
+{
+    GenerateTrainingSampleSet(pColor, pGray, pHSV);
+    m_strongClassifierBasePtr->Update(m_positiveSampleSet, m_negativeSampleSet);
+}
+
+// TrackObjectAndSaveState (ParticleFilterTracker.cpp:239-258)
+void ParticleFilterTracker::TrackObjectAndSaveState(int frameind, Matrixu* pColor, Matrixu* pGray, Matrixu* pHSV)
+{
+    std::vector<ParticleFilterTracker*> one(1, this);
+    TrackCameraObjects(m_ctx, one, frameind, pColor, pGray, pHSV, m_noise, 3);
+}
+
+void ParticleFilterTracker::ScoreCameraObjectsAsync(mct_ctx* ctx, std::vector<ParticleFilterTracker*>& trackers, const float* noiseDev)
+{
+    const int n = (int)trackers.size();
+    std::vector<mct_pf*> pfs(n); std::vector<mct_clf*> clfs(n);
+    std::vector<mct_track_params> tp(n); std::vector<float> u01(n);
+    for (int o = 0; o < n; o++) {
+        ParticleFilterTracker* t = trackers[o];
+        pfs[o] = t->m_particleFilterPtr->Handle(); clfs[o] = t->m_strongClassifierBasePtr->Handle();
+        tp[o].w0 = t->m_currentStateList[2]; tp[o].h0 = t->m_currentStateList[3];
+        tp[o].exponent = 20; tp[o].force_reset = 0; tp[o].resample = 1;
+        u01[o] = (float)(t->m_rng.Next() * 2.3283064365386962890625e-10);
+    }
+    chk(ctx, mct_track_score_async(ctx, n, pfs.data(), clfs.data(), tp.data(), noiseDev, 1, u01.data()));
+}
+
+void ParticleFilterTracker::TrackCameraObjects(mct_ctx* ctx, std::vector<ParticleFilterTracker*>& trackers, int frameind,
+                                               Matrixu* pColor, Matrixu* pGray, Matrixu* pHSV, const float* noise, int phases)
+{
+    const int n = (int)trackers.size();
+    if (n == 0) return;
+    if (phases & 1) {
+        if (!noise) throw MctHostError(MCT_E_ARG, "TrackCameraObjects: prediction noise not provided");
+        std::vector<mct_pf*> pfs(n); std::vector<mct_clf*> clfs(n);
+        std::vector<mct_track_params> tp(n); std::vector<float> u01(n);
+        std::vector<mct_pf_summary> summ(n);
+        for (int o = 0; o < n; o++) {
+            ParticleFilterTracker* t = trackers[o];
+            if (!t->m_isInitialized) throw MctHostError(MCT_E_STATE, "tracker not initialised");
+            pfs[o] = t->m_particleFilterPtr->Handle(); clfs[o] = t->m_strongClassifierBasePtr->Handle();
+            tp[o].w0 = t->m_currentStateList[2]; tp[o].h0 = t->m_currentStateList[3];
+            tp[o].exponent = 20; tp[o].force_reset = 0; tp[o].resample = 1;
+            u01[o] = (float)(t->m_rng.Peek() * 2.3283064365386962890625e-10);
+        }
+        // TrackObjectOnTheGivenFrame for every object of the camera in one batched device pass
+        chk(ctx, mct_track_score(ctx, n, pfs.data(), clfs.data(), tp.data(), noise, 0, u01.data(), summ.data()));
+        for (int o = 0; o < n; o++) {
+            ParticleFilterTracker* t = trackers[o];
+            if (summ[o].resampled) (void)t->m_rng.Next();        // the randfloat() inside ResampleParticles
+            t->m_particleFilterPtr->AdoptSummary(summ[o]);
+            t->StoreObjectState(frameind);
+        }
+    }
+    if (phases & 2) {
+        // UpdateClassifier: host enumerates the training boxes (RNG order), device does the rest, asynchronously
+        std::vector<mct_clf*> clfs(n);
+        std::vector<vectori> pc(n), pr(n), nc(n), nr(n);
+        std::vector<vectorf> psx(n), psy(n), nsx(n), nsy(n);
+        std::vector<mct_boxes> pb(n), nb(n);
+        for (int o = 0; o < n; o++) {
+            ParticleFilterTracker* t = trackers[o];
+            t->GenerateTrainingSampleSet(pColor, pGray, pHSV);
+            t->m_positiveSampleSet.ToBoxes(pc[o], pr[o], psx[o], psy[o]);
+            t->m_negativeSampleSet.ToBoxes(nc[o], nr[o], nsx[o], nsy[o]);
+            pb[o] = {(int)pc[o].size(), pc[o].data(), pr[o].data(), psx[o].data(), psy[o].data()};
+            nb[o] = {(int)nc[o].size(), nc[o].data(), nr[o].data(), nsx[o].data(), nsy[o].data()};
+            clfs[o] = t->m_strongClassifierBasePtr->Handle();
+        }
+        chk(ctx, mct_track_update(ctx, n, clfs.data(), pb.data(), nb.data()));
+    }
+}
+}  // namespace MultipleCameraTracking

@@ -1,0 +1,152 @@
+// mct_host_c.cpp -- flat C driver over the C++ host classes, for ctypes (tests, bench.py).
+// One "camera" = one mct_ctx + its Matrixu frame + the ParticleFilterTrackers of its objects, i.e. the slice of
+// Camera/Object (Camera.cpp:334-397, Object.cpp:198-358) that feeds the hot path.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mct_host.h"
+
+using namespace MultipleCameraTracking;
+
+struct mcth_object_params {
+    int feature_type, n_haar, n_bins, weak_type, strong_type;
+    int percent_selected;             // Percentage_Of_Weak_Classifiers_Selected (Object.cpp:235-236)
+    int n_particles;
+    float sd_x, sd_y, sd_sx, sd_sy;
+    float pos_radius_train, init_pos_radius_train;
+    int n_neg_train, init_n_neg_train, search_win;
+    int trajectory_option;
+    int64_t rng_seed;
+    float init_xywh[4];
+};
+
+struct mcth_camera {
+    mct_ctx* ctx;
+    Matrixu frame;
+    std::vector<ParticleFilterTracker*> trackers;
+    std::vector<mcth_object_params> params;
+    int n_frames;
+    std::string err;
+};
+
+extern "C" {
+const char* mcth_last_error(mcth_camera* c) { return c ? c->err.c_str() : "null camera"; }
+
+int mcth_camera_create(int device, void* stream, int n_frames, mcth_camera** out)
+{
+    *out = nullptr;
+    mct_ctx* ctx = nullptr;
+    int rc = mct_ctx_create(device, stream, &ctx);
+    if (rc) return rc;
+    mcth_camera* c = new mcth_camera{ctx, Matrixu(ctx), {}, {}, n_frames, ""};
+    *out = c;
+    return 0;
+}
+void mcth_camera_destroy(mcth_camera* c)
+{
+    if (!c) return;
+    for (auto* t : c->trackers) delete t;
+    mct_ctx_destroy(c->ctx);
+    delete c;
+}
+mct_ctx* mcth_camera_ctx(mcth_camera* c) { return c->ctx; }
+
+#define GUARD(body)                                                        \
+    try { body; return 0; }                                                \
+    catch (const MctHostError& e) { c->err = e.what(); return e.code ? e.code : -1; } \
+    catch (const std::exception& e) { c->err = e.what(); return -100; }
+
+int mcth_camera_set_frame(mcth_camera* c, const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2,
+                          int W, int H, int pitch, int is_device)
+{
+    GUARD(c->frame.SetFrame(gray, c0, c1, c2, W, H, pitch, is_device != 0));
+}
+
+int mcth_camera_add_object(mcth_camera* c, const mcth_object_params* p)
+{
+    GUARD({
+        c->params.push_back(*p);
+        c->trackers.push_back(new ParticleFilterTracker(c->ctx, p->rng_seed));
+    });
+}
+
+// frame 0: InitializeTracker for every object (Camera::InitializeCameraTrackers, Camera.cpp:278-321)
+int mcth_camera_init_trackers(mcth_camera* c)
+{
+    GUARD({
+        for (size_t o = 0; o < c->trackers.size(); o++) {
+            const mcth_object_params& p = c->params[o];
+            // Object::InitializeObjectParameters (Object.cpp:198-358)
+            Features::FeatureParametersPtr fp(new Features::FeatureParameters());
+            fp->type = (Features::FeatureType)p.feature_type;
+            fp->m_width = (uint)p.init_xywh[2]; fp->m_height = (uint)p.init_xywh[3];
+            fp->m_featureDimensionHaar = (uint)p.n_haar; fp->m_numberOfBins = (uint)p.n_bins;
+            const int F = (int)fp->GetFeatureDimension();
+            const int K = int(F * p.percent_selected / 100);
+            Classifier::StrongClassifierParametersBasePtr cp;
+            if (p.strong_type == MCT_STRONG_MILANYBOOST) cp.reset(new Classifier::MILAnyBoostClassifierParameters(K, F));
+            else cp.reset(new Classifier::MILBoostClassifierParameters(K, F));
+            cp->m_weakClassifierType = (Classifier::WeakClassifierType)p.weak_type;
+            cp->m_featureParametersPtr = fp;
+            TrackerParametersPtr tp(new ParticleFilterTrackerParameters());
+            tp->m_posRadiusTrain = p.pos_radius_train; tp->m_init_posTrainRadius = p.init_pos_radius_train;
+            tp->m_numberOfNegativeTrainingSamples = (uint)p.n_neg_train; tp->m_init_negNumTrain = (uint)p.init_n_neg_train;
+            tp->m_searchWindSize = (uint)p.search_win;
+            tp->m_outputTrajectoryOption = (PFTracker_TrajectoryOption)p.trajectory_option;
+            tp->m_numberOfParticles = p.n_particles;
+            tp->m_standardDeviationX = p.sd_x; tp->m_standardDeviationY = p.sd_y;
+            tp->m_standardDeviationScaleX = p.sd_sx; tp->m_standardDeviationScaleY = p.sd_sy;
+            tp->m_initState.assign(p.init_xywh, p.init_xywh + 4);
+            c->trackers[o]->InitializeTrackerWithParameters(&c->frame, &c->frame, 0, (uint)c->n_frames, tp, cp, &c->frame);
+        }
+    });
+}
+
+// one frame for all objects: phases bit0 = score path (TrackObjectOnTheGivenFrame + StoreObjectState),
+// bit1 = UpdateClassifier.  noise [n_obj][4][N]; out_boxes [n_obj][4] (m_states rows).
+int mcth_camera_track(mcth_camera* c, int frameind, const float* noise, int phases, int* out_boxes)
+{
+    GUARD({
+        ParticleFilterTracker::TrackCameraObjects(c->ctx, c->trackers, frameind, &c->frame, &c->frame, &c->frame, noise, phases);
+        if (out_boxes && (phases & 1))
+            for (size_t o = 0; o < c->trackers.size(); o++)
+                for (int q = 0; q < 4; q++) out_boxes[o * 4 + q] = c->trackers[o]->States()[(size_t)frameind * 4 + q];
+    });
+}
+
+// score path with device-resident noise, asynchronous (bench.py "value" leg)
+int mcth_camera_track_resident(mcth_camera* c, int frameind, const float* noise_dev)
+{
+    (void)frameind;
+    GUARD(ParticleFilterTracker::ScoreCameraObjectsAsync(c->ctx, c->trackers, noise_dev));
+}
+
+int mcth_camera_sync(mcth_camera* c) { return mct_sync(c->ctx); }
+long long mcth_camera_launches(mcth_camera* c) { return mct_launch_count(c->ctx); }
+
+// introspection for parity tests
+int mcth_object_selectors(mcth_camera* c, int o, int* idx)
+{
+    try { vectori s = c->trackers[o]->GetClassifier()->GetSelectorList(); for (size_t i = 0; i < s.size(); i++) idx[i] = s[i]; return (int)s.size(); }
+    catch (const std::exception& e) { c->err = e.what(); return -1; }
+}
+int mcth_object_state(mcth_camera* c, int o, float* cur6)
+{
+    const vectorf& s = c->trackers[o]->GetCurrentTrackerState();
+    for (int i = 0; i < 6; i++) cur6[i] = s[i];
+    return 0;
+}
+int mcth_object_particles(mcth_camera* c, int o, float* Nx5)
+{
+    return mct_pf_get_state(c->trackers[o]->GetParticleFilter()->Handle(), Nx5);
+}
+int mcth_object_last_train(mcth_camera* c, int o, int which, int* col, int* row, int cap)
+{
+    const Classifier::SampleSet& s = which == 0 ? c->trackers[o]->PositiveSet() : c->trackers[o]->NegativeSet();
+    int n = (int)s.Size() < cap ? (int)s.Size() : cap;
+    for (int i = 0; i < n; i++) { col[i] = s[i].m_col; row[i] = s[i].m_row; }
+    return n;
+}
+uint64_t mcth_object_rng_state(mcth_camera* c, int o) { return c->trackers[o]->Rng().state; }
+}
