@@ -196,7 +196,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    stream = torch.cuda.current_stream(dev)
+    # a dedicated (non-default) torch stream: the C-ABI launches on it and torch.cuda.Event times it
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
 
     seq, frames = make_sequence(rank)
     cam = mhost.Camera(local, n_frames=POOL + 8, stream=stream.cuda_stream)
