@@ -247,3 +247,253 @@ int mct_feature_color_rows(mct_clf* clf, const int* d_col, const int* d_row, con
     }
     return MCT_OK;
 }
+
+// ==========================================================================================
+// MDCH for Classify: only the SELECTED colour bins are read by the strong classifier
+// (MILBoostClassifier.cpp:351-361), so the test-set pass keeps, per box, one private fixed-point
+// accumulator per selected bin plus one "everything else" slot for the normaliser.
+//
+//   k_build_colormap : selector list -> bin->slot map, colour feature -> featN row   (once per Update)
+//   k_slot_image     : slot image S[y][x] = slotmap[bin(x,y)] per object               (once per frame)
+//   k_mdch_sel       : ONE THREAD PER BOX; the thread's accumulators live in shared memory as
+//                      hist[slot][lane] (bank == lane: conflict-free plain LDS/IADD/STS, no atomics --
+//                      shared atomics cost ~2 cycles per lane on sm_100a and were 80 % of the step);
+//                      the Gaussian weights of the common box size come from a per-CTA fixed-point LUT
+//                      (they depend on the offset inside the box only: cX - x = cols/2 - c exactly);
+//                      output rows [selected bin][box] are coalesced over the box index.
+//   k_mdch_big       : generic warp-per-box kernel for boxes the fast kernel leaves (more than
+//                      MCT_MDCH_SEG_PIX pixels, where a u32 accumulator would lose precision).
+// L1/L2-resident gather kernel: per box rows*cols slot reads (2 B) + LUT reads (broadcast) + smem RMW.
+// ==========================================================================================
+__global__ void k_build_colormap(const int* __restrict__ sel, const int* __restrict__ nsel, int n_haar, int n_color,
+                                 uint16_t* __restrict__ slotmap, int* __restrict__ colorrow, int* __restrict__ outbins,
+                                 int* __restrict__ nout)
+{
+    for (int b = threadIdx.x; b < n_color; b += blockDim.x) { slotmap[b] = 0; colorrow[b] = 0; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int n = 0;
+        const int ns = *nsel;
+        for (int s = 0; s < ns; s++) {
+            const int f = sel[s];
+            if (f < n_haar) continue;
+            const int b = f - n_haar;
+            if (slotmap[b] == 0) { outbins[n] = b; colorrow[b] = n; n++; slotmap[b] = (uint16_t)n; }
+        }
+        *nout = n;
+    }
+}
+int launch_build_colormap(mct_clf* clf)
+{
+    mct_ctx* ctx = clf->ctx;
+    if (!(clf->p.feature_type == MCT_FEAT_MDCH || clf->p.feature_type == MCT_FEAT_HAAR_MDCH)) return MCT_OK;
+    MCT_LAUNCH(ctx, "k_build_colormap", k_build_colormap<<<1, 256, 0, ctx->stream>>>(clf->d_sel, clf->d_nsel, clf->n_haar, clf->n_color,
+                                                                                  clf->d_slotmap, clf->d_colorrow, clf->d_outbins, clf->d_nout));
+    return MCT_OK;
+}
+
+__global__ void __launch_bounds__(256) k_slot_image(const ObjDesc* __restrict__ descs, const uint16_t* __restrict__ binimg, int npix)
+{
+    __shared__ uint16_t sm_map[4096];
+    const ObjDesc& d = descs[blockIdx.y];
+    if (d.slotimg == nullptr) return;
+    const int dim = d.n_color_rows;
+    for (int b = threadIdx.x; b < dim; b += blockDim.x) sm_map[b] = d.slotmap[b];
+    __syncthreads();
+    // 2 pixels per thread (u32 in, u32 out)
+    const int p = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (p + 1 < npix) {
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(binimg + p);
+        const uint32_t o = (uint32_t)sm_map[v & 0xffffu] | ((uint32_t)sm_map[v >> 16] << 16);
+        *reinterpret_cast<uint32_t*>(d.slotimg + p) = o;
+    } else if (p < npix) {
+        d.slotimg[p] = sm_map[binimg[p]];
+    }
+}
+
+#define MDS_WARPS 2
+#define MDS_LUT_CAP MCT_MDCH_SEG_PIX
+__global__ void __launch_bounds__(MDS_WARPS * 32)
+k_mdch_sel(const ObjDesc* __restrict__ descs, int W, int H, int max_slots)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    uint32_t* lut = (uint32_t*)smraw;                                   // [MDS_LUT_CAP] fixed-point weights of the ref box size
+    uint32_t* hist_all = lut + MDS_LUT_CAP;                             // [MDS_WARPS][max_slots][32]
+    __shared__ int s_ref, s_rows, s_cols;
+    const ObjDesc& d = descs[blockIdx.y];
+    if (d.slotimg == nullptr) return;
+    const int N = d.N;
+    if ((int)(blockIdx.x * blockDim.x) >= N) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = blockIdx.x * blockDim.x + tid;
+    uint32_t* hist = hist_all + (size_t)warp * max_slots * 32 + lane;   // element s at hist[s * 32]
+    const int n_out = *d.nout;
+    const int n_slots = n_out + 1;
+
+    bool valid = i < N && (d.valid == nullptr || d.valid[i] != 0);
+    int c0 = 0, r0 = 0, rows = 0, cols = 0, npix = 0;
+    if (valid) {
+        c0 = d.col[i]; r0 = d.row[i];
+        rows = __float2int_rn(__fmul_rn((float)d.ch0, d.sy[i]));
+        cols = __float2int_rn(__fmul_rn((float)d.cw0, d.sx[i]));
+        npix = rows * cols;
+    }
+    const bool big = valid && (npix > MDS_LUT_CAP || npix <= 0);
+    if (tid == 0) s_ref = 0x7fffffff;
+    __syncthreads();
+    if (valid && !big) atomicMin(&s_ref, tid);
+    __syncthreads();
+    if (s_ref == tid) { s_rows = rows; s_cols = cols; }
+    __syncthreads();
+    const int ref_rows = s_rows, ref_cols = s_cols;
+    if (s_ref != 0x7fffffff) {
+        // weight LUT of the reference box size (MultiDimensionalColorHistogram.cpp:66-69,87-89,107-110)
+        const int np = ref_rows * ref_cols;
+        int shift = __clz(np); if (shift > MCT_FIX_SHIFT_MAX) shift = MCT_FIX_SHIFT_MAX;
+        const float scale = (float)(1u << shift);
+        const float hx = __fdiv_rn((float)ref_cols, 2.0f), hy = __fdiv_rn((float)ref_rows, 2.0f);
+        const double ivx = 1.0 / (double)__fmul_rn(2.0f, __fmul_rn(hx, hx));
+        const double ivy = 1.0 / (double)__fmul_rn(2.0f, __fmul_rn(hy, hy));
+        for (int p = tid; p < np; p += blockDim.x) {
+            const int r = p / ref_cols, c = p - r * ref_cols;
+            const double dx = (double)__fsub_rn(hx, (float)c), dy = (double)__fsub_rn(hy, (float)r);
+            const float wd = (float)(dx * dx * ivx + dy * dy * ivy);
+            lut[p] = __float2uint_rn(__fmul_rn(expf(-wd), scale));
+        }
+    }
+    for (int s = 0; s < n_slots; s++) hist[s * 32] = 0u;
+    __syncthreads();
+
+    float inv_scale = 0.0f;
+    if (valid && !big) {
+        int shift = __clz(npix); if (shift > MCT_FIX_SHIFT_MAX) shift = MCT_FIX_SHIFT_MAX;
+        inv_scale = __fdiv_rn(1.0f, (float)(1u << shift));
+        const bool inside = c0 >= 0 && r0 >= 0 && c0 + cols <= W && r0 + rows <= H;
+        if (inside && rows == ref_rows && cols == ref_cols) {
+            // fast path: slot image gather + LUT weight + private accumulator
+            const uint16_t* img = d.slotimg + (size_t)r0 * W + c0;
+            const uint32_t* lr = lut;
+            for (int r = 0; r < rows; r++) {
+                int c = 0;
+                for (; c + 4 <= cols; c += 4) {
+                    const unsigned s0 = img[c], s1 = img[c + 1], s2 = img[c + 2], s3 = img[c + 3];
+                    const uint32_t w0 = lr[c], w1 = lr[c + 1], w2 = lr[c + 2], w3 = lr[c + 3];
+                    hist[s0 * 32] += w0; hist[s1 * 32] += w1; hist[s2 * 32] += w2; hist[s3 * 32] += w3;
+                }
+                for (; c < cols; c++) hist[(unsigned)img[c] * 32] += lr[c];
+                img += W; lr += cols;
+            }
+        } else {
+            // same arithmetic, weights computed per pixel (box size differs from the CTA's LUT, or box crosses the frame)
+            const float scale = (float)(1u << shift);
+            const float hx = __fdiv_rn((float)cols, 2.0f), hy = __fdiv_rn((float)rows, 2.0f);
+            const double ivx = 1.0 / (double)__fmul_rn(2.0f, __fmul_rn(hx, hx));
+            const double ivy = 1.0 / (double)__fmul_rn(2.0f, __fmul_rn(hy, hy));
+            for (int r = 0; r < rows; r++) {
+                const int yy = clampi(r0 + r, 0, H - 1);
+                const double dy = (double)__fsub_rn(hy, (float)r);
+                const double ay = dy * dy * ivy;
+                for (int c = 0; c < cols; c++) {
+                    const int xx = clampi(c0 + c, 0, W - 1);
+                    const double dx = (double)__fsub_rn(hx, (float)c);
+                    const float wd = (float)(dx * dx * ivx + ay);
+                    hist[(unsigned)d.slotimg[(size_t)yy * W + xx] * 32] += __float2uint_rn(__fmul_rn(expf(-wd), scale));
+                }
+            }
+        }
+    }
+    if (i < N) {
+        if (d.big) d.big[i] = big ? 1 : 0;
+        if (big && d.nbig) atomicAdd(d.nbig, 1);
+        // normalizeVec: bins / sum(bins); the sum over all nb^3 bins == sum over the slots (slot 0 = unselected bins)
+        uint32_t total = 0;
+        for (int s = 0; s < n_slots; s++) total += hist[s * 32];
+        const float S = __fmul_rn((float)total, inv_scale);
+        const bool ok = valid && !big;
+        for (int o = 0; o < n_out; o++)
+            d.featN[(size_t)o * d.ldN + i] = ok ? __fdiv_rn(__fmul_rn((float)hist[(o + 1) * 32], inv_scale), S) : 0.0f;
+    }
+}
+
+// generic warp-per-box pass over the boxes flagged by k_mdch_sel (segmented fixed point, all nb^3 bins in
+// shared memory), writing the selected bins only.  Exits immediately when nothing was flagged.
+__global__ void __launch_bounds__(MDCH_WARPS * 32)
+k_mdch_big(const ObjDesc* __restrict__ descs, const uint16_t* __restrict__ binimg, int W, int H)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const ObjDesc& d = descs[blockIdx.y];
+    if (d.slotimg == nullptr || d.nbig == nullptr || *d.nbig == 0) return;
+    const int nb = d.nb, dim = nb * nb * nb;
+    uint32_t* hist_all = (uint32_t*)smraw;
+    float* acc_all = (float*)(hist_all + MDCH_WARPS * dim);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* hist = hist_all + warp * dim;
+    float* acc = acc_all + warp * dim;
+    const int n_out = *d.nout;
+    for (int i = blockIdx.x * MDCH_WARPS + warp; i < d.N; i += gridDim.x * MDCH_WARPS) {
+        if (!d.big[i]) continue;
+        const int c0 = d.col[i], r0 = d.row[i];
+        const int rows = __float2int_rn(__fmul_rn((float)d.ch0, d.sy[i]));
+        const int cols = __float2int_rn(__fmul_rn((float)d.cw0, d.sx[i]));
+        const float hx = __fdiv_rn((float)cols, 2.0f), hy = __fdiv_rn((float)rows, 2.0f);
+        const float cX = __fadd_rn((float)c0, hx), cY = __fadd_rn((float)r0, hy);
+        const double ivx = 1.0 / (double)__fmul_rn(2.0f, __fmul_rn(hx, hx));
+        const double ivy = 1.0 / (double)__fmul_rn(2.0f, __fmul_rn(hy, hy));
+        for (int b = lane; b < dim; b += 32) { hist[b] = 0u; acc[b] = 0.0f; }
+        __syncwarp();
+        const int rows_per_seg = max(1, MCT_MDCH_SEG_PIX / max(cols, 1));
+        for (int rs = 0; rs < rows; rs += rows_per_seg) {
+            const int re = min(rows, rs + rows_per_seg);
+            const int npix = (re - rs) * cols;
+            int shift = __clz(max(npix, 1)); if (shift > MCT_FIX_SHIFT_MAX) shift = MCT_FIX_SHIFT_MAX;
+            const float scale = (float)(1u << shift);
+            int c = lane, r = rs;
+            while (c >= cols && r < re) { c -= cols; r++; }
+            while (r < re) {
+                const int yy = clampi(r0 + r, 0, H - 1), xx = clampi(c0 + c, 0, W - 1);
+                const unsigned bin = binimg[(size_t)yy * W + xx];
+                const double dx = (double)__fsub_rn(cX, (float)(c0 + c)), dy = (double)__fsub_rn(cY, (float)(r0 + r));
+                const float wd = (float)(dx * dx * ivx + dy * dy * ivy);
+                atomicAdd(&hist[bin], __float2uint_rn(__fmul_rn(expf(-wd), scale)));
+                c += 32;
+                while (c >= cols && r < re) { c -= cols; r++; }
+            }
+            __syncwarp();
+            const float inv = __fdiv_rn(1.0f, scale);
+            for (int b = lane; b < dim; b += 32) { acc[b] = __fadd_rn(acc[b], __fmul_rn((float)hist[b], inv)); hist[b] = 0u; }
+            __syncwarp();
+        }
+        float s = 0.0f;
+        for (int b = lane; b < dim; b += 32) s += acc[b];
+        s = warp_sum_f(s);
+        for (int o = lane; o < n_out; o += 32) d.featN[(size_t)o * d.ldN + i] = __fdiv_rn(acc[d.outbins[o]], s);
+        __syncwarp();
+    }
+}
+
+int launch_mdch_selected(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int max_slots)
+{
+    if (n_obj <= 0 || n_max <= 0) return MCT_OK;
+    const int npix = ctx->W * ctx->H;
+    dim3 g0(ceil_div(ceil_div(npix, 2), 256), n_obj);
+    MCT_LAUNCH(ctx, "k_slot_image", k_slot_image<<<g0, 256, 0, ctx->stream>>>(d_desc, ctx->binimg, npix));
+    size_t smem = (size_t)MDS_LUT_CAP * 4 + (size_t)MDS_WARPS * max_slots * 32 * 4;
+    static size_t s_attr = 48 * 1024;
+    if (smem > 220 * 1024) return mct_fail(ctx, MCT_E_UNSUPPORTED, "too many selected colour bins for the private-histogram kernel%s (%d)", "", max_slots);
+    if (smem > s_attr) {
+        MCT_CUDA(ctx, cudaFuncSetAttribute(k_mdch_sel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        s_attr = smem;
+    }
+    dim3 g1(ceil_div(n_max, MDS_WARPS * 32), n_obj);
+    MCT_LAUNCH(ctx, "k_mdch_sel", k_mdch_sel<<<g1, MDS_WARPS * 32, smem, ctx->stream>>>(d_desc, ctx->W, ctx->H, max_slots));
+    // generic fallback for flagged boxes (early exit when none)
+    size_t smem2 = (size_t)MDCH_WARPS * 512 * 8;
+    static size_t s_attr2 = 0;
+    if (smem2 > s_attr2) {
+        MCT_CUDA(ctx, cudaFuncSetAttribute(k_mdch_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        s_attr2 = smem2;
+    }
+    dim3 g2(ceil_div(n_max, MDCH_WARPS * 4), n_obj);
+    MCT_LAUNCH(ctx, "k_mdch_big", k_mdch_big<<<g2, MDCH_WARPS * 32, smem2, ctx->stream>>>(d_desc, ctx->binimg, ctx->W, ctx->H));
+    return MCT_OK;
+}

@@ -138,6 +138,36 @@ int launch_pf_testset(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max)
     return MCT_OK;
 }
 
+// Sequential f32 chains in reference order; the operands are fetched eight at a time so that the loop is
+// bound by the dependent FADD (4 cycles) and not by the shared/global load latency.
+__device__ __forceinline__ float chain_sum(const float* __restrict__ v, int n)
+{
+    float t = 0.0f;
+    int i = 0;
+    for (; i + 8 <= n; i += 8) {
+        const float a0 = v[i], a1 = v[i + 1], a2 = v[i + 2], a3 = v[i + 3], a4 = v[i + 4], a5 = v[i + 5], a6 = v[i + 6], a7 = v[i + 7];
+        t = __fadd_rn(t, a0); t = __fadd_rn(t, a1); t = __fadd_rn(t, a2); t = __fadd_rn(t, a3);
+        t = __fadd_rn(t, a4); t = __fadd_rn(t, a5); t = __fadd_rn(t, a6); t = __fadd_rn(t, a7);
+    }
+    for (; i < n; i++) t = __fadd_rn(t, v[i]);
+    return t;
+}
+// cdf[0] = 0, cdf[i] = cdf[i-1] + w[i]   (ParticleFilter.cpp:927-933; w[0] excluded -- reference quirk)
+__device__ __forceinline__ void chain_cdf(const float* __restrict__ w, float* __restrict__ cdf, int n)
+{
+    float c = 0.0f;
+    cdf[0] = 0.0f;
+    int i = 1;
+    for (; i + 8 <= n; i += 8) {
+        const float a0 = w[i], a1 = w[i + 1], a2 = w[i + 2], a3 = w[i + 3], a4 = w[i + 4], a5 = w[i + 5], a6 = w[i + 6], a7 = w[i + 7];
+        c = __fadd_rn(c, a0); cdf[i] = c;     c = __fadd_rn(c, a1); cdf[i + 1] = c;
+        c = __fadd_rn(c, a2); cdf[i + 2] = c; c = __fadd_rn(c, a3); cdf[i + 3] = c;
+        c = __fadd_rn(c, a4); cdf[i + 4] = c; c = __fadd_rn(c, a5); cdf[i + 5] = c;
+        c = __fadd_rn(c, a6); cdf[i + 6] = c; c = __fadd_rn(c, a7); cdf[i + 7] = c;
+    }
+    for (; i < n; i++) { c = __fadd_rn(c, w[i]); cdf[i] = c; }
+}
+
 // ------------------------------------------------------------------------------------------
 // ResampleParticles body (ParticleFilter.cpp:920-978).  sw = weights after the first normalisation
 // (shared or global), cdf = scratch of the same length.
@@ -145,21 +175,12 @@ __device__ void resample_body(const ObjDesc& d, float* sw, float* cdf, int force
 {
     const int N = d.N, tid = threadIdx.x, nt = blockDim.x;
     // NormalizeParticleWeights again (:924)
-    if (tid == 0) {
-        float total = 0.0f;
-        for (int i = 0; i < N; i++) total = __fadd_rn(total, sw[i]);
-        sh_f[0] = total;
-    }
+    if (tid == 0) sh_f[0] = chain_sum(sw, N);
     __syncthreads();
     const float total = sh_f[0];
     for (int i = tid; i < N; i += nt) sw[i] = (total != 0) ? __fdiv_rn(sw[i], total) : 1e-2f;
     __syncthreads();
-    // cdf[0] = 0 (w[0] excluded -- reference quirk), cdf[i] = cdf[i-1] + w[i]
-    if (tid == 0) {
-        float c = 0.0f;
-        cdf[0] = 0.0f;
-        for (int i = 1; i < N; i++) { c = __fadd_rn(c, sw[i]); cdf[i] = c; }
-    }
+    if (tid == 0) chain_cdf(sw, cdf, N);
     __syncthreads();
     const float invN = __fdiv_rn(1.0f, (float)N);
     const float seed = __fmul_rn(invN, d.u01);
@@ -239,11 +260,7 @@ __global__ void __launch_bounds__(PF_THREADS) k_pf_update(const ObjDesc* __restr
     }
     __syncthreads();
     // 2. NormalizeParticleWeights: sequential f32 total (:991-995)
-    if (tid == 0) {
-        float total = 0.0f;
-        for (int i = 0; i < N; i++) total = __fadd_rn(total, sw[i]);
-        sh_f[0] = total;
-    }
+    if (tid == 0) sh_f[0] = chain_sum(sw, N);
     __syncthreads();
     const float total = sh_f[0];
     __syncthreads();
@@ -433,16 +450,28 @@ __global__ void __launch_bounds__(PF_THREADS) k_pf_summary(const ObjDesc* __rest
             out->n_unique = N;
         }
     } else if (fs == MCT_PF_RESAMPLED) {
-        // run weights: the run-start thread sums its run in order
+        // run weights: the run-start thread sums its run in order.  Right after a forced resample every
+        // weight is exactly 1.0f, and an in-order f32 sum of L ones is exactly (float)L (L < 2^24): the run end
+        // is then found by binary search in the non-decreasing index list instead of walking the run.
+        int not_one = 0;
+        for (int i = tid; i < N; i += nt) not_one += (d.w[i] != 1.0f);
+        not_one = block_reduce_sum_i(not_one, sh_i);
         float mx = -CUDART_INF_F;
         int nruns = 0;
         for (int i = tid; i < N; i += nt) {
-            const bool start = (i == 0) || (d.residx[i] != d.residx[i - 1]);
+            const int v = d.residx[i];
+            const bool start = (i == 0) || (v != d.residx[i - 1]);
             float rw = 0.0f;
             if (start) {
                 nruns++;
-                rw = d.w[i];
-                for (int j = i + 1; j < N && d.residx[j] == d.residx[i]; j++) rw = __fadd_rn(rw, d.w[j]);
+                if (!not_one) {
+                    int lo = i + 1, hi = N;                      // first j > i with residx[j] != v
+                    while (lo < hi) { int mid = (lo + hi) >> 1; if (d.residx[mid] == v) lo = mid + 1; else hi = mid; }
+                    rw = (float)(lo - i);
+                } else {
+                    rw = d.w[i];
+                    for (int j = i + 1; j < N && d.residx[j] == v; j++) rw = __fadd_rn(rw, d.w[j]);
+                }
                 mx = fmaxf(mx, rw);
             }
             d.rw[i] = start ? rw : -1.0f;          // resampled-weight column doubles as run-weight scratch

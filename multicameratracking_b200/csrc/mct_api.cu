@@ -286,6 +286,22 @@ static int clf_ensure_test(mct_clf* clf, int n, int rows)
         clf->featN_cap = need;
     }
     clf->ldN = ldN;
+    if (clf->p.feature_type == MCT_FEAT_MDCH || clf->p.feature_type == MCT_FEAT_HAAR_MDCH) {
+        size_t px = (size_t)ctx->W * ctx->H + 2;
+        if (px > clf->slotimg_cap) {
+            MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (clf->d_slotimg) cudaFree(clf->d_slotimg);
+            MCT_CUDA(ctx, cudaMalloc(&clf->d_slotimg, px * sizeof(uint16_t)));
+            clf->slotimg_cap = px;
+        }
+        if (n > clf->big_cap) {
+            MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (clf->d_big) cudaFree(clf->d_big);
+            int cap = round_up(n, 256);
+            MCT_CUDA(ctx, cudaMalloc(&clf->d_big, (size_t)cap * 4));
+            clf->big_cap = cap;
+        }
+    }
     return MCT_OK;
 }
 
@@ -373,6 +389,12 @@ extern "C" int mct_classifier_create(mct_ctx* ctx, const mct_clf_params* p, cons
         for (int i = 0; i < n_color; i++) id[i] = i;
         MCT_CUDA(ctx, cudaMalloc(&c->d_colorrow, (size_t)n_color * 4));
         MCT_CUDA(ctx, cudaMemcpy(c->d_colorrow, id.data(), (size_t)n_color * 4, cudaMemcpyHostToDevice));
+        MCT_CUDA(ctx, cudaMalloc(&c->d_outbins, (size_t)n_color * 4));
+        MCT_CUDA(ctx, cudaMemcpy(c->d_outbins, id.data(), (size_t)n_color * 4, cudaMemcpyHostToDevice));
+        MCT_CUDA(ctx, cudaMalloc(&c->d_slotmap, (size_t)n_color * 2));
+        MCT_CUDA(ctx, cudaMemset(c->d_slotmap, 0, (size_t)n_color * 2));
+        MCT_CUDA(ctx, cudaMalloc(&c->d_nout, 4)); MCT_CUDA(ctx, cudaMemset(c->d_nout, 0, 4));
+        MCT_CUDA(ctx, cudaMalloc(&c->d_nbig, 4)); MCT_CUDA(ctx, cudaMemset(c->d_nbig, 0, 4));
     }
     *out = c;
     return MCT_OK;
@@ -385,7 +407,7 @@ extern "C" int mct_classifier_destroy(mct_clf* c)
     cudaStreamSynchronize(c->ctx->stream);
     void* ptrs[] = {c->d_rects, c->d_wts, c->d_nrect, c->d_weak, c->d_trained, c->d_sel, c->d_nsel, c->d_tcol, c->d_trow,
                     c->d_tsx, c->d_tsy, c->d_tw, c->d_featT, c->d_pred, c->d_col, c->d_row, c->d_sx, c->d_sy, c->d_featN,
-                    c->d_H, c->d_outbins, c->d_colorrow};
+                    c->d_H, c->d_outbins, c->d_colorrow, c->d_slotmap, c->d_nout, c->d_slotimg, c->d_big, c->d_nbig};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete c;
     return MCT_OK;
@@ -436,6 +458,7 @@ static int clf_train_common(mct_clf* c, int P, int Nn, const float* wpos, const 
     int rc;
     if ((rc = launch_weak_update(c, P, Nn, has_w))) return rc;
     if ((rc = launch_mil_select(c, P, Nn))) return rc;
+    if ((rc = launch_build_colormap(c))) return rc;
     c->lastP = P; c->lastNn = Nn;
     return MCT_OK;
 }
@@ -476,7 +499,10 @@ static void fill_clf_desc(ObjDesc* d, mct_clf* c)
     d->rects = c->d_rects; d->wts = c->d_wts; d->nrect = c->d_nrect;
     d->weak = c->d_weak; d->sel = c->d_sel; d->nsel = c->d_nsel;
     d->featN = c->d_featN; d->ldN = c->ldN; d->n_color_rows = c->n_color;
-    d->colorrow = c->d_colorrow; d->outbins = nullptr;
+    d->colorrow = c->d_colorrow; d->outbins = c->d_outbins;
+    const bool mdch = c->p.feature_type == MCT_FEAT_MDCH || c->p.feature_type == MCT_FEAT_HAAR_MDCH;
+    d->slotmap = c->d_slotmap; d->slotimg = mdch ? c->d_slotimg : nullptr; d->nout = c->d_nout; d->big = c->d_big; d->nbig = c->d_nbig;
+    d->cw0 = c->p.w0; d->ch0 = c->p.h0;
     d->F = c->F; d->n_haar = c->n_haar; d->nb = c->p.n_bins; d->weak_type = c->p.weak_type;
     d->feature_type = c->p.feature_type; d->cch_mode = c->p.cch_mode; d->K = c->K;
 }
@@ -491,6 +517,15 @@ static int classify_boxes_on_device(mct_clf* c, int n, int from_matrix, int log_
     h->N = n; h->ld = c->ldN;
     h->col = c->d_col; h->row = c->d_row; h->sx = c->d_sx; h->sy = c->d_sy; h->valid = nullptr; h->H = c->d_H;
     if ((rc = desc_commit(ctx, slot, 1))) return rc;
+    if (!from_matrix && c->n_color > 0) {
+        if (h->slotimg) {
+            if ((rc = launch_bin_image(ctx, c->p.n_bins))) return rc;
+            MCT_CUDA(ctx, cudaMemsetAsync(c->d_nbig, 0, 4, ctx->stream));
+            if ((rc = launch_mdch_selected(ctx, d, 1, n, (c->K < c->n_color ? c->K : c->n_color) + 1))) return rc;
+        } else if ((rc = mct_feature_color_rows(c, c->d_col, c->d_row, c->d_sx, c->d_sy, nullptr, n, nullptr, c->n_color,
+                                                c->d_featN, c->ldN)))
+            return rc;
+    }
     return launch_classify(ctx, d, 1, n, c->K, from_matrix, log_ratio);
 }
 
@@ -505,9 +540,6 @@ extern "C" int mct_classifier_classify(mct_clf* c, const mct_boxes* boxes, int l
     MCT_CUDA(ctx, cudaSetDevice(ctx->device));
     if ((rc = clf_ensure_test(c, n, c->n_color))) return rc;
     if ((rc = upload_boxes(ctx, boxes, c->d_col, c->d_row, c->d_sx, c->d_sy, 0))) return rc;
-    if (c->n_color > 0 &&
-        (rc = mct_feature_color_rows(c, c->d_col, c->d_row, c->d_sx, c->d_sy, nullptr, n, nullptr, c->n_color, c->d_featN, c->ldN)))
-        return rc;
     if ((rc = classify_boxes_on_device(c, n, 0, log_ratio))) return rc;
     MCT_CUDA(ctx, cudaMemcpyAsync(out_host, c->d_H, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     return mct_sync(ctx);
@@ -784,14 +816,27 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
     if ((rc = desc_commit(ctx, slot, n_obj))) return rc;
     if ((rc = launch_pf_predict(ctx, d, n_obj, n_max))) return rc;
     if ((rc = launch_pf_testset(ctx, d, n_obj, n_max))) return rc;
+    int any_mdch = 0, max_slots = 1;
     for (int o = 0; o < n_obj; o++) {
         mct_clf* c = clfs[o]; mct_pf* p = pfs[o];
-        if (c->n_color > 0) {
+        if (c->n_color <= 0) continue;
+        if (h[o].slotimg) {
+            any_mdch = 1;
+            int ms = (c->K < c->n_color ? c->K : c->n_color) + 1;
+            if (ms > max_slots) max_slots = ms;
+            MCT_CUDA(ctx, cudaMemsetAsync(c->d_nbig, 0, 4, ctx->stream));
+        } else {
             float* sx = p->d_state + 2 * (size_t)p->ld; float* sy = p->d_state + 3 * (size_t)p->ld;
             if ((rc = mct_feature_color_rows(c, p->d_col, p->d_row, sx, sy, p->d_valid, p->N, nullptr, c->n_color,
                                              c->d_featN, c->ldN)))
                 return rc;
         }
+    }
+    if (any_mdch) {
+        int nb = 0;
+        for (int o = 0; o < n_obj; o++) if (h[o].slotimg) nb = clfs[o]->p.n_bins;
+        if ((rc = launch_bin_image(ctx, nb))) return rc;
+        if ((rc = launch_mdch_selected(ctx, d, n_obj, n_max, max_slots))) return rc;
     }
     if ((rc = launch_classify(ctx, d, n_obj, n_max, K_max, 0, 1))) return rc;
     if ((rc = launch_pf_update(ctx, d, n_obj, n_max, 1))) return rc;

@@ -69,8 +69,13 @@ struct mct_clf {
     int* d_col; int* d_row; float* d_sx; float* d_sy;
     float* d_featN; size_t featN_cap;                   // [rows][ldN]
     float* d_H;
-    // selected colour rows map for classify
-    int* d_outbins; int* d_colorrow;                    // [n_color]: bins to write / feature -> row in featN
+    // selected colour rows map for classify (built on the device from the selector list after every Update)
+    int* d_outbins; int* d_colorrow;                    // [n_color]: bins to write / colour feature -> row in featN
+    uint16_t* d_slotmap;                                // [n_color]: joint bin -> private-histogram slot (0 = not selected)
+    int* d_nout;                                        // device: number of selected colour bins
+    uint16_t* d_slotimg; size_t slotimg_cap;            // per-frame slot image [H][W]
+    int* d_big; int big_cap;                            // per test box: 1 = left to the generic (large / odd box) kernel
+    int* d_nbig;                                        // device counter of such boxes
 };
 
 struct mct_pf {
@@ -107,7 +112,8 @@ struct ObjDesc {
     const float* weak; const int* sel; const int* nsel;
     float* featN; int ldN; int n_color_rows;
     const int* colorrow; const int* outbins;
-    int F, n_haar, nb, weak_type, feature_type, cch_mode, K, pad1;
+    const uint16_t* slotmap; uint16_t* slotimg; const int* nout; int* big; int* nbig;
+    int F, n_haar, nb, weak_type, feature_type, cch_mode, K, cw0, ch0, pad1;
 };
 
 // ------------------------------------------------------------------ error helpers
@@ -157,6 +163,10 @@ int mct_feature_matrix_full(mct_clf* clf, const int* d_col, const int* d_row, co
 // colour rows needed by Classify: the selected bins only (MDCH) / all 11 (CCH)
 int mct_feature_color_rows(mct_clf* clf, const int* d_col, const int* d_row, const float* d_sx, const float* d_sy,
                            const int* d_valid, int n, const int* d_outbins, int n_out, float* d_out, int ld);
+// MDCH rows of the selected bins for the test boxes of n_obj objects in one batched pass (slot image +
+// private-histogram kernel + generic fallback for large boxes)
+int launch_build_colormap(mct_clf* clf);
+int launch_mdch_selected(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int max_slots);
 int launch_classify(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int K_max, int from_matrix, int log_ratio);
 int launch_pf_predict(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max);
 int launch_pf_testset(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max);
