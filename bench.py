@@ -307,8 +307,10 @@ def run_ours(args):
         dom_name, (dom_ms, dom_n) = dom
         avg_us = 1e3 * dom_ms / max(dom_n, 1)
         rows, cols = seq.h0, seq.w0
+        mdch_bytes = N_OBJ * N_PART * (rows * cols * 3 + (N_BINS ** 3) * 4)   # B_mdch = N*rows*cols*3 + N*nb^3*4, all objects
         alg = {   # ALGORITHMIC bytes per launch, see DESIGN.md
             "k_mdch": N_PART * rows * cols * 3 + N_PART * (N_BINS ** 3) * 4,
+            "k_mdch_sel": mdch_bytes, "k_mdch_score": mdch_bytes,
             "k_classify": N_OBJ * N_PART * (50 * 4 * 16 + (CONFIG["selected"] - 50) * 4 + 4),
             "k_integral_band": W * H + (W + 1) * (H + 1) * 4,
             "k_pf_update": N_OBJ * N_PART * 44,

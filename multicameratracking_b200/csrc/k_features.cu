@@ -250,20 +250,29 @@ int mct_feature_color_rows(mct_clf* clf, const int* d_col, const int* d_row, con
 
 // ==========================================================================================
 // MDCH for Classify: only the SELECTED colour bins are read by the strong classifier
-// (MILBoostClassifier.cpp:351-361), so the test-set pass keeps, per box, one private fixed-point
-// accumulator per selected bin plus one "everything else" slot for the normaliser.
+// (MILBoostClassifier.cpp:351-361), so the test-set pass keeps, per box, one fixed-point accumulator per
+// selected bin ("slot"; slot 0 collects every unselected bin).
 //
-//   k_build_colormap : selector list -> bin->slot map, colour feature -> featN row   (once per Update)
-//   k_slot_image     : slot image S[y][x] = slotmap[bin(x,y)] per object               (once per frame)
-//   k_mdch_sel       : ONE THREAD PER BOX; the thread's accumulators live in shared memory as
-//                      hist[slot][lane] (bank == lane: conflict-free plain LDS/IADD/STS, no atomics --
-//                      shared atomics cost ~2 cycles per lane on sm_100a and were 80 % of the step);
-//                      the Gaussian weights of the common box size come from a per-CTA fixed-point LUT
-//                      (they depend on the offset inside the box only: cX - x = cols/2 - c exactly);
-//                      output rows [selected bin][box] are coalesced over the box index.
-//   k_mdch_big       : generic warp-per-box kernel for boxes the fast kernel leaves (more than
-//                      MCT_MDCH_SEG_PIX pixels, where a u32 accumulator would lose precision).
-// L1/L2-resident gather kernel: per box rows*cols slot reads (2 B) + LUT reads (broadcast) + smem RMW.
+//   k_build_colormap : selector list -> bin->slot map, colour feature -> featN row      (once per Update)
+//   k_mdch_sel       : persistent CTAs, each owning a contiguous chunk of ONE object's test boxes:
+//       1. bounding box of the chunk's boxes; the joint-bin image of that region is staged ONCE into shared
+//          memory as u8 slots (slot map applied while staging: 4 pixels per thread, one packed STS);
+//       2. the Gaussian weights depend on the offset inside the box only (cX - x = cols/2 - c exactly), so one
+//          fixed-point LUT per CTA serves every box of the common size (MultiDimensionalColorHistogram.cpp:
+//          66-69, 87-89, 107-110; weights in [e^-1, 1], scale 2^20 -> <= 2.6e-6 relative quantisation);
+//       3. T = cols/4 lanes per box, each lane owning a 4-pixel column strip and a PRIVATE histogram
+//          hist[slot][lane] (bank == lane: conflict-free plain LDS/IADD/STS -- shared atomics cost 2 cycles per
+//          lane on sm_100a, and warp match/redux aggregation 29 cycles per 32 pixels; both were measured slower,
+//          see tools/mdch_lab.cu).  The four read-modify-writes of a row are issued as 4 loads, a register
+//          forwarding network for equal slots, and 4 stores: one LDS latency per 4 pixels instead of four;
+//       4. the T partial histograms of a box are summed (skewed order: no bank conflicts) and normalised:
+//          normalizeVec (Public.h:270-275) divides by the sum over all nb^3 bins, which for a box inside the
+//          frame is the LUT total.
+//     Integer accumulation is order independent, so the result is run-to-run bit-stable.
+//   k_mdch_big       : generic warp-per-box kernel for the boxes k_mdch_sel flags (other size than the chunk's
+//                      common one, crossing the frame, > 128 columns, region larger than shared memory, or more
+//                      than 255 selected bins).
+// Shared-memory-resident gather kernel: per box rows*cols slot bytes + LUT words + private RMW traffic.
 // ==========================================================================================
 __global__ void k_build_colormap(const int* __restrict__ sel, const int* __restrict__ nsel, int n_haar, int n_color,
                                  uint16_t* __restrict__ slotmap, int* __restrict__ colorrow, int* __restrict__ outbins,
@@ -292,126 +301,188 @@ int launch_build_colormap(mct_clf* clf)
     return MCT_OK;
 }
 
-__global__ void __launch_bounds__(256) k_slot_image(const ObjDesc* __restrict__ descs, const uint16_t* __restrict__ binimg, int npix)
-{
-    __shared__ uint16_t sm_map[4096];
-    const ObjDesc& d = descs[blockIdx.y];
-    if (d.slotimg == nullptr) return;
-    const int dim = d.n_color_rows;
-    for (int b = threadIdx.x; b < dim; b += blockDim.x) sm_map[b] = d.slotmap[b];
-    __syncthreads();
-    // 2 pixels per thread (u32 in, u32 out)
-    const int p = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-    if (p + 1 < npix) {
-        const uint32_t v = *reinterpret_cast<const uint32_t*>(binimg + p);
-        const uint32_t o = (uint32_t)sm_map[v & 0xffffu] | ((uint32_t)sm_map[v >> 16] << 16);
-        *reinterpret_cast<uint32_t*>(d.slotimg + p) = o;
-    } else if (p < npix) {
-        d.slotimg[p] = sm_map[binimg[p]];
-    }
-}
-
-#define MDS_WARPS 2
-#define MDS_LUT_CAP MCT_MDCH_SEG_PIX
-__global__ void __launch_bounds__(MDS_WARPS * 32)
-k_mdch_sel(const ObjDesc* __restrict__ descs, int W, int H, int max_slots)
+#define MDS_WARPS 16
+#define MDS_SMEM (226 * 1024)
+__global__ void __launch_bounds__(MDS_WARPS * 32, 1)
+k_mdch_sel(const ObjDesc* __restrict__ descs, const uint16_t* __restrict__ binimg, int W, int H, int smem_bytes)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
-    uint32_t* lut = (uint32_t*)smraw;                                   // [MDS_LUT_CAP] fixed-point weights of the ref box size
-    uint32_t* hist_all = lut + MDS_LUT_CAP;                             // [MDS_WARPS][max_slots][32]
-    __shared__ int s_ref, s_rows, s_cols;
+    __shared__ int s_bb[4], s_ref, s_rows, s_cols;
+    __shared__ uint32_t s_tot[MDS_WARPS];
     const ObjDesc& d = descs[blockIdx.y];
-    if (d.slotimg == nullptr) return;
-    const int N = d.N;
-    if ((int)(blockIdx.x * blockDim.x) >= N) return;
+    if (d.slotmap == nullptr) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int i = blockIdx.x * blockDim.x + tid;
-    uint32_t* hist = hist_all + (size_t)warp * max_slots * 32 + lane;   // element s at hist[s * 32]
-    const int n_out = *d.nout;
-    const int n_slots = n_out + 1;
+    const int N = d.N;
+    const int chunk = (N + gridDim.x - 1) / gridDim.x;
+    const int i_begin = blockIdx.x * chunk, i_end = min(N, i_begin + chunk);
+    if (i_begin >= i_end) return;
+    const int n_out = *d.nout, n_slots = n_out + 1, dim = d.n_color_rows;
 
-    bool valid = i < N && (d.valid == nullptr || d.valid[i] != 0);
-    int c0 = 0, r0 = 0, rows = 0, cols = 0, npix = 0;
-    if (valid) {
-        c0 = d.col[i]; r0 = d.row[i];
-        rows = __float2int_rn(__fmul_rn((float)d.ch0, d.sy[i]));
-        cols = __float2int_rn(__fmul_rn((float)d.cw0, d.sx[i]));
-        npix = rows * cols;
+    // ---- 1. common box size of the chunk (first usable box) and bounding box of the conforming boxes
+    if (tid == 0) { s_ref = 0x7fffffff; s_bb[0] = 1 << 30; s_bb[1] = 1 << 30; s_bb[2] = -(1 << 30); s_bb[3] = -(1 << 30); }
+    __syncthreads();
+    // per-thread view of its boxes is recomputed where needed (registers are scarce in the main loop)
+    for (int i = i_begin + tid; i < i_end; i += blockDim.x) {
+        if (d.valid != nullptr && d.valid[i] == 0) continue;
+        const int rows = __float2int_rn(__fmul_rn((float)d.ch0, d.sy[i]));
+        const int cols = __float2int_rn(__fmul_rn((float)d.cw0, d.sx[i]));
+        const int c0 = d.col[i], r0 = d.row[i];
+        if (rows > 0 && cols > 0 && cols <= 128 && c0 >= 0 && r0 >= 0 && c0 + cols <= W && r0 + rows <= H) atomicMin(&s_ref, i);
     }
-    const bool big = valid && (npix > MDS_LUT_CAP || npix <= 0);
-    if (tid == 0) s_ref = 0x7fffffff;
     __syncthreads();
-    if (valid && !big) atomicMin(&s_ref, tid);
+    const int ref = s_ref;
+    if (tid == 0 && ref != 0x7fffffff) {
+        s_rows = __float2int_rn(__fmul_rn((float)d.ch0, d.sy[ref]));
+        s_cols = __float2int_rn(__fmul_rn((float)d.cw0, d.sx[ref]));
+    }
     __syncthreads();
-    if (s_ref == tid) { s_rows = rows; s_cols = cols; }
+    const int rows = ref != 0x7fffffff ? s_rows : 0, cols = ref != 0x7fffffff ? s_cols : 0;
+    const int colsp = (cols + 3) & ~3, T = max(colsp >> 2, 1), BPW = 32 / T;
+    {
+        int x0 = 1 << 30, y0 = 1 << 30, x1 = -(1 << 30), y1 = -(1 << 30);
+        for (int i = i_begin + tid; i < i_end; i += blockDim.x) {
+            if (d.valid != nullptr && d.valid[i] == 0) continue;
+            const int br = __float2int_rn(__fmul_rn((float)d.ch0, d.sy[i]));
+            const int bc = __float2int_rn(__fmul_rn((float)d.cw0, d.sx[i]));
+            const int c0 = d.col[i], r0 = d.row[i];
+            if (br == rows && bc == cols && c0 >= 0 && r0 >= 0 && c0 + cols <= W && r0 + rows <= H) {
+                x0 = min(x0, c0); y0 = min(y0, r0); x1 = max(x1, c0); y1 = max(y1, r0);
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+            x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+        }
+        if (lane == 0 && x1 >= x0) { atomicMin(&s_bb[0], x0); atomicMin(&s_bb[1], y0); atomicMax(&s_bb[2], x1); atomicMax(&s_bb[3], y1); }
+    }
     __syncthreads();
-    const int ref_rows = s_rows, ref_cols = s_cols;
-    if (s_ref != 0x7fffffff) {
-        // weight LUT of the reference box size (MultiDimensionalColorHistogram.cpp:66-69,87-89,107-110)
-        const int np = ref_rows * ref_cols;
-        int shift = __clz(np); if (shift > MCT_FIX_SHIFT_MAX) shift = MCT_FIX_SHIFT_MAX;
+    // ---- 2. shared-memory plan: LUT | slot map | per-warp private histograms | region
+    const int bx0 = s_bb[0] & ~3, by0 = s_bb[1];
+    const int RW = s_bb[2] + colsp - bx0, RH = s_bb[3] + rows - by0 + 1;      // +1 row: the row prefetch stays inside
+    const int RWp = ((RW + 3) & ~3) + 4;
+    uint32_t* lut = (uint32_t*)smraw;                                         // [(rows + 1)][colsp], last row zero
+    const size_t lut_b = (size_t)(rows + 1) * colsp * 4;
+    uint16_t* smap = (uint16_t*)(smraw + lut_b);                              // [dim]
+    const size_t map_b = ((size_t)dim * 2 + 15) & ~(size_t)15;
+    const size_t reg_b = ((size_t)RWp * max(RH, 0) + 15) & ~(size_t)15;
+    const size_t hist_b = (size_t)n_slots * 128;
+    int warps_used = 0;
+    bool fast = ref != 0x7fffffff && s_bb[2] >= s_bb[0] && n_slots <= 256 && T <= 32 && (W & 3) == 0 &&
+                lut_b + map_b + reg_b + hist_b <= (size_t)smem_bytes;
+    if (fast) warps_used = min(MDS_WARPS, (int)(((size_t)smem_bytes - lut_b - map_b - reg_b) / hist_b));
+    uint8_t* region = smraw + lut_b + map_b;
+    uint32_t* hist_all = (uint32_t*)(smraw + lut_b + map_b + reg_b);
+    if (!fast) {
+        // everything in this chunk goes to the generic kernel
+        for (int i = i_begin + tid; i < i_end; i += blockDim.x) {
+            const bool v = d.valid == nullptr || d.valid[i] != 0;
+            d.big[i] = v ? 1 : 0;
+            if (v) atomicAdd(d.nbig, 1);
+            else for (int o = 0; o < n_out; o++) d.featN[(size_t)o * d.ldN + i] = 0.0f;
+        }
+        return;
+    }
+    // ---- 3. LUT, slot map, region
+    int shift = __clz(rows * cols); if (shift > MCT_FIX_SHIFT_MAX) shift = MCT_FIX_SHIFT_MAX;
+    {
         const float scale = (float)(1u << shift);
-        const float hx = __fdiv_rn((float)ref_cols, 2.0f), hy = __fdiv_rn((float)ref_rows, 2.0f);
+        const float hx = __fdiv_rn((float)cols, 2.0f), hy = __fdiv_rn((float)rows, 2.0f);
         const double ivx = 1.0 / (double)__fmul_rn(2.0f, __fmul_rn(hx, hx));
         const double ivy = 1.0 / (double)__fmul_rn(2.0f, __fmul_rn(hy, hy));
-        for (int p = tid; p < np; p += blockDim.x) {
-            const int r = p / ref_cols, c = p - r * ref_cols;
-            const double dx = (double)__fsub_rn(hx, (float)c), dy = (double)__fsub_rn(hy, (float)r);
-            const float wd = (float)(dx * dx * ivx + dy * dy * ivy);
-            lut[p] = __float2uint_rn(__fmul_rn(expf(-wd), scale));
+        uint32_t part = 0;
+        for (int p = tid; p < (rows + 1) * colsp; p += blockDim.x) {
+            const int r = p / colsp, c = p - r * colsp;
+            uint32_t w = 0;
+            if (c < cols && r < rows) {
+                const double dx = (double)__fsub_rn(hx, (float)c), dy = (double)__fsub_rn(hy, (float)r);
+                const float wd = (float)(dx * dx * ivx + dy * dy * ivy);
+                w = __float2uint_rn(__fmul_rn(expf(-wd), scale));
+            }
+            lut[p] = w;
+            part += w;
         }
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) s_tot[warp] = part;
     }
-    for (int s = 0; s < n_slots; s++) hist[s * 32] = 0u;
+    for (int b = tid; b < dim; b += blockDim.x) smap[b] = d.slotmap[b];
     __syncthreads();
-
-    float inv_scale = 0.0f;
-    if (valid && !big) {
-        int shift = __clz(npix); if (shift > MCT_FIX_SHIFT_MAX) shift = MCT_FIX_SHIFT_MAX;
-        inv_scale = __fdiv_rn(1.0f, (float)(1u << shift));
-        const bool inside = c0 >= 0 && r0 >= 0 && c0 + cols <= W && r0 + rows <= H;
-        if (inside && rows == ref_rows && cols == ref_cols) {
-            // fast path: slot image gather + LUT weight + private accumulator
-            const uint16_t* img = d.slotimg + (size_t)r0 * W + c0;
-            const uint32_t* lr = lut;
-            for (int r = 0; r < rows; r++) {
-                int c = 0;
-                for (; c + 4 <= cols; c += 4) {
-                    const unsigned s0 = img[c], s1 = img[c + 1], s2 = img[c + 2], s3 = img[c + 3];
-                    const uint32_t w0 = lr[c], w1 = lr[c + 1], w2 = lr[c + 2], w3 = lr[c + 3];
-                    hist[s0 * 32] += w0; hist[s1 * 32] += w1; hist[s2 * 32] += w2; hist[s3 * 32] += w3;
-                }
-                for (; c < cols; c++) hist[(unsigned)img[c] * 32] += lr[c];
-                img += W; lr += cols;
-            }
-        } else {
-            // same arithmetic, weights computed per pixel (box size differs from the CTA's LUT, or box crosses the frame)
-            const float scale = (float)(1u << shift);
-            const float hx = __fdiv_rn((float)cols, 2.0f), hy = __fdiv_rn((float)rows, 2.0f);
-            const double ivx = 1.0 / (double)__fmul_rn(2.0f, __fmul_rn(hx, hx));
-            const double ivy = 1.0 / (double)__fmul_rn(2.0f, __fmul_rn(hy, hy));
-            for (int r = 0; r < rows; r++) {
-                const int yy = clampi(r0 + r, 0, H - 1);
-                const double dy = (double)__fsub_rn(hy, (float)r);
-                const double ay = dy * dy * ivy;
-                for (int c = 0; c < cols; c++) {
-                    const int xx = clampi(c0 + c, 0, W - 1);
-                    const double dx = (double)__fsub_rn(hx, (float)c);
-                    const float wd = (float)(dx * dx * ivx + ay);
-                    hist[(unsigned)d.slotimg[(size_t)yy * W + xx] * 32] += __float2uint_rn(__fmul_rn(expf(-wd), scale));
-                }
-            }
+    uint32_t total = 0;
+    for (int q = 0; q < MDS_WARPS; q++) total += s_tot[q];
+    {
+        const int qw = RWp >> 2;                                              // 4-pixel groups per region row
+        uint32_t* r32 = reinterpret_cast<uint32_t*>(region);
+        for (int g = tid; g < qw * RH; g += blockDim.x) {
+            const int y = g / qw, xg = g - y * qw;
+            const int yy = min(by0 + y, H - 1), xx = min(bx0 + 4 * xg, W - 4);
+            const uint2 px = *reinterpret_cast<const uint2*>(binimg + (size_t)yy * W + xx);
+            r32[g] = (uint32_t)smap[px.x & 0xffffu] | ((uint32_t)smap[px.x >> 16] << 8) |
+                     ((uint32_t)smap[px.y & 0xffffu] << 16) | ((uint32_t)smap[px.y >> 16] << 24);
         }
     }
-    if (i < N) {
-        if (d.big) d.big[i] = big ? 1 : 0;
-        if (big && d.nbig) atomicAdd(d.nbig, 1);
-        // normalizeVec: bins / sum(bins); the sum over all nb^3 bins == sum over the slots (slot 0 = unselected bins)
-        uint32_t total = 0;
-        for (int s = 0; s < n_slots; s++) total += hist[s * 32];
-        const float S = __fmul_rn((float)total, inv_scale);
-        const bool ok = valid && !big;
-        for (int o = 0; o < n_out; o++)
-            d.featN[(size_t)o * d.ldN + i] = ok ? __fdiv_rn(__fmul_rn((float)hist[(o + 1) * 32], inv_scale), S) : 0.0f;
+    __syncthreads();
+    // ---- 4. rounds of warps_used * BPW boxes
+    const float inv_scale = __fdiv_rn(1.0f, (float)(1u << shift));
+    const float S = __fmul_rn((float)total, inv_scale);
+    const int bw = lane / T, j = lane - bw * T;
+    const int q4 = colsp >> 2, rstep = RWp >> 2;
+    if (warp < warps_used) {
+        uint32_t* hist = hist_all + (size_t)warp * n_slots * 32 + lane;       // element s at hist[s * 32]
+        for (int base = i_begin + warp * BPW; base < i_end; base += warps_used * BPW) {
+            for (int s = 0; s < n_slots; s++) hist[s * 32] = 0u;
+            __syncwarp();
+            const int i = base + bw;
+            const bool mine = bw < BPW && i < i_end;
+            bool ok = false, valid = false;
+            if (mine) {
+                valid = d.valid == nullptr || d.valid[i] != 0;
+                if (valid) {
+                    const int br = __float2int_rn(__fmul_rn((float)d.ch0, d.sy[i]));
+                    const int bc = __float2int_rn(__fmul_rn((float)d.cw0, d.sx[i]));
+                    const int c0 = d.col[i], r0 = d.row[i];
+                    ok = br == rows && bc == cols && c0 >= 0 && r0 >= 0 && c0 + cols <= W && r0 + rows <= H;
+                    if (ok) {
+                        const int addr = (r0 - by0) * RWp + (c0 - bx0) + 4 * j;
+                        const uint4* l4 = reinterpret_cast<const uint4*>(lut) + j;
+                        const uint32_t* wp = reinterpret_cast<const uint32_t*>(region + (addr & ~3));
+                        const int sh = (addr & 3) * 8;
+                        uint32_t v = __funnelshift_r(wp[0], wp[1], sh);
+                        uint4 w = l4[0];
+                        for (int r = 0; r < rows; r++) {
+                            wp += rstep; l4 += q4;
+                            const uint32_t vn = __funnelshift_r(wp[0], wp[1], sh);    // next row (row `rows` is padding)
+                            const uint4 wn = l4[0];
+                            const uint32_t s0 = v & 0xffu, s1 = (v >> 8) & 0xffu, s2 = (v >> 16) & 0xffu, s3 = v >> 24;
+                            const uint32_t h0 = hist[s0 * 32], h1 = hist[s1 * 32], h2 = hist[s2 * 32], h3 = hist[s3 * 32];
+                            const uint32_t n0 = h0 + w.x;
+                            const uint32_t n1 = (s1 == s0 ? n0 : h1) + w.y;
+                            uint32_t t = (s2 == s0 ? n0 : h2); t = (s2 == s1 ? n1 : t);
+                            const uint32_t n2 = t + w.z;
+                            t = (s3 == s0 ? n0 : h3); t = (s3 == s1 ? n1 : t); t = (s3 == s2 ? n2 : t);
+                            const uint32_t n3 = t + w.w;
+                            hist[s0 * 32] = n0; hist[s1 * 32] = n1; hist[s2 * 32] = n2; hist[s3 * 32] = n3;
+                            v = vn; w = wn;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (mine) {
+                if (j == 0) {
+                    const int flag = (valid && !ok) ? 1 : 0;
+                    d.big[i] = flag;
+                    if (flag) atomicAdd(d.nbig, 1);
+                }
+                const uint32_t* hb = hist_all + (size_t)warp * n_slots * 32 + bw * T;
+                float* dst = d.featN + i;
+                for (int s = 1 + j; s < n_slots; s += T) {
+                    uint32_t t = 0;
+                    int qq = j;                                               // skewed start: the lanes of a box hit distinct banks
+                    for (int k = 0; k < T; k++) { t += hb[s * 32 + qq]; qq = (qq + 1 == T) ? 0 : qq + 1; }
+                    dst[(size_t)(s - 1) * d.ldN] = ok ? __fdiv_rn(__fmul_rn((float)t, inv_scale), S) : 0.0f;
+                }
+            }
+            __syncwarp();
+        }
     }
 }
 
@@ -422,7 +493,7 @@ k_mdch_big(const ObjDesc* __restrict__ descs, const uint16_t* __restrict__ binim
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     const ObjDesc& d = descs[blockIdx.y];
-    if (d.slotimg == nullptr || d.nbig == nullptr || *d.nbig == 0) return;
+    if (d.slotmap == nullptr || d.nbig == nullptr || *d.nbig == 0) return;
     const int nb = d.nb, dim = nb * nb * nb;
     uint32_t* hist_all = (uint32_t*)smraw;
     float* acc_all = (float*)(hist_all + MDCH_WARPS * dim);
@@ -473,19 +544,20 @@ k_mdch_big(const ObjDesc* __restrict__ descs, const uint16_t* __restrict__ binim
 
 int launch_mdch_selected(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int max_slots)
 {
+    (void)max_slots;
     if (n_obj <= 0 || n_max <= 0) return MCT_OK;
-    const int npix = ctx->W * ctx->H;
-    dim3 g0(ceil_div(ceil_div(npix, 2), 256), n_obj);
-    MCT_LAUNCH(ctx, "k_slot_image", k_slot_image<<<g0, 256, 0, ctx->stream>>>(d_desc, ctx->binimg, npix));
-    size_t smem = (size_t)MDS_LUT_CAP * 4 + (size_t)MDS_WARPS * max_slots * 32 * 4;
-    static size_t s_attr = 48 * 1024;
-    if (smem > 220 * 1024) return mct_fail(ctx, MCT_E_UNSUPPORTED, "too many selected colour bins for the private-histogram kernel%s (%d)", "", max_slots);
-    if (smem > s_attr) {
-        MCT_CUDA(ctx, cudaFuncSetAttribute(k_mdch_sel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        s_attr = smem;
+    static int s_attr = 0, s_sms = 0;
+    if (!s_attr) {
+        MCT_CUDA(ctx, cudaFuncSetAttribute(k_mdch_sel, cudaFuncAttributeMaxDynamicSharedMemorySize, MDS_SMEM));
+        MCT_CUDA(ctx, cudaDeviceGetAttribute(&s_sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        s_attr = 1;
     }
-    dim3 g1(ceil_div(n_max, MDS_WARPS * 32), n_obj);
-    MCT_LAUNCH(ctx, "k_mdch_sel", k_mdch_sel<<<g1, MDS_WARPS * 32, smem, ctx->stream>>>(d_desc, ctx->W, ctx->H, max_slots));
+    // one persistent CTA per SM, the SMs split evenly over the objects; each CTA owns a contiguous chunk of boxes
+    int per_obj = s_sms / n_obj;
+    if (per_obj < 1) per_obj = 1;
+    if (per_obj > ceil_div(n_max, 3)) per_obj = ceil_div(n_max, 3);
+    dim3 g1(per_obj, n_obj);
+    MCT_LAUNCH(ctx, "k_mdch_sel", k_mdch_sel<<<g1, MDS_WARPS * 32, MDS_SMEM, ctx->stream>>>(d_desc, ctx->binimg, ctx->W, ctx->H, MDS_SMEM));
     // generic fallback for flagged boxes (early exit when none)
     size_t smem2 = (size_t)MDCH_WARPS * 512 * 8;
     static size_t s_attr2 = 0;

@@ -287,13 +287,6 @@ static int clf_ensure_test(mct_clf* clf, int n, int rows)
     }
     clf->ldN = ldN;
     if (clf->p.feature_type == MCT_FEAT_MDCH || clf->p.feature_type == MCT_FEAT_HAAR_MDCH) {
-        size_t px = (size_t)ctx->W * ctx->H + 2;
-        if (px > clf->slotimg_cap) {
-            MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            if (clf->d_slotimg) cudaFree(clf->d_slotimg);
-            MCT_CUDA(ctx, cudaMalloc(&clf->d_slotimg, px * sizeof(uint16_t)));
-            clf->slotimg_cap = px;
-        }
         if (n > clf->big_cap) {
             MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             if (clf->d_big) cudaFree(clf->d_big);
@@ -407,7 +400,7 @@ extern "C" int mct_classifier_destroy(mct_clf* c)
     cudaStreamSynchronize(c->ctx->stream);
     void* ptrs[] = {c->d_rects, c->d_wts, c->d_nrect, c->d_weak, c->d_trained, c->d_sel, c->d_nsel, c->d_tcol, c->d_trow,
                     c->d_tsx, c->d_tsy, c->d_tw, c->d_featT, c->d_pred, c->d_col, c->d_row, c->d_sx, c->d_sy, c->d_featN,
-                    c->d_H, c->d_outbins, c->d_colorrow, c->d_slotmap, c->d_nout, c->d_slotimg, c->d_big, c->d_nbig};
+                    c->d_H, c->d_outbins, c->d_colorrow, c->d_slotmap, c->d_nout, c->d_big, c->d_nbig};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete c;
     return MCT_OK;
@@ -501,7 +494,7 @@ static void fill_clf_desc(ObjDesc* d, mct_clf* c)
     d->featN = c->d_featN; d->ldN = c->ldN; d->n_color_rows = c->n_color;
     d->colorrow = c->d_colorrow; d->outbins = c->d_outbins;
     const bool mdch = c->p.feature_type == MCT_FEAT_MDCH || c->p.feature_type == MCT_FEAT_HAAR_MDCH;
-    d->slotmap = c->d_slotmap; d->slotimg = mdch ? c->d_slotimg : nullptr; d->nout = c->d_nout; d->big = c->d_big; d->nbig = c->d_nbig;
+    d->slotmap = mdch ? c->d_slotmap : nullptr; d->nout = c->d_nout; d->big = c->d_big; d->nbig = c->d_nbig;
     d->cw0 = c->p.w0; d->ch0 = c->p.h0;
     d->F = c->F; d->n_haar = c->n_haar; d->nb = c->p.n_bins; d->weak_type = c->p.weak_type;
     d->feature_type = c->p.feature_type; d->cch_mode = c->p.cch_mode; d->K = c->K;
@@ -518,7 +511,7 @@ static int classify_boxes_on_device(mct_clf* c, int n, int from_matrix, int log_
     h->col = c->d_col; h->row = c->d_row; h->sx = c->d_sx; h->sy = c->d_sy; h->valid = nullptr; h->H = c->d_H;
     if ((rc = desc_commit(ctx, slot, 1))) return rc;
     if (!from_matrix && c->n_color > 0) {
-        if (h->slotimg) {
+        if (h->slotmap) {
             if ((rc = launch_bin_image(ctx, c->p.n_bins))) return rc;
             MCT_CUDA(ctx, cudaMemsetAsync(c->d_nbig, 0, 4, ctx->stream));
             if ((rc = launch_mdch_selected(ctx, d, 1, n, (c->K < c->n_color ? c->K : c->n_color) + 1))) return rc;
@@ -820,7 +813,7 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
     for (int o = 0; o < n_obj; o++) {
         mct_clf* c = clfs[o]; mct_pf* p = pfs[o];
         if (c->n_color <= 0) continue;
-        if (h[o].slotimg) {
+        if (h[o].slotmap) {
             any_mdch = 1;
             int ms = (c->K < c->n_color ? c->K : c->n_color) + 1;
             if (ms > max_slots) max_slots = ms;
@@ -834,7 +827,7 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
     }
     if (any_mdch) {
         int nb = 0;
-        for (int o = 0; o < n_obj; o++) if (h[o].slotimg) nb = clfs[o]->p.n_bins;
+        for (int o = 0; o < n_obj; o++) if (h[o].slotmap) nb = clfs[o]->p.n_bins;
         if ((rc = launch_bin_image(ctx, nb))) return rc;
         if ((rc = launch_mdch_selected(ctx, d, n_obj, n_max, max_slots))) return rc;
     }

@@ -73,7 +73,6 @@ struct mct_clf {
     int* d_outbins; int* d_colorrow;                    // [n_color]: bins to write / colour feature -> row in featN
     uint16_t* d_slotmap;                                // [n_color]: joint bin -> private-histogram slot (0 = not selected)
     int* d_nout;                                        // device: number of selected colour bins
-    uint16_t* d_slotimg; size_t slotimg_cap;            // per-frame slot image [H][W]
     int* d_big; int big_cap;                            // per test box: 1 = left to the generic (large / odd box) kernel
     int* d_nbig;                                        // device counter of such boxes
 };
@@ -112,7 +111,7 @@ struct ObjDesc {
     const float* weak; const int* sel; const int* nsel;
     float* featN; int ldN; int n_color_rows;
     const int* colorrow; const int* outbins;
-    const uint16_t* slotmap; uint16_t* slotimg; const int* nout; int* big; int* nbig;
+    const uint16_t* slotmap; const int* nout; int* big; int* nbig;
     int F, n_haar, nb, weak_type, feature_type, cch_mode, K, cw0, ch0, pad1;
 };
 
@@ -163,8 +162,8 @@ int mct_feature_matrix_full(mct_clf* clf, const int* d_col, const int* d_row, co
 // colour rows needed by Classify: the selected bins only (MDCH) / all 11 (CCH)
 int mct_feature_color_rows(mct_clf* clf, const int* d_col, const int* d_row, const float* d_sx, const float* d_sy,
                            const int* d_valid, int n, const int* d_outbins, int n_out, float* d_out, int ld);
-// MDCH rows of the selected bins for the test boxes of n_obj objects in one batched pass (slot image +
-// private-histogram kernel + generic fallback for large boxes)
+// MDCH rows of the selected bins for the test boxes of n_obj objects in one batched pass (persistent
+// private-histogram kernel + generic fallback for non-conforming boxes); slotmap == NULL marks a non-MDCH object
 int launch_build_colormap(mct_clf* clf);
 int launch_mdch_selected(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int max_slots);
 int launch_classify(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int K_max, int from_matrix, int log_ratio);
