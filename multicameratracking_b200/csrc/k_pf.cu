@@ -85,24 +85,27 @@ __device__ __forceinline__ float scale_step_dev(float s, float n, float msc, flo
     if (s < mins) s = mins;
     return s;
 }
-__global__ void __launch_bounds__(256) k_pf_predict(const ObjDesc* __restrict__ descs)
+__device__ __forceinline__ void predict_one(const ObjDesc& d, int i, const float* __restrict__ nz)
 {
-    const ObjDesc& d = descs[blockIdx.y];
     const int N = d.N;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) { d.st->filter_state = MCT_PF_PREDICTED; d.st->time_index += 1; }
-    if (i >= N) return;
-    const float* nz = d.noise;
     float sx = d.sx[i], sy = d.sy[i];
     d.cx[i] = (float)__float2int_rn(__fadd_rn(d.cx[i], __fmul_rn(sx, nz[i])));
     d.cy[i] = (float)__float2int_rn(__fadd_rn(d.cy[i], __fmul_rn(sy, nz[(size_t)N + i])));
     d.sx[i] = scale_step_dev(sx, nz[(size_t)2 * N + i], d.msc, d.maxs, d.mins);
     d.sy[i] = scale_step_dev(sy, nz[(size_t)3 * N + i], d.msc, d.maxs, d.mins);
 }
-int launch_pf_predict(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max)
+__global__ void __launch_bounds__(256) k_pf_predict(const ObjDesc* __restrict__ descs, const StepArgs sa)
+{
+    const ObjDesc& d = descs[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { d.st->filter_state = MCT_PF_PREDICTED; d.st->time_index += 1; }
+    if (i >= d.N) return;
+    predict_one(d, i, sa.noise_base + d.noise_off);
+}
+int launch_pf_predict(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, const StepArgs& sa)
 {
     dim3 g(ceil_div(n_max, 256), n_obj);
-    MCT_LAUNCH(ctx, "k_pf_predict", k_pf_predict<<<g, 256, 0, ctx->stream>>>(d_desc));
+    MCT_LAUNCH(ctx, "k_pf_predict", k_pf_predict<<<g, 256, 0, ctx->stream>>>(d_desc, sa));
     return MCT_OK;
 }
 
@@ -110,11 +113,8 @@ int launch_pf_predict(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max)
 // GenerateTestSampleSet (ParticleFilterTracker.cpp:1247-1305): box per particle; out-of-frame particles
 // get UpdateParticleWeight(p, 0) (weight *= 0 and the scale-ratio clamp); in-frame particles with a
 // non-zero weight form the test set (dense mask instead of the reference's compaction).
-__global__ void __launch_bounds__(256) k_pf_testset(const ObjDesc* __restrict__ descs, int fw, int fh)
+__device__ __forceinline__ void testset_one(const ObjDesc& d, int i, int fw, int fh)
 {
-    const ObjDesc& d = descs[blockIdx.y];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= d.N) return;
     float sx = d.sx[i], sy = d.sy[i];
     const float wf = __fmul_rn(sx, d.w0), hf = __fmul_rn(sy, d.h0);
     const float left = (float)__float2int_rn(__fsub_rn(d.cx[i], __fdiv_rn(wf, 2.0f)));
@@ -131,6 +131,32 @@ __global__ void __launch_bounds__(256) k_pf_testset(const ObjDesc* __restrict__ 
     d.col[i] = (int)left; d.row[i] = (int)top;
     d.valid[i] = v;
 }
+__global__ void __launch_bounds__(256) k_pf_testset(const ObjDesc* __restrict__ descs, int fw, int fh)
+{
+    const ObjDesc& d = descs[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.N) return;
+    testset_one(d, i, fw, fh);
+}
+// batched per-frame form: PredictWithBrownianMotion + GenerateTestSampleSet in one pass over the particles
+__global__ void __launch_bounds__(256) k_pf_predict_testset(const ObjDesc* __restrict__ descs, const StepArgs sa, int fw, int fh)
+{
+    const ObjDesc& d = descs[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        d.st->filter_state = MCT_PF_PREDICTED; d.st->time_index += 1;
+        if (d.nbig) *d.nbig = 0;                       // per-frame reset of the MDCH generic-path counter
+    }
+    if (i >= d.N) return;
+    predict_one(d, i, sa.noise_base + d.noise_off);
+    testset_one(d, i, fw, fh);
+}
+int launch_pf_predict_testset(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, const StepArgs& sa)
+{
+    dim3 g(ceil_div(n_max, 256), n_obj);
+    MCT_LAUNCH(ctx, "k_pf_predict_testset", k_pf_predict_testset<<<g, 256, 0, ctx->stream>>>(d_desc, sa, ctx->W, ctx->H));
+    return MCT_OK;
+}
 int launch_pf_testset(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max)
 {
     dim3 g(ceil_div(n_max, 256), n_obj);
@@ -138,40 +164,65 @@ int launch_pf_testset(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max)
     return MCT_OK;
 }
 
-// Sequential f32 chains in reference order; the operands are fetched eight at a time so that the loop is
-// bound by the dependent FADD (4 cycles) and not by the shared/global load latency.
+// Sequential f32 chains in reference order.  The dependent FADD (4 cycles) is the only thing on the critical
+// path: operands are fetched as float4 one 16-element block AHEAD into registers, so the load latency of block
+// k+1 hides behind the 64 cycles of adds of block k (the earlier scalar-load version paid LDS latency + issue per
+// 8 adds: 9.6 cycles per element instead of 4).  v / w / cdf must be 16-byte aligned.
+#define MCT_ADD4(t, q) t = __fadd_rn(t, q.x); t = __fadd_rn(t, q.y); t = __fadd_rn(t, q.z); t = __fadd_rn(t, q.w)
 __device__ __forceinline__ float chain_sum(const float* __restrict__ v, int n)
 {
     float t = 0.0f;
+    const float4* v4 = reinterpret_cast<const float4*>(v);
+    const int n4 = n >> 2;
     int i = 0;
-    for (; i + 8 <= n; i += 8) {
-        const float a0 = v[i], a1 = v[i + 1], a2 = v[i + 2], a3 = v[i + 3], a4 = v[i + 4], a5 = v[i + 5], a6 = v[i + 6], a7 = v[i + 7];
-        t = __fadd_rn(t, a0); t = __fadd_rn(t, a1); t = __fadd_rn(t, a2); t = __fadd_rn(t, a3);
-        t = __fadd_rn(t, a4); t = __fadd_rn(t, a5); t = __fadd_rn(t, a6); t = __fadd_rn(t, a7);
+    if (n4 >= 4) {
+        float4 b0 = v4[0], b1 = v4[1], b2 = v4[2], b3 = v4[3];
+#pragma unroll 1
+        for (i = 4; i + 4 <= n4; i += 4) {
+            const float4 c0 = v4[i], c1 = v4[i + 1], c2 = v4[i + 2], c3 = v4[i + 3];
+            MCT_ADD4(t, b0); MCT_ADD4(t, b1); MCT_ADD4(t, b2); MCT_ADD4(t, b3);
+            b0 = c0; b1 = c1; b2 = c2; b3 = c3;
+        }
+        MCT_ADD4(t, b0); MCT_ADD4(t, b1); MCT_ADD4(t, b2); MCT_ADD4(t, b3);
     }
-    for (; i < n; i++) t = __fadd_rn(t, v[i]);
+    for (int k = i * 4; k < n; k++) t = __fadd_rn(t, v[k]);
     return t;
 }
 // cdf[0] = 0, cdf[i] = cdf[i-1] + w[i]   (ParticleFilter.cpp:927-933; w[0] excluded -- reference quirk)
+#define MCT_CDF4(c, q, o) o.x = (c = __fadd_rn(c, q.x)); o.y = (c = __fadd_rn(c, q.y)); o.z = (c = __fadd_rn(c, q.z)); o.w = (c = __fadd_rn(c, q.w))
 __device__ __forceinline__ void chain_cdf(const float* __restrict__ w, float* __restrict__ cdf, int n)
 {
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    float4* c4 = reinterpret_cast<float4*>(cdf);
+    const int n4 = n >> 2;
     float c = 0.0f;
-    cdf[0] = 0.0f;
-    int i = 1;
-    for (; i + 8 <= n; i += 8) {
-        const float a0 = w[i], a1 = w[i + 1], a2 = w[i + 2], a3 = w[i + 3], a4 = w[i + 4], a5 = w[i + 5], a6 = w[i + 6], a7 = w[i + 7];
-        c = __fadd_rn(c, a0); cdf[i] = c;     c = __fadd_rn(c, a1); cdf[i + 1] = c;
-        c = __fadd_rn(c, a2); cdf[i + 2] = c; c = __fadd_rn(c, a3); cdf[i + 3] = c;
-        c = __fadd_rn(c, a4); cdf[i + 4] = c; c = __fadd_rn(c, a5); cdf[i + 5] = c;
-        c = __fadd_rn(c, a6); cdf[i + 6] = c; c = __fadd_rn(c, a7); cdf[i + 7] = c;
+    int i = 0;
+    if (n4 >= 3) {
+        // first block: element 0 contributes 0 (cdf[0] = 0, w[0] skipped)
+        float4 b0 = w4[0], b1 = w4[1];
+        b0.x = 0.0f;
+#pragma unroll 1
+        for (i = 2; i + 2 <= n4; i += 2) {
+            const float4 n0 = w4[i], n1 = w4[i + 1];
+            float4 o0, o1;
+            MCT_CDF4(c, b0, o0); MCT_CDF4(c, b1, o1);
+            c4[i - 2] = o0; c4[i - 1] = o1;
+            b0 = n0; b1 = n1;
+        }
+        float4 o0, o1;
+        MCT_CDF4(c, b0, o0); MCT_CDF4(c, b1, o1);
+        c4[i - 2] = o0; c4[i - 1] = o1;
+    } else {
+        cdf[0] = 0.0f;
+        i = 0;
     }
-    for (; i < n; i++) { c = __fadd_rn(c, w[i]); cdf[i] = c; }
+    for (int k = (i == 0 ? 1 : i * 4); k < n; k++) { c = __fadd_rn(c, w[k]); cdf[k] = c; }
 }
 
 // ------------------------------------------------------------------------------------------
 // ResampleParticles body (ParticleFilter.cpp:920-978).  sw = weights after the first normalisation
 // (shared or global), cdf = scratch of the same length.
-__device__ void resample_body(const ObjDesc& d, float* sw, float* cdf, int force, float* sh_f)
+__device__ void resample_body(const ObjDesc& d, float* sw, float* cdf, int force, float* sh_f, float u01)
 {
     const int N = d.N, tid = threadIdx.x, nt = blockDim.x;
     // NormalizeParticleWeights again (:924)
@@ -183,7 +234,7 @@ __device__ void resample_body(const ObjDesc& d, float* sw, float* cdf, int force
     if (tid == 0) chain_cdf(sw, cdf, N);
     __syncthreads();
     const float invN = __fdiv_rn(1.0f, (float)N);
-    const float seed = __fmul_rn(invN, d.u01);
+    const float seed = __fmul_rn(invN, u01);
     for (int i = tid; i < N; i += nt) {
         const float thr = __fadd_rn(seed, __fmul_rn(invN, (float)i));
         // idx = min(N-1, #{j : cdf[j] < thr})  == the reference's monotone walk
@@ -208,21 +259,25 @@ __device__ void resample_body(const ObjDesc& d, float* sw, float* cdf, int force
     }
 }
 
+__device__ void summary_body(const ObjDesc& d);
+
 // mode 0: d.H holds the classifier response; build the likelihood map ((H-min)/range)^exponent over the
 //         valid particles (ParticleFilterTracker.cpp:541-566) and use it as prob.
 // mode 1: d.H already holds prob, dense by particle (mask d.valid).
 // Then UpdateAllParticlesWeight (:680-717): w <- p*w (or p), scale clamp, Normalize, ResampleIfRequired.
-__global__ void __launch_bounds__(PF_THREADS) k_pf_update(const ObjDesc* __restrict__ descs, int mode, int smem_floats)
+__global__ void __launch_bounds__(PF_THREADS) k_pf_update(const ObjDesc* __restrict__ descs, const StepArgs sa, int mode, int smem_floats,
+                                                          int with_summary)
 {
-    extern __shared__ float smf[];
+    extern __shared__ __align__(16) float smf[];
     __shared__ float sh_f[32];
     __shared__ double sh_d[32];
     __shared__ int sh_i[32];
     __shared__ int s_decide;
     const ObjDesc& d = descs[blockIdx.x];
     const int N = d.N, tid = threadIdx.x, nt = blockDim.x;
-    float* sw = (2 * N <= smem_floats) ? smf : d.scratch;
-    float* cdf = (2 * N <= smem_floats) ? smf + N : d.scratch + d.ld;
+    const int N4 = (N + 3) & ~3;
+    float* sw = (2 * N4 <= smem_floats) ? smf : d.scratch;
+    float* cdf = (2 * N4 <= smem_floats) ? smf + N4 : d.scratch + d.ld;
 
     // 0. valid count, min / max of H over the test set
     float mn = CUDART_INF_F, mx = -CUDART_INF_F;
@@ -241,7 +296,11 @@ __global__ void __launch_bounds__(PF_THREADS) k_pf_update(const ObjDesc* __restr
             if (d.scored) atomicAdd(d.scored, (unsigned long long)cnt);
         }
     }
-    if (mode == 0 && cnt == 0) return;        // reference: ASSERT abort (ParticleFilterTracker.cpp:513)
+    if (mode == 0 && cnt == 0) {              // reference: ASSERT abort (ParticleFilterTracker.cpp:513)
+        __syncthreads();
+        if (with_summary) summary_body(d);    // the host sees n_valid == 0 -> MCT_E_EMPTY
+        return;
+    }
     const double dmn = (double)mn, range = (double)mx - (double)mn;
 
     // 1. weight update
@@ -293,17 +352,21 @@ __global__ void __launch_bounds__(PF_THREADS) k_pf_update(const ObjDesc* __restr
     }
     __syncthreads();
     if (s_decide) {
-        resample_body(d, sw, cdf, 1, sh_f);
+        resample_body(d, sw, cdf, 1, sh_f, sa.u01[blockIdx.x]);
         if (tid == 0) d.st->resampled = 1;
     } else {
         for (int i = tid; i < N; i += nt) d.w[i] = sw[i];
+    }
+    if (with_summary) {
+        __syncthreads();                       // the read-out reads state / weights written by other threads above
+        summary_body(d);
     }
 }
 
 static int pf_update_smem(mct_ctx* ctx, int n_max, int* smem_floats, size_t* smem_bytes)
 {
     // both chains' operands in shared memory when 2*N floats fit in 200 KB, else global scratch
-    size_t want = (size_t)2 * n_max * sizeof(float);
+    size_t want = (size_t)2 * round_up(n_max, 4) * sizeof(float);
     if (want > 200 * 1024) want = 0;
     *smem_bytes = want;
     *smem_floats = (int)(want / sizeof(float));
@@ -311,7 +374,7 @@ static int pf_update_smem(mct_ctx* ctx, int n_max, int* smem_floats, size_t* sme
     return MCT_OK;
 }
 
-int launch_pf_update(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int use_H)
+int launch_pf_update(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int use_H, const StepArgs& sa, int with_summary)
 {
     int sf; size_t sb;
     pf_update_smem(ctx, n_max, &sf, &sb);
@@ -320,24 +383,24 @@ int launch_pf_update(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, 
         MCT_CUDA(ctx, cudaFuncSetAttribute(k_pf_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
         s_attr = sb;
     }
-    MCT_LAUNCH(ctx, "k_pf_update", k_pf_update<<<n_obj, PF_THREADS, sb, ctx->stream>>>(d_desc, use_H ? 0 : 1, sf));
+    MCT_LAUNCH(ctx, "k_pf_update", k_pf_update<<<n_obj, PF_THREADS, sb, ctx->stream>>>(d_desc, sa, use_H ? 0 : 1, sf, with_summary));
     return MCT_OK;
 }
 
 // ResampleParticles(force) on its own (ParticleFilter.cpp:920-978)
-__global__ void __launch_bounds__(PF_THREADS) k_pf_resample(const ObjDesc* __restrict__ descs, int force, int smem_floats)
+__global__ void __launch_bounds__(PF_THREADS) k_pf_resample(const ObjDesc* __restrict__ descs, const StepArgs sa, int force, int smem_floats)
 {
-    extern __shared__ float smf[];
+    extern __shared__ __align__(16) float smf[];
     __shared__ float sh_f[32];
     const ObjDesc& d = descs[blockIdx.x];
-    const int N = d.N;
-    float* sw = (2 * N <= smem_floats) ? smf : d.scratch;
-    float* cdf = (2 * N <= smem_floats) ? smf + N : d.scratch + d.ld;
+    const int N = d.N, N4 = (N + 3) & ~3;
+    float* sw = (2 * N4 <= smem_floats) ? smf : d.scratch;
+    float* cdf = (2 * N4 <= smem_floats) ? smf + N4 : d.scratch + d.ld;
     for (int i = threadIdx.x; i < N; i += blockDim.x) sw[i] = d.w[i];
     __syncthreads();
-    resample_body(d, sw, cdf, force, sh_f);
+    resample_body(d, sw, cdf, force, sh_f, sa.u01[blockIdx.x]);
 }
-int launch_pf_resample_only(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int force)
+int launch_pf_resample_only(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int force, const StepArgs& sa)
 {
     int sf; size_t sb;
     pf_update_smem(ctx, n_max, &sf, &sb);
@@ -346,7 +409,7 @@ int launch_pf_resample_only(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int 
         MCT_CUDA(ctx, cudaFuncSetAttribute(k_pf_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
         s_attr = sb;
     }
-    MCT_LAUNCH(ctx, "k_pf_resample", k_pf_resample<<<n_obj, PF_THREADS, sb, ctx->stream>>>(d_desc, force, sf));
+    MCT_LAUNCH(ctx, "k_pf_resample", k_pf_resample<<<n_obj, PF_THREADS, sb, ctx->stream>>>(d_desc, sa, force, sf));
     return MCT_OK;
 }
 
@@ -406,13 +469,12 @@ int launch_pf_expand_prob(mct_ctx* ctx, const ObjDesc* d_desc, const float* d_pr
 // RESAMPLED: the resample index list is non-decreasing, so sorting it is the identity; unique runs are
 //            contiguous; run weights are summed in order; the reference then pairs the states in *index*
 //            order with the weights in *sorted* order (:799-806) -- kept.
-__global__ void __launch_bounds__(PF_THREADS) k_pf_summary(const ObjDesc* __restrict__ descs)
+__device__ void summary_body(const ObjDesc& d)
 {
     __shared__ float sh_f[32];
     __shared__ double sh_d[32];
     __shared__ int sh_i[32];
     __shared__ int s_first, s_last;
-    const ObjDesc& d = descs[blockIdx.x];
     const int N = d.N, tid = threadIdx.x, nt = blockDim.x;
     mct_pf_summary* out = d.summ;
     const int fs = d.st->filter_state;
@@ -499,6 +561,10 @@ __global__ void __launch_bounds__(PF_THREADS) k_pf_summary(const ObjDesc* __rest
         for (int q = 0; q < 5; q++) { out->ordered_first[q] = 0; out->highest_close[q] = 0; }
         out->n_unique = 0;
     }
+}
+__global__ void __launch_bounds__(PF_THREADS) k_pf_summary(const ObjDesc* __restrict__ descs)
+{
+    summary_body(descs[blockIdx.x]);
 }
 int launch_pf_summary(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max)
 {

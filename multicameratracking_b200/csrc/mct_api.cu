@@ -8,7 +8,6 @@
 char g_mct_err[512] = "";
 
 #define DESC_RING 32
-#define DESC_MAX_OBJ 64
 
 struct DescRing {
     ObjDesc* h;            // pinned [DESC_RING][DESC_MAX_OBJ]
@@ -71,6 +70,26 @@ static int desc_commit(mct_ctx* ctx, int slot, int n)
     return MCT_OK;
 }
 
+// Publish n descriptors (built by the caller in `src`) and return their device address.  The array is uploaded
+// only when it differs from the last published one: per-frame values (noise, u01) travel as kernel parameters
+// (StepArgs), so in steady state no descriptor copy is issued at all.  A published set lives in a ring slot that
+// is only reused 32 publishes later, after its copy event has completed.
+static int desc_publish(mct_ctx* ctx, const ObjDesc* src, int n, const ObjDesc** d_out)
+{
+    if (ctx->desc_last_d && ctx->desc_last_n == n && !memcmp(ctx->desc_last_h, src, (size_t)n * sizeof(ObjDesc))) {
+        *d_out = (const ObjDesc*)ctx->desc_last_d;
+        return MCT_OK;
+    }
+    ObjDesc *h, *d; int slot, rc;
+    if ((rc = desc_acquire(ctx, &h, &d, &slot))) return rc;
+    memcpy(h, src, (size_t)n * sizeof(ObjDesc));
+    if ((rc = desc_commit(ctx, slot, n))) return rc;
+    memcpy(ctx->desc_last_h, src, (size_t)n * sizeof(ObjDesc));
+    ctx->desc_last_d = d; ctx->desc_last_n = n;
+    *d_out = d;
+    return MCT_OK;
+}
+
 // ------------------------------------------------------------------------------------------ context
 extern "C" const char* mct_version(void) { return "mct-b200 0.1 (sm_100a)"; }
 extern "C" const char* mct_last_error(mct_ctx* ctx) { return ctx ? ctx->err : g_mct_err; }
@@ -102,8 +121,12 @@ extern "C" int mct_ctx_create(int device, void* cuda_stream, mct_ctx** out)
     for (int i = 0; i < DESC_RING; i++) MCT_CUDA(nullptr, cudaEventCreateWithFlags(&r->ev[i], cudaEventDisableTiming));
     r->next = 0;
     ctx->h_desc = r;
+    ctx->desc_last_h = malloc(sizeof(ObjDesc) * DESC_MAX_OBJ);
+    if (!ctx->desc_last_h) return mct_fail(nullptr, MCT_E_NOMEM, "out of host memory%s");
     ctx->summ_cap = DESC_MAX_OBJ;
-    MCT_CUDA(nullptr, cudaMallocHost(&ctx->h_summ, sizeof(mct_pf_summary) * DESC_MAX_OBJ));
+    MCT_CUDA(nullptr, cudaHostAlloc(&ctx->h_summ, sizeof(mct_pf_summary) * DESC_MAX_OBJ, cudaHostAllocMapped));
+    MCT_CUDA(nullptr, cudaHostGetDevicePointer((void**)&ctx->h_summ_dev, ctx->h_summ, 0));
+    memset(ctx->h_summ, 0, sizeof(mct_pf_summary) * DESC_MAX_OBJ);
     MCT_CUDA(nullptr, cudaMalloc(&ctx->d_scored, sizeof(unsigned long long)));
     MCT_CUDA(nullptr, cudaMemset(ctx->d_scored, 0, sizeof(unsigned long long)));
     *out = ctx;
@@ -166,6 +189,8 @@ extern "C" int mct_ctx_destroy(mct_ctx* ctx)
     if (ctx->d_tmp) cudaFree(ctx->d_tmp);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->h_summ) cudaFreeHost(ctx->h_summ);
+    if (ctx->d_noise_stage) cudaFree(ctx->d_noise_stage);
+    free(ctx->desc_last_h);
     DescRing* r = ring_of(ctx);
     if (r) {
         for (int i = 0; i < DESC_RING; i++) cudaEventDestroy(r->ev[i]);
@@ -503,13 +528,12 @@ static void fill_clf_desc(ObjDesc* d, mct_clf* c)
 static int classify_boxes_on_device(mct_clf* c, int n, int from_matrix, int log_ratio)
 {
     mct_ctx* ctx = c->ctx;
-    ObjDesc *h, *d; int slot, rc;
-    if ((rc = desc_acquire(ctx, &h, &d, &slot))) return rc;
+    ObjDesc hd; ObjDesc* h = &hd; const ObjDesc* d; int rc;
     memset(h, 0, sizeof(ObjDesc));
     fill_clf_desc(h, c);
     h->N = n; h->ld = c->ldN;
     h->col = c->d_col; h->row = c->d_row; h->sx = c->d_sx; h->sy = c->d_sy; h->valid = nullptr; h->H = c->d_H;
-    if ((rc = desc_commit(ctx, slot, 1))) return rc;
+    if ((rc = desc_publish(ctx, h, 1, &d))) return rc;
     if (!from_matrix && c->n_color > 0) {
         if (h->slotmap) {
             if ((rc = launch_bin_image(ctx, c->p.n_bins))) return rc;
@@ -629,7 +653,7 @@ static void fill_pf_desc(ObjDesc* d, mct_pf* p)
     d->cx = p->d_state; d->cy = p->d_state + ld; d->sx = p->d_state + 2 * ld; d->sy = p->d_state + 3 * ld; d->w = p->d_state + 4 * ld;
     d->rcx = p->d_res; d->rcy = p->d_res + ld; d->rsx = p->d_res + 2 * ld; d->rsy = p->d_res + 3 * ld; d->rw = p->d_res + 4 * ld;
     d->residx = p->d_residx; d->col = p->d_col; d->row = p->d_row; d->valid = p->d_valid;
-    d->H = p->d_H; d->noise = p->d_noise; d->scratch = p->d_scratch; d->st = p->d_st; d->summ = p->d_summ;
+    d->H = p->d_H; d->noise_off = 0; d->scratch = p->d_scratch; d->st = p->d_st; d->summ = p->d_summ;
     d->scored = p->ctx->d_scored;
     d->N = p->N; d->ld = p->ld;
     d->img_w = p->img_w; d->img_h = p->img_h; d->msc = p->msc; d->maxs = p->maxs; d->mins = p->mins;
@@ -695,17 +719,16 @@ extern "C" int mct_pf_get_resample_indices(mct_pf* p, int* out)
     return mct_sync(ctx);
 }
 
-static int pf_single_desc(mct_pf* p, ObjDesc** d_out, float w0, float h0, int force_reset, int resample, float u01)
+static int pf_single_desc(mct_pf* p, const ObjDesc** d_out, StepArgs* sa, float w0, float h0, int force_reset, int resample, float u01)
 {
     mct_ctx* ctx = p->ctx;
-    ObjDesc *h, *d; int slot, rc;
-    if ((rc = desc_acquire(ctx, &h, &d, &slot))) return rc;
-    memset(h, 0, sizeof(ObjDesc));
-    fill_pf_desc(h, p);
-    h->w0 = w0; h->h0 = h0; h->force_reset = force_reset; h->resample = resample; h->u01 = u01;
-    if ((rc = desc_commit(ctx, slot, 1))) return rc;
-    *d_out = d;
-    return MCT_OK;
+    ObjDesc hd;
+    memset(&hd, 0, sizeof(ObjDesc));
+    fill_pf_desc(&hd, p);
+    hd.w0 = w0; hd.h0 = h0; hd.force_reset = force_reset; hd.resample = resample;
+    memset(sa, 0, sizeof(*sa));
+    sa->noise_base = p->d_noise; sa->u01[0] = u01;
+    return desc_publish(ctx, &hd, 1, d_out);
 }
 
 extern "C" int mct_pf_predict(mct_pf* p, const float* noise, int noise_is_device, float w0, float h0)
@@ -716,9 +739,9 @@ extern "C" int mct_pf_predict(mct_pf* p, const float* noise, int noise_is_device
     MCT_CUDA(ctx, cudaSetDevice(ctx->device));
     MCT_CUDA(ctx, cudaMemcpyAsync(p->d_noise, noise, (size_t)4 * p->N * 4,
                                   noise_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
-    ObjDesc* d; int rc;
-    if ((rc = pf_single_desc(p, &d, w0, h0, 0, 1, 0.0f))) return rc;
-    if ((rc = launch_pf_predict(ctx, d, 1, p->N))) return rc;
+    const ObjDesc* d; StepArgs sa; int rc;
+    if ((rc = pf_single_desc(p, &d, &sa, w0, h0, 0, 1, 0.0f))) return rc;
+    if ((rc = launch_pf_predict(ctx, d, 1, p->N, sa))) return rc;
     return mct_sync(ctx);     // the host noise buffer may be reused by the caller
 }
 
@@ -731,10 +754,10 @@ extern "C" int mct_pf_update_all_weights(mct_pf* p, const float* prob, int n_pro
     if (n_prob > p->N) return mct_fail(ctx, MCT_E_ARG, "more probabilities than particles%s");
     MCT_CUDA(ctx, cudaSetDevice(ctx->device));
     if (n_prob > 0) MCT_CUDA(ctx, cudaMemcpyAsync(p->d_prob, prob, (size_t)n_prob * 4, cudaMemcpyHostToDevice, ctx->stream));
-    ObjDesc* d; int rc;
-    if ((rc = pf_single_desc(p, &d, 0, 0, force_reset, resample, u01))) return rc;
+    const ObjDesc* d; StepArgs sa; int rc;
+    if ((rc = pf_single_desc(p, &d, &sa, 0, 0, force_reset, resample, u01))) return rc;
     if ((rc = launch_pf_expand_prob(ctx, d, p->d_prob, n_prob, only_nonzero))) return rc;
-    if ((rc = launch_pf_update(ctx, d, 1, p->N, 0))) return rc;
+    if ((rc = launch_pf_update(ctx, d, 1, p->N, 0, sa, 0))) return rc;
     PfDev st;
     MCT_CUDA(ctx, cudaMemcpyAsync(&st, p->d_st, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
     if ((rc = mct_sync(ctx))) return rc;
@@ -748,9 +771,9 @@ extern "C" int mct_pf_resample(mct_pf* p, int force, float u01)
     mct_ctx* ctx = p->ctx;
     if (!p->initialized) return mct_fail(ctx, MCT_E_STATE, "particle filter not initialised%s");
     MCT_CUDA(ctx, cudaSetDevice(ctx->device));
-    ObjDesc* d; int rc;
-    if ((rc = pf_single_desc(p, &d, 0, 0, 0, 1, u01))) return rc;
-    if ((rc = launch_pf_resample_only(ctx, d, 1, p->N, force))) return rc;
+    const ObjDesc* d; StepArgs sa; int rc;
+    if ((rc = pf_single_desc(p, &d, &sa, 0, 0, 0, 1, u01))) return rc;
+    if ((rc = launch_pf_resample_only(ctx, d, 1, p->N, force, sa))) return rc;
     return mct_sync(ctx);
 }
 
@@ -759,8 +782,8 @@ extern "C" int mct_pf_get_summary(mct_pf* p, mct_pf_summary* out)
     if (!p || !out) return MCT_E_ARG;
     mct_ctx* ctx = p->ctx;
     MCT_CUDA(ctx, cudaSetDevice(ctx->device));
-    ObjDesc* d; int rc;
-    if ((rc = pf_single_desc(p, &d, 0, 0, 0, 1, 0.0f))) return rc;
+    const ObjDesc* d; StepArgs sa; int rc;
+    if ((rc = pf_single_desc(p, &d, &sa, 0, 0, 0, 1, 0.0f))) return rc;
     if ((rc = launch_pf_summary(ctx, d, 1, p->N))) return rc;
     MCT_CUDA(ctx, cudaMemcpyAsync(out, p->d_summ, sizeof(*out), cudaMemcpyDeviceToHost, ctx->stream));
     return mct_sync(ctx);
@@ -784,40 +807,50 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
     if (ctx->frame_id == 0) return mct_fail(ctx, MCT_E_STATE, "no frame set%s");
     MCT_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc, n_max = 0, K_max = 1;
-    size_t noff = 0;
+    size_t ntot = 0;
+    ObjDesc h[DESC_MAX_OBJ];
+    StepArgs sa;
     for (int o = 0; o < n_obj; o++) {
         mct_pf* p = pfs[o]; mct_clf* c = clfs[o];
         if (!p || !c || p->ctx != ctx || c->ctx != ctx) return mct_fail(ctx, MCT_E_ARG, "object handle belongs to another ctx%s");
         if (!p->initialized) return mct_fail(ctx, MCT_E_STATE, "particle filter not initialised%s");
         if ((rc = need_frame(c))) return rc;
         if ((rc = clf_ensure_test(c, p->N, c->n_color))) return rc;
-        MCT_CUDA(ctx, cudaMemcpyAsync(p->d_noise, noise + noff, (size_t)4 * p->N * 4,
-                                      noise_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
-        noff += (size_t)4 * p->N;
+        memset(&h[o], 0, sizeof(ObjDesc));
+        fill_pf_desc(&h[o], p);
+        fill_clf_desc(&h[o], c);
+        h[o].noise_off = (long long)ntot;
+        h[o].summ = ctx->h_summ_dev + o;               // the read-out is written straight into mapped pinned memory
+        h[o].w0 = params[o].w0; h[o].h0 = params[o].h0; h[o].exponent = params[o].exponent;
+        h[o].force_reset = params[o].force_reset; h[o].resample = params[o].resample;
+        sa.u01[o] = u01[o];
+        ntot += (size_t)4 * p->N;
         if (p->N > n_max) n_max = p->N;
         if (c->K > K_max) K_max = c->K;
     }
-    ObjDesc *h, *d; int slot;
-    if ((rc = desc_acquire(ctx, &h, &d, &slot))) return rc;
-    for (int o = 0; o < n_obj; o++) {
-        memset(&h[o], 0, sizeof(ObjDesc));
-        fill_pf_desc(&h[o], pfs[o]);
-        fill_clf_desc(&h[o], clfs[o]);
-        h[o].w0 = params[o].w0; h[o].h0 = params[o].h0; h[o].exponent = params[o].exponent;
-        h[o].force_reset = params[o].force_reset; h[o].resample = params[o].resample; h[o].u01 = u01[o];
+    // prediction noise: device pointers are used in place; host noise is staged with ONE copy
+    if (noise_is_device) sa.noise_base = noise;
+    else {
+        if (ntot > ctx->noise_stage_cap) {
+            MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (ctx->d_noise_stage) cudaFree(ctx->d_noise_stage);
+            MCT_CUDA(ctx, cudaMalloc(&ctx->d_noise_stage, ntot * sizeof(float)));
+            ctx->noise_stage_cap = ntot;
+        }
+        MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_noise_stage, noise, ntot * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        sa.noise_base = ctx->d_noise_stage;
     }
-    if ((rc = desc_commit(ctx, slot, n_obj))) return rc;
-    if ((rc = launch_pf_predict(ctx, d, n_obj, n_max))) return rc;
-    if ((rc = launch_pf_testset(ctx, d, n_obj, n_max))) return rc;
-    int any_mdch = 0, max_slots = 1;
+    const ObjDesc* d;
+    if ((rc = desc_publish(ctx, h, n_obj, &d))) return rc;
+    if ((rc = launch_pf_predict_testset(ctx, d, n_obj, n_max, sa))) return rc;
+    int any_mdch = 0, max_slots = 1, nb = 0;
     for (int o = 0; o < n_obj; o++) {
         mct_clf* c = clfs[o]; mct_pf* p = pfs[o];
         if (c->n_color <= 0) continue;
         if (h[o].slotmap) {
-            any_mdch = 1;
+            any_mdch = 1; nb = c->p.n_bins;
             int ms = (c->K < c->n_color ? c->K : c->n_color) + 1;
             if (ms > max_slots) max_slots = ms;
-            MCT_CUDA(ctx, cudaMemsetAsync(c->d_nbig, 0, 4, ctx->stream));
         } else {
             float* sx = p->d_state + 2 * (size_t)p->ld; float* sy = p->d_state + 3 * (size_t)p->ld;
             if ((rc = mct_feature_color_rows(c, p->d_col, p->d_row, sx, sy, p->d_valid, p->N, nullptr, c->n_color,
@@ -826,16 +859,11 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
         }
     }
     if (any_mdch) {
-        int nb = 0;
-        for (int o = 0; o < n_obj; o++) if (h[o].slotmap) nb = clfs[o]->p.n_bins;
         if ((rc = launch_bin_image(ctx, nb))) return rc;
         if ((rc = launch_mdch_selected(ctx, d, n_obj, n_max, max_slots))) return rc;
     }
     if ((rc = launch_classify(ctx, d, n_obj, n_max, K_max, 0, 1))) return rc;
-    if ((rc = launch_pf_update(ctx, d, n_obj, n_max, 1))) return rc;
-    if ((rc = launch_pf_summary(ctx, d, n_obj, n_max))) return rc;
-    for (int o = 0; o < n_obj; o++)
-        MCT_CUDA(ctx, cudaMemcpyAsync(&ctx->h_summ[o], pfs[o]->d_summ, sizeof(mct_pf_summary), cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = launch_pf_update(ctx, d, n_obj, n_max, 1, sa, 1))) return rc;
     return MCT_OK;
 }
 
@@ -878,10 +906,9 @@ extern "C" int mct_fuser_pack_foot_points(mct_ctx* ctx, int n_obj, mct_pf* const
     int rc = ensure_tmp(ctx, (size_t)n_obj * 4);
     if (rc) return rc;
     MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tmp, h0, (size_t)n_obj * 4, cudaMemcpyHostToDevice, ctx->stream));
-    ObjDesc *h, *d; int slot;
-    if ((rc = desc_acquire(ctx, &h, &d, &slot))) return rc;
+    ObjDesc h[DESC_MAX_OBJ]; const ObjDesc* d;
     for (int o = 0; o < n_obj; o++) { memset(&h[o], 0, sizeof(ObjDesc)); fill_pf_desc(&h[o], pfs[o]); }
-    if ((rc = desc_commit(ctx, slot, n_obj))) return rc;
+    if ((rc = desc_publish(ctx, h, n_obj, &d))) return rc;
     if ((rc = launch_foot_points(ctx, d, n_obj, ctx->d_tmp, dev_out))) return rc;
     return mct_sync(ctx);
 }

@@ -37,7 +37,9 @@ struct mct_ctx {
     uint16_t* binimg; size_t binimg_cap; int binimg_nb; long long binimg_frame;   // MDCH joint-bin image of the colour planes
     long long frame_id;
     void* d_desc; void* h_desc; size_t desc_cap;       // batched object descriptors (device + pinned host)
-    mct_pf_summary* h_summ; int summ_cap;              // pinned read-out buffer
+    void* desc_last_h; const void* desc_last_d; int desc_last_n;   // last published descriptor set (skip identical uploads)
+    mct_pf_summary* h_summ; mct_pf_summary* h_summ_dev; int summ_cap;   // pinned, device-mapped read-out buffer (kernels write it directly)
+    float* d_noise_stage; size_t noise_stage_cap;      // staging for host-provided prediction noise (one H2D per call)
     float* d_tmp; size_t tmp_cap;                      // scratch (sum_rects etc.)
     float* h_pin; size_t pin_cap;                      // pinned staging for small host arrays
     long long launches;
@@ -100,11 +102,11 @@ struct ObjDesc {
     float* cx; float* cy; float* sx; float* sy; float* w;
     float* rcx; float* rcy; float* rsx; float* rsy; float* rw;
     int* residx; int* col; int* row; int* valid;
-    float* H; const float* noise; float* scratch;
+    float* H; long long noise_off; float* scratch;      // noise_off: float offset of this object's 4 x N noise block in StepArgs::noise_base
     PfDev* st; mct_pf_summary* summ; unsigned long long* scored;
     int N, ld;
     float img_w, img_h, msc, maxs, mins;
-    float w0, h0, u01;
+    float w0, h0;
     int exponent, force_reset, resample, pad0;
     // classifier
     const int4* rects; const float* wts; const int* nrect;
@@ -113,6 +115,14 @@ struct ObjDesc {
     const int* colorrow; const int* outbins;
     const uint16_t* slotmap; const int* nout; int* big; int* nbig;
     int F, n_haar, nb, weak_type, feature_type, cch_mode, K, cw0, ch0, pad1;
+};
+
+// Per-call values that change every frame travel as kernel parameters, so that the ObjDesc array itself is
+// unchanged from frame to frame and its upload can be skipped (mct_api.cu: desc_publish).
+#define DESC_MAX_OBJ 64
+struct StepArgs {
+    const float* noise_base;       // [sum over objects of 4 * N] Gaussian rows (device)
+    float u01[DESC_MAX_OBJ];       // the randfloat() of ResampleParticles per object
 };
 
 // ------------------------------------------------------------------ error helpers
@@ -167,10 +177,13 @@ int mct_feature_color_rows(mct_clf* clf, const int* d_col, const int* d_row, con
 int launch_build_colormap(mct_clf* clf);
 int launch_mdch_selected(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int max_slots);
 int launch_classify(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int K_max, int from_matrix, int log_ratio);
-int launch_pf_predict(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max);
+int launch_pf_predict(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, const StepArgs& sa);
 int launch_pf_testset(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max);
-int launch_pf_update(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int use_H);
-int launch_pf_resample_only(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int force);
+// fused predict + test set (+ per-frame reset of the MDCH fallback counters) for the batched per-frame path
+int launch_pf_predict_testset(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, const StepArgs& sa);
+// with_summary: run the read-out (k_pf_summary body) at the end of the same kernel
+int launch_pf_update(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int use_H, const StepArgs& sa, int with_summary);
+int launch_pf_resample_only(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int force, const StepArgs& sa);
 int launch_pf_summary(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max);
 int launch_pf_expand_prob(mct_ctx* ctx, const ObjDesc* d_desc, const float* d_prob_compact, int n_prob, int only_nonzero);
 int launch_weak_update(mct_clf* clf, int P, int Nn, int has_weights);
