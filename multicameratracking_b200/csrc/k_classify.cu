@@ -63,6 +63,184 @@ k_classify(const ObjDesc* __restrict__ descs, const float* __restrict__ ii, int 
     d.H[i] = Hs;
 }
 
+// ------------------------------------------------------------------------------------------
+// k_classify_staged: the per-frame (test-set) form.  Persistent CTAs, each owning a contiguous chunk of ONE
+// object's boxes (the same chunking as k_mdch_sel):
+//   1. the K selected weak classifiers are staged in shared memory (as above);
+//   2. the bounding region of the chunk's boxes in the INTEGRAL IMAGE is staged once into shared memory
+//      (particles of an object cluster within a few sigma, so the region is ~150 KB at VGA); the 16 corner
+//      gathers per Haar feature then hit shared memory (random bank conflicts, ~3 wavefronts) instead of L1 with
+//      32 distinct lines per warp instruction -- the L1 wavefront rate was what bounded k_classify;
+//   3. four lanes share a box: lane q evaluates selectors q, q+4, ...; the responses are then added IN SELECTOR
+//      ORDER through shuffles, so H equals the reference's sequential f32 accumulation bit for bit;
+//   4. log(1e-5+p1) - log(1e-5+p0) is evaluated as one f64 log of the f64 quotient (half the f64 log count;
+//      identical after rounding to f32 except for sub-ulp ties).
+// Falls back to global gathers (same arithmetic) when the region does not fit.
+__device__ __forceinline__ float sum_rect_region(const float* __restrict__ reg, int rp, int ox, int oy, int W, int H,
+                                                 int x, int y, int w, int h)
+{
+    const int x0 = clampi(x, 0, W) - ox, x1 = clampi(x + w, 0, W) - ox;
+    const int y0 = clampi(y, 0, H) - oy, y1 = clampi(y + h, 0, H) - oy;
+    const float* r0 = reg + y0 * rp;
+    const float* r1 = reg + y1 * rp;
+    const float tl = r0[x0], tr = r0[x1], br = r1[x1], bl = r1[x0];
+    return __fsub_rn(__fsub_rn(__fadd_rn(br, tl), tr), bl);
+}
+__device__ __forceinline__ float haar_eval_region(const float* __restrict__ reg, int rp, int ox, int oy, int W, int H,
+                                                  const int4* rects, const float* wts, int nrect,
+                                                  int col, int row, float sx, float sy)
+{
+    float sum = 0.0f;
+    for (int k = 0; k < nrect; k++) {
+        const int4 r = rects[k];
+        const int x = __float2int_rn(__fmul_rn((float)r.x, sx)) + col;
+        const int y = __float2int_rn(__fmul_rn((float)r.y, sy)) + row;
+        const int h = __float2int_rn(__fmul_rn((float)r.w, sy));
+        const int w = __float2int_rn(__fmul_rn((float)r.z, sx));
+        sum = __fadd_rn(sum, __fmul_rn(wts[k], sum_rect_region(reg, rp, ox, oy, W, H, x, y, w, h)));
+    }
+    return __fdiv_rn(sum, __fmul_rn(sx, sy));
+}
+// ClassifyF with one f64 log: (float)log((1e-5 + p1) / (1e-5 + p0))
+__device__ __forceinline__ float weak_classify_ratio_dev(int weak_type, float x, const float* st)
+{
+    if (weak_type == MCT_WEAK_PERCEPTRON) return ((double)x * (double)st[0] > (double)st[1]) ? 1.0f : -1.0f;
+    const float d0 = __fsub_rn(x, st[0]), d1 = __fsub_rn(x, st[1]);
+    const float a0 = __fmul_rn(__fmul_rn(d0, d0), st[6]);
+    const float a1 = __fmul_rn(__fmul_rn(d1, d1), st[7]);
+    const double p0 = (double)__fmul_rn(expf(a0), st[4]);
+    const double p1 = (double)__fmul_rn(expf(a1), st[5]);
+    return (float)log((1e-5 + p1) / (1e-5 + p0));
+}
+
+#define CLS_THREADS 512
+#define CLS_SMEM (224 * 1024)
+__global__ void __launch_bounds__(CLS_THREADS, 1)
+k_classify_staged(const ObjDesc* __restrict__ descs, const float* __restrict__ ii, int iip, int W, int H, int log_ratio,
+                  int smem_bytes)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ int s_bb[4], s_ext[2];
+    const ObjDesc& d = descs[blockIdx.y];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int N = d.N;
+    const int chunk = (N + gridDim.x - 1) / gridDim.x;
+    const int i_begin = blockIdx.x * chunk, i_end = min(N, i_begin + chunk);
+    if (i_begin >= i_end) return;
+    const int nsel = *d.nsel, F = d.F;
+    SelEntry* se = (SelEntry*)smraw;
+    if (tid == 0) { s_bb[0] = 1 << 30; s_bb[1] = 1 << 30; s_bb[2] = -(1 << 30); s_bb[3] = -(1 << 30); s_ext[0] = 0; s_ext[1] = 0; }
+    __syncthreads();
+    // ---- 1. selected weak classifiers; extent of the selected Haar rects in the blob frame
+    int mxw = 0, mxh = 0;
+    for (int s = tid; s < nsel; s += blockDim.x) {
+        const int f = d.sel[s];
+        SelEntry& e = se[s];
+#pragma unroll
+        for (int q = 0; q < 8; q++) e.st[q] = d.weak[(size_t)q * F + f];
+        if (f < d.n_haar) {
+            e.nrect = d.nrect[f];
+            for (int k = 0; k < MCT_MAX_RECTS; k++) {
+                e.r[k] = d.rects[(size_t)f * MCT_MAX_RECTS + k];
+                e.w[k] = d.wts[(size_t)f * MCT_MAX_RECTS + k];
+                if (k < e.nrect) { mxw = max(mxw, e.r[k].x + e.r[k].z); mxh = max(mxh, e.r[k].y + e.r[k].w); }
+            }
+            e.row = 0;
+        } else {
+            e.nrect = 0;
+            e.row = d.colorrow[f - d.n_haar];
+        }
+    }
+    if (mxw > 0) { atomicMax(&s_ext[0], mxw); atomicMax(&s_ext[1], mxh); }
+    __syncthreads();
+    const int ext_w = s_ext[0], ext_h = s_ext[1];
+    // ---- 2. integral-image region of the chunk's valid boxes (Haar selectors only)
+    if (ext_w > 0) {
+        int x0 = 1 << 30, y0 = 1 << 30, x1 = -(1 << 30), y1 = -(1 << 30);
+        for (int i = i_begin + tid; i < i_end; i += blockDim.x) {
+            if (d.valid != nullptr && d.valid[i] == 0) continue;
+            const int c = d.col[i], r = d.row[i];
+            // round(a*s) + round(b*s) <= (a+b)*s + 1
+            const int ex = (int)ceilf((float)ext_w * d.sx[i]) + 2, ey = (int)ceilf((float)ext_h * d.sy[i]) + 2;
+            x0 = min(x0, c); y0 = min(y0, r); x1 = max(x1, c + ex); y1 = max(y1, r + ey);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+            x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+        }
+        if (lane == 0 && x1 >= x0) { atomicMin(&s_bb[0], x0); atomicMin(&s_bb[1], y0); atomicMax(&s_bb[2], x1); atomicMax(&s_bb[3], y1); }
+    }
+    __syncthreads();
+    const size_t se_b = ((size_t)max(nsel, 1) * sizeof(SelEntry) + 15) & ~(size_t)15;
+    float* region = (float*)(smraw + se_b);
+    const int bx0 = clampi(s_bb[0], 0, W), by0 = clampi(s_bb[1], 0, H);
+    const int bx1 = clampi(s_bb[2], 0, W), by1 = clampi(s_bb[3], 0, H);
+    const int RW = bx1 - bx0 + 1, RH = by1 - by0 + 1;
+    const int RWp = RW | 1;                                                   // odd pitch spreads rows over the banks
+    const bool have = ext_w > 0 && s_bb[2] >= s_bb[0];
+    const bool staged = have && se_b + (size_t)RWp * RH * 4 <= (size_t)smem_bytes;
+    if (staged) {
+        for (int y = tid >> 5; y < RH; y += CLS_THREADS / 32) {
+            const float* src = ii + (size_t)(by0 + y) * iip + bx0;
+            float* dst = region + y * RWp;
+            for (int x = lane; x < RW; x += 32) dst[x] = __ldg(src + x);
+        }
+    }
+    __syncthreads();
+    // ---- 3. four lanes per box
+    const int q = tid & 3;
+    const unsigned gmask = 0xfu << (lane & ~3);
+    for (int base = i_begin; base < i_end; base += CLS_THREADS / 4) {
+        const int i = base + (tid >> 2);
+        const bool live = i < i_end;
+        const bool ok = live && (d.valid == nullptr || d.valid[i] != 0);
+        int c = 0, r = 0; float fx = 1.0f, fy = 1.0f;
+        if (ok) { c = d.col[i]; r = d.row[i]; fx = d.sx[i]; fy = d.sy[i]; }
+        float Hs = 0.0f;
+        for (int s0 = 0; s0 < nsel; s0 += 4) {
+            const int s = s0 + q;
+            float v = 0.0f;
+            if (ok && s < nsel) {
+                const SelEntry& e = se[s];
+                float x;
+                if (e.nrect > 0) {
+                    if (staged) x = haar_eval_region(region, RWp, bx0, by0, W, H, e.r, e.w, e.nrect, c, r, fx, fy);
+                    else x = haar_eval_dev(ii, iip, W, H, e.r, e.w, e.nrect, c, r, fx, fy);
+                } else x = d.featN[(size_t)e.row * d.ldN + i];
+                v = weak_classify_ratio_dev(d.weak_type, x, e.st);
+            }
+            // ordered accumulation: responseList[i] += weak[k] in selector order (MILBoostClassifier.cpp:351-361)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float vj = __shfl_sync(gmask, v, (lane & ~3) + j);
+                if (s0 + j < nsel) Hs = __fadd_rn(Hs, vj);
+            }
+        }
+        if (live && q == 0) {
+            if (ok && !log_ratio) Hs = sigmoid_dev(Hs);
+            d.H[i] = ok ? Hs : 0.0f;
+        }
+    }
+}
+
+int launch_classify_staged(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int log_ratio)
+{
+    if (n_obj <= 0 || n_max <= 0) return MCT_OK;
+    static int s_attr = 0, s_sms = 0;
+    if (!s_attr) {
+        MCT_CUDA(ctx, cudaFuncSetAttribute(k_classify_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, CLS_SMEM));
+        MCT_CUDA(ctx, cudaDeviceGetAttribute(&s_sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        s_attr = 1;
+    }
+    int per_obj = s_sms / n_obj;
+    if (per_obj < 1) per_obj = 1;
+    if (per_obj > ceil_div(n_max, 32)) per_obj = ceil_div(n_max, 32);
+    dim3 g(per_obj, n_obj);
+    MCT_LAUNCH(ctx, "k_classify_staged", k_classify_staged<<<g, CLS_THREADS, CLS_SMEM, ctx->stream>>>(
+        d_desc, ctx->ii_base + MCT_II_LEAD, ctx->ii_pitch, ctx->W, ctx->H, log_ratio, CLS_SMEM));
+    return MCT_OK;
+}
+
 int launch_classify(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int K_max, int from_matrix, int log_ratio)
 {
     if (n_obj <= 0 || n_max <= 0) return MCT_OK;

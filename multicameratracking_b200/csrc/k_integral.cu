@@ -104,7 +104,189 @@ k_integral_band(const uint8_t* __restrict__ img, int W, int H, int pitch, int BH
         for (int c = tid; c <= W; c += nt) ii[c] = 0.0f;
 }
 
+// ------------------------------------------------------------------------------------------
+// Single-launch frame preparation (default path): integral image of all bands in ONE kernel, plus (optionally)
+// the MDCH joint-bin image on extra CTAs of the same launch.
+//   CTA b < n_bands : rows [b*BH, b*BH+BH): warp-per-row shuffle prefix -> shared memory; thread-per-column walk
+//                     turns it into the band-local integral; the band's last row (= band column totals, already
+//                     prefixed over x) is published to bandtot[b][*] with a release flag (flag value = frame id,
+//                     so the flags never need a reset); the CTA then acquires the flags of all bands above,
+//                     sums their totals per column (exact u32) and stores f32(base + local) with coalesced rows.
+//                     The frame is read from HBM exactly once and the table written once.
+//   CTA b >= n_bands: bin image, 4 pixels per thread (uchar4 loads, one 8-byte store).
+// Blocks wait on one another, so the launch is cooperative (co-residency guaranteed; grid <= 1 CTA per SM).
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+struct PrepArgs {
+    const uint8_t* gray; int W, H, pitch, BH, n_bands;
+    uint32_t* bandtot; unsigned* flags; unsigned epoch; float* ii; int iip;
+    const uint8_t* c0; const uint8_t* c1; const uint8_t* c2; int nb; int bw_shift; uint16_t* binimg; int n_binblocks;
+};
+
+__global__ void __launch_bounds__(512) k_frame_prep(const PrepArgs a)
+{
+    extern __shared__ uint32_t sm[];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int W = a.W, H = a.H;
+    if ((int)blockIdx.x >= a.n_bands) {
+        // ---- joint-bin image (MultiDimensionalColorHistogram.cpp:96-104); bw = 256/nb is a power of two here
+        const int q = blockIdx.x - a.n_bands;
+        const int groups = (W >> 2) * H;                                  // launch_integral guarantees W % 4 == 0, pitch % 4 == 0
+        const int wq = W >> 2, nb = a.nb, sh = a.bw_shift;
+        for (int g = q * nt + tid; g < groups; g += a.n_binblocks * nt) {
+            const int y = g / wq, x = (g - y * wq) << 2;
+            const size_t o = (size_t)y * a.pitch + x;
+            const uchar4 r = *reinterpret_cast<const uchar4*>(a.c0 + o);
+            const uchar4 gg = *reinterpret_cast<const uchar4*>(a.c1 + o);
+            const uchar4 bb = *reinterpret_cast<const uchar4*>(a.c2 + o);
+            const unsigned b0 = (r.x >> sh) + nb * (gg.x >> sh) + nb * nb * (bb.x >> sh);
+            const unsigned b1 = (r.y >> sh) + nb * (gg.y >> sh) + nb * nb * (bb.y >> sh);
+            const unsigned b2 = (r.z >> sh) + nb * (gg.z >> sh) + nb * nb * (bb.z >> sh);
+            const unsigned b3 = (r.w >> sh) + nb * (gg.w >> sh) + nb * nb * (bb.w >> sh);
+            *reinterpret_cast<uint2*>(a.binimg + (size_t)y * W + x) = make_uint2(b0 | (b1 << 16), b2 | (b3 << 16));
+        }
+        return;
+    }
+    const int b = blockIdx.x, BH = a.BH;
+    const int r0 = b * BH, nr = min(BH, H - r0);
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    uint32_t* rp = sm;                                                    // [BH][W]
+    const bool vec = ((a.pitch | (int)(size_t)a.gray) & 3) == 0;
+    // (1) row prefixes
+    for (int r = warp; r < nr; r += nwarps) {
+        const uint8_t* src = a.gray + (size_t)(r0 + r) * a.pitch;
+        uint32_t* dst = rp + (size_t)r * W;
+        uint32_t carry = 0;
+        for (int c0 = 0; c0 < W; c0 += 128) {
+            const int c = c0 + lane * 4;
+            uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+            if (c + 3 < W && vec) {
+                const uchar4 p = *reinterpret_cast<const uchar4*>(src + c);
+                v0 = p.x; v1 = p.y; v2 = p.z; v3 = p.w;
+            } else {
+                if (c + 0 < W) v0 = src[c + 0];
+                if (c + 1 < W) v1 = src[c + 1];
+                if (c + 2 < W) v2 = src[c + 2];
+                if (c + 3 < W) v3 = src[c + 3];
+            }
+            v1 += v0; v2 += v1; v3 += v2;
+            const uint32_t incl = warp_incl_scan(v3, lane);
+            const uint32_t off = carry + incl - v3;
+            if (c + 0 < W) dst[c + 0] = v0 + off;
+            if (c + 1 < W) dst[c + 1] = v1 + off;
+            if (c + 2 < W) dst[c + 2] = v2 + off;
+            if (c + 3 < W) dst[c + 3] = v3 + off;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    __syncthreads();
+    // (2) band-local integral in place + publish the band totals
+    uint32_t* tot = a.bandtot + (size_t)b * W;
+    for (int c = tid; c < W; c += nt) {
+        uint32_t acc = 0;
+        for (int r = 0; r < nr; r++) { acc += rp[(size_t)r * W + c]; rp[(size_t)r * W + c] = acc; }
+        tot[c] = acc;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) st_release_u32(a.flags + b, a.epoch);
+    // (3) wait for every band above (all CTAs are co-resident: cooperative launch)
+    for (int t = tid; t < b; t += nt) { while (ld_acquire_u32(a.flags + t) != a.epoch) { } }
+    __syncthreads();
+    // (4) base = totals of the bands above; store f32(base + local); a warp writes 32 consecutive columns of a row
+    float* ii = a.ii;
+    const int iip = a.iip;
+    for (int c = tid; c < W; c += nt) {
+        uint32_t base = 0;
+        for (int bb = 0; bb < b; bb++) base += __ldcg(a.bandtot + (size_t)bb * W + c);
+        for (int r = 0; r < nr; r++)
+            ii[(size_t)(r0 + r + 1) * iip + c + 1] = __uint2float_rn(base + rp[(size_t)r * W + c]);
+    }
+    for (int r = tid; r < nr; r += nt) ii[(size_t)(r0 + r + 1) * iip] = 0.0f;
+    if (b == 0)
+        for (int c = tid; c <= W; c += nt) ii[c] = 0.0f;
+}
+
+static int launch_integral_two_pass(mct_ctx* ctx);
+
 int launch_integral(mct_ctx* ctx)
+{
+    const int W = ctx->W, H = ctx->H;
+    static int s_coop = -1, s_sms = 0;
+    if (s_coop < 0) {
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+        cudaDeviceGetAttribute(&s_sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        s_coop = coop;
+    }
+    // band height: enough bands to spread over the SMs; BH*W u32 must fit in shared memory
+    int BH = 8;
+    while (ceil_div(H, BH) > s_sms / 2 && BH < 64) BH <<= 1;
+    const size_t smem = (size_t)BH * W * sizeof(uint32_t);
+    const int n_bands = ceil_div(H, BH);
+    if (!s_coop || smem > 200 * 1024 || n_bands > s_sms) return launch_integral_two_pass(ctx);
+    // the bin image rides along when an MDCH classifier has used this ctx before and the planes allow 4-pixel vectors
+    const int cnb = ctx->binimg_nb;
+    int with_bins = cnb > 0 && ctx->c0 && ctx->c1 && ctx->c2 && (W & 3) == 0 && (ctx->pitch & 3) == 0 &&
+                    ((((size_t)ctx->c0) | ((size_t)ctx->c1) | ((size_t)ctx->c2)) & 3) == 0 && (256 % cnb) == 0 &&
+                    ((256 / cnb) & (256 / cnb - 1)) == 0;
+    if (n_bands > 256) return launch_integral_two_pass(ctx);
+    if (!ctx->prep_flags) {
+        MCT_CUDA(ctx, cudaMalloc(&ctx->prep_flags, 256 * sizeof(unsigned)));
+        MCT_CUDA(ctx, cudaMemsetAsync(ctx->prep_flags, 0, 256 * sizeof(unsigned), ctx->stream));
+    }
+    size_t need = (size_t)n_bands * W;
+    if (need > ctx->bandsum_cap) {
+        if (ctx->bandsum) { MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->bandsum); }
+        MCT_CUDA(ctx, cudaMalloc(&ctx->bandsum, need * sizeof(uint32_t)));
+        ctx->bandsum_cap = need;
+    }
+    if (with_bins) {
+        size_t nb_need = (size_t)W * H;
+        if (nb_need > ctx->binimg_cap) {
+            if (ctx->binimg) { MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->binimg); }
+            MCT_CUDA(ctx, cudaMalloc(&ctx->binimg, nb_need * sizeof(uint16_t)));
+            ctx->binimg_cap = nb_need;
+        }
+    }
+    PrepArgs a;
+    a.gray = ctx->gray; a.W = W; a.H = H; a.pitch = ctx->pitch; a.BH = BH; a.n_bands = n_bands;
+    a.bandtot = ctx->bandsum; a.flags = ctx->prep_flags;
+    a.epoch = (unsigned)ctx->frame_id; a.ii = ctx->ii_base + MCT_II_LEAD; a.iip = ctx->ii_pitch;
+    a.c0 = ctx->c0; a.c1 = ctx->c1; a.c2 = ctx->c2; a.nb = cnb; a.bw_shift = 0; a.binimg = ctx->binimg;
+    a.n_binblocks = 0;
+    if (with_bins) {
+        const int bw = 256 / cnb;
+        while ((1 << a.bw_shift) < bw) a.bw_shift++;
+        a.n_binblocks = s_sms - n_bands;
+        if (a.n_binblocks > 64) a.n_binblocks = 64;
+        if (a.n_binblocks < 1) { with_bins = 0; a.n_binblocks = 0; }
+    }
+    static size_t s_attr = 0;
+    if (smem > s_attr) {
+        MCT_CUDA(ctx, cudaFuncSetAttribute(k_frame_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        s_attr = smem;
+    }
+    const int nt = 32 * (BH < 4 ? 4 : (BH > 16 ? 16 : BH));
+    void* args[] = {(void*)&a};
+    mct_prof_begin(ctx, "k_frame_prep");
+    MCT_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_frame_prep, dim3(n_bands + a.n_binblocks), dim3(nt), args, smem, ctx->stream));
+    mct_prof_end(ctx);
+    MCT_KERNEL_CHECK(ctx);
+    if (with_bins) ctx->binimg_frame = ctx->frame_id;
+    return MCT_OK;
+}
+
+static int launch_integral_two_pass(mct_ctx* ctx)
 {
     const int W = ctx->W, H = ctx->H;
     // band height: (BH + 1) * W u32 must fit in ~160 KB of shared memory

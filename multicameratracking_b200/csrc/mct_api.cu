@@ -185,6 +185,7 @@ extern "C" int mct_ctx_destroy(mct_ctx* ctx)
     for (int i = 0; i < 4; i++) if (ctx->own_planes[i]) cudaFree(ctx->own_planes[i]);
     if (ctx->ii_base) cudaFree(ctx->ii_base);
     if (ctx->bandsum) cudaFree(ctx->bandsum);
+    if (ctx->prep_flags) cudaFree(ctx->prep_flags);
     if (ctx->binimg) cudaFree(ctx->binimg);
     if (ctx->d_tmp) cudaFree(ctx->d_tmp);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
@@ -862,7 +863,8 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
         if ((rc = launch_bin_image(ctx, nb))) return rc;
         if ((rc = launch_mdch_selected(ctx, d, n_obj, n_max, max_slots))) return rc;
     }
-    if ((rc = launch_classify(ctx, d, n_obj, n_max, K_max, 0, 1))) return rc;
+    (void)K_max;
+    if ((rc = launch_classify_staged(ctx, d, n_obj, n_max, 1))) return rc;
     if ((rc = launch_pf_update(ctx, d, n_obj, n_max, 1, sa, 1))) return rc;
     return MCT_OK;
 }

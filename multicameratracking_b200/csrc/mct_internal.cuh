@@ -34,6 +34,7 @@ struct mct_ctx {
     uint8_t* own_planes[4]; size_t own_plane_cap;
     float* ii_base; int ii_pitch; size_t ii_cap;       // integral image storage; element (y,x) at ii_base[MCT_II_LEAD + y*ii_pitch + x]
     uint32_t* bandsum; size_t bandsum_cap;
+    unsigned* prep_flags;                              // [256] band-ready flags of k_frame_prep (value = frame id)
     uint16_t* binimg; size_t binimg_cap; int binimg_nb; long long binimg_frame;   // MDCH joint-bin image of the colour planes
     long long frame_id;
     void* d_desc; void* h_desc; size_t desc_cap;       // batched object descriptors (device + pinned host)
@@ -177,6 +178,7 @@ int mct_feature_color_rows(mct_clf* clf, const int* d_col, const int* d_row, con
 int launch_build_colormap(mct_clf* clf);
 int launch_mdch_selected(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int max_slots);
 int launch_classify(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int K_max, int from_matrix, int log_ratio);
+int launch_classify_staged(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int log_ratio);
 int launch_pf_predict(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, const StepArgs& sa);
 int launch_pf_testset(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max);
 // fused predict + test set (+ per-frame reset of the MDCH fallback counters) for the batched per-frame path
