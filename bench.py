@@ -240,6 +240,10 @@ def run_ours(args):
         t = pingpong(i, POOL)
         g, r, gg, b = planes_pin[t]
         cam._chk(cam.L.mcth_camera_set_frame(cam.h, vp(g.data_ptr()), vp(r.data_ptr()), vp(gg.data_ptr()), vp(b.data_ptr()), W, H, W, 0))
+        # the upload of the NEXT frame's planes (pinned host memory) is started now and overlaps this frame's kernels,
+        # as a video reader would decode ahead (Matrixu::PrefetchFrame); one frame is still copied per step
+        g2, r2, gg2, b2 = planes_pin[pingpong(i + 1, POOL)]
+        cam._chk(cam.L.mcth_camera_prefetch_frame(cam.h, vp(g2.data_ptr()), vp(r2.data_ptr()), vp(gg2.data_ptr()), vp(b2.data_ptr()), W, H, W))
         out = np.zeros((N_OBJ, 4), np.int32)
         cam._chk(cam.L.mcth_camera_track(cam.h, t, vp(noise_pin[i].data_ptr()), phases, out.ctypes.data_as(C.POINTER(C.c_int))))
         return out

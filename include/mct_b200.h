@@ -73,6 +73,12 @@ int mct_scored_particles(mct_ctx* ctx, unsigned long long* out, int reset);
  * Computes the (H+1)x(W+1) f32 integral image of gray: exact u32 prefix sums rounded once to f32. */
 int mct_frame_set(mct_ctx* ctx, const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2,
                   int W, int H, int pitch, int is_device);
+/* Optional double buffering of the upload (Camera.cpp:405-495 reads frame t+1 from the video while frame t is
+ * tracked): copies the NEXT frame's host planes (pinned memory for a truly asynchronous copy) into the ctx's back
+ * buffers on a separate copy stream, overlapping the kernels of the current frame.  A following mct_frame_set with
+ * the same pointers and geometry adopts the prefetched buffers instead of copying again. */
+int mct_frame_prefetch(mct_ctx* ctx, const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2,
+                       int W, int H, int pitch);
 /* dense (H+1)*(W+1) host copy of the integral image (tests) */
 int mct_frame_get_integral(mct_ctx* ctx, float* out_host);
 /* Matrixu::sumRect (Matrix.cpp:49-67): n rects {x,y,w,h} -> ((br+tl)-tr)-bl in f32.  Host in/out. */

@@ -24,7 +24,7 @@ PF_UNINIT, PF_INIT, PF_PREDICTED, PF_RESAMPLED = 0, 1, 2, 3
 # every symbol include/mct_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "mct_ctx_create", "mct_ctx_destroy", "mct_sync", "mct_last_error", "mct_version", "mct_launch_count",
-    "mct_ctx_stream", "mct_profile_enable", "mct_profile_read", "mct_scored_particles", "mct_frame_set", "mct_frame_get_integral", "mct_sum_rects", "mct_classifier_create",
+    "mct_ctx_stream", "mct_profile_enable", "mct_profile_read", "mct_scored_particles", "mct_frame_set", "mct_frame_prefetch", "mct_frame_get_integral", "mct_sum_rects", "mct_classifier_create",
     "mct_classifier_destroy", "mct_classifier_num_features", "mct_features_compute", "mct_classifier_update",
     "mct_classifier_update_from_features", "mct_classifier_classify", "mct_classifier_classify_from_features",
     "mct_classifier_get_selectors", "mct_classifier_get_weak_state", "mct_classifier_get_predictions",
@@ -92,6 +92,7 @@ def load():
     L.mct_profile_read.argtypes = [vp, C.c_int, C.c_char_p, _c_float_p, _c_int_p, _c_int_p]
     L.mct_scored_particles.argtypes = [vp, C.POINTER(C.c_ulonglong), C.c_int]
     L.mct_frame_set.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.mct_frame_prefetch.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int]
     L.mct_frame_get_integral.argtypes = [vp, _c_float_p]
     L.mct_sum_rects.argtypes = [vp, _c_int_p, C.c_int, _c_float_p]
     L.mct_classifier_create.argtypes = [vp, C.POINTER(ClfParams), C.POINTER(HaarTable), C.POINTER(vp)]
@@ -211,6 +212,15 @@ class Context:
         self._keep = (gray, planes)
         self.check(self.L.mct_frame_set(self.h, ptr(gray), ptr(planes[0]), ptr(planes[1]), ptr(planes[2]), W, H, W, 0))
         self.W, self.H = W, H
+
+    def frame_prefetch(self, gray, c0=None, c1=None, c2=None):
+        """Start the upload of the NEXT frame on the copy stream; frame_set with the same arrays adopts it."""
+        H, W = gray.shape
+        for a in (gray, c0, c1, c2):
+            assert a is None or (a.dtype == np.uint8 and a.flags["C_CONTIGUOUS"])
+        ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        self._keep_next = (gray, c0, c1, c2)
+        self.check(self.L.mct_frame_prefetch(self.h, ptr(gray), ptr(c0), ptr(c1), ptr(c2), W, H, W))
 
     def frame_set_device(self, W, H, pitch, gray_ptr, c0_ptr=0, c1_ptr=0, c2_ptr=0):
         """Adopt device-resident planes (e.g. torch uint8 tensors' data_ptr()) without a copy."""

@@ -183,6 +183,8 @@ extern "C" int mct_ctx_destroy(mct_ctx* ctx)
         delete ps;
     }
     for (int i = 0; i < 4; i++) if (ctx->own_planes[i]) cudaFree(ctx->own_planes[i]);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->ev_copy); cudaEventDestroy(ctx->ev_main); }
+    for (int i = 0; i < 4; i++) if (ctx->alt_planes[i]) cudaFree(ctx->alt_planes[i]);
     if (ctx->ii_base) cudaFree(ctx->ii_base);
     if (ctx->bandsum) cudaFree(ctx->bandsum);
     if (ctx->prep_flags) cudaFree(ctx->prep_flags);
@@ -227,11 +229,24 @@ extern "C" int mct_frame_set(mct_ctx* ctx, const uint8_t* gray, const uint8_t* c
     if (!gray || W < 4 || H < 4 || pitch < W) return mct_fail(ctx, MCT_E_ARG, "mct_frame_set: bad frame geometry%s");
     MCT_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint8_t* src[4] = {gray, c0, c1, c2};
+    const int dpp = round_up(W, 16);
     if (is_device) {
         ctx->gray = gray; ctx->c0 = c0; ctx->c1 = c1; ctx->c2 = c2;
         ctx->pitch = pitch;
+    } else if (ctx->pf_pending && ctx->pf_W == W && ctx->pf_H == H && ctx->pf_pitch == pitch && ctx->pf_src[0] == gray &&
+               ctx->pf_src[1] == c0 && ctx->pf_src[2] == c1 && ctx->pf_src[3] == c2) {
+        // adopt the prefetched back buffers: swap, and make the compute stream wait for the copy
+        for (int i = 0; i < 4; i++) { uint8_t* t = ctx->own_planes[i]; ctx->own_planes[i] = ctx->alt_planes[i]; ctx->alt_planes[i] = t; }
+        size_t tc = ctx->own_plane_cap; ctx->own_plane_cap = ctx->alt_plane_cap; ctx->alt_plane_cap = tc;
+        MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
+        ctx->pf_pending = 0;
+        ctx->gray = ctx->own_planes[0];
+        ctx->c0 = c0 ? ctx->own_planes[1] : nullptr;
+        ctx->c1 = c1 ? ctx->own_planes[2] : nullptr;
+        ctx->c2 = c2 ? ctx->own_planes[3] : nullptr;
+        ctx->pitch = dpp;
     } else {
-        int dp = round_up(W, 16);
+        int dp = dpp;
         size_t need = (size_t)dp * H;
         if (need > ctx->own_plane_cap) {
             MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -263,6 +278,41 @@ extern "C" int mct_frame_set(mct_ctx* ctx, const uint8_t* gray, const uint8_t* c
     }
     ctx->frame_id++;
     return launch_integral(ctx);
+}
+
+extern "C" int mct_frame_prefetch(mct_ctx* ctx, const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2,
+                                  int W, int H, int pitch)
+{
+    if (!ctx) return MCT_E_ARG;
+    if (!gray || W < 4 || H < 4 || pitch < W) return mct_fail(ctx, MCT_E_ARG, "mct_frame_prefetch: bad frame geometry%s");
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->copy_stream) {
+        MCT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        MCT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
+        MCT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming));
+    }
+    const int dp = round_up(W, 16);
+    const size_t need = (size_t)dp * H;
+    if (need > ctx->alt_plane_cap) {
+        MCT_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+        for (int i = 0; i < 4; i++) {
+            if (ctx->alt_planes[i]) cudaFree(ctx->alt_planes[i]);
+            MCT_CUDA(ctx, cudaMalloc(&ctx->alt_planes[i], need));
+        }
+        ctx->alt_plane_cap = need;
+    }
+    // the back buffers were the front buffers of the previous frame: everything enqueued on the compute stream so
+    // far (which includes their last readers) must finish before the copy overwrites them
+    MCT_CUDA(ctx, cudaEventRecord(ctx->ev_main, ctx->stream));
+    MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_main, 0));
+    const uint8_t* src[4] = {gray, c0, c1, c2};
+    for (int i = 0; i < 4; i++)
+        if (src[i])
+            MCT_CUDA(ctx, cudaMemcpy2DAsync(ctx->alt_planes[i], dp, src[i], pitch, W, H, cudaMemcpyHostToDevice, ctx->copy_stream));
+    MCT_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+    for (int i = 0; i < 4; i++) ctx->pf_src[i] = src[i];
+    ctx->pf_W = W; ctx->pf_H = H; ctx->pf_pitch = pitch; ctx->pf_pending = 1;
+    return MCT_OK;
 }
 
 extern "C" int mct_frame_get_integral(mct_ctx* ctx, float* out_host)

@@ -32,6 +32,9 @@ struct mct_ctx {
     int W, H, pitch;                       // current frame geometry (u8 planes)
     const uint8_t* gray; const uint8_t* c0; const uint8_t* c1; const uint8_t* c2;   // device planes in use
     uint8_t* own_planes[4]; size_t own_plane_cap;
+    uint8_t* alt_planes[4]; size_t alt_plane_cap;       // back buffers filled by mct_frame_prefetch on copy_stream
+    cudaStream_t copy_stream; cudaEvent_t ev_copy, ev_main;
+    const uint8_t* pf_src[4]; int pf_W, pf_H, pf_pitch, pf_pending;
     float* ii_base; int ii_pitch; size_t ii_cap;       // integral image storage; element (y,x) at ii_base[MCT_II_LEAD + y*ii_pitch + x]
     uint32_t* bandsum; size_t bandsum_cap;
     unsigned* prep_flags;                              // [256] band-ready flags of k_frame_prep (value = frame id)

@@ -48,6 +48,10 @@ void Matrixu::SetFrame(const uint8_t* gray, const uint8_t* c0, const uint8_t* c1
     chk(m_ctx, mct_frame_set(m_ctx, gray, c0, c1, c2, cols, rows, pitch, deviceResident ? 1 : 0));
     m_rows = rows; m_cols = cols; m_iiInit = true;
 }
+void Matrixu::PrefetchFrame(const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2, int cols, int rows, int pitch)
+{
+    chk(m_ctx, mct_frame_prefetch(m_ctx, gray, c0, c1, c2, cols, rows, pitch));
+}
 float Matrixu::sumRect(int x, int y, int w, int h) const
 {
     int r[4] = {x, y, w, h};

@@ -65,6 +65,8 @@ public:
     // upload gray (+ optional colour planes) and build the integral image  (Camera.cpp:460-491)
     void SetFrame(const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2, int cols, int rows,
                   int pitch, bool deviceResident = false);
+    // start the upload of the NEXT frame while the current one is tracked; SetFrame with the same pointers adopts it
+    void PrefetchFrame(const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2, int cols, int rows, int pitch);
     void initII() {}                      // done inside SetFrame; kept for call-site compatibility
     void FreeII() {}
     bool isInitII() const { return m_iiInit; }

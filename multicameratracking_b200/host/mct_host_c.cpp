@@ -63,6 +63,12 @@ int mcth_camera_set_frame(mcth_camera* c, const uint8_t* gray, const uint8_t* c0
     GUARD(c->frame.SetFrame(gray, c0, c1, c2, W, H, pitch, is_device != 0));
 }
 
+int mcth_camera_prefetch_frame(mcth_camera* c, const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2,
+                               int W, int H, int pitch)
+{
+    GUARD(c->frame.PrefetchFrame(gray, c0, c1, c2, W, H, pitch));
+}
+
 int mcth_camera_add_object(mcth_camera* c, const mcth_object_params* p)
 {
     GUARD({

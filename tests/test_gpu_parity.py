@@ -47,6 +47,22 @@ def test_integral_bit_exact(ctx, oracle, shape):
     np.testing.assert_array_equal(got, oracle.integral(img))
 
 
+def test_frame_prefetch_adopts_back_buffer(ctx, oracle):
+    """mct_frame_prefetch + mct_frame_set with the same host arrays == plain mct_frame_set (double-buffered upload)"""
+    seq = synth.Sequence(640, 480, 2)
+    f = [tuple(np.ascontiguousarray(p) for p in seq.frame(t)) for t in range(4)]
+    ctx.frame_set(*f[0])
+    for t in range(1, 4):
+        ctx.frame_prefetch(*f[t])
+        assert np.array_equal(ctx.integral(), oracle.integral(f[t - 1][0]))      # current frame untouched by the copy
+        ctx.frame_set(*f[t])                                                     # adopts the prefetched planes
+        assert np.array_equal(ctx.integral(), oracle.integral(f[t][0]))
+    # a prefetch that is not followed by the matching frame_set is simply ignored
+    ctx.frame_prefetch(*f[0])
+    ctx.frame_set(*f[2])
+    assert np.array_equal(ctx.integral(), oracle.integral(f[2][0]))
+
+
 def test_sum_rects_bit_exact(ctx, oracle):
     rng = np.random.default_rng(3)
     H, W = 480, 640
