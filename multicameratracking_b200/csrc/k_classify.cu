@@ -9,14 +9,6 @@
 // the reference's responseList[i] += weak[k] loop.
 #include "mct_internal.cuh"
 
-struct SelEntry {
-    int4  r[MCT_MAX_RECTS];
-    float w[MCT_MAX_RECTS];
-    float st[8];
-    int   nrect;      // >0: Haar feature; 0: colour feature, `row` indexes featN
-    int   row;
-};
-
 __global__ void __launch_bounds__(256)
 k_classify(const ObjDesc* __restrict__ descs, const float* __restrict__ ii, int iip, int W, int H,
            int from_matrix, int log_ratio)
@@ -113,47 +105,61 @@ __device__ __forceinline__ float weak_classify_ratio_dev(int weak_type, float x,
     return (float)log((1e-5 + p1) / (1e-5 + p0));
 }
 
+// ---- TMA 1-D bulk copies (cp.async.bulk -> SASS UBLKCP) completing on an mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
 #define CLS_THREADS 512
 #define CLS_SMEM (224 * 1024)
 __global__ void __launch_bounds__(CLS_THREADS, 1)
 k_classify_staged(const ObjDesc* __restrict__ descs, const float* __restrict__ ii, int iip, int W, int H, int log_ratio,
                   int smem_bytes)
 {
-    extern __shared__ __align__(16) unsigned char smraw[];
-    __shared__ int s_bb[4], s_ext[2];
+    extern __shared__ __align__(128) unsigned char smraw[];
+    __shared__ int s_bb[4];
+    __shared__ __align__(8) uint64_t s_bar[2];
     const ObjDesc& d = descs[blockIdx.y];
     const int tid = threadIdx.x, lane = tid & 31;
     const int N = d.N;
     const int chunk = (N + gridDim.x - 1) / gridDim.x;
     const int i_begin = blockIdx.x * chunk, i_end = min(N, i_begin + chunk);
     if (i_begin >= i_end) return;
-    const int nsel = *d.nsel, F = d.F;
     SelEntry* se = (SelEntry*)smraw;
-    if (tid == 0) { s_bb[0] = 1 << 30; s_bb[1] = 1 << 30; s_bb[2] = -(1 << 30); s_bb[3] = -(1 << 30); s_ext[0] = 0; s_ext[1] = 0; }
-    __syncthreads();
-    // ---- 1. selected weak classifiers; extent of the selected Haar rects in the blob frame
-    int mxw = 0, mxh = 0;
-    for (int s = tid; s < nsel; s += blockDim.x) {
-        const int f = d.sel[s];
-        SelEntry& e = se[s];
-#pragma unroll
-        for (int q = 0; q < 8; q++) e.st[q] = d.weak[(size_t)q * F + f];
-        if (f < d.n_haar) {
-            e.nrect = d.nrect[f];
-            for (int k = 0; k < MCT_MAX_RECTS; k++) {
-                e.r[k] = d.rects[(size_t)f * MCT_MAX_RECTS + k];
-                e.w[k] = d.wts[(size_t)f * MCT_MAX_RECTS + k];
-                if (k < e.nrect) { mxw = max(mxw, e.r[k].x + e.r[k].z); mxh = max(mxh, e.r[k].y + e.r[k].w); }
-            }
-            e.row = 0;
-        } else {
-            e.nrect = 0;
-            e.row = d.colorrow[f - d.n_haar];
-        }
+    const int Kcap = d.K;
+    const size_t se_b = (size_t)max(Kcap, 1) * sizeof(SelEntry);               // 160 B entries: a multiple of 16
+    if (tid == 0) {
+        s_bb[0] = 1 << 30; s_bb[1] = 1 << 30; s_bb[2] = -(1 << 30); s_bb[3] = -(1 << 30);
+        mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (mxw > 0) { atomicMax(&s_ext[0], mxw); atomicMax(&s_ext[1], mxh); }
     __syncthreads();
-    const int ext_w = s_ext[0], ext_h = s_ext[1];
+    // ---- 1. the prepared selected-classifier table arrives with ONE bulk copy while the boxes are scanned
+    if (tid == 0) {
+        mbar_expect_tx(&s_bar[0], (unsigned)se_b);
+        bulk_g2s(se, d.seltab, (unsigned)se_b, &s_bar[0]);
+    }
+    const int nsel = __ldg(d.selhdr), ext_w = __ldg(d.selhdr + 1), ext_h = __ldg(d.selhdr + 2);
     // ---- 2. integral-image region of the chunk's valid boxes (Haar selectors only)
     if (ext_w > 0) {
         int x0 = 1 << 30, y0 = 1 << 30, x1 = -(1 << 30), y1 = -(1 << 30);
@@ -171,23 +177,25 @@ k_classify_staged(const ObjDesc* __restrict__ descs, const float* __restrict__ i
         if (lane == 0 && x1 >= x0) { atomicMin(&s_bb[0], x0); atomicMin(&s_bb[1], y0); atomicMax(&s_bb[2], x1); atomicMax(&s_bb[3], y1); }
     }
     __syncthreads();
-    const size_t se_b = ((size_t)max(nsel, 1) * sizeof(SelEntry) + 15) & ~(size_t)15;
     float* region = (float*)(smraw + se_b);
     const int bx0 = clampi(s_bb[0], 0, W), by0 = clampi(s_bb[1], 0, H);
     const int bx1 = clampi(s_bb[2], 0, W), by1 = clampi(s_bb[3], 0, H);
-    const int RW = bx1 - bx0 + 1, RH = by1 - by0 + 1;
-    const int RWp = RW | 1;                                                   // odd pitch spreads rows over the banks
+    // x origin such that the source rows are 16-byte aligned (the table has a 3-float lead, MCT_II_LEAD)
+    const int ox = ((bx0 + 3) & ~3) - 3;
+    const int RH = by1 - by0 + 1;
+    const int RWc = (bx1 - ox + 1 + 3) & ~3;                                   // floats copied per row (multiple of 4)
+    const int RWp = (RWc & 4) ? RWc : RWc + 4;                                 // pitch/4 odd: rows spread over the banks
     const bool have = ext_w > 0 && s_bb[2] >= s_bb[0];
-    const bool staged = have && se_b + (size_t)RWp * RH * 4 <= (size_t)smem_bytes;
-    if (staged) {
-        for (int y = tid >> 5; y < RH; y += CLS_THREADS / 32) {
-            const float* src = ii + (size_t)(by0 + y) * iip + bx0;
-            float* dst = region + y * RWp;
-            for (int x = lane; x < RW; x += 32) dst[x] = __ldg(src + x);
-        }
+    const bool staged = have && se_b + (size_t)RWp * RH * 4 <= (size_t)smem_bytes && (size_t)RWc * RH * 4 < (1u << 20);
+    if (staged && tid < 32) {
+        if (lane == 0) mbar_expect_tx(&s_bar[1], (unsigned)(RWc * RH * 4));
+        __syncwarp();
+        for (int y = lane; y < RH; y += 32)
+            bulk_g2s(region + (size_t)y * RWp, ii + (size_t)(by0 + y) * iip + ox, (unsigned)(RWc * 4), &s_bar[1]);
     }
-    __syncthreads();
-    // ---- 3. four lanes per box
+    mbar_wait(&s_bar[0], 0);
+    if (staged) mbar_wait(&s_bar[1], 0);
+    // ---- 3. four lanes per box, two selectors in flight per lane
     const int q = tid & 3;
     const unsigned gmask = 0xfu << (lane & ~3);
     for (int base = i_begin; base < i_end; base += CLS_THREADS / 4) {
@@ -197,24 +205,29 @@ k_classify_staged(const ObjDesc* __restrict__ descs, const float* __restrict__ i
         int c = 0, r = 0; float fx = 1.0f, fy = 1.0f;
         if (ok) { c = d.col[i]; r = d.row[i]; fx = d.sx[i]; fy = d.sy[i]; }
         float Hs = 0.0f;
-        for (int s0 = 0; s0 < nsel; s0 += 4) {
-            const int s = s0 + q;
-            float v = 0.0f;
-            if (ok && s < nsel) {
-                const SelEntry& e = se[s];
-                float x;
-                if (e.nrect > 0) {
-                    if (staged) x = haar_eval_region(region, RWp, bx0, by0, W, H, e.r, e.w, e.nrect, c, r, fx, fy);
-                    else x = haar_eval_dev(ii, iip, W, H, e.r, e.w, e.nrect, c, r, fx, fy);
-                } else x = d.featN[(size_t)e.row * d.ldN + i];
-                v = weak_classify_ratio_dev(d.weak_type, x, e.st);
+        for (int s0 = 0; s0 < nsel; s0 += 8) {
+            float v[2] = {0.0f, 0.0f};
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int s = s0 + 4 * u + q;
+                if (ok && s < nsel) {
+                    const SelEntry& e = se[s];
+                    float x;
+                    if (e.nrect > 0) {
+                        if (staged) x = haar_eval_region(region, RWp, ox, by0, W, H, e.r, e.w, e.nrect, c, r, fx, fy);
+                        else x = haar_eval_dev(ii, iip, W, H, e.r, e.w, e.nrect, c, r, fx, fy);
+                    } else x = d.featN[(size_t)e.row * d.ldN + i];
+                    v[u] = weak_classify_ratio_dev(d.weak_type, x, e.st);
+                }
             }
             // ordered accumulation: responseList[i] += weak[k] in selector order (MILBoostClassifier.cpp:351-361)
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const float vj = __shfl_sync(gmask, v, (lane & ~3) + j);
-                if (s0 + j < nsel) Hs = __fadd_rn(Hs, vj);
-            }
+            for (int u = 0; u < 2; u++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float vj = __shfl_sync(gmask, v[u], (lane & ~3) + j);
+                    if (s0 + 4 * u + j < nsel) Hs = __fadd_rn(Hs, vj);
+                }
         }
         if (live && q == 0) {
             if (ok && !log_ratio) Hs = sigmoid_dev(Hs);

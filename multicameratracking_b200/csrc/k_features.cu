@@ -274,30 +274,63 @@ int mct_feature_color_rows(mct_clf* clf, const int* d_col, const int* d_row, con
 //                      than 255 selected bins).
 // Shared-memory-resident gather kernel: per box rows*cols slot bytes + LUT words + private RMW traffic.
 // ==========================================================================================
-__global__ void k_build_colormap(const int* __restrict__ sel, const int* __restrict__ nsel, int n_haar, int n_color,
+__global__ void k_build_colormap(const int* __restrict__ sel, const int* __restrict__ nsel, int n_haar, int n_color, int mdch,
                                  uint16_t* __restrict__ slotmap, int* __restrict__ colorrow, int* __restrict__ outbins,
-                                 int* __restrict__ nout)
+                                 int* __restrict__ nout, const int4* __restrict__ rects, const float* __restrict__ wts,
+                                 const int* __restrict__ nrect, const float* __restrict__ weak, int F, int K,
+                                 SelEntry* __restrict__ tab, int* __restrict__ hdr)
 {
-    for (int b = threadIdx.x; b < n_color; b += blockDim.x) { slotmap[b] = 0; colorrow[b] = 0; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int n = 0;
-        const int ns = *nsel;
-        for (int s = 0; s < ns; s++) {
-            const int f = sel[s];
-            if (f < n_haar) continue;
-            const int b = f - n_haar;
-            if (slotmap[b] == 0) { outbins[n] = b; colorrow[b] = n; n++; slotmap[b] = (uint16_t)n; }
+    __shared__ int s_ext[2];
+    const int ns = *nsel;
+    if (threadIdx.x == 0) { s_ext[0] = 0; s_ext[1] = 0; }
+    if (mdch) {
+        for (int b = threadIdx.x; b < n_color; b += blockDim.x) { slotmap[b] = 0; colorrow[b] = 0; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int n = 0;
+            for (int s = 0; s < ns; s++) {
+                const int f = sel[s];
+                if (f < n_haar) continue;
+                const int b = f - n_haar;
+                if (slotmap[b] == 0) { outbins[n] = b; colorrow[b] = n; n++; slotmap[b] = (uint16_t)n; }
+            }
+            *nout = n;
         }
-        *nout = n;
     }
+    __syncthreads();
+    // the prepared table read by k_classify_staged (entries beyond nsel are zero)
+    int mxw = 0, mxh = 0;
+    for (int s = threadIdx.x; s < K; s += blockDim.x) {
+        SelEntry e;
+        memset(&e, 0, sizeof(e));
+        if (s < ns) {
+            const int f = sel[s];
+            for (int q = 0; q < 8; q++) e.st[q] = weak[(size_t)q * F + f];
+            if (f < n_haar) {
+                e.nrect = nrect[f];
+                for (int k = 0; k < MCT_MAX_RECTS; k++) {
+                    e.r[k] = rects[(size_t)f * MCT_MAX_RECTS + k];
+                    e.w[k] = wts[(size_t)f * MCT_MAX_RECTS + k];
+                    if (k < e.nrect) { mxw = max(mxw, e.r[k].x + e.r[k].z); mxh = max(mxh, e.r[k].y + e.r[k].w); }
+                }
+            } else {
+                e.row = colorrow[f - n_haar];
+            }
+        }
+        tab[s] = e;
+    }
+    if (mxw > 0) { atomicMax(&s_ext[0], mxw); atomicMax(&s_ext[1], mxh); }
+    __syncthreads();
+    if (threadIdx.x == 0) { hdr[0] = ns < K ? ns : K; hdr[1] = s_ext[0]; hdr[2] = s_ext[1]; hdr[3] = 0; }
 }
 int launch_build_colormap(mct_clf* clf)
 {
     mct_ctx* ctx = clf->ctx;
-    if (!(clf->p.feature_type == MCT_FEAT_MDCH || clf->p.feature_type == MCT_FEAT_HAAR_MDCH)) return MCT_OK;
-    MCT_LAUNCH(ctx, "k_build_colormap", k_build_colormap<<<1, 256, 0, ctx->stream>>>(clf->d_sel, clf->d_nsel, clf->n_haar, clf->n_color,
-                                                                                  clf->d_slotmap, clf->d_colorrow, clf->d_outbins, clf->d_nout));
+    const int mdch = (clf->p.feature_type == MCT_FEAT_MDCH || clf->p.feature_type == MCT_FEAT_HAAR_MDCH) ? 1 : 0;
+    MCT_LAUNCH(ctx, "k_build_colormap", k_build_colormap<<<1, 256, 0, ctx->stream>>>(clf->d_sel, clf->d_nsel, clf->n_haar, clf->n_color, mdch,
+                                                                                  clf->d_slotmap, clf->d_colorrow, clf->d_outbins, clf->d_nout,
+                                                                                  clf->d_rects, clf->d_wts, clf->d_nrect, clf->d_weak, clf->F, clf->K,
+                                                                                  clf->d_seltab, clf->d_selhdr));
     return MCT_OK;
 }
 

@@ -448,6 +448,10 @@ extern "C" int mct_classifier_create(mct_ctx* ctx, const mct_clf_params* p, cons
     MCT_CUDA(ctx, cudaMemset(c->d_sel, 0, (size_t)F * 4));
     MCT_CUDA(ctx, cudaMalloc(&c->d_nsel, 4));
     MCT_CUDA(ctx, cudaMemset(c->d_nsel, 0, 4));
+    MCT_CUDA(ctx, cudaMalloc(&c->d_seltab, (size_t)K * sizeof(SelEntry)));
+    MCT_CUDA(ctx, cudaMemset(c->d_seltab, 0, (size_t)K * sizeof(SelEntry)));
+    MCT_CUDA(ctx, cudaMalloc(&c->d_selhdr, 16));
+    MCT_CUDA(ctx, cudaMemset(c->d_selhdr, 0, 16));
     MCT_CUDA(ctx, cudaMalloc(&c->d_tcol, (size_t)c->ldT * 4)); MCT_CUDA(ctx, cudaMalloc(&c->d_trow, (size_t)c->ldT * 4));
     MCT_CUDA(ctx, cudaMalloc(&c->d_tsx, (size_t)c->ldT * 4)); MCT_CUDA(ctx, cudaMalloc(&c->d_tsy, (size_t)c->ldT * 4));
     MCT_CUDA(ctx, cudaMalloc(&c->d_tw, (size_t)c->ldT * 4));
@@ -474,7 +478,7 @@ extern "C" int mct_classifier_destroy(mct_clf* c)
     if (!c) return MCT_OK;
     cudaSetDevice(c->ctx->device);
     cudaStreamSynchronize(c->ctx->stream);
-    void* ptrs[] = {c->d_rects, c->d_wts, c->d_nrect, c->d_weak, c->d_trained, c->d_sel, c->d_nsel, c->d_tcol, c->d_trow,
+    void* ptrs[] = {c->d_rects, c->d_wts, c->d_nrect, c->d_weak, c->d_trained, c->d_sel, c->d_nsel, c->d_seltab, c->d_selhdr, c->d_tcol, c->d_trow,
                     c->d_tsx, c->d_tsy, c->d_tw, c->d_featT, c->d_pred, c->d_col, c->d_row, c->d_sx, c->d_sy, c->d_featN,
                     c->d_H, c->d_outbins, c->d_colorrow, c->d_slotmap, c->d_nout, c->d_big, c->d_nbig};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -566,7 +570,7 @@ extern "C" int mct_classifier_update_from_features(mct_clf* c, const float* fpos
 static void fill_clf_desc(ObjDesc* d, mct_clf* c)
 {
     d->rects = c->d_rects; d->wts = c->d_wts; d->nrect = c->d_nrect;
-    d->weak = c->d_weak; d->sel = c->d_sel; d->nsel = c->d_nsel;
+    d->weak = c->d_weak; d->sel = c->d_sel; d->nsel = c->d_nsel; d->seltab = c->d_seltab; d->selhdr = c->d_selhdr;
     d->featN = c->d_featN; d->ldN = c->ldN; d->n_color_rows = c->n_color;
     d->colorrow = c->d_colorrow; d->outbins = c->d_outbins;
     const bool mdch = c->p.feature_type == MCT_FEAT_MDCH || c->p.feature_type == MCT_FEAT_HAAR_MDCH;

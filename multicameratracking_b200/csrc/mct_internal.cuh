@@ -24,6 +24,17 @@ struct PfDev {
     int   pad;
 };
 
+// One selected weak classifier, ready for Classify: Haar rect table (or the featN row of a colour feature) + the
+// 8-float weak state.  The table of a classifier is rebuilt on the device after every Update (k_build_colormap)
+// so that the per-frame kernels fetch it with one bulk copy instead of chasing selector -> feature -> state.
+struct SelEntry {
+    int4  r[MCT_MAX_RECTS];
+    float w[MCT_MAX_RECTS];
+    float st[8];
+    int   nrect;      // >0: Haar feature; 0: colour feature, `row` indexes featN
+    int   row;
+};
+
 // ------------------------------------------------------------------ host-side objects
 struct mct_ctx {
     int device;
@@ -62,6 +73,7 @@ struct mct_clf {
     float* d_weak; int* d_trained;
     // selection
     int* d_sel; int* d_nsel;
+    SelEntry* d_seltab; int* d_selhdr;                  // [K] prepared selected-classifier table; hdr = {nsel, ext_w, ext_h, 0}
     int cluster;                                       // requested cluster width (0 auto)
     // training buffers
     int max_train, ldT;
@@ -115,6 +127,7 @@ struct ObjDesc {
     // classifier
     const int4* rects; const float* wts; const int* nrect;
     const float* weak; const int* sel; const int* nsel;
+    const SelEntry* seltab; const int* selhdr;
     float* featN; int ldN; int n_color_rows;
     const int* colorrow; const int* outbins;
     const uint16_t* slotmap; const int* nout; int* big; int* nbig;
