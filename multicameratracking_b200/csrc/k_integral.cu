@@ -114,7 +114,7 @@ k_integral_band(const uint8_t* __restrict__ img, int W, int H, int pitch, int BH
 //                     sums their totals per column (exact u32) and stores f32(base + local) with coalesced rows.
 //                     The frame is read from HBM exactly once and the table written once.
 //   CTA b >= n_bands: bin image, 4 pixels per thread (uchar4 loads, one 8-byte store).
-// Blocks wait on one another, so the launch is cooperative (co-residency guaranteed; grid <= 1 CTA per SM).
+// Blocks wait on one another; see the ticket scheme at the top of the kernel for why this cannot deadlock.
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
 {
     unsigned v;
@@ -126,6 +126,14 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v)
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+#ifdef MCT_PREP_DEBUG
+__device__ unsigned long long g_prep_dbg[256 * 8];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define PREP_STAMP(k) do { if (threadIdx.x == 0) g_prep_dbg[s_ticket * 8 + (k)] = gtime(); } while (0)
+#else
+#define PREP_STAMP(k)
+#endif
+
 struct PrepArgs {
     const uint8_t* gray; int W, H, pitch, BH, n_bands;
     uint32_t* bandtot; unsigned* flags; unsigned epoch; float* ii; int iip;
@@ -135,13 +143,22 @@ struct PrepArgs {
 __global__ void __launch_bounds__(512) k_frame_prep(const PrepArgs a)
 {
     extern __shared__ uint32_t sm[];
+    __shared__ int s_ticket;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int W = a.W, H = a.H;
-    if ((int)blockIdx.x >= a.n_bands) {
+    // Work is handed out in ARRIVAL order (ticket counter), so the band that gets ticket b knows that every band
+    // < b is held by a CTA that is already running: the waits below cannot deadlock whatever the dispatch order or
+    // residency, and no cooperative launch is needed.  The last CTA to finish resets the two counters.
+    if (tid == 0) s_ticket = (int)atomicAdd(a.flags + 256, 1u);
+    __syncthreads();
+    const int ticket = s_ticket;
+    PREP_STAMP(0);
+    if (ticket >= a.n_bands) {
         // ---- joint-bin image (MultiDimensionalColorHistogram.cpp:96-104); bw = 256/nb is a power of two here
-        const int q = blockIdx.x - a.n_bands;
+        const int q = ticket - a.n_bands;
         const int groups = (W >> 2) * H;                                  // launch_integral guarantees W % 4 == 0, pitch % 4 == 0
         const int wq = W >> 2, nb = a.nb, sh = a.bw_shift;
+#pragma unroll 4
         for (int g = q * nt + tid; g < groups; g += a.n_binblocks * nt) {
             const int y = g / wq, x = (g - y * wq) << 2;
             const size_t o = (size_t)y * a.pitch + x;
@@ -154,30 +171,63 @@ __global__ void __launch_bounds__(512) k_frame_prep(const PrepArgs a)
             const unsigned b3 = (r.w >> sh) + nb * (gg.w >> sh) + nb * nb * (bb.w >> sh);
             *reinterpret_cast<uint2*>(a.binimg + (size_t)y * W + x) = make_uint2(b0 | (b1 << 16), b2 | (b3 << 16));
         }
+        __syncthreads();
+        PREP_STAMP(4);
+        if (tid == 0 && atomicAdd(a.flags + 257, 1u) == gridDim.x - 1) { a.flags[256] = 0; a.flags[257] = 0; }
         return;
     }
-    const int b = blockIdx.x, BH = a.BH;
+    const int b = ticket, BH = a.BH;
     const int r0 = b * BH, nr = min(BH, H - r0);
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     uint32_t* rp = sm;                                                    // [BH][W]
     const bool vec = ((a.pitch | (int)(size_t)a.gray) & 3) == 0;
-    // (1) row prefixes
+    // (1) row prefixes: ALL chunk loads of a row are issued before the first scan (the frame comes from HBM: one
+    //     latency per row instead of one per 128-pixel chunk)
     for (int r = warp; r < nr; r += nwarps) {
         const uint8_t* src = a.gray + (size_t)(r0 + r) * a.pitch;
         uint32_t* dst = rp + (size_t)r * W;
+        uchar4 px[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int c = k * 128 + lane * 4;
+            px[k] = make_uchar4(0, 0, 0, 0);
+            if (c < W) {
+                if (c + 3 < W && vec) px[k] = *reinterpret_cast<const uchar4*>(src + c);
+                else {
+                    px[k].x = src[c];
+                    if (c + 1 < W) px[k].y = src[c + 1];
+                    if (c + 2 < W) px[k].z = src[c + 2];
+                    if (c + 3 < W) px[k].w = src[c + 3];
+                }
+            }
+        }
         uint32_t carry = 0;
-        for (int c0 = 0; c0 < W; c0 += 128) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int c = k * 128 + lane * 4;
+            if (k * 128 < W) {
+                uint32_t v0 = px[k].x, v1 = px[k].y, v2 = px[k].z, v3 = px[k].w;
+                v1 += v0; v2 += v1; v3 += v2;
+                const uint32_t incl = warp_incl_scan(v3, lane);
+                const uint32_t off = carry + incl - v3;
+                if (c + 3 < W && (W & 3) == 0) *reinterpret_cast<uint4*>(dst + c) = make_uint4(v0 + off, v1 + off, v2 + off, v3 + off);
+                else {
+                    if (c + 0 < W) dst[c + 0] = v0 + off;
+                    if (c + 1 < W) dst[c + 1] = v1 + off;
+                    if (c + 2 < W) dst[c + 2] = v2 + off;
+                    if (c + 3 < W) dst[c + 3] = v3 + off;
+                }
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+        }
+        // frames wider than 2048 pixels: remaining chunks the simple way
+        for (int c0 = 2048; c0 < W; c0 += 128) {
             const int c = c0 + lane * 4;
             uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-            if (c + 3 < W && vec) {
-                const uchar4 p = *reinterpret_cast<const uchar4*>(src + c);
-                v0 = p.x; v1 = p.y; v2 = p.z; v3 = p.w;
-            } else {
-                if (c + 0 < W) v0 = src[c + 0];
-                if (c + 1 < W) v1 = src[c + 1];
-                if (c + 2 < W) v2 = src[c + 2];
-                if (c + 3 < W) v3 = src[c + 3];
-            }
+            if (c + 0 < W) v0 = src[c + 0];
+            if (c + 1 < W) v1 = src[c + 1];
+            if (c + 2 < W) v2 = src[c + 2];
+            if (c + 3 < W) v3 = src[c + 3];
             v1 += v0; v2 += v1; v3 += v2;
             const uint32_t incl = warp_incl_scan(v3, lane);
             const uint32_t off = carry + incl - v3;
@@ -189,6 +239,7 @@ __global__ void __launch_bounds__(512) k_frame_prep(const PrepArgs a)
         }
     }
     __syncthreads();
+    PREP_STAMP(1);
     // (2) band-local integral in place + publish the band totals
     uint32_t* tot = a.bandtot + (size_t)b * W;
     for (int c = tid; c < W; c += nt) {
@@ -199,14 +250,17 @@ __global__ void __launch_bounds__(512) k_frame_prep(const PrepArgs a)
     __threadfence();
     __syncthreads();
     if (tid == 0) st_release_u32(a.flags + b, a.epoch);
+    PREP_STAMP(2);
     // (3) wait for every band above (all CTAs are co-resident: cooperative launch)
     for (int t = tid; t < b; t += nt) { while (ld_acquire_u32(a.flags + t) != a.epoch) { } }
     __syncthreads();
+    PREP_STAMP(3);
     // (4) base = totals of the bands above; store f32(base + local); a warp writes 32 consecutive columns of a row
     float* ii = a.ii;
     const int iip = a.iip;
     for (int c = tid; c < W; c += nt) {
         uint32_t base = 0;
+#pragma unroll 8
         for (int bb = 0; bb < b; bb++) base += __ldcg(a.bandtot + (size_t)bb * W + c);
         for (int r = 0; r < nr; r++)
             ii[(size_t)(r0 + r + 1) * iip + c + 1] = __uint2float_rn(base + rp[(size_t)r * W + c]);
@@ -214,6 +268,9 @@ __global__ void __launch_bounds__(512) k_frame_prep(const PrepArgs a)
     for (int r = tid; r < nr; r += nt) ii[(size_t)(r0 + r + 1) * iip] = 0.0f;
     if (b == 0)
         for (int c = tid; c <= W; c += nt) ii[c] = 0.0f;
+    __syncthreads();
+    PREP_STAMP(4);
+    if (tid == 0 && atomicAdd(a.flags + 257, 1u) == gridDim.x - 1) { a.flags[256] = 0; a.flags[257] = 0; }
 }
 
 static int launch_integral_two_pass(mct_ctx* ctx);
@@ -233,16 +290,15 @@ int launch_integral(mct_ctx* ctx)
     while (ceil_div(H, BH) > s_sms / 2 && BH < 64) BH <<= 1;
     const size_t smem = (size_t)BH * W * sizeof(uint32_t);
     const int n_bands = ceil_div(H, BH);
-    if (!s_coop || smem > 200 * 1024 || n_bands > s_sms) return launch_integral_two_pass(ctx);
+    if (smem > 200 * 1024 || n_bands > 256) return launch_integral_two_pass(ctx);
     // the bin image rides along when an MDCH classifier has used this ctx before and the planes allow 4-pixel vectors
     const int cnb = ctx->binimg_nb;
     int with_bins = cnb > 0 && ctx->c0 && ctx->c1 && ctx->c2 && (W & 3) == 0 && (ctx->pitch & 3) == 0 &&
                     ((((size_t)ctx->c0) | ((size_t)ctx->c1) | ((size_t)ctx->c2)) & 3) == 0 && (256 % cnb) == 0 &&
                     ((256 / cnb) & (256 / cnb - 1)) == 0;
-    if (n_bands > 256) return launch_integral_two_pass(ctx);
     if (!ctx->prep_flags) {
-        MCT_CUDA(ctx, cudaMalloc(&ctx->prep_flags, 256 * sizeof(unsigned)));
-        MCT_CUDA(ctx, cudaMemsetAsync(ctx->prep_flags, 0, 256 * sizeof(unsigned), ctx->stream));
+        MCT_CUDA(ctx, cudaMalloc(&ctx->prep_flags, 260 * sizeof(unsigned)));          // [256] band flags, [256] ticket, [257] done
+        MCT_CUDA(ctx, cudaMemsetAsync(ctx->prep_flags, 0, 260 * sizeof(unsigned), ctx->stream));
     }
     size_t need = (size_t)n_bands * W;
     if (need > ctx->bandsum_cap) {
@@ -277,11 +333,7 @@ int launch_integral(mct_ctx* ctx)
         s_attr = smem;
     }
     const int nt = 32 * (BH < 4 ? 4 : (BH > 16 ? 16 : BH));
-    void* args[] = {(void*)&a};
-    mct_prof_begin(ctx, "k_frame_prep");
-    MCT_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_frame_prep, dim3(n_bands + a.n_binblocks), dim3(nt), args, smem, ctx->stream));
-    mct_prof_end(ctx);
-    MCT_KERNEL_CHECK(ctx);
+    MCT_LAUNCH(ctx, "k_frame_prep", k_frame_prep<<<n_bands + a.n_binblocks, nt, smem, ctx->stream>>>(a));
     if (with_bins) ctx->binimg_frame = ctx->frame_id;
     return MCT_OK;
 }
