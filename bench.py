@@ -230,7 +230,7 @@ def run_ours(args):
     def step_resident(i):
         t = pingpong(i, POOL)
         g, r, gg, b = planes_dev[t]
-        cam.set_frame_device(W, H, W, g.data_ptr(), r.data_ptr(), gg.data_ptr(), b.data_ptr())
+        cam.set_frame_device(W, H, W, g.data_ptr(), r.data_ptr(), gg.data_ptr(), b.data_ptr(), ready=True)   # static resident pool
         nz = noise_dev[i]
         rc = cam.L.mcth_camera_track_resident(cam.h, t, vp(nz.data_ptr()))
         if rc:

@@ -69,14 +69,20 @@ int mct_scored_particles(mct_ctx* ctx, unsigned long long* out, int reset);
  * gray is required; c0,c1,c2 are the colour planes the MDCH/CCH features read (R,G,B in that order,
  * Matrix.cpp:92-94, or H,S,V) and may be NULL when only Haar features are used.
  * is_device = 0: host pointers, copied H2D asynchronously on the ctx stream;
- * is_device = 1: device pointers adopted without a copy (must stay valid until the next frame_set).
+ * is_device = 1: device pointers adopted without a copy (must stay valid until the next frame_set); the planes are
+ *                taken to be produced by work already enqueued on the ctx stream (ordered after it);
+ * is_device = 2: same, but the planes are already complete, so the frame preparation may start at once and overlap
+ *                the previous frame's kernels (it runs on an internal stream into a second buffer set).
  * Computes the (H+1)x(W+1) f32 integral image of gray: exact u32 prefix sums rounded once to f32. */
 int mct_frame_set(mct_ctx* ctx, const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2,
                   int W, int H, int pitch, int is_device);
 /* Optional double buffering of the upload (Camera.cpp:405-495 reads frame t+1 from the video while frame t is
  * tracked): copies the NEXT frame's host planes (pinned memory for a truly asynchronous copy) into the ctx's back
  * buffers on a separate copy stream, overlapping the kernels of the current frame.  A following mct_frame_set with
- * the same pointers and geometry adopts the prefetched buffers instead of copying again. */
+ * the same pointers and geometry adopts the prefetched buffers instead of copying again.  The copy and the frame
+ * preparation are issued lazily (behind the current frame's noise copy and beside its particle-filter update in
+ * mct_track_score*, at the latest in the adopting mct_frame_set), so the host planes must stay valid and unchanged until
+ * the first mct_sync / mct_track_collect after the adopting mct_frame_set. */
 int mct_frame_prefetch(mct_ctx* ctx, const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2,
                        int W, int H, int pitch);
 /* dense (H+1)*(W+1) host copy of the integral image (tests) */

@@ -273,52 +273,40 @@ __global__ void __launch_bounds__(512) k_frame_prep(const PrepArgs a)
     if (tid == 0 && atomicAdd(a.flags + 257, 1u) == gridDim.x - 1) { a.flags[256] = 0; a.flags[257] = 0; }
 }
 
-static int launch_integral_two_pass(mct_ctx* ctx);
+static int launch_integral_two_pass(mct_ctx* ctx, const PrepTarget& t, cudaStream_t st);
 
-int launch_integral(mct_ctx* ctx)
+int launch_frame_prep(mct_ctx* ctx, const PrepTarget& t, cudaStream_t st, int* with_bins_out)
 {
-    const int W = ctx->W, H = ctx->H;
-    static int s_coop = -1, s_sms = 0;
-    if (s_coop < 0) {
-        int coop = 0;
-        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
-        cudaDeviceGetAttribute(&s_sms, cudaDevAttrMultiProcessorCount, ctx->device);
-        s_coop = coop;
-    }
+    const int W = t.W, H = t.H;
+    *with_bins_out = 0;
+    static int s_sms = 0;
+    if (!s_sms) cudaDeviceGetAttribute(&s_sms, cudaDevAttrMultiProcessorCount, ctx->device);
     // band height: enough bands to spread over the SMs; BH*W u32 must fit in shared memory
     int BH = 8;
     while (ceil_div(H, BH) > s_sms / 2 && BH < 64) BH <<= 1;
     const size_t smem = (size_t)BH * W * sizeof(uint32_t);
     const int n_bands = ceil_div(H, BH);
-    if (smem > 200 * 1024 || n_bands > 256) return launch_integral_two_pass(ctx);
+    if (smem > 200 * 1024 || n_bands > 256) return launch_integral_two_pass(ctx, t, st);
     // the bin image rides along when an MDCH classifier has used this ctx before and the planes allow 4-pixel vectors
     const int cnb = ctx->binimg_nb;
-    int with_bins = cnb > 0 && ctx->c0 && ctx->c1 && ctx->c2 && (W & 3) == 0 && (ctx->pitch & 3) == 0 &&
-                    ((((size_t)ctx->c0) | ((size_t)ctx->c1) | ((size_t)ctx->c2)) & 3) == 0 && (256 % cnb) == 0 &&
+    int with_bins = cnb > 0 && t.binimg && t.c0 && t.c1 && t.c2 && (W & 3) == 0 && (t.pitch & 3) == 0 &&
+                    ((((size_t)t.c0) | ((size_t)t.c1) | ((size_t)t.c2)) & 3) == 0 && (256 % cnb) == 0 &&
                     ((256 / cnb) & (256 / cnb - 1)) == 0;
     if (!ctx->prep_flags) {
         MCT_CUDA(ctx, cudaMalloc(&ctx->prep_flags, 260 * sizeof(unsigned)));          // [256] band flags, [256] ticket, [257] done
-        MCT_CUDA(ctx, cudaMemsetAsync(ctx->prep_flags, 0, 260 * sizeof(unsigned), ctx->stream));
+        MCT_CUDA(ctx, cudaMemsetAsync(ctx->prep_flags, 0, 260 * sizeof(unsigned), st));
     }
     size_t need = (size_t)n_bands * W;
     if (need > ctx->bandsum_cap) {
-        if (ctx->bandsum) { MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->bandsum); }
+        if (ctx->bandsum) { MCT_CUDA(ctx, cudaStreamSynchronize(st)); cudaFree(ctx->bandsum); }
         MCT_CUDA(ctx, cudaMalloc(&ctx->bandsum, need * sizeof(uint32_t)));
         ctx->bandsum_cap = need;
     }
-    if (with_bins) {
-        size_t nb_need = (size_t)W * H;
-        if (nb_need > ctx->binimg_cap) {
-            if (ctx->binimg) { MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->binimg); }
-            MCT_CUDA(ctx, cudaMalloc(&ctx->binimg, nb_need * sizeof(uint16_t)));
-            ctx->binimg_cap = nb_need;
-        }
-    }
     PrepArgs a;
-    a.gray = ctx->gray; a.W = W; a.H = H; a.pitch = ctx->pitch; a.BH = BH; a.n_bands = n_bands;
+    a.gray = t.gray; a.W = W; a.H = H; a.pitch = t.pitch; a.BH = BH; a.n_bands = n_bands;
     a.bandtot = ctx->bandsum; a.flags = ctx->prep_flags;
-    a.epoch = (unsigned)ctx->frame_id; a.ii = ctx->ii_base + MCT_II_LEAD; a.iip = ctx->ii_pitch;
-    a.c0 = ctx->c0; a.c1 = ctx->c1; a.c2 = ctx->c2; a.nb = cnb; a.bw_shift = 0; a.binimg = ctx->binimg;
+    a.epoch = ++ctx->prep_epoch; a.ii = t.ii_base + MCT_II_LEAD; a.iip = t.ii_pitch;
+    a.c0 = t.c0; a.c1 = t.c1; a.c2 = t.c2; a.nb = cnb; a.bw_shift = 0; a.binimg = t.binimg;
     a.n_binblocks = 0;
     if (with_bins) {
         const int bw = 256 / cnb;
@@ -333,14 +321,14 @@ int launch_integral(mct_ctx* ctx)
         s_attr = smem;
     }
     const int nt = 32 * (BH < 4 ? 4 : (BH > 16 ? 16 : BH));
-    MCT_LAUNCH(ctx, "k_frame_prep", k_frame_prep<<<n_bands + a.n_binblocks, nt, smem, ctx->stream>>>(a));
-    if (with_bins) ctx->binimg_frame = ctx->frame_id;
+    MCT_LAUNCH_ON(ctx, st, "k_frame_prep", k_frame_prep<<<n_bands + a.n_binblocks, nt, smem, st>>>(a));
+    *with_bins_out = with_bins;
     return MCT_OK;
 }
 
-static int launch_integral_two_pass(mct_ctx* ctx)
+static int launch_integral_two_pass(mct_ctx* ctx, const PrepTarget& t, cudaStream_t st)
 {
-    const int W = ctx->W, H = ctx->H;
+    const int W = t.W, H = t.H;
     // band height: (BH + 1) * W u32 must fit in ~160 KB of shared memory
     int BH = (160 * 1024 / 4 - W) / W;
     if (BH > 32) BH = 32;
@@ -348,12 +336,12 @@ static int launch_integral_two_pass(mct_ctx* ctx)
     int nb = ceil_div(H, BH);
     size_t need = (size_t)nb * W;
     if (need > ctx->bandsum_cap) {
-        if (ctx->bandsum) cudaFree(ctx->bandsum);
+        if (ctx->bandsum) { MCT_CUDA(ctx, cudaStreamSynchronize(st)); cudaFree(ctx->bandsum); }
         MCT_CUDA(ctx, cudaMalloc(&ctx->bandsum, need * sizeof(uint32_t)));
         ctx->bandsum_cap = need;
     }
     dim3 g1(ceil_div(W, 128), nb);
-    MCT_LAUNCH(ctx, "k_band_colsum", k_band_colsum<<<g1, 128, 0, ctx->stream>>>(ctx->gray, W, H, ctx->pitch, BH, ctx->bandsum));
+    MCT_LAUNCH_ON(ctx, st, "k_band_colsum", k_band_colsum<<<g1, 128, 0, st>>>(t.gray, W, H, t.pitch, BH, ctx->bandsum));
     size_t smem = (size_t)(BH + 1) * W * sizeof(uint32_t);
     static size_t s_attr = 0;
     if (smem > s_attr) {
@@ -362,8 +350,8 @@ static int launch_integral_two_pass(mct_ctx* ctx)
     }
     int nt = W >= 1024 ? 1024 : round_up(W, 32);
     if (nt < 128) nt = 128;
-    MCT_LAUNCH(ctx, "k_integral_band", k_integral_band<<<nb, nt, smem, ctx->stream>>>(ctx->gray, W, H, ctx->pitch, BH, ctx->bandsum,
-                                                  ctx->ii_base + MCT_II_LEAD, ctx->ii_pitch));
+    MCT_LAUNCH_ON(ctx, st, "k_integral_band", k_integral_band<<<nb, nt, smem, st>>>(t.gray, W, H, t.pitch, BH, ctx->bandsum,
+                                                                                t.ii_base + MCT_II_LEAD, t.ii_pitch));
     return MCT_OK;
 }
 
@@ -405,7 +393,7 @@ int launch_bin_image(mct_ctx* ctx, int nb)
     if (!ctx->c0 || !ctx->c1 || !ctx->c2) return mct_fail(ctx, MCT_E_STATE, "colour planes not set%s", "");
     size_t need = (size_t)ctx->W * ctx->H;
     if (need > ctx->binimg_cap) {
-        if (ctx->binimg) cudaFree(ctx->binimg);
+        if (ctx->binimg) { MCT_CUDA(ctx, cudaDeviceSynchronize()); cudaFree(ctx->binimg); }
         MCT_CUDA(ctx, cudaMalloc(&ctx->binimg, need * sizeof(uint16_t)));
         ctx->binimg_cap = need;
     }

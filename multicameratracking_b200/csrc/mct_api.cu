@@ -30,22 +30,24 @@ static cudaEvent_t prof_event(ProfState* ps)
     if (!ps->pool.empty()) { cudaEvent_t e = ps->pool.back(); ps->pool.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;
 }
-void mct_prof_begin(mct_ctx* ctx, const char* name)
+void mct_prof_begin_on(mct_ctx* ctx, const char* name, cudaStream_t st)
 {
     ProfState* ps = (ProfState*)ctx->prof;
     if (!ps || !ps->on) return;
     ps->cur = name; ps->cur_a = prof_event(ps);
-    cudaEventRecord(ps->cur_a, ctx->stream);
+    cudaEventRecord(ps->cur_a, st);
 }
-void mct_prof_end(mct_ctx* ctx)
+void mct_prof_end_on(mct_ctx* ctx, cudaStream_t st)
 {
     ProfState* ps = (ProfState*)ctx->prof;
     if (!ps || !ps->on || !ps->cur) return;
     cudaEvent_t b = prof_event(ps);
-    cudaEventRecord(b, ctx->stream);
+    cudaEventRecord(b, st);
     ps->entries.push_back({ps->cur, ps->cur_a, b});
     ps->cur = nullptr;
 }
+void mct_prof_begin(mct_ctx* ctx, const char* name) { mct_prof_begin_on(ctx, name, ctx->stream); }
+void mct_prof_end(mct_ctx* ctx) { mct_prof_end_on(ctx, ctx->stream); }
 
 static DescRing* ring_of(mct_ctx* ctx) { return (DescRing*)ctx->h_desc; }
 
@@ -147,6 +149,7 @@ extern "C" int mct_profile_read(mct_ctx* ctx, int max_kernels, char* names, floa
     ProfState* ps = (ProfState*)ctx->prof;
     if (!ps) return MCT_OK;
     MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->prep_stream) MCT_CUDA(ctx, cudaStreamSynchronize(ctx->prep_stream));
     int n = 0;
     for (ProfEntry& e : ps->entries) {
         float ms = 0.0f;
@@ -175,6 +178,7 @@ extern "C" int mct_ctx_destroy(mct_ctx* ctx)
     if (!ctx) return MCT_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->prep_stream) cudaStreamSynchronize(ctx->prep_stream);
     if (ctx->d_scored) cudaFree(ctx->d_scored);
     if (ctx->prof) {
         ProfState* ps = (ProfState*)ctx->prof;
@@ -183,8 +187,13 @@ extern "C" int mct_ctx_destroy(mct_ctx* ctx)
         delete ps;
     }
     for (int i = 0; i < 4; i++) if (ctx->own_planes[i]) cudaFree(ctx->own_planes[i]);
-    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->ev_copy); cudaEventDestroy(ctx->ev_main); }
-    for (int i = 0; i < 4; i++) if (ctx->alt_planes[i]) cudaFree(ctx->alt_planes[i]);
+    if (ctx->prep_stream) {
+        cudaStreamSynchronize(ctx->prep_stream); cudaStreamDestroy(ctx->prep_stream);
+        cudaEventDestroy(ctx->ev_ready); cudaEventDestroy(ctx->ev_mark[0]); cudaEventDestroy(ctx->ev_mark[1]); cudaEventDestroy(ctx->ev_gather);
+    }
+    for (int i = 0; i < 4; i++) if (ctx->back.planes[i]) cudaFree(ctx->back.planes[i]);
+    if (ctx->back.ii_base) cudaFree(ctx->back.ii_base);
+    if (ctx->back.binimg) cudaFree(ctx->back.binimg);
     if (ctx->ii_base) cudaFree(ctx->ii_base);
     if (ctx->bandsum) cudaFree(ctx->bandsum);
     if (ctx->prep_flags) cudaFree(ctx->prep_flags);
@@ -222,62 +231,156 @@ static int ensure_tmp(mct_ctx* ctx, size_t bytes)
 }
 
 // ------------------------------------------------------------------------------------------ frame
+// Two sets of per-frame buffers (planes, integral image, bin image).  Frame t+1 is uploaded and prepared on
+// prep_stream into the BACK set while the compute stream is still busy with frame t (its particle-filter update
+// occupies only n_obj SMs), then the sets are swapped and the compute stream waits for ev_ready.  A set is only
+// overwritten after the compute-stream marker recorded at the frame_set call that retired it.
+static int frame_streams(mct_ctx* ctx)
+{
+    if (ctx->prep_stream) return MCT_OK;
+    MCT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->prep_stream, cudaStreamNonBlocking));
+    MCT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
+    MCT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_mark[0], cudaEventDisableTiming));
+    MCT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_mark[1], cudaEventDisableTiming));
+    MCT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_gather, cudaEventDisableTiming));
+    return MCT_OK;
+}
+static void frame_swap(mct_ctx* ctx)
+{
+    FrameSet cur;
+    for (int i = 0; i < 4; i++) cur.planes[i] = ctx->own_planes[i];
+    cur.plane_cap = ctx->own_plane_cap; cur.ii_base = ctx->ii_base; cur.ii_cap = ctx->ii_cap;
+    cur.binimg = ctx->binimg; cur.binimg_cap = ctx->binimg_cap;
+    for (int i = 0; i < 4; i++) ctx->own_planes[i] = ctx->back.planes[i];
+    ctx->own_plane_cap = ctx->back.plane_cap; ctx->ii_base = ctx->back.ii_base; ctx->ii_cap = ctx->back.ii_cap;
+    ctx->binimg = ctx->back.binimg; ctx->binimg_cap = ctx->back.binimg_cap;
+    ctx->back = cur;
+}
+// grow the buffers of one set (rare: first frames / geometry change); growth waits for the whole device
+static int frame_ensure(mct_ctx* ctx, uint8_t** planes, size_t* plane_cap, float** ii_base, size_t* ii_cap, uint16_t** binimg,
+                        size_t* binimg_cap, int W, int H, bool host_planes)
+{
+    const size_t pneed = (size_t)round_up(W, 16) * H;
+    const size_t ineed = (size_t)MCT_II_LEAD + (size_t)(H + 1) * round_up(W + 1, 4) + 4;
+    const size_t bneed = (size_t)W * H;
+    const bool grow = (host_planes && pneed > *plane_cap) || ineed > *ii_cap || (ctx->binimg_nb > 0 && bneed > *binimg_cap);
+    if (!grow) return MCT_OK;
+    MCT_CUDA(ctx, cudaDeviceSynchronize());
+    if (host_planes && pneed > *plane_cap) {
+        for (int i = 0; i < 4; i++) {
+            if (planes[i]) cudaFree(planes[i]);
+            MCT_CUDA(ctx, cudaMalloc(&planes[i], pneed));
+        }
+        *plane_cap = pneed;
+    }
+    if (ineed > *ii_cap) {
+        if (*ii_base) cudaFree(*ii_base);
+        MCT_CUDA(ctx, cudaMalloc(ii_base, ineed * sizeof(float)));
+        *ii_cap = ineed;
+    }
+    if (ctx->binimg_nb > 0 && bneed > *binimg_cap) {
+        if (*binimg) cudaFree(*binimg);
+        MCT_CUDA(ctx, cudaMalloc(binimg, bneed * sizeof(uint16_t)));
+        *binimg_cap = bneed;
+    }
+    return MCT_OK;
+}
+
+// Frame prep of the prefetched (back) set.  It is deferred until the gather kernels of the current frame have been
+// launched (mct_track_score_async calls this right after the classify kernel), so that it runs beside the
+// particle-filter update, which occupies only n_obj SMs, instead of competing with the one-CTA-per-SM kernels.
+// Upload of the prefetched planes into the back set.  Also deferred: mct_track_score_async issues it right AFTER the
+// (small, latency-critical) noise copy of the current frame so that the 1.2 MB of planes never sit in front of it.
+static int prefetch_copy(mct_ctx* ctx)
+{
+    if (!ctx->pf_pending || ctx->pf_copied) return MCT_OK;
+    const int W = ctx->pf_W, H = ctx->pf_H, dpp = round_up(W, 16);
+    // the back set was the current set until the latest mct_frame_set: its readers are covered by the latest marker
+    MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->prep_stream, ctx->ev_mark[ctx->mark_idx], 0));
+    for (int i = 0; i < 4; i++)
+        if (ctx->pf_src[i])
+            MCT_CUDA(ctx, cudaMemcpy2DAsync(ctx->back.planes[i], dpp, ctx->pf_src[i], ctx->pf_pitch, W, H, cudaMemcpyHostToDevice,
+                                            ctx->prep_stream));
+    ctx->pf_copied = 1;
+    return MCT_OK;
+}
+static int prefetch_prep(mct_ctx* ctx)
+{
+    if (!ctx->pf_pending || ctx->pf_prepped) return MCT_OK;
+    int rc0 = prefetch_copy(ctx);
+    if (rc0) return rc0;
+    const int W = ctx->pf_W, H = ctx->pf_H, dpp = round_up(W, 16), iip = round_up(W + 1, 4);
+    PrepTarget t = {ctx->back.planes[0], ctx->pf_src[1] ? ctx->back.planes[1] : nullptr, ctx->pf_src[2] ? ctx->back.planes[2] : nullptr,
+                    ctx->pf_src[3] ? ctx->back.planes[3] : nullptr, W, H, dpp, ctx->back.ii_base, iip, ctx->back.binimg};
+    int with_bins = 0, rc;
+    if (ctx->has_gather) MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->prep_stream, ctx->ev_gather, 0));
+    if ((rc = launch_frame_prep(ctx, t, ctx->prep_stream, &with_bins))) return rc;
+    MCT_CUDA(ctx, cudaEventRecord(ctx->ev_ready, ctx->prep_stream));
+    ctx->pf_with_bins = with_bins; ctx->pf_prepped = 1;
+    return MCT_OK;
+}
+
 extern "C" int mct_frame_set(mct_ctx* ctx, const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2,
                              int W, int H, int pitch, int is_device)
 {
     if (!ctx) return MCT_E_ARG;
     if (!gray || W < 4 || H < 4 || pitch < W) return mct_fail(ctx, MCT_E_ARG, "mct_frame_set: bad frame geometry%s");
     MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = frame_streams(ctx))) return rc;
     const uint8_t* src[4] = {gray, c0, c1, c2};
-    const int dpp = round_up(W, 16);
+    const int dpp = round_up(W, 16), iip = round_up(W + 1, 4);
+    // marker: everything enqueued on the compute stream so far (all readers of the current set) ...
+    cudaEvent_t old_mark = ctx->ev_mark[ctx->mark_idx];
+    ctx->mark_idx ^= 1;
+    MCT_CUDA(ctx, cudaEventRecord(ctx->ev_mark[ctx->mark_idx], ctx->stream));
+    const bool adopt = !is_device && ctx->pf_pending && ctx->pf_W == W && ctx->pf_H == H && ctx->pf_pitch == pitch &&
+                       ctx->pf_src[0] == gray && ctx->pf_src[1] == c0 && ctx->pf_src[2] == c1 && ctx->pf_src[3] == c2;
+    int with_bins = 0;
+    if (adopt) {
+        // the back set already holds this frame, uploaded by mct_frame_prefetch (and normally prepared beside the
+        // previous frame's particle-filter update)
+        if ((rc = prefetch_prep(ctx))) return rc;
+        frame_swap(ctx);
+        with_bins = ctx->pf_with_bins;
+        ctx->pf_pending = 0;
+    } else {
+        ctx->pf_pending = 0;
+        // ... the back set was retired one frame_set call ago: its readers are covered by old_mark
+        if ((rc = frame_ensure(ctx, ctx->back.planes, &ctx->back.plane_cap, &ctx->back.ii_base, &ctx->back.ii_cap, &ctx->back.binimg,
+                               &ctx->back.binimg_cap, W, H, !is_device)))
+            return rc;
+        frame_swap(ctx);
+        MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->prep_stream, old_mark, 0));
+        // do not compete with the gather kernels of the frame in flight: start beside its particle-filter update
+        if (ctx->has_gather) MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->prep_stream, ctx->ev_gather, 0));
+        // is_device == 1: the caller's device planes are ordered after the work already enqueued on the compute stream
+        if (is_device == 1) MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->prep_stream, ctx->ev_mark[ctx->mark_idx], 0));
+        if (!is_device)
+            for (int i = 0; i < 4; i++)
+                if (src[i])
+                    MCT_CUDA(ctx, cudaMemcpy2DAsync(ctx->own_planes[i], dpp, src[i], pitch, W, H, cudaMemcpyHostToDevice, ctx->prep_stream));
+    }
     if (is_device) {
         ctx->gray = gray; ctx->c0 = c0; ctx->c1 = c1; ctx->c2 = c2;
         ctx->pitch = pitch;
-    } else if (ctx->pf_pending && ctx->pf_W == W && ctx->pf_H == H && ctx->pf_pitch == pitch && ctx->pf_src[0] == gray &&
-               ctx->pf_src[1] == c0 && ctx->pf_src[2] == c1 && ctx->pf_src[3] == c2) {
-        // adopt the prefetched back buffers: swap, and make the compute stream wait for the copy
-        for (int i = 0; i < 4; i++) { uint8_t* t = ctx->own_planes[i]; ctx->own_planes[i] = ctx->alt_planes[i]; ctx->alt_planes[i] = t; }
-        size_t tc = ctx->own_plane_cap; ctx->own_plane_cap = ctx->alt_plane_cap; ctx->alt_plane_cap = tc;
-        MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
-        ctx->pf_pending = 0;
+    } else {
         ctx->gray = ctx->own_planes[0];
         ctx->c0 = c0 ? ctx->own_planes[1] : nullptr;
         ctx->c1 = c1 ? ctx->own_planes[2] : nullptr;
         ctx->c2 = c2 ? ctx->own_planes[3] : nullptr;
         ctx->pitch = dpp;
-    } else {
-        int dp = dpp;
-        size_t need = (size_t)dp * H;
-        if (need > ctx->own_plane_cap) {
-            MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            for (int i = 0; i < 4; i++) {
-                if (ctx->own_planes[i]) cudaFree(ctx->own_planes[i]);
-                MCT_CUDA(ctx, cudaMalloc(&ctx->own_planes[i], need));
-            }
-            ctx->own_plane_cap = need;
-        }
-        for (int i = 0; i < 4; i++)
-            if (src[i])
-                MCT_CUDA(ctx, cudaMemcpy2DAsync(ctx->own_planes[i], dp, src[i], pitch, W, H, cudaMemcpyHostToDevice, ctx->stream));
-        ctx->gray = ctx->own_planes[0];
-        ctx->c0 = c0 ? ctx->own_planes[1] : nullptr;
-        ctx->c1 = c1 ? ctx->own_planes[2] : nullptr;
-        ctx->c2 = c2 ? ctx->own_planes[3] : nullptr;
-        ctx->pitch = dp;
     }
-    ctx->W = W; ctx->H = H;
-    int iip = round_up(W + 1, 4);
-    size_t need = (size_t)MCT_II_LEAD + (size_t)(H + 1) * iip + 4;
-    if (need > ctx->ii_cap || iip != ctx->ii_pitch) {
-        if (need > ctx->ii_cap) {
-            if (ctx->ii_base) { MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->ii_base); }
-            MCT_CUDA(ctx, cudaMalloc(&ctx->ii_base, need * sizeof(float)));
-            ctx->ii_cap = need;
-        }
-        ctx->ii_pitch = iip;
-    }
+    ctx->W = W; ctx->H = H; ctx->ii_pitch = iip;
     ctx->frame_id++;
-    return launch_integral(ctx);
+    if (!adopt) {
+        PrepTarget t = {ctx->gray, ctx->c0, ctx->c1, ctx->c2, W, H, ctx->pitch, ctx->ii_base, iip, ctx->binimg};
+        if ((rc = launch_frame_prep(ctx, t, ctx->prep_stream, &with_bins))) return rc;
+        MCT_CUDA(ctx, cudaEventRecord(ctx->ev_ready, ctx->prep_stream));
+    }
+    ctx->binimg_frame = with_bins ? ctx->frame_id : -1;
+    MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_ready, 0));
+    return MCT_OK;
 }
 
 extern "C" int mct_frame_prefetch(mct_ctx* ctx, const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2,
@@ -286,33 +389,15 @@ extern "C" int mct_frame_prefetch(mct_ctx* ctx, const uint8_t* gray, const uint8
     if (!ctx) return MCT_E_ARG;
     if (!gray || W < 4 || H < 4 || pitch < W) return mct_fail(ctx, MCT_E_ARG, "mct_frame_prefetch: bad frame geometry%s");
     MCT_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (!ctx->copy_stream) {
-        MCT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        MCT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
-        MCT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming));
-    }
-    const int dp = round_up(W, 16);
-    const size_t need = (size_t)dp * H;
-    if (need > ctx->alt_plane_cap) {
-        MCT_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
-        for (int i = 0; i < 4; i++) {
-            if (ctx->alt_planes[i]) cudaFree(ctx->alt_planes[i]);
-            MCT_CUDA(ctx, cudaMalloc(&ctx->alt_planes[i], need));
-        }
-        ctx->alt_plane_cap = need;
-    }
-    // the back buffers were the front buffers of the previous frame: everything enqueued on the compute stream so
-    // far (which includes their last readers) must finish before the copy overwrites them
-    MCT_CUDA(ctx, cudaEventRecord(ctx->ev_main, ctx->stream));
-    MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_main, 0));
+    int rc;
+    if ((rc = frame_streams(ctx))) return rc;
+    if ((rc = frame_ensure(ctx, ctx->back.planes, &ctx->back.plane_cap, &ctx->back.ii_base, &ctx->back.ii_cap, &ctx->back.binimg,
+                           &ctx->back.binimg_cap, W, H, true)))
+        return rc;
     const uint8_t* src[4] = {gray, c0, c1, c2};
-    for (int i = 0; i < 4; i++)
-        if (src[i])
-            MCT_CUDA(ctx, cudaMemcpy2DAsync(ctx->alt_planes[i], dp, src[i], pitch, W, H, cudaMemcpyHostToDevice, ctx->copy_stream));
-    MCT_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
     for (int i = 0; i < 4; i++) ctx->pf_src[i] = src[i];
-    ctx->pf_W = W; ctx->pf_H = H; ctx->pf_pitch = pitch; ctx->pf_pending = 1;
-    return MCT_OK;
+    ctx->pf_W = W; ctx->pf_H = H; ctx->pf_pitch = pitch; ctx->pf_pending = 1; ctx->pf_with_bins = 0; ctx->pf_prepped = 0; ctx->pf_copied = 0;
+    return MCT_OK;      // copy and frame prep follow in mct_track_score_async (or at the adopting mct_frame_set)
 }
 
 extern "C" int mct_frame_get_integral(mct_ctx* ctx, float* out_host)
@@ -895,6 +980,7 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
         MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_noise_stage, noise, ntot * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
         sa.noise_base = ctx->d_noise_stage;
     }
+    if (ctx->prep_stream && (rc = prefetch_copy(ctx))) return rc;      // next frame's planes: behind this frame's noise copy
     const ObjDesc* d;
     if ((rc = desc_publish(ctx, h, n_obj, &d))) return rc;
     if ((rc = launch_pf_predict_testset(ctx, d, n_obj, n_max, sa))) return rc;
@@ -919,6 +1005,12 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
     }
     (void)K_max;
     if ((rc = launch_classify_staged(ctx, d, n_obj, n_max, 1))) return rc;
+    // from here on the GPU is nearly idle (the update runs on n_obj SMs): next frame's preparation may start
+    if (ctx->prep_stream) {
+        MCT_CUDA(ctx, cudaEventRecord(ctx->ev_gather, ctx->stream));
+        ctx->has_gather = 1;
+        if ((rc = prefetch_prep(ctx))) return rc;
+    }
     if ((rc = launch_pf_update(ctx, d, n_obj, n_max, 1, sa, 1))) return rc;
     return MCT_OK;
 }

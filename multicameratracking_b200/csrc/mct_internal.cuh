@@ -36,6 +36,15 @@ struct SelEntry {
 };
 
 // ------------------------------------------------------------------ host-side objects
+struct FrameSet {              // one of the two sets of per-frame device buffers
+    uint8_t* planes[4]; size_t plane_cap;
+    float* ii_base; size_t ii_cap;
+    uint16_t* binimg; size_t binimg_cap;
+};
+struct PrepTarget {            // what one frame-prep launch reads and writes
+    const uint8_t *gray, *c0, *c1, *c2; int W, H, pitch;
+    float* ii_base; int ii_pitch; uint16_t* binimg;
+};
 struct mct_ctx {
     int device;
     cudaStream_t stream;
@@ -43,9 +52,12 @@ struct mct_ctx {
     int W, H, pitch;                       // current frame geometry (u8 planes)
     const uint8_t* gray; const uint8_t* c0; const uint8_t* c1; const uint8_t* c2;   // device planes in use
     uint8_t* own_planes[4]; size_t own_plane_cap;
-    uint8_t* alt_planes[4]; size_t alt_plane_cap;       // back buffers filled by mct_frame_prefetch on copy_stream
-    cudaStream_t copy_stream; cudaEvent_t ev_copy, ev_main;
-    const uint8_t* pf_src[4]; int pf_W, pf_H, pf_pitch, pf_pending;
+    // Double buffering of the frame: the planes / integral image / bin image of frame t+1 are produced on
+    // prep_stream into the BACK set while the compute stream still works on frame t (mct_api.cu, "frame").
+    FrameSet back;
+    cudaStream_t prep_stream; cudaEvent_t ev_ready, ev_mark[2], ev_gather; int mark_idx, has_gather;
+    unsigned prep_epoch;
+    const uint8_t* pf_src[4]; int pf_W, pf_H, pf_pitch, pf_pending, pf_with_bins, pf_prepped, pf_copied;
     float* ii_base; int ii_pitch; size_t ii_cap;       // integral image storage; element (y,x) at ii_base[MCT_II_LEAD + y*ii_pitch + x]
     uint32_t* bandsum; size_t bandsum_cap;
     unsigned* prep_flags;                              // [256] band-ready flags of k_frame_prep (value = frame id)
@@ -168,6 +180,8 @@ static inline int mct_fail(mct_ctx* ctx, int code, const char* fmt, const char* 
 // optional per-kernel CUDA-event timing on the launching stream (bench.py roofline); see mct_api.cu
 void mct_prof_begin(mct_ctx* ctx, const char* name);
 void mct_prof_end(mct_ctx* ctx);
+void mct_prof_begin_on(mct_ctx* ctx, const char* name, cudaStream_t st);
+void mct_prof_end_on(mct_ctx* ctx, cudaStream_t st);
 #define MCT_LAUNCH(ctx, name, ...)                                                           \
     do {                                                                                     \
         mct_prof_begin((ctx), (name));                                                       \
@@ -176,11 +190,21 @@ void mct_prof_end(mct_ctx* ctx);
         MCT_KERNEL_CHECK(ctx);                                                               \
     } while (0)
 
+#define MCT_LAUNCH_ON(ctx, st, name, ...)                                                    \
+    do {                                                                                     \
+        mct_prof_begin_on((ctx), (name), (st));                                              \
+        __VA_ARGS__;                                                                         \
+        mct_prof_end_on((ctx), (st));                                                        \
+        MCT_KERNEL_CHECK(ctx);                                                               \
+    } while (0)
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 
 // ------------------------------------------------------------------ kernel launchers (defined per .cu)
-int launch_integral(mct_ctx* ctx);
+// integral image (+ bin image when an MDCH classifier uses this ctx) of `t` on stream `st`; *with_bins tells whether
+// the bin image was produced
+int launch_frame_prep(mct_ctx* ctx, const PrepTarget& t, cudaStream_t st, int* with_bins);
 int launch_bin_image(mct_ctx* ctx, int nb);
 int launch_sum_rects(mct_ctx* ctx, const int* d_rects, int n, float* d_out);
 // full [F][ld] feature matrix of one box list (FeatureVector::Compute)

@@ -95,9 +95,11 @@ class Camera:
         ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
         self._chk(self.L.mcth_camera_set_frame(self.h, ptr(gray), ptr(pl[0]), ptr(pl[1]), ptr(pl[2]), W, H, W, 0))
 
-    def set_frame_device(self, W, H, pitch, gray_ptr, c0_ptr=0, c1_ptr=0, c2_ptr=0):
+    def set_frame_device(self, W, H, pitch, gray_ptr, c0_ptr=0, c1_ptr=0, c2_ptr=0, ready=False):
+        """device-resident planes; ready=True: the planes are already complete (no ordering against the ctx stream
+        needed), which lets the frame preparation overlap the previous frame's kernels"""
         vp = lambda p: C.c_void_p(p) if p else None
-        self._chk(self.L.mcth_camera_set_frame(self.h, vp(gray_ptr), vp(c0_ptr), vp(c1_ptr), vp(c2_ptr), W, H, pitch, 1))
+        self._chk(self.L.mcth_camera_set_frame(self.h, vp(gray_ptr), vp(c0_ptr), vp(c1_ptr), vp(c2_ptr), W, H, pitch, 2 if ready else 1))
 
     def init_trackers(self):
         self._chk(self.L.mcth_camera_init_trackers(self.h))

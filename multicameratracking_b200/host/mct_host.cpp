@@ -43,9 +43,9 @@ using Public::cvRound;
 
 // ================================================================================ Matrixu
 void Matrixu::SetFrame(const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2, int cols, int rows,
-                       int pitch, bool deviceResident)
+                       int pitch, int deviceMode)
 {
-    chk(m_ctx, mct_frame_set(m_ctx, gray, c0, c1, c2, cols, rows, pitch, deviceResident ? 1 : 0));
+    chk(m_ctx, mct_frame_set(m_ctx, gray, c0, c1, c2, cols, rows, pitch, deviceMode));
     m_rows = rows; m_cols = cols; m_iiInit = true;
 }
 void Matrixu::PrefetchFrame(const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2, int cols, int rows, int pitch)

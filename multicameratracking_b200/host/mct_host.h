@@ -63,8 +63,10 @@ class Matrixu {
 public:
     Matrixu(mct_ctx* ctx = nullptr) : m_ctx(ctx), m_rows(0), m_cols(0), m_iiInit(false) {}
     // upload gray (+ optional colour planes) and build the integral image  (Camera.cpp:460-491)
+    // deviceMode: 0 = host planes (copied), 1 = device planes ordered after the work already enqueued on the ctx stream,
+    //             2 = device planes that are already complete (lets the frame preparation overlap the previous frame)
     void SetFrame(const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2, int cols, int rows,
-                  int pitch, bool deviceResident = false);
+                  int pitch, int deviceMode = 0);
     // start the upload of the NEXT frame while the current one is tracked; SetFrame with the same pointers adopts it
     void PrefetchFrame(const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2, int cols, int rows, int pitch);
     void initII() {}                      // done inside SetFrame; kept for call-site compatibility

@@ -60,7 +60,7 @@ mct_ctx* mcth_camera_ctx(mcth_camera* c) { return c->ctx; }
 int mcth_camera_set_frame(mcth_camera* c, const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2,
                           int W, int H, int pitch, int is_device)
 {
-    GUARD(c->frame.SetFrame(gray, c0, c1, c2, W, H, pitch, is_device != 0));
+    GUARD(c->frame.SetFrame(gray, c0, c1, c2, W, H, pitch, is_device));
 }
 
 int mcth_camera_prefetch_frame(mcth_camera* c, const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2,

@@ -5,6 +5,8 @@
 char g_mct_err[512];
 void mct_prof_begin(mct_ctx*, const char*) {}
 void mct_prof_end(mct_ctx*) {}
+void mct_prof_begin_on(mct_ctx*, const char*, cudaStream_t) {}
+void mct_prof_end_on(mct_ctx*, cudaStream_t) {}
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA %s line %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
 int main(int argc, char** argv)
 {
@@ -20,11 +22,14 @@ int main(int argc, char** argv)
     CK(cudaMemcpy(pool, h.data(), h.size(), cudaMemcpyHostToDevice));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     auto setf = [&](int t) { uint8_t* b = pool + (size_t)(t % POOL) * 4 * W * H; ctx.gray = b; ctx.c0 = b + W * H; ctx.c1 = b + 2 * W * H; ctx.c2 = b + 3 * W * H; ctx.frame_id++; };
-    for (int t = 0; t < 5; t++) { setf(t); if (launch_integral(&ctx)) { printf("launch failed: %s\n", ctx.err); return 1; } }
+    int wb = 0;
+    auto prep = [&]() { PrepTarget t = {ctx.gray, ctx.c0, ctx.c1, ctx.c2, W, H, W, ctx.ii_base, ctx.ii_pitch, ctx.binimg}; return launch_frame_prep(&ctx, t, ctx.stream, &wb); };
+    if (ctx.binimg_nb) CK(cudaMalloc(&ctx.binimg, (size_t)W * H * 2));
+    for (int t = 0; t < 5; t++) { setf(t); if (prep()) { printf("launch failed: %s\n", ctx.err); return 1; } }
     CK(cudaStreamSynchronize(ctx.stream));
     const int n = 200;
     CK(cudaEventRecord(e0, ctx.stream));
-    for (int t = 0; t < n; t++) { setf(5 + t); launch_integral(&ctx); }
+    for (int t = 0; t < n; t++) { setf(5 + t); prep(); }
     CK(cudaEventRecord(e1, ctx.stream)); CK(cudaStreamSynchronize(ctx.stream));
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     printf("%dx%d nb=%d: %.2f us per frame_prep (back-to-back launches, %d-frame pool)\n", W, H, ctx.binimg_nb, 1e3 * ms / n, POOL);
