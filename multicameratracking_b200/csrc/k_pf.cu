@@ -270,7 +270,7 @@ __device__ void resample_body(const ObjDesc& d, float* sw, float* cdf, int force
     }
 }
 
-__device__ void summary_body(const ObjDesc& d);
+__device__ void summary_body(const ObjDesc& d, float* scratch);
 
 // mode 0: d.H holds the classifier response; build the likelihood map ((H-min)/range)^exponent over the
 //         valid particles (ParticleFilterTracker.cpp:541-566) and use it as prob.
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(PF_THREADS) k_pf_update(const ObjDesc* __restr
     }
     if (mode == 0 && cnt == 0) {              // reference: ASSERT abort (ParticleFilterTracker.cpp:513)
         __syncthreads();
-        if (with_summary) summary_body(d);    // the host sees n_valid == 0 -> MCT_E_EMPTY
+        if (with_summary) summary_body(d, nullptr);    // the host sees n_valid == 0 -> MCT_E_EMPTY
         return;
     }
     const double dmn = (double)mn, range = (double)mx - (double)mn;
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(PF_THREADS) k_pf_update(const ObjDesc* __restr
     }
     if (with_summary) {
         __syncthreads();                       // the read-out reads state / weights written by other threads above
-        summary_body(d);
+        summary_body(d, (2 * N4 <= smem_floats) ? smf : nullptr);   // sw / cdf are dead: reuse them as scratch
     }
 }
 
@@ -480,7 +480,9 @@ int launch_pf_expand_prob(mct_ctx* ctx, const ObjDesc* d_desc, const float* d_pr
 // RESAMPLED: the resample index list is non-decreasing, so sorting it is the identity; unique runs are
 //            contiguous; run weights are summed in order; the reference then pairs the states in *index*
 //            order with the weights in *sorted* order (:799-806) -- kept.
-__device__ void summary_body(const ObjDesc& d)
+// scratch: 2 * round_up(N, 4) floats of shared memory (or NULL): the resample index list and the run weights are
+// staged there so that the per-run binary searches and tie scans do not chase L2 latency.
+__device__ void summary_body(const ObjDesc& d, float* scratch)
 {
     __shared__ float sh_f[32];
     __shared__ double sh_d[32];
@@ -526,39 +528,46 @@ __device__ void summary_body(const ObjDesc& d)
         // run weights: the run-start thread sums its run in order.  Right after a forced resample every
         // weight is exactly 1.0f, and an in-order f32 sum of L ones is exactly (float)L (L < 2^24): the run end
         // is then found by binary search in the non-decreasing index list instead of walking the run.
+        const int* ridx = d.residx;
+        float* rw = d.rw;                          // without scratch the resampled-weight column doubles as run-weight scratch
+        if (scratch) {
+            int* si = reinterpret_cast<int*>(scratch);
+            for (int i = tid; i < N; i += nt) si[i] = d.residx[i];
+            ridx = si; rw = scratch + ((N + 3) & ~3);
+        }
         int not_one = 0;
         for (int i = tid; i < N; i += nt) not_one += (d.w[i] != 1.0f);
-        not_one = block_reduce_sum_i(not_one, sh_i);
+        not_one = block_reduce_sum_i(not_one, sh_i);          // (also orders the staging stores above)
         float mx = -CUDART_INF_F;
         int nruns = 0;
         for (int i = tid; i < N; i += nt) {
-            const int v = d.residx[i];
-            const bool start = (i == 0) || (v != d.residx[i - 1]);
-            float rw = 0.0f;
+            const int v = ridx[i];
+            const bool start = (i == 0) || (v != ridx[i - 1]);
+            float r = 0.0f;
             if (start) {
                 nruns++;
                 if (!not_one) {
                     int lo = i + 1, hi = N;                      // first j > i with residx[j] != v
-                    while (lo < hi) { int mid = (lo + hi) >> 1; if (d.residx[mid] == v) lo = mid + 1; else hi = mid; }
-                    rw = (float)(lo - i);
+                    while (lo < hi) { int mid = (lo + hi) >> 1; if (ridx[mid] == v) lo = mid + 1; else hi = mid; }
+                    r = (float)(lo - i);
                 } else {
-                    rw = d.w[i];
-                    for (int j = i + 1; j < N && d.residx[j] == v; j++) rw = __fadd_rn(rw, d.w[j]);
+                    r = d.w[i];
+                    for (int j = i + 1; j < N && ridx[j] == v; j++) r = __fadd_rn(r, d.w[j]);
                 }
-                mx = fmaxf(mx, rw);
+                mx = fmaxf(mx, r);
             }
-            d.rw[i] = start ? rw : -1.0f;          // resampled-weight column doubles as run-weight scratch
+            rw[i] = start ? r : -1.0f;
         }
         mx = block_reduce_minmax(mx, true, sh_f);
         nruns = block_reduce_sum_i(nruns, sh_i);
         int ties = 0;
-        for (int i = tid; i < N; i += nt) if (d.rw[i] == mx) ties++;
+        for (int i = tid; i < N; i += nt) if (rw[i] == mx) ties++;
         ties = block_reduce_sum_i(ties, sh_i);
         if (tid == 0) {
             // row (ties-1) of the ordered-unique matrix = state of the (ties-1)-th run in index order
             int want = ties - 1, ord = -1, b = 0;
             if (want > 0) {
-                for (int i = 0; i < N; i++) if (d.rw[i] >= 0.0f) { ord++; if (ord == want) { b = i; break; } }
+                for (int i = 0; i < N; i++) if (rw[i] >= 0.0f) { ord++; if (ord == want) { b = i; break; } }
             }
             out->ordered_first[0] = d.cx[0]; out->ordered_first[1] = d.cy[0]; out->ordered_first[2] = d.sx[0];
             out->ordered_first[3] = d.sy[0]; out->ordered_first[4] = mx;
@@ -566,8 +575,10 @@ __device__ void summary_body(const ObjDesc& d)
             out->highest_close[3] = d.sy[b]; out->highest_close[4] = mx;
             out->n_unique = nruns;
         }
-        __syncthreads();
-        for (int i = tid; i < N; i += nt) d.rw[i] = 1.0f;       // restore m_particlesResampledMatrix weights
+        if (!scratch) {
+            __syncthreads();
+            for (int i = tid; i < N; i += nt) d.rw[i] = 1.0f;   // restore m_particlesResampledMatrix weights
+        }
     } else if (tid == 0) {
         for (int q = 0; q < 5; q++) { out->ordered_first[q] = 0; out->highest_close[q] = 0; }
         out->n_unique = 0;
@@ -575,7 +586,7 @@ __device__ void summary_body(const ObjDesc& d)
 }
 __global__ void __launch_bounds__(PF_THREADS) k_pf_summary(const ObjDesc* __restrict__ descs)
 {
-    summary_body(descs[blockIdx.x]);
+    summary_body(descs[blockIdx.x], nullptr);
 }
 int launch_pf_summary(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max)
 {

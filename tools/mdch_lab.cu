@@ -217,7 +217,10 @@ __global__ void __launch_bounds__(WARPS * 32) v6_strips(Args a, const BBox* __re
 
 // ---------------------------------------------------------------- V7: persistent CTAs per object chunk; T = cols/4 lanes per box,
 // private hists, 4-way load-then-forward RMW batches (one LDS latency per 4 pixels), region bbox computed per CTA.
-template <int WARPS>
+__device__ unsigned long long g_dbg[64];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define STAMP(k) do { if (blockIdx.x == 3 && blockIdx.y == 2 && threadIdx.x == 0) g_dbg[k] = gtime(); } while (0)
+template <int WARPS, int FWD>
 __global__ void __launch_bounds__(WARPS * 32, 1) v7_forward(Args a, int ctas_per_obj, int region_cap)
 {
     extern __shared__ uint32_t sm[];
@@ -230,6 +233,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) v7_forward(Args a, int ctas_per
     uint16_t* smap = (uint16_t*)(lut + (rows + 1) * colsp);   // [512]
     uint32_t* hist_all = (uint32_t*)(smap + 512);             // [WARPS][n_slots][32]
     uint8_t* region = (uint8_t*)(hist_all + (size_t)WARPS * a.n_slots * 32);
+    STAMP(0);
     if (tid == 0) { s_bb[0] = 1 << 30; s_bb[1] = 1 << 30; s_bb[2] = -(1 << 30); s_bb[3] = -(1 << 30); }
     for (int b = tid; b < 512; b += blockDim.x) smap[b] = a.slotmap[o * 512 + b];
     __syncthreads();
@@ -245,6 +249,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) v7_forward(Args a, int ctas_per
         }
         if (lane == 0) { atomicMin(&s_bb[0], x0); atomicMin(&s_bb[1], y0); atomicMax(&s_bb[2], x1); atomicMax(&s_bb[3], y1); }
     }
+    STAMP(1);
     {   // LUT, zero padded to colsp
         const int np = rows * cols;
         int shift = __clz(np); if (shift > 20) shift = 20;
@@ -259,6 +264,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) v7_forward(Args a, int ctas_per
         }
     }
     __syncthreads();
+    STAMP(2);
     const int bx0 = s_bb[0] & ~3, by0 = s_bb[1];
     const int RW = s_bb[2] + colsp - bx0, RH = s_bb[3] + rows - by0 + 1;   // +1 row: the prefetch of row `rows` stays inside
     const int RWp = ((RW + 3) & ~3) + 4;
@@ -266,6 +272,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) v7_forward(Args a, int ctas_per
     {
         const int qw = RWp >> 2;                               // 4-pixel groups per region row (W % 4 == 0 assumed)
         uint32_t* r32 = reinterpret_cast<uint32_t*>(region);
+#pragma unroll 4
         for (int g = tid; g < qw * RH; g += blockDim.x) {
             const int y = g / qw, xg = g - y * qw;
             const int yy = min(by0 + y, a.H - 1), xx = min(bx0 + 4 * xg, a.W - 4);
@@ -275,10 +282,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) v7_forward(Args a, int ctas_per
         }
     }
     __syncthreads();
+    STAMP(3);
+    int rnd = 0;
     const int bw = lane / T, j = lane - bw * T;
     uint32_t* hist = hist_all + (size_t)warp * a.n_slots * 32 + lane;
     const int q = colsp >> 2;
     for (int base = i_begin + warp * BPW; base < i_end; base += WARPS * BPW) {
+        STAMP(4 + 3 * rnd);
         for (int s = 0; s < a.n_slots; s++) hist[s * 32] = 0;
         __syncwarp();
         const int i = base + bw;
@@ -298,29 +308,55 @@ __global__ void __launch_bounds__(WARPS * 32, 1) v7_forward(Args a, int ctas_per
                 const uint32_t vn = __funnelshift_r(wp[0], wp[1], sh);
                 const uint4 wn = l4[(r + 1) * q];
                 const uint32_t s0 = v & 0xffu, s1 = (v >> 8) & 0xffu, s2 = (v >> 16) & 0xffu, s3 = v >> 24;
-                const uint32_t h0 = hist[s0 * 32], h1 = hist[s1 * 32], h2 = hist[s2 * 32], h3 = hist[s3 * 32];
-                const uint32_t n0 = h0 + w.x;
-                const uint32_t n1 = (s1 == s0 ? n0 : h1) + w.y;
-                uint32_t t = (s2 == s0 ? n0 : h2); t = (s2 == s1 ? n1 : t);
-                const uint32_t n2 = t + w.z;
-                t = (s3 == s0 ? n0 : h3); t = (s3 == s1 ? n1 : t); t = (s3 == s2 ? n2 : t);
-                const uint32_t n3 = t + w.w;
-                hist[s0 * 32] = n0; hist[s1 * 32] = n1; hist[s2 * 32] = n2; hist[s3 * 32] = n3;
+                if (FWD == 4) {
+                    const uint32_t h0 = hist[s0 * 32], h1 = hist[s1 * 32], h2 = hist[s2 * 32], h3 = hist[s3 * 32];
+                    const uint32_t n0 = h0 + w.x;
+                    const uint32_t n1 = (s1 == s0 ? n0 : h1) + w.y;
+                    uint32_t t = (s2 == s0 ? n0 : h2); t = (s2 == s1 ? n1 : t);
+                    const uint32_t n2 = t + w.z;
+                    t = (s3 == s0 ? n0 : h3); t = (s3 == s1 ? n1 : t); t = (s3 == s2 ? n2 : t);
+                    const uint32_t n3 = t + w.w;
+                    hist[s0 * 32] = n0; hist[s1 * 32] = n1; hist[s2 * 32] = n2; hist[s3 * 32] = n3;
+                } else if (FWD == 2) {
+                    {
+                        const uint32_t h0 = hist[s0 * 32], h1 = hist[s1 * 32];
+                        const uint32_t n0 = h0 + w.x;
+                        const uint32_t n1 = (s1 == s0 ? n0 : h1) + w.y;
+                        hist[s0 * 32] = n0; hist[s1 * 32] = n1;
+                    }
+                    {
+                        const uint32_t h2 = hist[s2 * 32], h3 = hist[s3 * 32];
+                        const uint32_t n2 = h2 + w.z;
+                        const uint32_t n3 = (s3 == s2 ? n2 : h3) + w.w;
+                        hist[s2 * 32] = n2; hist[s3 * 32] = n3;
+                    }
+                } else {
+                    hist[s0 * 32] += w.x; hist[s1 * 32] += w.y; hist[s2 * 32] += w.z; hist[s3 * 32] += w.w;
+                }
                 v = vn; w = wn;
             }
         }
         __syncwarp();
+        STAMP(5 + 3 * rnd);
         if (ok) {
             const uint32_t* hb = hist_all + (size_t)warp * a.n_slots * 32 + bw * T;
-            for (int s = j; s < a.n_slots; s += T) {
-                uint32_t t = 0;
+            for (int s = j; s < a.n_slots; s += 2 * T) {
+                const int s2 = s + T;
+                const bool has2 = s2 < a.n_slots;
+                const uint32_t* r0p = hb + s * 32;
+                const uint32_t* r1p = hb + (has2 ? s2 : s) * 32;
+                uint32_t t0 = 0, t1 = 0;
                 int qq = j;                                   // skewed start: lanes of a box hit distinct banks
-                for (int k = 0; k < T; k++) { t += hb[s * 32 + qq]; qq = (qq + 1 == T) ? 0 : qq + 1; }
-                a.out[((size_t)o * a.n_slots + s) * a.N + i] = t;
+#pragma unroll 2
+                for (int k = 0; k < T; k++) { t0 += r0p[qq]; t1 += r1p[qq]; qq = (qq + 1 == T) ? 0 : qq + 1; }
+                a.out[((size_t)o * a.n_slots + s) * a.N + i] = t0;
+                if (has2) a.out[((size_t)o * a.n_slots + s2) * a.N + i] = t1;
             }
         }
         __syncwarp();
+        STAMP(6 + 3 * rnd); rnd++;
     }
+    STAMP(20);
 }
 
 // ---------------------------------------------------------------- microbench: match_any / redux throughput
@@ -456,18 +492,23 @@ int main(int argc, char** argv)
         const int bpc = WARPS * (32 / T); \
         run(label, [&] { v6_strips<T, WARPS><<<dim3((N + bpc - 1) / bpc, NOBJ), WARPS * 32, smem>>>(a, d_bb, d_l); }, false); \
         printf("   smem %zu B, grid %d x %d\n", smem, (N + bpc - 1) / bpc, NOBJ); } else printf("%s: smem %zu too large\n", label, smem); }
-#define RUN7(WARPS, CPO, label) { size_t fixed = (size_t)(rows + 1) * ((cols + 3) & ~3) * 4 + 1024 + (size_t)WARPS * n_slots * 32 * 4; \
+#define RUN7(WARPS, CPO, FWD, label) { size_t fixed = (size_t)(rows + 1) * ((cols + 3) & ~3) * 4 + 1024 + (size_t)WARPS * n_slots * 32 * 4; \
         size_t smem = fixed + maxreg + 8192; if (smem > 227 * 1024 - 64) smem = 227 * 1024 - 64; int cap = (int)(smem - fixed); \
-        CK(cudaFuncSetAttribute(v7_forward<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        run(label, [&] { v7_forward<WARPS><<<dim3(CPO, NOBJ), WARPS * 32, smem>>>(a, CPO, cap); }, false); \
+        CK((cudaFuncSetAttribute(v7_forward<WARPS, FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))); \
+        run(label, [&] { v7_forward<WARPS, FWD><<<dim3(CPO, NOBJ), WARPS * 32, smem>>>(a, CPO, cap); }, false); \
         printf("   region cap %d B\n", cap); }
-        RUN7(12, 18, "v7 fwd4 12w 18 cta/obj");
-        RUN7(12, 14, "v7 fwd4 12w 14 cta/obj");
-        RUN7(8, 18, "v7 fwd4  8w 18 cta/obj");
-        RUN7(13, 18, "v7 fwd4 13w 18 cta/obj");
-        RUN7(13, 17, "v7 fwd4 13w 17 cta/obj");
-        RUN7(7, 37, "v7 fwd4  7w 37 cta/obj");
-        RUN7(6, 37, "v7 fwd4  6w 37 cta/obj");
+        RUN7(13, 18, 2, "v7 fwd2 13w 18 cta/obj");
+        { unsigned long long hd[64]; CK(cudaMemcpyFromSymbol(hd, g_dbg, sizeof(hd))); printf("   stamps (us from kernel start of CTA(3,2) warp0):"); for (int k = 1; k <= 20; k++) if (hd[k]) printf(" [%d]%.2f", k, (double)(hd[k] - hd[0]) * 1e-3); printf("\n"); }
+        RUN7(13, 18, 1, "v7 fwd1 13w 18 cta/obj");
+        RUN7(16, 18, 2, "v7 fwd2 16w 18 cta/obj");
+        RUN7(16, 18, 1, "v7 fwd1 16w 18 cta/obj");
+        RUN7(12, 18, 4, "v7 fwd4 12w 18 cta/obj");
+        RUN7(12, 14, 4, "v7 fwd4 12w 14 cta/obj");
+        RUN7(8, 18, 4, "v7 fwd4  8w 18 cta/obj");
+        RUN7(13, 18, 4, "v7 fwd4 13w 18 cta/obj");
+        RUN7(13, 17, 4, "v7 fwd4 13w 17 cta/obj");
+        RUN7(7, 37, 4, "v7 fwd4  7w 37 cta/obj");
+        RUN7(6, 37, 4, "v7 fwd4  6w 37 cta/obj");
         RUN6(10, 4, "v6 10 lanes/box 4 cols  4w");
         RUN6(10, 8, "v6 10 lanes/box 4 cols  8w");
         RUN6(10, 12, "v6 10 lanes/box 4 cols 12w");
