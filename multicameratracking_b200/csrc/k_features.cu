@@ -8,8 +8,8 @@
 // ------------------------------------------------------------------------------------------
 // Haar: thread per box, blockIdx.y tiles the features (table reads are warp-uniform broadcasts).
 #define HAAR_FT 16
-__global__ void __launch_bounds__(256)
-k_haar_matrix(const float* __restrict__ ii, int iip, int W, int H,
+__device__ __forceinline__ void
+haar_matrix_body(const float* __restrict__ ii, int iip, int W, int H,
               const int4* __restrict__ rects, const float* __restrict__ wts, const int* __restrict__ nrect, int n_haar,
               const int* __restrict__ col, const int* __restrict__ row, const float* __restrict__ sx,
               const float* __restrict__ sy, int n, float* __restrict__ out, int ld)
@@ -19,6 +19,7 @@ k_haar_matrix(const float* __restrict__ ii, int iip, int W, int H,
     __shared__ int s_n[HAAR_FT];
     const int f0 = blockIdx.y * HAAR_FT;
     const int nf = min(HAAR_FT, n_haar - f0);
+    if (nf <= 0 || (int)(blockIdx.x * blockDim.x) >= n) return;       // block-uniform (batched launches use the largest grid)
     for (int t = threadIdx.x; t < nf * MCT_MAX_RECTS; t += blockDim.x) {
         s_r[t] = rects[(size_t)f0 * MCT_MAX_RECTS + t];
         s_w[t] = wts[(size_t)f0 * MCT_MAX_RECTS + t];
@@ -32,6 +33,22 @@ k_haar_matrix(const float* __restrict__ ii, int iip, int W, int H,
     for (int f = 0; f < nf; f++)
         out[(size_t)(f0 + f) * ld + i] =
             haar_eval_dev(ii, iip, W, H, s_r + f * MCT_MAX_RECTS, s_w + f * MCT_MAX_RECTS, s_n[f], c, r, fx, fy);
+}
+
+__global__ void __launch_bounds__(256)
+k_haar_matrix(const float* __restrict__ ii, int iip, int W, int H,
+              const int4* __restrict__ rects, const float* __restrict__ wts, const int* __restrict__ nrect, int n_haar,
+              const int* __restrict__ col, const int* __restrict__ row, const float* __restrict__ sx,
+              const float* __restrict__ sy, int n, float* __restrict__ out, int ld)
+{
+    haar_matrix_body(ii, iip, W, H, rects, wts, nrect, n_haar, col, row, sx, sy, n, out, ld);
+}
+// batched form: blockIdx.z = object (training sets of all objects of a camera)
+__global__ void __launch_bounds__(256)
+k_haar_matrix_batch(const TrainDesc* __restrict__ descs, const float* __restrict__ ii, int iip, int W, int H)
+{
+    const TrainDesc& d = descs[blockIdx.z];
+    haar_matrix_body(ii, iip, W, H, d.rects, d.wts, d.nrect, d.n_haar, d.col, d.row, d.sx, d.sy, d.P + d.Nn, d.featT, d.ldT);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -48,8 +65,8 @@ k_haar_matrix(const float* __restrict__ ii, int iip, int W, int H,
 //   - normalizeVec (Public.h:270-275): bins / sum(bins).
 #define MDCH_TILE 32
 #define MDCH_WARPS 8
-__global__ void __launch_bounds__(MDCH_WARPS * 32)
-k_mdch(const uint16_t* __restrict__ binimg, int W, int H, int nb, int w0, int h0,
+__device__ __forceinline__ void
+mdch_body(const uint16_t* __restrict__ binimg, int W, int H, int nb, int w0, int h0,
        const int* __restrict__ col, const int* __restrict__ row, const float* __restrict__ sx,
        const float* __restrict__ sy, const int* __restrict__ valid, int n,
        const int* __restrict__ outbins, int n_out, float* __restrict__ out, int ld)
@@ -63,6 +80,7 @@ k_mdch(const uint16_t* __restrict__ binimg, int W, int H, int nb, int w0, int h0
     uint32_t* hist = hist_all + warp * dim;
     float* acc = acc_all + warp * dim;
     const int i0 = blockIdx.x * MDCH_TILE;
+    if (i0 >= n) return;                                            // block-uniform (batched launches use the largest grid)
 
     for (int bi = warp; bi < MDCH_TILE; bi += MDCH_WARPS) {
         const int i = i0 + bi;
@@ -128,6 +146,24 @@ k_mdch(const uint16_t* __restrict__ binimg, int W, int H, int nb, int w0, int h0
         const int o = t / MDCH_TILE, bi = t % MDCH_TILE;
         if (bi < nbx) out[(size_t)o * ld + i0 + bi] = tile[o * (MDCH_TILE + 1) + bi];
     }
+}
+
+__global__ void __launch_bounds__(MDCH_WARPS * 32)
+k_mdch(const uint16_t* __restrict__ binimg, int W, int H, int nb, int w0, int h0,
+       const int* __restrict__ col, const int* __restrict__ row, const float* __restrict__ sx,
+       const float* __restrict__ sy, const int* __restrict__ valid, int n,
+       const int* __restrict__ outbins, int n_out, float* __restrict__ out, int ld)
+{
+    mdch_body(binimg, W, H, nb, w0, h0, col, row, sx, sy, valid, n, outbins, n_out, out, ld);
+}
+// batched form: blockIdx.y = object; all nb^3 bins into rows [n_haar, n_haar + nb^3) of the training matrix
+__global__ void __launch_bounds__(MDCH_WARPS * 32)
+k_mdch_batch(const TrainDesc* __restrict__ descs, const uint16_t* __restrict__ binimg, int W, int H)
+{
+    const TrainDesc& d = descs[blockIdx.y];
+    if (!(d.feature_type == MCT_FEAT_MDCH || d.feature_type == MCT_FEAT_HAAR_MDCH)) return;
+    mdch_body(binimg, W, H, d.nb, d.w0, d.h0, d.col, d.row, d.sx, d.sy, nullptr, d.P + d.Nn, nullptr, d.n_color,
+              d.featT + (size_t)d.n_haar * d.ldT, d.ldT);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -232,6 +268,35 @@ int mct_feature_matrix_full(mct_clf* clf, const int* d_col, const int* d_row, co
     return MCT_OK;
 }
 
+// training features of all objects: Haar rows + MDCH rows, two launches for the whole camera
+int launch_train_features(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj)
+{
+    int n_max = 0, nh_max = 0, any_mdch = 0, dim_max = 0, nb = 0;
+    for (int o = 0; o < n_obj; o++) {
+        n_max = max(n_max, h[o].P + h[o].Nn);
+        nh_max = max(nh_max, h[o].n_haar);
+        if (h[o].feature_type == MCT_FEAT_MDCH || h[o].feature_type == MCT_FEAT_HAAR_MDCH) { any_mdch = 1; dim_max = max(dim_max, h[o].n_color); nb = h[o].nb; }
+    }
+    if (n_max <= 0) return MCT_OK;
+    if (nh_max > 0) {
+        dim3 g(ceil_div(n_max, 256), ceil_div(nh_max, HAAR_FT), n_obj);
+        MCT_LAUNCH(ctx, "k_haar_matrix_batch", k_haar_matrix_batch<<<g, 256, 0, ctx->stream>>>(d, ctx->ii_base + MCT_II_LEAD, ctx->ii_pitch, ctx->W, ctx->H));
+    }
+    if (any_mdch) {
+        int rc = launch_bin_image(ctx, nb);
+        if (rc) return rc;
+        size_t smem = mdch_smem(dim_max, dim_max);
+        static size_t s_attr = 0;
+        if (smem > s_attr) {
+            MCT_CUDA(ctx, cudaFuncSetAttribute(k_mdch_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            s_attr = smem;
+        }
+        dim3 g(ceil_div(n_max, MDCH_TILE), n_obj);
+        MCT_LAUNCH(ctx, "k_mdch_batch", k_mdch_batch<<<g, MDCH_WARPS * 32, smem, ctx->stream>>>(d, ctx->binimg, ctx->W, ctx->H));
+    }
+    return MCT_OK;
+}
+
 // colour rows needed by classify: only the selected bins (rows 0..n_out) for MDCH; all 11 for CCH
 int mct_feature_color_rows(mct_clf* clf, const int* d_col, const int* d_row, const float* d_sx, const float* d_sy,
                            const int* d_valid, int n, const int* d_outbins, int n_out, float* d_out, int ld)
@@ -274,7 +339,7 @@ int mct_feature_color_rows(mct_clf* clf, const int* d_col, const int* d_row, con
 //                      than 255 selected bins).
 // Shared-memory-resident gather kernel: per box rows*cols slot bytes + LUT words + private RMW traffic.
 // ==========================================================================================
-__global__ void k_build_colormap(const int* __restrict__ sel, const int* __restrict__ nsel, int n_haar, int n_color, int mdch,
+__device__ __forceinline__ void build_colormap_body(const int* __restrict__ sel, const int* __restrict__ nsel, int n_haar, int n_color, int mdch,
                                  uint16_t* __restrict__ slotmap, int* __restrict__ colorrow, int* __restrict__ outbins,
                                  int* __restrict__ nout, const int4* __restrict__ rects, const float* __restrict__ wts,
                                  const int* __restrict__ nrect, const float* __restrict__ weak, int F, int K,
@@ -322,6 +387,27 @@ __global__ void k_build_colormap(const int* __restrict__ sel, const int* __restr
     if (mxw > 0) { atomicMax(&s_ext[0], mxw); atomicMax(&s_ext[1], mxh); }
     __syncthreads();
     if (threadIdx.x == 0) { hdr[0] = ns < K ? ns : K; hdr[1] = s_ext[0]; hdr[2] = s_ext[1]; hdr[3] = 0; }
+}
+__global__ void k_build_colormap(const int* __restrict__ sel, const int* __restrict__ nsel, int n_haar, int n_color, int mdch,
+                                 uint16_t* __restrict__ slotmap, int* __restrict__ colorrow, int* __restrict__ outbins,
+                                 int* __restrict__ nout, const int4* __restrict__ rects, const float* __restrict__ wts,
+                                 const int* __restrict__ nrect, const float* __restrict__ weak, int F, int K,
+                                 SelEntry* __restrict__ tab, int* __restrict__ hdr)
+{
+    build_colormap_body(sel, nsel, n_haar, n_color, mdch, slotmap, colorrow, outbins, nout, rects, wts, nrect, weak, F, K, tab, hdr);
+}
+__global__ void k_build_colormap_batch(const TrainDesc* __restrict__ descs)
+{
+    const TrainDesc& d = descs[blockIdx.x];
+    const int mdch = (d.feature_type == MCT_FEAT_MDCH || d.feature_type == MCT_FEAT_HAAR_MDCH) ? 1 : 0;
+    build_colormap_body(d.sel, d.nsel, d.n_haar, d.n_color, mdch, d.slotmap, d.colorrow, d.outbins, d.nout, d.rects, d.wts, d.nrect,
+                        d.weak, d.F, d.K, d.seltab, d.selhdr);
+}
+int launch_build_colormap_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj)
+{
+    (void)h;
+    MCT_LAUNCH(ctx, "k_build_colormap_batch", k_build_colormap_batch<<<n_obj, 256, 0, ctx->stream>>>(d));
+    return MCT_OK;
 }
 int launch_build_colormap(mct_clf* clf)
 {

@@ -34,8 +34,8 @@ __device__ __forceinline__ bool better_min(float v, int f, float bv, int bf)
     return (v < bv) || (v == bv && f < bf);
 }
 
-__global__ void __launch_bounds__(SEL_THREADS)
-k_milboost_select(const float* __restrict__ pred, int ld, int F, int P, int Nn, int K,
+__device__ __forceinline__ void
+milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int Nn, int K,
                   const float* __restrict__ weak, int weak_type, int* __restrict__ sel, int* __restrict__ nsel,
                   int FC)
 {
@@ -129,6 +129,22 @@ k_milboost_select(const float* __restrict__ pred, int ld, int F, int P, int Nn, 
     if (rank == 0 && tid == 0) *nsel = n_sel;
     cluster.sync();          // no CTA may exit while a peer can still write its slots
 }
+__global__ void __launch_bounds__(SEL_THREADS)
+k_milboost_select(const float* __restrict__ pred, int ld, int F, int P, int Nn, int K,
+                  const float* __restrict__ weak, int weak_type, int* __restrict__ sel, int* __restrict__ nsel,
+                  int FC)
+{
+    milboost_select_body(pred, ld, F, P, Nn, K, weak, weak_type, sel, nsel, FC);
+}
+// batched form: one cluster per object (blockIdx.y); objects of another strong-classifier type leave at once
+// (the whole cluster takes the same branch)
+__global__ void __launch_bounds__(SEL_THREADS)
+k_milboost_select_batch(const TrainDesc* __restrict__ descs, int FC)
+{
+    const TrainDesc& d = descs[blockIdx.y];
+    if (d.strong_type != MCT_STRONG_MILBOOST) return;
+    milboost_select_body(d.pred, d.ldT, d.F, d.P, d.Nn, d.K, d.weak, d.weak_type, d.sel, d.nsel, FC);
+}
 
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool better_max(float v, int f, float bv, int bf)
@@ -157,8 +173,8 @@ __device__ void block_argmax(float v, int f, float* out_v, int* out_f, SelSlot* 
 }
 
 #define ANY_THREADS 1024
-__global__ void __launch_bounds__(ANY_THREADS)
-k_anyboost_select(const float* __restrict__ pred, int ld, int F, int P, int Nn, int K,
+__device__ __forceinline__ void
+anyboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int Nn, int K,
                   int* __restrict__ sel, int* __restrict__ nsel)
 {
     const int M = P + Nn;
@@ -265,6 +281,18 @@ k_anyboost_select(const float* __restrict__ pred, int ld, int F, int P, int Nn, 
     }
     if (tid == 0) *nsel = n_sel < 0 ? 0 : n_sel;
 }
+__global__ void __launch_bounds__(ANY_THREADS)
+k_anyboost_select(const float* __restrict__ pred, int ld, int F, int P, int Nn, int K,
+                  int* __restrict__ sel, int* __restrict__ nsel)
+{
+    anyboost_select_body(pred, ld, F, P, Nn, K, sel, nsel);
+}
+__global__ void __launch_bounds__(ANY_THREADS) k_anyboost_select_batch(const TrainDesc* __restrict__ descs)
+{
+    const TrainDesc& d = descs[blockIdx.x];
+    if (d.strong_type != MCT_STRONG_MILANYBOOST) return;
+    anyboost_select_body(d.pred, d.ldT, d.F, d.P, d.Nn, d.K, d.sel, d.nsel);
+}
 
 // ------------------------------------------------------------------------------------------
 int launch_mil_select(mct_clf* clf, int P, int Nn)
@@ -321,5 +349,65 @@ int launch_mil_select(mct_clf* clf, int P, int Nn)
     MCT_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_milboost_select, pred, ld, F, P, Nn, K, weak, wt, sel, nsel, FC));
     mct_prof_end(ctx);
     MCT_KERNEL_CHECK(ctx);
+    return MCT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Batched selection for all objects of a camera: one launch per strong-classifier type.
+int launch_mil_select_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj, const int* cluster_req)
+{
+    int any_mil = 0, any_any = 0, F_max = 0, M_max = 0, F_any = 0, M_any = 0, creq = 0;
+    for (int o = 0; o < n_obj; o++) {
+        const int M = h[o].P + h[o].Nn;
+        if (h[o].strong_type == MCT_STRONG_MILANYBOOST) { any_any = 1; F_any = max(F_any, h[o].F); M_any = max(M_any, M); }
+        else { any_mil = 1; F_max = max(F_max, h[o].F); M_max = max(M_max, M); if (cluster_req && cluster_req[o] > creq) creq = cluster_req[o]; }
+    }
+    if (any_any) {
+        size_t smem = (size_t)(3 * M_any + F_any) * sizeof(float) + (size_t)F_any;
+        if (smem > 200 * 1024) return mct_fail(ctx, MCT_E_UNSUPPORTED, "training set too large for the AnyBoost kernel%s (M=%d)", "", M_any);
+        static size_t s_attr = 32 * 1024;
+        if (smem > s_attr) {
+            MCT_CUDA(ctx, cudaFuncSetAttribute(k_anyboost_select_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            s_attr = smem;
+        }
+        MCT_LAUNCH(ctx, "k_anyboost_select_batch", k_anyboost_select_batch<<<n_obj, ANY_THREADS, smem, ctx->stream>>>(d));
+    }
+    if (any_mil) {
+        const int F = F_max, M = M_max;
+        int C = creq;
+        if (C <= 0) { C = 1; while (C < SEL_MAX_CLUSTER && ceil_div(F, C) > 48) C <<= 1; }
+        if (C > SEL_MAX_CLUSTER) C = SEL_MAX_CLUSTER;
+        const int FL = ceil_div(F, C);
+        const size_t budget = 180 * 1024;
+        long fc_max = ((long)budget - (long)M * 4 - F) / ((long)M * 4) - 1;
+        if (fc_max < 1) return mct_fail(ctx, MCT_E_UNSUPPORTED, "training set too large for the MIL selection kernel%s (M=%d)", "", M);
+        int FC = FL < (int)fc_max ? FL : (int)fc_max;
+        if (FC > SEL_THREADS) FC = SEL_THREADS;
+        size_t smem = (size_t)M * 4 + (size_t)M * (FC + 1) * 4 + (size_t)F;
+        smem = (smem + 15) & ~(size_t)15;
+        static size_t s_attr = 0;
+        static int s_np = 0;
+        if (smem > s_attr) {
+            MCT_CUDA(ctx, cudaFuncSetAttribute(k_milboost_select_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            s_attr = smem;
+        }
+        if (C > 8 && !s_np) {
+            MCT_CUDA(ctx, cudaFuncSetAttribute(k_milboost_select_batch, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            s_np = 1;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(C, n_obj, 1);
+        cfg.blockDim = dim3(SEL_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        mct_prof_begin(ctx, "k_milboost_select_batch");
+        MCT_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_milboost_select_batch, d, FC));
+        mct_prof_end(ctx);
+        MCT_KERNEL_CHECK(ctx);
+    }
     return MCT_OK;
 }

@@ -64,8 +64,8 @@ __device__ __forceinline__ float norm_scale(const float* w, int n, int lane)
     return (float)(1.0 / (s + 1e-6));
 }
 
-__global__ void __launch_bounds__(256)
-k_weak_update(const float* __restrict__ feat, int ld, int F, int P, int Nn, int weak_type, float lr,
+__device__ __forceinline__ void
+weak_update_body(const float* __restrict__ feat, int ld, int F, int P, int Nn, int weak_type, float lr,
               const float* __restrict__ tw, float* __restrict__ weak, int* __restrict__ trained,
               float* __restrict__ pred)
 {
@@ -154,6 +154,28 @@ k_weak_update(const float* __restrict__ feat, int ld, int F, int P, int Nn, int 
     float* pr = pred + (size_t)f * ld;
     for (int i = lane; i < P + Nn; i += 32)
         pr[i] = weak_classify_dev(weak_type, xp[i], mu0, mu1, n0, n1, e0, e1);
+}
+
+__global__ void __launch_bounds__(256)
+k_weak_update(const float* __restrict__ feat, int ld, int F, int P, int Nn, int weak_type, float lr,
+              const float* __restrict__ tw, float* __restrict__ weak, int* __restrict__ trained,
+              float* __restrict__ pred)
+{
+    weak_update_body(feat, ld, F, P, Nn, weak_type, lr, tw, weak, trained, pred);
+}
+// batched form: blockIdx.y = object
+__global__ void __launch_bounds__(256) k_weak_update_batch(const TrainDesc* __restrict__ descs)
+{
+    const TrainDesc& d = descs[blockIdx.y];
+    weak_update_body(d.featT, d.ldT, d.F, d.P, d.Nn, d.weak_type, d.lr, d.tw, d.weak, d.trained, d.pred);
+}
+int launch_weak_update_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj)
+{
+    int F_max = 0;
+    for (int o = 0; o < n_obj; o++) F_max = max(F_max, h[o].F);
+    dim3 g(ceil_div(F_max, 8), n_obj);
+    MCT_LAUNCH(ctx, "k_weak_update_batch", k_weak_update_batch<<<g, 256, 0, ctx->stream>>>(d));
+    return MCT_OK;
 }
 
 int launch_weak_update(mct_clf* clf, int P, int Nn, int has_weights)

@@ -202,6 +202,9 @@ extern "C" int mct_ctx_destroy(mct_ctx* ctx)
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->h_summ) cudaFreeHost(ctx->h_summ);
     if (ctx->d_noise_stage) cudaFree(ctx->d_noise_stage);
+    if (ctx->h_tdesc) { cudaFreeHost(ctx->h_tdesc); cudaFree(ctx->d_tdesc); cudaEventDestroy(ctx->ev_train); }
+    if (ctx->h_train_stage) cudaFreeHost(ctx->h_train_stage);
+    if (ctx->d_train_stage) cudaFree(ctx->d_train_stage);
     free(ctx->desc_last_h);
     DescRing* r = ring_of(ctx);
     if (r) {
@@ -974,6 +977,9 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
         if (ntot > ctx->noise_stage_cap) {
             MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             if (ctx->d_noise_stage) cudaFree(ctx->d_noise_stage);
+    if (ctx->h_tdesc) { cudaFreeHost(ctx->h_tdesc); cudaFree(ctx->d_tdesc); cudaEventDestroy(ctx->ev_train); }
+    if (ctx->h_train_stage) cudaFreeHost(ctx->h_train_stage);
+    if (ctx->d_train_stage) cudaFree(ctx->d_train_stage);
             MCT_CUDA(ctx, cudaMalloc(&ctx->d_noise_stage, ntot * sizeof(float)));
             ctx->noise_stage_cap = ntot;
         }
@@ -1036,14 +1042,88 @@ extern "C" int mct_track_score(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, mct_
     return mct_track_collect(ctx, n_obj, summaries);
 }
 
+static void fill_train_desc(TrainDesc* t, mct_clf* c)
+{
+    memset(t, 0, sizeof(*t));
+    t->ldT = c->ldT; t->featT = c->d_featT; t->pred = c->d_pred;
+    t->rects = c->d_rects; t->wts = c->d_wts; t->nrect = c->d_nrect;
+    t->weak = c->d_weak; t->trained = c->d_trained; t->sel = c->d_sel; t->nsel = c->d_nsel;
+    t->slotmap = c->d_slotmap; t->colorrow = c->d_colorrow; t->outbins = c->d_outbins; t->nout = c->d_nout;
+    t->seltab = c->d_seltab; t->selhdr = c->d_selhdr;
+    t->F = c->F; t->K = c->K; t->n_haar = c->n_haar; t->n_color = c->n_color; t->nb = c->p.n_bins; t->w0 = c->p.w0; t->h0 = c->p.h0;
+    t->weak_type = c->p.weak_type; t->strong_type = c->p.strong_type; t->feature_type = c->p.feature_type; t->cch_mode = c->p.cch_mode;
+    t->lr = c->p.learning_rate;
+}
+
+// UpdateClassifier (ParticleFilterTracker.cpp:1013-1032) for all objects of a camera: ONE copy of the packed training
+// boxes, ONE descriptor copy and five batched launches (Haar rows, MDCH rows, weak update + predictions, greedy
+// selection with one cluster per object, selected-classifier tables) instead of 8 copies + 5 launches per object.
 extern "C" int mct_track_update(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, const mct_boxes* pos, const mct_boxes* neg)
 {
     if (!ctx || n_obj < 1 || !clfs || !pos || !neg) return MCT_E_ARG;
+    bool batchable = n_obj <= DESC_MAX_OBJ;
+    size_t total = 0;
     for (int o = 0; o < n_obj; o++) {
         if (!clfs[o] || clfs[o]->ctx != ctx) return mct_fail(ctx, MCT_E_ARG, "classifier handle belongs to another ctx%s");
-        int rc = mct_classifier_update(clfs[o], &pos[o], &neg[o], nullptr, nullptr);
-        if (rc) return rc;
+        if (clfs[o]->p.feature_type == MCT_FEAT_CCH) batchable = false;      // CCH classifiers take the per-object path
+        total += (size_t)pos[o].n + (size_t)neg[o].n;
     }
+    if (!batchable) {
+        for (int o = 0; o < n_obj; o++) {
+            int rc = mct_classifier_update(clfs[o], &pos[o], &neg[o], nullptr, nullptr);
+            if (rc) return rc;
+        }
+        return MCT_OK;
+    }
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if (!ctx->h_tdesc) {
+        MCT_CUDA(ctx, cudaMallocHost(&ctx->h_tdesc, sizeof(TrainDesc) * DESC_MAX_OBJ));
+        MCT_CUDA(ctx, cudaMalloc(&ctx->d_tdesc, sizeof(TrainDesc) * DESC_MAX_OBJ));
+        MCT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_train, cudaEventDisableTiming));
+    }
+    MCT_CUDA(ctx, cudaEventSynchronize(ctx->ev_train));                // the previous call's staging copies have executed
+    if (total > ctx->train_stage_cap) {
+        MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_train_stage) cudaFreeHost(ctx->h_train_stage);
+        if (ctx->d_train_stage) cudaFree(ctx->d_train_stage);
+        size_t cap = total + 1024;
+        MCT_CUDA(ctx, cudaMallocHost(&ctx->h_train_stage, cap * 4 * sizeof(int)));
+        MCT_CUDA(ctx, cudaMalloc(&ctx->d_train_stage, cap * 4 * sizeof(int)));
+        ctx->train_stage_cap = cap;
+    }
+    // pack: per object [col | row | sx | sy] x (P + Nn)
+    size_t off = 0;
+    std::vector<int> creq(n_obj, 0);
+    for (int o = 0; o < n_obj; o++) {
+        mct_clf* c = clfs[o];
+        if ((rc = need_frame(c))) return rc;
+        const int P = pos[o].n, Nn = neg[o].n, M = P + Nn;
+        if (P < 1 || Nn < 1) return mct_fail(ctx, MCT_E_ARG, "Update needs at least one positive and one negative sample%s");
+        if (M > c->max_train) return mct_fail(ctx, MCT_E_ARG, "training set exceeds max_train%s (%d)", "", M);
+        if (!pos[o].col || !pos[o].row || !pos[o].sx || !pos[o].sy || !neg[o].col || !neg[o].row || !neg[o].sx || !neg[o].sy)
+            return mct_fail(ctx, MCT_E_ARG, "box arrays are NULL%s");
+        int* hs = ctx->h_train_stage + off * 4;
+        memcpy(hs, pos[o].col, (size_t)P * 4);             memcpy(hs + P, neg[o].col, (size_t)Nn * 4);
+        memcpy(hs + M, pos[o].row, (size_t)P * 4);         memcpy(hs + M + P, neg[o].row, (size_t)Nn * 4);
+        memcpy(hs + 2 * M, pos[o].sx, (size_t)P * 4);      memcpy(hs + 2 * M + P, neg[o].sx, (size_t)Nn * 4);
+        memcpy(hs + 3 * M, pos[o].sy, (size_t)P * 4);      memcpy(hs + 3 * M + P, neg[o].sy, (size_t)Nn * 4);
+        TrainDesc* t = &ctx->h_tdesc[o];
+        fill_train_desc(t, c);
+        int* ds = ctx->d_train_stage + off * 4;
+        t->col = ds; t->row = ds + M; t->sx = (const float*)(ds + 2 * M); t->sy = (const float*)(ds + 3 * M); t->tw = nullptr;
+        t->P = P; t->Nn = Nn;
+        c->lastP = P; c->lastNn = Nn;
+        creq[o] = c->cluster;
+        off += (size_t)M;
+    }
+    MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_train_stage, ctx->h_train_stage, total * 4 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tdesc, ctx->h_tdesc, sizeof(TrainDesc) * n_obj, cudaMemcpyHostToDevice, ctx->stream));
+    MCT_CUDA(ctx, cudaEventRecord(ctx->ev_train, ctx->stream));
+    if ((rc = launch_train_features(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj))) return rc;
+    if ((rc = launch_weak_update_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj))) return rc;
+    if ((rc = launch_mil_select_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj, creq.data()))) return rc;
+    if ((rc = launch_build_colormap_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj))) return rc;
     return MCT_OK;
 }
 

@@ -36,6 +36,7 @@ struct SelEntry {
 };
 
 // ------------------------------------------------------------------ host-side objects
+struct TrainDesc;
 struct FrameSet {              // one of the two sets of per-frame device buffers
     uint8_t* planes[4]; size_t plane_cap;
     float* ii_base; size_t ii_cap;
@@ -66,7 +67,9 @@ struct mct_ctx {
     void* d_desc; void* h_desc; size_t desc_cap;       // batched object descriptors (device + pinned host)
     void* desc_last_h; const void* desc_last_d; int desc_last_n;   // last published descriptor set (skip identical uploads)
     mct_pf_summary* h_summ; mct_pf_summary* h_summ_dev; int summ_cap;   // pinned, device-mapped read-out buffer (kernels write it directly)
-    float* d_noise_stage; size_t noise_stage_cap;      // staging for host-provided prediction noise (one H2D per call)
+    float* d_noise_stage; size_t noise_stage_cap;
+    TrainDesc* h_tdesc; TrainDesc* d_tdesc; cudaEvent_t ev_train;   // batched UpdateClassifier descriptors (pinned + device)
+    int* h_train_stage; int* d_train_stage; size_t train_stage_cap;   // packed training boxes of all objects (4 x 4-byte arrays)      // staging for host-provided prediction noise (one H2D per call)
     float* d_tmp; size_t tmp_cap;                      // scratch (sum_rects etc.)
     float* h_pin; size_t pin_cap;                      // pinned staging for small host arrays
     long long launches;
@@ -144,6 +147,20 @@ struct ObjDesc {
     const int* colorrow; const int* outbins;
     const uint16_t* slotmap; const int* nout; int* big; int* nbig;
     int F, n_haar, nb, weak_type, feature_type, cch_mode, K, cw0, ch0, pad1;
+};
+
+// ------------------------------------------------------------------ batched training descriptor (UpdateClassifier)
+// One entry per object of a camera: all objects' classifiers are updated by the same handful of launches
+// (blockIdx.y / .z = object) instead of five launches + eight copies per object.
+struct TrainDesc {
+    const int* col; const int* row; const float* sx; const float* sy; const float* tw;   // P positives then Nn negatives
+    int P, Nn, ldT, pad0;
+    float* featT; float* pred;
+    const int4* rects; const float* wts; const int* nrect;
+    float* weak; int* trained; int* sel; int* nsel;
+    uint16_t* slotmap; int* colorrow; int* outbins; int* nout; SelEntry* seltab; int* selhdr;
+    int F, K, n_haar, n_color, nb, w0, h0, weak_type, strong_type, feature_type, cch_mode, pad1;
+    float lr; int pad2;
 };
 
 // Per-call values that change every frame travel as kernel parameters, so that the ObjDesc array itself is
@@ -230,6 +247,11 @@ int launch_pf_summary(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max)
 int launch_pf_expand_prob(mct_ctx* ctx, const ObjDesc* d_desc, const float* d_prob_compact, int n_prob, int only_nonzero);
 int launch_weak_update(mct_clf* clf, int P, int Nn, int has_weights);
 int launch_mil_select(mct_clf* clf, int P, int Nn);
+// batched UpdateClassifier of n_obj classifiers (device descriptor array d, host copy h)
+int launch_train_features(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj);
+int launch_weak_update_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj);
+int launch_mil_select_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj, const int* cluster_req);
+int launch_build_colormap_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj);
 int launch_foot_points(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, const float* d_h0, float* d_out);
 
 // ------------------------------------------------------------------ device helpers
