@@ -1,0 +1,80 @@
+"""Cross-camera exchange for the fusers: one camera per rank per GPU.
+
+The reference's CameraNetwork reads the other cameras' state through pointers inside one process
+(CameraNetwork.cpp:182-216 foot points for the geometric fuser, :276-320 training SampleSets for the appearance
+fuser).  With cameras sharded across GPUs the same payloads travel with ONE all-gather per frame:
+
+  geometric fuser   foot point of the highest-weight particle per object, float32 [n_obj][2], packed on the device by
+                    mct_fuser_pack_foot_points (ParticleFilterTracker.cpp:1223-1238); every rank then runs the tiny
+                    per-object fusion redundantly, so no broadcast is needed.
+  appearance fuser  per-object training FEATURE ROWS (instead of image pointers): float32 [F][P] and [F][Nn], padded to
+                    the largest count over ranks, plus the counts; each rank pools them in camera order and feeds
+                    mct_classifier_update_from_features (AppearanceBasedInformationFuser.cpp:44-90).
+
+Works on CUDA tensors with the NCCL backend (NVLink / NVSwitch) and on CPU tensors with gloo (tests).  There is no
+compute here: only packing, the collective and unpacking.
+"""
+import torch
+import torch.distributed as dist
+
+
+class CameraNetworkExchange:
+    def __init__(self, n_objects, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised (one process per camera / GPU)")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.n_objects = int(n_objects)
+
+    # ------------------------------------------------------------------ geometric fuser payload
+    def allgather_foot_points(self, local):
+        """local: float32 [n_obj][2] (this camera).  Returns [world][n_obj][2], index 0 = camera id = rank."""
+        local = local.contiguous()
+        if tuple(local.shape) != (self.n_objects, 2) or local.dtype != torch.float32:
+            raise ValueError("foot points must be float32 [%d][2]" % self.n_objects)
+        return self._allgather(local)
+
+    def _allgather(self, local):
+        """all_gather_into_tensor with the output concatenated along dim 0 (the form both NCCL and gloo accept)"""
+        local = local.contiguous()
+        flat = torch.empty((self.world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(flat, local, group=self.group)
+        return flat.view((self.world,) + tuple(local.shape))
+
+    # ------------------------------------------------------------------ appearance fuser payload
+    def allgather_feature_rows(self, fpos, fneg):
+        """fpos: float32 [F][P], fneg: float32 [F][Nn] of ONE object on this camera (P, Nn may differ per rank).
+        Returns (pooled_pos [F][sum P], pooled_neg [F][sum Nn], counts int64 [world][2]) in camera order."""
+        F = fpos.shape[0]
+        if fneg.shape[0] != F:
+            raise ValueError("positive and negative rows must have the same feature count")
+        dev = fpos.device
+        counts = torch.tensor([fpos.shape[1], fneg.shape[1]], dtype=torch.int64, device=dev)
+        allc = self._allgather(counts.view(1, 2)).view(self.world, 2)
+        pmax, nmax = int(allc[:, 0].max()), int(allc[:, 1].max())
+        pad = torch.zeros((F, pmax + nmax), dtype=torch.float32, device=dev)
+        pad[:, :fpos.shape[1]] = fpos
+        pad[:, pmax:pmax + fneg.shape[1]] = fneg
+        allp = self._allgather(pad)
+        pos = torch.cat([allp[r, :, :int(allc[r, 0])] for r in range(self.world)], dim=1)
+        neg = torch.cat([allp[r, :, pmax:pmax + int(allc[r, 1])] for r in range(self.world)], dim=1)
+        return pos.contiguous(), neg.contiguous(), allc
+
+    # ------------------------------------------------------------------ timing helper (bench.py)
+    def max_over_ranks(self, value, device=None):
+        t = torch.tensor([float(value)], dtype=torch.float64, device=device or "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return float(t.item())
+
+    def sum_over_ranks(self, value, device=None):
+        t = torch.tensor([float(value)], dtype=torch.float64, device=device or "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return float(t.item())
+
+
+def drop_samples(rng_next_float, n, threshold=0.5):
+    """AppearanceBasedInformationFuser.cpp:66-82: a pooled sample is kept iff randfloat() > RANDOM_SAMPLE_SELECTION_THRESHOLD
+    (0.5, :7), in order (all positives, then all negatives), one draw per sample from the MWC stream
+    (rng_next_float() -> float in [0,1))."""
+    return [i for i in range(n) if rng_next_float() > threshold]

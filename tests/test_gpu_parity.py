@@ -446,3 +446,161 @@ def test_fused_track_score_matches_oracle(ctx, oracle):
             pfs[o].set_state(so, opf.contents.filter_state)
     for x in clfs + pfs:
         x.close()
+
+
+# ---------------------------------------------------------------------------------- batched path, harder cases
+def _score_and_compare(ctx, oracle, seq, W, H, specs, N, sd, frames=(1, 2), haar_F=120):
+    """specs: list of (feature_type, weak_type, strong_type, K); one object each, scored in ONE mct_track_score call"""
+    w0, h0 = seq.w0, seq.h0
+    t, arrs = haar_table(oracle, haar_F, w0, h0)
+    gray, r, g, b = seq.frame(0)
+    ctx.frame_set(gray, r, g, b)
+    of = oracle.frame(gray, r, g, b)
+    clfs, oclfs, pfs, opfs = [], [], [], []
+    for o, (ft, wt, st, K) in enumerate(specs):
+        nh = haar_F if ft in (capi.FEAT_HAAR, capi.FEAT_HAAR_MDCH) else 0
+        clf = capi.StrongClassifier(ctx, ft, w0, h0, n_haar=nh, n_bins=8, weak_type=wt, strong_type=st, n_selected=K,
+                                    haar=arrs if nh else None)
+        oclf = oracle.clf_create(ft, nh, 8, w0, h0, wt, st, K, 0.85, t if nh else None)
+        pos, neg = _train_sets(oracle, seq, 0, o, seed=o + 1)
+        clf.Update(capi.make_boxes(*pos), capi.make_boxes(*neg))
+        oracle.clf_update(oclf, of, oracle.boxes(*pos), oracle.boxes(*neg))
+        assert clf.selectors().tolist() == oracle.clf_selectors(oclf).tolist()
+        x, y, w, h = seq.box(0, o)
+        pf, opf = _pf_pair(ctx, oracle, N, W=W, H=H, cx=x + w / 2, cy=y + h / 2)
+        clfs.append(clf); oclfs.append(oclf); pfs.append(pf); opfs.append(opf)
+    n = len(specs)
+    for frame in frames:
+        gray, r, g, b = seq.frame(frame)
+        ctx.frame_set(gray, r, g, b)
+        of = oracle.frame(gray, r, g, b)
+        nz = np.stack([synth.noise(N, sd, obj=o, t=frame) for o in range(n)])
+        u01 = [oracle.randfloat(oracle.rng(500 + o + 10 * frame)) for o in range(n)]
+        rngs = [oracle.rng(500 + o + 10 * frame) for o in range(n)]
+        summ = capi.track_score(ctx, pfs, clfs, [(w0, h0, 20, 0, 1)] * n, nz, u01)
+        for o in range(n):
+            opf = opfs[o]
+            oracle.lib.orc_pf_predict(opf, nz[o].ctypes.data_as(C.POINTER(C.c_float)), w0, h0)
+            col, row, sx, sy = oracle.pf_test_set(opf, w0, h0, W, H)
+            Ho = oracle.clf_classify(oclfs[o], of, oracle.boxes(col, row, sx, sy))
+            Hg, valid = pfs[o].last_response()
+            assert int(valid.sum()) == len(col) == summ[o].n_valid, (frame, o)
+            rel_close(Hg[valid != 0], Ho)
+            prob = oracle.likelihood_map(Ho, 20)
+            res = oracle.lib.orc_pf_update_all_weights(opf, prob.ctypes.data_as(C.POINTER(C.c_float)), 1, 0, 1, C.byref(rngs[o]))
+            assert bool(res) == bool(summ[o].resampled)
+            sg, so = pfs[o].state(), oracle.pf_state(opf)
+            np.testing.assert_array_equal(sg[:, :4], so[:, :4])
+            rel_close(sg[:, 4], so[:, 4], rtol=2e-4, scale=so[:, 4].max())
+            pfs[o].set_state(so, opf.contents.filter_state)
+    for x in clfs + pfs:
+        x.close()
+    for oc in oclfs:
+        oracle.lib.orc_clf_free(oc)
+
+
+def test_fused_mixed_types_scale_noise_and_border(ctx, oracle):
+    """one batched call over Haar / MDCH / Haar+MDCH / Perceptron / AnyBoost objects; scale noise makes the boxes differ
+    in size (the MDCH strip kernel hands them to the generic kernel) and the wide position noise pushes particles
+    over the frame border (invalid test samples)"""
+    seq = synth.Sequence(640, 480, 5)
+    specs = [(capi.FEAT_HAAR, capi.WEAK_STUMP, capi.STRONG_MILBOOST, 24),
+             (capi.FEAT_MDCH, capi.WEAK_STUMP, capi.STRONG_MILBOOST, 60),
+             (capi.FEAT_HAAR_MDCH, capi.WEAK_WSTUMP, capi.STRONG_MILBOOST, 126),
+             (capi.FEAT_HAAR, capi.WEAK_PERCEPTRON, capi.STRONG_MILBOOST, 24),
+             (capi.FEAT_MDCH, capi.WEAK_STUMP, capi.STRONG_MILANYBOOST, 102)]
+    _score_and_compare(ctx, oracle, seq, 640, 480, specs, N=700, sd=(60.0, 60.0, 0.04, 0.04))
+
+
+def test_fused_cfg4_shape_720p_mdch_anyboost(ctx, oracle):
+    """cfg 4 shape: 1280x720, 60x120 blobs, MDCH (512 -> 102 selected) + MILAnyBoost, several objects per camera"""
+    seq = synth.Sequence(1280, 720, 3)
+    assert (seq.w0, seq.h0) == (60, 120)
+    specs = [(capi.FEAT_MDCH, capi.WEAK_STUMP, capi.STRONG_MILANYBOOST, 102)] * 3
+    _score_and_compare(ctx, oracle, seq, 1280, 720, specs, N=400, sd=(20.0, 20.0, 1e-7, 1e-7), frames=(1,))
+
+
+def test_fused_cfg2_full_size_properties(ctx, oracle):
+    """BASELINE configs[1] at full size (8 objects x 2000 particles, Haar(250)+MDCH(512) -> 152, WeightedStumps): the
+    response of one object is compared with the oracle; all objects are checked through size-independent properties"""
+    seq = synth.Sequence(640, 480, 8)
+    w0, h0, N, F, K = seq.w0, seq.h0, 2000, 250, 152
+    t, arrs = haar_table(oracle, F, w0, h0)
+    gray, r, g, b = seq.frame(0)
+    ctx.frame_set(gray, r, g, b)
+    of = oracle.frame(gray, r, g, b)
+    clfs, pfs = [], []
+    oclf0 = oracle.clf_create(capi.FEAT_HAAR_MDCH, F, 8, w0, h0, capi.WEAK_WSTUMP, capi.STRONG_MILBOOST, K, 0.85, t)
+    for o in range(8):
+        clf = capi.StrongClassifier(ctx, capi.FEAT_HAAR_MDCH, w0, h0, n_haar=F, n_bins=8, weak_type=capi.WEAK_WSTUMP,
+                                    strong_type=capi.STRONG_MILBOOST, n_selected=K, haar=arrs)
+        pos, neg = _train_sets(oracle, seq, 0, o, seed=o + 1)
+        clf.Update(capi.make_boxes(*pos), capi.make_boxes(*neg))
+        if o == 0:
+            oracle.clf_update(oclf0, of, oracle.boxes(*pos), oracle.boxes(*neg))
+            assert clf.selectors().tolist() == oracle.clf_selectors(oclf0).tolist()
+        x, y, w, h = seq.box(0, o)
+        pf = capi.ParticleFilter(ctx, N, 640, 480); pf.Initialize(x + w / 2, y + h / 2)
+        clfs.append(clf); pfs.append(pf)
+    gray, r, g, b = seq.frame(1)
+    ctx.frame_set(gray, r, g, b)
+    of = oracle.frame(gray, r, g, b)
+    nz = np.stack([synth.noise(N, (20, 20, 1e-7, 1e-7), obj=o, t=1) for o in range(8)])
+    summ = capi.track_score(ctx, pfs, clfs, [(w0, h0, 20, 0, 1)] * 8, nz, [0.1 * (o + 1) for o in range(8)])
+    # object 0 against the oracle
+    opf = oracle.pf_create(N, 640, 480)
+    x, y, w, h = seq.box(0, 0)
+    oracle.lib.orc_pf_initialize(opf, x + w / 2, y + h / 2, 1, 1, 0.5, 10, 0.1)
+    oracle.lib.orc_pf_predict(opf, nz[0].ctypes.data_as(C.POINTER(C.c_float)), w0, h0)
+    col, row, sx, sy = oracle.pf_test_set(opf, w0, h0, 640, 480)
+    Ho = oracle.clf_classify(oclf0, of, oracle.boxes(col, row, sx, sy))
+    Hg, valid = pfs[0].last_response()
+    assert int(valid.sum()) == len(col) == summ[0].n_valid
+    rel_close(Hg[valid != 0], Ho)
+    # every object: properties that do not depend on the size
+    for o in range(8):
+        st = pfs[o].state()
+        assert summ[o].n_valid > 0 and np.isfinite(st).all()
+        if summ[o].resampled:
+            idx = pfs[o].resample_indices()
+            assert (np.diff(idx) >= 0).all() and idx.min() >= 0 and idx.max() < N       # systematic resampling is monotone
+            assert (st[:, 4] == 1).all()
+            assert summ[o].filter_state == capi.PF_RESAMPLED
+            np.testing.assert_array_equal(st[:, :4], pfs[o].resampled()[:, :4])
+        else:
+            assert abs(st[:, 4].sum() - 1.0) < 1e-3
+        assert 1 <= summ[o].n_unique <= N
+    for x in clfs + pfs:
+        x.close()
+    oracle.lib.orc_clf_free(oclf0)
+
+
+def test_edge_cases_errors_and_empty_inputs(ctx, oracle):
+    seq = synth.Sequence(640, 480, 1)
+    gray, r, g, b = seq.frame(0)
+    ctx.frame_set(gray, r, g, b)
+    t, arrs = haar_table(oracle, 40, seq.w0, seq.h0)
+    clf = capi.StrongClassifier(ctx, capi.FEAT_HAAR, seq.w0, seq.h0, n_haar=40, n_selected=8, haar=arrs)
+    e = np.zeros(0, np.int32); ef = np.zeros(0, np.float32)
+    assert clf.Classify(capi.make_boxes(e, e, ef, ef)).shape == (0,)                  # empty test set: nothing to do
+    with pytest.raises(capi.MctError):                                               # Update needs >= 1 positive and negative
+        clf.Update(capi.make_boxes(e, e, ef, ef), capi.make_boxes(e, e, ef, ef))
+    big = np.ones(5000, np.int32); bigf = np.ones(5000, np.float32)
+    with pytest.raises(capi.MctError):                                               # exceeds max_train
+        clf.Update(capi.make_boxes(big, big, bigf, bigf), capi.make_boxes(big[:3], big[:3], bigf[:3], bigf[:3]))
+    # an untrained classifier has no selectors: response is 0 everywhere
+    H = clf.Classify(capi.make_boxes(np.array([10, 20], np.int32), np.array([10, 20], np.int32), np.ones(2, np.float32), np.ones(2, np.float32)))
+    assert (H == 0).all()
+    # all particles out of the frame: the reference aborts (ParticleFilterTracker.cpp:513); here MCT_E_EMPTY
+    pos, neg = _train_sets(oracle, seq, 0, 0)
+    clf.Update(capi.make_boxes(*pos), capi.make_boxes(*neg))
+    pf = capi.ParticleFilter(ctx, 64, 640, 480); pf.Initialize(5.0, 5.0)
+    nz = np.zeros((1, 4, 64), np.float32)
+    with pytest.raises(capi.MctError) as ei:
+        capi.track_score(ctx, [pf], [clf], [(seq.w0, seq.h0, 20, 0, 1)], nz, [0.5])
+    assert ei.value.code == capi.E_EMPTY
+    # boxes partly outside the frame are clamped, never read out of bounds
+    col = np.array([-15, 630, 300], np.int32); row = np.array([-20, 470, 200], np.int32)
+    H = clf.Classify(capi.make_boxes(col, row, np.ones(3, np.float32), np.ones(3, np.float32)))
+    assert np.isfinite(H).all()
+    pf.close(); clf.close()

@@ -1,0 +1,81 @@
+"""Multi-camera host logic on CPU: world_size-2 gloo groups (one process per camera), 127.0.0.1 rendezvous.
+Covers the cross-camera exchange of multicameratracking_b200/network.py and the bench's max-over-ranks
+reduction; no GPU and no CUDA call."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from multicameratracking_b200.network import CameraNetworkExchange, drop_samples
+        n_obj, F = 3, 7
+        ex = CameraNetworkExchange(n_obj)
+        assert (ex.rank, ex.world) == (rank, world)
+        # geometric fuser: foot points, camera id = rank
+        local = torch.arange(n_obj * 2, dtype=torch.float32).reshape(n_obj, 2) + 100.0 * rank
+        allp = ex.allgather_foot_points(local)
+        assert tuple(allp.shape) == (world, n_obj, 2)
+        for r in range(world):
+            assert torch.equal(allp[r], torch.arange(n_obj * 2, dtype=torch.float32).reshape(n_obj, 2) + 100.0 * r)
+        with pytest.raises(ValueError):
+            ex.allgather_foot_points(torch.zeros(n_obj + 1, 2))
+        # appearance fuser: ragged feature rows, pooled in camera order
+        g = torch.Generator().manual_seed(1234)
+        P = [5, 2][rank % 2] + rank
+        Nn = [1, 4][rank % 2]
+        rows = {r: (torch.rand(F, [5, 2][r % 2] + r, generator=torch.Generator().manual_seed(10 + r)),
+                    torch.rand(F, [1, 4][r % 2], generator=torch.Generator().manual_seed(20 + r))) for r in range(world)}
+        fpos, fneg = rows[rank]
+        assert fpos.shape[1] == P and fneg.shape[1] == Nn
+        pos, neg, counts = ex.allgather_feature_rows(fpos, fneg)
+        assert torch.equal(pos, torch.cat([rows[r][0] for r in range(world)], dim=1))
+        assert torch.equal(neg, torch.cat([rows[r][1] for r in range(world)], dim=1))
+        assert counts.tolist() == [[rows[r][0].shape[1], rows[r][1].shape[1]] for r in range(world)]
+        # timing reduction used by bench.py: max over ranks, sum over ranks
+        assert ex.max_over_ranks(1.0 + rank) == float(world)
+        assert ex.sum_over_ranks(10.0) == 10.0 * world
+        # random sample dropping of the appearance fuser follows the MWC stream in order
+        seq = iter([0.9, 0.1, 0.6, 0.5, 0.51])
+        assert drop_samples(lambda: next(seq), 5) == [0, 2, 4]
+        q.put((rank, "ok"))
+    except BaseException as e:           # noqa: BLE001 - report to the parent
+        q.put((rank, "FAIL %r" % (e,)))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_camera_network_exchange_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_bench_shards_cameras_by_rank():
+    """one camera per rank: synthetic sequences and noise streams differ per camera and are reproducible"""
+    from multicameratracking_b200 import synth
+    a0 = synth.Sequence(320, 240, 2, camera=0, n_frames=4, obj_wh=(20, 30)).frame(1)[0]
+    a1 = synth.Sequence(320, 240, 2, camera=1, n_frames=4, obj_wh=(20, 30)).frame(1)[0]
+    b0 = synth.Sequence(320, 240, 2, camera=0, n_frames=4, obj_wh=(20, 30)).frame(1)[0]
+    assert np.array_equal(a0, b0) and not np.array_equal(a0, a1)
+    assert not np.array_equal(synth.noise(16, (1, 1, 1, 1), camera=0, obj=0, t=1), synth.noise(16, (1, 1, 1, 1), camera=1, obj=0, t=1))
