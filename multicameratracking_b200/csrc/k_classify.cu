@@ -139,7 +139,8 @@ k_classify_staged(const ObjDesc* __restrict__ descs, const float* __restrict__ i
     extern __shared__ __align__(128) unsigned char smraw[];
     __shared__ int s_bb[4];
     __shared__ __align__(8) uint64_t s_bar[2];
-    const ObjDesc& d = descs[blockIdx.y];
+    __shared__ ObjDesc s_desc;
+    const ObjDesc& d = load_desc(descs + blockIdx.y, &s_desc);
     const int tid = threadIdx.x, lane = tid & 31;
     const int N = d.N;
     const int chunk = (N + gridDim.x - 1) / gridDim.x;

@@ -428,7 +428,8 @@ k_mdch_sel(const ObjDesc* __restrict__ descs, const uint16_t* __restrict__ binim
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ int s_bb[4], s_ref, s_rows, s_cols;
     __shared__ uint32_t s_tot[MDS_WARPS];
-    const ObjDesc& d = descs[blockIdx.y];
+    __shared__ ObjDesc s_desc;
+    const ObjDesc& d = load_desc(descs + blockIdx.y, &s_desc);
     if (d.slotmap == nullptr) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = d.N;

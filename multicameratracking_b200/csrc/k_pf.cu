@@ -12,7 +12,19 @@
 #include "mct_internal.cuh"
 #include <math_constants.h>
 
-#define PF_THREADS 1024
+#define PF_THREADS 512
+
+#ifdef MCT_PF_DEBUG
+__device__ unsigned long long g_pf_dbg[64];      // [0..31] last launch without resampling, [32..63] last launch that resampled
+__shared__ unsigned long long s_pf_dbg[32];
+__device__ __forceinline__ unsigned long long pf_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define PF_STAMP(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) s_pf_dbg[k] = pf_gtime(); } while (0)
+#define PF_COMMIT(res) do { if (blockIdx.x == 0 && threadIdx.x == 0) for (int q_ = 0; q_ < 32; q_++) g_pf_dbg[((res) ? 32 : 0) + q_] = s_pf_dbg[q_]; } while (0)
+extern "C" int mct_debug_pf_stamps(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, g_pf_dbg, sizeof(unsigned long long) * 64); }
+#else
+#define PF_STAMP(k)
+#define PF_COMMIT(res)
+#endif
 
 __device__ __forceinline__ float block_reduce_minmax(float v, bool is_max, float* sh)
 {
@@ -50,6 +62,31 @@ __device__ __forceinline__ double block_reduce_sum_d(double v, double* sh)
     __syncthreads();
     return sh[0];
 }
+// count + min + max in one pass: two barriers instead of nine
+__device__ __forceinline__ void block_reduce_cnt_minmax(int& cnt, float& mn, float& mx, float* shf, int* shi)
+{
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) { shi[warp] = cnt; shf[warp] = mn; shf[32 + warp] = mx; }
+    __syncthreads();
+    cnt = 0; mn = CUDART_INF_F; mx = -CUDART_INF_F;
+    for (int q = 0; q < nw; q++) { cnt += shi[q]; mn = fminf(mn, shf[q]); mx = fmaxf(mx, shf[32 + q]); }
+}
+// five f64 sums in one pass
+__device__ __forceinline__ void block_reduce_sum_d5(double* acc, double* sh /* [5][32] */)
+{
+    for (int q = 0; q < 5; q++) acc[q] = warp_sum_d(acc[q]);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) for (int q = 0; q < 5; q++) sh[q * 32 + warp] = acc[q];
+    __syncthreads();
+    for (int q = 0; q < 5; q++) { double t = 0.0; for (int k = 0; k < nw; k++) t += sh[q * 32 + k]; acc[q] = t; }
+}
 __device__ __forceinline__ int block_reduce_sum_i(int v, int* sh)
 {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -76,6 +113,11 @@ __device__ __forceinline__ double ipow_d(double x, int n)
     while (n) { if (n & 1) r *= b; b *= b; n >>= 1; }
     return r;
 }
+
+// Correctly rounded f32 quotient through one f64 division: 53 >= 2*24 + 2 bits, so the double rounding is innocuous
+// (Figueroa) and the result equals __fdiv_rn bit for bit -- but f32 denormals (the ^20 likelihood map produces many)
+// are normal numbers in f64, so the division never takes the slow special-case path.
+__device__ __forceinline__ float fdiv_exact(float a, float b) { return (float)((double)a / (double)b); }
 
 // ParticleFilter::UpdateParticleWeight scale-ratio clamp (ParticleFilter.cpp:658-665): 1.2 and 0.9 are
 // double literals, so the comparison and the product are evaluated in double.
@@ -152,7 +194,8 @@ __global__ void __launch_bounds__(256) k_pf_testset(const ObjDesc* __restrict__ 
 // batched per-frame form: PredictWithBrownianMotion + GenerateTestSampleSet in one pass over the particles
 __global__ void __launch_bounds__(256) k_pf_predict_testset(const ObjDesc* __restrict__ descs, const StepArgs sa, int fw, int fh)
 {
-    const ObjDesc& d = descs[blockIdx.y];
+    __shared__ ObjDesc s_desc;
+    const ObjDesc& d = load_desc(descs + blockIdx.y, &s_desc);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         d.st->filter_state = MCT_PF_PREDICTED; d.st->time_index += 1;
@@ -175,59 +218,59 @@ int launch_pf_testset(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max)
     return MCT_OK;
 }
 
-// Sequential f32 chains in reference order.  The dependent FADD (4 cycles) is the only thing on the critical
-// path: operands are fetched as float4 one 16-element block AHEAD into registers, so the load latency of block
-// k+1 hides behind the 64 cycles of adds of block k (the earlier scalar-load version paid LDS latency + issue per
-// 8 adds: 9.6 cycles per element instead of 4).  v / w / cdf must be 16-byte aligned.
-#define MCT_ADD4(t, q) t = __fadd_rn(t, q.x); t = __fadd_rn(t, q.y); t = __fadd_rn(t, q.z); t = __fadd_rn(t, q.w)
-__device__ __forceinline__ float chain_sum(const float* __restrict__ v, int n)
+// Sequential f32 chains in reference order, run by ONE WARP out of registers.
+//   NormalizeParticleWeights (:987-1011) and the CDF (:927-933) are dependent FADD chains (4 cycles per element); any
+//   load, store or register move inside the chain costs extra (measured: 6.4 cycles per element with shared-memory
+//   operands, 12+ with the CDF stores).  Here lane L of warp 0 holds elements [64 L, 64 L + 64) of a 2048-element tile
+//   in registers; the lanes run their 64 adds one after the other (the running value hops from lane to lane with a
+//   shuffle), so the chain is pure FADD, and the CDF values stay in registers until the whole tile is done and are
+//   then written out by all lanes at once.
+//   Layout: element e of sw / cdf lives at index PIDX(e) = e + (e >> 6): one pad word per 64 elements makes the
+//   lane-blocked register loads and stores bank-conflict free.
+#define MCT_CH_PER 64
+#define PIDX(e) ((e) + ((e) >> 6))
+#define PLEN(n) ((n) + ((n) >> 6) + 4)
+// returns the sequential sum of w[0..n); all 32 lanes of the calling warp must call it
+__device__ __forceinline__ float warp_chain_sum(const float* __restrict__ w, int n, int lane)
 {
-    float t = 0.0f;
-    const float4* v4 = reinterpret_cast<const float4*>(v);
-    const int n4 = n >> 2;
-    int i = 0;
-    if (n4 >= 4) {
-        float4 b0 = v4[0], b1 = v4[1], b2 = v4[2], b3 = v4[3];
-#pragma unroll 1
-        for (i = 4; i + 4 <= n4; i += 4) {
-            const float4 c0 = v4[i], c1 = v4[i + 1], c2 = v4[i + 2], c3 = v4[i + 3];
-            MCT_ADD4(t, b0); MCT_ADD4(t, b1); MCT_ADD4(t, b2); MCT_ADD4(t, b3);
-            b0 = c0; b1 = c1; b2 = c2; b3 = c3;
+    float carry = 0.0f;
+    for (int t0 = 0; t0 < n; t0 += 32 * MCT_CH_PER) {
+        float r[MCT_CH_PER];
+        const int e0 = t0 + lane * MCT_CH_PER;
+#pragma unroll
+        for (int k = 0; k < MCT_CH_PER; k++) r[k] = (e0 + k < n) ? w[PIDX(e0) + k] : 0.0f;     // x + 0.0f == x: padding is inert
+        for (int L = 0; L < 32; L++) {
+            float c = carry;
+            if (lane == L) {
+#pragma unroll
+                for (int k = 0; k < MCT_CH_PER; k++) c = __fadd_rn(c, r[k]);
+            }
+            carry = __shfl_sync(0xffffffffu, c, L);
         }
-        MCT_ADD4(t, b0); MCT_ADD4(t, b1); MCT_ADD4(t, b2); MCT_ADD4(t, b3);
     }
-    for (int k = i * 4; k < n; k++) t = __fadd_rn(t, v[k]);
-    return t;
+    return carry;
 }
-// cdf[0] = 0, cdf[i] = cdf[i-1] + w[i]   (ParticleFilter.cpp:927-933; w[0] excluded -- reference quirk)
-#define MCT_CDF4(c, q, o) o.x = (c = __fadd_rn(c, q.x)); o.y = (c = __fadd_rn(c, q.y)); o.z = (c = __fadd_rn(c, q.z)); o.w = (c = __fadd_rn(c, q.w))
-__device__ __forceinline__ void chain_cdf(const float* __restrict__ w, float* __restrict__ cdf, int n)
+// cdf[0] = 0, cdf[i] = cdf[i-1] + w[i]  (ParticleFilter.cpp:927-933; w[0] excluded -- reference quirk)
+__device__ __forceinline__ void warp_chain_cdf(const float* __restrict__ w, float* __restrict__ cdf, int n, int lane)
 {
-    const float4* w4 = reinterpret_cast<const float4*>(w);
-    float4* c4 = reinterpret_cast<float4*>(cdf);
-    const int n4 = n >> 2;
-    float c = 0.0f;
-    int i = 0;
-    if (n4 >= 3) {
-        // first block: element 0 contributes 0 (cdf[0] = 0, w[0] skipped)
-        float4 b0 = w4[0], b1 = w4[1];
-        b0.x = 0.0f;
-#pragma unroll 1
-        for (i = 2; i + 2 <= n4; i += 2) {
-            const float4 n0 = w4[i], n1 = w4[i + 1];
-            float4 o0, o1;
-            MCT_CDF4(c, b0, o0); MCT_CDF4(c, b1, o1);
-            c4[i - 2] = o0; c4[i - 1] = o1;
-            b0 = n0; b1 = n1;
+    float carry = 0.0f;
+    for (int t0 = 0; t0 < n; t0 += 32 * MCT_CH_PER) {
+        float r[MCT_CH_PER];
+        const int e0 = t0 + lane * MCT_CH_PER;
+#pragma unroll
+        for (int k = 0; k < MCT_CH_PER; k++) r[k] = (e0 + k < n) ? w[PIDX(e0) + k] : 0.0f;
+        if (e0 == 0) r[0] = 0.0f;                         // w[0] does not enter the CDF
+        for (int L = 0; L < 32; L++) {
+            float c = carry;
+            if (lane == L) {
+#pragma unroll
+                for (int k = 0; k < MCT_CH_PER; k++) { c = __fadd_rn(c, r[k]); r[k] = c; }
+            }
+            carry = __shfl_sync(0xffffffffu, c, L);
         }
-        float4 o0, o1;
-        MCT_CDF4(c, b0, o0); MCT_CDF4(c, b1, o1);
-        c4[i - 2] = o0; c4[i - 1] = o1;
-    } else {
-        cdf[0] = 0.0f;
-        i = 0;
+#pragma unroll
+        for (int k = 0; k < MCT_CH_PER; k++) if (e0 + k < n) cdf[PIDX(e0) + k] = r[k];
     }
-    for (int k = (i == 0 ? 1 : i * 4); k < n; k++) { c = __fadd_rn(c, w[k]); cdf[k] = c; }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -236,37 +279,70 @@ __device__ __forceinline__ void chain_cdf(const float* __restrict__ w, float* __
 __device__ void resample_body(const ObjDesc& d, float* sw, float* cdf, int force, float* sh_f, float u01)
 {
     const int N = d.N, tid = threadIdx.x, nt = blockDim.x;
-    // NormalizeParticleWeights again (:924)
-    if (tid == 0) sh_f[0] = chain_sum(sw, N);
+    PF_STAMP(6);
+    // NormalizeParticleWeights again (:924): chain on warp 0, the divisions on all threads (tiny weights take the
+    // slow denormal path of the IEEE division: keep them off the serial warp)
+    if (tid < 32) { const float t2 = warp_chain_sum(sw, N, tid); if (tid == 0) sh_f[0] = t2; }
     __syncthreads();
     const float total = sh_f[0];
-    for (int i = tid; i < N; i += nt) sw[i] = (total != 0) ? __fdiv_rn(sw[i], total) : 1e-2f;
+    for (int i = tid; i < N; i += nt) sw[PIDX(i)] = (total != 0) ? fdiv_exact(sw[PIDX(i)], total) : 1e-2f;
     __syncthreads();
-    if (tid == 0) chain_cdf(sw, cdf, N);
+    // CDF (:927-933): warp 0, out of registers
+    if (tid < 32) warp_chain_cdf(sw, cdf, N, tid);
     __syncthreads();
+    PF_STAMP(7);
     const float invN = __fdiv_rn(1.0f, (float)N);
     const float seed = __fmul_rn(invN, u01);
-    for (int i = tid; i < N; i += nt) {
-        const float thr = __fadd_rn(seed, __fmul_rn(invN, (float)i));
-        // idx = min(N-1, #{j : cdf[j] < thr})  == the reference's monotone walk
-        int lo = 0, hi = N;
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            if (cdf[mid] < thr) lo = mid + 1; else hi = mid;
+    int top = 1;
+    while ((top << 1) <= N) top <<= 1;
+    for (int i0 = tid; i0 < N; i0 += 4 * nt) {
+        // idx = min(N-1, #{j : cdf[j] < thr})  == the reference's monotone walk; four branch-free
+        // lower-bound searches run in lock-step so that their shared-memory latencies overlap
+        float thr[4]; int lo[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { thr[k] = __fadd_rn(seed, __fmul_rn(invN, (float)(i0 + k * nt))); lo[k] = 0; }
+        for (int step = top; step > 0; step >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int m = lo[k] + step;
+                if (m <= N && cdf[PIDX(m - 1)] < thr[k]) lo[k] = m;
+            }
         }
-        const int idx = lo < N - 1 ? lo : N - 1;
-        d.residx[i] = idx;
-        d.rcx[i] = d.cx[idx]; d.rcy[i] = d.cy[idx]; d.rsx[i] = d.sx[idx]; d.rsy[i] = d.sy[idx];
-        d.rw[i] = 1.0f;
+        int idx[4]; float gx[4], gy[4], gsx[4], gsy[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            idx[k] = lo[k] < N - 1 ? lo[k] : N - 1;
+            gx[k] = d.cx[idx[k]]; gy[k] = d.cy[idx[k]]; gsx[k] = d.sx[idx[k]]; gsy[k] = d.sy[idx[k]];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = i0 + k * nt;
+            if (i < N) {
+                d.residx[i] = idx[k];
+                d.rcx[i] = gx[k]; d.rcy[i] = gy[k]; d.rsx[i] = gsx[k]; d.rsy[i] = gsy[k];
+                d.rw[i] = 1.0f;
+            }
+        }
     }
     __syncthreads();
+    PF_STAMP(8);
     if (force) {
-        for (int i = tid; i < N; i += nt) {
-            d.cx[i] = d.rcx[i]; d.cy[i] = d.rcy[i]; d.sx[i] = d.rsx[i]; d.sy[i] = d.rsy[i]; d.w[i] = 1.0f;
+        for (int i0 = tid; i0 < N; i0 += 4 * nt) {
+            float gx[4], gy[4], gsx[4], gsy[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int i = min(i0 + k * nt, N - 1);
+                gx[k] = d.rcx[i]; gy[k] = d.rcy[i]; gsx[k] = d.rsx[i]; gsy[k] = d.rsy[i];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int i = i0 + k * nt;
+                if (i < N) { d.cx[i] = gx[k]; d.cy[i] = gy[k]; d.sx[i] = gsx[k]; d.sy[i] = gsy[k]; d.w[i] = 1.0f; }
+            }
         }
         if (tid == 0) d.st->filter_state = MCT_PF_RESAMPLED;
     } else {
-        for (int i = tid; i < N; i += nt) d.w[i] = sw[i];
+        for (int i = tid; i < N; i += nt) d.w[i] = sw[PIDX(i)];
     }
 }
 
@@ -280,26 +356,31 @@ __global__ void __launch_bounds__(PF_THREADS) k_pf_update(const ObjDesc* __restr
                                                           int with_summary)
 {
     extern __shared__ __align__(16) float smf[];
-    __shared__ float sh_f[32];
+    __shared__ float sh_f[64];
     __shared__ double sh_d[32];
     __shared__ int sh_i[32];
     __shared__ int s_decide;
-    const ObjDesc& d = descs[blockIdx.x];
+    __shared__ ObjDesc s_desc;
+    const ObjDesc& d = load_desc(descs + blockIdx.x, &s_desc);
     const int N = d.N, tid = threadIdx.x, nt = blockDim.x;
-    const int N4 = (N + 3) & ~3;
+    const int N4 = (PLEN(N) + 3) & ~3;
     float* sw = (2 * N4 <= smem_floats) ? smf : d.scratch;
-    float* cdf = (2 * N4 <= smem_floats) ? smf + N4 : d.scratch + d.ld;
+    float* cdf = (2 * N4 <= smem_floats) ? smf + N4 : d.scratch + PLEN(d.ld);
 
+    PF_STAMP(0);
     // 0. valid count, min / max of H over the test set
     float mn = CUDART_INF_F, mx = -CUDART_INF_F;
     int cnt = 0;
-    for (int i = tid; i < N; i += nt)
-        if (d.valid[i]) { float h = d.H[i]; mn = fminf(mn, h); mx = fmaxf(mx, h); cnt++; }
-    cnt = block_reduce_sum_i(cnt, sh_i);
-    if (mode == 0) {
-        mn = block_reduce_minmax(mn, false, sh_f);
-        mx = block_reduce_minmax(mx, true, sh_f);
+    // (all per-particle loops below fetch four particles per thread before using any: the loads are L2 round trips)
+    for (int i0 = tid; i0 < N; i0 += 4 * nt) {
+        int vv[4]; float hh[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const int i = i0 + k * nt; vv[k] = (i < N) ? d.valid[i] : 0; hh[k] = (i < N) ? d.H[i] : 0.0f; }
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (vv[k]) { mn = fminf(mn, hh[k]); mx = fmaxf(mx, hh[k]); cnt++; }
     }
+    block_reduce_cnt_minmax(cnt, mn, mx, sh_f, sh_i);
+    __syncthreads();
     if (tid == 0) {
         d.st->n_valid = cnt; d.st->resampled = 0;
         if (mode == 0) {
@@ -313,34 +394,50 @@ __global__ void __launch_bounds__(PF_THREADS) k_pf_update(const ObjDesc* __restr
         return;
     }
     const double dmn = (double)mn, range = (double)mx - (double)mn;
-
+    PF_STAMP(1);
     // 1. weight update
-    for (int i = tid; i < N; i += nt) {
-        float w = d.w[i];
-        if (d.valid[i]) {
-            float p;
-            if (mode == 0) p = (range != 0) ? (float)ipow_d(((double)d.H[i] - dmn) / range, d.exponent) : 1.0f;
-            else p = d.H[i];
-            w = d.force_reset ? p : __fmul_rn(p, w);
-            float sx = d.sx[i], sy = d.sy[i];
-            scale_ratio_clamp(sx, sy);
-            d.sx[i] = sx; d.sy[i] = sy;
+    for (int i0 = tid; i0 < N; i0 += 4 * nt) {
+        int vv[4]; float hh[4], ww[4], xs[4], ys[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = i0 + k * nt;
+            const bool in = i < N;
+            vv[k] = in ? d.valid[i] : 0; hh[k] = in ? d.H[i] : 0.0f; ww[k] = in ? d.w[i] : 0.0f;
+            xs[k] = in ? d.sx[i] : 1.0f; ys[k] = in ? d.sy[i] : 1.0f;
         }
-        sw[i] = w;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = i0 + k * nt;
+            if (i >= N) continue;
+            float w = ww[k];
+            if (vv[k]) {
+                float p;
+                if (mode == 0) p = (range != 0) ? (float)ipow_d(((double)hh[k] - dmn) / range, d.exponent) : 1.0f;
+                else p = hh[k];
+                w = d.force_reset ? p : __fmul_rn(p, w);
+                float sx = xs[k], sy = ys[k];
+                scale_ratio_clamp(sx, sy);
+                d.sx[i] = sx; d.sy[i] = sy;
+            }
+            sw[PIDX(i)] = w;
+        }
     }
     __syncthreads();
-    // 2. NormalizeParticleWeights: sequential f32 total (:991-995)
-    if (tid == 0) sh_f[0] = chain_sum(sw, N);
+    PF_STAMP(2);
+    // 2. NormalizeParticleWeights: sequential f32 total (:991-995), warp 0 out of registers
+    if (tid < 32) { const float t1 = warp_chain_sum(sw, N, tid); if (tid == 0) sh_f[0] = t1; }
     __syncthreads();
+    PF_STAMP(3);
     const float total = sh_f[0];
     __syncthreads();
     double s2 = 0.0;
     for (int i = tid; i < N; i += nt) {
-        float w = (total != 0) ? __fdiv_rn(sw[i], total) : 1e-2f;
-        sw[i] = w;
+        float w = (total != 0) ? fdiv_exact(sw[PIDX(i)], total) : 1e-2f;
+        sw[PIDX(i)] = w;
         s2 += (double)w * (double)w;
     }
     s2 = block_reduce_sum_d(s2, sh_d);
+    PF_STAMP(4);
     // 3. ResampleIfRequired, WEIGHT_BASED (:845-910)
     if (tid == 0) {
         int decide = 0;
@@ -353,7 +450,7 @@ __global__ void __launch_bounds__(PF_THREADS) k_pf_update(const ObjDesc* __restr
             else if (lo >= thr) decide = 0;
             else {
                 float e = 0.0f;                                    // exact reference chain
-                for (int i = 0; i < N; i++) e = (float)((double)e + (double)sw[i] * (double)sw[i]);
+                for (int i = 0; i < N; i++) e = (float)((double)e + (double)sw[PIDX(i)] * (double)sw[PIDX(i)]);
                 neff_inv = e;
                 decide = (e != 0) && (__fdiv_rn(1.0f, e) < (float)thr);
             }
@@ -362,22 +459,26 @@ __global__ void __launch_bounds__(PF_THREADS) k_pf_update(const ObjDesc* __restr
         s_decide = decide;
     }
     __syncthreads();
+    PF_STAMP(5);
     if (s_decide) {
         resample_body(d, sw, cdf, 1, sh_f, sa.u01[blockIdx.x]);
         if (tid == 0) d.st->resampled = 1;
     } else {
-        for (int i = tid; i < N; i += nt) d.w[i] = sw[i];
+        for (int i = tid; i < N; i += nt) d.w[i] = sw[PIDX(i)];
     }
+    PF_STAMP(10);
     if (with_summary) {
         __syncthreads();                       // the read-out reads state / weights written by other threads above
-        summary_body(d, (2 * N4 <= smem_floats) ? smf : nullptr);   // sw / cdf are dead: reuse them as scratch
+        summary_body(d, (2 * N4 <= smem_floats) ? smf : nullptr);   // sw / cdf are dead: reuse them as scratch (2 * N4 floats)
     }
+    PF_STAMP(15);
+    PF_COMMIT(s_decide);
 }
 
 static int pf_update_smem(mct_ctx* ctx, int n_max, int* smem_floats, size_t* smem_bytes)
 {
     // both chains' operands in shared memory when 2*N floats fit in 200 KB, else global scratch
-    size_t want = (size_t)2 * round_up(n_max, 4) * sizeof(float);
+    size_t want = (size_t)2 * round_up(PLEN(n_max), 4) * sizeof(float);
     if (want > 200 * 1024) want = 0;
     *smem_bytes = want;
     *smem_floats = (int)(want / sizeof(float));
@@ -394,7 +495,8 @@ int launch_pf_update(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, 
         MCT_CUDA(ctx, cudaFuncSetAttribute(k_pf_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
         s_attr = sb;
     }
-    MCT_LAUNCH(ctx, "k_pf_update", k_pf_update<<<n_obj, PF_THREADS, sb, ctx->stream>>>(d_desc, sa, use_H ? 0 : 1, sf, with_summary));
+    const int nt = PF_THREADS;
+    MCT_LAUNCH(ctx, "k_pf_update", k_pf_update<<<n_obj, nt, sb, ctx->stream>>>(d_desc, sa, use_H ? 0 : 1, sf, with_summary));
     return MCT_OK;
 }
 
@@ -403,11 +505,12 @@ __global__ void __launch_bounds__(PF_THREADS) k_pf_resample(const ObjDesc* __res
 {
     extern __shared__ __align__(16) float smf[];
     __shared__ float sh_f[32];
-    const ObjDesc& d = descs[blockIdx.x];
-    const int N = d.N, N4 = (N + 3) & ~3;
+    __shared__ ObjDesc s_desc;
+    const ObjDesc& d = load_desc(descs + blockIdx.x, &s_desc);
+    const int N = d.N, N4 = (PLEN(N) + 3) & ~3;
     float* sw = (2 * N4 <= smem_floats) ? smf : d.scratch;
-    float* cdf = (2 * N4 <= smem_floats) ? smf + N4 : d.scratch + d.ld;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) sw[i] = d.w[i];
+    float* cdf = (2 * N4 <= smem_floats) ? smf + N4 : d.scratch + PLEN(d.ld);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) sw[PIDX(i)] = d.w[i];
     __syncthreads();
     resample_body(d, sw, cdf, force, sh_f, sa.u01[blockIdx.x]);
 }
@@ -485,7 +588,7 @@ int launch_pf_expand_prob(mct_ctx* ctx, const ObjDesc* d_desc, const float* d_pr
 __device__ void summary_body(const ObjDesc& d, float* scratch)
 {
     __shared__ float sh_f[32];
-    __shared__ double sh_d[32];
+    __shared__ double sh_d5[5 * 32];
     __shared__ int sh_i[32];
     __shared__ int s_first, s_last;
     const int N = d.N, tid = threadIdx.x, nt = blockDim.x;
@@ -493,13 +596,26 @@ __device__ void summary_body(const ObjDesc& d, float* scratch)
     const int fs = d.st->filter_state;
 
     double acc[5] = {0, 0, 0, 0, 0};
-    for (int i = tid; i < N; i += nt) {
-        const float w = d.w[i];
-        acc[0] += (double)__fmul_rn(d.cx[i], w); acc[1] += (double)__fmul_rn(d.cy[i], w);
-        acc[2] += (double)__fmul_rn(d.sx[i], w); acc[3] += (double)__fmul_rn(d.sy[i], w);
-        acc[4] += (double)w;
+    for (int i0 = tid; i0 < N; i0 += 4 * nt) {
+        float w[4], x[4], y[4], sx[4], sy[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = i0 + k * nt;
+            const bool in = i < N;
+            w[k] = in ? d.w[i] : 0.0f; x[k] = in ? d.cx[i] : 0.0f; y[k] = in ? d.cy[i] : 0.0f;
+            sx[k] = in ? d.sx[i] : 0.0f; sy[k] = in ? d.sy[i] : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (i0 + k * nt >= N) continue;
+            acc[0] += (double)__fmul_rn(x[k], w[k]); acc[1] += (double)__fmul_rn(y[k], w[k]);
+            acc[2] += (double)__fmul_rn(sx[k], w[k]); acc[3] += (double)__fmul_rn(sy[k], w[k]);
+            acc[4] += (double)w[k];
+        }
     }
-    for (int q = 0; q < 5; q++) acc[q] = block_reduce_sum_d(acc[q], sh_d);
+    PF_STAMP(11);
+    block_reduce_sum_d5(acc, sh_d5);
+    PF_STAMP(12);
     if (tid == 0) {
         for (int q = 0; q < 4; q++) out->average[q] = (float)(acc[q] / acc[4]);
         out->n_valid = d.st->n_valid; out->resampled = d.st->resampled; out->filter_state = fs;
@@ -558,6 +674,7 @@ __device__ void summary_body(const ObjDesc& d, float* scratch)
             }
             rw[i] = start ? r : -1.0f;
         }
+        PF_STAMP(13);
         mx = block_reduce_minmax(mx, true, sh_f);
         nruns = block_reduce_sum_i(nruns, sh_i);
         int ties = 0;
@@ -586,7 +703,8 @@ __device__ void summary_body(const ObjDesc& d, float* scratch)
 }
 __global__ void __launch_bounds__(PF_THREADS) k_pf_summary(const ObjDesc* __restrict__ descs)
 {
-    summary_body(descs[blockIdx.x], nullptr);
+    __shared__ ObjDesc s_desc;
+    summary_body(load_desc(descs + blockIdx.x, &s_desc), nullptr);
 }
 int launch_pf_summary(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max)
 {

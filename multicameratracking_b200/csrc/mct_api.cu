@@ -768,7 +768,7 @@ extern "C" int mct_pf_create(mct_ctx* ctx, int N, float image_w, float image_h, 
     MCT_CUDA(ctx, cudaMalloc(&p->d_col, ld * 4)); MCT_CUDA(ctx, cudaMalloc(&p->d_row, ld * 4));
     MCT_CUDA(ctx, cudaMalloc(&p->d_valid, ld * 4)); MCT_CUDA(ctx, cudaMalloc(&p->d_H, ld * 4));
     MCT_CUDA(ctx, cudaMalloc(&p->d_noise, 4 * ld * 4)); MCT_CUDA(ctx, cudaMalloc(&p->d_prob, ld * 4));
-    MCT_CUDA(ctx, cudaMalloc(&p->d_scratch, 2 * ld * 4));
+    MCT_CUDA(ctx, cudaMalloc(&p->d_scratch, 2 * (ld + ld / 64 + 64) * 4));   // sw | cdf in the padded chain layout (k_pf.cu PLEN)
     MCT_CUDA(ctx, cudaMalloc(&p->d_st, sizeof(PfDev))); MCT_CUDA(ctx, cudaMemset(p->d_st, 0, sizeof(PfDev)));
     MCT_CUDA(ctx, cudaMalloc(&p->d_summ, sizeof(mct_pf_summary)));
     MCT_CUDA(ctx, cudaMemset(p->d_summ, 0, sizeof(mct_pf_summary)));

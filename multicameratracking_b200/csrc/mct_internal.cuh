@@ -276,6 +276,16 @@ __device__ __forceinline__ float weak_classify_dev(int weak_type, float x, float
 // Public.h:169-172
 __device__ __forceinline__ float sigmoid_dev(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
 
+// The descriptor of this CTA's object, copied once into shared memory: every `d.field` through the global array is an
+// L2 round trip in front of the access it feeds, which is what bounds the small latency-bound kernels.
+__device__ __forceinline__ const ObjDesc& load_desc(const ObjDesc* __restrict__ g, ObjDesc* s)
+{
+    const int n = (int)(sizeof(ObjDesc) / sizeof(int));
+    for (int i = threadIdx.x; i < n; i += blockDim.x) reinterpret_cast<int*>(s)[i] = __ldg(reinterpret_cast<const int*>(g) + i);
+    __syncthreads();
+    return *s;
+}
+
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // Matrixu::sumRect (Matrix.cpp:49-67) on the padded integral image; coordinates are clamped to the
