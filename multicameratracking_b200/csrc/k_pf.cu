@@ -240,11 +240,12 @@ __device__ __forceinline__ float warp_chain_sum(const float* __restrict__ w, int
 #pragma unroll
         for (int k = 0; k < MCT_CH_PER; k++) r[k] = (e0 + k < n) ? w[PIDX(e0) + k] : 0.0f;     // x + 0.0f == x: padding is inert
         for (int L = 0; L < 32; L++) {
+            // branch-free: lanes other than L add +0.0f (exact identity for the non-negative running value), so the
+            // warp never diverges and the selects sit in the shadow of the 4-cycle dependent adds
+            const bool mine = lane == L;
             float c = carry;
-            if (lane == L) {
 #pragma unroll
-                for (int k = 0; k < MCT_CH_PER; k++) c = __fadd_rn(c, r[k]);
-            }
+            for (int k = 0; k < MCT_CH_PER; k++) c = __fadd_rn(c, mine ? r[k] : 0.0f);
             carry = __shfl_sync(0xffffffffu, c, L);
         }
     }
@@ -261,11 +262,10 @@ __device__ __forceinline__ void warp_chain_cdf(const float* __restrict__ w, floa
         for (int k = 0; k < MCT_CH_PER; k++) r[k] = (e0 + k < n) ? w[PIDX(e0) + k] : 0.0f;
         if (e0 == 0) r[0] = 0.0f;                         // w[0] does not enter the CDF
         for (int L = 0; L < 32; L++) {
+            const bool mine = lane == L;
             float c = carry;
-            if (lane == L) {
 #pragma unroll
-                for (int k = 0; k < MCT_CH_PER; k++) { c = __fadd_rn(c, r[k]); r[k] = c; }
-            }
+            for (int k = 0; k < MCT_CH_PER; k++) { c = __fadd_rn(c, mine ? r[k] : 0.0f); r[k] = mine ? c : r[k]; }
             carry = __shfl_sync(0xffffffffu, c, L);
         }
 #pragma unroll
@@ -285,6 +285,7 @@ __device__ void resample_body(const ObjDesc& d, float* sw, float* cdf, int force
     if (tid < 32) { const float t2 = warp_chain_sum(sw, N, tid); if (tid == 0) sh_f[0] = t2; }
     __syncthreads();
     const float total = sh_f[0];
+#pragma unroll 4
     for (int i = tid; i < N; i += nt) sw[PIDX(i)] = (total != 0) ? fdiv_exact(sw[PIDX(i)], total) : 1e-2f;
     __syncthreads();
     // CDF (:927-933): warp 0, out of registers
@@ -431,6 +432,7 @@ __global__ void __launch_bounds__(PF_THREADS) k_pf_update(const ObjDesc* __restr
     const float total = sh_f[0];
     __syncthreads();
     double s2 = 0.0;
+#pragma unroll 4
     for (int i = tid; i < N; i += nt) {
         float w = (total != 0) ? fdiv_exact(sw[PIDX(i)], total) : 1e-2f;
         sw[PIDX(i)] = w;
