@@ -24,7 +24,7 @@
 #include <math_constants.h>
 namespace cg = cooperative_groups;
 
-#define SEL_THREADS 256
+#define SEL_THREADS 1024
 #define SEL_MAX_CLUSTER 16
 
 struct SelSlot { float nll; int f; };

@@ -274,7 +274,8 @@ __device__ __forceinline__ float weak_classify_dev(int weak_type, float x, float
     return (float)(log(1e-5 + p1) - log(1e-5 + p0));
 }
 // Public.h:169-172
-__device__ __forceinline__ float sigmoid_dev(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+// (1.0f / y correctly rounded == __frcp_rn(y): same bits as the division, without its generic slow-path check)
+__device__ __forceinline__ float sigmoid_dev(float x) { return __frcp_rn(__fadd_rn(1.0f, expf(-x))); }
 
 // The descriptor of this CTA's object, copied once into shared memory: every `d.field` through the global array is an
 // L2 round trip in front of the access it feeds, which is what bounds the small latency-bound kernels.
