@@ -244,6 +244,8 @@ def run_ours(args):
         # as a video reader would decode ahead (Matrixu::PrefetchFrame); one frame is still copied per step
         g2, r2, gg2, b2 = planes_pin[pingpong(i + 1, POOL)]
         cam._chk(cam.L.mcth_camera_prefetch_frame(cam.h, vp(g2.data_ptr()), vp(r2.data_ptr()), vp(gg2.data_ptr()), vp(b2.data_ptr()), W, H, W))
+        if i + 1 < len(noise_pin):     # the next frame's Gaussian rows ride along as well (mct_noise_prefetch)
+            cam._chk(cam.L.mcth_camera_prefetch_noise(cam.h, vp(noise_pin[i + 1].data_ptr()), noise_pin[i + 1].numel()))
         out = np.zeros((N_OBJ, 4), np.int32)
         cam._chk(cam.L.mcth_camera_track(cam.h, t, vp(noise_pin[i].data_ptr()), phases, out.ctypes.data_as(C.POINTER(C.c_int))))
         return out
@@ -311,17 +313,23 @@ def run_ours(args):
         dom_name, (dom_ms, dom_n) = dom
         avg_us = 1e3 * dom_ms / max(dom_n, 1)
         rows, cols = seq.h0, seq.w0
-        mdch_bytes = N_OBJ * N_PART * (rows * cols * 3 + (N_BINS ** 3) * 4)   # B_mdch = N*rows*cols*3 + N*nb^3*4, all objects
-        alg = {   # ALGORITHMIC bytes per launch, see DESIGN.md
-            "k_mdch": N_PART * rows * cols * 3 + N_PART * (N_BINS ** 3) * 4,
-            "k_mdch_sel": mdch_bytes, "k_mdch_score": mdch_bytes,
-            "k_classify": N_OBJ * N_PART * (50 * 4 * 16 + (CONFIG["selected"] - 50) * 4 + 4),
-            "k_integral_band": W * H + (W + 1) * (H + 1) * 4,
-            "k_pf_update": N_OBJ * N_PART * 44,
-        }.get(dom_name, 0)
-        traffic = None
+        # ALGORITHMIC bytes per launch: what the reference's loads / stores amount to
+        n_tot = N_OBJ * N_PART
+        k_sel = CONFIG["selected"]
+        k_haar = int(np.mean([(cam.selectors(o) < N_HAAR).sum() for o in range(N_OBJ)]))      # selected Haar features (measured)
+        alg_all = {
+            "k_mdch_sel": n_tot * (rows * cols * 3 + (N_BINS ** 3) * 4),                      # B_mdch = N*rows*cols*3 + N*nb^3*4
+            "k_classify_staged": n_tot * (k_haar * 4 * 16 + (k_sel - k_haar) * 4 + 4),        # E[R_f] = 4 rects x 4 corners x 4 B
+            "k_frame_prep": W * H + (W + 1) * (H + 1) * 4 + 3 * W * H + 2 * W * H,            # integral + joint-bin image
+            "k_pf_update": n_tot * 44,
+            "k_pf_predict_testset": n_tot * 68,
+            "k_mdch_big": 0,
+        }
+        alg = alg_all.get(dom_name, 0)
+        traffic, traffic_all = None, {}
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(dom_name)
+            traffic_all = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+            traffic = traffic_all.get(dom_name)
         except Exception:
             pass
         achieved = alg / (avg_us * 1e-6) / 1e9 if avg_us > 0 else 0.0
@@ -337,7 +345,12 @@ def run_ours(args):
             "gpu_launches": int(launches_all),
             "roofline": {"kernel": dom_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
-                         "avg_launch_us": avg_us, "algorithmic_bytes_per_launch": alg, "kernel_time_shares": shares},
+                         "avg_launch_us": avg_us, "algorithmic_bytes_per_launch": alg, "kernel_time_shares": shares,
+                         "kernels": {k: {"avg_launch_us": round(1e3 * v[0] / max(v[1], 1), 2), "algorithmic_bytes": alg_all.get(k, 0),
+                                         "achieved_gbs": round(alg_all.get(k, 0) / max(1e3 * v[0] / max(v[1], 1), 1e-9) / 1e3, 1),
+                                         "dram_traffic_bytes": traffic_all.get(k)} for k, v in prof.items()},
+                         "note": "working set (~3 MB per camera) is L2/shared-memory resident: dram traffic << algorithmic bytes; "
+                                 "k_pf_update is bound by three sequential f32 add chains (bit-exact resampling), not by bandwidth"},
             "clocks": sampler.summary(),
         }
         if world == 1 and not args.no_cpu_baseline:

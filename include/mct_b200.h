@@ -19,6 +19,7 @@
  */
 #ifndef MCT_B200_H
 #define MCT_B200_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -213,6 +214,11 @@ int mct_track_score(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, mct_clf* const*
                     const mct_track_params* params /* [n_obj] */,
                     const float* noise, int noise_is_device, const float* u01,
                     mct_pf_summary* summaries);
+/* Optional: announce the host noise block ([n_obj][4][N], n_floats in total) of the NEXT mct_track_score* call.  It is
+ * uploaded on the internal copy stream while the current frame is being tracked; the next mct_track_score* called with
+ * the same host pointer then finds it on the device instead of copying it in front of its first kernel.  The host block
+ * must stay valid and unchanged until that call has been collected. */
+int mct_noise_prefetch(mct_ctx* ctx, const float* noise_host, size_t n_floats);
 /* asynchronous variant: no stream sync, summaries land in the ctx's pinned buffer; collect with
  * mct_track_collect (which synchronises). */
 int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, mct_clf* const* clfs,

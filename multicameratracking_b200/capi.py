@@ -30,7 +30,7 @@ SYMBOLS = [
     "mct_classifier_get_selectors", "mct_classifier_get_weak_state", "mct_classifier_get_predictions",
     "mct_classifier_set_cluster", "mct_pf_create", "mct_pf_destroy", "mct_pf_initialize", "mct_pf_predict",
     "mct_pf_update_all_weights", "mct_pf_resample", "mct_pf_get_state", "mct_pf_set_state", "mct_pf_get_resampled",
-    "mct_pf_get_resample_indices", "mct_pf_get_summary", "mct_track_score", "mct_track_score_async",
+    "mct_pf_get_resample_indices", "mct_pf_get_summary", "mct_track_score", "mct_noise_prefetch", "mct_track_score_async",
     "mct_track_collect", "mct_track_update", "mct_pf_get_last_response", "mct_fuser_pack_foot_points",
 ]
 
@@ -122,6 +122,7 @@ def load():
                                   _c_float_p, C.POINTER(PfSummary)]
     L.mct_track_score_async.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(TrackParams), vp, C.c_int,
                                         _c_float_p]
+    L.mct_noise_prefetch.argtypes = [vp, vp, C.c_size_t]
     L.mct_track_collect.argtypes = [vp, C.c_int, C.POINTER(PfSummary)]
     L.mct_track_update.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(Boxes), C.POINTER(Boxes)]
     L.mct_pf_get_last_response.argtypes = [vp, _c_float_p, _c_int_p]

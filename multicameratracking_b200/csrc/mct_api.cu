@@ -189,7 +189,7 @@ extern "C" int mct_ctx_destroy(mct_ctx* ctx)
     for (int i = 0; i < 4; i++) if (ctx->own_planes[i]) cudaFree(ctx->own_planes[i]);
     if (ctx->prep_stream) {
         cudaStreamSynchronize(ctx->prep_stream); cudaStreamDestroy(ctx->prep_stream);
-        cudaEventDestroy(ctx->ev_ready); cudaEventDestroy(ctx->ev_mark[0]); cudaEventDestroy(ctx->ev_mark[1]); cudaEventDestroy(ctx->ev_gather);
+        cudaEventDestroy(ctx->ev_ready); cudaEventDestroy(ctx->ev_mark[0]); cudaEventDestroy(ctx->ev_mark[1]); cudaEventDestroy(ctx->ev_gather); cudaEventDestroy(ctx->ev_noise);
     }
     for (int i = 0; i < 4; i++) if (ctx->back.planes[i]) cudaFree(ctx->back.planes[i]);
     if (ctx->back.ii_base) cudaFree(ctx->back.ii_base);
@@ -202,6 +202,7 @@ extern "C" int mct_ctx_destroy(mct_ctx* ctx)
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->h_summ) cudaFreeHost(ctx->h_summ);
     if (ctx->d_noise_stage) cudaFree(ctx->d_noise_stage);
+    for (int i = 0; i < 2; i++) if (ctx->d_noise_pf[i]) cudaFree(ctx->d_noise_pf[i]);
     if (ctx->h_tdesc) { cudaFreeHost(ctx->h_tdesc); cudaFree(ctx->d_tdesc); cudaEventDestroy(ctx->ev_train); }
     if (ctx->h_train_stage) cudaFreeHost(ctx->h_train_stage);
     if (ctx->d_train_stage) cudaFree(ctx->d_train_stage);
@@ -246,6 +247,7 @@ static int frame_streams(mct_ctx* ctx)
     MCT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_mark[0], cudaEventDisableTiming));
     MCT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_mark[1], cudaEventDisableTiming));
     MCT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_gather, cudaEventDisableTiming));
+    MCT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_noise, cudaEventDisableTiming));
     return MCT_OK;
 }
 static void frame_swap(mct_ctx* ctx)
@@ -971,12 +973,18 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
         if (p->N > n_max) n_max = p->N;
         if (c->K > K_max) K_max = c->K;
     }
-    // prediction noise: device pointers are used in place; host noise is staged with ONE copy
+    // prediction noise: device pointers are used in place; a block announced with mct_noise_prefetch is already on the
+    // device; any other host noise is staged with ONE copy
     if (noise_is_device) sa.noise_base = noise;
-    else {
+    else if (ctx->npf_ready && ctx->npf_ready_src == noise && ctx->npf_ready_n == ntot) {
+        MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_noise, 0));
+        sa.noise_base = ctx->d_noise_pf[ctx->noise_pf_cur];
+        ctx->npf_ready = 0;
+    } else {
         if (ntot > ctx->noise_stage_cap) {
             MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             if (ctx->d_noise_stage) cudaFree(ctx->d_noise_stage);
+    for (int i = 0; i < 2; i++) if (ctx->d_noise_pf[i]) cudaFree(ctx->d_noise_pf[i]);
     if (ctx->h_tdesc) { cudaFreeHost(ctx->h_tdesc); cudaFree(ctx->d_tdesc); cudaEventDestroy(ctx->ev_train); }
     if (ctx->h_train_stage) cudaFreeHost(ctx->h_train_stage);
     if (ctx->d_train_stage) cudaFree(ctx->d_train_stage);
@@ -987,6 +995,22 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
         sa.noise_base = ctx->d_noise_stage;
     }
     if (ctx->prep_stream && (rc = prefetch_copy(ctx))) return rc;      // next frame's planes: behind this frame's noise copy
+    if (ctx->npf_req && ctx->prep_stream) {
+        // next call's noise: into the other prefetch buffer (last read two frames ago; those kernels are covered by the
+        // marker of the latest mct_frame_set, which the copy stream waits for)
+        const int nb = ctx->noise_pf_cur ^ 1;
+        if (ctx->npf_req_n > ctx->noise_pf_cap[nb]) {
+            MCT_CUDA(ctx, cudaDeviceSynchronize());
+            if (ctx->d_noise_pf[nb]) cudaFree(ctx->d_noise_pf[nb]);
+            MCT_CUDA(ctx, cudaMalloc(&ctx->d_noise_pf[nb], ctx->npf_req_n * sizeof(float)));
+            ctx->noise_pf_cap[nb] = ctx->npf_req_n;
+        }
+        MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->prep_stream, ctx->ev_mark[ctx->mark_idx], 0));
+        MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_noise_pf[nb], ctx->npf_req_src, ctx->npf_req_n * sizeof(float), cudaMemcpyHostToDevice, ctx->prep_stream));
+        MCT_CUDA(ctx, cudaEventRecord(ctx->ev_noise, ctx->prep_stream));
+        ctx->noise_pf_cur = nb;
+        ctx->npf_ready_src = ctx->npf_req_src; ctx->npf_ready_n = ctx->npf_req_n; ctx->npf_ready = 1; ctx->npf_req = 0;
+    }
     const ObjDesc* d;
     if ((rc = desc_publish(ctx, h, n_obj, &d))) return rc;
     if ((rc = launch_pf_predict_testset(ctx, d, n_obj, n_max, sa))) return rc;
@@ -1018,6 +1042,15 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
         if ((rc = prefetch_prep(ctx))) return rc;
     }
     if ((rc = launch_pf_update(ctx, d, n_obj, n_max, 1, sa, 1))) return rc;
+    return MCT_OK;
+}
+
+extern "C" int mct_noise_prefetch(mct_ctx* ctx, const float* noise_host, size_t n_floats)
+{
+    if (!ctx || !noise_host || n_floats == 0) return MCT_E_ARG;
+    int rc = frame_streams(ctx);
+    if (rc) return rc;
+    ctx->npf_req_src = noise_host; ctx->npf_req_n = n_floats; ctx->npf_req = 1;
     return MCT_OK;
 }
 

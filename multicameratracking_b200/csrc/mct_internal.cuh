@@ -68,6 +68,10 @@ struct mct_ctx {
     void* desc_last_h; const void* desc_last_d; int desc_last_n;   // last published descriptor set (skip identical uploads)
     mct_pf_summary* h_summ; mct_pf_summary* h_summ_dev; int summ_cap;   // pinned, device-mapped read-out buffer (kernels write it directly)
     float* d_noise_stage; size_t noise_stage_cap;
+    float* d_noise_pf[2]; size_t noise_pf_cap[2]; int noise_pf_cur;         // prefetched noise blocks (mct_noise_prefetch)
+    const float* npf_ready_src; size_t npf_ready_n; int npf_ready;          // block already on the device, in d_noise_pf[noise_pf_cur]
+    const float* npf_req_src; size_t npf_req_n; int npf_req;               // block announced for the next call
+    cudaEvent_t ev_noise;
     TrainDesc* h_tdesc; TrainDesc* d_tdesc; cudaEvent_t ev_train;   // batched UpdateClassifier descriptors (pinned + device)
     int* h_train_stage; int* d_train_stage; size_t train_stage_cap;   // packed training boxes of all objects (4 x 4-byte arrays)      // staging for host-provided prediction noise (one H2D per call)
     float* d_tmp; size_t tmp_cap;                      // scratch (sum_rects etc.)

@@ -69,6 +69,14 @@ int mcth_camera_prefetch_frame(mcth_camera* c, const uint8_t* gray, const uint8_
     GUARD(c->frame.PrefetchFrame(gray, c0, c1, c2, W, H, pitch));
 }
 
+// announce the Gaussian rows of the NEXT mcth_camera_track call so that they are uploaded during the current frame
+int mcth_camera_prefetch_noise(mcth_camera* c, const float* noise, size_t n_floats)
+{
+    int rc = mct_noise_prefetch(c->ctx, noise, n_floats);
+    if (rc) c->err = mct_last_error(c->ctx);
+    return rc;
+}
+
 int mcth_camera_add_object(mcth_camera* c, const mcth_object_params* p)
 {
     GUARD({

@@ -604,3 +604,33 @@ def test_edge_cases_errors_and_empty_inputs(ctx, oracle):
     H = clf.Classify(capi.make_boxes(col, row, np.ones(3, np.float32), np.ones(3, np.float32)))
     assert np.isfinite(H).all()
     pf.close(); clf.close()
+
+
+def test_noise_prefetch_matches_inline_copy(ctx, oracle):
+    """mct_noise_prefetch: the announced block is uploaded during the previous call and gives identical results"""
+    seq = synth.Sequence(640, 480, 1)
+    w0, h0, N = seq.w0, seq.h0, 800
+    t, arrs = haar_table(oracle, 60, w0, h0)
+    gray, r, g, b = seq.frame(0)
+    ctx.frame_set(gray, r, g, b)
+    clf = capi.StrongClassifier(ctx, capi.FEAT_HAAR, w0, h0, n_haar=60, n_selected=12, haar=arrs)
+    pos, neg = _train_sets(oracle, seq, 0, 0)
+    clf.Update(capi.make_boxes(*pos), capi.make_boxes(*neg))
+    x, y, w, h = seq.box(0, 0)
+    nz = [np.ascontiguousarray(synth.noise(N, (20, 20, 1e-7, 1e-7), obj=0, t=k)[None]) for k in range(4)]
+    states = []
+    for use_prefetch in (False, True):
+        pf = capi.ParticleFilter(ctx, N, 640, 480); pf.Initialize(x + w / 2, y + h / 2)
+        out = []
+        for k in range(1, 4):
+            gray, r, g, b = seq.frame(k)
+            ctx.frame_set(gray, r, g, b)
+            if use_prefetch and k + 1 < 4:
+                ctx.check(ctx.L.mct_noise_prefetch(ctx.h, nz[k + 1].ctypes.data_as(C.c_void_p), nz[k + 1].size))
+            capi.track_score(ctx, [pf], [clf], [(w0, h0, 20, 0, 1)], nz[k], [0.3])
+            out.append(pf.state().copy())
+        states.append(out)
+        pf.close()
+    for a, bb in zip(*states):
+        np.testing.assert_array_equal(a, bb)
+    clf.close()
