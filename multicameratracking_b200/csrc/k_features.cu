@@ -63,8 +63,9 @@ k_haar_matrix_batch(const TrainDesc* __restrict__ descs, const float* __restrict
 //   - boxes with more than MCT_MDCH_SEG_PIX pixels are processed in row segments, each flushed to an
 //     f32 accumulator, so the u32 bins cannot overflow at any scale;
 //   - normalizeVec (Public.h:270-275): bins / sum(bins).
-#define MDCH_TILE 32
+#define MDCH_TILE 8
 #define MDCH_WARPS 8
+#define MDCH_CHUNK 1024
 __device__ __forceinline__ void
 mdch_body(const uint16_t* __restrict__ binimg, int W, int H, int nb, int w0, int h0,
        const int* __restrict__ col, const int* __restrict__ row, const float* __restrict__ sx,
@@ -76,9 +77,11 @@ mdch_body(const uint16_t* __restrict__ binimg, int W, int H, int nb, int w0, int
     uint32_t* hist_all = (uint32_t*)smraw;                         // [MDCH_WARPS][dim]
     float* acc_all = (float*)(hist_all + MDCH_WARPS * dim);        // [MDCH_WARPS][dim] f32 accumulators
     float* tile = acc_all + MDCH_WARPS * dim;                      // [n_out][MDCH_TILE+1]
+    uint16_t* buf_all = (uint16_t*)(tile + (size_t)n_out * (MDCH_TILE + 1));   // [MDCH_WARPS][MDCH_CHUNK]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* hist = hist_all + warp * dim;
     float* acc = acc_all + warp * dim;
+    uint16_t* buf = buf_all + warp * MDCH_CHUNK;
     const int i0 = blockIdx.x * MDCH_TILE;
     if (i0 >= n) return;                                            // block-uniform (batched launches use the largest grid)
 
@@ -108,19 +111,34 @@ mdch_body(const uint16_t* __restrict__ binimg, int W, int H, int nb, int w0, int
             int shift = __clz(max(npix, 1));
             if (shift > MCT_FIX_SHIFT_MAX) shift = MCT_FIX_SHIFT_MAX;
             const float scale = (float)(1u << shift);
-            // lanes stride over the flattened segment; (r, c) tracked incrementally
-            int c = lane, r = rs;
-            while (c >= cols && r < re) { c -= cols; r++; }
-            while (r < re) {
-                const int yy = clampi(r0 + r, 0, H - 1), xx = clampi(c0 + c, 0, W - 1);
-                const unsigned bin = binimg[(size_t)yy * W + xx];
-                const double dx = (double)__fsub_rn(cX, (float)(c0 + c));
-                const double dy = (double)__fsub_rn(cY, (float)(r0 + r));
-                const float wd = (float)(dx * dx * ivx + dy * dy * ivy);
-                const float wgt = expf(-wd);
-                atomicAdd(&hist[bin], __float2uint_rn(__fmul_rn(wgt, scale)));
-                c += 32;
-                while (c >= cols && r < re) { c -= cols; r++; }
+            // lanes stride over the flattened segment in chunks of MDCH_CHUNK pixels: the joint bins of a chunk are first
+            // fetched into a per-warp shared buffer with independent loads (8 in flight per lane; they come from L2, and
+            // issued one per iteration in front of the atomics they were what bounded this kernel), then binned.
+            const unsigned magic = 0xFFFFFFFFu / (unsigned)cols + 1u;       // p / cols == umulhi(p, magic) for p < 65536
+            for (int pc = 0; pc < npix; pc += MDCH_CHUNK) {
+#pragma unroll 8
+                for (int k = 0; k < MDCH_CHUNK / 32; k++) {
+                    const int q = lane + 32 * k, p = pc + q;
+                    if (p < npix) {
+                        const int r = (int)__umulhi((unsigned)p, magic), c = p - r * cols;
+                        const int yy = clampi(r0 + rs + r, 0, H - 1), xx = clampi(c0 + c, 0, W - 1);
+                        buf[q] = binimg[(size_t)yy * W + xx];
+                    }
+                }
+                __syncwarp();
+                for (int k = 0; k < MDCH_CHUNK / 32; k++) {
+                    const int q = lane + 32 * k, p = pc + q;
+                    if (p < npix) {
+                        const int r = (int)__umulhi((unsigned)p, magic), c = p - r * cols;
+                        const unsigned bin = buf[q];
+                        const double dx = (double)__fsub_rn(cX, (float)(c0 + c));
+                        const double dy = (double)__fsub_rn(cY, (float)(r0 + rs + r));
+                        const float wd = (float)(dx * dx * ivx + dy * dy * ivy);
+                        const float wgt = expf(-wd);
+                        atomicAdd(&hist[bin], __float2uint_rn(__fmul_rn(wgt, scale)));
+                    }
+                }
+                __syncwarp();
             }
             __syncwarp();
             const float inv = __fdiv_rn(1.0f, scale);
@@ -225,7 +243,8 @@ static int launch_haar_rows(mct_clf* clf, const int* d_col, const int* d_row, co
 
 static size_t mdch_smem(int dim, int n_out)
 {
-    return (size_t)MDCH_WARPS * dim * (sizeof(uint32_t) + sizeof(float)) + (size_t)n_out * (MDCH_TILE + 1) * sizeof(float);
+    return (size_t)MDCH_WARPS * dim * (sizeof(uint32_t) + sizeof(float)) + (size_t)n_out * (MDCH_TILE + 1) * sizeof(float) +
+           (size_t)MDCH_WARPS * MDCH_CHUNK * sizeof(uint16_t);
 }
 
 static int launch_mdch_rows(mct_clf* clf, const int* d_col, const int* d_row, const float* d_sx, const float* d_sy,
