@@ -68,31 +68,6 @@ k_classify(const ObjDesc* __restrict__ descs, const float* __restrict__ ii, int 
 //   4. log(1e-5+p1) - log(1e-5+p0) is evaluated as one f64 log of the f64 quotient (half the f64 log count;
 //      identical after rounding to f32 except for sub-ulp ties).
 // Falls back to global gathers (same arithmetic) when the region does not fit.
-__device__ __forceinline__ float sum_rect_region(const float* __restrict__ reg, int rp, int ox, int oy, int W, int H,
-                                                 int x, int y, int w, int h)
-{
-    const int x0 = clampi(x, 0, W) - ox, x1 = clampi(x + w, 0, W) - ox;
-    const int y0 = clampi(y, 0, H) - oy, y1 = clampi(y + h, 0, H) - oy;
-    const float* r0 = reg + y0 * rp;
-    const float* r1 = reg + y1 * rp;
-    const float tl = r0[x0], tr = r0[x1], br = r1[x1], bl = r1[x0];
-    return __fsub_rn(__fsub_rn(__fadd_rn(br, tl), tr), bl);
-}
-__device__ __forceinline__ float haar_eval_region(const float* __restrict__ reg, int rp, int ox, int oy, int W, int H,
-                                                  const int4* rects, const float* wts, int nrect,
-                                                  int col, int row, float sx, float sy)
-{
-    float sum = 0.0f;
-    for (int k = 0; k < nrect; k++) {
-        const int4 r = rects[k];
-        const int x = __float2int_rn(__fmul_rn((float)r.x, sx)) + col;
-        const int y = __float2int_rn(__fmul_rn((float)r.y, sy)) + row;
-        const int h = __float2int_rn(__fmul_rn((float)r.w, sy));
-        const int w = __float2int_rn(__fmul_rn((float)r.z, sx));
-        sum = __fadd_rn(sum, __fmul_rn(wts[k], sum_rect_region(reg, rp, ox, oy, W, H, x, y, w, h)));
-    }
-    return __fdiv_rn(sum, __fmul_rn(sx, sy));
-}
 // ClassifyF with one f64 log: (float)log((1e-5 + p1) / (1e-5 + p0))
 __device__ __forceinline__ float weak_classify_ratio_dev(int weak_type, float x, const float* st)
 {
@@ -103,31 +78,6 @@ __device__ __forceinline__ float weak_classify_ratio_dev(int weak_type, float x,
     const double p0 = (double)__fmul_rn(expf(a0), st[4]);
     const double p1 = (double)__fmul_rn(expf(a1), st[5]);
     return (float)log((1e-5 + p1) / (1e-5 + p0));
-}
-
-// ---- TMA 1-D bulk copies (cp.async.bulk -> SASS UBLKCP) completing on an mbarrier
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
-{
-    unsigned ok;
-    do {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
 }
 
 #define CLS_THREADS 512

@@ -4,6 +4,7 @@
 //   k_cch         : CultureColorHistogram::Compute (CultureColorHistogram.cpp:25-111)
 // Output is feature-major [F][ld] f32 (SampleSet.h:41-43), coalesced over the box index.
 #include "mct_internal.cuh"
+#include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------
 // Haar: thread per box, blockIdx.y tiles the features (table reads are warp-uniform broadcasts).
@@ -49,6 +50,185 @@ k_haar_matrix_batch(const TrainDesc* __restrict__ descs, const float* __restrict
 {
     const TrainDesc& d = descs[blockIdx.z];
     haar_matrix_body(ii, iip, W, H, d.rects, d.wts, d.nrect, d.n_haar, d.col, d.row, d.sx, d.sy, d.P + d.Nn, d.featT, d.ldT);
+}
+
+// ------------------------------------------------------------------------------------------
+// Tiled Haar matrix (large box lists anywhere in the frame, e.g. the N x F sweep of BASELINE configs[4]).
+// k_haar_matrix is bound by the L1 wavefront rate: a warp's 32 corner loads touch up to 32 different lines.  Here the
+// boxes are first binned by position into TS x TS tiles (k_tile_sort: counting sort in one CTA); one CTA per
+// (tile, feature chunk) then stages the integral-image region of its tile in shared memory with TMA bulk row copies and
+// gathers from there (bank conflicts instead of line misses).  Boxes whose extent exceeds the staged region (large
+// scales) take the global path inside the same kernel.  Arithmetic is identical to k_haar_matrix (bit-exact).
+#define HT_TS 64
+#define HT_FT 32
+#define HT_THREADS 256
+// one-CTA counting sort (small / medium lists): counts and cursors live in shared memory
+__global__ void __launch_bounds__(1024)
+k_tile_sort(const int* __restrict__ col, const int* __restrict__ row, int n, int W, int H, int tiles_x, int n_tiles,
+            int* __restrict__ start /* [n_tiles + 1] */, int* __restrict__ order /* [n] */)
+{
+    extern __shared__ int s_cnt[];                    // [n_tiles] counts, then cursors
+    __shared__ int s_part[32];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    for (int t = tid; t < n_tiles; t += nt) s_cnt[t] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+        const int tx = clampi(col[i], 0, W - 1) / HT_TS, ty = clampi(row[i], 0, H - 1) / HT_TS;
+        atomicAdd(&s_cnt[ty * tiles_x + tx], 1);
+    }
+    __syncthreads();
+    int base = 0;
+    for (int t0 = 0; t0 < n_tiles; t0 += nt) {
+        const int t = t0 + tid;
+        const int v = t < n_tiles ? s_cnt[t] : 0;
+        int inc = v;
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+        if (lane == 31) s_part[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int w = lane < (nt >> 5) ? s_part[lane] : 0, wi = w;
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += u; }
+            s_part[lane] = wi - w;
+        }
+        __syncthreads();
+        const int excl = base + s_part[warp] + inc - v;
+        if (t < n_tiles) { start[t] = excl; s_cnt[t] = excl; }
+        __syncthreads();
+        if (tid == nt - 1) s_part[0] = excl + v;
+        __syncthreads();
+        base = s_part[0];
+        __syncthreads();
+    }
+    if (tid == 0) start[n_tiles] = n;
+    for (int i = tid; i < n; i += nt) {
+        const int tx = clampi(col[i], 0, W - 1) / HT_TS, ty = clampi(row[i], 0, H - 1) / HT_TS;
+        order[atomicAdd(&s_cnt[ty * tiles_x + tx], 1)] = i;
+    }
+}
+
+__device__ __forceinline__ int tile_of(int c, int r, int W, int H, int tiles_x)
+{
+    return (clampi(r, 0, H - 1) / HT_TS) * tiles_x + clampi(c, 0, W - 1) / HT_TS;
+}
+// counting sort of the boxes by tile: count (grid over boxes) -> exclusive scan (one CTA) -> scatter (grid over boxes).
+// The order inside a tile is arbitrary (atomics); every box is computed independently, so results do not depend on it.
+__global__ void __launch_bounds__(256)
+k_tile_count(const int* __restrict__ col, const int* __restrict__ row, int n, int W, int H, int tiles_x, int* __restrict__ cnt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&cnt[tile_of(col[i], row[i], W, H, tiles_x)], 1);
+}
+__global__ void __launch_bounds__(1024)
+k_tile_scan(int* __restrict__ cnt /* in: counts, out: cursors */, int n_tiles, int n, int* __restrict__ start /* [n_tiles + 1] */)
+{
+    __shared__ int s_part[32];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    int base = 0;
+    for (int t0 = 0; t0 < n_tiles; t0 += nt) {
+        const int t = t0 + tid;
+        const int v = t < n_tiles ? cnt[t] : 0;
+        int inc = v;
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+        if (lane == 31) s_part[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int w = lane < (nt >> 5) ? s_part[lane] : 0, wi = w;
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += u; }
+            s_part[lane] = wi - w;
+        }
+        __syncthreads();
+        const int excl = base + s_part[warp] + inc - v;
+        if (t < n_tiles) { start[t] = excl; cnt[t] = excl; }
+        __syncthreads();
+        if (tid == nt - 1) s_part[0] = excl + v;
+        __syncthreads();
+        base = s_part[0];
+        __syncthreads();
+    }
+    if (tid == 0) start[n_tiles] = n;
+}
+__global__ void __launch_bounds__(256)
+k_tile_scatter(const int* __restrict__ col, const int* __restrict__ row, int n, int W, int H, int tiles_x, int* __restrict__ cursor,
+               int* __restrict__ order)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) order[atomicAdd(&cursor[tile_of(col[i], row[i], W, H, tiles_x)], 1)] = i;
+}
+
+__global__ void __launch_bounds__(HT_THREADS)
+k_haar_matrix_tiled(const float* __restrict__ ii, int iip, int W, int H,
+                    const int4* __restrict__ rects, const float* __restrict__ wts, const int* __restrict__ nrect, int n_haar,
+                    const int* __restrict__ col, const int* __restrict__ row, const float* __restrict__ sx,
+                    const float* __restrict__ sy, const int* __restrict__ start, const int* __restrict__ order, int tiles_x,
+                    int ext_w, int ext_h, int mxw, int mxh, float* __restrict__ out, int ld)
+{
+    extern __shared__ __align__(128) unsigned char smraw[];
+    __shared__ int4 s_r[HT_FT * MCT_MAX_RECTS];
+    __shared__ float s_w[HT_FT * MCT_MAX_RECTS];
+    __shared__ int s_n[HT_FT];
+    __shared__ __align__(8) uint64_t s_bar;
+    const int tile = blockIdx.x;
+    const int b0 = start[tile], b1 = start[tile + 1];
+    if (b0 >= b1) return;                                           // empty tile (block-uniform)
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int f0 = blockIdx.y * HT_FT, nf = min(HT_FT, n_haar - f0);
+    if (tid == 0) { mbar_init(&s_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    for (int t = tid; t < nf * MCT_MAX_RECTS; t += blockDim.x) {
+        s_r[t] = rects[(size_t)f0 * MCT_MAX_RECTS + t];
+        s_w[t] = wts[(size_t)f0 * MCT_MAX_RECTS + t];
+    }
+    for (int t = tid; t < nf; t += blockDim.x) s_n[t] = nrect[f0 + t];
+    __syncthreads();
+    // region of this tile in the integral image: positions [tx*TS, tx*TS + TS) + box extent, clipped to the table
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int bx0 = tx * HT_TS, by0 = ty * HT_TS;
+    const int bx1 = min(bx0 + HT_TS - 1 + ext_w, W), by1 = min(by0 + HT_TS - 1 + ext_h, H);
+    const int ox = ((bx0 + 3) & ~3) - 3;                            // 16-byte aligned source rows (3-float lead of the table)
+    const int RH = by1 - by0 + 1;
+    const int RWc = (bx1 - ox + 1 + 3) & ~3;
+    const int RWp = (RWc & 4) ? RWc : RWc + 4;
+    float* region = (float*)smraw;
+    if (tid < 32) {
+        if (lane == 0) mbar_expect_tx(&s_bar, (unsigned)(RWc * RH * 4));
+        __syncwarp();
+        for (int y = lane; y < RH; y += 32)
+            bulk_g2s(region + (size_t)y * RWp, ii + (size_t)(by0 + y) * iip + ox, (unsigned)(RWc * 4), &s_bar);
+    }
+    mbar_wait(&s_bar, 0);
+    const int nbox = b1 - b0;
+    if (nbox * 2 >= (int)blockDim.x) {
+        // dense tile: one thread per box, its position loaded once for the whole feature chunk
+        for (int j = b0 + tid; j < b1; j += blockDim.x) {
+            const int i = order[j];
+            const int c = col[i], r = row[i];
+            const float fx = sx[i], fy = sy[i];
+            // round(a*s) + round(b*s) <= (a+b)*s + 1: does every rect of this box stay inside the staged region?
+            // (corner coordinates are clamped to the table, so a region that reaches the table edge always suffices)
+            const int ex = (int)ceilf((float)mxw * fx) + 1, ey = (int)ceilf((float)mxh * fy) + 1;
+            const bool fits = (c + ex <= bx1 || bx1 >= W) && (r + ey <= by1 || by1 >= H);
+            for (int f = 0; f < nf; f++) {
+                float v;
+                if (fits) v = haar_eval_region(region, RWp, ox, by0, W, H, s_r + f * MCT_MAX_RECTS, s_w + f * MCT_MAX_RECTS, s_n[f], c, r, fx, fy);
+                else v = haar_eval_dev(ii, iip, W, H, s_r + f * MCT_MAX_RECTS, s_w + f * MCT_MAX_RECTS, s_n[f], c, r, fx, fy);
+                out[(size_t)(f0 + f) * ld + i] = v;
+            }
+        }
+    } else {
+        // sparse tile: work items = (feature, box) pairs, boxes fastest, so that every thread is busy
+        const int items = nbox * nf;
+        for (int item = tid; item < items; item += blockDim.x) {
+            const int f = item / nbox, jb = item - f * nbox;
+            const int i = order[b0 + jb];
+            const int c = col[i], r = row[i];
+            const float fx = sx[i], fy = sy[i];
+            const int ex = (int)ceilf((float)mxw * fx) + 1, ey = (int)ceilf((float)mxh * fy) + 1;
+            const bool fits = (c + ex <= bx1 || bx1 >= W) && (r + ey <= by1 || by1 >= H);
+            float v;
+            if (fits) v = haar_eval_region(region, RWp, ox, by0, W, H, s_r + f * MCT_MAX_RECTS, s_w + f * MCT_MAX_RECTS, s_n[f], c, r, fx, fy);
+            else v = haar_eval_dev(ii, iip, W, H, s_r + f * MCT_MAX_RECTS, s_w + f * MCT_MAX_RECTS, s_n[f], c, r, fx, fy);
+            out[(size_t)(f0 + f) * ld + i] = v;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -235,6 +415,44 @@ static int launch_haar_rows(mct_clf* clf, const int* d_col, const int* d_row, co
                             int n, float* d_out, int ld)
 {
     mct_ctx* ctx = clf->ctx;
+    // larger lists: bin the boxes into tiles and gather from shared memory
+    const int ext_w = clf->haar_mxw + 2, ext_h = clf->haar_mxh + 2;  // rect extent at scale 1 (+ rounding slack); larger boxes fall back per box
+    const int tiles_x = ceil_div(ctx->W, HT_TS), tiles_y = ceil_div(ctx->H, HT_TS), n_tiles = tiles_x * tiles_y;
+    const size_t reg_b = (size_t)(HT_TS + ext_w + 12) * (HT_TS + ext_h + 1) * 4;
+    // (the tiled path pays three tiny sort launches and one region staging per (tile, feature chunk): it wins once a
+    //  tile holds a few dozen boxes; MCT_HAAR_TILED=0/1 in the environment forces the choice for tests and sweeps)
+    static int s_force = -2;
+    if (s_force == -2) { const char* e = getenv("MCT_HAAR_TILED"); s_force = e ? atoi(e) : -1; }
+    const bool want = s_force >= 0 ? (s_force != 0 && n >= 2) : (n >= 1024 && n / n_tiles >= 24);
+    if (want && reg_b <= 200 * 1024 && n_tiles <= 8192 && ((size_t)ctx->ii_pitch & 3) == 0) {
+        const size_t need = (size_t)2 * n_tiles + 1 + (size_t)n;
+        if (need > clf->tsort_cap) {
+            MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (clf->d_tsort) cudaFree(clf->d_tsort);
+            MCT_CUDA(ctx, cudaMalloc(&clf->d_tsort, (need + 1024) * sizeof(int)));
+            clf->tsort_cap = need + 1024;
+        }
+        int* d_start = clf->d_tsort; int* d_cnt = clf->d_tsort + n_tiles + 1; int* d_order = d_cnt + n_tiles;
+        if (n <= 32768 && (size_t)n_tiles * sizeof(int) <= 40 * 1024) {
+            MCT_LAUNCH(ctx, "k_tile_sort", k_tile_sort<<<1, 1024, (size_t)n_tiles * sizeof(int), ctx->stream>>>(d_col, d_row, n, ctx->W, ctx->H, tiles_x,
+                                                                                                         n_tiles, d_start, d_order));
+        } else {
+            MCT_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, (size_t)n_tiles * sizeof(int), ctx->stream));
+            MCT_LAUNCH(ctx, "k_tile_sort", k_tile_count<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(d_col, d_row, n, ctx->W, ctx->H, tiles_x, d_cnt));
+            MCT_LAUNCH(ctx, "k_tile_sort", k_tile_scan<<<1, 1024, 0, ctx->stream>>>(d_cnt, n_tiles, n, d_start));
+            MCT_LAUNCH(ctx, "k_tile_sort", k_tile_scatter<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(d_col, d_row, n, ctx->W, ctx->H, tiles_x, d_cnt, d_order));
+        }
+        static size_t s_attr = 0;
+        if (reg_b > s_attr) {
+            MCT_CUDA(ctx, cudaFuncSetAttribute(k_haar_matrix_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)reg_b));
+            s_attr = reg_b;
+        }
+        dim3 g(n_tiles, ceil_div(clf->n_haar, HT_FT));
+        MCT_LAUNCH(ctx, "k_haar_matrix_tiled", k_haar_matrix_tiled<<<g, HT_THREADS, reg_b, ctx->stream>>>(
+            ctx->ii_base + MCT_II_LEAD, ctx->ii_pitch, ctx->W, ctx->H, clf->d_rects, clf->d_wts, clf->d_nrect, clf->n_haar,
+            d_col, d_row, d_sx, d_sy, d_start, d_order, tiles_x, ext_w, ext_h, clf->haar_mxw, clf->haar_mxh, d_out, ld));
+        return MCT_OK;
+    }
     dim3 g(ceil_div(n, 256), ceil_div(clf->n_haar, HAAR_FT));
     MCT_LAUNCH(ctx, "k_haar_matrix", k_haar_matrix<<<g, 256, 0, ctx->stream>>>(ctx->ii_base + MCT_II_LEAD, ctx->ii_pitch, ctx->W, ctx->H, clf->d_rects,
                                               clf->d_wts, clf->d_nrect, clf->n_haar, d_col, d_row, d_sx, d_sy, n, d_out, ld));

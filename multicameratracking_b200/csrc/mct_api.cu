@@ -518,6 +518,10 @@ extern "C" int mct_classifier_create(mct_ctx* ctx, const mct_clf_params* p, cons
             for (int k = 0; k < MCT_MAX_RECTS; k++) {
                 const int* s = haar->rects + ((size_t)f * MCT_MAX_RECTS + k) * 4;
                 r[(size_t)f * MCT_MAX_RECTS + k] = make_int4(s[0], s[1], s[2], s[3]);
+                if (k < haar->nrect[f]) {
+                    if (s[0] + s[2] > c->haar_mxw) c->haar_mxw = s[0] + s[2];
+                    if (s[1] + s[3] > c->haar_mxh) c->haar_mxh = s[1] + s[3];
+                }
             }
         }
         MCT_CUDA(ctx, cudaMalloc(&c->d_rects, r.size() * sizeof(int4)));
@@ -570,7 +574,7 @@ extern "C" int mct_classifier_destroy(mct_clf* c)
     cudaStreamSynchronize(c->ctx->stream);
     void* ptrs[] = {c->d_rects, c->d_wts, c->d_nrect, c->d_weak, c->d_trained, c->d_sel, c->d_nsel, c->d_seltab, c->d_selhdr, c->d_tcol, c->d_trow,
                     c->d_tsx, c->d_tsy, c->d_tw, c->d_featT, c->d_pred, c->d_col, c->d_row, c->d_sx, c->d_sy, c->d_featN,
-                    c->d_H, c->d_outbins, c->d_colorrow, c->d_slotmap, c->d_nout, c->d_big, c->d_nbig};
+                    c->d_H, c->d_outbins, c->d_colorrow, c->d_slotmap, c->d_nout, c->d_big, c->d_nbig, c->d_tsort};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete c;
     return MCT_OK;

@@ -88,6 +88,7 @@ struct mct_clf {
     int F, K, n_haar, n_color;
     // Haar table
     int4* d_rects; float* d_wts; int* d_nrect;
+    int haar_mxw, haar_mxh;                             // max over the table of rect.x + rect.w / rect.y + rect.h (blob frame)
     // weak state [8][F], trained flags
     float* d_weak; int* d_trained;
     // selection
@@ -110,6 +111,7 @@ struct mct_clf {
     int* d_outbins; int* d_colorrow;                    // [n_color]: bins to write / colour feature -> row in featN
     uint16_t* d_slotmap;                                // [n_color]: joint bin -> private-histogram slot (0 = not selected)
     int* d_nout;                                        // device: number of selected colour bins
+    int* d_tsort; size_t tsort_cap;                     // tiled Haar matrix: tile starts + box order (k_tile_sort)
     int* d_big; int big_cap;                            // per test box: 1 = left to the generic (large / odd box) kernel
     int* d_nbig;                                        // device counter of such boxes
 };
@@ -320,6 +322,59 @@ __device__ __forceinline__ float haar_eval_dev(const float* __restrict__ ii, int
     }
     return __fdiv_rn(sum, __fmul_rn(sx, sy));
 }
+
+// ---- the same on a region of the integral image staged in shared memory (origin ox, oy; pitch rp)
+__device__ __forceinline__ float sum_rect_region(const float* __restrict__ reg, int rp, int ox, int oy, int W, int H,
+                                                 int x, int y, int w, int h)
+{
+    const int x0 = clampi(x, 0, W) - ox, x1 = clampi(x + w, 0, W) - ox;
+    const int y0 = clampi(y, 0, H) - oy, y1 = clampi(y + h, 0, H) - oy;
+    const float* r0 = reg + y0 * rp;
+    const float* r1 = reg + y1 * rp;
+    const float tl = r0[x0], tr = r0[x1], br = r1[x1], bl = r1[x0];
+    return __fsub_rn(__fsub_rn(__fadd_rn(br, tl), tr), bl);
+}
+__device__ __forceinline__ float haar_eval_region(const float* __restrict__ reg, int rp, int ox, int oy, int W, int H,
+                                                  const int4* rects, const float* wts, int nrect,
+                                                  int col, int row, float sx, float sy)
+{
+    float sum = 0.0f;
+    for (int k = 0; k < nrect; k++) {
+        const int4 r = rects[k];
+        const int x = __float2int_rn(__fmul_rn((float)r.x, sx)) + col;
+        const int y = __float2int_rn(__fmul_rn((float)r.y, sy)) + row;
+        const int h = __float2int_rn(__fmul_rn((float)r.w, sy));
+        const int w = __float2int_rn(__fmul_rn((float)r.z, sx));
+        sum = __fadd_rn(sum, __fmul_rn(wts[k], sum_rect_region(reg, rp, ox, oy, W, H, x, y, w, h)));
+    }
+    return __fdiv_rn(sum, __fmul_rn(sx, sy));
+}
+
+// ---- TMA 1-D bulk copies (cp.async.bulk -> SASS UBLKCP) completing on an mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
 
 __device__ __forceinline__ float warp_sum_f(float v)
 {

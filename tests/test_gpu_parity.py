@@ -100,6 +100,35 @@ def test_haar_features_bit_exact(ctx, oracle, scales):
     clf.close()
 
 
+@pytest.mark.parametrize("scales", [False, True])
+@pytest.mark.parametrize("shape", [(640, 480), (1280, 720)])
+def test_haar_features_tiled_path_bit_exact(ctx, oracle, scales, shape):
+    """large box lists take the tile-sorted, TMA-staged kernel (k_tile_* + k_haar_matrix_tiled); scaled boxes that do
+    not fit the staged region fall back to global gathers inside it"""
+    W, H = shape
+    rng = np.random.default_rng(15)
+    seq = synth.Sequence(W, H, 1)
+    gray = seq.frame(0)[0]
+    ctx.frame_set(gray)
+    F, w0, h0 = 96, seq.w0, seq.h0
+    t, arrs = haar_table(oracle, F, w0, h0)
+    clf = capi.StrongClassifier(ctx, capi.FEAT_HAAR, w0, h0, n_haar=F, n_selected=16, haar=arrs)
+    n = 9000 if W == 640 else 12000
+    col, row, sx, sy = rand_boxes(rng, n, W, H, w0, h0, scales)
+    if scales:                                             # some boxes too large for the staged region -> per-box global path
+        sx[::7] = 1.6; sy[::5] = 1.7
+        col = np.minimum(col, W - np.rint(w0 * sx).astype(np.int32) - 3).astype(np.int32)
+        row = np.minimum(row, H - np.rint(h0 * sy).astype(np.int32) - 3).astype(np.int32)
+    got = clf.features(capi.make_boxes(col, row, sx, sy))
+    exp = np.zeros((F, n), np.float32)
+    ii = oracle.integral(gray)
+    ob = oracle.boxes(col, row, sx, sy)
+    oracle.lib.orc_haar_compute(t, ii.ctypes.data_as(C.POINTER(C.c_float)), W, C.byref(ob),
+                                exp.ctypes.data_as(C.POINTER(C.c_float)), n)
+    np.testing.assert_array_equal(got, exp)
+    clf.close()
+
+
 # ---------------------------------------------------------------------------------- a8, a9
 @pytest.mark.parametrize("scales", [False, True])
 def test_mdch_features(ctx, oracle, scales):
