@@ -60,7 +60,7 @@ k_haar_matrix_batch(const TrainDesc* __restrict__ descs, const float* __restrict
 // gathers from there (bank conflicts instead of line misses).  Boxes whose extent exceeds the staged region (large
 // scales) take the global path inside the same kernel.  Arithmetic is identical to k_haar_matrix (bit-exact).
 #define HT_TS 64
-#define HT_FT 32
+#define HT_FT 64
 #define HT_THREADS 256
 // one-CTA counting sort (small / medium lists): counts and cursors live in shared memory
 __global__ void __launch_bounds__(1024)
@@ -160,7 +160,7 @@ k_haar_matrix_tiled(const float* __restrict__ ii, int iip, int W, int H,
                     const int4* __restrict__ rects, const float* __restrict__ wts, const int* __restrict__ nrect, int n_haar,
                     const int* __restrict__ col, const int* __restrict__ row, const float* __restrict__ sx,
                     const float* __restrict__ sy, const int* __restrict__ start, const int* __restrict__ order, int tiles_x,
-                    int ext_w, int ext_h, int mxw, int mxh, float* __restrict__ out, int ld)
+                    int ext_w, int ext_h, int mxw, int mxh, int ft, float* __restrict__ out, int ld)
 {
     extern __shared__ __align__(128) unsigned char smraw[];
     __shared__ int4 s_r[HT_FT * MCT_MAX_RECTS];
@@ -171,7 +171,7 @@ k_haar_matrix_tiled(const float* __restrict__ ii, int iip, int W, int H,
     const int b0 = start[tile], b1 = start[tile + 1];
     if (b0 >= b1) return;                                           // empty tile (block-uniform)
     const int tid = threadIdx.x, lane = tid & 31;
-    const int f0 = blockIdx.y * HT_FT, nf = min(HT_FT, n_haar - f0);
+    const int f0 = blockIdx.y * ft, nf = min(ft, n_haar - f0);        // ft <= HT_FT features per CTA
     if (tid == 0) { mbar_init(&s_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     for (int t = tid; t < nf * MCT_MAX_RECTS; t += blockDim.x) {
         s_r[t] = rects[(size_t)f0 * MCT_MAX_RECTS + t];
@@ -423,7 +423,9 @@ static int launch_haar_rows(mct_clf* clf, const int* d_col, const int* d_row, co
     //  tile holds a few dozen boxes; MCT_HAAR_TILED=0/1 in the environment forces the choice for tests and sweeps)
     static int s_force = -2;
     if (s_force == -2) { const char* e = getenv("MCT_HAAR_TILED"); s_force = e ? atoi(e) : -1; }
-    const bool want = s_force >= 0 ? (s_force != 0 && n >= 2) : (n >= 1024 && n / n_tiles >= 24);
+    // a (tile, chunk) CTA does 16 * HT_FT gathers per box against one staged region: worth it from about one gather per staged float
+    const int ft = clf->n_haar <= 512 ? 32 : HT_FT;                 // smaller chunks keep enough CTAs in flight when F is small
+    const bool want = s_force >= 0 ? (s_force != 0 && n >= 2) : (n >= 1024 && (size_t)(n / n_tiles) * 16 * ft >= reg_b / 4);
     if (want && reg_b <= 200 * 1024 && n_tiles <= 8192 && ((size_t)ctx->ii_pitch & 3) == 0) {
         const size_t need = (size_t)2 * n_tiles + 1 + (size_t)n;
         if (need > clf->tsort_cap) {
@@ -447,10 +449,10 @@ static int launch_haar_rows(mct_clf* clf, const int* d_col, const int* d_row, co
             MCT_CUDA(ctx, cudaFuncSetAttribute(k_haar_matrix_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)reg_b));
             s_attr = reg_b;
         }
-        dim3 g(n_tiles, ceil_div(clf->n_haar, HT_FT));
+        dim3 g(n_tiles, ceil_div(clf->n_haar, ft));
         MCT_LAUNCH(ctx, "k_haar_matrix_tiled", k_haar_matrix_tiled<<<g, HT_THREADS, reg_b, ctx->stream>>>(
             ctx->ii_base + MCT_II_LEAD, ctx->ii_pitch, ctx->W, ctx->H, clf->d_rects, clf->d_wts, clf->d_nrect, clf->n_haar,
-            d_col, d_row, d_sx, d_sy, d_start, d_order, tiles_x, ext_w, ext_h, clf->haar_mxw, clf->haar_mxh, d_out, ld));
+            d_col, d_row, d_sx, d_sy, d_start, d_order, tiles_x, ext_w, ext_h, clf->haar_mxw, clf->haar_mxh, ft, d_out, ld));
         return MCT_OK;
     }
     dim3 g(ceil_div(n, 256), ceil_div(clf->n_haar, HAAR_FT));
