@@ -663,3 +663,37 @@ def test_noise_prefetch_matches_inline_copy(ctx, oracle):
     for a, bb in zip(*states):
         np.testing.assert_array_equal(a, bb)
     clf.close()
+
+
+def test_batched_update_mixed_classifier_types(ctx, oracle):
+    """mct_track_update (one batched pass for all objects) with different feature / weak / strong types per object:
+    weak state and selector lists must equal the oracle's per-object Update, over three frames (untrained + EMA)"""
+    seq = synth.Sequence(640, 480, 4)
+    w0, h0, F = seq.w0, seq.h0, 90
+    t, arrs = haar_table(oracle, F, w0, h0)
+    specs = [(capi.FEAT_HAAR, capi.WEAK_STUMP, capi.STRONG_MILBOOST, 18),
+             (capi.FEAT_MDCH, capi.WEAK_STUMP, capi.STRONG_MILANYBOOST, 102),
+             (capi.FEAT_HAAR_MDCH, capi.WEAK_WSTUMP, capi.STRONG_MILBOOST, 120),
+             (capi.FEAT_HAAR, capi.WEAK_PERCEPTRON, capi.STRONG_MILBOOST, 18)]
+    clfs, oclfs = [], []
+    for ft, wt, st, K in specs:
+        nh = F if ft in (capi.FEAT_HAAR, capi.FEAT_HAAR_MDCH) else 0
+        clfs.append(capi.StrongClassifier(ctx, ft, w0, h0, n_haar=nh, n_bins=8, weak_type=wt, strong_type=st, n_selected=K,
+                                          haar=arrs if nh else None))
+        oclfs.append(oracle.clf_create(ft, nh, 8, w0, h0, wt, st, K, 0.85, t if nh else None))
+    for frame in range(3):
+        gray, r, g, b = seq.frame(frame)
+        ctx.frame_set(gray, r, g, b)
+        of = oracle.frame(gray, r, g, b)
+        sets = [_train_sets(oracle, seq, frame, o, seed=10 * frame + o + 1) for o in range(4)]
+        capi.track_update(ctx, clfs, [capi.make_boxes(*s[0]) for s in sets], [capi.make_boxes(*s[1]) for s in sets])
+        for o in range(4):
+            oracle.clf_update(oclfs[o], of, oracle.boxes(*sets[o][0]), oracle.boxes(*sets[o][1]))
+            st_g, st_o = clfs[o].weak_state(), oracle.clf_weak_state(oclfs[o])
+            for q in range(2 if specs[o][1] == capi.WEAK_PERCEPTRON else 8):
+                rel_close(st_g[q], st_o[q], rtol=2e-5)
+            assert clfs[o].selectors().tolist() == oracle.clf_selectors(oclfs[o]).tolist(), (frame, o)
+    for c in clfs:
+        c.close()
+    for oc in oclfs:
+        oracle.lib.orc_clf_free(oc)
