@@ -77,6 +77,12 @@ int mct_scored_particles(mct_ctx* ctx, unsigned long long* out, int reset);
  * Computes the (H+1)x(W+1) f32 integral image of gray: exact u32 prefix sums rounded once to f32. */
 int mct_frame_set(mct_ctx* ctx, const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2,
                   int W, int H, int pitch, int is_device);
+/* The same from the PACKED BGR frame the reference's Camera reads (IplImage; Camera.cpp:449-494): the split into planar
+ * R,G,B (Matrix.cpp:70-100), the gray conversion (conv2BW, Matrix.cpp:518-533: OpenCV's fixed-point BGR2GRAY) and, with
+ * use_hsv, the 8-bit BGR2HSV conversion (conv2HSV, Matrix.cpp:535-580 -- the intended result; the reference stores it in
+ * the wrong matrix) run on the device, so only 3 bytes per pixel cross PCIe.  pitch_bytes >= 3*W.  is_device as above. */
+int mct_frame_set_bgr(mct_ctx* ctx, const uint8_t* bgr, int W, int H, int pitch_bytes, int use_hsv, int is_device);
+int mct_frame_prefetch_bgr(mct_ctx* ctx, const uint8_t* bgr_host, int W, int H, int pitch_bytes, int use_hsv);
 /* Optional double buffering of the upload (Camera.cpp:405-495 reads frame t+1 from the video while frame t is
  * tracked): copies the NEXT frame's host planes (pinned memory for a truly asynchronous copy) into the ctx's back
  * buffers on a separate copy stream, overlapping the kernels of the current frame.  A following mct_frame_set with
@@ -86,6 +92,8 @@ int mct_frame_set(mct_ctx* ctx, const uint8_t* gray, const uint8_t* c0, const ui
  * the first mct_sync / mct_track_collect after the adopting mct_frame_set. */
 int mct_frame_prefetch(mct_ctx* ctx, const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2,
                        int W, int H, int pitch);
+/* dense H*W host copies of the current frame's device planes gray, c0, c1, c2 (NULL pointers are skipped; tests) */
+int mct_frame_get_planes(mct_ctx* ctx, uint8_t* gray, uint8_t* c0, uint8_t* c1, uint8_t* c2);
 /* dense (H+1)*(W+1) host copy of the integral image (tests) */
 int mct_frame_get_integral(mct_ctx* ctx, float* out_host);
 /* Matrixu::sumRect (Matrix.cpp:49-67): n rects {x,y,w,h} -> ((br+tl)-tr)-bl in f32.  Host in/out. */

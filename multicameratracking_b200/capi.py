@@ -24,7 +24,7 @@ PF_UNINIT, PF_INIT, PF_PREDICTED, PF_RESAMPLED = 0, 1, 2, 3
 # every symbol include/mct_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "mct_ctx_create", "mct_ctx_destroy", "mct_sync", "mct_last_error", "mct_version", "mct_launch_count",
-    "mct_ctx_stream", "mct_profile_enable", "mct_profile_read", "mct_scored_particles", "mct_frame_set", "mct_frame_prefetch", "mct_frame_get_integral", "mct_sum_rects", "mct_classifier_create",
+    "mct_ctx_stream", "mct_profile_enable", "mct_profile_read", "mct_scored_particles", "mct_frame_set", "mct_frame_prefetch", "mct_frame_set_bgr", "mct_frame_prefetch_bgr", "mct_frame_get_planes", "mct_frame_get_integral", "mct_sum_rects", "mct_classifier_create",
     "mct_classifier_destroy", "mct_classifier_num_features", "mct_features_compute", "mct_classifier_update",
     "mct_classifier_update_from_features", "mct_classifier_classify", "mct_classifier_classify_from_features",
     "mct_classifier_get_selectors", "mct_classifier_get_weak_state", "mct_classifier_get_predictions",
@@ -93,6 +93,9 @@ def load():
     L.mct_scored_particles.argtypes = [vp, C.POINTER(C.c_ulonglong), C.c_int]
     L.mct_frame_set.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
     L.mct_frame_prefetch.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int]
+    L.mct_frame_set_bgr.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.mct_frame_prefetch_bgr.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.mct_frame_get_planes.argtypes = [vp, vp, vp, vp, vp]
     L.mct_frame_get_integral.argtypes = [vp, _c_float_p]
     L.mct_sum_rects.argtypes = [vp, _c_int_p, C.c_int, _c_float_p]
     L.mct_classifier_create.argtypes = [vp, C.POINTER(ClfParams), C.POINTER(HaarTable), C.POINTER(vp)]
@@ -213,6 +216,26 @@ class Context:
         self._keep = (gray, planes)
         self.check(self.L.mct_frame_set(self.h, ptr(gray), ptr(planes[0]), ptr(planes[1]), ptr(planes[2]), W, H, W, 0))
         self.W, self.H = W, H
+
+    def frame_set_bgr(self, bgr, use_hsv=False):
+        """packed BGR uint8 [H][W][3] (the frame the reference's Camera reads): planes, gray and HSV are made on the device"""
+        bgr = np.ascontiguousarray(bgr, np.uint8)
+        H, W = bgr.shape[:2]
+        self._keep = (bgr,)
+        self.check(self.L.mct_frame_set_bgr(self.h, bgr.ctypes.data_as(C.c_void_p), W, H, 3 * W, int(use_hsv), 0))
+        self.W, self.H = W, H
+
+    def frame_prefetch_bgr(self, bgr, use_hsv=False):
+        assert bgr.dtype == np.uint8 and bgr.flags["C_CONTIGUOUS"]
+        H, W = bgr.shape[:2]
+        self._keep_next = (bgr,)
+        self.check(self.L.mct_frame_prefetch_bgr(self.h, bgr.ctypes.data_as(C.c_void_p), W, H, 3 * W, int(use_hsv)))
+
+    def frame_planes(self):
+        """device planes gray, c0, c1, c2 of the current frame as host arrays (tests)"""
+        out = [np.empty((self.H, self.W), np.uint8) for _ in range(4)]
+        self.check(self.L.mct_frame_get_planes(self.h, *[o.ctypes.data_as(C.c_void_p) for o in out]))
+        return out
 
     def frame_prefetch(self, gray, c0=None, c1=None, c2=None):
         """Start the upload of the NEXT frame on the copy stream; frame_set with the same arrays adopts it."""

@@ -9,6 +9,7 @@
 //                     (c) thread-per-column walk down the band, coalesced f32 stores.
 // HBM-bound in principle (W*H u8 in, (W+1)*(H+1) f32 out); at 640x480 it is launch-latency bound.
 #include "mct_internal.cuh"
+#include <math.h>
 
 __global__ void k_band_colsum(const uint8_t* __restrict__ img, int W, int H, int pitch, int BH,
                               uint32_t* __restrict__ bandsum)
@@ -352,6 +353,54 @@ static int launch_integral_two_pass(mct_ctx* ctx, const PrepTarget& t, cudaStrea
     if (nt < 128) nt = 128;
     MCT_LAUNCH_ON(ctx, st, "k_integral_band", k_integral_band<<<nb, nt, smem, st>>>(t.gray, W, H, t.pitch, BH, ctx->bandsum,
                                                                                 t.ii_base + MCT_II_LEAD, t.ii_pitch));
+    return MCT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Frame pre-processing from the packed BGR image (Camera.cpp:449-494):
+//   planes   Matrix.cpp:70-100     channel 0 = R, 1 = G, 2 = B
+//   gray     Matrix.cpp:518-533    cvCvtColor BGR2GRAY = (R*4899 + G*9617 + B*1868 + 8192) >> 14
+//   HSV      Matrix.cpp:535-580    cvCvtColor BGR2HSV, 8-bit: fixed-point tables (hsv_shift 12, H in [0,180))
+// Integer arithmetic only: bit-exact against cv2 (tests/golden/cv2_gray.json, cv2_hsv.json via the oracle).
+__constant__ int c_sdiv[256];
+__constant__ int c_hdiv[256];
+__global__ void __launch_bounds__(256)
+k_bgr_unpack(const uint8_t* __restrict__ bgr, int spitch, int W, int H, int use_hsv, uint8_t* __restrict__ gray,
+             uint8_t* __restrict__ c0, uint8_t* __restrict__ c1, uint8_t* __restrict__ c2, int dpitch)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W || y >= H) return;
+    const uint8_t* p = bgr + (size_t)y * spitch + 3 * x;
+    const int b = p[0], g = p[1], r = p[2];
+    const size_t o = (size_t)y * dpitch + x;
+    gray[o] = (uint8_t)((r * 4899 + g * 9617 + b * 1868 + 8192) >> 14);
+    if (!use_hsv) { c0[o] = (uint8_t)r; c1[o] = (uint8_t)g; c2[o] = (uint8_t)b; return; }
+    const int v = max(max(b, g), r), vmin = min(min(b, g), r), diff = v - vmin;
+    const int vr = v == r ? -1 : 0, vg = v == g ? -1 : 0;
+    const int s = (diff * c_sdiv[v] + (1 << 11)) >> 12;
+    int h = (vr & (g - b)) + (~vr & ((vg & (b - r + 2 * diff)) + ((~vg) & (r - g + 4 * diff))));
+    h = (h * c_hdiv[diff] + (1 << 11)) >> 12;
+    h += h < 0 ? 180 : 0;
+    c0[o] = (uint8_t)h; c1[o] = (uint8_t)s; c2[o] = (uint8_t)v;
+}
+int launch_bgr_unpack(mct_ctx* ctx, const uint8_t* d_bgr, int spitch, int W, int H, int use_hsv, uint8_t* const planes[4], int dpitch,
+                      cudaStream_t st)
+{
+    static int s_tables = 0;
+    if (!s_tables) {
+        int sdiv[256], hdiv[256];
+        sdiv[0] = hdiv[0] = 0;
+        for (int i = 1; i < 256; i++) {       // saturate_cast<int>(double) == cvRound (half to even)
+            sdiv[i] = (int)lrint((double)(255 << 12) / (1.0 * i));
+            hdiv[i] = (int)lrint((double)(180 << 12) / (6.0 * i));
+        }
+        MCT_CUDA(ctx, cudaMemcpyToSymbolAsync(c_sdiv, sdiv, sizeof(sdiv), 0, cudaMemcpyHostToDevice, st));
+        MCT_CUDA(ctx, cudaMemcpyToSymbolAsync(c_hdiv, hdiv, sizeof(hdiv), 0, cudaMemcpyHostToDevice, st));
+        MCT_CUDA(ctx, cudaStreamSynchronize(st));          // the host tables live on this stack frame
+        s_tables = 1;
+    }
+    dim3 g(ceil_div(W, 256), H);
+    MCT_LAUNCH_ON(ctx, st, "k_bgr_unpack", k_bgr_unpack<<<g, 256, 0, st>>>(d_bgr, spitch, W, H, use_hsv, planes[0], planes[1], planes[2], planes[3], dpitch));
     return MCT_OK;
 }
 

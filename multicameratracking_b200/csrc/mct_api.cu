@@ -203,6 +203,7 @@ extern "C" int mct_ctx_destroy(mct_ctx* ctx)
     if (ctx->h_summ) cudaFreeHost(ctx->h_summ);
     if (ctx->d_noise_stage) cudaFree(ctx->d_noise_stage);
     for (int i = 0; i < 2; i++) if (ctx->d_noise_pf[i]) cudaFree(ctx->d_noise_pf[i]);
+    if (ctx->d_bgr_stage) cudaFree(ctx->d_bgr_stage);
     if (ctx->h_tdesc) { cudaFreeHost(ctx->h_tdesc); cudaFree(ctx->d_tdesc); cudaEventDestroy(ctx->ev_train); }
     if (ctx->h_train_stage) cudaFreeHost(ctx->h_train_stage);
     if (ctx->d_train_stage) cudaFree(ctx->d_train_stage);
@@ -294,6 +295,35 @@ static int frame_ensure(mct_ctx* ctx, uint8_t** planes, size_t* plane_cap, float
 // Frame prep of the prefetched (back) set.  It is deferred until the gather kernels of the current frame have been
 // launched (mct_track_score_async calls this right after the classify kernel), so that it runs beside the
 // particle-filter update, which occupies only n_obj SMs, instead of competing with the one-CTA-per-SM kernels.
+// Host -> device upload of one frame into `planes` on stream st: four planes, or the packed BGR image followed by the
+// unpack kernel (kind 1).  For device-resident BGR the unpack reads the caller's buffer directly.
+static int frame_upload(mct_ctx* ctx, int kind, const uint8_t* const src[4], int W, int H, int pitch, int is_device, int use_hsv,
+                        uint8_t* const planes[4], cudaStream_t st)
+{
+    const int dpp = round_up(W, 16);
+    if (kind == 0) {
+        if (is_device) return MCT_OK;
+        for (int i = 0; i < 4; i++)
+            if (src[i]) MCT_CUDA(ctx, cudaMemcpy2DAsync(planes[i], dpp, src[i], pitch, W, H, cudaMemcpyHostToDevice, st));
+        return MCT_OK;
+    }
+    const uint8_t* d_bgr = src[0];
+    int spitch = pitch;
+    if (!is_device) {
+        spitch = round_up(3 * W, 16);
+        const size_t need = (size_t)spitch * H;
+        if (need > ctx->bgr_stage_cap) {
+            MCT_CUDA(ctx, cudaDeviceSynchronize());
+            if (ctx->d_bgr_stage) cudaFree(ctx->d_bgr_stage);
+            MCT_CUDA(ctx, cudaMalloc(&ctx->d_bgr_stage, need));
+            ctx->bgr_stage_cap = need;
+        }
+        MCT_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_bgr_stage, spitch, src[0], pitch, (size_t)3 * W, H, cudaMemcpyHostToDevice, st));
+        d_bgr = ctx->d_bgr_stage;
+    }
+    return launch_bgr_unpack(ctx, d_bgr, spitch, W, H, use_hsv, planes, dpp, st);
+}
+
 // Upload of the prefetched planes into the back set.  Also deferred: mct_track_score_async issues it right AFTER the
 // (small, latency-critical) noise copy of the current frame so that the 1.2 MB of planes never sit in front of it.
 static int prefetch_copy(mct_ctx* ctx)
@@ -302,10 +332,9 @@ static int prefetch_copy(mct_ctx* ctx)
     const int W = ctx->pf_W, H = ctx->pf_H, dpp = round_up(W, 16);
     // the back set was the current set until the latest mct_frame_set: its readers are covered by the latest marker
     MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->prep_stream, ctx->ev_mark[ctx->mark_idx], 0));
-    for (int i = 0; i < 4; i++)
-        if (ctx->pf_src[i])
-            MCT_CUDA(ctx, cudaMemcpy2DAsync(ctx->back.planes[i], dpp, ctx->pf_src[i], ctx->pf_pitch, W, H, cudaMemcpyHostToDevice,
-                                            ctx->prep_stream));
+    (void)dpp;
+    int rc = frame_upload(ctx, ctx->pf_kind, ctx->pf_src, W, H, ctx->pf_pitch, 0, ctx->pf_hsv, ctx->back.planes, ctx->prep_stream);
+    if (rc) return rc;
     ctx->pf_copied = 1;
     return MCT_OK;
 }
@@ -315,8 +344,9 @@ static int prefetch_prep(mct_ctx* ctx)
     int rc0 = prefetch_copy(ctx);
     if (rc0) return rc0;
     const int W = ctx->pf_W, H = ctx->pf_H, dpp = round_up(W, 16), iip = round_up(W + 1, 4);
-    PrepTarget t = {ctx->back.planes[0], ctx->pf_src[1] ? ctx->back.planes[1] : nullptr, ctx->pf_src[2] ? ctx->back.planes[2] : nullptr,
-                    ctx->pf_src[3] ? ctx->back.planes[3] : nullptr, W, H, dpp, ctx->back.ii_base, iip, ctx->back.binimg};
+    const bool bgr = ctx->pf_kind == 1;
+    PrepTarget t = {ctx->back.planes[0], (bgr || ctx->pf_src[1]) ? ctx->back.planes[1] : nullptr, (bgr || ctx->pf_src[2]) ? ctx->back.planes[2] : nullptr,
+                    (bgr || ctx->pf_src[3]) ? ctx->back.planes[3] : nullptr, W, H, dpp, ctx->back.ii_base, iip, ctx->back.binimg};
     int with_bins = 0, rc;
     if (ctx->has_gather) MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->prep_stream, ctx->ev_gather, 0));
     if ((rc = launch_frame_prep(ctx, t, ctx->prep_stream, &with_bins))) return rc;
@@ -325,11 +355,11 @@ static int prefetch_prep(mct_ctx* ctx)
     return MCT_OK;
 }
 
-extern "C" int mct_frame_set(mct_ctx* ctx, const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2,
-                             int W, int H, int pitch, int is_device)
+static int frame_set_impl(mct_ctx* ctx, int kind, const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2,
+                          int W, int H, int pitch, int is_device, int use_hsv)
 {
     if (!ctx) return MCT_E_ARG;
-    if (!gray || W < 4 || H < 4 || pitch < W) return mct_fail(ctx, MCT_E_ARG, "mct_frame_set: bad frame geometry%s");
+    if (!gray || W < 4 || H < 4 || pitch < (kind ? 3 * W : W)) return mct_fail(ctx, MCT_E_ARG, "mct_frame_set: bad frame geometry%s");
     MCT_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc;
     if ((rc = frame_streams(ctx))) return rc;
@@ -339,8 +369,9 @@ extern "C" int mct_frame_set(mct_ctx* ctx, const uint8_t* gray, const uint8_t* c
     cudaEvent_t old_mark = ctx->ev_mark[ctx->mark_idx];
     ctx->mark_idx ^= 1;
     MCT_CUDA(ctx, cudaEventRecord(ctx->ev_mark[ctx->mark_idx], ctx->stream));
-    const bool adopt = !is_device && ctx->pf_pending && ctx->pf_W == W && ctx->pf_H == H && ctx->pf_pitch == pitch &&
-                       ctx->pf_src[0] == gray && ctx->pf_src[1] == c0 && ctx->pf_src[2] == c1 && ctx->pf_src[3] == c2;
+    const bool adopt = !is_device && ctx->pf_pending && ctx->pf_kind == kind && ctx->pf_hsv == use_hsv && ctx->pf_W == W && ctx->pf_H == H &&
+                       ctx->pf_pitch == pitch && ctx->pf_src[0] == gray && ctx->pf_src[1] == c0 && ctx->pf_src[2] == c1 && ctx->pf_src[3] == c2;
+    const bool own = kind == 1 || !is_device;               // planes live in the ctx's own buffers
     int with_bins = 0;
     if (adopt) {
         // the back set already holds this frame, uploaded by mct_frame_prefetch (and normally prepared beside the
@@ -353,7 +384,7 @@ extern "C" int mct_frame_set(mct_ctx* ctx, const uint8_t* gray, const uint8_t* c
         ctx->pf_pending = 0;
         // ... the back set was retired one frame_set call ago: its readers are covered by old_mark
         if ((rc = frame_ensure(ctx, ctx->back.planes, &ctx->back.plane_cap, &ctx->back.ii_base, &ctx->back.ii_cap, &ctx->back.binimg,
-                               &ctx->back.binimg_cap, W, H, !is_device)))
+                               &ctx->back.binimg_cap, W, H, own)))
             return rc;
         frame_swap(ctx);
         MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->prep_stream, old_mark, 0));
@@ -361,19 +392,16 @@ extern "C" int mct_frame_set(mct_ctx* ctx, const uint8_t* gray, const uint8_t* c
         if (ctx->has_gather) MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->prep_stream, ctx->ev_gather, 0));
         // is_device == 1: the caller's device planes are ordered after the work already enqueued on the compute stream
         if (is_device == 1) MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->prep_stream, ctx->ev_mark[ctx->mark_idx], 0));
-        if (!is_device)
-            for (int i = 0; i < 4; i++)
-                if (src[i])
-                    MCT_CUDA(ctx, cudaMemcpy2DAsync(ctx->own_planes[i], dpp, src[i], pitch, W, H, cudaMemcpyHostToDevice, ctx->prep_stream));
+        if ((rc = frame_upload(ctx, kind, src, W, H, pitch, is_device, use_hsv, ctx->own_planes, ctx->prep_stream))) return rc;
     }
-    if (is_device) {
+    if (!own) {
         ctx->gray = gray; ctx->c0 = c0; ctx->c1 = c1; ctx->c2 = c2;
         ctx->pitch = pitch;
     } else {
         ctx->gray = ctx->own_planes[0];
-        ctx->c0 = c0 ? ctx->own_planes[1] : nullptr;
-        ctx->c1 = c1 ? ctx->own_planes[2] : nullptr;
-        ctx->c2 = c2 ? ctx->own_planes[3] : nullptr;
+        ctx->c0 = (kind == 1 || c0) ? ctx->own_planes[1] : nullptr;
+        ctx->c1 = (kind == 1 || c1) ? ctx->own_planes[2] : nullptr;
+        ctx->c2 = (kind == 1 || c2) ? ctx->own_planes[3] : nullptr;
         ctx->pitch = dpp;
     }
     ctx->W = W; ctx->H = H; ctx->ii_pitch = iip;
@@ -388,11 +416,21 @@ extern "C" int mct_frame_set(mct_ctx* ctx, const uint8_t* gray, const uint8_t* c
     return MCT_OK;
 }
 
-extern "C" int mct_frame_prefetch(mct_ctx* ctx, const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2,
-                                  int W, int H, int pitch)
+extern "C" int mct_frame_set(mct_ctx* ctx, const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2,
+                             int W, int H, int pitch, int is_device)
+{
+    return frame_set_impl(ctx, 0, gray, c0, c1, c2, W, H, pitch, is_device, 0);
+}
+extern "C" int mct_frame_set_bgr(mct_ctx* ctx, const uint8_t* bgr, int W, int H, int pitch_bytes, int use_hsv, int is_device)
+{
+    return frame_set_impl(ctx, 1, bgr, nullptr, nullptr, nullptr, W, H, pitch_bytes, is_device, use_hsv ? 1 : 0);
+}
+
+static int frame_prefetch_impl(mct_ctx* ctx, int kind, const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2,
+                               int W, int H, int pitch, int use_hsv)
 {
     if (!ctx) return MCT_E_ARG;
-    if (!gray || W < 4 || H < 4 || pitch < W) return mct_fail(ctx, MCT_E_ARG, "mct_frame_prefetch: bad frame geometry%s");
+    if (!gray || W < 4 || H < 4 || pitch < (kind ? 3 * W : W)) return mct_fail(ctx, MCT_E_ARG, "mct_frame_prefetch: bad frame geometry%s");
     MCT_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc;
     if ((rc = frame_streams(ctx))) return rc;
@@ -402,7 +440,29 @@ extern "C" int mct_frame_prefetch(mct_ctx* ctx, const uint8_t* gray, const uint8
     const uint8_t* src[4] = {gray, c0, c1, c2};
     for (int i = 0; i < 4; i++) ctx->pf_src[i] = src[i];
     ctx->pf_W = W; ctx->pf_H = H; ctx->pf_pitch = pitch; ctx->pf_pending = 1; ctx->pf_with_bins = 0; ctx->pf_prepped = 0; ctx->pf_copied = 0;
+    ctx->pf_kind = kind; ctx->pf_hsv = use_hsv;
     return MCT_OK;      // copy and frame prep follow in mct_track_score_async (or at the adopting mct_frame_set)
+}
+extern "C" int mct_frame_prefetch(mct_ctx* ctx, const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2,
+                                  int W, int H, int pitch)
+{
+    return frame_prefetch_impl(ctx, 0, gray, c0, c1, c2, W, H, pitch, 0);
+}
+extern "C" int mct_frame_prefetch_bgr(mct_ctx* ctx, const uint8_t* bgr_host, int W, int H, int pitch_bytes, int use_hsv)
+{
+    return frame_prefetch_impl(ctx, 1, bgr_host, nullptr, nullptr, nullptr, W, H, pitch_bytes, use_hsv ? 1 : 0);
+}
+
+extern "C" int mct_frame_get_planes(mct_ctx* ctx, uint8_t* gray, uint8_t* c0, uint8_t* c1, uint8_t* c2)
+{
+    if (!ctx) return MCT_E_ARG;
+    if (ctx->frame_id == 0) return mct_fail(ctx, MCT_E_STATE, "no frame set%s");
+    uint8_t* dst[4] = {gray, c0, c1, c2};
+    const uint8_t* src[4] = {ctx->gray, ctx->c0, ctx->c1, ctx->c2};
+    for (int i = 0; i < 4; i++)
+        if (dst[i] && src[i])
+            MCT_CUDA(ctx, cudaMemcpy2DAsync(dst[i], ctx->W, src[i], ctx->pitch, ctx->W, ctx->H, cudaMemcpyDeviceToHost, ctx->stream));
+    return mct_sync(ctx);
 }
 
 extern "C" int mct_frame_get_integral(mct_ctx* ctx, float* out_host)
@@ -989,6 +1049,7 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
             MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             if (ctx->d_noise_stage) cudaFree(ctx->d_noise_stage);
     for (int i = 0; i < 2; i++) if (ctx->d_noise_pf[i]) cudaFree(ctx->d_noise_pf[i]);
+    if (ctx->d_bgr_stage) cudaFree(ctx->d_bgr_stage);
     if (ctx->h_tdesc) { cudaFreeHost(ctx->h_tdesc); cudaFree(ctx->d_tdesc); cudaEventDestroy(ctx->ev_train); }
     if (ctx->h_train_stage) cudaFreeHost(ctx->h_train_stage);
     if (ctx->d_train_stage) cudaFree(ctx->d_train_stage);

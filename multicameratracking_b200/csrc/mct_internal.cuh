@@ -58,7 +58,8 @@ struct mct_ctx {
     FrameSet back;
     cudaStream_t prep_stream; cudaEvent_t ev_ready, ev_mark[2], ev_gather; int mark_idx, has_gather;
     unsigned prep_epoch;
-    const uint8_t* pf_src[4]; int pf_W, pf_H, pf_pitch, pf_pending, pf_with_bins, pf_prepped, pf_copied;
+    const uint8_t* pf_src[4]; int pf_W, pf_H, pf_pitch, pf_pending, pf_with_bins, pf_prepped, pf_copied, pf_kind, pf_hsv;
+    uint8_t* d_bgr_stage; size_t bgr_stage_cap;         // packed BGR upload staging (consumed by k_bgr_unpack on the prep stream)
     float* ii_base; int ii_pitch; size_t ii_cap;       // integral image storage; element (y,x) at ii_base[MCT_II_LEAD + y*ii_pitch + x]
     uint32_t* bandsum; size_t bandsum_cap;
     unsigned* prep_flags;                              // [256] band-ready flags of k_frame_prep (value = frame id)
@@ -228,6 +229,9 @@ static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 // integral image (+ bin image when an MDCH classifier uses this ctx) of `t` on stream `st`; *with_bins tells whether
 // the bin image was produced
 int launch_frame_prep(mct_ctx* ctx, const PrepTarget& t, cudaStream_t st, int* with_bins);
+// packed BGR -> gray + planar R,G,B (or H,S,V) planes of pitch dpitch
+int launch_bgr_unpack(mct_ctx* ctx, const uint8_t* d_bgr, int spitch, int W, int H, int use_hsv, uint8_t* const planes[4], int dpitch,
+                      cudaStream_t st);
 int launch_bin_image(mct_ctx* ctx, int nb);
 int launch_sum_rects(mct_ctx* ctx, const int* d_rects, int n, float* d_out);
 // full [F][ld] feature matrix of one box list (FeatureVector::Compute)

@@ -74,6 +74,43 @@ float orc_sum_rect(const float* ii, int W, int x, int y, int w, int h)
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* Frame pre-processing (Camera.cpp:449-494; Matrix.cpp:70-100, 518-580)                        */
+/* ------------------------------------------------------------------------------------------ */
+static int orc_sat_round_div(double num, double den) { return (int)lrint(num / den); }   /* saturate_cast<int>(double) = cvRound */
+void orc_bgr_to_planes(const uint8_t* bgr, int W, int H, int pitch_bytes, int use_hsv,
+                       uint8_t* gray, uint8_t* c0, uint8_t* c1, uint8_t* c2)
+{
+    enum { HSV_SHIFT = 12 };
+    static int sdiv[256], hdiv[256], init = 0;
+    if (!init) {
+        sdiv[0] = hdiv[0] = 0;
+        for (int i = 1; i < 256; i++) {
+            sdiv[i] = orc_sat_round_div((double)(255 << HSV_SHIFT), 1.0 * i);
+            hdiv[i] = orc_sat_round_div((double)(180 << HSV_SHIFT), 6.0 * i);
+        }
+        init = 1;
+    }
+    for (int y = 0; y < H; y++) {
+        const uint8_t* p = bgr + (size_t)y * pitch_bytes;
+        for (int x = 0; x < W; x++) {
+            const int b = p[3 * x], g = p[3 * x + 1], r = p[3 * x + 2];
+            const size_t o = (size_t)y * W + x;
+            gray[o] = (uint8_t)((r * 4899 + g * 9617 + b * 1868 + 8192) >> 14);
+            if (!use_hsv) { c0[o] = (uint8_t)r; c1[o] = (uint8_t)g; c2[o] = (uint8_t)b; continue; }
+            int v = b > g ? b : g; if (r > v) v = r;
+            int vmin = b < g ? b : g; if (r < vmin) vmin = r;
+            const int diff = v - vmin;
+            const int vr = v == r ? -1 : 0, vg = v == g ? -1 : 0;
+            const int s = (diff * sdiv[v] + (1 << (HSV_SHIFT - 1))) >> HSV_SHIFT;
+            int h = (vr & (g - b)) + (~vr & ((vg & (b - r + 2 * diff)) + ((~vg) & (r - g + 4 * diff))));
+            h = (h * hdiv[diff] + (1 << (HSV_SHIFT - 1))) >> HSV_SHIFT;
+            h += h < 0 ? 180 : 0;
+            c0[o] = (uint8_t)h; c1[o] = (uint8_t)s; c2[o] = (uint8_t)v;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* Haar features                                                                               */
 /* ------------------------------------------------------------------------------------------ */
 /* HaarFeature.cpp:25-69 (draw order), HaarFeatureVector.cpp:24-29 (feature loop) */

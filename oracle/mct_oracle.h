@@ -35,6 +35,14 @@ int      orc_cvround(double v);
 void  orc_integral(const uint8_t* img, int W, int H, int pitch, float* ii /* (H+1)*(W+1) dense */);
 float orc_sum_rect(const float* ii, int W, int x, int y, int w, int h);
 
+/* ---- frame pre-processing upstream of the path: Camera.cpp:449-494, Matrix.cpp:70-100 (IplImage BGR -> planes, channel 0 = R,
+ * 1 = G, 2 = B), Matrix.cpp:518-533 (conv2BW = cvCvtColor BGR2GRAY), :535-580 (conv2HSV = cvCvtColor BGR2HSV; the reference writes
+ * the result into the wrong matrix -- SURVEY 8f row 1 -- here the INTENDED conversion).  OpenCV 8-bit formulas: gray =
+ * (R*4899 + G*9617 + B*1868 + 8192) >> 14; HSV = the fixed-point table algorithm (hsv_shift 12, H range 180).  Pinned against
+ * cv2 4.13 by tests/golden/cv2_gray.json and cv2_hsv.json.  use_hsv: planes c0,c1,c2 = H,S,V instead of R,G,B. */
+void orc_bgr_to_planes(const uint8_t* bgr, int W, int H, int pitch_bytes, int use_hsv,
+                       uint8_t* gray, uint8_t* c0, uint8_t* c1, uint8_t* c2 /* dense [H][W] */);
+
 /* ---- boxes = Sample (Sample.h:41-51), SoA ---- */
 typedef struct {
     int n;

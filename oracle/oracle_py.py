@@ -147,6 +147,14 @@ class Oracle:
     def randint(self, r, a, b):
         return self.lib.orc_randint(C.byref(r), a, b)
 
+    def bgr_to_planes(self, bgr, use_hsv=False):
+        """packed BGR [H][W][3] uint8 -> (gray, c0, c1, c2) planes: R,G,B or H,S,V"""
+        bgr = np.ascontiguousarray(bgr, np.uint8)
+        H, W = bgr.shape[:2]
+        out = [np.empty((H, W), np.uint8) for _ in range(4)]
+        self.lib.orc_bgr_to_planes(_up(bgr), W, H, 3 * W, int(use_hsv), *[_up(o) for o in out])
+        return out
+
     def integral(self, img):
         img = np.ascontiguousarray(img, dtype=np.uint8)
         H, W = img.shape

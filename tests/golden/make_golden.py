@@ -4,6 +4,7 @@
                  Public.cpp:10-23 uses) recovered from cv2.randu(CV_64F): cv2 returns
                  (int64)(u<<32 | carry) * 2^-64 + 0.5, so u = floor((v - 0.5) * 2^32 mod 2^32).
   cv2_gray.json  cv2.cvtColor(BGR2GRAY) on probe pixels (the conversion upstream of the path, Matrix.cpp:518-533)
+  cv2_hsv.json   cv2.cvtColor(BGR2HSV) (8-bit, H in [0,180)) on probe pixels incl. grey / saturated / tie cases
   cv2_round.json cvRound semantics probes (numpy rint == round-half-even == SSE cvtsd2si)
   hand.json      hand-computed integral / sumRect / resampler cases from SURVEY.md 8c
 """
@@ -30,6 +31,14 @@ def main():
     bgr = r.integers(0, 256, (1, 256, 3), dtype=np.uint8)
     g = cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY)
     json.dump({"bgr": bgr[0].tolist(), "gray": g[0].tolist()}, open(os.path.join(HERE, "cv2_gray.json"), "w"))
+
+    r2 = np.random.default_rng(4)
+    px = r2.integers(0, 256, (4000, 3), dtype=np.uint8)
+    edge = np.array([[0, 0, 0], [255, 255, 255], [10, 10, 10], [255, 0, 0], [0, 255, 0], [0, 0, 255], [255, 255, 0], [0, 255, 255],
+                     [255, 0, 255], [1, 0, 0], [0, 1, 0], [0, 0, 1], [200, 200, 199], [128, 127, 128], [5, 250, 5]], np.uint8)
+    bgr2 = np.concatenate([edge, px])[None]
+    hsv = cv2.cvtColor(bgr2, cv2.COLOR_BGR2HSV)
+    json.dump({"bgr": bgr2[0].tolist(), "hsv": hsv[0].tolist()}, open(os.path.join(HERE, "cv2_hsv.json"), "w"))
 
     probes = [2.5, 3.5, -2.5, -3.5, 0.5, 1.5, 0.49999, 2.500001, -0.5, 1e6 + 0.5]
     json.dump({"x": probes, "r": [int(np.rint(p)) for p in probes]}, open(os.path.join(HERE, "cv2_round.json"), "w"))

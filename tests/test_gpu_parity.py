@@ -697,3 +697,41 @@ def test_batched_update_mixed_classifier_types(ctx, oracle):
         c.close()
     for oc in oclfs:
         oracle.lib.orc_clf_free(oc)
+
+
+@pytest.mark.parametrize("use_hsv", [False, True])
+def test_frame_set_bgr_matches_oracle(ctx, oracle, use_hsv):
+    """packed BGR -> planar R,G,B / H,S,V + fixed-point gray on the device, bit-exact against the oracle
+    (itself pinned against cv2 goldens); the integral image follows from the device-made gray; prefetch adoption too"""
+    rng = np.random.default_rng(31)
+    for (H, W) in [(48, 64), (481, 643), (480, 640)]:
+        frames = [rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(3)]
+        frames[1][: H // 2] = (frames[1][: H // 2] // 64) * 64          # flat / saturated areas (grey ties in the HSV formula)
+        ctx.frame_set_bgr(frames[0], use_hsv)
+        for t in range(3):
+            if t > 0:
+                ctx.frame_set_bgr(frames[t], use_hsv)                  # adopts the prefetched upload when one is pending
+            if t + 1 < 3 and (W % 2 == 0):
+                ctx.frame_prefetch_bgr(frames[t + 1], use_hsv)
+            exp = oracle.bgr_to_planes(frames[t], use_hsv)
+            got = ctx.frame_planes()
+            for k in range(4):
+                np.testing.assert_array_equal(got[k], exp[k])
+            assert np.array_equal(ctx.integral(), oracle.integral(exp[0]))
+
+
+def test_mdch_features_from_bgr_frame(ctx, oracle):
+    """the colour-histogram features computed from a BGR-uploaded frame equal those from separately uploaded planes"""
+    seq = synth.Sequence(640, 480, 1)
+    gray, r, g, b = seq.frame(3)
+    bgr = np.ascontiguousarray(np.stack([b, g, r], axis=2))
+    clf = capi.StrongClassifier(ctx, capi.FEAT_MDCH, seq.w0, seq.h0, n_bins=8, n_selected=102)
+    rng = np.random.default_rng(32)
+    col, row, sx, sy = rand_boxes(rng, 150, 640, 480, seq.w0, seq.h0)
+    ctx.frame_set(gray, r, g, b)
+    a = clf.features(capi.make_boxes(col, row, sx, sy))
+    ctx.frame_set_bgr(bgr)
+    assert np.array_equal(ctx.frame_planes()[0], gray)                  # synth builds gray with the same fixed-point formula
+    bb = clf.features(capi.make_boxes(col, row, sx, sy))
+    np.testing.assert_array_equal(a, bb)
+    clf.close()
