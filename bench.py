@@ -215,6 +215,8 @@ def run_ours(args):
     # resident inputs: frame pool + per-step noise on the device; pinned copies for the e2e leg
     planes_dev = [[torch.from_numpy(p).to(dev) for p in fr] for fr in frames]
     planes_pin = [[torch.from_numpy(p).pin_memory() for p in fr] for fr in frames]
+    # the frame as the reference's Camera gets it from the video (packed BGR, Camera.cpp:449-494): the e2e leg uploads this
+    bgr_pin = [torch.from_numpy(np.ascontiguousarray(np.stack([fr[3], fr[2], fr[1]], axis=2))).pin_memory() for fr in frames]
     noise_np = [np.stack([synth.noise(N_PART, SD, camera=rank, obj=o, t=i) for o in range(N_OBJ)]) for i in range(total)]
     noise_dev = [torch.from_numpy(n).to(dev) for n in noise_np]
     noise_pin = [torch.from_numpy(n).pin_memory() for n in noise_np]
@@ -238,12 +240,16 @@ def run_ours(args):
 
     def step_e2e(i, phases):
         t = pingpong(i, POOL)
-        g, r, gg, b = planes_pin[t]
-        cam._chk(cam.L.mcth_camera_set_frame(cam.h, vp(g.data_ptr()), vp(r.data_ptr()), vp(gg.data_ptr()), vp(b.data_ptr()), W, H, W, 0))
-        # the upload of the NEXT frame's planes (pinned host memory) is started now and overlaps this frame's kernels,
-        # as a video reader would decode ahead (Matrixu::PrefetchFrame); one frame is still copied per step
-        g2, r2, gg2, b2 = planes_pin[pingpong(i + 1, POOL)]
-        cam._chk(cam.L.mcth_camera_prefetch_frame(cam.h, vp(g2.data_ptr()), vp(r2.data_ptr()), vp(gg2.data_ptr()), vp(b2.data_ptr()), W, H, W))
+        if (not args.e2e_bgr):
+            g, r, gg, b = planes_pin[t]
+            cam._chk(cam.L.mcth_camera_set_frame(cam.h, vp(g.data_ptr()), vp(r.data_ptr()), vp(gg.data_ptr()), vp(b.data_ptr()), W, H, W, 0))
+            # the upload of the NEXT frame (pinned host memory) is started now and overlaps this frame's kernels, as a video
+            # reader would decode ahead (Matrixu::PrefetchFrame); one frame is still copied per step
+            g2, r2, gg2, b2 = planes_pin[pingpong(i + 1, POOL)]
+            cam._chk(cam.L.mcth_camera_prefetch_frame(cam.h, vp(g2.data_ptr()), vp(r2.data_ptr()), vp(gg2.data_ptr()), vp(b2.data_ptr()), W, H, W))
+        else:
+            cam._chk(cam.L.mcth_camera_set_frame_bgr(cam.h, vp(bgr_pin[t].data_ptr()), W, H, 3 * W, 0, 0))
+            cam._chk(cam.L.mcth_camera_prefetch_frame_bgr(cam.h, vp(bgr_pin[pingpong(i + 1, POOL)].data_ptr()), W, H, 3 * W, 0))
         if i + 1 < len(noise_pin):     # the next frame's Gaussian rows ride along as well (mct_noise_prefetch)
             cam._chk(cam.L.mcth_camera_prefetch_noise(cam.h, vp(noise_pin[i + 1].data_ptr()), noise_pin[i + 1].numel()))
         out = np.zeros((N_OBJ, 4), np.int32)
@@ -339,7 +345,8 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
             "e2e": {"value": scored_e2e_all / (ms_e2e_max * 1e-3), "unit": "particles/s",
-                    "h2d_bytes_per_step": 4 * W * H + N_OBJ * 4 * N_PART * 4, "d2h_bytes_per_step": N_OBJ * C.sizeof(capi.PfSummary),
+                    "h2d_bytes_per_step": (4 if (not args.e2e_bgr) else 3) * W * H + N_OBJ * 4 * N_PART * 4,
+                    "input": "4 u8 planes (gray,R,G,B)" if (not args.e2e_bgr) else "packed BGR frame (split + gray conversion on the device)", "d2h_bytes_per_step": N_OBJ * C.sizeof(capi.PfSummary),
                     "ms_per_step": ms_e2e_max / args.steps},
             "tracked_frames_per_sec_per_camera": args.steps / (ms_full_max * 1e-3),
             "gpu_launches": int(launches_all),
@@ -368,6 +375,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-bgr", action="store_true", help="e2e leg uploads the packed BGR frame (split + gray on the device) instead of 4 planes")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -318,7 +318,8 @@ static int frame_upload(mct_ctx* ctx, int kind, const uint8_t* const src[4], int
             MCT_CUDA(ctx, cudaMalloc(&ctx->d_bgr_stage, need));
             ctx->bgr_stage_cap = need;
         }
-        MCT_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_bgr_stage, spitch, src[0], pitch, (size_t)3 * W, H, cudaMemcpyHostToDevice, st));
+        if (pitch == spitch) MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_bgr_stage, src[0], (size_t)spitch * H, cudaMemcpyHostToDevice, st));
+        else MCT_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_bgr_stage, spitch, src[0], pitch, (size_t)3 * W, H, cudaMemcpyHostToDevice, st));
         d_bgr = ctx->d_bgr_stage;
     }
     return launch_bgr_unpack(ctx, d_bgr, spitch, W, H, use_hsv, planes, dpp, st);
@@ -1048,11 +1049,6 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
         if (ntot > ctx->noise_stage_cap) {
             MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             if (ctx->d_noise_stage) cudaFree(ctx->d_noise_stage);
-    for (int i = 0; i < 2; i++) if (ctx->d_noise_pf[i]) cudaFree(ctx->d_noise_pf[i]);
-    if (ctx->d_bgr_stage) cudaFree(ctx->d_bgr_stage);
-    if (ctx->h_tdesc) { cudaFreeHost(ctx->h_tdesc); cudaFree(ctx->d_tdesc); cudaEventDestroy(ctx->ev_train); }
-    if (ctx->h_train_stage) cudaFreeHost(ctx->h_train_stage);
-    if (ctx->d_train_stage) cudaFree(ctx->d_train_stage);
             MCT_CUDA(ctx, cudaMalloc(&ctx->d_noise_stage, ntot * sizeof(float)));
             ctx->noise_stage_cap = ntot;
         }

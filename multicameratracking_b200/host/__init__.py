@@ -29,6 +29,8 @@ def load():
         L.mcth_camera_ctx.argtypes = [vp]; L.mcth_camera_ctx.restype = vp
         L.mcth_camera_set_frame.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
         L.mcth_camera_prefetch_frame.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int]
+        L.mcth_camera_set_frame_bgr.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.mcth_camera_prefetch_frame_bgr.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
         L.mcth_camera_prefetch_noise.argtypes = [vp, vp, C.c_size_t]
         L.mcth_camera_add_object.argtypes = [vp, C.POINTER(ObjectParams)]
         L.mcth_camera_init_trackers.argtypes = [vp]

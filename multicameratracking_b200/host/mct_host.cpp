@@ -48,6 +48,15 @@ void Matrixu::SetFrame(const uint8_t* gray, const uint8_t* c0, const uint8_t* c1
     chk(m_ctx, mct_frame_set(m_ctx, gray, c0, c1, c2, cols, rows, pitch, deviceMode));
     m_rows = rows; m_cols = cols; m_iiInit = true;
 }
+void Matrixu::SetFrameBGR(const uint8_t* bgr, int cols, int rows, int pitchBytes, bool useHSV, int deviceMode)
+{
+    chk(m_ctx, mct_frame_set_bgr(m_ctx, bgr, cols, rows, pitchBytes, useHSV ? 1 : 0, deviceMode));
+    m_rows = rows; m_cols = cols; m_iiInit = true;
+}
+void Matrixu::PrefetchFrameBGR(const uint8_t* bgr, int cols, int rows, int pitchBytes, bool useHSV)
+{
+    chk(m_ctx, mct_frame_prefetch_bgr(m_ctx, bgr, cols, rows, pitchBytes, useHSV ? 1 : 0));
+}
 void Matrixu::PrefetchFrame(const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2, int cols, int rows, int pitch)
 {
     chk(m_ctx, mct_frame_prefetch(m_ctx, gray, c0, c1, c2, cols, rows, pitch));

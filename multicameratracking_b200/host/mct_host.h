@@ -67,6 +67,9 @@ public:
     //             2 = device planes that are already complete (lets the frame preparation overlap the previous frame)
     void SetFrame(const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2, int cols, int rows,
                   int pitch, int deviceMode = 0);
+    // the packed BGR frame the reference's Camera reads (Camera.cpp:449-494): split, conv2BW and (useHSV) conv2HSV run on the device
+    void SetFrameBGR(const uint8_t* bgr, int cols, int rows, int pitchBytes, bool useHSV = false, int deviceMode = 0);
+    void PrefetchFrameBGR(const uint8_t* bgr, int cols, int rows, int pitchBytes, bool useHSV = false);
     // start the upload of the NEXT frame while the current one is tracked; SetFrame with the same pointers adopts it
     void PrefetchFrame(const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2, int cols, int rows, int pitch);
     void initII() {}                      // done inside SetFrame; kept for call-site compatibility

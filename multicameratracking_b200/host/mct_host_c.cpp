@@ -63,6 +63,14 @@ int mcth_camera_set_frame(mcth_camera* c, const uint8_t* gray, const uint8_t* c0
     GUARD(c->frame.SetFrame(gray, c0, c1, c2, W, H, pitch, is_device));
 }
 
+int mcth_camera_set_frame_bgr(mcth_camera* c, const uint8_t* bgr, int W, int H, int pitch_bytes, int use_hsv, int is_device)
+{
+    GUARD(c->frame.SetFrameBGR(bgr, W, H, pitch_bytes, use_hsv != 0, is_device));
+}
+int mcth_camera_prefetch_frame_bgr(mcth_camera* c, const uint8_t* bgr, int W, int H, int pitch_bytes, int use_hsv)
+{
+    GUARD(c->frame.PrefetchFrameBGR(bgr, W, H, pitch_bytes, use_hsv != 0));
+}
 int mcth_camera_prefetch_frame(mcth_camera* c, const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2,
                                int W, int H, int pitch)
 {
