@@ -190,8 +190,10 @@ static inline int mct_fail(mct_ctx* ctx, int code, const char* fmt, const char* 
 #define MCT_CUDA(ctx, call)                                                                 \
     do {                                                                                     \
         cudaError_t e__ = (call);                                                            \
-        if (e__ != cudaSuccess)                                                              \
+        if (e__ != cudaSuccess) {                                                            \
+            (void)cudaGetLastError();      /* do not let it resurface at the next launch check */ \
             return mct_fail((ctx), MCT_E_CUDA, "CUDA error: %s (line %d)", cudaGetErrorString(e__), __LINE__); \
+        }                                                                                    \
     } while (0)
 #define MCT_KERNEL_CHECK(ctx)                                                                \
     do {                                                                                     \

@@ -6,7 +6,7 @@ import bench
 from multicameratracking_b200 import capi
 L = capi.load()
 import torch
-args = type("A", (), dict(steps=7, warmup=3, gpus=1, no_cpu_baseline=True, impl="ours"))()
+args = type("A", (), dict(steps=7, warmup=3, gpus=1, no_cpu_baseline=True, impl="ours", e2e_bgr=False))()
 bench.run_ours(args)
 out = (C.c_ulonglong * 64)()
 L.mct_debug_pf_stamps.argtypes = [C.POINTER(C.c_ulonglong)]
