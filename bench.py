@@ -286,6 +286,13 @@ def run_ours(args):
     ms_e2e, scored_e2e, _ = timed(lambda i: step_e2e(i, 1), args.warmup, args.steps)
     # ---- 4. full frames (score + UpdateClassifier) through the host API ----
     ms_full, _, _ = timed(lambda i: step_e2e(i, 3), args.warmup, args.steps)
+    # per-kernel CUDA-event times of full frames (the UpdateClassifier kernels ride after the score path)
+    L.mct_profile_enable(ctx_h, 1)
+    n_pf = min(args.steps, 20)
+    for i in range(n_pf):
+        step_e2e(args.warmup + i, 3)
+    prof_full = capi.profile_read(L, ctx_h)
+    L.mct_profile_enable(ctx_h, 0)
 
     def allmax(x):
         if world == 1:
@@ -300,6 +307,25 @@ def run_ours(args):
         t = torch.tensor([x], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
+
+    # ---- 5. (N > 1) the cross-camera exchange of the geometric fuser: device-side pack + one NCCL allgather per frame
+    fuser = None
+    if world > 1:
+        from multicameratracking_b200.network import CameraNetworkExchange
+        ex = CameraNetworkExchange(N_OBJ)
+        pts = torch.zeros((N_OBJ, 2), dtype=torch.float32, device=dev)
+        for _ in range(5):
+            cam.pack_foot_points(pts.data_ptr()); allp = ex.allgather_foot_points(pts)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(50):
+            cam.pack_foot_points(pts.data_ptr()); allp = ex.allgather_foot_points(pts)
+        f1.record(stream)
+        barrier()
+        ok = bool(torch.equal(allp[rank], pts)) and tuple(allp.shape) == (world, N_OBJ, 2)
+        fuser = {"allgather_us_per_frame": allmax(1e3 * f0.elapsed_time(f1) / 50), "payload_bytes_per_rank": N_OBJ * 8, "verified": ok,
+                 "what": "mct_fuser_pack_foot_points + torch.distributed.all_gather_into_tensor (NCCL) per frame"}
 
     ms_max, ms_e2e_max, ms_full_max = allmax(ms), allmax(ms_e2e), allmax(ms_full)
     scored_all, scored_e2e_all = allsum(scored), allsum(scored_e2e)
@@ -349,6 +375,8 @@ def run_ours(args):
                     "input": "4 u8 planes (gray,R,G,B)" if (not args.e2e_bgr) else "packed BGR frame (split + gray conversion on the device)", "d2h_bytes_per_step": N_OBJ * C.sizeof(capi.PfSummary),
                     "ms_per_step": ms_e2e_max / args.steps},
             "tracked_frames_per_sec_per_camera": args.steps / (ms_full_max * 1e-3),
+            "full_frame": {"ms_per_frame": ms_full_max / args.steps,
+                           "kernel_us_per_frame": {k: round(1e3 * v[0] / n_pf, 2) for k, v in sorted(prof_full.items(), key=lambda kv: -kv[1][0])}},
             "gpu_launches": int(launches_all),
             "roofline": {"kernel": dom_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
@@ -360,6 +388,8 @@ def run_ours(args):
                                  "k_pf_update is bound by three sequential f32 add chains (bit-exact resampling), not by bandwidth"},
             "clocks": sampler.summary(),
         }
+        if fuser is not None:
+            out["fuser_exchange"] = fuser
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_leg()
         print(json.dumps(out))

@@ -427,6 +427,15 @@ def track_score(ctx, pfs, clfs, params, noise, u01, noise_device_ptr=None):
     return list(out)
 
 
+def pack_foot_points(ctx, pfs, h0, dev_out_ptr):
+    """mct_fuser_pack_foot_points: [n_obj][2] float32 on the device at dev_out_ptr (e.g. a torch tensor's data_ptr())."""
+    n = len(pfs)
+    vp = C.c_void_p
+    pa = (vp * n)(*[p.h for p in pfs])
+    hh = np.ascontiguousarray(h0, np.float32)
+    ctx.check(ctx.L.mct_fuser_pack_foot_points(ctx.h, n, pa, _fp(hh), vp(dev_out_ptr)))
+
+
 def track_update(ctx, clfs, pos_list, neg_list):
     n = len(clfs)
     vp = C.c_void_p

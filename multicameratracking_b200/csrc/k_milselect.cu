@@ -34,78 +34,145 @@ __device__ __forceinline__ bool better_min(float v, int f, float bv, int bf)
     return (v < bv) || (v == bv && f < bf);
 }
 
+// rows of terms per pass: MIL_RN negatives + MIL_PC positives per candidate; candidates per pass <= MIL_FC
+#define MIL_RN 32
+#define MIL_PC 64
+#define MIL_ROWS (MIL_RN + MIL_PC)
+#define MIL_FC 128
+
 __device__ __forceinline__ void
 milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int Nn, int K,
                   const float* __restrict__ weak, int weak_type, int* __restrict__ sel, int* __restrict__ nsel,
-                  int FC)
+                  int FC, int rows_in_smem)
 {
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
     const int M = P + Nn;
-    const int FCP = FC + 1;
+    const int FCP = FC | 1;                                  // odd row stride: the transposed stores hit 32 banks
+    const int FL = (F + C - 1) / C;
     extern __shared__ __align__(16) unsigned char smraw[];
     float* Hs = (float*)smraw;                               // [M]
-    float* scratch = Hs + M;                                 // [M][FC+1]
-    unsigned char* selflag = (unsigned char*)(scratch + (size_t)M * FCP);   // [F]
+    float* scratch = Hs + M;                                 // [MIL_ROWS][FCP] terms of the current pass, transposed
+    int* act = (int*)(scratch + (size_t)MIL_ROWS * FCP);     // [2][FC] compacted candidate lists (slot | need_pos << 16)
+    float* rows = (float*)(act + 2 * FC);                    // [FL][M] this CTA's candidate rows (optional)
+    unsigned char* selflag = (unsigned char*)(rows + (rows_in_smem ? (size_t)FL * M : 0));   // [F] 1 selected, 2 invalid
     __shared__ SelSlot slots[2][SEL_MAX_CLUSTER];
     __shared__ SelSlot s_best[SEL_THREADS / 32];
+    __shared__ int s_nact[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const int FL = (F + C - 1) / C;
     const int f_begin = rank * FL;
     const int f_end = min(F, f_begin + FL);
+    const int nw_c = (min(FC, FL) + 31) >> 5;                // warps that own candidates in phase 2
 
     for (int i = tid; i < M; i += blockDim.x) Hs[i] = 0.0f;
-    for (int f = tid; f < F; f += blockDim.x) selflag[f] = 0;
+    for (int f = tid; f < F; f += blockDim.x) {
+        unsigned char fl = 0;
+        if (weak_type != MCT_WEAK_PERCEPTRON && weak[0 * (size_t)F + f] == weak[1 * (size_t)F + f]) fl = 2;   // IsValidWeakClassifier: mu0 != mu1
+        selflag[f] = fl;
+    }
+    if (rows_in_smem)
+        for (int f = f_begin + warp; f < f_end; f += nwarps) {
+            const float* pr = pred + (size_t)f * ld;
+            float* dst = rows + (size_t)(f - f_begin) * M;
+            for (int i = lane; i < M; i += 32) dst[i] = pr[i];
+        }
     __syncthreads();
 
+    // (float)-log(1 - like + 1e-5) of a saturated bag (1 - like == 1.0f)
     double prev = 1000000.0;
     int n_sel = 0;
     for (int s = 0; s < K; s++) {
         float bv = CUDART_INF_F; int bf = 0x7fffffff;
         for (int fc = f_begin; fc < f_end; fc += FC) {
             const int nfc = min(FC, f_end - fc);
-            // phase 1: terms, coalesced over samples, transposed into scratch[i][fl]
-            for (int fl = warp; fl < nfc; fl += nwarps) {
-                const float* pr = pred + (size_t)(fc + fl) * ld;
-                for (int i = lane; i < M; i += 32) {
-                    const float sg = sigmoid_dev(__fadd_rn(Hs[i], pr[i]));
-                    float t;
-                    if (i < P) t = __fsub_rn(1.0f, sg);
-                    else t = -logf(__fsub_rn(__fadd_rn(1e-5f, 1.0f), sg));
-                    scratch[(size_t)i * FCP + fl] = t;
+            // The bag likelihood is the ordered f32 product of (1 - sigmoid) over the positives: it never grows, and once
+            // 1 - like rounds to 1.0f the later factors cannot change the NLL any more, so the positives are evaluated
+            // MIL_PC at a time and a candidate leaves the pass list as soon as its product saturates (bit-identical to the
+            // full chain).  The negatives' sum always runs to the end.
+            if (tid == 0) { s_nact[0] = 0; s_nact[1] = 0; }
+            __syncthreads();
+            float like = 1.0f, sn = 0.0f;
+            bool active = false, sat = false;
+            int col = 0;
+            if (tid < nfc && !selflag[fc + tid]) {
+                active = true;
+                col = atomicAdd(&s_nact[0], 1);
+                act[col] = tid | (1 << 16);
+            }
+            for (int it = 0;; it++) {
+                __syncthreads();
+                const int nact = s_nact[it & 1];
+                if (nact == 0) break;
+                const int n0 = it * MIL_RN, p0 = it * MIL_PC;
+                const int cntN = max(0, min(MIL_RN, Nn - n0)), cntP = max(0, min(MIL_PC, P - p0));
+                const int nbN = (cntN + 31) >> 5, nbP = (cntP + 31) >> 5, nblk = nbN + nbP;
+                const int* al = act + (it & 1) * FC;
+                // phase 1: terms, one warp per (candidate, 32 samples), transposed into scratch[row][col]
+                for (int u = warp; u < nact * nblk; u += nwarps) {
+                    const int a = u / nblk, b = u - a * nblk;
+                    const int e = al[a];
+                    const int slot = e & 0xffff;
+                    const float* pr = rows_in_smem ? rows + (size_t)(fc - f_begin + slot) * M : pred + (size_t)(fc + slot) * ld;
+                    if (b < nbN) {
+                        const int r = b * 32 + lane;
+                        if (r < cntN) {
+                            const int i = P + n0 + r;
+                            const float sg = sigmoid_dev(__fadd_rn(Hs[i], pr[i]));
+                            scratch[(size_t)r * FCP + a] = -logf(__fsub_rn(__fadd_rn(1e-5f, 1.0f), sg));
+                        }
+                    } else if (e >> 16) {
+                        const int r = (b - nbN) * 32 + lane;
+                        if (r < cntP) {
+                            const int i = p0 + r;
+                            const float sg = sigmoid_dev(__fadd_rn(Hs[i], pr[i]));
+                            scratch[(size_t)(MIL_RN + r) * FCP + a] = __fsub_rn(1.0f, sg);
+                        }
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) s_nact[it & 1] = 0;               // becomes the next-list counter of pass it + 1
+                // phase 2: ordered chains, one thread per candidate
+                if (active) {
+                    const float* sc = scratch + col;
+#pragma unroll 8
+                    for (int r = 0; r < cntN; r++) sn = __fadd_rn(sn, sc[(size_t)r * FCP]);
+                    if (!sat) {
+                        sc += (size_t)MIL_RN * FCP;
+#pragma unroll 8
+                        for (int r = 0; r < cntP; r++) like = __fmul_rn(like, sc[(size_t)r * FCP]);
+                        sat = __fsub_rn(1.0f, like) == 1.0f;
+                    }
+                    const bool more_p = !sat && (p0 + MIL_PC < P);
+                    if ((n0 + MIL_RN < Nn) || more_p) {
+                        col = atomicAdd(&s_nact[(it + 1) & 1], 1);
+                        act[((it + 1) & 1) * FC + col] = tid | ((int)more_p << 16);
+                    } else {
+                        active = false;
+                        const int f = fc + tid;
+                        const float posl = (float)(-log((double)__fsub_rn(1.0f, like) + 1e-5));
+                        const float nll = __fadd_rn(__fdiv_rn(posl, (float)P), __fdiv_rn(sn, (float)Nn));
+                        if (better_min(nll, f, bv, bf)) { bv = nll; bf = f; }
+                    }
                 }
             }
             __syncthreads();
-            // phase 2: ordered chains, one thread per candidate
-            if (tid < nfc) {
-                const int f = fc + tid;
-                float like = 1.0f;
-                for (int i = 0; i < P; i++) like = __fmul_rn(like, scratch[(size_t)i * FCP + tid]);
-                const float posl = (float)(-log((double)__fsub_rn(1.0f, like) + 1e-5));
-                float sn = 0.0f;
-                for (int j = P; j < M; j++) sn = __fadd_rn(sn, scratch[(size_t)j * FCP + tid]);
-                const float nll = __fadd_rn(__fdiv_rn(posl, (float)P), __fdiv_rn(sn, (float)Nn));
-                bool ok = !selflag[f];
-                if (ok && weak_type != MCT_WEAK_PERCEPTRON)
-                    ok = weak[0 * (size_t)F + f] != weak[1 * (size_t)F + f];      // IsValidWeakClassifier: mu0 != mu1
-                if (ok && better_min(nll, f, bv, bf)) { bv = nll; bf = f; }
+        }
+        // CTA argmin over the warps that own candidates
+        if (warp < nw_c) {
+            for (int o = 16; o > 0; o >>= 1) {
+                float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                int of = __shfl_xor_sync(0xffffffffu, bf, o);
+                if (better_min(ov, of, bv, bf)) { bv = ov; bf = of; }
             }
-            __syncthreads();
+            if (lane == 0) { s_best[warp].nll = bv; s_best[warp].f = bf; }
         }
-        // CTA argmin
-        for (int o = 16; o > 0; o >>= 1) {
-            float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            int of = __shfl_xor_sync(0xffffffffu, bf, o);
-            if (better_min(ov, of, bv, bf)) { bv = ov; bf = of; }
-        }
-        if (lane == 0) { s_best[warp].nll = bv; s_best[warp].f = bf; }
         __syncthreads();
         const int par = s & 1;
         if (tid < C) {
             float v = s_best[0].nll; int f = s_best[0].f;
-            for (int w = 1; w < nwarps; w++)
+            for (int w = 1; w < nw_c; w++)
                 if (better_min(s_best[w].nll, s_best[w].f, v, f)) { v = s_best[w].nll; f = s_best[w].f; }
             // publish into peer `tid`'s slot table (distributed shared memory)
             SelSlot* remote = cluster.map_shared_rank(&slots[0][0], tid);
@@ -132,18 +199,21 @@ milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int N
 __global__ void __launch_bounds__(SEL_THREADS)
 k_milboost_select(const float* __restrict__ pred, int ld, int F, int P, int Nn, int K,
                   const float* __restrict__ weak, int weak_type, int* __restrict__ sel, int* __restrict__ nsel,
-                  int FC)
+                  int FC, int rows_in_smem)
 {
-    milboost_select_body(pred, ld, F, P, Nn, K, weak, weak_type, sel, nsel, FC);
+    milboost_select_body(pred, ld, F, P, Nn, K, weak, weak_type, sel, nsel, FC, rows_in_smem);
 }
 // batched form: one cluster per object (blockIdx.y); objects of another strong-classifier type leave at once
 // (the whole cluster takes the same branch)
 __global__ void __launch_bounds__(SEL_THREADS)
-k_milboost_select_batch(const TrainDesc* __restrict__ descs, int FC)
+k_milboost_select_batch(const TrainDesc* __restrict__ descs, int FC, int FLmax, int Mmax)
 {
     const TrainDesc& d = descs[blockIdx.y];
     if (d.strong_type != MCT_STRONG_MILBOOST) return;
-    milboost_select_body(d.pred, d.ldT, d.F, d.P, d.Nn, d.K, d.weak, d.weak_type, d.sel, d.nsel, FC);
+    // the shared-memory plan was sized for (FLmax, Mmax): an object's rows fit iff its own FL * M does
+    const int FL = (d.F + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int rows_in_smem = FLmax > 0 && (size_t)FL * (d.P + d.Nn) <= (size_t)FLmax * Mmax && min(FC, FL) <= FC;
+    milboost_select_body(d.pred, d.ldT, d.F, d.P, d.Nn, d.K, d.weak, d.weak_type, d.sel, d.nsel, min(FC, max(FL, 1)), rows_in_smem);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -294,6 +364,19 @@ __global__ void __launch_bounds__(ANY_THREADS) k_anyboost_select_batch(const Tra
     anyboost_select_body(d.pred, d.ldT, d.F, d.P, d.Nn, d.K, d.sel, d.nsel);
 }
 
+
+// shared-memory plan of the MILBoost selection kernel: H[M] + terms[MIL_ROWS][FC|1] + lists[2][FC] + (rows[FL][M]) + flags[F]
+static size_t mil_smem_plan(int F, int M, int FL, int* FC_out, int* rows_out)
+{
+    int FC = FL < MIL_FC ? FL : MIL_FC;
+    if (FC < 1) FC = 1;
+    size_t base = (size_t)M * 4 + (size_t)MIL_ROWS * (FC | 1) * 4 + (size_t)2 * FC * 4 + (size_t)F;
+    size_t rows = (size_t)FL * M * 4;
+    int in_smem = base + rows <= (size_t)200 * 1024;
+    *FC_out = FC; *rows_out = in_smem;
+    size_t smem = base + (in_smem ? rows : 0);
+    return (smem + 15) & ~(size_t)15;
+}
 // ------------------------------------------------------------------------------------------
 int launch_mil_select(mct_clf* clf, int P, int Nn)
 {
@@ -315,14 +398,9 @@ int launch_mil_select(mct_clf* clf, int P, int Nn)
     if (C <= 0) { C = 1; while (C < SEL_MAX_CLUSTER && ceil_div(F, C) > 48) C <<= 1; }
     if (C > SEL_MAX_CLUSTER) C = SEL_MAX_CLUSTER;
     const int FL = ceil_div(F, C);
-    // candidates per chunk: the transposed tile [M][FC+1] must fit beside H[M] and the flags
-    const size_t budget = 180 * 1024;
-    long fc_max = ((long)budget - (long)M * 4 - F) / ((long)M * 4) - 1;
-    if (fc_max < 1) return mct_fail(ctx, MCT_E_UNSUPPORTED, "training set too large for the MIL selection kernel%s (M=%d)", "", M);
-    int FC = FL < (int)fc_max ? FL : (int)fc_max;
-    if (FC > SEL_THREADS) FC = SEL_THREADS;
-    size_t smem = (size_t)M * 4 + (size_t)M * (FC + 1) * 4 + (size_t)F;
-    smem = (smem + 15) & ~(size_t)15;
+    int FC, rows_in_smem;
+    const size_t smem = mil_smem_plan(F, M, FL, &FC, &rows_in_smem);
+    if (smem > 220 * 1024) return mct_fail(ctx, MCT_E_UNSUPPORTED, "training set too large for the MIL selection kernel%s (M=%d)", "", M);
     static size_t s_attr = 0;
     static int s_np = 0;
     if (smem > s_attr) {
@@ -346,7 +424,7 @@ int launch_mil_select(mct_clf* clf, int P, int Nn)
     int ld = clf->ldT, K = clf->K, wt = clf->p.weak_type;
     int* sel = clf->d_sel; int* nsel = clf->d_nsel;
     mct_prof_begin(ctx, "k_milboost_select");
-    MCT_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_milboost_select, pred, ld, F, P, Nn, K, weak, wt, sel, nsel, FC));
+    MCT_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_milboost_select, pred, ld, F, P, Nn, K, weak, wt, sel, nsel, FC, rows_in_smem));
     mct_prof_end(ctx);
     MCT_KERNEL_CHECK(ctx);
     return MCT_OK;
@@ -378,13 +456,10 @@ int launch_mil_select_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h
         if (C <= 0) { C = 1; while (C < SEL_MAX_CLUSTER && ceil_div(F, C) > 48) C <<= 1; }
         if (C > SEL_MAX_CLUSTER) C = SEL_MAX_CLUSTER;
         const int FL = ceil_div(F, C);
-        const size_t budget = 180 * 1024;
-        long fc_max = ((long)budget - (long)M * 4 - F) / ((long)M * 4) - 1;
-        if (fc_max < 1) return mct_fail(ctx, MCT_E_UNSUPPORTED, "training set too large for the MIL selection kernel%s (M=%d)", "", M);
-        int FC = FL < (int)fc_max ? FL : (int)fc_max;
-        if (FC > SEL_THREADS) FC = SEL_THREADS;
-        size_t smem = (size_t)M * 4 + (size_t)M * (FC + 1) * 4 + (size_t)F;
-        smem = (smem + 15) & ~(size_t)15;
+        int FC, rows_in_smem;
+        const size_t smem = mil_smem_plan(F, M, FL, &FC, &rows_in_smem);
+        if (smem > 220 * 1024) return mct_fail(ctx, MCT_E_UNSUPPORTED, "training set too large for the MIL selection kernel%s (M=%d)", "", M);
+        const int FLmax = rows_in_smem ? FL : 0, Mmax = M;
         static size_t s_attr = 0;
         static int s_np = 0;
         if (smem > s_attr) {
@@ -405,7 +480,7 @@ int launch_mil_select_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h
         attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         mct_prof_begin(ctx, "k_milboost_select_batch");
-        MCT_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_milboost_select_batch, d, FC));
+        MCT_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_milboost_select_batch, d, FC, FLmax, Mmax));
         mct_prof_end(ctx);
         MCT_KERNEL_CHECK(ctx);
     }

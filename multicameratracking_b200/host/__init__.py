@@ -36,6 +36,7 @@ def load():
         L.mcth_camera_init_trackers.argtypes = [vp]
         L.mcth_camera_track.argtypes = [vp, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]
         L.mcth_camera_track_resident.argtypes = [vp, C.c_int, vp]
+        L.mcth_camera_pack_foot_points.argtypes = [vp, vp]
         L.mcth_camera_sync.argtypes = [vp]
         L.mcth_camera_launches.argtypes = [vp]; L.mcth_camera_launches.restype = C.c_longlong
         L.mcth_object_selectors.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
@@ -114,6 +115,10 @@ class Camera:
         self._chk(self.L.mcth_camera_track(self.h, frameind, nz.ctypes.data_as(C.c_void_p), phases,
                                            out.ctypes.data_as(C.POINTER(C.c_int))))
         return out
+
+    def pack_foot_points(self, dev_out_ptr):
+        """geometric-fuser payload [n_obj][2] float32 written on the device (torch tensor data_ptr())"""
+        self._chk(self.L.mcth_camera_pack_foot_points(self.h, C.c_void_p(dev_out_ptr)))
 
     def sync(self):
         self._chk(self.L.mcth_camera_sync(self.h))

@@ -144,6 +144,18 @@ int mcth_camera_track_resident(mcth_camera* c, int frameind, const float* noise_
     GUARD(ParticleFilterTracker::ScoreCameraObjectsAsync(c->ctx, c->trackers, noise_dev));
 }
 
+// geometric-fuser payload of this camera: foot point of the highest-weight particle of every object, packed on
+// the device at dev_out [n_obj][2] (ready for an allgather on the same stream)
+int mcth_camera_pack_foot_points(mcth_camera* c, float* dev_out)
+{
+    const int n = (int)c->trackers.size();
+    std::vector<mct_pf*> pfs(n); std::vector<float> h0(n);
+    for (int o = 0; o < n; o++) { pfs[o] = c->trackers[o]->GetParticleFilter()->Handle(); h0[o] = c->trackers[o]->GetCurrentTrackerState()[3]; }
+    int rc = mct_fuser_pack_foot_points(c->ctx, n, pfs.data(), h0.data(), dev_out);
+    if (rc) c->err = mct_last_error(c->ctx);
+    return rc;
+}
+
 int mcth_camera_sync(mcth_camera* c) { return mct_sync(c->ctx); }
 long long mcth_camera_launches(mcth_camera* c) { return mct_launch_count(c->ctx); }
 

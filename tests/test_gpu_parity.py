@@ -735,3 +735,30 @@ def test_mdch_features_from_bgr_frame(ctx, oracle):
     bb = clf.features(capi.make_boxes(col, row, sx, sy))
     np.testing.assert_array_equal(a, bb)
     clf.close()
+
+
+def test_fuser_foot_points_payload(ctx, oracle):
+    """geometric-fuser payload: foot point (cx, cy + sy*h0/2) of the highest-weight particle, first maximum
+    (GetHighestWeightParticle, ParticleFilter.cpp:529-549; ParticleFilterTracker.cpp:1223-1238), packed on the device"""
+    import torch
+    rng = np.random.default_rng(41)
+    N, n_obj = 300, 3
+    pfs, exp, h0 = [], [], [90.0, 80.0, 60.0]
+    for o in range(n_obj):
+        pf = capi.ParticleFilter(ctx, N, 640, 480); pf.Initialize(320.0, 240.0)
+        st = np.zeros((N, 5), np.float32)
+        st[:, 0] = rng.uniform(50, 590, N).round(); st[:, 1] = rng.uniform(50, 430, N).round()
+        st[:, 2] = rng.uniform(0.8, 1.2, N); st[:, 3] = rng.uniform(0.8, 1.2, N)
+        st[:, 4] = rng.uniform(0, 1, N)
+        k = int(rng.integers(0, N - 5))
+        st[k, 4] = st[k + 3, 4] = 2.0                          # tie: the first maximum wins
+        pf.set_state(st)
+        a = int(np.argmax(st[:, 4]))
+        assert a == k
+        exp.append([st[a, 0], np.float32(st[a, 1] + np.float32(np.float32(st[a, 3] * np.float32(h0[o])) / np.float32(2.0)))])
+        pfs.append(pf)
+    out = torch.zeros((n_obj, 2), dtype=torch.float32, device="cuda")
+    capi.pack_foot_points(ctx, pfs, h0, out.data_ptr())
+    np.testing.assert_array_equal(out.cpu().numpy(), np.array(exp, np.float32))
+    for pf in pfs:
+        pf.close()
