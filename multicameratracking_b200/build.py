@@ -43,7 +43,7 @@ def build(force=False, verbose=False):
     for s in SOURCES:
         o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
         objs.append(o)
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("MCT_NVCC_EXTRA", "").split() + ["-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for s, p in procs:

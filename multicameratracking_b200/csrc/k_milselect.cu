@@ -34,37 +34,45 @@ __device__ __forceinline__ bool better_min(float v, int f, float bv, int bf)
     return (v < bv) || (v == bv && f < bf);
 }
 
-// rows of terms per pass: MIL_RN negatives + MIL_PC positives per candidate; candidates per pass <= MIL_FC
+// terms per pass and candidate: MIL_RN negatives + up to MIL_PC positives, kept per candidate in one padded row of
+// MIL_RS floats (MIL_RS % 32 == 4: the float4 reads of 8 neighbouring candidates cover the 32 banks once)
 #define MIL_RN 32
 #define MIL_PC 64
 #define MIL_ROWS (MIL_RN + MIL_PC)
+#define MIL_RS (MIL_ROWS + 4)
 #define MIL_FC 128
 
+#ifdef MCT_MIL_DEBUG
+// the read of barrier-protected state in front of the clock makes the stamp see the barrier's release, not its issue
+#define MIL_STAMP(k) { int v_ = *(volatile int*)&s_nact[0]; if (v_ == 0x7fffffff) dbg_pass += 1000; long long c_ = clock64(); dbg_t[k] += c_ - dbg_c; dbg_c = c_; }
+#else
+#define MIL_STAMP(k)
+#endif
+
+template <bool ROWS_SMEM>
 __device__ __forceinline__ void
 milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int Nn, int K,
                   const float* __restrict__ weak, int weak_type, int* __restrict__ sel, int* __restrict__ nsel,
-                  int FC, int rows_in_smem)
+                  int FC, int PC)
 {
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
     const int M = P + Nn;
-    const int FCP = FC | 1;                                  // odd row stride: the transposed stores hit 32 banks
     const int FL = (F + C - 1) / C;
     extern __shared__ __align__(16) unsigned char smraw[];
-    float* Hs = (float*)smraw;                               // [M]
-    float* scratch = Hs + M;                                 // [MIL_ROWS][FCP] terms of the current pass, transposed
-    int* act = (int*)(scratch + (size_t)MIL_ROWS * FCP);     // [2][FC] compacted candidate lists (slot | need_pos << 16)
-    float* rows = (float*)(act + 2 * FC);                    // [FL][M] this CTA's candidate rows (optional)
-    unsigned char* selflag = (unsigned char*)(rows + (rows_in_smem ? (size_t)FL * M : 0));   // [F] 1 selected, 2 invalid
+    float* scratch = (float*)smraw;                          // [FC][MIL_RS] terms of the current pass, one row per list entry
+    int* act = (int*)(scratch + (size_t)FC * MIL_RS);        // [2][FC] compacted candidate lists (slot | need_pos << 16)
+    float* Hs = (float*)(act + 2 * FC);                      // [M]
+    float* rows = Hs + M;                                    // [FL][M] this CTA's candidate rows (ROWS_SMEM)
+    unsigned char* selflag = (unsigned char*)(rows + (ROWS_SMEM ? (size_t)FL * M : 0));   // [F] 1 selected, 2 invalid
     __shared__ SelSlot slots[2][SEL_MAX_CLUSTER];
-    __shared__ SelSlot s_best[SEL_THREADS / 32];
+    __shared__ SelSlot s_cand[MIL_FC];
     __shared__ int s_nact[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int f_begin = rank * FL;
     const int f_end = min(F, f_begin + FL);
-    const int nw_c = (min(FC, FL) + 31) >> 5;                // warps that own candidates in phase 2
 
     for (int i = tid; i < M; i += blockDim.x) Hs[i] = 0.0f;
     for (int f = tid; f < F; f += blockDim.x) {
@@ -72,148 +80,231 @@ milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int N
         if (weak_type != MCT_WEAK_PERCEPTRON && weak[0 * (size_t)F + f] == weak[1 * (size_t)F + f]) fl = 2;   // IsValidWeakClassifier: mu0 != mu1
         selflag[f] = fl;
     }
-    if (rows_in_smem)
+    if (ROWS_SMEM)
         for (int f = f_begin + warp; f < f_end; f += nwarps) {
             const float* pr = pred + (size_t)f * ld;
-            float* dst = rows + (size_t)(f - f_begin) * M;
+            float* dst = rows + (f - f_begin) * M;
             for (int i = lane; i < M; i += 32) dst[i] = pr[i];
         }
+    if (tid == 0) { s_nact[0] = 0; s_nact[1] = 0; }
     __syncthreads();
 
-    // (float)-log(1 - like + 1e-5) of a saturated bag (1 - like == 1.0f)
+    // (float)-log(1 - like + 1e-5) of a saturated bag (1 - like == 1.0f): the f64 log leaves the per-round critical path
+    const float posl_sat = (float)(-log((double)1.0f + 1e-5));
+    const float fP = (float)P, fN = (float)Nn;
+#ifdef MCT_MIL_DEBUG
+    long long dbg_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long dbg_c = 0; int dbg_pass = 0;
+#endif
     double prev = 1000000.0;
     int n_sel = 0;
+    int g = 0;                  // running pass counter: list / counter parity continues across chunks and rounds
     for (int s = 0; s < K; s++) {
         float bv = CUDART_INF_F; int bf = 0x7fffffff;
+#ifdef MCT_MIL_DEBUG
+        dbg_c = clock64();
+#endif
         for (int fc = f_begin; fc < f_end; fc += FC) {
             const int nfc = min(FC, f_end - fc);
             // The bag likelihood is the ordered f32 product of (1 - sigmoid) over the positives: it never grows, and once
             // 1 - like rounds to 1.0f the later factors cannot change the NLL any more, so the positives are evaluated
-            // MIL_PC at a time and a candidate leaves the pass list as soon as its product saturates (bit-identical to the
+            // PC at a time and a candidate leaves the pass list as soon as its product saturates (bit-identical to the
             // full chain).  The negatives' sum always runs to the end.
-            if (tid == 0) { s_nact[0] = 0; s_nact[1] = 0; }
-            __syncthreads();
+            // Both counters are zero here (the previous list ran empty), and no thread can still be reading counter g & 1
+            // of an earlier pass: the last read was of the other parity.
             float like = 1.0f, sn = 0.0f;
             bool active = false, sat = false;
             int col = 0;
-            if (tid < nfc && !selflag[fc + tid]) {
-                active = true;
-                col = atomicAdd(&s_nact[0], 1);
-                act[col] = tid | (1 << 16);
+            if (tid < ((nfc + 31) & ~31)) {                     // whole warps: the list slots are handed out by ballot
+                active = tid < nfc && !selflag[fc + tid];
+                const unsigned bal = __ballot_sync(0xffffffffu, active);
+                int base = 0;
+                if (lane == 0 && bal) base = atomicAdd(&s_nact[g & 1], __popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (active) {
+                    col = base + __popc(bal & ((1u << lane) - 1u));
+                    act[(g & 1) * FC + col] = tid | (1 << 16);
+                }
             }
-            for (int it = 0;; it++) {
+            for (int it = 0;; it++, g++) {
                 __syncthreads();
-                const int nact = s_nact[it & 1];
-                if (nact == 0) break;
-                const int n0 = it * MIL_RN, p0 = it * MIL_PC;
-                const int cntN = max(0, min(MIL_RN, Nn - n0)), cntP = max(0, min(MIL_PC, P - p0));
+                const int nact = s_nact[g & 1];
+                if (nact == 0) { g++; break; }
+#ifdef MCT_MIL_DEBUG
+                dbg_pass++;
+#endif
+                MIL_STAMP(4)
+                const int n0 = it * MIL_RN, p0 = it * PC;
+                const int cntN = max(0, min(MIL_RN, Nn - n0)), cntP = max(0, min(PC, P - p0));
                 const int nbN = (cntN + 31) >> 5, nbP = (cntP + 31) >> 5, nblk = nbN + nbP;
-                const int* al = act + (it & 1) * FC;
-                // phase 1: terms, one warp per (candidate, 32 samples), transposed into scratch[row][col]
+                const unsigned magic = 65536u / (unsigned)nblk + 1u;        // u / nblk for u < 2^15, nblk <= 3
+                const int* al = act + (g & 1) * FC;
+                // phase 1: terms, one warp per (list entry, 32 samples); a block's tail is filled with the chain's neutral
+                // element so that phase 2 runs whole blocks
                 for (int u = warp; u < nact * nblk; u += nwarps) {
-                    const int a = u / nblk, b = u - a * nblk;
+                    const int a = (int)(((unsigned)u * magic) >> 16), b = u - a * nblk;
                     const int e = al[a];
                     const int slot = e & 0xffff;
-                    const float* pr = rows_in_smem ? rows + (size_t)(fc - f_begin + slot) * M : pred + (size_t)(fc + slot) * ld;
+                    const float* pr = ROWS_SMEM ? rows + (fc - f_begin + slot) * M : pred + (size_t)(fc + slot) * ld;
+                    float* dst = scratch + a * MIL_RS;
                     if (b < nbN) {
                         const int r = b * 32 + lane;
+                        float t = 0.0f;
                         if (r < cntN) {
                             const int i = P + n0 + r;
                             const float sg = sigmoid_dev(__fadd_rn(Hs[i], pr[i]));
-                            scratch[(size_t)r * FCP + a] = -logf(__fsub_rn(__fadd_rn(1e-5f, 1.0f), sg));
+                            t = -logf(__fsub_rn(__fadd_rn(1e-5f, 1.0f), sg));
                         }
+                        dst[r] = t;
                     } else if (e >> 16) {
                         const int r = (b - nbN) * 32 + lane;
+                        float t = 1.0f;
                         if (r < cntP) {
                             const int i = p0 + r;
-                            const float sg = sigmoid_dev(__fadd_rn(Hs[i], pr[i]));
-                            scratch[(size_t)(MIL_RN + r) * FCP + a] = __fsub_rn(1.0f, sg);
+                            t = __fsub_rn(1.0f, sigmoid_dev(__fadd_rn(Hs[i], pr[i])));
+                        }
+                        dst[MIL_RN + r] = t;
+                    }
+                }
+                MIL_STAMP(5)
+                __syncthreads();
+                MIL_STAMP(6)
+                if (tid == 0) s_nact[g & 1] = 0;                // becomes the next-list counter of pass g + 1
+                // phase 2: ordered chains, one thread per candidate; the sum and the product are independent chains and
+                // advance together
+                if (tid < ((nfc + 31) & ~31)) {
+                    bool again = false, more_p = false;
+                    if (active) {
+                        const float4* n4 = reinterpret_cast<const float4*>(scratch + col * MIL_RS);
+                        const float4* p4 = n4 + MIL_RN / 4;
+                        const bool doP = !sat && nbP > 0;
+                        if (nbN && doP) {
+#pragma unroll
+                            for (int k = 0; k < 8; k++) {
+                                const float4 x = n4[k], y = p4[k];
+                                sn = __fadd_rn(sn, x.x); like = __fmul_rn(like, y.x);
+                                sn = __fadd_rn(sn, x.y); like = __fmul_rn(like, y.y);
+                                sn = __fadd_rn(sn, x.z); like = __fmul_rn(like, y.z);
+                                sn = __fadd_rn(sn, x.w); like = __fmul_rn(like, y.w);
+                            }
+                        } else if (nbN) {
+#pragma unroll
+                            for (int k = 0; k < 8; k++) {
+                                const float4 x = n4[k];
+                                sn = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sn, x.x), x.y), x.z), x.w);
+                            }
+                        } else if (doP) {
+#pragma unroll
+                            for (int k = 0; k < 8; k++) {
+                                const float4 y = p4[k];
+                                like = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(like, y.x), y.y), y.z), y.w);
+                            }
+                        }
+                        if (doP) {
+                            for (int k = 8; k < nbP * 8; k++) {
+                                const float4 y = p4[k];
+                                like = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(like, y.x), y.y), y.z), y.w);
+                            }
+                            sat = __fsub_rn(1.0f, like) == 1.0f;
+                        }
+                        more_p = !sat && (p0 + PC < P);
+                        again = (n0 + MIL_RN < Nn) || more_p;
+                        if (!again) {
+                            active = false;
+                            const int f = fc + tid;
+                            const float posl = sat ? posl_sat : (float)(-log((double)__fsub_rn(1.0f, like) + 1e-5));
+                            const float nll = __fadd_rn(__fdiv_rn(posl, fP), __fdiv_rn(sn, fN));
+                            if (better_min(nll, f, bv, bf)) { bv = nll; bf = f; }
+                        }
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, again);
+                    if (bal) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(&s_nact[(g + 1) & 1], __popc(bal));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (again) {
+                            col = base + __popc(bal & ((1u << lane) - 1u));
+                            act[((g + 1) & 1) * FC + col] = tid | ((int)more_p << 16);
                         }
                     }
                 }
-                __syncthreads();
-                if (tid == 0) s_nact[it & 1] = 0;               // becomes the next-list counter of pass it + 1
-                // phase 2: ordered chains, one thread per candidate
-                if (active) {
-                    const float* sc = scratch + col;
-#pragma unroll 8
-                    for (int r = 0; r < cntN; r++) sn = __fadd_rn(sn, sc[(size_t)r * FCP]);
-                    if (!sat) {
-                        sc += (size_t)MIL_RN * FCP;
-#pragma unroll 8
-                        for (int r = 0; r < cntP; r++) like = __fmul_rn(like, sc[(size_t)r * FCP]);
-                        sat = __fsub_rn(1.0f, like) == 1.0f;
-                    }
-                    const bool more_p = !sat && (p0 + MIL_PC < P);
-                    if ((n0 + MIL_RN < Nn) || more_p) {
-                        col = atomicAdd(&s_nact[(it + 1) & 1], 1);
-                        act[((it + 1) & 1) * FC + col] = tid | ((int)more_p << 16);
-                    } else {
-                        active = false;
-                        const int f = fc + tid;
-                        const float posl = (float)(-log((double)__fsub_rn(1.0f, like) + 1e-5));
-                        const float nll = __fadd_rn(__fdiv_rn(posl, (float)P), __fdiv_rn(sn, (float)Nn));
-                        if (better_min(nll, f, bv, bf)) { bv = nll; bf = f; }
-                    }
-                }
+                MIL_STAMP(7)
             }
-            __syncthreads();
         }
-        // CTA argmin over the warps that own candidates
-        if (warp < nw_c) {
-            for (int o = 16; o > 0; o >>= 1) {
-                float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                int of = __shfl_xor_sync(0xffffffffu, bf, o);
-                if (better_min(ov, of, bv, bf)) { bv = ov; bf = of; }
-            }
-            if (lane == 0) { s_best[warp].nll = bv; s_best[warp].f = bf; }
-        }
+        MIL_STAMP(0)
+        // CTA argmin: the owning threads park their best in shared memory, warp 0 reduces and publishes
+        if (tid < FC) { s_cand[tid].nll = bv; s_cand[tid].f = bf; }
         __syncthreads();
         const int par = s & 1;
-        if (tid < C) {
-            float v = s_best[0].nll; int f = s_best[0].f;
-            for (int w = 1; w < nw_c; w++)
-                if (better_min(s_best[w].nll, s_best[w].f, v, f)) { v = s_best[w].nll; f = s_best[w].f; }
-            // publish into peer `tid`'s slot table (distributed shared memory)
-            SelSlot* remote = cluster.map_shared_rank(&slots[0][0], tid);
-            remote[par * SEL_MAX_CLUSTER + rank].nll = v;
-            remote[par * SEL_MAX_CLUSTER + rank].f = f;
+        if (warp == 0) {
+            float v = CUDART_INF_F; int f = 0x7fffffff;
+            for (int q = lane; q < FC; q += 32)
+                if (better_min(s_cand[q].nll, s_cand[q].f, v, f)) { v = s_cand[q].nll; f = s_cand[q].f; }
+            for (int o = 16; o > 0; o >>= 1) {
+                float ov = __shfl_xor_sync(0xffffffffu, v, o);
+                int of = __shfl_xor_sync(0xffffffffu, f, o);
+                if (better_min(ov, of, v, f)) { v = ov; f = of; }
+            }
+            if (lane < C) {
+                // publish into peer `lane`'s slot table (distributed shared memory)
+                SelSlot* remote = cluster.map_shared_rank(&slots[0][0], lane);
+                remote[par * SEL_MAX_CLUSTER + rank].nll = v;
+                remote[par * SEL_MAX_CLUSTER + rank].f = f;
+            }
         }
+        MIL_STAMP(1)
         cluster.sync();
-        float gv = slots[par][0].nll; int gf = slots[par][0].f;
-        for (int q = 1; q < C; q++)
-            if (better_min(slots[par][q].nll, slots[par][q].f, gv, gf)) { gv = slots[par][q].nll; gf = slots[par][q].f; }
+        MIL_STAMP(2)
+        // every thread reduces the C published bests the same way (2 slots per lane, then a butterfly)
+        float gv = CUDART_INF_F; int gf = 0x7fffffff;
+        if (lane < C) { gv = slots[par][lane].nll; gf = slots[par][lane].f; }
+        for (int o = 8; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, gv, o);
+            int of = __shfl_xor_sync(0xffffffffu, gf, o);
+            if (better_min(ov, of, gv, gf)) { gv = ov; gf = of; }
+        }
+        gv = __shfl_sync(0xffffffffu, gv, 0); gf = __shfl_sync(0xffffffffu, gf, 0);
         if (gf == 0x7fffffff) break;                               // nothing eligible (reference: UB read)
         if ((prev - (double)gv) < 1e-100) break;                   // :108-112 no improvement -> pop & stop
         prev = (double)gv;
         if (rank == 0 && tid == 0) sel[n_sel] = gf;
         n_sel++;
+        // the winner's row comes from L2: all CTAs of the cluster read the same 4 M bytes (a DSMEM read of the owner's copy
+        // queues 16 readers on one SM's shared-memory port and measured slower)
         const float* pb = pred + (size_t)gf * ld;
-        for (int i = tid; i < M; i += blockDim.x) Hs[i] = __fadd_rn(Hs[i], pb[i]);
+        for (int i = tid; i < M; i += blockDim.x) Hs[i] = __fadd_rn(Hs[i], __ldg(pb + i));
         if (tid == 0) selflag[gf] = 1;
         __syncthreads();
+        MIL_STAMP(3)
     }
+#ifdef MCT_MIL_DEBUG
+    if (tid == 0 && rank == 0 && blockIdx.y == 0)
+        printf("mil dbg: rounds %d passes %d | passes %lld argmin %lld csync %lld hs %lld clk | A %lld ph1 %lld B %lld ph2 %lld\n", n_sel, dbg_pass,
+               dbg_t[0], dbg_t[1], dbg_t[2], dbg_t[3], dbg_t[4], dbg_t[5], dbg_t[6], dbg_t[7]);
+#endif
     if (rank == 0 && tid == 0) *nsel = n_sel;
     cluster.sync();          // no CTA may exit while a peer can still write its slots
 }
 __global__ void __launch_bounds__(SEL_THREADS)
 k_milboost_select(const float* __restrict__ pred, int ld, int F, int P, int Nn, int K,
                   const float* __restrict__ weak, int weak_type, int* __restrict__ sel, int* __restrict__ nsel,
-                  int FC, int rows_in_smem)
+                  int FC, int rows_in_smem, int PC)
 {
-    milboost_select_body(pred, ld, F, P, Nn, K, weak, weak_type, sel, nsel, FC, rows_in_smem);
+    if (rows_in_smem) milboost_select_body<true>(pred, ld, F, P, Nn, K, weak, weak_type, sel, nsel, FC, PC);
+    else milboost_select_body<false>(pred, ld, F, P, Nn, K, weak, weak_type, sel, nsel, FC, PC);
 }
 // batched form: one cluster per object (blockIdx.y); objects of another strong-classifier type leave at once
 // (the whole cluster takes the same branch)
 __global__ void __launch_bounds__(SEL_THREADS)
-k_milboost_select_batch(const TrainDesc* __restrict__ descs, int FC, int FLmax, int Mmax)
+k_milboost_select_batch(const TrainDesc* __restrict__ descs, int FC, int FLmax, int Mmax, int PC)
 {
     const TrainDesc& d = descs[blockIdx.y];
     if (d.strong_type != MCT_STRONG_MILBOOST) return;
     // the shared-memory plan was sized for (FLmax, Mmax): an object's rows fit iff its own FL * M does
     const int FL = (d.F + (int)gridDim.x - 1) / (int)gridDim.x;
     const int rows_in_smem = FLmax > 0 && (size_t)FL * (d.P + d.Nn) <= (size_t)FLmax * Mmax && min(FC, FL) <= FC;
-    milboost_select_body(d.pred, d.ldT, d.F, d.P, d.Nn, d.K, d.weak, d.weak_type, d.sel, d.nsel, min(FC, max(FL, 1)), rows_in_smem);
+    const int fc = min(FC, max(FL, 1));
+    if (rows_in_smem) milboost_select_body<true>(d.pred, d.ldT, d.F, d.P, d.Nn, d.K, d.weak, d.weak_type, d.sel, d.nsel, fc, PC);
+    else milboost_select_body<false>(d.pred, d.ldT, d.F, d.P, d.Nn, d.K, d.weak, d.weak_type, d.sel, d.nsel, fc, PC);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -365,12 +456,19 @@ __global__ void __launch_bounds__(ANY_THREADS) k_anyboost_select_batch(const Tra
 }
 
 
-// shared-memory plan of the MILBoost selection kernel: H[M] + terms[MIL_ROWS][FC|1] + lists[2][FC] + (rows[FL][M]) + flags[F]
+// shared-memory plan of the MILBoost selection kernel: terms[FC][MIL_RS] + lists[2][FC] + H[M] + (rows[FL][M]) + flags[F]
+// positives per pass (<= MIL_PC); MCT_MIL_PC overrides for experiments
+static int mil_pc()
+{
+    static int pc = 0;
+    if (!pc) { const char* e = getenv("MCT_MIL_PC"); pc = e ? atoi(e) : 32; if (pc < 1 || pc > MIL_PC) pc = 32; }
+    return pc;
+}
 static size_t mil_smem_plan(int F, int M, int FL, int* FC_out, int* rows_out)
 {
     int FC = FL < MIL_FC ? FL : MIL_FC;
     if (FC < 1) FC = 1;
-    size_t base = (size_t)M * 4 + (size_t)MIL_ROWS * (FC | 1) * 4 + (size_t)2 * FC * 4 + (size_t)F;
+    size_t base = (size_t)M * 4 + (size_t)MIL_RS * FC * 4 + (size_t)2 * FC * 4 + (size_t)F;
     size_t rows = (size_t)FL * M * 4;
     int in_smem = base + rows <= (size_t)200 * 1024;
     *FC_out = FC; *rows_out = in_smem;
@@ -424,7 +522,7 @@ int launch_mil_select(mct_clf* clf, int P, int Nn)
     int ld = clf->ldT, K = clf->K, wt = clf->p.weak_type;
     int* sel = clf->d_sel; int* nsel = clf->d_nsel;
     mct_prof_begin(ctx, "k_milboost_select");
-    MCT_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_milboost_select, pred, ld, F, P, Nn, K, weak, wt, sel, nsel, FC, rows_in_smem));
+    MCT_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_milboost_select, pred, ld, F, P, Nn, K, weak, wt, sel, nsel, FC, rows_in_smem, mil_pc()));
     mct_prof_end(ctx);
     MCT_KERNEL_CHECK(ctx);
     return MCT_OK;
@@ -480,7 +578,7 @@ int launch_mil_select_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h
         attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         mct_prof_begin(ctx, "k_milboost_select_batch");
-        MCT_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_milboost_select_batch, d, FC, FLmax, Mmax));
+        MCT_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_milboost_select_batch, d, FC, FLmax, Mmax, mil_pc()));
         mct_prof_end(ctx);
         MCT_KERNEL_CHECK(ctx);
     }
