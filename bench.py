@@ -238,23 +238,42 @@ def run_ours(args):
         if rc:
             cam._chk(rc)
 
+    host_t = [0, 0, 0, 0, 0]      # ns spent in set_frame / prefetch_frame / prefetch_noise / track, and calls (MCT_BENCH_HOST_TIMING=1)
+    host_timing = os.environ.get("MCT_BENCH_HOST_TIMING") == "1"
+
+    # ctypes views of the (fixed) pinned buffers, made once: a C++ caller would pass the pointers directly
+    planes_ptr = None if args.e2e_bgr else [tuple(vp(x.data_ptr()) for x in pl) for pl in planes_pin]
+    bgr_ptr = [vp(x.data_ptr()) for x in bgr_pin] if args.e2e_bgr else None
+    noise_ptr = [vp(x.data_ptr()) for x in noise_pin]
+    noise_len = [x.numel() for x in noise_pin]
+    out_box = np.zeros((N_OBJ, 4), np.int32)
+    out_ptr = out_box.ctypes.data_as(C.POINTER(C.c_int))
+    Lh, camh = cam.L, cam.h
+
     def step_e2e(i, phases):
         t = pingpong(i, POOL)
-        if (not args.e2e_bgr):
-            g, r, gg, b = planes_pin[t]
-            cam._chk(cam.L.mcth_camera_set_frame(cam.h, vp(g.data_ptr()), vp(r.data_ptr()), vp(gg.data_ptr()), vp(b.data_ptr()), W, H, W, 0))
+        t0 = time.perf_counter_ns() if host_timing else 0
+        if planes_ptr is not None:
+            g, r, gg, b = planes_ptr[t]
+            cam._chk(Lh.mcth_camera_set_frame(camh, g, r, gg, b, W, H, W, 0))
+            t1 = time.perf_counter_ns() if host_timing else 0
             # the upload of the NEXT frame (pinned host memory) is started now and overlaps this frame's kernels, as a video
             # reader would decode ahead (Matrixu::PrefetchFrame); one frame is still copied per step
-            g2, r2, gg2, b2 = planes_pin[pingpong(i + 1, POOL)]
-            cam._chk(cam.L.mcth_camera_prefetch_frame(cam.h, vp(g2.data_ptr()), vp(r2.data_ptr()), vp(gg2.data_ptr()), vp(b2.data_ptr()), W, H, W))
+            g2, r2, gg2, b2 = planes_ptr[pingpong(i + 1, POOL)]
+            cam._chk(Lh.mcth_camera_prefetch_frame(camh, g2, r2, gg2, b2, W, H, W))
         else:
-            cam._chk(cam.L.mcth_camera_set_frame_bgr(cam.h, vp(bgr_pin[t].data_ptr()), W, H, 3 * W, 0, 0))
-            cam._chk(cam.L.mcth_camera_prefetch_frame_bgr(cam.h, vp(bgr_pin[pingpong(i + 1, POOL)].data_ptr()), W, H, 3 * W, 0))
-        if i + 1 < len(noise_pin):     # the next frame's Gaussian rows ride along as well (mct_noise_prefetch)
-            cam._chk(cam.L.mcth_camera_prefetch_noise(cam.h, vp(noise_pin[i + 1].data_ptr()), noise_pin[i + 1].numel()))
-        out = np.zeros((N_OBJ, 4), np.int32)
-        cam._chk(cam.L.mcth_camera_track(cam.h, t, vp(noise_pin[i].data_ptr()), phases, out.ctypes.data_as(C.POINTER(C.c_int))))
-        return out
+            cam._chk(Lh.mcth_camera_set_frame_bgr(camh, bgr_ptr[t], W, H, 3 * W, 0, 0))
+            t1 = time.perf_counter_ns() if host_timing else 0
+            cam._chk(Lh.mcth_camera_prefetch_frame_bgr(camh, bgr_ptr[pingpong(i + 1, POOL)], W, H, 3 * W, 0))
+        t2 = time.perf_counter_ns() if host_timing else 0
+        if i + 1 < len(noise_ptr):     # the next frame's Gaussian rows ride along as well (mct_noise_prefetch)
+            cam._chk(Lh.mcth_camera_prefetch_noise(camh, noise_ptr[i + 1], noise_len[i + 1]))
+        t3 = time.perf_counter_ns() if host_timing else 0
+        cam._chk(Lh.mcth_camera_track(camh, t, noise_ptr[i], phases, out_ptr))
+        if host_timing:
+            t4 = time.perf_counter_ns()
+            host_t[0] += t1 - t0; host_t[1] += t2 - t1; host_t[2] += t3 - t2; host_t[3] += t4 - t3; host_t[4] += 1
+        return out_box
 
     def timed(fn, n_warm, n_steps, offset=0):
         for i in range(n_warm):
@@ -285,6 +304,8 @@ def run_ours(args):
     # ---- 3. end to end through the host API, host buffers ----
     ms_e2e, scored_e2e, _ = timed(lambda i: step_e2e(i, 1), args.warmup, args.steps)
     # ---- 4. full frames (score + UpdateClassifier) through the host API ----
+    if host_timing:
+        sys.stderr.write("host us/step (score e2e): set_frame %.1f prefetch_frame %.1f prefetch_noise %.1f track %.1f\n" % tuple(1e-3 * x / max(1, host_t[4]) for x in host_t[:4]))
     ms_full, _, _ = timed(lambda i: step_e2e(i, 3), args.warmup, args.steps)
     # per-kernel CUDA-event times of full frames (the UpdateClassifier kernels ride after the score path)
     L.mct_profile_enable(ctx_h, 1)

@@ -1055,23 +1055,6 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
         MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_noise_stage, noise, ntot * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
         sa.noise_base = ctx->d_noise_stage;
     }
-    if (ctx->prep_stream && (rc = prefetch_copy(ctx))) return rc;      // next frame's planes: behind this frame's noise copy
-    if (ctx->npf_req && ctx->prep_stream) {
-        // next call's noise: into the other prefetch buffer (last read two frames ago; those kernels are covered by the
-        // marker of the latest mct_frame_set, which the copy stream waits for)
-        const int nb = ctx->noise_pf_cur ^ 1;
-        if (ctx->npf_req_n > ctx->noise_pf_cap[nb]) {
-            MCT_CUDA(ctx, cudaDeviceSynchronize());
-            if (ctx->d_noise_pf[nb]) cudaFree(ctx->d_noise_pf[nb]);
-            MCT_CUDA(ctx, cudaMalloc(&ctx->d_noise_pf[nb], ctx->npf_req_n * sizeof(float)));
-            ctx->noise_pf_cap[nb] = ctx->npf_req_n;
-        }
-        MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->prep_stream, ctx->ev_mark[ctx->mark_idx], 0));
-        MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_noise_pf[nb], ctx->npf_req_src, ctx->npf_req_n * sizeof(float), cudaMemcpyHostToDevice, ctx->prep_stream));
-        MCT_CUDA(ctx, cudaEventRecord(ctx->ev_noise, ctx->prep_stream));
-        ctx->noise_pf_cur = nb;
-        ctx->npf_ready_src = ctx->npf_req_src; ctx->npf_ready_n = ctx->npf_req_n; ctx->npf_ready = 1; ctx->npf_req = 0;
-    }
     const ObjDesc* d;
     if ((rc = desc_publish(ctx, h, n_obj, &d))) return rc;
     if ((rc = launch_pf_predict_testset(ctx, d, n_obj, n_max, sa))) return rc;
@@ -1100,9 +1083,28 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
     if (ctx->prep_stream) {
         MCT_CUDA(ctx, cudaEventRecord(ctx->ev_gather, ctx->stream));
         ctx->has_gather = 1;
-        if ((rc = prefetch_prep(ctx))) return rc;
     }
     if ((rc = launch_pf_update(ctx, d, n_obj, n_max, 1, sa, 1))) return rc;
+    // Only now, with this frame's whole chain queued, the housekeeping for the NEXT frame: every API call in front of the
+    // first launch is host time the GPU sits idle for (the caller waits for this frame's summaries before the next call)
+    if (ctx->prep_stream && (rc = prefetch_copy(ctx))) return rc;      // next frame's planes (behind this frame's noise copy)
+    if (ctx->npf_req && ctx->prep_stream) {
+        // next call's noise: into the other prefetch buffer (last read two frames ago; those kernels are covered by the
+        // marker of the latest mct_frame_set, which the copy stream waits for)
+        const int nb = ctx->noise_pf_cur ^ 1;
+        if (ctx->npf_req_n > ctx->noise_pf_cap[nb]) {
+            MCT_CUDA(ctx, cudaDeviceSynchronize());
+            if (ctx->d_noise_pf[nb]) cudaFree(ctx->d_noise_pf[nb]);
+            MCT_CUDA(ctx, cudaMalloc(&ctx->d_noise_pf[nb], ctx->npf_req_n * sizeof(float)));
+            ctx->noise_pf_cap[nb] = ctx->npf_req_n;
+        }
+        MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->prep_stream, ctx->ev_mark[ctx->mark_idx], 0));
+        MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_noise_pf[nb], ctx->npf_req_src, ctx->npf_req_n * sizeof(float), cudaMemcpyHostToDevice, ctx->prep_stream));
+        MCT_CUDA(ctx, cudaEventRecord(ctx->ev_noise, ctx->prep_stream));
+        ctx->noise_pf_cur = nb;
+        ctx->npf_ready_src = ctx->npf_req_src; ctx->npf_ready_n = ctx->npf_req_n; ctx->npf_ready = 1; ctx->npf_req = 0;
+    }
+    if (ctx->prep_stream && ctx->has_gather && (rc = prefetch_prep(ctx))) return rc;
     return MCT_OK;
 }
 
@@ -1131,9 +1133,24 @@ extern "C" int mct_track_score(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, mct_
                                const mct_track_params* params, const float* noise, int noise_is_device, const float* u01,
                                mct_pf_summary* summaries)
 {
+    // MCT_HOST_TIMING=1: host time spent issuing the frame's work vs waiting for its summaries (stderr, every 64 calls)
+    static int timing = -1;
+    if (timing < 0) { const char* e = getenv("MCT_HOST_TIMING"); timing = e && e[0] == '1'; }
+    if (!timing) {
+        int rc = mct_track_score_async(ctx, n_obj, pfs, clfs, params, noise, noise_is_device, u01);
+        if (rc) return rc;
+        return mct_track_collect(ctx, n_obj, summaries);
+    }
+    static double t_issue = 0, t_wait = 0; static int calls = 0;
+    auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
+    const double a = now();
     int rc = mct_track_score_async(ctx, n_obj, pfs, clfs, params, noise, noise_is_device, u01);
+    const double b = now();
     if (rc) return rc;
-    return mct_track_collect(ctx, n_obj, summaries);
+    rc = mct_track_collect(ctx, n_obj, summaries);
+    t_issue += b - a; t_wait += now() - b;
+    if (++calls == 64) { fprintf(stderr, "mct_track_score: issue %.1f us, wait %.1f us per call\n", t_issue / calls, t_wait / calls); calls = 0; t_issue = t_wait = 0; }
+    return rc;
 }
 
 static void fill_train_desc(TrainDesc* t, mct_clf* c)
