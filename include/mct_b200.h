@@ -210,7 +210,8 @@ int mct_pf_get_summary(mct_pf* pf, mct_pf_summary* out_host);
  * camera in a handful of batched launches: predict -> GenerateTestSampleSet (:1247-1305) -> Classify
  * (selected features only; identical result to the reference, which computes all F and reads K) ->
  * likelihood map ((H-min)/range)^exponent (:541-566) -> UpdateAllParticlesWeight -> Normalize ->
- * ResampleIfRequired -> read-out.  noise: [n_obj][4][N] (host or dev); u01: [n_obj] host.
+ * ResampleIfRequired -> read-out.  noise: [n_obj][4][N] (host or dev); u01: [n_obj] host.  noise == NULL selects the
+ * re-score variant (ParticleFilterTracker.cpp:1334-1482): the particles are scored where they are, without prediction.
  * summaries: [n_obj] host, valid after the call returns (the call synchronises the stream). */
 typedef struct {
     float w0, h0;           /* m_currentStateList[2], [3] */
@@ -243,6 +244,26 @@ int mct_pf_get_last_response(mct_pf* pf, float* out_N_host, int* valid_N_host);
 /* Packs the per-object payload the fusers exchange: foot point of the highest-weight
  * particle (cx, cy + sy*h0/2) (ParticleFilterTracker.cpp:1223-1238) into dev_out[n_obj][2] (dev),
  * ready for an NCCL allgather on the same stream. */
+/* ---- geometric-fuser feedback into one camera's particles (ParticleFilterTracker.cpp:1040-1125) ----
+ * mct_pf_ground_pdf: EstimateGroundPoint(false) (:1134-1160) + TransformWithHomography (GeometryBasedInformationFuser.cpp:
+ * 172-212) + MultiVariateNormalPdf (:111-163, exponent without the 1/2 as in the reference) for every particle, their total,
+ * and GetAverageofAllParticles (ParticleFilter.cpp:601-633) for the 20-pixel rearrangement test (:1090-1105) the caller
+ * makes.  H9: image -> ground homography (row-major f64); mean2 / cov4: the Kalman posterior (f32).  weights_host: optional
+ * [N] read-back of the per-particle pdf (all 1 when the covariance is unusable, :1063-1077). */
+typedef struct {
+    float total_weight;
+    float average[4];
+    int   usable_covariance;
+} mct_ground_pdf_result;
+int mct_pf_ground_pdf(mct_pf* pf, const double* H9, const float* mean2, const float* cov4, float h0,
+                      mct_ground_pdf_result* out, float* weights_host);
+/* RearrangeParticlesBasedOnGroundLocation (ParticleFilter.cpp:120-179, scale-changing form) followed by
+ * CheckForParticleRefinement (:173).  noise2xN: host [2][N], the (xRand, yRand) = randgaus(0, 10) pairs in particle order
+ * (drawn by the caller from the reference's MWC stream, Public.cpp:37-49).  The re-scoring that follows in the reference
+ * (UpdateParticleWeightsForRearrangedParticles, ParticleFilterTracker.cpp:1334-1482) is mct_track_score with noise == NULL
+ * (no prediction), exponent 1, force_reset 1, resample 1. */
+int mct_pf_rearrange_ground(mct_pf* pf, float mean_foot_x, float mean_foot_y, const float* noise2xN, float w0, float h0);
+
 int mct_fuser_pack_foot_points(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, const float* h0, float* dev_out);
 
 #ifdef __cplusplus

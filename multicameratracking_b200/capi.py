@@ -32,6 +32,7 @@ SYMBOLS = [
     "mct_pf_update_all_weights", "mct_pf_resample", "mct_pf_get_state", "mct_pf_set_state", "mct_pf_get_resampled",
     "mct_pf_get_resample_indices", "mct_pf_get_summary", "mct_track_score", "mct_noise_prefetch", "mct_track_score_async",
     "mct_track_collect", "mct_track_update", "mct_pf_get_last_response", "mct_fuser_pack_foot_points",
+    "mct_pf_ground_pdf", "mct_pf_rearrange_ground",
 ]
 
 
@@ -53,6 +54,10 @@ class ClfParams(C.Structure):
 
 class HaarTable(C.Structure):
     _fields_ = [("n_features", C.c_int), ("nrect", _c_int_p), ("rects", _c_int_p), ("weights", _c_float_p)]
+
+
+class GroundPdfResult(C.Structure):
+    _fields_ = [("total_weight", C.c_float), ("average", C.c_float * 4), ("usable_covariance", C.c_int)]
 
 
 class PfSummary(C.Structure):
@@ -130,6 +135,8 @@ def load():
     L.mct_track_update.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(Boxes), C.POINTER(Boxes)]
     L.mct_pf_get_last_response.argtypes = [vp, _c_float_p, _c_int_p]
     L.mct_fuser_pack_foot_points.argtypes = [vp, C.c_int, C.POINTER(vp), _c_float_p, vp]
+    L.mct_pf_ground_pdf.argtypes = [vp, C.POINTER(C.c_double), _c_float_p, _c_float_p, C.c_float, C.POINTER(GroundPdfResult), _c_float_p]
+    L.mct_pf_rearrange_ground.argtypes = [vp, C.c_float, C.c_float, _c_float_p, C.c_float, C.c_float]
     _lib = L
     return L
 
@@ -356,6 +363,22 @@ class ParticleFilter:
         ctx.check(ctx.L.mct_pf_create(ctx.h, n_particles, float(image_w), float(image_h), C.byref(h)))
         self.h = h
 
+    def ground_pdf(self, H, mean, cov, h0, want_weights=False):
+        """mct_pf_ground_pdf -> (total_weight, average[4], usable_covariance, weights or None)"""
+        Hd = np.ascontiguousarray(H, np.float64).reshape(9)
+        m = np.ascontiguousarray(mean, np.float32).reshape(2); c = np.ascontiguousarray(cov, np.float32).reshape(4)
+        res = GroundPdfResult()
+        w = np.zeros(self.N, np.float32) if want_weights else None
+        self.ctx.check(self.ctx.L.mct_pf_ground_pdf(self.h, Hd.ctypes.data_as(C.POINTER(C.c_double)), _fp(m), _fp(c), float(h0),
+                                                    C.byref(res), _fp(w) if want_weights else None))
+        return float(res.total_weight), np.array(list(res.average), np.float32), int(res.usable_covariance), w
+
+    def rearrange_ground(self, mean_foot, noise2xN, w0, h0):
+        """mct_pf_rearrange_ground (RearrangeParticlesBasedOnGroundLocation + CheckForParticleRefinement)"""
+        nz = np.ascontiguousarray(noise2xN, np.float32)
+        assert nz.shape == (2, self.N)
+        self.ctx.check(self.ctx.L.mct_pf_rearrange_ground(self.h, float(mean_foot[0]), float(mean_foot[1]), _fp(nz), float(w0), float(h0)))
+
     def close(self):
         if self.h:
             self.ctx.L.mct_pf_destroy(self.h)
@@ -420,6 +443,8 @@ def track_score(ctx, pfs, clfs, params, noise, u01, noise_device_ptr=None):
     out = (PfSummary * n)()
     if noise_device_ptr is not None:
         rc = ctx.L.mct_track_score(ctx.h, n, pa, ca, tp, vp(noise_device_ptr), 1, _fp(u), out)
+    elif noise is None:            # re-score variant: no prediction (UpdateParticleWeightsForRearrangedParticles)
+        rc = ctx.L.mct_track_score(ctx.h, n, pa, ca, tp, None, 0, _fp(u), out)
     else:
         nz = np.ascontiguousarray(noise, np.float32)
         rc = ctx.L.mct_track_score(ctx.h, n, pa, ca, tp, nz.ctypes.data_as(vp), 0, _fp(u), out)

@@ -138,6 +138,34 @@ __device__ __forceinline__ float scale_step_dev(float s, float n, float msc, flo
     if (s < mins) s = mins;
     return s;
 }
+
+// CheckForParticleRefinement (ParticleFilter.cpp:83-112) looks at the RESAMPLED matrix: a particle counts when its box's top-left
+// corner lies inside the image.  When no particle counts, ForceParticleFilterRefinement (:187-226) pulls the resampled centres
+// back towards the frame (quirk kept: the vertical correction uses scaleX, RS(row, 2)).
+__device__ __forceinline__ bool refine_valid_one(const ObjDesc& d, int i)
+{
+    const float left = __fsub_rn(d.rcx[i], __fdiv_rn(__fmul_rn(d.rsx[i], d.w0), 2.0f));
+    const float top = __fsub_rn(d.rcy[i], __fdiv_rn(__fmul_rn(d.rsy[i], d.h0), 2.0f));
+    return !(left < 0 || left >= d.img_w || top < 0 || top >= d.img_h);
+}
+__device__ __forceinline__ void force_refine_one(const ObjDesc& d, int i)
+{
+    const float cx = d.rcx[i], cy = d.rcy[i], sx = d.rsx[i], sy = d.rsy[i];
+    const float left = __fsub_rn(cx, __fdiv_rn(__fmul_rn(sx, d.w0), 2.0f));
+    const float top = __fsub_rn(cy, __fdiv_rn(__fmul_rn(sy, d.h0), 2.0f));
+    const float fx = cx, fy = __fadd_rn(cy, __fdiv_rn(__fmul_rn(sy, d.h0), 2.0f));
+    const float up = __fsub_rn(fy, __fdiv_rn(__fmul_rn(sx, d.h0), 2.0f));
+    if (left < 0) d.rcx[i] = fmaxf(fx, 0.0f);
+    if (left >= d.img_w) d.rcx[i] = fminf(fx, __fsub_rn(d.img_w, 1.0f));
+    if (top < 0) d.rcy[i] = fmaxf(up, 0.0f);
+    if (top >= d.img_h) d.rcy[i] = fminf(up, __fsub_rn(d.img_h, 1.0f));
+    d.rw[i] = 1.0f;
+}
+// The fused per-frame path spreads the check over two kernels: the predict kernel ORs {2 = check pending, 1 = some
+// particle counts} into PfDev::refine, k_pf_update (one CTA per object, the next kernel that touches the resampled
+// matrix) applies the refinement when the check is pending and nothing counted, and clears the flag.
+#define MCT_REFINE_PENDING 2
+#define MCT_REFINE_VALID 1
 __device__ __forceinline__ void predict_one(const ObjDesc& d, int i, const float* __restrict__ nz)
 {
     const int N = d.N;
@@ -188,6 +216,7 @@ __global__ void __launch_bounds__(256) k_pf_testset(const ObjDesc* __restrict__ 
 {
     const ObjDesc& d = descs[blockIdx.y];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && d.nbig) *d.nbig = 0;                 // (the re-score variant starts here: no predict kernel in front)
     if (i >= d.N) return;
     testset_one(d, i, fw, fh);
 }
@@ -201,7 +230,10 @@ __global__ void __launch_bounds__(256) k_pf_predict_testset(const ObjDesc* __res
         d.st->filter_state = MCT_PF_PREDICTED; d.st->time_index += 1;
         if (d.nbig) *d.nbig = 0;                       // per-frame reset of the MDCH generic-path counter
     }
-    if (i >= d.N) return;
+    const bool in = i < d.N;
+    const int any = __syncthreads_or(in && refine_valid_one(d, i));
+    if (threadIdx.x == 0) atomicOr(&d.st->refine, MCT_REFINE_PENDING | (any ? MCT_REFINE_VALID : 0));
+    if (!in) return;
     predict_one(d, i, sa.noise_base + d.noise_off);
     testset_one(d, i, fw, fh);
 }
@@ -369,6 +401,7 @@ __global__ void __launch_bounds__(PF_THREADS) k_pf_update(const ObjDesc* __restr
     float* cdf = (2 * N4 <= smem_floats) ? smf + N4 : d.scratch + PLEN(d.ld);
 
     PF_STAMP(0);
+    const int refine = d.st->refine;          // consumed after the first reduction: the load overlaps it
     // 0. valid count, min / max of H over the test set
     float mn = CUDART_INF_F, mx = -CUDART_INF_F;
     int cnt = 0;
@@ -381,8 +414,11 @@ __global__ void __launch_bounds__(PF_THREADS) k_pf_update(const ObjDesc* __restr
         for (int k = 0; k < 4; k++) if (vv[k]) { mn = fminf(mn, hh[k]); mx = fmaxf(mx, hh[k]); cnt++; }
     }
     block_reduce_cnt_minmax(cnt, mn, mx, sh_f, sh_i);
+    if (refine == MCT_REFINE_PENDING)         // CheckForParticleRefinement of this frame's predict found no particle in frame
+        for (int i = tid; i < N; i += nt) force_refine_one(d, i);
     __syncthreads();
     if (tid == 0) {
+        d.st->refine = 0;
         d.st->n_valid = cnt; d.st->resampled = 0;
         if (mode == 0) {
             d.st->max_response = cnt > 0 ? mx : 0.0f;
@@ -743,5 +779,103 @@ __global__ void __launch_bounds__(256) k_foot_points(const ObjDesc* __restrict__
 int launch_foot_points(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, const float* d_h0, float* d_out)
 {
     MCT_LAUNCH(ctx, "k_foot_points", k_foot_points<<<n_obj, 256, 0, ctx->stream>>>(d_desc, d_h0, d_out));
+    return MCT_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Geometric-fuser feedback
+//
+// k_pf_refine: CheckForParticleRefinement + ForceParticleFilterRefinement in one CTA per object, for the call sites
+// outside the fused per-frame path (mct_pf_predict, mct_pf_rearrange_ground).
+__global__ void __launch_bounds__(256) k_pf_refine(const ObjDesc* __restrict__ descs)
+{
+    const ObjDesc& d = descs[blockIdx.x];
+    int ok = 0;
+    for (int i = threadIdx.x; i < d.N; i += blockDim.x) ok |= refine_valid_one(d, i) ? 1 : 0;
+    const int any = __syncthreads_or(ok);
+    if (!any)
+        for (int i = threadIdx.x; i < d.N; i += blockDim.x) force_refine_one(d, i);
+    if (threadIdx.x == 0) d.st->refine = 0;
+}
+int launch_pf_refine(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj)
+{
+    MCT_LAUNCH(ctx, "k_pf_refine", k_pf_refine<<<n_obj, 256, 0, ctx->stream>>>(d_desc));
+    return MCT_OK;
+}
+
+// RearrangeParticlesBasedOnGroundLocation (ParticleFilter.cpp:120-179, shouldChangeTheScaleAccordingToOffset): every
+// particle's foot point is pulled onto the fused ground location (seen in this camera's image) plus noise by changing its
+// scale while its box's top-left corner stays where it was.  nz: [2][N] = the (xRand, yRand) pairs in particle order.
+__global__ void __launch_bounds__(256) k_pf_rearrange(const ObjDesc* __restrict__ descs, const float* __restrict__ nz, float mfx, float mfy)
+{
+    const ObjDesc& d = descs[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.N) return;
+    const float cx = d.cx[i], cy = d.cy[i], sx = d.sx[i], sy = d.sy[i];
+    const float hw = __fdiv_rn(d.w0, 2.0f), hh = __fdiv_rn(d.h0, 2.0f);
+    const float kx = (float)(2.0 / (double)d.w0), ky = (float)(1.0 / (double)d.h0);
+    const float xpos = fmaxf(0.0f, __fsub_rn(cx, __fmul_rn(hw, sx)));
+    const float ypos = fmaxf(0.0f, __fsub_rn(cy, __fmul_rn(hh, sy)));
+    const float fy = __fadd_rn(cy, __fmul_rn(hh, sy));
+    const float offx = __fadd_rn(__fsub_rn(mfx, cx), nz[i]);
+    const float offy = __fadd_rn(__fsub_rn(mfy, fy), nz[(size_t)d.N + i]);
+    const float nsx = fminf(fmaxf(__fadd_rn(__fmul_rn(kx, offx), sx), d.mins), d.maxs);
+    const float nsy = fminf(fmaxf(__fadd_rn(__fmul_rn(ky, offy), sy), d.mins), d.maxs);
+    d.sx[i] = nsx; d.sy[i] = nsy;
+    d.cx[i] = __fadd_rn(xpos, __fmul_rn(hw, nsx));
+    d.cy[i] = __fadd_rn(ypos, __fmul_rn(hh, nsy));
+}
+int launch_pf_rearrange(mct_ctx* ctx, const ObjDesc* d_desc, int n_max, const float* d_noise2, float mfx, float mfy)
+{
+    dim3 g(ceil_div(n_max, 256), 1);
+    MCT_LAUNCH(ctx, "k_pf_rearrange", k_pf_rearrange<<<g, 256, 0, ctx->stream>>>(d_desc, d_noise2, mfx, mfy));
+    return MCT_OK;
+}
+
+// UpdateParticlesWithGroundPDF, the per-particle part (ParticleFilterTracker.cpp:1054-1086): foot point
+// (cx, cy + sy*h0/2) -> ground plane through the camera's homography (f64, GeometryBasedInformationFuser.cpp:172-212)
+// -> multivariate normal pdf under the Kalman posterior (:111-163; the exponent has no 1/2, as in the reference), the total
+// weight, and GetAverageofAllParticles for the rearrangement test that follows on the host.
+__global__ void __launch_bounds__(256) k_ground_pdf(const ObjDesc* __restrict__ descs, const GroundArgs ga, float* __restrict__ wout,
+                                                    GroundOut* __restrict__ out)
+{
+    __shared__ double sh_d5[5 * 32];
+    __shared__ double sh_d[32];
+    const ObjDesc& d = descs[blockIdx.x];
+    const int N = d.N, tid = threadIdx.x, nt = blockDim.x;
+    double tot = 0.0, acc[5] = {0, 0, 0, 0, 0};
+    for (int i = tid; i < N; i += nt) {
+        const float cx = d.cx[i], cy = d.cy[i], sx = d.sx[i], sy = d.sy[i], w = d.w[i];
+        float pdf = 1.0f;
+        if (ga.usable) {
+            const double x = (double)cx, y = (double)__fadd_rn(cy, __fdiv_rn(__fmul_rn(sy, ga.h0), 2.0f));
+            const double t0 = __dadd_rn(__dadd_rn(__dmul_rn(ga.H[0], x), __dmul_rn(ga.H[1], y)), ga.H[2]);
+            const double t1 = __dadd_rn(__dadd_rn(__dmul_rn(ga.H[3], x), __dmul_rn(ga.H[4], y)), ga.H[5]);
+            const double t2 = __dadd_rn(__dadd_rn(__dmul_rn(ga.H[6], x), __dmul_rn(ga.H[7], y)), ga.H[8]);
+            const float gx = (float)(t0 / t2), gy = (float)(t1 / t2);
+            const float d0 = __fsub_rn(gx, ga.mean[0]), d1 = __fsub_rn(gy, ga.mean[1]);
+            const float q0 = (float)__dadd_rn(__dmul_rn((double)d0, (double)ga.ci[0]), __dmul_rn((double)d1, (double)ga.ci[2]));
+            const float q1 = (float)__dadd_rn(__dmul_rn((double)d0, (double)ga.ci[1]), __dmul_rn((double)d1, (double)ga.ci[3]));
+            const float prod = (float)__dadd_rn(__dmul_rn((double)q0, (double)d0), __dmul_rn((double)q1, (double)d1));
+            const float c = expf(-prod);
+            pdf = (float)(ga.a * (double)ga.b * (double)c);
+            if (pdf < 0) pdf = 0.0f;
+        }
+        if (wout) wout[i] = pdf;
+        tot += (double)pdf;
+        acc[0] += (double)__fmul_rn(cx, w); acc[1] += (double)__fmul_rn(cy, w);
+        acc[2] += (double)__fmul_rn(sx, w); acc[3] += (double)__fmul_rn(sy, w); acc[4] += (double)w;
+    }
+    tot = block_reduce_sum_d(tot, sh_d);
+    block_reduce_sum_d5(acc, sh_d5);
+    if (tid == 0) {
+        out->total_weight = (float)tot;
+        for (int q = 0; q < 4; q++) out->average[q] = (float)(acc[q] / acc[4]);
+    }
+}
+int launch_ground_pdf(mct_ctx* ctx, const ObjDesc* d_desc, const GroundArgs& ga, float* d_wout, GroundOut* d_out)
+{
+    MCT_LAUNCH(ctx, "k_ground_pdf", k_ground_pdf<<<1, 256, 0, ctx->stream>>>(d_desc, ga, d_wout, d_out));
     return MCT_OK;
 }

@@ -180,6 +180,7 @@ extern "C" int mct_ctx_destroy(mct_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->prep_stream) cudaStreamSynchronize(ctx->prep_stream);
     if (ctx->d_scored) cudaFree(ctx->d_scored);
+    if (ctx->d_ground_out) cudaFree(ctx->d_ground_out);
     if (ctx->prof) {
         ProfState* ps = (ProfState*)ctx->prof;
         for (ProfEntry& e : ps->entries) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -952,6 +953,62 @@ extern "C" int mct_pf_predict(mct_pf* p, const float* noise, int noise_is_device
     const ObjDesc* d; StepArgs sa; int rc;
     if ((rc = pf_single_desc(p, &d, &sa, w0, h0, 0, 1, 0.0f))) return rc;
     if ((rc = launch_pf_predict(ctx, d, 1, p->N, sa))) return rc;
+    if (w0 > 0 && h0 > 0 && (rc = launch_pf_refine(ctx, d, 1))) return rc;      // CheckForParticleRefinement (:328)
+    return mct_sync(ctx);     // the host noise buffer may be reused by the caller
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Geometric-fuser feedback
+extern "C" int mct_pf_ground_pdf(mct_pf* p, const double* H9, const float* mean2, const float* cov4, float h0,
+                                 mct_ground_pdf_result* out, float* weights_host)
+{
+    if (!p || !H9 || !mean2 || !cov4 || !out) return MCT_E_ARG;
+    mct_ctx* ctx = p->ctx;
+    if (!p->initialized) return mct_fail(ctx, MCT_E_STATE, "particle filter not initialised%s");
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    GroundArgs ga;
+    memset(&ga, 0, sizeof(ga));
+    for (int i = 0; i < 9; i++) ga.H[i] = H9[i];
+    ga.mean[0] = mean2[0]; ga.mean[1] = mean2[1]; ga.h0 = h0;
+    // cvDet / cvInvert of the 2x2 CV_32F covariance: f64 products, f32 store (GeometryBasedInformationFuser.cpp:119-133)
+    const double det = (double)cov4[0] * (double)cov4[3] - (double)cov4[1] * (double)cov4[2];
+    ga.usable = (det >= 0.0 && cov4[0] > 0) ? 1 : 0;       // ParticleFilterTracker.cpp:1063
+    if (ga.usable) {
+        if (det != 0.0) {
+            const double r = 1.0 / det;
+            ga.ci[0] = (float)((double)cov4[3] * r); ga.ci[1] = (float)(-(double)cov4[1] * r);
+            ga.ci[2] = (float)(-(double)cov4[2] * r); ga.ci[3] = (float)((double)cov4[0] * r);
+        }
+        const float detf = (float)det;
+        ga.b = 1.0f / sqrtf(detf);
+        const double s2pi = sqrt(6.283185307179586);
+        ga.a = 1.0 / (s2pi * s2pi);
+    }
+    const ObjDesc* d; StepArgs sa; int rc;
+    if ((rc = pf_single_desc(p, &d, &sa, 0, h0, 0, 1, 0.0f))) return rc;
+    if (!ctx->d_ground_out) MCT_CUDA(ctx, cudaMalloc(&ctx->d_ground_out, sizeof(GroundOut)));
+    if ((rc = launch_ground_pdf(ctx, d, ga, weights_host ? p->d_prob : nullptr, ctx->d_ground_out))) return rc;
+    GroundOut go;
+    MCT_CUDA(ctx, cudaMemcpyAsync(&go, ctx->d_ground_out, sizeof(go), cudaMemcpyDeviceToHost, ctx->stream));
+    if (weights_host) MCT_CUDA(ctx, cudaMemcpyAsync(weights_host, p->d_prob, (size_t)p->N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = mct_sync(ctx))) return rc;
+    out->total_weight = go.total_weight;
+    for (int q = 0; q < 4; q++) out->average[q] = go.average[q];
+    out->usable_covariance = ga.usable;
+    return MCT_OK;
+}
+
+extern "C" int mct_pf_rearrange_ground(mct_pf* p, float mean_foot_x, float mean_foot_y, const float* noise2xN, float w0, float h0)
+{
+    if (!p || !noise2xN || !(w0 > 0) || !(h0 > 0)) return MCT_E_ARG;
+    mct_ctx* ctx = p->ctx;
+    if (!p->initialized) return mct_fail(ctx, MCT_E_STATE, "particle filter not initialised%s");
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    MCT_CUDA(ctx, cudaMemcpyAsync(p->d_noise, noise2xN, (size_t)2 * p->N * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const ObjDesc* d; StepArgs sa; int rc;
+    if ((rc = pf_single_desc(p, &d, &sa, w0, h0, 0, 1, 0.0f))) return rc;
+    if ((rc = launch_pf_rearrange(ctx, d, p->N, p->d_noise, mean_foot_x, mean_foot_y))) return rc;
+    if ((rc = launch_pf_refine(ctx, d, 1))) return rc;                            // :173 CheckForParticleRefinement
     return mct_sync(ctx);     // the host noise buffer may be reused by the caller
 }
 
@@ -1013,8 +1070,9 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
                                      const mct_track_params* params, const float* noise, int noise_is_device,
                                      const float* u01)
 {
-    if (!ctx || n_obj < 1 || n_obj > DESC_MAX_OBJ || !pfs || !clfs || !params || !noise || !u01) return MCT_E_ARG;
+    if (!ctx || n_obj < 1 || n_obj > DESC_MAX_OBJ || !pfs || !clfs || !params || !u01) return MCT_E_ARG;
     if (ctx->frame_id == 0) return mct_fail(ctx, MCT_E_STATE, "no frame set%s");
+    const bool rescore = noise == nullptr;      // UpdateParticleWeightsForRearrangedParticles: no prediction step
     MCT_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc, n_max = 0, K_max = 1;
     size_t ntot = 0;
@@ -1040,7 +1098,7 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
     }
     // prediction noise: device pointers are used in place; a block announced with mct_noise_prefetch is already on the
     // device; any other host noise is staged with ONE copy
-    if (noise_is_device) sa.noise_base = noise;
+    if (noise_is_device || rescore) sa.noise_base = noise;
     else if (ctx->npf_ready && ctx->npf_ready_src == noise && ctx->npf_ready_n == ntot) {
         MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_noise, 0));
         sa.noise_base = ctx->d_noise_pf[ctx->noise_pf_cur];
@@ -1057,7 +1115,8 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
     }
     const ObjDesc* d;
     if ((rc = desc_publish(ctx, h, n_obj, &d))) return rc;
-    if ((rc = launch_pf_predict_testset(ctx, d, n_obj, n_max, sa))) return rc;
+    if (rescore) { if ((rc = launch_pf_testset(ctx, d, n_obj, n_max))) return rc; }
+    else if ((rc = launch_pf_predict_testset(ctx, d, n_obj, n_max, sa))) return rc;
     int any_mdch = 0, max_slots = 1, nb = 0;
     for (int o = 0; o < n_obj; o++) {
         mct_clf* c = clfs[o]; mct_pf* p = pfs[o];

@@ -21,7 +21,7 @@ struct PfDev {
     float neff_inv;
     float max_response;
     int   time_index;
-    int   pad;
+    int   refine;        // CheckForParticleRefinement hand-over between the predict kernel and k_pf_update (k_pf.cu)
 };
 
 // One selected weak classifier, ready for Classify: Haar rect table (or the featN row of a colour feature) + the
@@ -46,6 +46,7 @@ struct PrepTarget {            // what one frame-prep launch reads and writes
     const uint8_t *gray, *c0, *c1, *c2; int W, H, pitch;
     float* ii_base; int ii_pitch; uint16_t* binimg;
 };
+struct GroundOut;
 struct mct_ctx {
     int device;
     cudaStream_t stream;
@@ -81,6 +82,7 @@ struct mct_ctx {
     unsigned long long* d_scored;                      // device counter: test samples scored (sum of n_valid)
     void* prof;                                        // per-kernel event timing state (NULL = off)
     char err[512];
+    GroundOut* d_ground_out;     // read-out of k_ground_pdf
 };
 
 struct mct_clf {
@@ -116,6 +118,18 @@ struct mct_clf {
     int* d_big; int big_cap;                            // per test box: 1 = left to the generic (large / odd box) kernel
     int* d_nbig;                                        // device counter of such boxes
 };
+
+// geometric-fuser feedback: per-call arguments and read-out of k_ground_pdf
+struct GroundArgs {
+    double H[9];         // image -> ground homography
+    double a;            // 1 / pow(sqrt(2 pi), 2)
+    float mean[2];       // Kalman posterior mean
+    float ci[4];         // inverse covariance (cvInvert, f32)
+    float b;             // 1 / sqrt(det)
+    float h0;
+    int usable;          // det >= 0 && cov[0] > 0 (else every weight is 1)
+};
+struct GroundOut { float total_weight; float average[4]; };
 
 struct mct_pf {
     mct_ctx* ctx;
@@ -250,6 +264,9 @@ int launch_classify(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, i
 int launch_classify_staged(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int log_ratio);
 int launch_pf_predict(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, const StepArgs& sa);
 int launch_pf_testset(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max);
+int launch_pf_refine(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj);
+int launch_pf_rearrange(mct_ctx* ctx, const ObjDesc* d_desc, int n_max, const float* d_noise2, float mfx, float mfy);
+int launch_ground_pdf(mct_ctx* ctx, const ObjDesc* d_desc, const GroundArgs& ga, float* d_wout, GroundOut* d_out);
 // fused predict + test set (+ per-frame reset of the MDCH fallback counters) for the batched per-frame path
 int launch_pf_predict_testset(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, const StepArgs& sa);
 // with_summary: run the read-out (k_pf_summary body) at the end of the same kernel

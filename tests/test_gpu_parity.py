@@ -762,3 +762,161 @@ def test_fuser_foot_points_payload(ctx, oracle):
     np.testing.assert_array_equal(out.cpu().numpy(), np.array(exp, np.float32))
     for pf in pfs:
         pf.close()
+
+
+# ---------------------------------------------------------------------------------- geometric-fuser feedback
+def _plausible_homography(seed):
+    r = np.random.default_rng(seed)
+    return np.array([[r.uniform(0.8, 1.5), r.uniform(-0.2, 0.2), r.uniform(-100, 100)],
+                     [r.uniform(-0.2, 0.2), r.uniform(0.8, 1.5), r.uniform(-100, 100)],
+                     [r.uniform(-5e-4, 5e-4), r.uniform(-5e-4, 5e-4), 1.0]], np.float64)
+
+
+def test_ground_pdf_weights_total_and_average(ctx):
+    """UpdateParticlesWithGroundPDF, per-particle part (ParticleFilterTracker.cpp:1054-1086) against the numpy oracle:
+    pdf values within 2e-6 relative (expf differs in the last bit between libm and CUDA), total and average within 1e-6
+    (the device sums in f64, the reference sequentially in f32)"""
+    from oracle import fuser_oracle as fo
+    rng = np.random.default_rng(5)
+    N, h0 = 700, 80.0
+    pf = capi.ParticleFilter(ctx, N, 640, 480); pf.Initialize(320.0, 240.0)
+    st = np.zeros((N, 5), np.float32)
+    st[:, 0] = rng.uniform(200, 440, N).round(); st[:, 1] = rng.uniform(150, 330, N).round()
+    st[:, 2] = rng.uniform(0.8, 1.2, N); st[:, 3] = rng.uniform(0.8, 1.2, N); st[:, 4] = rng.uniform(0, 1, N)
+    pf.set_state(st)
+    H = _plausible_homography(1)
+    g = fo.transform_with_homography(fo.estimate_ground_points(st, h0), H)
+    mean = np.array([g[:, 0].mean(), g[:, 1].mean()], np.float32)
+    cov = np.array([[900.0, 120.0], [120.0, 1600.0]], np.float32)
+    tot, avg, usable, w = pf.ground_pdf(H, mean, cov, h0, want_weights=True)
+    wo, toto = fo.ground_pdf_weights(st, h0, H, mean, cov)
+    assert usable == 1 and wo.max() > 0
+    np.testing.assert_allclose(w, wo, rtol=2e-6, atol=1e-30)
+    assert abs(tot - float(toto)) <= 1e-6 * float(toto)
+    np.testing.assert_allclose(avg, fo.average_particle(st), rtol=1e-6)
+    # Kalman covariance the reference treats as unusable (negative determinant): every weight is 1 (:1073-1077)
+    tot2, _, usable2, w2 = pf.ground_pdf(H, mean, np.array([[1.0, 5.0], [5.0, 1.0]], np.float32), h0, want_weights=True)
+    assert usable2 == 0 and tot2 == float(N) and (w2 == 1.0).all()
+    pf.close()
+
+
+def test_rearrange_particles_on_ground_location_bit_exact(ctx):
+    """RearrangeParticlesBasedOnGroundLocation (ParticleFilter.cpp:120-179): f32 arithmetic in the reference's order,
+    including the scale clamps and the max(0, .) on the box corner"""
+    from oracle import fuser_oracle as fo
+    rng = np.random.default_rng(6)
+    N, w0, h0 = 1000, 40.0, 80.0
+    pf = capi.ParticleFilter(ctx, N, 640, 480); pf.Initialize(320.0, 240.0)
+    st = np.zeros((N, 5), np.float32)
+    st[:, 0] = rng.uniform(5, 635, N).round(); st[:, 1] = rng.uniform(5, 475, N).round()
+    st[:, 2] = rng.uniform(0.3, 3.0, N); st[:, 3] = rng.uniform(0.3, 3.0, N); st[:, 4] = rng.uniform(0, 1, N)
+    st[:5, 0] = 3.0; st[:5, 1] = 2.0                  # box corner left of / above the frame: clamped to 0
+    pf.set_state(st)
+    nz = (rng.standard_normal((2, N)) * 10).astype(np.float32)
+    nz[0, 5:10] = 4000.0; nz[1, 10:15] = -4000.0      # drive the scales into both clamps
+    pf.rearrange_ground((300.5, 260.25), nz, w0, h0)
+    exp = fo.rearrange_particles(st, (300.5, 260.25), nz, w0, h0)
+    got = pf.state()
+    np.testing.assert_array_equal(got, exp)
+    assert (got[5:10, 2] == 10.0).all() and (got[10:15, 3] == np.float32(0.1)).all()
+    pf.close()
+
+
+def test_particle_refinement_when_every_resampled_particle_left_the_frame(ctx):
+    """CheckForParticleRefinement / ForceParticleFilterRefinement (ParticleFilter.cpp:83-112, 187-226): no resampled
+    particle with its box corner inside the image -> centres pulled back (vertical correction with scaleX, as in the
+    reference), weights 1; with one particle inside nothing changes.  Both through mct_pf_predict and through the fused
+    per-frame call (flag handed from the predict kernel to the update kernel)."""
+    from oracle import fuser_oracle as fo
+    N, w0, h0 = 300, 40.0, 80.0
+    rng = np.random.default_rng(8)
+    for via_fused in (False, True):
+        for keep_one in (False, True):
+            pf = capi.ParticleFilter(ctx, N, 640, 480)
+            pf.Initialize(-30.0 if not keep_one else 300.0, -20.0 if not keep_one else 200.0)
+            rs0 = pf.resampled()
+            nz = np.zeros((4, N), np.float32)
+            if via_fused:
+                seq = synth.Sequence(640, 480, 1)
+                gray, r, g, b = seq.frame(0)
+                ctx.frame_set(gray, r, g, b)
+                clf = capi.StrongClassifier(ctx, capi.FEAT_MDCH, int(w0), int(h0), n_bins=8, n_selected=20)
+                orc = None
+                pos = (np.array([300, 301], np.int32), np.array([200, 200], np.int32), np.ones(2, np.float32), np.ones(2, np.float32))
+                neg = (np.array([100, 120], np.int32), np.array([100, 90], np.int32), np.ones(2, np.float32), np.ones(2, np.float32))
+                clf.Update(capi.make_boxes(*pos), capi.make_boxes(*neg))
+                try:
+                    capi.track_score(ctx, [pf], [clf], [(w0, h0, 20, 0, 1)], nz[None], [0.5])
+                except capi.MctError:
+                    assert not keep_one              # all particles off-frame: no test sample (reference: ASSERT abort)
+                clf.close()
+            else:
+                pf.PredictWithBrownianMotion(nz, w0, h0)
+            exp, forced = fo.check_refinement(rs0, w0, h0, 640, 480)
+            assert forced == (not keep_one)
+            got = pf.resampled()
+            if not (via_fused and keep_one):         # (a fused call that scores may also resample: skip the comparison then)
+                np.testing.assert_array_equal(got[:, :4], exp[:, :4])
+            pf.close()
+    del rng
+
+
+def test_rescore_rearranged_particles_matches_oracle(ctx, oracle):
+    """UpdateParticleWeightsForRearrangedParticles (ParticleFilterTracker.cpp:1334-1482) = mct_track_score without
+    prediction noise: test set from the particles where they are, Classify, likelihood with exponent 1, weights force-reset,
+    ResampleIfRequired"""
+    from oracle import fuser_oracle as fo
+    seq = synth.Sequence(640, 480, 2)
+    w0, h0 = seq.w0, seq.h0
+    N, F, K = 800, 120, 24
+    t, arrs = haar_table(oracle, F, w0, h0)
+    gray, r, g, b = seq.frame(0)
+    ctx.frame_set(gray, r, g, b)
+    of = oracle.frame(gray, r, g, b)
+    clfs, oclfs, pfs, opfs = [], [], [], []
+    for o, ft in enumerate((capi.FEAT_HAAR_MDCH, capi.FEAT_HAAR)):
+        clf = capi.StrongClassifier(ctx, ft, w0, h0, n_haar=F, n_bins=8, n_selected=K, haar=arrs)
+        oclf = oracle.clf_create(ft, F, 8, w0, h0, 0, 2, K, 0.85, t)
+        pos, neg = _train_sets(oracle, seq, 0, o, seed=o + 1)
+        clf.Update(capi.make_boxes(*pos), capi.make_boxes(*neg))
+        oracle.clf_update(oclf, of, oracle.boxes(*pos), oracle.boxes(*neg))
+        x, y, w, h = seq.box(0, o)
+        pf, opf = _pf_pair(ctx, oracle, N, cx=x + w / 2, cy=y + h / 2)
+        clfs.append(clf); oclfs.append(oclf); pfs.append(pf); opfs.append(opf)
+    gray, r, g, b = seq.frame(1)
+    ctx.frame_set(gray, r, g, b)
+    of = oracle.frame(gray, r, g, b)
+    # one ordinary frame first so that the particles are spread and weighted
+    nz = np.stack([synth.noise(N, (20, 20, 1e-7, 1e-7), obj=o, t=1) for o in range(2)])
+    capi.track_score(ctx, pfs, clfs, [(w0, h0, 20, 0, 1)] * 2, nz, [0.3, 0.6])
+    rng = np.random.default_rng(9)
+    for o in range(2):
+        st = pfs[o].state()
+        # fused ground location seen in this camera: 30 px to the right of / below the particles' mean foot
+        foot = (float(st[:, 0].mean()) + 30.0, float((st[:, 1] + st[:, 3] * h0 / 2).mean()) + 25.0)
+        nz2 = (rng.standard_normal((2, N)) * 10).astype(np.float32)
+        pfs[o].rearrange_ground(foot, nz2, w0, h0)
+        exp = fo.rearrange_particles(st, foot, nz2, w0, h0)
+        np.testing.assert_array_equal(pfs[o].state(), exp)
+        oracle.pf_state(opfs[o])[:] = exp
+    u01 = [oracle.randfloat(oracle.rng(900 + o)) for o in range(2)]
+    summ = capi.track_score(ctx, pfs, clfs, [(w0, h0, 1, 1, 1)] * 2, None, u01)
+    for o in range(2):
+        opf = opfs[o]
+        col, row, sx, sy = oracle.pf_test_set(opf, w0, h0, 640, 480)
+        assert len(col) == summ[o].n_valid and len(col) > 0
+        Ho = oracle.clf_classify(oclfs[o], of, oracle.boxes(col, row, sx, sy))
+        Hg, valid = pfs[o].last_response()
+        rel_close(Hg[valid != 0], Ho)
+        prob = oracle.likelihood_map(Ho, 1)
+        # (onlyNonZero, forceReset, resample) = (1, 1, 1)
+        rr = oracle.rng(900 + o)
+        res = oracle.lib.orc_pf_update_all_weights(opf, prob.ctypes.data_as(C.POINTER(C.c_float)), 1, 1, 1, C.byref(rr))
+        assert bool(res) == bool(summ[o].resampled)
+        sg, so = pfs[o].state(), oracle.pf_state(opf)
+        np.testing.assert_array_equal(sg[:, :4], so[:, :4])
+        rel_close(sg[:, 4], so[:, 4], rtol=2e-4, scale=so[:, 4].max())
+    for x in clfs + pfs:
+        x.close()
+    for oc in oclfs:
+        oracle.lib.orc_clf_free(oc)
