@@ -37,6 +37,16 @@ def load():
         L.mcth_camera_track.argtypes = [vp, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]
         L.mcth_camera_track_resident.argtypes = [vp, C.c_int, vp]
         L.mcth_camera_pack_foot_points.argtypes = [vp, vp]
+        dp, fp = C.POINTER(C.c_double), C.POINTER(C.c_float)
+        L.mcth_camera_ground_feedback.argtypes = [vp, C.c_int, dp, fp, fp, C.POINTER(C.c_int), fp]
+        L.mcth_fuser_create.argtypes = [C.c_int, dp, C.POINTER(vp)]
+        L.mcth_fuser_destroy.argtypes = [vp]
+        L.mcth_fuser_last_error.argtypes = [vp]; L.mcth_fuser_last_error.restype = C.c_char_p
+        L.mcth_fuser_initialize.argtypes = [vp, fp]
+        L.mcth_fuser_fuse.argtypes = [vp, fp]
+        L.mcth_fuser_get.argtypes = [vp, fp, fp, fp, fp]
+        L.mcth_fuser_intersection.argtypes = [C.c_int, dp, fp, dp]
+        L.mcth_randgaus.argtypes = [C.c_int64, C.c_float, C.c_int, fp]
         L.mcth_camera_sync.argtypes = [vp]
         L.mcth_camera_launches.argtypes = [vp]; L.mcth_camera_launches.restype = C.c_longlong
         L.mcth_object_selectors.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
@@ -120,6 +130,18 @@ class Camera:
         """geometric-fuser payload [n_obj][2] float32 written on the device (torch tensor data_ptr())"""
         self._chk(self.L.mcth_camera_pack_foot_points(self.h, C.c_void_p(dev_out_ptr)))
 
+    def ground_feedback(self, o, H, mean, cov):
+        """UpdateParticlesWithGroundPDF for object o (ParticleFilterTracker.cpp:1040-1125): the fused ground-plane estimate
+        (Kalman mean / covariance) is projected into this camera; when the particles' mean foot point is 20 px or more
+        away they are rearranged around it and re-scored.  Returns (rearranged, distance)."""
+        Hd = np.ascontiguousarray(H, np.float64).reshape(9)
+        m = np.ascontiguousarray(mean, np.float32).reshape(2); cv = np.ascontiguousarray(cov, np.float32).reshape(4)
+        r = C.c_int(0); d = C.c_float(0)
+        fp = C.POINTER(C.c_float)
+        self._chk(self.L.mcth_camera_ground_feedback(self.h, o, Hd.ctypes.data_as(C.POINTER(C.c_double)), m.ctypes.data_as(fp),
+                                                     cv.ctypes.data_as(fp), C.byref(r), C.byref(d)))
+        return bool(r.value), float(d.value)
+
     def sync(self):
         self._chk(self.L.mcth_camera_sync(self.h))
 
@@ -152,3 +174,70 @@ class Camera:
 
     def rng_state(self, o):
         return int(self.L.mcth_object_rng_state(self.h, o))
+
+
+class GeometricFuser:
+    """GeometryBasedInformationFuser of ONE object (principal-axis mode): every rank holds the same instance and feeds it
+    the same all-gathered foot points, so no broadcast of the Kalman state is needed."""
+
+    def __init__(self, homographies):
+        self.L = load()
+        Hs = np.ascontiguousarray(homographies, np.float64).reshape(-1, 9)
+        self.n_cameras = Hs.shape[0]
+        h = C.c_void_p()
+        rc = self.L.mcth_fuser_create(self.n_cameras, Hs.ctypes.data_as(C.POINTER(C.c_double)), C.byref(h))
+        if rc:
+            raise HostError("mcth_fuser_create failed (%d): at least two cameras are needed" % rc)
+        self.h = h
+        self.initialized = False
+
+    def _chk(self, rc):
+        if rc:
+            raise HostError("fuser error %d: %s" % (rc, self.L.mcth_fuser_last_error(self.h).decode()))
+
+    def _foot(self, foot):
+        f = np.ascontiguousarray(foot, np.float32)
+        if f.shape != (self.n_cameras, 2):
+            raise ValueError("foot points must be float32 [%d][2]" % self.n_cameras)
+        return f
+
+    def initialize(self, foot):
+        f = self._foot(foot)
+        self._chk(self.L.mcth_fuser_initialize(self.h, f.ctypes.data_as(C.POINTER(C.c_float))))
+        self.initialized = True
+
+    def fuse(self, foot):
+        """FuseInformation: InitializeKalman on the first call, predict + correct afterwards"""
+        if not self.initialized:
+            return self.initialize(foot)
+        f = self._foot(foot)
+        self._chk(self.L.mcth_fuser_fuse(self.h, f.ctypes.data_as(C.POINTER(C.c_float))))
+
+    def posterior(self):
+        """-> (mean[2], cov[2][2], state[4], P[4][4]) float32"""
+        fp = C.POINTER(C.c_float)
+        m = np.zeros(2, np.float32); cv = np.zeros(4, np.float32); st = np.zeros(4, np.float32); P = np.zeros(16, np.float32)
+        self._chk(self.L.mcth_fuser_get(self.h, m.ctypes.data_as(fp), cv.ctypes.data_as(fp), st.ctypes.data_as(fp), P.ctypes.data_as(fp)))
+        return m, cv.reshape(2, 2), st, P.reshape(4, 4)
+
+    def close(self):
+        if self.h:
+            self.L.mcth_fuser_destroy(self.h)
+            self.h = None
+
+
+def principal_axis_intersection(homographies, foot):
+    L = load()
+    Hs = np.ascontiguousarray(homographies, np.float64).reshape(-1, 9)
+    f = np.ascontiguousarray(foot, np.float32)
+    out = np.zeros(2, np.float64)
+    if L.mcth_fuser_intersection(Hs.shape[0], Hs.ctypes.data_as(C.POINTER(C.c_double)), f.ctypes.data_as(C.POINTER(C.c_float)),
+                                 out.ctypes.data_as(C.POINTER(C.c_double))):
+        raise HostError("principal-axis intersection failed (needs >= 2 cameras)")
+    return out
+
+
+def randgaus_stream(seed, sigma, n):
+    out = np.zeros(n, np.float32)
+    load().mcth_randgaus(seed, float(sigma), n, out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out

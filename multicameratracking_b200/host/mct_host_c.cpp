@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "mct_host.h"
+#include "mct_fuser.h"
 
 using namespace MultipleCameraTracking;
 
@@ -154,6 +155,70 @@ int mcth_camera_pack_foot_points(mcth_camera* c, float* dev_out)
     int rc = mct_fuser_pack_foot_points(c->ctx, n, pfs.data(), h0.data(), dev_out);
     if (rc) c->err = mct_last_error(c->ctx);
     return rc;
+}
+
+// ---- geometric fuser ----
+// feedback of the fused ground-plane estimate into object o of this camera (UpdateParticlesWithGroundPDF)
+int mcth_camera_ground_feedback(mcth_camera* c, int o, const double* H9, const float* mean2, const float* cov4, int* rearranged,
+                                float* distance)
+{
+    GUARD({
+        if (o < 0 || o >= (int)c->trackers.size()) throw MctHostError(MCT_E_ARG, "object index out of range");
+        Homography H; for (int i = 0; i < 9; i++) H[i] = H9[i];
+        const bool r = UpdateParticlesWithGroundPDF(c->ctx, c->trackers[o], mean2, cov4, H, distance);
+        if (rearranged) *rearranged = r ? 1 : 0;
+    });
+}
+
+struct mcth_fuser { GeometryBasedInformationFuser* f; std::string err; };
+int mcth_fuser_create(int n_cameras, const double* H /* [n_cameras][9] */, mcth_fuser** out)
+{
+    *out = nullptr;
+    try {
+        std::vector<Homography> list(n_cameras > 0 ? n_cameras : 0);
+        for (int c = 0; c < n_cameras; c++) for (int i = 0; i < 9; i++) list[c][i] = H[(size_t)c * 9 + i];
+        mcth_fuser* f = new mcth_fuser();
+        f->f = new GeometryBasedInformationFuser(list);
+        *out = f;
+        return 0;
+    } catch (const MctHostError& e) { return e.code ? e.code : -1; }
+    catch (const std::exception&) { return -100; }
+}
+void mcth_fuser_destroy(mcth_fuser* f) { if (f) { delete f->f; delete f; } }
+const char* mcth_fuser_last_error(mcth_fuser* f) { return f ? f->err.c_str() : "null fuser"; }
+#define FGUARD(body)                                                       \
+    try { body; return 0; }                                                \
+    catch (const MctHostError& e) { f->err = e.what(); return e.code ? e.code : -1; } \
+    catch (const std::exception& e) { f->err = e.what(); return -100; }
+int mcth_fuser_initialize(mcth_fuser* f, const float* foot /* [n_cameras][2] */) { FGUARD(f->f->InitializeKalman(foot)); }
+int mcth_fuser_fuse(mcth_fuser* f, const float* foot) { FGUARD(f->f->FuseInformation(foot)); }
+int mcth_fuser_get(mcth_fuser* f, float* mean2, float* cov4, float* state4, float* P16)
+{
+    FGUARD({
+        if (mean2) f->f->GetGroundPlaneKalmanMeanMatrix(mean2);
+        if (cov4) f->f->GetGroundPlaneKalmanCovarianceMatrix(cov4);
+        if (state4) memcpy(state4, f->f->StatePost(), 16);
+        if (P16) memcpy(P16, f->f->ErrorCovPost(), 64);
+    });
+}
+int mcth_fuser_intersection(int n_cameras, const double* H, const float* foot, double* out2)
+{
+    try {
+        std::vector<Homography> list(n_cameras > 0 ? n_cameras : 0);
+        for (int c = 0; c < n_cameras; c++) for (int i = 0; i < 9; i++) list[c][i] = H[(size_t)c * 9 + i];
+        const std::array<double, 2> g = GeometryBasedInformationFuser::EstimateGroundPlanePrincipleAxisIntersection(foot, list);
+        out2[0] = g[0]; out2[1] = g[1];
+        return 0;
+    } catch (...) { return -1; }
+}
+// randgaus(0, sigma) stream of a fresh MWC state (Public.cpp:37-49), for the parity tests
+int mcth_randgaus(int64_t seed, float sigma, int n, float* out)
+{
+    Public::RngStream s(seed);
+    Public::SetCurrentRng(&s);
+    for (int i = 0; i < n; i++) out[i] = Public::randgaus(0, sigma);
+    Public::SetCurrentRng(nullptr);
+    return 0;
 }
 
 int mcth_camera_sync(mcth_camera* c) { return mct_sync(c->ctx); }

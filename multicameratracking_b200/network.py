@@ -73,6 +73,46 @@ class CameraNetworkExchange:
         return float(t.item())
 
 
+class GeometricFusion:
+    """CameraNetwork::FuseGeometrically + FeedbackInformationFromGeometricFusion (CameraNetwork.cpp:94-268) with one camera
+    per rank: pack this camera's foot points on the device, ONE all-gather, then every rank runs the per-object fuser
+    (principal-axis intersection + Kalman; tiny, host side) on identical inputs and feeds the result back into its own
+    camera's particles (device: ground pdf, rearrangement, re-score)."""
+
+    def __init__(self, exchange, camera, homographies):
+        from .host import GeometricFuser
+        self.ex = exchange
+        self.cam = camera
+        self.H = [torch.as_tensor(h, dtype=torch.float64).reshape(3, 3).numpy() for h in homographies]
+        if len(self.H) != exchange.world:
+            raise ValueError("one homography per camera (rank) is needed")
+        self.fusers = [GeometricFuser(self.H) for _ in range(exchange.n_objects)]
+        self._foot = None
+
+    def step(self, device=None):
+        """one frame: returns (foot points [world][n_obj][2], [(rearranged, distance)] per object of this camera)"""
+        n = self.ex.n_objects
+        if self._foot is None:
+            self._foot = torch.zeros((n, 2), dtype=torch.float32, device=device or "cuda")
+        self.cam.pack_foot_points(self._foot.data_ptr())
+        allp = self.ex.allgather_foot_points(self._foot).cpu().numpy()
+        out = []
+        for o in range(n):
+            f = self.fusers[o]
+            first = not f.initialized
+            f.fuse(allp[:, o, :])
+            if first:
+                out.append((False, -1.0))          # the frame that initialises the filter gives no feedback yet
+                continue
+            mean, cov, _, _ = f.posterior()
+            out.append(self.cam.ground_feedback(o, self.H[self.ex.rank], mean, cov))
+        return allp, out
+
+    def close(self):
+        for f in self.fusers:
+            f.close()
+
+
 def drop_samples(rng_next_float, n, threshold=0.5):
     """AppearanceBasedInformationFuser.cpp:66-82: a pooled sample is kept iff randfloat() > RANDOM_SAMPLE_SELECTION_THRESHOLD
     (0.5, :7), in order (all positives, then all negatives), one draw per sample from the MWC stream

@@ -1,8 +1,11 @@
 """CPU tests of the drop-in boundary: libmct_b200.so builds for sm_100a, loads, exports every symbol
 include/mct_b200.h declares, and refuses to compute without a CUDA device (no CPU fallback)."""
 import ctypes as C
+import math
 import os
 import re
+
+import numpy as np
 
 import pytest
 
@@ -50,3 +53,65 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle_py" not in txt and "mct_oracle" not in txt and "libmct_oracle" not in txt, f
+
+
+# ---------------------------------------------------------------- host side of the geometric fuser (no GPU needed)
+def _fuser_gold():
+    import json
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cv2_fuser.json")))
+
+
+def test_host_fuser_principal_axis_matches_oracle_and_opencv():
+    from multicameratracking_b200 import host
+    from oracle import fuser_oracle as fo
+    for c in _fuser_gold()["svd"]:
+        foot = np.array(c["foot"], np.float32)
+        g = host.principal_axis_intersection(c["H"], foot)
+        np.testing.assert_allclose(g, np.array(c["g"]), rtol=1e-9)                  # cv2.SVDecomp
+        np.testing.assert_allclose(g, fo.principal_axis_intersection(foot, c["H"]), rtol=1e-9)
+
+
+def test_host_fuser_kalman_matches_oracle_and_opencv():
+    """cvCreateKalman(4, 2, 0) as InitializeKalman configures it; a fuser whose two cameras' axes meet where the golden
+    measurement sequence lies reproduces cv2.KalmanFilter's posterior"""
+    from multicameratracking_b200 import host
+    from oracle import fuser_oracle as fo
+    k = _fuser_gold()["kalman"]
+    # camera 0 sees ground x as image x, camera 1 sees ground y as image x: the intersection IS the foot-point pair
+    H0 = np.eye(3)
+    H1 = np.array([[0.0, 1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+    f = host.GeometricFuser([H0, H1])
+    kf = None
+    x0 = np.array(k["x0"], np.float32)
+    f.initialize(np.array([[x0[0], 0.0], [x0[1], 0.0]], np.float32))
+    kf = fo.KalmanCV(x0[0], x0[1])
+    for z, s, P in zip(k["z"], k["state_post"], k["cov_post"]):
+        z = np.array(z, np.float32)
+        f.fuse(np.array([[z[0], 7.0], [z[1], -3.0]], np.float32))
+        kf.update(z, np.array([[5, 0], [0, 5]], np.float32))
+        mean, cov, st, Pp = f.posterior()
+        np.testing.assert_allclose(st, np.array(s, np.float32), rtol=1e-5, atol=1e-5)           # cv2
+        np.testing.assert_allclose(Pp, np.array(P, np.float32), rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(st, kf.x_post[:, 0], rtol=1e-6, atol=1e-6)                   # oracle
+        np.testing.assert_allclose(cov, kf.cov(), rtol=1e-6, atol=1e-6)
+    f.close()
+    with pytest.raises(host.HostError):
+        host.GeometricFuser([H0])
+
+
+def test_host_randgaus_stream_matches_restatement(oracle):
+    """Public.cpp:37-49 polar Box-Muller over randfloat(), the noise of RearrangeParticlesBasedOnGroundLocation"""
+    from multicameratracking_b200 import host
+    got = host.randgaus_stream(4242, 10.0, 64)
+    r = oracle.rng(4242)
+    exp = []
+    for _ in range(64):
+        while True:
+            # `-1 + 2 * randfloat()` is float arithmetic in C++ (int * float), widened to double only on assignment
+            x = float(np.float32(-1) + np.float32(2) * np.float32(oracle.randfloat(r)))
+            y = float(np.float32(-1) + np.float32(2) * np.float32(oracle.randfloat(r)))
+            r2 = x * x + y * y
+            if not (r2 > 1.0 or r2 == 0):
+                break
+        exp.append(np.float32(np.float32(10.0 * y * math.sqrt(-2.0 * math.log(r2) / r2)) + np.float32(0)))   # libm, as the C++ side
+    np.testing.assert_array_equal(got, np.array(exp, np.float32))

@@ -77,3 +77,96 @@ def test_tracker_sequence_matches_oracle(oracle, cfg):
     for trk, clf, _ in otr:
         oracle.lib.orc_tracker_free(trk); oracle.lib.orc_clf_free(clf)
     cam.close()
+
+
+def test_geometric_fusion_feedback_two_cameras(oracle):
+    """Geometric fusion end to end for two cameras (both on this GPU, standing in for two ranks): per frame the foot
+    points are packed on the device, the per-object fuser (principal-axis intersection + Kalman) runs on the host, and the
+    feedback (ground pdf -> 20 px test -> rearrangement -> re-score) goes back into each camera's particles.  Checked
+    against the numpy oracle of the fuser arithmetic: decision, distance, rearranged particle states (bit-exact, with the
+    randgaus stream of the tracker's own MWC state) and the Kalman posterior."""
+    import torch
+    from oracle import fuser_oracle as fo
+    n_frames = 6
+    seq = synth.Sequence(640, 480, 3, n_frames=n_frames)
+    # Camera 1's ground plane is camera 0's with the axes swapped, and the tracked box's foot point lies on the diagonal
+    # (300, 300): the two principal axes meet at the foot itself.  The feedback then finds particles under the (tight)
+    # Kalman posterior, and the reference's foot of the AVERAGE particle -- cy + h0*sy, without the 1/2 -- lies ~40 px
+    # below the fused location, so the rearrangement branch runs.
+    box0 = (280, 220, 40, 80)
+    H = [np.eye(3), np.array([[0.0, 1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])]
+    over = dict(n_particles=400, n_haar=80)
+    p = dict(mhost.DEFAULTS); p.update(over)
+    cams = []
+    gray, r, g, b = seq.frame(0)
+    for c in range(2):
+        cam = mhost.Camera(0, n_frames)
+        cam.set_frame(gray, r, g, b)
+        cam.add_object(box0, rng_seed=11 + c, **over)
+        cam.init_trackers()
+        cams.append(cam)
+    fuser = mhost.GeometricFuser(H)
+    kf = None
+    N = p["n_particles"]
+    pts = torch.zeros((1, 2), dtype=torch.float32, device="cuda")
+    n_rearranged = 0
+    for t in range(1, n_frames):
+        gray, r, g, b = seq.frame(t)
+        foot = np.zeros((2, 2), np.float32)
+        for c, cam in enumerate(cams):
+            cam.set_frame(gray, r, g, b)
+            nz = np.stack([synth.noise(N, (p["sd_x"], p["sd_y"], p["sd_sx"], p["sd_sy"]), camera=c, obj=0, t=t)])
+            cam.track(t, nz, 1)
+            cam.pack_foot_points(pts.data_ptr()); cam.sync()
+            foot[c] = pts.cpu().numpy()[0]
+            st = cam.particles(0)
+            a = int(np.argmax(st[:, 4]))
+            assert foot[c, 0] == st[a, 0] and foot[c, 1] == np.float32(st[a, 1] + np.float32(st[a, 3] * np.float32(cam.state(0)[3])) / np.float32(2))
+        first = not fuser.initialized
+        fuser.fuse(foot)
+        g_or = fo.principal_axis_intersection(foot, H)
+        if first:
+            kf = fo.KalmanCV(np.float32(g_or[0]), np.float32(g_or[1]))
+        else:
+            kf.update(np.array([np.float32(g_or[0]), np.float32(g_or[1])], np.float32), np.array([[5, 0], [0, 5]], np.float32))
+        mean, cov, stp, P = fuser.posterior()
+        np.testing.assert_allclose(stp, kf.x_post[:, 0], rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(P, kf.P_post, rtol=1e-5, atol=1e-4)
+        if first:
+            continue
+        for c, cam in enumerate(cams):
+            st = cam.particles(0)
+            cur = cam.state(0)
+            tot, mf, dist, want = fo.ground_feedback_decision(st, cur[3], H[c], mean, cov)
+            rng0 = cam.rng_state(0)
+            got, d = cam.ground_feedback(0, H[c], mean, cov)
+            assert got == want, (t, c, dist, d)
+            if tot > 0:
+                assert abs(d - dist) <= 1e-3 * max(1.0, dist)
+            if got:
+                n_rearranged += 1
+                seed = rng0 if rng0 < (1 << 63) else rng0 - (1 << 64)
+                g2 = mhost.randgaus_stream(seed, 10.0, 2 * N)
+                nz2 = np.stack([g2[0::2], g2[1::2]])                   # (xRand, yRand) per particle, in order
+                exp = fo.rearrange_particles(st, mf, nz2, cur[2], cur[3])
+                now = cam.particles(0)
+                # the re-score that follows touches the states in two documented ways only: UpdateParticleWeight's scale-ratio
+                # clamp (ParticleFilter.cpp:658-665) and, when ResampleIfRequired fires, a resampling of these rows
+                cl = exp.copy()
+                for q in range(N):
+                    sx, sy = cl[q, 2], cl[q, 3]
+                    if float(np.float32(sx / sy)) > 1.2:
+                        cl[q, 3] = np.float32(0.9 * float(sx))
+                    elif float(np.float32(sy / sx)) > 1.2:
+                        cl[q, 2] = np.float32(0.9 * float(sy))
+                rows = {tuple(x) for x in exp[:, :4].tolist()} | {tuple(x) for x in cl[:, :4].tolist()}
+                assert all(tuple(x) in rows for x in now[:, :4].tolist())
+                # the particles now sit around the fused location seen in this camera (x; the foot's y is moved again by the
+                # scale-ratio clamp of the re-score)
+                assert abs(float(np.median(now[:, 0])) - float(mf[0])) < 15
+            else:
+                assert cam.rng_state(0) == rng0
+    assert n_rearranged >= 1
+    fuser.close()
+    for cam in cams:
+        cam.close()

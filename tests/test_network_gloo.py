@@ -58,6 +58,79 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+class _StandInCamera:
+    """duck-typed Camera for the CPU test: foot points written at the given address, feedback calls recorded"""
+
+    def __init__(self, foot):
+        self.foot = np.ascontiguousarray(foot, np.float32)
+        self.calls = []
+
+    def pack_foot_points(self, ptr):
+        import ctypes
+        ctypes.memmove(ptr, self.foot.ctypes.data, self.foot.nbytes)
+
+    def ground_feedback(self, o, H, mean, cov):
+        self.calls.append((o, np.array(H), np.array(mean), np.array(cov)))
+        return False, 0.0
+
+
+def _fusion_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from multicameratracking_b200.network import CameraNetworkExchange, GeometricFusion
+        from oracle import fuser_oracle as fo
+        n_obj = 2
+        H = [np.eye(3), np.array([[0.0, 1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])]
+        ex = CameraNetworkExchange(n_obj)
+        feet = lambda r, t: np.array([[100.0 + 10 * r + 3 * t, 50.0], [200.0 - 5 * r + t, 80.0]], np.float32)   # noqa: E731
+        cam = _StandInCamera(feet(rank, 0))
+        gf = GeometricFusion(ex, cam, H)
+        kfs = [None] * n_obj
+        for t in range(4):
+            cam.foot = feet(rank, t)
+            allp, out = gf.step(device="cpu")
+            assert allp.shape == (world, n_obj, 2)
+            for r in range(world):
+                np.testing.assert_array_equal(allp[r], feet(r, t))
+            for o in range(n_obj):
+                g = fo.principal_axis_intersection(allp[:, o, :], H)
+                if kfs[o] is None:
+                    kfs[o] = fo.KalmanCV(np.float32(g[0]), np.float32(g[1]))
+                    assert out[o] == (False, -1.0)
+                else:
+                    kfs[o].update(np.array([g[0], g[1]], np.float32), np.array([[5, 0], [0, 5]], np.float32))
+            if t > 0:                 # every rank fed its own camera with the SAME posterior, computed redundantly
+                last = cam.calls[-n_obj:]
+                for o, (oo, Hc, mean, cov) in enumerate(last):
+                    assert oo == o and np.array_equal(Hc, H[rank])
+                    np.testing.assert_allclose(mean, kfs[o].mean(), rtol=1e-5, atol=1e-4)
+                    np.testing.assert_allclose(cov, kfs[o].cov(), rtol=1e-5, atol=1e-4)
+        assert len(cam.calls) == 3 * n_obj
+        gf.close()
+        q.put((rank, "ok"))
+    except BaseException as e:           # noqa: BLE001 - report to the parent
+        q.put((rank, "FAIL %r" % (e,)))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_geometric_fusion_world2():
+    """FuseGeometrically + feedback with one camera per rank (gloo, CPU): the all-gathered foot points drive identical
+    per-object fusers on every rank; checked against the numpy oracle of the fuser arithmetic"""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_fusion_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
 def test_camera_network_exchange_world2():
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
