@@ -215,7 +215,8 @@ int mct_pf_get_summary(mct_pf* pf, mct_pf_summary* out_host);
  * summaries: [n_obj] host, valid after the call returns (the call synchronises the stream). */
 typedef struct {
     float w0, h0;           /* m_currentStateList[2], [3] */
-    int   exponent;         /* 20 (:556); 1 for the re-score variant (:1407) */
+    int   exponent;         /* 20 (:556); 1 for the re-score variant (:1407); 0 = the appearance fuser's map
+                             * sigmoid(H) instead of the min-max map (AppearanceBasedInformationFuser.cpp:98-121) */
     int   force_reset;      /* shouldForceReset */
     int   resample;         /* shouldResample */
 } mct_track_params;

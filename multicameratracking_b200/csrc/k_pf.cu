@@ -449,7 +449,11 @@ __global__ void __launch_bounds__(PF_THREADS) k_pf_update(const ObjDesc* __restr
             float w = ww[k];
             if (vv[k]) {
                 float p;
-                if (mode == 0) p = (range != 0) ? (float)ipow_d(((double)hh[k] - dmn) / range, d.exponent) : 1.0f;
+                if (mode == 0) {
+                    // exponent 0 selects the appearance fuser's map pow(sigmoid(H), 1) (AppearanceBasedInformationFuser.cpp:108-112)
+                    if (d.exponent == 0) p = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-hh[k])));
+                    else p = (range != 0) ? (float)ipow_d(((double)hh[k] - dmn) / range, d.exponent) : 1.0f;
+                }
                 else p = hh[k];
                 w = d.force_reset ? p : __fmul_rn(p, w);
                 float sx = xs[k], sy = ys[k];

@@ -26,6 +26,7 @@ class CameraNetworkExchange:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.n_objects = int(n_objects)
+        self.device = "cuda" if dist.get_backend(group) == "nccl" else "cpu"      # where the collectives' tensors live
 
     # ------------------------------------------------------------------ geometric fuser payload
     def allgather_foot_points(self, local):
@@ -111,6 +112,51 @@ class GeometricFusion:
     def close(self):
         for f in self.fusers:
             f.close()
+
+
+class AppearanceFusion:
+    """AppearanceBasedInformationFuser of ONE object on ONE camera (rank) with the other cameras' training samples arriving
+    as feature rows (AppearanceBasedInformationFuser.cpp:17-121, CameraNetwork.cpp:276-320).
+
+      global_clf   this rank's global appearance classifier of the object (capi.StrongClassifier made with
+                   learning_rate = 0, :28).  Every rank must build it from the SAME feature table (same Haar draws): rows
+                   computed on one camera are only meaningful to a classifier with the same features.
+      learn()      LearnGlobalAppearanceModel: feature rows of the local positive / negative boxes under the global
+                   classifier's features -> ONE all-gather -> pooled in camera order -> each sample kept iff
+                   randfloat() > 0.5 (positives first, then negatives) -> Update from the pooled rows
+      fuse()       FuseInformation + Object::UpdateParticleWeightUsingMultiCameraAppearanceModel (Object.cpp:496-528) +
+                   ForceParticleResampling (Object.cpp:445): particles scored in place by the global classifier, weight *=
+                   sigmoid(H), ResampleIfRequired, then ResampleParticles(false)
+    """
+
+    def __init__(self, exchange, ctx, global_clf):
+        self.ex = exchange
+        self.ctx = ctx
+        self.clf = global_clf
+        self.trained = False
+
+    def learn(self, pos_boxes, neg_boxes, rng_next_float):
+        """pos_boxes / neg_boxes: capi.make_boxes(...) of this camera's training sets for the object (current frame set)"""
+        dev = self.ex.device
+        fpos = torch.from_numpy(self.clf.features(pos_boxes)).to(dev)
+        fneg = torch.from_numpy(self.clf.features(neg_boxes)).to(dev)
+        pos, neg, counts = self.ex.allgather_feature_rows(fpos, fneg)
+        kp = drop_samples(rng_next_float, pos.shape[1])
+        kn = drop_samples(rng_next_float, neg.shape[1])
+        if not kp or not kn:
+            raise RuntimeError("appearance fusion: every pooled %s sample was dropped" % ("positive" if not kp else "negative"))
+        self.clf.update_from_features(pos[:, kp].contiguous().cpu().numpy(), neg[:, kn].contiguous().cpu().numpy())
+        self.trained = True
+        return counts, kp, kn
+
+    def fuse(self, pf, w0, h0, u01_update, u01_forced):
+        """returns the mct_pf_summary of the re-weighting call"""
+        from . import capi
+        if not self.trained:
+            raise RuntimeError("appearance fusion: learn() has not run")
+        summ = capi.track_score(self.ctx, [pf], [self.clf], [(w0, h0, 0, 0, 1)], None, [u01_update])[0]
+        pf.ResampleParticles(False, u01_forced)
+        return summ
 
 
 def drop_samples(rng_next_float, n, threshold=0.5):

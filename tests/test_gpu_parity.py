@@ -920,3 +920,91 @@ def test_rescore_rearranged_particles_matches_oracle(ctx, oracle):
         x.close()
     for oc in oclfs:
         oracle.lib.orc_clf_free(oc)
+
+
+# ---------------------------------------------------------------------------------- appearance fuser (cfg 4)
+class _LoopbackExchange:
+    """two cameras in one process: the 'all-gather' concatenates the rows both cameras computed (camera order)"""
+    device = "cpu"
+    world = 2
+
+    def __init__(self):
+        self.rows = {}
+
+    def allgather_feature_rows(self, fpos, fneg):
+        import torch
+        pos = torch.cat([self.rows[r][0] for r in range(2)], dim=1)
+        neg = torch.cat([self.rows[r][1] for r in range(2)], dim=1)
+        counts = torch.tensor([[self.rows[r][0].shape[1], self.rows[r][1].shape[1]] for r in range(2)])
+        return pos, neg, counts
+
+
+def test_appearance_fusion_pooled_update_and_particle_reweighting(oracle):
+    """LearnGlobalAppearanceModel + FuseInformation (AppearanceBasedInformationFuser.cpp:44-121) for one object seen by two
+    cameras: feature rows of both cameras' training boxes pooled in camera order, each sample kept iff randfloat() > 0.5,
+    global classifier (learning rate 0) updated from the rows; then camera 0's particles are re-weighted with
+    sigmoid(H_global) and resampled (Object.cpp:433-450, 496-528).  Oracle: the same steps on the CPU."""
+    import torch
+    from multicameratracking_b200.network import AppearanceFusion
+    W, H, N, F, K = 640, 480, 600, 100, 20
+    seqs = [synth.Sequence(W, H, 1, camera=c) for c in range(2)]
+    w0, h0 = seqs[0].w0, seqs[0].h0
+    t, arrs = haar_table(oracle, F, w0, h0)
+    ctxs = [capi.Context(0) for _ in range(2)]
+    frames, ofr, gclf, sets = [], [], [], []
+    for c in range(2):
+        gray, r, g, b = seqs[c].frame(1)
+        ctxs[c].frame_set(gray, r, g, b)
+        ofr.append(oracle.frame(gray, r, g, b)); frames.append((gray, r, g, b))
+        gclf.append(capi.StrongClassifier(ctxs[c], capi.FEAT_HAAR_MDCH, w0, h0, n_haar=F, n_bins=8, n_selected=K, haar=arrs,
+                                          learning_rate=0.0))
+        sets.append(_train_sets(oracle, seqs[c], 1, 0, seed=31 + c))
+    ogclf = oracle.clf_create(capi.FEAT_HAAR_MDCH, F, 8, w0, h0, 0, 2, K, 0.0, t)
+    ex = _LoopbackExchange()
+    for c in range(2):
+        ex.rows[c] = (torch.from_numpy(gclf[c].features(capi.make_boxes(*sets[c][0]))),
+                      torch.from_numpy(gclf[c].features(capi.make_boxes(*sets[c][1]))))
+    # oracle rows, pooled in camera order
+    opos = np.concatenate([oracle.clf_features(ogclf, ofr[c], oracle.boxes(*sets[c][0])) for c in range(2)], axis=1)
+    oneg = np.concatenate([oracle.clf_features(ogclf, ofr[c], oracle.boxes(*sets[c][1])) for c in range(2)], axis=1)
+    af = AppearanceFusion(ex, ctxs[0], gclf[0])
+    r_dev, r_or = oracle.rng(77), oracle.rng(77)
+    counts, kp, kn = af.learn(capi.make_boxes(*sets[0][0]), capi.make_boxes(*sets[0][1]), lambda: oracle.randfloat(r_dev))
+    okp = [i for i in range(opos.shape[1]) if oracle.randfloat(r_or) > 0.5]
+    okn = [i for i in range(oneg.shape[1]) if oracle.randfloat(r_or) > 0.5]
+    assert kp == okp and kn == okn and 0 < len(kp) < opos.shape[1]
+    assert counts.tolist() == [[len(sets[c][0][0]), len(sets[c][1][0])] for c in range(2)]
+    oracle.clf_update_from_features(ogclf, np.ascontiguousarray(opos[:, okp]), np.ascontiguousarray(oneg[:, okn]))
+    assert gclf[0].selectors().tolist() == oracle.clf_selectors(ogclf).tolist()
+    # camera 0's particles, spread and weighted
+    x, y, w, h = seqs[0].box(1, 0)
+    pf, opf = _pf_pair(ctxs[0], oracle, N, cx=x + w / 2, cy=y + h / 2)
+    nz = synth.noise(N, (15, 15, 0.02, 0.02), obj=0, t=1)
+    pf.PredictWithBrownianMotion(nz, w0, h0)
+    oracle.lib.orc_pf_predict(opf, nz.ctypes.data_as(C.POINTER(C.c_float)), w0, h0)
+    st = oracle.pf_state(opf)
+    st[:, 4] = np.random.default_rng(3).uniform(0.2, 1.0, N).astype(np.float32)
+    pf.set_state(st.copy(), opf.contents.filter_state)
+    u_a, u_b = oracle.randfloat(oracle.rng(555)), 0.81
+    summ = af.fuse(pf, w0, h0, u_a, u_b)
+    col, row, sx, sy = oracle.pf_test_set(opf, w0, h0, W, H)
+    assert summ.n_valid == len(col) > 0
+    Ho = oracle.clf_classify(ogclf, ofr[0], oracle.boxes(col, row, sx, sy))
+    Hg, valid = pf.last_response()
+    rel_close(Hg[valid != 0], Ho)
+    prob = (np.float32(1) / (np.float32(1) + np.exp(-Ho, dtype=np.float32))).astype(np.float32)
+    # UpdateParticleWeights(prob, onlyNonZero, no reset), ResampleIfRequired, then ForceParticleResampling
+    rr = oracle.rng(555)
+    res = oracle.lib.orc_pf_update_all_weights(opf, prob.ctypes.data_as(C.POINTER(C.c_float)), 1, 0, 1, C.byref(rr))
+    assert bool(res) == bool(summ.resampled)
+    oracle.lib.orc_pf_resample_u01(opf, 0, C.c_float(u_b))
+    sg, so = pf.state(), oracle.pf_state(opf)
+    np.testing.assert_array_equal(sg[:, :4], so[:, :4])
+    rel_close(sg[:, 4], so[:, 4], rtol=2e-4, scale=so[:, 4].max())
+    # the forced resampling draws from weights that agree to ~1e-4: at most a few threshold crossings differ
+    ig, io = pf.resample_indices(), oracle.pf_resample_idx(opf)
+    assert (ig != io).mean() < 0.02
+    pf.close()
+    for c in range(2):
+        gclf[c].close(); ctxs[c].close()
+    oracle.lib.orc_clf_free(ogclf)

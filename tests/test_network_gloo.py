@@ -116,6 +116,64 @@ def _fusion_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+class _StandInClassifier:
+    """duck-typed capi.StrongClassifier: feature rows are a deterministic function of the box columns"""
+
+    def __init__(self, F):
+        self.F = F
+        self.updated = None
+
+    def features(self, boxes):
+        cols = np.asarray(boxes, np.float32)
+        return (np.arange(self.F, dtype=np.float32)[:, None] * 1000.0 + cols[None, :]).astype(np.float32)
+
+    def update_from_features(self, fpos, fneg):
+        self.updated = (np.array(fpos), np.array(fneg))
+
+
+def _appearance_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from multicameratracking_b200.network import AppearanceFusion, CameraNetworkExchange
+        F = 5
+        ex = CameraNetworkExchange(1)
+        assert ex.device == "cpu"
+        clf = _StandInClassifier(F)
+        af = AppearanceFusion(ex, None, clf)
+        cols = {0: ([1, 2, 3, 4], [50, 51]), 1: ([11, 12], [60, 61, 62])}     # ragged per camera
+        draws = [0.9, 0.1, 0.6, 0.5, 0.51, 0.7, 0.2, 0.95, 0.3, 0.8, 0.99]   # 6 positives then 5 negatives
+        it = iter(draws)
+        counts, kp, kn = af.learn(cols[rank][0], cols[rank][1], lambda: next(it))
+        assert counts.tolist() == [[4, 2], [2, 3]]
+        assert kp == [0, 2, 4, 5] and kn == [1, 3, 4]
+        allpos = np.array(cols[0][0] + cols[1][0], np.float32); allneg = np.array(cols[0][1] + cols[1][1], np.float32)
+        np.testing.assert_array_equal(clf.updated[0][0], allpos[kp])        # feature row 0 carries the column itself
+        np.testing.assert_array_equal(clf.updated[1][0], allneg[kn])
+        assert clf.updated[0].shape == (F, 4) and clf.updated[1].shape == (F, 3)
+        q.put((rank, "ok"))
+    except BaseException as e:           # noqa: BLE001 - report to the parent
+        q.put((rank, "FAIL %r" % (e,)))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_appearance_fusion_pooling_world2():
+    """LearnGlobalAppearanceModel with one camera per rank (gloo, CPU): ragged per-camera training rows pooled in camera
+    order on every rank, then thinned by the randfloat() > 0.5 rule, positives first"""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_appearance_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
 def test_geometric_fusion_world2():
     """FuseGeometrically + feedback with one camera per rank (gloo, CPU): the all-gathered foot points drive identical
     per-object fusers on every rank; checked against the numpy oracle of the fuser arithmetic"""
