@@ -371,12 +371,12 @@ def run_ours(args):
         k_sel = CONFIG["selected"]
         k_haar = int(np.mean([(cam.selectors(o) < N_HAAR).sum() for o in range(N_OBJ)]))      # selected Haar features (measured)
         alg_all = {
-            "k_mdch_sel": n_tot * (rows * cols * 3 + (N_BINS ** 3) * 4),                      # B_mdch = N*rows*cols*3 + N*nb^3*4
+            # B_mdch = N*rows*cols*3 + N*nb^3*4, plus the predict / test-set prologue fused into the kernel (68 B per particle)
+            "k_mdch_sel": n_tot * (rows * cols * 3 + (N_BINS ** 3) * 4 + 68),
             "k_classify_staged": n_tot * (k_haar * 4 * 16 + (k_sel - k_haar) * 4 + 4),        # E[R_f] = 4 rects x 4 corners x 4 B
             "k_frame_prep": W * H + (W + 1) * (H + 1) * 4 + 3 * W * H + 2 * W * H,            # integral + joint-bin image
             "k_pf_update": n_tot * 44,
             "k_pf_predict_testset": n_tot * 68,
-            "k_mdch_big": 0,
         }
         alg = alg_all.get(dom_name, 0)
         traffic, traffic_all = None, {}

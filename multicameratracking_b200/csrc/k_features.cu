@@ -659,22 +659,70 @@ int launch_build_colormap(mct_clf* clf)
     return MCT_OK;
 }
 
+// generic warp-per-box pass over the boxes flagged by k_mdch_sel (segmented fixed point, all nb^3 bins in
+// shared memory), writing the selected bins only.  `first` / `stride` / `nwarps` describe the calling kernel's warp layout.
+// Everything another CTA of the same launch may have written (box geometry from the fused predict prologue, the flags) is
+// read with ld.cg: L1 is not coherent across SMs.
+__device__ __forceinline__ void mdch_big_body(const ObjDesc& d, const uint16_t* __restrict__ binimg, int W, int H,
+                                              unsigned char* smraw, int nwarps, int first, int stride)
+{
+    const int nb = d.nb, dim = nb * nb * nb;
+    uint32_t* hist_all = (uint32_t*)smraw;
+    float* acc_all = (float*)(hist_all + nwarps * dim);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* hist = hist_all + warp * dim;
+    float* acc = acc_all + warp * dim;
+    const int n_out = *d.nout;
+    for (int i = first; i < d.N; i += stride) {
+        if (!__ldcg(d.big + i)) continue;
+        const int c0 = __ldcg(d.col + i), r0 = __ldcg(d.row + i);
+        const int rows = __float2int_rn(__fmul_rn((float)d.ch0, __ldcg(d.sy + i)));
+        const int cols = __float2int_rn(__fmul_rn((float)d.cw0, __ldcg(d.sx + i)));
+        const float hx = __fdiv_rn((float)cols, 2.0f), hy = __fdiv_rn((float)rows, 2.0f);
+        const float cX = __fadd_rn((float)c0, hx), cY = __fadd_rn((float)r0, hy);
+        const double ivx = 1.0 / (double)__fmul_rn(2.0f, __fmul_rn(hx, hx));
+        const double ivy = 1.0 / (double)__fmul_rn(2.0f, __fmul_rn(hy, hy));
+        for (int b = lane; b < dim; b += 32) { hist[b] = 0u; acc[b] = 0.0f; }
+        __syncwarp();
+        const int rows_per_seg = max(1, MCT_MDCH_SEG_PIX / max(cols, 1));
+        for (int rs = 0; rs < rows; rs += rows_per_seg) {
+            const int re = min(rows, rs + rows_per_seg);
+            const int npix = (re - rs) * cols;
+            int shift = __clz(max(npix, 1)); if (shift > MCT_FIX_SHIFT_MAX) shift = MCT_FIX_SHIFT_MAX;
+            const float scale = (float)(1u << shift);
+            int c = lane, r = rs;
+            while (c >= cols && r < re) { c -= cols; r++; }
+            while (r < re) {
+                const int yy = clampi(r0 + r, 0, H - 1), xx = clampi(c0 + c, 0, W - 1);
+                const unsigned bin = binimg[(size_t)yy * W + xx];
+                const double dx = (double)__fsub_rn(cX, (float)(c0 + c)), dy = (double)__fsub_rn(cY, (float)(r0 + r));
+                const float wd = (float)(dx * dx * ivx + dy * dy * ivy);
+                atomicAdd(&hist[bin], __float2uint_rn(__fmul_rn(expf(-wd), scale)));
+                c += 32;
+                while (c >= cols && r < re) { c -= cols; r++; }
+            }
+            __syncwarp();
+            const float inv = __fdiv_rn(1.0f, scale);
+            for (int b = lane; b < dim; b += 32) { acc[b] = __fadd_rn(acc[b], __fmul_rn((float)hist[b], inv)); hist[b] = 0u; }
+            __syncwarp();
+        }
+        float s = 0.0f;
+        for (int b = lane; b < dim; b += 32) s += acc[b];
+        s = warp_sum_f(s);
+        for (int o = lane; o < n_out; o += 32) d.featN[(size_t)o * d.ldN + i] = __fdiv_rn(acc[d.outbins[o]], s);
+        __syncwarp();
+    }
+}
+
 #define MDS_WARPS 16
 #define MDS_SMEM (226 * 1024)
-__global__ void __launch_bounds__(MDS_WARPS * 32, 1)
-k_mdch_sel(const ObjDesc* __restrict__ descs, const uint16_t* __restrict__ binimg, int W, int H, int smem_bytes)
+// the gather over this CTA's chunk [i_begin, i_end) of the object's boxes
+__device__ __forceinline__ void mdch_sel_chunk(const ObjDesc& d, const uint16_t* __restrict__ binimg, int W, int H, int smem_bytes,
+                                               unsigned char* smraw, int i_begin, int i_end)
 {
-    extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ int s_bb[4], s_ref, s_rows, s_cols;
     __shared__ uint32_t s_tot[MDS_WARPS];
-    __shared__ ObjDesc s_desc;
-    const ObjDesc& d = load_desc(descs + blockIdx.y, &s_desc);
-    if (d.slotmap == nullptr) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int N = d.N;
-    const int chunk = (N + gridDim.x - 1) / gridDim.x;
-    const int i_begin = blockIdx.x * chunk, i_end = min(N, i_begin + chunk);
-    if (i_begin >= i_end) return;
     const int n_out = *d.nout, n_slots = n_out + 1, dim = d.n_color_rows;
 
     // ---- 1. common box size of the chunk (first usable box) and bounding box of the conforming boxes
@@ -845,63 +893,57 @@ k_mdch_sel(const ObjDesc* __restrict__ descs, const uint16_t* __restrict__ binim
     }
 }
 
-// generic warp-per-box pass over the boxes flagged by k_mdch_sel (segmented fixed point, all nb^3 bins in
-// shared memory), writing the selected bins only.  Exits immediately when nothing was flagged.
-__global__ void __launch_bounds__(MDCH_WARPS * 32)
-k_mdch_big(const ObjDesc* __restrict__ descs, const uint16_t* __restrict__ binimg, int W, int H)
+// Per-frame kernel of the colour features.  One persistent CTA per SM, the SMs split evenly over the objects, each CTA owns a
+// contiguous chunk of the object's particles.
+//   prologue (pre = 1 / 2): PredictWithBrownianMotion + GenerateTestSampleSet / GenerateTestSampleSet alone for the CTA's own
+//       particles -- the per-particle steps need nothing from other particles, so the predict kernel's launch folds away;
+//   gather: mdch_sel_chunk;
+//   tail: the CTA that finishes an object last (arrival counter, no waiting) runs the generic pass over the boxes the fast
+//       path flagged -- normally none, and the separate always-launched fallback kernel folds away as well.
+__global__ void __launch_bounds__(MDS_WARPS * 32, 1)
+k_mdch_sel(const ObjDesc* __restrict__ descs, const uint16_t* __restrict__ binimg, int W, int H, int smem_bytes, const StepArgs sa, int pre)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
-    const ObjDesc& d = descs[blockIdx.y];
-    if (d.slotmap == nullptr || d.nbig == nullptr || *d.nbig == 0) return;
-    const int nb = d.nb, dim = nb * nb * nb;
-    uint32_t* hist_all = (uint32_t*)smraw;
-    float* acc_all = (float*)(hist_all + MDCH_WARPS * dim);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t* hist = hist_all + warp * dim;
-    float* acc = acc_all + warp * dim;
-    const int n_out = *d.nout;
-    for (int i = blockIdx.x * MDCH_WARPS + warp; i < d.N; i += gridDim.x * MDCH_WARPS) {
-        if (!d.big[i]) continue;
-        const int c0 = d.col[i], r0 = d.row[i];
-        const int rows = __float2int_rn(__fmul_rn((float)d.ch0, d.sy[i]));
-        const int cols = __float2int_rn(__fmul_rn((float)d.cw0, d.sx[i]));
-        const float hx = __fdiv_rn((float)cols, 2.0f), hy = __fdiv_rn((float)rows, 2.0f);
-        const float cX = __fadd_rn((float)c0, hx), cY = __fadd_rn((float)r0, hy);
-        const double ivx = 1.0 / (double)__fmul_rn(2.0f, __fmul_rn(hx, hx));
-        const double ivy = 1.0 / (double)__fmul_rn(2.0f, __fmul_rn(hy, hy));
-        for (int b = lane; b < dim; b += 32) { hist[b] = 0u; acc[b] = 0.0f; }
-        __syncwarp();
-        const int rows_per_seg = max(1, MCT_MDCH_SEG_PIX / max(cols, 1));
-        for (int rs = 0; rs < rows; rs += rows_per_seg) {
-            const int re = min(rows, rs + rows_per_seg);
-            const int npix = (re - rs) * cols;
-            int shift = __clz(max(npix, 1)); if (shift > MCT_FIX_SHIFT_MAX) shift = MCT_FIX_SHIFT_MAX;
-            const float scale = (float)(1u << shift);
-            int c = lane, r = rs;
-            while (c >= cols && r < re) { c -= cols; r++; }
-            while (r < re) {
-                const int yy = clampi(r0 + r, 0, H - 1), xx = clampi(c0 + c, 0, W - 1);
-                const unsigned bin = binimg[(size_t)yy * W + xx];
-                const double dx = (double)__fsub_rn(cX, (float)(c0 + c)), dy = (double)__fsub_rn(cY, (float)(r0 + r));
-                const float wd = (float)(dx * dx * ivx + dy * dy * ivy);
-                atomicAdd(&hist[bin], __float2uint_rn(__fmul_rn(expf(-wd), scale)));
-                c += 32;
-                while (c >= cols && r < re) { c -= cols; r++; }
+    __shared__ ObjDesc s_desc;
+    __shared__ int s_ticket;
+    const ObjDesc& d = load_desc(descs + blockIdx.y, &s_desc);
+    const int tid = threadIdx.x;
+    const int N = d.N;
+    const int chunk = (N + gridDim.x - 1) / gridDim.x;
+    const int i_begin = min(N, (int)blockIdx.x * chunk), i_end = min(N, i_begin + chunk);
+    if (pre) {
+        if (blockIdx.x == 0 && tid == 0 && pre == 1) { d.st->filter_state = MCT_PF_PREDICTED; d.st->time_index += 1; }
+        int ok = 0;
+        for (int i = i_begin + tid; i < i_end; i += blockDim.x) {
+            if (pre == 1) {
+                ok |= refine_valid_one(d, i) ? 1 : 0;
+                predict_one(d, i, sa.noise_base + d.noise_off);
             }
-            __syncwarp();
-            const float inv = __fdiv_rn(1.0f, scale);
-            for (int b = lane; b < dim; b += 32) { acc[b] = __fadd_rn(acc[b], __fmul_rn((float)hist[b], inv)); hist[b] = 0u; }
-            __syncwarp();
+            testset_one(d, i, W, H);
         }
-        float s = 0.0f;
-        for (int b = lane; b < dim; b += 32) s += acc[b];
-        s = warp_sum_f(s);
-        for (int o = lane; o < n_out; o += 32) d.featN[(size_t)o * d.ldN + i] = __fdiv_rn(acc[d.outbins[o]], s);
-        __syncwarp();
+        if (pre == 1) {
+            const int any = __syncthreads_or(ok);
+            if (tid == 0) atomicOr(&d.st->refine, MCT_REFINE_PENDING | (any ? MCT_REFINE_VALID : 0));
+        }
+        __syncthreads();                      // the chunk's boxes are read back by other threads of this CTA
     }
+    if (d.slotmap == nullptr) return;         // object without colour features: nothing to gather, nobody runs a tail
+    if (i_begin < i_end) mdch_sel_chunk(d, binimg, W, H, smem_bytes, smraw, i_begin, i_end);
+    // ---- tail
+    __syncthreads();
+    if (tid == 0) { __threadfence(); s_ticket = atomicAdd(d.nbig + 1, 1); }
+    __syncthreads();
+    if (s_ticket != (int)gridDim.x - 1) return;
+    if (tid == 0) d.nbig[1] = 0;              // ready for the next launch
+    __threadfence();
+    if (__ldcg(d.nbig) == 0) return;
+    const int warp = tid >> 5;
+    mdch_big_body(d, binimg, W, H, smraw, MDS_WARPS, warp, MDS_WARPS);
+    __syncthreads();
+    if (tid == 0) *d.nbig = 0;                // counted again from zero by the next launch
 }
 
-int launch_mdch_selected(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int max_slots)
+int launch_mdch_selected(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int max_slots, const StepArgs& sa, int pre)
 {
     (void)max_slots;
     if (n_obj <= 0 || n_max <= 0) return MCT_OK;
@@ -916,15 +958,6 @@ int launch_mdch_selected(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_m
     if (per_obj < 1) per_obj = 1;
     if (per_obj > ceil_div(n_max, 3)) per_obj = ceil_div(n_max, 3);
     dim3 g1(per_obj, n_obj);
-    MCT_LAUNCH(ctx, "k_mdch_sel", k_mdch_sel<<<g1, MDS_WARPS * 32, MDS_SMEM, ctx->stream>>>(d_desc, ctx->binimg, ctx->W, ctx->H, MDS_SMEM));
-    // generic fallback for flagged boxes (early exit when none)
-    size_t smem2 = (size_t)MDCH_WARPS * 512 * 8;
-    static size_t s_attr2 = 0;
-    if (smem2 > s_attr2) {
-        MCT_CUDA(ctx, cudaFuncSetAttribute(k_mdch_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        s_attr2 = smem2;
-    }
-    dim3 g2(ceil_div(n_max, MDCH_WARPS * 4), n_obj);
-    MCT_LAUNCH(ctx, "k_mdch_big", k_mdch_big<<<g2, MDCH_WARPS * 32, smem2, ctx->stream>>>(d_desc, ctx->binimg, ctx->W, ctx->H));
+    MCT_LAUNCH(ctx, "k_mdch_sel", k_mdch_sel<<<g1, MDS_WARPS * 32, MDS_SMEM, ctx->stream>>>(d_desc, ctx->binimg, ctx->W, ctx->H, MDS_SMEM, sa, pre));
     return MCT_OK;
 }

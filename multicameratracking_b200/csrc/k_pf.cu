@@ -119,62 +119,6 @@ __device__ __forceinline__ double ipow_d(double x, int n)
 // are normal numbers in f64, so the division never takes the slow special-case path.
 __device__ __forceinline__ float fdiv_exact(float a, float b) { return (float)((double)a / (double)b); }
 
-// ParticleFilter::UpdateParticleWeight scale-ratio clamp (ParticleFilter.cpp:658-665): 1.2 and 0.9 are
-// double literals, so the comparison and the product are evaluated in double.
-__device__ __forceinline__ void scale_ratio_clamp(float& sx, float& sy)
-{
-    if ((double)__fdiv_rn(sx, sy) > 1.2) sy = (float)(0.9 * (double)sx);
-    else if ((double)__fdiv_rn(sy, sx) > 1.2) sx = (float)(0.9 * (double)sy);
-}
-
-// ------------------------------------------------------------------------------------------
-// PredictWithBrownianMotion (ParticleFilter.cpp:236-341).  x and y use the scale *before* its update.
-__device__ __forceinline__ float scale_step_dev(float s, float n, float msc, float maxs, float mins)
-{
-    if (msc > fabsf(n)) s = __fadd_rn(s, n);
-    else if (n < 0) s = __fsub_rn(s, msc);
-    else s = __fadd_rn(s, msc);
-    if (s > maxs) s = maxs;
-    if (s < mins) s = mins;
-    return s;
-}
-
-// CheckForParticleRefinement (ParticleFilter.cpp:83-112) looks at the RESAMPLED matrix: a particle counts when its box's top-left
-// corner lies inside the image.  When no particle counts, ForceParticleFilterRefinement (:187-226) pulls the resampled centres
-// back towards the frame (quirk kept: the vertical correction uses scaleX, RS(row, 2)).
-__device__ __forceinline__ bool refine_valid_one(const ObjDesc& d, int i)
-{
-    const float left = __fsub_rn(d.rcx[i], __fdiv_rn(__fmul_rn(d.rsx[i], d.w0), 2.0f));
-    const float top = __fsub_rn(d.rcy[i], __fdiv_rn(__fmul_rn(d.rsy[i], d.h0), 2.0f));
-    return !(left < 0 || left >= d.img_w || top < 0 || top >= d.img_h);
-}
-__device__ __forceinline__ void force_refine_one(const ObjDesc& d, int i)
-{
-    const float cx = d.rcx[i], cy = d.rcy[i], sx = d.rsx[i], sy = d.rsy[i];
-    const float left = __fsub_rn(cx, __fdiv_rn(__fmul_rn(sx, d.w0), 2.0f));
-    const float top = __fsub_rn(cy, __fdiv_rn(__fmul_rn(sy, d.h0), 2.0f));
-    const float fx = cx, fy = __fadd_rn(cy, __fdiv_rn(__fmul_rn(sy, d.h0), 2.0f));
-    const float up = __fsub_rn(fy, __fdiv_rn(__fmul_rn(sx, d.h0), 2.0f));
-    if (left < 0) d.rcx[i] = fmaxf(fx, 0.0f);
-    if (left >= d.img_w) d.rcx[i] = fminf(fx, __fsub_rn(d.img_w, 1.0f));
-    if (top < 0) d.rcy[i] = fmaxf(up, 0.0f);
-    if (top >= d.img_h) d.rcy[i] = fminf(up, __fsub_rn(d.img_h, 1.0f));
-    d.rw[i] = 1.0f;
-}
-// The fused per-frame path spreads the check over two kernels: the predict kernel ORs {2 = check pending, 1 = some
-// particle counts} into PfDev::refine, k_pf_update (one CTA per object, the next kernel that touches the resampled
-// matrix) applies the refinement when the check is pending and nothing counted, and clears the flag.
-#define MCT_REFINE_PENDING 2
-#define MCT_REFINE_VALID 1
-__device__ __forceinline__ void predict_one(const ObjDesc& d, int i, const float* __restrict__ nz)
-{
-    const int N = d.N;
-    float sx = d.sx[i], sy = d.sy[i];
-    d.cx[i] = (float)__float2int_rn(__fadd_rn(d.cx[i], __fmul_rn(sx, nz[i])));
-    d.cy[i] = (float)__float2int_rn(__fadd_rn(d.cy[i], __fmul_rn(sy, nz[(size_t)N + i])));
-    d.sx[i] = scale_step_dev(sx, nz[(size_t)2 * N + i], d.msc, d.maxs, d.mins);
-    d.sy[i] = scale_step_dev(sy, nz[(size_t)3 * N + i], d.msc, d.maxs, d.mins);
-}
 __global__ void __launch_bounds__(256) k_pf_predict(const ObjDesc* __restrict__ descs, const StepArgs sa)
 {
     const ObjDesc& d = descs[blockIdx.y];
@@ -190,28 +134,6 @@ int launch_pf_predict(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max,
     return MCT_OK;
 }
 
-// ------------------------------------------------------------------------------------------
-// GenerateTestSampleSet (ParticleFilterTracker.cpp:1247-1305): box per particle; out-of-frame particles
-// get UpdateParticleWeight(p, 0) (weight *= 0 and the scale-ratio clamp); in-frame particles with a
-// non-zero weight form the test set (dense mask instead of the reference's compaction).
-__device__ __forceinline__ void testset_one(const ObjDesc& d, int i, int fw, int fh)
-{
-    float sx = d.sx[i], sy = d.sy[i];
-    const float wf = __fmul_rn(sx, d.w0), hf = __fmul_rn(sy, d.h0);
-    const float left = (float)__float2int_rn(__fsub_rn(d.cx[i], __fdiv_rn(wf, 2.0f)));
-    const float top = (float)__float2int_rn(__fsub_rn(d.cy[i], __fdiv_rn(hf, 2.0f)));
-    const float width = (float)__float2int_rn(wf), height = (float)__float2int_rn(hf);
-    int v = 0;
-    if (left <= 0 || __fadd_rn(left, width) >= (float)(fw - 1) || top <= 0 || __fadd_rn(top, height) >= (float)(fh - 1)) {
-        d.w[i] = __fmul_rn(0.0f, d.w[i]);
-        scale_ratio_clamp(sx, sy);
-        d.sx[i] = sx; d.sy[i] = sy;
-    } else if (d.w[i] != 0) {
-        v = 1;
-    }
-    d.col[i] = (int)left; d.row[i] = (int)top;
-    d.valid[i] = v;
-}
 __global__ void __launch_bounds__(256) k_pf_testset(const ObjDesc* __restrict__ descs, int fw, int fh)
 {
     const ObjDesc& d = descs[blockIdx.y];

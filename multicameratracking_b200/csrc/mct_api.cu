@@ -623,7 +623,7 @@ extern "C" int mct_classifier_create(mct_ctx* ctx, const mct_clf_params* p, cons
         MCT_CUDA(ctx, cudaMalloc(&c->d_slotmap, (size_t)n_color * 2));
         MCT_CUDA(ctx, cudaMemset(c->d_slotmap, 0, (size_t)n_color * 2));
         MCT_CUDA(ctx, cudaMalloc(&c->d_nout, 4)); MCT_CUDA(ctx, cudaMemset(c->d_nout, 0, 4));
-        MCT_CUDA(ctx, cudaMalloc(&c->d_nbig, 4)); MCT_CUDA(ctx, cudaMemset(c->d_nbig, 0, 4));
+        MCT_CUDA(ctx, cudaMalloc(&c->d_nbig, 8)); MCT_CUDA(ctx, cudaMemset(c->d_nbig, 0, 8));     // [0] flagged boxes, [1] k_mdch_sel arrival counter
     }
     *out = c;
     return MCT_OK;
@@ -749,7 +749,8 @@ static int classify_boxes_on_device(mct_clf* c, int n, int from_matrix, int log_
         if (h->slotmap) {
             if ((rc = launch_bin_image(ctx, c->p.n_bins))) return rc;
             MCT_CUDA(ctx, cudaMemsetAsync(c->d_nbig, 0, 4, ctx->stream));
-            if ((rc = launch_mdch_selected(ctx, d, 1, n, (c->K < c->n_color ? c->K : c->n_color) + 1))) return rc;
+            StepArgs sa0; memset(&sa0, 0, sizeof(sa0));
+            if ((rc = launch_mdch_selected(ctx, d, 1, n, (c->K < c->n_color ? c->K : c->n_color) + 1, sa0, 0))) return rc;
         } else if ((rc = mct_feature_color_rows(c, c->d_col, c->d_row, c->d_sx, c->d_sy, nullptr, n, nullptr, c->n_color,
                                                 c->d_featN, c->ldN)))
             return rc;
@@ -1115,26 +1116,34 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
     }
     const ObjDesc* d;
     if ((rc = desc_publish(ctx, h, n_obj, &d))) return rc;
-    if (rescore) { if ((rc = launch_pf_testset(ctx, d, n_obj, n_max))) return rc; }
-    else if ((rc = launch_pf_predict_testset(ctx, d, n_obj, n_max, sa))) return rc;
-    int any_mdch = 0, max_slots = 1, nb = 0;
+    // Objects with MDCH colour features: the predict / test-set step of ALL objects rides in the prologue of k_mdch_sel
+    // (one launch less on the frame's critical path).  CCH objects compute their rows per object and need the boxes first.
+    int any_mdch = 0, any_cch = 0, max_slots = 1, nb = 0;
     for (int o = 0; o < n_obj; o++) {
-        mct_clf* c = clfs[o]; mct_pf* p = pfs[o];
+        mct_clf* c = clfs[o];
         if (c->n_color <= 0) continue;
         if (h[o].slotmap) {
             any_mdch = 1; nb = c->p.n_bins;
             int ms = (c->K < c->n_color ? c->K : c->n_color) + 1;
             if (ms > max_slots) max_slots = ms;
-        } else {
-            float* sx = p->d_state + 2 * (size_t)p->ld; float* sy = p->d_state + 3 * (size_t)p->ld;
-            if ((rc = mct_feature_color_rows(c, p->d_col, p->d_row, sx, sy, p->d_valid, p->N, nullptr, c->n_color,
-                                             c->d_featN, c->ldN)))
-                return rc;
-        }
+        } else any_cch = 1;
+    }
+    const bool fused_pre = any_mdch && !any_cch;
+    if (!fused_pre) {
+        if (rescore) { if ((rc = launch_pf_testset(ctx, d, n_obj, n_max))) return rc; }
+        else if ((rc = launch_pf_predict_testset(ctx, d, n_obj, n_max, sa))) return rc;
+    }
+    for (int o = 0; o < n_obj && any_cch; o++) {
+        mct_clf* c = clfs[o]; mct_pf* p = pfs[o];
+        if (c->n_color <= 0 || h[o].slotmap) continue;
+        float* sx = p->d_state + 2 * (size_t)p->ld; float* sy = p->d_state + 3 * (size_t)p->ld;
+        if ((rc = mct_feature_color_rows(c, p->d_col, p->d_row, sx, sy, p->d_valid, p->N, nullptr, c->n_color,
+                                         c->d_featN, c->ldN)))
+            return rc;
     }
     if (any_mdch) {
         if ((rc = launch_bin_image(ctx, nb))) return rc;
-        if ((rc = launch_mdch_selected(ctx, d, n_obj, n_max, max_slots))) return rc;
+        if ((rc = launch_mdch_selected(ctx, d, n_obj, n_max, max_slots, sa, fused_pre ? (rescore ? 2 : 1) : 0))) return rc;
     }
     (void)K_max;
     if ((rc = launch_classify_staged(ctx, d, n_obj, n_max, 1))) return rc;
