@@ -198,14 +198,25 @@ class Context:
         self.W = self.H = 0
         self._keep = None
 
+    @classmethod
+    def from_handle(cls, h):
+        """non-owning view of an existing mct_ctx (e.g. the one a host.Camera created)"""
+        self = cls.__new__(cls)
+        self.L = load()
+        self.h = h
+        self.W = self.H = 0
+        self._keep = None
+        self._borrowed = True
+        return self
+
     def check(self, rc):
         if rc:
             raise MctError(rc, self.L.mct_last_error(self.h).decode())
 
     def close(self):
-        if self.h:
+        if self.h and not getattr(self, "_borrowed", False):
             self.L.mct_ctx_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def sync(self):
         self.check(self.L.mct_sync(self.h))
@@ -363,6 +374,14 @@ class ParticleFilter:
         ctx.check(ctx.L.mct_pf_create(ctx.h, n_particles, float(image_w), float(image_h), C.byref(h)))
         self.h = h
 
+    @classmethod
+    def from_handle(cls, ctx, h, n_particles):
+        """non-owning view of an existing mct_pf"""
+        self = cls.__new__(cls)
+        self.ctx = ctx; self.N = n_particles; self.h = h
+        self._borrowed = True
+        return self
+
     def ground_pdf(self, H, mean, cov, h0, want_weights=False):
         """mct_pf_ground_pdf -> (total_weight, average[4], usable_covariance, weights or None)"""
         Hd = np.ascontiguousarray(H, np.float64).reshape(9)
@@ -380,7 +399,7 @@ class ParticleFilter:
         self.ctx.check(self.ctx.L.mct_pf_rearrange_ground(self.h, float(mean_foot[0]), float(mean_foot[1]), _fp(nz), float(w0), float(h0)))
 
     def close(self):
-        if self.h:
+        if self.h and not getattr(self, "_borrowed", False):
             self.ctx.L.mct_pf_destroy(self.h)
             self.h = None
 

@@ -47,6 +47,8 @@ def load():
         L.mcth_fuser_get.argtypes = [vp, fp, fp, fp, fp]
         L.mcth_fuser_intersection.argtypes = [C.c_int, dp, fp, dp]
         L.mcth_randgaus.argtypes = [C.c_int64, C.c_float, C.c_int, fp]
+        L.mcth_object_handles.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp)]
+        L.mcth_object_randfloat.argtypes = [vp, C.c_int]; L.mcth_object_randfloat.restype = C.c_float
         L.mcth_camera_sync.argtypes = [vp]
         L.mcth_camera_launches.argtypes = [vp]; L.mcth_camera_launches.restype = C.c_longlong
         L.mcth_object_selectors.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
@@ -119,7 +121,9 @@ class Camera:
         self._chk(self.L.mcth_camera_init_trackers(self.h))
 
     def track(self, frameind, noise, phases=3):
-        """noise: [n_obj][4][N] float32.  Returns [n_obj][4] boxes (x, y, w, h) when phases & 1."""
+        """noise: [n_obj][4][N] float32.  phases: bit 0 score + store the state, bit 1 UpdateClassifier, bit 2 (with bit 0)
+        score WITHOUT storing the state (fusion branch), bit 3 store the state from the particles as they are now (after the
+        fusers).  Returns [n_obj][4] boxes (x, y, w, h) of the stored state."""
         nz = np.ascontiguousarray(noise, np.float32)
         out = np.zeros((self.n_obj, 4), np.int32)
         self._chk(self.L.mcth_camera_track(self.h, frameind, nz.ctypes.data_as(C.c_void_p), phases,
@@ -141,6 +145,21 @@ class Camera:
         self._chk(self.L.mcth_camera_ground_feedback(self.h, o, Hd.ctypes.data_as(C.POINTER(C.c_double)), m.ctypes.data_as(fp),
                                                      cv.ctypes.data_as(fp), C.byref(r), C.byref(d)))
         return bool(r.value), float(d.value)
+
+    def capi_context(self):
+        """non-owning capi.Context on this camera's mct_ctx (same stream, same frame)"""
+        from .. import capi
+        return capi.Context.from_handle(C.c_void_p(self.L.mcth_camera_ctx(self.h)))
+
+    def particle_filter(self, o):
+        """non-owning capi.ParticleFilter of object o"""
+        from .. import capi
+        pf = C.c_void_p()
+        self._chk(self.L.mcth_object_handles(self.h, o, C.byref(pf), None))
+        return capi.ParticleFilter.from_handle(self.capi_context(), pf, self.N[o])
+
+    def randfloat(self, o):
+        return float(self.L.mcth_object_randfloat(self.h, o))
 
     def sync(self):
         self._chk(self.L.mcth_camera_sync(self.h))

@@ -511,7 +511,14 @@ void ParticleFilterTracker::TrackCameraObjects(mct_ctx* ctx, std::vector<Particl
             ParticleFilterTracker* t = trackers[o];
             if (summ[o].resampled) (void)t->m_rng.Next();        // the randfloat() inside ResampleParticles
             t->m_particleFilterPtr->AdoptSummary(summ[o]);
-            t->StoreObjectState(frameind);
+            if (!(phases & 4)) t->StoreObjectState(frameind);    // bit 2: TrackObjectWithoutSaveState (fusion branch, Object.cpp:433-450)
+        }
+    }
+    if (phases & 8) {
+        // StoreAllParticleFilterTrackerState (Camera.cpp:556-574) after the fusers changed the particles on the device
+        for (int o = 0; o < n; o++) {
+            trackers[o]->m_particleFilterPtr->Invalidate();
+            trackers[o]->StoreObjectState(frameind);
         }
     }
     if (phases & 2) {

@@ -263,6 +263,8 @@ public:
     mct_pf* Handle() const { return m_pf; }
     // fast path: adopt the read-out the fused scoring call already produced
     void AdoptSummary(const mct_pf_summary& s) { m_summary = s; m_summaryValid = true; m_hostStateValid = false; }
+    // the particles were changed on the device behind this object's back (fusers): read-outs are fetched again
+    void Invalidate() { m_summaryValid = false; m_hostStateValid = false; }
     const mct_pf_summary& Summary();
 private:
     void FetchState();

@@ -132,7 +132,7 @@ int mcth_camera_track(mcth_camera* c, int frameind, const float* noise, int phas
 {
     GUARD({
         ParticleFilterTracker::TrackCameraObjects(c->ctx, c->trackers, frameind, &c->frame, &c->frame, &c->frame, noise, phases);
-        if (out_boxes && (phases & 1))
+        if (out_boxes && (((phases & 1) && !(phases & 4)) || (phases & 8)))
             for (size_t o = 0; o < c->trackers.size(); o++)
                 for (int q = 0; q < 4; q++) out_boxes[o * 4 + q] = c->trackers[o]->States()[(size_t)frameind * 4 + q];
     });
@@ -155,6 +155,22 @@ int mcth_camera_pack_foot_points(mcth_camera* c, float* dev_out)
     int rc = mct_fuser_pack_foot_points(c->ctx, n, pfs.data(), h0.data(), dev_out);
     if (rc) c->err = mct_last_error(c->ctx);
     return rc;
+}
+
+// C-ABI handles of object o (particle filter, tracker classifier): for callers that drive extra device work on the camera's
+// own context, e.g. the appearance fuser's global classifier (network.AppearanceFusion)
+int mcth_object_handles(mcth_camera* c, int o, mct_pf** pf, mct_clf** clf)
+{
+    if (!c || o < 0 || o >= (int)c->trackers.size()) return MCT_E_ARG;
+    if (pf) *pf = c->trackers[o]->GetParticleFilter()->Handle();
+    if (clf) *clf = c->trackers[o]->GetClassifier()->Handle();
+    return 0;
+}
+// the tracker's MWC stream: next randfloat() (consumed) -- the appearance fuser's sample dropping draws from it
+float mcth_object_randfloat(mcth_camera* c, int o)
+{
+    Public::SetCurrentRng(&c->trackers[o]->Rng());
+    return Public::randfloat();
 }
 
 // ---- geometric fuser ----
