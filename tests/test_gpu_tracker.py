@@ -28,11 +28,16 @@ def _oracle_tracker(oracle, seq, o, f0, p, seed):
     return trk, clf, rng
 
 
-@pytest.mark.parametrize("cfg", ["cfg1_haar_milboost", "haarmdch_wstump_2obj", "mdch_anyboost_avg"])
+@pytest.mark.parametrize("cfg", ["cfg1_haar_milboost", "haarmdch_wstump_2obj", "mdch_anyboost_avg", "cfg2_full_size_8obj_2000"])
 def test_tracker_sequence_matches_oracle(oracle, cfg):
     n_frames = 12
     if cfg == "cfg1_haar_milboost":
         n_obj, over = 1, dict()
+    elif cfg == "cfg2_full_size_8obj_2000":
+        # BASELINE configs[1] at its full size: 8 objects, Haar(250) + MDCH(512) -> 152 selected, WeightedStumps + MILBoost,
+        # 2000 particles per object (the oracle needs ~1 s per frame for it)
+        n_frames = 6
+        n_obj, over = 8, dict(feature_type=3, weak_type=1, n_particles=2000, n_haar=250)
     elif cfg == "haarmdch_wstump_2obj":
         n_obj, over = 2, dict(feature_type=3, weak_type=1, n_particles=600, n_haar=100)
     else:
