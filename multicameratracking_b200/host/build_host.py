@@ -15,14 +15,24 @@ def build(force=False):
     deps = SRC + [os.path.join(HERE, "mct_host.h"), os.path.join(HERE, "mct_fuser.h"), os.path.join(PKG, "..", "include", "mct_b200.h")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
-    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    cmd = [gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", LIB] + SRC + [
-        "-L" + PKG, "-l:libmct_b200.so", "-Wl,-rpath,$ORIGIN/.."]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout)
-        raise RuntimeError("g++ failed building libmct_host.so")
-    return LIB
+    import fcntl
+    with open(os.path.join(HERE, ".build.lock"), "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)           # one builder at a time (ranks of a torchrun job)
+        try:
+            if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
+                return LIB
+            gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+            tmp = LIB + ".tmp.%d" % os.getpid()
+            cmd = [gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", tmp] + SRC + [
+                "-L" + PKG, "-l:libmct_b200.so", "-Wl,-rpath,$ORIGIN/.."]
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout)
+                raise RuntimeError("g++ failed building libmct_host.so")
+            os.replace(tmp, LIB)
+            return LIB
+        finally:
+            fcntl.flock(lk, fcntl.LOCK_UN)
 
 
 if __name__ == "__main__":
