@@ -154,6 +154,11 @@ int mct_classifier_update_from_features(mct_clf* clf, const float* fpos, int P, 
                                         const float* wpos, const float* wneg);
 /* StrongClassifierBase::Classify(set, isLogRatioEnabled) (MILBoostClassifier.cpp:339-374). */
 int mct_classifier_classify(mct_clf* clf, const mct_boxes* boxes, int log_ratio, float* out_host);
+/* SimpleTracker (the reference's default local tracker, SimpleTracker.cpp:280-342): the search windows of all objects of a
+ * camera are classified in one batched pass and only the first-maximum index and its response come back per object.
+ * boxes: [n_obj] test sample sets (host); best_idx / best_resp: [n_obj] host. */
+int mct_classify_argmax(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, const mct_boxes* boxes, int log_ratio,
+                        int* best_idx, float* best_resp);
 int mct_classifier_classify_from_features(mct_clf* clf, const float* feat, int n, int log_ratio, float* out_host);
 /* m_selectorList (StrongClassifierBase.h:63) */
 int mct_classifier_get_selectors(mct_clf* clf, int* idx_host, int* n);

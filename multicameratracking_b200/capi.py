@@ -32,7 +32,7 @@ SYMBOLS = [
     "mct_pf_update_all_weights", "mct_pf_resample", "mct_pf_get_state", "mct_pf_set_state", "mct_pf_get_resampled",
     "mct_pf_get_resample_indices", "mct_pf_get_summary", "mct_track_score", "mct_noise_prefetch", "mct_track_score_async",
     "mct_track_collect", "mct_track_update", "mct_pf_get_last_response", "mct_fuser_pack_foot_points",
-    "mct_pf_ground_pdf", "mct_pf_rearrange_ground",
+    "mct_pf_ground_pdf", "mct_pf_rearrange_ground", "mct_classify_argmax",
 ]
 
 
@@ -137,6 +137,7 @@ def load():
     L.mct_fuser_pack_foot_points.argtypes = [vp, C.c_int, C.POINTER(vp), _c_float_p, vp]
     L.mct_pf_ground_pdf.argtypes = [vp, C.POINTER(C.c_double), _c_float_p, _c_float_p, C.c_float, C.POINTER(GroundPdfResult), _c_float_p]
     L.mct_pf_rearrange_ground.argtypes = [vp, C.c_float, C.c_float, _c_float_p, C.c_float, C.c_float]
+    L.mct_classify_argmax.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(Boxes), C.c_int, _c_int_p, _c_float_p]
     _lib = L
     return L
 
@@ -304,9 +305,18 @@ class StrongClassifier:
         self.F = L.mct_classifier_num_features(h)
 
     def close(self):
-        if self.h:
+        if self.h and not getattr(self, "_borrowed", False):
             self.ctx.L.mct_classifier_destroy(self.h)
-            self.h = None
+        self.h = None
+
+    @classmethod
+    def from_handle(cls, ctx, h):
+        """non-owning view of an existing mct_clf"""
+        self = cls.__new__(cls)
+        self.ctx = ctx; self.h = h
+        self.F = ctx.L.mct_classifier_num_features(h)
+        self._borrowed = True
+        return self
 
     def GetNumberOfFeatures(self):
         return self.F
@@ -469,6 +479,17 @@ def track_score(ctx, pfs, clfs, params, noise, u01, noise_device_ptr=None):
         rc = ctx.L.mct_track_score(ctx.h, n, pa, ca, tp, nz.ctypes.data_as(vp), 0, _fp(u), out)
     ctx.check(rc)
     return list(out)
+
+
+def classify_argmax(ctx, clfs, boxes_list, log_ratio=True):
+    """mct_classify_argmax: (best index, best response) per object over its search window"""
+    n = len(clfs)
+    vp = C.c_void_p
+    ca = (vp * n)(*[c.h for c in clfs])
+    ba = (Boxes * n)(*boxes_list)
+    idx = np.zeros(n, np.int32); val = np.zeros(n, np.float32)
+    ctx.check(ctx.L.mct_classify_argmax(ctx.h, n, ca, ba, int(log_ratio), _ip(idx), _fp(val)))
+    return idx, val
 
 
 def pack_foot_points(ctx, pfs, h0, dev_out_ptr):

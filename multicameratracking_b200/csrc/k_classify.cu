@@ -8,6 +8,7 @@
 // [rows][ldN] matrix produced by k_mdch / k_cch.  H accumulates in selector order in f32, exactly like
 // the reference's responseList[i] += weak[k] loop.
 #include "mct_internal.cuh"
+#include <math_constants.h>
 
 __global__ void __launch_bounds__(256)
 k_classify(const ObjDesc* __restrict__ descs, const float* __restrict__ ii, int iip, int W, int H,
@@ -217,5 +218,41 @@ int launch_classify(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, i
     dim3 g(ceil_div(n_max, 256), n_obj);
     MCT_LAUNCH(ctx, "k_classify", k_classify<<<g, 256, smem, ctx->stream>>>(d_desc, ctx->ii_base ? ctx->ii_base + MCT_II_LEAD : nullptr, ctx->ii_pitch,
                                               ctx->W, ctx->H, from_matrix, log_ratio));
+    return MCT_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// SimpleTracker's decision (SimpleTracker.cpp:316-323): index and value of the largest response over the search window,
+// first occurrence on ties (max_idx, Public.h:256-268).  One CTA per object over d.H[0 .. N).
+struct ArgmaxOut { int idx; float val; };
+__global__ void __launch_bounds__(256) k_response_argmax(const ObjDesc* __restrict__ descs, ArgmaxOut* __restrict__ out)
+{
+    __shared__ float s_v[8];
+    __shared__ int s_i[8];
+    const ObjDesc& d = descs[blockIdx.x];
+    float bv = -CUDART_INF_F; int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < d.N; i += blockDim.x) {
+        const float v = d.H[i];
+        if (v > bv || (v == bv && i < bi) || bi == 0x7fffffff) { bv = v; bi = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_v[warp] = bv; s_i[warp] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++)
+            if (s_i[w] != 0x7fffffff && (bi == 0x7fffffff || s_v[w] > bv || (s_v[w] == bv && s_i[w] < bi))) { bv = s_v[w]; bi = s_i[w]; }
+        out[blockIdx.x].idx = bi == 0x7fffffff ? -1 : bi;
+        out[blockIdx.x].val = bv;
+    }
+}
+int launch_response_argmax(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, void* d_out)
+{
+    MCT_LAUNCH(ctx, "k_response_argmax", k_response_argmax<<<n_obj, 256, 0, ctx->stream>>>(d_desc, (ArgmaxOut*)d_out));
     return MCT_OK;
 }

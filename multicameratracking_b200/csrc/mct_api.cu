@@ -181,6 +181,7 @@ extern "C" int mct_ctx_destroy(mct_ctx* ctx)
     if (ctx->prep_stream) cudaStreamSynchronize(ctx->prep_stream);
     if (ctx->d_scored) cudaFree(ctx->d_scored);
     if (ctx->d_ground_out) cudaFree(ctx->d_ground_out);
+    if (ctx->d_argmax) cudaFree(ctx->d_argmax);
     if (ctx->prof) {
         ProfState* ps = (ProfState*)ctx->prof;
         for (ProfEntry& e : ps->entries) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -772,6 +773,63 @@ extern "C" int mct_classifier_classify(mct_clf* c, const mct_boxes* boxes, int l
     if ((rc = classify_boxes_on_device(c, n, 0, log_ratio))) return rc;
     MCT_CUDA(ctx, cudaMemcpyAsync(out_host, c->d_H, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     return mct_sync(ctx);
+}
+
+// SimpleTracker::TrackObjectOnTheGivenFrame's device part for all objects of a camera (SimpleTracker.cpp:280-342): the
+// strong classifiers score their search windows in one batched pass and only {best index, best response} per object comes
+// back.  boxes[o]: the test sample set of object o (host).  NaN responses are never picked unless all are NaN.
+extern "C" int mct_classify_argmax(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, const mct_boxes* boxes, int log_ratio,
+                                   int* best_idx, float* best_resp)
+{
+    if (!ctx || n_obj < 1 || n_obj > DESC_MAX_OBJ || !clfs || !boxes || !best_idx || !best_resp) return MCT_E_ARG;
+    if (ctx->frame_id == 0) return mct_fail(ctx, MCT_E_STATE, "no frame set%s");
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    ObjDesc h[DESC_MAX_OBJ];
+    int rc, n_max = 0, K_max = 1, any_mdch = 0, max_slots = 1, nb = 0;
+    for (int o = 0; o < n_obj; o++) {
+        mct_clf* c = clfs[o];
+        if (!c || c->ctx != ctx) return mct_fail(ctx, MCT_E_ARG, "classifier handle belongs to another ctx%s");
+        if (boxes[o].n < 1) return mct_fail(ctx, MCT_E_EMPTY, "object %s%d has an empty search window", "", o);
+        if ((rc = need_frame(c))) return rc;
+        if ((rc = clf_ensure_test(c, boxes[o].n, c->n_color))) return rc;
+        if ((rc = upload_boxes(ctx, &boxes[o], c->d_col, c->d_row, c->d_sx, c->d_sy, 0))) return rc;
+        memset(&h[o], 0, sizeof(ObjDesc));
+        fill_clf_desc(&h[o], c);
+        h[o].N = boxes[o].n; h[o].ld = c->ldN;
+        h[o].col = c->d_col; h[o].row = c->d_row; h[o].sx = c->d_sx; h[o].sy = c->d_sy; h[o].valid = nullptr; h[o].H = c->d_H;
+        if (boxes[o].n > n_max) n_max = boxes[o].n;
+        if (c->K > K_max) K_max = c->K;
+        if (c->n_color > 0 && h[o].slotmap) {
+            any_mdch = 1; nb = c->p.n_bins;
+            int ms = (c->K < c->n_color ? c->K : c->n_color) + 1;
+            if (ms > max_slots) max_slots = ms;
+        }
+    }
+    const ObjDesc* d;
+    if ((rc = desc_publish(ctx, h, n_obj, &d))) return rc;
+    for (int o = 0; o < n_obj; o++) {          // CCH rows per object (the reference's degenerate histogram; rarely configured)
+        mct_clf* c = clfs[o];
+        if (c->n_color > 0 && !h[o].slotmap &&
+            (rc = mct_feature_color_rows(c, c->d_col, c->d_row, c->d_sx, c->d_sy, nullptr, boxes[o].n, nullptr, c->n_color, c->d_featN, c->ldN)))
+            return rc;
+    }
+    if (any_mdch) {
+        StepArgs sa0; memset(&sa0, 0, sizeof(sa0));
+        if ((rc = launch_bin_image(ctx, nb))) return rc;
+        if ((rc = launch_mdch_selected(ctx, d, n_obj, n_max, max_slots, sa0, 0))) return rc;
+    }
+    if ((rc = launch_classify(ctx, d, n_obj, n_max, K_max, 0, log_ratio))) return rc;
+    if (ctx->argmax_cap < n_obj) {
+        if (ctx->d_argmax) cudaFree(ctx->d_argmax);
+        MCT_CUDA(ctx, cudaMalloc(&ctx->d_argmax, (size_t)DESC_MAX_OBJ * 8));
+        ctx->argmax_cap = DESC_MAX_OBJ;
+    }
+    if ((rc = launch_response_argmax(ctx, d, n_obj, ctx->d_argmax))) return rc;
+    struct { int idx; float val; } out[DESC_MAX_OBJ];
+    MCT_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_argmax, (size_t)n_obj * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = mct_sync(ctx))) return rc;
+    for (int o = 0; o < n_obj; o++) { best_idx[o] = out[o].idx; best_resp[o] = out[o].val; }
+    return MCT_OK;
 }
 
 extern "C" int mct_classifier_classify_from_features(mct_clf* c, const float* feat, int n, int log_ratio, float* out_host)

@@ -82,6 +82,7 @@ struct mct_ctx {
     unsigned long long* d_scored;                      // device counter: test samples scored (sum of n_valid)
     void* prof;                                        // per-kernel event timing state (NULL = off)
     char err[512];
+    void* d_argmax; int argmax_cap;   // read-out of k_response_argmax [n_obj] {idx, val}
     GroundOut* d_ground_out;     // read-out of k_ground_pdf
 };
 
@@ -265,6 +266,7 @@ int launch_classify_staged(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n
 int launch_pf_predict(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, const StepArgs& sa);
 int launch_pf_testset(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max);
 int launch_pf_refine(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj);
+int launch_response_argmax(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, void* d_out);
 int launch_pf_rearrange(mct_ctx* ctx, const ObjDesc* d_desc, int n_max, const float* d_noise2, float mfx, float mfy);
 int launch_ground_pdf(mct_ctx* ctx, const ObjDesc* d_desc, const GroundArgs& ga, float* d_wout, GroundOut* d_out);
 // fused predict + test set (+ per-frame reset of the MDCH fallback counters) for the batched per-frame path

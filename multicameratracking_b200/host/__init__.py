@@ -47,6 +47,13 @@ def load():
         L.mcth_fuser_get.argtypes = [vp, fp, fp, fp, fp]
         L.mcth_fuser_intersection.argtypes = [C.c_int, dp, fp, dp]
         L.mcth_randgaus.argtypes = [C.c_int64, C.c_float, C.c_int, fp]
+        L.mcth_camera_add_simple_object.argtypes = [vp, C.POINTER(ObjectParams)]
+        L.mcth_camera_init_simple.argtypes = [vp]
+        L.mcth_camera_track_simple.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double)]
+        L.mcth_simple_selectors.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
+        L.mcth_simple_rng_state.argtypes = [vp, C.c_int]; L.mcth_simple_rng_state.restype = C.c_uint64
+        L.mcth_simple_last_test_size.argtypes = [vp, C.c_int]
+        L.mcth_simple_classifier.argtypes = [vp, C.c_int]; L.mcth_simple_classifier.restype = vp
         L.mcth_object_handles.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp)]
         L.mcth_object_randfloat.argtypes = [vp, C.c_int]; L.mcth_object_randfloat.restype = C.c_float
         L.mcth_camera_sync.argtypes = [vp]
@@ -102,6 +109,45 @@ class Camera:
         self._chk(self.L.mcth_camera_add_object(self.h, C.byref(op)))
         self.n_obj += 1
         self.N.append(p["n_particles"])
+
+    # ---- SimpleTracker objects (Local_Tracker_Type 0, the reference's default)
+    def add_simple_object(self, init_xywh, **kw):
+        p = dict(DEFAULTS); p.update(kw)
+        op = ObjectParams()
+        for k, v in p.items():
+            setattr(op, k, v)
+        op.init_xywh = (C.c_float * 4)(*[float(x) for x in init_xywh])
+        self._chk(self.L.mcth_camera_add_simple_object(self.h, C.byref(op)))
+        self.n_simple = getattr(self, "n_simple", 0) + 1
+
+    def init_simple(self):
+        self._chk(self.L.mcth_camera_init_simple(self.h))
+
+    def track_simple(self, frameind):
+        """one frame for all SimpleTracker objects: returns (states [n][4] float32 x, y, w, h; best responses [n])"""
+        n = getattr(self, "n_simple", 0)
+        st = np.zeros((n, 4), np.float32); rs = np.zeros(n, np.float64)
+        self._chk(self.L.mcth_camera_track_simple(self.h, frameind, st.ctypes.data_as(C.POINTER(C.c_float)),
+                                                  rs.ctypes.data_as(C.POINTER(C.c_double))))
+        return st, rs
+
+    def simple_selectors(self, o):
+        idx = np.zeros(4096, np.int32)
+        n = self.L.mcth_simple_selectors(self.h, o, idx.ctypes.data_as(C.POINTER(C.c_int)))
+        if n < 0:
+            self._chk(n)
+        return idx[:n].copy()
+
+    def simple_classifier(self, o):
+        """non-owning capi.StrongClassifier of SimpleTracker object o (introspection)"""
+        from .. import capi
+        return capi.StrongClassifier.from_handle(self.capi_context(), C.c_void_p(self.L.mcth_simple_classifier(self.h, o)))
+
+    def simple_rng_state(self, o):
+        return int(self.L.mcth_simple_rng_state(self.h, o))
+
+    def simple_last_test_size(self, o):
+        return int(self.L.mcth_simple_last_test_size(self.h, o))
 
     def set_frame(self, gray, c0=None, c1=None, c2=None):
         gray = np.ascontiguousarray(gray, np.uint8)

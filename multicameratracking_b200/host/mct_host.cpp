@@ -539,4 +539,125 @@ void ParticleFilterTracker::TrackCameraObjects(mct_ctx* ctx, std::vector<Particl
         chk(ctx, mct_track_update(ctx, n, clfs.data(), pb.data(), nb.data()));
     }
 }
+
+// ================================================================================ SimpleTracker
+SimpleTracker::SimpleTracker(mct_ctx* ctx, int64_t rngSeed)
+    : m_ctx(ctx), m_rng(rngSeed), m_currentStateList(4, 0.0f), m_lastResponse(0), m_lastTestSetSize(0), m_isInitialized(false)
+{
+}
+
+// SimpleTracker.cpp:35-108
+void SimpleTracker::InitializeTrackerWithParameters(Matrixu* pColor, Matrixu* pGray, int, uint videoLength, TrackerParametersPtr tp,
+                                                    Classifier::StrongClassifierParametersBasePtr cp, Matrixu* pHSV)
+{
+    Public::SetCurrentRng(&m_rng);
+    m_params = std::dynamic_pointer_cast<SimpleTrackerParameters>(tp);
+    if (!m_params) { m_params = SimpleTrackerParametersPtr(new SimpleTrackerParameters()); static_cast<ParticleFilterTrackerParameters&>(*m_params) = *tp; }
+    m_states.assign((size_t)videoLength * 4, 0.0f);
+    m_strongClassifierBasePtr = Classifier::StrongClassifierFactory::CreateAndInitializeClassifier(cp, m_ctx);
+    for (int i = 0; i < 4; i++) m_currentStateList[i] = tp->m_initState[i];
+    Classifier::SampleSet pos, neg;
+    pos.SampleImage(pGray, (int)(uint)m_currentStateList[0], (int)(uint)m_currentStateList[1], (int)(uint)m_currentStateList[2],
+                    (int)(uint)m_currentStateList[3], tp->m_init_posTrainRadius, 0, 1000000, pColor, pHSV);
+    neg.SampleImage(pGray, (int)(uint)m_currentStateList[0], (int)(uint)m_currentStateList[1], (int)(uint)m_currentStateList[2],
+                    (int)(uint)m_currentStateList[3], 2.0f * tp->m_searchWindSize, 1.5f * tp->m_init_posTrainRadius,
+                    (int)tp->m_init_negNumTrain, pColor, pHSV);
+    if (pos.Size() < 1 || neg.Size() < 1) throw MctHostError(MCT_E_EMPTY, "SimpleTracker: empty initial training set");
+    m_strongClassifierBasePtr->Update(pos, neg);
+    m_isInitialized = true;
+}
+
+// :472-493
+void SimpleTracker::GenerateTestSampleSet(Matrixu* pColor, Matrixu* pGray, Matrixu* pHSV)
+{
+    Public::SetCurrentRng(&m_rng);
+    m_testSampleSet.Clear();
+    m_testSampleSet.SampleImage(pGray, (int)m_currentStateList[0], (int)m_currentStateList[1], (int)m_currentStateList[2],
+                                (int)m_currentStateList[3], (float)m_params->m_searchWindSize, 0, 1000000, pColor, pHSV);
+}
+
+// :350-455
+void SimpleTracker::GenerateTrainingSampleSet(Matrixu* pColor, Matrixu* pGray, Matrixu* pHSV)
+{
+    Public::SetCurrentRng(&m_rng);
+    m_positiveSampleSet.Clear();
+    if (m_params->m_posRadiusTrain == 1) {
+        Classifier::Sample smp;
+        smp.m_col = (int)m_currentStateList[0]; smp.m_row = (int)m_currentStateList[1];
+        smp.m_width = (int)m_currentStateList[2]; smp.m_height = (int)m_currentStateList[3];
+        smp.m_scaleX = 1; smp.m_scaleY = 1; smp.m_weight = 1.0f;
+        m_positiveSampleSet.PushBackSample(smp);
+    } else {
+        m_positiveSampleSet.SampleImage(pGray, (int)m_currentStateList[0], (int)m_currentStateList[1], (int)m_currentStateList[2],
+                                        (int)m_currentStateList[3], m_params->m_posRadiusTrain, 0,
+                                        (int)m_params->m_maximumNumberOfPositiveTrainingSamples, pColor, pHSV);
+    }
+    m_negativeSampleSet.Clear();
+    if (m_params->m_negSampleStrategy == 0)
+        m_negativeSampleSet.SampleImage(pGray, m_params->m_numberOfNegativeTrainingSamples, (int)m_currentStateList[2],
+                                        (int)m_currentStateList[3], pColor, pHSV);
+    else
+        m_negativeSampleSet.SampleImage(pGray, (int)m_currentStateList[0], (int)m_currentStateList[1], (int)m_currentStateList[2],
+                                        (int)m_currentStateList[3], 1.5f * m_params->m_searchWindSize, m_params->m_posRadiusTrain + 5,
+                                        (int)m_params->m_numberOfNegativeTrainingSamples, pColor, pHSV);
+}
+
+// :258-270
+void SimpleTracker::UpdateClassifier(Matrixu* pColor, Matrixu* pGray, Matrixu* pHSV)
+{
+    GenerateTrainingSampleSet(pColor, pGray, pHSV);
+    m_strongClassifierBasePtr->Update(m_positiveSampleSet, m_negativeSampleSet);
+}
+
+void SimpleTracker::TrackObjectAndSaveState(int frameind, Matrixu* pColor, Matrixu* pGray, Matrixu* pHSV)
+{
+    std::vector<SimpleTracker*> one(1, this);
+    TrackCameraObjects(m_ctx, one, frameind, pColor, pGray, pHSV, nullptr);
+}
+
+void SimpleTracker::TrackCameraObjects(mct_ctx* ctx, std::vector<SimpleTracker*>& trackers, int frameind, Matrixu* pColor,
+                                       Matrixu* pGray, Matrixu* pHSV, double* responses)
+{
+    const int n = (int)trackers.size();
+    if (n == 0) return;
+    // 1. search windows (host enumeration, each tracker's own RNG stream), scored in one batched device pass
+    std::vector<mct_clf*> clfs(n);
+    std::vector<vectori> tc(n), tr(n); std::vector<vectorf> tsx(n), tsy(n);
+    std::vector<mct_boxes> tb(n);
+    for (int o = 0; o < n; o++) {
+        SimpleTracker* t = trackers[o];
+        if (!t->m_isInitialized) throw MctHostError(MCT_E_STATE, "tracker not initialised");
+        t->GenerateTestSampleSet(pColor, pGray, pHSV);
+        t->m_testSampleSet.ToBoxes(tc[o], tr[o], tsx[o], tsy[o]);
+        t->m_lastTestSetSize = (int)tc[o].size();
+        tb[o] = {(int)tc[o].size(), tc[o].data(), tr[o].data(), tsx[o].data(), tsy[o].data()};
+        clfs[o] = t->m_strongClassifierBasePtr->Handle();
+    }
+    std::vector<int> best(n); std::vector<float> resp(n);
+    chk(ctx, mct_classify_argmax(ctx, n, clfs.data(), tb.data(), 1 /* m_shouldNotUseSigmoid */, best.data(), resp.data()));
+    // 2. new position = the best box (:316-323), then UpdateClassifier for all objects in one batched pass
+    std::vector<vectori> pc(n), pr(n), nc(n), nr(n);
+    std::vector<vectorf> psx(n), psy(n), nsx(n), nsy(n);
+    std::vector<mct_boxes> pb(n), nb(n);
+    for (int o = 0; o < n; o++) {
+        SimpleTracker* t = trackers[o];
+        if (best[o] < 0) throw MctHostError(MCT_E_EMPTY, "SimpleTracker: no response");
+        t->m_lastResponse = resp[o];
+        if (responses) responses[o] = resp[o];
+        t->m_currentStateList[1] = (float)tr[o][best[o]];
+        t->m_currentStateList[0] = (float)tc[o][best[o]];
+        t->m_testSampleSet.Clear();
+        t->GenerateTrainingSampleSet(pColor, pGray, pHSV);
+        t->m_positiveSampleSet.ToBoxes(pc[o], pr[o], psx[o], psy[o]);
+        t->m_negativeSampleSet.ToBoxes(nc[o], nr[o], nsx[o], nsy[o]);
+        pb[o] = {(int)pc[o].size(), pc[o].data(), pr[o].data(), psx[o].data(), psy[o].data()};
+        nb[o] = {(int)nc[o].size(), nc[o].data(), nr[o].data(), nsx[o].data(), nsy[o].data()};
+    }
+    chk(ctx, mct_track_update(ctx, n, clfs.data(), pb.data(), nb.data()));
+    for (int o = 0; o < n; o++) {
+        SimpleTracker* t = trackers[o];
+        if ((size_t)frameind * 4 + 3 < t->m_states.size())
+            for (int s = 0; s < 4; s++) t->m_states[(size_t)frameind * 4 + s] = t->m_currentStateList[s];
+    }
+}
 }  // namespace MultipleCameraTracking

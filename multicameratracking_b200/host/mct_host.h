@@ -279,6 +279,7 @@ typedef std::shared_ptr<ParticleFilter> ParticleFilterPtr;
 // TrackerParameters.h:135-196 (only the fields the hot path reads)
 enum PFTracker_TrajectoryOption { PARTICLE_HIGHEST_WEIGHT = 0, PARTICLE_AVERAGE = 1 };
 struct ParticleFilterTrackerParameters {
+    virtual ~ParticleFilterTrackerParameters() {}
     uint m_numberOfNegativeTrainingSamples = 15, m_init_negNumTrain = 1000;
     float m_posRadiusTrain = 1, m_init_posTrainRadius = 3;
     uint m_maximumNumberOfPositiveTrainingSamples = 100000;
@@ -359,6 +360,48 @@ private:
     Classifier::SampleSet m_positiveSampleSet, m_negativeSampleSet;
     std::vector<int> m_states;
     const float* m_noise;
+    bool m_isInitialized;
+};
+
+// SimpleTracker.h: the reference's default local tracker (Local_Tracker_Type 0): exhaustive search window around the
+// current position, the classifier's maximum response decides (SimpleTracker.cpp:280-342).
+struct SimpleTrackerParameters : public ParticleFilterTrackerParameters {
+    uint m_negSampleStrategy = 1;          // TrackerParameters.cpp:81; 0 = negatives from all over the image (:425-433)
+};
+typedef std::shared_ptr<SimpleTrackerParameters> SimpleTrackerParametersPtr;
+class SimpleTracker : public Tracker {
+public:
+    SimpleTracker(mct_ctx* ctx, int64_t rngSeed = 1);
+    void InitializeTrackerWithParameters(Matrixu* pFrameImageColor, Matrixu* pFrameImageGray, int frameInd, uint videoLength,
+                                         TrackerParametersPtr trackerParametersPtr,
+                                         Classifier::StrongClassifierParametersBasePtr clfparamsPtr,
+                                         Matrixu* pFrameImageHSV = nullptr) override;
+    void TrackObjectAndSaveState(int frameind, Matrixu* pFrameImageColor, Matrixu* pFrameImageGray,
+                                 Matrixu* pFrameImageHSV = nullptr) override;
+    void GenerateTrainingSampleSet(Matrixu* pFrameImageColor, Matrixu* pFrameImageGray, Matrixu* pFrameImageHSV = nullptr) override;
+    void GenerateTestSampleSet(Matrixu* pFrameImageColor, Matrixu* pFrameImageGray, Matrixu* pFrameImageHSV) override;
+    void GetTrainingSampleSets(Classifier::SampleSet& pos, Classifier::SampleSet& neg) override { pos = m_positiveSampleSet; neg = m_negativeSampleSet; }
+    void UpdateClassifier(Matrixu* pFrameImageColor, Matrixu* pFrameImageGray, Matrixu* pFrameImageHSV = nullptr) override;
+    const vectorf& GetCurrentTrackerState() const override { return m_currentStateList; }
+    void SaveStates() override {}
+    const std::vector<float>& States() const { return m_states; }      // [frame][4] x, y, w, h (SimpleTracker.cpp:145-148)
+    Classifier::StrongClassifierBasePtr GetClassifier() const { return m_strongClassifierBasePtr; }
+    Public::RngStream& Rng() { return m_rng; }
+    double LastResponse() const { return m_lastResponse; }
+    int LastTestSetSize() const { return m_lastTestSetSize; }
+    // all objects of a camera in one batched device pass per phase (search windows scored together, classifiers updated
+    // together); responses[o] = the value TrackObjectOnTheGivenFrame returns
+    static void TrackCameraObjects(mct_ctx* ctx, std::vector<SimpleTracker*>& trackers, int frameind, Matrixu* pFrameImageColor,
+                                   Matrixu* pFrameImageGray, Matrixu* pFrameImageHSV, double* responses = nullptr);
+private:
+    mct_ctx* m_ctx;
+    Public::RngStream m_rng;
+    SimpleTrackerParametersPtr m_params;
+    Classifier::StrongClassifierBasePtr m_strongClassifierBasePtr;
+    vectorf m_currentStateList;            // leftX, topY, w, h
+    Classifier::SampleSet m_positiveSampleSet, m_negativeSampleSet, m_testSampleSet;
+    std::vector<float> m_states;
+    double m_lastResponse; int m_lastTestSetSize;
     bool m_isInitialized;
 };
 }  // namespace MultipleCameraTracking

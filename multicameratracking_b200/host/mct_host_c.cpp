@@ -27,6 +27,8 @@ struct mcth_camera {
     Matrixu frame;
     std::vector<ParticleFilterTracker*> trackers;
     std::vector<mcth_object_params> params;
+    std::vector<SimpleTracker*> simple;                 // Local_Tracker_Type 0 objects (their own list and params)
+    std::vector<mcth_object_params> simple_params;
     int n_frames;
     std::string err;
 };
@@ -40,13 +42,14 @@ int mcth_camera_create(int device, void* stream, int n_frames, mcth_camera** out
     mct_ctx* ctx = nullptr;
     int rc = mct_ctx_create(device, stream, &ctx);
     if (rc) return rc;
-    mcth_camera* c = new mcth_camera{ctx, Matrixu(ctx), {}, {}, n_frames, ""};
+    mcth_camera* c = new mcth_camera{ctx, Matrixu(ctx), {}, {}, {}, {}, n_frames, ""};
     *out = c;
     return 0;
 }
 void mcth_camera_destroy(mcth_camera* c)
 {
     if (!c) return;
+    for (auto* t : c->simple) delete t;
     for (auto* t : c->trackers) delete t;
     mct_ctx_destroy(c->ctx);
     delete c;
@@ -93,6 +96,61 @@ int mcth_camera_add_object(mcth_camera* c, const mcth_object_params* p)
         c->trackers.push_back(new ParticleFilterTracker(c->ctx, p->rng_seed));
     });
 }
+
+// ---- SimpleTracker objects (the reference's default local tracker) ----
+static void make_params(const mcth_object_params& p, Classifier::StrongClassifierParametersBasePtr& cp, SimpleTrackerParametersPtr& tp)
+{
+    Features::FeatureParametersPtr fp(new Features::FeatureParameters());
+    fp->type = (Features::FeatureType)p.feature_type;
+    fp->m_width = (uint)p.init_xywh[2]; fp->m_height = (uint)p.init_xywh[3];
+    fp->m_featureDimensionHaar = (uint)p.n_haar; fp->m_numberOfBins = (uint)p.n_bins;
+    const int F = (int)fp->GetFeatureDimension();
+    const int K = int(F * p.percent_selected / 100);
+    if (p.strong_type == MCT_STRONG_MILANYBOOST) cp.reset(new Classifier::MILAnyBoostClassifierParameters(K, F));
+    else cp.reset(new Classifier::MILBoostClassifierParameters(K, F));
+    cp->m_weakClassifierType = (Classifier::WeakClassifierType)p.weak_type;
+    cp->m_featureParametersPtr = fp;
+    tp.reset(new SimpleTrackerParameters());
+    tp->m_posRadiusTrain = p.pos_radius_train; tp->m_init_posTrainRadius = p.init_pos_radius_train;
+    tp->m_numberOfNegativeTrainingSamples = (uint)p.n_neg_train; tp->m_init_negNumTrain = (uint)p.init_n_neg_train;
+    tp->m_searchWindSize = (uint)p.search_win;
+    tp->m_initState.assign(p.init_xywh, p.init_xywh + 4);
+}
+int mcth_camera_add_simple_object(mcth_camera* c, const mcth_object_params* p)
+{
+    GUARD({
+        c->simple_params.push_back(*p);
+        c->simple.push_back(new SimpleTracker(c->ctx, p->rng_seed));
+    });
+}
+int mcth_camera_init_simple(mcth_camera* c)
+{
+    GUARD({
+        for (size_t o = 0; o < c->simple.size(); o++) {
+            Classifier::StrongClassifierParametersBasePtr cp; SimpleTrackerParametersPtr tp;
+            make_params(c->simple_params[o], cp, tp);
+            c->simple[o]->InitializeTrackerWithParameters(&c->frame, &c->frame, 0, (uint)c->n_frames, tp, cp, &c->frame);
+        }
+    });
+}
+// one frame for all SimpleTracker objects: out_state [n][4] = m_states row (x, y, w, h), out_resp [n] = best response
+int mcth_camera_track_simple(mcth_camera* c, int frameind, float* out_state, double* out_resp)
+{
+    GUARD({
+        SimpleTracker::TrackCameraObjects(c->ctx, c->simple, frameind, &c->frame, &c->frame, &c->frame, out_resp);
+        if (out_state)
+            for (size_t o = 0; o < c->simple.size(); o++)
+                for (int q = 0; q < 4; q++) out_state[o * 4 + q] = c->simple[o]->GetCurrentTrackerState()[q];
+    });
+}
+int mcth_simple_selectors(mcth_camera* c, int o, int* idx)
+{
+    try { vectori s = c->simple[o]->GetClassifier()->GetSelectorList(); for (size_t i = 0; i < s.size(); i++) idx[i] = s[i]; return (int)s.size(); }
+    catch (const std::exception& e) { c->err = e.what(); return -1; }
+}
+mct_clf* mcth_simple_classifier(mcth_camera* c, int o) { return c->simple[o]->GetClassifier()->Handle(); }
+uint64_t mcth_simple_rng_state(mcth_camera* c, int o) { return c->simple[o]->Rng().state; }
+int mcth_simple_last_test_size(mcth_camera* c, int o) { return c->simple[o]->LastTestSetSize(); }
 
 // frame 0: InitializeTracker for every object (Camera::InitializeCameraTrackers, Camera.cpp:278-321)
 int mcth_camera_init_trackers(mcth_camera* c)

@@ -1165,3 +1165,88 @@ void orc_tracker_track(orc_tracker* t, const orc_frame* f, const float* noise, i
     if (phases & 1) { tracker_score(t, f, noise); tracker_store(t, out_box); }
     if (phases & 2) tracker_update(t, f);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * SimpleTracker (the reference's default local tracker, SimpleTracker.cpp): exhaustive search window.
+ * Restated for the default strategies: positives = disc of radius pos_radius_train (or the single current box when the
+ * radius is 1, :375-386), negatives = ring [pos_radius_train + 5, 1.5 * search_win) (m_negSampleStrategy 1, :436-447). */
+struct orc_simple {
+    orc_tracker_params tp;
+    orc_clf* clf;
+    orc_rng* rng;
+    float cur[4];                 /* m_currentStateList: leftX, topY, w, h */
+    int ok, last_n, last_best;
+    int *col, *row; float *sx, *sy, *H;
+    int *pcol, *prow, *ncol, *nrow; float* one;
+    int P, Nn;
+};
+#define SIMPLE_CAP 16384
+static void simple_update(orc_simple* t, const orc_frame* f)
+{
+    if (t->tp.pos_radius_train == 1) {                                     /* :375-386 */
+        t->pcol[0] = (int)t->cur[0]; t->prow[0] = (int)t->cur[1]; t->P = 1;
+    } else {
+        t->P = orc_sample_ring(t->rng, f->W, f->H, (int)t->cur[0], (int)t->cur[1], (int)t->cur[2], (int)t->cur[3],
+                               t->tp.pos_radius_train, 0, t->tp.max_pos_train, 1, 1, t->pcol, t->prow, SIMPLE_CAP);
+    }
+    t->Nn = orc_sample_ring(t->rng, f->W, f->H, (int)t->cur[0], (int)t->cur[1], (int)t->cur[2], (int)t->cur[3],
+                            1.5f * t->tp.search_win, t->tp.pos_radius_train + 5, t->tp.n_neg_train, 1, 1,
+                            t->ncol, t->nrow, SIMPLE_CAP);
+    orc_boxes pb = {t->P, t->pcol, t->prow, t->one, t->one};
+    orc_boxes nb = {t->Nn, t->ncol, t->nrow, t->one, t->one};
+    orc_clf_update(t->clf, f, &pb, &nb, NULL, NULL);                       /* :262 (no size check in the reference) */
+}
+/* SimpleTracker::InitializeTrackerWithParameters :35-108 */
+orc_simple* orc_simple_create(const orc_tracker_params* tp, orc_clf* clf, const orc_frame* f0, const float init[4], orc_rng* r)
+{
+    orc_simple* t = (orc_simple*)calloc(1, sizeof(*t));
+    t->tp = *tp; t->clf = clf; t->rng = r;
+    t->col = (int*)malloc(SIMPLE_CAP * 4); t->row = (int*)malloc(SIMPLE_CAP * 4);
+    t->sx = (float*)malloc(SIMPLE_CAP * 4); t->sy = (float*)malloc(SIMPLE_CAP * 4); t->H = (float*)malloc(SIMPLE_CAP * 4);
+    t->pcol = (int*)malloc(SIMPLE_CAP * 4); t->prow = (int*)malloc(SIMPLE_CAP * 4);
+    t->ncol = (int*)malloc(SIMPLE_CAP * 4); t->nrow = (int*)malloc(SIMPLE_CAP * 4);
+    t->one = (float*)malloc(SIMPLE_CAP * 4);
+    for (int i = 0; i < SIMPLE_CAP; i++) { t->one[i] = 1.0f; t->sx[i] = 1.0f; t->sy[i] = 1.0f; }
+    for (int i = 0; i < 4; i++) t->cur[i] = init[i];
+    t->P = orc_sample_ring(r, f0->W, f0->H, (int)(unsigned)t->cur[0], (int)(unsigned)t->cur[1], (int)(unsigned)t->cur[2],
+                           (int)(unsigned)t->cur[3], tp->init_pos_radius_train, 0, 1000000, 1, 1, t->pcol, t->prow, SIMPLE_CAP);
+    t->Nn = orc_sample_ring(r, f0->W, f0->H, (int)(unsigned)t->cur[0], (int)(unsigned)t->cur[1], (int)(unsigned)t->cur[2],
+                            (int)(unsigned)t->cur[3], 2.0f * tp->search_win, 1.5f * tp->init_pos_radius_train,
+                            tp->init_n_neg_train, 1, 1, t->ncol, t->nrow, SIMPLE_CAP);
+    t->ok = !(t->P < 1 || t->Nn < 1);
+    if (t->ok) {
+        orc_boxes pb = {t->P, t->pcol, t->prow, t->one, t->one};
+        orc_boxes nb = {t->Nn, t->ncol, t->nrow, t->one, t->one};
+        orc_clf_update(clf, f0, &pb, &nb, NULL, NULL);
+    }
+    return t;
+}
+void orc_simple_free(orc_simple* t)
+{
+    if (!t) return;
+    free(t->col); free(t->row); free(t->sx); free(t->sy); free(t->H);
+    free(t->pcol); free(t->prow); free(t->ncol); free(t->nrow); free(t->one); free(t);
+}
+/* TrackObjectAndSaveState :116-150 -> TrackObjectOnTheGivenFrame :280-342.  Returns the best response; out_state = the
+   m_states row (x, y, w, h as floats). */
+double orc_simple_track(orc_simple* t, const orc_frame* f, float out_state[4])
+{
+    /* GenerateTestSampleSet :472-493: every position within search_win of the current one */
+    int n = orc_sample_ring(t->rng, f->W, f->H, (int)t->cur[0], (int)t->cur[1], (int)t->cur[2], (int)t->cur[3],
+                            (float)t->tp.search_win, 0, 1000000, 1, 1, t->col, t->row, SIMPLE_CAP);
+    t->last_n = n;
+    if (n < 1) { t->ok = 0; return 0; }
+    orc_boxes tb = {n, t->col, t->row, t->sx, t->sy};
+    orc_clf_classify(t->clf, f, &tb, 1, t->H);                            /* m_shouldNotUseSigmoid = true (DefaultParameters.h:12) */
+    int best = 0;                                                         /* max_idx: first maximum (Public.h:256-268) */
+    for (int i = 1; i < n; i++) if (t->H[i] > t->H[best]) best = i;
+    t->last_best = best;
+    double resp = t->H[best];
+    t->cur[1] = (float)t->row[best];
+    t->cur[0] = (float)t->col[best];
+    simple_update(t, f);
+    for (int s = 0; s < 4; s++) out_state[s] = t->cur[s];
+    return resp;
+}
+int orc_simple_last_n(const orc_simple* t) { return t->last_n; }
+int orc_simple_last_best(const orc_simple* t) { return t->last_best; }

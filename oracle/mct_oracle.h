@@ -173,6 +173,15 @@ const float* orc_tracker_state(const orc_tracker* t);     /* m_currentStateList[
 /* last training sets (for parity tests of the update path) */
 int  orc_tracker_last_train(const orc_tracker* t, int which /*0 pos,1 neg*/, int* col, int* row, float* sx, float* sy, int cap);
 
+/* SimpleTracker (SimpleTracker.cpp), default strategies; shares orc_tracker_params (n_particles etc. unused) */
+typedef struct orc_simple orc_simple;
+orc_simple* orc_simple_create(const orc_tracker_params* tp, orc_clf* clf /* owned by caller */, const orc_frame* f0,
+                              const float init_xywh[4], orc_rng* r /* shared stream */);
+void orc_simple_free(orc_simple* t);
+double orc_simple_track(orc_simple* t, const orc_frame* f, float out_state[4]);
+int orc_simple_last_n(const orc_simple* t);
+int orc_simple_last_best(const orc_simple* t);
+
 #ifdef __cplusplus
 }
 #endif

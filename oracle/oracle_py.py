@@ -128,6 +128,12 @@ class Oracle:
         L.orc_tracker_create.argtypes = [C.POINTER(TrackerParams), C.c_void_p, C.POINTER(Frame), _c_float_p, C.POINTER(Rng)]
         L.orc_tracker_create.restype = C.c_void_p
         L.orc_tracker_free.argtypes = [C.c_void_p]
+        L.orc_simple_create.argtypes = [C.POINTER(TrackerParams), C.c_void_p, C.POINTER(Frame), _c_float_p, C.POINTER(Rng)]
+        L.orc_simple_create.restype = C.c_void_p
+        L.orc_simple_free.argtypes = [C.c_void_p]
+        L.orc_simple_track.argtypes = [C.c_void_p, C.POINTER(Frame), _c_float_p]; L.orc_simple_track.restype = C.c_double
+        L.orc_simple_last_n.argtypes = [C.c_void_p]; L.orc_simple_last_n.restype = C.c_int
+        L.orc_simple_last_best.argtypes = [C.c_void_p]; L.orc_simple_last_best.restype = C.c_int
         L.orc_tracker_track.argtypes = [C.c_void_p, C.POINTER(Frame), _c_float_p, _c_int_p, C.c_int]
         L.orc_tracker_last_valid.argtypes = [C.c_void_p]; L.orc_tracker_last_valid.restype = C.c_int
         L.orc_tracker_pf.argtypes = [C.c_void_p]; L.orc_tracker_pf.restype = C.POINTER(Pf)
