@@ -31,11 +31,6 @@ with open(os.path.join(pr, "%s_launch_summary.txt" % tag), "w") as f:
         f.write("%-70s %5d %9.1f %9.1f %6.1f%%\n" % (k, len(v), sum(v) / len(v), min(v), 100 * sum(v) / tot))
 print(open(os.path.join(pr, "%s_launch_summary.txt" % tag)).read())
 
-# ---- full-set capture
-rep = os.path.join(go, "prof_%s.ncu-rep" % tag)
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rr = list(csv.reader(raw.splitlines()))
-hdr = rr[0]
 want = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "sm__cycles_elapsed.max", "smsp__inst_executed.sum",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -48,26 +43,40 @@ want = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "sm_
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"]
-idx = [(w, hdr.index(w)) for w in want if w in hdr]
-units = rr[1]
 traffic = {}
 try:
     traffic = json.load(open(os.path.join(pr, "roofline_traffic.json")))
 except Exception:
     pass
-seen = set()
-for vals in rr[2:]:
-    name = vals[hdr.index("Kernel Name")].split("(")[0]
-    if name in seen:
-        continue
-    seen.add(name)
-    with open(os.path.join(pr, "%s_full_%s.csv" % (tag, name)), "w") as f:
-        f.write("metric,unit,value\n")
-        for w, i in idx:
-            f.write("%s,%s,%s\n" % (w, units[i], vals[i]))
-    def num(m):
-        v = float(vals[hdr.index(m)].replace(",", "")); u = units[hdr.index(m)].lower()
-        return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
-    traffic[name] = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+
+
+# ---- full-set captures (score path, and the UpdateClassifier kernels when captured)
+def full(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(raw.splitlines()))
+    if len(rr) < 3:
+        return
+    hdr = rr[0]
+    idx = [(w, hdr.index(w)) for w in want if w in hdr]
+    units = rr[1]
+    seen = set()
+    for vals in rr[2:]:
+        name = vals[hdr.index("Kernel Name")].split("(")[0]
+        if name in seen:
+            continue
+        seen.add(name)
+        with open(os.path.join(pr, "%s_full_%s.csv" % (tag, name)), "w") as f:
+            f.write("metric,unit,value\n")
+            for w, i in idx:
+                f.write("%s,%s,%s\n" % (w, units[i], vals[i]))
+        def num(m):
+            v = float(vals[hdr.index(m)].replace(",", "")); u = units[hdr.index(m)].lower()
+            return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+        traffic[name] = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+
+
+for rep in ("prof_%s.ncu-rep" % tag, "prof_%s_upd.ncu-rep" % tag):
+    if os.path.exists(os.path.join(go, rep)):
+        full(os.path.join(go, rep))
 json.dump(traffic, open(os.path.join(pr, "roofline_traffic.json"), "w"), indent=1)
 print("roofline_traffic.json:", traffic)
