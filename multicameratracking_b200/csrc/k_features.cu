@@ -359,9 +359,212 @@ __global__ void __launch_bounds__(MDCH_WARPS * 32)
 k_mdch_batch(const TrainDesc* __restrict__ descs, const uint16_t* __restrict__ binimg, int W, int H)
 {
     const TrainDesc& d = descs[blockIdx.y];
-    if (!(d.feature_type == MCT_FEAT_MDCH || d.feature_type == MCT_FEAT_HAAR_MDCH)) return;
+    if (!(d.feature_type == MCT_FEAT_MDCH || d.feature_type == MCT_FEAT_HAAR_MDCH) || d.mdch_fast) return;
     mdch_body(binimg, W, H, d.nb, d.w0, d.h0, d.col, d.row, d.sx, d.sy, nullptr, d.P + d.Nn, nullptr, d.n_color,
               d.featT + (size_t)d.n_haar * d.ldT, d.ldT);
+}
+
+// ------------------------------------------------------------------------------------------
+// MDCH rows of the TRAINING boxes (UpdateClassifier): all nb^3 bins of ~335 boxes per object.
+// The training boxes of an object come in two groups (positives in a disc of radius ~10 px, negatives in a ring), every box of a
+// group has the same size and the boxes overlap almost completely.  Instead of walking every box's pixels (1.07 M atomic
+// histogram updates per object in k_mdch_batch), the group's bounding region (a few thousand pixels) is sorted by joint
+// bin once, and then box k's bin-b value is the sum over the region's pixels of bin b of the box's weight at that pixel:
+//     U[b][k] = sum_{p : bin(p) = b} E[offset(p) + base(k)]
+// where E is the box's Gaussian weight table (fixed point, the same quantisation as mdch_body / k_mdch_sel) embedded in
+// a zero field large enough that every (pixel, box) pair of the region lands inside it -- no bounds test, no atomics in
+// the inner loop, lanes = boxes read consecutive table words.  Integer sums: identical to the per-box histograms.
+//   k_mdch_train_prep    (group, object): table total, counting sort of the region's pixels by bin
+//   k_mdch_train_main    (chunk, group, object): thread = box, walks its chunk of the sorted list, flushes per bin
+//   k_mdch_train_finish  (bins, object): u32 -> normalised f32 rows, accumulators zeroed for the next frame
+// counting sort with one private histogram per warp (no cross-warp contention, no match.any): [warp][dim] counts ->
+// per-(bin, warp) start offsets -> scatter
+#define MTP_WARPS 32
+__global__ void __launch_bounds__(MTP_WARPS * 32) k_mdch_train_prep(const TrainDesc* __restrict__ descs, const uint16_t* __restrict__ binimg, int W, int H)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ unsigned s_part[32];
+    __shared__ unsigned s_base[1024];
+    const TrainDesc& d = descs[blockIdx.y];
+    if (!d.mdch_fast) return;
+    const MdchGroup g = d.grp[blockIdx.x];
+    if (g.n <= 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x;
+    const int dim = d.n_color;
+    unsigned* hist = (unsigned*)smraw;                               // [MTP_WARPS][dim]
+    uint16_t* sbin = (uint16_t*)(hist + MTP_WARPS * dim);            // [npx] joint bins of the region
+    for (int q = tid; q < MTP_WARPS * dim; q += nt) hist[q] = 0u;
+    // region bins into shared memory, eight independent loads in flight per thread (pixels outside the frame take the
+    // clamped pixel, as the per-box kernels do)
+    for (int p0 = tid; p0 < g.npx; p0 += 8 * nt) {
+        uint16_t v[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int p = min(p0 + q * nt, g.npx - 1);
+            const int y = p / g.RW, x = p - y * g.RW;
+            v[q] = binimg[(size_t)clampi(g.y0 + y, 0, H - 1) * W + clampi(g.x0 + x, 0, W - 1)];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) if (p0 + q * nt < g.npx) sbin[p0 + q * nt] = v[q];
+    }
+    // fixed-point total of the weight table
+    {
+        const float scale = (float)(1u << g.shift);
+        const float hx = __fdiv_rn((float)g.cols, 2.0f), hy = __fdiv_rn((float)g.rows, 2.0f);
+        const double ivx = 1.0 / (double)__fmul_rn(2.0f, __fmul_rn(hx, hx));
+        const double ivy = 1.0 / (double)__fmul_rn(2.0f, __fmul_rn(hy, hy));
+        unsigned part = 0;
+        for (int p = tid; p < g.rows * g.cols; p += nt) {
+            const int r = p / g.cols, c = p - r * g.cols;
+            const double dx = (double)__fsub_rn(hx, (float)c), dy = (double)__fsub_rn(hy, (float)r);
+            const float wd = (float)(dx * dx * ivx + dy * dy * ivy);
+            part += __float2uint_rn(__fmul_rn(expf(-wd), scale));
+        }
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) s_part[warp] = part;
+    }
+    __syncthreads();
+    if (tid == 0) { unsigned t = 0; for (int q = 0; q < (nt >> 5); q++) t += s_part[q]; d.mtot[blockIdx.x] = t; }
+    // each warp owns a contiguous slice of the region (so that the scatter below is stable per warp)
+    const int per_w = (g.npx + MTP_WARPS - 1) / MTP_WARPS;
+    const int w_begin = warp * per_w, w_end = min(g.npx, w_begin + per_w);
+    unsigned* myh = hist + warp * dim;
+    for (int p = w_begin + lane; p < w_end; p += 32) atomicAdd(&myh[sbin[p]], 1u);
+    __syncthreads();
+    // per bin: exclusive scan over the warps, then the bins' bases
+    unsigned tot = 0;
+    if (tid < dim) {
+        for (int w = 0; w < MTP_WARPS; w++) { const unsigned c = hist[w * dim + tid]; hist[w * dim + tid] = tot; tot += c; }
+    }
+    {
+        unsigned inc = tot;                                           // block-wide exclusive scan of tot over tid < dim (<= 1024)
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_part[warp] = inc;
+        __syncthreads();
+        unsigned wb = 0;
+        for (int w = 0; w < warp; w++) wb += s_part[w];
+        s_base[tid] = wb + inc - tot;
+    }
+    __syncthreads();
+    uint32_t* list = d.mlist + g.list_off;
+    for (int p = w_begin + lane; p < w_end; p += 32) {
+        const unsigned bin = sbin[p];
+        const unsigned pos = s_base[bin] + atomicAdd(&myh[bin], 1u);
+        const int y = p / g.RW, x = p - y * g.RW;
+        list[pos] = (bin << 22) | ((unsigned)y << 11) | (unsigned)x;
+    }
+}
+
+// thread = (box, slice of the CTA's list chunk); lanes of a warp are consecutive boxes of the same slice.
+// EXT: the box's weight table sits in a zero field [2 RH - rows][2 RW - cols] so that every (pixel, box) pair of the region
+// indexes it without a bounds test (used when the field is small: the positives' disc); otherwise bounds-tested lookups.
+#define MTR_THREADS 384
+#define MTR_EXT_WORDS 12288
+template <bool EXT>
+__device__ __forceinline__ void mdch_train_walk(const TrainDesc& d, const MdchGroup& g, const uint32_t* __restrict__ tab, const uint32_t* __restrict__ sl,
+                                                int npx)
+{
+    const int tid = threadIdx.x;
+    const int B = min((g.n + 31) & ~31, (int)blockDim.x);         // boxes per pass
+    const int S = blockDim.x / B;                                  // list slices walked side by side
+    const int kk = tid % B, s = tid / B;
+    if (s >= S) return;
+    const int len = (npx + S - 1) / S;
+    const int p0 = s * len, p1 = min(npx, p0 + len);
+    if (p0 >= p1) return;
+    const unsigned ldT = (unsigned)d.ldT;
+    const int EW = 2 * g.RW - g.cols;
+    for (int k0 = 0; k0 < g.n; k0 += B) {
+        const int k = k0 + kk;
+        if (k >= g.n) continue;
+        const int i = g.first + k;
+        const int cxk = d.col[i] - g.x0, cyk = d.row[i] - g.y0;              // box corner in region coordinates
+        const int base = (g.RH - g.rows - cyk) * EW + (g.RW - g.cols - cxk);
+        uint32_t* acc_col = d.macc + i;
+        unsigned cur = sl[p0] >> 22, acc = 0;
+#pragma unroll 4
+        for (int p = p0; p < p1; p++) {
+            const unsigned w = sl[p];
+            const unsigned b = w >> 22;
+            if (b != cur) {                                                    // warp-uniform: the warp walks one slice
+                if (acc) atomicAdd(acc_col + (size_t)cur * ldT, acc);
+                acc = 0; cur = b;
+            }
+            if (EXT) acc += tab[(int)(w & 0x3fffffu) + base];
+            else {
+                const unsigned dx = (w & 0x7ffu) - (unsigned)cxk, dy = ((w >> 11) & 0x7ffu) - (unsigned)cyk;
+                if (dx < (unsigned)g.cols && dy < (unsigned)g.rows) acc += tab[dy * g.cols + dx];
+            }
+        }
+        if (acc) atomicAdd(acc_col + (size_t)cur * ldT, acc);
+    }
+}
+__global__ void __launch_bounds__(MTR_THREADS) k_mdch_train_main(const TrainDesc* __restrict__ descs, int smem_tab_words)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const TrainDesc& d = descs[blockIdx.z];
+    if (!d.mdch_fast) return;
+    const MdchGroup g = d.grp[blockIdx.y];
+    const int c_begin = blockIdx.x * g.chunk_px;
+    if (g.n <= 0 || c_begin >= g.npx) return;
+    const int c_end = min(g.npx, c_begin + g.chunk_px), npx = c_end - c_begin;
+    const int tid = threadIdx.x;
+    uint32_t* tab = (uint32_t*)smraw;                            // weight table (plain or embedded in the zero field)
+    uint32_t* sl = tab + smem_tab_words;                         // this CTA's chunk of the sorted list
+    const int EW = 2 * g.RW - g.cols, EH = 2 * g.RH - g.rows;
+    const bool ext = EW * EH <= MTR_EXT_WORDS;
+    if (ext) {
+        for (int p = tid; p < EW * EH; p += blockDim.x) tab[p] = 0u;
+        // list words carry (y, x) in 11-bit fields; the zero-field form wants y * EW + x
+        for (int p = tid; p < npx; p += blockDim.x) {
+            const unsigned w = d.mlist[g.list_off + c_begin + p];
+            sl[p] = (w & 0xffc00000u) | (((w >> 11) & 0x7ffu) * (unsigned)EW + (w & 0x7ffu));
+        }
+    } else {
+        for (int p = tid; p < npx; p += blockDim.x) sl[p] = d.mlist[g.list_off + c_begin + p];
+    }
+    __syncthreads();
+    {
+        const float scale = (float)(1u << g.shift);
+        const float hx = __fdiv_rn((float)g.cols, 2.0f), hy = __fdiv_rn((float)g.rows, 2.0f);
+        const double ivx = 1.0 / (double)__fmul_rn(2.0f, __fmul_rn(hx, hx));
+        const double ivy = 1.0 / (double)__fmul_rn(2.0f, __fmul_rn(hy, hy));
+        for (int p = tid; p < g.rows * g.cols; p += blockDim.x) {
+            const int r = p / g.cols, c = p - r * g.cols;
+            const double dx = (double)__fsub_rn(hx, (float)c), dy = (double)__fsub_rn(hy, (float)r);
+            const float wd = (float)(dx * dx * ivx + dy * dy * ivy);
+            const uint32_t wq = __float2uint_rn(__fmul_rn(expf(-wd), scale));
+            if (ext) tab[(r + g.RH - g.rows) * EW + c + g.RW - g.cols] = wq;
+            else tab[p] = wq;
+        }
+    }
+    __syncthreads();
+    if (ext) mdch_train_walk<true>(d, g, tab, sl, npx);
+    else mdch_train_walk<false>(d, g, tab, sl, npx);
+}
+
+// u32 sums -> normalised f32 rows; the accumulators are left zero for the next frame.  Flat over (bin, box), four
+// independent elements per thread.
+__global__ void __launch_bounds__(256) k_mdch_train_finish(const TrainDesc* __restrict__ descs)
+{
+    const TrainDesc& d = descs[blockIdx.y];
+    if (!d.mdch_fast) return;
+    const int n = d.P + d.Nn, first1 = d.grp[1].first, ld = d.ldT;
+    const int total = d.n_color * ld;
+    const int e0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (e0 >= total) return;
+    const float is0 = __fdiv_rn(1.0f, (float)(1u << d.grp[0].shift)), is1 = __fdiv_rn(1.0f, (float)(1u << d.grp[1].shift));
+    const float S0 = __fmul_rn((float)d.mtot[0], is0), S1 = __fmul_rn((float)d.mtot[1], is1);
+    const uint4 t = *reinterpret_cast<const uint4*>(d.macc + e0);            // ld is a multiple of 4
+    *reinterpret_cast<uint4*>(d.macc + e0) = make_uint4(0u, 0u, 0u, 0u);
+    const int b = e0 / ld, i = e0 - b * ld;
+    const unsigned tv[4] = {t.x, t.y, t.z, t.w};
+    float* dst = d.featT + (size_t)(d.n_haar + b) * ld + i;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (i + q >= n) break;
+        dst[q] = (i + q >= first1) ? __fdiv_rn(__fmul_rn((float)tv[q], is1), S1) : __fdiv_rn(__fmul_rn((float)tv[q], is0), S0);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -524,14 +727,49 @@ int launch_train_features(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, 
     if (any_mdch) {
         int rc = launch_bin_image(ctx, nb);
         if (rc) return rc;
-        size_t smem = mdch_smem(dim_max, dim_max);
-        static size_t s_attr = 0;
-        if (smem > s_attr) {
-            MCT_CUDA(ctx, cudaFuncSetAttribute(k_mdch_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            s_attr = smem;
+        // objects whose two groups qualified on the host take the pixel-list kernels; the others the generic per-box kernel
+        int n_fast = 0, n_slow = 0, nch = 1, tab_words = 0, chunk_words = 0, npx_max = 0, ld_max = 0;
+        for (int o = 0; o < n_obj; o++) {
+            if (!(h[o].feature_type == MCT_FEAT_MDCH || h[o].feature_type == MCT_FEAT_HAAR_MDCH)) continue;
+            if (h[o].mdch_fast) {
+                n_fast++;
+                ld_max = max(ld_max, h[o].ldT);
+                for (int gi = 0; gi < 2; gi++) {
+                    const MdchGroup& g = h[o].grp[gi];
+                    nch = max(nch, g.nchunk);
+                    const int ext = (2 * g.RW - g.cols) * (2 * g.RH - g.rows);
+                    tab_words = max(tab_words, ext <= MTR_EXT_WORDS ? ext : g.rows * g.cols);
+                    chunk_words = max(chunk_words, g.chunk_px);
+                    npx_max = max(npx_max, g.npx);
+                }
+            } else n_slow++;
         }
-        dim3 g(ceil_div(n_max, MDCH_TILE), n_obj);
-        MCT_LAUNCH(ctx, "k_mdch_batch", k_mdch_batch<<<g, MDCH_WARPS * 32, smem, ctx->stream>>>(d, ctx->binimg, ctx->W, ctx->H));
+        if (n_fast) {
+            const size_t smem_main = (size_t)(tab_words + chunk_words) * 4;
+            const size_t smem_prep = (size_t)MTP_WARPS * dim_max * 4 + (size_t)npx_max * 2 + 16;
+            static size_t s_attr_m = 48 * 1024, s_attr_p = 48 * 1024;
+            if (smem_main > s_attr_m) {
+                MCT_CUDA(ctx, cudaFuncSetAttribute(k_mdch_train_main, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_main));
+                s_attr_m = smem_main;
+            }
+            if (smem_prep > s_attr_p) {
+                MCT_CUDA(ctx, cudaFuncSetAttribute(k_mdch_train_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep));
+                s_attr_p = smem_prep;
+            }
+            MCT_LAUNCH(ctx, "k_mdch_train_prep", k_mdch_train_prep<<<dim3(2, n_obj), MTP_WARPS * 32, smem_prep, ctx->stream>>>(d, ctx->binimg, ctx->W, ctx->H));
+            MCT_LAUNCH(ctx, "k_mdch_train_main", k_mdch_train_main<<<dim3(nch, 2, n_obj), MTR_THREADS, smem_main, ctx->stream>>>(d, tab_words));
+            MCT_LAUNCH(ctx, "k_mdch_train_finish", k_mdch_train_finish<<<dim3(ceil_div(dim_max * ld_max, 1024), n_obj), 256, 0, ctx->stream>>>(d));
+        }
+        if (n_slow) {
+            size_t smem = mdch_smem(dim_max, dim_max);
+            static size_t s_attr = 0;
+            if (smem > s_attr) {
+                MCT_CUDA(ctx, cudaFuncSetAttribute(k_mdch_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                s_attr = smem;
+            }
+            dim3 g(ceil_div(n_max, MDCH_TILE), n_obj);
+            MCT_LAUNCH(ctx, "k_mdch_batch", k_mdch_batch<<<g, MDCH_WARPS * 32, smem, ctx->stream>>>(d, ctx->binimg, ctx->W, ctx->H));
+        }
     }
     return MCT_OK;
 }

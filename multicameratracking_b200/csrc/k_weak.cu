@@ -153,7 +153,7 @@ weak_update_body(const float* __restrict__ feat, int ld, int F, int P, int Nn, i
     // predictions (ClassifySetF) for positives then negatives
     float* pr = pred + (size_t)f * ld;
     for (int i = lane; i < P + Nn; i += 32)
-        pr[i] = weak_classify_dev(weak_type, xp[i], mu0, mu1, n0, n1, e0, e1);
+        pr[i] = weak_classify_q_dev(weak_type, xp[i], mu0, mu1, n0, n1, e0, e1);
 }
 
 __global__ void __launch_bounds__(256)

@@ -182,6 +182,9 @@ extern "C" int mct_ctx_destroy(mct_ctx* ctx)
     if (ctx->d_scored) cudaFree(ctx->d_scored);
     if (ctx->d_ground_out) cudaFree(ctx->d_ground_out);
     if (ctx->d_argmax) cudaFree(ctx->d_argmax);
+    if (ctx->d_mlist) cudaFree(ctx->d_mlist);
+    if (ctx->d_macc) cudaFree(ctx->d_macc);
+    if (ctx->d_mtot) cudaFree(ctx->d_mtot);
     if (ctx->prof) {
         ProfState* ps = (ProfState*)ctx->prof;
         for (ProfEntry& e : ps->entries) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -821,6 +824,9 @@ extern "C" int mct_classify_argmax(mct_ctx* ctx, int n_obj, mct_clf* const* clfs
     if ((rc = launch_classify(ctx, d, n_obj, n_max, K_max, 0, log_ratio))) return rc;
     if (ctx->argmax_cap < n_obj) {
         if (ctx->d_argmax) cudaFree(ctx->d_argmax);
+    if (ctx->d_mlist) cudaFree(ctx->d_mlist);
+    if (ctx->d_macc) cudaFree(ctx->d_macc);
+    if (ctx->d_mtot) cudaFree(ctx->d_mtot);
         MCT_CUDA(ctx, cudaMalloc(&ctx->d_argmax, (size_t)DESC_MAX_OBJ * 8));
         ctx->argmax_cap = DESC_MAX_OBJ;
     }
@@ -1292,6 +1298,36 @@ static void fill_train_desc(TrainDesc* t, mct_clf* c)
     t->lr = c->p.learning_rate;
 }
 
+// Host side of the pixel-list MDCH kernels (k_features.cu, k_mdch_train_*): one group = boxes [first, first + n) of the same
+// size; returns false when the group has to take the generic per-box kernel.
+static bool mdch_group_plan(MdchGroup* g, const mct_boxes* b, int first, int w0, int h0, int dim)
+{
+    memset(g, 0, sizeof(*g));
+    g->first = first; g->n = b->n;
+    if (b->n < 1 || dim > 1024) return false;
+    const float sx = b->sx[0], sy = b->sy[0];
+    int x0 = b->col[0], x1 = b->col[0], y0 = b->row[0], y1 = b->row[0];
+    for (int i = 0; i < b->n; i++) {
+        if (b->sx[i] != sx || b->sy[i] != sy) return false;
+        x0 = std::min(x0, b->col[i]); x1 = std::max(x1, b->col[i]);
+        y0 = std::min(y0, b->row[i]); y1 = std::max(y1, b->row[i]);
+    }
+    g->rows = (int)lrintf((float)h0 * sy); g->cols = (int)lrintf((float)w0 * sx);      // __float2int_rn(__fmul_rn(.)), as the kernels
+    if (g->rows < 1 || g->cols < 1 || g->rows * g->cols > MCT_MDCH_SEG_PIX) return false;
+    g->x0 = x0; g->y0 = y0; g->RW = x1 - x0 + g->cols; g->RH = y1 - y0 + g->rows;
+    g->EW = 0; g->EH = 0;
+    g->npx = g->RW * g->RH;
+    if (g->npx > 65536 || g->RW > 2047 || g->RH > 2047) return false;
+    // one CTA walks chunk_px list entries: S slices side by side (S = threads / boxes per pass), ~160 entries per thread
+    const int T = 384;
+    const int B = std::min((g->n + 31) & ~31, T), S = T / B;
+    g->chunk_px = S * 160;
+    g->nchunk = (g->npx + g->chunk_px - 1) / g->chunk_px;
+    int shift = __builtin_clz((unsigned)(g->rows * g->cols));
+    g->shift = shift > MCT_FIX_SHIFT_MAX ? MCT_FIX_SHIFT_MAX : shift;
+    return true;
+}
+
 // UpdateClassifier (ParticleFilterTracker.cpp:1013-1032) for all objects of a camera: ONE copy of the packed training
 // boxes, ONE descriptor copy and five batched launches (Haar rows, MDCH rows, weak update + predictions, greedy
 // selection with one cluster per object, selected-classifier tables) instead of 8 copies + 5 launches per object.
@@ -1330,7 +1366,7 @@ extern "C" int mct_track_update(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, c
         ctx->train_stage_cap = cap;
     }
     // pack: per object [col | row | sx | sy] x (P + Nn)
-    size_t off = 0;
+    size_t off = 0, mlist_words = 0, macc_words = 0;
     std::vector<int> creq(n_obj, 0);
     for (int o = 0; o < n_obj; o++) {
         mct_clf* c = clfs[o];
@@ -1353,6 +1389,41 @@ extern "C" int mct_track_update(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, c
         c->lastP = P; c->lastNn = Nn;
         creq[o] = c->cluster;
         off += (size_t)M;
+        // MDCH training rows: both groups of equal-size boxes inside a small region -> pixel-list kernels
+        t->mdch_fast = 0;
+        if ((c->p.feature_type == MCT_FEAT_MDCH || c->p.feature_type == MCT_FEAT_HAAR_MDCH) && !getenv("MCT_MDCH_TRAIN_GENERIC")) {
+            const bool ok0 = mdch_group_plan(&t->grp[0], &pos[o], 0, c->p.w0, c->p.h0, c->n_color);
+            const bool ok1 = mdch_group_plan(&t->grp[1], &neg[o], P, c->p.w0, c->p.h0, c->n_color);
+            if (ok0 && ok1) {
+                t->mdch_fast = 1;
+                t->grp[0].list_off = 0; t->grp[1].list_off = t->grp[0].npx;
+                mlist_words += (size_t)t->grp[0].npx + t->grp[1].npx;
+                macc_words += (size_t)c->n_color * c->ldT;
+            }
+        }
+    }
+    // work buffers of the pixel-list kernels (accumulators are zero between launches: k_mdch_train_finish clears what it reads)
+    if (mlist_words > ctx->mlist_cap || macc_words > ctx->macc_cap || !ctx->d_mtot) {
+        MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (mlist_words > ctx->mlist_cap) {
+            if (ctx->d_mlist) cudaFree(ctx->d_mlist);
+            MCT_CUDA(ctx, cudaMalloc(&ctx->d_mlist, (mlist_words + 4096) * 4)); ctx->mlist_cap = mlist_words + 4096;
+        }
+        if (macc_words > ctx->macc_cap) {
+            if (ctx->d_macc) cudaFree(ctx->d_macc);
+            MCT_CUDA(ctx, cudaMalloc(&ctx->d_macc, (macc_words + 4096) * 4)); ctx->macc_cap = macc_words + 4096;
+            MCT_CUDA(ctx, cudaMemset(ctx->d_macc, 0, ctx->macc_cap * 4));
+        }
+        if (!ctx->d_mtot) MCT_CUDA(ctx, cudaMalloc(&ctx->d_mtot, (size_t)DESC_MAX_OBJ * 2 * 4));
+    }
+    {
+        size_t lo = 0, ao = 0;
+        for (int o = 0; o < n_obj; o++) {
+            TrainDesc* t = &ctx->h_tdesc[o];
+            if (!t->mdch_fast) continue;
+            t->mlist = ctx->d_mlist + lo; t->macc = ctx->d_macc + ao; t->mtot = ctx->d_mtot + 2 * o;
+            lo += (size_t)t->grp[0].npx + t->grp[1].npx; ao += (size_t)clfs[o]->n_color * clfs[o]->ldT;
+        }
     }
     MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_train_stage, ctx->h_train_stage, total * 4 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tdesc, ctx->h_tdesc, sizeof(TrainDesc) * n_obj, cudaMemcpyHostToDevice, ctx->stream));

@@ -83,6 +83,7 @@ struct mct_ctx {
     void* prof;                                        // per-kernel event timing state (NULL = off)
     char err[512];
     void* d_argmax; int argmax_cap;   // read-out of k_response_argmax [n_obj] {idx, val}
+    uint32_t* d_mlist; size_t mlist_cap; uint32_t* d_macc; size_t macc_cap; uint32_t* d_mtot;   // k_mdch_train_* work buffers
     GroundOut* d_ground_out;     // read-out of k_ground_pdf
 };
 
@@ -174,6 +175,17 @@ struct ObjDesc {
 // ------------------------------------------------------------------ batched training descriptor (UpdateClassifier)
 // One entry per object of a camera: all objects' classifiers are updated by the same handful of launches
 // (blockIdx.y / .z = object) instead of five launches + eight copies per object.
+// One group of training boxes of one object (the positives, or the negatives): same box size, corners inside one bounding
+// region.  Filled on the host (mct_track_update); n == 0 or ok == 0 sends the object to the generic kernel.
+struct MdchGroup {
+    int first, n;              // box index range [first, first + n) in the object's training set
+    int rows, cols;            // common box size in pixels
+    int x0, y0, RW, RH;        // bounding region of the boxes (image coordinates of its corner, extent)
+    int EW, EH;                // extended weight table: E[(dy + RH - rows) * EW + dx + RW - cols], zero outside the box
+    int list_off, npx;         // this group's slice of the sorted pixel list
+    int nchunk, chunk_px;      // list chunks (one CTA each)
+    int shift, pad;
+};
 struct TrainDesc {
     const int* col; const int* row; const float* sx; const float* sy; const float* tw;   // P positives then Nn negatives
     int P, Nn, ldT, pad0;
@@ -182,7 +194,11 @@ struct TrainDesc {
     float* weak; int* trained; int* sel; int* nsel;
     uint16_t* slotmap; int* colorrow; int* outbins; int* nout; SelEntry* seltab; int* selhdr;
     int F, K, n_haar, n_color, nb, w0, h0, weak_type, strong_type, feature_type, cch_mode, pad1;
-    float lr; int pad2;
+    float lr; int mdch_fast;               // mdch_fast: both groups eligible for the pixel-list kernels
+    MdchGroup grp[2];
+    uint32_t* mlist;                       // sorted pixel lists of both groups ((bin << 22) | offset in the extended table)
+    uint32_t* macc;                        // [n_color][ldT] u32 accumulators (zero between launches)
+    uint32_t* mtot;                        // [2] fixed-point total of each group's weight table
 };
 
 // Per-call values that change every frame travel as kernel parameters, so that the ObjDesc array itself is
@@ -303,6 +319,19 @@ __device__ __forceinline__ float weak_classify_dev(int weak_type, float x, float
     double p0 = (double)__fmul_rn(expf(a0), n0);
     double p1 = (double)__fmul_rn(expf(a1), n1);
     return (float)(log(1e-5 + p1) - log(1e-5 + p0));
+}
+// the same value with ONE f64 log (of the f64 quotient): identical after rounding to f32 except for sub-ulp ties; used where
+// the f64 logs dominate (test-set classification, training predictions)
+__device__ __forceinline__ float weak_classify_q_dev(int weak_type, float x, float mu0, float mu1,
+                                                     float n0, float n1, float e0, float e1)
+{
+    if (weak_type == MCT_WEAK_PERCEPTRON) return ((double)x * (double)mu0 > (double)mu1) ? 1.0f : -1.0f;
+    const float d0 = __fsub_rn(x, mu0), d1 = __fsub_rn(x, mu1);
+    const float a0 = __fmul_rn(__fmul_rn(d0, d0), e0);
+    const float a1 = __fmul_rn(__fmul_rn(d1, d1), e1);
+    const double p0 = (double)__fmul_rn(expf(a0), n0);
+    const double p1 = (double)__fmul_rn(expf(a1), n1);
+    return (float)log((1e-5 + p1) / (1e-5 + p0));
 }
 // Public.h:169-172
 // (1.0f / y correctly rounded == __frcp_rn(y): same bits as the division, without its generic slow-path check)

@@ -1008,3 +1008,60 @@ def test_appearance_fusion_pooled_update_and_particle_reweighting(oracle):
     for c in range(2):
         gclf[c].close(); ctxs[c].close()
     oracle.lib.orc_clf_free(ogclf)
+
+
+def test_mdch_training_rows_pixel_list_kernels(ctx, oracle):
+    """UpdateClassifier's MDCH rows through the pixel-list kernels (k_mdch_train_*: region sorted by bin, thread = box) against
+    the oracle's per-box histograms and against the generic per-box kernel: weak state within 2e-5 / 2e-6, same selectors.
+    Cases: ordinary training sets, a set hanging over the frame border (clamped pixels), different scales for the positive
+    and the negative group, and a set with mixed scales inside one group (falls back to the generic kernel)."""
+    import os
+    seq = synth.Sequence(640, 480, 3)
+    w0, h0 = seq.w0, seq.h0
+    gray, r, g, b = seq.frame(0)
+    ctx.frame_set(gray, r, g, b)
+    of = oracle.frame(gray, r, g, b)
+    one = lambda n, v=1.0: np.full(n, v, np.float32)                     # noqa: E731
+    rr = oracle.rng(5)
+    pc, pr = oracle.sample_ring(rr, 640, 480, 3, 2, w0, h0, 10.0, 0.0, 100000)          # disc around the frame corner
+    nc, nr = oracle.sample_ring(rr, 640, 480, 3, 2, w0, h0, 30.0, 25.0, 30)
+    pc = pc - 6; pr = pr - 5                                                             # push part of it outside the frame
+    sets = [_train_sets(oracle, seq, 0, 0, seed=1),
+            ((pc, pr, one(len(pc)), one(len(pc))), (nc, nr, one(len(nc)), one(len(nc)))),
+            None, None]
+    p2, n2 = _train_sets(oracle, seq, 0, 1, seed=2)
+    sets[2] = ((p2[0], p2[1], one(len(p2[0]), 1.15), one(len(p2[0]), 0.9)), (n2[0], n2[1], one(len(n2[0]), 1.3), one(len(n2[0]), 1.3)))
+    p3, n3 = _train_sets(oracle, seq, 0, 2, seed=3)
+    mix = one(len(p3[0])); mix[::7] = 1.1
+    sets[3] = ((p3[0], p3[1], mix, one(len(p3[0]))), n3)
+    for variant in ("fast", "generic"):
+        if variant == "generic":
+            os.environ["MCT_MDCH_TRAIN_GENERIC"] = "1"
+        try:
+            clfs = [capi.StrongClassifier(ctx, capi.FEAT_MDCH, w0, h0, n_bins=8, weak_type=capi.WEAK_STUMP, strong_type=capi.STRONG_MILBOOST,
+                                          n_selected=102) for _ in sets]
+            oclfs = [oracle.clf_create(capi.FEAT_MDCH, 0, 8, w0, h0, 0, 2, 102, 0.85, None) for _ in sets]
+            for rep in range(2):                                          # untrained, then the learning-rate blend
+                capi.track_update(ctx, clfs, [capi.make_boxes(*s[0]) for s in sets], [capi.make_boxes(*s[1]) for s in sets])
+                for o, s in enumerate(sets):
+                    if o == 1:
+                        continue         # boxes partly outside the frame: the reference reads out of bounds there (no oracle);
+                                         # the two device paths clamp the pixel coordinates and are compared with each other below
+                    oracle.clf_update(oclfs[o], of, oracle.boxes(*s[0]), oracle.boxes(*s[1]))
+                    st_g, st_o = clfs[o].weak_state(), oracle.clf_weak_state(oclfs[o])
+                    for q in range(8):
+                        rel_close(st_g[q], st_o[q], rtol=2e-5)
+                    assert clfs[o].selectors().tolist() == oracle.clf_selectors(oclfs[o]).tolist(), (variant, rep, o)
+            states = [c.weak_state() for c in clfs]
+            if variant == "fast":
+                fast_states = states
+            else:
+                for a, bb in zip(fast_states, states):
+                    for q in range(8):
+                        rel_close(a[q], bb[q], rtol=2e-6)
+            for c in clfs:
+                c.close()
+            for oc in oclfs:
+                oracle.lib.orc_clf_free(oc)
+        finally:
+            os.environ.pop("MCT_MDCH_TRAIN_GENERIC", None)
