@@ -378,37 +378,42 @@ k_mdch_batch(const TrainDesc* __restrict__ descs, const uint16_t* __restrict__ b
 //   k_mdch_train_main    (chunk, group, object): thread = box, walks its chunk of the sorted list, flushes per bin
 //   k_mdch_train_finish  (bins, object): u32 -> normalised f32 rows, accumulators zeroed for the next frame
 // counting sort with one private histogram per warp (no cross-warp contention, no match.any): [warp][dim] counts ->
-// per-(bin, warp) start offsets -> scatter
-#define MTP_WARPS 32
+// per-(bin, warp) start offsets -> scatter.  The region is cut into MTP_PARTS row-major parts, one CTA each; a part's
+// sorted pixels occupy the same list range as its unsorted ones, so the list is a concatenation of sorted parts (the walk
+// only needs runs of equal bins, not a global order).
+#define MTP_WARPS 8
+#define MTP_PARTS 4
 __global__ void __launch_bounds__(MTP_WARPS * 32) k_mdch_train_prep(const TrainDesc* __restrict__ descs, const uint16_t* __restrict__ binimg, int W, int H)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ unsigned s_part[32];
     __shared__ unsigned s_base[1024];
-    const TrainDesc& d = descs[blockIdx.y];
+    const TrainDesc& d = descs[blockIdx.z];
     if (!d.mdch_fast) return;
-    const MdchGroup g = d.grp[blockIdx.x];
+    const MdchGroup g = d.grp[blockIdx.y];
     if (g.n <= 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x;
     const int dim = d.n_color;
+    const int part_len = (g.npx + MTP_PARTS - 1) / MTP_PARTS;
+    const int q_begin = blockIdx.x * part_len, q_end = min(g.npx, q_begin + part_len), qn = q_end - q_begin;
     unsigned* hist = (unsigned*)smraw;                               // [MTP_WARPS][dim]
-    uint16_t* sbin = (uint16_t*)(hist + MTP_WARPS * dim);            // [npx] joint bins of the region
+    uint16_t* sbin = (uint16_t*)(hist + MTP_WARPS * dim);            // [part_len] joint bins of this part
     for (int q = tid; q < MTP_WARPS * dim; q += nt) hist[q] = 0u;
-    // region bins into shared memory, eight independent loads in flight per thread (pixels outside the frame take the
+    // the part's bins into shared memory, eight independent loads in flight per thread (pixels outside the frame take the
     // clamped pixel, as the per-box kernels do)
-    for (int p0 = tid; p0 < g.npx; p0 += 8 * nt) {
+    for (int p0 = tid; p0 < qn; p0 += 8 * nt) {
         uint16_t v[8];
 #pragma unroll
         for (int q = 0; q < 8; q++) {
-            const int p = min(p0 + q * nt, g.npx - 1);
+            const int p = q_begin + min(p0 + q * nt, qn - 1);
             const int y = p / g.RW, x = p - y * g.RW;
             v[q] = binimg[(size_t)clampi(g.y0 + y, 0, H - 1) * W + clampi(g.x0 + x, 0, W - 1)];
         }
 #pragma unroll
-        for (int q = 0; q < 8; q++) if (p0 + q * nt < g.npx) sbin[p0 + q * nt] = v[q];
+        for (int q = 0; q < 8; q++) if (p0 + q * nt < qn) sbin[p0 + q * nt] = v[q];
     }
-    // fixed-point total of the weight table
-    {
+    // fixed-point total of the weight table (part 0 only)
+    if (blockIdx.x == 0) {
         const float scale = (float)(1u << g.shift);
         const float hx = __fdiv_rn((float)g.cols, 2.0f), hy = __fdiv_rn((float)g.rows, 2.0f);
         const double ivx = 1.0 / (double)__fmul_rn(2.0f, __fmul_rn(hx, hx));
@@ -424,45 +429,53 @@ __global__ void __launch_bounds__(MTP_WARPS * 32) k_mdch_train_prep(const TrainD
         if (lane == 0) s_part[warp] = part;
     }
     __syncthreads();
-    if (tid == 0) { unsigned t = 0; for (int q = 0; q < (nt >> 5); q++) t += s_part[q]; d.mtot[blockIdx.x] = t; }
-    // each warp owns a contiguous slice of the region (so that the scatter below is stable per warp)
-    const int per_w = (g.npx + MTP_WARPS - 1) / MTP_WARPS;
-    const int w_begin = warp * per_w, w_end = min(g.npx, w_begin + per_w);
+    if (blockIdx.x == 0 && tid == 0) { unsigned t = 0; for (int q = 0; q < (nt >> 5); q++) t += s_part[q]; d.mtot[blockIdx.y] = t; }
+    if (qn <= 0) return;
+    // each warp owns a contiguous slice of the part
+    const int per_w = (qn + MTP_WARPS - 1) / MTP_WARPS;
+    const int w_begin = warp * per_w, w_end = min(qn, w_begin + per_w);
     unsigned* myh = hist + warp * dim;
     for (int p = w_begin + lane; p < w_end; p += 32) atomicAdd(&myh[sbin[p]], 1u);
     __syncthreads();
-    // per bin: exclusive scan over the warps, then the bins' bases
-    unsigned tot = 0;
-    if (tid < dim) {
-        for (int w = 0; w < MTP_WARPS; w++) { const unsigned c = hist[w * dim + tid]; hist[w * dim + tid] = tot; tot += c; }
-    }
-    {
-        unsigned inc = tot;                                           // block-wide exclusive scan of tot over tid < dim (<= 1024)
+    // per bin: exclusive scan over the warps, then the bins' bases (threads cover the bins in rounds of blockDim)
+    unsigned carry = 0;
+    for (int b0 = 0; b0 < dim; b0 += nt) {
+        const int bq = b0 + tid;
+        unsigned tot = 0;
+        if (bq < dim)
+            for (int w = 0; w < MTP_WARPS; w++) { const unsigned c = hist[w * dim + bq]; hist[w * dim + bq] = tot; tot += c; }
+        unsigned inc = tot;
         for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        __syncthreads();
         if (lane == 31) s_part[warp] = inc;
         __syncthreads();
-        unsigned wb = 0;
-        for (int w = 0; w < warp; w++) wb += s_part[w];
-        s_base[tid] = wb + inc - tot;
+        unsigned wb = carry, all = 0;
+        for (int w = 0; w < (nt >> 5); w++) { if (w < warp) wb += s_part[w]; all += s_part[w]; }
+        if (bq < dim) s_base[bq] = wb + inc - tot;
+        carry += all;
     }
     __syncthreads();
-    uint32_t* list = d.mlist + g.list_off;
+    uint32_t* list = d.mlist + g.list_off + q_begin;
     for (int p = w_begin + lane; p < w_end; p += 32) {
         const unsigned bin = sbin[p];
         const unsigned pos = s_base[bin] + atomicAdd(&myh[bin], 1u);
-        const int y = p / g.RW, x = p - y * g.RW;
+        const int pp = q_begin + p;
+        const int y = pp / g.RW, x = pp - y * g.RW;
         list[pos] = (bin << 22) | ((unsigned)y << 11) | (unsigned)x;
     }
 }
 
 // thread = (box, slice of the CTA's list chunk); lanes of a warp are consecutive boxes of the same slice.
+// The chunk's runs of equal bins are found once per CTA; a thread then sums a run's table words in a register with no
+// bin test in the loop, and adds the sum to the (bin, box) accumulator with one global integer add.
 // EXT: the box's weight table sits in a zero field [2 RH - rows][2 RW - cols] so that every (pixel, box) pair of the region
 // indexes it without a bounds test (used when the field is small: the positives' disc); otherwise bounds-tested lookups.
 #define MTR_THREADS 384
 #define MTR_EXT_WORDS 12288
+struct MtrRun { unsigned bin; int start, end; int pad; };
 template <bool EXT>
 __device__ __forceinline__ void mdch_train_walk(const TrainDesc& d, const MdchGroup& g, const uint32_t* __restrict__ tab, const uint32_t* __restrict__ sl,
-                                                int npx)
+                                                const MtrRun* __restrict__ runs, int nruns, int npx)
 {
     const int tid = threadIdx.x;
     const int B = min((g.n + 31) & ~31, (int)blockDim.x);         // boxes per pass
@@ -481,27 +494,33 @@ __device__ __forceinline__ void mdch_train_walk(const TrainDesc& d, const MdchGr
         const int cxk = d.col[i] - g.x0, cyk = d.row[i] - g.y0;              // box corner in region coordinates
         const int base = (g.RH - g.rows - cyk) * EW + (g.RW - g.cols - cxk);
         uint32_t* acc_col = d.macc + i;
-        unsigned cur = sl[p0] >> 22, acc = 0;
-#pragma unroll 4
-        for (int p = p0; p < p1; p++) {
-            const unsigned w = sl[p];
-            const unsigned b = w >> 22;
-            if (b != cur) {                                                    // warp-uniform: the warp walks one slice
-                if (acc) atomicAdd(acc_col + (size_t)cur * ldT, acc);
-                acc = 0; cur = b;
+        for (int r = 0; r < nruns; r++) {
+            const MtrRun rn = runs[r];
+            const int a = max(rn.start, p0), e = min(rn.end, p1);           // warp-uniform
+            if (a >= e) continue;
+            unsigned acc = 0;
+            if (EXT) {
+                int p = a;
+                for (; p + 4 <= e; p += 4) {
+                    const unsigned w0 = sl[p], w1 = sl[p + 1], w2 = sl[p + 2], w3 = sl[p + 3];
+                    acc += tab[(int)w0 + base] + tab[(int)w1 + base] + tab[(int)w2 + base] + tab[(int)w3 + base];
+                }
+                for (; p < e; p++) acc += tab[(int)sl[p] + base];
+            } else {
+                for (int p = a; p < e; p++) {
+                    const unsigned w = sl[p];
+                    const unsigned dx = (w & 0x7ffu) - (unsigned)cxk, dy = (w >> 11) - (unsigned)cyk;
+                    if (dx < (unsigned)g.cols && dy < (unsigned)g.rows) acc += tab[dy * g.cols + dx];
+                }
             }
-            if (EXT) acc += tab[(int)(w & 0x3fffffu) + base];
-            else {
-                const unsigned dx = (w & 0x7ffu) - (unsigned)cxk, dy = ((w >> 11) & 0x7ffu) - (unsigned)cyk;
-                if (dx < (unsigned)g.cols && dy < (unsigned)g.rows) acc += tab[dy * g.cols + dx];
-            }
+            if (acc) atomicAdd(acc_col + (size_t)rn.bin * ldT, acc);
         }
-        if (acc) atomicAdd(acc_col + (size_t)cur * ldT, acc);
     }
 }
-__global__ void __launch_bounds__(MTR_THREADS) k_mdch_train_main(const TrainDesc* __restrict__ descs, int smem_tab_words)
+__global__ void __launch_bounds__(MTR_THREADS) k_mdch_train_main(const TrainDesc* __restrict__ descs, int smem_tab_words, int smem_chunk_words)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ int s_nruns;
     const TrainDesc& d = descs[blockIdx.z];
     if (!d.mdch_fast) return;
     const MdchGroup g = d.grp[blockIdx.y];
@@ -510,20 +529,46 @@ __global__ void __launch_bounds__(MTR_THREADS) k_mdch_train_main(const TrainDesc
     const int c_end = min(g.npx, c_begin + g.chunk_px), npx = c_end - c_begin;
     const int tid = threadIdx.x;
     uint32_t* tab = (uint32_t*)smraw;                            // weight table (plain or embedded in the zero field)
-    uint32_t* sl = tab + smem_tab_words;                         // this CTA's chunk of the sorted list
+    uint32_t* sl = tab + smem_tab_words;                         // the chunk's table offsets (or packed (y, x))
+    MtrRun* runs = (MtrRun*)(sl + smem_chunk_words);             // [<= npx]
     const int EW = 2 * g.RW - g.cols, EH = 2 * g.RH - g.rows;
     const bool ext = EW * EH <= MTR_EXT_WORDS;
-    if (ext) {
-        for (int p = tid; p < EW * EH; p += blockDim.x) tab[p] = 0u;
-        // list words carry (y, x) in 11-bit fields; the zero-field form wants y * EW + x
-        for (int p = tid; p < npx; p += blockDim.x) {
-            const unsigned w = d.mlist[g.list_off + c_begin + p];
-            sl[p] = (w & 0xffc00000u) | (((w >> 11) & 0x7ffu) * (unsigned)EW + (w & 0x7ffu));
-        }
-    } else {
-        for (int p = tid; p < npx; p += blockDim.x) sl[p] = d.mlist[g.list_off + c_begin + p];
+    if (tid == 0) s_nruns = 0;
+    if (ext) for (int p = tid; p < EW * EH; p += blockDim.x) tab[p] = 0u;
+    __syncthreads();
+    // the chunk's list: table offsets into sl, bins into sb
+    uint16_t* sb = (uint16_t*)(runs + smem_chunk_words);         // [npx]
+    const uint32_t* gl = d.mlist + g.list_off + c_begin;
+    for (int p = tid; p < npx; p += blockDim.x) {
+        const unsigned w = gl[p];
+        const unsigned y = (w >> 11) & 0x7ffu, x = w & 0x7ffu;
+        sl[p] = ext ? (y * (unsigned)EW + x) : ((y << 11) | x);
+        sb[p] = (uint16_t)(w >> 22);
     }
     __syncthreads();
+    // runs of equal bins (a bin may occur in several runs when the chunk straddles sorted parts): every thread takes a
+    // contiguous stretch, counts the run starts in it, a block scan numbers them
+    {
+        __shared__ int s_w[MTR_THREADS / 32];
+        const int per = (npx + (int)blockDim.x - 1) / (int)blockDim.x;
+        const int a0 = min(npx, tid * per), a1 = min(npx, a0 + per);
+        int cnt = 0;
+        for (int p = a0; p < a1; p++) cnt += (p == 0 || sb[p - 1] != sb[p]) ? 1 : 0;
+        int inc = cnt;
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        int wb = 0, all = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { if (w < warp) wb += s_w[w]; all += s_w[w]; }
+        int idx = wb + inc - cnt - 1;                            // run that contains the element in front of a0
+        for (int p = a0; p < a1; p++) {
+            const unsigned bin = sb[p];
+            if (p == 0 || sb[p - 1] != bin) { idx++; runs[idx].bin = bin; runs[idx].start = p; }
+            if (p == npx - 1 || sb[p + 1] != bin) runs[idx].end = p + 1;
+        }
+        if (tid == 0) s_nruns = all;
+    }
     {
         const float scale = (float)(1u << g.shift);
         const float hx = __fdiv_rn((float)g.cols, 2.0f), hy = __fdiv_rn((float)g.rows, 2.0f);
@@ -539,25 +584,26 @@ __global__ void __launch_bounds__(MTR_THREADS) k_mdch_train_main(const TrainDesc
         }
     }
     __syncthreads();
-    if (ext) mdch_train_walk<true>(d, g, tab, sl, npx);
-    else mdch_train_walk<false>(d, g, tab, sl, npx);
+    if (ext) mdch_train_walk<true>(d, g, tab, sl, runs, s_nruns, npx);
+    else mdch_train_walk<false>(d, g, tab, sl, runs, s_nruns, npx);
 }
 
-// u32 sums -> normalised f32 rows; the accumulators are left zero for the next frame.  Flat over (bin, box), four
-// independent elements per thread.
+// u32 sums -> normalised f32 rows; the accumulators are left zero for the next frame.  Flat over (bin, box quad), the
+// four elements of a thread are independent.
 __global__ void __launch_bounds__(256) k_mdch_train_finish(const TrainDesc* __restrict__ descs)
 {
     const TrainDesc& d = descs[blockIdx.y];
     if (!d.mdch_fast) return;
     const int n = d.P + d.Nn, first1 = d.grp[1].first, ld = d.ldT;
-    const int total = d.n_color * ld;
-    const int e0 = (blockIdx.x * 256 + threadIdx.x) * 4;
-    if (e0 >= total) return;
+    const int nq = (n + 3) >> 2;                                  // quads per row
+    const int u = blockIdx.x * 256 + threadIdx.x;
+    if (u >= d.n_color * nq) return;
+    const int b = u / nq, i = (u - b * nq) * 4;
     const float is0 = __fdiv_rn(1.0f, (float)(1u << d.grp[0].shift)), is1 = __fdiv_rn(1.0f, (float)(1u << d.grp[1].shift));
     const float S0 = __fmul_rn((float)d.mtot[0], is0), S1 = __fmul_rn((float)d.mtot[1], is1);
-    const uint4 t = *reinterpret_cast<const uint4*>(d.macc + e0);            // ld is a multiple of 4
-    *reinterpret_cast<uint4*>(d.macc + e0) = make_uint4(0u, 0u, 0u, 0u);
-    const int b = e0 / ld, i = e0 - b * ld;
+    uint32_t* src = d.macc + (size_t)b * ld + i;                  // ld is a multiple of 4, the buffer 16-byte aligned
+    const uint4 t = *reinterpret_cast<const uint4*>(src);
+    *reinterpret_cast<uint4*>(src) = make_uint4(0u, 0u, 0u, 0u);
     const unsigned tv[4] = {t.x, t.y, t.z, t.w};
     float* dst = d.featT + (size_t)(d.n_haar + b) * ld + i;
 #pragma unroll
@@ -728,12 +774,12 @@ int launch_train_features(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, 
         int rc = launch_bin_image(ctx, nb);
         if (rc) return rc;
         // objects whose two groups qualified on the host take the pixel-list kernels; the others the generic per-box kernel
-        int n_fast = 0, n_slow = 0, nch = 1, tab_words = 0, chunk_words = 0, npx_max = 0, ld_max = 0;
+        int n_fast = 0, n_slow = 0, nch = 1, tab_words = 0, chunk_words = 0, npx_max = 0, n_train_max = 0;
         for (int o = 0; o < n_obj; o++) {
             if (!(h[o].feature_type == MCT_FEAT_MDCH || h[o].feature_type == MCT_FEAT_HAAR_MDCH)) continue;
             if (h[o].mdch_fast) {
                 n_fast++;
-                ld_max = max(ld_max, h[o].ldT);
+                n_train_max = max(n_train_max, h[o].P + h[o].Nn);
                 for (int gi = 0; gi < 2; gi++) {
                     const MdchGroup& g = h[o].grp[gi];
                     nch = max(nch, g.nchunk);
@@ -745,8 +791,8 @@ int launch_train_features(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, 
             } else n_slow++;
         }
         if (n_fast) {
-            const size_t smem_main = (size_t)(tab_words + chunk_words) * 4;
-            const size_t smem_prep = (size_t)MTP_WARPS * dim_max * 4 + (size_t)npx_max * 2 + 16;
+            const size_t smem_main = (size_t)(tab_words + chunk_words) * 4 + (size_t)chunk_words * sizeof(MtrRun) + (size_t)chunk_words * 2 + 16;
+            const size_t smem_prep = (size_t)MTP_WARPS * dim_max * 4 + (size_t)ceil_div(npx_max, MTP_PARTS) * 2 + 16;
             static size_t s_attr_m = 48 * 1024, s_attr_p = 48 * 1024;
             if (smem_main > s_attr_m) {
                 MCT_CUDA(ctx, cudaFuncSetAttribute(k_mdch_train_main, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_main));
@@ -756,9 +802,9 @@ int launch_train_features(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, 
                 MCT_CUDA(ctx, cudaFuncSetAttribute(k_mdch_train_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep));
                 s_attr_p = smem_prep;
             }
-            MCT_LAUNCH(ctx, "k_mdch_train_prep", k_mdch_train_prep<<<dim3(2, n_obj), MTP_WARPS * 32, smem_prep, ctx->stream>>>(d, ctx->binimg, ctx->W, ctx->H));
-            MCT_LAUNCH(ctx, "k_mdch_train_main", k_mdch_train_main<<<dim3(nch, 2, n_obj), MTR_THREADS, smem_main, ctx->stream>>>(d, tab_words));
-            MCT_LAUNCH(ctx, "k_mdch_train_finish", k_mdch_train_finish<<<dim3(ceil_div(dim_max * ld_max, 1024), n_obj), 256, 0, ctx->stream>>>(d));
+            MCT_LAUNCH(ctx, "k_mdch_train_prep", k_mdch_train_prep<<<dim3(MTP_PARTS, 2, n_obj), MTP_WARPS * 32, smem_prep, ctx->stream>>>(d, ctx->binimg, ctx->W, ctx->H));
+            MCT_LAUNCH(ctx, "k_mdch_train_main", k_mdch_train_main<<<dim3(nch, 2, n_obj), MTR_THREADS, smem_main, ctx->stream>>>(d, tab_words, chunk_words));
+            MCT_LAUNCH(ctx, "k_mdch_train_finish", k_mdch_train_finish<<<dim3(ceil_div(dim_max * ceil_div(n_train_max, 4), 256), n_obj), 256, 0, ctx->stream>>>(d));
         }
         if (n_slow) {
             size_t smem = mdch_smem(dim_max, dim_max);

@@ -139,30 +139,45 @@ milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int N
                 const unsigned magic = 65536u / (unsigned)nblk + 1u;        // u / nblk for u < 2^15, nblk <= 3
                 const int* al = act + (g & 1) * FC;
                 // phase 1: terms, one warp per (list entry, 32 samples); a block's tail is filled with the chain's neutral
-                // element so that phase 2 runs whole blocks
-                for (int u = warp; u < nact * nblk; u += nwarps) {
-                    const int a = (int)(((unsigned)u * magic) >> 16), b = u - a * nblk;
-                    const int e = al[a];
-                    const int slot = e & 0xffff;
-                    const float* pr = ROWS_SMEM ? rows + (fc - f_begin + slot) * M : pred + (size_t)(fc + slot) * ld;
-                    float* dst = scratch + a * MIL_RS;
-                    if (b < nbN) {
-                        const int r = b * 32 + lane;
-                        float t = 0.0f;
-                        if (r < cntN) {
-                            const int i = P + n0 + r;
-                            const float sg = sigmoid_dev(__fadd_rn(Hs[i], pr[i]));
-                            t = -logf(__fsub_rn(__fadd_rn(1e-5f, 1.0f), sg));
+                // element so that phase 2 runs whole blocks.  Three units per trip: their exp / reciprocal chains are
+                // independent and interleave (the pass is bound by the latency of those chains, not by issue slots).
+                const int nunits = nact * nblk;
+                for (int u0 = warp; u0 < nunits; u0 += 3 * nwarps) {
+                    float xv[3]; int kind[3]; float* dp[3];
+#pragma unroll
+                    for (int j = 0; j < 3; j++) {
+                        const int u = u0 + j * nwarps;
+                        kind[j] = 0; xv[j] = 0.0f; dp[j] = scratch;
+                        if (u < nunits) {
+                            const int a = (int)(((unsigned)u * magic) >> 16), bb = u - a * nblk;
+                            const int e = al[a];
+                            const int slot = e & 0xffff;
+                            const float* pr = ROWS_SMEM ? rows + (fc - f_begin + slot) * M : pred + (size_t)(fc + slot) * ld;
+                            float* dst = scratch + a * MIL_RS;
+                            if (bb < nbN) {
+                                const int r = bb * 32 + lane;
+                                kind[j] = (r < cntN) ? 1 : 3;                 // 3: tail of a negative block -> 0
+                                dp[j] = dst + r;
+                                if (r < cntN) { const int i = P + n0 + r; xv[j] = __fadd_rn(Hs[i], pr[i]); }
+                            } else if (e >> 16) {
+                                const int r = (bb - nbN) * 32 + lane;
+                                kind[j] = (r < cntP) ? 2 : 4;                 // 4: tail of a positive block -> 1
+                                dp[j] = dst + MIL_RN + r;
+                                if (r < cntP) { const int i = p0 + r; xv[j] = __fadd_rn(Hs[i], pr[i]); }
+                            }
                         }
-                        dst[r] = t;
-                    } else if (e >> 16) {
-                        const int r = (b - nbN) * 32 + lane;
-                        float t = 1.0f;
-                        if (r < cntP) {
-                            const int i = p0 + r;
-                            t = __fsub_rn(1.0f, sigmoid_dev(__fadd_rn(Hs[i], pr[i])));
-                        }
-                        dst[MIL_RN + r] = t;
+                    }
+                    float sg[3];
+#pragma unroll
+                    for (int j = 0; j < 3; j++) sg[j] = sigmoid_dev(xv[j]);
+#pragma unroll
+                    for (int j = 0; j < 3; j++) {
+                        if (kind[j] == 0) continue;
+                        float t;
+                        if (kind[j] == 1) t = -logf(__fsub_rn(__fadd_rn(1e-5f, 1.0f), sg[j]));
+                        else if (kind[j] == 2) t = __fsub_rn(1.0f, sg[j]);
+                        else t = (kind[j] == 3) ? 0.0f : 1.0f;
+                        *dp[j] = t;
                     }
                 }
                 MIL_STAMP(5)
