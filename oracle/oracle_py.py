@@ -17,8 +17,11 @@ _c_u8_p = C.POINTER(C.c_uint8)
 
 def build(force=False):
     so = os.path.join(_HERE, "libmct_oracle.so")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(_HERE, "mct_oracle.c")):
+    omp = os.path.join(_HERE, "libmct_oracle_omp.so")
+    src = max(os.path.getmtime(os.path.join(_HERE, "mct_oracle.c")), os.path.getmtime(os.path.join(_HERE, "mct_oracle.h")))
+    if force or not os.path.exists(so) or os.path.getmtime(so) < src:
         subprocess.run(["make", "-C", _HERE, "-B", "libmct_oracle.so"], check=True, capture_output=True)
+    if force or not os.path.exists(omp) or os.path.getmtime(omp) < src:
         subprocess.run(["make", "-C", _HERE, "-B", "libmct_oracle_omp.so"], check=False, capture_output=True)
     return so
 
