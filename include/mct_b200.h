@@ -263,6 +263,10 @@ typedef struct {
 } mct_ground_pdf_result;
 int mct_pf_ground_pdf(mct_pf* pf, const double* H9, const float* mean2, const float* cov4, float h0,
                       mct_ground_pdf_result* out, float* weights_host);
+/* The same for all objects of a camera in one launch and one read-back (FeedbackInformationFromGeometricFusion's loop,
+ * CameraNetwork.cpp:105-121): H9 is the camera's homography, mean2 [n_obj][2], cov4 [n_obj][4], h0 [n_obj], out [n_obj]. */
+int mct_fuser_ground_pdf(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, const double* H9, const float* mean2,
+                         const float* cov4, const float* h0, mct_ground_pdf_result* out);
 /* RearrangeParticlesBasedOnGroundLocation (ParticleFilter.cpp:120-179, scale-changing form) followed by
  * CheckForParticleRefinement (:173).  noise2xN: host [2][N], the (xRand, yRand) = randgaus(0, 10) pairs in particle order
  * (drawn by the caller from the reference's MWC stream, Public.cpp:37-49).  The re-scoring that follows in the reference

@@ -763,9 +763,11 @@ int launch_pf_rearrange(mct_ctx* ctx, const ObjDesc* d_desc, int n_max, const fl
 // (cx, cy + sy*h0/2) -> ground plane through the camera's homography (f64, GeometryBasedInformationFuser.cpp:172-212)
 // -> multivariate normal pdf under the Kalman posterior (:111-163; the exponent has no 1/2, as in the reference), the total
 // weight, and GetAverageofAllParticles for the rearrangement test that follows on the host.
-__global__ void __launch_bounds__(256) k_ground_pdf(const ObjDesc* __restrict__ descs, const GroundArgs ga, float* __restrict__ wout,
-                                                    GroundOut* __restrict__ out)
+__global__ void __launch_bounds__(256) k_ground_pdf(const ObjDesc* __restrict__ descs, const GroundArgs* __restrict__ gas, float* __restrict__ wout,
+                                                    GroundOut* __restrict__ outs)
 {
+    const GroundArgs ga = gas[blockIdx.x];
+    GroundOut* out = outs + blockIdx.x;
     __shared__ double sh_d5[5 * 32];
     __shared__ double sh_d[32];
     const ObjDesc& d = descs[blockIdx.x];
@@ -800,8 +802,9 @@ __global__ void __launch_bounds__(256) k_ground_pdf(const ObjDesc* __restrict__ 
         for (int q = 0; q < 4; q++) out->average[q] = (float)(acc[q] / acc[4]);
     }
 }
-int launch_ground_pdf(mct_ctx* ctx, const ObjDesc* d_desc, const GroundArgs& ga, float* d_wout, GroundOut* d_out)
+// one CTA per object; d_wout (optional per-particle read-back) is only meaningful for n_obj == 1
+int launch_ground_pdf(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, const GroundArgs* d_ga, float* d_wout, GroundOut* d_out)
 {
-    MCT_LAUNCH(ctx, "k_ground_pdf", k_ground_pdf<<<1, 256, 0, ctx->stream>>>(d_desc, ga, d_wout, d_out));
+    MCT_LAUNCH(ctx, "k_ground_pdf", k_ground_pdf<<<n_obj, 256, 0, ctx->stream>>>(d_desc, d_ga, d_wout, d_out));
     return MCT_OK;
 }

@@ -181,6 +181,7 @@ extern "C" int mct_ctx_destroy(mct_ctx* ctx)
     if (ctx->prep_stream) cudaStreamSynchronize(ctx->prep_stream);
     if (ctx->d_scored) cudaFree(ctx->d_scored);
     if (ctx->d_ground_out) cudaFree(ctx->d_ground_out);
+    if (ctx->d_ground_args) cudaFree(ctx->d_ground_args);
     if (ctx->d_argmax) cudaFree(ctx->d_argmax);
     if (ctx->d_mlist) cudaFree(ctx->d_mlist);
     if (ctx->d_macc) cudaFree(ctx->d_macc);
@@ -1024,6 +1025,66 @@ extern "C" int mct_pf_predict(mct_pf* p, const float* noise, int noise_is_device
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Geometric-fuser feedback
+static void ground_args_fill(GroundArgs* ga, const double* H9, const float* mean2, const float* cov4, float h0)
+{
+    memset(ga, 0, sizeof(*ga));
+    for (int i = 0; i < 9; i++) ga->H[i] = H9[i];
+    ga->mean[0] = mean2[0]; ga->mean[1] = mean2[1]; ga->h0 = h0;
+    // cvDet / cvInvert of the 2x2 CV_32F covariance: f64 products, f32 store (GeometryBasedInformationFuser.cpp:119-133)
+    const double det = (double)cov4[0] * (double)cov4[3] - (double)cov4[1] * (double)cov4[2];
+    ga->usable = (det >= 0.0 && cov4[0] > 0) ? 1 : 0;       // ParticleFilterTracker.cpp:1063
+    if (ga->usable) {
+        if (det != 0.0) {
+            const double r = 1.0 / det;
+            ga->ci[0] = (float)((double)cov4[3] * r); ga->ci[1] = (float)(-(double)cov4[1] * r);
+            ga->ci[2] = (float)(-(double)cov4[2] * r); ga->ci[3] = (float)((double)cov4[0] * r);
+        }
+        const float detf = (float)det;
+        ga->b = 1.0f / sqrtf(detf);
+        const double s2pi = sqrt(6.283185307179586);
+        ga->a = 1.0 / (s2pi * s2pi);
+    }
+}
+static int ground_buffers(mct_ctx* ctx)
+{
+    if (!ctx->d_ground_out) MCT_CUDA(ctx, cudaMalloc(&ctx->d_ground_out, sizeof(GroundOut) * DESC_MAX_OBJ));
+    if (!ctx->d_ground_args) MCT_CUDA(ctx, cudaMalloc(&ctx->d_ground_args, sizeof(GroundArgs) * DESC_MAX_OBJ));
+    return MCT_OK;
+}
+// all objects of a camera in one launch and one read-back (H9: the camera's homography; mean2 / cov4 / h0: per object)
+extern "C" int mct_fuser_ground_pdf(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, const double* H9, const float* mean2,
+                                    const float* cov4, const float* h0, mct_ground_pdf_result* out)
+{
+    if (!ctx || n_obj < 1 || n_obj > DESC_MAX_OBJ || !pfs || !H9 || !mean2 || !cov4 || !h0 || !out) return MCT_E_ARG;
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    ObjDesc h[DESC_MAX_OBJ];
+    GroundArgs ga[DESC_MAX_OBJ];
+    for (int o = 0; o < n_obj; o++) {
+        mct_pf* p = pfs[o];
+        if (!p || p->ctx != ctx) return mct_fail(ctx, MCT_E_ARG, "particle filter belongs to another ctx%s");
+        if (!p->initialized) return mct_fail(ctx, MCT_E_STATE, "particle filter not initialised%s");
+        memset(&h[o], 0, sizeof(ObjDesc));
+        fill_pf_desc(&h[o], p);
+        h[o].h0 = h0[o];
+        ground_args_fill(&ga[o], H9, mean2 + 2 * o, cov4 + 4 * o, h0[o]);
+    }
+    int rc;
+    if ((rc = ground_buffers(ctx))) return rc;
+    const ObjDesc* d;
+    if ((rc = desc_publish(ctx, h, n_obj, &d))) return rc;
+    MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_ground_args, ga, sizeof(GroundArgs) * n_obj, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = launch_ground_pdf(ctx, d, n_obj, ctx->d_ground_args, nullptr, ctx->d_ground_out))) return rc;
+    GroundOut go[DESC_MAX_OBJ];
+    MCT_CUDA(ctx, cudaMemcpyAsync(go, ctx->d_ground_out, sizeof(GroundOut) * n_obj, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = mct_sync(ctx))) return rc;
+    for (int o = 0; o < n_obj; o++) {
+        out[o].total_weight = go[o].total_weight;
+        for (int q = 0; q < 4; q++) out[o].average[q] = go[o].average[q];
+        out[o].usable_covariance = ga[o].usable;
+    }
+    return MCT_OK;
+}
+
 extern "C" int mct_pf_ground_pdf(mct_pf* p, const double* H9, const float* mean2, const float* cov4, float h0,
                                  mct_ground_pdf_result* out, float* weights_host)
 {
@@ -1032,27 +1093,12 @@ extern "C" int mct_pf_ground_pdf(mct_pf* p, const double* H9, const float* mean2
     if (!p->initialized) return mct_fail(ctx, MCT_E_STATE, "particle filter not initialised%s");
     MCT_CUDA(ctx, cudaSetDevice(ctx->device));
     GroundArgs ga;
-    memset(&ga, 0, sizeof(ga));
-    for (int i = 0; i < 9; i++) ga.H[i] = H9[i];
-    ga.mean[0] = mean2[0]; ga.mean[1] = mean2[1]; ga.h0 = h0;
-    // cvDet / cvInvert of the 2x2 CV_32F covariance: f64 products, f32 store (GeometryBasedInformationFuser.cpp:119-133)
-    const double det = (double)cov4[0] * (double)cov4[3] - (double)cov4[1] * (double)cov4[2];
-    ga.usable = (det >= 0.0 && cov4[0] > 0) ? 1 : 0;       // ParticleFilterTracker.cpp:1063
-    if (ga.usable) {
-        if (det != 0.0) {
-            const double r = 1.0 / det;
-            ga.ci[0] = (float)((double)cov4[3] * r); ga.ci[1] = (float)(-(double)cov4[1] * r);
-            ga.ci[2] = (float)(-(double)cov4[2] * r); ga.ci[3] = (float)((double)cov4[0] * r);
-        }
-        const float detf = (float)det;
-        ga.b = 1.0f / sqrtf(detf);
-        const double s2pi = sqrt(6.283185307179586);
-        ga.a = 1.0 / (s2pi * s2pi);
-    }
+    ground_args_fill(&ga, H9, mean2, cov4, h0);
     const ObjDesc* d; StepArgs sa; int rc;
     if ((rc = pf_single_desc(p, &d, &sa, 0, h0, 0, 1, 0.0f))) return rc;
-    if (!ctx->d_ground_out) MCT_CUDA(ctx, cudaMalloc(&ctx->d_ground_out, sizeof(GroundOut)));
-    if ((rc = launch_ground_pdf(ctx, d, ga, weights_host ? p->d_prob : nullptr, ctx->d_ground_out))) return rc;
+    if ((rc = ground_buffers(ctx))) return rc;
+    MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_ground_args, &ga, sizeof(GroundArgs), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = launch_ground_pdf(ctx, d, 1, ctx->d_ground_args, weights_host ? p->d_prob : nullptr, ctx->d_ground_out))) return rc;
     GroundOut go;
     MCT_CUDA(ctx, cudaMemcpyAsync(&go, ctx->d_ground_out, sizeof(go), cudaMemcpyDeviceToHost, ctx->stream));
     if (weights_host) MCT_CUDA(ctx, cudaMemcpyAsync(weights_host, p->d_prob, (size_t)p->N * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -47,6 +47,7 @@ struct PrepTarget {            // what one frame-prep launch reads and writes
     float* ii_base; int ii_pitch; uint16_t* binimg;
 };
 struct GroundOut;
+struct GroundArgs;
 struct mct_ctx {
     int device;
     cudaStream_t stream;
@@ -84,7 +85,8 @@ struct mct_ctx {
     char err[512];
     void* d_argmax; int argmax_cap;   // read-out of k_response_argmax [n_obj] {idx, val}
     uint32_t* d_mlist; size_t mlist_cap; uint32_t* d_macc; size_t macc_cap; uint32_t* d_mtot;   // k_mdch_train_* work buffers
-    GroundOut* d_ground_out;     // read-out of k_ground_pdf
+    GroundOut* d_ground_out;     // read-out of k_ground_pdf [DESC_MAX_OBJ]
+    GroundArgs* d_ground_args;   // its per-object arguments [DESC_MAX_OBJ]
 };
 
 struct mct_clf {
@@ -284,7 +286,7 @@ int launch_pf_testset(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max)
 int launch_pf_refine(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj);
 int launch_response_argmax(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, void* d_out);
 int launch_pf_rearrange(mct_ctx* ctx, const ObjDesc* d_desc, int n_max, const float* d_noise2, float mfx, float mfy);
-int launch_ground_pdf(mct_ctx* ctx, const ObjDesc* d_desc, const GroundArgs& ga, float* d_wout, GroundOut* d_out);
+int launch_ground_pdf(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, const GroundArgs* d_ga, float* d_wout, GroundOut* d_out);
 // fused predict + test set (+ per-frame reset of the MDCH fallback counters) for the batched per-frame path
 int launch_pf_predict_testset(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, const StepArgs& sa);
 // with_summary: run the read-out (k_pf_summary body) at the end of the same kernel

@@ -39,12 +39,14 @@ def load():
         L.mcth_camera_pack_foot_points.argtypes = [vp, vp]
         dp, fp = C.POINTER(C.c_double), C.POINTER(C.c_float)
         L.mcth_camera_ground_feedback.argtypes = [vp, C.c_int, dp, fp, fp, C.POINTER(C.c_int), fp]
+        L.mcth_camera_ground_feedback_all.argtypes = [vp, dp, fp, fp, C.POINTER(C.c_int), fp]
         L.mcth_fuser_create.argtypes = [C.c_int, dp, C.POINTER(vp)]
         L.mcth_fuser_destroy.argtypes = [vp]
         L.mcth_fuser_last_error.argtypes = [vp]; L.mcth_fuser_last_error.restype = C.c_char_p
         L.mcth_fuser_initialize.argtypes = [vp, fp]
         L.mcth_fuser_fuse.argtypes = [vp, fp]
         L.mcth_fuser_get.argtypes = [vp, fp, fp, fp, fp]
+        L.mcth_fuser_fuse_many.argtypes = [C.POINTER(vp), C.c_int, fp, C.c_int, fp, fp, C.POINTER(C.c_int)]
         L.mcth_fuser_intersection.argtypes = [C.c_int, dp, fp, dp]
         L.mcth_randgaus.argtypes = [C.c_int64, C.c_float, C.c_int, fp]
         L.mcth_camera_add_simple_object.argtypes = [vp, C.POINTER(ObjectParams)]
@@ -207,6 +209,18 @@ class Camera:
     def randfloat(self, o):
         return float(self.L.mcth_object_randfloat(self.h, o))
 
+    def ground_feedback_all(self, H, means, covs):
+        """ground_feedback for every object of the camera with ONE device pass for the pdfs: means [n][2], covs [n][2][2].
+        Returns [(rearranged, distance)] per object."""
+        n = self.n_obj
+        Hd = np.ascontiguousarray(H, np.float64).reshape(9)
+        m = np.ascontiguousarray(means, np.float32).reshape(n, 2); cv = np.ascontiguousarray(covs, np.float32).reshape(n, 4)
+        r = np.zeros(n, np.int32); d = np.zeros(n, np.float32)
+        fp = C.POINTER(C.c_float)
+        self._chk(self.L.mcth_camera_ground_feedback_all(self.h, Hd.ctypes.data_as(C.POINTER(C.c_double)), m.ctypes.data_as(fp),
+                                                         cv.ctypes.data_as(fp), r.ctypes.data_as(C.POINTER(C.c_int)), d.ctypes.data_as(fp)))
+        return [(bool(r[o]), float(d[o])) for o in range(n)]
+
     def sync(self):
         self._chk(self.L.mcth_camera_sync(self.h))
 
@@ -289,6 +303,25 @@ class GeometricFuser:
         if self.h:
             self.L.mcth_fuser_destroy(self.h)
             self.h = None
+
+
+def fuse_many(fusers, allp):
+    """one frame for the fusers of all objects in one call: allp float32 [n_cameras][n_obj][2].
+    Returns (means [n_obj][2], covs [n_obj][2][2], fresh [n_obj] bool: initialised by this frame)"""
+    L = load()
+    n = len(fusers)
+    a = np.ascontiguousarray(allp, np.float32)
+    assert a.shape[1:] == (n, 2)
+    hs = (C.c_void_p * n)(*[f.h for f in fusers])
+    means = np.zeros((n, 2), np.float32); covs = np.zeros((n, 4), np.float32); fresh = np.zeros(n, np.int32)
+    fp = C.POINTER(C.c_float)
+    rc = L.mcth_fuser_fuse_many(hs, n, a.ctypes.data_as(fp), a.shape[0], means.ctypes.data_as(fp), covs.ctypes.data_as(fp),
+                                fresh.ctypes.data_as(C.POINTER(C.c_int)))
+    if rc:
+        raise HostError("fuser error %d" % rc)
+    for f, fr in zip(fusers, fresh):
+        f.initialized = True
+    return means, covs.reshape(n, 2, 2), fresh.astype(bool)
 
 
 def principal_axis_intersection(homographies, foot):

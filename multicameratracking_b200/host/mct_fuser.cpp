@@ -168,14 +168,12 @@ void GeometryBasedInformationFuser::GetGroundPlaneKalmanCovarianceMatrix(float c
     cov[0] = m_errorCovPost[0]; cov[1] = m_errorCovPost[1]; cov[2] = m_errorCovPost[4]; cov[3] = m_errorCovPost[5];
 }
 
-bool UpdateParticlesWithGroundPDF(mct_ctx* ctx, ParticleFilterTracker* t, const float mean[2], const float cov[4],
-                                  const Homography& H, float* distanceOut)
+// the part of UpdateParticlesWithGroundPDF behind the pdf evaluation (:1088-1123)
+static bool feedback_after_pdf(mct_ctx* ctx, ParticleFilterTracker* t, const mct_ground_pdf_result& res, const float mean[2],
+                               const Homography& H, float* distanceOut)
 {
     const vectorf& cur = t->GetCurrentTrackerState();
     mct_pf* pf = t->GetParticleFilter()->Handle();
-    mct_ground_pdf_result res;
-    int rc = mct_pf_ground_pdf(pf, H.data(), mean, cov, cur[3], &res, nullptr);
-    if (rc) throw MctHostError(rc, mct_last_error(ctx));
     if (distanceOut) *distanceOut = -1.0f;
     if (!(res.total_weight > 0.0)) return false;                                   // :1088
     // FindMeanFootPositionOnImagePlane (:1168-1194): the Kalman mean back through the inverse homography
@@ -192,7 +190,7 @@ bool UpdateParticlesWithGroundPDF(mct_ctx* ctx, ParticleFilterTracker* t, const 
     std::vector<float> nz((size_t)2 * N);
     Public::SetCurrentRng(&t->Rng());
     for (int r = 0; r < N; r++) { nz[r] = Public::randgaus(0, 10.0f); nz[(size_t)N + r] = Public::randgaus(0, 10.0f); }
-    rc = mct_pf_rearrange_ground(pf, meanFoot[0], meanFoot[1], nz.data(), cur[2], cur[3]);
+    int rc = mct_pf_rearrange_ground(pf, meanFoot[0], meanFoot[1], nz.data(), cur[2], cur[3]);
     if (rc) throw MctHostError(rc, mct_last_error(ctx));
     // UpdateParticleWeightsForRearrangedParticles (:1334-1482): score in place, exponent 1, weights reset, resample
     mct_clf* clf = t->GetClassifier()->Handle();
@@ -204,5 +202,33 @@ bool UpdateParticlesWithGroundPDF(mct_ctx* ctx, ParticleFilterTracker* t, const 
     if (summ.resampled) (void)t->Rng().Next();
     t->GetParticleFilter()->AdoptSummary(summ);
     return true;
+}
+
+bool UpdateParticlesWithGroundPDF(mct_ctx* ctx, ParticleFilterTracker* t, const float mean[2], const float cov[4],
+                                  const Homography& H, float* distanceOut)
+{
+    const vectorf& cur = t->GetCurrentTrackerState();
+    mct_ground_pdf_result res;
+    int rc = mct_pf_ground_pdf(t->GetParticleFilter()->Handle(), H.data(), mean, cov, cur[3], &res, nullptr);
+    if (rc) throw MctHostError(rc, mct_last_error(ctx));
+    return feedback_after_pdf(ctx, t, res, mean, H, distanceOut);
+}
+
+void UpdateParticlesWithGroundPDF(mct_ctx* ctx, std::vector<ParticleFilterTracker*>& trackers, const float* means, const float* covs,
+                                  const Homography& H, int* rearranged, float* distances)
+{
+    const int n = (int)trackers.size();
+    if (n == 0) return;
+    std::vector<mct_pf*> pfs(n); std::vector<float> h0(n);
+    std::vector<mct_ground_pdf_result> res(n);
+    for (int o = 0; o < n; o++) { pfs[o] = trackers[o]->GetParticleFilter()->Handle(); h0[o] = trackers[o]->GetCurrentTrackerState()[3]; }
+    int rc = mct_fuser_ground_pdf(ctx, n, pfs.data(), H.data(), means, covs, h0.data(), res.data());
+    if (rc) throw MctHostError(rc, mct_last_error(ctx));
+    for (int o = 0; o < n; o++) {
+        float dist = -1.0f;
+        const bool r = feedback_after_pdf(ctx, trackers[o], res[o], means + 2 * o, H, &dist);
+        if (rearranged) rearranged[o] = r ? 1 : 0;
+        if (distances) distances[o] = dist;
+    }
 }
 }  // namespace MultipleCameraTracking

@@ -50,6 +50,11 @@ private:
 // MWC stream in the reference's order (Public.cpp:37-49).
 bool UpdateParticlesWithGroundPDF(mct_ctx* ctx, ParticleFilterTracker* tracker, const float mean[2], const float cov[4],
                                   const Homography& homography, float* distanceOut = nullptr);
+// The same for all objects of one camera (the object loop of FeedbackInformationFromGeometricFusion, CameraNetwork.cpp:105-121):
+// ONE device pass + read-back for the ground pdfs of all objects, then rearrangement + re-score for the objects that need it.
+// means [n][2], covs [n][4]; rearranged / distances (optional) [n].
+void UpdateParticlesWithGroundPDF(mct_ctx* ctx, std::vector<ParticleFilterTracker*>& trackers, const float* means, const float* covs,
+                                  const Homography& homography, int* rearranged = nullptr, float* distances = nullptr);
 }  // namespace MultipleCameraTracking
 
 namespace Public {

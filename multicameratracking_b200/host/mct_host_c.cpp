@@ -244,6 +244,15 @@ int mcth_camera_ground_feedback(mcth_camera* c, int o, const double* H9, const f
     });
 }
 
+// all objects of the camera: one device pass for the pdfs (means [n][2], covs [n][4]; rearranged / distance [n])
+int mcth_camera_ground_feedback_all(mcth_camera* c, const double* H9, const float* means, const float* covs, int* rearranged, float* distance)
+{
+    GUARD({
+        Homography H; for (int i = 0; i < 9; i++) H[i] = H9[i];
+        UpdateParticlesWithGroundPDF(c->ctx, c->trackers, means, covs, H, rearranged, distance);
+    });
+}
+
 struct mcth_fuser { GeometryBasedInformationFuser* f; std::string err; };
 int mcth_fuser_create(int n_cameras, const double* H /* [n_cameras][9] */, mcth_fuser** out)
 {
@@ -274,6 +283,25 @@ int mcth_fuser_get(mcth_fuser* f, float* mean2, float* cov4, float* state4, floa
         if (state4) memcpy(state4, f->f->StatePost(), 16);
         if (P16) memcpy(P16, f->f->ErrorCovPost(), 64);
     });
+}
+// one frame for the fusers of all objects: allp [n_cameras][n_obj][2] (the all-gathered foot points); a fuser that is not
+// initialised yet is initialised from this frame (fresh[o] = 1, no feedback for it); means [n_obj][2], covs [n_obj][4]
+int mcth_fuser_fuse_many(mcth_fuser** fs, int n_obj, const float* allp, int n_cameras, float* means, float* covs, int* fresh)
+{
+    for (int o = 0; o < n_obj; o++) {
+        mcth_fuser* f = fs[o];
+        try {
+            std::vector<float> foot((size_t)n_cameras * 2);
+            for (int c = 0; c < n_cameras; c++) { foot[2 * c] = allp[((size_t)c * n_obj + o) * 2]; foot[2 * c + 1] = allp[((size_t)c * n_obj + o) * 2 + 1]; }
+            const bool first = !f->f->IsInitialized();
+            if (first) f->f->InitializeKalman(foot.data()); else f->f->FuseInformation(foot.data());
+            if (fresh) fresh[o] = first ? 1 : 0;
+            f->f->GetGroundPlaneKalmanMeanMatrix(means + 2 * o);
+            f->f->GetGroundPlaneKalmanCovarianceMatrix(covs + 4 * o);
+        } catch (const MctHostError& e) { f->err = e.what(); return e.code ? e.code : -1; }
+        catch (const std::exception& e) { f->err = e.what(); return -100; }
+    }
+    return 0;
 }
 int mcth_fuser_intersection(int n_cameras, const double* H, const float* foot, double* out2)
 {

@@ -144,7 +144,8 @@ def test_geometric_fusion_feedback_two_cameras(oracle):
             cur = cam.state(0)
             tot, mf, dist, want = fo.ground_feedback_decision(st, cur[3], H[c], mean, cov)
             rng0 = cam.rng_state(0)
-            got, d = cam.ground_feedback(0, H[c], mean, cov)
+            # camera 0 through the per-object call, camera 1 through the batched one (one device pass for all objects)
+            got, d = cam.ground_feedback(0, H[c], mean, cov) if c == 0 else cam.ground_feedback_all(H[c], [mean], [cov])[0]
             assert got == want, (t, c, dist, d)
             if tot > 0:
                 assert abs(d - dist) <= 1e-3 * max(1.0, dist)

@@ -69,9 +69,9 @@ def main():
                                     strong_type=capi.STRONG_MILANYBOOST, n_selected=102, learning_rate=0.0)
         gclf.append(clf); af.append(AppearanceFusion(ex, ctx, clf))
 
-    ev = lambda: torch.cuda.Event(enable_timing=True)          # noqa: E731
-    t_geo, t_app_learn, t_app_fuse, n_rearr, n_geo, n_learn = 0.0, 0.0, 0.0, 0, 0, 0
+    n_rearr = 0
     post_ok = True
+    fuse_ms, geo_ms, learn_ms, geo_parts = [], [], [], []
     n_learn_all = 0
     t0 = time.time()
     for t in range(1, args.frames + 1):
@@ -81,19 +81,20 @@ def main():
         cam.track(t, nz, 1 | 4)                                # TrackObjectWithoutSaveState: score path, state not stored yet
         # appearance re-weighting with the global model (Object.cpp:433-450)
         if t > 2 and t % args.refresh == 0 and all(a.trained for a in af):
-            e0, e1 = ev(), ev(); e0.record(stream)
+            cam.sync()
             for o in range(n_obj):
                 cur = cam.state(o)
                 pf = cam.particle_filter(o)
+                tt = time.perf_counter()
                 af[o].fuse(pf, float(cur[2]), float(cur[3]), cam.randfloat(o), cam.randfloat(o))
-            e1.record(stream); torch.cuda.synchronize()
-            t_app_fuse += e0.elapsed_time(e1)
+                fuse_ms.append(round(1e3 * (time.perf_counter() - tt), 2))
         # geometric fusion + feedback (CameraNetwork.cpp:94-268)
-        e0, e1 = ev(), ev(); e0.record(stream)
+        cam.sync(); tt = time.perf_counter()
         allp, fb = gf.step(device=dev)
-        e1.record(stream); torch.cuda.synchronize()
+        cam.sync()
         if t > 1:                                              # (frame 1 carries NCCL's lazy communicator set-up)
-            t_geo += e0.elapsed_time(e1); n_geo += 1
+            geo_ms.append(1e3 * (time.perf_counter() - tt))
+            geo_parts.append(dict(gf.last_ms))
         n_rearr += sum(1 for x in fb if x[0])
         # every rank holds the same Kalman posterior (computed redundantly from the all-gathered foot points)
         post = torch.tensor(np.concatenate([np.concatenate([f.posterior()[2], f.posterior()[3].ravel()]) for f in gf.fusers]), device=dev)
@@ -104,7 +105,7 @@ def main():
         cam.sync()
         # LearnGlobalAppearanceModel every refresh frames (CameraNetwork.cpp:276-320)
         if (t + 1) % args.refresh == 0:
-            e0, e1 = ev(), ev(); e0.record(stream)
+            cam.sync(); tt = time.perf_counter()
             for o in range(n_obj):
                 cur = cam.state(o)
                 pc, pr = cam.last_train(o, 0); nc, nr = cam.last_train(o, 1)
@@ -112,17 +113,20 @@ def main():
                 pos = capi.make_boxes(pc, pr, one(len(pc), cur[4]), one(len(pc), cur[5]))
                 neg = capi.make_boxes(nc, nr, one(len(nc), min(cur[4], 10.0)), one(len(nc), min(cur[5], 10.0)))
                 af[o].learn(pos, neg, lambda o=o: cam.randfloat(o))
-            e1.record(stream); torch.cuda.synchronize()
+            cam.sync()
             if n_learn_all > 0:                                # (first refresh: first ragged all-gather shapes)
-                t_app_learn += e0.elapsed_time(e1); n_learn += 1
+                learn_ms.append(1e3 * (time.perf_counter() - tt))
             n_learn_all += 1
     wall = time.time() - t0
     red = lambda v: ex.max_over_ranks(v, device=dev)          # noqa: E731
+    med = lambda v: float(np.median(v)) if len(v) else 0.0    # noqa: E731
     out = {"what": "multi-camera tracking with geometric + appearance fusion over NCCL, one camera per GPU",
            "n_gpus": world, "frames": args.frames, "objects_per_camera": n_obj, "particles_per_object": N, "feature_type": args.feature,
-           "geometric_fusion_ms_per_frame": red(t_geo / max(n_geo, 1)), "rearranged_objects_total": ex.sum_over_ranks(n_rearr, device=dev),
-           "appearance_learn_ms_per_refresh": red(t_app_learn / max(n_learn, 1)), "appearance_learn_refreshes": n_learn,
-           "appearance_fuse_ms_total": red(t_app_fuse), "kalman_posterior_identical_on_all_ranks": bool(post_ok),
+           "timing": "host wall clock around each step with the camera's stream drained before and after, median, max over ranks",
+           "geometric_fusion_ms_per_frame": red(med(geo_ms)),
+           "geometric_fusion_stages_ms_rank0": {k: round(med([g[k] for g in geo_parts]), 3) for k in (geo_parts[0] if geo_parts else {})}, "rearranged_objects_total": ex.sum_over_ranks(n_rearr, device=dev),
+           "appearance_learn_ms_per_refresh_all_objects": red(med(learn_ms)), "appearance_learn_refreshes": len(learn_ms),
+           "appearance_fuse_ms_per_object": red(med(fuse_ms[n_obj:])), "kalman_posterior_identical_on_all_ranks": bool(post_ok),
            "selectors_global_obj0": gclf[0].selectors()[:8].tolist(), "wall_s": red(wall)}
     if rank == 0:
         print(json.dumps(out))
