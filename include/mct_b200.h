@@ -274,6 +274,16 @@ int mct_fuser_ground_pdf(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, const doub
  * (no prediction), exponent 1, force_reset 1, resample 1. */
 int mct_pf_rearrange_ground(mct_pf* pf, float mean_foot_x, float mean_foot_y, const float* noise2xN, float w0, float h0);
 
+/* The same exchange WITHOUT a collective library: every camera's receive buffer is exported with CUDA IPC and the kernel that
+ * computes the foot points stores them straight into all cameras' buffers over NVLink, then a bounded wait gathers
+ * everybody's frame (replaces CameraNetwork.cpp:182-216 + the all-gather).  Set-up: mct_p2p_create on every rank, exchange the
+ * 64-byte handles by any means (e.g. torch.distributed.all_gather_object), mct_p2p_open with all of them, barrier.
+ * mct_fuser_exchange_foot_points: host_out [world][n_obj][2]; every camera calls it once per frame; timeout_ms <= 0 -> 2000. */
+int mct_p2p_create(mct_ctx* ctx, int world, int rank, unsigned char* ipc_handle_out64);
+int mct_p2p_open(mct_ctx* ctx, const unsigned char* all_handles);
+int mct_p2p_destroy(mct_ctx* ctx);
+int mct_fuser_exchange_foot_points(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, const float* h0, float* host_out, int timeout_ms);
+
 int mct_fuser_pack_foot_points(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, const float* h0, float* dev_out);
 
 #ifdef __cplusplus

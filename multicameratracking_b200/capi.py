@@ -32,7 +32,8 @@ SYMBOLS = [
     "mct_pf_update_all_weights", "mct_pf_resample", "mct_pf_get_state", "mct_pf_set_state", "mct_pf_get_resampled",
     "mct_pf_get_resample_indices", "mct_pf_get_summary", "mct_track_score", "mct_noise_prefetch", "mct_track_score_async",
     "mct_track_collect", "mct_track_update", "mct_pf_get_last_response", "mct_fuser_pack_foot_points",
-    "mct_pf_ground_pdf", "mct_pf_rearrange_ground", "mct_classify_argmax", "mct_fuser_ground_pdf",
+    "mct_pf_ground_pdf", "mct_pf_rearrange_ground", "mct_classify_argmax", "mct_fuser_ground_pdf", "mct_p2p_create", "mct_p2p_open", "mct_p2p_destroy",
+    "mct_fuser_exchange_foot_points",
 ]
 
 
@@ -138,6 +139,10 @@ def load():
     L.mct_pf_ground_pdf.argtypes = [vp, C.POINTER(C.c_double), _c_float_p, _c_float_p, C.c_float, C.POINTER(GroundPdfResult), _c_float_p]
     L.mct_pf_rearrange_ground.argtypes = [vp, C.c_float, C.c_float, _c_float_p, C.c_float, C.c_float]
     L.mct_fuser_ground_pdf.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_double), _c_float_p, _c_float_p, _c_float_p, C.POINTER(GroundPdfResult)]
+    L.mct_p2p_create.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+    L.mct_p2p_open.argtypes = [vp, C.c_char_p]
+    L.mct_p2p_destroy.argtypes = [vp]
+    L.mct_fuser_exchange_foot_points.argtypes = [vp, C.c_int, C.POINTER(vp), _c_float_p, _c_float_p, C.c_int]
     L.mct_classify_argmax.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(Boxes), C.c_int, _c_int_p, _c_float_p]
     _lib = L
     return L

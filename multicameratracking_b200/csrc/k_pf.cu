@@ -710,6 +710,80 @@ int launch_foot_points(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, const flo
 
 
 // ------------------------------------------------------------------------------------------
+// The geometric fuser's exchange over NVLink peer memory, fused with the kernel that produces the payload:
+// k_foot_points_push computes this camera's foot points and stores them straight into slot [rank] of EVERY camera's
+// receive buffer (peer pointers opened through CUDA IPC), then publishes the frame's sequence number in every buffer's
+// flag word; k_foot_points_wait (same stream, next launch) waits until all cameras' flags carry the sequence number and
+// hands the gathered points to the host through mapped pinned memory.  Two buffers by sequence parity: a camera can run at
+// most one frame ahead of the slowest one (it needs everybody's flag of frame t before it finishes frame t), so the frame it
+// may already be writing never collides with the one still being read.  The wait is bounded (timeout -> error flag).
+__global__ void __launch_bounds__(256) k_foot_points_push(const ObjDesc* __restrict__ descs, const float* __restrict__ h0, P2PPeers peers,
+                                                          int world, int rank, unsigned seq, unsigned* __restrict__ ticket)
+{
+    __shared__ float sh_f[32];
+    __shared__ int s_first;
+    const ObjDesc& d = descs[blockIdx.x];
+    const int N = d.N, tid = threadIdx.x, nt = blockDim.x, par = seq & 1u;
+    float mx = -CUDART_INF_F;
+    for (int i = tid; i < N; i += nt) mx = fmaxf(mx, d.w[i]);
+    mx = block_reduce_minmax(mx, true, sh_f);
+    if (tid == 0) s_first = N;
+    __syncthreads();
+    int lf = N;
+    for (int i = tid; i < N; i += nt) if (d.w[i] == mx) lf = min(lf, i);
+    if (lf < N) atomicMin(&s_first, lf);
+    __syncthreads();
+    if (tid != 0) return;
+    const int a = s_first < N ? s_first : 0;
+    const float fx = d.cx[a], fy = __fadd_rn(d.cy[a], __fdiv_rn(__fmul_rn(d.sy[a], h0[blockIdx.x]), 2.0f));
+    for (int r = 0; r < world; r++) {
+        float* slot = peers.p[r]->data[par][rank][blockIdx.x];
+        slot[0] = fx; slot[1] = fy;
+    }
+    __threadfence_system();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {                 // the last object of this camera publishes the frame
+        *ticket = 0u;
+        __threadfence_system();
+        for (int r = 0; r < world; r++) {
+            unsigned* f = &peers.p[r]->flags[par][rank];
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(seq) : "memory");
+        }
+    }
+}
+__global__ void __launch_bounds__(64) k_foot_points_wait(P2PBuf* __restrict__ mine, int world, int n_obj, unsigned seq, float* __restrict__ out,
+                                                         unsigned long long timeout_ns, int* __restrict__ status)
+{
+    const int par = seq & 1u, tid = threadIdx.x;
+    __shared__ int s_bad;
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+    if (tid < world) {
+        unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        const unsigned* f = &mine->flags[par][tid];
+        for (;;) {
+            unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if (v == seq) break;
+            unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > timeout_ns) { s_bad = 1; break; }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) *status = s_bad;
+    for (int q = tid; q < world * n_obj * 2; q += blockDim.x) {
+        const int r = q / (n_obj * 2), rem = q - r * n_obj * 2;
+        out[q] = mine->data[par][r][rem >> 1][rem & 1];
+    }
+}
+int launch_foot_points_exchange(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, const float* d_h0, const P2PPeers& peers, int world, int rank,
+                                unsigned seq, unsigned* d_ticket, float* d_out, unsigned long long timeout_ns, int* d_status)
+{
+    MCT_LAUNCH(ctx, "k_foot_points_push", k_foot_points_push<<<n_obj, 256, 0, ctx->stream>>>(d_desc, d_h0, peers, world, rank, seq, d_ticket));
+    MCT_LAUNCH(ctx, "k_foot_points_wait", k_foot_points_wait<<<1, 64, 0, ctx->stream>>>(peers.p[rank], world, n_obj, seq, d_out, timeout_ns, d_status));
+    return MCT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // Geometric-fuser feedback
 //
 // k_pf_refine: CheckForParticleRefinement + ForceParticleFilterRefinement in one CTA per object, for the call sites

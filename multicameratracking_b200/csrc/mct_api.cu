@@ -180,6 +180,7 @@ extern "C" int mct_ctx_destroy(mct_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->prep_stream) cudaStreamSynchronize(ctx->prep_stream);
     if (ctx->d_scored) cudaFree(ctx->d_scored);
+    mct_p2p_destroy(ctx);
     if (ctx->d_ground_out) cudaFree(ctx->d_ground_out);
     if (ctx->d_ground_args) cudaFree(ctx->d_ground_args);
     if (ctx->d_argmax) cudaFree(ctx->d_argmax);
@@ -1478,6 +1479,86 @@ extern "C" int mct_track_update(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, c
     if ((rc = launch_weak_update_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj))) return rc;
     if ((rc = launch_mil_select_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj, creq.data()))) return rc;
     if ((rc = launch_build_colormap_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj))) return rc;
+    return MCT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Peer-memory exchange of the geometric fuser's payload (no NCCL): every camera's receive buffer is exported with CUDA IPC,
+// the cameras open each other's buffers once, and per frame ONE kernel computes the foot points and stores them into all
+// buffers over NVLink (k_pf.cu).
+extern "C" int mct_p2p_create(mct_ctx* ctx, int world, int rank, unsigned char* ipc_handle_out64)
+{
+    if (!ctx || world < 1 || world > MCT_P2P_MAXW || rank < 0 || rank >= world || !ipc_handle_out64) return MCT_E_ARG;
+    if (ctx->p2p_world) return mct_fail(ctx, MCT_E_STATE, "peer exchange already created%s");
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    P2PBuf* mine = nullptr;
+    MCT_CUDA(ctx, cudaMalloc(&mine, sizeof(P2PBuf)));
+    MCT_CUDA(ctx, cudaMemset(mine, 0, sizeof(P2PBuf)));
+    MCT_CUDA(ctx, cudaMalloc(&ctx->d_p2p_ticket, 4)); MCT_CUDA(ctx, cudaMemset(ctx->d_p2p_ticket, 0, 4));
+    MCT_CUDA(ctx, cudaHostAlloc(&ctx->h_p2p_out, sizeof(float) * MCT_P2P_MAXW * 64 * 2, cudaHostAllocMapped));
+    MCT_CUDA(ctx, cudaHostGetDevicePointer(&ctx->h_p2p_out_dev, ctx->h_p2p_out, 0));
+    MCT_CUDA(ctx, cudaHostAlloc(&ctx->h_p2p_status, sizeof(int), cudaHostAllocMapped));
+    MCT_CUDA(ctx, cudaHostGetDevicePointer(&ctx->h_p2p_status_dev, ctx->h_p2p_status, 0));
+    MCT_CUDA(ctx, cudaDeviceSynchronize());
+    cudaIpcMemHandle_t hnd;
+    MCT_CUDA(ctx, cudaIpcGetMemHandle(&hnd, mine));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(ipc_handle_out64, &hnd, 64);
+    memset(&ctx->p2p, 0, sizeof(ctx->p2p));
+    ctx->p2p.p[rank] = mine; ctx->p2p_world = world; ctx->p2p_rank = rank; ctx->p2p_seq = 0;
+    return MCT_OK;
+}
+extern "C" int mct_p2p_open(mct_ctx* ctx, const unsigned char* all_handles /* [world][64] */)
+{
+    if (!ctx || !all_handles || !ctx->p2p_world) return MCT_E_ARG;
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int r = 0; r < ctx->p2p_world; r++) {
+        if (r == ctx->p2p_rank) continue;
+        cudaIpcMemHandle_t hnd; memcpy(&hnd, all_handles + (size_t)r * 64, 64);
+        void* p = nullptr;
+        MCT_CUDA(ctx, cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+        ctx->p2p.p[r] = (P2PBuf*)p;
+    }
+    return MCT_OK;
+}
+extern "C" int mct_p2p_destroy(mct_ctx* ctx)
+{
+    if (!ctx || !ctx->p2p_world) return MCT_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int r = 0; r < ctx->p2p_world; r++) {
+        if (!ctx->p2p.p[r]) continue;
+        if (r == ctx->p2p_rank) cudaFree(ctx->p2p.p[r]); else cudaIpcCloseMemHandle(ctx->p2p.p[r]);
+    }
+    if (ctx->d_p2p_ticket) cudaFree(ctx->d_p2p_ticket);
+    if (ctx->h_p2p_out) cudaFreeHost(ctx->h_p2p_out);
+    if (ctx->h_p2p_status) cudaFreeHost(ctx->h_p2p_status);
+    memset(&ctx->p2p, 0, sizeof(ctx->p2p));
+    ctx->p2p_world = 0; ctx->d_p2p_ticket = nullptr; ctx->h_p2p_out = nullptr; ctx->h_p2p_status = nullptr;
+    return MCT_OK;
+}
+// one frame: host_out [world][n_obj][2] = the foot points of every camera (index = rank); all cameras must call it once per frame
+extern "C" int mct_fuser_exchange_foot_points(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, const float* h0, float* host_out, int timeout_ms)
+{
+    if (!ctx || n_obj < 1 || n_obj > DESC_MAX_OBJ || !pfs || !h0 || !host_out) return MCT_E_ARG;
+    if (!ctx->p2p_world) return mct_fail(ctx, MCT_E_STATE, "peer exchange not created%s");
+    for (int r = 0; r < ctx->p2p_world; r++) if (!ctx->p2p.p[r]) return mct_fail(ctx, MCT_E_STATE, "peer buffers not opened%s");
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = ensure_tmp(ctx, (size_t)n_obj * 4);
+    if (rc) return rc;
+    MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tmp, h0, (size_t)n_obj * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ObjDesc h[DESC_MAX_OBJ]; const ObjDesc* d;
+    for (int o = 0; o < n_obj; o++) { memset(&h[o], 0, sizeof(ObjDesc)); fill_pf_desc(&h[o], pfs[o]); }
+    if ((rc = desc_publish(ctx, h, n_obj, &d))) return rc;
+    const unsigned seq = ++ctx->p2p_seq;
+    *ctx->h_p2p_status = 0;
+    const unsigned long long tns = (unsigned long long)(timeout_ms > 0 ? timeout_ms : 2000) * 1000000ull;
+    if ((rc = launch_foot_points_exchange(ctx, d, n_obj, (const float*)ctx->d_tmp, ctx->p2p, ctx->p2p_world, ctx->p2p_rank, seq, ctx->d_p2p_ticket,
+                                          ctx->h_p2p_out_dev, tns, ctx->h_p2p_status_dev)))
+        return rc;
+    if ((rc = mct_sync(ctx))) return rc;
+    if (*ctx->h_p2p_status) return mct_fail(ctx, MCT_E_STATE, "peer exchange timed out: a camera did not publish its frame%s");
+    memcpy(host_out, ctx->h_p2p_out, sizeof(float) * (size_t)ctx->p2p_world * n_obj * 2);
     return MCT_OK;
 }
 

@@ -48,6 +48,13 @@ struct PrepTarget {            // what one frame-prep launch reads and writes
 };
 struct GroundOut;
 struct GroundArgs;
+// peer-memory exchange of the geometric fuser's payload (k_pf.cu: k_foot_points_push / _wait)
+#define MCT_P2P_MAXW 16
+struct P2PBuf {
+    unsigned flags[2][MCT_P2P_MAXW];                       // [parity][camera] sequence number of the last frame published
+    float data[2][MCT_P2P_MAXW][64][2];                    // [parity][camera][object] foot point
+};
+struct P2PPeers { P2PBuf* p[MCT_P2P_MAXW]; };
 struct mct_ctx {
     int device;
     cudaStream_t stream;
@@ -85,6 +92,7 @@ struct mct_ctx {
     char err[512];
     void* d_argmax; int argmax_cap;   // read-out of k_response_argmax [n_obj] {idx, val}
     uint32_t* d_mlist; size_t mlist_cap; uint32_t* d_macc; size_t macc_cap; uint32_t* d_mtot;   // k_mdch_train_* work buffers
+    P2PPeers p2p; int p2p_world, p2p_rank; unsigned p2p_seq; unsigned* d_p2p_ticket; float* h_p2p_out; float* h_p2p_out_dev; int* h_p2p_status; int* h_p2p_status_dev;
     GroundOut* d_ground_out;     // read-out of k_ground_pdf [DESC_MAX_OBJ]
     GroundArgs* d_ground_args;   // its per-object arguments [DESC_MAX_OBJ]
 };
@@ -284,6 +292,8 @@ int launch_classify_staged(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n
 int launch_pf_predict(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, const StepArgs& sa);
 int launch_pf_testset(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max);
 int launch_pf_refine(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj);
+int launch_foot_points_exchange(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, const float* d_h0, const P2PPeers& peers, int world, int rank,
+                                unsigned seq, unsigned* d_ticket, float* d_out, unsigned long long timeout_ns, int* d_status);
 int launch_response_argmax(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, void* d_out);
 int launch_pf_rearrange(mct_ctx* ctx, const ObjDesc* d_desc, int n_max, const float* d_noise2, float mfx, float mfy);
 int launch_ground_pdf(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, const GroundArgs* d_ga, float* d_wout, GroundOut* d_out);

@@ -56,6 +56,7 @@ def load():
         L.mcth_simple_rng_state.argtypes = [vp, C.c_int]; L.mcth_simple_rng_state.restype = C.c_uint64
         L.mcth_simple_last_test_size.argtypes = [vp, C.c_int]
         L.mcth_simple_classifier.argtypes = [vp, C.c_int]; L.mcth_simple_classifier.restype = vp
+        L.mcth_camera_exchange_foot_points.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
         L.mcth_object_handles.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp)]
         L.mcth_object_randfloat.argtypes = [vp, C.c_int]; L.mcth_object_randfloat.restype = C.c_float
         L.mcth_camera_sync.argtypes = [vp]
@@ -208,6 +209,24 @@ class Camera:
 
     def randfloat(self, o):
         return float(self.L.mcth_object_randfloat(self.h, o))
+
+    def p2p_setup(self, rank, world, allgather_bytes):
+        """peer-memory exchange set-up: allgather_bytes(b: bytes) -> list of every rank's bytes (e.g. through
+        torch.distributed.all_gather_object); the caller puts a barrier behind it"""
+        from .. import capi
+        ctx = self.capi_context()
+        buf = C.create_string_buffer(64)
+        ctx.check(ctx.L.mct_p2p_create(ctx.h, world, rank, buf))
+        allh = allgather_bytes(bytes(buf.raw))
+        assert len(allh) == world and all(len(x) == 64 for x in allh)
+        ctx.check(ctx.L.mct_p2p_open(ctx.h, b"".join(allh)))
+        self._p2p_world = world
+
+    def exchange_foot_points(self, timeout_ms=2000):
+        """foot points of all cameras [world][n_obj][2] through the peer-memory kernels (every camera calls this once per frame)"""
+        out = np.zeros((self._p2p_world, self.n_obj, 2), np.float32)
+        self._chk(self.L.mcth_camera_exchange_foot_points(self.h, out.ctypes.data_as(C.POINTER(C.c_float)), int(timeout_ms)))
+        return out
 
     def ground_feedback_all(self, H, means, covs):
         """ground_feedback for every object of the camera with ONE device pass for the pdfs: means [n][2], covs [n][2][2].

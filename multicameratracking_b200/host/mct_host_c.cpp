@@ -231,6 +231,18 @@ float mcth_object_randfloat(mcth_camera* c, int o)
     return Public::randfloat();
 }
 
+// the same payload exchanged with all cameras over NVLink peer memory (mct_p2p_* set up on c->ctx beforehand):
+// host_out [world][n_obj][2]
+int mcth_camera_exchange_foot_points(mcth_camera* c, float* host_out, int timeout_ms)
+{
+    const int n = (int)c->trackers.size();
+    std::vector<mct_pf*> pfs(n); std::vector<float> h0(n);
+    for (int o = 0; o < n; o++) { pfs[o] = c->trackers[o]->GetParticleFilter()->Handle(); h0[o] = c->trackers[o]->GetCurrentTrackerState()[3]; }
+    int rc = mct_fuser_exchange_foot_points(c->ctx, n, pfs.data(), h0.data(), host_out, timeout_ms);
+    if (rc) c->err = mct_last_error(c->ctx);
+    return rc;
+}
+
 // ---- geometric fuser ----
 // feedback of the fused ground-plane estimate into object o of this camera (UpdateParticlesWithGroundPDF)
 int mcth_camera_ground_feedback(mcth_camera* c, int o, const double* H9, const float* mean2, const float* cov4, int* rearranged,

@@ -80,8 +80,18 @@ class GeometricFusion:
     (principal-axis intersection + Kalman; tiny, host side) on identical inputs and feeds the result back into its own
     camera's particles (device: ground pdf, rearrangement, re-score)."""
 
-    def __init__(self, exchange, camera, homographies):
+    def __init__(self, exchange, camera, homographies, p2p=False):
+        """p2p: exchange the foot points with the library's own peer-memory kernels (NVLink stores into every camera's
+        receive buffer, fused with the foot-point kernel) instead of an NCCL all-gather"""
         from .host import GeometricFuser
+        self.p2p = bool(p2p)
+        if self.p2p:
+            def gather(b):
+                out = [None] * exchange.world
+                dist.all_gather_object(out, b, group=exchange.group)
+                return out
+            camera.p2p_setup(exchange.rank, exchange.world, gather)
+            dist.barrier(group=exchange.group)
         self.ex = exchange
         self.cam = camera
         self.H = [torch.as_tensor(h, dtype=torch.float64).reshape(3, 3).numpy() for h in homographies]
@@ -99,8 +109,11 @@ class GeometricFusion:
         if self._foot is None:
             self._foot = torch.zeros((n, 2), dtype=torch.float32, device=device or "cuda")
         t0 = time.perf_counter()
-        self.cam.pack_foot_points(self._foot.data_ptr())
-        allp = self.ex.allgather_foot_points(self._foot).cpu().numpy()
+        if self.p2p:
+            allp = self.cam.exchange_foot_points()
+        else:
+            self.cam.pack_foot_points(self._foot.data_ptr())
+            allp = self.ex.allgather_foot_points(self._foot).cpu().numpy()
         t1 = time.perf_counter()
         means, covs, fresh = fuse_many(self.fusers, allp)
         t2 = time.perf_counter()

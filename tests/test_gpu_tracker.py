@@ -238,3 +238,69 @@ def test_simple_tracker_sequence_matches_oracle(oracle, cfg):
     for trk, clf, _ in otr:
         oracle.lib.orc_simple_free(trk); oracle.lib.orc_clf_free(clf)
     cam.close()
+
+
+def _p2p_worker(rank, world, port, q):
+    import os
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)          # plumbing only: the payload moves over NVLink
+    try:
+        seq = synth.Sequence(640, 480, 3, camera=rank, n_frames=6)
+        cam = mhost.Camera(rank, 6)
+        gray, r, g, b = seq.frame(0)
+        cam.set_frame(gray, r, g, b)
+        for o in range(3):
+            cam.add_object(seq.box(0, o), rng_seed=100 * rank + o + 1, n_particles=300, n_haar=60)
+        cam.init_trackers()
+
+        def gather(bts):
+            out = [None] * world
+            dist.all_gather_object(out, bts)
+            return out
+        cam.p2p_setup(rank, world, gather)
+        dist.barrier()
+        pts = torch.zeros((3, 2), dtype=torch.float32, device="cuda")
+        for t in range(1, 5):
+            gray, r, g, b = seq.frame(t)
+            cam.set_frame(gray, r, g, b)
+            nz = np.stack([synth.noise(300, (20, 20, 1e-7, 1e-7), camera=rank, obj=o, t=t) for o in range(3)])
+            cam.track(t, nz, 1)
+            allp = cam.exchange_foot_points(timeout_ms=5000)
+            cam.pack_foot_points(pts.data_ptr()); cam.sync()
+            mine = pts.cpu().numpy()
+            assert np.array_equal(allp[rank], mine)
+            every = [None] * world
+            dist.all_gather_object(every, mine)
+            for rr in range(world):
+                assert np.array_equal(allp[rr], every[rr]), (t, rr)
+        cam.close()
+        q.put((rank, "ok"))
+    except BaseException as e:           # noqa: BLE001
+        q.put((rank, "FAIL %r" % (e,)))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_memory_foot_point_exchange_two_gpus():
+    """the geometric fuser's payload exchanged by the library's own kernels over NVLink peer memory (CUDA IPC buffers, stores
+    from the foot-point kernel, bounded wait): every camera ends each frame with every camera's foot points, identical to
+    the locally packed ones.  Needs two GPUs."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_p2p_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res

@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--particles", type=int, default=1000)
     ap.add_argument("--refresh", type=int, default=3)
     ap.add_argument("--feature", type=int, default=3, help="0 Haar, 2 MDCH, 3 Haar+MDCH")
+    ap.add_argument("--p2p", action="store_true", help="foot points through the peer-memory kernels instead of the NCCL all-gather")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -58,7 +59,7 @@ def main():
     for c in range(world):
         a = 2 * np.pi * c / max(world, 2) + 0.3
         Hs.append(np.array([[np.cos(a), -np.sin(a), 40.0 * c], [np.sin(a), np.cos(a), -25.0 * c], [1e-4 * c, -5e-5 * c, 1.0]]))
-    gf = GeometricFusion(ex, cam, Hs)
+    gf = GeometricFusion(ex, cam, Hs, p2p=args.p2p)
 
     # appearance fuser: one global classifier per object, the SAME feature table on every rank (seeded by the object id)
     # (colour-histogram features: the table is the same on every rank by construction; cfg 3 uses MDCH + MILAnyBoost)
@@ -121,7 +122,7 @@ def main():
     red = lambda v: ex.max_over_ranks(v, device=dev)          # noqa: E731
     med = lambda v: float(np.median(v)) if len(v) else 0.0    # noqa: E731
     out = {"what": "multi-camera tracking with geometric + appearance fusion over NCCL, one camera per GPU",
-           "n_gpus": world, "frames": args.frames, "objects_per_camera": n_obj, "particles_per_object": N, "feature_type": args.feature,
+           "n_gpus": world, "foot_point_exchange": "peer-memory kernels (NVLink stores)" if args.p2p else "NCCL all-gather", "frames": args.frames, "objects_per_camera": n_obj, "particles_per_object": N, "feature_type": args.feature,
            "timing": "host wall clock around each step with the camera's stream drained before and after, median, max over ranks",
            "geometric_fusion_ms_per_frame": red(med(geo_ms)),
            "geometric_fusion_stages_ms_rank0": {k: round(med([g[k] for g in geo_parts]), 3) for k in (geo_parts[0] if geo_parts else {})}, "rearranged_objects_total": ex.sum_over_ranks(n_rearr, device=dev),
