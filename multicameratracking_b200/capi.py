@@ -33,7 +33,7 @@ SYMBOLS = [
     "mct_pf_get_resample_indices", "mct_pf_get_summary", "mct_track_score", "mct_noise_prefetch", "mct_track_score_async",
     "mct_track_collect", "mct_track_update", "mct_pf_get_last_response", "mct_fuser_pack_foot_points",
     "mct_pf_ground_pdf", "mct_pf_rearrange_ground", "mct_classify_argmax", "mct_fuser_ground_pdf", "mct_p2p_create", "mct_p2p_open", "mct_p2p_destroy",
-    "mct_fuser_exchange_foot_points",
+    "mct_fuser_exchange_foot_points", "mct_features_compute_dev", "mct_classifier_update_from_features_dev",
 ]
 
 
@@ -143,6 +143,8 @@ def load():
     L.mct_p2p_open.argtypes = [vp, C.c_char_p]
     L.mct_p2p_destroy.argtypes = [vp]
     L.mct_fuser_exchange_foot_points.argtypes = [vp, C.c_int, C.POINTER(vp), _c_float_p, _c_float_p, C.c_int]
+    L.mct_features_compute_dev.argtypes = [vp, C.POINTER(Boxes), vp, C.c_int]
+    L.mct_classifier_update_from_features_dev.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int]
     L.mct_classify_argmax.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(Boxes), C.c_int, _c_int_p, _c_float_p]
     _lib = L
     return L
@@ -334,6 +336,14 @@ class StrongClassifier:
         out = np.zeros((self.F, max(boxes.n, 1)), np.float32)
         self.ctx.check(self.ctx.L.mct_features_compute(self.h, C.byref(boxes), _fp(out)))
         return out[:, :boxes.n] if boxes.n else out[:, :0]
+
+    def features_dev(self, boxes, dev_ptr, ld):
+        """feature rows [F][n] written to device memory at dev_ptr (leading dimension ld floats)"""
+        self.ctx.check(self.ctx.L.mct_features_compute_dev(self.h, C.byref(boxes), C.c_void_p(dev_ptr), int(ld)))
+
+    def update_from_features_dev(self, pos_ptr, ld_pos, P, neg_ptr, ld_neg, Nn):
+        self.ctx.check(self.ctx.L.mct_classifier_update_from_features_dev(self.h, C.c_void_p(pos_ptr), int(ld_pos), int(P),
+                                                                          C.c_void_p(neg_ptr), int(ld_neg), int(Nn)))
 
     def Update(self, pos, neg, wpos=None, wneg=None):
         wp = None if wpos is None else _fp(np.ascontiguousarray(wpos, np.float32))

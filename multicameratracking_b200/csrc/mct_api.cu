@@ -714,6 +714,37 @@ extern "C" int mct_classifier_update(mct_clf* c, const mct_boxes* pos, const mct
     return clf_train_common(c, P, Nn, wpos, wneg);
 }
 
+// device-resident variants for the appearance fuser's exchange (rows stay in HBM between the feature kernels, the NCCL
+// all-gather and the update): dev_out / dev_fpos / dev_fneg are device pointers with the given leading dimensions
+extern "C" int mct_features_compute_dev(mct_clf* c, const mct_boxes* boxes, float* dev_out, int ld_out)
+{
+    if (!c || !boxes || (boxes->n > 0 && (!dev_out || ld_out < boxes->n))) return MCT_E_ARG;
+    mct_ctx* ctx = c->ctx;
+    int rc = need_frame(c);
+    if (rc) return rc;
+    const int n = boxes->n;
+    if (n <= 0) return MCT_OK;
+    if ((rc = clf_ensure_test(c, n, c->F))) return rc;
+    if ((rc = upload_boxes(ctx, boxes, c->d_col, c->d_row, c->d_sx, c->d_sy, 0))) return rc;
+    if ((rc = mct_feature_matrix_full(c, c->d_col, c->d_row, c->d_sx, c->d_sy, n, c->d_featN, c->ldN))) return rc;
+    MCT_CUDA(ctx, cudaMemcpy2DAsync(dev_out, (size_t)ld_out * 4, c->d_featN, (size_t)c->ldN * 4, (size_t)n * 4, c->F,
+                                    cudaMemcpyDeviceToDevice, ctx->stream));
+    return mct_sync(ctx);          // the host box arrays may be reused by the caller
+}
+extern "C" int mct_classifier_update_from_features_dev(mct_clf* c, const float* dev_fpos, int ld_pos, int P, const float* dev_fneg,
+                                                       int ld_neg, int Nn)
+{
+    if (!c || !dev_fpos || !dev_fneg || ld_pos < P || ld_neg < Nn) return MCT_E_ARG;
+    mct_ctx* ctx = c->ctx;
+    if (P < 1 || Nn < 1) return mct_fail(ctx, MCT_E_ARG, "Update needs at least one positive and one negative sample%s");
+    if (P + Nn > c->max_train) return mct_fail(ctx, MCT_E_ARG, "training set exceeds max_train%s (%d)", "", P + Nn);
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    MCT_CUDA(ctx, cudaMemcpy2DAsync(c->d_featT, (size_t)c->ldT * 4, dev_fpos, (size_t)ld_pos * 4, (size_t)P * 4, c->F,
+                                    cudaMemcpyDeviceToDevice, ctx->stream));
+    MCT_CUDA(ctx, cudaMemcpy2DAsync(c->d_featT + P, (size_t)c->ldT * 4, dev_fneg, (size_t)ld_neg * 4, (size_t)Nn * 4, c->F,
+                                    cudaMemcpyDeviceToDevice, ctx->stream));
+    return clf_train_common(c, P, Nn, nullptr, nullptr);
+}
 extern "C" int mct_classifier_update_from_features(mct_clf* c, const float* fpos, int P, const float* fneg, int Nn,
                                                    const float* wpos, const float* wneg)
 {

@@ -154,16 +154,32 @@ class AppearanceFusion:
         self.trained = False
 
     def learn(self, pos_boxes, neg_boxes, rng_next_float):
-        """pos_boxes / neg_boxes: capi.make_boxes(...) of this camera's training sets for the object (current frame set)"""
+        """pos_boxes / neg_boxes: capi.make_boxes(...) of this camera's training sets for the object (current frame set).
+        With NCCL the rows never leave the device: feature kernels -> all-gather -> column selection -> update."""
         dev = self.ex.device
-        fpos = torch.from_numpy(self.clf.features(pos_boxes)).to(dev)
-        fneg = torch.from_numpy(self.clf.features(neg_boxes)).to(dev)
+        on_device = dev == "cuda" and hasattr(self.clf, "features_dev") and hasattr(pos_boxes, "n")
+        if on_device:
+            F, P, Nn = self.clf.F, int(pos_boxes.n), int(neg_boxes.n)
+            fpos = torch.empty((F, P), dtype=torch.float32, device="cuda")
+            fneg = torch.empty((F, Nn), dtype=torch.float32, device="cuda")
+            torch.cuda.current_stream().synchronize()          # the C-ABI works on the camera's stream
+            self.clf.features_dev(pos_boxes, fpos.data_ptr(), P)
+            self.clf.features_dev(neg_boxes, fneg.data_ptr(), Nn)
+        else:
+            fpos = torch.from_numpy(self.clf.features(pos_boxes)).to(dev)
+            fneg = torch.from_numpy(self.clf.features(neg_boxes)).to(dev)
         pos, neg, counts = self.ex.allgather_feature_rows(fpos, fneg)
         kp = drop_samples(rng_next_float, pos.shape[1])
         kn = drop_samples(rng_next_float, neg.shape[1])
         if not kp or not kn:
             raise RuntimeError("appearance fusion: every pooled %s sample was dropped" % ("positive" if not kp else "negative"))
-        self.clf.update_from_features(pos[:, kp].contiguous().cpu().numpy(), neg[:, kn].contiguous().cpu().numpy())
+        if on_device:
+            sp = pos[:, torch.as_tensor(kp, device="cuda")].contiguous()
+            sn = neg[:, torch.as_tensor(kn, device="cuda")].contiguous()
+            torch.cuda.current_stream().synchronize()
+            self.clf.update_from_features_dev(sp.data_ptr(), len(kp), len(kp), sn.data_ptr(), len(kn), len(kn))
+        else:
+            self.clf.update_from_features(pos[:, kp].contiguous().cpu().numpy(), neg[:, kn].contiguous().cpu().numpy())
         self.trained = True
         return counts, kp, kn
 
