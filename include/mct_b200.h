@@ -40,7 +40,7 @@ enum { MCT_FEAT_HAAR = 0, MCT_FEAT_CCH = 1, MCT_FEAT_MDCH = 2, MCT_FEAT_HAAR_MDC
 /* Classifier::WeakClassifierType (WeakClassifierBase.h:13-16) */
 enum { MCT_WEAK_STUMP = 0, MCT_WEAK_WSTUMP = 1, MCT_WEAK_PERCEPTRON = 2 };
 /* Classifier::StrongClassifierType (ClassifierParameters.h:11-18) */
-enum { MCT_STRONG_MILBOOST = 2, MCT_STRONG_MILANYBOOST = 4 };
+enum { MCT_STRONG_ADABOOST = 0, MCT_STRONG_MILBOOST = 2, MCT_STRONG_MILANYBOOST = 4 };   /* ClassifierParameters.h:11-18 */
 /* ParticleFilter::State (ParticleFilter.h:33-37) */
 enum { MCT_PF_UNINIT = 0, MCT_PF_INIT = 1, MCT_PF_PREDICTED = 2, MCT_PF_RESAMPLED = 3 };
 
@@ -170,6 +170,8 @@ int mct_classifier_classify_from_features(mct_clf* clf, const float* feat, int n
 int mct_classifier_get_selectors(mct_clf* clf, int* idx_host, int* n);
 /* weak-classifier state, 8 rows x F: mu0,mu1,sig0,sig1,n0,n1,e0,e1 (OnlineStumpsWeakClassifier.h:33-40);
  * perceptron: rows 0,1 = m_weightList[0], [1] */
+/* AdaBoost (AdaBoostClassifier.cpp): voting weights m_alphaList of the selected weak classifiers, in selector order */
+int mct_classifier_get_alphas(mct_clf* clf, float* alphas_host, int* n);
 int mct_classifier_get_weak_state(mct_clf* clf, float* out8xF_host);
 /* last Update's weak predictions [F][P+Nn] (positives first) -- parity tests */
 int mct_classifier_get_predictions(mct_clf* clf, float* out_host, int* P, int* Nn);

@@ -18,7 +18,7 @@ _c_u8_p = C.POINTER(C.c_uint8)
 OK, E_ARG, E_CUDA, E_STATE, E_EMPTY, E_NOMEM, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 FEAT_HAAR, FEAT_CCH, FEAT_MDCH, FEAT_HAAR_MDCH = 0, 1, 2, 3
 WEAK_STUMP, WEAK_WSTUMP, WEAK_PERCEPTRON = 0, 1, 2
-STRONG_MILBOOST, STRONG_MILANYBOOST = 2, 4
+STRONG_ADABOOST, STRONG_MILBOOST, STRONG_MILANYBOOST = 0, 2, 4
 PF_UNINIT, PF_INIT, PF_PREDICTED, PF_RESAMPLED = 0, 1, 2, 3
 
 # every symbol include/mct_b200.h declares (checked by tests/test_abi.py)
@@ -33,7 +33,7 @@ SYMBOLS = [
     "mct_pf_get_resample_indices", "mct_pf_get_summary", "mct_track_score", "mct_noise_prefetch", "mct_track_score_async",
     "mct_track_collect", "mct_track_update", "mct_pf_get_last_response", "mct_fuser_pack_foot_points",
     "mct_pf_ground_pdf", "mct_pf_rearrange_ground", "mct_classify_argmax", "mct_fuser_ground_pdf", "mct_p2p_create", "mct_p2p_open", "mct_p2p_destroy",
-    "mct_fuser_exchange_foot_points", "mct_features_compute_dev", "mct_classifier_update_from_features_dev",
+    "mct_fuser_exchange_foot_points", "mct_classifier_get_alphas", "mct_features_compute_dev", "mct_classifier_update_from_features_dev",
 ]
 
 
@@ -145,6 +145,7 @@ def load():
     L.mct_fuser_exchange_foot_points.argtypes = [vp, C.c_int, C.POINTER(vp), _c_float_p, _c_float_p, C.c_int]
     L.mct_features_compute_dev.argtypes = [vp, C.POINTER(Boxes), vp, C.c_int]
     L.mct_classifier_update_from_features_dev.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int]
+    L.mct_classifier_get_alphas.argtypes = [vp, _c_float_p, _c_int_p]
     L.mct_classify_argmax.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(Boxes), C.c_int, _c_int_p, _c_float_p]
     _lib = L
     return L
@@ -368,6 +369,12 @@ class StrongClassifier:
         self.ctx.check(self.ctx.L.mct_classifier_classify_from_features(self.h, _fp(feat), feat.shape[1], int(log_ratio),
                                                                         _fp(out)))
         return out[:feat.shape[1]]
+
+    def alphas(self):
+        """AdaBoost voting weights of the selected weak classifiers (empty for the MIL classifiers)"""
+        a = np.zeros(4096, np.float32); n = C.c_int(0)
+        self.ctx.check(self.ctx.L.mct_classifier_get_alphas(self.h, _fp(a), C.byref(n)))
+        return a[:n.value].copy()
 
     def selectors(self):
         idx = np.zeros(self.F, np.int32)

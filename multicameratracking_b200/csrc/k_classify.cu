@@ -26,6 +26,7 @@ k_classify(const ObjDesc* __restrict__ descs, const float* __restrict__ ii, int 
         SelEntry& e = se[s];
 #pragma unroll
         for (int q = 0; q < 8; q++) e.st[q] = d.weak[(size_t)q * F + f];
+        if (d.alpha) e.st[2] = d.alpha[s];                     // AdaBoost: the vote weight rides in the (unused) sigma0 slot
         if (f < d.n_haar && !from_matrix) {
             e.nrect = d.nrect[f];
             for (int k = 0; k < MCT_MAX_RECTS; k++) {
@@ -50,9 +51,10 @@ k_classify(const ObjDesc* __restrict__ descs, const float* __restrict__ ii, int 
         float x;
         if (e.nrect > 0) x = haar_eval_dev(ii, iip, W, H, e.r, e.w, e.nrect, c, r, fx, fy);
         else x = d.featN[(size_t)e.row * d.ldN + i];
-        Hs = __fadd_rn(Hs, weak_classify_dev(d.weak_type, x, e.st[0], e.st[1], e.st[4], e.st[5], e.st[6], e.st[7]));
+        if (d.alpha) Hs = __fadd_rn(Hs, weak_classify_bool_dev(d.weak_type, x, e.st[0], e.st[1], e.st[4], e.st[5], e.st[6], e.st[7]) ? e.st[2] : -e.st[2]);
+        else Hs = __fadd_rn(Hs, weak_classify_dev(d.weak_type, x, e.st[0], e.st[1], e.st[4], e.st[5], e.st[6], e.st[7]));
     }
-    if (!log_ratio) Hs = sigmoid_dev(Hs);
+    if (!log_ratio) Hs = sigmoid_dev(d.alpha ? __fmul_rn(2.0f, Hs) : Hs);     // AdaBoost: sigmoid(2 H) (:208)
     d.H[i] = Hs;
 }
 
@@ -169,7 +171,8 @@ k_classify_staged(const ObjDesc* __restrict__ descs, const float* __restrict__ i
                         if (staged) x = haar_eval_region(region, RWp, ox, by0, W, H, e.r, e.w, e.nrect, c, r, fx, fy);
                         else x = haar_eval_dev(ii, iip, W, H, e.r, e.w, e.nrect, c, r, fx, fy);
                     } else x = d.featN[(size_t)e.row * d.ldN + i];
-                    v[u] = weak_classify_ratio_dev(d.weak_type, x, e.st);
+                    v[u] = d.alpha ? (weak_classify_bool_dev(d.weak_type, x, e.st[0], e.st[1], e.st[4], e.st[5], e.st[6], e.st[7]) ? e.st[2] : -e.st[2])
+                                   : weak_classify_ratio_dev(d.weak_type, x, e.st);
                 }
             }
             // ordered accumulation: responseList[i] += weak[k] in selector order (MILBoostClassifier.cpp:351-361)
@@ -182,7 +185,7 @@ k_classify_staged(const ObjDesc* __restrict__ descs, const float* __restrict__ i
                 }
         }
         if (live && q == 0) {
-            if (ok && !log_ratio) Hs = sigmoid_dev(Hs);
+            if (ok && !log_ratio) Hs = sigmoid_dev(d.alpha ? __fmul_rn(2.0f, Hs) : Hs);
             d.H[i] = ok ? Hs : 0.0f;
         }
     }

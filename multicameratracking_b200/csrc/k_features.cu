@@ -866,7 +866,7 @@ __device__ __forceinline__ void build_colormap_body(const int* __restrict__ sel,
                                  uint16_t* __restrict__ slotmap, int* __restrict__ colorrow, int* __restrict__ outbins,
                                  int* __restrict__ nout, const int4* __restrict__ rects, const float* __restrict__ wts,
                                  const int* __restrict__ nrect, const float* __restrict__ weak, int F, int K,
-                                 SelEntry* __restrict__ tab, int* __restrict__ hdr)
+                                 SelEntry* __restrict__ tab, int* __restrict__ hdr, const float* __restrict__ alpha = nullptr)
 {
     __shared__ int s_ext[2];
     const int ns = *nsel;
@@ -894,6 +894,7 @@ __device__ __forceinline__ void build_colormap_body(const int* __restrict__ sel,
         if (s < ns) {
             const int f = sel[s];
             for (int q = 0; q < 8; q++) e.st[q] = weak[(size_t)q * F + f];
+            if (alpha) e.st[2] = alpha[s];                    // AdaBoost: the vote weight rides in the (unused) sigma0 slot
             if (f < n_haar) {
                 e.nrect = nrect[f];
                 for (int k = 0; k < MCT_MAX_RECTS; k++) {
@@ -915,16 +916,16 @@ __global__ void k_build_colormap(const int* __restrict__ sel, const int* __restr
                                  uint16_t* __restrict__ slotmap, int* __restrict__ colorrow, int* __restrict__ outbins,
                                  int* __restrict__ nout, const int4* __restrict__ rects, const float* __restrict__ wts,
                                  const int* __restrict__ nrect, const float* __restrict__ weak, int F, int K,
-                                 SelEntry* __restrict__ tab, int* __restrict__ hdr)
+                                 SelEntry* __restrict__ tab, int* __restrict__ hdr, const float* __restrict__ alpha)
 {
-    build_colormap_body(sel, nsel, n_haar, n_color, mdch, slotmap, colorrow, outbins, nout, rects, wts, nrect, weak, F, K, tab, hdr);
+    build_colormap_body(sel, nsel, n_haar, n_color, mdch, slotmap, colorrow, outbins, nout, rects, wts, nrect, weak, F, K, tab, hdr, alpha);
 }
 __global__ void k_build_colormap_batch(const TrainDesc* __restrict__ descs)
 {
     const TrainDesc& d = descs[blockIdx.x];
     const int mdch = (d.feature_type == MCT_FEAT_MDCH || d.feature_type == MCT_FEAT_HAAR_MDCH) ? 1 : 0;
     build_colormap_body(d.sel, d.nsel, d.n_haar, d.n_color, mdch, d.slotmap, d.colorrow, d.outbins, d.nout, d.rects, d.wts, d.nrect,
-                        d.weak, d.F, d.K, d.seltab, d.selhdr);
+                        d.weak, d.F, d.K, d.seltab, d.selhdr, d.strong_type == MCT_STRONG_ADABOOST ? d.alpha : nullptr);
 }
 int launch_build_colormap_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj)
 {
@@ -939,7 +940,8 @@ int launch_build_colormap(mct_clf* clf)
     MCT_LAUNCH(ctx, "k_build_colormap", k_build_colormap<<<1, 256, 0, ctx->stream>>>(clf->d_sel, clf->d_nsel, clf->n_haar, clf->n_color, mdch,
                                                                                   clf->d_slotmap, clf->d_colorrow, clf->d_outbins, clf->d_nout,
                                                                                   clf->d_rects, clf->d_wts, clf->d_nrect, clf->d_weak, clf->F, clf->K,
-                                                                                  clf->d_seltab, clf->d_selhdr));
+                                                                                  clf->d_seltab, clf->d_selhdr,
+                                                                                  clf->p.strong_type == MCT_STRONG_ADABOOST ? clf->d_alpha : nullptr));
     return MCT_OK;
 }
 

@@ -491,10 +491,133 @@ static size_t mil_smem_plan(int F, int M, int FL, int* FC_out, int* rows_out)
     return (smem + 15) & ~(size_t)15;
 }
 // ------------------------------------------------------------------------------------------
+// k_adaboost_select: AdaBoostClassifier::Update selection loop (AdaBoostClassifier.cpp:62-171), online boosting with running
+// TP / FP / TN / FN weights per (selector, weak classifier).  One CTA per classifier, one thread per weak classifier:
+//   prologue  the weak classifiers' boolean labels for the P + Nn training samples, packed 32 per word in shared memory;
+//   round s   every thread adds the sample weights to its four counters IN SAMPLE ORDER (the reference accumulates
+//             straight onto the running counters in f32), forms err = (FP+FN)/(FP+FN+TP+TN); block arg-min over the not yet
+//             selected classifiers (ties -> lowest index; std::sort's tie order is unspecified in the reference);
+//             alpha = clamp(0.5f * logf((1-err)/(err+1e-5f)), 0, 10); sample weights *= 1/(2-2err) (correct) or 1/(2err).
+#define ADA_THREADS 1024
+__device__ __forceinline__ void
+adaboost_select_body(const float* __restrict__ feat, int ld, int F, int P, int Nn, int K, const float* __restrict__ weak, int weak_type,
+                     float* __restrict__ cnt, float* __restrict__ alpha, int* __restrict__ sel, int* __restrict__ nsel)
+{
+    const int M = P + Nn, W32 = (M + 31) >> 5;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    float* lam = (float*)smraw;                          // [M] sample weights (positives then negatives)
+    unsigned* bits = (unsigned*)(lam + M);               // [F][W32] labels
+    unsigned char* selflag = (unsigned char*)(bits + (size_t)F * W32);
+    __shared__ SelSlot sh[ADA_THREADS / 32];
+    __shared__ float s_corw, s_incorw;
+    __shared__ int s_best;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const float lp = __fdiv_rn(0.5f, (float)P), ln = __fdiv_rn(0.5f, (float)Nn);
+    for (int i = tid; i < M; i += nt) lam[i] = i < P ? lp : ln;
+    for (int f = tid; f < F; f += nt) selflag[f] = 0;
+    // labels: one warp per weak classifier, a ballot per 32 samples
+    {
+        const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+        for (int f = warp; f < F; f += nw) {
+            const float mu0 = weak[0 * (size_t)F + f], mu1 = weak[1 * (size_t)F + f];
+            const float n0 = weak[4 * (size_t)F + f], n1 = weak[5 * (size_t)F + f], e0 = weak[6 * (size_t)F + f], e1 = weak[7 * (size_t)F + f];
+            const float* x = feat + (size_t)f * ld;
+            for (int w = 0; w < W32; w++) {
+                const int i = w * 32 + lane;
+                const bool b = i < M && weak_classify_bool_dev(weak_type, x[i], mu0, mu1, n0, n1, e0, e1);
+                const unsigned bal = __ballot_sync(0xffffffffu, b);
+                if (lane == 0) bits[(size_t)f * W32 + w] = bal;
+            }
+        }
+    }
+    __syncthreads();
+    const size_t KF = (size_t)K * F;
+    for (int s = 0; s < K; s++) {
+        float bv = CUDART_INF_F; int bf = 0x7fffffff;
+        for (int f = tid; f < F; f += nt) {
+            float* c0 = cnt + (size_t)s * F + f;
+            float tp = c0[0], fp = c0[KF], tn = c0[2 * KF], fn = c0[3 * KF];
+            const unsigned* bw = bits + (size_t)f * W32;
+            for (int i = 0; i < P; i++) {
+                const float l = lam[i];
+                if ((bw[i >> 5] >> (i & 31)) & 1u) tp = __fadd_rn(tp, l); else fp = __fadd_rn(fp, l);
+            }
+            for (int i = P; i < M; i++) {
+                const float l = lam[i];
+                if ((bw[i >> 5] >> (i & 31)) & 1u) fn = __fadd_rn(fn, l); else tn = __fadd_rn(tn, l);
+            }
+            c0[0] = tp; c0[KF] = fp; c0[2 * KF] = tn; c0[3 * KF] = fn;
+            const float num = __fadd_rn(fp, fn);
+            const float err = __fdiv_rn(num, __fadd_rn(__fadd_rn(num, tp), tn));
+            if (!selflag[f] && better_min(err, f, bv, bf)) { bv = err; bf = f; }
+        }
+        // block arg-min
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int of = __shfl_xor_sync(0xffffffffu, bf, o);
+            if (better_min(ov, of, bv, bf)) { bv = ov; bf = of; }
+        }
+        if ((tid & 31) == 0) { sh[tid >> 5].nll = bv; sh[tid >> 5].f = bf; }
+        __syncthreads();
+        if (tid == 0) {
+            float v = sh[0].nll; int f = sh[0].f;
+            for (int w = 1; w < (nt >> 5); w++) if (better_min(sh[w].nll, sh[w].f, v, f)) { v = sh[w].nll; f = sh[w].f; }
+            s_best = f;
+            if (f != 0x7fffffff) {
+                sel[s] = f; selflag[f] = 1;
+                const float minerr = v;
+                float a = __fmul_rn(0.5f, logf(__fdiv_rn(__fsub_rn(1.0f, minerr), __fadd_rn(minerr, 0.00001f))));
+                a = fmaxf(0.0f, fminf(a, 10.0f));
+                alpha[s] = a;
+                s_corw = __fdiv_rn(1.0f, __fsub_rn(2.0f, __fmul_rn(2.0f, minerr)));
+                s_incorw = __fdiv_rn(1.0f, __fmul_rn(2.0f, minerr));
+            }
+        }
+        __syncthreads();
+        const int best = s_best;
+        if (best == 0x7fffffff) { if (tid == 0) *nsel = s; return; }       // every weak classifier already selected (K > F cannot happen)
+        const unsigned* bb = bits + (size_t)best * W32;
+        const float corw = s_corw, incorw = s_incorw;
+        for (int i = tid; i < M; i += nt) {
+            const bool lab = (bb[i >> 5] >> (i & 31)) & 1u;
+            const bool correct = i < P ? lab : !lab;
+            lam[i] = __fmul_rn(lam[i], correct ? corw : incorw);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) *nsel = K;
+}
+__global__ void __launch_bounds__(ADA_THREADS) k_adaboost_select_batch(const TrainDesc* __restrict__ descs)
+{
+    const TrainDesc& d = descs[blockIdx.x];
+    if (d.strong_type != MCT_STRONG_ADABOOST) return;
+    adaboost_select_body(d.featT, d.ldT, d.F, d.P, d.Nn, d.K, d.weak, d.weak_type, d.ada_cnt, d.alpha, d.sel, d.nsel);
+}
+__global__ void __launch_bounds__(ADA_THREADS) k_adaboost_select(const float* __restrict__ feat, int ld, int F, int P, int Nn, int K,
+                                                                 const float* __restrict__ weak, int weak_type, float* __restrict__ cnt,
+                                                                 float* __restrict__ alpha, int* __restrict__ sel, int* __restrict__ nsel)
+{
+    adaboost_select_body(feat, ld, F, P, Nn, K, weak, weak_type, cnt, alpha, sel, nsel);
+}
+static size_t ada_smem(int F, int M) { return (size_t)M * 4 + (size_t)F * ((M + 31) / 32) * 4 + (size_t)F + 16; }
+
+// ------------------------------------------------------------------------------------------
 int launch_mil_select(mct_clf* clf, int P, int Nn)
 {
     mct_ctx* ctx = clf->ctx;
     const int F = clf->F, M = P + Nn;
+    if (clf->p.strong_type == MCT_STRONG_ADABOOST) {
+        const size_t smem = ada_smem(F, M);
+        if (smem > 200 * 1024) return mct_fail(ctx, MCT_E_UNSUPPORTED, "training set too large for the AdaBoost kernel%s (M=%d)", "", M);
+        static size_t s_attr_a = 32 * 1024;
+        if (smem > s_attr_a) {
+            MCT_CUDA(ctx, cudaFuncSetAttribute(k_adaboost_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            s_attr_a = smem;
+        }
+        MCT_LAUNCH(ctx, "k_adaboost_select", k_adaboost_select<<<1, ADA_THREADS, smem, ctx->stream>>>(clf->d_featT, clf->ldT, F, P, Nn, clf->K, clf->d_weak,
+                                                                                           clf->p.weak_type, clf->d_ada_cnt, clf->d_alpha, clf->d_sel, clf->d_nsel));
+        return MCT_OK;
+    }
     if (clf->p.strong_type == MCT_STRONG_MILANYBOOST) {
         size_t smem = (size_t)(3 * M + F) * sizeof(float) + (size_t)F;
         if (smem > 200 * 1024) return mct_fail(ctx, MCT_E_UNSUPPORTED, "training set too large for the AnyBoost kernel%s (M=%d)", "", M);
@@ -547,11 +670,22 @@ int launch_mil_select(mct_clf* clf, int P, int Nn)
 // Batched selection for all objects of a camera: one launch per strong-classifier type.
 int launch_mil_select_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj, const int* cluster_req)
 {
-    int any_mil = 0, any_any = 0, F_max = 0, M_max = 0, F_any = 0, M_any = 0, creq = 0;
+    int any_mil = 0, any_any = 0, any_ada = 0, F_max = 0, M_max = 0, F_any = 0, M_any = 0, creq = 0;
+    size_t smem_ada = 0;
     for (int o = 0; o < n_obj; o++) {
         const int M = h[o].P + h[o].Nn;
+        if (h[o].strong_type == MCT_STRONG_ADABOOST) { any_ada = 1; smem_ada = max(smem_ada, ada_smem(h[o].F, M)); continue; }
         if (h[o].strong_type == MCT_STRONG_MILANYBOOST) { any_any = 1; F_any = max(F_any, h[o].F); M_any = max(M_any, M); }
         else { any_mil = 1; F_max = max(F_max, h[o].F); M_max = max(M_max, M); if (cluster_req && cluster_req[o] > creq) creq = cluster_req[o]; }
+    }
+    if (any_ada) {
+        if (smem_ada > 200 * 1024) return mct_fail(ctx, MCT_E_UNSUPPORTED, "training set too large for the AdaBoost kernel%s");
+        static size_t s_attr_a = 32 * 1024;
+        if (smem_ada > s_attr_a) {
+            MCT_CUDA(ctx, cudaFuncSetAttribute(k_adaboost_select_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ada));
+            s_attr_a = smem_ada;
+        }
+        MCT_LAUNCH(ctx, "k_adaboost_select_batch", k_adaboost_select_batch<<<n_obj, ADA_THREADS, smem_ada, ctx->stream>>>(d));
     }
     if (any_any) {
         size_t smem = (size_t)(3 * M_any + F_any) * sizeof(float) + (size_t)F_any;

@@ -562,7 +562,7 @@ extern "C" int mct_classifier_create(mct_ctx* ctx, const mct_clf_params* p, cons
         (p->n_bins < 1 || p->n_bins > 8 || 256 % p->n_bins != 0))
         return mct_fail(ctx, MCT_E_UNSUPPORTED, "Color_Number_Of_Bins must divide 256 and be <= 8%s (%d)", "", p->n_bins);
     if (p->weak_type < 0 || p->weak_type > 2) return mct_fail(ctx, MCT_E_ARG, "unknown weak classifier type%s (%d)", "", p->weak_type);
-    if (p->strong_type != MCT_STRONG_MILBOOST && p->strong_type != MCT_STRONG_MILANYBOOST)
+    if (p->strong_type != MCT_STRONG_MILBOOST && p->strong_type != MCT_STRONG_MILANYBOOST && p->strong_type != MCT_STRONG_ADABOOST)
         return mct_fail(ctx, MCT_E_UNSUPPORTED, "strong classifier type not on the hot path%s (%d)", "", p->strong_type);
     if (n_haar > 0 && (!haar || haar->n_features != n_haar || !haar->nrect || !haar->rects || !haar->weights))
         return mct_fail(ctx, MCT_E_ARG, "Haar table missing or of the wrong size%s");
@@ -614,6 +614,15 @@ extern "C" int mct_classifier_create(mct_ctx* ctx, const mct_clf_params* p, cons
     MCT_CUDA(ctx, cudaMemset(c->d_seltab, 0, (size_t)K * sizeof(SelEntry)));
     MCT_CUDA(ctx, cudaMalloc(&c->d_selhdr, 16));
     MCT_CUDA(ctx, cudaMemset(c->d_selhdr, 0, 16));
+    if (p->strong_type == MCT_STRONG_ADABOOST) {
+        // running TP / FP / TN / FN weights, initial value 1 (AdaBoostClassifier.cpp:27-36), and the voting weights
+        const size_t nc = (size_t)4 * K * c->F;
+        std::vector<float> ones(nc, 1.0f);
+        MCT_CUDA(ctx, cudaMalloc(&c->d_ada_cnt, nc * 4));
+        MCT_CUDA(ctx, cudaMemcpy(c->d_ada_cnt, ones.data(), nc * 4, cudaMemcpyHostToDevice));
+        MCT_CUDA(ctx, cudaMalloc(&c->d_alpha, (size_t)K * 4));
+        MCT_CUDA(ctx, cudaMemset(c->d_alpha, 0, (size_t)K * 4));
+    }
     MCT_CUDA(ctx, cudaMalloc(&c->d_tcol, (size_t)c->ldT * 4)); MCT_CUDA(ctx, cudaMalloc(&c->d_trow, (size_t)c->ldT * 4));
     MCT_CUDA(ctx, cudaMalloc(&c->d_tsx, (size_t)c->ldT * 4)); MCT_CUDA(ctx, cudaMalloc(&c->d_tsy, (size_t)c->ldT * 4));
     MCT_CUDA(ctx, cudaMalloc(&c->d_tw, (size_t)c->ldT * 4));
@@ -642,7 +651,7 @@ extern "C" int mct_classifier_destroy(mct_clf* c)
     cudaStreamSynchronize(c->ctx->stream);
     void* ptrs[] = {c->d_rects, c->d_wts, c->d_nrect, c->d_weak, c->d_trained, c->d_sel, c->d_nsel, c->d_seltab, c->d_selhdr, c->d_tcol, c->d_trow,
                     c->d_tsx, c->d_tsy, c->d_tw, c->d_featT, c->d_pred, c->d_col, c->d_row, c->d_sx, c->d_sy, c->d_featN,
-                    c->d_H, c->d_outbins, c->d_colorrow, c->d_slotmap, c->d_nout, c->d_big, c->d_nbig, c->d_tsort};
+                    c->d_H, c->d_outbins, c->d_colorrow, c->d_slotmap, c->d_nout, c->d_big, c->d_nbig, c->d_tsort, c->d_ada_cnt, c->d_alpha};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete c;
     return MCT_OK;
@@ -764,6 +773,7 @@ static void fill_clf_desc(ObjDesc* d, mct_clf* c)
 {
     d->rects = c->d_rects; d->wts = c->d_wts; d->nrect = c->d_nrect;
     d->weak = c->d_weak; d->sel = c->d_sel; d->nsel = c->d_nsel; d->seltab = c->d_seltab; d->selhdr = c->d_selhdr;
+    d->alpha = c->p.strong_type == MCT_STRONG_ADABOOST ? c->d_alpha : nullptr;
     d->featN = c->d_featN; d->ldN = c->ldN; d->n_color_rows = c->n_color;
     d->colorrow = c->d_colorrow; d->outbins = c->d_outbins;
     const bool mdch = c->p.feature_type == MCT_FEAT_MDCH || c->p.feature_type == MCT_FEAT_HAAR_MDCH;
@@ -898,6 +908,22 @@ extern "C" int mct_classifier_get_selectors(mct_clf* c, int* idx_host, int* n)
         return mct_sync(ctx);
     }
     return MCT_OK;
+}
+extern "C" int mct_classifier_get_alphas(mct_clf* c, float* alphas_host, int* n)
+{
+    if (!c || !alphas_host || !n) return MCT_E_ARG;
+    mct_ctx* ctx = c->ctx;
+    *n = 0;
+    if (c->p.strong_type != MCT_STRONG_ADABOOST) return MCT_OK;
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    int ns = 0;
+    MCT_CUDA(ctx, cudaMemcpyAsync(&ns, c->d_nsel, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    int rc = mct_sync(ctx);
+    if (rc) return rc;
+    if (ns > c->K) ns = c->K;
+    MCT_CUDA(ctx, cudaMemcpyAsync(alphas_host, c->d_alpha, (size_t)ns * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    *n = ns;
+    return mct_sync(ctx);
 }
 extern "C" int mct_classifier_get_weak_state(mct_clf* c, float* out)
 {
@@ -1371,6 +1397,7 @@ static void fill_train_desc(TrainDesc* t, mct_clf* c)
     t->weak = c->d_weak; t->trained = c->d_trained; t->sel = c->d_sel; t->nsel = c->d_nsel;
     t->slotmap = c->d_slotmap; t->colorrow = c->d_colorrow; t->outbins = c->d_outbins; t->nout = c->d_nout;
     t->seltab = c->d_seltab; t->selhdr = c->d_selhdr;
+    t->ada_cnt = c->d_ada_cnt; t->alpha = c->d_alpha;
     t->F = c->F; t->K = c->K; t->n_haar = c->n_haar; t->n_color = c->n_color; t->nb = c->p.n_bins; t->w0 = c->p.w0; t->h0 = c->p.h0;
     t->weak_type = c->p.weak_type; t->strong_type = c->p.strong_type; t->feature_type = c->p.feature_type; t->cch_mode = c->p.cch_mode;
     t->lr = c->p.learning_rate;

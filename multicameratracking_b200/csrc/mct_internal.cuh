@@ -129,6 +129,7 @@ struct mct_clf {
     int* d_tsort; size_t tsort_cap;                     // tiled Haar matrix: tile starts + box order (k_tile_sort)
     int* d_big; int big_cap;                            // per test box: 1 = left to the generic (large / odd box) kernel
     int* d_nbig;                                        // device counter of such boxes
+    float* d_ada_cnt; float* d_alpha;                   // AdaBoost state ([4][K][F], initial value 1; [K])
 };
 
 // geometric-fuser feedback: per-call arguments and read-out of k_ground_pdf
@@ -176,6 +177,7 @@ struct ObjDesc {
     const int4* rects; const float* wts; const int* nrect;
     const float* weak; const int* sel; const int* nsel;
     const SelEntry* seltab; const int* selhdr;
+    const float* alpha;                         // AdaBoost voting weights per selector (NULL for the MIL classifiers)
     float* featN; int ldN; int n_color_rows;
     const int* colorrow; const int* outbins;
     const uint16_t* slotmap; const int* nout; int* big; int* nbig;
@@ -209,6 +211,7 @@ struct TrainDesc {
     uint32_t* mlist;                       // sorted pixel lists of both groups ((bin << 22) | offset in the extended table)
     uint32_t* macc;                        // [n_color][ldT] u32 accumulators (zero between launches)
     uint32_t* mtot;                        // [2] fixed-point total of each group's weight table
+    float* ada_cnt; float* alpha;          // AdaBoost: [4][K][F] running TP / FP / TN / FN weights, [K] voting weights
 };
 
 // Per-call values that change every frame travel as kernel parameters, so that the ObjDesc array itself is
@@ -344,6 +347,19 @@ __device__ __forceinline__ float weak_classify_q_dev(int weak_type, float x, flo
     const double p0 = (double)__fmul_rn(expf(a0), n0);
     const double p1 = (double)__fmul_rn(expf(a1), n1);
     return (float)log((1e-5 + p1) / (1e-5 + p0));
+}
+// AdaBoostClassifier::Classify vote of one selected weak classifier (AdaBoostClassifier.cpp:196-203): +alpha if the weak
+// classifier says "object" (OnlineStumps::Classify compares the two class likelihoods, .cpp:68-75; the other weak types take
+// the sign of ClassifyF), -alpha otherwise
+__device__ __forceinline__ bool weak_classify_bool_dev(int weak_type, float x, float mu0, float mu1, float n0, float n1, float e0, float e1)
+{
+    if (weak_type == MCT_WEAK_STUMP) {
+        const float d0 = __fsub_rn(x, mu0), d1 = __fsub_rn(x, mu1);
+        const float p0 = __fmul_rn(expf(__fmul_rn(__fmul_rn(d0, d0), e0)), n0);
+        const float p1 = __fmul_rn(expf(__fmul_rn(__fmul_rn(d1, d1), e1)), n1);
+        return p1 > p0;
+    }
+    return weak_classify_dev(weak_type, x, mu0, mu1, n0, n1, e0, e1) > 0.0f;
 }
 // Public.h:169-172
 // (1.0f / y correctly rounded == __frcp_rn(y): same bits as the division, without its generic slow-path check)

@@ -281,13 +281,23 @@ vectori StrongClassifierBase::GetSelectorList()
     return s;
 }
 
+vectorf AdaBoostClassifier::GetAlphaList()
+{
+    vectorf a(4096); int n = 0;
+    int rc = mct_classifier_get_alphas(m_clf, a.data(), &n);
+    if (rc) throw MctHostError(rc, mct_last_error(m_ctx));
+    a.resize(n);
+    return a;
+}
+
 StrongClassifierBasePtr StrongClassifierFactory::CreateAndInitializeClassifier(StrongClassifierParametersBasePtr p, mct_ctx* ctx)
 {
     if (!p) throw MctHostError(MCT_E_ARG, "CreateAndInitializeClassifier: NULL parameters");
     switch (p->GetClassifierType()) {
         case ONLINE_STOCHASTIC_BOOST_MIL: return StrongClassifierBasePtr(new MILBoostClassifier(ctx, p));
         case ONLINE_ANY_BOOST_MIL: return StrongClassifierBasePtr(new MILAnyBoostClassifier(ctx, p));
-        default: throw MctHostError(MCT_E_UNSUPPORTED, "strong classifier type is outside the B200 hot path (AdaBoost / MILEnsemble)");
+        case ONLINE_ADABOOST: return StrongClassifierBasePtr(new AdaBoostClassifier(ctx, p));
+        default: throw MctHostError(MCT_E_UNSUPPORTED, "strong classifier type is outside the B200 hot path (MILEnsemble)");
     }
 }
 }  // namespace Classifier

@@ -206,6 +206,9 @@ typedef std::shared_ptr<StrongClassifierParametersBase> StrongClassifierParamete
 struct MILBoostClassifierParameters : StrongClassifierParametersBase {
     MILBoostClassifierParameters(int k, int f) : StrongClassifierParametersBase(ONLINE_STOCHASTIC_BOOST_MIL, k, f) {}
 };
+struct AdaBoostClassifierParameters : StrongClassifierParametersBase {          // ClassifierParameters.h:68-85
+    AdaBoostClassifierParameters(int k, int f) : StrongClassifierParametersBase(ONLINE_ADABOOST, k, f) {}
+};
 struct MILAnyBoostClassifierParameters : StrongClassifierParametersBase {
     MILAnyBoostClassifierParameters(int k, int f) : StrongClassifierParametersBase(ONLINE_ANY_BOOST_MIL, k, f) {}
 };
@@ -230,6 +233,12 @@ protected:
 typedef std::shared_ptr<StrongClassifierBase> StrongClassifierBasePtr;
 class MILBoostClassifier : public StrongClassifierBase { public: using StrongClassifierBase::StrongClassifierBase; };
 class MILAnyBoostClassifier : public StrongClassifierBase { public: using StrongClassifierBase::StrongClassifierBase; };
+// AdaBoostClassifier.h: online boosting (Oza / Grabner); GetAlphaList = m_alphaList of the selected weak classifiers
+class AdaBoostClassifier : public StrongClassifierBase {
+public:
+    using StrongClassifierBase::StrongClassifierBase;
+    vectorf GetAlphaList();
+};
 
 // StrongClassifierFactory.h:9 (+ the device context the classifier lives on)
 struct StrongClassifierFactory {

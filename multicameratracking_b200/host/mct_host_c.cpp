@@ -107,6 +107,7 @@ static void make_params(const mcth_object_params& p, Classifier::StrongClassifie
     const int F = (int)fp->GetFeatureDimension();
     const int K = int(F * p.percent_selected / 100);
     if (p.strong_type == MCT_STRONG_MILANYBOOST) cp.reset(new Classifier::MILAnyBoostClassifierParameters(K, F));
+    else if (p.strong_type == MCT_STRONG_ADABOOST) cp.reset(new Classifier::AdaBoostClassifierParameters(K, F));
     else cp.reset(new Classifier::MILBoostClassifierParameters(K, F));
     cp->m_weakClassifierType = (Classifier::WeakClassifierType)p.weak_type;
     cp->m_featureParametersPtr = fp;
@@ -167,6 +168,7 @@ int mcth_camera_init_trackers(mcth_camera* c)
             const int K = int(F * p.percent_selected / 100);
             Classifier::StrongClassifierParametersBasePtr cp;
             if (p.strong_type == MCT_STRONG_MILANYBOOST) cp.reset(new Classifier::MILAnyBoostClassifierParameters(K, F));
+            else if (p.strong_type == MCT_STRONG_ADABOOST) cp.reset(new Classifier::AdaBoostClassifierParameters(K, F));
             else cp.reset(new Classifier::MILBoostClassifierParameters(K, F));
             cp->m_weakClassifierType = (Classifier::WeakClassifierType)p.weak_type;
             cp->m_featureParametersPtr = fp;

@@ -283,6 +283,8 @@ struct orc_clf {
     int* trained;
     int* sel; int n_sel;
     int cch_mode;
+    float *cTP, *cFP, *cTN, *cFN;                         /* AdaBoost: [K][F] running counts, initial value 1 (AdaBoostClassifier.cpp:27-36) */
+    float* alpha; float sum_alpha;                        /* [K] */
 };
 
 /* StrongClassifierBase.cpp:8-129 (K clamp :20-23; weak clf ctor: lr 0.85 then SetLearningRate) */
@@ -310,6 +312,12 @@ orc_clf* orc_clf_create(int feature_type, int n_haar, int nb, int w0, int h0, in
     c->pw0 = (float*)calloc(F, 4); c->pw1 = (float*)calloc(F, 4);
     c->trained = (int*)calloc(F, sizeof(int));
     c->sel = (int*)calloc(F, sizeof(int));
+    if (strong_type == ORC_STRONG_ADABOOST) {
+        size_t n = (size_t)c->K * F;
+        c->cTP = (float*)malloc(n * 4); c->cFP = (float*)malloc(n * 4); c->cTN = (float*)malloc(n * 4); c->cFN = (float*)malloc(n * 4);
+        for (size_t i = 0; i < n; i++) { c->cTP[i] = 1.0f; c->cFP[i] = 1.0f; c->cTN[i] = 1.0f; c->cFN[i] = 1.0f; }
+        c->alpha = (float*)calloc((size_t)c->K, 4);
+    }
     for (int f = 0; f < F; f++) { c->sig0[f] = 1; c->sig1[f] = 1; }  /* OnlineStumps::Initialize :53-60 */
     c->n_sel = 0;
     return c;
@@ -319,7 +327,8 @@ void orc_clf_free(orc_clf* c)
     if (!c) return;
     orc_haar_free(c->haar);
     free(c->mu0); free(c->mu1); free(c->sig0); free(c->sig1); free(c->n0); free(c->n1); free(c->e0); free(c->e1);
-    free(c->pw0); free(c->pw1); free(c->trained); free(c->sel); free(c);
+    free(c->pw0); free(c->pw1); free(c->trained); free(c->sel);
+    free(c->cTP); free(c->cFP); free(c->cTN); free(c->cFN); free(c->alpha); free(c);
 }
 int orc_clf_num_features(const orc_clf* c) { return c->F; }
 
@@ -620,6 +629,57 @@ static void milanyboost_select(orc_clf* c, const float* pp, int P, const float* 
 }
 
 /* MILBoostClassifier.cpp:15-157 / MILAnyBoostClassifier.cpp:14-254 from feature matrices */
+/* WeakClassifier::Classify (bool): OnlineStumps :68-75 compares the two class likelihoods, WeightedStumps (header :25) and
+   Perceptron (:61-68) take the sign of ClassifyF */
+static int weak_classify_bool(const orc_clf* c, int f, float xx)
+{
+    if (c->weak_type == ORC_WEAK_STUMP) {
+        float d0 = xx - c->mu0[f], d1 = xx - c->mu1[f];
+        float a0 = d0 * d0; a0 = a0 * c->e0[f];
+        float a1 = d1 * d1; a1 = a1 * c->e1[f];
+        double p0 = (double)(expf(a0) * c->n0[f]);
+        double p1 = (double)(expf(a1) * c->n1[f]);
+        return p1 > p0;
+    }
+    return weak_classify(c, f, xx) > 0;
+}
+/* AdaBoostClassifier::Update selection loop (AdaBoostClassifier.cpp:62-171): online boosting with running TP/FP/TN/FN
+   weights per (selector, weak classifier).  bp [F][P], bn [F][Nn] = ClassifySet labels.  sort_order sorts errs in place,
+   so errs[k] IS the error of order[k]; ties in std::sort are unspecified in the reference, index order here. */
+static void adaboost_select(orc_clf* c, const unsigned char* bp, int P, const unsigned char* bn, int Nn)
+{
+    int F = c->F, K = c->K;
+    float* poslam = (float*)malloc((size_t)(P > 0 ? P : 1) * 4);
+    float* neglam = (float*)malloc((size_t)(Nn > 0 ? Nn : 1) * 4);
+    for (int i = 0; i < P; i++) poslam[i] = .5f / (float)P;
+    for (int j = 0; j < Nn; j++) neglam[j] = .5f / (float)Nn;
+    vi_t* errs = (vi_t*)malloc((size_t)F * sizeof(vi_t));
+    c->sum_alpha = 0.0f; c->n_sel = 0;
+    for (int s = 0; s < K; s++) {
+        float *TP = c->cTP + (size_t)s * F, *FP = c->cFP + (size_t)s * F, *TN = c->cTN + (size_t)s * F, *FN = c->cFN + (size_t)s * F;
+        for (int w = 0; w < F; w++) {
+            for (int i = 0; i < P; i++) { if (bp[(size_t)w * P + i]) TP[w] += poslam[i]; else FP[w] += poslam[i]; }
+            for (int j = 0; j < Nn; j++) { if (!bn[(size_t)w * Nn + j]) TN[w] += neglam[j]; else FN[w] += neglam[j]; }
+            errs[w].v = (FP[w] + FN[w]) / (FP[w] + FN[w] + TP[w] + TN[w]);
+            errs[w].i = w;
+        }
+        qsort(errs, (size_t)F, sizeof(vi_t), cmp_asc);
+        float minerr = 0; int bestind = 0, found = 0;
+        for (int k = 0; k < F; k++) {
+            if (!in_list(c->sel, c->n_sel, errs[k].i)) { c->sel[c->n_sel++] = errs[k].i; minerr = errs[k].v; bestind = errs[k].i; found = 1; break; }
+        }
+        (void)found;
+        float a = 0.5f * logf((1 - minerr) / (minerr + 0.00001f));
+        if (a > (float)10) a = (float)10;
+        if (a < (float)0) a = (float)0;
+        c->alpha[s] = a;
+        c->sum_alpha += a;
+        float corw = 1 / (2 - 2 * minerr), incorw = 1 / (2 * minerr);
+        for (int j = 0; j < P; j++) poslam[j] *= (bp[(size_t)bestind * P + j] == 1) ? corw : incorw;
+        for (int j = 0; j < Nn; j++) neglam[j] *= (bn[(size_t)bestind * Nn + j] == 0) ? corw : incorw;
+    }
+    free(poslam); free(neglam); free(errs);
+}
 void orc_clf_update_from_features(orc_clf* c, const float* fpos, int P, const float* fneg, int Nn,
                                   const float* wpos, const float* wneg)
 {
@@ -641,7 +701,17 @@ void orc_clf_update_from_features(orc_clf* c, const float* fpos, int P, const fl
         for (int i = 0; i < P; i++) pp[(size_t)f * P + i] = weak_classify(c, f, xp[i]);
         for (int j = 0; j < Nn; j++) pn[(size_t)f * Nn + j] = weak_classify(c, f, xn[j]);
     }
-    if (c->strong_type == ORC_STRONG_MILANYBOOST) milanyboost_select(c, pp, P, pn, Nn);
+    if (c->strong_type == ORC_STRONG_ADABOOST) {
+        unsigned char* bp = (unsigned char*)malloc((size_t)F * (P > 0 ? P : 1));
+        unsigned char* bn = (unsigned char*)malloc((size_t)F * (Nn > 0 ? Nn : 1));
+        for (int f = 0; f < F; f++) {
+            for (int i = 0; i < P; i++) bp[(size_t)f * P + i] = (unsigned char)weak_classify_bool(c, f, fpos[(size_t)f * P + i]);
+            for (int j = 0; j < Nn; j++) bn[(size_t)f * Nn + j] = (unsigned char)weak_classify_bool(c, f, fneg[(size_t)f * Nn + j]);
+        }
+        adaboost_select(c, bp, P, bn, Nn);
+        free(bp); free(bn);
+    }
+    else if (c->strong_type == ORC_STRONG_MILANYBOOST) milanyboost_select(c, pp, P, pn, Nn);
     else milboost_select(c, pp, P, pn, Nn);
     free(pp); free(pn); free(pwn); free(nwn);
 }
@@ -662,6 +732,14 @@ void orc_clf_update(orc_clf* c, const orc_frame* f, const orc_boxes* pos, const 
 void orc_clf_classify_from_features(const orc_clf* c, const float* feat, int n, int ld, int log_ratio, float* out)
 {
     for (int i = 0; i < n; i++) out[i] = 0.0f;
+    if (c->strong_type == ORC_STRONG_ADABOOST) {                   /* AdaBoostClassifier::Classify :181-224 */
+        for (int s = 0; s < c->n_sel; s++) {
+            int f = c->sel[s];
+            for (int i = 0; i < n; i++) out[i] += weak_classify_bool(c, f, feat[(size_t)f * ld + i]) ? c->alpha[s] : -c->alpha[s];
+        }
+        if (!log_ratio) for (int i = 0; i < n; i++) out[i] = sigmoidf_(2 * out[i]);
+        return;
+    }
     for (int s = 0; s < c->n_sel; s++) {
         int f = c->sel[s];
         for (int i = 0; i < n; i++) out[i] += weak_classify(c, f, feat[(size_t)f * ld + i]);
@@ -675,6 +753,12 @@ void orc_clf_classify(const orc_clf* c, const orc_frame* f, const orc_boxes* b, 
     orc_clf_features(c, f, b, feat, b->n);      /* the reference computes ALL F (:345-348) */
     orc_clf_classify_from_features(c, feat, b->n, b->n, log_ratio, out);
     free(feat);
+}
+int orc_clf_get_alphas(const orc_clf* c, float* a)
+{
+    if (!c->alpha) return 0;
+    for (int i = 0; i < c->n_sel; i++) a[i] = c->alpha[i];
+    return c->n_sel;
 }
 int orc_clf_get_selectors(const orc_clf* c, int* idx)
 {

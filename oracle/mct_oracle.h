@@ -75,7 +75,7 @@ void orc_cch_compute(const uint8_t* hue, int pitch, int w0, int h0, const orc_bo
 /* ---- strong classifier (StrongClassifierBase + MILBoost / MILAnyBoost + weak clfs) ---- */
 enum { ORC_FEAT_HAAR = 0, ORC_FEAT_CCH = 1, ORC_FEAT_MDCH = 2, ORC_FEAT_HAAR_MDCH = 3 };   /* FeatureParameters.h:12-16 */
 enum { ORC_WEAK_STUMP = 0, ORC_WEAK_WSTUMP = 1, ORC_WEAK_PERCEPTRON = 2 };                 /* WeakClassifierBase.h:13-16 */
-enum { ORC_STRONG_MILBOOST = 2, ORC_STRONG_MILANYBOOST = 4 };                              /* ClassifierParameters.h:11-18 */
+enum { ORC_STRONG_ADABOOST = 0, ORC_STRONG_MILBOOST = 2, ORC_STRONG_MILANYBOOST = 4 };                              /* ClassifierParameters.h:11-18 */
 
 typedef struct {
     const uint8_t* gray; const uint8_t* c0; const uint8_t* c1; const uint8_t* c2;
@@ -101,6 +101,7 @@ void orc_clf_classify_from_features(const orc_clf* c, const float* feat, int n, 
 int  orc_clf_get_selectors(const orc_clf* c, int* idx);
 /* weak state rows: mu0,mu1,sig0,sig1,n0,n1,e0,e1 (stumps) or w0,thr (perceptron, rows 0,1) */
 void orc_clf_get_weak_state(const orc_clf* c, float* out8xF);
+int  orc_clf_get_alphas(const orc_clf* c, float* alphas);   /* AdaBoost voting weights of the selected weak classifiers */
 void orc_clf_set_threads(int n);   /* honours the reference's (compiled-out) omp pragmas when built with -fopenmp */
 
 /* ---- likelihood map: ParticleFilterTracker.cpp:541-566 ---- */

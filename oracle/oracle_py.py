@@ -104,6 +104,7 @@ class Oracle:
         L.orc_clf_classify_from_features.argtypes = [C.c_void_p, _c_float_p, C.c_int, C.c_int, C.c_int, _c_float_p]
         L.orc_clf_get_selectors.argtypes = [C.c_void_p, _c_int_p]; L.orc_clf_get_selectors.restype = C.c_int
         L.orc_clf_get_weak_state.argtypes = [C.c_void_p, _c_float_p]
+        L.orc_clf_get_alphas.argtypes = [C.c_void_p, _c_float_p]; L.orc_clf_get_alphas.restype = C.c_int
         L.orc_clf_set_threads.argtypes = [C.c_int]
         L.orc_likelihood_map.argtypes = [_c_float_p, C.c_int, C.c_int]
         L.orc_pf_create.argtypes = [C.c_int, C.c_float, C.c_float]; L.orc_pf_create.restype = C.POINTER(Pf)
@@ -239,6 +240,11 @@ class Oracle:
         idx = np.zeros(F, np.int32)
         n = self.lib.orc_clf_get_selectors(clf, _ip(idx))
         return idx[:n].copy()
+
+    def clf_alphas(self, clf):
+        a = np.zeros(4096, np.float32)
+        n = self.lib.orc_clf_get_alphas(clf, _fp(a))
+        return a[:n].copy()
 
     def clf_weak_state(self, clf):
         F = self.lib.orc_clf_num_features(clf)

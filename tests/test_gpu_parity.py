@@ -210,6 +210,9 @@ CASES = [
     ("haarmdch_wstump_milboost", capi.FEAT_HAAR_MDCH, capi.WEAK_WSTUMP, capi.STRONG_MILBOOST, 250, 152),
     ("mdch_stump_anyboost", capi.FEAT_MDCH, capi.WEAK_STUMP, capi.STRONG_MILANYBOOST, 0, 102),
     ("haar_stump_anyboost", capi.FEAT_HAAR, capi.WEAK_STUMP, capi.STRONG_MILANYBOOST, 250, 50),
+    ("haar_stump_adaboost", capi.FEAT_HAAR, capi.WEAK_STUMP, capi.STRONG_ADABOOST, 250, 50),
+    ("haarmdch_wstump_adaboost", capi.FEAT_HAAR_MDCH, capi.WEAK_WSTUMP, capi.STRONG_ADABOOST, 100, 60),
+    ("haar_perceptron_adaboost", capi.FEAT_HAAR, capi.WEAK_PERCEPTRON, capi.STRONG_ADABOOST, 60, 12),
 ]
 
 
@@ -238,15 +241,27 @@ def test_update_and_classify(ctx, oracle, case):
             rel_close(st_g[q], st_o[q], rtol=2e-5)
         sel_g, sel_o = clf.selectors().tolist(), oracle.clf_selectors(oclf).tolist()
         assert sel_g == sel_o, (name, frame)
+        ada = stype == capi.STRONG_ADABOOST
+        if ada:                                  # voting weights (AdaBoostClassifier.cpp:147-150)
+            rel_close(clf.alphas(), oracle.clf_alphas(oclf), rtol=2e-5)
         # Classify on fresh boxes
         col, row, sx, sy = rand_boxes(rng, 500, 640, 480, w0, h0, frame == 2)
         Hg = clf.Classify(capi.make_boxes(col, row, sx, sy))
         Ho = oracle.clf_classify(oclf, of, oracle.boxes(col, row, sx, sy))
-        rel_close(Hg, Ho)
+        if ada:
+            # H is a sum of +-alpha votes: a box sitting on a weak classifier's decision boundary may flip one vote between libm
+            # and CUDA (expf differs in the last bit); everything else agrees to 1e-5
+            bad = np.abs(Hg - Ho) > 1e-5 * np.maximum(1.0, np.abs(Ho))
+            assert bad.mean() <= 0.01, (name, frame, int(bad.sum()))
+        else:
+            rel_close(Hg, Ho)
         if frame == 0:
             Pg = clf.Classify(capi.make_boxes(col, row, sx, sy), False)
             Po = oracle.clf_classify(oclf, of, oracle.boxes(col, row, sx, sy), False)
-            rel_close(Pg, Po)
+            if ada:
+                assert (np.abs(Pg - Po) > 1e-5).mean() <= 0.01
+            else:
+                rel_close(Pg, Po)
     clf.close()
     oracle.lib.orc_clf_free(oclf)
 

@@ -178,7 +178,7 @@ def test_geometric_fusion_feedback_two_cameras(oracle):
         cam.close()
 
 
-@pytest.mark.parametrize("cfg", ["haar_milboost", "haarmdch_3obj", "single_positive_r1"])
+@pytest.mark.parametrize("cfg", ["haar_milboost", "haarmdch_3obj", "single_positive_r1", "haar_adaboost"])
 def test_simple_tracker_sequence_matches_oracle(oracle, cfg):
     """SimpleTracker (the reference's default Local_Tracker_Type 0, SimpleTracker.cpp): exhaustive search window scored by the
     strong classifier, best response wins, classifier updated around the new position.  All objects of the camera go through
@@ -189,6 +189,9 @@ def test_simple_tracker_sequence_matches_oracle(oracle, cfg):
         n_obj, over = 1, dict(search_win=20)
     elif cfg == "haarmdch_3obj":
         n_obj, over = 3, dict(feature_type=3, weak_type=1, n_haar=100, search_win=15)
+    elif cfg == "haar_adaboost":
+        # the reference's other default pairing: SimpleTracker + online AdaBoost (Tracker_Strong_Classifier_Type 2 in config.cfg)
+        n_obj, over = 2, dict(strong_type=0, search_win=15, n_haar=150)
     else:
         # posRadiusTrain 1: the single current box is the only positive (SimpleTracker.cpp:375-386).
         # (MILAnyBoost on top of empty MDCH bins is avoided here on purpose: its retry branch subtracts and re-adds prediction
