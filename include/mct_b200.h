@@ -40,7 +40,7 @@ enum { MCT_FEAT_HAAR = 0, MCT_FEAT_CCH = 1, MCT_FEAT_MDCH = 2, MCT_FEAT_HAAR_MDC
 /* Classifier::WeakClassifierType (WeakClassifierBase.h:13-16) */
 enum { MCT_WEAK_STUMP = 0, MCT_WEAK_WSTUMP = 1, MCT_WEAK_PERCEPTRON = 2 };
 /* Classifier::StrongClassifierType (ClassifierParameters.h:11-18) */
-enum { MCT_STRONG_ADABOOST = 0, MCT_STRONG_MILBOOST = 2, MCT_STRONG_MILANYBOOST = 4 };   /* ClassifierParameters.h:11-18 */
+enum { MCT_STRONG_ADABOOST = 0, MCT_STRONG_MILBOOST = 2, MCT_STRONG_MILENSEMBLE = 3, MCT_STRONG_MILANYBOOST = 4 };   /* ClassifierParameters.h:11-18 */
 /* ParticleFilter::State (ParticleFilter.h:33-37) */
 enum { MCT_PF_UNINIT = 0, MCT_PF_INIT = 1, MCT_PF_PREDICTED = 2, MCT_PF_RESAMPLED = 3 };
 
@@ -124,6 +124,8 @@ typedef struct {
     int   cch_mode;          /* 0 = reference_exact, 1 = intended */
     int   max_train;         /* capacity for P + Nn training boxes (0 -> 4096) */
     int   max_test;          /* capacity for test boxes per classify call (0 -> 65536) */
+    float pct_retained;      /* MILEnsemble only: Percentage_Of_Weak_Classifiers_Retained, in percent
+                              * (MILEnsembleClassifierParameters, ClassifierParameters.h:105-117; stored / 100.0f, :52) */
 } mct_clf_params;
 
 /* Haar table generated on the host with the reference RNG order (HaarFeature.cpp:25-69). */

@@ -18,7 +18,7 @@ _c_u8_p = C.POINTER(C.c_uint8)
 OK, E_ARG, E_CUDA, E_STATE, E_EMPTY, E_NOMEM, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 FEAT_HAAR, FEAT_CCH, FEAT_MDCH, FEAT_HAAR_MDCH = 0, 1, 2, 3
 WEAK_STUMP, WEAK_WSTUMP, WEAK_PERCEPTRON = 0, 1, 2
-STRONG_ADABOOST, STRONG_MILBOOST, STRONG_MILANYBOOST = 0, 2, 4
+STRONG_ADABOOST, STRONG_MILBOOST, STRONG_MILENSEMBLE, STRONG_MILANYBOOST = 0, 2, 3, 4
 PF_UNINIT, PF_INIT, PF_PREDICTED, PF_RESAMPLED = 0, 1, 2, 3
 
 # every symbol include/mct_b200.h declares (checked by tests/test_abi.py)
@@ -50,7 +50,7 @@ class Boxes(C.Structure):
 class ClfParams(C.Structure):
     _fields_ = [("feature_type", C.c_int), ("n_haar", C.c_int), ("n_bins", C.c_int), ("w0", C.c_int), ("h0", C.c_int),
                 ("weak_type", C.c_int), ("strong_type", C.c_int), ("n_selected", C.c_int), ("learning_rate", C.c_float),
-                ("cch_mode", C.c_int), ("max_train", C.c_int), ("max_test", C.c_int)]
+                ("cch_mode", C.c_int), ("max_train", C.c_int), ("max_test", C.c_int), ("pct_retained", C.c_float)]
 
 
 class HaarTable(C.Structure):
@@ -296,11 +296,11 @@ class StrongClassifier:
     """StrongClassifierBase behind StrongClassifierFactory::CreateAndInitializeClassifier."""
 
     def __init__(self, ctx, feature_type, w0, h0, n_haar=0, n_bins=8, weak_type=WEAK_STUMP, strong_type=STRONG_MILBOOST,
-                 n_selected=0, learning_rate=0.85, haar=None, cch_mode=0, max_train=4096):
+                 n_selected=0, learning_rate=0.85, haar=None, cch_mode=0, max_train=4096, pct_retained=0.0):
         self.ctx = ctx
         L = ctx.L
         p = ClfParams(feature_type, n_haar, n_bins, w0, h0, weak_type, strong_type, n_selected, learning_rate, cch_mode,
-                      max_train, 0)
+                      max_train, 0, pct_retained)
         ht = None
         if haar is not None:
             nrect, rects, weights = haar

@@ -602,10 +602,271 @@ __global__ void __launch_bounds__(ADA_THREADS) k_adaboost_select(const float* __
 static size_t ada_smem(int F, int M) { return (size_t)M * 4 + (size_t)F * ((M + 31) / 32) * 4 + (size_t)F + 16; }
 
 // ------------------------------------------------------------------------------------------
+// k_ensemble_retain / k_ensemble_select: MILEnsembleClassifier::Update (MILEnsembleClassifier.cpp:14-157) and
+// RetainBestPerformingWeakClassifiers (:206-337).  Same greedy bag-likelihood selection as MILBoost with three differences
+// that matter for the bits: (1) the previous frame's selectors are re-ranked on the new samples with their OLD weak state
+// and the best pct% of them are kept (f32 product chain, :270); (2) the main loop accumulates the positive bag product and
+// the negative sum in DOUBLE (:88, :100) and has no IsValidWeakClassifier test (:114); (3) sort_order (Public.h:213-228)
+// sorts the values in place, so `negLogLikelihoodList[order[k]]` (:131, :321) is the value of RANK order[k], not the chosen
+// candidate's -- that value is what the next round's stopping test sees.  It is reproduced with an exact rank sort
+// (ties -> lowest index, like the oracle; std::sort's tie order is unspecified).
+// One thread-block cluster per classifier, candidates split over its CTAs; per round
+//   terms   all threads: 1 - sigmoid(H + p) / -logf(1e-5f + 1 - sigmoid(H + p)) of the CTA's candidates into shared rows,
+//   chains  one thread per candidate, in sample order (f32 or f64 as the reference has it) -> nll into a global row,
+//   cluster barrier, every CTA reads all nll, ranks its own candidates (warp per candidate) into the sorted row and
+//   takes the block arg-min over the unselected candidates, cluster barrier, every CTA applies the same decision.
+// Rows written by other CTAs of the cluster during the kernel are read with ld.cg (L2), never through L1 / the nc path.
+#define ENS_THREADS 1024
+#define ENS_MAX_CLUSTER 8
+template <bool RETAIN>
+__device__ __forceinline__ void
+ensemble_body(const float* __restrict__ feat, float* pred, int ld, int F, int P, int Nn, int K, const float* __restrict__ weak, int weak_type,
+              float pct, int* sel, int* nsel, int* keep, float* ensH, float* gscr, int FC)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    const int M = P + Nn, MS = M | 1;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    float* Hs = (float*)smraw;                       // [M]
+    float* nllS = Hs + M;                            // [F] all candidates' nll of the round
+    int* cand = (int*)(nllS + F);                    // [F] candidate -> weak classifier index
+    float* terms = (float*)(cand + F);               // [FC][MS]
+    unsigned char* flag = (unsigned char*)(terms + (size_t)FC * MS);   // [F] candidate already taken
+    __shared__ SelSlot sh[ENS_THREADS / 32];
+    __shared__ int s_best, s_stop;
+    float* gnll = gscr; float* gsorted = gscr + F;
+
+    const int n0 = *nsel;                            // previous selectors (RETAIN) / retained selectors (select)
+    int NC, rounds_end, n_sel;
+    if (RETAIN) {
+        NC = n0;
+        for (int q = tid; q < NC; q += nt) { cand[q] = sel[q]; flag[q] = 0; }
+        for (int i = tid; i < M; i += nt) Hs[i] = 0.0f;
+        n_sel = 0;
+        rounds_end = (int)__fmul_rn(pct, (float)n0);                         // :214
+        if (rounds_end > NC) rounds_end = NC;
+    } else {
+        NC = F;
+        for (int q = tid; q < NC; q += nt) { cand[q] = q; flag[q] = 0; }
+        for (int i = tid; i < M; i += nt) Hs[i] = ensH[i];
+        __syncthreads();
+        for (int q = tid; q < n0; q += nt) flag[sel[q]] = 1;
+        n_sel = n0;
+        rounds_end = K;
+    }
+    cluster.sync();                                  // everybody holds its copy of sel / nsel before CTA 0 rewrites them
+    if (RETAIN) {
+        if (rank == 0) {
+            for (int f = tid; f < F; f += nt) keep[f] = 0;
+            if (n0 == 0 || rounds_end == 0) {
+                for (int i = tid; i < M; i += nt) ensH[i] = 0.0f;
+                if (tid == 0) *nsel = 0;
+            }
+        }
+        if (n0 == 0 || rounds_end == 0) return;
+    }
+    const int FL = (NC + C - 1) / C;
+    const int q0 = min(NC, rank * FL), q1 = min(NC, q0 + FL);
+    if (RETAIN) {
+        // predictions of the previous selectors on the new samples, old weak state (:251-257)
+        for (int idx = tid; idx < (q1 - q0) * M; idx += nt) {
+            const int c = idx / M, i = idx - c * M, f = cand[q0 + c];
+            const float mu0 = weak[0 * (size_t)F + f], mu1 = weak[1 * (size_t)F + f];
+            const float a0 = weak[4 * (size_t)F + f], a1 = weak[5 * (size_t)F + f], e0 = weak[6 * (size_t)F + f], e1 = weak[7 * (size_t)F + f];
+            pred[(size_t)f * ld + i] = weak_classify_q_dev(weak_type, feat[(size_t)f * ld + i], mu0, mu1, a0, a1, e0, e1);
+        }
+        __threadfence();
+        cluster.sync();
+    }
+    double prev = 1000000.0;
+    const float fP = (float)P, fN = (float)Nn;
+    for (int s = n_sel; s < rounds_end; s++) {
+        for (int c0 = q0; c0 < q1; c0 += FC) {
+            const int nc = min(FC, q1 - c0);
+            for (int idx = tid; idx < nc * M; idx += nt) {
+                const int c = idx / M, i = idx - c * M;
+                const float x = __fadd_rn(Hs[i], __ldcg(pred + (size_t)cand[c0 + c] * ld + i));
+                const float sg = sigmoid_dev(x);
+                terms[(size_t)c * MS + i] = i < P ? __fsub_rn(1.0f, sg) : -logf(__fsub_rn(__fadd_rn(1e-5f, 1.0f), sg));
+            }
+            __syncthreads();
+            if (tid < nc) {
+                const float* row = terms + (size_t)tid * MS;
+                float posl, negl;
+                if (RETAIN) {
+                    float like = 1.0f;
+                    for (int i = 0; i < P; i++) like = __fmul_rn(like, row[i]);
+                    posl = (float)(-log((double)__fsub_rn(1.0f, like) + 1e-5));
+                    float a = 0.0f;
+                    for (int j = P; j < M; j++) a = __fadd_rn(a, row[j]);
+                    negl = a;
+                } else {
+                    double like = 1.0;
+                    for (int i = 0; i < P; i++) like = __dmul_rn(like, (double)row[i]);
+                    posl = (float)(-log(__dadd_rn(__dsub_rn(1.0, like), 1e-5)));
+                    double a = 0.0;
+                    for (int j = P; j < M; j++) a = __dadd_rn(a, (double)row[j]);
+                    negl = (float)a;
+                }
+                gnll[c0 + tid] = __fadd_rn(__fdiv_rn(posl, fP), __fdiv_rn(negl, fN));
+            }
+            __syncthreads();
+        }
+        __threadfence();
+        cluster.sync();
+        for (int q = tid; q < NC; q += nt) nllS[q] = __ldcg(gnll + q);
+        __syncthreads();
+        // rank of the CTA's own candidates in the stable ascending order -> sorted row
+        for (int q = q0 + warp; q < q1; q += nw) {
+            const float v = nllS[q];
+            int cnt = 0;
+            for (int u = lane; u < NC; u += 32) { const float o = nllS[u]; cnt += (o < v || (o == v && u < q)) ? 1 : 0; }
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (lane == 0) gsorted[cnt] = v;
+        }
+        // first candidate of the order that is not taken yet
+        float bv = CUDART_INF_F; int bf = 0x7fffffff;
+        for (int q = tid; q < NC; q += nt) { const float v = nllS[q]; if (!flag[q] && better_min(v, q, bv, bf)) { bv = v; bf = q; } }
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int of = __shfl_xor_sync(0xffffffffu, bf, o);
+            if (better_min(ov, of, bv, bf)) { bv = ov; bf = of; }
+        }
+        if (lane == 0) { sh[warp].nll = bv; sh[warp].f = bf; }
+        __threadfence();
+        cluster.sync();
+        if (tid == 0) {
+            float v = sh[0].nll; int f = sh[0].f;
+            for (int w = 1; w < nw; w++) if (better_min(sh[w].nll, sh[w].f, v, f)) { v = sh[w].nll; f = sh[w].f; }
+            int stop = 0;
+            if (f == 0x7fffffff) stop = 1;                                       // every candidate taken (:304-307)
+            else if ((prev - (double)v) < 1e-100) stop = 1;                      // :122-127 / :309-314 push then pop
+            s_best = f; s_stop = stop;
+        }
+        __syncthreads();
+        if (s_stop) break;
+        const int best = s_best, bw = cand[best];
+        prev = (double)__ldcg(gsorted + best);                                   // negLogLikelihoodList[order[k]] after the in-place sort
+        for (int i = tid; i < M; i += nt) Hs[i] = __fadd_rn(Hs[i], __ldcg(pred + (size_t)bw * ld + i));
+        if (tid == 0) { flag[best] = 1; if (rank == 0) { sel[n_sel] = bw; if (RETAIN) keep[bw] = 1; } }
+        n_sel++;
+        __syncthreads();
+    }
+    if (rank == 0) {
+        if (RETAIN) for (int i = tid; i < M; i += nt) ensH[i] = Hs[i];
+        if (tid == 0) *nsel = n_sel;
+    }
+}
+__global__ void __launch_bounds__(ENS_THREADS) k_ensemble_retain_batch(const TrainDesc* __restrict__ descs, int FC)
+{
+    const TrainDesc& d = descs[blockIdx.y];
+    if (d.strong_type != MCT_STRONG_MILENSEMBLE) return;
+    ensemble_body<true>(d.featT, d.pred, d.ldT, d.F, d.P, d.Nn, d.K, d.weak, d.weak_type, d.pct_retained, d.sel, d.nsel, d.keep, d.ensH, d.ensH + d.ldT, FC);
+}
+__global__ void __launch_bounds__(ENS_THREADS) k_ensemble_select_batch(const TrainDesc* __restrict__ descs, int FC)
+{
+    const TrainDesc& d = descs[blockIdx.y];
+    if (d.strong_type != MCT_STRONG_MILENSEMBLE) return;
+    ensemble_body<false>(d.featT, d.pred, d.ldT, d.F, d.P, d.Nn, d.K, d.weak, d.weak_type, d.pct_retained, d.sel, d.nsel, d.keep, d.ensH, d.ensH + d.ldT, FC);
+}
+__global__ void __launch_bounds__(ENS_THREADS)
+k_ensemble_retain(const float* __restrict__ feat, float* pred, int ld, int F, int P, int Nn, int K, const float* __restrict__ weak, int weak_type,
+                  float pct, int* sel, int* nsel, int* keep, float* ensH, int FC)
+{
+    ensemble_body<true>(feat, pred, ld, F, P, Nn, K, weak, weak_type, pct, sel, nsel, keep, ensH, ensH + ld, FC);
+}
+__global__ void __launch_bounds__(ENS_THREADS)
+k_ensemble_select(const float* __restrict__ feat, float* pred, int ld, int F, int P, int Nn, int K, const float* __restrict__ weak, int weak_type,
+                  float pct, int* sel, int* nsel, int* keep, float* ensH, int FC)
+{
+    ensemble_body<false>(feat, pred, ld, F, P, Nn, K, weak, weak_type, pct, sel, nsel, keep, ensH, ensH + ld, FC);
+}
+// cluster width and candidate chunk of the ensemble kernels: NC candidates (K for the retain step, F for the selection)
+static size_t ens_plan(int F, int M, int NC, int* C_out, int* FC_out)
+{
+    int C = 1;
+    while (C < ENS_MAX_CLUSTER && NC / (2 * C) >= 24) C <<= 1;
+    const int FL = ceil_div(NC, C), MS = M | 1;
+    const size_t base = (size_t)M * 4 + (size_t)F * 8 + (size_t)F;
+    int FC = (int)(((size_t)160 * 1024) / ((size_t)MS * 4));
+    if (FC > FL) FC = FL;
+    if (FC > ENS_THREADS) FC = ENS_THREADS;
+    if (FC < 1) FC = 1;
+    *C_out = C; *FC_out = FC;
+    return (base + (size_t)FC * MS * 4 + 15) & ~(size_t)15;
+}
+template <typename KernT, typename... Args>
+static int ens_launch(mct_ctx* ctx, const char* name, KernT kern, size_t* attr_state, dim3 grid, int C, size_t smem, Args... args)
+{
+    if (smem > 220 * 1024) return mct_fail(ctx, MCT_E_UNSUPPORTED, "training set too large for the MILEnsemble kernels%s");
+    if (smem > *attr_state) {
+        MCT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        *attr_state = smem;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(ENS_THREADS, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    mct_prof_begin(ctx, name);
+    MCT_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, args...));
+    mct_prof_end(ctx);
+    MCT_KERNEL_CHECK(ctx);
+    return MCT_OK;
+}
+int launch_ensemble_retain(mct_clf* clf, int P, int Nn)
+{
+    if (clf->p.strong_type != MCT_STRONG_MILENSEMBLE) return MCT_OK;
+    int C, FC;
+    const size_t smem = ens_plan(clf->F, P + Nn, clf->K, &C, &FC);
+    static size_t s_attr = 0;
+    return ens_launch(clf->ctx, "k_ensemble_retain", k_ensemble_retain, &s_attr, dim3(C, 1, 1), C, smem, (const float*)clf->d_featT, clf->d_pred, clf->ldT,
+                      clf->F, P, Nn, clf->K, (const float*)clf->d_weak, clf->p.weak_type, clf->p.pct_retained / 100.0f, clf->d_sel, clf->d_nsel,
+                      clf->d_keep, clf->d_ensH, FC);
+}
+static int launch_ensemble_select(mct_clf* clf, int P, int Nn)
+{
+    int C, FC;
+    const size_t smem = ens_plan(clf->F, P + Nn, clf->F, &C, &FC);
+    static size_t s_attr = 0;
+    return ens_launch(clf->ctx, "k_ensemble_select", k_ensemble_select, &s_attr, dim3(C, 1, 1), C, smem, (const float*)clf->d_featT, clf->d_pred, clf->ldT,
+                      clf->F, P, Nn, clf->K, (const float*)clf->d_weak, clf->p.weak_type, clf->p.pct_retained / 100.0f, clf->d_sel, clf->d_nsel,
+                      clf->d_keep, clf->d_ensH, FC);
+}
+// batched forms: the plan covers the largest ensemble classifier of the camera
+static int ens_batch_plan(const TrainDesc* h, int n_obj, int retain, int* C_out, int* FC_out, size_t* smem_out)
+{
+    int any = 0, F = 0, M = 0, NC = 0;
+    for (int o = 0; o < n_obj; o++) {
+        if (h[o].strong_type != MCT_STRONG_MILENSEMBLE) continue;
+        any = 1; F = max(F, h[o].F); M = max(M, h[o].P + h[o].Nn); NC = max(NC, retain ? h[o].K : h[o].F);
+    }
+    if (any) *smem_out = ens_plan(F, M, NC, C_out, FC_out);
+    return any;
+}
+int launch_ensemble_retain_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj)
+{
+    int C, FC; size_t smem;
+    if (!ens_batch_plan(h, n_obj, 1, &C, &FC, &smem)) return MCT_OK;
+    static size_t s_attr = 0;
+    return ens_launch(ctx, "k_ensemble_retain_batch", k_ensemble_retain_batch, &s_attr, dim3(C, n_obj, 1), C, smem, d, FC);
+}
+static int launch_ensemble_select_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj)
+{
+    int C, FC; size_t smem;
+    if (!ens_batch_plan(h, n_obj, 0, &C, &FC, &smem)) return MCT_OK;
+    static size_t s_attr = 0;
+    return ens_launch(ctx, "k_ensemble_select_batch", k_ensemble_select_batch, &s_attr, dim3(C, n_obj, 1), C, smem, d, FC);
+}
+
+// ------------------------------------------------------------------------------------------
 int launch_mil_select(mct_clf* clf, int P, int Nn)
 {
     mct_ctx* ctx = clf->ctx;
     const int F = clf->F, M = P + Nn;
+    if (clf->p.strong_type == MCT_STRONG_MILENSEMBLE) return launch_ensemble_select(clf, P, Nn);
     if (clf->p.strong_type == MCT_STRONG_ADABOOST) {
         const size_t smem = ada_smem(F, M);
         if (smem > 200 * 1024) return mct_fail(ctx, MCT_E_UNSUPPORTED, "training set too large for the AdaBoost kernel%s (M=%d)", "", M);
@@ -672,8 +933,10 @@ int launch_mil_select_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h
 {
     int any_mil = 0, any_any = 0, any_ada = 0, F_max = 0, M_max = 0, F_any = 0, M_any = 0, creq = 0;
     size_t smem_ada = 0;
+    { int rc = launch_ensemble_select_batch(ctx, d, h, n_obj); if (rc) return rc; }
     for (int o = 0; o < n_obj; o++) {
         const int M = h[o].P + h[o].Nn;
+        if (h[o].strong_type == MCT_STRONG_MILENSEMBLE) continue;
         if (h[o].strong_type == MCT_STRONG_ADABOOST) { any_ada = 1; smem_ada = max(smem_ada, ada_smem(h[o].F, M)); continue; }
         if (h[o].strong_type == MCT_STRONG_MILANYBOOST) { any_any = 1; F_any = max(F_any, h[o].F); M_any = max(M_any, M); }
         else { any_mil = 1; F_max = max(F_max, h[o].F); M_max = max(M_max, M); if (cluster_req && cluster_req[o] > creq) creq = cluster_req[o]; }

@@ -67,7 +67,7 @@ __device__ __forceinline__ float norm_scale(const float* w, int n, int lane)
 __device__ __forceinline__ void
 weak_update_body(const float* __restrict__ feat, int ld, int F, int P, int Nn, int weak_type, float lr,
               const float* __restrict__ tw, float* __restrict__ weak, int* __restrict__ trained,
-              float* __restrict__ pred)
+              float* __restrict__ pred, const int* __restrict__ keep)
 {
     const int lane = threadIdx.x & 31;
     const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -77,9 +77,15 @@ weak_update_body(const float* __restrict__ feat, int ld, int F, int P, int Nn, i
     float mu0 = weak[0 * (size_t)F + f], mu1 = weak[1 * (size_t)F + f];
     float sig0 = weak[2 * (size_t)F + f], sig1 = weak[3 * (size_t)F + f];
     float n0 = 0, n1 = 0, e0 = 0, e1 = 0;
-    const int was_trained = trained[f];
+    int was_trained = trained[f];
+    // MILEnsemble (MILEnsembleClassifier.cpp:56-72): a retained weak classifier keeps its state and is only evaluated;
+    // every other one is re-initialised (mu = 0, sig = 1, untrained) and trained from scratch on this set
+    const bool kept = keep != nullptr && keep[f] != 0;
+    if (keep != nullptr && !kept) { mu0 = 0.0f; mu1 = 0.0f; sig0 = 1.0f; sig1 = 1.0f; was_trained = 0; }
 
-    if (weak_type == MCT_WEAK_STUMP) {
+    if (kept) {
+        // state as loaded (the derived rows below are a function of sig0 / sig1 only)
+    } else if (weak_type == MCT_WEAK_STUMP) {
         // OnlineStumpsWeakClassifier::Update (OnlineStumpsWeakClassifier.cpp:99-151)
         const double sp = row_sum_d(xp, P, lane), sn = row_sum_d(xn, Nn, lane);
         const float pm = P > 0 ? (float)(sp / (double)P) : 0.0f;
@@ -159,15 +165,15 @@ weak_update_body(const float* __restrict__ feat, int ld, int F, int P, int Nn, i
 __global__ void __launch_bounds__(256)
 k_weak_update(const float* __restrict__ feat, int ld, int F, int P, int Nn, int weak_type, float lr,
               const float* __restrict__ tw, float* __restrict__ weak, int* __restrict__ trained,
-              float* __restrict__ pred)
+              float* __restrict__ pred, const int* __restrict__ keep)
 {
-    weak_update_body(feat, ld, F, P, Nn, weak_type, lr, tw, weak, trained, pred);
+    weak_update_body(feat, ld, F, P, Nn, weak_type, lr, tw, weak, trained, pred, keep);
 }
 // batched form: blockIdx.y = object
 __global__ void __launch_bounds__(256) k_weak_update_batch(const TrainDesc* __restrict__ descs)
 {
     const TrainDesc& d = descs[blockIdx.y];
-    weak_update_body(d.featT, d.ldT, d.F, d.P, d.Nn, d.weak_type, d.lr, d.tw, d.weak, d.trained, d.pred);
+    weak_update_body(d.featT, d.ldT, d.F, d.P, d.Nn, d.weak_type, d.lr, d.tw, d.weak, d.trained, d.pred, d.keep);
 }
 int launch_weak_update_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj)
 {
@@ -183,6 +189,7 @@ int launch_weak_update(mct_clf* clf, int P, int Nn, int has_weights)
     mct_ctx* ctx = clf->ctx;
     MCT_LAUNCH(ctx, "k_weak_update", k_weak_update<<<ceil_div(clf->F, 8), 256, 0, ctx->stream>>>(clf->d_featT, clf->ldT, clf->F, P, Nn, clf->p.weak_type,
                                                                clf->p.learning_rate, has_weights ? clf->d_tw : nullptr,
-                                                               clf->d_weak, clf->d_trained, clf->d_pred));
+                                                               clf->d_weak, clf->d_trained, clf->d_pred,
+                                                               clf->p.strong_type == MCT_STRONG_MILENSEMBLE ? clf->d_keep : nullptr));
     return MCT_OK;
 }

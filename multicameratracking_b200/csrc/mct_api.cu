@@ -562,8 +562,11 @@ extern "C" int mct_classifier_create(mct_ctx* ctx, const mct_clf_params* p, cons
         (p->n_bins < 1 || p->n_bins > 8 || 256 % p->n_bins != 0))
         return mct_fail(ctx, MCT_E_UNSUPPORTED, "Color_Number_Of_Bins must divide 256 and be <= 8%s (%d)", "", p->n_bins);
     if (p->weak_type < 0 || p->weak_type > 2) return mct_fail(ctx, MCT_E_ARG, "unknown weak classifier type%s (%d)", "", p->weak_type);
-    if (p->strong_type != MCT_STRONG_MILBOOST && p->strong_type != MCT_STRONG_MILANYBOOST && p->strong_type != MCT_STRONG_ADABOOST)
-        return mct_fail(ctx, MCT_E_UNSUPPORTED, "strong classifier type not on the hot path%s (%d)", "", p->strong_type);
+    if (p->strong_type != MCT_STRONG_MILBOOST && p->strong_type != MCT_STRONG_MILANYBOOST && p->strong_type != MCT_STRONG_ADABOOST &&
+        p->strong_type != MCT_STRONG_MILENSEMBLE)
+        return mct_fail(ctx, MCT_E_UNSUPPORTED, "unknown strong classifier type%s (%d)", "", p->strong_type);
+    if (p->strong_type == MCT_STRONG_MILENSEMBLE && !(p->pct_retained >= 0.0f && p->pct_retained <= 100.0f))
+        return mct_fail(ctx, MCT_E_ARG, "Percentage_Of_Weak_Classifiers_Retained outside [0, 100]%s");
     if (n_haar > 0 && (!haar || haar->n_features != n_haar || !haar->nrect || !haar->rects || !haar->weights))
         return mct_fail(ctx, MCT_E_ARG, "Haar table missing or of the wrong size%s");
     if (p->w0 < 4 || p->h0 < 4) return mct_fail(ctx, MCT_E_ARG, "object blob too small%s");
@@ -623,6 +626,13 @@ extern "C" int mct_classifier_create(mct_ctx* ctx, const mct_clf_params* p, cons
         MCT_CUDA(ctx, cudaMalloc(&c->d_alpha, (size_t)K * 4));
         MCT_CUDA(ctx, cudaMemset(c->d_alpha, 0, (size_t)K * 4));
     }
+    if (p->strong_type == MCT_STRONG_MILENSEMBLE) {
+        // retained flags; hypothesis left by the retain step followed by the round's nll / sorted rows
+        MCT_CUDA(ctx, cudaMalloc(&c->d_keep, (size_t)F * 4));
+        MCT_CUDA(ctx, cudaMemset(c->d_keep, 0, (size_t)F * 4));
+        MCT_CUDA(ctx, cudaMalloc(&c->d_ensH, ((size_t)c->ldT + 2 * (size_t)F) * 4));
+        MCT_CUDA(ctx, cudaMemset(c->d_ensH, 0, ((size_t)c->ldT + 2 * (size_t)F) * 4));
+    }
     MCT_CUDA(ctx, cudaMalloc(&c->d_tcol, (size_t)c->ldT * 4)); MCT_CUDA(ctx, cudaMalloc(&c->d_trow, (size_t)c->ldT * 4));
     MCT_CUDA(ctx, cudaMalloc(&c->d_tsx, (size_t)c->ldT * 4)); MCT_CUDA(ctx, cudaMalloc(&c->d_tsy, (size_t)c->ldT * 4));
     MCT_CUDA(ctx, cudaMalloc(&c->d_tw, (size_t)c->ldT * 4));
@@ -651,7 +661,8 @@ extern "C" int mct_classifier_destroy(mct_clf* c)
     cudaStreamSynchronize(c->ctx->stream);
     void* ptrs[] = {c->d_rects, c->d_wts, c->d_nrect, c->d_weak, c->d_trained, c->d_sel, c->d_nsel, c->d_seltab, c->d_selhdr, c->d_tcol, c->d_trow,
                     c->d_tsx, c->d_tsy, c->d_tw, c->d_featT, c->d_pred, c->d_col, c->d_row, c->d_sx, c->d_sy, c->d_featN,
-                    c->d_H, c->d_outbins, c->d_colorrow, c->d_slotmap, c->d_nout, c->d_big, c->d_nbig, c->d_tsort, c->d_ada_cnt, c->d_alpha};
+                    c->d_H, c->d_outbins, c->d_colorrow, c->d_slotmap, c->d_nout, c->d_big, c->d_nbig, c->d_tsort, c->d_ada_cnt, c->d_alpha,
+                    c->d_keep, c->d_ensH};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete c;
     return MCT_OK;
@@ -700,6 +711,7 @@ static int clf_train_common(mct_clf* c, int P, int Nn, const float* wpos, const 
         MCT_CUDA(ctx, cudaMemcpyAsync(c->d_tw + P, wneg, (size_t)Nn * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
     int rc;
+    if ((rc = launch_ensemble_retain(c, P, Nn))) return rc;
     if ((rc = launch_weak_update(c, P, Nn, has_w))) return rc;
     if ((rc = launch_mil_select(c, P, Nn))) return rc;
     if ((rc = launch_build_colormap(c))) return rc;
@@ -1398,6 +1410,8 @@ static void fill_train_desc(TrainDesc* t, mct_clf* c)
     t->slotmap = c->d_slotmap; t->colorrow = c->d_colorrow; t->outbins = c->d_outbins; t->nout = c->d_nout;
     t->seltab = c->d_seltab; t->selhdr = c->d_selhdr;
     t->ada_cnt = c->d_ada_cnt; t->alpha = c->d_alpha;
+    const bool ens = c->p.strong_type == MCT_STRONG_MILENSEMBLE;
+    t->keep = ens ? c->d_keep : nullptr; t->ensH = c->d_ensH; t->pct_retained = ens ? c->p.pct_retained / 100.0f : 0.0f;
     t->F = c->F; t->K = c->K; t->n_haar = c->n_haar; t->n_color = c->n_color; t->nb = c->p.n_bins; t->w0 = c->p.w0; t->h0 = c->p.h0;
     t->weak_type = c->p.weak_type; t->strong_type = c->p.strong_type; t->feature_type = c->p.feature_type; t->cch_mode = c->p.cch_mode;
     t->lr = c->p.learning_rate;
@@ -1534,6 +1548,7 @@ extern "C" int mct_track_update(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, c
     MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tdesc, ctx->h_tdesc, sizeof(TrainDesc) * n_obj, cudaMemcpyHostToDevice, ctx->stream));
     MCT_CUDA(ctx, cudaEventRecord(ctx->ev_train, ctx->stream));
     if ((rc = launch_train_features(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj))) return rc;
+    if ((rc = launch_ensemble_retain_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj))) return rc;
     if ((rc = launch_weak_update_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj))) return rc;
     if ((rc = launch_mil_select_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj, creq.data()))) return rc;
     if ((rc = launch_build_colormap_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj))) return rc;

@@ -130,6 +130,7 @@ struct mct_clf {
     int* d_big; int big_cap;                            // per test box: 1 = left to the generic (large / odd box) kernel
     int* d_nbig;                                        // device counter of such boxes
     float* d_ada_cnt; float* d_alpha;                   // AdaBoost state ([4][K][F], initial value 1; [K])
+    int* d_keep; float* d_ensH;                         // MILEnsemble: [F] retained flags, [ldT] hypothesis left by the retain step
 };
 
 // geometric-fuser feedback: per-call arguments and read-out of k_ground_pdf
@@ -212,6 +213,8 @@ struct TrainDesc {
     uint32_t* macc;                        // [n_color][ldT] u32 accumulators (zero between launches)
     uint32_t* mtot;                        // [2] fixed-point total of each group's weight table
     float* ada_cnt; float* alpha;          // AdaBoost: [4][K][F] running TP / FP / TN / FN weights, [K] voting weights
+    int* keep; float* ensH;                // MILEnsemble: [F] retained flags (NULL for the other types), [ldT] hypothesis
+    float pct_retained; int pad2;          // MILEnsemble: m_percentageOfRetainedWeakClassifiers (already / 100.0f)
 };
 
 // Per-call values that change every frame travel as kernel parameters, so that the ObjDesc array itself is
@@ -309,6 +312,9 @@ int launch_pf_summary(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max)
 int launch_pf_expand_prob(mct_ctx* ctx, const ObjDesc* d_desc, const float* d_prob_compact, int n_prob, int only_nonzero);
 int launch_weak_update(mct_clf* clf, int P, int Nn, int has_weights);
 int launch_mil_select(mct_clf* clf, int P, int Nn);
+// MILEnsemble: RetainBestPerformingWeakClassifiers, in front of the weak update (no-op for the other strong types)
+int launch_ensemble_retain(mct_clf* clf, int P, int Nn);
+int launch_ensemble_retain_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj);
 // batched UpdateClassifier of n_obj classifiers (device descriptor array d, host copy h)
 int launch_train_features(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj);
 int launch_weak_update_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj);

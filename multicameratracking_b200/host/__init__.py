@@ -15,7 +15,8 @@ class ObjectParams(C.Structure):
                 ("sd_x", C.c_float), ("sd_y", C.c_float), ("sd_sx", C.c_float), ("sd_sy", C.c_float),
                 ("pos_radius_train", C.c_float), ("init_pos_radius_train", C.c_float),
                 ("n_neg_train", C.c_int), ("init_n_neg_train", C.c_int), ("search_win", C.c_int),
-                ("trajectory_option", C.c_int), ("rng_seed", C.c_int64), ("init_xywh", C.c_float * 4)]
+                ("trajectory_option", C.c_int), ("rng_seed", C.c_int64), ("init_xywh", C.c_float * 4),
+                ("percent_retained", C.c_float)]
 
 
 def load():
@@ -77,7 +78,7 @@ class HostError(RuntimeError):
 # config.cfg values
 DEFAULTS = dict(feature_type=0, n_haar=250, n_bins=8, weak_type=0, strong_type=2, percent_selected=20, n_particles=1000,
                 sd_x=20.0, sd_y=20.0, sd_sx=1e-7, sd_sy=1e-7, pos_radius_train=10.0, init_pos_radius_train=7.0,
-                n_neg_train=30, init_n_neg_train=30, search_win=20, trajectory_option=0, rng_seed=1)
+                n_neg_train=30, init_n_neg_train=30, search_win=20, trajectory_option=0, rng_seed=1, percent_retained=0.0)
 
 
 class Camera:

@@ -238,6 +238,7 @@ StrongClassifierBase::StrongClassifierBase(mct_ctx* ctx, StrongClassifierParamet
     cp.n_selected = p->m_numberOfSelectedWeakClassifiers;
     cp.learning_rate = p->m_learningRate;
     cp.cch_mode = fp.m_cultureColorMode;
+    cp.pct_retained = p->m_percentageOfRetainedWeakClassifiers * 100.0f;
     const auto& hf = m_featureVectorPtr->HaarFeatures();
     std::vector<int> nrect(hf.size()), rects(hf.size() * MCT_MAX_RECTS * 4, 0);
     std::vector<float> wts(hf.size() * MCT_MAX_RECTS, 0.0f);
@@ -297,7 +298,8 @@ StrongClassifierBasePtr StrongClassifierFactory::CreateAndInitializeClassifier(S
         case ONLINE_STOCHASTIC_BOOST_MIL: return StrongClassifierBasePtr(new MILBoostClassifier(ctx, p));
         case ONLINE_ANY_BOOST_MIL: return StrongClassifierBasePtr(new MILAnyBoostClassifier(ctx, p));
         case ONLINE_ADABOOST: return StrongClassifierBasePtr(new AdaBoostClassifier(ctx, p));
-        default: throw MctHostError(MCT_E_UNSUPPORTED, "strong classifier type is outside the B200 hot path (MILEnsemble)");
+        case ONLINE_ENSEMBLE_BOOST_MIL: return StrongClassifierBasePtr(new MILEnsembleClassifier(ctx, p));
+        default: throw MctHostError(MCT_E_UNSUPPORTED, "unknown strong classifier type");
     }
 }
 }  // namespace Classifier

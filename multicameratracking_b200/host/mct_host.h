@@ -191,16 +191,18 @@ enum StrongClassifierType { ONLINE_ADABOOST = 0, ONLINE_STOCHASTIC_BOOST_MIL = 2
 // ClassifierParameters.h:38-65
 struct StrongClassifierParametersBase {
     StrongClassifierParametersBase(StrongClassifierType t, int numberOfSelectedWeakClassifiers, int totalNumberOfWeakClassifiers,
-                                   float learningRate = 0.85f)
+                                   float learningRate = 0.85f, float percentageOfRetainedWeakClassifiers = 0)
         : m_type(t), m_weakClassifierType(STUMP), m_learningRate(learningRate),
           m_numberOfSelectedWeakClassifiers(numberOfSelectedWeakClassifiers),
-          m_totalNumberOfWeakClassifiers(totalNumberOfWeakClassifiers) {}
+          m_totalNumberOfWeakClassifiers(totalNumberOfWeakClassifiers),
+          m_percentageOfRetainedWeakClassifiers(percentageOfRetainedWeakClassifiers / 100.0f) {}    // ClassifierParameters.h:52
     StrongClassifierType GetClassifierType() const { return m_type; }
     StrongClassifierType m_type;
     Features::FeatureParametersPtr m_featureParametersPtr;
     WeakClassifierType m_weakClassifierType;
     float m_learningRate;
     int m_numberOfSelectedWeakClassifiers, m_totalNumberOfWeakClassifiers;
+    float m_percentageOfRetainedWeakClassifiers;
 };
 typedef std::shared_ptr<StrongClassifierParametersBase> StrongClassifierParametersBasePtr;
 struct MILBoostClassifierParameters : StrongClassifierParametersBase {
@@ -208,6 +210,10 @@ struct MILBoostClassifierParameters : StrongClassifierParametersBase {
 };
 struct AdaBoostClassifierParameters : StrongClassifierParametersBase {          // ClassifierParameters.h:68-85
     AdaBoostClassifierParameters(int k, int f) : StrongClassifierParametersBase(ONLINE_ADABOOST, k, f) {}
+};
+struct MILEnsembleClassifierParameters : StrongClassifierParametersBase {       // ClassifierParameters.h:105-117
+    MILEnsembleClassifierParameters(int k, int f, float percentageOfRetainedWeakClassifiers)
+        : StrongClassifierParametersBase(ONLINE_ENSEMBLE_BOOST_MIL, k, f, 0.85f, percentageOfRetainedWeakClassifiers) {}
 };
 struct MILAnyBoostClassifierParameters : StrongClassifierParametersBase {
     MILAnyBoostClassifierParameters(int k, int f) : StrongClassifierParametersBase(ONLINE_ANY_BOOST_MIL, k, f) {}
@@ -233,6 +239,8 @@ protected:
 typedef std::shared_ptr<StrongClassifierBase> StrongClassifierBasePtr;
 class MILBoostClassifier : public StrongClassifierBase { public: using StrongClassifierBase::StrongClassifierBase; };
 class MILAnyBoostClassifier : public StrongClassifierBase { public: using StrongClassifierBase::StrongClassifierBase; };
+// MILEnsembleClassifier.h: retained selectors re-ranked on the new samples, every other weak classifier trained from scratch
+class MILEnsembleClassifier : public StrongClassifierBase { public: using StrongClassifierBase::StrongClassifierBase; };
 // AdaBoostClassifier.h: online boosting (Oza / Grabner); GetAlphaList = m_alphaList of the selected weak classifiers
 class AdaBoostClassifier : public StrongClassifierBase {
 public:

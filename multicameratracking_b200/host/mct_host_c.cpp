@@ -20,6 +20,7 @@ struct mcth_object_params {
     int trajectory_option;
     int64_t rng_seed;
     float init_xywh[4];
+    float percent_retained;           // Percentage_Of_Weak_Classifiers_Retained (MILEnsemble, Object.cpp:254-262)
 };
 
 struct mcth_camera {
@@ -107,6 +108,7 @@ static void make_params(const mcth_object_params& p, Classifier::StrongClassifie
     const int F = (int)fp->GetFeatureDimension();
     const int K = int(F * p.percent_selected / 100);
     if (p.strong_type == MCT_STRONG_MILANYBOOST) cp.reset(new Classifier::MILAnyBoostClassifierParameters(K, F));
+    else if (p.strong_type == MCT_STRONG_MILENSEMBLE) cp.reset(new Classifier::MILEnsembleClassifierParameters(K, F, p.percent_retained));
     else if (p.strong_type == MCT_STRONG_ADABOOST) cp.reset(new Classifier::AdaBoostClassifierParameters(K, F));
     else cp.reset(new Classifier::MILBoostClassifierParameters(K, F));
     cp->m_weakClassifierType = (Classifier::WeakClassifierType)p.weak_type;
@@ -168,6 +170,7 @@ int mcth_camera_init_trackers(mcth_camera* c)
             const int K = int(F * p.percent_selected / 100);
             Classifier::StrongClassifierParametersBasePtr cp;
             if (p.strong_type == MCT_STRONG_MILANYBOOST) cp.reset(new Classifier::MILAnyBoostClassifierParameters(K, F));
+            else if (p.strong_type == MCT_STRONG_MILENSEMBLE) cp.reset(new Classifier::MILEnsembleClassifierParameters(K, F, p.percent_retained));
             else if (p.strong_type == MCT_STRONG_ADABOOST) cp.reset(new Classifier::AdaBoostClassifierParameters(K, F));
             else cp.reset(new Classifier::MILBoostClassifierParameters(K, F));
             cp->m_weakClassifierType = (Classifier::WeakClassifierType)p.weak_type;

@@ -285,6 +285,7 @@ struct orc_clf {
     int cch_mode;
     float *cTP, *cFP, *cTN, *cFN;                         /* AdaBoost: [K][F] running counts, initial value 1 (AdaBoostClassifier.cpp:27-36) */
     float* alpha; float sum_alpha;                        /* [K] */
+    float pct_retained;                                   /* MILEnsemble: m_percentageOfRetainedWeakClassifiers (= pct / 100.0f, ClassifierParameters.h:52) */
 };
 
 /* StrongClassifierBase.cpp:8-129 (K clamp :20-23; weak clf ctor: lr 0.85 then SetLearningRate) */
@@ -331,6 +332,8 @@ void orc_clf_free(orc_clf* c)
     free(c->cTP); free(c->cFP); free(c->cTN); free(c->cFN); free(c->alpha); free(c);
 }
 int orc_clf_num_features(const orc_clf* c) { return c->F; }
+/* MILEnsembleClassifierParameters (ClassifierParameters.h:105-117): the percentage is stored divided by 100.0f (:52) */
+void orc_clf_set_retained(orc_clf* c, float percentage) { c->pct_retained = percentage / 100.0f; }
 
 /* FeatureVector::Compute by type (HaarAndColorHistogramFeatureVector.cpp:33-44: Haar rows then MDCH rows) */
 void orc_clf_features(const orc_clf* c, const orc_frame* f, const orc_boxes* b, float* out, int ld)
@@ -680,6 +683,121 @@ static void adaboost_select(orc_clf* c, const unsigned char* bp, int P, const un
     }
     free(poslam); free(neglam); free(errs);
 }
+
+/* ---- MILEnsembleClassifier (MILEnsembleClassifier.cpp:14-337) ------------------------------------------------
+   sort_order (Public.h:213-228) sorts the VALUES in place as well, so after it `negLogLikelihoodList[k]` is the k-th
+   smallest value (the chosen one's) while `negLogLikelihoodList[order[k]]` (:131, :321) is the value of RANK order[k] --
+   a quirk that feeds the stopping test of the following rounds; restated as written.  Ties -> lowest index. */
+static void sort_order_f(const float* v, int n, float* sorted, int* order)
+{
+    vi_t* a = (vi_t*)malloc((size_t)(n > 0 ? n : 1) * sizeof(vi_t));
+    for (int i = 0; i < n; i++) { a[i].v = v[i]; a[i].i = i; }
+    qsort(a, (size_t)n, sizeof(vi_t), cmp_asc);
+    for (int i = 0; i < n; i++) { sorted[i] = a[i].v; order[i] = a[i].i; }
+    free(a);
+}
+/* RetainBestPerformingWeakClassifiers (:206-337).  f32 positive chain (:270), predictions from the weak state of the
+   previous frame on the new samples; Hp / Hn come back advanced by the retained selectors. */
+static void ensemble_retain(orc_clf* c, const float* fpos, int P, const float* fneg, int Nn, float* Hp, float* Hn)
+{
+    const int n_prev = c->n_sel;
+    const int n_retain = (int)(c->pct_retained * (float)n_prev);             /* :214 float * size_t */
+    if (n_prev == 0) return;
+    if (n_retain == 0) { c->n_sel = 0; return; }
+    int* prev = (int*)malloc((size_t)n_prev * sizeof(int));
+    for (int i = 0; i < n_prev; i++) prev[i] = c->sel[i];
+    c->n_sel = 0;
+    float* pp = (float*)malloc((size_t)n_prev * P * 4);
+    float* pn = (float*)malloc((size_t)n_prev * Nn * 4);
+    for (int q = 0; q < n_prev; q++) {
+        int f = prev[q];
+        for (int i = 0; i < P; i++) pp[(size_t)q * P + i] = weak_classify(c, f, fpos[(size_t)f * P + i]);
+        for (int j = 0; j < Nn; j++) pn[(size_t)q * Nn + j] = weak_classify(c, f, fneg[(size_t)f * Nn + j]);
+    }
+    float* nll = (float*)malloc((size_t)n_prev * 4);
+    float* sorted = (float*)malloc((size_t)n_prev * 4);
+    int* order = (int*)malloc((size_t)n_prev * sizeof(int));
+    double previousNLL = 1000000;
+    for (int s = 0; s < n_retain; s++) {
+        for (int q = 0; q < n_prev; q++) {
+            float like = 1.0f;
+            for (int i = 0; i < P; i++) like *= (1 - sigmoidf_(Hp[i] + pp[(size_t)q * P + i]));
+            float posl = (float)-log(1 - like + 1e-5);
+            like = 0.0f;
+            for (int j = 0; j < Nn; j++) like += (float)-logf(1e-5f + 1 - sigmoidf_(Hn[j] + pn[(size_t)q * Nn + j]));
+            nll[q] = posl / (float)P + like / (float)Nn;
+        }
+        sort_order_f(nll, n_prev, sorted, order);
+        int k = 0;
+        for (; k < n_prev; k++) if (!in_list(c->sel, c->n_sel, prev[order[k]])) break;
+        if (k == n_prev) break;                                               /* :304-307 */
+        if ((previousNLL - (double)sorted[k]) < 1e-100) break;                /* :309-314 push then pop */
+        c->sel[c->n_sel++] = prev[order[k]];
+        previousNLL = sorted[order[k]];                                       /* :318 value at rank order[k] */
+        const int q = order[k];
+        for (int i = 0; i < P; i++) Hp[i] += pp[(size_t)q * P + i];
+        for (int j = 0; j < Nn; j++) Hn[j] += pn[(size_t)q * Nn + j];
+    }
+    free(prev); free(pp); free(pn); free(nll); free(sorted); free(order);
+}
+/* MILEnsembleClassifier::Update (:14-157).  Retained weak classifiers keep their state and are only evaluated (:59-65);
+   every other one is re-initialised and trained from scratch on this frame's samples (:67-72).  The positive bag
+   likelihood and the negative sum are DOUBLE accumulators here (:88, :100), unlike MILBoost and the retain step. */
+static void milensemble_update(orc_clf* c, const float* fpos, int P, const float* fneg, int Nn,
+                               const float* pwn, const float* nwn)
+{
+    int F = c->F;
+    float* Hp = (float*)calloc((size_t)(P > 0 ? P : 1), 4);
+    float* Hn = (float*)calloc((size_t)(Nn > 0 ? Nn : 1), 4);
+    ensemble_retain(c, fpos, P, fneg, Nn, Hp, Hn);
+    float* pp = (float*)malloc((size_t)F * (P > 0 ? P : 1) * 4);
+    float* pn = (float*)malloc((size_t)F * (Nn > 0 ? Nn : 1) * 4);
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+#endif
+    for (int f = 0; f < F; f++) {
+        const float* xp = fpos + (size_t)f * P;
+        const float* xn = fneg + (size_t)f * Nn;
+        if (!in_list(c->sel, c->n_sel, f)) {
+            c->mu0[f] = 0; c->mu1[f] = 0; c->sig0[f] = 1; c->sig1[f] = 1; c->trained[f] = 0;     /* Initialize() */
+            if (c->weak_type == ORC_WEAK_STUMP) stump_update(c, f, xp, P, xn, Nn);
+            else if (c->weak_type == ORC_WEAK_WSTUMP) wstump_update(c, f, xp, P, xn, Nn, pwn, nwn);
+            else perceptron_update(c, f, xp, P, xn, Nn);
+        }
+        for (int i = 0; i < P; i++) pp[(size_t)f * P + i] = weak_classify(c, f, xp[i]);
+        for (int j = 0; j < Nn; j++) pn[(size_t)f * Nn + j] = weak_classify(c, f, xn[j]);
+    }
+    float* nll = (float*)malloc((size_t)F * 4);
+    float* sorted = (float*)malloc((size_t)F * 4);
+    int* order = (int*)malloc((size_t)F * sizeof(int));
+    double previousNLL = 1000000;
+    for (int s = c->n_sel; s < c->K; s++) {
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+#endif
+        for (int w = 0; w < F; w++) {
+            double like = 1.0f;
+            for (int i = 0; i < P; i++) like *= (1 - sigmoidf_(Hp[i] + pp[(size_t)w * P + i]));
+            float posl = (float)-log(1 - like + 1e-5);
+            like = 0.0f;
+            for (int j = 0; j < Nn; j++) like += (float)-logf(1e-5f + 1 - sigmoidf_(Hn[j] + pn[(size_t)w * Nn + j]));
+            float negl = (float)like;
+            nll[w] = posl / (float)P + negl / (float)Nn;
+        }
+        sort_order_f(nll, F, sorted, order);
+        int k = 0;
+        for (; k < F; k++) if (!in_list(c->sel, c->n_sel, order[k])) break;   /* no IsValidWeakClassifier test here (:114) */
+        if (k == F) break;                                                    /* reference: out-of-range read (UB) */
+        if ((previousNLL - (double)sorted[k]) < 1e-100) break;                /* :122-127 */
+        const int best = order[k];
+        c->sel[c->n_sel++] = best;
+        previousNLL = sorted[order[k]];                                       /* :131 value at rank order[k] */
+        for (int i = 0; i < P; i++) Hp[i] += pp[(size_t)best * P + i];
+        for (int j = 0; j < Nn; j++) Hn[j] += pn[(size_t)best * Nn + j];
+    }
+    free(Hp); free(Hn); free(pp); free(pn); free(nll); free(sorted); free(order);
+}
+
 void orc_clf_update_from_features(orc_clf* c, const float* fpos, int P, const float* fneg, int Nn,
                                   const float* wpos, const float* wneg)
 {
@@ -689,6 +807,11 @@ void orc_clf_update_from_features(orc_clf* c, const float* fpos, int P, const fl
     float* pwn = (float*)malloc((size_t)(P > 0 ? P : 1) * 4);
     float* nwn = (float*)malloc((size_t)(Nn > 0 ? Nn : 1) * 4);
     if (c->weak_type == ORC_WEAK_WSTUMP) { normalize_w(wpos, P, pwn); normalize_w(wneg, Nn, nwn); }
+    if (c->strong_type == ORC_STRONG_MILENSEMBLE) {
+        milensemble_update(c, fpos, P, fneg, Nn, pwn, nwn);
+        free(pp); free(pn); free(pwn); free(nwn);
+        return;
+    }
 #ifdef _OPENMP
 #pragma omp parallel for num_threads(g_threads) schedule(static)
 #endif

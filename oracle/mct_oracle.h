@@ -75,7 +75,7 @@ void orc_cch_compute(const uint8_t* hue, int pitch, int w0, int h0, const orc_bo
 /* ---- strong classifier (StrongClassifierBase + MILBoost / MILAnyBoost + weak clfs) ---- */
 enum { ORC_FEAT_HAAR = 0, ORC_FEAT_CCH = 1, ORC_FEAT_MDCH = 2, ORC_FEAT_HAAR_MDCH = 3 };   /* FeatureParameters.h:12-16 */
 enum { ORC_WEAK_STUMP = 0, ORC_WEAK_WSTUMP = 1, ORC_WEAK_PERCEPTRON = 2 };                 /* WeakClassifierBase.h:13-16 */
-enum { ORC_STRONG_ADABOOST = 0, ORC_STRONG_MILBOOST = 2, ORC_STRONG_MILANYBOOST = 4 };                              /* ClassifierParameters.h:11-18 */
+enum { ORC_STRONG_ADABOOST = 0, ORC_STRONG_MILBOOST = 2, ORC_STRONG_MILENSEMBLE = 3, ORC_STRONG_MILANYBOOST = 4 };                              /* ClassifierParameters.h:11-18 */
 
 typedef struct {
     const uint8_t* gray; const uint8_t* c0; const uint8_t* c1; const uint8_t* c2;
@@ -88,6 +88,8 @@ orc_clf* orc_clf_create(int feature_type, int n_haar, int nb, int w0, int h0, in
                         int strong_type, int K, float lr, const orc_haar_table* haar /* copied; may be NULL */);
 void orc_clf_free(orc_clf* c);
 int  orc_clf_num_features(const orc_clf* c);
+/* MILEnsemble only: Percentage_Of_Weak_Classifiers_Retained (MILEnsembleClassifierParameters, ClassifierParameters.h:105-117) */
+void orc_clf_set_retained(orc_clf* c, float percentage);
 /* FeatureVector::Compute: out [F][n], ld */
 void orc_clf_features(const orc_clf* c, const orc_frame* f, const orc_boxes* b, float* out, int ld);
 /* StrongClassifierBase::Update(pos,neg); wpos/wneg NULL => uniform 1.0 (SURVEY a12 decision) */

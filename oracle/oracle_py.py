@@ -96,6 +96,7 @@ class Oracle:
         L.orc_clf_create.argtypes = [C.c_int] * 8 + [C.c_float, C.POINTER(HaarTable)]
         L.orc_clf_create.restype = C.c_void_p
         L.orc_clf_free.argtypes = [C.c_void_p]
+        L.orc_clf_set_retained.argtypes = [C.c_void_p, C.c_float]; L.orc_clf_set_retained.restype = None
         L.orc_clf_num_features.argtypes = [C.c_void_p]; L.orc_clf_num_features.restype = C.c_int
         L.orc_clf_features.argtypes = [C.c_void_p, C.POINTER(Frame), C.POINTER(Boxes), _c_float_p, C.c_int]
         L.orc_clf_update.argtypes = [C.c_void_p, C.POINTER(Frame), C.POINTER(Boxes), C.POINTER(Boxes), _c_float_p, _c_float_p]
@@ -204,8 +205,11 @@ class Oracle:
         f._keep = (gray, planes, ii)
         return f
 
-    def clf_create(self, feature_type, n_haar, nb, w0, h0, weak_type, strong_type, K, lr, haar):
-        return self.lib.orc_clf_create(feature_type, n_haar, nb, w0, h0, weak_type, strong_type, K, lr, haar)
+    def clf_create(self, feature_type, n_haar, nb, w0, h0, weak_type, strong_type, K, lr, haar, pct_retained=0.0):
+        c = self.lib.orc_clf_create(feature_type, n_haar, nb, w0, h0, weak_type, strong_type, K, lr, haar)
+        if pct_retained:
+            self.lib.orc_clf_set_retained(c, pct_retained)
+        return c
 
     def clf_features(self, clf, frame, boxes):
         F = self.lib.orc_clf_num_features(clf)

@@ -213,22 +213,30 @@ CASES = [
     ("haar_stump_adaboost", capi.FEAT_HAAR, capi.WEAK_STUMP, capi.STRONG_ADABOOST, 250, 50),
     ("haarmdch_wstump_adaboost", capi.FEAT_HAAR_MDCH, capi.WEAK_WSTUMP, capi.STRONG_ADABOOST, 100, 60),
     ("haar_perceptron_adaboost", capi.FEAT_HAAR, capi.WEAK_PERCEPTRON, capi.STRONG_ADABOOST, 60, 12),
+    # MILEnsemble (MILEnsembleClassifier.cpp): last element = Percentage_Of_Weak_Classifiers_Retained
+    ("haar_stump_ensemble_r50", capi.FEAT_HAAR, capi.WEAK_STUMP, capi.STRONG_MILENSEMBLE, 250, 50, 50.0),
+    ("haarmdch_wstump_ensemble_r30", capi.FEAT_HAAR_MDCH, capi.WEAK_WSTUMP, capi.STRONG_MILENSEMBLE, 250, 152, 30.0),
+    ("mdch_perceptron_ensemble_r60", capi.FEAT_MDCH, capi.WEAK_PERCEPTRON, capi.STRONG_MILENSEMBLE, 0, 40, 60.0),
+    ("haar_stump_ensemble_r0", capi.FEAT_HAAR, capi.WEAK_STUMP, capi.STRONG_MILENSEMBLE, 60, 12, 0.0),
+    ("haar_stump_ensemble_r100", capi.FEAT_HAAR, capi.WEAK_STUMP, capi.STRONG_MILENSEMBLE, 60, 12, 100.0),
 ]
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_update_and_classify(ctx, oracle, case):
-    name, ftype, wtype, stype, n_haar, K = case
-    seq = synth.Sequence(640, 480, 2)
+    name, ftype, wtype, stype, n_haar, K = case[:6]
+    pct = case[6] if len(case) > 6 else 0.0
+    seq = synth.Sequence(640, 480, 2, n_frames=5)
     w0, h0 = seq.w0, seq.h0
     t = arrs = None
     if n_haar:
         t, arrs = haar_table(oracle, n_haar, w0, h0)
     clf = capi.StrongClassifier(ctx, ftype, w0, h0, n_haar=n_haar, n_bins=8, weak_type=wtype, strong_type=stype,
-                                n_selected=K, haar=arrs)
-    oclf = oracle.clf_create(ftype, n_haar, 8, w0, h0, wtype, stype, K, 0.85, t)
+                                n_selected=K, haar=arrs, pct_retained=pct)
+    oclf = oracle.clf_create(ftype, n_haar, 8, w0, h0, wtype, stype, K, 0.85, t, pct_retained=pct)
     rng = np.random.default_rng(21)
-    for frame in range(3):                      # first Update (untrained branch) + two EMA updates
+    n_frames = 5 if stype == capi.STRONG_MILENSEMBLE else 3
+    for frame in range(n_frames):               # first Update (untrained branch) + EMA updates (ensemble: retain steps)
         gray, r, g, b = seq.frame(frame)
         ctx.frame_set(gray, r, g, b)
         of = oracle.frame(gray, r, g, b)
@@ -680,7 +688,8 @@ def test_noise_prefetch_matches_inline_copy(ctx, oracle):
     clf.close()
 
 
-def test_batched_update_mixed_classifier_types(ctx, oracle):
+@pytest.mark.parametrize("with_ensemble", [False, True])
+def test_batched_update_mixed_classifier_types(ctx, oracle, with_ensemble):
     """mct_track_update (one batched pass for all objects) with different feature / weak / strong types per object:
     weak state and selector lists must equal the oracle's per-object Update, over three frames (untrained + EMA)"""
     seq = synth.Sequence(640, 480, 4)
@@ -690,12 +699,15 @@ def test_batched_update_mixed_classifier_types(ctx, oracle):
              (capi.FEAT_MDCH, capi.WEAK_STUMP, capi.STRONG_MILANYBOOST, 102),
              (capi.FEAT_HAAR_MDCH, capi.WEAK_WSTUMP, capi.STRONG_MILBOOST, 120),
              (capi.FEAT_HAAR, capi.WEAK_PERCEPTRON, capi.STRONG_MILBOOST, 18)]
+    specs_ens = {1: (capi.FEAT_MDCH, capi.WEAK_STUMP, capi.STRONG_MILENSEMBLE, 102), 3: (capi.FEAT_HAAR, capi.WEAK_WSTUMP, capi.STRONG_MILENSEMBLE, 18)}
+    if with_ensemble:
+        specs = [specs_ens.get(i, s) for i, s in enumerate(specs)]
     clfs, oclfs = [], []
     for ft, wt, st, K in specs:
         nh = F if ft in (capi.FEAT_HAAR, capi.FEAT_HAAR_MDCH) else 0
         clfs.append(capi.StrongClassifier(ctx, ft, w0, h0, n_haar=nh, n_bins=8, weak_type=wt, strong_type=st, n_selected=K,
-                                          haar=arrs if nh else None))
-        oclfs.append(oracle.clf_create(ft, nh, 8, w0, h0, wt, st, K, 0.85, t if nh else None))
+                                          haar=arrs if nh else None, pct_retained=40.0))
+        oclfs.append(oracle.clf_create(ft, nh, 8, w0, h0, wt, st, K, 0.85, t if nh else None, pct_retained=40.0))
     for frame in range(3):
         gray, r, g, b = seq.frame(frame)
         ctx.frame_set(gray, r, g, b)

@@ -18,7 +18,8 @@ def _oracle_tracker(oracle, seq, o, f0, p, seed):
     t = oracle.haar_generate(rng, p["n_haar"], seq.w0, seq.h0) if p["feature_type"] in (0, 3) else None
     F = {0: p["n_haar"], 1: 11, 2: 512, 3: p["n_haar"] + 512}[p["feature_type"]]
     K = int(F * p["percent_selected"] / 100)
-    clf = oracle.clf_create(p["feature_type"], p["n_haar"], p["n_bins"], seq.w0, seq.h0, p["weak_type"], p["strong_type"], K, 0.85, t)
+    clf = oracle.clf_create(p["feature_type"], p["n_haar"], p["n_bins"], seq.w0, seq.h0, p["weak_type"], p["strong_type"], K, 0.85, t,
+                            pct_retained=p.get("percent_retained", 0.0))
     tp = oracle_py.TrackerParams(p["n_particles"], p["sd_x"], p["sd_y"], p["sd_sx"], p["sd_sy"], p["pos_radius_train"],
                                  p["init_pos_radius_train"], p["n_neg_train"], p["init_n_neg_train"], 100000,
                                  p["search_win"], p["trajectory_option"], 0, 0, 30)
@@ -28,7 +29,8 @@ def _oracle_tracker(oracle, seq, o, f0, p, seed):
     return trk, clf, rng
 
 
-@pytest.mark.parametrize("cfg", ["cfg1_haar_milboost", "haarmdch_wstump_2obj", "mdch_anyboost_avg", "cfg2_full_size_8obj_2000"])
+@pytest.mark.parametrize("cfg", ["cfg1_haar_milboost", "haarmdch_wstump_2obj", "mdch_anyboost_avg", "cfg2_full_size_8obj_2000",
+                                 "haar_ensemble_2obj"])
 def test_tracker_sequence_matches_oracle(oracle, cfg):
     n_frames = 12
     if cfg == "cfg1_haar_milboost":
@@ -40,6 +42,9 @@ def test_tracker_sequence_matches_oracle(oracle, cfg):
         n_obj, over = 8, dict(feature_type=3, weak_type=1, n_particles=2000, n_haar=250)
     elif cfg == "haarmdch_wstump_2obj":
         n_obj, over = 2, dict(feature_type=3, weak_type=1, n_particles=600, n_haar=100)
+    elif cfg == "haar_ensemble_2obj":
+        # Tracker_Strong_Classifier_Type 3 (MILEnsemble), half of the previous selectors re-ranked and retained every frame
+        n_obj, over = 2, dict(strong_type=3, n_particles=500, n_haar=120, percent_retained=50.0)
     else:
         n_obj, over = 1, dict(feature_type=2, strong_type=4, n_particles=500, trajectory_option=1)
     seq = synth.Sequence(640, 480, n_obj, n_frames=n_frames)
