@@ -296,6 +296,35 @@ int mct_fuser_exchange_foot_points(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, 
 
 int mct_fuser_pack_foot_points(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, const float* h0, float* dev_out);
 
+/* ---------------------------------------------------------------- training samples from the particles -------
+ * ParticleFilterTracker::GeneratePositiveTrainingSampleSet, the strategies that read the particle filter
+ * (ParticleFilterTracker.cpp:743-892; PFTracker_Positive_Sample_Strategy, TrackerParameters.h:42-51), for all objects
+ * of a camera in one device pass over the device-resident particles:
+ *   1 SAMPLE_POS_GREEDY           the first min(#ordered unique, max_pos) ordered unique particles with non-zero weight
+ *                                 whose box lies inside the frame (FindOrderedUniqueParticles, ParticleFilter.cpp:728-815);
+ *   2 SAMPLE_POS_SEMI_GREEDY      the same, additionally closer than 8 px to the current state's centre;
+ *   3 SAMPLE_POS_PARTICLE_RANDOM  every in-frame resampled particle kept iff randfloat() < max_pos / N: draw k of the
+ *                                 tracker's multiply-with-carry stream belongs to the k-th in-frame particle, reproduced
+ *                                 in parallel by jumping the generator ahead (state_n = A^n state_0 mod (A 2^32 - 1)).
+ * The read-out also carries what SAMPLE_NEG_PARTICLE_RANDOM (:939-995) needs from the particles: the largest
+ * |x - centre|, |y - centre| over the ordered unique particles.  Boxes come back as [n_obj][cap] host arrays. */
+typedef struct {
+    int   strategy;                  /* 1, 2 or 3 (0 = only the negative-strategy read-out) */
+    int   max_pos;                   /* m_maxNumPositiveExamples */
+    float cur[6];                    /* m_currentStateList: leftX, topY, width, height, scaleX, scaleY */
+    int   frame_w, frame_h;
+    unsigned long long rng_state;    /* the tracker's cvRNG state (strategy 3) */
+} mct_train_gen;
+typedef struct {
+    int   n_pos;                     /* boxes written for this object (<= cap) */
+    int   n_unique;                  /* GetNumberOfOrderedUniqueParticles */
+    float max_dx, max_dy;            /* over the ordered unique particles */
+    unsigned long long rng_state;    /* state after the draws of strategy 3 (unchanged otherwise) */
+    int   n_draws, pad;
+} mct_train_gen_out;
+int mct_pf_training_boxes(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, const mct_train_gen* gen, int cap,
+                          int* col, int* row, float* sx, float* sy, mct_train_gen_out* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,7 @@ SYMBOLS = [
     "mct_track_collect", "mct_track_update", "mct_pf_get_last_response", "mct_fuser_pack_foot_points",
     "mct_pf_ground_pdf", "mct_pf_rearrange_ground", "mct_classify_argmax", "mct_fuser_ground_pdf", "mct_p2p_create", "mct_p2p_open", "mct_p2p_destroy",
     "mct_fuser_exchange_foot_points", "mct_classifier_get_alphas", "mct_features_compute_dev", "mct_classifier_update_from_features_dev",
+    "mct_pf_training_boxes",
 ]
 
 
@@ -51,6 +52,16 @@ class ClfParams(C.Structure):
     _fields_ = [("feature_type", C.c_int), ("n_haar", C.c_int), ("n_bins", C.c_int), ("w0", C.c_int), ("h0", C.c_int),
                 ("weak_type", C.c_int), ("strong_type", C.c_int), ("n_selected", C.c_int), ("learning_rate", C.c_float),
                 ("cch_mode", C.c_int), ("max_train", C.c_int), ("max_test", C.c_int), ("pct_retained", C.c_float)]
+
+
+class TrainGen(C.Structure):
+    _fields_ = [("strategy", C.c_int), ("max_pos", C.c_int), ("cur", C.c_float * 6), ("frame_w", C.c_int), ("frame_h", C.c_int),
+                ("rng_state", C.c_uint64)]
+
+
+class TrainGenOut(C.Structure):
+    _fields_ = [("n_pos", C.c_int), ("n_unique", C.c_int), ("max_dx", C.c_float), ("max_dy", C.c_float), ("rng_state", C.c_uint64),
+                ("n_draws", C.c_int), ("pad", C.c_int)]
 
 
 class HaarTable(C.Structure):
@@ -147,6 +158,8 @@ def load():
     L.mct_classifier_update_from_features_dev.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int]
     L.mct_classifier_get_alphas.argtypes = [vp, _c_float_p, _c_int_p]
     L.mct_classify_argmax.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(Boxes), C.c_int, _c_int_p, _c_float_p]
+    L.mct_pf_training_boxes.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(TrainGen), C.c_int, _c_int_p, _c_int_p, _c_float_p, _c_float_p,
+                                        C.POINTER(TrainGenOut)]
     _lib = L
     return L
 
@@ -522,6 +535,28 @@ def pack_foot_points(ctx, pfs, h0, dev_out_ptr):
     pa = (vp * n)(*[p.h for p in pfs])
     hh = np.ascontiguousarray(h0, np.float32)
     ctx.check(ctx.L.mct_fuser_pack_foot_points(ctx.h, n, pa, _fp(hh), vp(dev_out_ptr)))
+
+
+def training_boxes(ctx, pfs, gens, cap):
+    """mct_pf_training_boxes: gens = [(strategy, max_pos, cur[6], frame_w, frame_h, rng_state)]; returns per object
+    (col, row, sx, sy, TrainGenOut)"""
+    n = len(pfs)
+    vp = C.c_void_p
+    pa = (vp * n)(*[p.h for p in pfs])
+    ga = (TrainGen * n)()
+    for o, (st, mp, cur, fw, fh, rs) in enumerate(gens):
+        ga[o].strategy = st; ga[o].max_pos = mp; ga[o].frame_w = fw; ga[o].frame_h = fh; ga[o].rng_state = rs
+        for i in range(6):
+            ga[o].cur[i] = float(cur[i])
+    col = np.zeros((n, cap), np.int32); row = np.zeros((n, cap), np.int32)
+    sx = np.zeros((n, cap), np.float32); sy = np.zeros((n, cap), np.float32)
+    out = (TrainGenOut * n)()
+    ctx.check(ctx.L.mct_pf_training_boxes(ctx.h, n, pa, ga, cap, _ip(col), _ip(row), _fp(sx), _fp(sy), out))
+    res = []
+    for o in range(n):
+        k = out[o].n_pos
+        res.append((col[o, :k].copy(), row[o, :k].copy(), sx[o, :k].copy(), sy[o, :k].copy(), out[o]))
+    return res
 
 
 def track_update(ctx, clfs, pos_list, neg_list):

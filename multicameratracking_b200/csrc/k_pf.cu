@@ -882,3 +882,195 @@ int launch_ground_pdf(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, const Grou
     MCT_LAUNCH(ctx, "k_ground_pdf", k_ground_pdf<<<n_obj, 256, 0, ctx->stream>>>(d_desc, d_ga, d_wout, d_out));
     return MCT_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// k_train_from_particles: GeneratePositiveTrainingSampleSet strategies GREEDY / SEMI_GREEDY / PARTICLE_RANDOM
+// (ParticleFilterTracker.cpp:743-892) and the particle read-out of SAMPLE_NEG_PARTICLE_RANDOM (:939-964).
+// One CTA per object.  Ordered unique particles (ParticleFilter.cpp:728-815):
+//   RESAMPLED  rows = run starts of the (non-decreasing) resample index list in index order; the weights column holds
+//              the run weights sorted descending (:799-806), so "weight != 0" holds for the first nz rows, nz = runs with
+//              a non-zero member (weights are non-negative);
+//   PREDICTED  rows = particles by weight descending, ties by index: exact rank by counting.
+// PARTICLE_RANDOM consumes one randfloat() per in-frame resampled particle, in particle order: the k-th in-frame
+// particle gets draw k, computed by jumping the multiply-with-carry generator (Public.cpp:15-23: state = lo * A + hi)
+// ahead: state_n = A^n * state_0 mod (A * 2^32 - 1) once the state is below the modulus (two plain steps).
+#define MWC_A 4164903690ull
+#define MWC_M ((MWC_A << 32) - 1ull)
+__device__ __forceinline__ unsigned long long mwc_step(unsigned long long s) { return (s & 0xffffffffull) * MWC_A + (s >> 32); }
+__device__ __forceinline__ unsigned long long mwc_mulmod(unsigned long long a, unsigned long long b)
+{
+    return (unsigned long long)(((unsigned __int128)a * (unsigned __int128)b) % (unsigned __int128)MWC_M);
+}
+// pw[k] = A^(2^k) mod M; s0 must already be <= M (two plain steps taken)
+__device__ __forceinline__ unsigned long long mwc_jump(unsigned long long s, unsigned n, const unsigned long long* pw)
+{
+    for (int k = 0; n; k++, n >>= 1) if (n & 1u) s = mwc_mulmod(s, pw[k]);
+    return s;
+}
+// state after n draws from s0
+__device__ __forceinline__ unsigned long long mwc_after(unsigned long long s0, unsigned long long s2, unsigned n, const unsigned long long* pw)
+{
+    if (n == 0) return s0;
+    if (n == 1) return mwc_step(s0);
+    return mwc_jump(s2, n - 2, pw);
+}
+// in-order position of the flagged threads of this tile (exclusive) and the tile total
+__device__ __forceinline__ int block_compact(bool flag, int* sh /* [33] */, int* total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    const int inwarp = __popc(bal & ((1u << lane) - 1u));
+    __syncthreads();
+    if (lane == 0) sh[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, tot = 0;
+    for (int w = 0; w < nw; w++) { const int c = sh[w]; if (w < warp) before += c; tot += c; }
+    *total = tot;
+    return before + inwarp;
+}
+__device__ __forceinline__ bool particle_box_in_frame(float a0, float a1, float a2, float a3, float w0, float h0, int fw, int fh, int* lx, int* ty)
+{
+    const float wf = __fmul_rn(a2, w0), hf = __fmul_rn(a3, h0);
+    const int leftX = __float2int_rn(__fsub_rn(a0, __fdiv_rn(wf, 2.0f))), topY = __float2int_rn(__fsub_rn(a1, __fdiv_rn(hf, 2.0f)));
+    const int width = __float2int_rn(wf), height = __float2int_rn(hf);
+    *lx = leftX; *ty = topY;
+    return leftX > 0 && topY > 0 && leftX + width < fw - 1 && topY + height < fh - 1;
+}
+__global__ void __launch_bounds__(PF_THREADS)
+k_train_from_particles(const ObjDesc* __restrict__ descs, const mct_train_gen* __restrict__ gens, int cap, int* __restrict__ col, int* __restrict__ row,
+                       float* __restrict__ sx, float* __restrict__ sy, mct_train_gen_out* __restrict__ outs)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ ObjDesc s_desc;
+    __shared__ int sh_c[33];
+    __shared__ float sh_f[32];
+    __shared__ int sh_i[32];
+    __shared__ unsigned long long s_pw[32];
+    const ObjDesc& d = load_desc(descs + blockIdx.x, &s_desc);
+    const mct_train_gen g = gens[blockIdx.x];
+    const int N = d.N, tid = threadIdx.x, nt = blockDim.x;
+    const int fs = d.st->filter_state;
+    int* o_col = col + (size_t)blockIdx.x * cap; int* o_row = row + (size_t)blockIdx.x * cap;
+    float* o_sx = sx + (size_t)blockIdx.x * cap; float* o_sy = sy + (size_t)blockIdx.x * cap;
+    float* sw = (float*)smraw;                         // [N] weights (PREDICTED rank pass)
+    int* rowidx = (int*)(sw + ((N + 3) & ~3));         // [max_pos] particle index of the first ordered unique rows
+    const int max_pos = g.max_pos > 0 ? g.max_pos : 0;
+    const float w0 = g.cur[2], h0 = g.cur[3];
+    const float ccx = __fadd_rn(g.cur[0], __fdiv_rn(__fmul_rn(g.cur[2], g.cur[4]), 2.0f));
+    const float ccy = __fadd_rn(g.cur[1], __fdiv_rn(__fmul_rn(g.cur[3], g.cur[5]), 2.0f));
+
+    // ---- ordered unique particles: first max_pos rows, count, non-zero rows, largest centre distances
+    int n_uniq = 0, nz = 0x7fffffff;
+    float mdx = 0.0f, mdy = 0.0f;
+    if (fs == MCT_PF_RESAMPLED) {
+        int base = 0, nzc = 0;
+        for (int i0 = 0; i0 < N; i0 += nt) {
+            const int i = i0 + tid;
+            const bool start = i < N && (i == 0 || d.residx[i] != d.residx[i - 1]);
+            int tot;
+            const int q = base + block_compact(start, sh_c, &tot);
+            if (start) {
+                if (q < max_pos) rowidx[q] = i;
+                const int v = d.residx[i];
+                bool any = false;
+                for (int j = i; j < N && d.residx[j] == v; j++) if (d.w[j] != 0.0f) { any = true; break; }
+                nzc += any ? 1 : 0;
+                mdx = fmaxf(mdx, fabsf(__fsub_rn(d.cx[i], ccx))); mdy = fmaxf(mdy, fabsf(__fsub_rn(d.cy[i], ccy)));
+            }
+            base += tot;
+        }
+        n_uniq = base;
+        nz = block_reduce_sum_i(nzc, sh_i);
+    } else if (fs == MCT_PF_PREDICTED) {
+        for (int i = tid; i < N; i += nt) sw[i] = d.w[i];
+        __syncthreads();
+        for (int i = tid; i < N; i += nt) {
+            const float v = sw[i];
+            int rank = 0;
+            for (int j = 0; j < N; j++) { const float o = sw[j]; rank += (o > v || (o == v && j < i)) ? 1 : 0; }
+            if (rank < max_pos) rowidx[rank] = i;
+            mdx = fmaxf(mdx, fabsf(__fsub_rn(d.cx[i], ccx))); mdy = fmaxf(mdy, fabsf(__fsub_rn(d.cy[i], ccy)));
+        }
+        n_uniq = N;
+    }
+    mdx = block_reduce_minmax(mdx, true, sh_f);
+    mdy = block_reduce_minmax(mdy, true, sh_f);
+    __syncthreads();
+
+    int n_pos = 0, n_draws = 0;
+    unsigned long long rng_after = g.rng_state;
+    if (g.strategy == 1 || g.strategy == 2) {
+        const int n = min(n_uniq, max_pos);
+        int base = 0;
+        for (int q0 = 0; q0 < n; q0 += nt) {
+            const int q = q0 + tid;
+            bool ok = false; int lx = 0, ty = 0; float a2 = 0, a3 = 0;
+            if (q < n) {
+                const int i = rowidx[q];
+                const float a0 = d.cx[i], a1 = d.cy[i]; a2 = d.sx[i]; a3 = d.sy[i];
+                const bool wnz = fs == MCT_PF_RESAMPLED ? q < nz : d.w[i] != 0.0f;
+                ok = wnz && particle_box_in_frame(a0, a1, a2, a3, w0, h0, g.frame_w, g.frame_h, &lx, &ty);
+                if (g.strategy == 2) {
+                    const double ddx = (double)__fsub_rn(ccx, a0), ddy = (double)__fsub_rn(ccy, a1);
+                    const float dist = (float)sqrt(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));
+                    ok = ok && dist < 8.0f;
+                }
+            }
+            int tot;
+            const int pos = base + block_compact(ok, sh_c, &tot);
+            if (ok && pos < cap) { o_col[pos] = lx; o_row[pos] = ty; o_sx[pos] = a2; o_sy[pos] = a3; }
+            base += tot;
+        }
+        n_pos = min(base, cap);
+    } else if (g.strategy == 3) {
+        const unsigned long long s0 = g.rng_state, s2 = mwc_step(mwc_step(s0));
+        if (tid == 0) {
+            unsigned long long p = MWC_A % MWC_M;
+            for (int k = 0; k < 32; k++) { s_pw[k] = p; p = mwc_mulmod(p, p); }
+        }
+        __syncthreads();
+        const float prob = __fdiv_rn((float)g.max_pos, (float)N);
+        int base_in = 0, base_keep = 0;
+        for (int i0 = 0; i0 < N; i0 += nt) {
+            const int i = i0 + tid;
+            int lx = 0, ty = 0; float a2 = 0, a3 = 0;
+            bool in = false;
+            if (i < N) { a2 = d.rsx[i]; a3 = d.rsy[i]; in = particle_box_in_frame(d.rcx[i], d.rcy[i], a2, a3, w0, h0, g.frame_w, g.frame_h, &lx, &ty); }
+            int tot_in;
+            const int k = base_in + block_compact(in, sh_c, &tot_in);
+            bool keep = false;
+            if (in) {
+                const unsigned long long s = mwc_after(s0, s2, (unsigned)k + 1u, s_pw);
+                const float rf = (float)((double)(unsigned)(s & 0xffffffffull) * 2.3283064365386962890625e-10);
+                keep = rf < prob;
+            }
+            int tot_keep;
+            const int pos = base_keep + block_compact(keep, sh_c, &tot_keep);
+            if (keep && pos < cap && pos < max_pos) { o_col[pos] = lx; o_row[pos] = ty; o_sx[pos] = a2; o_sy[pos] = a3; }
+            base_in += tot_in; base_keep += tot_keep;
+        }
+        n_draws = base_in;
+        n_pos = min(min(base_keep, max_pos), cap);
+        rng_after = mwc_after(s0, s2, (unsigned)base_in, s_pw);
+    }
+    if (tid == 0) {
+        mct_train_gen_out o;
+        o.n_pos = n_pos; o.n_unique = n_uniq; o.max_dx = mdx; o.max_dy = mdy; o.rng_state = rng_after; o.n_draws = n_draws; o.pad = 0;
+        outs[blockIdx.x] = o;
+    }
+}
+int launch_train_from_particles(mct_ctx* ctx, const ObjDesc* d_desc, const ObjDesc* h_desc, int n_obj, const mct_train_gen* d_gen, int max_pos_max,
+                                int cap, int* d_col, int* d_row, float* d_sx, float* d_sy, mct_train_gen_out* d_out)
+{
+    int n_max = 0;
+    for (int o = 0; o < n_obj; o++) n_max = max(n_max, h_desc[o].N);
+    const size_t smem = ((size_t)((n_max + 3) & ~3) + (size_t)max(max_pos_max, 1)) * 4;
+    if (smem > 200 * 1024) return mct_fail(ctx, MCT_E_UNSUPPORTED, "too many particles for the training-sample kernel%s (%d)", "", n_max);
+    static size_t s_attr = 48 * 1024;
+    if (smem > s_attr) {
+        MCT_CUDA(ctx, cudaFuncSetAttribute(k_train_from_particles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        s_attr = smem;
+    }
+    MCT_LAUNCH(ctx, "k_train_from_particles", k_train_from_particles<<<n_obj, PF_THREADS, smem, ctx->stream>>>(d_desc, d_gen, cap, d_col, d_row, d_sx, d_sy, d_out));
+    return MCT_OK;
+}

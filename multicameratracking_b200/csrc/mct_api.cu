@@ -1648,3 +1648,37 @@ extern "C" int mct_fuser_pack_foot_points(mct_ctx* ctx, int n_obj, mct_pf* const
     if ((rc = launch_foot_points(ctx, d, n_obj, ctx->d_tmp, dev_out))) return rc;
     return mct_sync(ctx);
 }
+
+extern "C" int mct_pf_training_boxes(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, const mct_train_gen* gen, int cap,
+                                     int* col, int* row, float* sx, float* sy, mct_train_gen_out* out)
+{
+    if (!ctx || n_obj < 1 || n_obj > DESC_MAX_OBJ || !pfs || !gen || cap < 1 || !col || !row || !sx || !sy || !out) return MCT_E_ARG;
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    int max_pos = 1;
+    for (int o = 0; o < n_obj; o++) {
+        if (!pfs[o] || !pfs[o]->initialized) return mct_fail(ctx, MCT_E_STATE, "particle filter not initialised%s");
+        if (gen[o].strategy < 0 || gen[o].strategy > 3 || gen[o].max_pos < 0) return mct_fail(ctx, MCT_E_ARG, "bad training-sample strategy%s");
+        if (gen[o].max_pos > max_pos) max_pos = gen[o].max_pos;
+    }
+    // scratch: gen[n] | out[n] | col,row,sx,sy [n][cap]
+    const size_t off_out = (size_t)n_obj * sizeof(mct_train_gen), off_box = off_out + (size_t)n_obj * sizeof(mct_train_gen_out);
+    const size_t box_bytes = (size_t)n_obj * cap * 4;
+    int rc = ensure_tmp(ctx, off_box + 4 * box_bytes);
+    if (rc) return rc;
+    unsigned char* base = (unsigned char*)ctx->d_tmp;
+    mct_train_gen* d_gen = (mct_train_gen*)base;
+    mct_train_gen_out* d_out = (mct_train_gen_out*)(base + off_out);
+    int* d_col = (int*)(base + off_box); int* d_row = (int*)(base + off_box + box_bytes);
+    float* d_sx = (float*)(base + off_box + 2 * box_bytes); float* d_sy = (float*)(base + off_box + 3 * box_bytes);
+    MCT_CUDA(ctx, cudaMemcpyAsync(d_gen, gen, (size_t)n_obj * sizeof(mct_train_gen), cudaMemcpyHostToDevice, ctx->stream));
+    ObjDesc h[DESC_MAX_OBJ]; const ObjDesc* d;
+    for (int o = 0; o < n_obj; o++) { memset(&h[o], 0, sizeof(ObjDesc)); fill_pf_desc(&h[o], pfs[o]); }
+    if ((rc = desc_publish(ctx, h, n_obj, &d))) return rc;
+    if ((rc = launch_train_from_particles(ctx, d, h, n_obj, d_gen, max_pos, cap, d_col, d_row, d_sx, d_sy, d_out))) return rc;
+    MCT_CUDA(ctx, cudaMemcpyAsync(out, d_out, (size_t)n_obj * sizeof(mct_train_gen_out), cudaMemcpyDeviceToHost, ctx->stream));
+    MCT_CUDA(ctx, cudaMemcpyAsync(col, d_col, box_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MCT_CUDA(ctx, cudaMemcpyAsync(row, d_row, box_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MCT_CUDA(ctx, cudaMemcpyAsync(sx, d_sx, box_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MCT_CUDA(ctx, cudaMemcpyAsync(sy, d_sy, box_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return mct_sync(ctx);
+}

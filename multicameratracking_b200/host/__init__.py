@@ -16,7 +16,8 @@ class ObjectParams(C.Structure):
                 ("pos_radius_train", C.c_float), ("init_pos_radius_train", C.c_float),
                 ("n_neg_train", C.c_int), ("init_n_neg_train", C.c_int), ("search_win", C.c_int),
                 ("trajectory_option", C.c_int), ("rng_seed", C.c_int64), ("init_xywh", C.c_float * 4),
-                ("percent_retained", C.c_float)]
+                ("percent_retained", C.c_float), ("pos_strategy", C.c_int), ("neg_strategy", C.c_int),
+                ("max_num_pos_examples", C.c_int)]
 
 
 def load():
@@ -78,7 +79,8 @@ class HostError(RuntimeError):
 # config.cfg values
 DEFAULTS = dict(feature_type=0, n_haar=250, n_bins=8, weak_type=0, strong_type=2, percent_selected=20, n_particles=1000,
                 sd_x=20.0, sd_y=20.0, sd_sx=1e-7, sd_sy=1e-7, pos_radius_train=10.0, init_pos_radius_train=7.0,
-                n_neg_train=30, init_n_neg_train=30, search_win=20, trajectory_option=0, rng_seed=1, percent_retained=0.0)
+                n_neg_train=30, init_n_neg_train=30, search_win=20, trajectory_option=0, rng_seed=1, percent_retained=0.0,
+                pos_strategy=0, neg_strategy=0, max_num_pos_examples=30)
 
 
 class Camera:

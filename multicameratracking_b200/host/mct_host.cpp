@@ -441,12 +441,9 @@ void ParticleFilterTracker::StoreObjectState(int frameind)
     }
 }
 
-// GenerateTrainingSampleSet (ParticleFilterTracker.cpp:647-688), strategies SAMPLE_POS/NEG_SIMPLETRACKER (:723-736, :921-937)
-void ParticleFilterTracker::GenerateTrainingSampleSet(Matrixu* pColor, Matrixu* pGray, Matrixu* pHSV)
+// GenerateTrainingSampleSet (ParticleFilterTracker.cpp:647-688): current state from the particles (:655-672) ...
+void ParticleFilterTracker::PrepareTrainingState()
 {
-    Public::SetCurrentRng(&m_rng);
-    if (m_params->m_positiveSampleStrategy != 0 || m_params->m_negativeSampleStrategy != 0)
-        throw MctHostError(MCT_E_UNSUPPORTED, "only the SIMPLETRACKER training-sample strategies are on the hot path");
     vectorf a;
     if (m_params->m_outputTrajectoryOption == PARTICLE_HIGHEST_WEIGHT) m_particleFilterPtr->GetOrderedUniqueParticles(0, a);
     else m_particleFilterPtr->GetAverageofAllParticles(a);
@@ -454,20 +451,72 @@ void ParticleFilterTracker::GenerateTrainingSampleSet(Matrixu* pColor, Matrixu* 
     m_currentStateList[0] = std::max(a[0] - widthFloat / 2, 0.0f);
     m_currentStateList[1] = std::max(a[1] - heightFloat / 2, 0.0f);
     m_currentStateList[4] = a[2]; m_currentStateList[5] = a[3];
+}
+void ParticleFilterTracker::FillTrainGen(mct_train_gen& g, Matrixu* pColor, Matrixu* pGray) const
+{
+    memset(&g, 0, sizeof(g));
+    g.strategy = m_params->m_positiveSampleStrategy; g.max_pos = m_params->m_maxNumPositiveExamples;
+    for (int i = 0; i < 6; i++) g.cur[i] = m_currentStateList[i];
+    Matrixu* m = pGray ? pGray : pColor;
+    if (!m) throw MctHostError(MCT_E_ARG, "GenerateTrainingSampleSet: no image given");
+    g.frame_w = m->cols(); g.frame_h = m->rows();
+    g.rng_state = m_rng.state;
+}
+// ... then GeneratePositiveTrainingSampleSet (:697-906) and GenerateNegativeTrainingSampleSet (:913-1004).  The strategies that
+// walk the particles (GREEDY, SEMI_GREEDY, PARTICLE_RANDOM positives; the distances of PARTICLE_RANDOM negatives) were evaluated
+// on the device (`readout` + box arrays); the disc / ring / rectangle enumerations stay here with the tracker's RNG stream.
+void ParticleFilterTracker::BuildTrainingSets(Matrixu* pColor, Matrixu* pGray, Matrixu* pHSV, const mct_train_gen_out* readout,
+                                              const int* col, const int* row, const float* sx, const float* sy)
+{
+    Public::SetCurrentRng(&m_rng);
+    const int ps = m_params->m_positiveSampleStrategy, ns = m_params->m_negativeSampleStrategy;
+    if (ps < 0 || ps > 3 || ns < 0 || ns > 1) throw MctHostError(MCT_E_ARG, "unknown training-sample strategy");
+    if ((ps != 0 || ns != 0) && !readout) throw MctHostError(MCT_E_STATE, "BuildTrainingSets: particle read-out missing");
     m_positiveSampleSet.Clear();
-    m_positiveSampleSet.SampleImage(pGray, (int)m_currentStateList[0], (int)m_currentStateList[1], (int)m_currentStateList[2],
-                                    (int)m_currentStateList[3], m_params->m_posRadiusTrain, 0,
-                                    (int)m_params->m_maximumNumberOfPositiveTrainingSamples, pColor, pHSV,
-                                    m_currentStateList[4], m_currentStateList[5]);
+    if (ps != 0) {
+        for (int i = 0; i < readout->n_pos; i++)
+            m_positiveSampleSet.PushBackSample(pGray, col[i], row[i], Public::cvRound((double)m_currentStateList[2]),
+                                               Public::cvRound((double)m_currentStateList[3]), 1, pColor, pHSV, sx[i], sy[i]);
+        m_rng.state = readout->rng_state;                              // the randfloat() draws of PARTICLE_RANDOM (:867)
+    }
+    if (ps == 0 || (ps == 1 && m_positiveSampleSet.Size() == 0))       // SIMPLETRACKER (:727-741) / GREEDY's fall-back (:779-793)
+        m_positiveSampleSet.SampleImage(pGray, (int)m_currentStateList[0], (int)m_currentStateList[1], (int)m_currentStateList[2],
+                                        (int)m_currentStateList[3], m_params->m_posRadiusTrain, 0,
+                                        (int)m_params->m_maximumNumberOfPositiveTrainingSamples, pColor, pHSV,
+                                        m_currentStateList[4], m_currentStateList[5]);
     const float maxs = m_particleFilterPtr->GetMaxScale();
+    const float nsx = std::min(m_currentStateList[4], maxs), nsy = std::min(m_currentStateList[5], maxs);
     m_negativeSampleSet.Clear();
-    m_negativeSampleSet.SampleImage(pGray, cvRound((double)m_currentStateList[0]), cvRound((double)m_currentStateList[1]),
-                                    cvRound((double)m_currentStateList[2]), cvRound((double)m_currentStateList[3]),
-                                    1.5f * m_params->m_searchWindSize, m_params->m_posRadiusTrain + 15,
-                                    (int)m_params->m_numberOfNegativeTrainingSamples, pColor, pHSV,
-                                    std::min(m_currentStateList[4], maxs), std::min(m_currentStateList[5], maxs));
+    if (ns == 0) {
+        m_negativeSampleSet.SampleImage(pGray, cvRound((double)m_currentStateList[0]), cvRound((double)m_currentStateList[1]),
+                                        cvRound((double)m_currentStateList[2]), cvRound((double)m_currentStateList[3]),
+                                        1.5f * m_params->m_searchWindSize, m_params->m_posRadiusTrain + 15,
+                                        (int)m_params->m_numberOfNegativeTrainingSamples, pColor, pHSV, nsx, nsy);
+    } else {
+        // SAMPLE_NEG_PARTICLE_RANDOM (:939-995): keep away from the spread of the unique particles, within [radius + 5, 15]
+        float minimumDistanceX = std::max(readout->max_dx, (float)m_params->m_posRadiusTrain + 5);
+        float minimumDistanceY = std::max(readout->max_dy, (float)m_params->m_posRadiusTrain + 5);
+        minimumDistanceX = std::min(minimumDistanceX, 15.0f); minimumDistanceY = std::min(minimumDistanceY, 15.0f);
+        const float maximumDistance = 1.5f * m_params->m_searchWindSize;
+        m_negativeSampleSet.SampleImage(pGray, cvRound((double)m_currentStateList[0]), cvRound((double)m_currentStateList[1]),
+                                        cvRound((double)m_currentStateList[2]), cvRound((double)m_currentStateList[3]),
+                                        maximumDistance, maximumDistance, minimumDistanceX, minimumDistanceY,
+                                        (int)m_params->m_numberOfNegativeTrainingSamples, pColor, pHSV, nsx, nsy);
+    }
     if (m_positiveSampleSet.Size() < 1 || m_negativeSampleSet.Size() < 1)
         throw MctHostError(MCT_E_EMPTY, "GenerateTrainingSampleSet: empty training set");
+}
+void ParticleFilterTracker::GenerateTrainingSampleSet(Matrixu* pColor, Matrixu* pGray, Matrixu* pHSV)
+{
+    PrepareTrainingState();
+    if (!NeedsParticleReadout()) { BuildTrainingSets(pColor, pGray, pHSV, nullptr, nullptr, nullptr, nullptr, nullptr); return; }
+    mct_train_gen g; mct_train_gen_out go;
+    FillTrainGen(g, pColor, pGray);
+    const int cap = std::max(1, g.max_pos);
+    vectori col(cap), row(cap); vectorf sx(cap), sy(cap);
+    mct_pf* pf = m_particleFilterPtr->Handle();
+    chk(m_ctx, mct_pf_training_boxes(m_ctx, 1, &pf, &g, cap, col.data(), row.data(), sx.data(), sy.data(), &go));
+    BuildTrainingSets(pColor, pGray, pHSV, &go, col.data(), row.data(), sx.data(), sy.data());
 }
 
 // UpdateClassifier (ParticleFilterTracker.cpp:1013-1032)
@@ -539,9 +588,30 @@ void ParticleFilterTracker::TrackCameraObjects(mct_ctx* ctx, std::vector<Particl
         std::vector<vectori> pc(n), pr(n), nc(n), nr(n);
         std::vector<vectorf> psx(n), psy(n), nsx(n), nsy(n);
         std::vector<mct_boxes> pb(n), nb(n);
+        // particle-reading strategies: one device pass for all objects of the camera that ask for it
+        std::vector<int> rd; std::vector<mct_pf*> rpf; std::vector<mct_train_gen> rg;
+        int cap = 1;
         for (int o = 0; o < n; o++) {
             ParticleFilterTracker* t = trackers[o];
-            t->GenerateTrainingSampleSet(pColor, pGray, pHSV);
+            t->PrepareTrainingState();
+            if (!t->NeedsParticleReadout()) continue;
+            mct_train_gen g; t->FillTrainGen(g, pColor, pGray);
+            rd.push_back(o); rpf.push_back(t->m_particleFilterPtr->Handle()); rg.push_back(g);
+            cap = std::max(cap, g.max_pos);
+        }
+        std::vector<mct_train_gen_out> ro(rd.size());
+        vectori rcol(rd.size() * cap), rrow(rd.size() * cap); vectorf rsx(rd.size() * cap), rsy(rd.size() * cap);
+        if (!rd.empty())
+            chk(ctx, mct_pf_training_boxes(ctx, (int)rd.size(), rpf.data(), rg.data(), cap, rcol.data(), rrow.data(), rsx.data(), rsy.data(), ro.data()));
+        size_t k = 0;
+        for (int o = 0; o < n; o++) {
+            ParticleFilterTracker* t = trackers[o];
+            if (k < rd.size() && rd[k] == o) {
+                t->BuildTrainingSets(pColor, pGray, pHSV, &ro[k], rcol.data() + k * cap, rrow.data() + k * cap, rsx.data() + k * cap, rsy.data() + k * cap);
+                k++;
+            } else {
+                t->BuildTrainingSets(pColor, pGray, pHSV, nullptr, nullptr, nullptr, nullptr, nullptr);
+            }
             t->m_positiveSampleSet.ToBoxes(pc[o], pr[o], psx[o], psy[o]);
             t->m_negativeSampleSet.ToBoxes(nc[o], nr[o], nsx[o], nsy[o]);
             pb[o] = {(int)pc[o].size(), pc[o].data(), pr[o].data(), psx[o].data(), psy[o].data()};

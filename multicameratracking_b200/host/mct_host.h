@@ -306,7 +306,9 @@ struct ParticleFilterTrackerParameters {
     PFTracker_TrajectoryOption m_outputTrajectoryOption = PARTICLE_AVERAGE;
     int m_numberOfParticles = 50;
     float m_standardDeviationX = 5, m_standardDeviationY = 5, m_standardDeviationScaleX = 0, m_standardDeviationScaleY = 0;
-    int m_positiveSampleStrategy = 0, m_negativeSampleStrategy = 0;   // SAMPLE_POS/NEG_SIMPLETRACKER (config.cfg defaults)
+    // PFTracker_Positive_Sample_Strategy: 0 SIMPLETRACKER, 1 GREEDY, 2 SEMI_GREEDY, 3 PARTICLE_RANDOM;
+    // PFTracker_Negative_Sample_Strategy: 0 SIMPLETRACKER, 1 PARTICLE_RANDOM (TrackerParameters.h:42-58; config.cfg defaults 0 / 0)
+    int m_positiveSampleStrategy = 0, m_negativeSampleStrategy = 0;
     int m_maxNumPositiveExamples = 30;
 };
 typedef std::shared_ptr<ParticleFilterTrackerParameters> TrackerParametersPtr;
@@ -342,6 +344,14 @@ public:
     void TrackObjectAndSaveState(int frameind, Matrixu* pFrameImageColor, Matrixu* pFrameImageGray,
                                  Matrixu* pFrameImageHSV = nullptr) override;
     void GenerateTrainingSampleSet(Matrixu* pFrameImageColor, Matrixu* pFrameImageGray, Matrixu* pFrameImageHSV = nullptr) override;
+    // the three steps of GenerateTrainingSampleSet, split so that TrackCameraObjects can read the particles of all objects of a
+    // camera in ONE device pass (mct_pf_training_boxes): state from the particles (:655-672), the request for the particle
+    // strategies, and the sample sets themselves (:697-1004)
+    void PrepareTrainingState();
+    bool NeedsParticleReadout() const { return m_params->m_positiveSampleStrategy != 0 || m_params->m_negativeSampleStrategy != 0; }
+    void FillTrainGen(mct_train_gen& g, Matrixu* pFrameImageColor, Matrixu* pFrameImageGray) const;
+    void BuildTrainingSets(Matrixu* pFrameImageColor, Matrixu* pFrameImageGray, Matrixu* pFrameImageHSV, const mct_train_gen_out* readout,
+                           const int* col, const int* row, const float* sx, const float* sy);
     void GenerateTestSampleSet(Matrixu*, Matrixu*, Matrixu*) override {}   // fused into the device scoring call
     void GetTrainingSampleSets(Classifier::SampleSet& pos, Classifier::SampleSet& neg) override { pos = m_positiveSampleSet; neg = m_negativeSampleSet; }
     void UpdateClassifier(Matrixu* pFrameImageColor, Matrixu* pFrameImageGray, Matrixu* pFrameImageHSV = nullptr) override;

@@ -21,6 +21,8 @@ struct mcth_object_params {
     int64_t rng_seed;
     float init_xywh[4];
     float percent_retained;           // Percentage_Of_Weak_Classifiers_Retained (MILEnsemble, Object.cpp:254-262)
+    int pos_strategy, neg_strategy;   // PfTracker_Positive / Negative_Sample_Strategy (Object.cpp:316-342)
+    int max_num_pos_examples;         // PfTracker_Max_Num_Positive_Examples (Object.cpp:313)
 };
 
 struct mcth_camera {
@@ -181,6 +183,8 @@ int mcth_camera_init_trackers(mcth_camera* c)
             tp->m_searchWindSize = (uint)p.search_win;
             tp->m_outputTrajectoryOption = (PFTracker_TrajectoryOption)p.trajectory_option;
             tp->m_numberOfParticles = p.n_particles;
+            tp->m_positiveSampleStrategy = p.pos_strategy; tp->m_negativeSampleStrategy = p.neg_strategy;
+            if (p.max_num_pos_examples > 0) tp->m_maxNumPositiveExamples = p.max_num_pos_examples;
             tp->m_standardDeviationX = p.sd_x; tp->m_standardDeviationY = p.sd_y;
             tp->m_standardDeviationScaleX = p.sd_sx; tp->m_standardDeviationScaleY = p.sd_sy;
             tp->m_initState.assign(p.init_xywh, p.init_xywh + 4);

@@ -1334,7 +1334,95 @@ static void tracker_store(orc_tracker* t, int out_box[4])
     out_box[2] = orc_cvround((double)(t->cur[2] * t->cur[4]));
     out_box[3] = orc_cvround((double)(t->cur[3] * t->cur[5]));
 }
-/* UpdateClassifier :1013-1032 -> GenerateTrainingSampleSet :647-688, strategies 0/0 (:723-736, :921-937) */
+/* GeneratePositiveTrainingSampleSet (ParticleFilterTracker.cpp:697-906): the four strategies of
+   PFTracker_Positive_Sample_Strategy (TrackerParameters.h:42-51).  Boxes carry the particle's own scales. */
+static int box_in_frame(int leftX, int topY, int width, int height, int fw, int fh)
+{
+    return leftX > 0 && topY > 0 && leftX + width < fw - 1 && topY + height < fh - 1;
+}
+static void particle_box(const orc_tracker* t, const float* a, int* leftX, int* topY, int* width, int* height)
+{
+    float widthFloat = a[2] * t->cur[2], heightFloat = a[3] * t->cur[3];
+    *leftX = orc_cvround((double)(a[0] - widthFloat / 2));
+    *topY = orc_cvround((double)(a[1] - heightFloat / 2));
+    *width = orc_cvround((double)widthFloat);
+    *height = orc_cvround((double)heightFloat);
+}
+static void positive_ring(orc_tracker* t, const orc_frame* f)
+{
+    t->P = orc_sample_ring(t->rng, f->W, f->H, (int)t->cur[0], (int)t->cur[1], (int)t->cur[2], (int)t->cur[3],
+                           t->tp.pos_radius_train, 0, t->tp.max_pos_train, t->cur[4], t->cur[5],
+                           t->pcol, t->prow, TRAIN_CAP);
+    fill_scale(t->psx, t->P, t->cur[4]); fill_scale(t->psy, t->P, t->cur[5]);
+}
+static void tracker_gen_positive(orc_tracker* t, const orc_frame* f)
+{
+    const int strategy = t->tp.pos_strategy, maxpos = t->tp.max_num_pos_examples;
+    int lx, ty, w, h;
+    t->P = 0;
+    if (strategy == 0) { positive_ring(t, f); return; }                         /* SAMPLE_POS_SIMPLETRACKER :727-741 */
+    if (strategy == 1 || strategy == 2) {                                       /* GREEDY :743-795, SEMI_GREEDY :797-843 */
+        orc_pf_find_ordered_unique(t->pf);
+        int n = t->pf->n_uniq < maxpos ? t->pf->n_uniq : maxpos;
+        float ccx = t->cur[0] + t->cur[2] * t->cur[4] / 2, ccy = t->cur[1] + t->cur[3] * t->cur[5] / 2;
+        for (int q = 0; q < n && t->P < TRAIN_CAP; q++) {
+            const float* a = t->pf->uniq + (size_t)q * 5;
+            particle_box(t, a, &lx, &ty, &w, &h);
+            float dist = (float)sqrt(pow((double)(ccx - a[0]), 2) + pow((double)(ccy - a[1]), 2));
+            if (a[4] != 0 && box_in_frame(lx, ty, w, h, f->W, f->H) && (strategy == 1 || dist < 8)) {
+                t->pcol[t->P] = lx; t->prow[t->P] = ty; t->psx[t->P] = a[2]; t->psy[t->P] = a[3]; t->P++;
+            }
+        }
+        if (strategy == 1 && t->P == 0) positive_ring(t, f);                    /* :779-793 fall back to the disc */
+        return;
+    }
+    /* SAMPLE_POS_PARTICLE_RANDOM :845-892: one randfloat() per in-frame resampled particle */
+    int N = t->pf->N, i = 0;
+    float prob = (float)maxpos / N;
+    for (int q = 0; q < N; q++) {
+        const float* a = t->pf->resampled + (size_t)q * 5;
+        particle_box(t, a, &lx, &ty, &w, &h);
+        if (box_in_frame(lx, ty, w, h, f->W, f->H)) {
+            if (orc_randfloat(t->rng) < prob) {
+                if (i < TRAIN_CAP) { t->pcol[i] = lx; t->prow[i] = ty; t->psx[i] = a[2]; t->psy[i] = a[3]; }
+                i++;
+            }
+        }
+    }
+    t->P = i < maxpos ? i : maxpos;
+}
+/* GenerateNegativeTrainingSampleSet (:913-1004) */
+static void tracker_gen_negative(orc_tracker* t, const orc_frame* f)
+{
+    float maxs = t->pf->max_scale;
+    float nsx = t->cur[4] < maxs ? t->cur[4] : maxs, nsy = t->cur[5] < maxs ? t->cur[5] : maxs;
+    if (t->tp.neg_strategy == 0) {                                              /* SAMPLE_NEG_SIMPLETRACKER :921-937 */
+        t->Nn = orc_sample_ring(t->rng, f->W, f->H, orc_cvround((double)t->cur[0]), orc_cvround((double)t->cur[1]),
+                                orc_cvround((double)t->cur[2]), orc_cvround((double)t->cur[3]),
+                                1.5f * t->tp.search_win, t->tp.pos_radius_train + 15, t->tp.n_neg_train, nsx, nsy,
+                                t->ncol, t->nrow, TRAIN_CAP);
+    } else {                                                                    /* SAMPLE_NEG_PARTICLE_RANDOM :939-995 */
+        float mindx = 0.0f, mindy = 0.0f;
+        float ccx = t->cur[0] + t->cur[2] * t->cur[4] / 2, ccy = t->cur[1] + t->cur[3] * t->cur[5] / 2;
+        orc_pf_find_ordered_unique(t->pf);
+        for (int q = 0; q < t->pf->n_uniq; q++) {
+            const float* a = t->pf->uniq + (size_t)q * 5;
+            if (fabsf(a[0] - ccx) > mindx) mindx = fabsf(a[0] - ccx);
+            if (fabsf(a[1] - ccy) > mindy) mindy = fabsf(a[1] - ccy);
+        }
+        float lo = (float)t->tp.pos_radius_train + 5;
+        if (mindx < lo) mindx = lo;
+        if (mindy < lo) mindy = lo;
+        if (mindx > 15.0f) mindx = 15.0f;
+        if (mindy > 15.0f) mindy = 15.0f;
+        float maxd = 1.5f * t->tp.search_win;
+        t->Nn = orc_sample_rect(t->rng, f->W, f->H, orc_cvround((double)t->cur[0]), orc_cvround((double)t->cur[1]),
+                                orc_cvround((double)t->cur[2]), orc_cvround((double)t->cur[3]),
+                                maxd, maxd, mindx, mindy, t->tp.n_neg_train, nsx, nsy, t->ncol, t->nrow, TRAIN_CAP);
+    }
+    fill_scale(t->nsx, t->Nn, nsx); fill_scale(t->nsy, t->Nn, nsy);
+}
+/* UpdateClassifier :1013-1032 -> GenerateTrainingSampleSet :647-688 */
 static void tracker_update(orc_tracker* t, const orc_frame* f)
 {
     float a[5];
@@ -1349,18 +1437,9 @@ static void tracker_update(orc_tracker* t, const orc_frame* f)
     t->cur[0] = l > 0.0f ? l : 0.0f;
     t->cur[1] = tp_ > 0.0f ? tp_ : 0.0f;
     t->cur[4] = a[2]; t->cur[5] = a[3];
-    t->P = orc_sample_ring(t->rng, f->W, f->H, (int)t->cur[0], (int)t->cur[1], (int)t->cur[2], (int)t->cur[3],
-                           t->tp.pos_radius_train, 0, t->tp.max_pos_train, t->cur[4], t->cur[5],
-                           t->pcol, t->prow, TRAIN_CAP);
-    fill_scale(t->psx, t->P, t->cur[4]); fill_scale(t->psy, t->P, t->cur[5]);
+    tracker_gen_positive(t, f);
     if (t->P == 0) pf_force_refinement(t->pf, t->cur[2], t->cur[3]);  /* :898-901 */
-    float maxs = t->pf->max_scale;
-    float nsx = t->cur[4] < maxs ? t->cur[4] : maxs, nsy = t->cur[5] < maxs ? t->cur[5] : maxs;
-    t->Nn = orc_sample_ring(t->rng, f->W, f->H, orc_cvround((double)t->cur[0]), orc_cvround((double)t->cur[1]),
-                            orc_cvround((double)t->cur[2]), orc_cvround((double)t->cur[3]),
-                            1.5f * t->tp.search_win, t->tp.pos_radius_train + 15, t->tp.n_neg_train, nsx, nsy,
-                            t->ncol, t->nrow, TRAIN_CAP);
-    fill_scale(t->nsx, t->Nn, nsx); fill_scale(t->nsy, t->Nn, nsy);
+    tracker_gen_negative(t, f);
     if (t->P < 1 || t->Nn < 1) { t->ok = 0; return; }
     orc_boxes pb = {t->P, t->pcol, t->prow, t->psx, t->psy};
     orc_boxes nb = {t->Nn, t->ncol, t->nrow, t->nsx, t->nsy};

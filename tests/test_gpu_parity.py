@@ -404,6 +404,93 @@ def test_update_all_weights_and_resample_bit_exact(ctx, oracle, N):
     pf.close(); oracle.lib.orc_pf_free(opf)
 
 
+def _cvround(v):
+    return int(np.rint(np.float64(v)))
+
+
+def _particle_box(a, cur, fw, fh):
+    """leftX, topY and the in-frame test of ParticleFilterTracker.cpp:754-764 in f32"""
+    f = np.float32
+    wf, hf = f(a[2]) * f(cur[2]), f(a[3]) * f(cur[3])
+    lx, ty = _cvround(f(a[0]) - wf / f(2)), _cvround(f(a[1]) - hf / f(2))
+    w, h = _cvround(wf), _cvround(hf)
+    return lx, ty, (lx > 0 and ty > 0 and lx + w < fw - 1 and ty + h < fh - 1)
+
+
+@pytest.mark.parametrize("N", [700, 2000])
+def test_training_boxes_from_particles_all_strategies(ctx, oracle, N):
+    """mct_pf_training_boxes (GREEDY / SEMI_GREEDY / PARTICLE_RANDOM positives, distances for PARTICLE_RANDOM negatives) against a
+    restatement of ParticleFilterTracker.cpp:743-892, :939-964 on the oracle's ordered-unique / resampled matrices, in the
+    PREDICTED state (rows by weight) and the RESAMPLED state (rows = runs of the index list); bit-exact incl. the RNG state"""
+    rng = np.random.default_rng(N)
+    W, H = 640, 480
+    pf, opf = _pf_pair(ctx, oracle, N, W, H, cx=70.0, cy=400.0)       # near the border: some boxes leave the frame
+    cur = np.array([50.0, 360.0, 40.0, 80.0, 1.0, 1.0], np.float32)
+    f = np.float32
+    ccx, ccy = f(cur[0] + cur[2] * cur[4] / f(2)), f(cur[1] + cur[3] * cur[5] / f(2))
+    nz = synth.noise(N, (12, 12, 0.02, 0.02))
+    pf.PredictWithBrownianMotion(nz, 40, 80)
+    oracle.lib.orc_pf_predict(opf, nz.ctypes.data_as(C.POINTER(C.c_float)), 40, 80)
+    seen = set()
+    for rnd, peaked in enumerate([False, True, False, True]):
+        st = oracle.pf_state(opf)
+        m = int((st[:, 4] != 0).sum())
+        prob = rng.uniform(0.2, 1.0, m).astype(np.float32)
+        prob[rng.integers(0, m, m // 10)] = prob[0]                   # ties in the weight order
+        if peaked:
+            prob = (prob * 1e-4).astype(np.float32)
+            prob[rng.integers(0, m, 5)] = 1.0                        # N_eff collapses below 1 % of N -> resample
+        r = oracle.rng(100 + rnd); peek = oracle.rng(100 + rnd)
+        u01 = oracle.randfloat(peek)
+        res_o = oracle.lib.orc_pf_update_all_weights(opf, prob.ctypes.data_as(C.POINTER(C.c_float)), 1, 0, 1, C.byref(r))
+        assert pf.UpdateAllParticlesWeight(prob, True, False, True, u01) == bool(res_o)
+        seen.add(bool(res_o))
+        opf.contents.uniq_valid = 0
+        oracle.lib.orc_pf_find_ordered_unique(opf)
+        nu = opf.contents.n_uniq
+        uniq = np.ctypeslib.as_array(opf.contents.uniq, (N * 5,)).reshape(N, 5)[:nu].copy()
+        res_m = oracle.pf_resampled(opf).copy()
+        for max_pos in (30, 400):
+            seed = 7 + rnd
+            gens = [(1, max_pos, cur, W, H, seed), (2, max_pos, cur, W, H, seed), (3, max_pos, cur, W, H, seed), (0, max_pos, cur, W, H, seed)]
+            out = capi.training_boxes(ctx, [pf] * 4, gens, max_pos)
+            # GREEDY / SEMI_GREEDY
+            for k, strat in ((0, 1), (1, 2)):
+                exp = []
+                for q in range(min(nu, max_pos)):
+                    a = uniq[q]
+                    lx, ty, ok = _particle_box(a, cur, W, H)
+                    dist = f(np.sqrt(np.float64(ccx - f(a[0])) ** 2 + np.float64(ccy - f(a[1])) ** 2))
+                    if a[4] != 0 and ok and (strat == 1 or dist < 8):
+                        exp.append((lx, ty, a[2], a[3]))
+                col, row, sx, sy, o = out[k]
+                assert o.n_unique == nu and o.n_pos == len(exp), (rnd, strat, o.n_pos, len(exp))
+                assert list(zip(col.tolist(), row.tolist(), sx.tolist(), sy.tolist())) == [(a, b, float(c), float(d)) for a, b, c, d in exp]
+                assert o.rng_state == seed and o.n_draws == 0
+                assert o.max_dx == np.abs(uniq[:, 0] - ccx).max() and o.max_dy == np.abs(uniq[:, 1] - ccy).max()
+            # PARTICLE_RANDOM: one randfloat() per in-frame resampled particle, in particle order
+            rr = oracle.rng(seed)
+            pr = f(max_pos) / f(N)
+            exp, draws = [], 0
+            for q in range(N):
+                a = res_m[q]
+                lx, ty, ok = _particle_box(a, cur, W, H)
+                if ok:
+                    draws += 1
+                    if oracle.randfloat(rr) < pr:
+                        exp.append((lx, ty, a[2], a[3]))
+            exp = exp[:max_pos]
+            col, row, sx, sy, o = out[2]
+            assert o.n_draws == draws and o.rng_state == rr.state, (rnd, o.n_draws, draws)
+            assert list(zip(col.tolist(), row.tolist(), sx.tolist(), sy.tolist())) == [(a, b, float(c), float(d)) for a, b, c, d in exp]
+            assert out[3][4].n_pos == 0 and out[3][4].max_dx == out[0][4].max_dx
+        nz = synth.noise(N, (12, 12, 0.02, 0.02), t=rnd + 1)
+        pf.PredictWithBrownianMotion(nz, 40, 80)
+        oracle.lib.orc_pf_predict(opf, nz.ctypes.data_as(C.POINTER(C.c_float)), 40, 80)
+    assert seen == {False, True}
+    pf.close(); oracle.lib.orc_pf_free(opf)
+
+
 def test_resample_particles_forced_and_unforced(ctx, oracle):
     N = 3000
     rng = np.random.default_rng(9)

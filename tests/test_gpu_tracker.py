@@ -22,7 +22,8 @@ def _oracle_tracker(oracle, seq, o, f0, p, seed):
                             pct_retained=p.get("percent_retained", 0.0))
     tp = oracle_py.TrackerParams(p["n_particles"], p["sd_x"], p["sd_y"], p["sd_sx"], p["sd_sy"], p["pos_radius_train"],
                                  p["init_pos_radius_train"], p["n_neg_train"], p["init_n_neg_train"], 100000,
-                                 p["search_win"], p["trajectory_option"], 0, 0, 30)
+                                 p["search_win"], p["trajectory_option"], p.get("pos_strategy", 0), p.get("neg_strategy", 0),
+                                 p.get("max_num_pos_examples", 30))
     x, y, w, h = seq.box(0, o)
     init = np.array([x, y, w, h], np.float32)
     trk = oracle.lib.orc_tracker_create(C.byref(tp), clf, C.byref(f0), init.ctypes.data_as(C.POINTER(C.c_float)), C.byref(rng))
@@ -30,7 +31,7 @@ def _oracle_tracker(oracle, seq, o, f0, p, seed):
 
 
 @pytest.mark.parametrize("cfg", ["cfg1_haar_milboost", "haarmdch_wstump_2obj", "mdch_anyboost_avg", "cfg2_full_size_8obj_2000",
-                                 "haar_ensemble_2obj"])
+                                 "haar_ensemble_2obj", "greedy_pos_random_neg", "semi_greedy_pos", "particle_random_pos"])
 def test_tracker_sequence_matches_oracle(oracle, cfg):
     n_frames = 12
     if cfg == "cfg1_haar_milboost":
@@ -42,6 +43,14 @@ def test_tracker_sequence_matches_oracle(oracle, cfg):
         n_obj, over = 8, dict(feature_type=3, weak_type=1, n_particles=2000, n_haar=250)
     elif cfg == "haarmdch_wstump_2obj":
         n_obj, over = 2, dict(feature_type=3, weak_type=1, n_particles=600, n_haar=100)
+    elif cfg == "greedy_pos_random_neg":
+        # PfTracker_Positive_Sample_Strategy 1 (ordered unique particles) + Negative 1 (rectangle ring sized by the particle spread)
+        n_obj, over = 2, dict(n_particles=600, n_haar=100, pos_strategy=1, neg_strategy=1, max_num_pos_examples=60)
+    elif cfg == "semi_greedy_pos":
+        n_obj, over = 1, dict(n_particles=600, n_haar=100, pos_strategy=2, max_num_pos_examples=300, sd_x=4.0, sd_y=4.0)
+    elif cfg == "particle_random_pos":
+        # one randfloat() per in-frame resampled particle: the device jumps the tracker's RNG stream ahead
+        n_obj, over = 2, dict(n_particles=800, n_haar=100, pos_strategy=3, neg_strategy=1, max_num_pos_examples=50, trajectory_option=1)
     elif cfg == "haar_ensemble_2obj":
         # Tracker_Strong_Classifier_Type 3 (MILEnsemble), half of the previous selectors re-ranked and retained every frame
         n_obj, over = 2, dict(strong_type=3, n_particles=500, n_haar=120, percent_retained=50.0)
