@@ -325,6 +325,29 @@ typedef struct {
 int mct_pf_training_boxes(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, const mct_train_gen* gen, int cap,
                           int* col, int* row, float* sx, float* sy, mct_train_gen_out* out);
 
+/* SampleSet::SampleImage, ring form (SampleSet.cpp:82-168) and rectangle form (:180-262), followed by
+ * SelectSamplesUniformlyFromLargerSet (:331-361), for a batch of regions in one device pass: candidates are enumerated in the
+ * reference's row-major order, candidate k owns draw k of the tracker's RNG stream (jump-ahead, see mct_pf_training_boxes) and
+ * survives iff !(randfloat() > (max_n + 1) / n_candidates); the survivors keep their order and are cut at max_n.  No draws
+ * happen when the probability is >= 1.  col / row: [n_regions][cap] host arrays. */
+typedef struct {
+    int   kind;                      /* 0 ring: p = {outerCircleRadius, innerCircleRadius}; 1 rectangle: p = {maxDX, maxDY, minDX, minDY} */
+    int   x, y, width, height;       /* SampleImage arguments */
+    float p[4];
+    int   max_n;                     /* maximumNumberOfSamples */
+    float scale_x, scale_y;
+    int   frame_w, frame_h;          /* image cols / rows */
+    unsigned long long rng_state;
+} mct_sample_region;
+typedef struct {
+    int n;                           /* samples kept (<= cap) */
+    int n_candidates;                /* size of the larger set */
+    int n_draws, pad;                /* randfloat() calls consumed */
+    unsigned long long rng_state;    /* state after them */
+} mct_sample_region_out;
+int mct_sample_regions(mct_ctx* ctx, int n_regions, const mct_sample_region* regions, int cap, int* col, int* row,
+                       mct_sample_region_out* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,7 +34,7 @@ SYMBOLS = [
     "mct_track_collect", "mct_track_update", "mct_pf_get_last_response", "mct_fuser_pack_foot_points",
     "mct_pf_ground_pdf", "mct_pf_rearrange_ground", "mct_classify_argmax", "mct_fuser_ground_pdf", "mct_p2p_create", "mct_p2p_open", "mct_p2p_destroy",
     "mct_fuser_exchange_foot_points", "mct_classifier_get_alphas", "mct_features_compute_dev", "mct_classifier_update_from_features_dev",
-    "mct_pf_training_boxes",
+    "mct_pf_training_boxes", "mct_sample_regions",
 ]
 
 
@@ -62,6 +62,16 @@ class TrainGen(C.Structure):
 class TrainGenOut(C.Structure):
     _fields_ = [("n_pos", C.c_int), ("n_unique", C.c_int), ("max_dx", C.c_float), ("max_dy", C.c_float), ("rng_state", C.c_uint64),
                 ("n_draws", C.c_int), ("pad", C.c_int)]
+
+
+class SampleRegion(C.Structure):
+    _fields_ = [("kind", C.c_int), ("x", C.c_int), ("y", C.c_int), ("width", C.c_int), ("height", C.c_int), ("p", C.c_float * 4),
+                ("max_n", C.c_int), ("scale_x", C.c_float), ("scale_y", C.c_float), ("frame_w", C.c_int), ("frame_h", C.c_int),
+                ("rng_state", C.c_uint64)]
+
+
+class SampleRegionOut(C.Structure):
+    _fields_ = [("n", C.c_int), ("n_candidates", C.c_int), ("n_draws", C.c_int), ("pad", C.c_int), ("rng_state", C.c_uint64)]
 
 
 class HaarTable(C.Structure):
@@ -160,6 +170,7 @@ def load():
     L.mct_classify_argmax.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(Boxes), C.c_int, _c_int_p, _c_float_p]
     L.mct_pf_training_boxes.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(TrainGen), C.c_int, _c_int_p, _c_int_p, _c_float_p, _c_float_p,
                                         C.POINTER(TrainGenOut)]
+    L.mct_sample_regions.argtypes = [vp, C.c_int, C.POINTER(SampleRegion), C.c_int, _c_int_p, _c_int_p, C.POINTER(SampleRegionOut)]
     _lib = L
     return L
 
@@ -557,6 +568,24 @@ def training_boxes(ctx, pfs, gens, cap):
         k = out[o].n_pos
         res.append((col[o, :k].copy(), row[o, :k].copy(), sx[o, :k].copy(), sy[o, :k].copy(), out[o]))
     return res
+
+
+def sample_regions(ctx, regions, cap):
+    """mct_sample_regions: regions = [dict(kind, x, y, width, height, p, max_n, scale_x, scale_y, frame_w, frame_h, rng_state)];
+    returns per region (col, row, SampleRegionOut)"""
+    n = len(regions)
+    ra = (SampleRegion * n)()
+    for i, g in enumerate(regions):
+        for k, v in g.items():
+            if k == "p":
+                for j in range(4):
+                    ra[i].p[j] = float(v[j]) if j < len(v) else 0.0
+            else:
+                setattr(ra[i], k, v)
+    col = np.zeros((n, cap), np.int32); row = np.zeros((n, cap), np.int32)
+    out = (SampleRegionOut * n)()
+    ctx.check(ctx.L.mct_sample_regions(ctx.h, n, ra, cap, _ip(col), _ip(row), out))
+    return [(col[i, :out[i].n].copy(), row[i, :out[i].n].copy(), out[i]) for i in range(n)]
 
 
 def track_update(ctx, clfs, pos_list, neg_list):

@@ -1074,3 +1074,76 @@ int launch_train_from_particles(mct_ctx* ctx, const ObjDesc* d_desc, const ObjDe
     MCT_LAUNCH(ctx, "k_train_from_particles", k_train_from_particles<<<n_obj, PF_THREADS, smem, ctx->stream>>>(d_desc, d_gen, cap, d_col, d_row, d_sx, d_sy, d_out));
     return MCT_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// k_sample_regions: SampleSet::SampleImage (ring :82-168, rectangle :180-262) + SelectSamplesUniformlyFromLargerSet (:331-361).
+// One CTA per region; pass 1 counts the candidates (the keep probability needs the count), pass 2 gives candidate k draw k.
+__device__ __forceinline__ bool region_candidate(const mct_sample_region& g, int r, int c, float o2, float i2)
+{
+    if (g.kind == 0) {
+        const int dist = (g.y - r) * (g.y - r) + (g.x - c) * (g.x - c);
+        return (float)dist < o2 && (float)dist >= i2;
+    }
+    const int dx = abs(g.x - c), dy = abs(g.y - r);
+    return (float)dx >= g.p[2] || (float)dy >= g.p[3];
+}
+__global__ void __launch_bounds__(PF_THREADS)
+k_sample_regions(const mct_sample_region* __restrict__ regs, int cap, int* __restrict__ col, int* __restrict__ row, mct_sample_region_out* __restrict__ outs)
+{
+    __shared__ int sh_c[33];
+    __shared__ int sh_i[32];
+    __shared__ unsigned long long s_pw[32];
+    const mct_sample_region g = regs[blockIdx.x];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    int* o_col = col + (size_t)blockIdx.x * cap; int* o_row = row + (size_t)blockIdx.x * cap;
+    const int scaledW = __float2int_rn(__fmul_rn((float)g.width, g.scale_x)), scaledH = __float2int_rn(__fmul_rn((float)g.height, g.scale_y));
+    const int nrows = g.frame_h - scaledH - 1, ncols = g.frame_w - scaledW - 1;
+    const int ry = (int)(g.kind == 0 ? g.p[0] : g.p[1]), rx = (int)g.p[0];
+    const int minrow = max(0, g.y - ry), maxrow = min(nrows - 1, g.y + ry);
+    const int mincol = max(0, g.x - rx), maxcol = min(ncols - 1, g.x + rx);
+    const int RW = maxcol - mincol + 1, RH = maxrow - minrow + 1;
+    const int cells = (RW > 0 && RH > 0) ? RW * RH : 0;
+    const float o2 = __fmul_rn(g.p[0], g.p[0]), i2 = __fmul_rn(g.p[1], g.p[1]);
+    int cnt = 0;
+    for (int e = tid; e < cells; e += nt) cnt += region_candidate(g, minrow + e / RW, mincol + e % RW, o2, i2) ? 1 : 0;
+    const int n_cand = block_reduce_sum_i(cnt, sh_i);
+    const int n_list = n_cand;
+    const float prob = __fdiv_rn((float)(g.max_n + 1), (float)(unsigned)n_list);
+    const bool thin = prob < 1.0f;
+    const unsigned long long s0 = g.rng_state, s2 = mwc_step(mwc_step(s0));
+    if (tid == 0) {
+        unsigned long long p = MWC_A % MWC_M;
+        for (int k = 0; k < 32; k++) { s_pw[k] = p; p = mwc_mulmod(p, p); }
+    }
+    __syncthreads();
+    int base_c = 0, base_k = 0;
+    for (int e0 = 0; e0 < cells; e0 += nt) {
+        const int e = e0 + tid;
+        const int r = minrow + e / max(RW, 1), c = mincol + e % max(RW, 1);
+        const bool cand = e < cells && region_candidate(g, r, c, o2, i2);
+        int tot_c;
+        const int k = base_c + block_compact(cand, sh_c, &tot_c);
+        bool keep = cand && k < n_list;
+        if (keep && thin) {
+            const unsigned long long s = mwc_after(s0, s2, (unsigned)k + 1u, s_pw);
+            const float rf = (float)((double)(unsigned)(s & 0xffffffffull) * 2.3283064365386962890625e-10);
+            keep = !(rf > prob);
+        }
+        int tot_k;
+        const int pos = base_k + block_compact(keep, sh_c, &tot_k);
+        if (keep && pos < cap && (!thin || pos < g.max_n)) { o_col[pos] = c; o_row[pos] = r; }
+        base_c += tot_c; base_k += tot_k;
+    }
+    if (tid == 0) {
+        mct_sample_region_out o;
+        o.n = min(thin ? min(base_k, g.max_n) : n_list, cap);
+        o.n_candidates = n_cand; o.n_draws = thin ? n_list : 0; o.pad = 0;
+        o.rng_state = thin ? mwc_after(s0, s2, (unsigned)n_list, s_pw) : s0;
+        outs[blockIdx.x] = o;
+    }
+}
+int launch_sample_regions(mct_ctx* ctx, int n, const mct_sample_region* d_reg, int cap, int* d_col, int* d_row, mct_sample_region_out* d_out)
+{
+    MCT_LAUNCH(ctx, "k_sample_regions", k_sample_regions<<<n, PF_THREADS, 0, ctx->stream>>>(d_reg, cap, d_col, d_row, d_out));
+    return MCT_OK;
+}

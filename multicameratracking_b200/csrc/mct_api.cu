@@ -1682,3 +1682,31 @@ extern "C" int mct_pf_training_boxes(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
     MCT_CUDA(ctx, cudaMemcpyAsync(sy, d_sy, box_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return mct_sync(ctx);
 }
+
+extern "C" int mct_sample_regions(mct_ctx* ctx, int n_regions, const mct_sample_region* regions, int cap, int* col, int* row,
+                                  mct_sample_region_out* out)
+{
+    if (!ctx || n_regions < 1 || !regions || cap < 1 || !col || !row || !out) return MCT_E_ARG;
+    for (int i = 0; i < n_regions; i++) {
+        const mct_sample_region& g = regions[i];
+        if (g.kind < 0 || g.kind > 1 || g.max_n < 0) return mct_fail(ctx, MCT_E_ARG, "bad sample region%s (%d)", "", i);
+        // the reference asserts these (SampleSet.cpp:97, :203-204)
+        if (g.kind == 0 ? !(g.p[0] > g.p[1]) : !(g.p[0] > g.p[2] && g.p[1] > g.p[3]))
+            return mct_fail(ctx, MCT_E_ARG, "sample region: outer extent must exceed the inner one%s (%d)", "", i);
+    }
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t off_out = (size_t)n_regions * sizeof(mct_sample_region), off_box = off_out + (size_t)n_regions * sizeof(mct_sample_region_out);
+    const size_t box_bytes = (size_t)n_regions * cap * 4;
+    int rc = ensure_tmp(ctx, off_box + 2 * box_bytes);
+    if (rc) return rc;
+    unsigned char* base = (unsigned char*)ctx->d_tmp;
+    mct_sample_region* d_reg = (mct_sample_region*)base;
+    mct_sample_region_out* d_out = (mct_sample_region_out*)(base + off_out);
+    int* d_col = (int*)(base + off_box); int* d_row = (int*)(base + off_box + box_bytes);
+    MCT_CUDA(ctx, cudaMemcpyAsync(d_reg, regions, off_out, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = launch_sample_regions(ctx, n_regions, d_reg, cap, d_col, d_row, d_out))) return rc;
+    MCT_CUDA(ctx, cudaMemcpyAsync(out, d_out, (size_t)n_regions * sizeof(mct_sample_region_out), cudaMemcpyDeviceToHost, ctx->stream));
+    MCT_CUDA(ctx, cudaMemcpyAsync(col, d_col, box_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MCT_CUDA(ctx, cudaMemcpyAsync(row, d_row, box_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return mct_sync(ctx);
+}

@@ -321,6 +321,7 @@ int launch_weak_update_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* 
 int launch_mil_select_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj, const int* cluster_req);
 int launch_build_colormap_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj);
 int launch_foot_points(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, const float* d_h0, float* d_out);
+int launch_sample_regions(mct_ctx* ctx, int n, const mct_sample_region* d_reg, int cap, int* d_col, int* d_row, mct_sample_region_out* d_out);
 int launch_train_from_particles(mct_ctx* ctx, const ObjDesc* d_desc, const ObjDesc* h_desc, int n_obj, const mct_train_gen* d_gen, int max_pos_max,
                                 int cap, int* d_col, int* d_row, float* d_sx, float* d_sy, mct_train_gen_out* d_out);
 

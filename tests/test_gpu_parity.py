@@ -491,6 +491,44 @@ def test_training_boxes_from_particles_all_strategies(ctx, oracle, N):
     pf.close(); oracle.lib.orc_pf_free(opf)
 
 
+def test_sample_regions_ring_and_rectangle_match_oracle(ctx, oracle):
+    """mct_sample_regions (SampleSet::SampleImage ring / rectangle forms + SelectSamplesUniformlyFromLargerSet on the device,
+    draws by RNG jump-ahead) against the oracle's sequential samplers: same boxes, same order, same RNG state afterwards"""
+    W, H = 640, 480
+    cases = []
+    rng = np.random.default_rng(3)
+    for i in range(24):
+        x, y = int(rng.integers(-5, 620)), int(rng.integers(-5, 470))
+        if i % 6 == 0:
+            x, y = (3, 4) if i % 12 == 0 else (598, 396)                 # clipped by the frame
+        sxy = (1.0, 1.0) if i % 3 else (1.2, 0.9)
+        if i % 2 == 0:
+            outer, inner = [(10.0, 0.0), (30.0, 25.0), (40.0, 10.5), (7.5, 7.0)][(i // 2) % 4]
+            max_n = [100000, 30, 65, 5][(i // 2) % 4]
+            cases.append(dict(kind=0, x=x, y=y, width=40, height=80, p=[outer, inner], max_n=max_n, scale_x=sxy[0], scale_y=sxy[1],
+                              frame_w=W, frame_h=H, rng_state=1000 + i))
+        else:
+            p = [(30.0, 30.0, 15.0, 15.0), (30.0, 24.0, 12.5, 6.0), (12.0, 9.0, 0.0, 0.0)][(i // 2) % 3]
+            max_n = [30, 200, 100000][(i // 2) % 3]
+            cases.append(dict(kind=1, x=x, y=y, width=40, height=80, p=list(p), max_n=max_n, scale_x=sxy[0], scale_y=sxy[1],
+                              frame_w=W, frame_h=H, rng_state=(1 << 64) - 1 if i == 5 else 77 + i))
+    res = capi.sample_regions(ctx, cases, 16384)
+    n_thinned = 0
+    for g, (col, row, o) in zip(cases, res):
+        r = oracle.rng(1); r.state = g["rng_state"]
+        if g["kind"] == 0:
+            oc, orow = oracle.sample_ring(r, W, H, g["x"], g["y"], 40, 80, g["p"][0], g["p"][1], g["max_n"], g["scale_x"], g["scale_y"])
+        else:
+            oc, orow = oracle.sample_rect(r, W, H, g["x"], g["y"], 40, 80, g["p"][0], g["p"][1], g["p"][2], g["p"][3], g["max_n"],
+                                          g["scale_x"], g["scale_y"])
+        np.testing.assert_array_equal(col, oc); np.testing.assert_array_equal(row, orow)
+        assert o.rng_state == r.state, g
+        n_thinned += o.n_draws > 0
+    assert n_thinned >= 8
+    with pytest.raises(capi.MctError):
+        capi.sample_regions(ctx, [dict(cases[0], p=[5.0, 5.0])], 64)      # the reference asserts outer > inner
+
+
 def test_resample_particles_forced_and_unforced(ctx, oracle):
     N = 3000
     rng = np.random.default_rng(9)
