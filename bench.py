@@ -430,6 +430,22 @@ def run_ours(args):
         except Exception:
             pass
         achieved = alg / (avg_us * 1e-6) / 1e9 if avg_us > 0 else 0.0
+        # on-chip ceilings: the gather kernels work out of shared memory / L2, so their traffic there (ncu counters of
+        # the committed capture, per launch) is set against this pool's measured shared-memory and L2 read peaks (tools/peaks_lab.cu)
+        onchip = None
+        try:
+            pk = json.load(open(os.path.join(ROOT, "profiles", "r01_peaks.json")))
+            oc = json.load(open(os.path.join(ROOT, "profiles", "roofline_onchip.json"))).get(dom_name)
+            if oc and avg_us > 0:
+                smem_b = oc["smem_wavefronts"] * 128.0
+                onchip = {"smem_peak_gbs": pk["smem_read_gbs"], "l2_peak_gbs": pk["l2_read_gbs"], "peaks_source": "profiles/r01_peaks.json (tools/peaks_lab.cu)",
+                          "smem_bytes_per_launch": smem_b, "smem_achieved_gbs": smem_b / (avg_us * 1e-6) / 1e9,
+                          "smem_frac": smem_b / (avg_us * 1e-6) / 1e9 / pk["smem_read_gbs"],
+                          "smem_bank_conflict_share": oc["smem_bank_conflict_wavefronts"] / max(oc["smem_wavefronts"], 1.0),
+                          "l2_bytes_per_launch": oc["l2_bytes"], "l2_achieved_gbs": oc["l2_bytes"] / (avg_us * 1e-6) / 1e9,
+                          "counters_source": "profiles/roofline_onchip.json (ncu --set full, per launch)"}
+        except Exception:
+            pass
         shares = {k: round(v[0] / tot, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
         out = {
             "metric": METRIC, "value": scored_all / (ms_max * 1e-3), "unit": "particles/s", "n_gpus": world,
@@ -445,7 +461,7 @@ def run_ours(args):
             "gpu_launches": int(launches_all),
             "roofline": {"kernel": dom_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
-                         "avg_launch_us": avg_us, "algorithmic_bytes_per_launch": alg, "kernel_time_shares": shares,
+                         "avg_launch_us": avg_us, "algorithmic_bytes_per_launch": alg, "kernel_time_shares": shares, "onchip": onchip,
                          "kernels": {k: {"avg_launch_us": round(1e3 * v[0] / max(v[1], 1), 2), "algorithmic_bytes": alg_all.get(k, 0),
                                          "achieved_gbs": round(alg_all.get(k, 0) / max(1e3 * v[0] / max(v[1], 1), 1e-9) / 1e3, 1),
                                          "dram_traffic_bytes": traffic_all.get(k)} for k, v in prof.items()},

@@ -92,6 +92,35 @@ static void frame_limits(Matrixu* gray, Matrixu* rgb, Matrixu* hsv, int width, i
     numberOfColumns = m->cols() - scaledWidth - 1;
 }
 
+// The candidates of both region forms are runs of consecutive columns per row, so the larger set is never materialised:
+// pass 1 adds up the run lengths (the keep probability of SelectSamplesUniformlyFromLargerSet needs the count), pass 2 walks
+// the runs in the reference's row-major order, draws one randfloat() per candidate when the set is thinned, and stores the
+// survivors only.  Same samples, same order and same RNG draws as enumerate-then-erase (SampleSet.cpp:82-168, :180-262, :331-361).
+struct ColumnRun { int row, c0, c1; };
+static int isqrt_floor(int v)
+{
+    int r = (int)std::sqrt((double)v);
+    while (r * r > v) r--;
+    while ((r + 1) * (r + 1) <= v) r++;
+    return r;
+}
+void SampleSet::TakeRuns(const std::vector<ColumnRun>& runs, int maximumNumberOfSamples, Matrixu* gray, int width, int height,
+                         Matrixu* rgb, Matrixu* hsv, float scaleX, float scaleY)
+{
+    size_t n = 0;
+    for (const ColumnRun& q : runs) n += (size_t)(q.c1 - q.c0 + 1);
+    m_sampleList.clear();
+    const float probability = ((float)(maximumNumberOfSamples + 1)) / (float)(uint)n;
+    const bool thin = probability < 1;
+    m_sampleList.reserve(thin ? (size_t)maximumNumberOfSamples + 64 : n);
+    for (const ColumnRun& q : runs)
+        for (int c = q.c0; c <= q.c1; c++) {
+            if (thin && Public::randfloat() > probability) continue;
+            PushBackSample(gray, c, q.row, width, height, 1.0f, rgb, hsv, scaleX, scaleY);
+        }
+    if (thin && m_sampleList.size() > (size_t)maximumNumberOfSamples) m_sampleList.resize((size_t)maximumNumberOfSamples);
+}
+
 void SampleSet::SampleImage(Matrixu* gray, int x, int y, int width, int height, float outerCircleRadius,
                             float innerCircleRadius, int maximumNumberOfSamples, Matrixu* rgb, Matrixu* hsv,
                             float scaleX, float scaleY)
@@ -102,14 +131,27 @@ void SampleSet::SampleImage(Matrixu* gray, int x, int y, int width, int height, 
     const float outerSq = outerCircleRadius * outerCircleRadius, innerSq = innerCircleRadius * innerCircleRadius;
     const int minrow = std::max(0, y - (int)outerCircleRadius), maxrow = std::min(nrows - 1, y + (int)outerCircleRadius);
     const int mincol = std::max(0, x - (int)outerCircleRadius), maxcol = std::min(ncols - 1, x + (int)outerCircleRadius);
-    m_sampleList.clear();
-    for (int r = minrow; r <= maxrow; r++)
-        for (int c = mincol; c <= maxcol; c++) {
-            const int dist = (y - r) * (y - r) + (x - c) * (x - c);
-            if ((float)dist < outerSq && (float)dist >= innerSq)
-                PushBackSample(gray, c, r, width, height, 1.0f, rgb, hsv, scaleX, scaleY);
+    // (float)dist < outerSq && (float)dist >= innerSq for an integer dist (exact in f32 here)  <=>  dLo <= dist <= dHi
+    const int dHi = (int)std::ceil(outerSq) - 1, dLo = (int)std::ceil(innerSq);
+    std::vector<ColumnRun> runs;
+    for (int r = minrow; r <= maxrow; r++) {
+        const int dy2 = (y - r) * (y - r);
+        if (dHi - dy2 < 0) continue;
+        const int b = isqrt_floor(dHi - dy2);                                   // |x - c| <= b
+        int a = 0;                                                              // |x - c| >= a
+        if (dLo - dy2 > 0) { a = isqrt_floor(dLo - dy2 - 1) + 1; }
+        if (a > b) continue;
+        if (a == 0) {
+            const int c0 = std::max(mincol, x - b), c1 = std::min(maxcol, x + b);
+            if (c0 <= c1) runs.push_back({r, c0, c1});
+        } else {
+            int c0 = std::max(mincol, x - b), c1 = std::min(maxcol, x - a);
+            if (c0 <= c1) runs.push_back({r, c0, c1});
+            c0 = std::max(mincol, x + a); c1 = std::min(maxcol, x + b);
+            if (c0 <= c1) runs.push_back({r, c0, c1});
         }
-    SelectSamplesUniformlyFromLargerSet(maximumNumberOfSamples);
+    }
+    TakeRuns(runs, maximumNumberOfSamples, gray, width, height, rgb, hsv, scaleX, scaleY);
 }
 
 void SampleSet::SampleImage(Matrixu* gray, int x, int y, int width, int height, float maximumDistanceX,
@@ -122,14 +164,21 @@ void SampleSet::SampleImage(Matrixu* gray, int x, int y, int width, int height, 
     frame_limits(gray, rgb, hsv, width, height, scaleX, scaleY, nrows, ncols);
     const int minrow = std::max(0, y - (int)maximumDistanceY), maxrow = std::min(nrows - 1, y + (int)maximumDistanceY);
     const int mincol = std::max(0, x - (int)maximumDistanceX), maxcol = std::min(ncols - 1, x + (int)maximumDistanceX);
-    m_sampleList.clear();
-    for (int r = minrow; r <= maxrow; r++)
-        for (int c = mincol; c <= maxcol; c++) {
-            const int dx = std::abs(x - c), dy = std::abs(y - r);
-            if ((float)dx >= minimumDistanceX || (float)dy >= minimumDistanceY)
-                PushBackSample(gray, c, r, width, height, 1.0f, rgb, hsv, scaleX, scaleY);
+    // (float)dx >= minimumDistanceX for an integer dx >= 0  <=>  dx >= aX
+    const int aX = minimumDistanceX > 0 ? (int)std::ceil(minimumDistanceX) : 0;
+    std::vector<ColumnRun> runs;
+    for (int r = minrow; r <= maxrow; r++) {
+        const int dy = std::abs(y - r);
+        if ((float)dy >= minimumDistanceY || aX == 0) {
+            if (mincol <= maxcol) runs.push_back({r, mincol, maxcol});
+            continue;
         }
-    SelectSamplesUniformlyFromLargerSet(maximumNumberOfSamples);
+        int c0 = mincol, c1 = std::min(maxcol, x - aX);
+        if (c0 <= c1) runs.push_back({r, c0, c1});
+        c0 = std::max(mincol, x + aX); c1 = maxcol;
+        if (c0 <= c1) runs.push_back({r, c0, c1});
+    }
+    TakeRuns(runs, maximumNumberOfSamples, gray, width, height, rgb, hsv, scaleX, scaleY);
 }
 
 void SampleSet::SampleImage(Matrixu* gray, uint numberOfSamples, int w, int h, Matrixu* rgb, Matrixu* hsv, float scaleX,

@@ -62,6 +62,8 @@ int         cvRound(double v);            // round-half-to-even
 class Matrixu {
 public:
     Matrixu(mct_ctx* ctx = nullptr) : m_ctx(ctx), m_rows(0), m_cols(0), m_iiInit(false) {}
+    // size-only matrix without a device frame (host-side sample enumeration: SampleSet::SampleImage reads rows() / cols() only)
+    Matrixu(int rows, int cols) : m_ctx(nullptr), m_rows(rows), m_cols(cols), m_iiInit(false) {}
     // upload gray (+ optional colour planes) and build the integral image  (Camera.cpp:460-491)
     // deviceMode: 0 = host planes (copied), 1 = device planes ordered after the work already enqueued on the ctx stream,
     //             2 = device planes that are already complete (lets the frame preparation overlap the previous frame)
@@ -95,12 +97,16 @@ struct Sample {
                m_height(0), m_weight(1.0f), m_scaleX(1), m_scaleY(1), m_cameraID(0) {}
 };
 
+struct ColumnRun;          // {row, first column, last column}: a run of candidate samples (mct_host.cpp)
 // SampleSet.h:13-94.  Feature matrix is feature-major [F][N] (m_featureMatrix[ftr](sample)).
 class SampleSet {
 public:
     size_t Size() const { return m_sampleList.size(); }
     void Resize(size_t n) { m_sampleList.resize(n); }
     void Clear() { m_featureMatrix.clear(); m_numFeatures = 0; m_sampleList.clear(); }
+    // samples of the column runs, thinned like SelectSamplesUniformlyFromLargerSet (mct_host.cpp)
+    void TakeRuns(const std::vector<ColumnRun>& runs, int maximumNumberOfSamples, Matrixu* gray, int width, int height,
+                  Matrixu* rgb, Matrixu* hsv, float scaleX, float scaleY);
     Sample& operator[](int i) { return m_sampleList[i]; }
     const Sample& operator[](int i) const { return m_sampleList[i]; }
     void PushBackSample(const Sample& s) { m_sampleList.push_back(s); }

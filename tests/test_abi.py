@@ -115,3 +115,22 @@ def test_host_randgaus_stream_matches_restatement(oracle):
                 break
         exp.append(np.float32(np.float32(10.0 * y * math.sqrt(-2.0 * math.log(r2) / r2)) + np.float32(0)))   # libm, as the C++ side
     np.testing.assert_array_equal(got, np.array(exp, np.float32))
+
+
+def test_host_sampler_equals_the_naive_listing(tmp_path):
+    """SampleSet::SampleImage of the host mirror enumerates the candidates as per-row column runs and never builds the larger
+    set; tests/cpp/host_sampler_check.cpp compares it with the naive enumerate-then-thin listing of SampleSet.cpp on 20 000
+    random regions (samples, order, RNG state).  Host code only: runs without a GPU."""
+    import subprocess
+    from multicameratracking_b200 import build
+    from multicameratracking_b200.host import build_host
+    lib_dev, lib_host = build.build(), build_host.build()
+    hd, dd = os.path.dirname(lib_host), os.path.dirname(lib_dev)
+    exe = str(tmp_path / "host_sampler_check")
+    cmd = ["g++", "-O2", "-std=c++17", os.path.join(ROOT, "tests", "cpp", "host_sampler_check.cpp"), "-o", exe,
+           "-I", hd, "-I", os.path.join(ROOT, "include"), "-L", hd, "-lmct_host", "-L", dd, "-lmct_b200",
+           "-Wl,-rpath," + hd, "-Wl,-rpath," + dd]
+    subprocess.run(cmd, check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "bad 0" in r.stdout and int(r.stdout.split("thinned cases")[1]) > 1000

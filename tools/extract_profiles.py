@@ -48,6 +48,11 @@ try:
     traffic = json.load(open(os.path.join(pr, "roofline_traffic.json")))
 except Exception:
     pass
+onchip = {}          # per kernel and launch: shared-memory wavefronts, L2 bytes (bench.py sets them against tools/peaks_lab.cu's peaks)
+try:
+    onchip = json.load(open(os.path.join(pr, "roofline_onchip.json")))
+except Exception:
+    pass
 
 
 # ---- full-set captures (score path, and the UpdateClassifier kernels when captured)
@@ -73,6 +78,9 @@ def full(rep):
             v = float(vals[hdr.index(m)].replace(",", "")); u = units[hdr.index(m)].lower()
             return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
         traffic[name] = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+        onchip[name] = {"smem_wavefronts": num("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
+                        "smem_bank_conflict_wavefronts": num("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
+                        "l2_bytes": num("lts__t_bytes.sum")}
 
 
 for rep in ("prof_%s.ncu-rep" % tag, "prof_%s_upd.ncu-rep" % tag):
@@ -80,3 +88,5 @@ for rep in ("prof_%s.ncu-rep" % tag, "prof_%s_upd.ncu-rep" % tag):
         full(os.path.join(go, rep))
 json.dump(traffic, open(os.path.join(pr, "roofline_traffic.json"), "w"), indent=1)
 print("roofline_traffic.json:", traffic)
+json.dump(onchip, open(os.path.join(pr, "roofline_onchip.json"), "w"), indent=1)
+print("roofline_onchip.json:", onchip)
