@@ -442,7 +442,8 @@ def run_ours(args):
                           "smem_bytes_per_launch": smem_b, "smem_achieved_gbs": smem_b / (avg_us * 1e-6) / 1e9,
                           "smem_frac": smem_b / (avg_us * 1e-6) / 1e9 / pk["smem_read_gbs"],
                           "smem_bank_conflict_share": oc["smem_bank_conflict_wavefronts"] / max(oc["smem_wavefronts"], 1.0),
-                          "l2_bytes_per_launch": oc["l2_bytes"], "l2_achieved_gbs": oc["l2_bytes"] / (avg_us * 1e-6) / 1e9,
+                          "l2_read_bytes_per_launch": oc.get("l2_bytes"),
+                          "l2_achieved_gbs": (oc["l2_bytes"] / (avg_us * 1e-6) / 1e9) if oc.get("l2_bytes") else None,
                           "counters_source": "profiles/roofline_onchip.json (ncu --set full, per launch)"}
         except Exception:
             pass

@@ -80,7 +80,7 @@ def full(rep):
         traffic[name] = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
         onchip[name] = {"smem_wavefronts": num("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
                         "smem_bank_conflict_wavefronts": num("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
-                        "l2_bytes": num("lts__t_bytes.sum")}
+                        "l2_bytes": num("l1tex__m_xbar2l1tex_read_bytes.sum") if "l1tex__m_xbar2l1tex_read_bytes.sum" in hdr else None}
 
 
 for rep in ("prof_%s.ncu-rep" % tag, "prof_%s_upd.ncu-rep" % tag):
