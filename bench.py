@@ -233,7 +233,7 @@ def run_ours(args):
         t = pingpong(i, POOL)
         g, r, gg, b = planes_dev[t]
         cam.set_frame_device(W, H, W, g.data_ptr(), r.data_ptr(), gg.data_ptr(), b.data_ptr(), ready=True)   # static resident pool
-        nz = noise_dev[i]
+        nz = noise_dev[i % total]
         rc = cam.L.mcth_camera_track_resident(cam.h, t, vp(nz.data_ptr()))
         if rc:
             cam._chk(rc)
@@ -266,16 +266,23 @@ def run_ours(args):
             t1 = time.perf_counter_ns() if host_timing else 0
             cam._chk(Lh.mcth_camera_prefetch_frame_bgr(camh, bgr_ptr[pingpong(i + 1, POOL)], W, H, 3 * W, 0))
         t2 = time.perf_counter_ns() if host_timing else 0
-        if i + 1 < len(noise_ptr):     # the next frame's Gaussian rows ride along as well (mct_noise_prefetch)
-            cam._chk(Lh.mcth_camera_prefetch_noise(camh, noise_ptr[i + 1], noise_len[i + 1]))
+        # the next frame's Gaussian rows ride along as well (mct_noise_prefetch)
+        cam._chk(Lh.mcth_camera_prefetch_noise(camh, noise_ptr[(i + 1) % total], noise_len[(i + 1) % total]))
         t3 = time.perf_counter_ns() if host_timing else 0
-        cam._chk(Lh.mcth_camera_track(camh, t, noise_ptr[i], phases, out_ptr))
+        cam._chk(Lh.mcth_camera_track(camh, t, noise_ptr[i % total], phases, out_ptr))
         if host_timing:
             t4 = time.perf_counter_ns()
             host_t[0] += t1 - t0; host_t[1] += t2 - t1; host_t[2] += t3 - t2; host_t[3] += t4 - t3; host_t[4] += 1
         return out_box
 
-    def timed(fn, n_warm, n_steps, offset=0):
+    # The legs below run on the same trackers one after the other, so the frame counter keeps running across them (the
+    # synthetic objects move continuously through the ping-pong pool; a leg that restarted at frame 0 would find the objects
+    # far from where the previous leg left the trackers, and lost trackers spread their particles over the slow paths).
+    clock = [0]
+
+    def timed(fn, n_warm, n_steps):
+        offset = clock[0]
+        clock[0] += n_warm + n_steps
         for i in range(n_warm):
             fn(offset + i)
         barrier()
@@ -298,7 +305,8 @@ def run_ours(args):
     # ---- 2. per-kernel CUDA-event timing of the same steps (roofline of the dominant kernel) ----
     L.mct_profile_enable(ctx_h, 1)
     for i in range(args.steps):
-        step_resident(args.warmup + i)
+        step_resident(clock[0] + i)
+    clock[0] += args.steps
     prof = capi.profile_read(L, ctx_h)
     L.mct_profile_enable(ctx_h, 0)
     # ---- 3. end to end through the host API, host buffers ----
@@ -311,7 +319,8 @@ def run_ours(args):
     L.mct_profile_enable(ctx_h, 1)
     n_pf = min(args.steps, 20)
     for i in range(n_pf):
-        step_e2e(args.warmup + i, 3)
+        step_e2e(clock[0] + i, 3)
+    clock[0] += n_pf
     prof_full = capi.profile_read(L, ctx_h)
     L.mct_profile_enable(ctx_h, 0)
 

@@ -1002,11 +1002,12 @@ __device__ __forceinline__ void mdch_big_body(const ObjDesc& d, const uint16_t* 
 
 #define MDS_WARPS 16
 #define MDS_SMEM (226 * 1024)
+#define MDS_MIN_WARPS 8           // fewer private histograms than this in the single-group plan -> row-band plan
 // the gather over this CTA's chunk [i_begin, i_end) of the object's boxes
 __device__ __forceinline__ void mdch_sel_chunk(const ObjDesc& d, const uint16_t* __restrict__ binimg, int W, int H, int smem_bytes,
                                                unsigned char* smraw, int i_begin, int i_end)
 {
-    __shared__ int s_bb[4], s_ref, s_rows, s_cols;
+    __shared__ int s_bb[4], s_ref, s_rows, s_cols, s_nord, s_gend;
     __shared__ uint32_t s_tot[MDS_WARPS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_out = *d.nout, n_slots = n_out + 1, dim = d.n_color_rows;
@@ -1049,22 +1050,54 @@ __device__ __forceinline__ void mdch_sel_chunk(const ObjDesc& d, const uint16_t*
         if (lane == 0 && x1 >= x0) { atomicMin(&s_bb[0], x0); atomicMin(&s_bb[1], y0); atomicMax(&s_bb[2], x1); atomicMax(&s_bb[3], y1); }
     }
     __syncthreads();
-    // ---- 2. shared-memory plan: LUT | slot map | per-warp private histograms | region
-    const int bx0 = s_bb[0] & ~3, by0 = s_bb[1];
-    const int RW = s_bb[2] + colsp - bx0, RH = s_bb[3] + rows - by0 + 1;      // +1 row: the row prefetch stays inside
-    const int RWp = ((RW + 3) & ~3) + 4;
-    uint32_t* lut = (uint32_t*)smraw;                                         // [(rows + 1)][colsp], last row zero
+    // ---- 2. shared-memory plan
+    //   single group : LUT | slot map | region of the whole chunk | per-warp private histograms (what is left, <= MDS_WARPS)
+    //   row bands    : LUT | slot map | row-sorted box list | row counters | region budget | histograms of `wm` warps
+    // The second plan takes over when the chunk's bounding region leaves fewer than MDS_MIN_WARPS histograms (particles spread
+    // over the frame, e.g. a tracker that lost its object): the conforming boxes are counting-sorted by their top row and cut
+    // greedily into groups whose bounding region fits the budget; each group is staged and gathered like a small chunk.
+    const int n_c = i_end - i_begin;
     const size_t lut_b = (size_t)(rows + 1) * colsp * 4;
+    uint32_t* lut = (uint32_t*)smraw;                                         // [(rows + 1)][colsp], last row zero
     uint16_t* smap = (uint16_t*)(smraw + lut_b);                              // [dim]
     const size_t map_b = ((size_t)dim * 2 + 15) & ~(size_t)15;
-    const size_t reg_b = ((size_t)RWp * max(RH, 0) + 15) & ~(size_t)15;
     const size_t hist_b = (size_t)n_slots * 128;
+    const bool usable = ref != 0x7fffffff && s_bb[2] >= s_bb[0] && n_slots <= 256 && T <= 32 && (W & 3) == 0;
     int warps_used = 0;
-    bool fast = ref != 0x7fffffff && s_bb[2] >= s_bb[0] && n_slots <= 256 && T <= 32 && (W & 3) == 0 &&
-                lut_b + map_b + reg_b + hist_b <= (size_t)smem_bytes;
-    if (fast) warps_used = min(MDS_WARPS, (int)(((size_t)smem_bytes - lut_b - map_b - reg_b) / hist_b));
     uint8_t* region = smraw + lut_b + map_b;
-    uint32_t* hist_all = (uint32_t*)(smraw + lut_b + map_b + reg_b);
+    uint32_t* hist_all = nullptr;
+    bool fast = false, banded = false;
+    uint16_t *ord_i = nullptr, *ord_c = nullptr, *ord_r = nullptr;
+    int* rowcnt = nullptr;
+    size_t band_budget = 0;
+    if (usable) {
+        const int bx0 = s_bb[0] & ~3, by0 = s_bb[1];
+        const int RW = s_bb[2] + colsp - bx0, RH = s_bb[3] + rows - by0 + 1;  // +1 row: the row prefetch stays inside
+        const int RWp = ((RW + 3) & ~3) + 4;
+        const size_t reg_b = ((size_t)RWp * RH + 15) & ~(size_t)15;
+        if (lut_b + map_b + reg_b + hist_b <= (size_t)smem_bytes) {
+            warps_used = min(MDS_WARPS, (int)(((size_t)smem_bytes - lut_b - map_b - reg_b) / hist_b));
+            hist_all = (uint32_t*)(smraw + lut_b + map_b + reg_b);
+            fast = true;
+        }
+        if ((!fast || warps_used < MDS_MIN_WARPS) && n_c < 65536 && W < 65536 && H < 65536) {
+            const size_t ord_b = (((size_t)n_c * 6) + 15) & ~(size_t)15, cnt_b = (((size_t)H + 2) * 4 + 15) & ~(size_t)15;
+            const size_t one_box = (size_t)(colsp + 8) * (rows + 1) + 16;
+            for (int wm = MDS_MIN_WARPS; wm >= 1 && !banded; wm >>= 1) {
+                const size_t fixed = lut_b + map_b + ord_b + cnt_b + (size_t)wm * hist_b;
+                if (wm <= warps_used) break;                                   // the single group is at least as good
+                if (fixed + 4 * one_box <= (size_t)smem_bytes) {
+                    banded = true; fast = true;
+                    band_budget = ((size_t)smem_bytes - fixed) & ~(size_t)15;
+                    warps_used = wm;
+                    ord_i = (uint16_t*)(smraw + lut_b + map_b); ord_c = ord_i + n_c; ord_r = ord_c + n_c;
+                    rowcnt = (int*)(smraw + lut_b + map_b + ord_b);
+                    region = smraw + lut_b + map_b + ord_b + cnt_b;
+                    hist_all = (uint32_t*)(region + band_budget);
+                }
+            }
+        }
+    }
     if (!fast) {
         // everything in this chunk goes to the generic kernel
         for (int i = i_begin + tid; i < i_end; i += blockDim.x) {
@@ -1075,7 +1108,7 @@ __device__ __forceinline__ void mdch_sel_chunk(const ObjDesc& d, const uint16_t*
         }
         return;
     }
-    // ---- 3. LUT, slot map, region
+    // ---- 3. LUT, slot map
     int shift = __clz(rows * cols); if (shift > MCT_FIX_SHIFT_MAX) shift = MCT_FIX_SHIFT_MAX;
     {
         const float scale = (float)(1u << shift);
@@ -1098,84 +1131,159 @@ __device__ __forceinline__ void mdch_sel_chunk(const ObjDesc& d, const uint16_t*
         if (lane == 0) s_tot[warp] = part;
     }
     for (int b = tid; b < dim; b += blockDim.x) smap[b] = d.slotmap[b];
-    __syncthreads();
-    uint32_t total = 0;
-    for (int q = 0; q < MDS_WARPS; q++) total += s_tot[q];
-    {
-        const int qw = RWp >> 2;                                              // 4-pixel groups per region row
-        uint32_t* r32 = reinterpret_cast<uint32_t*>(region);
-        for (int g = tid; g < qw * RH; g += blockDim.x) {
-            const int y = g / qw, xg = g - y * qw;
-            const int yy = min(by0 + y, H - 1), xx = min(bx0 + 4 * xg, W - 4);
-            const uint2 px = *reinterpret_cast<const uint2*>(binimg + (size_t)yy * W + xx);
-            r32[g] = (uint32_t)smap[px.x & 0xffffu] | ((uint32_t)smap[px.x >> 16] << 8) |
-                     ((uint32_t)smap[px.y & 0xffffu] << 16) | ((uint32_t)smap[px.y >> 16] << 24);
+    if (banded) {
+        // counting sort of the conforming boxes by top row; everything else is flagged for the generic pass right away
+        for (int r = tid; r < H + 2; r += blockDim.x) rowcnt[r] = 0;
+        if (tid == 0) s_nord = 0;
+        __syncthreads();
+        for (int i = i_begin + tid; i < i_end; i += blockDim.x) {
+            const bool v = d.valid == nullptr || d.valid[i] != 0;
+            bool okb = false;
+            int r0 = 0;
+            if (v) {
+                const int br = __float2int_rn(__fmul_rn((float)d.ch0, d.sy[i]));
+                const int bc = __float2int_rn(__fmul_rn((float)d.cw0, d.sx[i]));
+                const int c0 = d.col[i]; r0 = d.row[i];
+                okb = br == rows && bc == cols && c0 >= 0 && r0 >= 0 && c0 + cols <= W && r0 + rows <= H;
+            }
+            if (okb) { atomicAdd(&rowcnt[r0 + 1], 1); atomicAdd(&s_nord, 1); }
+            else {
+                d.big[i] = v ? 1 : 0;
+                if (v) atomicAdd(d.nbig, 1);
+                for (int o = 0; o < n_out; o++) d.featN[(size_t)o * d.ldN + i] = 0.0f;
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {                                                      // rowcnt[r] := first list position of row r
+            int carry = 0;
+            for (int r0 = 0; r0 < H + 2; r0 += 32) {
+                const int r = r0 + lane;
+                int v = r < H + 2 ? rowcnt[r] : 0;
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+                if (r < H + 2) rowcnt[r] = carry + v;
+                carry += __shfl_sync(0xffffffffu, v, 31);
+            }
+        }
+        __syncthreads();
+        for (int i = i_begin + tid; i < i_end; i += blockDim.x) {
+            if (d.valid != nullptr && d.valid[i] == 0) continue;
+            const int br = __float2int_rn(__fmul_rn((float)d.ch0, d.sy[i]));
+            const int bc = __float2int_rn(__fmul_rn((float)d.cw0, d.sx[i]));
+            const int c0 = d.col[i], r0 = d.row[i];
+            if (br == rows && bc == cols && c0 >= 0 && r0 >= 0 && c0 + cols <= W && r0 + rows <= H) {
+                const int pos = atomicAdd(&rowcnt[r0], 1);
+                ord_i[pos] = (uint16_t)(i - i_begin); ord_c[pos] = (uint16_t)c0; ord_r[pos] = (uint16_t)r0;
+            }
         }
     }
     __syncthreads();
-    // ---- 4. rounds of warps_used * BPW boxes
+    uint32_t total = 0;
+    for (int q = 0; q < MDS_WARPS; q++) total += s_tot[q];
     const float inv_scale = __fdiv_rn(1.0f, (float)(1u << shift));
     const float S = __fmul_rn((float)total, inv_scale);
     const int bw = lane / T, j = lane - bw * T;
-    const int q4 = colsp >> 2, rstep = RWp >> 2;
-    if (warp < warps_used) {
-        uint32_t* hist = hist_all + (size_t)warp * n_slots * 32 + lane;       // element s at hist[s * 32]
-        for (int base = i_begin + warp * BPW; base < i_end; base += warps_used * BPW) {
-            for (int s = 0; s < n_slots; s++) hist[s * 32] = 0u;
-            __syncwarp();
-            const int i = base + bw;
-            const bool mine = bw < BPW && i < i_end;
-            bool ok = false, valid = false;
-            if (mine) {
-                valid = d.valid == nullptr || d.valid[i] != 0;
-                if (valid) {
-                    const int br = __float2int_rn(__fmul_rn((float)d.ch0, d.sy[i]));
-                    const int bc = __float2int_rn(__fmul_rn((float)d.cw0, d.sx[i]));
-                    const int c0 = d.col[i], r0 = d.row[i];
-                    ok = br == rows && bc == cols && c0 >= 0 && r0 >= 0 && c0 + cols <= W && r0 + rows <= H;
-                    if (ok) {
-                        const int addr = (r0 - by0) * RWp + (c0 - bx0) + 4 * j;
-                        const uint4* l4 = reinterpret_cast<const uint4*>(lut) + j;
-                        const uint32_t* wp = reinterpret_cast<const uint32_t*>(region + (addr & ~3));
-                        const int sh = (addr & 3) * 8;
-                        uint32_t v = __funnelshift_r(wp[0], wp[1], sh);
-                        uint4 w = l4[0];
-                        for (int r = 0; r < rows; r++) {
-                            wp += rstep; l4 += q4;
-                            const uint32_t vn = __funnelshift_r(wp[0], wp[1], sh);    // next row (row `rows` is padding)
-                            const uint4 wn = l4[0];
-                            const uint32_t s0 = v & 0xffu, s1 = (v >> 8) & 0xffu, s2 = (v >> 16) & 0xffu, s3 = v >> 24;
-                            const uint32_t h0 = hist[s0 * 32], h1 = hist[s1 * 32], h2 = hist[s2 * 32], h3 = hist[s3 * 32];
-                            const uint32_t n0 = h0 + w.x;
-                            const uint32_t n1 = (s1 == s0 ? n0 : h1) + w.y;
-                            uint32_t t = (s2 == s0 ? n0 : h2); t = (s2 == s1 ? n1 : t);
-                            const uint32_t n2 = t + w.z;
-                            t = (s3 == s0 ? n0 : h3); t = (s3 == s1 ? n1 : t); t = (s3 == s2 ? n2 : t);
-                            const uint32_t n3 = t + w.w;
-                            hist[s0 * 32] = n0; hist[s1 * 32] = n1; hist[s2 * 32] = n2; hist[s3 * 32] = n3;
-                            v = vn; w = wn;
+    const int q4 = colsp >> 2;
+    // ---- 4. per group: stage the region, then rounds of warps_used * BPW boxes
+    int g_begin = banded ? 0 : i_begin;
+    const int g_stop = banded ? s_nord : i_end;
+    while (g_begin < g_stop) {
+        int g_end = i_end;
+        if (banded) {
+            if (tid == 0) {
+                // greedy cut of the row-sorted list: the largest prefix whose bounding region fits the budget
+                int minc = ord_c[g_begin], maxc = minc;
+                const int rfirst = ord_r[g_begin];
+                int rlast = rfirst, k = g_begin + 1;
+                for (; k < g_stop; k++) {
+                    const int c = ord_c[k], r = ord_r[k];
+                    const int nmin = min(minc, c), nmax = max(maxc, c);
+                    const int rwp = ((nmax + colsp - (nmin & ~3) + 3) & ~3) + 4;
+                    if ((size_t)rwp * (r + rows - rfirst + 1) + 16 > band_budget) break;
+                    minc = nmin; maxc = nmax; rlast = r;
+                }
+                s_bb[0] = minc; s_bb[1] = rfirst; s_bb[2] = maxc; s_bb[3] = rlast; s_gend = k;
+            }
+            __syncthreads();
+            g_end = s_gend;
+        }
+        const int bx0 = s_bb[0] & ~3, by0 = s_bb[1];
+        const int RW = s_bb[2] + colsp - bx0, RH = s_bb[3] + rows - by0 + 1;
+        const int RWp = ((RW + 3) & ~3) + 4;
+        const int rstep = RWp >> 2;
+        {
+            const int qw = RWp >> 2;                                          // 4-pixel groups per region row
+            uint32_t* r32 = reinterpret_cast<uint32_t*>(region);
+            for (int g = tid; g < qw * RH; g += blockDim.x) {
+                const int y = g / qw, xg = g - y * qw;
+                const int yy = min(by0 + y, H - 1), xx = min(bx0 + 4 * xg, W - 4);
+                const uint2 px = *reinterpret_cast<const uint2*>(binimg + (size_t)yy * W + xx);
+                r32[g] = (uint32_t)smap[px.x & 0xffffu] | ((uint32_t)smap[px.x >> 16] << 8) |
+                         ((uint32_t)smap[px.y & 0xffffu] << 16) | ((uint32_t)smap[px.y >> 16] << 24);
+            }
+        }
+        __syncthreads();
+        if (warp < warps_used) {
+            uint32_t* hist = hist_all + (size_t)warp * n_slots * 32 + lane;   // element s at hist[s * 32]
+            for (int base = g_begin + warp * BPW; base < g_end; base += warps_used * BPW) {
+                for (int s = 0; s < n_slots; s++) hist[s * 32] = 0u;
+                __syncwarp();
+                const int k = base + bw;
+                const bool mine = bw < BPW && k < g_end;
+                const int i = mine ? (banded ? i_begin + (int)ord_i[k] : k) : 0;
+                bool ok = false, valid = false;
+                if (mine) {
+                    valid = d.valid == nullptr || d.valid[i] != 0;
+                    if (valid) {
+                        const int br = __float2int_rn(__fmul_rn((float)d.ch0, d.sy[i]));
+                        const int bc = __float2int_rn(__fmul_rn((float)d.cw0, d.sx[i]));
+                        const int c0 = d.col[i], r0 = d.row[i];
+                        ok = br == rows && bc == cols && c0 >= 0 && r0 >= 0 && c0 + cols <= W && r0 + rows <= H;
+                        if (ok) {
+                            const int addr = (r0 - by0) * RWp + (c0 - bx0) + 4 * j;
+                            const uint4* l4 = reinterpret_cast<const uint4*>(lut) + j;
+                            const uint32_t* wp = reinterpret_cast<const uint32_t*>(region + (addr & ~3));
+                            const int sh = (addr & 3) * 8;
+                            uint32_t v = __funnelshift_r(wp[0], wp[1], sh);
+                            uint4 w = l4[0];
+                            for (int r = 0; r < rows; r++) {
+                                wp += rstep; l4 += q4;
+                                const uint32_t vn = __funnelshift_r(wp[0], wp[1], sh);    // next row (row `rows` is padding)
+                                const uint4 wn = l4[0];
+                                const uint32_t s0 = v & 0xffu, s1 = (v >> 8) & 0xffu, s2 = (v >> 16) & 0xffu, s3 = v >> 24;
+                                const uint32_t h0 = hist[s0 * 32], h1 = hist[s1 * 32], h2 = hist[s2 * 32], h3 = hist[s3 * 32];
+                                const uint32_t n0 = h0 + w.x;
+                                const uint32_t n1 = (s1 == s0 ? n0 : h1) + w.y;
+                                uint32_t t = (s2 == s0 ? n0 : h2); t = (s2 == s1 ? n1 : t);
+                                const uint32_t n2 = t + w.z;
+                                t = (s3 == s0 ? n0 : h3); t = (s3 == s1 ? n1 : t); t = (s3 == s2 ? n2 : t);
+                                const uint32_t n3 = t + w.w;
+                                hist[s0 * 32] = n0; hist[s1 * 32] = n1; hist[s2 * 32] = n2; hist[s3 * 32] = n3;
+                                v = vn; w = wn;
+                            }
                         }
                     }
                 }
-            }
-            __syncwarp();
-            if (mine) {
-                if (j == 0) {
-                    const int flag = (valid && !ok) ? 1 : 0;
-                    d.big[i] = flag;
-                    if (flag) atomicAdd(d.nbig, 1);
+                __syncwarp();
+                if (mine) {
+                    if (j == 0) {
+                        const int flag = (valid && !ok) ? 1 : 0;
+                        d.big[i] = flag;
+                        if (flag) atomicAdd(d.nbig, 1);
+                    }
+                    const uint32_t* hb = hist_all + (size_t)warp * n_slots * 32 + bw * T;
+                    float* dst = d.featN + i;
+                    for (int s = 1 + j; s < n_slots; s += T) {
+                        uint32_t t = 0;
+                        int qq = j;                                           // skewed start: the lanes of a box hit distinct banks
+                        for (int k2 = 0; k2 < T; k2++) { t += hb[s * 32 + qq]; qq = (qq + 1 == T) ? 0 : qq + 1; }
+                        dst[(size_t)(s - 1) * d.ldN] = ok ? __fdiv_rn(__fmul_rn((float)t, inv_scale), S) : 0.0f;
+                    }
                 }
-                const uint32_t* hb = hist_all + (size_t)warp * n_slots * 32 + bw * T;
-                float* dst = d.featN + i;
-                for (int s = 1 + j; s < n_slots; s += T) {
-                    uint32_t t = 0;
-                    int qq = j;                                               // skewed start: the lanes of a box hit distinct banks
-                    for (int k = 0; k < T; k++) { t += hb[s * 32 + qq]; qq = (qq + 1 == T) ? 0 : qq + 1; }
-                    dst[(size_t)(s - 1) * d.ldN] = ok ? __fdiv_rn(__fmul_rn((float)t, inv_scale), S) : 0.0f;
-                }
+                __syncwarp();
             }
-            __syncwarp();
         }
+        g_begin = g_end;
+        if (banded) __syncthreads();                                          // the next group rewrites s_bb and the region
     }
 }
 

@@ -689,6 +689,17 @@ def test_fused_mixed_types_scale_noise_and_border(ctx, oracle):
     _score_and_compare(ctx, oracle, seq, 640, 480, specs, N=700, sd=(60.0, 60.0, 0.04, 0.04))
 
 
+@pytest.mark.parametrize("N", [600, 4000])
+def test_fused_particles_spread_over_the_whole_frame(ctx, oracle, N):
+    """a lost tracker: equal-size boxes scattered over the whole frame (position noise of 150 / 120 px).  The bounding region of a
+    CTA's chunk no longer fits shared memory, so k_mdch_sel takes its row-band plan (boxes counting-sorted by top row, greedy
+    groups staged one after the other); many particles also leave the frame.  Responses, weights and resampling as the oracle's"""
+    seq = synth.Sequence(640, 480, 2)
+    specs = [(capi.FEAT_MDCH, capi.WEAK_STUMP, capi.STRONG_MILBOOST, 60),
+             (capi.FEAT_HAAR_MDCH, capi.WEAK_WSTUMP, capi.STRONG_MILBOOST, 126)]
+    _score_and_compare(ctx, oracle, seq, 640, 480, specs, N=N, sd=(150.0, 120.0, 1e-7, 1e-7), frames=(1, 2, 3))
+
+
 def test_fused_cfg4_shape_720p_mdch_anyboost(ctx, oracle):
     """cfg 4 shape: 1280x720, 60x120 blobs, MDCH (512 -> 102 selected) + MILAnyBoost, several objects per camera"""
     seq = synth.Sequence(1280, 720, 3)
