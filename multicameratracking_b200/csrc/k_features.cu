@@ -766,9 +766,21 @@ int launch_train_features(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, 
         if (h[o].feature_type == MCT_FEAT_MDCH || h[o].feature_type == MCT_FEAT_HAAR_MDCH) { any_mdch = 1; dim_max = max(dim_max, h[o].n_color); nb = h[o].nb; }
     }
     if (n_max <= 0) return MCT_OK;
+    bool forked = false;
     if (nh_max > 0) {
         dim3 g(ceil_div(n_max, 256), ceil_div(nh_max, HAAR_FT), n_obj);
-        MCT_LAUNCH(ctx, "k_haar_matrix_batch", k_haar_matrix_batch<<<g, 256, 0, ctx->stream>>>(d, ctx->ii_base + MCT_II_LEAD, ctx->ii_pitch, ctx->W, ctx->H));
+        // the Haar rows and the MDCH rows of the training boxes are independent: with both feature families present the Haar matrix
+        // runs on a side stream beside the three MDCH kernels and joins in front of the weak-classifier update
+        if (any_mdch && ctx->train_stream && !getenv("MCT_TRAIN_SERIAL")) {
+            MCT_CUDA(ctx, cudaEventRecord(ctx->ev_tfork, ctx->stream));
+            MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->train_stream, ctx->ev_tfork, 0));
+            MCT_LAUNCH_ON(ctx, ctx->train_stream, "k_haar_matrix_batch",
+                          k_haar_matrix_batch<<<g, 256, 0, ctx->train_stream>>>(d, ctx->ii_base + MCT_II_LEAD, ctx->ii_pitch, ctx->W, ctx->H));
+            MCT_CUDA(ctx, cudaEventRecord(ctx->ev_tjoin, ctx->train_stream));
+            forked = true;
+        } else {
+            MCT_LAUNCH(ctx, "k_haar_matrix_batch", k_haar_matrix_batch<<<g, 256, 0, ctx->stream>>>(d, ctx->ii_base + MCT_II_LEAD, ctx->ii_pitch, ctx->W, ctx->H));
+        }
     }
     if (any_mdch) {
         int rc = launch_bin_image(ctx, nb);
@@ -817,6 +829,7 @@ int launch_train_features(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, 
             MCT_LAUNCH(ctx, "k_mdch_batch", k_mdch_batch<<<g, MDCH_WARPS * 32, smem, ctx->stream>>>(d, ctx->binimg, ctx->W, ctx->H));
         }
     }
+    if (forked) MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_tjoin, 0));
     return MCT_OK;
 }
 

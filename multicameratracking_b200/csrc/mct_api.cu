@@ -212,6 +212,10 @@ extern "C" int mct_ctx_destroy(mct_ctx* ctx)
     for (int i = 0; i < 2; i++) if (ctx->d_noise_pf[i]) cudaFree(ctx->d_noise_pf[i]);
     if (ctx->d_bgr_stage) cudaFree(ctx->d_bgr_stage);
     if (ctx->h_tdesc) { cudaFreeHost(ctx->h_tdesc); cudaFree(ctx->d_tdesc); cudaEventDestroy(ctx->ev_train); }
+    if (ctx->train_stream) {
+        cudaStreamSynchronize(ctx->train_stream); cudaStreamDestroy(ctx->train_stream);
+        cudaEventDestroy(ctx->ev_tfork); cudaEventDestroy(ctx->ev_tjoin);
+    }
     if (ctx->h_train_stage) cudaFreeHost(ctx->h_train_stage);
     if (ctx->d_train_stage) cudaFree(ctx->d_train_stage);
     free(ctx->desc_last_h);
@@ -1473,6 +1477,9 @@ extern "C" int mct_track_update(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, c
         MCT_CUDA(ctx, cudaMallocHost(&ctx->h_tdesc, sizeof(TrainDesc) * DESC_MAX_OBJ));
         MCT_CUDA(ctx, cudaMalloc(&ctx->d_tdesc, sizeof(TrainDesc) * DESC_MAX_OBJ));
         MCT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_train, cudaEventDisableTiming));
+        MCT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->train_stream, cudaStreamNonBlocking));
+        MCT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_tfork, cudaEventDisableTiming));
+        MCT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_tjoin, cudaEventDisableTiming));
     }
     MCT_CUDA(ctx, cudaEventSynchronize(ctx->ev_train));                // the previous call's staging copies have executed
     if (total > ctx->train_stage_cap) {

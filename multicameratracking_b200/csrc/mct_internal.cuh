@@ -83,6 +83,7 @@ struct mct_ctx {
     const float* npf_req_src; size_t npf_req_n; int npf_req;               // block announced for the next call
     cudaEvent_t ev_noise;
     TrainDesc* h_tdesc; TrainDesc* d_tdesc; cudaEvent_t ev_train;   // batched UpdateClassifier descriptors (pinned + device)
+    cudaStream_t train_stream; cudaEvent_t ev_tfork, ev_tjoin;      // the training Haar rows run beside the MDCH rows
     int* h_train_stage; int* d_train_stage; size_t train_stage_cap;   // packed training boxes of all objects (4 x 4-byte arrays)      // staging for host-provided prediction noise (one H2D per call)
     float* d_tmp; size_t tmp_cap;                      // scratch (sum_rects etc.)
     float* h_pin; size_t pin_cap;                      // pinned staging for small host arrays
