@@ -112,13 +112,29 @@ void SampleSet::TakeRuns(const std::vector<ColumnRun>& runs, int maximumNumberOf
     m_sampleList.clear();
     const float probability = ((float)(maximumNumberOfSamples + 1)) / (float)(uint)n;
     const bool thin = probability < 1;
-    m_sampleList.reserve(thin ? (size_t)maximumNumberOfSamples + 64 : n);
+    Sample proto;                                   // everything but the position is common to the set
+    proto.m_pImgGray = gray; proto.m_pImgColor = rgb; proto.m_pImgHSV = hsv;
+    proto.m_width = width; proto.m_height = height; proto.m_weight = 1.0f; proto.m_scaleX = scaleX; proto.m_scaleY = scaleY;
+    if (!thin) {
+        m_sampleList.resize(n, proto);
+        size_t k = 0;
+        for (const ColumnRun& q : runs)
+            for (int c = q.c0; c <= q.c1; c++, k++) { m_sampleList[k].m_col = c; m_sampleList[k].m_row = q.row; }
+        return;
+    }
+    // one randfloat() per candidate, in order (Public.cpp:15-23); the stream's state lives in a register during the walk
+    Public::RngStream* rng = Public::CurrentRng();
+    uint64_t st = rng->state;
+    m_sampleList.reserve((size_t)maximumNumberOfSamples + 64);
     for (const ColumnRun& q : runs)
         for (int c = q.c0; c <= q.c1; c++) {
-            if (thin && Public::randfloat() > probability) continue;
-            PushBackSample(gray, c, q.row, width, height, 1.0f, rgb, hsv, scaleX, scaleY);
+            st = (uint64_t)(uint32_t)st * 4164903690U + (st >> 32);
+            if ((float)((uint32_t)st * 2.3283064365386962890625e-10) > probability) continue;
+            proto.m_col = c; proto.m_row = q.row;
+            m_sampleList.push_back(proto);
         }
-    if (thin && m_sampleList.size() > (size_t)maximumNumberOfSamples) m_sampleList.resize((size_t)maximumNumberOfSamples);
+    rng->state = st;
+    if (m_sampleList.size() > (size_t)maximumNumberOfSamples) m_sampleList.resize((size_t)maximumNumberOfSamples);
 }
 
 void SampleSet::SampleImage(Matrixu* gray, int x, int y, int width, int height, float outerCircleRadius,
