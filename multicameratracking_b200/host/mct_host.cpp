@@ -6,7 +6,10 @@
 #include "mct_host.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
+#include <cstdio>
 #include <cstring>
 
 static void chk(mct_ctx* ctx, int rc)
@@ -653,6 +656,10 @@ void ParticleFilterTracker::TrackCameraObjects(mct_ctx* ctx, std::vector<Particl
         std::vector<vectori> pc(n), pr(n), nc(n), nr(n);
         std::vector<vectorf> psx(n), psy(n), nsx(n), nsy(n);
         std::vector<mct_boxes> pb(n), nb(n);
+        // MCT_HOST_TIMING=1: host time of the training-set generation and of the mct_track_update call (stderr, every 64 frames)
+        static const bool timing = getenv("MCT_HOST_TIMING") != nullptr;
+        static double t_gen = 0, t_upd = 0; static int t_calls = 0;
+        const auto tp0 = std::chrono::steady_clock::now();
         // particle-reading strategies: one device pass for all objects of the camera that ask for it
         std::vector<int> rd; std::vector<mct_pf*> rpf; std::vector<mct_train_gen> rg;
         int cap = 1;
@@ -683,7 +690,18 @@ void ParticleFilterTracker::TrackCameraObjects(mct_ctx* ctx, std::vector<Particl
             nb[o] = {(int)nc[o].size(), nc[o].data(), nr[o].data(), nsx[o].data(), nsy[o].data()};
             clfs[o] = t->m_strongClassifierBasePtr->Handle();
         }
+        const auto tp1 = std::chrono::steady_clock::now();
         chk(ctx, mct_track_update(ctx, n, clfs.data(), pb.data(), nb.data()));
+        if (timing) {
+            const auto tp2 = std::chrono::steady_clock::now();
+            t_gen += std::chrono::duration<double, std::micro>(tp1 - tp0).count();
+            t_upd += std::chrono::duration<double, std::micro>(tp2 - tp1).count();
+            if (++t_calls == 64) {
+                fprintf(stderr, "UpdateClassifier host side: training sets %.1f us, mct_track_update (plan + copies + launches) %.1f us per frame\n",
+                        t_gen / t_calls, t_upd / t_calls);
+                t_gen = t_upd = 0; t_calls = 0;
+            }
+        }
     }
 }
 
