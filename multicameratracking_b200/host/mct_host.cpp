@@ -20,7 +20,8 @@ static void chk(mct_ctx* ctx, int rc)
 // ================================================================================ Public
 namespace Public {
 static RngStream g_default(1);              // static CvRNG rng_state = cvRNG(1)   (Public.h:156)
-static RngStream* g_cur = &g_default;
+// per host thread: one thread per camera / GPU may drive its trackers concurrently with the others (threading)
+static thread_local RngStream* g_cur = nullptr;
 
 uint32_t RngStream::Next()
 {
@@ -34,12 +35,12 @@ uint32_t RngStream::Peek() const
     uint64_t t = (uint64_t)(uint32_t)state * 4164903690U + (state >> 32);
     return (uint32_t)t;
 }
-void SetCurrentRng(RngStream* s) { g_cur = s ? s : &g_default; }
-RngStream* CurrentRng() { return g_cur; }
-void randinitalize(const int init) { g_cur->Seed(init); }
-int randint(const int mn, const int mx) { return (int)(g_cur->Next() % (unsigned)(mx - mn + 1) + (unsigned)mn); }
-float randfloat() { return (float)(g_cur->Next() * 2.3283064365386962890625e-10); }
-float peekfloat() { return (float)(g_cur->Peek() * 2.3283064365386962890625e-10); }
+void SetCurrentRng(RngStream* s) { g_cur = s; }
+RngStream* CurrentRng() { return g_cur ? g_cur : &g_default; }
+void randinitalize(const int init) { CurrentRng()->Seed(init); }
+int randint(const int mn, const int mx) { return (int)(CurrentRng()->Next() % (unsigned)(mx - mn + 1) + (unsigned)mn); }
+float randfloat() { return (float)(CurrentRng()->Next() * 2.3283064365386962890625e-10); }
+float peekfloat() { return (float)(CurrentRng()->Peek() * 2.3283064365386962890625e-10); }
 int cvRound(double v) { return (int)std::lrint(v); }
 }  // namespace Public
 using Public::cvRound;
