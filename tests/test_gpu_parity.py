@@ -1102,7 +1102,8 @@ class _LoopbackExchange:
         return pos, neg, counts
 
 
-def test_appearance_fusion_pooled_update_and_particle_reweighting(oracle):
+@pytest.mark.parametrize("gtype", ["milboost_stump", "milensemble_perceptron"])
+def test_appearance_fusion_pooled_update_and_particle_reweighting(oracle, gtype):
     """LearnGlobalAppearanceModel + FuseInformation (AppearanceBasedInformationFuser.cpp:44-121) for one object seen by two
     cameras: feature rows of both cameras' training boxes pooled in camera order, each sample kept iff randfloat() > 0.5,
     global classifier (learning rate 0) updated from the rows; then camera 0's particles are re-weighted with
@@ -1110,6 +1111,9 @@ def test_appearance_fusion_pooled_update_and_particle_reweighting(oracle):
     import torch
     from multicameratracking_b200.network import AppearanceFusion
     W, H, N, F, K = 640, 480, 600, 100, 20
+    # Appearance_Fusion_Strong_Classifier_Type 3 = MILEnsemble over perceptrons (Object.cpp:168-178), 2 = MILBoost
+    g_strong, g_weak, g_pct = (capi.STRONG_MILENSEMBLE, capi.WEAK_PERCEPTRON, 50.0) if gtype == "milensemble_perceptron" else \
+                              (capi.STRONG_MILBOOST, capi.WEAK_STUMP, 0.0)
     seqs = [synth.Sequence(W, H, 1, camera=c) for c in range(2)]
     w0, h0 = seqs[0].w0, seqs[0].h0
     t, arrs = haar_table(oracle, F, w0, h0)
@@ -1120,9 +1124,9 @@ def test_appearance_fusion_pooled_update_and_particle_reweighting(oracle):
         ctxs[c].frame_set(gray, r, g, b)
         ofr.append(oracle.frame(gray, r, g, b)); frames.append((gray, r, g, b))
         gclf.append(capi.StrongClassifier(ctxs[c], capi.FEAT_HAAR_MDCH, w0, h0, n_haar=F, n_bins=8, n_selected=K, haar=arrs,
-                                          learning_rate=0.0))
+                                          learning_rate=0.0, weak_type=g_weak, strong_type=g_strong, pct_retained=g_pct))
         sets.append(_train_sets(oracle, seqs[c], 1, 0, seed=31 + c))
-    ogclf = oracle.clf_create(capi.FEAT_HAAR_MDCH, F, 8, w0, h0, 0, 2, K, 0.0, t)
+    ogclf = oracle.clf_create(capi.FEAT_HAAR_MDCH, F, 8, w0, h0, g_weak, g_strong, K, 0.0, t, pct_retained=g_pct)
     ex = _LoopbackExchange()
     for c in range(2):
         ex.rows[c] = (torch.from_numpy(gclf[c].features(capi.make_boxes(*sets[c][0]))),
@@ -1139,6 +1143,14 @@ def test_appearance_fusion_pooled_update_and_particle_reweighting(oracle):
     assert counts.tolist() == [[len(sets[c][0][0]), len(sets[c][1][0])] for c in range(2)]
     oracle.clf_update_from_features(ogclf, np.ascontiguousarray(opos[:, okp]), np.ascontiguousarray(oneg[:, okn]))
     assert gclf[0].selectors().tolist() == oracle.clf_selectors(ogclf).tolist()
+    if g_strong == capi.STRONG_MILENSEMBLE:
+        # a second refresh: half of the selectors are re-ranked on the newly pooled rows and retained
+        counts, kp, kn = af.learn(capi.make_boxes(*sets[0][0]), capi.make_boxes(*sets[0][1]), lambda: oracle.randfloat(r_dev))
+        okp = [i for i in range(opos.shape[1]) if oracle.randfloat(r_or) > 0.5]
+        okn = [i for i in range(oneg.shape[1]) if oracle.randfloat(r_or) > 0.5]
+        assert kp == okp and kn == okn
+        oracle.clf_update_from_features(ogclf, np.ascontiguousarray(opos[:, okp]), np.ascontiguousarray(oneg[:, okn]))
+        assert gclf[0].selectors().tolist() == oracle.clf_selectors(ogclf).tolist()
     # camera 0's particles, spread and weighted
     x, y, w, h = seqs[0].box(1, 0)
     pf, opf = _pf_pair(ctxs[0], oracle, N, cx=x + w / 2, cy=y + h / 2)
