@@ -488,6 +488,18 @@ def test_training_boxes_from_particles_all_strategies(ctx, oracle, N):
         pf.PredictWithBrownianMotion(nz, 40, 80)
         oracle.lib.orc_pf_predict(opf, nz.ctypes.data_as(C.POINTER(C.c_float)), 40, 80)
     assert seen == {False, True}
+    # every particle's box crosses the frame border: no positive comes back (GREEDY then falls back to the disc on the host,
+    # ParticleFilterTracker.cpp:779-793); PARTICLE_RANDOM reads the RESAMPLED matrix (GetResampledParticle), which still holds
+    # the last resampling: one draw per in-frame row of it
+    m = oracle.pf_state(opf).copy()
+    m[:, 0] = 5.0; m[:, 1] = 470.0; m[:, 4] = 1.0 / N
+    pf.set_state(m, capi.PF_PREDICTED)
+    out = capi.training_boxes(ctx, [pf] * 3, [(s, 50, cur, W, H, 99) for s in (1, 2, 3)], 50)
+    for col, row, sx, sy, o in out[:2]:
+        assert o.n_pos == 0 and len(col) == 0 and o.n_unique == N
+    assert out[2][4].n_draws == sum(_particle_box(a, cur, W, H)[2] for a in pf.resampled())
+    with pytest.raises(capi.MctError):
+        capi.training_boxes(ctx, [pf], [(7, 50, cur, W, H, 1)], 50)           # unknown strategy
     pf.close(); oracle.lib.orc_pf_free(opf)
 
 
