@@ -84,6 +84,9 @@ __device__ __forceinline__ float weak_classify_ratio_dev(int weak_type, float x,
 }
 
 #define CLS_THREADS 512
+#ifndef CLS_UF
+#define CLS_UF 4              // selectors in flight per lane (8 measured the same)
+#endif
 #define CLS_SMEM (224 * 1024)
 __global__ void __launch_bounds__(CLS_THREADS, 1)
 k_classify_staged(const ObjDesc* __restrict__ descs, const float* __restrict__ ii, int iip, int W, int H, int log_ratio,
@@ -159,25 +162,35 @@ k_classify_staged(const ObjDesc* __restrict__ descs, const float* __restrict__ i
         int c = 0, r = 0; float fx = 1.0f, fy = 1.0f;
         if (ok) { c = d.col[i]; r = d.row[i]; fx = d.sx[i]; fy = d.sy[i]; }
         float Hs = 0.0f;
-        for (int s0 = 0; s0 < nsel; s0 += 8) {
-            float v[2] = {0.0f, 0.0f};
+        for (int s0 = 0; s0 < nsel; s0 += 4 * CLS_UF) {
+            float v[CLS_UF];
+            // the inputs of CLS_UF selectors per lane are fetched before any of them is evaluated: the colour rows come from L2
+            // (one round trip per selector), so the trips of a step overlap instead of queueing behind each other's f64 log
+            float x[CLS_UF]; bool on[CLS_UF];
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
+            for (int u = 0; u < CLS_UF; u++) {
                 const int s = s0 + 4 * u + q;
-                if (ok && s < nsel) {
+                on[u] = ok && s < nsel;
+                x[u] = 0.0f; v[u] = 0.0f;
+                if (on[u]) {
                     const SelEntry& e = se[s];
-                    float x;
                     if (e.nrect > 0) {
-                        if (staged) x = haar_eval_region(region, RWp, ox, by0, W, H, e.r, e.w, e.nrect, c, r, fx, fy);
-                        else x = haar_eval_dev(ii, iip, W, H, e.r, e.w, e.nrect, c, r, fx, fy);
-                    } else x = d.featN[(size_t)e.row * d.ldN + i];
-                    v[u] = d.alpha ? (weak_classify_bool_dev(d.weak_type, x, e.st[0], e.st[1], e.st[4], e.st[5], e.st[6], e.st[7]) ? e.st[2] : -e.st[2])
-                                   : weak_classify_ratio_dev(d.weak_type, x, e.st);
+                        if (staged) x[u] = haar_eval_region(region, RWp, ox, by0, W, H, e.r, e.w, e.nrect, c, r, fx, fy);
+                        else x[u] = haar_eval_dev(ii, iip, W, H, e.r, e.w, e.nrect, c, r, fx, fy);
+                    } else x[u] = d.featN[(size_t)e.row * d.ldN + i];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < CLS_UF; u++) {
+                if (on[u]) {
+                    const SelEntry& e = se[s0 + 4 * u + q];
+                    v[u] = d.alpha ? (weak_classify_bool_dev(d.weak_type, x[u], e.st[0], e.st[1], e.st[4], e.st[5], e.st[6], e.st[7]) ? e.st[2] : -e.st[2])
+                                   : weak_classify_ratio_dev(d.weak_type, x[u], e.st);
                 }
             }
             // ordered accumulation: responseList[i] += weak[k] in selector order (MILBoostClassifier.cpp:351-361)
 #pragma unroll
-            for (int u = 0; u < 2; u++)
+            for (int u = 0; u < CLS_UF; u++)
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const float vj = __shfl_sync(gmask, v[u], (lane & ~3) + j);
