@@ -93,7 +93,7 @@ k_classify_staged(const ObjDesc* __restrict__ descs, const float* __restrict__ i
                   int smem_bytes)
 {
     extern __shared__ __align__(128) unsigned char smraw[];
-    __shared__ int s_bb[4];
+    __shared__ int s_bb[4], s_ctr[3];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ ObjDesc s_desc;
     const ObjDesc& d = load_desc(descs + blockIdx.y, &s_desc);
@@ -107,6 +107,7 @@ k_classify_staged(const ObjDesc* __restrict__ descs, const float* __restrict__ i
     const size_t se_b = (size_t)max(Kcap, 1) * sizeof(SelEntry);               // 160 B entries: a multiple of 16
     if (tid == 0) {
         s_bb[0] = 1 << 30; s_bb[1] = 1 << 30; s_bb[2] = -(1 << 30); s_bb[3] = -(1 << 30);
+        s_ctr[0] = 0; s_ctr[1] = 0; s_ctr[2] = 0;
         mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -120,13 +121,16 @@ k_classify_staged(const ObjDesc* __restrict__ descs, const float* __restrict__ i
     // ---- 2. integral-image region of the chunk's valid boxes (Haar selectors only)
     if (ext_w > 0) {
         int x0 = 1 << 30, y0 = 1 << 30, x1 = -(1 << 30), y1 = -(1 << 30);
+        int sxc = 0, syc = 0, nb = 0;                                          // sum of the box centres (window placement below)
         for (int i = i_begin + tid; i < i_end; i += blockDim.x) {
             if (d.valid != nullptr && d.valid[i] == 0) continue;
             const int c = d.col[i], r = d.row[i];
             // round(a*s) + round(b*s) <= (a+b)*s + 1
             const int ex = (int)ceilf((float)ext_w * d.sx[i]) + 2, ey = (int)ceilf((float)ext_h * d.sy[i]) + 2;
             x0 = min(x0, c); y0 = min(y0, r); x1 = max(x1, c + ex); y1 = max(y1, r + ey);
+            sxc += c + (ex >> 1); syc += r + (ey >> 1); nb++;
         }
+        if (nb) { atomicAdd(&s_ctr[0], sxc); atomicAdd(&s_ctr[1], syc); atomicAdd(&s_ctr[2], nb); }
         for (int o = 16; o > 0; o >>= 1) {
             x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o));
             x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
@@ -135,8 +139,26 @@ k_classify_staged(const ObjDesc* __restrict__ descs, const float* __restrict__ i
     }
     __syncthreads();
     float* region = (float*)(smraw + se_b);
-    const int bx0 = clampi(s_bb[0], 0, W), by0 = clampi(s_bb[1], 0, H);
-    const int bx1 = clampi(s_bb[2], 0, W), by1 = clampi(s_bb[3], 0, H);
+    int bx0 = clampi(s_bb[0], 0, W), by0 = clampi(s_bb[1], 0, H);
+    int bx1 = clampi(s_bb[2], 0, W), by1 = clampi(s_bb[3], 0, H);
+    // When the bounding region of ALL boxes does not fit, a window of the same aspect around the mean box centre is staged
+    // instead (the bounding box is set by a few outliers of the particle cloud); boxes inside the window evaluate from shared
+    // memory, only the outliers gather from global memory.  (The launch lasts as long as its slowest CTA.)
+    bool partial = false;
+    {
+        const size_t budget = ((size_t)smem_bytes - se_b) / 4;                // floats
+        const size_t full = (size_t)(bx1 - bx0 + 12) * (size_t)(by1 - by0 + 1);
+        if (ext_w > 0 && s_bb[2] >= s_bb[0] && s_ctr[2] > 0 && full > budget) {
+            const float f = sqrtf((float)budget / (float)full) * 0.97f;
+            const int ww = (int)((float)(bx1 - bx0 + 1) * f), wh = (int)((float)(by1 - by0 + 1) * f);
+            const int mx = s_ctr[0] / s_ctr[2], my = s_ctr[1] / s_ctr[2];
+            if (ww > 2 * ext_w + 8 && wh > 2 * ext_h + 8) {
+                const int nx0 = clampi(mx - ww / 2, bx0, bx1 - ww + 1), ny0 = clampi(my - wh / 2, by0, by1 - wh + 1);
+                bx0 = nx0; by0 = ny0; bx1 = nx0 + ww - 1; by1 = ny0 + wh - 1;
+                partial = true;
+            }
+        }
+    }
     // x origin such that the source rows are 16-byte aligned (the table has a 3-float lead, MCT_II_LEAD)
     const int ox = ((bx0 + 3) & ~3) - 3;
     const int RH = by1 - by0 + 1;
@@ -161,6 +183,11 @@ k_classify_staged(const ObjDesc* __restrict__ descs, const float* __restrict__ i
         const bool ok = live && (d.valid == nullptr || d.valid[i] != 0);
         int c = 0, r = 0; float fx = 1.0f, fy = 1.0f;
         if (ok) { c = d.col[i]; r = d.row[i]; fx = d.sx[i]; fy = d.sy[i]; }
+        bool in_win = staged;
+        if (partial && ok) {
+            const int ex = (int)ceilf((float)ext_w * fx) + 2, ey = (int)ceilf((float)ext_h * fy) + 2;
+            in_win = staged && c >= bx0 && r >= by0 && c + ex <= bx1 && r + ey <= by1;
+        }
         float Hs = 0.0f;
         for (int s0 = 0; s0 < nsel; s0 += 4 * CLS_UF) {
             float v[CLS_UF];
@@ -175,7 +202,7 @@ k_classify_staged(const ObjDesc* __restrict__ descs, const float* __restrict__ i
                 if (on[u]) {
                     const SelEntry& e = se[s];
                     if (e.nrect > 0) {
-                        if (staged) x[u] = haar_eval_region(region, RWp, ox, by0, W, H, e.r, e.w, e.nrect, c, r, fx, fy);
+                        if (in_win) x[u] = haar_eval_region(region, RWp, ox, by0, W, H, e.r, e.w, e.nrect, c, r, fx, fy);
                         else x[u] = haar_eval_dev(ii, iip, W, H, e.r, e.w, e.nrect, c, r, fx, fy);
                     } else x[u] = d.featN[(size_t)e.row * d.ldN + i];
                 }
