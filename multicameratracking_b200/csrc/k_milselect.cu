@@ -133,8 +133,11 @@ milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int N
                 dbg_pass++;
 #endif
                 MIL_STAMP(4)
-                const int n0 = it * MIL_RN, p0 = it * PC;
-                const int cntN = max(0, min(MIL_RN, Nn - n0)), cntP = max(0, min(PC, P - p0));
+                // the first pass takes PC positives (most bags saturate inside it); a bag that did not saturate is unlikely to do so
+                // soon, so the later passes take MIL_PC at a time: fewer passes (barriers) when the classes do not separate
+                const int pcur = it == 0 ? PC : MIL_PC;
+                const int n0 = it * MIL_RN, p0 = it == 0 ? 0 : PC + (it - 1) * MIL_PC;
+                const int cntN = max(0, min(MIL_RN, Nn - n0)), cntP = max(0, min(pcur, P - p0));
                 const int nbN = (cntN + 31) >> 5, nbP = (cntP + 31) >> 5, nblk = nbN + nbP;
                 const unsigned magic = 65536u / (unsigned)nblk + 1u;        // u / nblk for u < 2^15, nblk <= 3
                 const int* al = act + (g & 1) * FC;
@@ -221,7 +224,7 @@ milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int N
                             }
                             sat = __fsub_rn(1.0f, like) == 1.0f;
                         }
-                        more_p = !sat && (p0 + PC < P);
+                        more_p = !sat && (p0 + pcur < P);
                         again = (n0 + MIL_RN < Nn) || more_p;
                         if (!again) {
                             active = false;
