@@ -37,7 +37,7 @@ __device__ __forceinline__ bool better_min(float v, int f, float bv, int bf)
 // terms per pass and candidate: MIL_RN negatives + up to MIL_PC positives, kept per candidate in one padded row of
 // MIL_RS floats (MIL_RS % 32 == 4: the float4 reads of 8 neighbouring candidates cover the 32 banks once)
 #define MIL_RN 32
-#define MIL_PC 64
+#define MIL_PC 128
 #define MIL_ROWS (MIL_RN + MIL_PC)
 #define MIL_RS (MIL_ROWS + 4)
 #define MIL_FC 128
@@ -139,7 +139,7 @@ milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int N
                 const int n0 = it * MIL_RN, p0 = it == 0 ? 0 : PC + (it - 1) * MIL_PC;
                 const int cntN = max(0, min(MIL_RN, Nn - n0)), cntP = max(0, min(pcur, P - p0));
                 const int nbN = (cntN + 31) >> 5, nbP = (cntP + 31) >> 5, nblk = nbN + nbP;
-                const unsigned magic = 65536u / (unsigned)nblk + 1u;        // u / nblk for u < 2^15, nblk <= 3
+                const unsigned magic = 65536u / (unsigned)nblk + 1u;        // u / nblk exactly for u < 2^11, nblk <= 5
                 const int* al = act + (g & 1) * FC;
                 // phase 1: terms, one warp per (list entry, 32 samples); a block's tail is filled with the chain's neutral
                 // element so that phase 2 runs whole blocks.  Three units per trip: their exp / reciprocal chains are
