@@ -289,8 +289,16 @@ def run_ours(args):
     out_ptr = out_box.ctypes.data_as(C.POINTER(C.c_int))
     Lh, camh = cam.L, cam.h
 
+    # one call per video frame (mcth_camera_step: make frame t current, announce frame t+1 and its noise, track)
+    plane_arr = None if args.e2e_bgr else [(vp * 4)(*pl) for pl in planes_ptr]
+
     def step_e2e(i, phases):
         t = pingpong(i, POOL)
+        if plane_arr is not None and not host_timing:
+            j = (i + 1) % total
+            cam._chk(Lh.mcth_camera_step(camh, t, plane_arr[t], plane_arr[pingpong(i + 1, POOL)], W, H, W, noise_ptr[i % total], noise_ptr[j],
+                                         noise_len[j], phases, out_ptr))
+            return out_box
         t0 = time.perf_counter_ns() if host_timing else 0
         if planes_ptr is not None:
             g, r, gg, b = planes_ptr[t]

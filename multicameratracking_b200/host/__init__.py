@@ -37,6 +37,7 @@ def load():
         L.mcth_camera_add_object.argtypes = [vp, C.POINTER(ObjectParams)]
         L.mcth_camera_init_trackers.argtypes = [vp]
         L.mcth_camera_track.argtypes = [vp, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]
+        L.mcth_camera_step.argtypes = [vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_size_t, C.c_int, C.POINTER(C.c_int)]
         L.mcth_camera_track_resident.argtypes = [vp, C.c_int, vp]
         L.mcth_camera_pack_foot_points.argtypes = [vp, vp]
         dp, fp = C.POINTER(C.c_double), C.POINTER(C.c_float)
@@ -180,6 +181,26 @@ class Camera:
         out = np.zeros((self.n_obj, 4), np.int32)
         self._chk(self.L.mcth_camera_track(self.h, frameind, nz.ctypes.data_as(C.c_void_p), phases,
                                            out.ctypes.data_as(C.POINTER(C.c_int))))
+        return out
+
+    def step(self, frameind, planes, next_planes, noise, next_noise=None, phases=3):
+        """mcth_camera_step: make `planes` (gray, c0, c1, c2 uint8 arrays) the current frame, announce the next frame and its noise
+        (uploaded while this frame is tracked), track.  The arrays must stay alive until the next call."""
+        pl = [np.ascontiguousarray(p, np.uint8) for p in planes]
+        H, W = pl[0].shape
+        pa = (C.c_void_p * 4)(*[p.ctypes.data for p in pl])
+        na = None
+        if next_planes is not None:
+            npl = [np.ascontiguousarray(p, np.uint8) for p in next_planes]
+            na = (C.c_void_p * 4)(*[p.ctypes.data for p in npl])
+            self._keep_next = npl
+        nz = np.ascontiguousarray(noise, np.float32)
+        nn = np.ascontiguousarray(next_noise, np.float32) if next_noise is not None else None
+        self._keep_step = (pl, nz, nn)
+        out = np.zeros((self.n_obj, 4), np.int32)
+        self._chk(self.L.mcth_camera_step(self.h, frameind, pa, na, W, H, W, nz.ctypes.data_as(C.c_void_p),
+                                          nn.ctypes.data_as(C.c_void_p) if nn is not None else None, nn.size if nn is not None else 0,
+                                          phases, out.ctypes.data_as(C.POINTER(C.c_int))))
         return out
 
     def pack_foot_points(self, dev_out_ptr):

@@ -205,6 +205,26 @@ int mcth_camera_track(mcth_camera* c, int frameind, const float* noise, int phas
     });
 }
 
+// One video frame in one call (the body of the reference's per-frame loop, CameraNetwork.cpp:549-554 / Camera.cpp:449-494):
+// make frame t current, announce frame t+1 and its Gaussian rows (uploaded while frame t is tracked; NULL = nothing to
+// announce), track.  planes / next_planes: gray, c0, c1, c2 host pointers.
+int mcth_camera_step(mcth_camera* c, int frameind, const uint8_t* const* planes, const uint8_t* const* next_planes, int W, int H, int pitch,
+                     const float* noise, const float* next_noise, size_t n_noise_floats, int phases, int* out_boxes)
+{
+    GUARD({
+        c->frame.SetFrame(planes[0], planes[1], planes[2], planes[3], W, H, pitch, 0);
+        if (next_planes) c->frame.PrefetchFrame(next_planes[0], next_planes[1], next_planes[2], next_planes[3], W, H, pitch);
+        if (next_noise) {
+            const int rc = mct_noise_prefetch(c->ctx, next_noise, n_noise_floats);
+            if (rc) throw MctHostError(rc, mct_last_error(c->ctx));
+        }
+        ParticleFilterTracker::TrackCameraObjects(c->ctx, c->trackers, frameind, &c->frame, &c->frame, &c->frame, noise, phases);
+        if (out_boxes && (((phases & 1) && !(phases & 4)) || (phases & 8)))
+            for (size_t o = 0; o < c->trackers.size(); o++)
+                for (int q = 0; q < 4; q++) out_boxes[o * 4 + q] = c->trackers[o]->States()[(size_t)frameind * 4 + q];
+    });
+}
+
 // score path with device-resident noise, asynchronous (bench.py "value" leg)
 int mcth_camera_track_resident(mcth_camera* c, int frameind, const float* noise_dev)
 {

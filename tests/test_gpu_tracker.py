@@ -97,6 +97,37 @@ def test_tracker_sequence_matches_oracle(oracle, cfg):
         oracle.lib.orc_tracker_free(trk); oracle.lib.orc_clf_free(clf)
     cam.close()
 
+def test_single_call_frame_step_equals_separate_calls():
+    """mcth_camera_step (set frame + announce the next frame and noise + track, one call per video frame) gives the same boxes,
+    selectors and RNG states as set_frame / track"""
+    n_frames, n_obj = 8, 2
+    seq = synth.Sequence(640, 480, n_obj, n_frames=n_frames)
+    over = dict(feature_type=3, weak_type=1, n_particles=500, n_haar=60)
+    p = dict(mhost.DEFAULTS); p.update(over)
+    cams = []
+    for _ in range(2):
+        cam = mhost.Camera(0, n_frames)
+        cam.set_frame(*seq.frame(0))
+        for o in range(n_obj):
+            cam.add_object(seq.box(0, o), rng_seed=o + 1, **over)
+        cam.init_trackers()
+        cams.append(cam)
+    frames = [tuple(np.ascontiguousarray(x) for x in seq.frame(t)) for t in range(n_frames)]
+    noise = [np.stack([synth.noise(p["n_particles"], (p["sd_x"], p["sd_y"], p["sd_sx"], p["sd_sy"]), obj=o, t=t) for o in range(n_obj)])
+             for t in range(n_frames)]
+    for t in range(1, n_frames):
+        cams[0].set_frame(*frames[t])
+        a = cams[0].track(t, noise[t], 3)
+        nxt = t + 1 < n_frames
+        b = cams[1].step(t, frames[t], frames[t + 1] if nxt else None, noise[t], noise[t + 1] if nxt else None, 3)
+        np.testing.assert_array_equal(a, b)
+        for o in range(n_obj):
+            assert cams[0].rng_state(o) == cams[1].rng_state(o)
+            assert cams[0].selectors(o).tolist() == cams[1].selectors(o).tolist()
+    for cam in cams:
+        cam.close()
+
+
 
 def test_geometric_fusion_feedback_two_cameras(oracle):
     """Geometric fusion end to end for two cameras (both on this GPU, standing in for two ranks): per frame the foot
