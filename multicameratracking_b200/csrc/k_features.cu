@@ -1137,7 +1137,10 @@ __device__ __forceinline__ void mdch_sel_chunk(const ObjDesc& d, const uint16_t*
                 const float wd = (float)(dx * dx * ivx + dy * dy * ivy);
                 w = __float2uint_rn(__fmul_rn(expf(-wd), scale));
             }
-            lut[p] = w;
+            // four planes [k][r][T]: plane k holds the weights of column 4 j + k, so that the lanes of a box (and of the other boxes
+            // of the warp, which read the same addresses) load consecutive words -- one wavefront per load; the former [r][colsp]
+            // layout read 16 bytes per lane and cost 6 wavefronts per row (40-word rows wrap around the 32 banks)
+            lut[(size_t)(c & 3) * (rows + 1) * T + r * T + (c >> 2)] = w;
             part += w;
         }
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
@@ -1195,7 +1198,6 @@ __device__ __forceinline__ void mdch_sel_chunk(const ObjDesc& d, const uint16_t*
     const float inv_scale = __fdiv_rn(1.0f, (float)(1u << shift));
     const float S = __fmul_rn((float)total, inv_scale);
     const int bw = lane / T, j = lane - bw * T;
-    const int q4 = colsp >> 2;
     // ---- 4. per group: stage the region, then rounds of warps_used * BPW boxes
     int g_begin = banded ? 0 : i_begin;
     const int g_stop = banded ? s_nord : i_end;
@@ -1253,15 +1255,16 @@ __device__ __forceinline__ void mdch_sel_chunk(const ObjDesc& d, const uint16_t*
                         ok = br == rows && bc == cols && c0 >= 0 && r0 >= 0 && c0 + cols <= W && r0 + rows <= H;
                         if (ok) {
                             const int addr = (r0 - by0) * RWp + (c0 - bx0) + 4 * j;
-                            const uint4* l4 = reinterpret_cast<const uint4*>(lut) + j;
+                            const uint32_t* lp = lut + j;
+                            const int PS = (rows + 1) * T;                    // plane stride
                             const uint32_t* wp = reinterpret_cast<const uint32_t*>(region + (addr & ~3));
                             const int sh = (addr & 3) * 8;
                             uint32_t v = __funnelshift_r(wp[0], wp[1], sh);
-                            uint4 w = l4[0];
+                            uint4 w = make_uint4(lp[0], lp[PS], lp[2 * PS], lp[3 * PS]);
                             for (int r = 0; r < rows; r++) {
-                                wp += rstep; l4 += q4;
+                                wp += rstep; lp += T;
                                 const uint32_t vn = __funnelshift_r(wp[0], wp[1], sh);    // next row (row `rows` is padding)
-                                const uint4 wn = l4[0];
+                                const uint4 wn = make_uint4(lp[0], lp[PS], lp[2 * PS], lp[3 * PS]);
                                 const uint32_t s0 = v & 0xffu, s1 = (v >> 8) & 0xffu, s2 = (v >> 16) & 0xffu, s3 = v >> 24;
                                 const uint32_t h0 = hist[s0 * 32], h1 = hist[s1 * 32], h2 = hist[s2 * 32], h3 = hist[s3 * 32];
                                 const uint32_t n0 = h0 + w.x;
