@@ -897,10 +897,28 @@ int launch_ground_pdf(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, const Grou
 #define MWC_A 4164903690ull
 #define MWC_M ((MWC_A << 32) - 1ull)
 __device__ __forceinline__ unsigned long long mwc_step(unsigned long long s) { return (s & 0xffffffffull) * MWC_A + (s >> 32); }
+// a * b mod M for a, b < M by Barrett reduction: q = floor(hi * mu / 2^64) with mu = floor(2^128 / M) = 2^64 + MWC_MU_LO
+// underestimates the quotient by at most 2 (checked on 2e5 random pairs and by the parity tests against the sequential stream);
+// a generic 128-bit modulo costs ~1000 instructions per call and made the jump-ahead the slowest part of the kernels
+#define MWC_MU_LO 0x07fe96ee8b5642a8ull
 __device__ __forceinline__ unsigned long long mwc_mulmod(unsigned long long a, unsigned long long b)
 {
-    return (unsigned long long)(((unsigned __int128)a * (unsigned __int128)b) % (unsigned __int128)MWC_M);
+    const unsigned long long lo = a * b, hi = __umul64hi(a, b);
+    const unsigned long long q = hi + __umul64hi(hi, MWC_MU_LO);
+    const unsigned long long qlo = q * MWC_M, qhi = __umul64hi(q, MWC_M);
+    unsigned long long rlo = lo - qlo;
+    unsigned long long rhi = hi - qhi - (lo < qlo ? 1ull : 0ull);
+    while (rhi != 0ull || rlo >= MWC_M) { rhi -= (rlo < MWC_M ? 1ull : 0ull); rlo -= MWC_M; }
+    return rlo;
 }
+// A^(2^k) mod M, k = 0..31
+__constant__ unsigned long long c_mwc_pw[32] = {
+    0x00000000f83f630aull, 0xf0badf95453cbc64ull, 0x5bb3ca800e155d1full, 0x17d406e4d579f267ull, 0xb4e603a4edcddfc5ull, 0x6cbe3044aad17ec3ull,
+    0xdd6cfbc2b97fc301ull, 0x4ddc089a9cb56ba1ull, 0x233e7431a129a78dull, 0xdc6d3202a2123589ull, 0x0e4f486bf3391191ull, 0x3899ee7ead25bea8ull,
+    0x7d789128b6481463ull, 0x02f797587e026b06ull, 0x71505662b47474f9ull, 0x7ffea99b8bf62055ull, 0x4c8dab023bc54a8eull, 0xcdee9b4a3bd4bf9aull,
+    0x783227907a7eae0eull, 0x86f2f38cf3cd17b9ull, 0xc73dfa3fdfcc6159ull, 0xf6e194fd40a1c691ull, 0xba2151430bc11a33ull, 0x80c6cf827191eec5ull,
+    0xdf99a36ffd0b83a5ull, 0x73a1b24b33fe2045ull, 0x01fb902f184234bdull, 0xacfff6883014bc66ull, 0xb4a1db6974c2abf6ull, 0xa7367cf9ce7befc8ull,
+    0x107eabd8a843b13bull, 0xb0d2605fe7d077ccull};
 // pw[k] = A^(2^k) mod M; s0 must already be <= M (two plain steps taken)
 __device__ __forceinline__ unsigned long long mwc_jump(unsigned long long s, unsigned n, const unsigned long long* pw)
 {
@@ -982,14 +1000,50 @@ k_train_from_particles(const ObjDesc* __restrict__ descs, const mct_train_gen* _
         n_uniq = base;
         nz = block_reduce_sum_i(nzc, sh_i);
     } else if (fs == MCT_PF_PREDICTED) {
-        for (int i = tid; i < N; i += nt) sw[i] = d.w[i];
-        __syncthreads();
+        // Only the first max_pos rows are needed.  Weights are non-negative, so their bit patterns order like the values: a radix
+        // select (4 passes of 8 bits over a shared histogram) finds the max_pos-th largest pattern, and exact ranks (ties by
+        // index) are then counted only for the particles at or above it, one warp per candidate.
+        __shared__ unsigned s_hist[256];
+        __shared__ unsigned s_prefix, s_want;
         for (int i = tid; i < N; i += nt) {
-            const float v = sw[i];
-            int rank = 0;
-            for (int j = 0; j < N; j++) { const float o = sw[j]; rank += (o > v || (o == v && j < i)) ? 1 : 0; }
-            if (rank < max_pos) rowidx[rank] = i;
+            sw[i] = d.w[i];
             mdx = fmaxf(mdx, fabsf(__fsub_rn(d.cx[i], ccx))); mdy = fmaxf(mdy, fabsf(__fsub_rn(d.cy[i], ccy)));
+        }
+        if (tid == 0) { s_prefix = 0u; s_want = (unsigned)min(max(max_pos, 1), N); }
+        __syncthreads();
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            for (int b = tid; b < 256; b += nt) s_hist[b] = 0u;
+            __syncthreads();
+            const unsigned prefix = s_prefix, himask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+            for (int i = tid; i < N; i += nt) {
+                const unsigned u = __float_as_uint(sw[i]);
+                if ((u & himask) == prefix) atomicAdd(&s_hist[(u >> shift) & 0xffu], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned want = s_want, b = 255;
+                for (;; b--) { const unsigned c = s_hist[b]; if (c >= want || b == 0) break; want -= c; }
+                s_want = want; s_prefix = prefix | (b << shift);
+            }
+            __syncthreads();
+        }
+        const float thr = __uint_as_float(s_prefix);                     // the min(max_pos, N)-th largest weight
+        {
+            const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+            for (int i0 = warp * 32; i0 < N; i0 += nw * 32) {
+                const int i = i0 + lane;
+                unsigned cand = __ballot_sync(0xffffffffu, i < N && sw[i] >= thr);
+                while (cand) {
+                    const int src = __ffs(cand) - 1;
+                    cand &= cand - 1;
+                    const int ci = i0 + src;
+                    const float v = sw[ci];
+                    int cnt = 0;
+                    for (int j = lane; j < N; j += 32) { const float o = sw[j]; cnt += (o > v || (o == v && j < ci)) ? 1 : 0; }
+                    cnt = __reduce_add_sync(0xffffffffu, cnt);
+                    if (lane == 0 && cnt < max_pos) rowidx[cnt] = ci;
+                }
+            }
         }
         n_uniq = N;
     }
@@ -1024,10 +1078,7 @@ k_train_from_particles(const ObjDesc* __restrict__ descs, const mct_train_gen* _
         n_pos = min(base, cap);
     } else if (g.strategy == 3) {
         const unsigned long long s0 = g.rng_state, s2 = mwc_step(mwc_step(s0));
-        if (tid == 0) {
-            unsigned long long p = MWC_A % MWC_M;
-            for (int k = 0; k < 32; k++) { s_pw[k] = p; p = mwc_mulmod(p, p); }
-        }
+        if (tid < 32) s_pw[tid] = c_mwc_pw[tid];
         __syncthreads();
         const float prob = __fdiv_rn((float)g.max_pos, (float)N);
         int base_in = 0, base_keep = 0;
@@ -1111,10 +1162,7 @@ k_sample_regions(const mct_sample_region* __restrict__ regs, int cap, int* __res
     const float prob = __fdiv_rn((float)(g.max_n + 1), (float)(unsigned)n_list);
     const bool thin = prob < 1.0f;
     const unsigned long long s0 = g.rng_state, s2 = mwc_step(mwc_step(s0));
-    if (tid == 0) {
-        unsigned long long p = MWC_A % MWC_M;
-        for (int k = 0; k < 32; k++) { s_pw[k] = p; p = mwc_mulmod(p, p); }
-    }
+    if (tid < 32) s_pw[tid] = c_mwc_pw[tid];
     __syncthreads();
     int base_c = 0, base_k = 0;
     for (int e0 = 0; e0 < cells; e0 += nt) {
