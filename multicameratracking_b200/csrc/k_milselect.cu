@@ -752,6 +752,11 @@ ensemble_body(const float* __restrict__ feat, float* pred, int ld, int F, int P,
         const int best = s_best, bw = cand[best];
         prev = (double)__ldcg(gsorted + best);                                   // negLogLikelihoodList[order[k]] after the in-place sort
         for (int i = tid; i < M; i += nt) Hs[i] = __fadd_rn(Hs[i], __ldcg(pred + (size_t)bw * ld + i));
+        if (RETAIN) {
+            // "not already included" is a test on the FEATURE (count(m_selectorList, previouslySelected[order[k]]), :296): the list
+            // a new classifier starts with is K copies of feature 0 (StrongClassifierBase.cpp:91), so all its slots go at once
+            for (int q = tid; q < NC; q += nt) if (cand[q] == bw) flag[q] = 1;
+        }
         if (tid == 0) { flag[best] = 1; if (rank == 0) { sel[n_sel] = bw; if (RETAIN) keep[bw] = 1; } }
         n_sel++;
         __syncthreads();

@@ -617,6 +617,12 @@ extern "C" int mct_classifier_create(mct_ctx* ctx, const mct_clf_params* p, cons
     MCT_CUDA(ctx, cudaMemset(c->d_sel, 0, (size_t)F * 4));
     MCT_CUDA(ctx, cudaMalloc(&c->d_nsel, 4));
     MCT_CUDA(ctx, cudaMemset(c->d_nsel, 0, 4));
+    if (p->strong_type == MCT_STRONG_MILENSEMBLE) {
+        // m_selectorList.resize(K, 0) (StrongClassifierBase.cpp:91): K copies of feature 0.  MILEnsemble alone does not clear the list
+        // before its first retain step, so untrained weak classifier 0 is retained by the first Update and never trained while it stays
+        // (pinned against the reference build: tests/test_ref_pins_oracle.py::test_strong_classifier_update_and_classify[*ensemble])
+        MCT_CUDA(ctx, cudaMemcpy(c->d_nsel, &K, 4, cudaMemcpyHostToDevice));
+    }
     MCT_CUDA(ctx, cudaMalloc(&c->d_seltab, (size_t)K * sizeof(SelEntry)));
     MCT_CUDA(ctx, cudaMemset(c->d_seltab, 0, (size_t)K * sizeof(SelEntry)));
     MCT_CUDA(ctx, cudaMalloc(&c->d_selhdr, 16));

@@ -320,7 +320,11 @@ orc_clf* orc_clf_create(int feature_type, int n_haar, int nb, int w0, int h0, in
         c->alpha = (float*)calloc((size_t)c->K, 4);
     }
     for (int f = 0; f < F; f++) { c->sig0[f] = 1; c->sig1[f] = 1; }  /* OnlineStumps::Initialize :53-60 */
-    c->n_sel = 0;
+    /* StrongClassifierBase.cpp:91: m_selectorList.resize(K, 0) -- the list starts as K ZEROS, not empty.  MILBoost / MILAnyBoost /
+       AdaBoost clear it at the top of Update; MILEnsemble does not: its first RetainBestPerformingWeakClassifiers sees K copies
+       of feature 0, retains it once (untrained), and MILEnsemble::Update then never trains feature 0 while it stays retained
+       (pinned against the reference build, tests/test_ref_pins_oracle.py).  Perceptron::Initialize leaves the weights (0, 0). */
+    c->n_sel = strong_type == ORC_STRONG_MILENSEMBLE ? c->K : 0;
     return c;
 }
 void orc_clf_free(orc_clf* c)

@@ -1,0 +1,30 @@
+/* Shim for building the UNMODIFIED reference sources (test infrastructure, see oracle/build_ref.py).
+ * boost::shared_ptr and its casts are the std ones.
+ *
+ * MCT_REF_STABLE_TIES (default build): the reference ranks weak classifiers with std::sort on the VALUE only
+ * (Public.h:211-245, SortableElement::operator<), so the order of candidates with exactly equal scores is whatever the
+ * standard library's std::sort happens to do -- unspecified by the C++ standard, different between the MSVC runtime of the
+ * shipped VS2008 solution and libstdc++.  This header is included by Public.h after <algorithm>; with the flag set, the two
+ * std::sort calls resolve to a conforming implementation that keeps equal elements in index order (std::stable_sort).
+ * oracle/build_ref.py also builds libmct_ref_native.so without the flag (libstdc++ introsort);
+ * tests/test_ref_pins_oracle.py shows the two differ only where scores tie exactly. */
+#ifndef MCT_SHIM_BOOST_SHARED_PTR
+#define MCT_SHIM_BOOST_SHARED_PTR
+#include <memory>
+#include <algorithm>
+#include <numeric>
+#include <list>
+namespace boost {
+using std::shared_ptr;
+using std::static_pointer_cast;
+using std::dynamic_pointer_cast;
+using std::const_pointer_cast;
+using std::make_shared;
+}
+#ifdef MCT_REF_STABLE_TIES
+namespace std {
+template <class It> inline void mct_sort_ties_in_index_order(It a, It b) { std::stable_sort(a, b); }
+}
+#define sort mct_sort_ties_in_index_order
+#endif
+#endif

@@ -1,0 +1,2 @@
+/* shim: see mct_cvshim.h */
+#include "mct_cvshim.h"
