@@ -84,7 +84,10 @@ weak_update_body(const float* __restrict__ feat, int ld, int F, int P, int Nn, i
     if (keep != nullptr && !kept) { mu0 = 0.0f; mu1 = 0.0f; sig0 = 1.0f; sig1 = 1.0f; was_trained = 0; }
 
     if (kept) {
-        // state as loaded (the derived rows below are a function of sig0 / sig1 only)
+        // state as stored, derived rows included: the classifier a fresh MILEnsemble retains first (K copies of feature 0,
+        // StrongClassifierBase.cpp:91) was never trained; its m_n / m_e are uninitialised memory in the reference
+        // (OnlineStumpsWeakClassifier.cpp:53-60), zero here and in the oracle
+        n0 = weak[4 * (size_t)F + f]; n1 = weak[5 * (size_t)F + f]; e0 = weak[6 * (size_t)F + f]; e1 = weak[7 * (size_t)F + f];
     } else if (weak_type == MCT_WEAK_STUMP) {
         // OnlineStumpsWeakClassifier::Update (OnlineStumpsWeakClassifier.cpp:99-151)
         const double sp = row_sum_d(xp, P, lane), sn = row_sum_d(xn, Nn, lane);
@@ -143,7 +146,7 @@ weak_update_body(const float* __restrict__ feat, int ld, int F, int P, int Nn, i
         w0 = __shfl_sync(0xffffffffu, w0, 0);
         mu0 = w0; mu1 = w1;
     }
-    if (weak_type != MCT_WEAK_PERCEPTRON) {
+    if (weak_type != MCT_WEAK_PERCEPTRON && !kept) {
         n0 = __fdiv_rn(1.0f, __fsqrt_rn(sig0));          // 1.0f / pow(sig, 0.5f)
         n1 = __fdiv_rn(1.0f, __fsqrt_rn(sig1));
         e1 = __fdiv_rn(-1.0f, __fmul_rn(2.0f, sig1));    // the reference's +1e-99f is 0 in f32
