@@ -160,6 +160,17 @@ int mct_classifier_update_from_features_dev(mct_clf* clf, const float* dev_fpos,
                                             int ld_neg, int Nn);
 int mct_classifier_update_from_features(mct_clf* clf, const float* fpos, int P, const float* fneg, int Nn,
                                         const float* wpos, const float* wneg);
+/* Learner side of AppearanceBasedInformationFuser::LearnGlobalAppearanceModel (AppearanceBasedInformationFuser.cpp:44-90):
+ * the sample sets CameraNetwork::GenerateTrainingSampleSetsForAppearanceFusion (CameraNetwork.cpp:276-320) pools arrive as
+ * feature rows in device exchange buffers.  Training column j (positives first) = the feature column starting at element
+ * col_offset_host[j] of dev_rows, feature rows row_stride elements apart; the caller lists only the samples that survived
+ * the randfloat() > 0.5 drop rule (:66-82), in pooled order. */
+int mct_classifier_update_from_gathered(mct_clf* clf, const float* dev_rows, const int* col_offset_host, long long row_stride,
+                                        int P, int Nn);
+/* device buffers on the ctx's device (exchange buffers) and a copy ordered on the ctx's stream (any direction, peers included) */
+int mct_dev_alloc(mct_ctx* ctx, size_t bytes, void** out);
+int mct_dev_free(mct_ctx* ctx, void* p);
+int mct_dev_copy(mct_ctx* ctx, void* dst, const void* src, size_t bytes);
 /* StrongClassifierBase::Classify(set, isLogRatioEnabled) (MILBoostClassifier.cpp:339-374). */
 int mct_classifier_classify(mct_clf* clf, const mct_boxes* boxes, int log_ratio, float* out_host);
 /* SimpleTracker (the reference's default local tracker, SimpleTracker.cpp:280-342): the search windows of all objects of a
@@ -199,6 +210,9 @@ int mct_pf_update_all_weights(mct_pf* pf, const float* prob_host, int n_prob, in
                               int force_reset, int resample, float u01, int* resampled);
 /* ParticleFilter::ResampleParticles(force) (ParticleFilter.cpp:920-978) */
 int mct_pf_resample(mct_pf* pf, int force_state_change, float u01);
+/* the same for all objects of a camera in one launch, stream-ordered (no synchronisation): Object.cpp:449 forces a
+ * resampling of every object every frame when a fuser is on.  u01 [n_obj] host. */
+int mct_pf_resample_many(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, int force_state_change, const float* u01);
 /* m_particlesStateMatrix / m_particlesResampledMatrix / m_resampleIndexList */
 int mct_pf_get_state(mct_pf* pf, float* out_Nx5_host);
 int mct_pf_set_state(mct_pf* pf, const float* in_Nx5_host, int filter_state);
@@ -295,6 +309,9 @@ int mct_p2p_destroy(mct_ctx* ctx);
 int mct_fuser_exchange_foot_points(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, const float* h0, float* host_out, int timeout_ms);
 
 int mct_fuser_pack_foot_points(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, const float* h0, float* dev_out);
+/* the same payload read back to the host, host_out [n_obj][2] (what CameraNetwork::FuseGeometrically, CameraNetwork.cpp:182-216,
+ * collects from every camera) */
+int mct_fuser_foot_points(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, const float* h0, float* host_out);
 
 /* ---------------------------------------------------------------- training samples from the particles -------
  * ParticleFilterTracker::GeneratePositiveTrainingSampleSet, the strategies that read the particle filter

@@ -776,6 +776,56 @@ extern "C" int mct_classifier_update_from_features_dev(mct_clf* c, const float* 
                                     cudaMemcpyDeviceToDevice, ctx->stream));
     return clf_train_common(c, P, Nn, nullptr, nullptr);
 }
+// Appearance fuser, learner side (AppearanceBasedInformationFuser.cpp:44-90): the pooled sample sets of all cameras arrive as
+// feature rows in exchange buffers; column j of this Update's training matrix is the feature column that starts at element
+// col_offset[j] of dev_rows (rows row_stride elements apart).  The kept samples (randfloat() > 0.5, :66-82) are gathered
+// straight into the classifier's training matrix: no intermediate pooled copy.
+__global__ void __launch_bounds__(256) k_gather_columns(const float* __restrict__ src, const int* __restrict__ off, long long row_stride,
+                                                        int n, int F, float* __restrict__ dst, int ld)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const float* s = src + off[j];
+    for (int f = blockIdx.y; f < F; f += gridDim.y) dst[(size_t)f * ld + j] = s[(size_t)f * row_stride];
+}
+extern "C" int mct_classifier_update_from_gathered(mct_clf* c, const float* dev_rows, const int* col_offset_host, long long row_stride, int P, int Nn)
+{
+    if (!c || !dev_rows || !col_offset_host || row_stride < 1) return MCT_E_ARG;
+    mct_ctx* ctx = c->ctx;
+    if (P < 1 || Nn < 1) return mct_fail(ctx, MCT_E_ARG, "Update needs at least one positive and one negative sample%s");
+    if (P + Nn > c->max_train) return mct_fail(ctx, MCT_E_ARG, "training set exceeds max_train%s (%d)", "", P + Nn);
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    MCT_CUDA(ctx, cudaMemcpyAsync(c->d_tcol, col_offset_host, (size_t)(P + Nn) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const int n = P + Nn;
+    MCT_LAUNCH(ctx, "k_gather_columns", k_gather_columns<<<dim3(ceil_div(n, 256), c->F < 64 ? c->F : 64), 256, 0, ctx->stream>>>(
+                   dev_rows, c->d_tcol, row_stride, n, c->F, c->d_featT, c->ldT));
+    return clf_train_common(c, P, Nn, nullptr, nullptr);
+}
+// plain device buffers on the ctx's device (exchange buffers of the appearance fuser) and stream-ordered copies between them
+extern "C" int mct_dev_alloc(mct_ctx* ctx, size_t bytes, void** out)
+{
+    if (!ctx || !out) return MCT_E_ARG;
+    *out = nullptr;
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    MCT_CUDA(ctx, cudaMalloc(out, bytes ? bytes : 1));
+    return MCT_OK;
+}
+extern "C" int mct_dev_free(mct_ctx* ctx, void* p)
+{
+    if (!ctx) return MCT_E_ARG;
+    if (!p) return MCT_OK;
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    MCT_CUDA(ctx, cudaFree(p));
+    return MCT_OK;
+}
+extern "C" int mct_dev_copy(mct_ctx* ctx, void* dst, const void* src, size_t bytes)
+{
+    if (!ctx || (bytes && (!dst || !src))) return MCT_E_ARG;
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    MCT_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
+    return MCT_OK;
+}
 extern "C" int mct_classifier_update_from_features(mct_clf* c, const float* fpos, int P, const float* fneg, int Nn,
                                                    const float* wpos, const float* wneg)
 {
@@ -1235,6 +1285,27 @@ extern "C" int mct_pf_resample(mct_pf* p, int force, float u01)
     return mct_sync(ctx);
 }
 
+// ResampleParticles(force) for all objects of a camera in one launch (Object.cpp:449: the fusion path forces a resampling
+// of every object every frame); u01 [n_obj] host
+extern "C" int mct_pf_resample_many(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, int force, const float* u01)
+{
+    if (!ctx || n_obj < 1 || n_obj > DESC_MAX_OBJ || !pfs || !u01) return MCT_E_ARG;
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    ObjDesc h[DESC_MAX_OBJ]; const ObjDesc* d; StepArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    int n_max = 0;
+    for (int o = 0; o < n_obj; o++) {
+        if (!pfs[o] || !pfs[o]->initialized) return mct_fail(ctx, MCT_E_STATE, "particle filter not initialised%s");
+        memset(&h[o], 0, sizeof(ObjDesc)); fill_pf_desc(&h[o], pfs[o]);
+        h[o].resample = 1;
+        sa.u01[o] = u01[o];
+        if (pfs[o]->N > n_max) n_max = pfs[o]->N;
+    }
+    int rc;
+    if ((rc = desc_publish(ctx, h, n_obj, &d))) return rc;
+    return launch_pf_resample_only(ctx, d, n_obj, n_max, force, sa);
+}
+
 extern "C" int mct_pf_get_summary(mct_pf* p, mct_pf_summary* out)
 {
     if (!p || !out) return MCT_E_ARG;
@@ -1659,6 +1730,23 @@ extern "C" int mct_fuser_pack_foot_points(mct_ctx* ctx, int n_obj, mct_pf* const
     for (int o = 0; o < n_obj; o++) { memset(&h[o], 0, sizeof(ObjDesc)); fill_pf_desc(&h[o], pfs[o]); }
     if ((rc = desc_publish(ctx, h, n_obj, &d))) return rc;
     if ((rc = launch_foot_points(ctx, d, n_obj, ctx->d_tmp, dev_out))) return rc;
+    return mct_sync(ctx);
+}
+
+// the same payload read back to the host: host_out [n_obj][2] (CameraNetwork::FuseGeometrically gathers it from every camera)
+extern "C" int mct_fuser_foot_points(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, const float* h0, float* host_out)
+{
+    if (!ctx || n_obj < 1 || n_obj > DESC_MAX_OBJ || !pfs || !h0 || !host_out) return MCT_E_ARG;
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = ensure_tmp(ctx, (size_t)n_obj * 4 + (size_t)n_obj * 8);
+    if (rc) return rc;
+    float* d_out = (float*)ctx->d_tmp + n_obj;
+    MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tmp, h0, (size_t)n_obj * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ObjDesc h[DESC_MAX_OBJ]; const ObjDesc* d;
+    for (int o = 0; o < n_obj; o++) { memset(&h[o], 0, sizeof(ObjDesc)); fill_pf_desc(&h[o], pfs[o]); }
+    if ((rc = desc_publish(ctx, h, n_obj, &d))) return rc;
+    if ((rc = launch_foot_points(ctx, d, n_obj, (const float*)ctx->d_tmp, d_out))) return rc;
+    MCT_CUDA(ctx, cudaMemcpyAsync(host_out, d_out, (size_t)n_obj * 8, cudaMemcpyDeviceToHost, ctx->stream));
     return mct_sync(ctx);
 }
 

@@ -69,6 +69,7 @@ def load():
         L.mcth_object_particles.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
         L.mcth_object_last_train.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]
         L.mcth_object_rng_state.argtypes = [vp, C.c_int]; L.mcth_object_rng_state.restype = C.c_uint64
+        L.mcth_object_box.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int)]
         _lib = L
     return _lib
 
@@ -294,6 +295,12 @@ class Camera:
                                           row.ctypes.data_as(C.POINTER(C.c_int)), 16384)
         return col[:n].copy(), row[:n].copy()
 
+    def boxes(self, o, frameind):
+        """m_states row (x, y, w, h) stored for a frame"""
+        out = (C.c_int * 4)()
+        self._chk(self.L.mcth_object_box(self.h, o, frameind, out))
+        return list(out)
+
     def rng_state(self, o):
         return int(self.L.mcth_object_rng_state(self.h, o))
 
@@ -382,3 +389,114 @@ def randgaus_stream(seed, sigma, n):
     out = np.zeros(n, np.float32)
     load().mcth_randgaus(seed, float(sigma), n, out.ctypes.data_as(C.POINTER(C.c_float)))
     return out
+
+
+class NetworkParams(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("geometric_fusion", "appearance_fusion", "af_strong", "af_weak", "af_pct_selected",
+                                       "af_pct_retained", "af_refresh")]
+
+
+_AG_HOST = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
+_AG_ROWS = C.CFUNCTYPE(None, C.c_void_p, C.c_size_t, C.c_void_p)
+
+
+class Exchange(C.Structure):
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("user", C.c_void_p), ("allgather_host", _AG_HOST), ("allgather_rows", _AG_ROWS)]
+
+
+class Network:
+    """CameraNetwork (mct_network.h): the reference's per-frame schedule over the cameras of a network, fusers included.
+
+      cameras        this process' Camera objects (objects added, trackers NOT yet initialised, frame 0 set)
+      camera_ids     their indices in the whole network (None: 0 .. len - 1)
+      n_cameras      cameras in the whole network (None: len(cameras), i.e. everything lives in this process)
+      homographies   [n_cameras][3][3] image -> ground plane (geometric fuser)
+      exchange       (rank, world, allgather_host(send_ptr, recv_ptr, nbytes), allgather_rows(nbytes, stream_ptr)) when the
+                     network spans processes (one camera per process); see network.TorchExchange
+    """
+
+    def __init__(self, cameras, homographies=None, camera_ids=None, n_cameras=None, exchange=None, geometric_fusion=0,
+                 appearance_fusion=0, af_strong=1, af_weak=0, af_pct_selected=20, af_pct_retained=0, af_refresh=1):
+        self.L = L = load()
+        vp = C.c_void_p
+        L.mcth_network_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_double),
+                                          C.POINTER(NetworkParams), C.POINTER(Exchange), C.POINTER(vp)]
+        L.mcth_network_destroy.argtypes = [vp]
+        L.mcth_network_last_error.argtypes = [vp]; L.mcth_network_last_error.restype = C.c_char_p
+        L.mcth_network_init.argtypes = [vp]
+        L.mcth_network_track.argtypes = [vp, C.c_int, C.POINTER(vp)]
+        L.mcth_network_row_bytes.argtypes = [vp]; L.mcth_network_row_bytes.restype = C.c_size_t
+        L.mcth_network_set_row_buffers.argtypes = [vp, vp, vp]
+        L.mcth_network_kalman.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.mcth_network_global_selectors.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.mcth_network_global_classifier.argtypes = [vp, C.c_int, C.c_int]; L.mcth_network_global_classifier.restype = vp
+        L.mcth_network_last_rearranged.argtypes = [vp, C.c_int, C.c_int]
+        L.mcth_network_stage_ms.argtypes = [vp, C.POINTER(C.c_double)]
+        self.cameras = list(cameras)
+        n_local = len(self.cameras)
+        ids = list(range(n_local)) if camera_ids is None else list(camera_ids)
+        nc = n_local if n_cameras is None else int(n_cameras)
+        self.n_cameras = nc
+        Hp = None
+        if homographies is not None:
+            self._H = np.ascontiguousarray(homographies, np.float64).reshape(nc, 9)
+            Hp = self._H.ctypes.data_as(C.POINTER(C.c_double))
+        p = NetworkParams(geometric_fusion, appearance_fusion, af_strong, af_weak, af_pct_selected, af_pct_retained, af_refresh)
+        self._ex = None
+        exp = None
+        if exchange is not None:
+            rank, world, ag_host, ag_rows = exchange
+            self._cb = (_AG_HOST(lambda user, s, r, n: ag_host(s, r, n)), _AG_ROWS(lambda user, n, st: ag_rows(n, st)))
+            self._ex = Exchange(rank, world, None, self._cb[0], self._cb[1])
+            exp = C.byref(self._ex)
+        h = vp()
+        cams = (vp * n_local)(*[c.h for c in self.cameras])
+        rc = L.mcth_network_create(cams, (C.c_int * n_local)(*ids), n_local, nc, Hp, C.byref(p), exp, C.byref(h))
+        self.h = h
+        if rc:
+            raise HostError("mcth_network_create failed (%d): %s" % (rc, L.mcth_network_last_error(h).decode()))
+
+    def _chk(self, rc):
+        if rc:
+            raise HostError("network error %d: %s" % (rc, self.L.mcth_network_last_error(self.h).decode()))
+
+    def init(self):
+        """trackers of every local camera (frame 0 already set), global classifiers, geometric fusers"""
+        self._chk(self.L.mcth_network_init(self.h))
+
+    def row_bytes(self):
+        return int(self.L.mcth_network_row_bytes(self.h))
+
+    def set_row_buffers(self, send_ptr, recv_ptr):
+        self._chk(self.L.mcth_network_set_row_buffers(self.h, C.c_void_p(send_ptr), C.c_void_p(recv_ptr)))
+
+    def track(self, frameind, noise):
+        """noise: per local camera a float32 array [n_obj][4][N].  The cameras' frames are already set."""
+        keep = [np.ascontiguousarray(z, np.float32) for z in noise]
+        ptrs = (C.c_void_p * len(keep))(*[z.ctypes.data for z in keep])
+        self._chk(self.L.mcth_network_track(self.h, frameind, ptrs))
+
+    def kalman(self, o):
+        st = np.zeros(4, np.float32); P = np.zeros(16, np.float32)
+        if self.L.mcth_network_kalman(self.h, o, st.ctypes.data_as(C.POINTER(C.c_float)), P.ctypes.data_as(C.POINTER(C.c_float))):
+            raise HostError("no geometric fuser")
+        return st, P.reshape(4, 4)
+
+    def global_selectors(self, local_cam, o):
+        idx = np.zeros(4096, np.int32)
+        n = self.L.mcth_network_global_selectors(self.h, local_cam, o, idx.ctypes.data_as(C.POINTER(C.c_int)))
+        if n < 0:
+            raise HostError(self.L.mcth_network_last_error(self.h).decode())
+        return idx[:n].copy()
+
+    def last_rearranged(self, local_cam, o):
+        return int(self.L.mcth_network_last_rearranged(self.h, local_cam, o))
+
+    def stage_ms(self):
+        out = (C.c_double * 8)()
+        self.L.mcth_network_stage_ms(self.h, out)
+        return dict(zip(("score", "reweight", "geo_exchange", "geo_fusers", "geo_feedback", "update", "learn", "store"), list(out)))
+
+    def close(self):
+        if self.h:
+            self.L.mcth_network_destroy(self.h); self.h = None

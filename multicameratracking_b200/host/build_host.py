@@ -6,13 +6,15 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libmct_host.so")
-SRC = [os.path.join(HERE, "mct_host.cpp"), os.path.join(HERE, "mct_fuser.cpp"), os.path.join(HERE, "mct_host_c.cpp")]
+SRC = [os.path.join(HERE, "mct_host.cpp"), os.path.join(HERE, "mct_fuser.cpp"), os.path.join(HERE, "mct_host_c.cpp"),
+       os.path.join(HERE, "mct_network.cpp")]
 
 
 def build(force=False):
     from .. import build as core
     core.build()
-    deps = SRC + [os.path.join(HERE, "mct_host.h"), os.path.join(HERE, "mct_fuser.h"), os.path.join(PKG, "..", "include", "mct_b200.h")]
+    deps = SRC + [os.path.join(HERE, "mct_host.h"), os.path.join(HERE, "mct_fuser.h"), os.path.join(HERE, "mct_host_c.h"),
+                  os.path.join(HERE, "mct_network.h"), os.path.join(PKG, "..", "include", "mct_b200.h")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     import fcntl

@@ -10,31 +10,7 @@
 
 using namespace MultipleCameraTracking;
 
-struct mcth_object_params {
-    int feature_type, n_haar, n_bins, weak_type, strong_type;
-    int percent_selected;             // Percentage_Of_Weak_Classifiers_Selected (Object.cpp:235-236)
-    int n_particles;
-    float sd_x, sd_y, sd_sx, sd_sy;
-    float pos_radius_train, init_pos_radius_train;
-    int n_neg_train, init_n_neg_train, search_win;
-    int trajectory_option;
-    int64_t rng_seed;
-    float init_xywh[4];
-    float percent_retained;           // Percentage_Of_Weak_Classifiers_Retained (MILEnsemble, Object.cpp:254-262)
-    int pos_strategy, neg_strategy;   // PfTracker_Positive / Negative_Sample_Strategy (Object.cpp:316-342)
-    int max_num_pos_examples;         // PfTracker_Max_Num_Positive_Examples (Object.cpp:313)
-};
-
-struct mcth_camera {
-    mct_ctx* ctx;
-    Matrixu frame;
-    std::vector<ParticleFilterTracker*> trackers;
-    std::vector<mcth_object_params> params;
-    std::vector<SimpleTracker*> simple;                 // Local_Tracker_Type 0 objects (their own list and params)
-    std::vector<mcth_object_params> simple_params;
-    int n_frames;
-    std::string err;
-};
+#include "mct_host_c.h"
 
 extern "C" {
 const char* mcth_last_error(mcth_camera* c) { return c ? c->err.c_str() : "null camera"; }
@@ -391,4 +367,88 @@ int mcth_object_last_train(mcth_camera* c, int o, int which, int* col, int* row,
     return n;
 }
 uint64_t mcth_object_rng_state(mcth_camera* c, int o) { return c->trackers[o]->Rng().state; }
+// m_states row of a frame (x, y, w, h as stored by StoreObjectState)
+int mcth_object_box(mcth_camera* c, int o, int frameind, int* out4)
+{
+    if (!c || o < 0 || o >= (int)c->trackers.size()) return MCT_E_ARG;
+    const std::vector<int>& st = c->trackers[o]->States();
+    if (frameind < 0 || (size_t)frameind * 4 + 3 >= st.size()) return MCT_E_ARG;
+    for (int q = 0; q < 4; q++) out4[q] = st[(size_t)frameind * 4 + q];
+    return 0;
+}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// CameraNetwork (mct_network.h) behind a flat C interface.  exchange == NULL: all cameras of the network live in this process.
+#include "mct_network.h"
+
+struct mcth_network_params {
+    int geometric_fusion, appearance_fusion, af_strong, af_weak, af_pct_selected, af_pct_retained, af_refresh;
+};
+struct mcth_exchange {
+    int rank, world;
+    void* user;
+    void (*allgather_host)(void* user, const void* send, void* recv, size_t bytes);
+    void (*allgather_rows)(void* user, size_t bytes, void* stream);
+};
+namespace {
+struct CallbackExchange : public NetworkExchange {
+    mcth_exchange e;
+    explicit CallbackExchange(const mcth_exchange& x) : e(x) {}
+    int Rank() const override { return e.rank; }
+    int World() const override { return e.world; }
+    void AllGatherHost(const void* send, void* recv, size_t bytes) override { e.allgather_host(e.user, send, recv, bytes); }
+    void AllGatherRows(size_t bytes, void* stream) override { e.allgather_rows(e.user, bytes, stream); }
+};
+}  // namespace
+struct mcth_network { CameraNetwork* net; CallbackExchange* ex; std::string err; };
+
+extern "C" {
+const char* mcth_network_last_error(mcth_network* n) { return n ? n->err.c_str() : "null network"; }
+int mcth_network_create(mcth_camera* const* cams, const int* cam_ids, int n_local, int n_cameras, const double* H,
+                        const mcth_network_params* p, const mcth_exchange* exchange, mcth_network** out)
+{
+    *out = nullptr;
+    mcth_network* n = new mcth_network{nullptr, nullptr, ""};
+    try {
+        std::vector<mcth_camera*> cl(cams, cams + n_local);
+        std::vector<int> ids(cam_ids, cam_ids + n_local);
+        std::vector<Homography> hs;
+        if (H) { hs.resize(n_cameras); for (int c = 0; c < n_cameras; c++) for (int i = 0; i < 9; i++) hs[c][i] = H[(size_t)c * 9 + i]; }
+        NetworkParameters np;
+        np.geometricFusionType = p->geometric_fusion; np.appearanceFusionType = p->appearance_fusion;
+        np.appearanceFusionStrongClassifierType = p->af_strong; np.appearanceFusionWeakClassifierType = p->af_weak;
+        np.afPercentageOfWeakClassifiersSelected = p->af_pct_selected; np.afPercentageOfWeakClassifiersRetained = p->af_pct_retained;
+        np.appearanceFusionRefreshRate = p->af_refresh;
+        if (exchange) n->ex = new CallbackExchange(*exchange);
+        n->net = new CameraNetwork(cl, ids, n_cameras, hs, np, n->ex);
+        *out = n;
+        return 0;
+    } catch (const MctHostError& e) { n->err = e.what(); *out = n; return e.code ? e.code : -1; }
+    catch (const std::exception& e) { n->err = e.what(); *out = n; return -100; }
+}
+void mcth_network_destroy(mcth_network* n) { if (n) { delete n->net; delete n->ex; delete n; } }
+#define NGUARD(body)                                                       \
+    try { body; return 0; }                                                \
+    catch (const MctHostError& e) { n->err = e.what(); return e.code ? e.code : -1; } \
+    catch (const std::exception& e) { n->err = e.what(); return -100; }
+int mcth_network_init(mcth_network* n) { NGUARD(n->net->InitializeCameraNetwork()); }
+int mcth_network_track(mcth_network* n, int frame, const float* const* noise) { NGUARD(n->net->TrackObjectsOnCurrentFrame(frame, noise)); }
+size_t mcth_network_row_bytes(mcth_network* n) { return n->net->RowBufferBytes(); }
+int mcth_network_set_row_buffers(mcth_network* n, void* send_dev, void* recv_dev) { NGUARD(n->net->SetRowBuffers(send_dev, recv_dev)); }
+int mcth_network_kalman(mcth_network* n, int o, float* state4, float* P16)
+{
+    const GeometryBasedInformationFuser* f = n->net->GeometricFuser(o);
+    if (!f) return -1;
+    memcpy(state4, f->StatePost(), 16); memcpy(P16, f->ErrorCovPost(), 64);
+    return 0;
+}
+int mcth_network_global_selectors(mcth_network* n, int local_cam, int o, int* idx)
+{
+    try { vectori s = n->net->GlobalClassifier(local_cam, o)->GetSelectorList(); for (size_t i = 0; i < s.size(); i++) idx[i] = s[i]; return (int)s.size(); }
+    catch (const std::exception& e) { n->err = e.what(); return -1; }
+}
+mct_clf* mcth_network_global_classifier(mcth_network* n, int local_cam, int o) { return n->net->GlobalClassifier(local_cam, o)->Handle(); }
+int mcth_network_last_rearranged(mcth_network* n, int local_cam, int o) { return n->net->LastRearranged(local_cam, o); }
+int mcth_network_stage_ms(mcth_network* n, double* out8) { memcpy(out8, n->net->StageMilliseconds(), 8 * sizeof(double)); return 0; }
 }

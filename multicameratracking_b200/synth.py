@@ -58,3 +58,54 @@ def noise(n_particles, sd, camera=0, obj=0, t=0):
     for k in range(4):
         out[k] = (rng.standard_normal(n_particles) * sd[k]).astype(np.float32)
     return out
+
+
+class MultiViewScene:
+    """C cameras looking at the same O objects on one ground plane (BASELINE configs[2] / [3]).  The objects move on the
+    ground (world coordinates); camera c sees the FOOT of object o at  centre + s * R(theta_c) (P - world_centre)  and the
+    object's box stands on that foot point (foot = bottom centre).  The image -> ground homography of camera c is the
+    inverse of that affine map, so the cameras' principal axes (vertical image lines through the foot points, mapped to the
+    ground) meet at the object's ground position: a geometrically consistent input for GeometryBasedInformationFuser."""
+
+    def __init__(self, n_cameras, n_objects, W=640, H=480, n_frames=100, obj_wh=None, seed=7):
+        self.C, self.O, self.W, self.H = n_cameras, n_objects, W, H
+        self.seqs = [Sequence(W, H, n_objects, camera=c, n_frames=n_frames, obj_wh=obj_wh) for c in range(n_cameras)]
+        w0, h0 = self.seqs[0].w0, self.seqs[0].h0
+        rng = np.random.default_rng(seed)
+        half = 0.28 * min(W, H)                           # world square [-half, half]^2 around the origin
+        self.P0 = rng.uniform(-0.8 * half, 0.8 * half, (n_objects, 2))
+        self.v = rng.uniform(-1.0, 1.0, (n_objects, 2))
+        self.A = rng.uniform(2, 8, (n_objects, 2))
+        self.om = rng.uniform(0.05, 0.2, (n_objects, 2))
+        self.half = half
+        self.theta = [0.35 + c * np.pi / max(n_cameras, 2) for c in range(n_cameras)]
+        self.scale = 1.0
+        self.centre = np.array([W / 2.0, (H + h0) / 2.0])
+        self.homographies = []
+        for c in range(n_cameras):
+            M = self._affine(c)
+            self.homographies.append(np.linalg.inv(M))
+            self.seqs[c].box = (lambda t, o, c=c: self.box(c, t, o))
+
+    def _affine(self, c):
+        th, s = self.theta[c], self.scale
+        R = s * np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+        M = np.eye(3)
+        M[:2, :2] = R
+        M[:2, 2] = self.centre
+        return M                                           # ground (x, y, 1) -> image foot point
+
+    def ground(self, t, o):
+        p = self.P0[o] + self.v[o] * t + self.A[o] * np.sin(self.om[o] * t)
+        return np.clip(p, -self.half, self.half)
+
+    def box(self, c, t, o):
+        w0, h0 = self.seqs[c].w0, self.seqs[c].h0
+        g = self.ground(t, o)
+        f = self._affine(c) @ np.array([g[0], g[1], 1.0])
+        x = int(round(float(np.clip(f[0] - w0 / 2.0, 4, self.W - w0 - 5))))
+        y = int(round(float(np.clip(f[1] - h0, 4, self.H - h0 - 5))))
+        return x, y, w0, h0
+
+    def frame(self, c, t):
+        return self.seqs[c].frame(t)

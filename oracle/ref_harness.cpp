@@ -60,6 +60,15 @@ using namespace MultipleCameraTracking;
 
 extern "C" void mct_shim_set_noise(const float* rows, size_t n);
 extern "C" size_t mct_shim_noise_consumed();
+extern "C" { extern uint64_t* mct_shim_rng_override; }
+
+/* abortError -> exit(0) inside the reference throws MctRefAbort (ref_shim/boost/shared_ptr.hpp); entry points that can reach
+ * an assertion of the reference return -1 / NULL instead of ending the process */
+static int g_aborts = 0;
+#define REF_TRY(body, fail)                                                                         \
+    try { body; }                                                                                   \
+    catch (const MctRefAbort&) { g_aborts++; mct_shim_rng_override = 0; mct_shim_set_noise(NULL, 0); return fail; }
+extern "C" int ref_abort_count(void) { return g_aborts; }
 
 namespace {
 struct Frame {
@@ -115,6 +124,8 @@ void ref_set_log(int verbose)
     g_verboseMode = verbose != 0;
     g_detailedLog = false;
     if (!g_logFile.is_open()) g_logFile.open("/dev/null");
+    /* the reference also prints progress straight to std::cout (selector lists, foot points, ...) */
+    if (verbose) std::cout.clear(); else std::cout.setstate(std::ios_base::failbit);
 }
 
 /* ---- frames: Matrixu planes + initII (Matrix.cpp:33-47, Camera.cpp:449-494) ---- */
@@ -206,14 +217,15 @@ void ref_clf_features(void* cp, void* fr, int n, const int* col, const int* row,
     int F = c->clf->GetNumberOfFeatures();
     for (int f = 0; f < F; f++) for (int i = 0; i < n; i++) out[(size_t)f * ld + i] = set.GetFeatureValue(i, f);
 }
-void ref_clf_update(void* cp, void* fr, int np, const int* pcol, const int* prow, const float* psx, const float* psy, int nn,
+int ref_clf_update(void* cp, void* fr, int np, const int* pcol, const int* prow, const float* psx, const float* psy, int nn,
                     const int* ncol, const int* nrow, const float* nsx, const float* nsy)
 {
     Clf* c = (Clf*)cp;
     Classifier::SampleSet pos, neg;
     fill_set(pos, (Frame*)fr, np, pcol, prow, psx, psy, c->w0, c->h0);
     fill_set(neg, (Frame*)fr, nn, ncol, nrow, nsx, nsy, c->w0, c->h0);
-    c->clf->Update(pos, neg);
+    REF_TRY(c->clf->Update(pos, neg), -1);
+    return 0;
 }
 void ref_clf_classify(void* cp, void* fr, int n, const int* col, const int* row, const float* sx, const float* sy, int log_ratio, float* out)
 {
@@ -438,12 +450,18 @@ void* ref_tracker_create(int particle_filter, const ref_tracker_params* tp, int 
         t->simple.reset(new SimpleTracker(NULL));
         t->base = t->simple.get();
     }
-    t->base->InitializeTrackerWithParameters(color, &f->gray, 0, n_frames, p, cp, NULL, NULL, hsv, NULL);
+    REF_TRY(t->base->InitializeTrackerWithParameters(color, &f->gray, 0, n_frames, p, cp, NULL, NULL, hsv, NULL), (delete t, (void*)NULL));
     return t;
 }
 void ref_tracker_free(void* t) { delete (Trk*)t; }
 /* phases bit0: TrackObjectOnTheGivenFrame + StoreObjectState; bit1: UpdateClassifier (TrackObjectAndSaveState :239-258) */
-void ref_tracker_track(void* tp, void* fr, const float* noise4xN, int out_box[4], int phases)
+static void tracker_track_body(void* tp, void* fr, const float* noise4xN, int out_box[4], int phases);
+int ref_tracker_track(void* tp, void* fr, const float* noise4xN, int out_box[4], int phases)
+{
+    REF_TRY(tracker_track_body(tp, fr, noise4xN, out_box, phases), -1);
+    return 0;
+}
+static void tracker_track_body(void* tp, void* fr, const float* noise4xN, int out_box[4], int phases)
 {
     Trk* t = (Trk*)tp; Frame* f = (Frame*)fr;
     Matrixu* color = f->color.rows() ? &f->color : NULL;
@@ -494,4 +512,282 @@ void ref_tracker_weak_state(void* tp, float* out8xF)
 }
 int ref_tracker_test_set_size(void* tp) { Trk* t = (Trk*)tp; return t->pft ? (int)t->pft->m_testSampleSet.Size() : (int)t->simple->m_testSampleSet.Size(); }
 
+}  // extern "C"
+
+/* ============================================================================================================
+ * Multi-camera schedule: CameraNetwork::TrackObjectsOnCurrentFrame (CameraNetwork.cpp:537-613) over the reference's own
+ * Object / ParticleFilterTracker / GeometryBasedInformationFuser / AppearanceBasedInformationFuser classes.
+ *
+ * Why not the reference's CameraNetwork / Camera objects themselves: Camera reads videos, homographies and ground-truth
+ * files from disk inside its constructor (Camera.cpp:90-190), and the per-pair streams need a hook between objects.  The loops below are those of CameraNetwork.cpp / Camera.cpp line by line (cited), everything inside
+ * them is the reference's code.  Each (camera, object) pair draws from its own MWC stream (mct_shim_rng_override), the
+ * convention of the sharded B200 path; with every pair seeded to share ONE stream object the draws are the reference's
+ * global sequence.
+ * ============================================================================================================ */
+typedef struct {
+    int n_cameras, n_objects, n_frames;
+    int feature_type, n_haar, n_bins, use_hsv, strong_type, weak_type, pct_selected, pct_retained;
+    int n_particles;
+    float sd_x, sd_y, sd_sx, sd_sy;
+    int pos_radius_train, init_pos_radius_train, n_neg_train, init_n_neg_train, search_win, neg_sample_strategy;
+    int trajectory_option, pos_strategy, neg_strategy, max_num_pos_examples;
+    int geometric_fusion;                 /* 0 / 1 */
+    int appearance_fusion;                /* 0 none, 1 culture colour, 2 MDCH */
+    int af_strong, af_weak, af_pct_selected, af_pct_retained, af_refresh;
+    int shared_stream;                    /* 1: all pairs draw from stream [0][0] (the reference's single global stream) */
+} ref_net_cfg;
+
+namespace {
+struct Net;
+struct NetBase : public CameraNetworkBase {
+    Net* net;
+    virtual void GenerateTrainingSampleSetsForAppearanceFusion(const int objectId, Classifier::SampleSet& pos, Classifier::SampleSet& neg);
+    virtual void TrackObjectsOnCurrentFrame(const int) {}
+    virtual void SaveCameraNetworkState() {}
+};
+struct Net {
+    ref_net_cfg cfg;
+    CameraTrackingParametersPtr ctp;
+    std::vector<CvMat*> H;
+    std::vector<std::vector<ObjectPtr> > obj;          /* [camera][object] */
+    std::vector<Frame*> frames;                        /* current frame of every camera */
+    std::vector<GeometryBasedInformationFuserPtr> gf;  /* per object */
+    std::vector<uint64_t> streams;                     /* [camera][object] */
+    std::vector<CvMat*> ground;                        /* m_groundPlaneParticlesPtrList */
+    NetBase* base;
+    CameraNetworkBasePtr basePtr;
+    uint64_t* stream(int c, int o) { return cfg.shared_stream ? &streams[0] : &streams[(size_t)c * cfg.n_objects + o]; }
+    void select(int c, int o) { mct_shim_rng_override = stream(c, o); }
+    Matrixu* color(int c) { return frames[c]->color.rows() ? &frames[c]->color : NULL; }
+    Matrixu* gray(int c) {
+        /* Camera::PrepareCurrentFrameForTracking (Camera.cpp:449-494): a gray image exists only for the Haar feature types */
+        return (cfg.feature_type == Features::HAAR_LIKE || cfg.feature_type == Features::HAAR_COLOR_HISTOGRAM) ? &frames[c]->gray : NULL;
+    }
+    Matrixu* hsv(int c) { return ctp->m_HSVRequired ? &frames[c]->hsv : NULL; }
+};
+/* CameraNetwork.cpp:276-320 */
+void NetBase::GenerateTrainingSampleSetsForAppearanceFusion(const int objectId, Classifier::SampleSet& positiveSampleSet, Classifier::SampleSet& negativeSampleSet)
+{
+    uint64_t* saved = mct_shim_rng_override;
+    for (int cameraIndex = 0; cameraIndex < net->cfg.n_cameras; cameraIndex++) {
+        Classifier::SampleSet objectPositiveSampleSet, objectNegativeSampleSet;
+        net->select(cameraIndex, objectId);
+        net->obj[cameraIndex][objectId]->GenerateTrainingSampleSetsForAppearanceFusion(objectPositiveSampleSet, objectNegativeSampleSet,
+                                                                                     net->color(cameraIndex), net->gray(cameraIndex), net->hsv(cameraIndex));
+        for (int i = 0; i < (int)objectPositiveSampleSet.Size(); i++) { objectPositiveSampleSet[i].m_cameraID = cameraIndex; positiveSampleSet.PushBackSample(objectPositiveSampleSet[i]); }
+        for (int i = 0; i < (int)objectNegativeSampleSet.Size(); i++) negativeSampleSet.PushBackSample(objectNegativeSampleSet[i]);
+    }
+    mct_shim_rng_override = saved;
+}
+}  // namespace
+
+extern "C" {
+static void* net_create_body(const ref_net_cfg* cfg, const double* homographies, const float* init_xywh, const int64_t* seeds);
+void* ref_net_create(const ref_net_cfg* cfg, const double* homographies /* [C][9] */, const float* init_xywh /* [C][O][4] */,
+                     const int64_t* seeds /* [C][O] */)
+{
+    REF_TRY(return net_create_body(cfg, homographies, init_xywh, seeds), (void*)NULL);
+}
+static void* net_create_body(const ref_net_cfg* cfg, const double* homographies, const float* init_xywh, const int64_t* seeds)
+{
+    ref_set_log(0);
+    Net* n = new Net();
+    n->cfg = *cfg;
+    InputParameters& g = g_configInput;
+    memset(&g, 0, sizeof(g));
+    g.m_numOfFrames = cfg->n_frames; g.m_startFrameIndex = 0; g.m_trialNumber = 1;
+    g.m_loadVideoWithColor = 1; g.m_loadVideoFromImgs = 1;
+    strcpy(g.m_outputDirectoryNameCstr, "/tmp"); strcpy(g.m_inputDirectoryNameCstr, "/tmp");
+    strcpy(g.m_dataFilesNameCstr, "mct"); strcpy(g.m_intializationDirectoryCstr, "init");
+    g.m_trackerFeatureType = cfg->feature_type + 1; g.m_useHSVColor = cfg->use_hsv; g.m_numofBinsColor = cfg->n_bins;
+    g.m_trackerFeatureParameter = cfg->n_haar;
+    g.m_percentageOfWeakClassifiersSelected = cfg->pct_selected; g.m_percentageOfWeakClassifiersRetained = cfg->pct_retained;
+    g.m_localTrackerType = 1;
+    g.m_posRadiusTrain = cfg->pos_radius_train; g.m_initPosRadiusTrain = cfg->init_pos_radius_train;
+    g.m_numNegExamples = cfg->n_neg_train; g.m_initNumNegExampes = cfg->init_n_neg_train;
+    g.m_searchWindowSize = cfg->search_win; g.m_negSampleStrategy = cfg->neg_sample_strategy;
+    g.m_numOfParticles = cfg->n_particles;
+    g.m_PFTrackerStdDevX = cfg->sd_x; g.m_PFTrackerStdDevY = cfg->sd_y; g.m_PFTrackerStdDevScaleX = cfg->sd_sx; g.m_PFTrackerStdDevScaleY = cfg->sd_sy;
+    g.m_PFTrackerNumDispParticles = 0; g.m_PfTrackerMaxNumPositiveExamples = cfg->max_num_pos_examples;
+    g.m_PFOutputTrajectoryOption = cfg->trajectory_option;
+    g.m_PfTrackerPositiveExampleStrategy = cfg->pos_strategy; g.m_PfTrackerNegativeExampleStrategy = cfg->neg_strategy;
+    g.m_geometricFusionType = cfg->geometric_fusion; g.m_appearanceFusionType = cfg->appearance_fusion;
+    g.m_appearanceFusionStrongClassifierType = cfg->af_strong; g.m_appearanceFusionWeakClassifierType = cfg->af_weak + 1;
+    g.m_AFRefreshRate = cfg->af_refresh > 0 ? cfg->af_refresh : 1;
+    g.m_AFpercentageOfWeakClassifiersSelected = cfg->af_pct_selected; g.m_AFpercentageOfWeakClassifiersRetained = cfg->af_pct_retained;
+    n->ctp.reset(new CameraTrackingParameters(&g, PARTICLE_FILTER_TRACKER, (Classifier::StrongClassifierType)cfg->strong_type,
+                                              (Classifier::WeakClassifierType)cfg->weak_type, (Features::FeatureType)cfg->feature_type,
+                                              (GeometricFusionType)cfg->geometric_fusion, cfg->n_particles,
+                                              (AppearanceFusionType)cfg->appearance_fusion,
+                                              (AppearanceFusionStrongClassifierType)cfg->af_strong,
+                                              (Classifier::WeakClassifierType)cfg->af_weak));
+    n->streams.resize((size_t)cfg->n_cameras * cfg->n_objects);
+    n->obj.resize(cfg->n_cameras);
+    n->frames.assign(cfg->n_cameras, (Frame*)NULL);
+    for (int c = 0; c < cfg->n_cameras; c++) {
+        CvMat* H = cvCreateMat(3, 3, CV_64FC1);
+        for (int i = 0; i < 9; i++) H->data.db[i] = homographies ? homographies[c * 9 + i] : (i % 4 == 0 ? 1.0 : 0.0);
+        n->H.push_back(H);
+        for (int o = 0; o < cfg->n_objects; o++) {
+            int64_t seed = seeds[(size_t)c * cfg->n_objects + o];
+            n->streams[(size_t)c * cfg->n_objects + o] = seed ? (uint64_t)seed : (uint64_t)(int64_t)-1;
+            /* Camera::InitializeCameraParameters (Camera.cpp:139-150, 251-270): objects with their initial state */
+            ObjectPtr op(new Object(o, c, true, n->ctp, H));
+            vectorf st(5);
+            for (int k = 0; k < 4; k++) st[k] = init_xywh[((size_t)c * cfg->n_objects + o) * 4 + k];
+            st[4] = 0;
+            n->select(c, o);
+            op->InitializeObjectParameters(st, "/tmp/mct_ref");      /* creates the appearance fuser's classifier too (Object.cpp:203-216) */
+            n->obj[c].push_back(op);
+        }
+    }
+    n->base = new NetBase(); n->base->net = n;
+    n->basePtr = n->base;                                  /* CameraNetworkBasePtr is a raw pointer (CameraNetworkBase.h) */
+    mct_shim_rng_override = 0;
+    return n;
+}
+void ref_net_free(void* np)
+{
+    Net* n = (Net*)np;
+    if (!n) return;
+    mct_shim_rng_override = 0;
+    delete n->base;
+    delete n;
+}
+/* frame 0: Camera::InitializeCameraTrackers (Camera.cpp:278-321) for every camera in order, then CameraNetwork::InitializeGeometricFuser (:380-470) */
+static void net_init_body(void* np, void* const* frames);
+int ref_net_init(void* np, void* const* frames)
+{
+    REF_TRY(net_init_body(np, frames), -1);
+    return 0;
+}
+static void net_init_body(void* np, void* const* frames)
+{
+    Net* n = (Net*)np;
+    const ref_net_cfg& cfg = n->cfg;
+    for (int c = 0; c < cfg.n_cameras; c++) {
+        n->frames[c] = (Frame*)frames[c];
+        for (int o = 0; o < cfg.n_objects; o++) {
+            n->select(c, o);
+            n->obj[c][o]->InitializeObjectTracker(n->color(c), n->gray(c), 0, cfg.n_frames, NULL, NULL, n->hsv(c), NULL);
+        }
+    }
+    if (cfg.geometric_fusion) {
+        n->gf.resize(cfg.n_objects); n->ground.assign(cfg.n_objects, (CvMat*)NULL);
+        for (int o = 0; o < cfg.n_objects; o++) {
+            n->ground[o] = cvCreateMat(cfg.n_cameras, 2, CV_32FC1);
+            for (int c = 0; c < cfg.n_cameras; c++) {
+                CvMat* p = n->obj[c][o]->GetAverageParticleFootPositionOnImagePlaneForGeometricFusion();
+                GeometryBasedInformationFuser::CopyMatrix(p, n->ground[o], 0, c, 2);
+            }
+            n->gf[o].reset(new GeometryBasedInformationFuser(cfg.n_cameras, n->ground[o], GeometryBasedInformationFuser::PRINCIPAL_AXIS_INTERSECTION, n->H));
+        }
+    }
+    mct_shim_rng_override = 0;
+}
+/* one frame.  noise [C][O][4][N]: the cv::randn rows of each tracker's PredictWithBrownianMotion */
+static void net_track_body(void* np, int frameIndex, void* const* frames, const float* noise);
+int ref_net_track(void* np, int frameIndex, void* const* frames, const float* noise)
+{
+    REF_TRY(net_track_body(np, frameIndex, frames, noise), -1);
+    return 0;
+}
+static void net_track_body(void* np, int frameIndex, void* const* frames, const float* noise)
+{
+    Net* n = (Net*)np;
+    const ref_net_cfg& cfg = n->cfg;
+    const size_t per = (size_t)4 * cfg.n_particles;
+    /* CameraNetwork.cpp:549-554 -> Camera::TrackCameraFrame (Camera.cpp:334-397) -> Object::TrackObjectFrame (Object.cpp:411-455) */
+    for (int c = 0; c < cfg.n_cameras; c++) {
+        n->frames[c] = (Frame*)frames[c];
+        for (int o = 0; o < cfg.n_objects; o++) {
+            n->select(c, o);
+            mct_shim_set_noise(noise + ((size_t)c * cfg.n_objects + o) * per, per);
+            n->obj[c][o]->TrackObjectFrame(frameIndex, n->color(c), n->gray(c), NULL, NULL, n->hsv(c));
+            mct_shim_set_noise(NULL, 0);
+        }
+    }
+    if (!cfg.geometric_fusion && !cfg.appearance_fusion) { mct_shim_rng_override = 0; return; }                 /* :557-561 */
+    if (cfg.geometric_fusion) {
+        /* FuseGeometrically (:175-268), principal-axis branch */
+        for (int o = 0; o < cfg.n_objects; o++) {
+            n->ground[o] = cvCreateMat(cfg.n_cameras, 2, CV_32FC1);                                               /* (:191, leaked there too) */
+            for (int c = 0; c < cfg.n_cameras; c++) {
+                CvMat* p = n->obj[c][o]->GetAverageParticleFootPositionOnImagePlaneForGeometricFusion();
+                GeometryBasedInformationFuser::CopyMatrix(p, n->ground[o], 0, c, 2);
+            }
+        }
+        for (int o = 0; o < cfg.n_objects; o++) n->gf[o]->FuseInformation(n->ground[o]);
+        if (frameIndex > 0) {
+            /* FeedbackInformationFromGeometricFusion (:94-128) */
+            for (int c = 0; c < cfg.n_cameras; c++)
+                for (int o = 0; o < cfg.n_objects; o++) {
+                    CvMat* mean = n->gf[o]->GetGroundPlaneKalmanMeanMatrix(frameIndex);
+                    CvMat* cov = n->gf[o]->GetGroundPlaneKalmanCovarianceMatrix();
+                    n->select(c, o);
+                    n->obj[c][o]->UpdateParticleWeightsWithGroundPDF(mean, cov, n->color(c), n->gray(c), n->hsv(c));
+                    cvReleaseMat(&mean); cvReleaseMat(&cov);
+                }
+        }
+    }
+    /* :583-587 -> Camera::LearnLocalAppearanceModel (Camera.cpp:610-640) */
+    for (int c = 0; c < cfg.n_cameras; c++)
+        for (int o = 0; o < cfg.n_objects; o++) {
+            n->select(c, o);
+            n->obj[c][o]->UpdateParticleFilterTrackerAppearanceModel(n->color(c), n->gray(c), NULL, n->hsv(c));
+        }
+    /* :589-600 -> Camera::LearnGlobalAppearanceModel (Camera.cpp:722-740) */
+    if (cfg.appearance_fusion && (frameIndex + 1) % n->ctp->m_appearanceFusionRefreshRate == 0)
+        for (int c = 0; c < cfg.n_cameras; c++)
+            for (int o = 0; o < cfg.n_objects; o++) {
+                n->select(c, o);
+                n->obj[c][o]->LearnGlobalAppearanceModel(n->basePtr);
+            }
+    /* :602-608 -> Camera::StoreAllParticleFilterTrackerState (Camera.cpp:553-575) */
+    for (int c = 0; c < cfg.n_cameras; c++)
+        for (int o = 0; o < cfg.n_objects; o++) n->obj[c][o]->StoreParticleFilterTrackerState(frameIndex);
+    mct_shim_rng_override = 0;
+}
+static ParticleFilterTracker* net_pft(Net* n, int c, int o) { return static_cast<ParticleFilterTracker*>(n->obj[c][o]->m_trackerPtr.get()); }
+void ref_net_box(void* np, int c, int o, int frame, float* out4)
+{
+    ParticleFilterTracker* t = net_pft((Net*)np, c, o);
+    for (int k = 0; k < 4; k++) out4[k] = t->m_states(frame, k);
+}
+void* ref_net_pf(void* np, int c, int o) { return net_pft((Net*)np, c, o)->m_particleFilterPtr.get(); }
+void ref_net_state(void* np, int c, int o, float* out6) { const vectorf& s = net_pft((Net*)np, c, o)->GetCurrentTrackerState(); for (int i = 0; i < 6; i++) out6[i] = s[i]; }
+int ref_net_selectors(void* np, int c, int o, int global, int* idx)
+{
+    Net* n = (Net*)np;
+    Classifier::StrongClassifierBase* clf = global ? n->obj[c][o]->m_appearanceFuserPtr->m_strongClassifierBasePtr.get()
+                                                   : net_pft(n, c, o)->m_strongClassifierBasePtr.get();
+    for (size_t i = 0; i < clf->m_selectorList.size(); i++) idx[i] = clf->m_selectorList[i];
+    return (int)clf->m_selectorList.size();
+}
+void ref_net_weak_state(void* np, int c, int o, int global, float* out8xF)
+{
+    Net* n = (Net*)np;
+    Classifier::StrongClassifierBase* clf = global ? n->obj[c][o]->m_appearanceFuserPtr->m_strongClassifierBasePtr.get()
+                                                   : net_pft(n, c, o)->m_strongClassifierBasePtr.get();
+    int F = (int)clf->m_weakClassifierPtrList.size();
+    for (int f = 0; f < F; f++) weak_state(clf->m_weakClassifierPtrList[f], out8xF, F, f);
+}
+int ref_net_kalman(void* np, int o, float* state4, float* P16)
+{
+    Net* n = (Net*)np;
+    if (n->gf.empty()) return -1;
+    CvKalman* k = n->gf[o]->m_pKalman;
+    for (int i = 0; i < 4; i++) state4[i] = k->state_post->data.fl[i];
+    for (int i = 0; i < 16; i++) P16[i] = k->error_cov_post->data.fl[i];
+    return 0;
+}
+uint64_t ref_net_rng_state(void* np, int c, int o) { return *((Net*)np)->stream(c, o); }
+int ref_net_last_train(void* np, int c, int o, int which, int* col, int* row, int cap)
+{
+    ParticleFilterTracker* t = net_pft((Net*)np, c, o);
+    Classifier::SampleSet& s = which == 0 ? t->m_positiveSampleSet : t->m_negativeSampleSet;
+    int m = (int)s.Size();
+    for (int i = 0; i < m && i < cap; i++) { col[i] = s[i].m_col; row[i] = s[i].m_row; }
+    return m;
+}
 }  // extern "C"

@@ -36,6 +36,10 @@ class TrackerParams(C.Structure):
                 ("neg_strategy", C.c_int), ("max_num_pos_examples", C.c_int)]
 
 
+class RefAbort(RuntimeError):
+    """the reference hit one of its own assertions (abortError, Public.h:288-308: it would have exit(0)ed)"""
+
+
 class Ref:
     _lib = None
 
@@ -76,7 +80,7 @@ class Ref:
         L.ref_clf_haar_table.argtypes = [vp, _c_int_p, _c_int_p, _c_float_p]; L.ref_clf_haar_table.restype = i
         box = [i, _c_int_p, _c_int_p, _c_float_p, _c_float_p]
         L.ref_clf_features.argtypes = [vp, vp] + box + [_c_float_p, i]
-        L.ref_clf_update.argtypes = [vp, vp] + box + box
+        L.ref_clf_update.argtypes = [vp, vp] + box + box; L.ref_clf_update.restype = i
         L.ref_clf_classify.argtypes = [vp, vp] + box + [i, _c_float_p]
         L.ref_clf_get_selectors.argtypes = [vp, _c_int_p]; L.ref_clf_get_selectors.restype = i
         L.ref_clf_get_alphas.argtypes = [vp, _c_float_p]; L.ref_clf_get_alphas.restype = i
@@ -103,7 +107,7 @@ class Ref:
         L.ref_tracker_create.argtypes = [i, C.POINTER(TrackerParams)] + [i] * 6 + [f, i, f, vp, _c_float_p, i]
         L.ref_tracker_create.restype = vp
         L.ref_tracker_free.argtypes = [vp]
-        L.ref_tracker_track.argtypes = [vp, vp, _c_float_p, _c_int_p, i]
+        L.ref_tracker_track.argtypes = [vp, vp, _c_float_p, _c_int_p, i]; L.ref_tracker_track.restype = i
         L.ref_tracker_state.argtypes = [vp, _c_float_p]
         L.ref_tracker_states_row.argtypes = [vp, i, _c_float_p]
         L.ref_tracker_pf.argtypes = [vp]; L.ref_tracker_pf.restype = vp
@@ -171,7 +175,8 @@ class Ref:
 
     def clf_update(self, clf, fr, pos, neg):
         bp, k1 = self._box(*pos); bn, k2 = self._box(*neg)
-        self.lib.ref_clf_update(clf, fr[0], *bp, *bn)
+        if self.lib.ref_clf_update(clf, fr[0], *bp, *bn):
+            raise RefAbort("the reference aborted inside StrongClassifierBase::Update (message on stderr)")
 
     def clf_classify(self, clf, fr, col, row, sx, sy, log_ratio=True):
         b, keep = self._box(col, row, sx, sy)
@@ -260,12 +265,15 @@ class Ref:
         init = np.ascontiguousarray(init_xywh, np.float32)
         t = self.lib.ref_tracker_create(int(particle_filter), C.byref(tp), feature_type, n_haar, nb, weak_type, strong_type, K, lr,
                                         use_hsv, pct_retained, fr[0], _fp(init), n_frames)
+        if not t:
+            raise RefAbort("the reference aborted inside InitializeTrackerWithParameters (message on stderr)")
         return t, tp.n_particles
 
     def tracker_track(self, t, fr, noise4xN, phases=3):
         nz = None if noise4xN is None else np.ascontiguousarray(noise4xN, np.float32)
         box = np.zeros(4, np.int32)
-        self.lib.ref_tracker_track(t[0], fr[0], _fp(nz), _ip(box), phases)
+        if self.lib.ref_tracker_track(t[0], fr[0], _fp(nz), _ip(box), phases):
+            raise RefAbort("the reference aborted inside TrackObjectAndSaveState (message on stderr)")
         return box
 
     def tracker_state(self, t):
@@ -283,3 +291,115 @@ class Ref:
         out = np.zeros((8, F), np.float32)
         self.lib.ref_tracker_weak_state(t[0], _fp(out))
         return out
+
+
+class NetCfg(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("n_cameras", "n_objects", "n_frames", "feature_type", "n_haar", "n_bins", "use_hsv", "strong_type",
+                                       "weak_type", "pct_selected", "pct_retained", "n_particles")] + \
+               [(k, C.c_float) for k in ("sd_x", "sd_y", "sd_sx", "sd_sy")] + \
+               [(k, C.c_int) for k in ("pos_radius_train", "init_pos_radius_train", "n_neg_train", "init_n_neg_train", "search_win",
+                                       "neg_sample_strategy", "trajectory_option", "pos_strategy", "neg_strategy", "max_num_pos_examples",
+                                       "geometric_fusion", "appearance_fusion", "af_strong", "af_weak", "af_pct_selected", "af_pct_retained",
+                                       "af_refresh", "shared_stream")]
+
+
+NET_DEFAULTS = dict(feature_type=0, n_haar=250, n_bins=8, use_hsv=0, strong_type=2, weak_type=0, pct_selected=20, pct_retained=0,
+                    n_particles=1000, sd_x=20.0, sd_y=20.0, sd_sx=1e-7, sd_sy=1e-7, pos_radius_train=10, init_pos_radius_train=7,
+                    n_neg_train=30, init_n_neg_train=30, search_win=20, neg_sample_strategy=1, trajectory_option=0, pos_strategy=0,
+                    neg_strategy=0, max_num_pos_examples=30, geometric_fusion=0, appearance_fusion=0, af_strong=1, af_weak=0,
+                    af_pct_selected=20, af_pct_retained=0, af_refresh=1, shared_stream=0)
+
+
+class RefNetwork:
+    """The reference's multi-camera frame loop (CameraNetwork.cpp:537-613) over its own Object / tracker / fuser classes, one MWC
+    stream per (camera, object) pair (ref_harness.cpp, second half)."""
+
+    def __init__(self, ref, n_cameras, n_objects, n_frames, homographies, init_xywh, seeds, **kw):
+        L = ref.lib
+        vp, i = C.c_void_p, C.c_int
+        L.ref_net_create.argtypes = [C.POINTER(NetCfg), C.POINTER(C.c_double), _c_float_p, C.POINTER(C.c_int64)]; L.ref_net_create.restype = vp
+        L.ref_net_free.argtypes = [vp]
+        L.ref_net_init.argtypes = [vp, C.POINTER(vp)]
+        L.ref_net_track.argtypes = [vp, i, C.POINTER(vp), _c_float_p]; L.ref_net_track.restype = i
+        L.ref_net_init.restype = i
+        L.ref_net_box.argtypes = [vp, i, i, i, _c_float_p]
+        L.ref_net_pf.argtypes = [vp, i, i]; L.ref_net_pf.restype = vp
+        L.ref_net_state.argtypes = [vp, i, i, _c_float_p]
+        L.ref_net_selectors.argtypes = [vp, i, i, i, _c_int_p]; L.ref_net_selectors.restype = i
+        L.ref_net_weak_state.argtypes = [vp, i, i, i, _c_float_p]
+        L.ref_net_kalman.argtypes = [vp, i, _c_float_p, _c_float_p]; L.ref_net_kalman.restype = i
+        L.ref_net_rng_state.argtypes = [vp, i, i]; L.ref_net_rng_state.restype = C.c_uint64
+        L.ref_net_last_train.argtypes = [vp, i, i, i, _c_int_p, _c_int_p, i]; L.ref_net_last_train.restype = i
+        self.ref, self.L = ref, L
+        p = dict(NET_DEFAULTS); p.update(kw)
+        cfg = NetCfg(n_cameras=n_cameras, n_objects=n_objects, n_frames=n_frames, **p)
+        self.cfg, self.C, self.O, self.N = cfg, n_cameras, n_objects, p["n_particles"]
+        H = None if homographies is None else np.ascontiguousarray(homographies, np.float64).reshape(n_cameras, 9)
+        init = np.ascontiguousarray(init_xywh, np.float32).reshape(n_cameras, n_objects, 4)
+        sd = np.ascontiguousarray(seeds, np.int64).reshape(n_cameras, n_objects)
+        self.h = L.ref_net_create(C.byref(cfg), None if H is None else H.ctypes.data_as(C.POINTER(C.c_double)), _fp(init),
+                                  sd.ctypes.data_as(C.POINTER(C.c_int64)))
+        if not self.h:
+            raise RefAbort("the reference aborted while the objects were created (message on stderr)")
+        self.frames = None
+
+    def _set_frames(self, planes):
+        """planes: per camera (gray, c0, c1, c2)"""
+        new = [self.ref.frame(*p) for p in planes]
+        arr = (C.c_void_p * self.C)(*[f[0] for f in new])
+        return new, arr
+
+    def init(self, planes):
+        self.frames, arr = self._set_frames(planes)
+        if self.L.ref_net_init(self.h, arr):
+            raise RefAbort("the reference aborted while initialising the trackers (message on stderr)")
+
+    def track(self, frame_index, planes, noise):
+        """noise: float32 [C][O][4][N]"""
+        new, arr = self._set_frames(planes)
+        nz = np.ascontiguousarray(noise, np.float32)
+        assert nz.shape == (self.C, self.O, 4, self.N)
+        rc = self.L.ref_net_track(self.h, frame_index, arr, _fp(nz))
+        if rc:
+            raise RefAbort("the reference aborted in frame %d (message on stderr)" % frame_index)
+        for f in self.frames:
+            self.ref.frame_free(f)
+        self.frames = new
+
+    def box(self, c, o, frame):
+        out = np.zeros(4, np.float32); self.L.ref_net_box(self.h, c, o, frame, _fp(out)); return out
+
+    def particles(self, c, o):
+        return self.ref.pf_get((self.L.ref_net_pf(self.h, c, o), self.N))
+
+    def state(self, c, o):
+        out = np.zeros(6, np.float32); self.L.ref_net_state(self.h, c, o, _fp(out)); return out
+
+    def selectors(self, c, o, global_clf=False):
+        idx = np.zeros(4096, np.int32)
+        n = self.L.ref_net_selectors(self.h, c, o, int(global_clf), _ip(idx))
+        return idx[:n].copy()
+
+    def weak_state(self, c, o, F, global_clf=False):
+        out = np.zeros((8, F), np.float32); self.L.ref_net_weak_state(self.h, c, o, int(global_clf), _fp(out)); return out
+
+    def kalman(self, o):
+        st = np.zeros(4, np.float32); P = np.zeros(16, np.float32)
+        self.L.ref_net_kalman(self.h, o, _fp(st), _fp(P))
+        return st, P.reshape(4, 4)
+
+    def rng_state(self, c, o):
+        return int(self.L.ref_net_rng_state(self.h, c, o))
+
+    def last_train(self, c, o, which, cap=65536):
+        col = np.zeros(cap, np.int32); row = np.zeros(cap, np.int32)
+        n = self.L.ref_net_last_train(self.h, c, o, which, _ip(col), _ip(row), cap)
+        return col[:n].copy(), row[:n].copy()
+
+    def close(self):
+        if self.h:
+            self.L.ref_net_free(self.h); self.h = None
+        if self.frames:
+            for f in self.frames:
+                self.ref.frame_free(f)
+            self.frames = None

@@ -21,6 +21,12 @@ using std::dynamic_pointer_cast;
 using std::const_pointer_cast;
 using std::make_shared;
 }
+/* The reference reports every failed assertion through abortError (Public.h:288-308), which prints and calls exit(0): a test
+ * process would end with status 0 in the middle of a run.  Here exit() inside the reference sources throws instead (not a
+ * std::exception, so the reference's own catch blocks do not see it); ref_harness.cpp turns it into an error return. */
+struct MctRefAbort { int code; };
+[[noreturn]] inline void mct_shim_exit(int code) { throw MctRefAbort{code}; }
+#define exit(code) mct_shim_exit(code)
 #ifdef MCT_REF_STABLE_TIES
 namespace std {
 template <class It> inline void mct_sort_ties_in_index_order(It a, It b) { std::stable_sort(a, b); }

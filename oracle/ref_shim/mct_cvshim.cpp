@@ -18,6 +18,8 @@ void mct_shim_not_on_path(const char* what)
     abort();
 }
 
+extern "C" { uint64_t* mct_shim_rng_override = 0; }
+
 /* ---- injected noise rows (cv::randn / cv::randu) ---- */
 static const float* g_noise = 0;
 static size_t g_noise_n = 0, g_noise_pos = 0;

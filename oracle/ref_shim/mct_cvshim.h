@@ -66,10 +66,22 @@ static inline CvScalar cvRealScalar(double a) { return cvScalar(a); }
 
 /* ---- RNG (types_c.h: CV_RNG_COEFF) ---- */
 static inline CvRNG cvRNG(int64_t seed = -1) { CvRNG r = seed ? (uint64_t)seed : (uint64_t)(int64_t)-1; return r; }
+/* Stream multiplexing for the multi-camera harness: the reference draws everything from ONE global stream (Public.h:156),
+ * which serialises cameras and objects.  The B200 path gives every (camera, object) pair its own stream so that cameras
+ * can run on different GPUs; ref_harness.cpp points this override at the stream of the (camera, object) whose reference
+ * method it is about to call.  NULL (default) = the reference's own global stream, untouched. */
+#ifdef __cplusplus
+extern "C" {
+#endif
+extern uint64_t* mct_shim_rng_override;
+#ifdef __cplusplus
+}
+#endif
 static inline unsigned cvRandInt(CvRNG* rng) {
-    uint64_t t = *rng;
+    CvRNG* r = mct_shim_rng_override ? (CvRNG*)mct_shim_rng_override : rng;
+    uint64_t t = *r;
     t = (uint64_t)(unsigned)t * 4164903690U + (t >> 32);
-    *rng = t;
+    *r = t;
     return (unsigned)t;
 }
 static inline double cvRandReal(CvRNG* rng) { return cvRandInt(rng) * 2.3283064365386962890625e-10; }

@@ -1,0 +1,93 @@
+"""Multi-camera parity (BASELINE configs[2] / [3]): the product's CameraNetwork (host/mct_network.cpp over the C-ABI, all
+cameras of the network on this GPU) against THE REFERENCE'S OWN CODE running the same schedule (oracle/_ref: Object,
+ParticleFilterTracker, GeometryBasedInformationFuser, AppearanceBasedInformationFuser compiled from /root/reference/src and
+driven by ref_harness.cpp's restatement of CameraNetwork::TrackObjectsOnCurrentFrame, CameraNetwork.cpp:537-613).
+
+Same synthetic multi-view scene, same prediction noise, one MWC stream per (camera, object) pair on both sides.  Bar: tracked
+boxes within 1 px, selector lists (local and global classifiers) and every pair's RNG state equal after every frame, the
+geometric fuser's Kalman state within 1e-4 relative."""
+import numpy as np
+import pytest
+
+from multicameratracking_b200 import host as mhost
+from multicameratracking_b200 import synth
+from oracle.ref_py import Ref, RefNetwork
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not Ref.available(), reason="oracle/_ref not built")]
+
+CASES = {
+    # name: (cameras, objects, frames, W, H, per-object overrides, network settings)
+    "geometric_2x2_haar": (2, 2, 6, 640, 480, dict(n_particles=400, n_haar=80), dict(geometric_fusion=1)),
+    "appearance_2x2_mdch": (2, 2, 6, 640, 480, dict(n_particles=300, feature_type=2, strong_type=2), dict(appearance_fusion=2, af_refresh=1)),
+    "both_3x2_haarmdch_refresh2": (3, 2, 7, 640, 480, dict(n_particles=300, feature_type=3, n_haar=60), dict(geometric_fusion=1, appearance_fusion=2, af_refresh=2)),
+    # BASELINE configs[2] at its full shape: 4 cameras x 8 objects, Haar(250) + MILBoost, 1000 particles, geometric fuser
+    "cfg2_full_4x8_geometric": (4, 8, 6, 640, 480, dict(), dict(geometric_fusion=1)),
+}
+
+
+def _noise(scene, N, p, t):
+    return np.stack([np.stack([synth.noise(N, (p["sd_x"], p["sd_y"], p["sd_sx"], p["sd_sy"]), camera=c, obj=o, t=t) for o in range(scene.O)])
+                     for c in range(scene.C)])
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_camera_network_matches_reference(case):
+    Cn, On, T, W, H, over, netkw = CASES[case]
+    ref = Ref()
+    scene = synth.MultiViewScene(Cn, On, W, H, n_frames=T)
+    p = dict(mhost.DEFAULTS); p.update(over)
+    N = p["n_particles"]
+    init = np.array([[scene.box(c, 0, o) for o in range(On)] for c in range(Cn)], np.float32)
+    seeds = np.array([[1000 * c + o + 1 for o in range(On)] for c in range(Cn)])
+    rkw = dict(feature_type=p["feature_type"], n_haar=p["n_haar"], n_bins=p["n_bins"], strong_type=p["strong_type"], weak_type=p["weak_type"],
+               pct_selected=p["percent_selected"], n_particles=N, sd_x=p["sd_x"], sd_y=p["sd_y"], sd_sx=p["sd_sx"], sd_sy=p["sd_sy"],
+               pos_radius_train=int(p["pos_radius_train"]), init_pos_radius_train=int(p["init_pos_radius_train"]), n_neg_train=p["n_neg_train"],
+               init_n_neg_train=p["init_n_neg_train"], search_win=p["search_win"], trajectory_option=p["trajectory_option"])
+    rkw.update(netkw)
+    rnet = RefNetwork(ref, Cn, On, T, scene.homographies, init, seeds, **rkw)
+    rnet.init([scene.frame(c, 0) for c in range(Cn)])
+    cams = []
+    for c in range(Cn):
+        cam = mhost.Camera(0, T)
+        cam.set_frame(*scene.frame(c, 0))
+        for o in range(On):
+            cam.add_object(scene.box(c, 0, o), rng_seed=int(seeds[c, o]), **over)
+        cams.append(cam)
+    net = mhost.Network(cams, scene.homographies, **netkw)
+    net.init()
+    F = {0: p["n_haar"], 1: 11, 2: 512, 3: p["n_haar"] + 512}[p["feature_type"]]
+    for c in range(Cn):
+        for o in range(On):
+            assert cams[c].selectors(o).tolist() == rnet.selectors(c, o).tolist(), (case, "init", c, o)
+            assert cams[c].rng_state(o) == rnet.rng_state(c, o), (case, "init", c, o)
+    if netkw.get("geometric_fusion"):
+        for o in range(On):
+            np.testing.assert_allclose(net.kalman(o)[0], rnet.kalman(o)[0], rtol=1e-5, atol=1e-3)
+    worst = 0
+    for t in range(1, T):
+        planes = [scene.frame(c, t) for c in range(Cn)]
+        nz = _noise(scene, N, p, t)
+        rnet.track(t, planes, nz)
+        for c in range(Cn):
+            cams[c].set_frame(*planes[c])
+        net.track(t, [nz[c] for c in range(Cn)])
+        for c in range(Cn):
+            cams[c].sync()
+            for o in range(On):
+                rb = rnet.box(c, o, t)
+                gb = np.array(cams[c].boxes(o, t), np.float32)
+                d = float(np.abs(rb - gb).max())
+                worst = max(worst, d)
+                assert d <= 1, (case, t, c, o, rb, gb)
+                assert cams[c].rng_state(o) == rnet.rng_state(c, o), (case, t, c, o, "RNG streams diverged")
+                assert cams[c].selectors(o).tolist() == rnet.selectors(c, o).tolist(), (case, t, c, o)
+                if netkw.get("appearance_fusion") and (t + 1) % netkw.get("af_refresh", 1) == 0:
+                    assert net.global_selectors(c, o).tolist() == rnet.selectors(c, o, True).tolist(), (case, t, c, o, "global classifier")
+        if netkw.get("geometric_fusion"):
+            for o in range(On):
+                a, Pa = net.kalman(o); b, Pb = rnet.kalman(o)
+                np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-3, err_msg="%s frame %d object %d Kalman state" % (case, t, o))
+                np.testing.assert_allclose(Pa, Pb, rtol=1e-4, atol=1e-4)
+    net.close(); rnet.close()
+    for cam in cams:
+        cam.close()
