@@ -29,8 +29,17 @@ namespace cg = cooperative_groups;
 
 struct SelSlot { float nll; int f; };
 
+// Order of the candidates = the reference's sort_order (Public.h:211-228) with its two unspecified points pinned: exactly tied
+// scores keep index order (a stable sort), and NaN scores -- the appearance fuser's classifiers (learning rate 0) get sigma = 0
+// for colour bins that are empty in a class, hence n = inf, e = -inf and NaN responses -- rank LAST (std::sort on them is
+// undefined behaviour in the reference; oracle/ref_shim/boost/shared_ptr.hpp gives the reference build the same order).
+// f == 0x7fffffff marks "no candidate yet".
 __device__ __forceinline__ bool better_min(float v, int f, float bv, int bf)
 {
+    if (f == 0x7fffffff) return false;
+    if (bf == 0x7fffffff) return true;
+    const bool vn = v != v, bn = bv != bv;
+    if (vn | bn) return bn && (!vn || f < bf);
     return (v < bv) || (v == bv && f < bf);
 }
 
@@ -328,6 +337,10 @@ k_milboost_select_batch(const TrainDesc* __restrict__ descs, int FC, int FLmax, 
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool better_max(float v, int f, float bv, int bf)
 {
+    if (f == 0x7fffffff) return false;
+    if (bf == 0x7fffffff) return true;
+    const bool vn = v != v, bn = bv != bv;
+    if (vn | bn) return bn && (!vn || f < bf);            // NaN scores last in the descending order too (sort_order_des)
     return (v > bv) || (v == bv && f < bf);
 }
 // block argmax over (value desc, index asc); returns through shared

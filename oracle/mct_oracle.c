@@ -507,6 +507,12 @@ static int weak_valid(const orc_clf* c, int f)
 static float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-1 * x)); }
 
 static int in_list(const int* l, int n, int v) { for (int i = 0; i < n; i++) if (l[i] == v) return 1; return 0; }
+/* Order of sort_order / sort_order_des (Public.h:211-245) with its two unspecified points pinned the way oracle/_ref is built
+   (ref_shim/boost/shared_ptr.hpp): exactly tied scores keep index order, NaN scores rank last.  NaN scores are real: the
+   appearance fuser's classifiers (learning rate 0) get sigma = 0 for colour bins that are empty in a class on their second
+   Update, hence n = inf, e = -inf and NaN responses; std::sort on them is undefined behaviour in the reference. */
+static int lt_nanlast(float a, float b) { int an = a != a, bn = b != b; if (an || bn) return !an && bn; return a < b; }
+static int gt_nanlast(float a, float b) { int an = a != a, bn = b != b; if (an || bn) return !an && bn; return a > b; }
 
 /* MILBoostClassifier.cpp:61-131 (selection).  pp [F][P], pn [F][Nn].
    sort_order (Public.h:213-228) is std::sort on values only; ties -> smallest index (stable). */
@@ -534,7 +540,7 @@ static void milboost_select(orc_clf* c, const float* pp, int P, const float* pn,
         int best = -1;
         for (int w = 0; w < F; w++) {
             if (in_list(c->sel, c->n_sel, w) || !weak_valid(c, w)) continue;
-            if (best < 0 || nll[w] < nll[best]) best = w;
+            if (best < 0 || lt_nanlast(nll[w], nll[best])) best = w;
         }
         if (best < 0) break;                                      /* reference: out-of-range read (UB) */
         if ((previousNLL - nll[best]) < 1e-100) break;            /* :108-112 push then pop */
@@ -551,15 +557,15 @@ typedef struct { float v; int i; } vi_t;
 static int cmp_desc(const void* a, const void* b)
 {
     const vi_t* x = (const vi_t*)a; const vi_t* y = (const vi_t*)b;
-    if (x->v > y->v) return -1;
-    if (x->v < y->v) return 1;
+    if (gt_nanlast(x->v, y->v)) return -1;
+    if (gt_nanlast(y->v, x->v)) return 1;
     return x->i - y->i;
 }
 static int cmp_asc(const void* a, const void* b)
 {
     const vi_t* x = (const vi_t*)a; const vi_t* y = (const vi_t*)b;
-    if (x->v < y->v) return -1;
-    if (x->v > y->v) return 1;
+    if (lt_nanlast(x->v, y->v)) return -1;
+    if (lt_nanlast(y->v, x->v)) return 1;
     return x->i - y->i;
 }
 

@@ -5,7 +5,8 @@
  * (Public.h:211-245, SortableElement::operator<), so the order of candidates with exactly equal scores is whatever the
  * standard library's std::sort happens to do -- unspecified by the C++ standard, different between the MSVC runtime of the
  * shipped VS2008 solution and libstdc++.  This header is included by Public.h after <algorithm>; with the flag set, the two
- * std::sort calls resolve to a conforming implementation that keeps equal elements in index order (std::stable_sort).
+ * std::sort calls resolve to a conforming implementation that keeps equal elements in index order (std::stable_sort) and
+ * ranks NaN scores last.
  * oracle/build_ref.py also builds libmct_ref_native.so without the flag (libstdc++ introsort);
  * tests/test_ref_pins_oracle.py shows the two differ only where scores tie exactly. */
 #ifndef MCT_SHIM_BOOST_SHARED_PTR
@@ -29,7 +30,18 @@ struct MctRefAbort { int code; };
 #define exit(code) mct_shim_exit(code)
 #ifdef MCT_REF_STABLE_TIES
 namespace std {
-template <class It> inline void mct_sort_ties_in_index_order(It a, It b) { std::stable_sort(a, b); }
+/* Elements are SortableElement / SortableElementRev (Public.h:180-197): operator< compares _val only (ascending resp.
+ * descending).  NaN scores rank last in both: std::sort with a comparison that is not a strict weak order (NaN) is undefined
+ * behaviour in the reference, and NaN scores do occur (appearance fuser, learning rate 0, empty colour bins). */
+template <class It> inline void mct_sort_ties_in_index_order(It a, It b)
+{
+    typedef typename std::iterator_traits<It>::value_type E;
+    std::stable_sort(a, b, [](const E& x, const E& y) {
+        const bool xn = x._val != x._val, yn = y._val != y._val;
+        if (xn || yn) return !xn && yn;
+        return x < y;
+    });
+}
 }
 #define sort mct_sort_ties_in_index_order
 #endif
