@@ -46,6 +46,33 @@ CONFIG = {"workload": "configs[1]: 1 camera/GPU, 8 objects, Haar(250)+MDCH(512) 
           "l2_policy": "inputs larger than L2: %d-frame device-resident pool (157 MB) cycled" % POOL}
 
 
+# BASELINE.json configs[0..4].  0 / 1: one camera per GPU without a fuser (replicas, no data-path collective); 2 / 3: the camera
+# network with a fuser (one camera per rank under torchrun, or all cameras on this GPU when run alone); 4: Haar scoring sweep.
+CONFIGS = {
+    0: dict(W=640, H=480, n_obj=1, n_part=1000, n_haar=250, feat=0, weak=0, strong=2,
+            workload="configs[0]: 1 camera, 1 object, Haar(250) -> 50 selected, OnlineStumps+MILBoost, 1000 particles, 640x480 synthetic"),
+    1: dict(W=640, H=480, n_obj=8, n_part=2000, n_haar=250, feat=3, weak=1, strong=2, workload=CONFIG["workload"]),
+    2: dict(W=640, H=480, n_obj=8, n_part=1000, n_haar=250, feat=0, weak=0, strong=2, cameras=4, camouflage=None,
+            net=dict(geometric_fusion=1),
+            workload="configs[2]: 4 cameras x 8 objects, Haar(250) -> 50 selected, OnlineStumps+MILBoost, 1000 particles/object, 640x480, "
+                     "GeometryBasedInformationFuser (principal-axis intersection + Kalman) with feedback, one camera per GPU"),
+    3: dict(W=1280, H=720, n_obj=16, n_part=1000, n_haar=0, feat=2, weak=0, strong=4, cameras=8, camouflage=30,
+            net=dict(appearance_fusion=2, af_refresh=1),
+            workload="configs[3]: 8 cameras x 16 objects, 1280x720, MDCH(512) -> 102 selected, OnlineStumps+MILAnyBoost, 1000 particles/object, "
+                     "AppearanceBasedInformationFuser (MILBoost over MDCH, refresh every frame), one camera per GPU"),
+}
+
+
+def configure(k):
+    global W, H, N_OBJ, N_PART, N_HAAR, FEAT, WEAK, STRONG, CONFIG
+    c = CONFIGS[k]
+    W, H, N_OBJ, N_PART, N_HAAR, FEAT, WEAK, STRONG = c["W"], c["H"], c["n_obj"], c["n_part"], c["n_haar"], c["feat"], c["weak"], c["strong"]
+    F = {0: N_HAAR, 2: N_BINS ** 3, 3: N_HAAR + N_BINS ** 3}[FEAT]
+    CONFIG = {"workload": c["workload"], "frame": [W, H], "objects_per_camera": N_OBJ, "particles_per_object": N_PART, "features": F,
+              "selected": int(F * PCT / 100),
+              "l2_policy": "inputs larger than L2: %d-frame device-resident pool (%d MB) cycled" % (POOL, POOL * 4 * W * H // 1000000)}
+
+
 def pingpong(i, n):
     """frame index sequence 1,2,..,n-1,n-2,..,1,2.. so that object motion stays continuous"""
     period = 2 * (n - 2)
@@ -94,7 +121,7 @@ class ClockSampler(threading.Thread):
                     pass
                 if self.stop_flag:
                     return
-                time.sleep(0.001)
+                time.sleep(0.05)         # 20 samples per second: no measurable load on the host cores the ranks share
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while True:
@@ -133,12 +160,12 @@ def make_sequence(camera):
 def oracle_setup(orc, seq, frames):
     from oracle import oracle_py
     f0 = orc.frame(*frames[0])
-    F = N_HAAR + N_BINS ** 3
+    F = CONFIG["features"]
     K = int(F * PCT / 100)
     trackers = []
     for o in range(N_OBJ):
         rng = orc.rng(o + 1)
-        t = orc.haar_generate(rng, N_HAAR, seq.w0, seq.h0)
+        t = orc.haar_generate(rng, N_HAAR, seq.w0, seq.h0) if N_HAAR > 0 else None
         clf = orc.clf_create(FEAT, N_HAAR, N_BINS, seq.w0, seq.h0, WEAK, STRONG, K, 0.85, t)
         tp = oracle_py.TrackerParams(N_PART, SD[0], SD[1], SD[2], SD[3], 10.0, 7.0, 30, 30, 100000, 20, 0, 0, 0, 30)
         init = np.array(seq.box(0, o), np.float32)
@@ -194,30 +221,68 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     val = scored / dt
     sample = "%d steps x %d of %d objects x %d particles (score path incl. integral image)" % (args.steps, n_o, N_OBJ, N_PART)
+    ref_build = reference_build_leg(seq, frames)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "particles/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
         "cpu_baseline": {"value": val, "unit": "particles/s", "cores": kind_threads, "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        "e2e": {"value": val, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "reference_build": ref_build}))
+
+
+def reference_build_leg(seq, frames):
+    """The reference's OWN code (oracle/_ref = /root/reference/src compiled against header shims), single thread as it ships
+    (obj/Makefile has no -fopenmp), on a bounded sample: one object, score path only.  Reported next to the OpenMP port above,
+    which is the stronger baseline and stays the line's value."""
+    try:
+        from multicameratracking_b200 import synth
+        from oracle.ref_py import Ref, TrackerParams
+        if not Ref.available():
+            return {"unavailable": "oracle/_ref not built and /root/reference absent"}
+        ref = Ref()
+        weak = 0 if WEAK == 1 else WEAK          # WeightedStumps dereferences NULL weight lists in the reference (SURVEY a12)
+        fr = ref.frame(*frames[0])
+        ref.seed(1)
+        tp = TrackerParams(N_PART, SD[0], SD[1], SD[2], SD[3], 10.0, 7.0, 30, 30, 100000, 20, 0, 0, 0, 30)
+        trk = ref.tracker_create(True, tp, FEAT, max(N_HAAR, 1), N_BINS, weak, STRONG, CONFIG["selected"], 0.85, fr,
+                                 np.array(seq.box(0, 0), np.float32), 64)
+        n, scored, t0 = 0, 0, time.perf_counter()
+        while time.perf_counter() - t0 < 10.0 and n < 20:
+            f2 = ref.frame(*frames[pingpong(n, POOL)])
+            ref.tracker_track(trk, f2, synth.noise(N_PART, SD, obj=0, t=n + 1), 1)
+            scored += ref.lib.ref_tracker_test_set_size(trk[0])
+            ref.frame_free(f2)
+            n += 1
+        dt = time.perf_counter() - t0
+        return {"value": scored / dt, "unit": "particles/s", "cores": 1, "kind": "reference",
+                "sample": "%d frames x 1 of %d objects x %d particles, score path incl. initII%s" % (
+                    n, N_OBJ, N_PART, "; OnlineStumps in place of WeightedStumps (the reference crashes on its NULL weight lists)" if WEAK == 1 else "")}
+    except Exception as e:                      # noqa: BLE001
+        return {"unavailable": repr(e)}
 
 
 # ------------------------------------------------------------------------------------------------ our arm
-def cpu_baseline_leg():
-    """oracle (single thread, as the reference ships) on a bounded sample: a few frames of 2 objects"""
+def cpu_baseline_leg(phases=1):
+    """oracle (single thread, as the reference ships) on a bounded sample: a few frames of 2 objects.  phases=3: full frames
+    (score path + UpdateClassifier), reported as tracked frames/s per camera (the second metric of BASELINE.json)"""
     from oracle.oracle_py import Oracle
     orc = Oracle(omp=False)
     seq, frames = make_sequence(0)
     trackers = oracle_setup(orc, seq, frames)
-    objs = [0, 1]
+    objs = [0, 1][:N_OBJ]
     oracle_score_frame(orc, trackers, frames, 1, objs)
     scored, t0, n = 0, time.perf_counter(), 0
-    while time.perf_counter() - t0 < 12.0 and n < 40:
-        scored += oracle_score_frame(orc, trackers, frames, pingpong(n + 1, POOL), objs)
+    while time.perf_counter() - t0 < (12.0 if phases == 1 else 8.0) and n < 40:
+        scored += oracle_score_frame(orc, trackers, frames, pingpong(n + 1, POOL), objs, phases)
         n += 1
     dt = time.perf_counter() - t0
+    if phases != 1:
+        # frames/s for a whole camera = measured object-frames/s divided by the objects per camera
+        return {"value": n * len(objs) / float(N_OBJ) / dt, "unit": "tracked frames/s per camera", "cores": 1, "kind": "port",
+                "sample": "%d full frames (score + UpdateClassifier) x %d of %d objects x %d particles, single thread" % (n, len(objs), N_OBJ, N_PART)}
     return {"value": scored / dt, "unit": "particles/s", "cores": 1, "kind": "port",
-            "sample": "%d frames x 2 of %d objects x %d particles, single thread (reference builds compile omp out)" % (n, N_OBJ, N_PART)}
+            "sample": "%d frames x %d of %d objects x %d particles, single thread (reference builds compile omp out)" % (n, len(objs), N_OBJ, N_PART)}
 
 
 def run_ours(args):
@@ -505,6 +570,9 @@ def run_ours(args):
         except Exception:
             pass
         shares = {k: round(v[0] / tot, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+        # what really bounds the dominant kernel (ncu: DRAM traffic is ~1 % of the algorithmic bytes, everything is staged on chip)
+        bound = {"k_mdch_sel": "smem", "k_classify_staged": "smem/latency", "k_pf_update": "latency", "k_frame_prep": "hbm",
+                 "k_haar_matrix_batch": "l1/l2", "k_pf_predict_testset": "latency"}.get(dom_name, "hbm")
         out = {
             "metric": METRIC, "value": scored_all / (ms_max * 1e-3), "unit": "particles/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -517,7 +585,9 @@ def run_ours(args):
             "full_frame": {"ms_per_frame": ms_full_max / args.steps,
                            "kernel_us_per_frame": {k: round(1e3 * v[0] / n_pf, 2) for k, v in sorted(prof_full.items(), key=lambda kv: -kv[1][0])}},
             "gpu_launches": int(launches_all),
-            "roofline": {"kernel": dom_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"kernel": dom_name, "bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "achieved_is": "ALGORITHMIC bytes per launch / launch time (SURVEY 8d), set against the HBM copy peak as the contract asks; "
+                                        "the limiter named in `bound` and its own fraction are in `onchip`",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                          "avg_launch_us": avg_us, "algorithmic_bytes_per_launch": alg, "kernel_time_shares": shares, "onchip": onchip,
                          "kernels": {k: {"avg_launch_us": round(1e3 * v[0] / max(v[1], 1), 2), "algorithmic_bytes": alg_all.get(k, 0),
@@ -531,10 +601,227 @@ def run_ours(args):
             out["fuser_exchange"] = fuser
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_leg()
+            out["cpu_baseline_full_frame"] = cpu_baseline_leg(phases=3)
         print(json.dumps(out))
     cam.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ configs[2] / [3]: the camera network
+NET_POOL = 24          # frames per camera in the host pool of the network runs (uploaded every step: these runs are end to end)
+
+
+def network_scene(n_cameras):
+    from multicameratracking_b200 import synth
+    c = CONFIGS[2] if CONFIG["workload"].startswith("configs[2]") else CONFIGS[3]
+    return c, synth.MultiViewScene(n_cameras, N_OBJ, W, H, n_frames=NET_POOL, camouflage=c["camouflage"])
+
+
+def run_network(args):
+    """One step = one frame of the whole per-frame schedule of CameraNetwork::TrackObjectsOnCurrentFrame (CameraNetwork.cpp:537-613)
+    for this rank's camera: frame upload, score path, fuser exchange INSIDE the step, feedback / re-weighting, UpdateClassifier,
+    (appearance) global model refresh, state read-out.  Under torchrun: one camera per rank, exchange over NCCL; alone: all cameras
+    of the configuration on this GPU (exchange in process)."""
+    import torch
+    import torch.distributed as dist
+    from multicameratracking_b200 import synth
+    from multicameratracking_b200 import host as mhost
+    from multicameratracking_b200.network import TorchExchange
+
+    rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = CONFIGS[args.config]
+    n_cameras = world if world > 1 else cfg["cameras"]
+    _, scene = network_scene(n_cameras)
+    my = [rank] if world > 1 else list(range(n_cameras))
+    total = args.steps + args.warmup
+    frames = {c: [scene.frame(c, t) for t in range(NET_POOL)] for c in my}
+    over = dict(feature_type=FEAT, n_haar=max(N_HAAR, 1), n_bins=N_BINS, weak_type=WEAK, strong_type=STRONG, percent_selected=PCT, n_particles=N_PART,
+                sd_x=SD[0], sd_y=SD[1], sd_sx=SD[2], sd_sy=SD[3])
+    cams = []
+    for c in my:
+        cam = mhost.Camera(local, n_frames=total + 8)
+        cam.set_frame(*frames[c][0])
+        for o in range(N_OBJ):
+            cam.add_object(scene.box(c, 0, o), rng_seed=1000 * c + o + 1, **over)
+        cams.append(cam)
+    ex = TorchExchange() if world > 1 else None
+    net = mhost.Network(cams, scene.homographies, camera_ids=my, n_cameras=n_cameras, exchange=ex.as_tuple() if ex else None, **cfg["net"])
+    net.init()
+    if ex:
+        ex.bind_rows(net)
+    noise = {c: [np.stack([synth.noise(N_PART, SD, camera=c, obj=o, t=i + 1) for o in range(N_OBJ)]) for i in range(total)] for c in my}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stages = {}
+
+    def step(i):
+        t = pingpong(i, NET_POOL)
+        for k, c in enumerate(my):
+            cams[k].set_frame(*frames[c][t])
+        net.track(i + 1, [noise[c][i] for c in my])
+        for k, v in net.stage_ms().items():
+            stages[k] = stages.get(k, 0.0) + v
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    stages.clear()
+    l0 = sum(cam.launches for cam in cams)
+    sampler = ClockSampler(local); sampler.start()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    for cam in cams:
+        cam.sync()
+    dt = time.perf_counter() - t0
+    barrier()
+    sampler.stop_flag = True
+    launches = sum(cam.launches for cam in cams) - l0
+
+    def allmax(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); return float(tt.item())
+
+    def allsum(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device=dev); dist.all_reduce(tt, op=dist.ReduceOp.SUM); return float(tt.item())
+
+    dt_max = allmax(dt); launches_all = allsum(launches)
+    st = {k: allmax(v / args.steps) for k, v in sorted(stages.items())}
+    if rank == 0:
+        cam_frames = n_cameras * args.steps
+        h2d = len(my) * (4 * W * H + N_OBJ * 4 * N_PART * 4)
+        val = cam_frames / dt_max
+        out = {"metric": "camera_frames_tracked_per_sec", "value": val, "unit": "camera-frames/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": 1e3 * dt_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic", "config": dict(CONFIG, cameras=n_cameras, cameras_per_gpu=len(my), fusers=cfg["net"],
+                                                                 l2_policy="inputs uploaded from host memory every step (end to end)"),
+               "timing": "host wall clock around the timed steps with every camera stream drained at the end, max over ranks: the network's "
+                         "schedule synchronises with the device several times per frame (training-set generation, fuser decisions), so the "
+                         "host clock is the device timeline",
+               "tracked_frames_per_sec_per_camera": args.steps / dt_max / (len(my) if world == 1 else 1),
+               "particles_scored_per_sec": cam_frames * N_OBJ * N_PART / dt_max,
+               "e2e": {"value": val, "unit": "camera-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": len(my) * N_OBJ * 80,
+                       "note": "the network path IS end to end: host frames and noise in, boxes out, every step"},
+               "stage_ms_per_frame": {k: round(v, 4) for k, v in st.items()},
+               "gpu_launches": int(launches_all), "roofline": None, "clocks": sampler.summary()}
+        print(json.dumps(out))
+    net.close()
+    for cam in cams:
+        cam.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_network_reference(args):
+    """The reference's own code (oracle/_ref: /root/reference/src compiled against header shims) running the same multi-camera schedule on
+    the host CPU, single thread as the reference ships; a bounded sample of the workload (fewer cameras / objects when a frame takes long)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from multicameratracking_b200 import synth
+    from oracle.ref_py import Ref, RefNetwork
+    if not Ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built and /root/reference is absent"}))
+        return
+    cfg = CONFIGS[args.config]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_cameras = world if world > 1 else cfg["cameras"]
+    # bounded sample: configs[3] needs ~80 s per frame at its full shape
+    sc, so = (n_cameras, N_OBJ) if args.config == 2 else (2, 4)
+    steps, warm = (min(args.steps, 4), 1) if args.config == 2 else (2, 1)
+    scene = synth.MultiViewScene(sc, so, W, H, n_frames=NET_POOL, camouflage=cfg["camouflage"])
+    init = np.array([[scene.box(c, 0, o) for o in range(so)] for c in range(sc)], np.float32)
+    seeds = np.array([[1000 * c + o + 1 for o in range(so)] for c in range(sc)])
+    ref = Ref()
+    net = RefNetwork(ref, sc, so, steps + warm + 2, scene.homographies, init, seeds, feature_type=FEAT, n_haar=max(N_HAAR, 1), strong_type=STRONG,
+                     weak_type=WEAK, n_particles=N_PART, **cfg["net"])
+    net.init([scene.frame(c, 0) for c in range(sc)])
+    nz = lambda t: np.stack([np.stack([synth.noise(N_PART, SD, camera=c, obj=o, t=t) for o in range(so)]) for c in range(sc)])   # noqa: E731
+    for i in range(warm):
+        net.track(i + 1, [scene.frame(c, pingpong(i, NET_POOL)) for c in range(sc)], nz(i + 1))
+    t0 = time.perf_counter()
+    for i in range(warm, warm + steps):
+        net.track(i + 1, [scene.frame(c, pingpong(i, NET_POOL)) for c in range(sc)], nz(i + 1))
+    dt = time.perf_counter() - t0
+    net.close()
+    # camera-frames/s normalised to the configuration's objects per camera
+    val = sc * steps * (so / float(N_OBJ)) / dt
+    sample = "%d frames x %d cameras x %d of %d objects x %d particles, full schedule with fusers, reference build single thread" % (steps, sc, so, N_OBJ, N_PART)
+    print(json.dumps({"impl": "reference", "metric": "camera_frames_tracked_per_sec", "value": val, "unit": "camera-frames/s", "n_gpus": args.gpus,
+                      "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f32", "data": "synthetic", "config": dict(CONFIG, cameras=n_cameras),
+                      "cpu_baseline": {"value": val, "unit": "camera-frames/s", "cores": 1, "kind": "reference", "sample": sample},
+                      "e2e": {"value": val, "unit": "camera-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ------------------------------------------------------------------------------------------------ configs[4]: Haar scoring sweep
+def run_sweep(args):
+    """roofline characterisation of the Haar rectangle-sum gather (FeatureVector::Compute): N boxes x F features x frame size"""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    if args.impl == "reference":
+        print(json.dumps({"impl": "reference", "unavailable": "configs[4] is a roofline sweep of the GPU kernel; the CPU arm of the path is --config 0 / 1"}))
+        return
+    import torch
+    from multicameratracking_b200 import capi, synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    ctx = capi.Context(0)
+    L = capi.load()
+    peak = 6545.0
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    pts = []
+    for (w, h) in [(640, 480), (1280, 720), (1920, 1080)]:
+        seq = synth.Sequence(w, h, 1)
+        ctx.frame_set(seq.frame(0)[0])
+        for F in (250, 2000):
+            arrs = synth.haar_table(1, F, seq.w0, seq.h0)
+            sumR = int(arrs[0].sum())
+            clf = capi.StrongClassifier(ctx, capi.FEAT_HAAR, seq.w0, seq.h0, n_haar=F, n_selected=max(1, F // 5), haar=arrs)
+            for N in (1000, 8000, 64000):
+                rng = np.random.default_rng(5)
+                bx = capi.make_boxes(rng.integers(1, w - seq.w0 - 2, N).astype(np.int32), rng.integers(1, h - seq.h0 - 2, N).astype(np.int32),
+                                     np.ones(N, np.float32), np.ones(N, np.float32))
+                for _ in range(max(3, args.warmup)):
+                    clf.features(bx)
+                capi.profile_enable(L, ctx.h, True)
+                for _ in range(5):
+                    clf.features(bx)
+                prof = capi.profile_read(L, ctx.h)
+                capi.profile_enable(L, ctx.h, False)
+                ms = sum(v[0] for k, v in prof.items() if k.startswith("k_haar") or k.startswith("k_tile"))
+                n = max(v[1] for k, v in prof.items() if k.startswith("k_haar"))
+                us = 1e3 * ms / n
+                alg = N * sumR * 16 + N * F * 4
+                pts.append({"frame": [w, h], "N": N, "F": F, "us": round(us, 2), "kernels": sorted(k for k in prof if k.startswith("k_haar") or k.startswith("k_tile")),
+                            "algorithmic_bytes": alg, "achieved_gbs": round(alg / us / 1e3, 1), "frac_of_hbm_peak": round(alg / us / 1e3 / peak, 3),
+                            "rect_sums_per_s_G": round(N * sumR / us / 1e3, 2)})
+            clf.close()
+    best = max(pts, key=lambda q: q["achieved_gbs"])
+    print(json.dumps({"metric": "haar_rect_sums_per_sec", "value": best["rect_sums_per_s_G"] * 1e9, "unit": "rect-sums/s", "n_gpus": 1, "steps": 5,
+                      "warmup": max(3, args.warmup), "ms_per_step": best["us"] * 1e-3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "configs[4]: Haar scoring sweep, N boxes x F features x frame size, uniformly random boxes", "best_point": best},
+                      "roofline": {"kernel": "k_haar_matrix(_tiled)", "bound": "smem/L2 (staged gather) - reported against the HBM copy peak in algorithmic bytes",
+                                   "achieved": best["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": best["frac_of_hbm_peak"], "traffic": None},
+                      "points": pts, "gpu_launches": 5 * len(pts)}))
+    ctx.close()
 
 
 def main():
@@ -545,9 +832,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-bgr", action="store_true", help="e2e leg uploads the packed BGR frame (split + gray on the device) instead of 4 planes")
+    ap.add_argument("--config", type=int, default=1, choices=[0, 1, 2, 3, 4],
+                    help="BASELINE.json configs[k]; 1 (default) is the configuration the headline metric is quoted on")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.config == 4:
+        return run_sweep(args)
+    configure(args.config)
+    if args.config in (2, 3):
+        return run_network_reference(args) if args.impl == "reference" else run_network(args)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -198,3 +198,60 @@ def drop_samples(rng_next_float, n, threshold=0.5):
     (0.5, :7), in order (all positives, then all negatives), one draw per sample from the MWC stream
     (rng_next_float() -> float in [0,1))."""
     return [i for i in range(n) if rng_next_float() > threshold]
+
+
+class TorchExchange:
+    """NetworkExchange for host.Network over torch.distributed: rank r holds camera r (one process per camera per GPU).
+
+    Small host payloads (foot points, counts) travel as CUDA (NCCL) or CPU (gloo) tensors; the appearance fuser's feature rows
+    are all-gathered between two device buffers this object owns (torch tensors, so that NCCL can use them) and hands to the
+    network with bind_rows()."""
+
+    def __init__(self, group=None, device=None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised (one process per camera / GPU)")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.cuda = dist.get_backend(group) == "nccl"
+        self.device = device if device is not None else ("cuda" if self.cuda else "cpu")
+        self._small = {}
+        self.send = self.recv = None
+
+    def as_tuple(self):
+        return (self.rank, self.world, self.allgather_host, self.allgather_rows)
+
+    def allgather_host(self, send_ptr, recv_ptr, nbytes):
+        import ctypes as C
+        nbytes = int(nbytes)
+        if nbytes not in self._small:
+            pin = self.cuda
+            self._small[nbytes] = (torch.empty(nbytes, dtype=torch.uint8, pin_memory=pin), torch.empty(nbytes * self.world, dtype=torch.uint8, pin_memory=pin),
+                                   torch.empty(nbytes, dtype=torch.uint8, device=self.device), torch.empty(nbytes * self.world, dtype=torch.uint8, device=self.device))
+        hs, hr, ds, dr = self._small[nbytes]
+        C.memmove(hs.data_ptr(), send_ptr, nbytes)
+        if self.cuda:
+            ds.copy_(hs, non_blocking=True)
+            dist.all_gather_into_tensor(dr, ds, group=self.group)
+            hr.copy_(dr, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        else:
+            dist.all_gather_into_tensor(hr, hs, group=self.group)
+        C.memmove(recv_ptr, hr.data_ptr(), nbytes * self.world)
+
+    def bind_rows(self, network):
+        """allocate the feature-row exchange buffers and give them to the network (after network.init())"""
+        n = network.row_bytes()
+        if n == 0:
+            return
+        self.send = torch.empty(n, dtype=torch.uint8, device=self.device)
+        self.recv = torch.empty(n * self.world, dtype=torch.uint8, device=self.device)
+        network.set_row_buffers(self.send.data_ptr(), self.recv.data_ptr())
+
+    def allgather_rows(self, nbytes, stream_ptr):
+        if self.cuda:
+            st = torch.cuda.ExternalStream(int(stream_ptr))
+            with torch.cuda.stream(st):
+                dist.all_gather_into_tensor(self.recv, self.send, group=self.group)     # ordered on the camera's own stream
+        else:
+            dist.all_gather_into_tensor(self.recv, self.send, group=self.group)

@@ -12,8 +12,14 @@ def gray_from_rgb(r, g, b):
 
 
 class Sequence:
-    def __init__(self, W=640, H=480, n_objects=1, camera=0, n_frames=100, obj_wh=None):
+    def __init__(self, W=640, H=480, n_objects=1, camera=0, n_frames=100, obj_wh=None, camouflage=None):
+        """camouflage: None = objects with their own mean colour (clearly separable from the background); a number d = the
+        object is the local background shifted by a per-object colour offset of magnitude <= d (plus its texture): colour
+        histograms of object and surroundings overlap, as in real footage.  MILAnyBoost needs that: on perfectly separable
+        samples its first weak classifier saturates the bag likelihood, no second one can improve it, and the reference
+        aborts with "Could not find best 2 weak classifiers" (MILAnyBoostClassifier.cpp:102-131)."""
         self.W, self.H, self.n_objects, self.n_frames = W, H, n_objects, n_frames
+        self.camouflage = camouflage
         self.w0, self.h0 = obj_wh if obj_wh else OBJ_WH.get((W, H), (40, 80))
         rng = np.random.default_rng(1000 + camera)
         yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
@@ -23,6 +29,8 @@ class Sequence:
             bg.append(a + 40 * np.sin(fx * xx + ph[0]) * np.cos(fy * yy + ph[1]))
         self.bg = np.stack(bg)
         self.colors = rng.uniform(30, 225, (n_objects, 3)).astype(np.float32)
+        if camouflage is not None:
+            self.offsets = (np.random.default_rng(77 + camera).uniform(-1, 1, (n_objects, 3)) * float(camouflage)).astype(np.float32)
         self.tex = rng.uniform(-25, 25, (n_objects, 3, self.h0, self.w0)).astype(np.float32)
         m = 2 * 20 + 8
         self.x0 = rng.uniform(m, W - self.w0 - m, n_objects)
@@ -45,7 +53,10 @@ class Sequence:
         img = self.bg + rng.uniform(-8, 8, self.bg.shape).astype(np.float32)
         for o in range(self.n_objects):
             x, y, w, h = self.box(t, o)
-            img[:, y:y + h, x:x + w] = self.colors[o][:, None, None] + self.tex[o]
+            if self.camouflage is None:
+                img[:, y:y + h, x:x + w] = self.colors[o][:, None, None] + self.tex[o]
+            else:
+                img[:, y:y + h, x:x + w] += self.offsets[o][:, None, None] + self.tex[o]
         img = np.clip(img, 0, 255).astype(np.uint8)
         r, g, b = img[0], img[1], img[2]
         return gray_from_rgb(r, g, b), np.ascontiguousarray(r), np.ascontiguousarray(g), np.ascontiguousarray(b)
@@ -67,9 +78,9 @@ class MultiViewScene:
     inverse of that affine map, so the cameras' principal axes (vertical image lines through the foot points, mapped to the
     ground) meet at the object's ground position: a geometrically consistent input for GeometryBasedInformationFuser."""
 
-    def __init__(self, n_cameras, n_objects, W=640, H=480, n_frames=100, obj_wh=None, seed=7):
+    def __init__(self, n_cameras, n_objects, W=640, H=480, n_frames=100, obj_wh=None, seed=7, camouflage=None):
         self.C, self.O, self.W, self.H = n_cameras, n_objects, W, H
-        self.seqs = [Sequence(W, H, n_objects, camera=c, n_frames=n_frames, obj_wh=obj_wh) for c in range(n_cameras)]
+        self.seqs = [Sequence(W, H, n_objects, camera=c, n_frames=n_frames, obj_wh=obj_wh, camouflage=camouflage) for c in range(n_cameras)]
         w0, h0 = self.seqs[0].w0, self.seqs[0].h0
         rng = np.random.default_rng(seed)
         half = 0.28 * min(W, H)                           # world square [-half, half]^2 around the origin
@@ -109,3 +120,29 @@ class MultiViewScene:
 
     def frame(self, c, t):
         return self.seqs[c].frame(t)
+
+
+def haar_table(seed, F, w0, h0):
+    """HaarFeature::Generate (HaarFeature.cpp:25-69) for F features of a w0 x h0 blob, drawn from OpenCV's multiply-with-carry
+    stream seeded like randinitalize(seed) (Public.cpp:10-23), in the reference's draw order.  Returns (nrect [F], rects
+    [F][6][4], weights [F][6]) as capi.StrongClassifier(haar=...) takes them."""
+    state = [seed if seed else (1 << 64) - 1]
+
+    def nxt():
+        t = state[0]
+        t = (t & 0xffffffff) * 4164903690 + (t >> 32)
+        state[0] = t & ((1 << 64) - 1)
+        return state[0] & 0xffffffff
+
+    randint = lambda a, b: nxt() % (b - a + 1) + a                      # noqa: E731
+    randfloat = lambda: np.float32(nxt() * 2.3283064365386962890625e-10)  # noqa: E731
+    nrect = np.zeros(F, np.int32); rects = np.zeros((F, 6, 4), np.int32); wts = np.zeros((F, 6), np.float32)
+    for f in range(F):
+        n = randint(2, 6)
+        nrect[f] = n
+        for k in range(n):
+            wts[f, k] = np.float32(randfloat() * np.float32(2) - np.float32(1))
+            x = randint(0, w0 - 3); y = randint(0, h0 - 3)
+            rects[f, k] = (x, y, randint(1, w0 - x - 2), randint(1, h0 - y - 2))
+        randint(0, 0)                                                   # the channel draw (one channel)
+    return nrect, rects, wts

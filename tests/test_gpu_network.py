@@ -13,7 +13,8 @@ from multicameratracking_b200 import host as mhost
 from multicameratracking_b200 import synth
 from oracle.ref_py import Ref, RefNetwork
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not Ref.available(), reason="oracle/_ref not built")]
+pytestmark = pytest.mark.gpu
+needs_ref = pytest.mark.skipif(not Ref.available(), reason="oracle/_ref not built")
 
 CASES = {
     # name: (cameras, objects, frames, W, H, per-object overrides, network settings)
@@ -30,6 +31,7 @@ def _noise(scene, N, p, t):
                      for c in range(scene.C)])
 
 
+@needs_ref
 @pytest.mark.parametrize("case", list(CASES))
 def test_camera_network_matches_reference(case):
     Cn, On, T, W, H, over, netkw = CASES[case]
@@ -89,5 +91,74 @@ def test_camera_network_matches_reference(case):
                 np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-3, err_msg="%s frame %d object %d Kalman state" % (case, t, o))
                 np.testing.assert_allclose(Pa, Pb, rtol=1e-4, atol=1e-4)
     net.close(); rnet.close()
+    for cam in cams:
+        cam.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Full-shape configurations against REFERENCE-GENERATED golden files (tests/golden/ref_*.json, made by
+# tests/golden/make_ref_golden.py from the reference build in the development container): nothing of the reference is
+# needed on the GPU box, the synthetic inputs are regenerated from their seeds.
+import importlib.util
+import json
+import os
+
+_G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _golden_module():
+    spec = importlib.util.spec_from_file_location("make_ref_golden", os.path.join(_G, "make_ref_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.mark.parametrize("name", ["cfg2_full", "cfg3_full"])
+def test_camera_network_full_shape_matches_reference_golden(name):
+    path = os.path.join(_G, "ref_%s.json" % name)
+    if not os.path.exists(path):
+        pytest.skip("golden file %s not generated" % path)
+    gold = json.load(open(path))
+    mg = _golden_module()
+    cs = mg.CASES[name]
+    Cn, On, T = cs["cameras"], cs["objects"], cs["frames"]
+    p = dict(mg.OBJ_DEFAULTS); p.update(cs["obj"])
+    N = p["n_particles"]
+    scene = synth.MultiViewScene(Cn, On, cs["W"], cs["H"], n_frames=T, camouflage=cs["camouflage"])
+    seeds = mg.seeds_for(Cn, On)
+    cams = []
+    for c in range(Cn):
+        cam = mhost.Camera(0, T)
+        cam.set_frame(*scene.frame(c, 0))
+        for o in range(On):
+            cam.add_object(scene.box(c, 0, o), rng_seed=int(seeds[c, o]), **cs["obj"])
+        cams.append(cam)
+    net = mhost.Network(cams, scene.homographies, **cs["net"])
+    net.init()
+    pairs = [(c, o) for c in range(Cn) for o in range(On)]
+    for k, (c, o) in enumerate(pairs):
+        assert cams[c].selectors(o).tolist() == gold["init"]["selectors"][k], (name, "init", c, o)
+        assert str(cams[c].rng_state(o)) == gold["init"]["rng"][k], (name, "init", c, o)
+    for fr in gold["frames"]:
+        t = fr["t"]
+        for c in range(Cn):
+            cams[c].set_frame(*scene.frame(c, t))
+        nz = mg.noise_for(scene, N, p, t)
+        net.track(t, [nz[c] for c in range(Cn)])
+        for c in range(Cn):
+            cams[c].sync()
+        for k, (c, o) in enumerate(pairs):
+            gb = np.array(cams[c].boxes(o, t)); rb = np.array(fr["boxes"][k])
+            assert np.abs(gb - rb).max() <= 1, (name, t, c, o, gb, rb)
+            assert str(cams[c].rng_state(o)) == fr["rng"][k], (name, t, c, o, "RNG streams diverged")
+            assert cams[c].selectors(o).tolist() == fr["selectors"][k], (name, t, c, o)
+            if "global_selectors" in fr:
+                assert net.global_selectors(c, o).tolist() == fr["global_selectors"][k], (name, t, c, o, "global classifier")
+        if "kalman" in fr:
+            for o in range(On):
+                a, Pa = net.kalman(o)
+                np.testing.assert_allclose(a, np.array(fr["kalman"][o], np.float32), rtol=1e-4, atol=1e-3)
+                np.testing.assert_allclose(Pa.ravel(), np.array(fr["kalman_P"][o], np.float32), rtol=1e-4, atol=1e-4)
+    net.close()
     for cam in cams:
         cam.close()

@@ -210,3 +210,65 @@ def test_bench_shards_cameras_by_rank():
     b0 = synth.Sequence(320, 240, 2, camera=0, n_frames=4, obj_wh=(20, 30)).frame(1)[0]
     assert np.array_equal(a0, b0) and not np.array_equal(a0, a1)
     assert not np.array_equal(synth.noise(16, (1, 1, 1, 1), camera=0, obj=0, t=1), synth.noise(16, (1, 1, 1, 1), camera=1, obj=0, t=1))
+
+
+class _StandInNetwork:
+    """what TorchExchange.bind_rows needs from host.Network"""
+
+    def __init__(self, nbytes):
+        self.nbytes = nbytes
+        self.ptrs = None
+
+    def row_bytes(self):
+        return self.nbytes
+
+    def set_row_buffers(self, send, recv):
+        self.ptrs = (send, recv)
+
+
+def _torch_exchange_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import ctypes as C
+        from multicameratracking_b200.network import TorchExchange
+        ex = TorchExchange()
+        r, w, ag_host, ag_rows = ex.as_tuple()
+        assert (r, w) == (rank, world)
+        # host payload through raw pointers, as the C++ CameraNetwork calls it (foot points: 8 objects x 2 floats; counts)
+        for n in (64, 24):
+            send = (np.arange(n, dtype=np.uint8) + 100 * rank).astype(np.uint8)
+            recv = np.zeros(n * world, np.uint8)
+            ag_host(send.ctypes.data, recv.ctypes.data, n)
+            for k in range(world):
+                assert np.array_equal(recv[k * n:(k + 1) * n], (np.arange(n, dtype=np.uint8) + 100 * k).astype(np.uint8))
+        # feature rows: the exchange owns the buffers and hands their addresses to the network
+        net = _StandInNetwork(4096)
+        ex.bind_rows(net)
+        assert net.ptrs == (ex.send.data_ptr(), ex.recv.data_ptr())
+        rows = np.full(4096, rank + 1, np.uint8)
+        C.memmove(net.ptrs[0], rows.ctypes.data, 4096)
+        ag_rows(4096, 0)
+        got = np.frombuffer((C.c_uint8 * (4096 * world)).from_address(net.ptrs[1]), np.uint8)
+        for k in range(world):
+            assert (got[k * 4096:(k + 1) * 4096] == k + 1).all()
+        q.put((rank, "ok"))
+    except BaseException as e:           # noqa: BLE001
+        q.put((rank, "FAIL %r" % (e,)))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_torch_exchange_two_ranks_gloo():
+    """the NetworkExchange implementation bench.py and tools/ use under torchrun, on CPU tensors with gloo"""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_torch_exchange_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
