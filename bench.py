@@ -641,22 +641,38 @@ def run_network(args):
     _, scene = network_scene(n_cameras)
     my = [rank] if world > 1 else list(range(n_cameras))
     total = args.steps + args.warmup
-    frames = {c: [scene.frame(c, t) for t in range(NET_POOL)] for c in my}
+    SEG = 8            # frames per tracking segment, see build()
+    frames = {c: [scene.frame(c, t) for t in range(SEG + 1)] for c in my}
     over = dict(feature_type=FEAT, n_haar=max(N_HAAR, 1), n_bins=N_BINS, weak_type=WEAK, strong_type=STRONG, percent_selected=PCT, n_particles=N_PART,
                 sd_x=SD[0], sd_y=SD[1], sd_sx=SD[2], sd_sy=SD[3])
-    cams = []
-    for c in my:
-        cam = mhost.Camera(local, n_frames=total + 8)
-        cam.set_frame(*frames[c][0])
-        for o in range(N_OBJ):
-            cam.add_object(scene.box(c, 0, o), rng_seed=1000 * c + o + 1, **over)
-        cams.append(cam)
     ex = TorchExchange() if world > 1 else None
-    net = mhost.Network(cams, scene.homographies, camera_ids=my, n_cameras=n_cameras, exchange=ex.as_tuple() if ex else None, **cfg["net"])
-    net.init()
-    if ex:
-        ex.bind_rows(net)
-    noise = {c: [np.stack([synth.noise(N_PART, SD, camera=c, obj=o, t=i + 1) for o in range(N_OBJ)]) for i in range(total)] for c in my}
+    state = {"cams": [], "net": None}
+
+    def build():
+        """(Re)initialise the trackers on frame 0 of the scene -- untimed.  The reference's geometric feedback is not a stable
+        controller on long synthetic sequences (its rearrangement triggers whenever the average particle's foot, computed with
+        h0 instead of h0 / 2, is 20 px from the fused estimate, ParticleFilterTracker.cpp:1093-1105, and rescales the particles
+        by the offset); the reference itself runs into its empty-training-set assertion after ~17 frames of this scene.  The
+        bench therefore tracks segments of SEG frames from a fresh initialisation; every timed step is a regular frame of the
+        schedule."""
+        if state["net"] is not None:
+            state["net"].close()
+            for cam in state["cams"]:
+                cam.close()
+        cams = []
+        for c in my:
+            cam = mhost.Camera(local, n_frames=SEG + 4)
+            cam.set_frame(*frames[c][0])
+            for o in range(N_OBJ):
+                cam.add_object(scene.box(c, 0, o), rng_seed=1000 * c + o + 1, **over)
+            cams.append(cam)
+        net = mhost.Network(cams, scene.homographies, camera_ids=my, n_cameras=n_cameras, exchange=ex.as_tuple() if ex else None, **cfg["net"])
+        net.init()
+        if ex:
+            ex.bind_rows(net)
+        state["cams"], state["net"] = cams, net
+
+    noise = {c: [np.stack([synth.noise(N_PART, SD, camera=c, obj=o, t=k + 1) for o in range(N_OBJ)]) for k in range(SEG)] for c in my}
 
     def barrier():
         if world > 1:
@@ -664,30 +680,36 @@ def run_network(args):
         torch.cuda.synchronize()
 
     stages = {}
+    timed = {"s": 0.0, "launches": 0}
 
-    def step(i):
-        t = pingpong(i, NET_POOL)
-        for k, c in enumerate(my):
-            cams[k].set_frame(*frames[c][t])
-        net.track(i + 1, [noise[c][i] for c in my])
-        for k, v in net.stage_ms().items():
-            stages[k] = stages.get(k, 0.0) + v
+    def step(i, record):
+        k = i % SEG
+        if k == 0:
+            build()
+            barrier()
+        cams, net = state["cams"], state["net"]
+        l0 = sum(cam.launches for cam in cams)
+        t0 = time.perf_counter()
+        for j, c in enumerate(my):
+            cams[j].set_frame(*frames[c][k + 1])
+        net.track(k + 1, [noise[c][k] for c in my])
+        for cam in cams:
+            cam.sync()
+        dt = time.perf_counter() - t0
+        if record:
+            timed["s"] += dt
+            timed["launches"] += sum(cam.launches for cam in cams) - l0
+            for kk, v in net.stage_ms().items():
+                stages[kk] = stages.get(kk, 0.0) + v
 
-    for i in range(args.warmup):
-        step(i)
-    barrier()
-    stages.clear()
-    l0 = sum(cam.launches for cam in cams)
     sampler = ClockSampler(local); sampler.start()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        step(args.warmup + i)
-    for cam in cams:
-        cam.sync()
-    dt = time.perf_counter() - t0
+    for i in range(total):
+        step(i, i >= args.warmup)
     barrier()
     sampler.stop_flag = True
-    launches = sum(cam.launches for cam in cams) - l0
+    dt = timed["s"]
+    launches = timed["launches"]
+    cams, net = state["cams"], state["net"]
 
     def allmax(x):
         if world == 1:
@@ -709,9 +731,9 @@ def run_network(args):
                "warmup": args.warmup, "ms_per_step": 1e3 * dt_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic", "config": dict(CONFIG, cameras=n_cameras, cameras_per_gpu=len(my), fusers=cfg["net"],
                                                                  l2_policy="inputs uploaded from host memory every step (end to end)"),
-               "timing": "host wall clock around the timed steps with every camera stream drained at the end, max over ranks: the network's "
-                         "schedule synchronises with the device several times per frame (training-set generation, fuser decisions), so the "
-                         "host clock is the device timeline",
+               "timing": "host wall clock around every timed step with the camera streams drained at its end, summed over the steps, max over "
+                         "ranks: the network's schedule synchronises with the device several times per frame (training-set generation, fuser "
+                         "decisions), so the host clock is the device timeline; trackers are re-initialised (untimed) every 8 frames",
                "tracked_frames_per_sec_per_camera": args.steps / dt_max / (len(my) if world == 1 else 1),
                "particles_scored_per_sec": cam_frames * N_OBJ * N_PART / dt_max,
                "e2e": {"value": val, "unit": "camera-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": len(my) * N_OBJ * 80,

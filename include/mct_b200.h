@@ -167,6 +167,17 @@ int mct_classifier_update_from_features(mct_clf* clf, const float* fpos, int P, 
  * the randfloat() > 0.5 drop rule (:66-82), in pooled order. */
 int mct_classifier_update_from_gathered(mct_clf* clf, const float* dev_rows, const int* col_offset_host, long long row_stride,
                                         int P, int Nn);
+/* The two halves of one learner round of the appearance fuser for ALL objects of a camera (batched forms of
+ * mct_features_compute_dev / mct_classifier_update_from_gathered):
+ *  - every camera: feature rows of the freshly generated training sets of all its objects under the objects' global
+ *    classifiers, written into the exchange buffer (object o at dev_rows + o * obj_stride floats, feature rows ld floats apart,
+ *    positives from column 0, negatives from column ld_pos); stream-ordered, the box arrays may be reused at once;
+ *  - the learner: per object the kept columns gathered into the global classifier's training matrix and ONE batched Update.
+ *    col_offsets_host: the objects' offset lists back to back (P[0] + Nn[0] entries, then P[1] + Nn[1], ...). */
+int mct_train_features_many_dev(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, const mct_boxes* pos, const mct_boxes* neg,
+                                float* dev_rows, size_t obj_stride, int ld, int ld_pos);
+int mct_track_update_from_gathered(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, const float* dev_rows, const int* col_offsets_host,
+                                   long long row_stride, const int* P, const int* Nn);
 /* device buffers on the ctx's device (exchange buffers) and a copy ordered on the ctx's stream (any direction, peers included) */
 int mct_dev_alloc(mct_ctx* ctx, size_t bytes, void** out);
 int mct_dev_free(mct_ctx* ctx, void* p);

@@ -1531,6 +1531,11 @@ static bool mdch_group_plan(MdchGroup* g, const mct_boxes* b, int first, int w0,
 // UpdateClassifier (ParticleFilterTracker.cpp:1013-1032) for all objects of a camera: ONE copy of the packed training
 // boxes, ONE descriptor copy and five batched launches (Haar rows, MDCH rows, weak update + predictions, greedy
 // selection with one cluster per object, selected-classifier tables) instead of 8 copies + 5 launches per object.
+// stages the training boxes of all objects, fills the TrainDescs and launches the feature kernels: afterwards every classifier's
+// training matrix d_featT holds its rows [F][P + Nn] (stream-ordered, no synchronisation)
+static int train_stage_and_features(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, const mct_boxes* pos, const mct_boxes* neg, std::vector<int>& creq);
+static int train_descs_ready(mct_ctx* ctx);
+
 extern "C" int mct_track_update(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, const mct_boxes* pos, const mct_boxes* neg)
 {
     if (!ctx || n_obj < 1 || !clfs || !pos || !neg) return MCT_E_ARG;
@@ -1548,8 +1553,18 @@ extern "C" int mct_track_update(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, c
         }
         return MCT_OK;
     }
-    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<int> creq;
     int rc;
+    if ((rc = train_stage_and_features(ctx, n_obj, clfs, pos, neg, creq))) return rc;
+    if ((rc = launch_ensemble_retain_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj))) return rc;
+    if ((rc = launch_weak_update_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj))) return rc;
+    if ((rc = launch_mil_select_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj, creq.data()))) return rc;
+    if ((rc = launch_build_colormap_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj))) return rc;
+    return MCT_OK;
+}
+
+static int train_descs_ready(mct_ctx* ctx)
+{
     if (!ctx->h_tdesc) {
         MCT_CUDA(ctx, cudaMallocHost(&ctx->h_tdesc, sizeof(TrainDesc) * DESC_MAX_OBJ));
         MCT_CUDA(ctx, cudaMalloc(&ctx->d_tdesc, sizeof(TrainDesc) * DESC_MAX_OBJ));
@@ -1559,6 +1574,16 @@ extern "C" int mct_track_update(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, c
         MCT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_tjoin, cudaEventDisableTiming));
     }
     MCT_CUDA(ctx, cudaEventSynchronize(ctx->ev_train));                // the previous call's staging copies have executed
+    return MCT_OK;
+}
+
+static int train_stage_and_features(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, const mct_boxes* pos, const mct_boxes* neg, std::vector<int>& creq_out)
+{
+    size_t total = 0;
+    for (int o = 0; o < n_obj; o++) total += (size_t)pos[o].n + (size_t)neg[o].n;
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = train_descs_ready(ctx))) return rc;
     if (total > ctx->train_stage_cap) {
         MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (ctx->h_train_stage) cudaFreeHost(ctx->h_train_stage);
@@ -1632,6 +1657,67 @@ extern "C" int mct_track_update(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, c
     MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tdesc, ctx->h_tdesc, sizeof(TrainDesc) * n_obj, cudaMemcpyHostToDevice, ctx->stream));
     MCT_CUDA(ctx, cudaEventRecord(ctx->ev_train, ctx->stream));
     if ((rc = launch_train_features(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj))) return rc;
+    creq_out = creq;
+    return MCT_OK;
+}
+
+// Appearance fuser, every camera's side of one learner round (CameraNetwork.cpp:276-320 with SampleSets replaced by feature rows):
+// the feature rows of all objects' freshly generated training sets, computed in ONE batched pass under each object's global
+// classifier and written into the exchange buffer: object o at dev_rows + o * obj_stride floats, rows `ld` floats apart,
+// positives from column 0, negatives from column ld_pos.  Stream-ordered, no synchronisation; the box arrays may be reused.
+extern "C" int mct_train_features_many_dev(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, const mct_boxes* pos, const mct_boxes* neg,
+                                           float* dev_rows, size_t obj_stride, int ld, int ld_pos)
+{
+    if (!ctx || n_obj < 1 || n_obj > DESC_MAX_OBJ || !clfs || !pos || !neg || !dev_rows || ld_pos < 1 || ld <= ld_pos) return MCT_E_ARG;
+    for (int o = 0; o < n_obj; o++) {
+        if (!clfs[o] || clfs[o]->ctx != ctx) return mct_fail(ctx, MCT_E_ARG, "classifier handle belongs to another ctx%s");
+        if (clfs[o]->p.feature_type == MCT_FEAT_CCH) return mct_fail(ctx, MCT_E_UNSUPPORTED, "batched training rows: culture colour classifiers take mct_features_compute_dev%s");
+        if (pos[o].n > ld_pos || neg[o].n > ld - ld_pos) return mct_fail(ctx, MCT_E_ARG, "training set larger than the exchange buffer%s");
+    }
+    std::vector<int> creq;
+    int rc;
+    if ((rc = train_stage_and_features(ctx, n_obj, clfs, pos, neg, creq))) return rc;
+    for (int o = 0; o < n_obj; o++) {
+        mct_clf* c = clfs[o];
+        float* base = dev_rows + (size_t)o * obj_stride;
+        MCT_CUDA(ctx, cudaMemcpy2DAsync(base, (size_t)ld * 4, c->d_featT, (size_t)c->ldT * 4, (size_t)pos[o].n * 4, c->F, cudaMemcpyDeviceToDevice, ctx->stream));
+        MCT_CUDA(ctx, cudaMemcpy2DAsync(base + ld_pos, (size_t)ld * 4, c->d_featT + pos[o].n, (size_t)c->ldT * 4, (size_t)neg[o].n * 4, c->F,
+                                        cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return MCT_OK;
+}
+
+// The learner's side for all its objects at once: per object the kept columns are gathered into the classifier's training matrix
+// (see mct_classifier_update_from_gathered), then ONE batched Update (weak classifiers, selection, colour map) for all of them.
+// col_offsets_host: the objects' offset lists back to back (P[0] + Nn[0] entries, then P[1] + Nn[1], ...).
+extern "C" int mct_track_update_from_gathered(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, const float* dev_rows, const int* col_offsets_host,
+                                              long long row_stride, const int* P, const int* Nn)
+{
+    if (!ctx || n_obj < 1 || n_obj > DESC_MAX_OBJ || !clfs || !dev_rows || !col_offsets_host || !P || !Nn || row_stride < 1) return MCT_E_ARG;
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = train_descs_ready(ctx))) return rc;
+    std::vector<int> creq(n_obj, 0);
+    size_t off = 0;
+    for (int o = 0; o < n_obj; o++) {
+        mct_clf* c = clfs[o];
+        if (!c || c->ctx != ctx) return mct_fail(ctx, MCT_E_ARG, "classifier handle belongs to another ctx%s");
+        if (P[o] < 1 || Nn[o] < 1) return mct_fail(ctx, MCT_E_ARG, "Update needs at least one positive and one negative sample%s");
+        const int M = P[o] + Nn[o];
+        if (M > c->max_train) return mct_fail(ctx, MCT_E_ARG, "training set exceeds max_train%s (%d)", "", M);
+        MCT_CUDA(ctx, cudaMemcpyAsync(c->d_tcol, col_offsets_host + off, (size_t)M * 4, cudaMemcpyHostToDevice, ctx->stream));
+        MCT_LAUNCH(ctx, "k_gather_columns", k_gather_columns<<<dim3(ceil_div(M, 256), c->F < 64 ? c->F : 64), 256, 0, ctx->stream>>>(
+                       dev_rows, c->d_tcol, row_stride, M, c->F, c->d_featT, c->ldT));
+        TrainDesc* t = &ctx->h_tdesc[o];
+        fill_train_desc(t, c);
+        t->col = nullptr; t->row = nullptr; t->sx = nullptr; t->sy = nullptr; t->tw = nullptr;
+        t->P = P[o]; t->Nn = Nn[o]; t->mdch_fast = 0;
+        c->lastP = P[o]; c->lastNn = Nn[o];
+        creq[o] = c->cluster;
+        off += (size_t)M;
+    }
+    MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tdesc, ctx->h_tdesc, sizeof(TrainDesc) * n_obj, cudaMemcpyHostToDevice, ctx->stream));
+    MCT_CUDA(ctx, cudaEventRecord(ctx->ev_train, ctx->stream));
     if ((rc = launch_ensemble_retain_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj))) return rc;
     if ((rc = launch_weak_update_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj))) return rc;
     if ((rc = launch_mil_select_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj, creq.data()))) return rc;

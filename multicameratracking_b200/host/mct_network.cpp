@@ -219,23 +219,35 @@ void CameraNetwork::LearnGlobalAppearanceModel()
     const int n = m_numberOfObjects, F = m_afFeatures, C = m_numberOfCameras;
     std::vector<int> counts((size_t)C * n * 2), mine((size_t)m_cameras.size() * n * 2);
     for (int learner = 0; learner < C; learner++) {
-        // 1. every camera: GenerateTrainingSampleSet for every object, feature rows into its send buffer
+        // 1. every camera: GenerateTrainingSampleSet for every object (host: RNG order), feature rows of all objects into its send
+        //    buffer in one batched device pass
         for (size_t i = 0; i < m_cameras.size(); i++) {
             mcth_camera* cam = m_cameras[i];
-            float* rows = (float*)m_sendRows[i];
+            std::vector<vectori> pc(n), pr(n), nc(n), nr(n);
+            std::vector<vectorf> psx(n), psy(n), nsx(n), nsy(n);
+            std::vector<mct_boxes> pb(n), nb(n);
+            std::vector<mct_clf*> gl(n);
+            bool batched = m_params.appearanceFusionType == 2;
             for (int o = 0; o < n; o++) {
                 ParticleFilterTracker* t = cam->trackers[o];
                 t->GenerateTrainingSampleSet(&cam->frame, &cam->frame, &cam->frame);
-                vectori pc, pr, nc, nr; vectorf psx, psy, nsx, nsy;
-                t->PositiveSet().ToBoxes(pc, pr, psx, psy); t->NegativeSet().ToBoxes(nc, nr, nsx, nsy);
-                const int P = (int)pc.size(), Nn = (int)nc.size();
+                t->PositiveSet().ToBoxes(pc[o], pr[o], psx[o], psy[o]); t->NegativeSet().ToBoxes(nc[o], nr[o], nsx[o], nsy[o]);
+                const int P = (int)pc[o].size(), Nn = (int)nc[o].size();
                 if (P > m_ldPos || Nn > m_ldRow - m_ldPos) throw MctHostError(MCT_E_ARG, "appearance fusion: training set larger than the exchange buffer");
-                mct_boxes pb = {P, pc.data(), pr.data(), psx.data(), psy.data()}, nb = {Nn, nc.data(), nr.data(), nsx.data(), nsy.data()};
-                float* base = rows + (size_t)o * F * m_ldRow;
-                mct_clf* g = m_globalClassifiers[i][o]->Handle();
-                chk(cam->ctx, mct_features_compute_dev(g, &pb, base, m_ldRow));
-                chk(cam->ctx, mct_features_compute_dev(g, &nb, base + m_ldPos, m_ldRow));
+                pb[o] = {P, pc[o].data(), pr[o].data(), psx[o].data(), psy[o].data()};
+                nb[o] = {Nn, nc[o].data(), nr[o].data(), nsx[o].data(), nsy[o].data()};
+                gl[o] = m_globalClassifiers[i][o]->Handle();
                 mine[(i * n + o) * 2] = P; mine[(i * n + o) * 2 + 1] = Nn;
+            }
+            float* rows = (float*)m_sendRows[i];
+            if (batched) {
+                chk(cam->ctx, mct_train_features_many_dev(cam->ctx, n, gl.data(), pb.data(), nb.data(), rows, (size_t)F * m_ldRow, m_ldRow, m_ldPos));
+            } else {
+                for (int o = 0; o < n; o++) {
+                    float* base = rows + (size_t)o * F * m_ldRow;
+                    chk(cam->ctx, mct_features_compute_dev(gl[o], &pb[o], base, m_ldRow));
+                    chk(cam->ctx, mct_features_compute_dev(gl[o], &nb[o], base + m_ldPos, m_ldRow));
+                }
             }
         }
         // 2. rows and counts to the learner
@@ -255,9 +267,10 @@ void CameraNetwork::LearnGlobalAppearanceModel()
         // 3. the learner: pooled order = positives of camera 0..C-1, then negatives of camera 0..C-1
         mcth_camera* cam = m_cameras[li];
         const size_t camStride = (size_t)n * F * m_ldRow;
+        std::vector<int> off, Pk(n), Nk(n);
+        std::vector<mct_clf*> gl(n);
         for (int o = 0; o < n; o++) {
             Public::SetCurrentRng(&cam->trackers[o]->Rng());
-            std::vector<int> off;
             int P = 0, Nn = 0;
             for (int c = 0; c < C; c++)
                 for (int s = 0; s < counts[((size_t)c * n + o) * 2]; s++)
@@ -266,8 +279,17 @@ void CameraNetwork::LearnGlobalAppearanceModel()
                 for (int s = 0; s < counts[((size_t)c * n + o) * 2 + 1]; s++)
                     if (Public::randfloat() > 0.5f) { off.push_back((int)(c * camStride + (size_t)o * F * m_ldRow + m_ldPos + s)); Nn++; }
             if (P < 1 || Nn < 1) throw MctHostError(MCT_E_EMPTY, "appearance fusion: every pooled sample of a class was dropped");
-            chk(cam->ctx, mct_classifier_update_from_gathered(m_globalClassifiers[li][o]->Handle(), (const float*)m_recvRows[li], off.data(), m_ldRow, P, Nn));
+            Pk[o] = P; Nk[o] = Nn; gl[o] = m_globalClassifiers[li][o]->Handle();
             m_globalTrained[li][o] = 1;
+        }
+        if (m_params.appearanceFusionType == 2) {
+            chk(cam->ctx, mct_track_update_from_gathered(cam->ctx, n, gl.data(), (const float*)m_recvRows[li], off.data(), m_ldRow, Pk.data(), Nk.data()));
+        } else {
+            size_t at = 0;
+            for (int o = 0; o < n; o++) {
+                chk(cam->ctx, mct_classifier_update_from_gathered(gl[o], (const float*)m_recvRows[li], off.data() + at, m_ldRow, Pk[o], Nk[o]));
+                at += (size_t)Pk[o] + Nk[o];
+            }
         }
         chk(cam->ctx, mct_sync(cam->ctx));             // the offsets above are host vectors
     }
