@@ -641,7 +641,7 @@ def run_network(args):
     _, scene = network_scene(n_cameras)
     my = [rank] if world > 1 else list(range(n_cameras))
     total = args.steps + args.warmup
-    SEG = 8            # frames per tracking segment, see build()
+    SEG = 3 if cfg["net"].get("geometric_fusion") else 12      # frames per tracking segment, see build()
     frames = {c: [scene.frame(c, t) for t in range(SEG + 1)] for c in my}
     over = dict(feature_type=FEAT, n_haar=max(N_HAAR, 1), n_bins=N_BINS, weak_type=WEAK, strong_type=STRONG, percent_selected=PCT, n_particles=N_PART,
                 sd_x=SD[0], sd_y=SD[1], sd_sx=SD[2], sd_sy=SD[3])
@@ -652,9 +652,10 @@ def run_network(args):
         """(Re)initialise the trackers on frame 0 of the scene -- untimed.  The reference's geometric feedback is not a stable
         controller on long synthetic sequences (its rearrangement triggers whenever the average particle's foot, computed with
         h0 instead of h0 / 2, is 20 px from the fused estimate, ParticleFilterTracker.cpp:1093-1105, and rescales the particles
-        by the offset); the reference itself runs into its empty-training-set assertion after ~17 frames of this scene.  The
-        bench therefore tracks segments of SEG frames from a fresh initialisation; every timed step is a regular frame of the
-        schedule."""
+        by the offset: with the 40 x 80 objects of the synthetic specification it fires EVERY frame); the reference itself runs into
+        its sampler / empty-training-set assertions after 4 (2 cameras) to 17 (4 cameras) frames of this scene, and so does this
+        path, on the same frame.  The bench therefore tracks short segments from a fresh initialisation; every timed step is a
+        regular frame of the schedule (with the appearance fuser, whose re-weighting starts at frame 3, segments are 12 frames)."""
         if state["net"] is not None:
             state["net"].close()
             for cam in state["cams"]:
@@ -733,7 +734,7 @@ def run_network(args):
                                                                  l2_policy="inputs uploaded from host memory every step (end to end)"),
                "timing": "host wall clock around every timed step with the camera streams drained at its end, summed over the steps, max over "
                          "ranks: the network's schedule synchronises with the device several times per frame (training-set generation, fuser "
-                         "decisions), so the host clock is the device timeline; trackers are re-initialised (untimed) every 8 frames",
+                         "decisions), so the host clock is the device timeline; trackers are re-initialised (untimed) every %d frames" % SEG,
                "tracked_frames_per_sec_per_camera": args.steps / dt_max / (len(my) if world == 1 else 1),
                "particles_scored_per_sec": cam_frames * N_OBJ * N_PART / dt_max,
                "e2e": {"value": val, "unit": "camera-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": len(my) * N_OBJ * 80,
