@@ -35,6 +35,9 @@ SYMBOLS = [
     "mct_pf_ground_pdf", "mct_pf_rearrange_ground", "mct_classify_argmax", "mct_fuser_ground_pdf", "mct_p2p_create", "mct_p2p_open", "mct_p2p_destroy",
     "mct_fuser_exchange_foot_points", "mct_classifier_get_alphas", "mct_features_compute_dev", "mct_classifier_update_from_features_dev",
     "mct_pf_training_boxes", "mct_sample_regions",
+    # called by the C++ host schedule (host/mct_network.cpp), listed so that load() checks they are exported
+    "mct_classifier_update_from_gathered", "mct_dev_alloc", "mct_dev_copy", "mct_dev_free", "mct_fuser_foot_points",
+    "mct_pf_resample_many", "mct_track_update_from_gathered", "mct_train_features_many_dev",
 ]
 
 
