@@ -154,7 +154,8 @@ int mct_classifier_update(mct_clf* clf, const mct_boxes* pos, const mct_boxes* n
  * sample sets arrive as feature rows after the cross-camera allgather. */
 /* device-resident forms for the appearance fuser (AppearanceBasedInformationFuser.cpp:44-90 with the pooled SampleSets replaced by
  * feature rows): the rows [F][n] are written to / read from device memory with the given leading dimensions, so that they
- * can go through an NCCL all-gather without touching the host. */
+ * can go through an NCCL all-gather without touching the host.  Both calls have consumed / filled the caller's device buffers
+ * when they return (the staging copies are waited for), so a stream-ordered allocator may recycle them at once. */
 int mct_features_compute_dev(mct_clf* clf, const mct_boxes* boxes, float* dev_out, int ld_out);
 int mct_classifier_update_from_features_dev(mct_clf* clf, const float* dev_fpos, int ld_pos, int P, const float* dev_fneg,
                                             int ld_neg, int Nn);

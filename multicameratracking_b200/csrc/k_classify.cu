@@ -234,12 +234,9 @@ k_classify_staged(const ObjDesc* __restrict__ descs, const float* __restrict__ i
 int launch_classify_staged(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int log_ratio)
 {
     if (n_obj <= 0 || n_max <= 0) return MCT_OK;
-    static int s_attr = 0, s_sms = 0;
-    if (!s_attr) {
-        MCT_CUDA(ctx, cudaFuncSetAttribute(k_classify_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, CLS_SMEM));
-        MCT_CUDA(ctx, cudaDeviceGetAttribute(&s_sms, cudaDevAttrMultiProcessorCount, ctx->device));
-        s_attr = 1;
-    }
+    static size_t s_attr[MCT_MAX_DEV];
+    if (int rc_ = mct_smem_attr(ctx, k_classify_staged, s_attr, CLS_SMEM, 0)) return rc_;
+    const int s_sms = ctx->sms;
     int per_obj = s_sms / n_obj;
     if (per_obj < 1) per_obj = 1;
     if (per_obj > ceil_div(n_max, 32)) per_obj = ceil_div(n_max, 32);
@@ -253,11 +250,8 @@ int launch_classify(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, i
 {
     if (n_obj <= 0 || n_max <= 0) return MCT_OK;
     size_t smem = (size_t)(K_max > 0 ? K_max : 1) * sizeof(SelEntry);
-    static size_t s_attr = 48 * 1024;
-    if (smem > s_attr) {
-        MCT_CUDA(ctx, cudaFuncSetAttribute(k_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        s_attr = smem;
-    }
+    static size_t s_attr[MCT_MAX_DEV];
+    if (int rc_ = mct_smem_attr(ctx, k_classify, s_attr, smem, 48 * 1024)) return rc_;
     dim3 g(ceil_div(n_max, 256), n_obj);
     MCT_LAUNCH(ctx, "k_classify", k_classify<<<g, 256, smem, ctx->stream>>>(d_desc, ctx->ii_base ? ctx->ii_base + MCT_II_LEAD : nullptr, ctx->ii_pitch,
                                               ctx->W, ctx->H, from_matrix, log_ratio));

@@ -693,11 +693,8 @@ static int launch_haar_rows(mct_clf* clf, const int* d_col, const int* d_row, co
             MCT_LAUNCH(ctx, "k_tile_sort", k_tile_scan<<<1, 1024, 0, ctx->stream>>>(d_cnt, n_tiles, n, d_start));
             MCT_LAUNCH(ctx, "k_tile_sort", k_tile_scatter<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(d_col, d_row, n, ctx->W, ctx->H, tiles_x, d_cnt, d_order));
         }
-        static size_t s_attr = 0;
-        if (reg_b > s_attr) {
-            MCT_CUDA(ctx, cudaFuncSetAttribute(k_haar_matrix_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)reg_b));
-            s_attr = reg_b;
-        }
+        static size_t s_attr[MCT_MAX_DEV];
+        if (int rc_ = mct_smem_attr(ctx, k_haar_matrix_tiled, s_attr, reg_b, 0)) return rc_;
         dim3 g(n_tiles, ceil_div(clf->n_haar, ft));
         MCT_LAUNCH(ctx, "k_haar_matrix_tiled", k_haar_matrix_tiled<<<g, HT_THREADS, reg_b, ctx->stream>>>(
             ctx->ii_base + MCT_II_LEAD, ctx->ii_pitch, ctx->W, ctx->H, clf->d_rects, clf->d_wts, clf->d_nrect, clf->n_haar,
@@ -725,11 +722,8 @@ static int launch_mdch_rows(mct_clf* clf, const int* d_col, const int* d_row, co
     if (rc) return rc;
     const int dim = clf->n_color;
     size_t smem = mdch_smem(dim, n_out);
-    static size_t s_attr = 0;
-    if (smem > s_attr) {
-        MCT_CUDA(ctx, cudaFuncSetAttribute(k_mdch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        s_attr = smem;
-    }
+    static size_t s_attr[MCT_MAX_DEV];
+    if (int rc_ = mct_smem_attr(ctx, k_mdch, s_attr, smem, 0)) return rc_;
     MCT_LAUNCH(ctx, "k_mdch", k_mdch<<<ceil_div(n, MDCH_TILE), MDCH_WARPS * 32, smem, ctx->stream>>>(
         ctx->binimg, ctx->W, ctx->H, clf->p.n_bins, clf->p.w0, clf->p.h0, d_col, d_row, d_sx, d_sy, d_valid, n,
         d_outbins, n_out, d_out, ld));
@@ -805,26 +799,17 @@ int launch_train_features(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, 
         if (n_fast) {
             const size_t smem_main = (size_t)(tab_words + chunk_words) * 4 + (size_t)chunk_words * sizeof(MtrRun) + (size_t)chunk_words * 2 + 16;
             const size_t smem_prep = (size_t)MTP_WARPS * dim_max * 4 + (size_t)ceil_div(npx_max, MTP_PARTS) * 2 + 16;
-            static size_t s_attr_m = 48 * 1024, s_attr_p = 48 * 1024;
-            if (smem_main > s_attr_m) {
-                MCT_CUDA(ctx, cudaFuncSetAttribute(k_mdch_train_main, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_main));
-                s_attr_m = smem_main;
-            }
-            if (smem_prep > s_attr_p) {
-                MCT_CUDA(ctx, cudaFuncSetAttribute(k_mdch_train_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep));
-                s_attr_p = smem_prep;
-            }
+            static size_t s_attr_m[MCT_MAX_DEV], s_attr_p[MCT_MAX_DEV];
+            if (int rc_ = mct_smem_attr(ctx, k_mdch_train_main, s_attr_m, smem_main, 48 * 1024)) return rc_;
+            if (int rc_ = mct_smem_attr(ctx, k_mdch_train_prep, s_attr_p, smem_prep, 48 * 1024)) return rc_;
             MCT_LAUNCH(ctx, "k_mdch_train_prep", k_mdch_train_prep<<<dim3(MTP_PARTS, 2, n_obj), MTP_WARPS * 32, smem_prep, ctx->stream>>>(d, ctx->binimg, ctx->W, ctx->H));
             MCT_LAUNCH(ctx, "k_mdch_train_main", k_mdch_train_main<<<dim3(nch, 2, n_obj), MTR_THREADS, smem_main, ctx->stream>>>(d, tab_words, chunk_words));
             MCT_LAUNCH(ctx, "k_mdch_train_finish", k_mdch_train_finish<<<dim3(ceil_div(dim_max * ceil_div(n_train_max, 4), 256), n_obj), 256, 0, ctx->stream>>>(d));
         }
         if (n_slow) {
             size_t smem = mdch_smem(dim_max, dim_max);
-            static size_t s_attr = 0;
-            if (smem > s_attr) {
-                MCT_CUDA(ctx, cudaFuncSetAttribute(k_mdch_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                s_attr = smem;
-            }
+            static size_t s_attr[MCT_MAX_DEV];
+            if (int rc_ = mct_smem_attr(ctx, k_mdch_batch, s_attr, smem, 0)) return rc_;
             dim3 g(ceil_div(n_max, MDCH_TILE), n_obj);
             MCT_LAUNCH(ctx, "k_mdch_batch", k_mdch_batch<<<g, MDCH_WARPS * 32, smem, ctx->stream>>>(d, ctx->binimg, ctx->W, ctx->H));
         }
@@ -1357,12 +1342,9 @@ int launch_mdch_selected(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_m
 {
     (void)max_slots;
     if (n_obj <= 0 || n_max <= 0) return MCT_OK;
-    static int s_attr = 0, s_sms = 0;
-    if (!s_attr) {
-        MCT_CUDA(ctx, cudaFuncSetAttribute(k_mdch_sel, cudaFuncAttributeMaxDynamicSharedMemorySize, MDS_SMEM));
-        MCT_CUDA(ctx, cudaDeviceGetAttribute(&s_sms, cudaDevAttrMultiProcessorCount, ctx->device));
-        s_attr = 1;
-    }
+    static size_t s_attr[MCT_MAX_DEV];
+    if (int rc_ = mct_smem_attr(ctx, k_mdch_sel, s_attr, MDS_SMEM, 0)) return rc_;
+    const int s_sms = ctx->sms;
     // one persistent CTA per SM, the SMs split evenly over the objects; each CTA owns a contiguous chunk of boxes
     int per_obj = s_sms / n_obj;
     if (per_obj < 1) per_obj = 1;

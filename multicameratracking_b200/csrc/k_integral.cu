@@ -280,8 +280,7 @@ int launch_frame_prep(mct_ctx* ctx, const PrepTarget& t, cudaStream_t st, int* w
 {
     const int W = t.W, H = t.H;
     *with_bins_out = 0;
-    static int s_sms = 0;
-    if (!s_sms) cudaDeviceGetAttribute(&s_sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const int s_sms = ctx->sms;
     // band height: enough bands to spread over the SMs; BH*W u32 must fit in shared memory
     int BH = 8;
     while (ceil_div(H, BH) > s_sms / 2 && BH < 64) BH <<= 1;
@@ -316,11 +315,8 @@ int launch_frame_prep(mct_ctx* ctx, const PrepTarget& t, cudaStream_t st, int* w
         if (a.n_binblocks > 64) a.n_binblocks = 64;
         if (a.n_binblocks < 1) { with_bins = 0; a.n_binblocks = 0; }
     }
-    static size_t s_attr = 0;
-    if (smem > s_attr) {
-        MCT_CUDA(ctx, cudaFuncSetAttribute(k_frame_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        s_attr = smem;
-    }
+    static size_t s_attr[MCT_MAX_DEV];
+    if (int rc_ = mct_smem_attr(ctx, k_frame_prep, s_attr, smem, 0)) return rc_;
     const int nt = 32 * (BH < 4 ? 4 : (BH > 16 ? 16 : BH));
     MCT_LAUNCH_ON(ctx, st, "k_frame_prep", k_frame_prep<<<n_bands + a.n_binblocks, nt, smem, st>>>(a));
     *with_bins_out = with_bins;
@@ -344,11 +340,8 @@ static int launch_integral_two_pass(mct_ctx* ctx, const PrepTarget& t, cudaStrea
     dim3 g1(ceil_div(W, 128), nb);
     MCT_LAUNCH_ON(ctx, st, "k_band_colsum", k_band_colsum<<<g1, 128, 0, st>>>(t.gray, W, H, t.pitch, BH, ctx->bandsum));
     size_t smem = (size_t)(BH + 1) * W * sizeof(uint32_t);
-    static size_t s_attr = 0;
-    if (smem > s_attr) {
-        MCT_CUDA(ctx, cudaFuncSetAttribute(k_integral_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        s_attr = smem;
-    }
+    static size_t s_attr[MCT_MAX_DEV];
+    if (int rc_ = mct_smem_attr(ctx, k_integral_band, s_attr, smem, 0)) return rc_;
     int nt = W >= 1024 ? 1024 : round_up(W, 32);
     if (nt < 128) nt = 128;
     MCT_LAUNCH_ON(ctx, st, "k_integral_band", k_integral_band<<<nb, nt, smem, st>>>(t.gray, W, H, t.pitch, BH, ctx->bandsum,
@@ -386,7 +379,8 @@ k_bgr_unpack(const uint8_t* __restrict__ bgr, int spitch, int W, int H, int use_
 int launch_bgr_unpack(mct_ctx* ctx, const uint8_t* d_bgr, int spitch, int W, int H, int use_hsv, uint8_t* const planes[4], int dpitch,
                       cudaStream_t st)
 {
-    static int s_tables = 0;
+    static int s_tables_dev[MCT_MAX_DEV];             // the __constant__ tables are per device
+    int& s_tables = s_tables_dev[ctx->device];
     if (!s_tables) {
         int sdiv[256], hdiv[256];
         sdiv[0] = hdiv[0] = 0;

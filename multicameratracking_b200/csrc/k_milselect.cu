@@ -821,10 +821,7 @@ template <typename KernT, typename... Args>
 static int ens_launch(mct_ctx* ctx, const char* name, KernT kern, size_t* attr_state, dim3 grid, int C, size_t smem, Args... args)
 {
     if (smem > 220 * 1024) return mct_fail(ctx, MCT_E_UNSUPPORTED, "training set too large for the MILEnsemble kernels%s");
-    if (smem > *attr_state) {
-        MCT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        *attr_state = smem;
-    }
+    if (int rc_ = mct_smem_attr(ctx, kern, attr_state, smem, 0)) return rc_;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(ENS_THREADS, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
@@ -842,8 +839,8 @@ int launch_ensemble_retain(mct_clf* clf, int P, int Nn)
     if (clf->p.strong_type != MCT_STRONG_MILENSEMBLE) return MCT_OK;
     int C, FC;
     const size_t smem = ens_plan(clf->F, P + Nn, clf->K, &C, &FC);
-    static size_t s_attr = 0;
-    return ens_launch(clf->ctx, "k_ensemble_retain", k_ensemble_retain, &s_attr, dim3(C, 1, 1), C, smem, (const float*)clf->d_featT, clf->d_pred, clf->ldT,
+    static size_t s_attr[MCT_MAX_DEV];
+    return ens_launch(clf->ctx, "k_ensemble_retain", k_ensemble_retain, s_attr, dim3(C, 1, 1), C, smem, (const float*)clf->d_featT, clf->d_pred, clf->ldT,
                       clf->F, P, Nn, clf->K, (const float*)clf->d_weak, clf->p.weak_type, clf->p.pct_retained / 100.0f, clf->d_sel, clf->d_nsel,
                       clf->d_keep, clf->d_ensH, FC);
 }
@@ -851,8 +848,8 @@ static int launch_ensemble_select(mct_clf* clf, int P, int Nn)
 {
     int C, FC;
     const size_t smem = ens_plan(clf->F, P + Nn, clf->F, &C, &FC);
-    static size_t s_attr = 0;
-    return ens_launch(clf->ctx, "k_ensemble_select", k_ensemble_select, &s_attr, dim3(C, 1, 1), C, smem, (const float*)clf->d_featT, clf->d_pred, clf->ldT,
+    static size_t s_attr[MCT_MAX_DEV];
+    return ens_launch(clf->ctx, "k_ensemble_select", k_ensemble_select, s_attr, dim3(C, 1, 1), C, smem, (const float*)clf->d_featT, clf->d_pred, clf->ldT,
                       clf->F, P, Nn, clf->K, (const float*)clf->d_weak, clf->p.weak_type, clf->p.pct_retained / 100.0f, clf->d_sel, clf->d_nsel,
                       clf->d_keep, clf->d_ensH, FC);
 }
@@ -871,15 +868,15 @@ int launch_ensemble_retain_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDe
 {
     int C, FC; size_t smem;
     if (!ens_batch_plan(h, n_obj, 1, &C, &FC, &smem)) return MCT_OK;
-    static size_t s_attr = 0;
-    return ens_launch(ctx, "k_ensemble_retain_batch", k_ensemble_retain_batch, &s_attr, dim3(C, n_obj, 1), C, smem, d, FC);
+    static size_t s_attr[MCT_MAX_DEV];
+    return ens_launch(ctx, "k_ensemble_retain_batch", k_ensemble_retain_batch, s_attr, dim3(C, n_obj, 1), C, smem, d, FC);
 }
 static int launch_ensemble_select_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj)
 {
     int C, FC; size_t smem;
     if (!ens_batch_plan(h, n_obj, 0, &C, &FC, &smem)) return MCT_OK;
-    static size_t s_attr = 0;
-    return ens_launch(ctx, "k_ensemble_select_batch", k_ensemble_select_batch, &s_attr, dim3(C, n_obj, 1), C, smem, d, FC);
+    static size_t s_attr[MCT_MAX_DEV];
+    return ens_launch(ctx, "k_ensemble_select_batch", k_ensemble_select_batch, s_attr, dim3(C, n_obj, 1), C, smem, d, FC);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -891,11 +888,8 @@ int launch_mil_select(mct_clf* clf, int P, int Nn)
     if (clf->p.strong_type == MCT_STRONG_ADABOOST) {
         const size_t smem = ada_smem(F, M);
         if (smem > 200 * 1024) return mct_fail(ctx, MCT_E_UNSUPPORTED, "training set too large for the AdaBoost kernel%s (M=%d)", "", M);
-        static size_t s_attr_a = 32 * 1024;
-        if (smem > s_attr_a) {
-            MCT_CUDA(ctx, cudaFuncSetAttribute(k_adaboost_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            s_attr_a = smem;
-        }
+        static size_t s_attr_a[MCT_MAX_DEV];
+        if (int rc_ = mct_smem_attr(ctx, k_adaboost_select, s_attr_a, smem, 32 * 1024)) return rc_;
         MCT_LAUNCH(ctx, "k_adaboost_select", k_adaboost_select<<<1, ADA_THREADS, smem, ctx->stream>>>(clf->d_featT, clf->ldT, F, P, Nn, clf->K, clf->d_weak,
                                                                                            clf->p.weak_type, clf->d_ada_cnt, clf->d_alpha, clf->d_sel, clf->d_nsel));
         return MCT_OK;
@@ -903,11 +897,8 @@ int launch_mil_select(mct_clf* clf, int P, int Nn)
     if (clf->p.strong_type == MCT_STRONG_MILANYBOOST) {
         size_t smem = (size_t)(3 * M + F) * sizeof(float) + (size_t)F;
         if (smem > 200 * 1024) return mct_fail(ctx, MCT_E_UNSUPPORTED, "training set too large for the AnyBoost kernel%s (M=%d)", "", M);
-        static size_t s_attr = 32 * 1024;
-        if (smem > s_attr) {
-            MCT_CUDA(ctx, cudaFuncSetAttribute(k_anyboost_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            s_attr = smem;
-        }
+        static size_t s_attr[MCT_MAX_DEV];
+        if (int rc_ = mct_smem_attr(ctx, k_anyboost_select, s_attr, smem, 32 * 1024)) return rc_;
         MCT_LAUNCH(ctx, "k_anyboost_select", k_anyboost_select<<<1, ANY_THREADS, smem, ctx->stream>>>(clf->d_pred, clf->ldT, F, P, Nn, clf->K, clf->d_sel, clf->d_nsel));
         return MCT_OK;
     }
@@ -919,15 +910,12 @@ int launch_mil_select(mct_clf* clf, int P, int Nn)
     int FC, rows_in_smem;
     const size_t smem = mil_smem_plan(F, M, FL, &FC, &rows_in_smem);
     if (smem > 220 * 1024) return mct_fail(ctx, MCT_E_UNSUPPORTED, "training set too large for the MIL selection kernel%s (M=%d)", "", M);
-    static size_t s_attr = 0;
-    static int s_np = 0;
-    if (smem > s_attr) {
-        MCT_CUDA(ctx, cudaFuncSetAttribute(k_milboost_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        s_attr = smem;
-    }
-    if (C > 8 && !s_np) {
+    static size_t s_attr[MCT_MAX_DEV];
+    static int s_np[MCT_MAX_DEV];
+    if (int rc_ = mct_smem_attr(ctx, k_milboost_select, s_attr, smem, 0)) return rc_;
+    if (C > 8 && !s_np[ctx->device]) {
         MCT_CUDA(ctx, cudaFuncSetAttribute(k_milboost_select, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        s_np = 1;
+        s_np[ctx->device] = 1;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(C, 1, 1);
@@ -964,21 +952,15 @@ int launch_mil_select_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h
     }
     if (any_ada) {
         if (smem_ada > 200 * 1024) return mct_fail(ctx, MCT_E_UNSUPPORTED, "training set too large for the AdaBoost kernel%s");
-        static size_t s_attr_a = 32 * 1024;
-        if (smem_ada > s_attr_a) {
-            MCT_CUDA(ctx, cudaFuncSetAttribute(k_adaboost_select_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ada));
-            s_attr_a = smem_ada;
-        }
+        static size_t s_attr_a[MCT_MAX_DEV];
+        if (int rc_ = mct_smem_attr(ctx, k_adaboost_select_batch, s_attr_a, smem_ada, 32 * 1024)) return rc_;
         MCT_LAUNCH(ctx, "k_adaboost_select_batch", k_adaboost_select_batch<<<n_obj, ADA_THREADS, smem_ada, ctx->stream>>>(d));
     }
     if (any_any) {
         size_t smem = (size_t)(3 * M_any + F_any) * sizeof(float) + (size_t)F_any;
         if (smem > 200 * 1024) return mct_fail(ctx, MCT_E_UNSUPPORTED, "training set too large for the AnyBoost kernel%s (M=%d)", "", M_any);
-        static size_t s_attr = 32 * 1024;
-        if (smem > s_attr) {
-            MCT_CUDA(ctx, cudaFuncSetAttribute(k_anyboost_select_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            s_attr = smem;
-        }
+        static size_t s_attr[MCT_MAX_DEV];
+        if (int rc_ = mct_smem_attr(ctx, k_anyboost_select_batch, s_attr, smem, 32 * 1024)) return rc_;
         MCT_LAUNCH(ctx, "k_anyboost_select_batch", k_anyboost_select_batch<<<n_obj, ANY_THREADS, smem, ctx->stream>>>(d));
     }
     if (any_mil) {
@@ -991,15 +973,12 @@ int launch_mil_select_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h
         const size_t smem = mil_smem_plan(F, M, FL, &FC, &rows_in_smem);
         if (smem > 220 * 1024) return mct_fail(ctx, MCT_E_UNSUPPORTED, "training set too large for the MIL selection kernel%s (M=%d)", "", M);
         const int FLmax = rows_in_smem ? FL : 0, Mmax = M;
-        static size_t s_attr = 0;
-        static int s_np = 0;
-        if (smem > s_attr) {
-            MCT_CUDA(ctx, cudaFuncSetAttribute(k_milboost_select_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            s_attr = smem;
-        }
-        if (C > 8 && !s_np) {
+        static size_t s_attr[MCT_MAX_DEV];
+        static int s_np[MCT_MAX_DEV];
+        if (int rc_ = mct_smem_attr(ctx, k_milboost_select_batch, s_attr, smem, 0)) return rc_;
+        if (C > 8 && !s_np[ctx->device]) {
             MCT_CUDA(ctx, cudaFuncSetAttribute(k_milboost_select_batch, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-            s_np = 1;
+            s_np[ctx->device] = 1;
         }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(C, n_obj, 1);

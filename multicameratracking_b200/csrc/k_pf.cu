@@ -454,11 +454,8 @@ int launch_pf_update(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, 
 {
     int sf; size_t sb;
     pf_update_smem(ctx, n_max, &sf, &sb);
-    static size_t s_attr = 32 * 1024;
-    if (sb > s_attr) {
-        MCT_CUDA(ctx, cudaFuncSetAttribute(k_pf_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
-        s_attr = sb;
-    }
+    static size_t s_attr[MCT_MAX_DEV];
+    if (int rc_ = mct_smem_attr(ctx, k_pf_update, s_attr, sb, 32 * 1024)) return rc_;
     const int nt = PF_THREADS;
     MCT_LAUNCH(ctx, "k_pf_update", k_pf_update<<<n_obj, nt, sb, ctx->stream>>>(d_desc, sa, use_H ? 0 : 1, sf, with_summary));
     return MCT_OK;
@@ -482,11 +479,8 @@ int launch_pf_resample_only(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int 
 {
     int sf; size_t sb;
     pf_update_smem(ctx, n_max, &sf, &sb);
-    static size_t s_attr = 32 * 1024;
-    if (sb > s_attr) {
-        MCT_CUDA(ctx, cudaFuncSetAttribute(k_pf_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
-        s_attr = sb;
-    }
+    static size_t s_attr[MCT_MAX_DEV];
+    if (int rc_ = mct_smem_attr(ctx, k_pf_resample, s_attr, sb, 32 * 1024)) return rc_;
     MCT_LAUNCH(ctx, "k_pf_resample", k_pf_resample<<<n_obj, PF_THREADS, sb, ctx->stream>>>(d_desc, sa, force, sf));
     return MCT_OK;
 }
@@ -1117,11 +1111,8 @@ int launch_train_from_particles(mct_ctx* ctx, const ObjDesc* d_desc, const ObjDe
     for (int o = 0; o < n_obj; o++) n_max = max(n_max, h_desc[o].N);
     const size_t smem = ((size_t)((n_max + 3) & ~3) + (size_t)max(max_pos_max, 1)) * 4;
     if (smem > 200 * 1024) return mct_fail(ctx, MCT_E_UNSUPPORTED, "too many particles for the training-sample kernel%s (%d)", "", n_max);
-    static size_t s_attr = 48 * 1024;
-    if (smem > s_attr) {
-        MCT_CUDA(ctx, cudaFuncSetAttribute(k_train_from_particles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        s_attr = smem;
-    }
+    static size_t s_attr[MCT_MAX_DEV];
+    if (int rc_ = mct_smem_attr(ctx, k_train_from_particles, s_attr, smem, 48 * 1024)) return rc_;
     MCT_LAUNCH(ctx, "k_train_from_particles", k_train_from_particles<<<n_obj, PF_THREADS, smem, ctx->stream>>>(d_desc, d_gen, cap, d_col, d_row, d_sx, d_sy, d_out));
     return MCT_OK;
 }

@@ -6,6 +6,7 @@
 #include <vector>
 
 char g_mct_err[512] = "";
+std::mutex g_mct_attr_mu;
 
 #define DESC_RING 32
 
@@ -107,12 +108,13 @@ extern "C" int mct_ctx_create(int device, void* cuda_stream, mct_ctx** out)
     if (e != cudaSuccess || ndev == 0)
         return mct_fail(nullptr, MCT_E_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
                         cudaGetErrorString(e));
-    if (device < 0 || device >= ndev) return mct_fail(nullptr, MCT_E_ARG, "device index out of range%s (%d)", "", device);
+    if (device < 0 || device >= ndev || device >= MCT_MAX_DEV) return mct_fail(nullptr, MCT_E_ARG, "device index out of range%s (%d)", "", device);
     MCT_CUDA(nullptr, cudaSetDevice(device));
     mct_ctx* ctx = new (std::nothrow) mct_ctx();
     if (!ctx) return mct_fail(nullptr, MCT_E_NOMEM, "out of host memory%s");
     memset(ctx, 0, sizeof(*ctx));
     ctx->device = device;
+    MCT_CUDA(nullptr, cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device));
     ctx->binimg_frame = -1;
     if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false; }
     else { MCT_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
@@ -774,6 +776,8 @@ extern "C" int mct_classifier_update_from_features_dev(mct_clf* c, const float* 
                                     cudaMemcpyDeviceToDevice, ctx->stream));
     MCT_CUDA(ctx, cudaMemcpy2DAsync(c->d_featT + P, (size_t)c->ldT * 4, dev_fneg, (size_t)ld_neg * 4, (size_t)Nn * 4, c->F,
                                     cudaMemcpyDeviceToDevice, ctx->stream));
+    // the caller's buffers have been consumed when this call returns (a caching allocator may hand them out again at once)
+    MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return clf_train_common(c, P, Nn, nullptr, nullptr);
 }
 // Appearance fuser, learner side (AppearanceBasedInformationFuser.cpp:44-90): the pooled sample sets of all cameras arrive as

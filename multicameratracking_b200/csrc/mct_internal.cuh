@@ -57,6 +57,7 @@ struct P2PBuf {
 struct P2PPeers { P2PBuf* p[MCT_P2P_MAXW]; };
 struct mct_ctx {
     int device;
+    int sms;                               // multiprocessors of this ctx's device
     cudaStream_t stream;
     bool own_stream;
     int W, H, pitch;                       // current frame geometry (u8 planes)
@@ -271,6 +272,26 @@ void mct_prof_end_on(mct_ctx* ctx, cudaStream_t st);
         mct_prof_end_on((ctx), (st));                                                        \
         MCT_KERNEL_CHECK(ctx);                                                               \
     } while (0)
+
+// Per-device launch state.  Function attributes (opt-in dynamic shared memory, non-portable cluster sizes) and __constant__
+// uploads belong to ONE device: every launcher keeps its high-water mark in a table indexed by ctx->device, so ctxs on several
+// GPUs of one process are independent (INTEGRATION.md "threads and devices").  The mutex makes check + set atomic for host
+// threads that drive different ctxs.
+#define MCT_MAX_DEV 64
+#include <mutex>
+extern std::mutex g_mct_attr_mu;
+template <typename KernT>
+static inline int mct_smem_attr(mct_ctx* ctx, KernT kern, size_t* high_water /* [MCT_MAX_DEV] */, size_t need, size_t floor_bytes)
+{
+    std::lock_guard<std::mutex> lock(g_mct_attr_mu);
+    size_t& cur = high_water[ctx->device];
+    if (cur < floor_bytes) cur = floor_bytes;
+    if (need > cur) {
+        MCT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+        cur = need;
+    }
+    return MCT_OK;
+}
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }

@@ -720,6 +720,32 @@ def test_fused_cfg4_shape_720p_mdch_anyboost(ctx, oracle):
     _score_and_compare(ctx, oracle, seq, 1280, 720, specs, N=400, sd=(20.0, 20.0, 1e-7, 1e-7), frames=(1,))
 
 
+def test_two_devices_in_one_process(ctx, oracle):
+    """ctxs on devices 0 and 1 of ONE process are independent: function attributes (opt-in shared memory of
+    k_mdch_sel / k_classify_staged / k_frame_prep, cluster sizes) and the __constant__ HSV tables are kept per device.
+    Device 1 goes first for everything device 0 has not touched in this process; needs two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(5)
+    bgr = rng.integers(0, 256, (1080, 1920, 3), dtype=np.uint8)       # 1080p: k_frame_prep opts into > 48 KB of shared memory
+    c1 = capi.Context(1)
+    try:
+        for c in (c1, ctx):
+            c.frame_set_bgr(bgr, True)
+            exp = oracle.bgr_to_planes(bgr, True)
+            got = c.frame_planes()
+            for k in range(4):
+                np.testing.assert_array_equal(got[k], exp[k])
+            assert np.array_equal(c.integral(), oracle.integral(exp[0]))
+        seq = synth.Sequence(640, 480, 2)
+        specs = [(capi.FEAT_HAAR_MDCH, capi.WEAK_WSTUMP, capi.STRONG_MILBOOST, 60), (capi.FEAT_MDCH, capi.WEAK_STUMP, capi.STRONG_MILANYBOOST, 102)]
+        for c in (c1, ctx):
+            _score_and_compare(c, oracle, seq, 640, 480, specs, N=600, sd=(20.0, 20.0, 1e-7, 1e-7), frames=(1,))
+    finally:
+        c1.close()
+
+
 def test_fused_cfg2_full_size_properties(ctx, oracle):
     """BASELINE configs[1] at full size (8 objects x 2000 particles, Haar(250)+MDCH(512) -> 152, WeightedStumps): the
     response of one object is compared with the oracle; all objects are checked through size-independent properties"""
