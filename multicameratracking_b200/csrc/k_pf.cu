@@ -439,6 +439,343 @@ __global__ void __launch_bounds__(PF_THREADS) k_pf_update(const ObjDesc* __restr
     PF_COMMIT(s_decide);
 }
 
+// ------------------------------------------------------------------------------------------
+// k_pf_update_fast: the same step for N <= 4 * PF_THREADS particles with the particle matrix staged ONCE.
+//   * every thread owns particles tid + k * PF_THREADS (k < 4); the five state columns are read once (one round trip to
+//     L2) into shared memory, every later pass (weight update, both normalisations, the resampler's gather, the copy back
+//     into the state, the read-out) works out of shared memory and registers;
+//   * the three ordered f32 chains run on warp 0 with CH elements per lane, CH chosen so that 32 * CH just covers N
+//     (a chain over N = 1000 no longer walks a 2048-element tile);
+//   * the resampled rows are written to the resampled matrix AND back into the state from the registers that did the gather;
+//   * the read-out is one pass + ONE block reduction (average sums, run statistics / arg-max together).
+// Results are bit-identical to k_pf_update (same expressions, same chain order); k_pf_update stays for larger N.
+struct PfRed { double acc[5]; float mx; int a, b; };      // a / b: ties, runs (RESAMPLED) or first / last arg-max (PREDICTED)
+
+template <int CH>
+__device__ __forceinline__ float warp_chain_sum_t(const float* __restrict__ w, int n, int lane)
+{
+    float r[CH];
+    const int e0 = lane * CH;
+#pragma unroll
+    for (int k = 0; k < CH; k++) r[k] = (e0 + k < n) ? w[PIDX(e0) + k] : 0.0f;
+    float carry = 0.0f;
+    const int nl = (n + CH - 1) / CH;                         // lanes that hold elements
+    for (int L = 0; L < nl; L++) {
+        const bool mine = lane == L;
+        float c = carry;
+#pragma unroll
+        for (int k = 0; k < CH; k++) c = __fadd_rn(c, mine ? r[k] : 0.0f);
+        carry = __shfl_sync(0xffffffffu, c, L);
+    }
+    return carry;
+}
+template <int CH>
+__device__ __forceinline__ void warp_chain_cdf_t(const float* __restrict__ w, float* __restrict__ cdf, int n, int lane)
+{
+    float r[CH];
+    const int e0 = lane * CH;
+#pragma unroll
+    for (int k = 0; k < CH; k++) r[k] = (e0 + k < n) ? w[PIDX(e0) + k] : 0.0f;
+    if (e0 == 0) r[0] = 0.0f;                                 // w[0] does not enter the CDF (reference quirk, :927-933)
+    float carry = 0.0f;
+    const int nl = (n + CH - 1) / CH;
+    for (int L = 0; L < nl; L++) {
+        // the owning lane turns its block into prefix sums in place (r[k] += r[k-1]: one dependent FADD per element, nothing
+        // else in the loop body; tools/chain_lab.cu: 6.3 cycles per element against 7.9 for the select form)
+        float c = carry;
+        if (lane == L) {
+            r[0] = __fadd_rn(c, r[0]);
+#pragma unroll
+            for (int k = 1; k < CH; k++) r[k] = __fadd_rn(r[k - 1], r[k]);
+            c = r[CH - 1];
+        }
+        carry = __shfl_sync(0xffffffffu, c, L);
+    }
+#pragma unroll
+    for (int k = 0; k < CH; k++) if (e0 + k < n) cdf[PIDX(e0) + k] = r[k];
+}
+
+template <int CH>
+__global__ void __launch_bounds__(PF_THREADS, 1) k_pf_update_fast(const ObjDesc* __restrict__ descs, const StepArgs sa, int mode, int with_summary)
+{
+    extern __shared__ __align__(16) float smf[];
+    __shared__ float sh_f[64];
+    __shared__ double sh_d[32];
+    __shared__ int sh_i[32];
+    __shared__ int s_decide;
+    __shared__ PfRed s_red[PF_THREADS / 32];
+    __shared__ ObjDesc s_desc;
+    const ObjDesc& d = load_desc(descs + blockIdx.x, &s_desc);
+    const int N = d.N, tid = threadIdx.x;
+    constexpr int nt = PF_THREADS;
+    const int NP = (PLEN(N) + 3) & ~3, N4 = (N + 3) & ~3;
+    float* sw = smf; float* cdf = smf + NP;
+    float* ccx = cdf + NP; float* ccy = ccx + N4; float* csx = ccy + N4; float* csy = csx + N4;
+
+    PF_STAMP(0);
+    const int refine = d.st->refine;
+    // 0. the particle matrix, once
+    int vv[4]; float hh[4], ww[4], xs[4], ys[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int i = tid + k * nt;
+        const bool in = i < N;
+        vv[k] = in ? d.valid[i] : 0; hh[k] = in ? d.H[i] : 0.0f; ww[k] = in ? d.w[i] : 0.0f;
+        xs[k] = in ? d.sx[i] : 1.0f; ys[k] = in ? d.sy[i] : 1.0f;
+        const float x = in ? d.cx[i] : 0.0f, y = in ? d.cy[i] : 0.0f;
+        if (in) { ccx[i] = x; ccy[i] = y; }
+    }
+    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (vv[k]) { mn = fminf(mn, hh[k]); mx = fmaxf(mx, hh[k]); cnt++; }
+    block_reduce_cnt_minmax(cnt, mn, mx, sh_f, sh_i);
+    if (refine == MCT_REFINE_PENDING)
+        for (int i = tid; i < N; i += nt) force_refine_one(d, i);
+    const float max_response = cnt > 0 ? mx : 0.0f;
+    if (tid == 0) {
+        d.st->refine = 0;
+        d.st->n_valid = cnt; d.st->resampled = 0;
+        if (mode == 0) {
+            d.st->max_response = max_response;
+            if (d.scored) atomicAdd(d.scored, (unsigned long long)cnt);
+        }
+    }
+    if (mode == 0 && cnt == 0) {
+        __syncthreads();
+        if (with_summary) summary_body(d, nullptr);
+        return;
+    }
+    const double dmn = (double)mn, range = (double)mx - (double)mn;
+    PF_STAMP(1);
+    // 1. weight update
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int i = tid + k * nt;
+        if (i >= N) continue;
+        float w = ww[k];
+        float sx = xs[k], sy = ys[k];
+        if (vv[k]) {
+            float p;
+            if (mode == 0) {
+                if (d.exponent == 0) p = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-hh[k])));
+                else p = (range != 0) ? (float)ipow_d(((double)hh[k] - dmn) / range, d.exponent) : 1.0f;
+            }
+            else p = hh[k];
+            w = d.force_reset ? p : __fmul_rn(p, w);
+            scale_ratio_clamp(sx, sy);
+            d.sx[i] = sx; d.sy[i] = sy;
+        }
+        csx[i] = sx; csy[i] = sy;
+        sw[PIDX(i)] = w;
+        ww[k] = w;
+    }
+    __syncthreads();
+    PF_STAMP(2);
+    // 2. NormalizeParticleWeights (:987-1011)
+    if (tid < 32) { const float t1 = warp_chain_sum_t<CH>(sw, N, tid); if (tid == 0) sh_f[0] = t1; }
+    __syncthreads();
+    PF_STAMP(3);
+    const float total = sh_f[0];
+    double s2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int i = tid + k * nt;
+        if (i >= N) continue;
+        const float w = (total != 0) ? fdiv_exact(ww[k], total) : 1e-2f;
+        ww[k] = w;
+        sw[PIDX(i)] = w;
+        s2 += (double)w * (double)w;
+    }
+    s2 = block_reduce_sum_d(s2, sh_d);
+    PF_STAMP(4);
+    // 3. ResampleIfRequired, WEIGHT_BASED (:845-910)
+    float neff_inv = (float)s2;
+    if (tid == 0) {
+        int decide = 0;
+        if (d.resample && s2 != 0.0) {
+            const double thr = (double)(float)((double)N * 0.01);
+            const double m = (double)N * 1.2e-7 + 1e-6;
+            const double hi = 1.0 / (s2 * (1.0 - m)), lo = 1.0 / (s2 * (1.0 + m));
+            if (hi < thr) decide = 1;
+            else if (lo >= thr) decide = 0;
+            else {
+                float e = 0.0f;
+                for (int i = 0; i < N; i++) e = (float)((double)e + (double)sw[PIDX(i)] * (double)sw[PIDX(i)]);
+                neff_inv = e;
+                decide = (e != 0) && (__fdiv_rn(1.0f, e) < (float)thr);
+            }
+        }
+        d.st->neff_inv = neff_inv;
+        s_decide = decide;
+    }
+    __syncthreads();
+    PF_STAMP(5);
+    const int decide = s_decide;
+    const int fs_in = d.st->filter_state;
+    float gx[4], gy[4], gsx[4], gsy[4];
+    int* sidx = reinterpret_cast<int*>(sw);              // resample index list (sw is dead once the CDF exists)
+    if (decide) {
+        // ResampleParticles(true) (:920-978)
+        PF_STAMP(6);
+        if (tid < 32) { const float t2 = warp_chain_sum_t<CH>(sw, N, tid); if (tid == 0) sh_f[1] = t2; }
+        __syncthreads();
+        PF_STAMP(16);
+        const float total2 = sh_f[1];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = tid + k * nt;
+            if (i < N) sw[PIDX(i)] = (total2 != 0) ? fdiv_exact(ww[k], total2) : 1e-2f;
+        }
+        __syncthreads();
+        PF_STAMP(17);
+        if (tid < 32) warp_chain_cdf_t<CH>(sw, cdf, N, tid);
+        __syncthreads();
+        PF_STAMP(7);
+        const float invN = __fdiv_rn(1.0f, (float)N);
+        const float seed = __fmul_rn(invN, sa.u01[blockIdx.x]);
+        int top = 1;
+        while ((top << 1) <= N) top <<= 1;
+        float thr[4]; int lo[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { thr[k] = __fadd_rn(seed, __fmul_rn(invN, (float)(tid + k * nt))); lo[k] = 0; }
+        for (int step = top; step > 0; step >>= 1) {
+            // branch-free: the four loads of a step are independent and in flight together
+            int m[4]; float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { m[k] = lo[k] + step; v[k] = cdf[PIDX(min(m[k], N) - 1)]; }
+#pragma unroll
+            for (int k = 0; k < 4; k++) lo[k] = (m[k] <= N && v[k] < thr[k]) ? m[k] : lo[k];
+        }
+        PF_STAMP(18);
+        int idx[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            idx[k] = lo[k] < N - 1 ? lo[k] : N - 1;
+            gx[k] = ccx[idx[k]]; gy[k] = ccy[idx[k]]; gsx[k] = csx[idx[k]]; gsy[k] = csy[idx[k]];
+        }
+        __syncthreads();                                  // every search has read the CDF / sw region: sidx may overwrite it
+        PF_STAMP(19);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = tid + k * nt;
+            if (i < N) {
+                sidx[i] = idx[k];
+                d.residx[i] = idx[k];
+                d.rcx[i] = gx[k]; d.rcy[i] = gy[k]; d.rsx[i] = gsx[k]; d.rsy[i] = gsy[k]; d.rw[i] = 1.0f;
+                d.cx[i] = gx[k]; d.cy[i] = gy[k]; d.sx[i] = gsx[k]; d.sy[i] = gsy[k]; d.w[i] = 1.0f;
+            }
+        }
+        if (tid == 0) { d.st->filter_state = MCT_PF_RESAMPLED; d.st->resampled = 1; }
+        PF_STAMP(8);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const int i = tid + k * nt; if (i < N) d.w[i] = ww[k]; }
+    }
+    PF_STAMP(10);
+    if (!with_summary) { PF_COMMIT(decide); return; }
+    const int fs = decide ? MCT_PF_RESAMPLED : fs_in;
+    if (!decide && fs != MCT_PF_PREDICTED) {
+        // (re-score of an already resampled filter, or a filter that was never predicted: the generic read-out)
+        __syncthreads();
+        summary_body(d, smf);
+        PF_COMMIT(decide);
+        return;
+    }
+    // ---- read-out: one pass, one reduction
+    PfRed me;
+#pragma unroll
+    for (int q = 0; q < 5; q++) me.acc[q] = 0.0;
+    me.mx = -CUDART_INF_F; me.a = decide ? 0 : N; me.b = decide ? 0 : -1;
+    float* rwf = cdf;                                     // run weight per run start, -1 elsewhere (RESAMPLED)
+    if (decide) {
+        __syncthreads();                                  // sidx complete
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = tid + k * nt;
+            if (i >= N) continue;
+            // every weight is exactly 1.0f: x * 1.0f == x and an in-order f32 sum of L ones is exactly (float)L
+            me.acc[0] += (double)gx[k]; me.acc[1] += (double)gy[k]; me.acc[2] += (double)gsx[k]; me.acc[3] += (double)gsy[k]; me.acc[4] += 1.0;
+            const int v = sidx[i];
+            const bool start = (i == 0) || (v != sidx[i - 1]);
+            float r = -1.0f;
+            if (start) {
+                int lo2 = i + 1, hi2 = N;                 // first j > i with sidx[j] != v
+                while (lo2 < hi2) { const int mid = (lo2 + hi2) >> 1; if (sidx[mid] == v) lo2 = mid + 1; else hi2 = mid; }
+                r = (float)(lo2 - i);
+                me.b++;
+                if (r > me.mx) { me.mx = r; me.a = 1; } else if (r == me.mx) me.a++;
+            }
+            rwf[i] = r;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = tid + k * nt;
+            if (i >= N) continue;
+            const float w = ww[k];
+            me.acc[0] += (double)__fmul_rn(ccx[i], w); me.acc[1] += (double)__fmul_rn(ccy[i], w);
+            me.acc[2] += (double)__fmul_rn(csx[i], w); me.acc[3] += (double)__fmul_rn(csy[i], w);
+            me.acc[4] += (double)w;
+            if (w > me.mx) { me.mx = w; me.a = i; me.b = i; } else if (w == me.mx) { me.a = min(me.a, i); me.b = max(me.b, i); }
+        }
+    }
+    PF_STAMP(11);
+    auto merge = [&](PfRed& x, const PfRed& y) {
+#pragma unroll
+        for (int q = 0; q < 5; q++) x.acc[q] += y.acc[q];
+        if (decide) {
+            x.b += y.b;
+            if (y.mx > x.mx) { x.mx = y.mx; x.a = y.a; } else if (y.mx == x.mx) x.a += y.a;
+        } else {
+            if (y.mx > x.mx) { x.mx = y.mx; x.a = y.a; x.b = y.b; }
+            else if (y.mx == x.mx) { x.a = min(x.a, y.a); x.b = max(x.b, y.b); }
+        }
+    };
+    auto shfl = [&](const PfRed& x, int o) {
+        PfRed y;
+#pragma unroll
+        for (int q = 0; q < 5; q++) y.acc[q] = __shfl_xor_sync(0xffffffffu, x.acc[q], o);
+        y.mx = __shfl_xor_sync(0xffffffffu, x.mx, o); y.a = __shfl_xor_sync(0xffffffffu, x.a, o); y.b = __shfl_xor_sync(0xffffffffu, x.b, o);
+        return y;
+    };
+    // (the f64 sums are combined in a fixed tree: lanes by xor-shuffle, then the 16 warp partials in warp order)
+    for (int o = 16; o > 0; o >>= 1) { const PfRed y = shfl(me, o); merge(me, y); }
+    PF_STAMP(12);
+    if ((tid & 31) == 0) s_red[tid >> 5] = me;
+    __syncthreads();
+    PF_STAMP(13);
+    if (tid == 0) {
+        PfRed t = s_red[0];
+        for (int q = 1; q < nt / 32; q++) merge(t, s_red[q]);
+        mct_pf_summary* out = d.summ;
+        for (int q = 0; q < 4; q++) out->average[q] = (float)(t.acc[q] / t.acc[4]);
+        out->n_valid = cnt; out->resampled = decide; out->filter_state = fs;
+        out->neff_inv = neff_inv; out->max_response = (mode == 0) ? max_response : d.st->max_response;
+        if (decide) {
+            // row (ties-1) of the ordered-unique matrix = state of the (ties-1)-th run in index order (:799-806 pairing quirk)
+            const int want = t.a - 1;
+            int ord = -1, b = 0;
+            if (want > 0) for (int i = 0; i < N; i++) if (rwf[i] >= 0.0f) { ord++; if (ord == want) { b = i; break; } }
+            const int s0 = sidx[0], sb = sidx[b];
+            out->ordered_first[0] = ccx[s0]; out->ordered_first[1] = ccy[s0]; out->ordered_first[2] = csx[s0];
+            out->ordered_first[3] = csy[s0]; out->ordered_first[4] = t.mx;
+            out->highest_close[0] = ccx[sb]; out->highest_close[1] = ccy[sb]; out->highest_close[2] = csx[sb];
+            out->highest_close[3] = csy[sb]; out->highest_close[4] = t.mx;
+            out->n_unique = t.b;
+        } else {
+            const int a = t.a < N ? t.a : 0, b = t.b >= 0 ? t.b : 0;
+            out->ordered_first[0] = ccx[a]; out->ordered_first[1] = ccy[a]; out->ordered_first[2] = csx[a];
+            out->ordered_first[3] = csy[a]; out->ordered_first[4] = sw[PIDX(a)];
+            out->highest_close[0] = ccx[b]; out->highest_close[1] = ccy[b]; out->highest_close[2] = csx[b];
+            out->highest_close[3] = csy[b]; out->highest_close[4] = sw[PIDX(b)];
+            out->n_unique = N;
+        }
+    }
+    PF_STAMP(15);
+    PF_COMMIT(decide);
+}
+
 static int pf_update_smem(mct_ctx* ctx, int n_max, int* smem_floats, size_t* smem_bytes)
 {
     // both chains' operands in shared memory when 2*N floats fit in 200 KB, else global scratch
@@ -452,6 +789,24 @@ static int pf_update_smem(mct_ctx* ctx, int n_max, int* smem_floats, size_t* sme
 
 int launch_pf_update(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int use_H, const StepArgs& sa, int with_summary)
 {
+    if (n_max <= 4 * PF_THREADS && !getenv("MCT_PF_GENERIC")) {
+        const size_t fb = ((size_t)2 * round_up(PLEN(n_max), 4) + (size_t)4 * round_up(n_max, 4)) * sizeof(float);
+        const int mode = use_H ? 0 : 1;
+        if (n_max <= 32 * 16) {
+            static size_t s_a16[MCT_MAX_DEV];
+            if (int rc_ = mct_smem_attr(ctx, k_pf_update_fast<16>, s_a16, fb, 32 * 1024)) return rc_;
+            MCT_LAUNCH(ctx, "k_pf_update", k_pf_update_fast<16><<<n_obj, PF_THREADS, fb, ctx->stream>>>(d_desc, sa, mode, with_summary));
+        } else if (n_max <= 32 * 32) {
+            static size_t s_a32[MCT_MAX_DEV];
+            if (int rc_ = mct_smem_attr(ctx, k_pf_update_fast<32>, s_a32, fb, 32 * 1024)) return rc_;
+            MCT_LAUNCH(ctx, "k_pf_update", k_pf_update_fast<32><<<n_obj, PF_THREADS, fb, ctx->stream>>>(d_desc, sa, mode, with_summary));
+        } else {
+            static size_t s_a64[MCT_MAX_DEV];
+            if (int rc_ = mct_smem_attr(ctx, k_pf_update_fast<64>, s_a64, fb, 32 * 1024)) return rc_;
+            MCT_LAUNCH(ctx, "k_pf_update", k_pf_update_fast<64><<<n_obj, PF_THREADS, fb, ctx->stream>>>(d_desc, sa, mode, with_summary));
+        }
+        return MCT_OK;
+    }
     int sf; size_t sb;
     pf_update_smem(ctx, n_max, &sf, &sb);
     static size_t s_attr[MCT_MAX_DEV];

@@ -15,9 +15,10 @@ names = {0: "start", 1: "after count/min/max", 2: "after weight update", 3: "aft
          6: "after chain2", 7: "after divide+cdf chain", 8: "after search+gather", 10: "after resample/copy", 11: "summary: before average",
          12: "after average", 13: "after run weights", 15: "end"}
 names[6] = "resample: before normalise+cdf"
+names.update({16: "after chain2", 17: "after divide", 18: "after search", 19: "after gather+barrier", 12: "summary: after warp reduce", 13: "summary: after barrier"})
 for base, lab in ((0, "no resample"), (32, "RESAMPLED")):
     print("----", lab)
     t0 = out[base]
-    for k in sorted(names):
+    for k in sorted(names, key=lambda k: out[base + k]):
         if out[base + k] and out[base + k] >= t0:
             print("%-32s %8.2f us" % (names[k], (out[base + k] - t0) * 1e-3))
