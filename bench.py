@@ -426,9 +426,12 @@ def run_ours(args):
     ms, scored, launches = timed(step_resident, args.warmup, args.steps)
     sampler.stop_flag = True
     # ---- 3. per-kernel CUDA-event timing of the same steps (roofline of the dominant kernel) ----
+    # (every step is drained before the next one is issued: in the free-running leg above the host runs ahead and the preparation
+    #  of frame t+1 shares the SMs with the kernels of frame t, which would be charged to whichever kernel it delays)
     L.mct_profile_enable(ctx_h, 1)
     for i in range(args.steps):
         step_resident(clock[0] + i)
+        cam.sync()
     clock[0] += args.steps
     prof = capi.profile_read(L, ctx_h)
     L.mct_profile_enable(ctx_h, 0)

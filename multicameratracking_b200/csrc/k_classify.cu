@@ -52,6 +52,7 @@ k_classify(const ObjDesc* __restrict__ descs, const float* __restrict__ ii, int 
         if (e.nrect > 0) x = haar_eval_dev(ii, iip, W, H, e.r, e.w, e.nrect, c, r, fx, fy);
         else x = d.featN[(size_t)e.row * d.ldN + i];
         if (d.alpha) Hs = __fadd_rn(Hs, weak_classify_bool_dev(d.weak_type, x, e.st[0], e.st[1], e.st[4], e.st[5], e.st[6], e.st[7]) ? e.st[2] : -e.st[2]);
+        else if (d.color_resp && e.nrect == 0) Hs = __fadd_rn(Hs, x);          // featN already holds the response (k_mdch_sel)
         else Hs = __fadd_rn(Hs, weak_classify_dev(d.weak_type, x, e.st[0], e.st[1], e.st[4], e.st[5], e.st[6], e.st[7]));
     }
     if (!log_ratio) Hs = sigmoid_dev(d.alpha ? __fmul_rn(2.0f, Hs) : Hs);     // AdaBoost: sigmoid(2 H) (:208)
@@ -83,6 +84,15 @@ __device__ __forceinline__ float weak_classify_ratio_dev(int weak_type, float x,
     return (float)log((1e-5 + p1) / (1e-5 + p0));
 }
 
+#ifdef MCT_CLS_DEBUG
+// per-CTA phase stamps of the last k_classify_staged launch (tools/cls_stamps.py): [cta][8] globaltimer values
+__device__ unsigned long long g_cls_dbg[256 * 8];
+__device__ __forceinline__ unsigned long long cls_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define CLS_STAMP(k) do { if (threadIdx.x == 0) g_cls_dbg[((blockIdx.y * gridDim.x + blockIdx.x) & 255) * 8 + (k)] = cls_gtime(); } while (0)
+extern "C" int mct_debug_cls_stamps(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, g_cls_dbg, sizeof(unsigned long long) * 256 * 8); }
+#else
+#define CLS_STAMP(k)
+#endif
 #define CLS_THREADS 512
 #ifndef CLS_UF
 #define CLS_UF 4              // selectors in flight per lane (8 measured the same)
@@ -96,9 +106,11 @@ k_classify_staged(const ObjDesc* __restrict__ descs, const float* __restrict__ i
     __shared__ int s_bb[4], s_ctr[3];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ ObjDesc s_desc;
+    CLS_STAMP(0);
     const ObjDesc& d = load_desc(descs + blockIdx.y, &s_desc);
     const int tid = threadIdx.x, lane = tid & 31;
     const int N = d.N;
+    CLS_STAMP(1);
     const int chunk = (N + gridDim.x - 1) / gridDim.x;
     const int i_begin = blockIdx.x * chunk, i_end = min(N, i_begin + chunk);
     if (i_begin >= i_end) return;
@@ -123,10 +135,13 @@ k_classify_staged(const ObjDesc* __restrict__ descs, const float* __restrict__ i
         int x0 = 1 << 30, y0 = 1 << 30, x1 = -(1 << 30), y1 = -(1 << 30);
         int sxc = 0, syc = 0, nb = 0;                                          // sum of the box centres (window placement below)
         for (int i = i_begin + tid; i < i_end; i += blockDim.x) {
-            if (d.valid != nullptr && d.valid[i] == 0) continue;
+            // (all five loads are issued before the validity test: one round trip to L2 instead of two)
+            const int vld = d.valid != nullptr ? d.valid[i] : 1;
             const int c = d.col[i], r = d.row[i];
+            const float bsx = d.sx[i], bsy = d.sy[i];
+            if (vld == 0) continue;
             // round(a*s) + round(b*s) <= (a+b)*s + 1
-            const int ex = (int)ceilf((float)ext_w * d.sx[i]) + 2, ey = (int)ceilf((float)ext_h * d.sy[i]) + 2;
+            const int ex = (int)ceilf((float)ext_w * bsx) + 2, ey = (int)ceilf((float)ext_h * bsy) + 2;
             x0 = min(x0, c); y0 = min(y0, r); x1 = max(x1, c + ex); y1 = max(y1, r + ey);
             sxc += c + (ex >> 1); syc += r + (ey >> 1); nb++;
         }
@@ -138,6 +153,7 @@ k_classify_staged(const ObjDesc* __restrict__ descs, const float* __restrict__ i
         if (lane == 0 && x1 >= x0) { atomicMin(&s_bb[0], x0); atomicMin(&s_bb[1], y0); atomicMax(&s_bb[2], x1); atomicMax(&s_bb[3], y1); }
     }
     __syncthreads();
+    CLS_STAMP(2);
     float* region = (float*)(smraw + se_b);
     int bx0 = clampi(s_bb[0], 0, W), by0 = clampi(s_bb[1], 0, H);
     int bx1 = clampi(s_bb[2], 0, W), by1 = clampi(s_bb[3], 0, H);
@@ -166,14 +182,32 @@ k_classify_staged(const ObjDesc* __restrict__ descs, const float* __restrict__ i
     const int RWp = (RWc & 4) ? RWc : RWc + 4;                                 // pitch/4 odd: rows spread over the banks
     const bool have = ext_w > 0 && s_bb[2] >= s_bb[0];
     const bool staged = have && se_b + (size_t)RWp * RH * 4 <= (size_t)smem_bytes && (size_t)RWc * RH * 4 < (1u << 20);
-    if (staged && tid < 32) {
-        if (lane == 0) mbar_expect_tx(&s_bar[1], (unsigned)(RWc * RH * 4));
-        __syncwarp();
-        for (int y = lane; y < RH; y += 32)
-            bulk_g2s(region + (size_t)y * RWp, ii + (size_t)(by0 + y) * iip + ox, (unsigned)(RWc * 4), &s_bar[1]);
+    if (staged) {
+        // The region arrives through 16-byte loads of ALL threads, six in flight per thread (two or three round trips to L2 for
+        // ~150 KB).  One bulk copy per row (~200 UBLKCP of ~700 B per CTA) was measured at 11.7 us of mbarrier wait per launch
+        // (profiles/r02a: 31 % of the kernel's stall samples): the copy engine serialises small copies.
+        const int q4 = RWc >> 2, n4 = q4 * RH;
+        const float* src0 = ii + (size_t)by0 * iip + ox;
+        for (int g0 = tid; g0 < n4; g0 += CLS_THREADS * 6) {
+            float4 v[6]; int off[6];
+#pragma unroll
+            for (int u = 0; u < 6; u++) {
+                const int g = g0 + u * CLS_THREADS;
+                off[u] = -1;
+                if (g < n4) {
+                    const int y = g / q4, x4 = g - y * q4;
+                    v[u] = __ldg(reinterpret_cast<const float4*>(src0 + (size_t)y * iip) + x4);
+                    off[u] = y * RWp + 4 * x4;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 6; u++) if (off[u] >= 0) *reinterpret_cast<float4*>(region + off[u]) = v[u];
+        }
     }
+    CLS_STAMP(3);
     mbar_wait(&s_bar[0], 0);
-    if (staged) mbar_wait(&s_bar[1], 0);
+    __syncthreads();
+    CLS_STAMP(4);
     // ---- 3. four lanes per box, two selectors in flight per lane
     const int q = tid & 3;
     const unsigned gmask = 0xfu << (lane & ~3);
@@ -211,7 +245,8 @@ k_classify_staged(const ObjDesc* __restrict__ descs, const float* __restrict__ i
             for (int u = 0; u < CLS_UF; u++) {
                 if (on[u]) {
                     const SelEntry& e = se[s0 + 4 * u + q];
-                    v[u] = d.alpha ? (weak_classify_bool_dev(d.weak_type, x[u], e.st[0], e.st[1], e.st[4], e.st[5], e.st[6], e.st[7]) ? e.st[2] : -e.st[2])
+                    if (d.color_resp && e.nrect == 0) v[u] = x[u];             // the colour kernel left the response itself in featN
+                    else v[u] = d.alpha ? (weak_classify_bool_dev(d.weak_type, x[u], e.st[0], e.st[1], e.st[4], e.st[5], e.st[6], e.st[7]) ? e.st[2] : -e.st[2])
                                    : weak_classify_ratio_dev(d.weak_type, x[u], e.st);
                 }
             }
@@ -229,6 +264,12 @@ k_classify_staged(const ObjDesc* __restrict__ descs, const float* __restrict__ i
             d.H[i] = ok ? Hs : 0.0f;
         }
     }
+    CLS_STAMP(5);
+#ifdef MCT_CLS_DEBUG
+    __syncthreads();
+    CLS_STAMP(6);
+    if (threadIdx.x == 0) g_cls_dbg[((blockIdx.y * gridDim.x + blockIdx.x) & 255) * 8 + 7] = (unsigned long long)(staged ? 1 : 0) | ((unsigned long long)(partial ? 1 : 0) << 1) | ((unsigned long long)nsel << 8) | ((unsigned long long)(RWp * RH) << 24);
+#endif
 }
 
 int launch_classify_staged(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, int log_ratio)

@@ -864,7 +864,8 @@ __device__ __forceinline__ void build_colormap_body(const int* __restrict__ sel,
                                  uint16_t* __restrict__ slotmap, int* __restrict__ colorrow, int* __restrict__ outbins,
                                  int* __restrict__ nout, const int4* __restrict__ rects, const float* __restrict__ wts,
                                  const int* __restrict__ nrect, const float* __restrict__ weak, int F, int K,
-                                 SelEntry* __restrict__ tab, int* __restrict__ hdr, const float* __restrict__ alpha = nullptr)
+                                 SelEntry* __restrict__ tab, int* __restrict__ hdr, const float* __restrict__ alpha = nullptr,
+                                 float* __restrict__ rowst = nullptr)
 {
     __shared__ int s_ext[2];
     const int ns = *nsel;
@@ -902,6 +903,8 @@ __device__ __forceinline__ void build_colormap_body(const int* __restrict__ sel,
                 }
             } else {
                 e.row = colorrow[f - n_haar];
+                // weak state by colour row, for the response evaluation fused into k_mdch_sel (a bin selected twice has one state)
+                if (rowst && mdch) for (int q = 0; q < 8; q++) rowst[(size_t)e.row * 8 + q] = e.st[q];
             }
         }
         tab[s] = e;
@@ -914,16 +917,16 @@ __global__ void k_build_colormap(const int* __restrict__ sel, const int* __restr
                                  uint16_t* __restrict__ slotmap, int* __restrict__ colorrow, int* __restrict__ outbins,
                                  int* __restrict__ nout, const int4* __restrict__ rects, const float* __restrict__ wts,
                                  const int* __restrict__ nrect, const float* __restrict__ weak, int F, int K,
-                                 SelEntry* __restrict__ tab, int* __restrict__ hdr, const float* __restrict__ alpha)
+                                 SelEntry* __restrict__ tab, int* __restrict__ hdr, const float* __restrict__ alpha, float* __restrict__ rowst)
 {
-    build_colormap_body(sel, nsel, n_haar, n_color, mdch, slotmap, colorrow, outbins, nout, rects, wts, nrect, weak, F, K, tab, hdr, alpha);
+    build_colormap_body(sel, nsel, n_haar, n_color, mdch, slotmap, colorrow, outbins, nout, rects, wts, nrect, weak, F, K, tab, hdr, alpha, rowst);
 }
 __global__ void k_build_colormap_batch(const TrainDesc* __restrict__ descs)
 {
     const TrainDesc& d = descs[blockIdx.x];
     const int mdch = (d.feature_type == MCT_FEAT_MDCH || d.feature_type == MCT_FEAT_HAAR_MDCH) ? 1 : 0;
     build_colormap_body(d.sel, d.nsel, d.n_haar, d.n_color, mdch, d.slotmap, d.colorrow, d.outbins, d.nout, d.rects, d.wts, d.nrect,
-                        d.weak, d.F, d.K, d.seltab, d.selhdr, d.strong_type == MCT_STRONG_ADABOOST ? d.alpha : nullptr);
+                        d.weak, d.F, d.K, d.seltab, d.selhdr, d.strong_type == MCT_STRONG_ADABOOST ? d.alpha : nullptr, d.rowst);
 }
 int launch_build_colormap_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj)
 {
@@ -939,7 +942,7 @@ int launch_build_colormap(mct_clf* clf)
                                                                                   clf->d_slotmap, clf->d_colorrow, clf->d_outbins, clf->d_nout,
                                                                                   clf->d_rects, clf->d_wts, clf->d_nrect, clf->d_weak, clf->F, clf->K,
                                                                                   clf->d_seltab, clf->d_selhdr,
-                                                                                  clf->p.strong_type == MCT_STRONG_ADABOOST ? clf->d_alpha : nullptr));
+                                                                                  clf->p.strong_type == MCT_STRONG_ADABOOST ? clf->d_alpha : nullptr, clf->d_rowst));
     return MCT_OK;
 }
 
@@ -993,7 +996,14 @@ __device__ __forceinline__ void mdch_big_body(const ObjDesc& d, const uint16_t* 
         float s = 0.0f;
         for (int b = lane; b < dim; b += 32) s += acc[b];
         s = warp_sum_f(s);
-        for (int o = lane; o < n_out; o += 32) d.featN[(size_t)o * d.ldN + i] = __fdiv_rn(acc[d.outbins[o]], s);
+        for (int o = lane; o < n_out; o += 32) {
+            float x = __fdiv_rn(acc[d.outbins[o]], s);
+            if (d.color_resp) {
+                const float* st = d.rowst + (size_t)o * 8;
+                x = weak_classify_q_dev(d.weak_type, x, st[0], st[1], st[4], st[5], st[6], st[7]);
+            }
+            d.featN[(size_t)o * d.ldN + i] = x;
+        }
         __syncwarp();
     }
 }
@@ -1273,11 +1283,35 @@ __device__ __forceinline__ void mdch_sel_chunk(const ObjDesc& d, const uint16_t*
                     }
                     const uint32_t* hb = hist_all + (size_t)warp * n_slots * 32 + bw * T;
                     float* dst = d.featN + i;
-                    for (int s = 1 + j; s < n_slots; s += T) {
-                        uint32_t t = 0;
-                        int qq = j;                                           // skewed start: the lanes of a box hit distinct banks
-                        for (int k2 = 0; k2 < T; k2++) { t += hb[s * 32 + qq]; qq = (qq + 1 == T) ? 0 : qq + 1; }
-                        dst[(size_t)(s - 1) * d.ldN] = ok ? __fdiv_rn(__fmul_rn((float)t, inv_scale), S) : 0.0f;
+                    if (!d.color_resp) {
+                        for (int s = 1 + j; s < n_slots; s += T) {
+                            uint32_t t = 0;
+                            int qq = j;                                       // skewed start: the lanes of a box hit distinct banks
+                            for (int k2 = 0; k2 < T; k2++) { t += hb[s * 32 + qq]; qq = (qq + 1 == T) ? 0 : qq + 1; }
+                            dst[(size_t)(s - 1) * d.ldN] = ok ? __fdiv_rn(__fmul_rn((float)t, inv_scale), S) : 0.0f;
+                        }
+                    } else {
+                        // fused ClassifyF of the selector that owns the bin: the bin value never leaves the SM, featN receives the
+                        // response the classify kernel adds in selector order.  Two slots per step: their exp / log chains overlap.
+                        const float4* rst = reinterpret_cast<const float4*>(d.rowst);
+                        for (int s = 1 + j; s < n_slots; s += 2 * T) {
+                            const int s2 = s + T;
+                            const bool two = s2 < n_slots;
+                            uint32_t t = 0, t2 = 0;
+                            int qq = j;
+                            for (int k2 = 0; k2 < T; k2++) {
+                                t += hb[s * 32 + qq];
+                                if (two) t2 += hb[s2 * 32 + qq];
+                                qq = (qq + 1 == T) ? 0 : qq + 1;
+                            }
+                            const float4 a0 = __ldg(rst + 2 * (s - 1)), a1 = __ldg(rst + 2 * (s - 1) + 1);
+                            const float4 b0 = __ldg(rst + 2 * (two ? s2 - 1 : s - 1)), b1 = __ldg(rst + 2 * (two ? s2 - 1 : s - 1) + 1);
+                            const float x = __fdiv_rn(__fmul_rn((float)t, inv_scale), S), x2 = __fdiv_rn(__fmul_rn((float)t2, inv_scale), S);
+                            const float r1 = weak_classify_q_dev(d.weak_type, x, a0.x, a0.y, a1.x, a1.y, a1.z, a1.w);
+                            const float r2 = weak_classify_q_dev(d.weak_type, x2, b0.x, b0.y, b1.x, b1.y, b1.z, b1.w);
+                            dst[(size_t)(s - 1) * d.ldN] = ok ? r1 : 0.0f;
+                            if (two) dst[(size_t)(s2 - 1) * d.ldN] = ok ? r2 : 0.0f;
+                        }
                     }
                 }
                 __syncwarp();

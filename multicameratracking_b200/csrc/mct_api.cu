@@ -660,6 +660,7 @@ extern "C" int mct_classifier_create(mct_ctx* ctx, const mct_clf_params* p, cons
         MCT_CUDA(ctx, cudaMalloc(&c->d_slotmap, (size_t)n_color * 2));
         MCT_CUDA(ctx, cudaMemset(c->d_slotmap, 0, (size_t)n_color * 2));
         MCT_CUDA(ctx, cudaMalloc(&c->d_nout, 4)); MCT_CUDA(ctx, cudaMemset(c->d_nout, 0, 4));
+        MCT_CUDA(ctx, cudaMalloc(&c->d_rowst, (size_t)n_color * 8 * 4)); MCT_CUDA(ctx, cudaMemset(c->d_rowst, 0, (size_t)n_color * 8 * 4));
         MCT_CUDA(ctx, cudaMalloc(&c->d_nbig, 8)); MCT_CUDA(ctx, cudaMemset(c->d_nbig, 0, 8));     // [0] flagged boxes, [1] k_mdch_sel arrival counter
     }
     *out = c;
@@ -674,7 +675,7 @@ extern "C" int mct_classifier_destroy(mct_clf* c)
     void* ptrs[] = {c->d_rects, c->d_wts, c->d_nrect, c->d_weak, c->d_trained, c->d_sel, c->d_nsel, c->d_seltab, c->d_selhdr, c->d_tcol, c->d_trow,
                     c->d_tsx, c->d_tsy, c->d_tw, c->d_featT, c->d_pred, c->d_col, c->d_row, c->d_sx, c->d_sy, c->d_featN,
                     c->d_H, c->d_outbins, c->d_colorrow, c->d_slotmap, c->d_nout, c->d_big, c->d_nbig, c->d_tsort, c->d_ada_cnt, c->d_alpha,
-                    c->d_keep, c->d_ensH};
+                    c->d_keep, c->d_ensH, c->d_rowst};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete c;
     return MCT_OK;
@@ -854,6 +855,7 @@ static void fill_clf_desc(ObjDesc* d, mct_clf* c)
     d->colorrow = c->d_colorrow; d->outbins = c->d_outbins;
     const bool mdch = c->p.feature_type == MCT_FEAT_MDCH || c->p.feature_type == MCT_FEAT_HAAR_MDCH;
     d->slotmap = mdch ? c->d_slotmap : nullptr; d->nout = c->d_nout; d->big = c->d_big; d->nbig = c->d_nbig;
+    d->rowst = c->d_rowst; d->color_resp = 0;
     d->cw0 = c->p.w0; d->ch0 = c->p.h0;
     d->F = c->F; d->n_haar = c->n_haar; d->nb = c->p.n_bins; d->weak_type = c->p.weak_type;
     d->feature_type = c->p.feature_type; d->cch_mode = c->p.cch_mode; d->K = c->K;
@@ -1354,6 +1356,9 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
         fill_pf_desc(&h[o], p);
         fill_clf_desc(&h[o], c);
         h[o].noise_off = (long long)ntot;
+        // MDCH objects of the MIL classifiers: the colour kernel evaluates the selected colour weak classifiers where the bin
+        // values are (shared memory) and leaves their responses in featN; the classify kernel only adds them in selector order
+        h[o].color_resp = (h[o].slotmap != nullptr && h[o].alpha == nullptr && !getenv("MCT_NO_COLOR_RESP")) ? 1 : 0;
         h[o].summ = ctx->h_summ_dev + o;               // the read-out is written straight into mapped pinned memory
         h[o].w0 = params[o].w0; h[o].h0 = params[o].h0; h[o].exponent = params[o].exponent;
         h[o].force_reset = params[o].force_reset; h[o].resample = params[o].resample;
@@ -1492,7 +1497,7 @@ static void fill_train_desc(TrainDesc* t, mct_clf* c)
     t->ldT = c->ldT; t->featT = c->d_featT; t->pred = c->d_pred;
     t->rects = c->d_rects; t->wts = c->d_wts; t->nrect = c->d_nrect;
     t->weak = c->d_weak; t->trained = c->d_trained; t->sel = c->d_sel; t->nsel = c->d_nsel;
-    t->slotmap = c->d_slotmap; t->colorrow = c->d_colorrow; t->outbins = c->d_outbins; t->nout = c->d_nout;
+    t->slotmap = c->d_slotmap; t->colorrow = c->d_colorrow; t->outbins = c->d_outbins; t->nout = c->d_nout; t->rowst = c->d_rowst;
     t->seltab = c->d_seltab; t->selhdr = c->d_selhdr;
     t->ada_cnt = c->d_ada_cnt; t->alpha = c->d_alpha;
     const bool ens = c->p.strong_type == MCT_STRONG_MILENSEMBLE;

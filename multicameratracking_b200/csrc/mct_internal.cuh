@@ -128,6 +128,7 @@ struct mct_clf {
     int* d_outbins; int* d_colorrow;                    // [n_color]: bins to write / colour feature -> row in featN
     uint16_t* d_slotmap;                                // [n_color]: joint bin -> private-histogram slot (0 = not selected)
     int* d_nout;                                        // device: number of selected colour bins
+    float* d_rowst;                                     // [n_color][8]: weak state of the selector that owns colour row r (fused responses)
     int* d_tsort; size_t tsort_cap;                     // tiled Haar matrix: tile starts + box order (k_tile_sort)
     int* d_big; int big_cap;                            // per test box: 1 = left to the generic (large / odd box) kernel
     int* d_nbig;                                        // device counter of such boxes
@@ -184,7 +185,9 @@ struct ObjDesc {
     float* featN; int ldN; int n_color_rows;
     const int* colorrow; const int* outbins;
     const uint16_t* slotmap; const int* nout; int* big; int* nbig;
-    int F, n_haar, nb, weak_type, feature_type, cch_mode, K, cw0, ch0, pad1;
+    int F, n_haar, nb, weak_type, feature_type, cch_mode, K, cw0, ch0;
+    int color_resp;      // 1: the per-frame colour kernel leaves ClassifyF(x) of the owning selector in featN instead of the bin value x
+    const float* rowst;  // [n_color_rows][8] weak state per colour row (valid when color_resp)
 };
 
 // ------------------------------------------------------------------ batched training descriptor (UpdateClassifier)
@@ -207,7 +210,7 @@ struct TrainDesc {
     float* featT; float* pred;
     const int4* rects; const float* wts; const int* nrect;
     float* weak; int* trained; int* sel; int* nsel;
-    uint16_t* slotmap; int* colorrow; int* outbins; int* nout; SelEntry* seltab; int* selhdr;
+    uint16_t* slotmap; int* colorrow; int* outbins; int* nout; SelEntry* seltab; int* selhdr; float* rowst;
     int F, K, n_haar, n_color, nb, w0, h0, weak_type, strong_type, feature_type, cch_mode, pad1;
     float lr; int mdch_fast;               // mdch_fast: both groups eligible for the pixel-list kernels
     MdchGroup grp[2];
