@@ -711,6 +711,24 @@ def run_network(args):
         step(i, i >= args.warmup)
     barrier()
     sampler.stop_flag = True
+    # per-kernel CUDA-event times of one more (untimed) segment of the first local camera: what the frame's device time is made of
+    kernel_us = None
+    if os.environ.get("MCT_BENCH_KERNELS", "1") == "1":
+        from multicameratracking_b200 import capi
+        Lc = capi.load()
+        prof_acc, prof_frames = {}, 0
+        for i in range(SEG):
+            if i == 0:
+                build(); barrier()
+                ctx0 = C.c_void_p(state["cams"][0].L.mcth_camera_ctx(state["cams"][0].h))
+            Lc.mct_profile_enable(ctx0, 1)
+            step(i, False)
+            for kname, (ms_k, n_k) in capi.profile_read(Lc, ctx0).items():
+                acc = prof_acc.setdefault(kname, [0.0, 0]); acc[0] += ms_k; acc[1] += n_k
+            Lc.mct_profile_enable(ctx0, 0)
+            prof_frames += 1
+        kernel_us = {k: [round(1e3 * v[0] / prof_frames, 1), round(v[1] / prof_frames, 1)] for k, v in sorted(prof_acc.items(), key=lambda kv: -kv[1][0])}
+        barrier()
     dt = timed["s"]
     launches = timed["launches"]
     cams, net = state["cams"], state["net"]
@@ -743,6 +761,7 @@ def run_network(args):
                "e2e": {"value": val, "unit": "camera-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": len(my) * N_OBJ * 80,
                        "note": "the network path IS end to end: host frames and noise in, boxes out, every step"},
                "stage_ms_per_frame": {k: round(v, 4) for k, v in st.items()},
+               "kernel_us_per_frame_camera0": kernel_us,      # {kernel: [us per frame, launches per frame]}, CUDA events, rank 0's first camera
                "gpu_launches": int(launches_all), "roofline": None, "clocks": sampler.summary()}
         print(json.dumps(out))
     net.close()

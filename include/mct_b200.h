@@ -172,11 +172,14 @@ int mct_classifier_update_from_gathered(mct_clf* clf, const float* dev_rows, con
  * mct_features_compute_dev / mct_classifier_update_from_gathered):
  *  - every camera: feature rows of the freshly generated training sets of all its objects under the objects' global
  *    classifiers, written into the exchange buffer (object o at dev_rows + o * obj_stride floats, feature rows ld floats apart,
- *    positives from column 0, negatives from column ld_pos); stream-ordered, the box arrays may be reused at once;
+ *    positives from column 0, negatives from column ld_pos); stream-ordered, the box arrays may be reused at once.
+ *    reuse_pos_rows (or NULL): the rows an earlier call wrote for IDENTICAL positive boxes (same layout) -- the learner rounds
+ *    of one frame regenerate the same positives and only re-thin the negative ring, so the positive columns are copied from
+ *    there and only the negative boxes are evaluated;
  *  - the learner: per object the kept columns gathered into the global classifier's training matrix and ONE batched Update.
  *    col_offsets_host: the objects' offset lists back to back (P[0] + Nn[0] entries, then P[1] + Nn[1], ...). */
 int mct_train_features_many_dev(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, const mct_boxes* pos, const mct_boxes* neg,
-                                float* dev_rows, size_t obj_stride, int ld, int ld_pos);
+                                float* dev_rows, size_t obj_stride, int ld, int ld_pos, const float* reuse_pos_rows);
 int mct_track_update_from_gathered(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, const float* dev_rows, const int* col_offsets_host,
                                    long long row_stride, const int* P, const int* Nn);
 /* device buffers on the ctx's device (exchange buffers) and a copy ordered on the ctx's stream (any direction, peers included) */
@@ -245,6 +248,9 @@ typedef struct {
     float highest_close[5]; /* GetHighestOrderedUniqueParticleCloseToTheGivenState (:557-593) */
 } mct_pf_summary;
 int mct_pf_get_summary(mct_pf* pf, mct_pf_summary* out_host);
+/* the read-outs of several objects of one camera in one launch and one synchronisation
+ * (Camera::StoreAllParticleFilterTrackerState, Camera.cpp:556-574) */
+int mct_pf_get_summary_many(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, mct_pf_summary* out_host /* [n_obj] */);
 
 /* ---------------------------------------------------------------- fused per-frame path ---- */
 /* One call = TrackObjectOnTheGivenFrame (ParticleFilterTracker.cpp:468-639) for n_obj objects of this
@@ -309,6 +315,10 @@ int mct_fuser_ground_pdf(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, const doub
  * (UpdateParticleWeightsForRearrangedParticles, ParticleFilterTracker.cpp:1334-1482) is mct_track_score with noise == NULL
  * (no prediction), exponent 1, force_reset 1, resample 1. */
 int mct_pf_rearrange_ground(mct_pf* pf, float mean_foot_x, float mean_foot_y, const float* noise2xN, float w0, float h0);
+/* the same for several objects of a camera in one pass: mean_foot_xy [n_obj][2]; noise host, object o's [2][N] block behind
+ * the blocks of the objects in front of it; w0 / h0 [n_obj] */
+int mct_pf_rearrange_ground_many(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, const float* mean_foot_xy, const float* noise,
+                                 const float* w0, const float* h0);
 
 /* The same exchange WITHOUT a collective library: every camera's receive buffer is exported with CUDA IPC and the kernel that
  * computes the foot points stores them straight into all cameras' buffers over NVLink, then a bounded wait gathers

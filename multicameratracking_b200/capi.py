@@ -38,6 +38,7 @@ SYMBOLS = [
     # called by the C++ host schedule (host/mct_network.cpp), listed so that load() checks they are exported
     "mct_classifier_update_from_gathered", "mct_dev_alloc", "mct_dev_copy", "mct_dev_free", "mct_fuser_foot_points",
     "mct_pf_resample_many", "mct_track_update_from_gathered", "mct_train_features_many_dev",
+    "mct_pf_get_summary_many", "mct_pf_rearrange_ground_many",
 ]
 
 

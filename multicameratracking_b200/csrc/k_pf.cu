@@ -1156,11 +1156,14 @@ int launch_pf_refine(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj)
 // RearrangeParticlesBasedOnGroundLocation (ParticleFilter.cpp:120-179, shouldChangeTheScaleAccordingToOffset): every
 // particle's foot point is pulled onto the fused ground location (seen in this camera's image) plus noise by changing its
 // scale while its box's top-left corner stays where it was.  nz: [2][N] = the (xRand, yRand) pairs in particle order.
-__global__ void __launch_bounds__(256) k_pf_rearrange(const ObjDesc* __restrict__ descs, const float* __restrict__ nz, float mfx, float mfy)
+// (batched form: object blockIdx.y takes its mean foot point from ra and its noise block at nz + ra.noise_off[object])
+__global__ void __launch_bounds__(256) k_pf_rearrange(const ObjDesc* __restrict__ descs, const float* __restrict__ nz_base, const RearrangeArgs ra)
 {
     const ObjDesc& d = descs[blockIdx.y];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.N) return;
+    const float* nz = nz_base + ra.noise_off[blockIdx.y];
+    const float mfx = ra.mfx[blockIdx.y], mfy = ra.mfy[blockIdx.y];
     const float cx = d.cx[i], cy = d.cy[i], sx = d.sx[i], sy = d.sy[i];
     const float hw = __fdiv_rn(d.w0, 2.0f), hh = __fdiv_rn(d.h0, 2.0f);
     const float kx = (float)(2.0 / (double)d.w0), ky = (float)(1.0 / (double)d.h0);
@@ -1175,10 +1178,10 @@ __global__ void __launch_bounds__(256) k_pf_rearrange(const ObjDesc* __restrict_
     d.cx[i] = __fadd_rn(xpos, __fmul_rn(hw, nsx));
     d.cy[i] = __fadd_rn(ypos, __fmul_rn(hh, nsy));
 }
-int launch_pf_rearrange(mct_ctx* ctx, const ObjDesc* d_desc, int n_max, const float* d_noise2, float mfx, float mfy)
+int launch_pf_rearrange(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, const float* d_noise2, const RearrangeArgs& ra)
 {
-    dim3 g(ceil_div(n_max, 256), 1);
-    MCT_LAUNCH(ctx, "k_pf_rearrange", k_pf_rearrange<<<g, 256, 0, ctx->stream>>>(d_desc, d_noise2, mfx, mfy));
+    dim3 g(ceil_div(n_max, 256), n_obj);
+    MCT_LAUNCH(ctx, "k_pf_rearrange", k_pf_rearrange<<<g, 256, 0, ctx->stream>>>(d_desc, d_noise2, ra));
     return MCT_OK;
 }
 

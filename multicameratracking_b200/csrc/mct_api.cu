@@ -1254,8 +1254,43 @@ extern "C" int mct_pf_rearrange_ground(mct_pf* p, float mean_foot_x, float mean_
     MCT_CUDA(ctx, cudaMemcpyAsync(p->d_noise, noise2xN, (size_t)2 * p->N * 4, cudaMemcpyHostToDevice, ctx->stream));
     const ObjDesc* d; StepArgs sa; int rc;
     if ((rc = pf_single_desc(p, &d, &sa, w0, h0, 0, 1, 0.0f))) return rc;
-    if ((rc = launch_pf_rearrange(ctx, d, p->N, p->d_noise, mean_foot_x, mean_foot_y))) return rc;
+    RearrangeArgs ra; ra.mfx[0] = mean_foot_x; ra.mfy[0] = mean_foot_y; ra.noise_off[0] = 0;
+    if ((rc = launch_pf_rearrange(ctx, d, 1, p->N, p->d_noise, ra))) return rc;
     if ((rc = launch_pf_refine(ctx, d, 1))) return rc;                            // :173 CheckForParticleRefinement
+    return mct_sync(ctx);     // the host noise buffer may be reused by the caller
+}
+
+// the same for several objects of a camera in one pass (the geometric fuser's feedback rearranges every object whose average
+// particle lies 20 px from the fused estimate): noise host [sum over objects of 2 * N], object o's block after the blocks of
+// the objects in front of it; mean_foot_xy [n_obj][2]
+extern "C" int mct_pf_rearrange_ground_many(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, const float* mean_foot_xy, const float* noise,
+                                            const float* w0, const float* h0)
+{
+    if (!ctx || n_obj < 1 || n_obj > DESC_MAX_OBJ || !pfs || !mean_foot_xy || !noise || !w0 || !h0) return MCT_E_ARG;
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    ObjDesc h[DESC_MAX_OBJ]; const ObjDesc* d; RearrangeArgs ra;
+    size_t ntot = 0; int n_max = 0;
+    for (int o = 0; o < n_obj; o++) {
+        mct_pf* p = pfs[o];
+        if (!p || p->ctx != ctx || !p->initialized) return mct_fail(ctx, MCT_E_STATE, "particle filter not initialised%s");
+        if (!(w0[o] > 0) || !(h0[o] > 0)) return MCT_E_ARG;
+        memset(&h[o], 0, sizeof(ObjDesc)); fill_pf_desc(&h[o], p);
+        h[o].w0 = w0[o]; h[o].h0 = h0[o]; h[o].resample = 1;
+        ra.mfx[o] = mean_foot_xy[2 * o]; ra.mfy[o] = mean_foot_xy[2 * o + 1]; ra.noise_off[o] = (long long)ntot;
+        ntot += (size_t)2 * p->N;
+        if (p->N > n_max) n_max = p->N;
+    }
+    if (ntot > ctx->noise_stage_cap) {
+        MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_noise_stage) cudaFree(ctx->d_noise_stage);
+        MCT_CUDA(ctx, cudaMalloc(&ctx->d_noise_stage, ntot * sizeof(float)));
+        ctx->noise_stage_cap = ntot;
+    }
+    MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_noise_stage, noise, ntot * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    int rc;
+    if ((rc = desc_publish(ctx, h, n_obj, &d))) return rc;
+    if ((rc = launch_pf_rearrange(ctx, d, n_obj, n_max, ctx->d_noise_stage, ra))) return rc;
+    if ((rc = launch_pf_refine(ctx, d, n_obj))) return rc;
     return mct_sync(ctx);     // the host noise buffer may be reused by the caller
 }
 
@@ -1322,6 +1357,28 @@ extern "C" int mct_pf_get_summary(mct_pf* p, mct_pf_summary* out)
     if ((rc = launch_pf_summary(ctx, d, 1, p->N))) return rc;
     MCT_CUDA(ctx, cudaMemcpyAsync(out, p->d_summ, sizeof(*out), cudaMemcpyDeviceToHost, ctx->stream));
     return mct_sync(ctx);
+}
+
+// read-outs of several objects of a camera: one launch, one synchronisation (Camera::StoreAllParticleFilterTrackerState)
+extern "C" int mct_pf_get_summary_many(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, mct_pf_summary* out)
+{
+    if (!ctx || n_obj < 1 || n_obj > DESC_MAX_OBJ || !pfs || !out) return MCT_E_ARG;
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    ObjDesc h[DESC_MAX_OBJ]; const ObjDesc* d;
+    int n_max = 0;
+    for (int o = 0; o < n_obj; o++) {
+        if (!pfs[o] || pfs[o]->ctx != ctx || !pfs[o]->initialized) return mct_fail(ctx, MCT_E_STATE, "particle filter not initialised%s");
+        memset(&h[o], 0, sizeof(ObjDesc)); fill_pf_desc(&h[o], pfs[o]);
+        h[o].summ = ctx->h_summ_dev + o;               // straight into mapped pinned memory
+        h[o].resample = 1;
+        if (pfs[o]->N > n_max) n_max = pfs[o]->N;
+    }
+    int rc;
+    if ((rc = desc_publish(ctx, h, n_obj, &d))) return rc;
+    if ((rc = launch_pf_summary(ctx, d, n_obj, n_max))) return rc;
+    if ((rc = mct_sync(ctx))) return rc;
+    memcpy(out, ctx->h_summ, sizeof(mct_pf_summary) * n_obj);
+    return MCT_OK;
 }
 
 extern "C" int mct_pf_get_last_response(mct_pf* p, float* out, int* valid)
@@ -1674,8 +1731,11 @@ static int train_stage_and_features(mct_ctx* ctx, int n_obj, mct_clf* const* clf
 // the feature rows of all objects' freshly generated training sets, computed in ONE batched pass under each object's global
 // classifier and written into the exchange buffer: object o at dev_rows + o * obj_stride floats, rows `ld` floats apart,
 // positives from column 0, negatives from column ld_pos.  Stream-ordered, no synchronisation; the box arrays may be reused.
+// reuse_pos_rows != NULL: rows of an earlier call (same layout) whose POSITIVE boxes were identical -- the learner rounds of one
+// frame regenerate the same positives and only re-thin the negative ring; the positive columns are then copied from there and
+// only the negative boxes go through the feature kernels.
 extern "C" int mct_train_features_many_dev(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, const mct_boxes* pos, const mct_boxes* neg,
-                                           float* dev_rows, size_t obj_stride, int ld, int ld_pos)
+                                           float* dev_rows, size_t obj_stride, int ld, int ld_pos, const float* reuse_pos_rows)
 {
     if (!ctx || n_obj < 1 || n_obj > DESC_MAX_OBJ || !clfs || !pos || !neg || !dev_rows || ld_pos < 1 || ld <= ld_pos) return MCT_E_ARG;
     for (int o = 0; o < n_obj; o++) {
@@ -1685,12 +1745,22 @@ extern "C" int mct_train_features_many_dev(mct_ctx* ctx, int n_obj, mct_clf* con
     }
     std::vector<int> creq;
     int rc;
-    if ((rc = train_stage_and_features(ctx, n_obj, clfs, pos, neg, creq))) return rc;
+    std::vector<mct_boxes> pos1;
+    if (reuse_pos_rows) {                       // one positive box keeps the staging / planning code on its usual path
+        pos1.assign(pos, pos + n_obj);
+        for (int o = 0; o < n_obj; o++) if (pos1[o].n > 1) pos1[o].n = 1;
+    }
+    const mct_boxes* pp = reuse_pos_rows ? pos1.data() : pos;
+    if ((rc = train_stage_and_features(ctx, n_obj, clfs, pp, neg, creq))) return rc;
     for (int o = 0; o < n_obj; o++) {
         mct_clf* c = clfs[o];
         float* base = dev_rows + (size_t)o * obj_stride;
-        MCT_CUDA(ctx, cudaMemcpy2DAsync(base, (size_t)ld * 4, c->d_featT, (size_t)c->ldT * 4, (size_t)pos[o].n * 4, c->F, cudaMemcpyDeviceToDevice, ctx->stream));
-        MCT_CUDA(ctx, cudaMemcpy2DAsync(base + ld_pos, (size_t)ld * 4, c->d_featT + pos[o].n, (size_t)c->ldT * 4, (size_t)neg[o].n * 4, c->F,
+        if (reuse_pos_rows)
+            MCT_CUDA(ctx, cudaMemcpy2DAsync(base, (size_t)ld * 4, reuse_pos_rows + (size_t)o * obj_stride, (size_t)ld * 4, (size_t)pos[o].n * 4, c->F,
+                                            cudaMemcpyDeviceToDevice, ctx->stream));
+        else
+            MCT_CUDA(ctx, cudaMemcpy2DAsync(base, (size_t)ld * 4, c->d_featT, (size_t)c->ldT * 4, (size_t)pos[o].n * 4, c->F, cudaMemcpyDeviceToDevice, ctx->stream));
+        MCT_CUDA(ctx, cudaMemcpy2DAsync(base + ld_pos, (size_t)ld * 4, c->d_featT + pp[o].n, (size_t)c->ldT * 4, (size_t)neg[o].n * 4, c->F,
                                         cudaMemcpyDeviceToDevice, ctx->stream));
     }
     return MCT_OK;

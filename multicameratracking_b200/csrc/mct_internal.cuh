@@ -230,6 +230,9 @@ struct StepArgs {
     float u01[DESC_MAX_OBJ];       // the randfloat() of ResampleParticles per object
 };
 
+// per-object arguments of the batched RearrangeParticlesBasedOnGroundLocation launch
+struct RearrangeArgs { float mfx[DESC_MAX_OBJ], mfy[DESC_MAX_OBJ]; long long noise_off[DESC_MAX_OBJ]; };
+
 // ------------------------------------------------------------------ error helpers
 extern char g_mct_err[512];
 static inline int mct_fail(mct_ctx* ctx, int code, const char* fmt, const char* a = "", int b = 0)
@@ -326,7 +329,7 @@ int launch_pf_refine(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj);
 int launch_foot_points_exchange(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, const float* d_h0, const P2PPeers& peers, int world, int rank,
                                 unsigned seq, unsigned* d_ticket, float* d_out, unsigned long long timeout_ns, int* d_status);
 int launch_response_argmax(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, void* d_out);
-int launch_pf_rearrange(mct_ctx* ctx, const ObjDesc* d_desc, int n_max, const float* d_noise2, float mfx, float mfy);
+int launch_pf_rearrange(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, const float* d_noise2, const RearrangeArgs& ra);
 int launch_ground_pdf(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, const GroundArgs* d_ga, float* d_wout, GroundOut* d_out);
 // fused predict + test set (+ per-frame reset of the MDCH fallback counters) for the batched per-frame path
 int launch_pf_predict_testset(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, const StepArgs& sa);

@@ -401,7 +401,7 @@ _AG_ROWS = C.CFUNCTYPE(None, C.c_void_p, C.c_size_t, C.c_void_p)
 
 
 class Exchange(C.Structure):
-    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("user", C.c_void_p), ("allgather_host", _AG_HOST), ("allgather_rows", _AG_ROWS)]
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("user", C.c_void_p), ("allgather_host", _AG_HOST), ("alltoall_rows", _AG_ROWS)]
 
 
 class Network:
@@ -411,7 +411,7 @@ class Network:
       camera_ids     their indices in the whole network (None: 0 .. len - 1)
       n_cameras      cameras in the whole network (None: len(cameras), i.e. everything lives in this process)
       homographies   [n_cameras][3][3] image -> ground plane (geometric fuser)
-      exchange       (rank, world, allgather_host(send_ptr, recv_ptr, nbytes), allgather_rows(nbytes, stream_ptr)) when the
+      exchange       (rank, world, allgather_host(send_ptr, recv_ptr, nbytes), alltoall_rows(slot_bytes, stream_ptr)) when the
                      network spans processes (one camera per process); see network.TorchExchange
     """
 

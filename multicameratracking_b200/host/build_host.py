@@ -25,7 +25,7 @@ def build(force=False):
                 return LIB
             gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
             tmp = LIB + ".tmp.%d" % os.getpid()
-            cmd = [gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", tmp] + SRC + [
+            cmd = [gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-pthread", "-o", tmp] + SRC + [
                 "-L" + PKG, "-l:libmct_b200.so", "-Wl,-rpath,$ORIGIN/.."]
             r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
             if r.returncode != 0:

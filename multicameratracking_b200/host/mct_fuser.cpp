@@ -1,7 +1,9 @@
 // mct_fuser.cpp -- see mct_fuser.h
 #include "mct_fuser.h"
 
+#include <algorithm>
 #include <cmath>
+#include <thread>
 #include <cstring>
 
 namespace Public {
@@ -224,11 +226,70 @@ void UpdateParticlesWithGroundPDF(mct_ctx* ctx, std::vector<ParticleFilterTracke
     for (int o = 0; o < n; o++) { pfs[o] = trackers[o]->GetParticleFilter()->Handle(); h0[o] = trackers[o]->GetCurrentTrackerState()[3]; }
     int rc = mct_fuser_ground_pdf(ctx, n, pfs.data(), H.data(), means, covs, h0.data(), res.data());
     if (rc) throw MctHostError(rc, mct_last_error(ctx));
+    // the host part of :1088-1105 per object; the objects that rearrange then go through ONE batched rearrangement pass and ONE
+    // batched re-scoring call (every object draws from its own MWC stream, so the order across objects is free)
+    std::vector<int> R;
+    std::vector<float> meanFoot, nz, w0v, h0v;
+    std::vector<size_t> nzAt;
+    const Homography Hinv = GeometryBasedInformationFuser::Invert(H);
     for (int o = 0; o < n; o++) {
-        float dist = -1.0f;
-        const bool r = feedback_after_pdf(ctx, trackers[o], res[o], means + 2 * o, H, &dist);
-        if (rearranged) rearranged[o] = r ? 1 : 0;
-        if (distances) distances[o] = dist;
+        ParticleFilterTracker* t = trackers[o];
+        const vectorf& cur = t->GetCurrentTrackerState();
+        if (rearranged) rearranged[o] = 0;
+        if (distances) distances[o] = -1.0f;
+        if (!(res[o].total_weight > 0.0)) continue;
+        double img[2];
+        GeometryBasedInformationFuser::TransformWithHomography(means + 2 * o, 1, Hinv, img);
+        const float mf[2] = {(float)img[0], (float)img[1]};
+        const float footX = res[o].average[0], footY = res[o].average[1] + cur[3] * res[o].average[3];
+        const double distance = std::sqrt(std::pow((double)(mf[0] - footX), 2) + std::pow((double)(footY - mf[1]), 2));
+        if (distances) distances[o] = (float)distance;
+        if (distance < 20) continue;
+        const int N = t->GetParticleFilter()->GetNumberOfParticles();
+        nzAt.push_back(nz.size());
+        nz.resize(nz.size() + (size_t)2 * N);
+        R.push_back(o); meanFoot.push_back(mf[0]); meanFoot.push_back(mf[1]); w0v.push_back(cur[2]); h0v.push_back(cur[3]);
+        if (rearranged) rearranged[o] = 1;
+    }
+    if (R.empty()) return;
+    const int m = (int)R.size();
+    // RearrangeParticlesBasedOnGroundLocation: (xRand, yRand) = randgaus(0, 10) per particle, in particle order, from the object's
+    // own MWC stream.  The polar method rejects a data-dependent number of draws, so a stream is sequential (~30 ns per value);
+    // the objects' streams are independent and are drawn side by side on host threads.
+    auto draw = [&](int k) {
+        ParticleFilterTracker* t = trackers[R[k]];
+        const int N = t->GetParticleFilter()->GetNumberOfParticles();
+        float* z = nz.data() + nzAt[k];
+        Public::SetCurrentRng(&t->Rng());
+        for (int r = 0; r < N; r++) { z[r] = Public::randgaus(0, 10.0f); z[(size_t)N + r] = Public::randgaus(0, 10.0f); }
+    };
+    {
+        const int nth = std::min(m, std::max(1, (int)std::thread::hardware_concurrency() / 8));
+        if (nth <= 1) for (int k = 0; k < m; k++) draw(k);
+        else {
+            std::vector<std::thread> th;
+            for (int q = 1; q < nth; q++) th.emplace_back([&, q] { for (int k = q; k < m; k += nth) draw(k); });
+            for (int k = 0; k < m; k += nth) draw(k);
+            for (std::thread& x : th) x.join();
+        }
+    }
+    std::vector<mct_pf*> rp(m); std::vector<mct_clf*> rc2(m); std::vector<mct_track_params> tp(m); std::vector<float> u01(m);
+    std::vector<mct_pf_summary> summ(m);
+    for (int k = 0; k < m; k++) {
+        ParticleFilterTracker* t = trackers[R[k]];
+        rp[k] = t->GetParticleFilter()->Handle(); rc2[k] = t->GetClassifier()->Handle();
+        tp[k].w0 = w0v[k]; tp[k].h0 = h0v[k]; tp[k].exponent = 1; tp[k].force_reset = 1; tp[k].resample = 1;
+        u01[k] = (float)(t->Rng().Peek() * 2.3283064365386962890625e-10);
+    }
+    rc = mct_pf_rearrange_ground_many(ctx, m, rp.data(), meanFoot.data(), nz.data(), w0v.data(), h0v.data());
+    if (rc) throw MctHostError(rc, mct_last_error(ctx));
+    // UpdateParticleWeightsForRearrangedParticles (:1334-1482): score in place, exponent 1, weights reset, resample
+    rc = mct_track_score(ctx, m, rp.data(), rc2.data(), tp.data(), nullptr, 0, u01.data(), summ.data());
+    if (rc) throw MctHostError(rc, mct_last_error(ctx));
+    for (int k = 0; k < m; k++) {
+        ParticleFilterTracker* t = trackers[R[k]];
+        if (summ[k].resampled) (void)t->Rng().Next();
+        t->GetParticleFilter()->AdoptSummary(summ[k]);
     }
 }
 }  // namespace MultipleCameraTracking

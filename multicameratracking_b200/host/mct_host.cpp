@@ -617,6 +617,17 @@ void ParticleFilterTracker::ScoreCameraObjectsAsync(mct_ctx* ctx, std::vector<Pa
     chk(ctx, mct_track_score_async(ctx, n, pfs.data(), clfs.data(), tp.data(), noiseDev, 1, u01.data()));
 }
 
+void ParticleFilterTracker::EnsureSummaries(mct_ctx* ctx, std::vector<ParticleFilterTracker*>& trackers)
+{
+    std::vector<mct_pf*> pfs; std::vector<ParticleFilterTracker*> who;
+    for (ParticleFilterTracker* t : trackers)
+        if (t->m_isInitialized && !t->m_particleFilterPtr->SummaryValid()) { pfs.push_back(t->m_particleFilterPtr->Handle()); who.push_back(t); }
+    if (pfs.empty()) return;
+    std::vector<mct_pf_summary> summ(pfs.size());
+    chk(ctx, mct_pf_get_summary_many(ctx, (int)pfs.size(), pfs.data(), summ.data()));
+    for (size_t k = 0; k < who.size(); k++) who[k]->m_particleFilterPtr->AdoptSummary(summ[k]);
+}
+
 void ParticleFilterTracker::TrackCameraObjects(mct_ctx* ctx, std::vector<ParticleFilterTracker*>& trackers, int frameind,
                                                Matrixu* pColor, Matrixu* pGray, Matrixu* pHSV, const float* noise, int phases)
 {
@@ -646,8 +657,12 @@ void ParticleFilterTracker::TrackCameraObjects(mct_ctx* ctx, std::vector<Particl
     }
     if (phases & 8) {
         // StoreAllParticleFilterTrackerState (Camera.cpp:556-574) after the fusers changed the particles on the device
+        // (one read-out launch and one synchronisation for all objects of the camera)
+        std::vector<mct_pf*> pfs(n); std::vector<mct_pf_summary> summ(n);
+        for (int o = 0; o < n; o++) pfs[o] = trackers[o]->m_particleFilterPtr->Handle();
+        chk(ctx, mct_pf_get_summary_many(ctx, n, pfs.data(), summ.data()));
         for (int o = 0; o < n; o++) {
-            trackers[o]->m_particleFilterPtr->Invalidate();
+            trackers[o]->m_particleFilterPtr->AdoptSummary(summ[o]);
             trackers[o]->StoreObjectState(frameind);
         }
     }
@@ -661,6 +676,7 @@ void ParticleFilterTracker::TrackCameraObjects(mct_ctx* ctx, std::vector<Particl
         static const bool timing = getenv("MCT_HOST_TIMING") != nullptr;
         static double t_gen = 0, t_upd = 0; static int t_calls = 0;
         const auto tp0 = std::chrono::steady_clock::now();
+        EnsureSummaries(ctx, trackers);
         // particle-reading strategies: one device pass for all objects of the camera that ask for it
         std::vector<int> rd; std::vector<mct_pf*> rpf; std::vector<mct_train_gen> rg;
         int cap = 1;

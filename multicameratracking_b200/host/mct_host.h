@@ -289,6 +289,7 @@ public:
     // the particles were changed on the device behind this object's back (fusers): read-outs are fetched again
     void Invalidate() { m_summaryValid = false; m_hostStateValid = false; }
     const mct_pf_summary& Summary();
+    bool SummaryValid() const { return m_summaryValid; }
 private:
     void FetchState();
     mct_ctx* m_ctx; mct_pf* m_pf;
@@ -383,6 +384,9 @@ public:
     // read-out lands in the ctx's pinned buffer (mct_track_collect).  The resampler draw is consumed
     // unconditionally, so this form is for throughput runs, not for parity runs.
     static void ScoreCameraObjectsAsync(mct_ctx* ctx, std::vector<ParticleFilterTracker*>& trackers, const float* noiseDev);
+    // the read-outs of all trackers whose particles changed on the device since the last one: ONE launch and ONE synchronisation
+    // instead of one of each per object (in front of loops that read the particle filters object by object)
+    static void EnsureSummaries(mct_ctx* ctx, std::vector<ParticleFilterTracker*>& trackers);
 private:
     mct_ctx* m_ctx;
     Public::RngStream m_rng;

@@ -389,7 +389,7 @@ struct mcth_exchange {
     int rank, world;
     void* user;
     void (*allgather_host)(void* user, const void* send, void* recv, size_t bytes);
-    void (*allgather_rows)(void* user, size_t bytes, void* stream);
+    void (*alltoall_rows)(void* user, size_t slot_bytes, void* stream);
 };
 namespace {
 struct CallbackExchange : public NetworkExchange {
@@ -398,7 +398,7 @@ struct CallbackExchange : public NetworkExchange {
     int Rank() const override { return e.rank; }
     int World() const override { return e.world; }
     void AllGatherHost(const void* send, void* recv, size_t bytes) override { e.allgather_host(e.user, send, recv, bytes); }
-    void AllGatherRows(size_t bytes, void* stream) override { e.allgather_rows(e.user, bytes, stream); }
+    void AllToAllRows(size_t slotBytes, void* stream) override { e.alltoall_rows(e.user, slotBytes, stream); }
 };
 }  // namespace
 struct mcth_network { CameraNetwork* net; CallbackExchange* ex; std::string err; };

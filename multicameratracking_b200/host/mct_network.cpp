@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "mct_host_c.h"
@@ -115,7 +117,7 @@ void CameraNetwork::InitializeCameraNetwork()
         if (!m_exchange) {
             m_sendRows.assign(m_cameras.size(), nullptr); m_recvRows.assign(m_cameras.size(), nullptr);
             for (size_t i = 0; i < m_cameras.size(); i++) {
-                chk(m_cameras[i]->ctx, mct_dev_alloc(m_cameras[i]->ctx, m_rowBytes, &m_sendRows[i]));
+                chk(m_cameras[i]->ctx, mct_dev_alloc(m_cameras[i]->ctx, m_rowBytes * m_numberOfCameras, &m_sendRows[i]));
                 chk(m_cameras[i]->ctx, mct_dev_alloc(m_cameras[i]->ctx, m_rowBytes * m_numberOfCameras, &m_recvRows[i]));
             }
             m_ownRowBuffers = true;
@@ -211,23 +213,43 @@ void CameraNetwork::ForceParticleResampling(int i)
 // CameraNetwork.cpp:589-600 -> Camera::LearnGlobalAppearanceModel (Camera.cpp:722-740) -> AppearanceBasedInformationFuser::
 // LearnGlobalAppearanceModel (:44-90).  The reference runs, for every learner camera c and object o, GenerateTrainingSampleSets-
 // ForAppearanceFusion over ALL cameras (CameraNetwork.cpp:276-320): every tracker regenerates its training sets once per learner
-// (the negative ring is thinned with fresh randfloat() draws each time).  One round per learner keeps that order: all cameras
-// regenerate and publish feature rows under the (identical) global feature definition, the learner pools them in camera order,
-// drops samples with its own draws (:66-82) and updates its global classifiers.
+// (the negative ring is thinned with fresh randfloat() draws each time), and the learner drops pooled samples with its own draws
+// (:66-82).  What orders the rounds is therefore the HOST side only (each tracker's MWC stream: regenerate, regenerate, ...,
+// with the drop draws of the round in which its camera learns in between); the device work of a round depends on nothing from
+// the other rounds.  So:
+//   round L = 0 .. C-1 : every camera regenerates its sets (host RNG) and launches the feature rows of all its objects into send
+//                        slot L (asynchronous); the (P, Nn) counts of the round go round (small host exchange); the learner
+//                        camera L draws its drop decisions (host RNG) and keeps the column offsets;
+//   then               : ONE all-to-all of the row buffers (camera c's slot L goes to camera L) and ONE batched Update of the
+//                        global classifiers per camera -- all cameras learn at the same time instead of one after the other.
 void CameraNetwork::LearnGlobalAppearanceModel()
 {
     const int n = m_numberOfObjects, F = m_afFeatures, C = m_numberOfCameras;
-    std::vector<int> counts((size_t)C * n * 2), mine((size_t)m_cameras.size() * n * 2);
+    const size_t nl = m_cameras.size();
+    const size_t slotFloats = (size_t)n * F * m_ldRow;                         // one camera's rows of one round
+    std::vector<int> counts((size_t)C * n * 2), mine(nl * n * 2);
+    struct LearnerPlan { std::vector<int> off, Pk, Nk; };
+    std::vector<LearnerPlan> plan(nl);
+    const bool batched = m_params.appearanceFusionType == 2;
+    // MCT_HOST_TIMING=1: where the host time of this stage goes (stderr, every 16 calls)
+    static const bool timing = getenv("MCT_HOST_TIMING") != nullptr;
+    static double tacc[6] = {0, 0, 0, 0, 0, 0}; static int tcalls = 0;
+    double tm = now_ms();
+    auto lap = [&](int k) { if (timing) { const double t = now_ms(); tacc[k] += t - tm; tm = t; } };
+    // positives of the first round per local camera: later rounds regenerate the same boxes (the tracker state does not change
+    // between the rounds and the positive strategy draws nothing unless it thins), which is checked, not assumed
+    std::vector<std::vector<vectori>> pc0(nl), pr0(nl);
+    std::vector<std::vector<vectorf>> psx0(nl), psy0(nl);
     for (int learner = 0; learner < C; learner++) {
-        // 1. every camera: GenerateTrainingSampleSet for every object (host: RNG order), feature rows of all objects into its send
-        //    buffer in one batched device pass
-        for (size_t i = 0; i < m_cameras.size(); i++) {
+        // 1. every camera: GenerateTrainingSampleSet for every object (host: RNG order), feature rows of all objects into send
+        //    slot `learner` in one batched device pass
+        for (size_t i = 0; i < nl; i++) {
             mcth_camera* cam = m_cameras[i];
             std::vector<vectori> pc(n), pr(n), nc(n), nr(n);
             std::vector<vectorf> psx(n), psy(n), nsx(n), nsy(n);
             std::vector<mct_boxes> pb(n), nb(n);
             std::vector<mct_clf*> gl(n);
-            bool batched = m_params.appearanceFusionType == 2;
+            ParticleFilterTracker::EnsureSummaries(cam->ctx, cam->trackers);
             for (int o = 0; o < n; o++) {
                 ParticleFilterTracker* t = cam->trackers[o];
                 t->GenerateTrainingSampleSet(&cam->frame, &cam->frame, &cam->frame);
@@ -239,9 +261,14 @@ void CameraNetwork::LearnGlobalAppearanceModel()
                 gl[o] = m_globalClassifiers[i][o]->Handle();
                 mine[(i * n + o) * 2] = P; mine[(i * n + o) * 2 + 1] = Nn;
             }
-            float* rows = (float*)m_sendRows[i];
+            lap(0);
+            float* rows = (float*)m_sendRows[i] + (size_t)learner * slotFloats;
             if (batched) {
-                chk(cam->ctx, mct_train_features_many_dev(cam->ctx, n, gl.data(), pb.data(), nb.data(), rows, (size_t)F * m_ldRow, m_ldRow, m_ldPos));
+                bool same = learner > 0;
+                if (learner == 0) { pc0[i] = pc; pr0[i] = pr; psx0[i] = psx; psy0[i] = psy; }
+                else for (int o = 0; o < n && same; o++) same = pc[o] == pc0[i][o] && pr[o] == pr0[i][o] && psx[o] == psx0[i][o] && psy[o] == psy0[i][o];
+                chk(cam->ctx, mct_train_features_many_dev(cam->ctx, n, gl.data(), pb.data(), nb.data(), rows, (size_t)F * m_ldRow, m_ldRow, m_ldPos,
+                                                          same ? (const float*)m_sendRows[i] : nullptr));
             } else {
                 for (int o = 0; o < n; o++) {
                     float* base = rows + (size_t)o * F * m_ldRow;
@@ -250,48 +277,67 @@ void CameraNetwork::LearnGlobalAppearanceModel()
                 }
             }
         }
-        // 2. rows and counts to the learner
+        lap(1);
+        // 2. the counts of the round to everybody (the learner needs them before its next regeneration)
+        if (m_exchange) m_exchange->AllGatherHost(mine.data(), counts.data(), (size_t)n * 2 * sizeof(int));
+        else for (size_t i = 0; i < nl; i++) std::memcpy(counts.data() + (size_t)m_cameraIds[i] * n * 2, mine.data() + i * n * 2, (size_t)n * 2 * sizeof(int));
+        lap(2);
         int li = -1;                                   // local index of the learner camera, if it lives here
-        for (size_t i = 0; i < m_cameras.size(); i++) if (m_cameraIds[i] == learner) li = (int)i;
-        if (m_exchange) {
-            m_exchange->AllGatherHost(mine.data(), counts.data(), (size_t)n * 2 * sizeof(int));
-            m_exchange->AllGatherRows(m_rowBytes, mct_ctx_stream(m_cameras[0]->ctx));
-        } else {
-            for (size_t i = 0; i < m_cameras.size(); i++) {
-                std::memcpy(counts.data() + (size_t)m_cameraIds[i] * n * 2, mine.data() + i * n * 2, (size_t)n * 2 * sizeof(int));
-                chk(m_cameras[i]->ctx, mct_sync(m_cameras[i]->ctx));
-                chk(m_cameras[li]->ctx, mct_dev_copy(m_cameras[li]->ctx, (char*)m_recvRows[li] + (size_t)m_cameraIds[i] * m_rowBytes, m_sendRows[i], m_rowBytes));
-            }
-        }
+        for (size_t i = 0; i < nl; i++) if (m_cameraIds[i] == learner) li = (int)i;
         if (li < 0) continue;
-        // 3. the learner: pooled order = positives of camera 0..C-1, then negatives of camera 0..C-1
+        // 3. the learner's drop rule: pooled order = positives of camera 0..C-1, then negatives of camera 0..C-1; offsets address
+        //    its receive buffer [camera][object][F][ldRow]
         mcth_camera* cam = m_cameras[li];
-        const size_t camStride = (size_t)n * F * m_ldRow;
-        std::vector<int> off, Pk(n), Nk(n);
-        std::vector<mct_clf*> gl(n);
+        LearnerPlan& lp = plan[li];
+        lp.Pk.assign(n, 0); lp.Nk.assign(n, 0);
         for (int o = 0; o < n; o++) {
             Public::SetCurrentRng(&cam->trackers[o]->Rng());
             int P = 0, Nn = 0;
             for (int c = 0; c < C; c++)
                 for (int s = 0; s < counts[((size_t)c * n + o) * 2]; s++)
-                    if (Public::randfloat() > 0.5f) { off.push_back((int)(c * camStride + (size_t)o * F * m_ldRow + s)); P++; }
+                    if (Public::randfloat() > 0.5f) { lp.off.push_back((int)(c * slotFloats + (size_t)o * F * m_ldRow + s)); P++; }
             for (int c = 0; c < C; c++)
                 for (int s = 0; s < counts[((size_t)c * n + o) * 2 + 1]; s++)
-                    if (Public::randfloat() > 0.5f) { off.push_back((int)(c * camStride + (size_t)o * F * m_ldRow + m_ldPos + s)); Nn++; }
+                    if (Public::randfloat() > 0.5f) { lp.off.push_back((int)(c * slotFloats + (size_t)o * F * m_ldRow + m_ldPos + s)); Nn++; }
             if (P < 1 || Nn < 1) throw MctHostError(MCT_E_EMPTY, "appearance fusion: every pooled sample of a class was dropped");
-            Pk[o] = P; Nk[o] = Nn; gl[o] = m_globalClassifiers[li][o]->Handle();
+            lp.Pk[o] = P; lp.Nk[o] = Nn;
             m_globalTrained[li][o] = 1;
         }
-        if (m_params.appearanceFusionType == 2) {
-            chk(cam->ctx, mct_track_update_from_gathered(cam->ctx, n, gl.data(), (const float*)m_recvRows[li], off.data(), m_ldRow, Pk.data(), Nk.data()));
+    }
+    lap(3);
+    // 4. rows to their learners
+    if (m_exchange) {
+        m_exchange->AllToAllRows(m_rowBytes, mct_ctx_stream(m_cameras[0]->ctx));
+    } else {
+        for (size_t i = 0; i < nl; i++) chk(m_cameras[i]->ctx, mct_sync(m_cameras[i]->ctx));
+        for (size_t li = 0; li < nl; li++)
+            for (size_t i = 0; i < nl; i++)
+                chk(m_cameras[li]->ctx, mct_dev_copy(m_cameras[li]->ctx, (char*)m_recvRows[li] + (size_t)m_cameraIds[i] * m_rowBytes,
+                                                     (char*)m_sendRows[i] + (size_t)m_cameraIds[li] * m_rowBytes, m_rowBytes));
+    }
+    lap(4);
+    // 5. every local camera updates its global classifiers (one batched pass per camera, the cameras side by side)
+    for (size_t li = 0; li < nl; li++) {
+        mcth_camera* cam = m_cameras[li];
+        LearnerPlan& lp = plan[li];
+        std::vector<mct_clf*> gl(n);
+        for (int o = 0; o < n; o++) gl[o] = m_globalClassifiers[li][o]->Handle();
+        if (batched) {
+            chk(cam->ctx, mct_track_update_from_gathered(cam->ctx, n, gl.data(), (const float*)m_recvRows[li], lp.off.data(), m_ldRow, lp.Pk.data(), lp.Nk.data()));
         } else {
             size_t at = 0;
             for (int o = 0; o < n; o++) {
-                chk(cam->ctx, mct_classifier_update_from_gathered(gl[o], (const float*)m_recvRows[li], off.data() + at, m_ldRow, Pk[o], Nk[o]));
-                at += (size_t)Pk[o] + Nk[o];
+                chk(cam->ctx, mct_classifier_update_from_gathered(gl[o], (const float*)m_recvRows[li], lp.off.data() + at, m_ldRow, lp.Pk[o], lp.Nk[o]));
+                at += (size_t)lp.Pk[o] + lp.Nk[o];
             }
         }
-        chk(cam->ctx, mct_sync(cam->ctx));             // the offsets above are host vectors
+    }
+    for (size_t li = 0; li < nl; li++) chk(m_cameras[li]->ctx, mct_sync(m_cameras[li]->ctx));      // the offsets above are host vectors
+    lap(5);
+    if (timing && ++tcalls == 16) {
+        fprintf(stderr, "LearnGlobalAppearanceModel host ms per frame: training sets %.3f, feature-row launches %.3f, counts exchange %.3f, drop rule %.3f, "
+                        "row exchange %.3f, update + drain %.3f\n", tacc[0] / 16, tacc[1] / 16, tacc[2] / 16, tacc[3] / 16, tacc[4] / 16, tacc[5] / 16);
+        tcalls = 0; for (double& x : tacc) x = 0;
     }
 }
 

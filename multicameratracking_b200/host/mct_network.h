@@ -48,9 +48,10 @@ public:
     virtual int World() const = 0;
     // recv = [World][bytes] in rank order; host memory
     virtual void AllGatherHost(const void* send, void* recv, size_t bytes) = 0;
-    // all-gather of the device row buffers registered with CameraNetwork::SetRowBuffers (send -> recv[World][bytes]);
-    // must be ordered after the work already enqueued on `stream` and complete (or stream-ordered) when it returns
-    virtual void AllGatherRows(size_t bytes, void* stream) = 0;
+    // all-to-all of the device row buffers registered with CameraNetwork::SetRowBuffers, both [World][slotBytes]:
+    // recv slot c = camera c's send slot Rank().  Must be ordered after the work already enqueued on `stream` and complete
+    // (or stream-ordered) when it returns
+    virtual void AllToAllRows(size_t slotBytes, void* stream) = 0;
 };
 
 class CameraNetwork {
@@ -66,7 +67,7 @@ public:
     // :537-613.  noise[i]: prediction noise of local camera i, host [n_obj][4][N].  The cameras' frames are already set.
     void TrackObjectsOnCurrentFrame(int frameIndex, const float* const* noise);
     // multi-process runs with a collective library: the embedding owns the exchange buffers (e.g. torch tensors for NCCL)
-    size_t RowBufferBytes() const { return m_rowBytes; }
+    size_t RowBufferBytes() const { return m_rowBytes * (size_t)m_numberOfCameras; }     // of EACH of the two buffers
     void SetRowBuffers(void* sendDev, void* recvDev);
 
     // introspection (parity tests)
@@ -93,8 +94,9 @@ private:
     std::vector<std::vector<Classifier::StrongClassifierBasePtr>> m_globalClassifiers;        // [local camera][object]
     std::vector<std::vector<char>> m_globalTrained;
     std::vector<std::vector<int>> m_lastRearranged;
-    // appearance-fuser exchange buffers: per camera [object][F][ldRow] feature rows (positives from column 0, negatives from
-    // column ldPos), and the (P, Nn) counts
+    // appearance-fuser exchange buffers, per local camera [numberOfCameras slots][object][F][ldRow] feature rows (positives from
+    // column 0, negatives from column ldPos).  Send slot L = this camera's rows of learner round L; receive slot c = camera c's
+    // rows of the round in which THIS camera learns.  m_rowBytes = bytes of one slot.
     int m_afFeatures, m_ldPos, m_ldRow;
     size_t m_rowBytes;
     std::vector<void*> m_sendRows, m_recvRows;             // per local camera (device)

@@ -219,7 +219,7 @@ class TorchExchange:
         self.send = self.recv = None
 
     def as_tuple(self):
-        return (self.rank, self.world, self.allgather_host, self.allgather_rows)
+        return (self.rank, self.world, self.allgather_host, self.alltoall_rows)
 
     def allgather_host(self, send_ptr, recv_ptr, nbytes):
         import ctypes as C
@@ -244,14 +244,23 @@ class TorchExchange:
         n = network.row_bytes()
         if n == 0:
             return
+        # both buffers hold one slot per camera: send slot L = this camera's rows of learner round L, recv slot c = camera c's rows
+        # of the round in which this camera learns
         self.send = torch.empty(n, dtype=torch.uint8, device=self.device)
-        self.recv = torch.empty(n * self.world, dtype=torch.uint8, device=self.device)
+        self.recv = torch.empty(n, dtype=torch.uint8, device=self.device)
         network.set_row_buffers(self.send.data_ptr(), self.recv.data_ptr())
 
-    def allgather_rows(self, nbytes, stream_ptr):
+    def alltoall_rows(self, slot_bytes, stream_ptr):
+        """recv slot c <- camera c's send slot `rank`: one collective per frame for the appearance fuser's feature rows"""
         if self.cuda:
             st = torch.cuda.ExternalStream(int(stream_ptr))
             with torch.cuda.stream(st):
-                dist.all_gather_into_tensor(self.recv, self.send, group=self.group)     # ordered on the camera's own stream
+                dist.all_to_all_single(self.recv, self.send, group=self.group)          # ordered on the camera's own stream
         else:
-            dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+            # gloo has no all-to-all: gather everything and keep the slots addressed to this rank (CPU tests, small worlds)
+            slot = int(slot_bytes)
+            full = torch.empty(self.send.numel() * self.world, dtype=torch.uint8)
+            dist.all_gather_into_tensor(full, self.send, group=self.group)
+            per = self.send.numel()
+            for c in range(self.world):
+                self.recv[c * slot:(c + 1) * slot] = full[c * per + self.rank * slot: c * per + (self.rank + 1) * slot]

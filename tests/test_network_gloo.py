@@ -233,7 +233,7 @@ def _torch_exchange_worker(rank, world, port, q):
         import ctypes as C
         from multicameratracking_b200.network import TorchExchange
         ex = TorchExchange()
-        r, w, ag_host, ag_rows = ex.as_tuple()
+        r, w, ag_host, a2a_rows = ex.as_tuple()
         assert (r, w) == (rank, world)
         # host payload through raw pointers, as the C++ CameraNetwork calls it (foot points: 8 objects x 2 floats; counts)
         for n in (64, 24):
@@ -243,15 +243,17 @@ def _torch_exchange_worker(rank, world, port, q):
             for k in range(world):
                 assert np.array_equal(recv[k * n:(k + 1) * n], (np.arange(n, dtype=np.uint8) + 100 * k).astype(np.uint8))
         # feature rows: the exchange owns the buffers and hands their addresses to the network
-        net = _StandInNetwork(4096)
+        slot = 2048
+        net = _StandInNetwork(slot * world)
         ex.bind_rows(net)
         assert net.ptrs == (ex.send.data_ptr(), ex.recv.data_ptr())
-        rows = np.full(4096, rank + 1, np.uint8)
-        C.memmove(net.ptrs[0], rows.ctypes.data, 4096)
-        ag_rows(4096, 0)
-        got = np.frombuffer((C.c_uint8 * (4096 * world)).from_address(net.ptrs[1]), np.uint8)
-        for k in range(world):
-            assert (got[k * 4096:(k + 1) * 4096] == k + 1).all()
+        # send slot L carries (rank, L); after the all-to-all recv slot c must carry (c, rank)
+        rows = np.concatenate([np.full(slot, 16 * rank + L, np.uint8) for L in range(world)])
+        C.memmove(net.ptrs[0], rows.ctypes.data, slot * world)
+        a2a_rows(slot, 0)
+        got = np.frombuffer((C.c_uint8 * (slot * world)).from_address(net.ptrs[1]), np.uint8)
+        for c in range(world):
+            assert (got[c * slot:(c + 1) * slot] == 16 * c + rank).all()
         q.put((rank, "ok"))
     except BaseException as e:           # noqa: BLE001
         q.put((rank, "FAIL %r" % (e,)))
