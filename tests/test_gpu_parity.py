@@ -720,6 +720,76 @@ def test_fused_cfg4_shape_720p_mdch_anyboost(ctx, oracle):
     _score_and_compare(ctx, oracle, seq, 1280, 720, specs, N=400, sd=(20.0, 20.0, 1e-7, 1e-7), frames=(1,))
 
 
+def test_selected_count_clamp_matches_oracle(ctx, oracle):
+    """StrongClassifierBase.cpp:20-23: a selected count outside [1, F] becomes F / 2 (mct_classifier_create); the selector lists of
+    the first Update then equal the oracle's, which is pinned to the reference build on this"""
+    seq = synth.Sequence(640, 480, 1)
+    F = 40
+    t, arrs = haar_table(oracle, F, seq.w0, seq.h0)
+    gray, r, g, b = seq.frame(0)
+    ctx.frame_set(gray, r, g, b)
+    of = oracle.frame(gray, r, g, b)
+    pos, neg = _train_sets(oracle, seq, 0, 0, seed=3)
+    for K in (0, F + 7, F):
+        clf = capi.StrongClassifier(ctx, capi.FEAT_HAAR, seq.w0, seq.h0, n_haar=F, n_selected=K, haar=arrs)
+        oclf = oracle.clf_create(capi.FEAT_HAAR, F, 8, seq.w0, seq.h0, 0, 2, K, 0.85, t)
+        clf.Update(capi.make_boxes(*pos), capi.make_boxes(*neg))
+        oracle.clf_update(oclf, of, oracle.boxes(*pos), oracle.boxes(*neg))
+        got, want = clf.selectors().tolist(), oracle.clf_selectors(oclf).tolist()
+        assert got == want, K
+        assert len(got) <= (F if K == F else F // 2)
+        clf.close(); oracle.lib.orc_clf_free(oclf)
+
+
+def test_fused_sequence_without_reseeding(ctx, oracle):
+    """four frames of the fused scoring path with NO hand-over of the oracle's state between the frames: the GPU particle filter
+    runs on its own results.  Contract: positions / scales and resample decisions are exact as long as
+    the resample index lists agree (they do here), weights agree to 2e-4 of the largest weight (a 1e-5 response error passes
+    through the ^20 likelihood map), classifier responses to 1e-5 of the largest response."""
+    seq = synth.Sequence(640, 480, 2)
+    w0, h0, N, F, K = seq.w0, seq.h0, 1500, 120, 40
+    t, arrs = haar_table(oracle, F, w0, h0)
+    gray, r, g, b = seq.frame(0)
+    ctx.frame_set(gray, r, g, b)
+    of = oracle.frame(gray, r, g, b)
+    clfs, oclfs, pfs, opfs = [], [], [], []
+    for o, ft in enumerate((capi.FEAT_HAAR, capi.FEAT_HAAR_MDCH)):
+        clf = capi.StrongClassifier(ctx, ft, w0, h0, n_haar=F, n_bins=8, n_selected=K, haar=arrs)
+        oclf = oracle.clf_create(ft, F, 8, w0, h0, 0, 2, K, 0.85, t)
+        pos, neg = _train_sets(oracle, seq, 0, o, seed=o + 1)
+        clf.Update(capi.make_boxes(*pos), capi.make_boxes(*neg))
+        oracle.clf_update(oclf, of, oracle.boxes(*pos), oracle.boxes(*neg))
+        x, y, w, h = seq.box(0, o)
+        pf, opf = _pf_pair(ctx, oracle, N, cx=x + w / 2, cy=y + h / 2)
+        clfs.append(clf); oclfs.append(oclf); pfs.append(pf); opfs.append(opf)
+    for frame in range(1, 5):
+        gray, r, g, b = seq.frame(frame)
+        ctx.frame_set(gray, r, g, b)
+        of = oracle.frame(gray, r, g, b)
+        nz = np.stack([synth.noise(N, (20, 20, 1e-7, 1e-7), obj=o, t=frame) for o in range(2)])
+        u01 = [oracle.randfloat(oracle.rng(900 + o + 10 * frame)) for o in range(2)]
+        rngs = [oracle.rng(900 + o + 10 * frame) for o in range(2)]
+        summ = capi.track_score(ctx, pfs, clfs, [(w0, h0, 20, 0, 1)] * 2, nz, u01)
+        for o in range(2):
+            opf = opfs[o]
+            oracle.lib.orc_pf_predict(opf, nz[o].ctypes.data_as(C.POINTER(C.c_float)), w0, h0)
+            col, row, sx, sy = oracle.pf_test_set(opf, w0, h0, 640, 480)
+            Ho = oracle.clf_classify(oclfs[o], of, oracle.boxes(col, row, sx, sy))
+            Hg, valid = pfs[o].last_response()
+            assert int(valid.sum()) == len(col) == summ[o].n_valid, (frame, o)
+            rel_close(Hg[valid != 0], Ho)
+            prob = oracle.likelihood_map(Ho, 20)
+            res = oracle.lib.orc_pf_update_all_weights(opf, prob.ctypes.data_as(C.POINTER(C.c_float)), 1, 0, 1, C.byref(rngs[o]))
+            assert bool(res) == bool(summ[o].resampled), (frame, o)
+            sg, so = pfs[o].state(), oracle.pf_state(opf)
+            np.testing.assert_array_equal(sg[:, :4], so[:, :4], err_msg="frame %d object %d" % (frame, o))
+            rel_close(sg[:, 4], so[:, 4], rtol=2e-4, scale=so[:, 4].max())
+    for x in clfs + pfs:
+        x.close()
+    for oc in oclfs:
+        oracle.lib.orc_clf_free(oc)
+
+
 def test_two_devices_in_one_process(ctx, oracle):
     """ctxs on devices 0 and 1 of ONE process are independent: function attributes (opt-in shared memory of
     k_mdch_sel / k_classify_staged / k_frame_prep, cluster sizes) and the __constant__ HSV tables are kept per device.
@@ -748,23 +818,31 @@ def test_two_devices_in_one_process(ctx, oracle):
 
 def test_fused_cfg2_full_size_properties(ctx, oracle):
     """BASELINE configs[1] at full size (8 objects x 2000 particles, Haar(250)+MDCH(512) -> 152, WeightedStumps): the
-    response of one object is compared with the oracle; all objects are checked through size-independent properties"""
+    responses, resample decisions and states of ALL eight objects are compared with the oracle (its OpenMP build when present);
+    size-independent properties on top"""
+    try:
+        from oracle.oracle_py import Oracle
+        import os as _os
+        oracle = Oracle(omp=True)
+        oracle.lib.orc_clf_set_threads(_os.cpu_count() or 1)
+    except OSError:
+        pass
     seq = synth.Sequence(640, 480, 8)
     w0, h0, N, F, K = seq.w0, seq.h0, 2000, 250, 152
     t, arrs = haar_table(oracle, F, w0, h0)
     gray, r, g, b = seq.frame(0)
     ctx.frame_set(gray, r, g, b)
     of = oracle.frame(gray, r, g, b)
-    clfs, pfs = [], []
-    oclf0 = oracle.clf_create(capi.FEAT_HAAR_MDCH, F, 8, w0, h0, capi.WEAK_WSTUMP, capi.STRONG_MILBOOST, K, 0.85, t)
+    clfs, pfs, oclfs = [], [], []
     for o in range(8):
         clf = capi.StrongClassifier(ctx, capi.FEAT_HAAR_MDCH, w0, h0, n_haar=F, n_bins=8, weak_type=capi.WEAK_WSTUMP,
                                     strong_type=capi.STRONG_MILBOOST, n_selected=K, haar=arrs)
         pos, neg = _train_sets(oracle, seq, 0, o, seed=o + 1)
         clf.Update(capi.make_boxes(*pos), capi.make_boxes(*neg))
-        if o == 0:
-            oracle.clf_update(oclf0, of, oracle.boxes(*pos), oracle.boxes(*neg))
-            assert clf.selectors().tolist() == oracle.clf_selectors(oclf0).tolist()
+        oclf = oracle.clf_create(capi.FEAT_HAAR_MDCH, F, 8, w0, h0, capi.WEAK_WSTUMP, capi.STRONG_MILBOOST, K, 0.85, t)
+        oracle.clf_update(oclf, of, oracle.boxes(*pos), oracle.boxes(*neg))
+        assert clf.selectors().tolist() == oracle.clf_selectors(oclf).tolist(), o
+        oclfs.append(oclf)
         x, y, w, h = seq.box(0, o)
         pf = capi.ParticleFilter(ctx, N, 640, 480); pf.Initialize(x + w / 2, y + h / 2)
         clfs.append(clf); pfs.append(pf)
@@ -772,17 +850,26 @@ def test_fused_cfg2_full_size_properties(ctx, oracle):
     ctx.frame_set(gray, r, g, b)
     of = oracle.frame(gray, r, g, b)
     nz = np.stack([synth.noise(N, (20, 20, 1e-7, 1e-7), obj=o, t=1) for o in range(8)])
-    summ = capi.track_score(ctx, pfs, clfs, [(w0, h0, 20, 0, 1)] * 8, nz, [0.1 * (o + 1) for o in range(8)])
-    # object 0 against the oracle
-    opf = oracle.pf_create(N, 640, 480)
-    x, y, w, h = seq.box(0, 0)
-    oracle.lib.orc_pf_initialize(opf, x + w / 2, y + h / 2, 1, 1, 0.5, 10, 0.1)
-    oracle.lib.orc_pf_predict(opf, nz[0].ctypes.data_as(C.POINTER(C.c_float)), w0, h0)
-    col, row, sx, sy = oracle.pf_test_set(opf, w0, h0, 640, 480)
-    Ho = oracle.clf_classify(oclf0, of, oracle.boxes(col, row, sx, sy))
-    Hg, valid = pfs[0].last_response()
-    assert int(valid.sum()) == len(col) == summ[0].n_valid
-    rel_close(Hg[valid != 0], Ho)
+    u01 = [oracle.randfloat(oracle.rng(40 + o)) for o in range(8)]
+    summ = capi.track_score(ctx, pfs, clfs, [(w0, h0, 20, 0, 1)] * 8, nz, u01)
+    # every object against the oracle: response, resample decision, particle state
+    for o in range(8):
+        opf = oracle.pf_create(N, 640, 480)
+        x, y, w, h = seq.box(0, o)
+        oracle.lib.orc_pf_initialize(opf, x + w / 2, y + h / 2, 1, 1, 0.5, 10, 0.1)
+        oracle.lib.orc_pf_predict(opf, nz[o].ctypes.data_as(C.POINTER(C.c_float)), w0, h0)
+        col, row, sx, sy = oracle.pf_test_set(opf, w0, h0, 640, 480)
+        Ho = oracle.clf_classify(oclfs[o], of, oracle.boxes(col, row, sx, sy))
+        Hg, valid = pfs[o].last_response()
+        assert int(valid.sum()) == len(col) == summ[o].n_valid, o
+        rel_close(Hg[valid != 0], Ho)
+        prob = oracle.likelihood_map(Ho, 20)
+        rr = oracle.rng(40 + o)
+        res = oracle.lib.orc_pf_update_all_weights(opf, prob.ctypes.data_as(C.POINTER(C.c_float)), 1, 0, 1, C.byref(rr))
+        assert bool(res) == bool(summ[o].resampled), o
+        sg, so = pfs[o].state(), oracle.pf_state(opf)
+        np.testing.assert_array_equal(sg[:, :4], so[:, :4], err_msg="object %d" % o)
+        rel_close(sg[:, 4], so[:, 4], rtol=2e-4, scale=so[:, 4].max())
     # every object: properties that do not depend on the size
     for o in range(8):
         st = pfs[o].state()
@@ -798,7 +885,8 @@ def test_fused_cfg2_full_size_properties(ctx, oracle):
         assert 1 <= summ[o].n_unique <= N
     for x in clfs + pfs:
         x.close()
-    oracle.lib.orc_clf_free(oclf0)
+    for oc in oclfs:
+        oracle.lib.orc_clf_free(oc)
 
 
 def test_edge_cases_errors_and_empty_inputs(ctx, oracle):

@@ -129,6 +129,49 @@ def test_single_call_frame_step_equals_separate_calls():
 
 
 
+def test_free_running_score_path_equals_track_up_to_the_unconditional_draw():
+    """ScoreCameraObjectsAsync (the free-running, device-resident leg bench.py times as `value`) draws the resampler's randfloat()
+    for every frame without waiting for the read-out; TrackCameraObjects draws it only when the frame resampled.  That draw is
+    the ONLY difference: with one extra randfloat() consumed on the synchronous side after every frame that did not resample,
+    the two paths agree bit for bit (particles and RNG state) over a sequence with both kinds of frames."""
+    import torch
+    n_frames, n_obj = 7, 3
+    seq = synth.Sequence(640, 480, n_obj, n_frames=n_frames)
+    over = dict(feature_type=3, weak_type=1, n_particles=700, n_haar=80)
+    p = dict(mhost.DEFAULTS); p.update(over)
+    cams = []
+    for _ in range(2):
+        cam = mhost.Camera(0, n_frames)
+        cam.set_frame(*seq.frame(0))
+        for o in range(n_obj):
+            cam.add_object(seq.box(0, o), rng_seed=o + 1, **over)
+        cam.init_trackers()
+        cams.append(cam)
+    N = p["n_particles"]
+    kinds = set()
+    for t in range(1, n_frames):
+        fr = [np.ascontiguousarray(x) for x in seq.frame(t)]
+        nz = np.stack([synth.noise(N, (p["sd_x"], p["sd_y"], p["sd_sx"], p["sd_sy"]), obj=o, t=t) for o in range(n_obj)])
+        cams[0].set_frame(*fr)
+        cams[0].track(t, nz, 1)
+        cams[1].set_frame(*fr)
+        nzd = torch.from_numpy(nz).cuda()
+        torch.cuda.synchronize()
+        cams[1]._chk(cams[1].L.mcth_camera_track_resident(cams[1].h, t, C.c_void_p(nzd.data_ptr())))
+        cams[1].sync()
+        for o in range(n_obj):
+            a, b = cams[0].particles(o), cams[1].particles(o)
+            np.testing.assert_array_equal(a, b)
+            resampled = bool((a[:, 4] == 1).all())
+            kinds.add(resampled)
+            if not resampled:
+                cams[0].randfloat(o)                     # the draw the free-running path spent on this frame anyway
+            assert cams[0].rng_state(o) == cams[1].rng_state(o), (t, o)
+    assert True in kinds, "no frame resampled: the test does not cover the draw"
+    for cam in cams:
+        cam.close()
+
+
 def test_geometric_fusion_feedback_two_cameras(oracle):
     """Geometric fusion end to end for two cameras (both on this GPU, standing in for two ranks): per frame the foot
     points are packed on the device, the per-object fuser (principal-axis intersection + Kalman) runs on the host, and the
