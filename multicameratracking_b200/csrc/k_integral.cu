@@ -135,9 +135,17 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 #define PREP_STAMP(k)
 #endif
 
+// flag words of k_frame_prep, one per 128-byte line: [256] band flags, [32] group flags, the ticket and the done counter
+#define PREP_GROUP 8
+#define PREP_CPT 4                // columns per thread whose loads are in flight together
+#define PREP_BAND_FLAG(b) ((b) * 32)
+#define PREP_GROUP_FLAG(g) ((256 + (g)) * 32)
+#define PREP_TICKET (288 * 32)
+#define PREP_DONE (289 * 32)
+#define PREP_FLAG_WORDS (290 * 32)
 struct PrepArgs {
     const uint8_t* gray; int W, H, pitch, BH, n_bands;
-    uint32_t* bandtot; unsigned* flags; unsigned epoch; float* ii; int iip;
+    uint32_t* bandtot; uint32_t* grptot; unsigned* flags; unsigned epoch; float* ii; int iip;
     const uint8_t* c0; const uint8_t* c1; const uint8_t* c2; int nb; int bw_shift; uint16_t* binimg; int n_binblocks;
 };
 
@@ -150,7 +158,7 @@ __global__ void __launch_bounds__(512) k_frame_prep(const PrepArgs a)
     // Work is handed out in ARRIVAL order (ticket counter), so the band that gets ticket b knows that every band
     // < b is held by a CTA that is already running: the waits below cannot deadlock whatever the dispatch order or
     // residency, and no cooperative launch is needed.  The last CTA to finish resets the two counters.
-    if (tid == 0) s_ticket = (int)atomicAdd(a.flags + 256, 1u);
+    if (tid == 0) s_ticket = (int)atomicAdd(a.flags + PREP_TICKET, 1u);
     __syncthreads();
     const int ticket = s_ticket;
     PREP_STAMP(0);
@@ -174,7 +182,7 @@ __global__ void __launch_bounds__(512) k_frame_prep(const PrepArgs a)
         }
         __syncthreads();
         PREP_STAMP(4);
-        if (tid == 0 && atomicAdd(a.flags + 257, 1u) == gridDim.x - 1) { a.flags[256] = 0; a.flags[257] = 0; }
+        if (tid == 0 && atomicAdd(a.flags + PREP_DONE, 1u) == gridDim.x - 1) { a.flags[PREP_TICKET] = 0; a.flags[PREP_DONE] = 0; }
         return;
     }
     const int b = ticket, BH = a.BH;
@@ -250,28 +258,78 @@ __global__ void __launch_bounds__(512) k_frame_prep(const PrepArgs a)
     }
     __threadfence();
     __syncthreads();
-    if (tid == 0) st_release_u32(a.flags + b, a.epoch);
+    if (tid == 0) st_release_u32(a.flags + PREP_BAND_FLAG(b), a.epoch);
     PREP_STAMP(2);
-    // (3) wait for every band above (all CTAs are co-resident: cooperative launch)
-    for (int t = tid; t < b; t += nt) { while (ld_acquire_u32(a.flags + t) != a.epoch) { } }
+    // (3) Two levels instead of "every band sums every band above it" (B^2 / 2 rows of totals read from L2, 59 dependent-ish loads
+    //     for the last band at VGA, 67 at 1080p): bands form groups of PREP_GROUP; the LAST band of a group adds up the group's
+    //     totals and publishes them; a band's base = the totals of the groups in front of its own + the totals of the bands in
+    //     front of it inside its group: at most (PREP_GROUP - 1) + n_groups rows.  Every wait is for a lower ticket (bands in
+    //     front, leaders of groups in front), so the arrival-order argument above still holds.  Flags live 128 bytes apart and
+    //     are polled by one lane each with a back-off: the former all-threads spin on two cache lines delayed the very stores it
+    //     was waiting for (5 us between the last publication and the first waiter getting through at VGA).
+    const int g = b / PREP_GROUP, first = g * PREP_GROUP, last = min(first + PREP_GROUP, a.n_bands) - 1;
+    if (tid < b - first) { while (ld_acquire_u32(a.flags + PREP_BAND_FLAG(first + tid)) != a.epoch) __nanosleep(40); }
+    __syncthreads();
+    if (b == last) {
+        uint32_t* gt = a.grptot + (size_t)g * W;
+        // (all loads of a thread's columns are issued before any is used: one round trip to L2 per wait level, not one per column)
+        for (int c0 = tid; c0 < W; c0 += PREP_CPT * nt) {
+            uint32_t v[PREP_CPT][PREP_GROUP - 1];
+#pragma unroll
+            for (int k = 0; k < PREP_CPT; k++)
+#pragma unroll
+                for (int bb = 0; bb < PREP_GROUP - 1; bb++) {
+                    const int c = c0 + k * nt;
+                    v[k][bb] = (c < W && first + bb < b) ? __ldcg(a.bandtot + (size_t)(first + bb) * W + c) : 0u;
+                }
+#pragma unroll
+            for (int k = 0; k < PREP_CPT; k++) {
+                const int c = c0 + k * nt;
+                if (c >= W) continue;
+                uint32_t acc = rp[(size_t)(nr - 1) * W + c];              // own total
+#pragma unroll
+                for (int bb = 0; bb < PREP_GROUP - 1; bb++) acc += v[k][bb];
+                gt[c] = acc;
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) st_release_u32(a.flags + PREP_GROUP_FLAG(g), a.epoch);
+    }
+    for (int t = tid; t < g; t += nt) { while (ld_acquire_u32(a.flags + PREP_GROUP_FLAG(t)) != a.epoch) __nanosleep(40); }
     __syncthreads();
     PREP_STAMP(3);
-    // (4) base = totals of the bands above; store f32(base + local); a warp writes 32 consecutive columns of a row
+    // (4) store f32(base + local); a warp writes 32 consecutive columns of a row
     float* ii = a.ii;
     const int iip = a.iip;
-    for (int c = tid; c < W; c += nt) {
-        uint32_t base = 0;
+    for (int c0 = tid; c0 < W; c0 += PREP_CPT * nt) {
+        uint32_t base[PREP_CPT];
+#pragma unroll
+        for (int k = 0; k < PREP_CPT; k++) {
+            const int c = c0 + k * nt;
+            uint32_t acc = 0;
+            if (c < W) {
 #pragma unroll 8
-        for (int bb = 0; bb < b; bb++) base += __ldcg(a.bandtot + (size_t)bb * W + c);
-        for (int r = 0; r < nr; r++)
-            ii[(size_t)(r0 + r + 1) * iip + c + 1] = __uint2float_rn(base + rp[(size_t)r * W + c]);
+                for (int gg = 0; gg < g; gg++) acc += __ldcg(a.grptot + (size_t)gg * W + c);
+#pragma unroll
+                for (int bb = 0; bb < PREP_GROUP - 1; bb++) if (first + bb < b) acc += __ldcg(a.bandtot + (size_t)(first + bb) * W + c);
+            }
+            base[k] = acc;
+        }
+#pragma unroll
+        for (int k = 0; k < PREP_CPT; k++) {
+            const int c = c0 + k * nt;
+            if (c >= W) continue;
+            for (int r = 0; r < nr; r++)
+                ii[(size_t)(r0 + r + 1) * iip + c + 1] = __uint2float_rn(base[k] + rp[(size_t)r * W + c]);
+        }
     }
     for (int r = tid; r < nr; r += nt) ii[(size_t)(r0 + r + 1) * iip] = 0.0f;
     if (b == 0)
         for (int c = tid; c <= W; c += nt) ii[c] = 0.0f;
     __syncthreads();
     PREP_STAMP(4);
-    if (tid == 0 && atomicAdd(a.flags + 257, 1u) == gridDim.x - 1) { a.flags[256] = 0; a.flags[257] = 0; }
+    if (tid == 0 && atomicAdd(a.flags + PREP_DONE, 1u) == gridDim.x - 1) { a.flags[PREP_TICKET] = 0; a.flags[PREP_DONE] = 0; }
 }
 
 static int launch_integral_two_pass(mct_ctx* ctx, const PrepTarget& t, cudaStream_t st);
@@ -293,10 +351,11 @@ int launch_frame_prep(mct_ctx* ctx, const PrepTarget& t, cudaStream_t st, int* w
                     ((((size_t)t.c0) | ((size_t)t.c1) | ((size_t)t.c2)) & 3) == 0 && (256 % cnb) == 0 &&
                     ((256 / cnb) & (256 / cnb - 1)) == 0;
     if (!ctx->prep_flags) {
-        MCT_CUDA(ctx, cudaMalloc(&ctx->prep_flags, 260 * sizeof(unsigned)));          // [256] band flags, [256] ticket, [257] done
-        MCT_CUDA(ctx, cudaMemsetAsync(ctx->prep_flags, 0, 260 * sizeof(unsigned), st));
+        MCT_CUDA(ctx, cudaMalloc(&ctx->prep_flags, PREP_FLAG_WORDS * sizeof(unsigned)));
+        MCT_CUDA(ctx, cudaMemsetAsync(ctx->prep_flags, 0, PREP_FLAG_WORDS * sizeof(unsigned), st));
     }
-    size_t need = (size_t)n_bands * W;
+    const int n_groups = ceil_div(n_bands, PREP_GROUP);
+    size_t need = (size_t)(n_bands + n_groups) * W;                               // band totals, then group totals
     if (need > ctx->bandsum_cap) {
         if (ctx->bandsum) { MCT_CUDA(ctx, cudaStreamSynchronize(st)); cudaFree(ctx->bandsum); }
         MCT_CUDA(ctx, cudaMalloc(&ctx->bandsum, need * sizeof(uint32_t)));
@@ -304,7 +363,7 @@ int launch_frame_prep(mct_ctx* ctx, const PrepTarget& t, cudaStream_t st, int* w
     }
     PrepArgs a;
     a.gray = t.gray; a.W = W; a.H = H; a.pitch = t.pitch; a.BH = BH; a.n_bands = n_bands;
-    a.bandtot = ctx->bandsum; a.flags = ctx->prep_flags;
+    a.bandtot = ctx->bandsum; a.grptot = ctx->bandsum + (size_t)n_bands * W; a.flags = ctx->prep_flags;
     a.epoch = ++ctx->prep_epoch; a.ii = t.ii_base + MCT_II_LEAD; a.iip = t.ii_pitch;
     a.c0 = t.c0; a.c1 = t.c1; a.c2 = t.c2; a.nb = cnb; a.bw_shift = 0; a.binimg = t.binimg;
     a.n_binblocks = 0;

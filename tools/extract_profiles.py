@@ -67,6 +67,8 @@ def full(rep):
     seen = set()
     for vals in rr[2:]:
         name = vals[hdr.index("Kernel Name")].split("(")[0]
+        # the launch names bench.py reports: no "void", no template arguments; k_pf_update_fast<CH> is launched as k_pf_update
+        name = name.replace("void ", "").split("<")[0].replace("k_pf_update_fast", "k_pf_update")
         if name in seen:
             continue
         seen.add(name)

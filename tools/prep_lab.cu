@@ -3,6 +3,7 @@
 #include "../multicameratracking_b200/csrc/k_integral.cu"
 #include <vector>
 char g_mct_err[512];
+std::mutex g_mct_attr_mu;
 void mct_prof_begin(mct_ctx*, const char*) {}
 void mct_prof_end(mct_ctx*) {}
 void mct_prof_begin_on(mct_ctx*, const char*, cudaStream_t) {}
@@ -13,6 +14,7 @@ int main(int argc, char** argv)
     const int W = argc > 1 ? atoi(argv[1]) : 640, H = argc > 2 ? atoi(argv[2]) : 480, POOL = 96;
     mct_ctx ctx; memset(&ctx, 0, sizeof(ctx));
     CK(cudaStreamCreate(&ctx.stream));
+    cudaDeviceGetAttribute(&ctx.sms, cudaDevAttrMultiProcessorCount, 0);
     ctx.W = W; ctx.H = H; ctx.pitch = W; ctx.binimg_nb = argc > 3 ? atoi(argv[3]) : 8; ctx.binimg_frame = -1;
     ctx.ii_pitch = (W + 1 + 3) & ~3;
     CK(cudaMalloc(&ctx.ii_base, ((size_t)(H + 1) * ctx.ii_pitch + 16) * 4));
@@ -38,6 +40,17 @@ int main(int argc, char** argv)
     CK(cudaMemcpyFromSymbol(hd, g_prep_dbg, sizeof(hd)));
     unsigned long long t0 = ~0ull;
     for (int b = 0; b < 130; b++) if (hd[b * 8] && hd[b * 8] < t0) t0 = hd[b * 8];
+    for (int k = 1; k < 5; k++) {
+        double mx = 0, sum = 0; int arg = -1, cnt = 0;
+        for (int b = 0; b < 256; b++) {
+            if (!hd[b * 8] || !hd[b * 8 + k] || hd[b * 8 + k] < t0 || (k < 4 && !hd[b * 8 + 1])) continue;
+            const double v = (double)(hd[b * 8 + k] - t0) * 1e-3;
+            if (v > 1e6) continue;
+            sum += v; cnt++;
+            if (v > mx) { mx = v; arg = b; }
+        }
+        printf("stamp %d: mean %.2f max %.2f us (ticket %d) over %d CTAs\n", k, cnt ? sum / cnt : 0.0, mx, arg, cnt);
+    }
     for (int b = 0; b < 130; b += 10) { printf("ticket %3d:", b); for (int k = 0; k < 6; k++) printf(" %7.2f", (double)(hd[b * 8 + k] - t0) * 1e-3); printf(" us\n"); }
 #endif
     return 0;
