@@ -686,11 +686,13 @@ def run_network(args):
     stages = {}
     timed = {"s": 0.0, "launches": 0}
 
-    def step(i, record):
+    def step(i, record, after_build=None):
         k = i % SEG
         if k == 0:
             build()
             barrier()
+            if after_build:
+                after_build()
         cams, net = state["cams"], state["net"]
         l0 = sum(cam.launches for cam in cams)
         t0 = time.perf_counter()
@@ -717,16 +719,18 @@ def run_network(args):
         from multicameratracking_b200 import capi
         Lc = capi.load()
         prof_acc, prof_frames = {}, 0
+        holder = {}
+
+        def profile_on():          # (the segment's first step re-creates the cameras: take the context of the NEW first camera)
+            holder["ctx"] = C.c_void_p(state["cams"][0].L.mcth_camera_ctx(state["cams"][0].h))
+            Lc.mct_profile_enable(holder["ctx"], 1)
+
         for i in range(SEG):
-            if i == 0:
-                build(); barrier()
-                ctx0 = C.c_void_p(state["cams"][0].L.mcth_camera_ctx(state["cams"][0].h))
-            Lc.mct_profile_enable(ctx0, 1)
-            step(i, False)
-            for kname, (ms_k, n_k) in capi.profile_read(Lc, ctx0).items():
+            step(i, False, after_build=profile_on)
+            for kname, (ms_k, n_k) in capi.profile_read(Lc, holder["ctx"]).items():
                 acc = prof_acc.setdefault(kname, [0.0, 0]); acc[0] += ms_k; acc[1] += n_k
-            Lc.mct_profile_enable(ctx0, 0)
             prof_frames += 1
+        Lc.mct_profile_enable(holder["ctx"], 0)
         kernel_us = {k: [round(1e3 * v[0] / prof_frames, 1), round(v[1] / prof_frames, 1)] for k, v in sorted(prof_acc.items(), key=lambda kv: -kv[1][0])}
         barrier()
     dt = timed["s"]

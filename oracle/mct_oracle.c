@@ -7,7 +7,7 @@
  * double; exp/log of a float argument are the float overloads).
  *
  * Build: see oracle/Makefile (-O2 -ffp-contract=off so no FMA contraction changes f32 results).
- * PARITY: unpinned against a built reference (IPP/OpenCV 2.3.1/Boost absent) -- see header.
+ * PARITY: pinned row by row to the reference's own code (oracle/_ref, tests/test_ref_pins_oracle.py) -- see header.
  */
 #include "mct_oracle.h"
 #include <math.h>

@@ -9,12 +9,17 @@
  * function cites the reference file:line it follows (paths relative to /root/reference/src).
  *
  * PARITY PINNING STATUS (see DESIGN.md "Oracle"):
- *   - pinned:   MWC RNG stream (cv2 4.13 same generator; SURVEY 8c goldens), cvRound half-to-even,
- *               hand-computed integral / sumRect / resampler vectors (tests/golden/).
- *   - UNPINNED: the reference cannot be built here (needs Intel IPP + OpenCV 2.3.1 + Boost, none
- *               present) and ships no tests, fixtures or golden vectors.  IPP-internal arithmetic
- *               (ippiIntegral f32 accumulation order, ippiMean/StdDev summation) is restated as
- *               "exact integer / f64 accumulation, rounded once" -- parity unpinned for those.
+ *   - PINNED TO THE REFERENCE'S OWN CODE: oracle/_ref/libmct_ref.so is the unmodified reference (the .cpp files under /root/reference/src)
+ *               compiled where it lies against header shims for IPP / OpenCV / Boost (oracle/build_ref.py, oracle/ref_shim/)
+ *               and driven through oracle/ref_harness.cpp; tests/test_ref_pins_oracle.py runs it and this file on the same
+ *               seeded inputs for every row of SURVEY 8a (bit-exact for integer / index / ordered-f32 work, 1e-5 elsewhere),
+ *               the tracker loop and the multi-camera schedule included.
+ *   - also pinned: MWC RNG stream, BGR->gray / HSV, cvRound, cvInvert / SVD / Kalman against cv2 4.13 (tests/golden/cv2_*.json),
+ *               hand-computed integral / sumRect / resampler vectors (tests/golden/hand.json).
+ *   - STATED ASSUMPTIONS THAT REMAIN (oracle/ref_shim/ipp.h): closed-source IPP arithmetic (ippiIntegral accumulation, ippiMean /
+ *               StdDev summation) is the shim's restatement -- exact integer / f64 accumulation, rounded once -- and std::sort's
+ *               order of exactly tied scores is unspecified by the language (the _ref build keeps ties in index order; the
+ *               native-libstdc++ build is tested to differ in nothing else).
  */
 #ifndef MCT_ORACLE_H
 #define MCT_ORACLE_H
