@@ -387,6 +387,45 @@ typedef struct {
 int mct_sample_regions(mct_ctx* ctx, int n_regions, const mct_sample_region* regions, int cap, int* col, int* row,
                        mct_sample_region_out* out);
 
+/* ---------------------------------------------------------------- the whole frame on the device ---- */
+/* The tracker's multiply-with-carry stream (Public.cpp:15-23, `rng_state`) as DEVICE-resident state of the particle filter:
+ * after mct_pf_rng_set, mct_track_score* called with u01 == NULL takes the randfloat() of ResampleParticles
+ * (ParticleFilter.cpp:940) from that stream -- consumed iff the filter resamples, as in the reference -- and
+ * mct_track_update_default draws the thinning decisions of SelectSamplesUniformlyFromLargerSet from it.  mct_pf_rng_get
+ * synchronises the stream and returns the current state (the host mirror adopts it when host-side code needs the stream). */
+int mct_pf_rng_set(mct_pf* pf, unsigned long long state);
+int mct_pf_rng_get(mct_pf* pf, unsigned long long* state);
+
+/* GenerateTrainingSampleSet with the default strategies (SAMPLE_POS_SIMPLETRACKER / SAMPLE_NEG_SIMPLETRACKER,
+ * ParticleFilterTracker.cpp:647-741, 913-937) + UpdateClassifier (:1013-1032) for n_obj objects, queued behind the frame's
+ * mct_track_score* with NO host round trip: one kernel reads the particle read-out where k_pf_update left it, derives
+ * m_currentStateList (:655-672), enumerates the positive disc and the negative ring (SampleSet.cpp:82-168), thins them with
+ * the device-resident stream (:331-361; candidate k takes draw k by jump-ahead), writes the boxes, the set sizes and the plan
+ * of the colour-histogram kernels straight into the device-side descriptors; the update kernels are launched from upper
+ * bounds.  Same boxes, same order, same draws as the host enumeration (mct_track_update).  Asynchronous. */
+typedef struct {
+    float w0, h0;                 /* m_currentStateList[2], [3] */
+    int   trajectory_option;      /* m_outputTrajectoryOption: 0 = highest-weight particle, 1 = average of all particles */
+    float pos_radius;             /* m_posRadiusTrain */
+    int   max_pos;                /* m_maximumNumberOfPositiveTrainingSamples */
+    float neg_outer, neg_inner;   /* 1.5 * m_searchWindSize, m_posRadiusTrain + 15 (:926-930) */
+    int   max_neg;                /* m_numberOfNegativeTrainingSamples */
+    float scale_hint_x, scale_hint_y;   /* last known state scale; sizes the launches only: a wrong hint costs time, never results */
+} mct_train_default;
+typedef struct {
+    int P, Nn;                    /* sizes of the positive / negative set */
+    int status;                   /* MCT_OK; MCT_E_EMPTY: no particle in the frame or an empty set -- the classifier was left untouched */
+    int mdch_fast;                /* the colour rows took the pixel-list kernels (diagnostic) */
+    unsigned long long rng_state; /* the stream after this frame's draws */
+    float cur[6];                 /* m_currentStateList after GenerateTrainingSampleSet */
+    int n_draws, pad;             /* randfloat() calls of the two thinning passes */
+} mct_train_default_out;
+int mct_track_update_default(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, mct_clf* const* clfs, const mct_train_default* gen /* [n_obj] */);
+/* synchronises the stream; out [n_obj] (or NULL: only the status is checked); returns the first object's error, if any */
+int mct_track_update_default_collect(mct_ctx* ctx, int n_obj, mct_train_default_out* out);
+/* the boxes generated for object `obj` by the last mct_track_update_default (positives first; tests / diagnostics; synchronises) */
+int mct_track_update_default_boxes(mct_ctx* ctx, int obj, int cap, int* col, int* row, float* sx, float* sy, int* P, int* Nn);
+
 #ifdef __cplusplus
 }
 #endif

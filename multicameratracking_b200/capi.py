@@ -39,6 +39,9 @@ SYMBOLS = [
     "mct_classifier_update_from_gathered", "mct_dev_alloc", "mct_dev_copy", "mct_dev_free", "mct_fuser_foot_points",
     "mct_pf_resample_many", "mct_track_update_from_gathered", "mct_train_features_many_dev",
     "mct_pf_get_summary_many", "mct_pf_rearrange_ground_many",
+    # whole frame on the device
+    "mct_pf_rng_set", "mct_pf_rng_get", "mct_track_update_default", "mct_track_update_default_collect",
+    "mct_track_update_default_boxes",
 ]
 
 
@@ -56,6 +59,17 @@ class ClfParams(C.Structure):
     _fields_ = [("feature_type", C.c_int), ("n_haar", C.c_int), ("n_bins", C.c_int), ("w0", C.c_int), ("h0", C.c_int),
                 ("weak_type", C.c_int), ("strong_type", C.c_int), ("n_selected", C.c_int), ("learning_rate", C.c_float),
                 ("cch_mode", C.c_int), ("max_train", C.c_int), ("max_test", C.c_int), ("pct_retained", C.c_float)]
+
+
+class TrainDefault(C.Structure):
+    _fields_ = [("w0", C.c_float), ("h0", C.c_float), ("trajectory_option", C.c_int), ("pos_radius", C.c_float), ("max_pos", C.c_int),
+                ("neg_outer", C.c_float), ("neg_inner", C.c_float), ("max_neg", C.c_int), ("scale_hint_x", C.c_float),
+                ("scale_hint_y", C.c_float)]
+
+
+class TrainDefaultOut(C.Structure):
+    _fields_ = [("P", C.c_int), ("Nn", C.c_int), ("status", C.c_int), ("mdch_fast", C.c_int), ("rng_state", C.c_uint64),
+                ("cur", C.c_float * 6), ("n_draws", C.c_int), ("pad", C.c_int)]
 
 
 class TrainGen(C.Structure):
@@ -175,6 +189,12 @@ def load():
     L.mct_pf_training_boxes.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(TrainGen), C.c_int, _c_int_p, _c_int_p, _c_float_p, _c_float_p,
                                         C.POINTER(TrainGenOut)]
     L.mct_sample_regions.argtypes = [vp, C.c_int, C.POINTER(SampleRegion), C.c_int, _c_int_p, _c_int_p, C.POINTER(SampleRegionOut)]
+    L.mct_pf_rng_set.argtypes = [vp, C.c_uint64]
+    L.mct_pf_rng_get.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.mct_track_update_default.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(TrainDefault)]
+    L.mct_track_update_default_collect.argtypes = [vp, C.c_int, C.POINTER(TrainDefaultOut)]
+    L.mct_track_update_default_boxes.argtypes = [vp, C.c_int, C.c_int, _c_int_p, _c_int_p, _c_float_p, _c_float_p,
+                                                 C.POINTER(C.c_int), C.POINTER(C.c_int)]
     _lib = L
     return L
 
@@ -530,6 +550,51 @@ def track_score(ctx, pfs, clfs, params, noise, u01, noise_device_ptr=None):
         rc = ctx.L.mct_track_score(ctx.h, n, pa, ca, tp, nz.ctypes.data_as(vp), 0, _fp(u), out)
     ctx.check(rc)
     return list(out)
+
+
+def pf_rng_set(pf, state):
+    pf.ctx.check(pf.ctx.L.mct_pf_rng_set(pf.h, C.c_uint64(int(state))))
+
+
+def pf_rng_get(pf):
+    st = C.c_uint64(0)
+    pf.ctx.check(pf.ctx.L.mct_pf_rng_get(pf.h, C.byref(st)))
+    return int(st.value)
+
+
+def track_score_dev_rng(ctx, pfs, clfs, params, noise):
+    """mct_track_score with u01 == NULL: the resampler draw comes from every object's device-resident stream (pf_rng_set)."""
+    n = len(pfs)
+    vp = C.c_void_p
+    pa = (vp * n)(*[p.h for p in pfs]); ca = (vp * n)(*[c.h for c in clfs])
+    tp = (TrackParams * n)(*[TrackParams(*p) for p in params])
+    out = (PfSummary * n)()
+    nz = np.ascontiguousarray(noise, np.float32)
+    ctx.check(ctx.L.mct_track_score(ctx.h, n, pa, ca, tp, nz.ctypes.data_as(vp), 0, None, out))
+    return list(out)
+
+
+def track_update_default(ctx, pfs, clfs, gens, collect=True):
+    """mct_track_update_default (+ _collect): gens = [TrainDefault(...)] per object; returns the read-outs when collected."""
+    n = len(pfs)
+    vp = C.c_void_p
+    pa = (vp * n)(*[p.h for p in pfs]); ca = (vp * n)(*[c.h for c in clfs])
+    ga = (TrainDefault * n)(*gens)
+    ctx.check(ctx.L.mct_track_update_default(ctx.h, n, pa, ca, ga))
+    if not collect:
+        return None
+    out = (TrainDefaultOut * n)()
+    ctx.check(ctx.L.mct_track_update_default_collect(ctx.h, n, out))
+    return list(out)
+
+
+def track_update_default_boxes(ctx, obj, cap=8192):
+    """boxes of object `obj` generated by the last track_update_default: (col, row, sx, sy, P, Nn)"""
+    col = np.zeros(cap, np.int32); row = np.zeros(cap, np.int32); sx = np.zeros(cap, np.float32); sy = np.zeros(cap, np.float32)
+    P = C.c_int(0); Nn = C.c_int(0)
+    ctx.check(ctx.L.mct_track_update_default_boxes(ctx.h, obj, cap, _ip(col), _ip(row), _fp(sx), _fp(sy), C.byref(P), C.byref(Nn)))
+    m = min(P.value + Nn.value, cap)
+    return col[:m], row[:m], sx[:m], sy[:m], P.value, Nn.value
 
 
 def classify_argmax(ctx, clfs, boxes_list, log_ratio=True):

@@ -471,7 +471,6 @@ __global__ void __launch_bounds__(MTP_WARPS * 32) k_mdch_train_prep(const TrainD
 // EXT: the box's weight table sits in a zero field [2 RH - rows][2 RW - cols] so that every (pixel, box) pair of the region
 // indexes it without a bounds test (used when the field is small: the positives' disc); otherwise bounds-tested lookups.
 #define MTR_THREADS 384
-#define MTR_EXT_WORDS 12288
 struct MtrRun { unsigned bin; int start, end; int pad; };
 template <bool EXT>
 __device__ __forceinline__ void mdch_train_walk(const TrainDesc& d, const MdchGroup& g, const uint32_t* __restrict__ tab, const uint32_t* __restrict__ sl,
@@ -532,7 +531,7 @@ __global__ void __launch_bounds__(MTR_THREADS) k_mdch_train_main(const TrainDesc
     uint32_t* sl = tab + smem_tab_words;                         // the chunk's table offsets (or packed (y, x))
     MtrRun* runs = (MtrRun*)(sl + smem_chunk_words);             // [<= npx]
     const int EW = 2 * g.RW - g.cols, EH = 2 * g.RH - g.rows;
-    const bool ext = EW * EH <= MTR_EXT_WORDS;
+    const bool ext = g.EW != 0;                                  // decided with the plan (host: mdch_group_plan; device: k_train_gen_default)
     if (tid == 0) s_nruns = 0;
     if (ext) for (int p = tid; p < EW * EH; p += blockDim.x) tab[p] = 0u;
     __syncthreads();
@@ -751,11 +750,11 @@ int mct_feature_matrix_full(mct_clf* clf, const int* d_col, const int* d_row, co
 }
 
 // training features of all objects: Haar rows + MDCH rows, two launches for the whole camera
-int launch_train_features(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj)
+int launch_train_features(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj, const TrainLaunchBounds* lb)
 {
-    int n_max = 0, nh_max = 0, any_mdch = 0, dim_max = 0, nb = 0;
+    int n_max = lb ? lb->n_max : 0, nh_max = 0, any_mdch = 0, dim_max = 0, nb = 0;
     for (int o = 0; o < n_obj; o++) {
-        n_max = max(n_max, h[o].P + h[o].Nn);
+        if (!lb) n_max = max(n_max, h[o].P + h[o].Nn);
         nh_max = max(nh_max, h[o].n_haar);
         if (h[o].feature_type == MCT_FEAT_MDCH || h[o].feature_type == MCT_FEAT_HAAR_MDCH) { any_mdch = 1; dim_max = max(dim_max, h[o].n_color); nb = h[o].nb; }
     }
@@ -781,7 +780,13 @@ int launch_train_features(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, 
         if (rc) return rc;
         // objects whose two groups qualified on the host take the pixel-list kernels; the others the generic per-box kernel
         int n_fast = 0, n_slow = 0, nch = 1, tab_words = 0, chunk_words = 0, npx_max = 0, n_train_max = 0;
-        for (int o = 0; o < n_obj; o++) {
+        if (lb) {
+            // sizes and plans are decided by k_train_gen_default: both kernel families are launched from the bounds, every
+            // object takes one of them (TrainDesc::mdch_fast on the device)
+            n_fast = lb->nch > 0 ? 1 : 0; n_slow = 1;
+            nch = max(lb->nch, 1); tab_words = lb->tab_words; chunk_words = lb->chunk_words; npx_max = lb->npx_max; n_train_max = lb->n_train_max;
+        }
+        for (int o = 0; o < n_obj && !lb; o++) {
             if (!(h[o].feature_type == MCT_FEAT_MDCH || h[o].feature_type == MCT_FEAT_HAAR_MDCH)) continue;
             if (h[o].mdch_fast) {
                 n_fast++;
@@ -924,6 +929,7 @@ __global__ void k_build_colormap(const int* __restrict__ sel, const int* __restr
 __global__ void k_build_colormap_batch(const TrainDesc* __restrict__ descs)
 {
     const TrainDesc& d = descs[blockIdx.x];
+    if (d.P < 1 || d.Nn < 1) return;              // empty training set decided on the device (k_train_gen_default): classifier left as it is
     const int mdch = (d.feature_type == MCT_FEAT_MDCH || d.feature_type == MCT_FEAT_HAAR_MDCH) ? 1 : 0;
     build_colormap_body(d.sel, d.nsel, d.n_haar, d.n_color, mdch, d.slotmap, d.colorrow, d.outbins, d.nout, d.rects, d.wts, d.nrect,
                         d.weak, d.F, d.K, d.seltab, d.selhdr, d.strong_type == MCT_STRONG_ADABOOST ? d.alpha : nullptr, d.rowst);

@@ -326,6 +326,7 @@ k_milboost_select_batch(const TrainDesc* __restrict__ descs, int FC, int FLmax, 
 {
     const TrainDesc& d = descs[blockIdx.y];
     if (d.strong_type != MCT_STRONG_MILBOOST) return;
+    if (d.P < 1 || d.Nn < 1) return;              // empty training set decided on the device (k_train_gen_default): classifier left as it is
     // the shared-memory plan was sized for (FLmax, Mmax): an object's rows fit iff its own FL * M does
     const int FL = (d.F + (int)gridDim.x - 1) / (int)gridDim.x;
     const int rows_in_smem = FLmax > 0 && (size_t)FL * (d.P + d.Nn) <= (size_t)FLmax * Mmax && min(FC, FL) <= FC;
@@ -483,6 +484,7 @@ __global__ void __launch_bounds__(ANY_THREADS) k_anyboost_select_batch(const Tra
 {
     const TrainDesc& d = descs[blockIdx.x];
     if (d.strong_type != MCT_STRONG_MILANYBOOST) return;
+    if (d.P < 1 || d.Nn < 1) return;              // empty training set decided on the device (k_train_gen_default): classifier left as it is
     anyboost_select_body(d.pred, d.ldT, d.F, d.P, d.Nn, d.K, d.sel, d.nsel);
 }
 
@@ -607,6 +609,7 @@ __global__ void __launch_bounds__(ADA_THREADS) k_adaboost_select_batch(const Tra
 {
     const TrainDesc& d = descs[blockIdx.x];
     if (d.strong_type != MCT_STRONG_ADABOOST) return;
+    if (d.P < 1 || d.Nn < 1) return;              // empty training set decided on the device (k_train_gen_default): classifier left as it is
     adaboost_select_body(d.featT, d.ldT, d.F, d.P, d.Nn, d.K, d.weak, d.weak_type, d.ada_cnt, d.alpha, d.sel, d.nsel);
 }
 __global__ void __launch_bounds__(ADA_THREADS) k_adaboost_select(const float* __restrict__ feat, int ld, int F, int P, int Nn, int K,
@@ -783,12 +786,14 @@ __global__ void __launch_bounds__(ENS_THREADS) k_ensemble_retain_batch(const Tra
 {
     const TrainDesc& d = descs[blockIdx.y];
     if (d.strong_type != MCT_STRONG_MILENSEMBLE) return;
+    if (d.P < 1 || d.Nn < 1) return;              // empty training set decided on the device (k_train_gen_default): classifier left as it is
     ensemble_body<true>(d.featT, d.pred, d.ldT, d.F, d.P, d.Nn, d.K, d.weak, d.weak_type, d.pct_retained, d.sel, d.nsel, d.keep, d.ensH, d.ensH + d.ldT, FC);
 }
 __global__ void __launch_bounds__(ENS_THREADS) k_ensemble_select_batch(const TrainDesc* __restrict__ descs, int FC)
 {
     const TrainDesc& d = descs[blockIdx.y];
     if (d.strong_type != MCT_STRONG_MILENSEMBLE) return;
+    if (d.P < 1 || d.Nn < 1) return;              // empty training set decided on the device (k_train_gen_default): classifier left as it is
     ensemble_body<false>(d.featT, d.pred, d.ldT, d.F, d.P, d.Nn, d.K, d.weak, d.weak_type, d.pct_retained, d.sel, d.nsel, d.keep, d.ensH, d.ensH + d.ldT, FC);
 }
 __global__ void __launch_bounds__(ENS_THREADS)

@@ -119,6 +119,29 @@ __device__ __forceinline__ double ipow_d(double x, int n)
 // are normal numbers in f64, so the division never takes the slow special-case path.
 __device__ __forceinline__ float fdiv_exact(float a, float b) { return (float)((double)a / (double)b); }
 
+// The randfloat() of ResampleParticles (ParticleFilter.cpp:940): from the call's arguments, or peeked from the object's
+// device-resident multiply-with-carry stream (Public.cpp:15-23); resample_consume advances that stream (ONE thread, after a barrier
+// behind every thread's peek) when the filter did resample -- the reference draws only inside ResampleParticles.
+__device__ __forceinline__ float resample_draw(const ObjDesc& d, const StepArgs& sa, int obj)
+{
+    if (!sa.dev_rng) return sa.u01[obj];
+    const unsigned long long s = d.trk->rng;
+    const unsigned long long n = (s & 0xffffffffull) * 4164903690ull + (s >> 32);
+    return (float)((double)(unsigned)(n & 0xffffffffull) * 2.3283064365386962890625e-10);
+}
+__device__ __forceinline__ void resample_consume(const ObjDesc& d, const StepArgs& sa)
+{
+    if (!sa.dev_rng) return;
+    const unsigned long long s = d.trk->rng;
+    d.trk->rng = (s & 0xffffffffull) * 4164903690ull + (s >> 32);
+}
+// the part of the read-out that GenerateTrainingSampleSet consumes, mirrored into device memory (PfTrk)
+__device__ __forceinline__ void trk_set_avg(const ObjDesc& d, int q, float v) { if (d.trk) d.trk->avg[q] = v; }
+__device__ __forceinline__ void trk_set_first(const ObjDesc& d, float x, float y, float sx, float sy)
+{
+    if (d.trk) { d.trk->first[0] = x; d.trk->first[1] = y; d.trk->first[2] = sx; d.trk->first[3] = sy; }
+}
+
 __global__ void __launch_bounds__(256) k_pf_predict(const ObjDesc* __restrict__ descs, const StepArgs sa)
 {
     const ObjDesc& d = descs[blockIdx.y];
@@ -425,8 +448,8 @@ __global__ void __launch_bounds__(PF_THREADS) k_pf_update(const ObjDesc* __restr
     __syncthreads();
     PF_STAMP(5);
     if (s_decide) {
-        resample_body(d, sw, cdf, 1, sh_f, sa.u01[blockIdx.x]);
-        if (tid == 0) d.st->resampled = 1;
+        resample_body(d, sw, cdf, 1, sh_f, resample_draw(d, sa, blockIdx.x));
+        if (tid == 0) { d.st->resampled = 1; resample_consume(d, sa); }
     } else {
         for (int i = tid; i < N; i += nt) d.w[i] = sw[PIDX(i)];
     }
@@ -633,7 +656,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) k_pf_update_fast(const ObjDesc*
         __syncthreads();
         PF_STAMP(7);
         const float invN = __fdiv_rn(1.0f, (float)N);
-        const float seed = __fmul_rn(invN, sa.u01[blockIdx.x]);
+        const float seed = __fmul_rn(invN, resample_draw(d, sa, blockIdx.x));
         int top = 1;
         while ((top << 1) <= N) top <<= 1;
         float thr[4]; int lo[4];
@@ -666,7 +689,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) k_pf_update_fast(const ObjDesc*
                 d.cx[i] = gx[k]; d.cy[i] = gy[k]; d.sx[i] = gsx[k]; d.sy[i] = gsy[k]; d.w[i] = 1.0f;
             }
         }
-        if (tid == 0) { d.st->filter_state = MCT_PF_RESAMPLED; d.st->resampled = 1; }
+        if (tid == 0) { d.st->filter_state = MCT_PF_RESAMPLED; d.st->resampled = 1; resample_consume(d, sa); }
         PF_STAMP(8);
     } else {
 #pragma unroll
@@ -749,7 +772,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) k_pf_update_fast(const ObjDesc*
         PfRed t = s_red[0];
         for (int q = 1; q < nt / 32; q++) merge(t, s_red[q]);
         mct_pf_summary* out = d.summ;
-        for (int q = 0; q < 4; q++) out->average[q] = (float)(t.acc[q] / t.acc[4]);
+        for (int q = 0; q < 4; q++) { const float v = (float)(t.acc[q] / t.acc[4]); out->average[q] = v; trk_set_avg(d, q, v); }
         out->n_valid = cnt; out->resampled = decide; out->filter_state = fs;
         out->neff_inv = neff_inv; out->max_response = (mode == 0) ? max_response : d.st->max_response;
         if (decide) {
@@ -760,6 +783,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) k_pf_update_fast(const ObjDesc*
             const int s0 = sidx[0], sb = sidx[b];
             out->ordered_first[0] = ccx[s0]; out->ordered_first[1] = ccy[s0]; out->ordered_first[2] = csx[s0];
             out->ordered_first[3] = csy[s0]; out->ordered_first[4] = t.mx;
+            trk_set_first(d, ccx[s0], ccy[s0], csx[s0], csy[s0]);
             out->highest_close[0] = ccx[sb]; out->highest_close[1] = ccy[sb]; out->highest_close[2] = csx[sb];
             out->highest_close[3] = csy[sb]; out->highest_close[4] = t.mx;
             out->n_unique = t.b;
@@ -767,6 +791,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) k_pf_update_fast(const ObjDesc*
             const int a = t.a < N ? t.a : 0, b = t.b >= 0 ? t.b : 0;
             out->ordered_first[0] = ccx[a]; out->ordered_first[1] = ccy[a]; out->ordered_first[2] = csx[a];
             out->ordered_first[3] = csy[a]; out->ordered_first[4] = sw[PIDX(a)];
+            trk_set_first(d, ccx[a], ccy[a], csx[a], csy[a]);
             out->highest_close[0] = ccx[b]; out->highest_close[1] = ccy[b]; out->highest_close[2] = csx[b];
             out->highest_close[3] = csy[b]; out->highest_close[4] = sw[PIDX(b)];
             out->n_unique = N;
@@ -930,7 +955,7 @@ __device__ void summary_body(const ObjDesc& d, float* scratch)
     block_reduce_sum_d5(acc, sh_d5);
     PF_STAMP(12);
     if (tid == 0) {
-        for (int q = 0; q < 4; q++) out->average[q] = (float)(acc[q] / acc[4]);
+        for (int q = 0; q < 4; q++) { const float v = (float)(acc[q] / acc[4]); out->average[q] = v; trk_set_avg(d, q, v); }
         out->n_valid = d.st->n_valid; out->resampled = d.st->resampled; out->filter_state = fs;
         out->neff_inv = d.st->neff_inv; out->max_response = d.st->max_response;
     }
@@ -949,6 +974,7 @@ __device__ void summary_body(const ObjDesc& d, float* scratch)
             int a = s_first < N ? s_first : 0, b = s_last >= 0 ? s_last : 0;
             out->ordered_first[0] = d.cx[a]; out->ordered_first[1] = d.cy[a]; out->ordered_first[2] = d.sx[a];
             out->ordered_first[3] = d.sy[a]; out->ordered_first[4] = d.w[a];
+            trk_set_first(d, d.cx[a], d.cy[a], d.sx[a], d.sy[a]);
             out->highest_close[0] = d.cx[b]; out->highest_close[1] = d.cy[b]; out->highest_close[2] = d.sx[b];
             out->highest_close[3] = d.sy[b]; out->highest_close[4] = d.w[b];
             out->n_unique = N;
@@ -1001,6 +1027,7 @@ __device__ void summary_body(const ObjDesc& d, float* scratch)
             }
             out->ordered_first[0] = d.cx[0]; out->ordered_first[1] = d.cy[0]; out->ordered_first[2] = d.sx[0];
             out->ordered_first[3] = d.sy[0]; out->ordered_first[4] = mx;
+            trk_set_first(d, d.cx[0], d.cy[0], d.sx[0], d.sy[0]);
             out->highest_close[0] = d.cx[b]; out->highest_close[1] = d.cy[b]; out->highest_close[2] = d.sx[b];
             out->highest_close[3] = d.sy[b]; out->highest_close[4] = mx;
             out->n_unique = nruns;
@@ -1011,6 +1038,7 @@ __device__ void summary_body(const ObjDesc& d, float* scratch)
         }
     } else if (tid == 0) {
         for (int q = 0; q < 5; q++) { out->ordered_first[q] = 0; out->highest_close[q] = 0; }
+        trk_set_first(d, 0.0f, 0.0f, 0.0f, 0.0f);
         out->n_unique = 0;
     }
 }
@@ -1487,15 +1515,13 @@ __device__ __forceinline__ bool region_candidate(const mct_sample_region& g, int
     const int dx = abs(g.x - c), dy = abs(g.y - r);
     return (float)dx >= g.p[2] || (float)dy >= g.p[3];
 }
-__global__ void __launch_bounds__(PF_THREADS)
-k_sample_regions(const mct_sample_region* __restrict__ regs, int cap, int* __restrict__ col, int* __restrict__ row, mct_sample_region_out* __restrict__ outs)
+// body shared by k_sample_regions and k_train_gen_default: all threads of the CTA call it; the result lands in *res (shared memory)
+// and is visible to every thread on return.  bbox (shared int[4], or NULL): min col, max col, min row, max row of the KEPT samples.
+__device__ void sample_region_body(const mct_sample_region& g, int cap, int* __restrict__ o_col, int* __restrict__ o_row,
+                                   mct_sample_region_out* res, int* bbox, int* sh_c /* [33] */, int* sh_i /* [32] */,
+                                   const unsigned long long* s_pw /* [32] shared copy of c_mwc_pw */)
 {
-    __shared__ int sh_c[33];
-    __shared__ int sh_i[32];
-    __shared__ unsigned long long s_pw[32];
-    const mct_sample_region g = regs[blockIdx.x];
     const int tid = threadIdx.x, nt = blockDim.x;
-    int* o_col = col + (size_t)blockIdx.x * cap; int* o_row = row + (size_t)blockIdx.x * cap;
     const int scaledW = __float2int_rn(__fmul_rn((float)g.width, g.scale_x)), scaledH = __float2int_rn(__fmul_rn((float)g.height, g.scale_y));
     const int nrows = g.frame_h - scaledH - 1, ncols = g.frame_w - scaledW - 1;
     const int ry = (int)(g.kind == 0 ? g.p[0] : g.p[1]), rx = (int)g.p[0];
@@ -1504,6 +1530,7 @@ k_sample_regions(const mct_sample_region* __restrict__ regs, int cap, int* __res
     const int RW = maxcol - mincol + 1, RH = maxrow - minrow + 1;
     const int cells = (RW > 0 && RH > 0) ? RW * RH : 0;
     const float o2 = __fmul_rn(g.p[0], g.p[0]), i2 = __fmul_rn(g.p[1], g.p[1]);
+    if (bbox && tid == 0) { bbox[0] = 0x7fffffff; bbox[1] = -0x7fffffff; bbox[2] = 0x7fffffff; bbox[3] = -0x7fffffff; }
     int cnt = 0;
     for (int e = tid; e < cells; e += nt) cnt += region_candidate(g, minrow + e / RW, mincol + e % RW, o2, i2) ? 1 : 0;
     const int n_cand = block_reduce_sum_i(cnt, sh_i);
@@ -1511,9 +1538,8 @@ k_sample_regions(const mct_sample_region* __restrict__ regs, int cap, int* __res
     const float prob = __fdiv_rn((float)(g.max_n + 1), (float)(unsigned)n_list);
     const bool thin = prob < 1.0f;
     const unsigned long long s0 = g.rng_state, s2 = mwc_step(mwc_step(s0));
-    if (tid < 32) s_pw[tid] = c_mwc_pw[tid];
-    __syncthreads();
     int base_c = 0, base_k = 0;
+    int bx0 = 0x7fffffff, bx1 = -0x7fffffff, by0 = 0x7fffffff, by1 = -0x7fffffff;
     for (int e0 = 0; e0 < cells; e0 += nt) {
         const int e = e0 + tid;
         const int r = minrow + e / max(RW, 1), c = mincol + e % max(RW, 1);
@@ -1528,19 +1554,138 @@ k_sample_regions(const mct_sample_region* __restrict__ regs, int cap, int* __res
         }
         int tot_k;
         const int pos = base_k + block_compact(keep, sh_c, &tot_k);
-        if (keep && pos < cap && (!thin || pos < g.max_n)) { o_col[pos] = c; o_row[pos] = r; }
+        if (keep && pos < cap && (!thin || pos < g.max_n)) {
+            o_col[pos] = c; o_row[pos] = r;
+            bx0 = min(bx0, c); bx1 = max(bx1, c); by0 = min(by0, r); by1 = max(by1, r);
+        }
         base_c += tot_c; base_k += tot_k;
     }
+    if (bbox && bx0 <= bx1) { atomicMin(&bbox[0], bx0); atomicMax(&bbox[1], bx1); atomicMin(&bbox[2], by0); atomicMax(&bbox[3], by1); }
     if (tid == 0) {
         mct_sample_region_out o;
         o.n = min(thin ? min(base_k, g.max_n) : n_list, cap);
         o.n_candidates = n_cand; o.n_draws = thin ? n_list : 0; o.pad = 0;
         o.rng_state = thin ? mwc_after(s0, s2, (unsigned)n_list, s_pw) : s0;
-        outs[blockIdx.x] = o;
+        *res = o;
     }
+    __syncthreads();
+}
+__global__ void __launch_bounds__(PF_THREADS)
+k_sample_regions(const mct_sample_region* __restrict__ regs, int cap, int* __restrict__ col, int* __restrict__ row, mct_sample_region_out* __restrict__ outs)
+{
+    __shared__ int sh_c[33];
+    __shared__ int sh_i[32];
+    __shared__ unsigned long long s_pw[32];
+    __shared__ mct_sample_region_out s_res;
+    const mct_sample_region g = regs[blockIdx.x];
+    if (threadIdx.x < 32) s_pw[threadIdx.x] = c_mwc_pw[threadIdx.x];
+    __syncthreads();
+    sample_region_body(g, cap, col + (size_t)blockIdx.x * cap, row + (size_t)blockIdx.x * cap, &s_res, nullptr, sh_c, sh_i, s_pw);
+    if (threadIdx.x == 0) outs[blockIdx.x] = s_res;
 }
 int launch_sample_regions(mct_ctx* ctx, int n, const mct_sample_region* d_reg, int cap, int* d_col, int* d_row, mct_sample_region_out* d_out)
 {
     MCT_LAUNCH(ctx, "k_sample_regions", k_sample_regions<<<n, PF_THREADS, 0, ctx->stream>>>(d_reg, cap, d_col, d_row, d_out));
+    return MCT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_train_gen_default: GenerateTrainingSampleSet with the default strategies for all objects of a camera, on the device, queued
+// behind the frame's k_pf_update (one CTA per object):
+//   m_currentStateList from the particle read-out (ParticleFilterTracker.cpp:655-672; PfTrk holds what k_pf_update left),
+//   positives = disc of m_posRadiusTrain around the state's corner (:727-741), negatives = ring between m_posRadiusTrain + 15 and
+//   1.5 m_searchWindSize (:926-937), both thinned like SelectSamplesUniformlyFromLargerSet with the tracker's own stream (positives
+//   first), boxes written behind each other into the object's slot of the training stage; then the set sizes and the plan of the
+//   pixel-list colour-histogram kernels (the device form of mdch_group_plan, mct_api.cu) go straight into the object's TrainDesc.
+// A plan outside what the host sized the launches for (TrainGenDev::*_b) sends the object to the generic per-box kernel.
+__device__ bool gen_group_plan(MdchGroup* g, int first, int n, float sx, float sy, const int* bbox, const TrainGenDev& q, int gi)
+{
+    MdchGroup z = {};
+    z.first = first; z.n = n;
+    *g = z;
+    if (n < 1 || q.dim > 1024) return false;
+    z.rows = __float2int_rn(__fmul_rn((float)q.ch0, sy)); z.cols = __float2int_rn(__fmul_rn((float)q.cw0, sx));
+    if (z.rows < 1 || z.cols < 1 || z.rows * z.cols > MCT_MDCH_SEG_PIX) return false;
+    z.x0 = bbox[0]; z.y0 = bbox[2]; z.RW = bbox[1] - bbox[0] + z.cols; z.RH = bbox[3] - bbox[2] + z.rows;
+    z.npx = z.RW * z.RH;
+    if (z.npx > 65536 || z.RW > 2047 || z.RH > 2047 || z.npx > q.npx_b[gi]) return false;
+    const int ext = (2 * z.RW - z.cols) * (2 * z.RH - z.rows);
+    z.EW = (ext <= MTR_EXT_WORDS && ext <= q.tab_b) ? 1 : 0; z.EH = 0;
+    if (!z.EW && z.rows * z.cols > q.tab_b) return false;
+    const int T = 384;
+    const int B = min((n + 31) & ~31, T), S = T / B;
+    z.chunk_px = S * 160;
+    z.nchunk = (z.npx + z.chunk_px - 1) / z.chunk_px;
+    if (z.nchunk > q.nch_b) return false;
+    const int shift = __clz(z.rows * z.cols);
+    z.shift = shift > MCT_FIX_SHIFT_MAX ? MCT_FIX_SHIFT_MAX : shift;
+    *g = z;
+    return true;
+}
+__global__ void __launch_bounds__(PF_THREADS)
+k_train_gen_default(const TrainGenDev* __restrict__ gens, TrainDesc* __restrict__ descs, mct_train_default_out* __restrict__ outs)
+{
+    __shared__ int sh_c[33];
+    __shared__ int sh_i[32];
+    __shared__ unsigned long long s_pw[32];
+    __shared__ mct_sample_region_out s_res[2];
+    __shared__ int s_bbox[2][4];
+    const TrainGenDev q = gens[blockIdx.x];
+    TrainDesc& t = descs[blockIdx.x];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid < 32) s_pw[tid] = c_mwc_pw[tid];
+    __syncthreads();
+    const float* a = q.opt == 0 ? q.trk->first : q.trk->avg;
+    const float a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3];
+    const int n_valid = q.st->n_valid;
+    const unsigned long long rng0 = q.trk->rng;
+    float cur[6];
+    {
+        const float wf = __fmul_rn(a2, q.w0), hf = __fmul_rn(a3, q.h0);
+        const float x = __fsub_rn(a0, __fdiv_rn(wf, 2.0f)), y = __fsub_rn(a1, __fdiv_rn(hf, 2.0f));
+        cur[0] = x < 0.0f ? 0.0f : x; cur[1] = y < 0.0f ? 0.0f : y; cur[2] = q.w0; cur[3] = q.h0; cur[4] = a2; cur[5] = a3;
+    }
+    int* col = q.stage; int* row = q.stage + q.mcap;
+    float* sx = (float*)(q.stage + 2 * q.mcap); float* sy = (float*)(q.stage + 3 * q.mcap);
+    int P = 0, Nn = 0;
+    unsigned long long rng = rng0;
+    int n_draws = 0;
+    float nsx = 1.0f, nsy = 1.0f;
+    const bool usable = n_valid > 0 && a0 == a0 && a1 == a1 && a2 == a2 && a3 == a3;
+    if (usable) {
+        mct_sample_region g;
+        g.kind = 0; g.x = (int)cur[0]; g.y = (int)cur[1]; g.width = (int)cur[2]; g.height = (int)cur[3];
+        g.p[0] = q.pos_radius; g.p[1] = 0.0f; g.p[2] = 0.0f; g.p[3] = 0.0f;
+        g.max_n = q.max_pos; g.scale_x = cur[4]; g.scale_y = cur[5]; g.frame_w = q.frame_w; g.frame_h = q.frame_h; g.rng_state = rng;
+        sample_region_body(g, q.cap_pos, col, row, &s_res[0], s_bbox[0], sh_c, sh_i, s_pw);
+        P = s_res[0].n; rng = s_res[0].rng_state; n_draws = s_res[0].n_draws;
+        nsx = fminf(cur[4], q.maxs); nsy = fminf(cur[5], q.maxs);
+        g.x = __float2int_rn(cur[0]); g.y = __float2int_rn(cur[1]); g.width = __float2int_rn(cur[2]); g.height = __float2int_rn(cur[3]);
+        g.p[0] = q.neg_outer; g.p[1] = q.neg_inner;
+        g.max_n = q.max_neg; g.scale_x = nsx; g.scale_y = nsy; g.rng_state = rng;
+        sample_region_body(g, q.cap_neg, col + P, row + P, &s_res[1], s_bbox[1], sh_c, sh_i, s_pw);
+        Nn = s_res[1].n; rng = s_res[1].rng_state; n_draws += s_res[1].n_draws;
+        for (int i = tid; i < P + Nn; i += nt) { sx[i] = i < P ? cur[4] : nsx; sy[i] = i < P ? cur[5] : nsy; }
+    }
+    if (tid == 0) {
+        const bool ok = usable && P >= 1 && Nn >= 1;
+        int fast = 0;
+        if (ok && q.mdch) {
+            const bool ok0 = gen_group_plan(&t.grp[0], 0, P, cur[4], cur[5], s_bbox[0], q, 0);
+            const bool ok1 = gen_group_plan(&t.grp[1], P, Nn, nsx, nsy, s_bbox[1], q, 1);
+            if (ok0 && ok1) { fast = 1; t.grp[0].list_off = 0; t.grp[1].list_off = t.grp[0].npx; }
+        }
+        t.P = ok ? P : 0; t.Nn = ok ? Nn : 0; t.mdch_fast = fast;
+        q.trk->rng = rng;
+        mct_train_default_out o;
+        o.P = P; o.Nn = Nn; o.status = ok ? MCT_OK : MCT_E_EMPTY; o.mdch_fast = fast; o.rng_state = rng;
+        for (int k = 0; k < 6; k++) o.cur[k] = cur[k];
+        o.n_draws = n_draws; o.pad = 0;
+        outs[blockIdx.x] = o;
+    }
+}
+int launch_train_gen_default(mct_ctx* ctx, int n_obj, const TrainGenDev* d_gen, TrainDesc* d_tdesc, mct_train_default_out* d_out)
+{
+    MCT_LAUNCH(ctx, "k_train_gen_default", k_train_gen_default<<<n_obj, PF_THREADS, 0, ctx->stream>>>(d_gen, d_tdesc, d_out));
     return MCT_OK;
 }

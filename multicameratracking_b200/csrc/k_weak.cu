@@ -176,6 +176,7 @@ k_weak_update(const float* __restrict__ feat, int ld, int F, int P, int Nn, int 
 __global__ void __launch_bounds__(256) k_weak_update_batch(const TrainDesc* __restrict__ descs)
 {
     const TrainDesc& d = descs[blockIdx.y];
+    if (d.P < 1 || d.Nn < 1) return;              // empty training set decided on the device (k_train_gen_default): classifier left as it is
     weak_update_body(d.featT, d.ldT, d.F, d.P, d.Nn, d.weak_type, d.lr, d.tw, d.weak, d.trained, d.pred, d.keep);
 }
 int launch_weak_update_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj)

@@ -220,6 +220,10 @@ extern "C" int mct_ctx_destroy(mct_ctx* ctx)
     }
     if (ctx->h_train_stage) cudaFreeHost(ctx->h_train_stage);
     if (ctx->d_train_stage) cudaFree(ctx->d_train_stage);
+    if (ctx->d_gen) cudaFree(ctx->d_gen);
+    if (ctx->h_gen_out) cudaFreeHost(ctx->h_gen_out);
+    free(ctx->gen_shadow); free(ctx->tdesc_shadow);
+    if (ctx->has_ev_score) cudaEventDestroy(ctx->ev_score);
     free(ctx->desc_last_h);
     DescRing* r = ring_of(ctx);
     if (r) {
@@ -1014,6 +1018,10 @@ extern "C" int mct_classifier_get_predictions(mct_clf* c, float* out, int* P, in
 {
     if (!c || !out || !P || !Nn) return MCT_E_ARG;
     mct_ctx* ctx = c->ctx;
+    if (c->lastP < 0 && ctx->gen_pending) {              // the last Update took its set sizes on the device: fetch them
+        int rc = mct_track_update_default_collect(ctx, ctx->gen_n, nullptr);
+        if (rc && rc != MCT_E_EMPTY) return rc;
+    }
     *P = c->lastP; *Nn = c->lastNn;
     int M = c->lastP + c->lastNn;
     if (M <= 0) return MCT_OK;
@@ -1040,6 +1048,7 @@ extern "C" int mct_pf_create(mct_ctx* ctx, int N, float image_w, float image_h, 
     MCT_CUDA(ctx, cudaMalloc(&p->d_noise, 4 * ld * 4)); MCT_CUDA(ctx, cudaMalloc(&p->d_prob, ld * 4));
     MCT_CUDA(ctx, cudaMalloc(&p->d_scratch, 2 * (ld + ld / 64 + 64) * 4));   // sw | cdf in the padded chain layout (k_pf.cu PLEN)
     MCT_CUDA(ctx, cudaMalloc(&p->d_st, sizeof(PfDev))); MCT_CUDA(ctx, cudaMemset(p->d_st, 0, sizeof(PfDev)));
+    MCT_CUDA(ctx, cudaMalloc(&p->d_trk, sizeof(PfTrk))); MCT_CUDA(ctx, cudaMemset(p->d_trk, 0, sizeof(PfTrk)));
     MCT_CUDA(ctx, cudaMalloc(&p->d_summ, sizeof(mct_pf_summary)));
     MCT_CUDA(ctx, cudaMemset(p->d_summ, 0, sizeof(mct_pf_summary)));
     MCT_CUDA(ctx, cudaMemset(p->d_state, 0, 5 * ld * 4)); MCT_CUDA(ctx, cudaMemset(p->d_res, 0, 5 * ld * 4));
@@ -1054,7 +1063,7 @@ extern "C" int mct_pf_destroy(mct_pf* p)
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
     void* ptrs[] = {p->d_state, p->d_res, p->d_residx, p->d_col, p->d_row, p->d_valid, p->d_H, p->d_noise, p->d_prob,
-                    p->d_scratch, p->d_st, p->d_summ};
+                    p->d_scratch, p->d_st, p->d_summ, p->d_trk};
     for (void* q : ptrs) if (q) cudaFree(q);
     delete p;
     return MCT_OK;
@@ -1067,6 +1076,7 @@ static void fill_pf_desc(ObjDesc* d, mct_pf* p)
     d->rcx = p->d_res; d->rcy = p->d_res + ld; d->rsx = p->d_res + 2 * ld; d->rsy = p->d_res + 3 * ld; d->rw = p->d_res + 4 * ld;
     d->residx = p->d_residx; d->col = p->d_col; d->row = p->d_row; d->valid = p->d_valid;
     d->H = p->d_H; d->noise_off = 0; d->scratch = p->d_scratch; d->st = p->d_st; d->summ = p->d_summ;
+    d->trk = p->d_trk;
     d->scored = p->ctx->d_scored;
     d->N = p->N; d->ld = p->ld;
     d->img_w = p->img_w; d->img_h = p->img_h; d->msc = p->msc; d->maxs = p->maxs; d->mins = p->mins;
@@ -1395,7 +1405,7 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
                                      const mct_track_params* params, const float* noise, int noise_is_device,
                                      const float* u01)
 {
-    if (!ctx || n_obj < 1 || n_obj > DESC_MAX_OBJ || !pfs || !clfs || !params || !u01) return MCT_E_ARG;
+    if (!ctx || n_obj < 1 || n_obj > DESC_MAX_OBJ || !pfs || !clfs || !params) return MCT_E_ARG;
     if (ctx->frame_id == 0) return mct_fail(ctx, MCT_E_STATE, "no frame set%s");
     const bool rescore = noise == nullptr;      // UpdateParticleWeightsForRearrangedParticles: no prediction step
     MCT_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1419,11 +1429,12 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
         h[o].summ = ctx->h_summ_dev + o;               // the read-out is written straight into mapped pinned memory
         h[o].w0 = params[o].w0; h[o].h0 = params[o].h0; h[o].exponent = params[o].exponent;
         h[o].force_reset = params[o].force_reset; h[o].resample = params[o].resample;
-        sa.u01[o] = u01[o];
+        sa.u01[o] = u01 ? u01[o] : 0.0f;
         ntot += (size_t)4 * p->N;
         if (p->N > n_max) n_max = p->N;
         if (c->K > K_max) K_max = c->K;
     }
+    sa.dev_rng = u01 ? 0 : 1;                          // u01 == NULL: every object draws from its device-resident stream (mct_pf_rng_set)
     // prediction noise: device pointers are used in place; a block announced with mct_noise_prefetch is already on the
     // device; any other host noise is staged with ONE copy
     if (noise_is_device || rescore) sa.noise_base = noise;
@@ -1480,6 +1491,11 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
         ctx->has_gather = 1;
     }
     if ((rc = launch_pf_update(ctx, d, n_obj, n_max, 1, sa, 1))) return rc;
+    // the read-outs are complete behind this point: mct_track_collect waits for it, not for whatever the caller queues next
+    // (the frame's UpdateClassifier when it runs from the device, mct_track_update_default)
+    if (!ctx->has_ev_score) { MCT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_score, cudaEventDisableTiming)); ctx->has_ev_score = 1; }
+    MCT_CUDA(ctx, cudaEventRecord(ctx->ev_score, ctx->stream));
+    ctx->score_gen_seq = ctx->gen_seq;                 // every device-side UpdateClassifier queued so far completes in front of that event
     // Only now, with this frame's whole chain queued, the housekeeping for the NEXT frame: every API call in front of the
     // first launch is host time the GPU sits idle for (the caller waits for this frame's summaries before the next call)
     if (ctx->prep_stream && (rc = prefetch_copy(ctx))) return rc;      // next frame's planes (behind this frame's noise copy)
@@ -1515,9 +1531,21 @@ extern "C" int mct_noise_prefetch(mct_ctx* ctx, const float* noise_host, size_t 
 extern "C" int mct_track_collect(mct_ctx* ctx, int n_obj, mct_pf_summary* summaries)
 {
     if (!ctx || n_obj < 1 || n_obj > DESC_MAX_OBJ || !summaries) return MCT_E_ARG;
-    int rc = mct_sync(ctx);
-    if (rc) return rc;
+    if (ctx->has_ev_score) MCT_CUDA(ctx, cudaEventSynchronize(ctx->ev_score));
+    else { int rc = mct_sync(ctx); if (rc) return rc; }
     memcpy(summaries, ctx->h_summ, sizeof(mct_pf_summary) * n_obj);
+    if (ctx->h_gen_out && ctx->score_gen_seq > ctx->gen_checked_seq) {
+        // the device-side UpdateClassifier of the PREVIOUS frame has completed (it was queued in front of this frame's kernels):
+        // an empty training set it met is reported here, one frame late
+        const mct_train_default_out* res = ctx->h_gen_out + (ctx->score_gen_seq & 1) * DESC_MAX_OBJ;
+        ctx->gen_checked_seq = ctx->score_gen_seq;
+        if (ctx->gen_checked_seq == ctx->gen_seq) ctx->gen_pending = 0;
+        for (int o = 0; o < ctx->gen_n; o++) {
+            if (ctx->gen_clfs[o] && ctx->gen_checked_seq == ctx->gen_seq) { ctx->gen_clfs[o]->lastP = res[o].P; ctx->gen_clfs[o]->lastNn = res[o].Nn; }
+            if (res[o].status != MCT_OK)
+                return mct_fail(ctx, res[o].status, "object %s%d: the previous frame's training set was empty (classifier left as it was)", "", o);
+        }
+    }
     for (int o = 0; o < n_obj; o++)
         if (summaries[o].n_valid == 0)
             return mct_fail(ctx, MCT_E_EMPTY, "object %s%d has no valid test sample (all particles out of frame)", "", o);
@@ -1581,7 +1609,7 @@ static bool mdch_group_plan(MdchGroup* g, const mct_boxes* b, int first, int w0,
     g->rows = (int)lrintf((float)h0 * sy); g->cols = (int)lrintf((float)w0 * sx);      // __float2int_rn(__fmul_rn(.)), as the kernels
     if (g->rows < 1 || g->cols < 1 || g->rows * g->cols > MCT_MDCH_SEG_PIX) return false;
     g->x0 = x0; g->y0 = y0; g->RW = x1 - x0 + g->cols; g->RH = y1 - y0 + g->rows;
-    g->EW = 0; g->EH = 0;
+    g->EW = ((2 * g->RW - g->cols) * (2 * g->RH - g->rows) <= MTR_EXT_WORDS) ? 1 : 0; g->EH = 0;
     g->npx = g->RW * g->RH;
     if (g->npx > 65536 || g->RW > 2047 || g->RH > 2047) return false;
     // one CTA walks chunk_px list entries: S slices side by side (S = threads / boxes per pass), ~160 entries per thread
@@ -1721,6 +1749,7 @@ static int train_stage_and_features(mct_ctx* ctx, int n_obj, mct_clf* const* clf
     }
     MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_train_stage, ctx->h_train_stage, total * 4 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tdesc, ctx->h_tdesc, sizeof(TrainDesc) * n_obj, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->tdesc_gen_valid = 0;
     MCT_CUDA(ctx, cudaEventRecord(ctx->ev_train, ctx->stream));
     if ((rc = launch_train_features(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj))) return rc;
     creq_out = creq;
@@ -1796,11 +1825,220 @@ extern "C" int mct_track_update_from_gathered(mct_ctx* ctx, int n_obj, mct_clf* 
         off += (size_t)M;
     }
     MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tdesc, ctx->h_tdesc, sizeof(TrainDesc) * n_obj, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->tdesc_gen_valid = 0;
     MCT_CUDA(ctx, cudaEventRecord(ctx->ev_train, ctx->stream));
     if ((rc = launch_ensemble_retain_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj))) return rc;
     if ((rc = launch_weak_update_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj))) return rc;
     if ((rc = launch_mil_select_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj, creq.data()))) return rc;
     if ((rc = launch_build_colormap_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj))) return rc;
+    return MCT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The whole frame on the device: the tracker's stream as device-resident state, and UpdateClassifier with the
+// default-strategy training sets generated by k_train_gen_default (k_pf.cu) behind the frame's k_pf_update.
+extern "C" int mct_pf_rng_set(mct_pf* p, unsigned long long state)
+{
+    if (!p) return MCT_E_ARG;
+    mct_ctx* ctx = p->ctx;
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    MCT_CUDA(ctx, cudaMemcpyAsync(&p->d_trk->rng, &state, sizeof(state), cudaMemcpyHostToDevice, ctx->stream));
+    return mct_sync(ctx);                       // `state` is a stack value of the caller's frame
+}
+extern "C" int mct_pf_rng_get(mct_pf* p, unsigned long long* state)
+{
+    if (!p || !state) return MCT_E_ARG;
+    mct_ctx* ctx = p->ctx;
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    MCT_CUDA(ctx, cudaMemcpyAsync(state, &p->d_trk->rng, sizeof(*state), cudaMemcpyDeviceToHost, ctx->stream));
+    return mct_sync(ctx);
+}
+
+// candidates of SampleSet::SampleImage's ring form when the frame does not clip it (SampleSet.cpp:106-140)
+static int ring_count_unclipped(float outer, float inner)
+{
+    static float s_o[8], s_i[8]; static int s_n[8], s_used = 0;      // a handful of (outer, inner) pairs per process
+    for (int k = 0; k < s_used; k++) if (s_o[k] == outer && s_i[k] == inner) return s_n[k];
+    const int R = (int)outer;
+    const float o2 = outer * outer, i2 = inner * inner;
+    int n = 0;
+    for (int dy = -R; dy <= R; dy++)
+        for (int dx = -R; dx <= R; dx++) { const int d = dx * dx + dy * dy; n += ((float)d < o2 && (float)d >= i2) ? 1 : 0; }
+    if (s_used < 8) { s_o[s_used] = outer; s_i[s_used] = inner; s_n[s_used] = n; s_used++; }
+    return n;
+}
+
+extern "C" int mct_track_update_default(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, mct_clf* const* clfs, const mct_train_default* gen)
+{
+    if (!ctx || n_obj < 1 || n_obj > DESC_MAX_OBJ || !pfs || !clfs || !gen) return MCT_E_ARG;
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if (!ctx->d_gen) {
+        MCT_CUDA(ctx, cudaMalloc(&ctx->d_gen, sizeof(TrainGenDev) * DESC_MAX_OBJ));
+        MCT_CUDA(ctx, cudaHostAlloc(&ctx->h_gen_out, sizeof(mct_train_default_out) * DESC_MAX_OBJ * 2, cudaHostAllocMapped));
+        MCT_CUDA(ctx, cudaHostGetDevicePointer(&ctx->h_gen_out_dev, ctx->h_gen_out, 0));
+        memset(ctx->h_gen_out, 0, sizeof(mct_train_default_out) * DESC_MAX_OBJ * 2);
+        ctx->gen_shadow = calloc(DESC_MAX_OBJ, sizeof(TrainGenDev));
+        ctx->tdesc_shadow = calloc(DESC_MAX_OBJ, sizeof(TrainDesc));
+        if (!ctx->gen_shadow || !ctx->tdesc_shadow) return mct_fail(ctx, MCT_E_NOMEM, "out of host memory%s");
+    }
+    if (!ctx->h_tdesc && (rc = train_descs_ready(ctx))) return rc;
+    std::vector<TrainGenDev> hg(n_obj); std::vector<TrainDesc> ht(n_obj);
+    TrainGenDev* g = hg.data(); TrainDesc* tds = ht.data();
+    std::vector<int> creq(n_obj, 0);
+    TrainLaunchBounds lb = {0, 0, 0, 0, 0, 0};
+    size_t stage_words = 0, mlist_words = 0, macc_words = 0;
+    for (int o = 0; o < n_obj; o++) {
+        mct_pf* p = pfs[o]; mct_clf* c = clfs[o];
+        if (!p || !c || p->ctx != ctx || c->ctx != ctx) return mct_fail(ctx, MCT_E_ARG, "object handle belongs to another ctx%s");
+        if (!p->initialized) return mct_fail(ctx, MCT_E_STATE, "particle filter not initialised%s");
+        if (c->p.feature_type == MCT_FEAT_CCH) return mct_fail(ctx, MCT_E_UNSUPPORTED, "device-side training sets: culture colour classifiers take mct_track_update%s");
+        if ((rc = need_frame(c))) return rc;
+        const mct_train_default& q = gen[o];
+        if (!(q.pos_radius > 0.0f) || !(q.neg_outer > q.neg_inner) || q.max_pos < 0 || q.max_neg < 0) return mct_fail(ctx, MCT_E_ARG, "training-sample radii / counts out of range%s");
+        const int cnt_p = ring_count_unclipped(q.pos_radius, 0.0f), cnt_n = ring_count_unclipped(q.neg_outer, q.neg_inner);
+        const int Pb = std::max(1, (int)std::min<long long>(cnt_p, (long long)q.max_pos + 1)), Nb = std::max(1, (int)std::min<long long>(cnt_n, (long long)q.max_neg + 1));
+        const int Mb = Pb + Nb;
+        if (Mb > c->max_train) return mct_fail(ctx, MCT_E_ARG, "training set exceeds max_train%s (%d)", "", Mb);
+        const int mcap = round_up(Mb, 4);
+        TrainGenDev& d = g[o];
+        memset(&d, 0, sizeof(d));
+        d.trk = p->d_trk; d.st = p->d_st; d.mcap = mcap; d.cap_pos = Pb; d.cap_neg = Nb;
+        d.w0 = q.w0; d.h0 = q.h0; d.opt = q.trajectory_option;
+        d.pos_radius = q.pos_radius; d.max_pos = q.max_pos; d.neg_outer = q.neg_outer; d.neg_inner = q.neg_inner; d.max_neg = q.max_neg;
+        d.maxs = p->maxs; d.frame_w = ctx->W; d.frame_h = ctx->H;
+        d.cw0 = c->p.w0; d.ch0 = c->p.h0; d.dim = c->n_color;
+        d.mdch = (c->p.feature_type == MCT_FEAT_MDCH || c->p.feature_type == MCT_FEAT_HAAR_MDCH) && !getenv("MCT_MDCH_TRAIN_GENERIC");
+        TrainDesc* t = &tds[o];
+        fill_train_desc(t, c);
+        t->P = Pb; t->Nn = Nb;                       // upper bounds: the launches are sized from them, the kernel writes the real sizes
+        t->mdch_fast = d.mdch;
+        creq[o] = c->cluster;
+        lb.n_max = std::max(lb.n_max, Mb);
+        if (d.mdch) {
+            // bounds of the pixel-list plan from the hinted scale (+ 2 pixels of slack on the box size)
+            const float shx = q.scale_hint_x > 0 ? q.scale_hint_x : 1.0f, shy = q.scale_hint_y > 0 ? q.scale_hint_y : 1.0f;
+            const float hsx[2] = {shx, std::min(shx, p->maxs)}, hsy[2] = {shy, std::min(shy, p->maxs)};
+            const int R[2] = {(int)q.pos_radius, (int)q.neg_outer}, nb_[2] = {Pb, Nb};
+            for (int gi = 0; gi < 2; gi++) {
+                const int cols = (int)lrintf((float)c->p.w0 * hsx[gi]) + 2, rows = (int)lrintf((float)c->p.h0 * hsy[gi]) + 2;
+                const int RW = 2 * R[gi] + cols, RH = 2 * R[gi] + rows;
+                const int npx = std::min(RW * RH, 65536);
+                d.npx_b[gi] = npx;
+                const int ext = (2 * RW - cols) * (2 * RH - rows);
+                d.tab_b = std::max(d.tab_b, ext <= MTR_EXT_WORDS ? ext : std::min(rows * cols, MCT_MDCH_SEG_PIX));
+                const int B = std::min((nb_[gi] + 31) & ~31, 384), S = 384 / B;
+                d.nch_b = std::max(d.nch_b, (npx + S * 160 - 1) / (S * 160));
+                lb.npx_max = std::max(lb.npx_max, npx);
+            }
+            lb.nch = std::max(lb.nch, d.nch_b); lb.tab_words = std::max(lb.tab_words, d.tab_b);
+            lb.chunk_words = 12 * 160;               // the longest chunk a group can ask for (32 boxes or fewer: 12 slices of 160)
+            lb.n_train_max = std::max(lb.n_train_max, Mb);
+            mlist_words += (size_t)d.npx_b[0] + d.npx_b[1];
+            macc_words += (size_t)c->n_color * c->ldT;
+        }
+        stage_words += (size_t)4 * mcap;
+    }
+    // buffers (grow-only; growing synchronises)
+    if (stage_words > ctx->train_stage_cap * 4) {
+        MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_train_stage) cudaFreeHost(ctx->h_train_stage);
+        if (ctx->d_train_stage) cudaFree(ctx->d_train_stage);
+        const size_t cap = stage_words / 4 + 1024;
+        MCT_CUDA(ctx, cudaMallocHost(&ctx->h_train_stage, cap * 4 * sizeof(int)));
+        MCT_CUDA(ctx, cudaMalloc(&ctx->d_train_stage, cap * 4 * sizeof(int)));
+        ctx->train_stage_cap = cap;
+        ctx->tdesc_gen_valid = 0;
+    }
+    if (mlist_words > ctx->mlist_cap || macc_words > ctx->macc_cap || !ctx->d_mtot) {
+        MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (mlist_words > ctx->mlist_cap) {
+            if (ctx->d_mlist) cudaFree(ctx->d_mlist);
+            MCT_CUDA(ctx, cudaMalloc(&ctx->d_mlist, (mlist_words + 4096) * 4)); ctx->mlist_cap = mlist_words + 4096;
+        }
+        if (macc_words > ctx->macc_cap) {
+            if (ctx->d_macc) cudaFree(ctx->d_macc);
+            MCT_CUDA(ctx, cudaMalloc(&ctx->d_macc, (macc_words + 4096) * 4)); ctx->macc_cap = macc_words + 4096;
+            MCT_CUDA(ctx, cudaMemset(ctx->d_macc, 0, ctx->macc_cap * 4));
+        }
+        if (!ctx->d_mtot) MCT_CUDA(ctx, cudaMalloc(&ctx->d_mtot, (size_t)DESC_MAX_OBJ * 2 * 4));
+        ctx->tdesc_gen_valid = 0;
+    }
+    {
+        size_t so = 0, lo = 0, ao = 0;
+        for (int o = 0; o < n_obj; o++) {
+            TrainGenDev& d = g[o]; TrainDesc* t = &tds[o];
+            d.stage = ctx->d_train_stage + so;
+            t->col = d.stage; t->row = d.stage + d.mcap; t->sx = (const float*)(d.stage + 2 * d.mcap); t->sy = (const float*)(d.stage + 3 * d.mcap); t->tw = nullptr;
+            so += (size_t)4 * d.mcap;
+            if (d.mdch) {
+                t->mlist = ctx->d_mlist + lo; t->macc = ctx->d_macc + ao; t->mtot = ctx->d_mtot + 2 * o;
+                lo += (size_t)d.npx_b[0] + d.npx_b[1]; ao += (size_t)clfs[o]->n_color * clfs[o]->ldT;
+            }
+        }
+    }
+    // arguments and descriptors travel only when they differ from what the device already holds (the kernel rewrites every
+    // per-frame field of the descriptors itself)
+    if (ctx->gen_shadow_n != n_obj || memcmp(ctx->gen_shadow, g, sizeof(TrainGenDev) * n_obj) != 0) {
+        memcpy(ctx->gen_shadow, g, sizeof(TrainGenDev) * n_obj); ctx->gen_shadow_n = n_obj;
+        MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_gen, ctx->gen_shadow, sizeof(TrainGenDev) * n_obj, cudaMemcpyHostToDevice, ctx->stream));
+        MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));       // pageable source: rare (a changed hint or object set)
+    }
+    if (!ctx->tdesc_gen_valid || ctx->tdesc_shadow_n != n_obj || memcmp(ctx->tdesc_shadow, tds, sizeof(TrainDesc) * n_obj) != 0) {
+        if ((rc = train_descs_ready(ctx))) return rc;
+        memcpy(ctx->tdesc_shadow, tds, sizeof(TrainDesc) * n_obj); ctx->tdesc_shadow_n = n_obj;
+        memcpy(ctx->h_tdesc, tds, sizeof(TrainDesc) * n_obj);
+        MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tdesc, ctx->h_tdesc, sizeof(TrainDesc) * n_obj, cudaMemcpyHostToDevice, ctx->stream));
+        MCT_CUDA(ctx, cudaEventRecord(ctx->ev_train, ctx->stream));
+        ctx->tdesc_gen_valid = 1;
+    }
+    for (int o = 0; o < n_obj; o++) { ctx->gen_clfs[o] = clfs[o]; clfs[o]->lastP = -1; clfs[o]->lastNn = -1; }
+    ctx->gen_n = n_obj; ctx->gen_pending = 1; ctx->gen_seq++;
+    if ((rc = launch_train_gen_default(ctx, n_obj, ctx->d_gen, ctx->d_tdesc, ctx->h_gen_out_dev + (ctx->gen_seq & 1) * DESC_MAX_OBJ))) return rc;
+    if ((rc = launch_train_features(ctx, ctx->d_tdesc, tds, n_obj, &lb))) return rc;
+    if ((rc = launch_ensemble_retain_batch(ctx, ctx->d_tdesc, tds, n_obj))) return rc;
+    if ((rc = launch_weak_update_batch(ctx, ctx->d_tdesc, tds, n_obj))) return rc;
+    if ((rc = launch_mil_select_batch(ctx, ctx->d_tdesc, tds, n_obj, creq.data()))) return rc;
+    if ((rc = launch_build_colormap_batch(ctx, ctx->d_tdesc, tds, n_obj))) return rc;
+    return MCT_OK;
+}
+
+extern "C" int mct_track_update_default_collect(mct_ctx* ctx, int n_obj, mct_train_default_out* out)
+{
+    if (!ctx || n_obj < 1 || n_obj > DESC_MAX_OBJ) return MCT_E_ARG;
+    if (!ctx->h_gen_out || ctx->gen_n < n_obj) return mct_fail(ctx, MCT_E_STATE, "no device-side UpdateClassifier to collect%s");
+    int rc = mct_sync(ctx);
+    if (rc) return rc;
+    ctx->gen_pending = 0; ctx->gen_checked_seq = ctx->gen_seq;
+    const mct_train_default_out* res = ctx->h_gen_out + (ctx->gen_seq & 1) * DESC_MAX_OBJ;
+    if (out) memcpy(out, res, sizeof(mct_train_default_out) * n_obj);
+    for (int o = 0; o < n_obj; o++) {
+        const mct_train_default_out& r = res[o];
+        if (ctx->gen_clfs[o]) { ctx->gen_clfs[o]->lastP = r.status == MCT_OK ? r.P : 0; ctx->gen_clfs[o]->lastNn = r.status == MCT_OK ? r.Nn : 0; }
+    }
+    for (int o = 0; o < n_obj; o++)
+        if (res[o].status != MCT_OK)
+            return mct_fail(ctx, res[o].status, "object %s%d: empty training set (classifier left as it was)", "", o);
+    return MCT_OK;
+}
+
+// the boxes k_train_gen_default produced for object `obj` of the last mct_track_update_default (tests / diagnostics): positives
+// first, then negatives; synchronises
+extern "C" int mct_track_update_default_boxes(mct_ctx* ctx, int obj, int cap, int* col, int* row, float* sx, float* sy, int* P, int* Nn)
+{
+    if (!ctx || obj < 0 || cap < 0 || !P || !Nn) return MCT_E_ARG;
+    if (!ctx->h_gen_out || obj >= ctx->gen_n || obj >= ctx->gen_shadow_n) return mct_fail(ctx, MCT_E_STATE, "no device-side UpdateClassifier to read%s");
+    int rc = mct_sync(ctx);
+    if (rc) return rc;
+    const mct_train_default_out& r = ctx->h_gen_out[(ctx->gen_seq & 1) * DESC_MAX_OBJ + obj];
+    *P = r.P; *Nn = r.Nn;
+    const TrainGenDev& g = ((const TrainGenDev*)ctx->gen_shadow)[obj];
+    const int n = std::min(r.P + r.Nn, cap);
+    if (n <= 0) return MCT_OK;
+    if (col) MCT_CUDA(ctx, cudaMemcpy(col, g.stage, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    if (row) MCT_CUDA(ctx, cudaMemcpy(row, g.stage + g.mcap, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    if (sx) MCT_CUDA(ctx, cudaMemcpy(sx, g.stage + 2 * g.mcap, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    if (sy) MCT_CUDA(ctx, cudaMemcpy(sy, g.stage + 3 * g.mcap, (size_t)n * 4, cudaMemcpyDeviceToHost));
     return MCT_OK;
 }
 

@@ -23,6 +23,15 @@ struct PfDev {
     int   time_index;
     int   refine;        // CheckForParticleRefinement hand-over between the predict kernel and k_pf_update (k_pf.cu)
 };
+// Device-resident tracker state of one object (mct_pf::d_trk): what GenerateTrainingSampleSet reads from the particle filter
+// (ParticleFilterTracker.cpp:655-672), kept next to the mapped host read-out so that the training-sample kernel of the same
+// frame needs no host round trip, and the tracker's multiply-with-carry stream when it lives on the device (mct_pf_rng_set).
+struct PfTrk {
+    unsigned long long rng;      // Public::rng_state of this tracker (Public.cpp:15-23)
+    float avg[4];                // GetAverageofAllParticles
+    float first[4];              // GetOrderedUniqueParticles(0)
+    int   n_valid, pad;
+};
 
 // One selected weak classifier, ready for Classify: Haar rect table (or the featN row of a colour feature) + the
 // 8-float weak state.  The table of a classifier is rebuilt on the device after every Update (k_build_colormap)
@@ -95,6 +104,14 @@ struct mct_ctx {
     void* d_argmax; int argmax_cap;   // read-out of k_response_argmax [n_obj] {idx, val}
     uint32_t* d_mlist; size_t mlist_cap; uint32_t* d_macc; size_t macc_cap; uint32_t* d_mtot;   // k_mdch_train_* work buffers
     P2PPeers p2p; int p2p_world, p2p_rank; unsigned p2p_seq; unsigned* d_p2p_ticket; float* h_p2p_out; float* h_p2p_out_dev; int* h_p2p_status; int* h_p2p_status_dev;
+    // whole frame on the device (mct_track_update_default): per-object generator arguments (uploaded when they change), the mapped
+    // read-out of k_train_gen_default, the descriptor set last uploaded for it, the event behind the frame's k_pf_update
+    struct TrainGenDev* d_gen; void* gen_shadow; int gen_shadow_n;
+    mct_train_default_out* h_gen_out; mct_train_default_out* h_gen_out_dev;
+    void* tdesc_shadow; int tdesc_shadow_n; int tdesc_gen_valid;
+    mct_clf* gen_clfs[64]; int gen_n; int gen_pending;
+    long long gen_seq, score_gen_seq, gen_checked_seq;   // read-outs alternate between two buffers (gen_seq & 1); see mct_track_collect
+    cudaEvent_t ev_score; int has_ev_score;
     GroundOut* d_ground_out;     // read-out of k_ground_pdf [DESC_MAX_OBJ]
     GroundArgs* d_ground_args;   // its per-object arguments [DESC_MAX_OBJ]
 };
@@ -161,6 +178,7 @@ struct mct_pf {
     float* d_prob;       // ld
     float* d_scratch;    // 2*ld (cdf / weights when N too large for smem)
     PfDev* d_st;
+    PfTrk* d_trk;
     mct_pf_summary* d_summ;
     int initialized;
 };
@@ -173,6 +191,7 @@ struct ObjDesc {
     int* residx; int* col; int* row; int* valid;
     float* H; long long noise_off; float* scratch;      // noise_off: float offset of this object's 4 x N noise block in StepArgs::noise_base
     PfDev* st; mct_pf_summary* summ; unsigned long long* scored;
+    PfTrk* trk;
     int N, ld;
     float img_w, img_h, msc, maxs, mins;
     float w0, h0;
@@ -195,11 +214,12 @@ struct ObjDesc {
 // (blockIdx.y / .z = object) instead of five launches + eight copies per object.
 // One group of training boxes of one object (the positives, or the negatives): same box size, corners inside one bounding
 // region.  Filled on the host (mct_track_update); n == 0 or ok == 0 sends the object to the generic kernel.
+#define MTR_EXT_WORDS 12288    // largest extended weight table of k_mdch_train_main (words of shared memory)
 struct MdchGroup {
     int first, n;              // box index range [first, first + n) in the object's training set
     int rows, cols;            // common box size in pixels
     int x0, y0, RW, RH;        // bounding region of the boxes (image coordinates of its corner, extent)
-    int EW, EH;                // extended weight table: E[(dy + RH - rows) * EW + dx + RW - cols], zero outside the box
+    int EW, EH;                // EW != 0: the walk uses the extended weight table E[(dy + RH - rows) * (2 RW - cols) + dx + RW - cols], zero outside the box
     int list_off, npx;         // this group's slice of the sorted pixel list
     int nchunk, chunk_px;      // list chunks (one CTA each)
     int shift, pad;
@@ -228,6 +248,7 @@ struct TrainDesc {
 struct StepArgs {
     const float* noise_base;       // [sum over objects of 4 * N] Gaussian rows (device)
     float u01[DESC_MAX_OBJ];       // the randfloat() of ResampleParticles per object
+    int dev_rng = 0;               // 1: the draw comes from the object's device-resident stream (PfTrk::rng), which advances iff it resamples
 };
 
 // per-object arguments of the batched RearrangeParticlesBasedOnGroundLocation launch
@@ -344,7 +365,24 @@ int launch_mil_select(mct_clf* clf, int P, int Nn);
 int launch_ensemble_retain(mct_clf* clf, int P, int Nn);
 int launch_ensemble_retain_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj);
 // batched UpdateClassifier of n_obj classifiers (device descriptor array d, host copy h)
-int launch_train_features(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj);
+// launch bounds of the training-feature kernels when the set sizes and the colour-histogram plan are decided on the device
+// (mct_track_update_default): grids and shared memory from upper bounds, CTAs outside the actual plan leave at once
+struct TrainLaunchBounds { int n_max, nch, tab_words, chunk_words, npx_max, n_train_max; };
+int launch_train_features(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj, const TrainLaunchBounds* lb = nullptr);
+// per-object arguments of k_train_gen_default (device array, re-uploaded only when they change)
+struct TrainGenDev {
+    PfTrk* trk; const PfDev* st;
+    int* stage; int mcap;                 // [4][mcap] col | row | sx | sy of the object's training boxes (positives first)
+    int cap_pos, cap_neg;
+    float w0, h0; int opt;                // m_currentStateList[2], [3]; 0 = highest-weight particle, 1 = average
+    float pos_radius; int max_pos;
+    float neg_outer, neg_inner; int max_neg;
+    float maxs;                           // ParticleFilter::GetMaxScale()
+    int frame_w, frame_h;
+    int mdch, cw0, ch0, dim;              // colour-histogram rows wanted; classifier blob size; nb^3
+    int npx_b[2], tab_b, nch_b;           // what the launch was sized for (a plan beyond it takes the generic kernel)
+};
+int launch_train_gen_default(mct_ctx* ctx, int n_obj, const TrainGenDev* d_gen, TrainDesc* d_tdesc, mct_train_default_out* d_out);
 int launch_weak_update_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj);
 int launch_mil_select_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj, const int* cluster_req);
 int launch_build_colormap_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj);

@@ -70,8 +70,19 @@ def load():
         L.mcth_object_last_train.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]
         L.mcth_object_rng_state.argtypes = [vp, C.c_int]; L.mcth_object_rng_state.restype = C.c_uint64
         L.mcth_object_box.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.mcth_set_device_training_sets.argtypes = [C.c_int]; L.mcth_set_device_training_sets.restype = None
         _lib = L
     return _lib
+
+
+def set_device_training_sets(on):
+    """Whole frame on the device (k_train_gen_default behind the scoring kernels, the trackers' streams device-resident) on / off
+    for this process; off = the host enumerates the default-strategy training sets (ParticleFilterTracker::BuildTrainingSets)."""
+    load().mcth_set_device_training_sets(1 if on else 0)
+
+
+def device_training_sets():
+    return bool(load().mcth_get_device_training_sets())
 
 
 class HostError(RuntimeError):

@@ -462,8 +462,10 @@ void ParticleFilterTracker::InitializeTrackerWithParameters(Matrixu* pColor, Mat
                                                             TrackerParametersPtr tp,
                                                             Classifier::StrongClassifierParametersBasePtr cp, Matrixu* pHSV)
 {
+    PullRng();
     Public::SetCurrentRng(&m_rng);
     m_params = tp;
+    m_isColorCulture = cp->m_featureParametersPtr && cp->m_featureParametersPtr->GetFeatureType() == Features::CULTURE_COLOR_HISTOGRAM;
     m_states.assign((size_t)videoLength * 4, 0);
     m_strongClassifierBasePtr = Classifier::StrongClassifierFactory::CreateAndInitializeClassifier(cp, m_ctx);
     for (int i = 0; i < 4; i++) m_currentStateList[i] = tp->m_initState[i];
@@ -485,6 +487,28 @@ void ParticleFilterTracker::InitializeTrackerWithParameters(Matrixu* pColor, Mat
                                     m_currentStateList[1] + m_currentStateList[3] / 2, m_currentStateList[4],
                                     m_currentStateList[5]);
     m_isInitialized = true;
+}
+
+void ParticleFilterTracker::PullRng()
+{
+    if (!m_rngOnDevice) return;
+    unsigned long long st = 0;
+    chk(m_ctx, mct_pf_rng_get(m_particleFilterPtr->Handle(), &st));
+    m_rng.state = st;
+    m_rngOnDevice = false;
+}
+void ParticleFilterTracker::PushRng()
+{
+    if (m_rngOnDevice) return;
+    chk(m_ctx, mct_pf_rng_set(m_particleFilterPtr->Handle(), m_rng.state));
+    m_rngOnDevice = true;
+}
+static int g_deviceTrainingSets = -1;
+void ParticleFilterTracker::SetDeviceTrainingSets(bool on) { g_deviceTrainingSets = on ? 1 : 0; }
+bool ParticleFilterTracker::DeviceTrainingSets()
+{
+    if (g_deviceTrainingSets < 0) g_deviceTrainingSets = getenv("MCT_HOST_TRAINING_SETS") ? 0 : 1;
+    return g_deviceTrainingSets != 0;
 }
 
 // StoreObjectState (ParticleFilterTracker.cpp:286-393)
@@ -529,7 +553,7 @@ void ParticleFilterTracker::FillTrainGen(mct_train_gen& g, Matrixu* pColor, Matr
     Matrixu* m = pGray ? pGray : pColor;
     if (!m) throw MctHostError(MCT_E_ARG, "GenerateTrainingSampleSet: no image given");
     g.frame_w = m->cols(); g.frame_h = m->rows();
-    g.rng_state = m_rng.state;
+    g.rng_state = const_cast<ParticleFilterTracker*>(this)->Rng().state;
 }
 // ... then GeneratePositiveTrainingSampleSet (:697-906) and GenerateNegativeTrainingSampleSet (:913-1004).  The strategies that
 // walk the particles (GREEDY, SEMI_GREEDY, PARTICLE_RANDOM positives; the distances of PARTICLE_RANDOM negatives) were evaluated
@@ -537,6 +561,7 @@ void ParticleFilterTracker::FillTrainGen(mct_train_gen& g, Matrixu* pColor, Matr
 void ParticleFilterTracker::BuildTrainingSets(Matrixu* pColor, Matrixu* pGray, Matrixu* pHSV, const mct_train_gen_out* readout,
                                               const int* col, const int* row, const float* sx, const float* sy)
 {
+    PullRng();
     Public::SetCurrentRng(&m_rng);
     const int ps = m_params->m_positiveSampleStrategy, ns = m_params->m_negativeSampleStrategy;
     if (ps < 0 || ps > 3 || ns < 0 || ns > 1) throw MctHostError(MCT_E_ARG, "unknown training-sample strategy");
@@ -612,7 +637,7 @@ void ParticleFilterTracker::ScoreCameraObjectsAsync(mct_ctx* ctx, std::vector<Pa
         pfs[o] = t->m_particleFilterPtr->Handle(); clfs[o] = t->m_strongClassifierBasePtr->Handle();
         tp[o].w0 = t->m_currentStateList[2]; tp[o].h0 = t->m_currentStateList[3];
         tp[o].exponent = 20; tp[o].force_reset = 0; tp[o].resample = 1;
-        u01[o] = (float)(t->m_rng.Next() * 2.3283064365386962890625e-10);
+        u01[o] = (float)(t->Rng().Next() * 2.3283064365386962890625e-10);
     }
     chk(ctx, mct_track_score_async(ctx, n, pfs.data(), clfs.data(), tp.data(), noiseDev, 1, u01.data()));
 }
@@ -633,6 +658,45 @@ void ParticleFilterTracker::TrackCameraObjects(mct_ctx* ctx, std::vector<Particl
 {
     const int n = (int)trackers.size();
     if (n == 0) return;
+    if (phases == 3 && DeviceTrainingSets()) {
+        // Whole frame on the device: scoring, the default-strategy training sets (k_train_gen_default) and UpdateClassifier are
+        // queued back to back; the host waits for the read-outs only (the update kernels of this frame run while the caller
+        // prepares the next one).  The trackers' streams live on the device meanwhile.
+        bool eligible = noise != nullptr;
+        for (ParticleFilterTracker* t : trackers)
+            eligible = eligible && t->m_isInitialized && !t->NeedsParticleReadout() && !t->m_isColorCulture;
+        if (eligible) {
+            std::vector<mct_pf*> pfs(n); std::vector<mct_clf*> clfs(n);
+            std::vector<mct_track_params> tp(n); std::vector<mct_train_default> gen(n);
+            std::vector<mct_pf_summary> summ(n);
+            for (int o = 0; o < n; o++) {
+                ParticleFilterTracker* t = trackers[o];
+                t->PushRng();
+                pfs[o] = t->m_particleFilterPtr->Handle(); clfs[o] = t->m_strongClassifierBasePtr->Handle();
+                tp[o].w0 = t->m_currentStateList[2]; tp[o].h0 = t->m_currentStateList[3];
+                tp[o].exponent = 20; tp[o].force_reset = 0; tp[o].resample = 1;
+                mct_train_default& g = gen[o];
+                memset(&g, 0, sizeof(g));
+                g.w0 = t->m_currentStateList[2]; g.h0 = t->m_currentStateList[3];
+                g.trajectory_option = (int)t->m_params->m_outputTrajectoryOption;
+                g.pos_radius = t->m_params->m_posRadiusTrain; g.max_pos = (int)t->m_params->m_maximumNumberOfPositiveTrainingSamples;
+                g.neg_outer = 1.5f * t->m_params->m_searchWindSize; g.neg_inner = t->m_params->m_posRadiusTrain + 15;
+                g.max_neg = (int)t->m_params->m_numberOfNegativeTrainingSamples;
+                g.scale_hint_x = t->m_currentStateList[4]; g.scale_hint_y = t->m_currentStateList[5];
+            }
+            chk(ctx, mct_track_score_async(ctx, n, pfs.data(), clfs.data(), tp.data(), noise, 0, nullptr));
+            chk(ctx, mct_track_update_default(ctx, n, pfs.data(), clfs.data(), gen.data()));
+            chk(ctx, mct_track_collect(ctx, n, summ.data()));
+            for (int o = 0; o < n; o++) {
+                ParticleFilterTracker* t = trackers[o];
+                t->m_particleFilterPtr->AdoptSummary(summ[o]);
+                t->StoreObjectState(frameind);
+                t->PrepareTrainingState();                  // m_currentStateList as GenerateTrainingSampleSet leaves it (:655-672)
+                t->m_positiveSampleSet.Clear(); t->m_negativeSampleSet.Clear();
+            }
+            return;
+        }
+    }
     if (phases & 1) {
         if (!noise) throw MctHostError(MCT_E_ARG, "TrackCameraObjects: prediction noise not provided");
         std::vector<mct_pf*> pfs(n); std::vector<mct_clf*> clfs(n);
@@ -644,13 +708,13 @@ void ParticleFilterTracker::TrackCameraObjects(mct_ctx* ctx, std::vector<Particl
             pfs[o] = t->m_particleFilterPtr->Handle(); clfs[o] = t->m_strongClassifierBasePtr->Handle();
             tp[o].w0 = t->m_currentStateList[2]; tp[o].h0 = t->m_currentStateList[3];
             tp[o].exponent = 20; tp[o].force_reset = 0; tp[o].resample = 1;
-            u01[o] = (float)(t->m_rng.Peek() * 2.3283064365386962890625e-10);
+            u01[o] = (float)(t->Rng().Peek() * 2.3283064365386962890625e-10);
         }
         // TrackObjectOnTheGivenFrame for every object of the camera in one batched device pass
         chk(ctx, mct_track_score(ctx, n, pfs.data(), clfs.data(), tp.data(), noise, 0, u01.data(), summ.data()));
         for (int o = 0; o < n; o++) {
             ParticleFilterTracker* t = trackers[o];
-            if (summ[o].resampled) (void)t->m_rng.Next();        // the randfloat() inside ResampleParticles
+            if (summ[o].resampled) (void)t->Rng().Next();        // the randfloat() inside ResampleParticles
             t->m_particleFilterPtr->AdoptSummary(summ[o]);
             if (!(phases & 4)) t->StoreObjectState(frameind);    // bit 2: TrackObjectWithoutSaveState (fusion branch, Object.cpp:433-450)
         }

@@ -371,7 +371,16 @@ public:
     bool IsInitialized() const { return m_isInitialized; }
     Classifier::StrongClassifierBasePtr GetClassifier() const { return m_strongClassifierBasePtr; }
     ParticleFilterPtr GetParticleFilter() const { return m_particleFilterPtr; }
-    Public::RngStream& Rng() { return m_rng; }
+    // the tracker's stream; when the last frames ran with the stream on the device (TrackCameraObjects, whole frame on the
+    // device) its state is fetched back first (one synchronisation) and host-side draws continue from there
+    Public::RngStream& Rng() { PullRng(); return m_rng; }
+    void PullRng();
+    void PushRng();
+    // whole frame on the device: default-strategy training sets generated by k_train_gen_default behind the frame's scoring
+    // kernels (no host round trip).  On by default for the configurations it covers; MCT_HOST_TRAINING_SETS=1 in the
+    // environment or SetDeviceTrainingSets(false) keeps the host enumeration.
+    static void SetDeviceTrainingSets(bool on);
+    static bool DeviceTrainingSets();
     const Classifier::SampleSet& PositiveSet() const { return m_positiveSampleSet; }
     const Classifier::SampleSet& NegativeSet() const { return m_negativeSampleSet; }
 
@@ -390,6 +399,8 @@ public:
 private:
     mct_ctx* m_ctx;
     Public::RngStream m_rng;
+    bool m_rngOnDevice = false;            // m_rng is stale: the stream lives in the particle filter's device state
+    bool m_isColorCulture = false;         // culture colour features: training rows take the per-object path
     TrackerParametersPtr m_params;
     Classifier::StrongClassifierBasePtr m_strongClassifierBasePtr;
     ParticleFilterPtr m_particleFilterPtr;

@@ -367,6 +367,9 @@ int mcth_object_last_train(mcth_camera* c, int o, int which, int* col, int* row,
     return n;
 }
 uint64_t mcth_object_rng_state(mcth_camera* c, int o) { return c->trackers[o]->Rng().state; }
+// whole frame on the device (default-strategy training sets from k_train_gen_default) on / off for this process
+void mcth_set_device_training_sets(int on) { ParticleFilterTracker::SetDeviceTrainingSets(on != 0); }
+int mcth_get_device_training_sets(void) { return ParticleFilterTracker::DeviceTrainingSets() ? 1 : 0; }
 // m_states row of a frame (x, y, w, h as stored by StoreObjectState)
 int mcth_object_box(mcth_camera* c, int o, int frameind, int* out4)
 {

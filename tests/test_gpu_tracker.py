@@ -30,10 +30,33 @@ def _oracle_tracker(oracle, seq, o, f0, p, seed):
     return trk, clf, rng
 
 
+def _oracle_last_train(oracle, trk, which, cap=8192):
+    col = np.zeros(cap, np.int32); row = np.zeros(cap, np.int32); sx = np.zeros(cap, np.float32); sy = np.zeros(cap, np.float32)
+    ip, fp = C.POINTER(C.c_int), C.POINTER(C.c_float)
+    n = oracle.lib.orc_tracker_last_train(trk, which, col.ctypes.data_as(ip), row.ctypes.data_as(ip), sx.ctypes.data_as(fp), sy.ctypes.data_as(fp), cap)
+    return col[:n], row[:n], sx[:n], sy[:n]
+
+
 @pytest.mark.parametrize("cfg", ["cfg1_haar_milboost", "haarmdch_wstump_2obj", "mdch_anyboost_avg", "cfg2_full_size_8obj_2000",
                                  "haar_ensemble_2obj", "greedy_pos_random_neg", "semi_greedy_pos", "particle_random_pos"])
 def test_tracker_sequence_matches_oracle(oracle, cfg):
+    _tracker_sequence(oracle, cfg)
+
+
+@pytest.mark.parametrize("cfg", ["cfg1_haar_milboost", "haarmdch_wstump_2obj", "mdch_anyboost_avg"])
+def test_tracker_sequence_matches_oracle_with_host_training_sets(oracle, cfg):
+    """the host enumeration of the default-strategy training sets (the path of round 1) stays covered: same sequences, with the
+    device-side generation switched off"""
+    mhost.set_device_training_sets(False)
+    try:
+        _tracker_sequence(oracle, cfg)
+    finally:
+        mhost.set_device_training_sets(True)
+
+
+def _tracker_sequence(oracle, cfg):
     n_frames = 12
+    device_sets = mhost.device_training_sets() and cfg not in ("greedy_pos_random_neg", "semi_greedy_pos", "particle_random_pos")
     if cfg == "cfg1_haar_milboost":
         n_obj, over = 1, dict()
     elif cfg == "cfg2_full_size_8obj_2000":
@@ -90,6 +113,19 @@ def test_tracker_sequence_matches_oracle(oracle, cfg):
             # the RNG streams stay in lock-step (same resample decisions, same thinning draws)
             assert cam.rng_state(o) == otr[o][2].state, (cfg, t, o)
             assert cam.selectors(o).tolist() == oracle.clf_selectors(otr[o][1]).tolist(), (cfg, t, o)
+            if device_sets:
+                # the boxes k_train_gen_default wrote (positives, then negatives) against the oracle's SampleImage + thinning
+                col, row, sx, sy, P, Nn = capi.track_update_default_boxes(cam.capi_context(), o)
+                oc, orw, osx, osy = _oracle_last_train(oracle, otr[o][0], 0)
+                nc, nr, nsx, nsy = _oracle_last_train(oracle, otr[o][0], 1)
+                assert (P, Nn) == (len(oc), len(nc)), (cfg, t, o, P, Nn, len(oc), len(nc))
+                np.testing.assert_array_equal(col, np.concatenate([oc, nc])); np.testing.assert_array_equal(row, np.concatenate([orw, nr]))
+                # scales = the state's scale as the read-out of this frame reports it (exactly), which agrees with the oracle's to
+                # 1e-6: PARTICLE_AVERAGE is a f64 tree against the reference's f32 chain, and PARTICLE_HIGHEST_WEIGHT picks between
+                # particles of the same pixel cell whose weights agree to the response tolerance (their scales differ by an ulp)
+                st = cam.state(o)
+                np.testing.assert_array_equal(sx[:P], np.full(P, st[4], np.float32)); np.testing.assert_array_equal(sy[:P], np.full(P, st[5], np.float32))
+                np.testing.assert_allclose(sx, np.concatenate([osx, nsx]), rtol=1e-6, atol=0); np.testing.assert_allclose(sy, np.concatenate([osy, nsy]), rtol=1e-6, atol=0)
             # sanity only: the tracker (reference algorithm) stays in the neighbourhood of the synthetic object
             gx, gy, gw, gh = seq.box(t, o)
             assert abs(boxes[o][0] - gx) <= 60 and abs(boxes[o][1] - gy) <= 60
