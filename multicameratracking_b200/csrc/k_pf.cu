@@ -1517,9 +1517,138 @@ __device__ __forceinline__ bool region_candidate(const mct_sample_region& g, int
 }
 // body shared by k_sample_regions and k_train_gen_default: all threads of the CTA call it; the result lands in *res (shared memory)
 // and is visible to every thread on return.  bbox (shared int[4], or NULL): min col, max col, min row, max row of the KEPT samples.
+// The candidates (a sparse ring inside its bounding square) are first compacted, in row-major order, into a shared list; the
+// thinning then runs densely over that list: a thread owns a block of consecutive candidates, jumps the stream ONCE to its block's
+// first draw and steps it from there (a jump is ~10 modular multiplications of ~80 instructions, a step is three) -- with one jump
+// per candidate inside the square's row-major walk nearly every warp paid the full jump for a few live lanes (39 us per frame).
+// Regions whose candidates do not fit the list keep the walk with one jump per candidate.
+__device__ __forceinline__ int block_excl_scan_i(int v, int* sh /* [33] */, int* total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    __syncthreads();
+    if (lane == 31) sh[warp] = inc;
+    __syncthreads();
+    int before = 0, tot = 0;
+    for (int w = 0; w < nw; w++) { const int c = sh[w]; if (w < warp) before += c; tot += c; }
+    *total = tot;
+    return before + inc - v;
+}
+#define SR_LIST_CAP 6144
+// Ring / disc form by rows: the candidates of a row are at most two runs of consecutive columns, known in closed form
+// ((float)dist < o2 && (float)dist >= i2 for an integer dist  <=>  ceil(i2) <= dist <= ceil(o2) - 1; the same bounds as the host
+// sampler, host/mct_host.cpp SampleImage).  One thread per row describes its runs, one block scan numbers the candidates, and a
+// thread then owns a block of consecutive candidates: no per-cell work at all.  Returns false (nothing written) when the region
+// does not fit this plan; the caller then takes the cell walk.
+#define SR_ROWS_CAP 512
+__device__ __forceinline__ int isqrt_floor_dev(int v)
+{
+    int r = (int)sqrtf((float)v);
+    while (r * r > v) r--;
+    while ((r + 1) * (r + 1) <= v) r++;
+    return r;
+}
+__device__ bool sample_ring_rows(const mct_sample_region& g, int cap, int* __restrict__ o_col, int* __restrict__ o_row,
+                                 mct_sample_region_out* res, int* bbox, int* sh_c, const unsigned long long* s_pw, int* s_buf,
+                                 int minrow, int mincol, int maxcol, int RH, float o2, float i2)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    int* a0 = s_buf; int* an = s_buf + SR_ROWS_CAP; int* b0 = s_buf + 2 * SR_ROWS_CAP; int* bn = s_buf + 3 * SR_ROWS_CAP;
+    int* pre = s_buf + 4 * SR_ROWS_CAP;                                   // [RH + 1] candidates in front of row r
+    const int dHi = (int)ceilf(o2) - 1, dLo = (int)ceilf(i2);
+    int cnt = 0;
+    if (tid < RH) {
+        const int r = minrow + tid;
+        const int dy2 = (g.y - r) * (g.y - r);
+        int sa = 0, na = 0, sb = 0, nb = 0;
+        if (dHi - dy2 >= 0 && mincol <= maxcol) {
+            const int b = isqrt_floor_dev(dHi - dy2);                     // |x - c| <= b
+            const int a = (dLo - dy2 > 0) ? isqrt_floor_dev(dLo - dy2 - 1) + 1 : 0;   // |x - c| >= a
+            if (a <= b) {
+                if (a == 0) {
+                    const int c0 = max(mincol, g.x - b), c1 = min(maxcol, g.x + b);
+                    if (c0 <= c1) { sa = c0; na = c1 - c0 + 1; }
+                } else {
+                    int c0 = max(mincol, g.x - b), c1 = min(maxcol, g.x - a);
+                    if (c0 <= c1) { sa = c0; na = c1 - c0 + 1; }
+                    c0 = max(mincol, g.x + a); c1 = min(maxcol, g.x + b);
+                    if (c0 <= c1) { sb = c0; nb = c1 - c0 + 1; }
+                }
+            }
+        }
+        a0[tid] = sa; an[tid] = na; b0[tid] = sb; bn[tid] = nb;
+        cnt = na + nb;
+    }
+    PF_STAMP(20);
+    int n_cand;
+    const int before = block_excl_scan_i(cnt, sh_c, &n_cand);
+    PF_STAMP(21);
+    if (n_cand > 32 * nt) { __syncthreads(); return false; }               // (uniform: every thread sees the same total)
+    if (tid < RH) pre[tid] = before;
+    if (tid == 0) pre[RH] = n_cand;
+    __syncthreads();
+    const int n_list = n_cand;
+    const float prob = __fdiv_rn((float)(g.max_n + 1), (float)(unsigned)n_list);
+    const bool thin = prob < 1.0f;
+    const unsigned long long s0 = g.rng_state, s2 = mwc_step(mwc_step(s0));
+    const int B = max(thin ? 8 : 1, (n_cand + nt - 1) / nt);               // (a jump per thread when thinning: longer blocks)
+    const int k0 = tid * B, k1 = min(n_cand, k0 + B);
+    // the stream after all draws: by a thread that owns no candidates when there is one (beside the others' jumps)
+    unsigned long long rng_after = s0;
+    const int fin = (n_cand + B - 1) / B < nt ? nt - 1 : 0;
+    if (thin && tid == fin) rng_after = mwc_after(s0, s2, (unsigned)n_list, s_pw);
+    unsigned keepmask = 0u;
+    int r0 = 0;
+    if (k0 < k1) {
+        int lo = 0, hi = RH - 1;                                          // last row with pre[row] <= k0
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (pre[mid] <= k0) lo = mid; else hi = mid - 1; }
+        r0 = lo;
+        if (thin) {
+            unsigned long long st = mwc_after(s0, s2, (unsigned)k0, s_pw);
+            for (int k = k0; k < k1; k++) {
+                st = mwc_step(st);
+                const float rf = (float)((double)(unsigned)(st & 0xffffffffull) * 2.3283064365386962890625e-10);
+                if (!(rf > prob)) keepmask |= 1u << (k - k0);
+            }
+        } else keepmask = (k1 - k0 >= 32) ? 0xffffffffu : ((1u << (k1 - k0)) - 1u);
+    }
+    PF_STAMP(22);
+    int tot_k;
+    int pos = block_excl_scan_i(__popc(keepmask), sh_c, &tot_k);
+    PF_STAMP(23);
+    int bx0 = 0x7fffffff, bx1 = -0x7fffffff, by0 = 0x7fffffff, by1 = -0x7fffffff;
+    if (k0 < k1) {
+        int r = r0, off = k0 - pre[r0];
+        for (int k = k0; k < k1; k++) {
+            while (off >= an[r] + bn[r]) { off -= an[r] + bn[r]; r++; }   // (rows without candidates are skipped)
+            if ((keepmask >> (k - k0)) & 1u) {
+                if (pos < cap && (!thin || pos < g.max_n)) {
+                    const int c = off < an[r] ? a0[r] + off : b0[r] + (off - an[r]);
+                    const int rr = minrow + r;
+                    o_col[pos] = c; o_row[pos] = rr;
+                    bx0 = min(bx0, c); bx1 = max(bx1, c); by0 = min(by0, rr); by1 = max(by1, rr);
+                }
+                pos++;
+            }
+            off++;
+        }
+    }
+    if (bbox && bx0 <= bx1) { atomicMin(&bbox[0], bx0); atomicMax(&bbox[1], bx1); atomicMin(&bbox[2], by0); atomicMax(&bbox[3], by1); }
+    if (tid == fin) {
+        mct_sample_region_out o;
+        o.n = min(thin ? min(tot_k, g.max_n) : n_list, cap);
+        o.n_candidates = n_cand; o.n_draws = thin ? n_list : 0; o.pad = 0;
+        o.rng_state = rng_after;
+        *res = o;
+    }
+    __syncthreads();
+    return true;
+}
 __device__ void sample_region_body(const mct_sample_region& g, int cap, int* __restrict__ o_col, int* __restrict__ o_row,
                                    mct_sample_region_out* res, int* bbox, int* sh_c /* [33] */, int* sh_i /* [32] */,
-                                   const unsigned long long* s_pw /* [32] shared copy of c_mwc_pw */)
+                                   const unsigned long long* s_pw /* [32] shared copy of c_mwc_pw */, int* s_list /* [SR_LIST_CAP] shared */)
 {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int scaledW = __float2int_rn(__fmul_rn((float)g.width, g.scale_x)), scaledH = __float2int_rn(__fmul_rn((float)g.height, g.scale_y));
@@ -1531,39 +1660,82 @@ __device__ void sample_region_body(const mct_sample_region& g, int cap, int* __r
     const int cells = (RW > 0 && RH > 0) ? RW * RH : 0;
     const float o2 = __fmul_rn(g.p[0], g.p[0]), i2 = __fmul_rn(g.p[1], g.p[1]);
     if (bbox && tid == 0) { bbox[0] = 0x7fffffff; bbox[1] = -0x7fffffff; bbox[2] = 0x7fffffff; bbox[3] = -0x7fffffff; }
-    int cnt = 0;
-    for (int e = tid; e < cells; e += nt) cnt += region_candidate(g, minrow + e / RW, mincol + e % RW, o2, i2) ? 1 : 0;
-    const int n_cand = block_reduce_sum_i(cnt, sh_i);
+    if (g.kind == 0 && RH <= SR_ROWS_CAP && RH <= nt && sample_ring_rows(g, cap, o_col, o_row, res, bbox, sh_c, s_pw, s_list,
+                                                                          minrow, mincol, maxcol, RH, o2, i2)) return;
+    // the candidates, counted and (as far as the list reaches) compacted in row-major order
+    int n_cand = 0;
+    for (int e0 = 0; e0 < cells; e0 += nt) {
+        const int e = e0 + tid;
+        const bool cand = e < cells && region_candidate(g, minrow + e / max(RW, 1), mincol + e % max(RW, 1), o2, i2);
+        int tot_c;
+        const int k = n_cand + block_compact(cand, sh_c, &tot_c);
+        if (cand && k < SR_LIST_CAP) s_list[k] = e;
+        n_cand += tot_c;
+    }
+    __syncthreads();
+    (void)sh_i;
     const int n_list = n_cand;
     const float prob = __fdiv_rn((float)(g.max_n + 1), (float)(unsigned)n_list);
     const bool thin = prob < 1.0f;
     const unsigned long long s0 = g.rng_state, s2 = mwc_step(mwc_step(s0));
-    int base_c = 0, base_k = 0;
     int bx0 = 0x7fffffff, bx1 = -0x7fffffff, by0 = 0x7fffffff, by1 = -0x7fffffff;
-    for (int e0 = 0; e0 < cells; e0 += nt) {
-        const int e = e0 + tid;
-        const int r = minrow + e / max(RW, 1), c = mincol + e % max(RW, 1);
-        const bool cand = e < cells && region_candidate(g, r, c, o2, i2);
-        int tot_c;
-        const int k = base_c + block_compact(cand, sh_c, &tot_c);
-        bool keep = cand && k < n_list;
-        if (keep && thin) {
-            const unsigned long long s = mwc_after(s0, s2, (unsigned)k + 1u, s_pw);
-            const float rf = (float)((double)(unsigned)(s & 0xffffffffull) * 2.3283064365386962890625e-10);
-            keep = !(rf > prob);
+    int n_kept;
+    if (n_cand <= SR_LIST_CAP && (n_cand + nt - 1) / nt <= 32) {
+        // candidate k takes draw k: blocks of B consecutive candidates per thread
+        const int B = max(8, (n_cand + nt - 1) / nt);                    // <= 12 for a full list
+        const int k0 = tid * B, k1 = min(n_cand, k0 + B);
+        unsigned keepmask = 0u;
+        if (k0 < k1) {
+            if (thin) {
+                unsigned long long st = mwc_after(s0, s2, (unsigned)k0, s_pw);
+                for (int k = k0; k < k1; k++) {
+                    st = mwc_step(st);
+                    const float rf = (float)((double)(unsigned)(st & 0xffffffffull) * 2.3283064365386962890625e-10);
+                    if (!(rf > prob)) keepmask |= 1u << (k - k0);
+                }
+            } else keepmask = (k1 - k0 >= 32) ? 0xffffffffu : ((1u << (k1 - k0)) - 1u);
         }
         int tot_k;
-        const int pos = base_k + block_compact(keep, sh_c, &tot_k);
-        if (keep && pos < cap && (!thin || pos < g.max_n)) {
-            o_col[pos] = c; o_row[pos] = r;
-            bx0 = min(bx0, c); bx1 = max(bx1, c); by0 = min(by0, r); by1 = max(by1, r);
+        int pos = block_excl_scan_i(__popc(keepmask), sh_c, &tot_k);
+        for (int k = k0; k < k1; k++) {
+            if (!((keepmask >> (k - k0)) & 1u)) continue;
+            if (pos < cap && (!thin || pos < g.max_n)) {
+                const int e = s_list[k];
+                const int r = minrow + e / RW, c = mincol + e % RW;
+                o_col[pos] = c; o_row[pos] = r;
+                bx0 = min(bx0, c); bx1 = max(bx1, c); by0 = min(by0, r); by1 = max(by1, r);
+            }
+            pos++;
         }
-        base_c += tot_c; base_k += tot_k;
+        n_kept = tot_k;
+    } else {
+        int base_c = 0, base_k = 0;
+        for (int e0 = 0; e0 < cells; e0 += nt) {
+            const int e = e0 + tid;
+            const int r = minrow + e / max(RW, 1), c = mincol + e % max(RW, 1);
+            const bool cand = e < cells && region_candidate(g, r, c, o2, i2);
+            int tot_c;
+            const int k = base_c + block_compact(cand, sh_c, &tot_c);
+            bool keep = cand && k < n_list;
+            if (keep && thin) {
+                const unsigned long long s = mwc_after(s0, s2, (unsigned)k + 1u, s_pw);
+                const float rf = (float)((double)(unsigned)(s & 0xffffffffull) * 2.3283064365386962890625e-10);
+                keep = !(rf > prob);
+            }
+            int tot_k;
+            const int pos = base_k + block_compact(keep, sh_c, &tot_k);
+            if (keep && pos < cap && (!thin || pos < g.max_n)) {
+                o_col[pos] = c; o_row[pos] = r;
+                bx0 = min(bx0, c); bx1 = max(bx1, c); by0 = min(by0, r); by1 = max(by1, r);
+            }
+            base_c += tot_c; base_k += tot_k;
+        }
+        n_kept = base_k;
     }
     if (bbox && bx0 <= bx1) { atomicMin(&bbox[0], bx0); atomicMax(&bbox[1], bx1); atomicMin(&bbox[2], by0); atomicMax(&bbox[3], by1); }
     if (tid == 0) {
         mct_sample_region_out o;
-        o.n = min(thin ? min(base_k, g.max_n) : n_list, cap);
+        o.n = min(thin ? min(n_kept, g.max_n) : n_list, cap);
         o.n_candidates = n_cand; o.n_draws = thin ? n_list : 0; o.pad = 0;
         o.rng_state = thin ? mwc_after(s0, s2, (unsigned)n_list, s_pw) : s0;
         *res = o;
@@ -1577,10 +1749,11 @@ k_sample_regions(const mct_sample_region* __restrict__ regs, int cap, int* __res
     __shared__ int sh_i[32];
     __shared__ unsigned long long s_pw[32];
     __shared__ mct_sample_region_out s_res;
+    __shared__ int s_list[SR_LIST_CAP];
     const mct_sample_region g = regs[blockIdx.x];
     if (threadIdx.x < 32) s_pw[threadIdx.x] = c_mwc_pw[threadIdx.x];
     __syncthreads();
-    sample_region_body(g, cap, col + (size_t)blockIdx.x * cap, row + (size_t)blockIdx.x * cap, &s_res, nullptr, sh_c, sh_i, s_pw);
+    sample_region_body(g, cap, col + (size_t)blockIdx.x * cap, row + (size_t)blockIdx.x * cap, &s_res, nullptr, sh_c, sh_i, s_pw, s_list);
     if (threadIdx.x == 0) outs[blockIdx.x] = s_res;
 }
 int launch_sample_regions(mct_ctx* ctx, int n, const mct_sample_region* d_reg, int cap, int* d_col, int* d_row, mct_sample_region_out* d_out)
@@ -1630,11 +1803,14 @@ k_train_gen_default(const TrainGenDev* __restrict__ gens, TrainDesc* __restrict_
     __shared__ unsigned long long s_pw[32];
     __shared__ mct_sample_region_out s_res[2];
     __shared__ int s_bbox[2][4];
+    __shared__ int s_list[SR_LIST_CAP];
+    PF_STAMP(0);
     const TrainGenDev q = gens[blockIdx.x];
     TrainDesc& t = descs[blockIdx.x];
     const int tid = threadIdx.x, nt = blockDim.x;
     if (tid < 32) s_pw[tid] = c_mwc_pw[tid];
     __syncthreads();
+    PF_STAMP(1);
     const float* a = q.opt == 0 ? q.trk->first : q.trk->avg;
     const float a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3];
     const int n_valid = q.st->n_valid;
@@ -1652,19 +1828,22 @@ k_train_gen_default(const TrainGenDev* __restrict__ gens, TrainDesc* __restrict_
     int n_draws = 0;
     float nsx = 1.0f, nsy = 1.0f;
     const bool usable = n_valid > 0 && a0 == a0 && a1 == a1 && a2 == a2 && a3 == a3;
+    PF_STAMP(2);
     if (usable) {
         mct_sample_region g;
         g.kind = 0; g.x = (int)cur[0]; g.y = (int)cur[1]; g.width = (int)cur[2]; g.height = (int)cur[3];
         g.p[0] = q.pos_radius; g.p[1] = 0.0f; g.p[2] = 0.0f; g.p[3] = 0.0f;
         g.max_n = q.max_pos; g.scale_x = cur[4]; g.scale_y = cur[5]; g.frame_w = q.frame_w; g.frame_h = q.frame_h; g.rng_state = rng;
-        sample_region_body(g, q.cap_pos, col, row, &s_res[0], s_bbox[0], sh_c, sh_i, s_pw);
+        sample_region_body(g, q.cap_pos, col, row, &s_res[0], s_bbox[0], sh_c, sh_i, s_pw, s_list);
         P = s_res[0].n; rng = s_res[0].rng_state; n_draws = s_res[0].n_draws;
+        PF_STAMP(3);
         nsx = fminf(cur[4], q.maxs); nsy = fminf(cur[5], q.maxs);
         g.x = __float2int_rn(cur[0]); g.y = __float2int_rn(cur[1]); g.width = __float2int_rn(cur[2]); g.height = __float2int_rn(cur[3]);
         g.p[0] = q.neg_outer; g.p[1] = q.neg_inner;
         g.max_n = q.max_neg; g.scale_x = nsx; g.scale_y = nsy; g.rng_state = rng;
-        sample_region_body(g, q.cap_neg, col + P, row + P, &s_res[1], s_bbox[1], sh_c, sh_i, s_pw);
+        sample_region_body(g, q.cap_neg, col + P, row + P, &s_res[1], s_bbox[1], sh_c, sh_i, s_pw, s_list);
         Nn = s_res[1].n; rng = s_res[1].rng_state; n_draws += s_res[1].n_draws;
+        PF_STAMP(4);
         for (int i = tid; i < P + Nn; i += nt) { sx[i] = i < P ? cur[4] : nsx; sy[i] = i < P ? cur[5] : nsy; }
     }
     if (tid == 0) {
@@ -1683,6 +1862,8 @@ k_train_gen_default(const TrainGenDev* __restrict__ gens, TrainDesc* __restrict_
         o.n_draws = n_draws; o.pad = 0;
         outs[blockIdx.x] = o;
     }
+    PF_STAMP(5);
+    PF_COMMIT(0);
 }
 int launch_train_gen_default(mct_ctx* ctx, int n_obj, const TrainGenDev* d_gen, TrainDesc* d_tdesc, mct_train_default_out* d_out)
 {
