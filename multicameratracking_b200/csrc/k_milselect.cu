@@ -365,26 +365,64 @@ __device__ void block_argmax(float v, int f, float* out_v, int* out_f, SelSlot* 
     __syncthreads();
 }
 
-#define ANY_THREADS 1024
+// MILAnyBoost on a thread-block cluster (round 2; one CTA per classifier before: every round re-read the F x M prediction
+// matrix from L2 with 32 distinct lines per warp load and ran the F ordered objective chains on one SM, ~20 us per round).
+// The F candidates are split over the C CTAs of the cluster; a CTA stages its candidates' prediction rows ONCE in shared memory
+// (row pitch odd: lane = candidate reads conflict-free, the weight is a broadcast) -- the rows do not change across the rounds.
+// Every CTA keeps its own copy of the hypothesis H and repeats the M-long sigmoid pass and the ordered bag chain (identical
+// arithmetic on identical data: all CTAs take the same decisions without talking); per round the CTAs exchange only their
+// best (objective, index) pair through distributed shared memory across ONE cluster barrier.  Same expressions and the same
+// order per candidate as before; (value desc, index asc) is a total order, so the reduction tree does not matter.
+#define ANY_THREADS 256
+#define ANY_MAX_CLUSTER 8
+template <bool ROWS_SMEM>
 __device__ __forceinline__ void
 anyboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int Nn, int K,
                   int* __restrict__ sel, int* __restrict__ nsel)
 {
-    const int M = P + Nn;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int M = P + Nn, Mp = M | 1;
+    const int FL = (F + C - 1) / C;
+    const int f_begin = rank * FL, f_end = min(F, f_begin + FL), nf = max(0, f_end - f_begin);
     extern __shared__ __align__(16) unsigned char smraw[];
     float* Hs = (float*)smraw;              // [M]  hypothesis
     float* pi = Hs + M;                     // [M]  instance probabilities
     float* tq = pi + M;                     // [M]  chain terms, later instance weights
-    float* obj = tq + M;                    // [F]  last objective values
-    unsigned char* selflag = (unsigned char*)(obj + F);
+    float* obj = tq + M;                    // [FL] last objective values of this CTA's candidates
+    float* rows = obj + FL;                 // [FL][Mp] their prediction rows (ROWS_SMEM)
+    unsigned char* selflag = (unsigned char*)(rows + (ROWS_SMEM ? (size_t)FL * Mp : 0));   // [F]
     __shared__ SelSlot sh[ANY_THREADS / 32];
+    __shared__ SelSlot slots[2][ANY_MAX_CLUSTER];
     __shared__ float s_pbag, s_nll;
     __shared__ int s_action;                // 0 continue normally, 1 special retry, 2 pop & stop
-    const int tid = threadIdx.x, nt = blockDim.x;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
 
     for (int i = tid; i < M; i += nt) Hs[i] = 0.0f;
-    for (int f = tid; f < F; f += nt) { selflag[f] = 0; obj[f] = 0.0f; }
+    for (int f = tid; f < F; f += nt) selflag[f] = 0;
+    for (int f = tid; f < FL; f += nt) obj[f] = 0.0f;
+    if (ROWS_SMEM)
+        for (int f = warp; f < nf; f += nwarps) {
+            const float* pr = pred + (size_t)(f_begin + f) * ld;
+            float* dst = rows + (size_t)f * Mp;
+            for (int i = lane; i < M; i += 32) dst[i] = pr[i];
+        }
     __syncthreads();
+    int xc = 0;                             // exchange counter (slot parity)
+    // cluster-wide argmax of the CTAs' (v, f): identical result in every thread of every CTA
+    auto exchange = [&](float v, int f, float* gv, int* gf) {
+        const int par = xc & 1; xc++;
+        if (tid < C) {
+            SelSlot* remote = cluster.map_shared_rank(&slots[0][0], tid);
+            remote[par * ANY_MAX_CLUSTER + rank].nll = v;
+            remote[par * ANY_MAX_CLUSTER + rank].f = f;
+        }
+        cluster.sync();
+        float bv = slots[par][0].nll; int bf = slots[par][0].f;
+        for (int q = 1; q < C; q++)
+            if (better_max(slots[par][q].nll, slots[par][q].f, bv, bf)) { bv = slots[par][q].nll; bf = slots[par][q].f; }
+        *gv = bv; *gf = bf;
+    };
     double prev = 1000000.0;
     int n_sel = 0;
     float cur_v = 0.0f; int cur_f = -1;     // position k in the last sorted order
@@ -424,15 +462,17 @@ anyboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int N
             __syncthreads();
             n_sel--;
             float bv = -CUDART_INF_F; int bf = 0x7fffffff;
-            for (int f = tid; f < F; f += nt) {
-                const float v = obj[f];
+            for (int fl = tid; fl < nf; fl += nt) {
+                const int f = f_begin + fl;
+                const float v = obj[fl];
                 const bool after = (v < cur_v) || (v == cur_v && f > cur_f);
                 if (after && !selflag[f] && better_max(v, f, bv, bf)) { bv = v; bf = f; }
             }
-            float gv; int gf;
-            block_argmax(bv, bf, &gv, &gf, sh);
+            float lv; int lf, gf; float gv;
+            block_argmax(bv, bf, &lv, &lf, sh);
+            exchange(lv, lf, &gv, &gf);
             if (gf == 0x7fffffff) break;                          // reference: abortError
-            if (tid == 0) { sel[n_sel] = gf; selflag[gf] = 1; }
+            if (tid == 0) { if (rank == 0) sel[n_sel] = gf; selflag[gf] = 1; }
             n_sel++;
             last_sel = gf; cur_v = gv; cur_f = gf;
             const float* pb = pred + (size_t)gf * ld;
@@ -453,18 +493,26 @@ anyboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int N
         __syncthreads();
         // objective: ordered f32 chain per candidate (:176-189)
         float bv = -CUDART_INF_F; int bf = 0x7fffffff;
-        for (int f = tid; f < F; f += nt) {
-            const float* pr = pred + (size_t)f * ld;
+        for (int fl = tid; fl < nf; fl += nt) {
+            const int f = f_begin + fl;
             float o = 0.0f;
-            for (int i = 0; i < M; i++) o = __fadd_rn(o, __fmul_rn(tq[i], pr[i]));
-            obj[f] = o;
+            if (ROWS_SMEM) {
+                const float* pr = rows + (size_t)fl * Mp;
+#pragma unroll 8
+                for (int i = 0; i < M; i++) o = __fadd_rn(o, __fmul_rn(tq[i], pr[i]));
+            } else {
+                const float* pr = pred + (size_t)f * ld;
+                for (int i = 0; i < M; i++) o = __fadd_rn(o, __fmul_rn(tq[i], pr[i]));
+            }
+            obj[fl] = o;
             if (!selflag[f] && better_max(o, f, bv, bf)) { bv = o; bf = f; }
         }
         have_order = 1;
-        float gv; int gf;
-        block_argmax(bv, bf, &gv, &gf, sh);
+        float lv; int lf, gf; float gv;
+        block_argmax(bv, bf, &lv, &lf, sh);
+        exchange(lv, lf, &gv, &gf);
         if (gf == 0x7fffffff) break;                              // all selected (:203-207)
-        if (tid == 0) { sel[n_sel] = gf; selflag[gf] = 1; }
+        if (tid == 0) { if (rank == 0) sel[n_sel] = gf; selflag[gf] = 1; }
         n_sel++;
         last_sel = gf; cur_v = gv; cur_f = gf;
         const float* pb = pred + (size_t)gf * ld;
@@ -472,20 +520,41 @@ anyboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int N
         for (int i = tid; i < M; i += nt) Hs[i] = __fadd_rn(Hs[i], pb[i]);
         __syncthreads();
     }
-    if (tid == 0) *nsel = n_sel < 0 ? 0 : n_sel;
+    if (rank == 0 && tid == 0) *nsel = n_sel < 0 ? 0 : n_sel;
+    cluster.sync();          // no CTA may exit while a peer can still write its slots
+}
+// shared-memory plan: H, pi, tq [M] + obj [FL] + rows [FL][M | 1] (when they fit) + flags [F]
+static size_t any_smem_plan(int F, int M, int C, int* rows_in_smem)
+{
+    const int FL = ceil_div(F, C);
+    const size_t base = (size_t)(3 * M + FL) * sizeof(float) + (size_t)round_up(F, 16);
+    const size_t rows = (size_t)FL * (M | 1) * sizeof(float);
+    *rows_in_smem = base + rows <= 200 * 1024 ? 1 : 0;
+    return base + (*rows_in_smem ? rows : 0);
+}
+static int any_cluster_width(int F)
+{
+    int C = 1;
+    while (C < ANY_MAX_CLUSTER && ceil_div(F, C) > 64) C <<= 1;
+    return C;
 }
 __global__ void __launch_bounds__(ANY_THREADS)
 k_anyboost_select(const float* __restrict__ pred, int ld, int F, int P, int Nn, int K,
-                  int* __restrict__ sel, int* __restrict__ nsel)
+                  int* __restrict__ sel, int* __restrict__ nsel, int rows_in_smem)
 {
-    anyboost_select_body(pred, ld, F, P, Nn, K, sel, nsel);
+    if (rows_in_smem) anyboost_select_body<true>(pred, ld, F, P, Nn, K, sel, nsel);
+    else anyboost_select_body<false>(pred, ld, F, P, Nn, K, sel, nsel);
 }
-__global__ void __launch_bounds__(ANY_THREADS) k_anyboost_select_batch(const TrainDesc* __restrict__ descs)
+// batched form: one cluster per object (blockIdx.y); the plan was sized for (F_max, M_max): an object's rows fit iff its own do
+__global__ void __launch_bounds__(ANY_THREADS) k_anyboost_select_batch(const TrainDesc* __restrict__ descs, int rows_words)
 {
-    const TrainDesc& d = descs[blockIdx.x];
+    const TrainDesc& d = descs[blockIdx.y];
     if (d.strong_type != MCT_STRONG_MILANYBOOST) return;
     if (d.P < 1 || d.Nn < 1) return;              // empty training set decided on the device (k_train_gen_default): classifier left as it is
-    anyboost_select_body(d.pred, d.ldT, d.F, d.P, d.Nn, d.K, d.sel, d.nsel);
+    const int FL = (d.F + (int)gridDim.x - 1) / (int)gridDim.x;
+    const bool fit = rows_words > 0 && (size_t)FL * ((d.P + d.Nn) | 1) <= (size_t)rows_words;
+    if (fit) anyboost_select_body<true>(d.pred, d.ldT, d.F, d.P, d.Nn, d.K, d.sel, d.nsel);
+    else anyboost_select_body<false>(d.pred, d.ldT, d.F, d.P, d.Nn, d.K, d.sel, d.nsel);
 }
 
 
@@ -839,6 +908,22 @@ static int ens_launch(mct_ctx* ctx, const char* name, KernT kern, size_t* attr_s
     MCT_KERNEL_CHECK(ctx);
     return MCT_OK;
 }
+template <typename KernT, typename... Args>
+static int any_launch(mct_ctx* ctx, const char* name, KernT kern, size_t* attr_state, dim3 grid, int C, size_t smem, Args... args)
+{
+    if (int rc_ = mct_smem_attr(ctx, kern, attr_state, smem, 0)) return rc_;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(ANY_THREADS, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    mct_prof_begin(ctx, name);
+    MCT_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, args...));
+    mct_prof_end(ctx);
+    MCT_KERNEL_CHECK(ctx);
+    return MCT_OK;
+}
 int launch_ensemble_retain(mct_clf* clf, int P, int Nn)
 {
     if (clf->p.strong_type != MCT_STRONG_MILENSEMBLE) return MCT_OK;
@@ -900,12 +985,13 @@ int launch_mil_select(mct_clf* clf, int P, int Nn)
         return MCT_OK;
     }
     if (clf->p.strong_type == MCT_STRONG_MILANYBOOST) {
-        size_t smem = (size_t)(3 * M + F) * sizeof(float) + (size_t)F;
+        const int C = any_cluster_width(F);
+        int rows_in_smem;
+        const size_t smem = any_smem_plan(F, M, C, &rows_in_smem);
         if (smem > 200 * 1024) return mct_fail(ctx, MCT_E_UNSUPPORTED, "training set too large for the AnyBoost kernel%s (M=%d)", "", M);
         static size_t s_attr[MCT_MAX_DEV];
-        if (int rc_ = mct_smem_attr(ctx, k_anyboost_select, s_attr, smem, 32 * 1024)) return rc_;
-        MCT_LAUNCH(ctx, "k_anyboost_select", k_anyboost_select<<<1, ANY_THREADS, smem, ctx->stream>>>(clf->d_pred, clf->ldT, F, P, Nn, clf->K, clf->d_sel, clf->d_nsel));
-        return MCT_OK;
+        return any_launch(ctx, "k_anyboost_select", k_anyboost_select, s_attr, dim3(C, 1, 1), C, smem, (const float*)clf->d_pred, clf->ldT, F, P, Nn, clf->K,
+                          clf->d_sel, clf->d_nsel, rows_in_smem);
     }
     // cluster width: enough CTAs that each owns <= ~48 candidates, capped at 16 (non-portable size)
     int C = clf->cluster;
@@ -962,11 +1048,13 @@ int launch_mil_select_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h
         MCT_LAUNCH(ctx, "k_adaboost_select_batch", k_adaboost_select_batch<<<n_obj, ADA_THREADS, smem_ada, ctx->stream>>>(d));
     }
     if (any_any) {
-        size_t smem = (size_t)(3 * M_any + F_any) * sizeof(float) + (size_t)F_any;
+        const int C = any_cluster_width(F_any);
+        int rows_in_smem;
+        const size_t smem = any_smem_plan(F_any, M_any, C, &rows_in_smem);
         if (smem > 200 * 1024) return mct_fail(ctx, MCT_E_UNSUPPORTED, "training set too large for the AnyBoost kernel%s (M=%d)", "", M_any);
+        const int rows_words = rows_in_smem ? ceil_div(F_any, C) * (M_any | 1) : 0;
         static size_t s_attr[MCT_MAX_DEV];
-        if (int rc_ = mct_smem_attr(ctx, k_anyboost_select_batch, s_attr, smem, 32 * 1024)) return rc_;
-        MCT_LAUNCH(ctx, "k_anyboost_select_batch", k_anyboost_select_batch<<<n_obj, ANY_THREADS, smem, ctx->stream>>>(d));
+        if (int rc_ = any_launch(ctx, "k_anyboost_select_batch", k_anyboost_select_batch, s_attr, dim3(C, n_obj, 1), C, smem, d, rows_words)) return rc_;
     }
     if (any_mil) {
         const int F = F_max, M = M_max;

@@ -1778,7 +1778,7 @@ __device__ bool gen_group_plan(MdchGroup* g, int first, int n, float sx, float s
     *g = z;
     if (n < 1 || q.dim > 1024) return false;
     z.rows = __float2int_rn(__fmul_rn((float)q.ch0, sy)); z.cols = __float2int_rn(__fmul_rn((float)q.cw0, sx));
-    if (z.rows < 1 || z.cols < 1 || z.rows * z.cols > MCT_MDCH_SEG_PIX) return false;
+    if (z.rows < 1 || z.cols < 1 || z.rows * z.cols > MCT_MDCH_TRAIN_PIX) return false;
     z.x0 = bbox[0]; z.y0 = bbox[2]; z.RW = bbox[1] - bbox[0] + z.cols; z.RH = bbox[3] - bbox[2] + z.rows;
     z.npx = z.RW * z.RH;
     if (z.npx > 65536 || z.RW > 2047 || z.RH > 2047 || z.npx > q.npx_b[gi]) return false;

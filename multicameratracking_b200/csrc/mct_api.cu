@@ -1607,7 +1607,7 @@ static bool mdch_group_plan(MdchGroup* g, const mct_boxes* b, int first, int w0,
         y0 = std::min(y0, b->row[i]); y1 = std::max(y1, b->row[i]);
     }
     g->rows = (int)lrintf((float)h0 * sy); g->cols = (int)lrintf((float)w0 * sx);      // __float2int_rn(__fmul_rn(.)), as the kernels
-    if (g->rows < 1 || g->cols < 1 || g->rows * g->cols > MCT_MDCH_SEG_PIX) return false;
+    if (g->rows < 1 || g->cols < 1 || g->rows * g->cols > MCT_MDCH_TRAIN_PIX) return false;
     g->x0 = x0; g->y0 = y0; g->RW = x1 - x0 + g->cols; g->RH = y1 - y0 + g->rows;
     g->EW = ((2 * g->RW - g->cols) * (2 * g->RH - g->rows) <= MTR_EXT_WORDS) ? 1 : 0; g->EH = 0;
     g->npx = g->RW * g->RH;
@@ -1926,7 +1926,7 @@ extern "C" int mct_track_update_default(mct_ctx* ctx, int n_obj, mct_pf* const* 
                 const int npx = std::min(RW * RH, 65536);
                 d.npx_b[gi] = npx;
                 const int ext = (2 * RW - cols) * (2 * RH - rows);
-                d.tab_b = std::max(d.tab_b, ext <= MTR_EXT_WORDS ? ext : std::min(rows * cols, MCT_MDCH_SEG_PIX));
+                d.tab_b = std::max(d.tab_b, ext <= MTR_EXT_WORDS ? ext : std::min(rows * cols, MCT_MDCH_TRAIN_PIX));
                 const int B = std::min((nb_[gi] + 31) & ~31, 384), S = 384 / B;
                 d.nch_b = std::max(d.nch_b, (npx + S * 160 - 1) / (S * 160));
                 lb.npx_max = std::max(lb.npx_max, npx);

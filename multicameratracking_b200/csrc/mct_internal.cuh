@@ -11,6 +11,7 @@
 #define MCT_II_LEAD 3          // integral rows start 3 floats into a 16B-aligned row so that column 1 is 16B aligned
 #define MCT_FIX_SHIFT_MAX 20   // MDCH fixed-point histogram scale 2^20
 #define MCT_MDCH_SEG_PIX 4096  // pixels per fixed-point segment (u32 cannot overflow: 4096 * 2^20 = 2^32 excluded by weight <= 1 and shift rule)
+#define MCT_MDCH_TRAIN_PIX 8191 // largest box of the pixel-list training kernels: one fixed-point segment at 2^clz(pixels) >= 2^19 (8191 * 2^19 < 2^32)
 
 // ------------------------------------------------------------------ per-object device status
 struct PfDev {
