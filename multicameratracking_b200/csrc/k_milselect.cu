@@ -43,6 +43,27 @@ __device__ __forceinline__ bool better_min(float v, int f, float bv, int bf)
     return (v < bv) || (v == bv && f < bf);
 }
 
+// warp-wide arg-min in the order of better_min with two redux instructions instead of a five-step shuffle butterfly: the score
+// is mapped to a u32 whose unsigned order is the scores' order (NaN last, -0 == +0), ties and the "no candidate" mark
+// (f == 0x7fffffff, which loses against everything) are settled by the index; the score's own bits come from the winning lane.
+__device__ __forceinline__ unsigned score_key(float v, int f)
+{
+    if (f == 0x7fffffff || v != v) return 0xffffffffu;
+    if (v == 0.0f) return 0x80000000u;
+    const unsigned u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ void warp_argmin(float& v, int& f)
+{
+    const unsigned key = score_key(v, f);
+    const unsigned m = __reduce_min_sync(0xffffffffu, key);
+    const unsigned fm = __reduce_min_sync(0xffffffffu, key == m ? (unsigned)f : 0x7fffffffu);
+    const unsigned who = __ballot_sync(0xffffffffu, key == m && (unsigned)f == fm);
+    const int src = who ? __ffs(who) - 1 : 0;
+    v = __shfl_sync(0xffffffffu, v, src);
+    f = (int)fm;
+}
+
 // terms per pass and candidate: MIL_RN negatives + up to MIL_PC positives, kept per candidate in one padded row of
 // MIL_RS floats (MIL_RS % 32 == 4: the float4 reads of 8 neighbouring candidates cover the 32 banks once)
 #define MIL_RN 32
@@ -259,18 +280,20 @@ milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int N
         }
         MIL_STAMP(0)
         // CTA argmin: the owning threads park their best in shared memory, warp 0 reduces and publishes
-        if (tid < FC) { s_cand[tid].nll = bv; s_cand[tid].f = bf; }
+        // (one candidate per thread: the warps that own candidates reduce their registers, warp 0 combines the few warp bests)
+        const int ncw = (min(FC, FL) + 31) >> 5;
+        if (warp < ncw) {
+            float v = bv; int f = bf;
+            warp_argmin(v, f);
+            if (lane == 0) { s_cand[warp].nll = v; s_cand[warp].f = f; }
+        }
         __syncthreads();
         const int par = s & 1;
         if (warp == 0) {
             float v = CUDART_INF_F; int f = 0x7fffffff;
-            for (int q = lane; q < FC; q += 32)
-                if (better_min(s_cand[q].nll, s_cand[q].f, v, f)) { v = s_cand[q].nll; f = s_cand[q].f; }
-            for (int o = 16; o > 0; o >>= 1) {
-                float ov = __shfl_xor_sync(0xffffffffu, v, o);
-                int of = __shfl_xor_sync(0xffffffffu, f, o);
-                if (better_min(ov, of, v, f)) { v = ov; f = of; }
-            }
+            if (lane < ncw) { v = s_cand[lane].nll; f = s_cand[lane].f; }
+            if (ncw > 1) warp_argmin(v, f);
+            else { v = __shfl_sync(0xffffffffu, v, 0); f = __shfl_sync(0xffffffffu, f, 0); }
             if (lane < C) {
                 // publish into peer `lane`'s slot table (distributed shared memory)
                 SelSlot* remote = cluster.map_shared_rank(&slots[0][0], lane);
@@ -284,12 +307,7 @@ milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int N
         // every thread reduces the C published bests the same way (2 slots per lane, then a butterfly)
         float gv = CUDART_INF_F; int gf = 0x7fffffff;
         if (lane < C) { gv = slots[par][lane].nll; gf = slots[par][lane].f; }
-        for (int o = 8; o > 0; o >>= 1) {
-            float ov = __shfl_xor_sync(0xffffffffu, gv, o);
-            int of = __shfl_xor_sync(0xffffffffu, gf, o);
-            if (better_min(ov, of, gv, gf)) { gv = ov; gf = of; }
-        }
-        gv = __shfl_sync(0xffffffffu, gv, 0); gf = __shfl_sync(0xffffffffu, gf, 0);
+        warp_argmin(gv, gf);
         if (gf == 0x7fffffff) break;                               // nothing eligible (reference: UB read)
         if ((prev - (double)gv) < 1e-100) break;                   // :108-112 no improvement -> pop & stop
         prev = (double)gv;
