@@ -101,8 +101,10 @@ milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int N
     __shared__ int s_nact[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const int f_begin = rank * FL;
-    const int f_end = min(F, f_begin + FL);
+    // candidate l of this CTA is feature rank + l * C: every CTA gets the same mix of feature families (with contiguous ranges the
+    // CTAs that owned the Haar features carried 48 live candidates per round and the ones with colour bins, many of them empty
+    // in both classes and therefore invalid, a dozen: the cluster barrier waited for the former)
+    const int nl = F > rank ? (F - rank + C - 1) / C : 0;
 
     for (int i = tid; i < M; i += blockDim.x) Hs[i] = 0.0f;
     for (int f = tid; f < F; f += blockDim.x) {
@@ -111,9 +113,9 @@ milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int N
         selflag[f] = fl;
     }
     if (ROWS_SMEM)
-        for (int f = f_begin + warp; f < f_end; f += nwarps) {
-            const float* pr = pred + (size_t)f * ld;
-            float* dst = rows + (f - f_begin) * M;
+        for (int l = warp; l < nl; l += nwarps) {
+            const float* pr = pred + (size_t)(rank + l * C) * ld;
+            float* dst = rows + l * M;
             for (int i = lane; i < M; i += 32) dst[i] = pr[i];
         }
     if (tid == 0) { s_nact[0] = 0; s_nact[1] = 0; }
@@ -133,8 +135,8 @@ milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int N
 #ifdef MCT_MIL_DEBUG
         dbg_c = clock64();
 #endif
-        for (int fc = f_begin; fc < f_end; fc += FC) {
-            const int nfc = min(FC, f_end - fc);
+        for (int fc = 0; fc < nl; fc += FC) {
+            const int nfc = min(FC, nl - fc);
             // The bag likelihood is the ordered f32 product of (1 - sigmoid) over the positives: it never grows, and once
             // 1 - like rounds to 1.0f the later factors cannot change the NLL any more, so the positives are evaluated
             // PC at a time and a candidate leaves the pass list as soon as its product saturates (bit-identical to the
@@ -145,7 +147,7 @@ milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int N
             bool active = false, sat = false;
             int col = 0;
             if (tid < ((nfc + 31) & ~31)) {                     // whole warps: the list slots are handed out by ballot
-                active = tid < nfc && !selflag[fc + tid];
+                active = tid < nfc && !selflag[rank + (fc + tid) * C];
                 const unsigned bal = __ballot_sync(0xffffffffu, active);
                 int base = 0;
                 if (lane == 0 && bal) base = atomicAdd(&s_nact[g & 1], __popc(bal));
@@ -185,7 +187,7 @@ milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int N
                             const int a = (int)(((unsigned)u * magic) >> 16), bb = u - a * nblk;
                             const int e = al[a];
                             const int slot = e & 0xffff;
-                            const float* pr = ROWS_SMEM ? rows + (fc - f_begin + slot) * M : pred + (size_t)(fc + slot) * ld;
+                            const float* pr = ROWS_SMEM ? rows + (fc + slot) * M : pred + (size_t)(rank + (fc + slot) * C) * ld;
                             float* dst = scratch + a * MIL_RS;
                             if (bb < nbN) {
                                 const int r = bb * 32 + lane;
@@ -258,7 +260,7 @@ milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int N
                         again = (n0 + MIL_RN < Nn) || more_p;
                         if (!again) {
                             active = false;
-                            const int f = fc + tid;
+                            const int f = rank + (fc + tid) * C;
                             const float posl = sat ? posl_sat : (float)(-log((double)__fsub_rn(1.0f, like) + 1e-5));
                             const float nll = __fadd_rn(__fdiv_rn(posl, fP), __fdiv_rn(sn, fN));
                             if (better_min(nll, f, bv, bf)) { bv = nll; bf = f; }
