@@ -586,6 +586,8 @@ def run_ours(args):
                     "ms_per_step": ms_e2e_max / args.steps},
             "tracked_frames_per_sec_per_camera": args.steps / (ms_full_max * 1e-3),
             "full_frame": {"ms_per_frame": ms_full_max / args.steps,
+                           "training_sets": ("device: k_train_gen_default behind the frame's k_pf_update, tracker streams device-resident, no host round trip"
+                                             if mhost.device_training_sets() else "host enumeration (MCT_HOST_TRAINING_SETS=1)"),
                            "kernel_us_per_frame": {k: round(1e3 * v[0] / n_pf, 2) for k, v in sorted(prof_full.items(), key=lambda kv: -kv[1][0])}},
             "gpu_launches": int(launches_all),
             "roofline": {"kernel": dom_name, "bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s",

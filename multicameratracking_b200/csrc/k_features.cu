@@ -759,6 +759,7 @@ int launch_train_features(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, 
         if (h[o].feature_type == MCT_FEAT_MDCH || h[o].feature_type == MCT_FEAT_HAAR_MDCH) { any_mdch = 1; dim_max = max(dim_max, h[o].n_color); nb = h[o].nb; }
     }
     if (n_max <= 0) return MCT_OK;
+    if (any_mdch) { int rc = launch_bin_image(ctx, nb); if (rc) return rc; }     // (in front of the fork: both streams read it)
     bool forked = false;
     if (nh_max > 0) {
         dim3 g(ceil_div(n_max, 256), ceil_div(nh_max, HAAR_FT), n_obj);
@@ -769,15 +770,12 @@ int launch_train_features(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, 
             MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->train_stream, ctx->ev_tfork, 0));
             MCT_LAUNCH_ON(ctx, ctx->train_stream, "k_haar_matrix_batch",
                           k_haar_matrix_batch<<<g, 256, 0, ctx->train_stream>>>(d, ctx->ii_base + MCT_II_LEAD, ctx->ii_pitch, ctx->W, ctx->H));
-            MCT_CUDA(ctx, cudaEventRecord(ctx->ev_tjoin, ctx->train_stream));
             forked = true;
         } else {
             MCT_LAUNCH(ctx, "k_haar_matrix_batch", k_haar_matrix_batch<<<g, 256, 0, ctx->stream>>>(d, ctx->ii_base + MCT_II_LEAD, ctx->ii_pitch, ctx->W, ctx->H));
         }
     }
     if (any_mdch) {
-        int rc = launch_bin_image(ctx, nb);
-        if (rc) return rc;
         // objects whose two groups qualified on the host take the pixel-list kernels; the others the generic per-box kernel
         int n_fast = 0, n_slow = 0, nch = 1, tab_words = 0, chunk_words = 0, npx_max = 0, n_train_max = 0;
         if (lb) {
@@ -816,10 +814,16 @@ int launch_train_features(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, 
             static size_t s_attr[MCT_MAX_DEV];
             if (int rc_ = mct_smem_attr(ctx, k_mdch_batch, s_attr, smem, 0)) return rc_;
             dim3 g(ceil_div(n_max, MDCH_TILE), n_obj);
-            MCT_LAUNCH(ctx, "k_mdch_batch", k_mdch_batch<<<g, MDCH_WARPS * 32, smem, ctx->stream>>>(d, ctx->binimg, ctx->W, ctx->H));
+            // device-decided plans: the generic kernel is launched for the objects whose plan left the launch bounds -- normally
+            // none, every CTA leaves at once -- so it rides on the side stream behind the Haar rows, off the critical path
+            if (lb && forked) MCT_LAUNCH_ON(ctx, ctx->train_stream, "k_mdch_batch", k_mdch_batch<<<g, MDCH_WARPS * 32, smem, ctx->train_stream>>>(d, ctx->binimg, ctx->W, ctx->H));
+            else MCT_LAUNCH(ctx, "k_mdch_batch", k_mdch_batch<<<g, MDCH_WARPS * 32, smem, ctx->stream>>>(d, ctx->binimg, ctx->W, ctx->H));
         }
     }
-    if (forked) MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_tjoin, 0));
+    if (forked) {
+        MCT_CUDA(ctx, cudaEventRecord(ctx->ev_tjoin, ctx->train_stream));
+        MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_tjoin, 0));
+    }
     return MCT_OK;
 }
 
