@@ -10,5 +10,5 @@ $CMD > gpurun_out/plain_${TAG}b.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"k_mdch_sel|k_classify_staged|k_pf_update|k_frame_prep" -s 60 -c 5 -o gpurun_out/prof_${TAG} $CMD > gpurun_out/ncu_full_${TAG}.log 2>&1
 tail -n 2 gpurun_out/ncu_full_${TAG}.log
 # UpdateClassifier kernels (full frames leg)
-ncu --set full --clock-control none --import-source on -k regex:"k_milboost_select_batch|k_mdch_train_main|k_weak_update_batch|k_haar_matrix_batch" -s 12 -c 4 -o gpurun_out/prof_${TAG}_upd $CMD > gpurun_out/ncu_full_${TAG}_upd.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_milboost_select_batch|k_mdch_train_main|k_weak_update_batch|k_haar_matrix_batch|k_train_gen_default" -s 16 -c 5 -o gpurun_out/prof_${TAG}_upd $CMD > gpurun_out/ncu_full_${TAG}_upd.log 2>&1
 tail -n 2 gpurun_out/ncu_full_${TAG}_upd.log
