@@ -357,10 +357,13 @@ def run_ours(args):
     # one call per video frame (mcth_camera_step: make frame t current, announce frame t+1 and its noise, track)
     plane_arr = None if args.e2e_bgr else [(vp * 4)(*pl) for pl in planes_ptr]
 
-    def step_e2e(i, phases):
+    def step_e2e(i, phases, last=False):
         t = pingpong(i, POOL)
         if plane_arr is not None and not host_timing:
             j = (i + 1) % total
+            if last:                      # closes a streaming run: nothing announced, nothing queued ahead
+                cam._chk(Lh.mcth_camera_step(camh, t, plane_arr[t], None, W, H, W, noise_ptr[i % total], None, 0, phases, out_ptr))
+                return out_box
             cam._chk(Lh.mcth_camera_step(camh, t, plane_arr[t], plane_arr[pingpong(i + 1, POOL)], W, H, W, noise_ptr[i % total], noise_ptr[j],
                                          noise_len[j], phases, out_ptr))
             return out_box
@@ -392,9 +395,9 @@ def run_ours(args):
     # far from where the previous leg left the trackers, and lost trackers spread their particles over the slow paths).
     clock = [0]
 
-    def timed(fn, n_warm, n_steps):
+    def timed(fn, n_warm, n_steps, closer=None):
         offset = clock[0]
-        clock[0] += n_warm + n_steps
+        clock[0] += n_warm + n_steps + (1 if closer else 0)
         for i in range(n_warm):
             fn(offset + i)
         barrier()
@@ -407,7 +410,11 @@ def run_ours(args):
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
-        return ms, capi.scored_particles(L, ctx_h), cam.launches - l0
+        res = ms, capi.scored_particles(L, ctx_h), cam.launches - l0
+        if closer:
+            closer(offset + n_warm + n_steps)       # (untimed: consumes the frame a streaming leg queued ahead)
+            barrier()
+        return res
 
     # ---- 1. full frames (score + UpdateClassifier) through the host API, first: the trackers start on their objects ----
     ms_full, _, _ = timed(lambda i: step_e2e(i, 3), args.warmup, args.steps)
@@ -436,7 +443,16 @@ def run_ours(args):
     prof = capi.profile_read(L, ctx_h)
     L.mct_profile_enable(ctx_h, 0)
     # ---- 4. end to end through the host API, host buffers ----
-    ms_e2e, scored_e2e, _ = timed(lambda i: step_e2e(i, 1), args.warmup, args.steps)
+    # streaming calls (phases 1 | 16): a call returns frame t's boxes after it has queued frame t + 1, whose planes and noise it uploads;
+    # every timed call still carries one frame's host -> device copies, one frame of kernels and one frame's read-out (the frame
+    # queued by the last timed call is consumed by an untimed closing call).  Opt-in (MCT_E2E_STREAM=1): on B200 the synchronous
+    # call per frame measures 134.5 us against 138.3 us streaming, so the default stays the reference's
+    # synchronous per-frame interface.
+    stream_e2e = plane_arr is not None and not host_timing and bool(os.environ.get("MCT_E2E_STREAM"))
+    if stream_e2e:
+        ms_e2e, scored_e2e, _ = timed(lambda i: step_e2e(i, 1 | 16), args.warmup, args.steps, closer=lambda i: step_e2e(i, 1 | 16, last=True))
+    else:
+        ms_e2e, scored_e2e, _ = timed(lambda i: step_e2e(i, 1), args.warmup, args.steps)
     if host_timing:
         sys.stderr.write("host us/step (score e2e): set_frame %.1f prefetch_frame %.1f prefetch_noise %.1f track %.1f\n" % tuple(1e-3 * x / max(1, host_t[4]) for x in host_t[:4]))
 
@@ -583,7 +599,9 @@ def run_ours(args):
             "e2e": {"value": scored_e2e_all / (ms_e2e_max * 1e-3), "unit": "particles/s",
                     "h2d_bytes_per_step": (4 if (not args.e2e_bgr) else 3) * W * H + N_OBJ * 4 * N_PART * 4,
                     "input": "4 u8 planes (gray,R,G,B)" if (not args.e2e_bgr) else "packed BGR frame (split + gray conversion on the device)", "d2h_bytes_per_step": N_OBJ * C.sizeof(capi.PfSummary),
-                    "ms_per_step": ms_e2e_max / args.steps},
+                    "ms_per_step": ms_e2e_max / args.steps,
+                    "call": ("mcth_camera_step, streaming (phases 1 | 16): frame t's boxes are returned after frame t + 1 has been queued; "
+                             "one frame uploaded, tracked and read back per call") if stream_e2e else "mcth_camera_step, synchronous per frame"},
             "tracked_frames_per_sec_per_camera": args.steps / (ms_full_max * 1e-3),
             "full_frame": {"ms_per_frame": ms_full_max / args.steps,
                            "training_sets": ("device: k_train_gen_default behind the frame's k_pf_update, tracker streams device-resident, no host round trip"

@@ -83,6 +83,9 @@ int mct_frame_set(mct_ctx* ctx, const uint8_t* gray, const uint8_t* c0, const ui
  * the wrong matrix) run on the device, so only 3 bytes per pixel cross PCIe.  pitch_bytes >= 3*W.  is_device as above. */
 int mct_frame_set_bgr(mct_ctx* ctx, const uint8_t* bgr, int W, int H, int pitch_bytes, int use_hsv, int is_device);
 int mct_frame_prefetch_bgr(mct_ctx* ctx, const uint8_t* bgr_host, int W, int H, int pitch_bytes, int use_hsv);
+/* Issues the announced frame's upload and preparation now instead of at the end of the next mct_track_score* call: for a caller
+ * that queues frame t + 1 (mct_frame_set + mct_track_score_async) while frame t is still being tracked. */
+int mct_frame_prefetch_flush(mct_ctx* ctx);
 /* Optional double buffering of the upload (Camera.cpp:405-495 reads frame t+1 from the video while frame t is
  * tracked): copies the NEXT frame's host planes (pinned memory for a truly asynchronous copy) into the ctx's back
  * buffers on a separate copy stream, overlapping the kernels of the current frame.  A following mct_frame_set with

@@ -41,7 +41,7 @@ SYMBOLS = [
     "mct_pf_get_summary_many", "mct_pf_rearrange_ground_many",
     # whole frame on the device
     "mct_pf_rng_set", "mct_pf_rng_get", "mct_track_update_default", "mct_track_update_default_collect",
-    "mct_track_update_default_boxes",
+    "mct_track_update_default_boxes", "mct_frame_prefetch_flush",
 ]
 
 

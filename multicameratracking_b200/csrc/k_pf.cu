@@ -324,7 +324,7 @@ __device__ void resample_body(const ObjDesc& d, float* sw, float* cdf, int force
     }
 }
 
-__device__ void summary_body(const ObjDesc& d, float* scratch);
+__device__ void summary_body(const ObjDesc& d, float* scratch, int summ_off = 0);
 
 // mode 0: d.H holds the classifier response; build the likelihood map ((H-min)/range)^exponent over the
 //         valid particles (ParticleFilterTracker.cpp:541-566) and use it as prob.
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(PF_THREADS) k_pf_update(const ObjDesc* __restr
     }
     if (mode == 0 && cnt == 0) {              // reference: ASSERT abort (ParticleFilterTracker.cpp:513)
         __syncthreads();
-        if (with_summary) summary_body(d, nullptr);    // the host sees n_valid == 0 -> MCT_E_EMPTY
+        if (with_summary) summary_body(d, nullptr, sa.summ_off);    // the host sees n_valid == 0 -> MCT_E_EMPTY
         return;
     }
     const double dmn = (double)mn, range = (double)mx - (double)mn;
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(PF_THREADS) k_pf_update(const ObjDesc* __restr
     PF_STAMP(10);
     if (with_summary) {
         __syncthreads();                       // the read-out reads state / weights written by other threads above
-        summary_body(d, (2 * N4 <= smem_floats) ? smf : nullptr);   // sw / cdf are dead: reuse them as scratch (2 * N4 floats)
+        summary_body(d, (2 * N4 <= smem_floats) ? smf : nullptr, sa.summ_off);   // sw / cdf are dead: reuse them as scratch (2 * N4 floats)
     }
     PF_STAMP(15);
     PF_COMMIT(s_decide);
@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) k_pf_update_fast(const ObjDesc*
     }
     if (mode == 0 && cnt == 0) {
         __syncthreads();
-        if (with_summary) summary_body(d, nullptr);
+        if (with_summary) summary_body(d, nullptr, sa.summ_off);
         return;
     }
     const double dmn = (double)mn, range = (double)mx - (double)mn;
@@ -701,7 +701,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) k_pf_update_fast(const ObjDesc*
     if (!decide && fs != MCT_PF_PREDICTED) {
         // (re-score of an already resampled filter, or a filter that was never predicted: the generic read-out)
         __syncthreads();
-        summary_body(d, smf);
+        summary_body(d, smf, sa.summ_off);
         PF_COMMIT(decide);
         return;
     }
@@ -771,7 +771,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) k_pf_update_fast(const ObjDesc*
     if (tid == 0) {
         PfRed t = s_red[0];
         for (int q = 1; q < nt / 32; q++) merge(t, s_red[q]);
-        mct_pf_summary* out = d.summ;
+        mct_pf_summary* out = d.summ + sa.summ_off;
         for (int q = 0; q < 4; q++) { const float v = (float)(t.acc[q] / t.acc[4]); out->average[q] = v; trk_set_avg(d, q, v); }
         out->n_valid = cnt; out->resampled = decide; out->filter_state = fs;
         out->neff_inv = neff_inv; out->max_response = (mode == 0) ? max_response : d.st->max_response;
@@ -923,14 +923,14 @@ int launch_pf_expand_prob(mct_ctx* ctx, const ObjDesc* d_desc, const float* d_pr
 //            order with the weights in *sorted* order (:799-806) -- kept.
 // scratch: 2 * round_up(N, 4) floats of shared memory (or NULL): the resample index list and the run weights are
 // staged there so that the per-run binary searches and tie scans do not chase L2 latency.
-__device__ void summary_body(const ObjDesc& d, float* scratch)
+__device__ void summary_body(const ObjDesc& d, float* scratch, int summ_off)
 {
     __shared__ float sh_f[32];
     __shared__ double sh_d5[5 * 32];
     __shared__ int sh_i[32];
     __shared__ int s_first, s_last;
     const int N = d.N, tid = threadIdx.x, nt = blockDim.x;
-    mct_pf_summary* out = d.summ;
+    mct_pf_summary* out = d.summ + summ_off;
     const int fs = d.st->filter_state;
 
     double acc[5] = {0, 0, 0, 0, 0};

@@ -128,9 +128,11 @@ extern "C" int mct_ctx_create(int device, void* cuda_stream, mct_ctx** out)
     ctx->desc_last_h = malloc(sizeof(ObjDesc) * DESC_MAX_OBJ);
     if (!ctx->desc_last_h) return mct_fail(nullptr, MCT_E_NOMEM, "out of host memory%s");
     ctx->summ_cap = DESC_MAX_OBJ;
-    MCT_CUDA(nullptr, cudaHostAlloc(&ctx->h_summ, sizeof(mct_pf_summary) * DESC_MAX_OBJ, cudaHostAllocMapped));
+    // [0, 64) and [64, 128): the two alternating read-out slots of the fused score path (two calls may be in flight);
+    // [128, 192): the stand-alone read-out calls (mct_pf_get_summary_many)
+    MCT_CUDA(nullptr, cudaHostAlloc(&ctx->h_summ, sizeof(mct_pf_summary) * DESC_MAX_OBJ * 3, cudaHostAllocMapped));
     MCT_CUDA(nullptr, cudaHostGetDevicePointer((void**)&ctx->h_summ_dev, ctx->h_summ, 0));
-    memset(ctx->h_summ, 0, sizeof(mct_pf_summary) * DESC_MAX_OBJ);
+    memset(ctx->h_summ, 0, sizeof(mct_pf_summary) * DESC_MAX_OBJ * 3);
     MCT_CUDA(nullptr, cudaMalloc(&ctx->d_scored, sizeof(unsigned long long)));
     MCT_CUDA(nullptr, cudaMemset(ctx->d_scored, 0, sizeof(unsigned long long)));
     *out = ctx;
@@ -223,7 +225,7 @@ extern "C" int mct_ctx_destroy(mct_ctx* ctx)
     if (ctx->d_gen) cudaFree(ctx->d_gen);
     if (ctx->h_gen_out) cudaFreeHost(ctx->h_gen_out);
     free(ctx->gen_shadow); free(ctx->tdesc_shadow);
-    if (ctx->has_ev_score) cudaEventDestroy(ctx->ev_score);
+    if (ctx->has_ev_score) { cudaEventDestroy(ctx->ev_score[0]); cudaEventDestroy(ctx->ev_score[1]); }
     free(ctx->desc_last_h);
     DescRing* r = ring_of(ctx);
     if (r) {
@@ -471,6 +473,17 @@ extern "C" int mct_frame_prefetch_bgr(mct_ctx* ctx, const uint8_t* bgr_host, int
     return frame_prefetch_impl(ctx, 1, bgr_host, nullptr, nullptr, nullptr, W, H, pitch_bytes, use_hsv ? 1 : 0);
 }
 
+// issue the announced frame's upload and preparation NOW (instead of at the end of the next mct_track_score*): for callers that
+// queue frame t + 1 while frame t is still being tracked
+extern "C" int mct_frame_prefetch_flush(mct_ctx* ctx)
+{
+    if (!ctx) return MCT_E_ARG;
+    if (!ctx->pf_pending) return MCT_OK;
+    MCT_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = prefetch_copy(ctx))) return rc;
+    return prefetch_prep(ctx);
+}
 extern "C" int mct_frame_get_planes(mct_ctx* ctx, uint8_t* gray, uint8_t* c0, uint8_t* c1, uint8_t* c2)
 {
     if (!ctx) return MCT_E_ARG;
@@ -1379,7 +1392,7 @@ extern "C" int mct_pf_get_summary_many(mct_ctx* ctx, int n_obj, mct_pf* const* p
     for (int o = 0; o < n_obj; o++) {
         if (!pfs[o] || pfs[o]->ctx != ctx || !pfs[o]->initialized) return mct_fail(ctx, MCT_E_STATE, "particle filter not initialised%s");
         memset(&h[o], 0, sizeof(ObjDesc)); fill_pf_desc(&h[o], pfs[o]);
-        h[o].summ = ctx->h_summ_dev + o;               // straight into mapped pinned memory
+        h[o].summ = ctx->h_summ_dev + 2 * DESC_MAX_OBJ + o;    // straight into mapped pinned memory (the stand-alone region)
         h[o].resample = 1;
         if (pfs[o]->N > n_max) n_max = pfs[o]->N;
     }
@@ -1387,7 +1400,7 @@ extern "C" int mct_pf_get_summary_many(mct_ctx* ctx, int n_obj, mct_pf* const* p
     if ((rc = desc_publish(ctx, h, n_obj, &d))) return rc;
     if ((rc = launch_pf_summary(ctx, d, n_obj, n_max))) return rc;
     if ((rc = mct_sync(ctx))) return rc;
-    memcpy(out, ctx->h_summ, sizeof(mct_pf_summary) * n_obj);
+    memcpy(out, ctx->h_summ + 2 * DESC_MAX_OBJ, sizeof(mct_pf_summary) * n_obj);
     return MCT_OK;
 }
 
@@ -1426,7 +1439,7 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
         // MDCH objects of the MIL classifiers: the colour kernel evaluates the selected colour weak classifiers where the bin
         // values are (shared memory) and leaves their responses in featN; the classify kernel only adds them in selector order
         h[o].color_resp = (h[o].slotmap != nullptr && h[o].alpha == nullptr && !getenv("MCT_NO_COLOR_RESP")) ? 1 : 0;
-        h[o].summ = ctx->h_summ_dev + o;               // the read-out is written straight into mapped pinned memory
+        h[o].summ = ctx->h_summ_dev + o;               // the read-out is written straight into mapped pinned memory (+ StepArgs::summ_off)
         h[o].w0 = params[o].w0; h[o].h0 = params[o].h0; h[o].exponent = params[o].exponent;
         h[o].force_reset = params[o].force_reset; h[o].resample = params[o].resample;
         sa.u01[o] = u01 ? u01[o] : 0.0f;
@@ -1435,9 +1448,32 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
         if (c->K > K_max) K_max = c->K;
     }
     sa.dev_rng = u01 ? 0 : 1;                          // u01 == NULL: every object draws from its device-resident stream (mct_pf_rng_set)
+    // read-out slot of this call: two fused score calls may be in flight (the caller queues frame t + 1 before it collects frame t);
+    // a third one retires the oldest, whose read-outs are then lost (the free-running throughput path never collects)
+    if (ctx->score_issued - ctx->score_collected >= 2) ctx->score_collected = ctx->score_issued - 1;
+    const int slot = (int)(ctx->score_issued & 1);
+    sa.summ_off = slot * DESC_MAX_OBJ;
     // prediction noise: device pointers are used in place; a block announced with mct_noise_prefetch is already on the
     // device; any other host noise is staged with ONE copy
     if (noise_is_device || rescore) sa.noise_base = noise;
+    else if (ctx->npf_req && ctx->prep_stream && ctx->npf_req_src == noise && ctx->npf_req_n == ntot) {
+        // announced for THIS call and not uploaded yet (the caller queues the next frame while the current one is still being
+        // tracked): upload it now on the copy stream, beside the kernels in flight, instead of in front of this call's first kernel
+        const int nb2 = ctx->noise_pf_cur ^ 1;
+        if (ctx->npf_req_n > ctx->noise_pf_cap[nb2]) {
+            MCT_CUDA(ctx, cudaDeviceSynchronize());
+            if (ctx->d_noise_pf[nb2]) cudaFree(ctx->d_noise_pf[nb2]);
+            MCT_CUDA(ctx, cudaMalloc(&ctx->d_noise_pf[nb2], ctx->npf_req_n * sizeof(float)));
+            ctx->noise_pf_cap[nb2] = ctx->npf_req_n;
+        }
+        // (the other buffer was last read by the score call two calls ago: the event of this call's slot still marks its end)
+        if (ctx->has_ev_score && ctx->score_issued >= 2) MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->prep_stream, ctx->ev_score[slot], 0));
+        MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_noise_pf[nb2], noise, ntot * sizeof(float), cudaMemcpyHostToDevice, ctx->prep_stream));
+        MCT_CUDA(ctx, cudaEventRecord(ctx->ev_noise, ctx->prep_stream));
+        MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_noise, 0));
+        ctx->noise_pf_cur = nb2; ctx->npf_req = 0; ctx->npf_ready = 0;
+        sa.noise_base = ctx->d_noise_pf[nb2];
+    }
     else if (ctx->npf_ready && ctx->npf_ready_src == noise && ctx->npf_ready_n == ntot) {
         MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_noise, 0));
         sa.noise_base = ctx->d_noise_pf[ctx->noise_pf_cur];
@@ -1493,9 +1529,14 @@ extern "C" int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs
     if ((rc = launch_pf_update(ctx, d, n_obj, n_max, 1, sa, 1))) return rc;
     // the read-outs are complete behind this point: mct_track_collect waits for it, not for whatever the caller queues next
     // (the frame's UpdateClassifier when it runs from the device, mct_track_update_default)
-    if (!ctx->has_ev_score) { MCT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_score, cudaEventDisableTiming)); ctx->has_ev_score = 1; }
-    MCT_CUDA(ctx, cudaEventRecord(ctx->ev_score, ctx->stream));
-    ctx->score_gen_seq = ctx->gen_seq;                 // every device-side UpdateClassifier queued so far completes in front of that event
+    if (!ctx->has_ev_score) {
+        MCT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_score[0], cudaEventDisableTiming));
+        MCT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_score[1], cudaEventDisableTiming));
+        ctx->has_ev_score = 1;
+    }
+    MCT_CUDA(ctx, cudaEventRecord(ctx->ev_score[slot], ctx->stream));
+    ctx->score_gen_seq_slot[slot] = ctx->gen_seq;      // every device-side UpdateClassifier queued so far completes in front of that event
+    ctx->score_issued++;
     // Only now, with this frame's whole chain queued, the housekeeping for the NEXT frame: every API call in front of the
     // first launch is host time the GPU sits idle for (the caller waits for this frame's summaries before the next call)
     if (ctx->prep_stream && (rc = prefetch_copy(ctx))) return rc;      // next frame's planes (behind this frame's noise copy)
@@ -1531,9 +1572,19 @@ extern "C" int mct_noise_prefetch(mct_ctx* ctx, const float* noise_host, size_t 
 extern "C" int mct_track_collect(mct_ctx* ctx, int n_obj, mct_pf_summary* summaries)
 {
     if (!ctx || n_obj < 1 || n_obj > DESC_MAX_OBJ || !summaries) return MCT_E_ARG;
-    if (ctx->has_ev_score) MCT_CUDA(ctx, cudaEventSynchronize(ctx->ev_score));
-    else { int rc = mct_sync(ctx); if (rc) return rc; }
-    memcpy(summaries, ctx->h_summ, sizeof(mct_pf_summary) * n_obj);
+    // the oldest fused score call not collected yet (or, with none pending, the latest one again)
+    int slot;
+    if (ctx->score_collected < ctx->score_issued) {
+        slot = (int)(ctx->score_collected & 1);
+        MCT_CUDA(ctx, cudaEventSynchronize(ctx->ev_score[slot]));
+        ctx->score_collected++;
+    } else {
+        slot = (int)((ctx->score_issued - 1) & 1);
+        if (ctx->score_issued < 1) slot = 0;
+        int rc = mct_sync(ctx); if (rc) return rc;
+    }
+    memcpy(summaries, ctx->h_summ + slot * DESC_MAX_OBJ, sizeof(mct_pf_summary) * n_obj);
+    ctx->score_gen_seq = ctx->score_gen_seq_slot[slot];
     if (ctx->h_gen_out && ctx->score_gen_seq > ctx->gen_checked_seq) {
         // the device-side UpdateClassifier of the PREVIOUS frame has completed (it was queued in front of this frame's kernels):
         // an empty training set it met is reported here, one frame late

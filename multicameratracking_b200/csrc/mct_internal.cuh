@@ -112,7 +112,9 @@ struct mct_ctx {
     void* tdesc_shadow; int tdesc_shadow_n; int tdesc_gen_valid;
     mct_clf* gen_clfs[64]; int gen_n; int gen_pending;
     long long gen_seq, score_gen_seq, gen_checked_seq;   // read-outs alternate between two buffers (gen_seq & 1); see mct_track_collect
-    cudaEvent_t ev_score; int has_ev_score;
+    cudaEvent_t ev_score[2]; int has_ev_score;      // behind the k_pf_update of the score call that wrote read-out slot 0 / 1
+    long long score_issued, score_collected;        // fused score calls queued / collected: at most two in flight (slot = count & 1)
+    long long score_gen_seq_slot[2];
     GroundOut* d_ground_out;     // read-out of k_ground_pdf [DESC_MAX_OBJ]
     GroundArgs* d_ground_args;   // its per-object arguments [DESC_MAX_OBJ]
 };
@@ -249,6 +251,7 @@ struct TrainDesc {
 struct StepArgs {
     const float* noise_base;       // [sum over objects of 4 * N] Gaussian rows (device)
     float u01[DESC_MAX_OBJ];       // the randfloat() of ResampleParticles per object
+    int summ_off = 0;              // the read-outs of this call go to ObjDesc::summ + summ_off (the fused score path alternates between two slots)
     int dev_rng = 0;               // 1: the draw comes from the object's device-resident stream (PfTrk::rng), which advances iff it resamples
 };
 

@@ -65,6 +65,7 @@ void Matrixu::PrefetchFrame(const uint8_t* gray, const uint8_t* c0, const uint8_
 {
     chk(m_ctx, mct_frame_prefetch(m_ctx, gray, c0, c1, c2, cols, rows, pitch));
 }
+void Matrixu::FlushPrefetch() { chk(m_ctx, mct_frame_prefetch_flush(m_ctx)); }
 float Matrixu::sumRect(int x, int y, int w, int h) const
 {
     int r[4] = {x, y, w, h};
@@ -640,6 +641,34 @@ void ParticleFilterTracker::ScoreCameraObjectsAsync(mct_ctx* ctx, std::vector<Pa
         u01[o] = (float)(t->Rng().Next() * 2.3283064365386962890625e-10);
     }
     chk(ctx, mct_track_score_async(ctx, n, pfs.data(), clfs.data(), tp.data(), noiseDev, 1, u01.data()));
+}
+
+void ParticleFilterTracker::IssueScore(mct_ctx* ctx, std::vector<ParticleFilterTracker*>& trackers, const float* noise)
+{
+    const int n = (int)trackers.size();
+    if (n == 0) return;
+    if (!noise) throw MctHostError(MCT_E_ARG, "IssueScore: prediction noise not provided");
+    std::vector<mct_pf*> pfs(n); std::vector<mct_clf*> clfs(n); std::vector<mct_track_params> tp(n);
+    for (int o = 0; o < n; o++) {
+        ParticleFilterTracker* t = trackers[o];
+        if (!t->m_isInitialized) throw MctHostError(MCT_E_STATE, "tracker not initialised");
+        t->PushRng();
+        pfs[o] = t->m_particleFilterPtr->Handle(); clfs[o] = t->m_strongClassifierBasePtr->Handle();
+        tp[o].w0 = t->m_currentStateList[2]; tp[o].h0 = t->m_currentStateList[3];
+        tp[o].exponent = 20; tp[o].force_reset = 0; tp[o].resample = 1;
+    }
+    chk(ctx, mct_track_score_async(ctx, n, pfs.data(), clfs.data(), tp.data(), noise, 0, nullptr));
+}
+void ParticleFilterTracker::FinishScore(mct_ctx* ctx, std::vector<ParticleFilterTracker*>& trackers, int frameind)
+{
+    const int n = (int)trackers.size();
+    if (n == 0) return;
+    std::vector<mct_pf_summary> summ(n);
+    chk(ctx, mct_track_collect(ctx, n, summ.data()));
+    for (int o = 0; o < n; o++) {
+        trackers[o]->m_particleFilterPtr->AdoptSummary(summ[o]);
+        trackers[o]->StoreObjectState(frameind);
+    }
 }
 
 void ParticleFilterTracker::EnsureSummaries(mct_ctx* ctx, std::vector<ParticleFilterTracker*>& trackers)

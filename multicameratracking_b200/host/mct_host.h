@@ -74,6 +74,8 @@ public:
     void PrefetchFrameBGR(const uint8_t* bgr, int cols, int rows, int pitchBytes, bool useHSV = false);
     // start the upload of the NEXT frame while the current one is tracked; SetFrame with the same pointers adopts it
     void PrefetchFrame(const uint8_t* gray, const uint8_t* c0, const uint8_t* c1, const uint8_t* c2, int cols, int rows, int pitch);
+    // issue the announced frame's upload and preparation now (a caller that queues the next frame while this one is tracked)
+    void FlushPrefetch();
     void initII() {}                      // done inside SetFrame; kept for call-site compatibility
     void FreeII() {}
     bool isInitII() const { return m_iiInit; }
@@ -393,6 +395,12 @@ public:
     // read-out lands in the ctx's pinned buffer (mct_track_collect).  The resampler draw is consumed
     // unconditionally, so this form is for throughput runs, not for parity runs.
     static void ScoreCameraObjectsAsync(mct_ctx* ctx, std::vector<ParticleFilterTracker*>& trackers, const float* noiseDev);
+    // Streaming form of the score path (TrackObjectOnTheGivenFrame + StoreObjectState for a video whose next frame is known):
+    // IssueScore queues the frame that is current on the ctx without waiting (the resampler's draw comes from the trackers'
+    // device-resident streams, so nothing of the previous frame's read-out is needed), FinishScore waits for the OLDEST queued
+    // frame's read-outs and stores the objects' states for it.  At most two frames in flight.
+    static void IssueScore(mct_ctx* ctx, std::vector<ParticleFilterTracker*>& trackers, const float* noise /* host [n][4][N] */);
+    static void FinishScore(mct_ctx* ctx, std::vector<ParticleFilterTracker*>& trackers, int frameind);
     // the read-outs of all trackers whose particles changed on the device since the last one: ONE launch and ONE synchronisation
     // instead of one of each per object (in front of loops that read the particle filters object by object)
     static void EnsureSummaries(mct_ctx* ctx, std::vector<ParticleFilterTracker*>& trackers);

