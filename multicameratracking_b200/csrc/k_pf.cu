@@ -771,7 +771,10 @@ __global__ void __launch_bounds__(PF_THREADS, 1) k_pf_update_fast(const ObjDesc*
     if (tid == 0) {
         PfRed t = s_red[0];
         for (int q = 1; q < nt / 32; q++) merge(t, s_red[q]);
-        mct_pf_summary* out = d.summ + sa.summ_off;
+        // (the record is assembled in registers and leaves as five 16-byte stores: the destination is mapped host memory, every
+        //  store a posted write over PCIe)
+        __align__(16) mct_pf_summary rec;
+        mct_pf_summary* out = &rec;
         for (int q = 0; q < 4; q++) { const float v = (float)(t.acc[q] / t.acc[4]); out->average[q] = v; trk_set_avg(d, q, v); }
         out->n_valid = cnt; out->resampled = decide; out->filter_state = fs;
         out->neff_inv = neff_inv; out->max_response = (mode == 0) ? max_response : d.st->max_response;
@@ -796,6 +799,11 @@ __global__ void __launch_bounds__(PF_THREADS, 1) k_pf_update_fast(const ObjDesc*
             out->highest_close[3] = csy[b]; out->highest_close[4] = sw[PIDX(b)];
             out->n_unique = N;
         }
+        static_assert(sizeof(mct_pf_summary) == 80, "read-out record: five 16-byte words");
+        uint4* dst = reinterpret_cast<uint4*>(d.summ + sa.summ_off);
+        const uint4* src = reinterpret_cast<const uint4*>(&rec);
+#pragma unroll
+        for (int q = 0; q < 5; q++) dst[q] = src[q];
     }
     PF_STAMP(15);
     PF_COMMIT(decide);
