@@ -94,6 +94,14 @@ static int desc_publish(mct_ctx* ctx, const ObjDesc* src, int n, const ObjDesc**
 }
 
 // ------------------------------------------------------------------------------------------ context
+// Staging buffers of UpdateClassifier parked between contexts: a harness that re-creates its cameras (bench.py's network legs build
+// fresh trackers every few frames) otherwise pays the pinned / device allocations of the first batched Update inside a frame
+// -- about a millisecond per context with peer mappings in place (one camera per process).  One parked set per device.
+#include <mutex>
+struct StageCache { int* h_stage; int* d_stage; size_t cap; TrainDesc* h_tdesc; TrainDesc* d_tdesc; };
+static StageCache g_stage_cache[MCT_MAX_DEV];
+static std::mutex g_stage_mu;
+
 extern "C" const char* mct_version(void) { return "mct-b200 0.1 (sm_100a)"; }
 extern "C" const char* mct_last_error(mct_ctx* ctx) { return ctx ? ctx->err : g_mct_err; }
 extern "C" long long mct_launch_count(mct_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -215,7 +223,19 @@ extern "C" int mct_ctx_destroy(mct_ctx* ctx)
     if (ctx->d_noise_stage) cudaFree(ctx->d_noise_stage);
     for (int i = 0; i < 2; i++) if (ctx->d_noise_pf[i]) cudaFree(ctx->d_noise_pf[i]);
     if (ctx->d_bgr_stage) cudaFree(ctx->d_bgr_stage);
-    if (ctx->h_tdesc) { cudaFreeHost(ctx->h_tdesc); cudaFree(ctx->d_tdesc); cudaEventDestroy(ctx->ev_train); }
+    {
+        std::lock_guard<std::mutex> lk(g_stage_mu);
+        StageCache& sc = g_stage_cache[ctx->device < MCT_MAX_DEV ? ctx->device : 0];
+        if (ctx->h_tdesc) {
+            if (!sc.h_tdesc && ctx->device < MCT_MAX_DEV) { sc.h_tdesc = ctx->h_tdesc; sc.d_tdesc = ctx->d_tdesc; }
+            else { cudaFreeHost(ctx->h_tdesc); cudaFree(ctx->d_tdesc); }
+            cudaEventDestroy(ctx->ev_train);
+        }
+        if (ctx->h_train_stage && ctx->d_train_stage && !sc.h_stage && ctx->device < MCT_MAX_DEV) {
+            sc.h_stage = ctx->h_train_stage; sc.d_stage = ctx->d_train_stage; sc.cap = ctx->train_stage_cap;
+            ctx->h_train_stage = nullptr; ctx->d_train_stage = nullptr;
+        }
+    }
     if (ctx->train_stream) {
         cudaStreamSynchronize(ctx->train_stream); cudaStreamDestroy(ctx->train_stream);
         cudaEventDestroy(ctx->ev_tfork); cudaEventDestroy(ctx->ev_tjoin);
@@ -1708,11 +1728,27 @@ extern "C" int mct_track_update(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, c
     return MCT_OK;
 }
 
+static void stage_take_parked(mct_ctx* ctx, size_t need_boxes)
+{
+    std::lock_guard<std::mutex> lk(g_stage_mu);
+    if (ctx->device >= MCT_MAX_DEV) return;
+    StageCache& sc = g_stage_cache[ctx->device];
+    if (!sc.h_stage || sc.cap < need_boxes) return;
+    ctx->h_train_stage = sc.h_stage; ctx->d_train_stage = sc.d_stage; ctx->train_stage_cap = sc.cap;
+    sc.h_stage = nullptr; sc.d_stage = nullptr; sc.cap = 0;
+}
 static int train_descs_ready(mct_ctx* ctx)
 {
     if (!ctx->h_tdesc) {
-        MCT_CUDA(ctx, cudaMallocHost(&ctx->h_tdesc, sizeof(TrainDesc) * DESC_MAX_OBJ));
-        MCT_CUDA(ctx, cudaMalloc(&ctx->d_tdesc, sizeof(TrainDesc) * DESC_MAX_OBJ));
+        {
+            std::lock_guard<std::mutex> lk(g_stage_mu);
+            StageCache& sc = g_stage_cache[ctx->device < MCT_MAX_DEV ? ctx->device : 0];
+            if (sc.h_tdesc && ctx->device < MCT_MAX_DEV) { ctx->h_tdesc = sc.h_tdesc; ctx->d_tdesc = sc.d_tdesc; sc.h_tdesc = nullptr; sc.d_tdesc = nullptr; }
+        }
+        if (!ctx->h_tdesc) {
+            MCT_CUDA(ctx, cudaMallocHost(&ctx->h_tdesc, sizeof(TrainDesc) * DESC_MAX_OBJ));
+            MCT_CUDA(ctx, cudaMalloc(&ctx->d_tdesc, sizeof(TrainDesc) * DESC_MAX_OBJ));
+        }
         MCT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_train, cudaEventDisableTiming));
         MCT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->train_stream, cudaStreamNonBlocking));
         MCT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_tfork, cudaEventDisableTiming));
@@ -1729,6 +1765,7 @@ static int train_stage_and_features(mct_ctx* ctx, int n_obj, mct_clf* const* clf
     MCT_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc;
     if ((rc = train_descs_ready(ctx))) return rc;
+    if (total > ctx->train_stage_cap && !ctx->h_train_stage) stage_take_parked(ctx, total);
     if (total > ctx->train_stage_cap) {
         MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (ctx->h_train_stage) cudaFreeHost(ctx->h_train_stage);
@@ -1776,7 +1813,7 @@ static int train_stage_and_features(mct_ctx* ctx, int n_obj, mct_clf* const* clf
         }
     }
     // work buffers of the pixel-list kernels (accumulators are zero between launches: k_mdch_train_finish clears what it reads)
-    if (mlist_words > ctx->mlist_cap || macc_words > ctx->macc_cap || !ctx->d_mtot) {
+    if (mlist_words > ctx->mlist_cap || macc_words > ctx->macc_cap || (mlist_words > 0 && !ctx->d_mtot)) {
         MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (mlist_words > ctx->mlist_cap) {
             if (ctx->d_mlist) cudaFree(ctx->d_mlist);
@@ -1991,6 +2028,7 @@ extern "C" int mct_track_update_default(mct_ctx* ctx, int n_obj, mct_pf* const* 
         stage_words += (size_t)4 * mcap;
     }
     // buffers (grow-only; growing synchronises)
+    if (stage_words > ctx->train_stage_cap * 4 && !ctx->h_train_stage) stage_take_parked(ctx, stage_words / 4 + 1);
     if (stage_words > ctx->train_stage_cap * 4) {
         MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (ctx->h_train_stage) cudaFreeHost(ctx->h_train_stage);
