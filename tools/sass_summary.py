@@ -11,7 +11,7 @@ elf = subprocess.run(["cuobjdump", "-lelf", lib], capture_output=True, text=True
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 pats = collections.OrderedDict([("UBLKCP", r"\bUBLKCP"), ("UTMALDG", r"\bUTMALDG"), ("SYNCS", r"\bSYNCS"), ("UCGABAR", r"\bUCGABAR"), ("MAPA", r"\bMAPA"),
                                 ("BAR", r"\bBAR\."), ("ATOMS", r"\bATOMS"), ("LDS", r"\bLDS"), ("STS", r"\bSTS"), ("DFMA/DMUL/DADD", r"\bD(FMA|MUL|ADD)"),
-                                ("MUFU", r"\bMUFU"), ("SHFL", r"\bSHFL"), ("REDUX", r"\bREDUX")])
+                                ("MUFU", r"\bMUFU"), ("SHFL", r"\bSHFL"), ("REDUX", r"\bC?REDUX")])
 cur, counts, order, ninst = None, {}, [], collections.Counter()
 for line in sass.splitlines():
     m = re.search(r"Function : (\S+)", line)
