@@ -346,7 +346,10 @@ def run_ours(args):
     host_timing = os.environ.get("MCT_BENCH_HOST_TIMING") == "1"
 
     # ctypes views of the (fixed) pinned buffers, made once: a C++ caller would pass the pointers directly
-    planes_ptr = None if args.e2e_bgr else [tuple(vp(x.data_ptr()) for x in pl) for pl in planes_pin]
+    # Haar-only classifiers read the gray plane only (FeatureParameters.cpp:16-20): the colour planes are then not handed to the
+    # library at all (NULL planes are part of the interface), so they are neither uploaded nor binned
+    gray_only = FEAT == 0 and not args.e2e_bgr
+    planes_ptr = None if args.e2e_bgr else [tuple(vp(x.data_ptr()) if (k == 0 or not gray_only) else None for k, x in enumerate(pl)) for pl in planes_pin]
     bgr_ptr = [vp(x.data_ptr()) for x in bgr_pin] if args.e2e_bgr else None
     noise_ptr = [vp(x.data_ptr()) for x in noise_pin]
     noise_len = [x.numel() for x in noise_pin]
@@ -597,8 +600,8 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
             "e2e": {"value": scored_e2e_all / (ms_e2e_max * 1e-3), "unit": "particles/s",
-                    "h2d_bytes_per_step": (4 if (not args.e2e_bgr) else 3) * W * H + N_OBJ * 4 * N_PART * 4,
-                    "input": "4 u8 planes (gray,R,G,B)" if (not args.e2e_bgr) else "packed BGR frame (split + gray conversion on the device)", "d2h_bytes_per_step": N_OBJ * C.sizeof(capi.PfSummary),
+                    "h2d_bytes_per_step": (1 if gray_only else (4 if (not args.e2e_bgr) else 3)) * W * H + N_OBJ * 4 * N_PART * 4,
+                    "input": ("gray u8 plane (Haar-only classifiers read nothing else)" if gray_only else "4 u8 planes (gray,R,G,B)") if (not args.e2e_bgr) else "packed BGR frame (split + gray conversion on the device)", "d2h_bytes_per_step": N_OBJ * C.sizeof(capi.PfSummary),
                     "ms_per_step": ms_e2e_max / args.steps,
                     "call": ("mcth_camera_step, streaming (phases 1 | 16): frame t's boxes are returned after frame t + 1 has been queued; "
                              "one frame uploaded, tracked and read back per call") if stream_e2e else "mcth_camera_step, synchronous per frame"},
