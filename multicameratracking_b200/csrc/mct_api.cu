@@ -2005,7 +2005,9 @@ extern "C" int mct_track_update_default(mct_ctx* ctx, int n_obj, mct_pf* const* 
         lb.n_max = std::max(lb.n_max, Mb);
         if (d.mdch) {
             // bounds of the pixel-list plan from the hinted scale (+ 2 pixels of slack on the box size)
-            const float shx = q.scale_hint_x > 0 ? q.scale_hint_x : 1.0f, shy = q.scale_hint_y > 0 ? q.scale_hint_y : 1.0f;
+            float shx = q.scale_hint_x > 0 ? q.scale_hint_x : 1.0f, shy = q.scale_hint_y > 0 ? q.scale_hint_y : 1.0f;
+            // (test hook: a deliberately wrong hint, so that the plans leave the launch bounds and the objects take the generic kernel)
+            if (const char* e = getenv("MCT_TEST_HINT_SCALE")) { const float k = (float)atof(e); if (k > 0) { shx *= k; shy *= k; } }
             const float hsx[2] = {shx, std::min(shx, p->maxs)}, hsy[2] = {shy, std::min(shy, p->maxs)};
             const int R[2] = {(int)q.pos_radius, (int)q.neg_outer}, nb_[2] = {Pb, Nb};
             for (int gi = 0; gi < 2; gi++) {

@@ -54,8 +54,18 @@ def test_tracker_sequence_matches_oracle_with_host_training_sets(oracle, cfg):
         mhost.set_device_training_sets(True)
 
 
-def _tracker_sequence(oracle, cfg):
+def test_device_training_sets_with_a_wrong_scale_hint_take_the_generic_kernel(oracle, monkeypatch):
+    """mct_track_update_default sizes its launches from the last known state scale; a plan that leaves those bounds must cost
+    time only: with the hint halved the pixel-list plans of the colour rows do not fit, every object takes the generic per-box
+    kernel (mdch_fast == 0 in the read-out), and boxes, stream states and selector lists still equal the oracle's"""
+    monkeypatch.setenv("MCT_TEST_HINT_SCALE", "0.5")
+    fast = _tracker_sequence(oracle, "haarmdch_wstump_2obj", want_fast_flags=True)
+    assert fast and not any(fast), fast
+
+
+def _tracker_sequence(oracle, cfg, want_fast_flags=False):
     n_frames = 12
+    fast_flags = []
     device_sets = mhost.device_training_sets() and cfg not in ("greedy_pos_random_neg", "semi_greedy_pos", "particle_random_pos")
     if cfg == "cfg1_haar_milboost":
         n_obj, over = 1, dict()
@@ -116,6 +126,11 @@ def _tracker_sequence(oracle, cfg):
             if device_sets:
                 # the boxes k_train_gen_default wrote (positives, then negatives) against the oracle's SampleImage + thinning
                 col, row, sx, sy, P, Nn = capi.track_update_default_boxes(cam.capi_context(), o)
+                if want_fast_flags:
+                    cctx = cam.capi_context()
+                    outs = (capi.TrainDefaultOut * n_obj)()
+                    cctx.check(cctx.L.mct_track_update_default_collect(cctx.h, n_obj, outs))
+                    fast_flags.append(int(outs[o].mdch_fast))
                 oc, orw, osx, osy = _oracle_last_train(oracle, otr[o][0], 0)
                 nc, nr, nsx, nsy = _oracle_last_train(oracle, otr[o][0], 1)
                 assert (P, Nn) == (len(oc), len(nc)), (cfg, t, o, P, Nn, len(oc), len(nc))
@@ -132,6 +147,7 @@ def _tracker_sequence(oracle, cfg):
     for trk, clf, _ in otr:
         oracle.lib.orc_tracker_free(trk); oracle.lib.orc_clf_free(clf)
     cam.close()
+    return fast_flags
 
 def test_single_call_frame_step_equals_separate_calls():
     """mcth_camera_step (set frame + announce the next frame and noise + track, one call per video frame) gives the same boxes,
