@@ -130,6 +130,10 @@ k_classify_staged(const ObjDesc* __restrict__ descs, const float* __restrict__ i
         bulk_g2s(se, d.seltab, (unsigned)se_b, &s_bar[0]);
     }
     const int nsel = __ldg(d.selhdr), ext_w = __ldg(d.selhdr + 1), ext_h = __ldg(d.selhdr + 2);
+    // everything above reads what earlier frames' kernels left (descriptor, selector table); the boxes, the valid flags and the colour
+    // responses come from the producer in front of this launch
+    pdl_wait();
+    pdl_trigger();
     // ---- 2. integral-image region of the chunk's valid boxes (Haar selectors only)
     if (ext_w > 0) {
         int x0 = 1 << 30, y0 = 1 << 30, x1 = -(1 << 30), y1 = -(1 << 30);
@@ -282,8 +286,8 @@ int launch_classify_staged(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n
     if (per_obj < 1) per_obj = 1;
     if (per_obj > ceil_div(n_max, 32)) per_obj = ceil_div(n_max, 32);
     dim3 g(per_obj, n_obj);
-    MCT_LAUNCH(ctx, "k_classify_staged", k_classify_staged<<<g, CLS_THREADS, CLS_SMEM, ctx->stream>>>(
-        d_desc, ctx->ii_base + MCT_II_LEAD, ctx->ii_pitch, ctx->W, ctx->H, log_ratio, CLS_SMEM));
+    MCT_LAUNCH_PDL(ctx, "k_classify_staged", k_classify_staged, g, dim3(CLS_THREADS), (size_t)CLS_SMEM,
+                   d_desc, (const float*)(ctx->ii_base + MCT_II_LEAD), ctx->ii_pitch, ctx->W, ctx->H, log_ratio, (int)CLS_SMEM);
     return MCT_OK;
 }
 

@@ -1371,6 +1371,7 @@ k_mdch_sel(const ObjDesc* __restrict__ descs, const uint16_t* __restrict__ binim
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ ObjDesc s_desc;
     __shared__ int s_ticket;
+    pdl_trigger();                            // k_classify_staged may take the SMs this kernel's CTAs leave and run up to its pdl_wait()
     const ObjDesc& d = load_desc(descs + blockIdx.y, &s_desc);
     const int tid = threadIdx.x;
     const int N = d.N;

@@ -534,6 +534,8 @@ __global__ void __launch_bounds__(PF_THREADS, 1) k_pf_update_fast(const ObjDesc*
     const int NP = (PLEN(N) + 3) & ~3, N4 = (N + 3) & ~3;
     float* sw = smf; float* cdf = smf + NP;
     float* ccx = cdf + NP; float* ccy = ccx + N4; float* csx = ccy + N4; float* csy = csx + N4;
+    pdl_wait();                                // (the descriptor is older than the frame; everything below reads the producer's output)
+    pdl_trigger();
 
     PF_STAMP(0);
     const int refine = d.st->refine;
@@ -828,15 +830,15 @@ int launch_pf_update(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max, 
         if (n_max <= 32 * 16) {
             static size_t s_a16[MCT_MAX_DEV];
             if (int rc_ = mct_smem_attr(ctx, k_pf_update_fast<16>, s_a16, fb, 32 * 1024)) return rc_;
-            MCT_LAUNCH(ctx, "k_pf_update", k_pf_update_fast<16><<<n_obj, PF_THREADS, fb, ctx->stream>>>(d_desc, sa, mode, with_summary));
+            MCT_LAUNCH_PDL(ctx, "k_pf_update", k_pf_update_fast<16>, dim3(n_obj), dim3(PF_THREADS), fb, d_desc, sa, mode, with_summary);
         } else if (n_max <= 32 * 32) {
             static size_t s_a32[MCT_MAX_DEV];
             if (int rc_ = mct_smem_attr(ctx, k_pf_update_fast<32>, s_a32, fb, 32 * 1024)) return rc_;
-            MCT_LAUNCH(ctx, "k_pf_update", k_pf_update_fast<32><<<n_obj, PF_THREADS, fb, ctx->stream>>>(d_desc, sa, mode, with_summary));
+            MCT_LAUNCH_PDL(ctx, "k_pf_update", k_pf_update_fast<32>, dim3(n_obj), dim3(PF_THREADS), fb, d_desc, sa, mode, with_summary);
         } else {
             static size_t s_a64[MCT_MAX_DEV];
             if (int rc_ = mct_smem_attr(ctx, k_pf_update_fast<64>, s_a64, fb, 32 * 1024)) return rc_;
-            MCT_LAUNCH(ctx, "k_pf_update", k_pf_update_fast<64><<<n_obj, PF_THREADS, fb, ctx->stream>>>(d_desc, sa, mode, with_summary));
+            MCT_LAUNCH_PDL(ctx, "k_pf_update", k_pf_update_fast<64>, dim3(n_obj), dim3(PF_THREADS), fb, d_desc, sa, mode, with_summary);
         }
         return MCT_OK;
     }
@@ -1818,6 +1820,7 @@ k_train_gen_default(const TrainGenDev* __restrict__ gens, TrainDesc* __restrict_
     const int tid = threadIdx.x, nt = blockDim.x;
     if (tid < 32) s_pw[tid] = c_mwc_pw[tid];
     __syncthreads();
+    pdl_wait();                                // the read-out mirror and the stream state come from the frame's k_pf_update
     PF_STAMP(1);
     const float* a = q.opt == 0 ? q.trk->first : q.trk->avg;
     const float a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3];
@@ -1873,8 +1876,10 @@ k_train_gen_default(const TrainGenDev* __restrict__ gens, TrainDesc* __restrict_
     PF_STAMP(5);
     PF_COMMIT(0);
 }
-int launch_train_gen_default(mct_ctx* ctx, int n_obj, const TrainGenDev* d_gen, TrainDesc* d_tdesc, mct_train_default_out* d_out)
+int launch_train_gen_default(mct_ctx* ctx, int n_obj, const TrainGenDev* d_gen, TrainDesc* d_tdesc, mct_train_default_out* d_out, bool fresh_args)
 {
-    MCT_LAUNCH(ctx, "k_train_gen_default", k_train_gen_default<<<n_obj, PF_THREADS, 0, ctx->stream>>>(d_gen, d_tdesc, d_out));
+    // (arguments or descriptors uploaded in front of this launch: the plain launch keeps the kernel behind the copies)
+    if (fresh_args) MCT_LAUNCH(ctx, "k_train_gen_default", k_train_gen_default<<<n_obj, PF_THREADS, 0, ctx->stream>>>(d_gen, d_tdesc, d_out));
+    else MCT_LAUNCH_PDL(ctx, "k_train_gen_default", k_train_gen_default, dim3(n_obj), dim3(PF_THREADS), (size_t)0, d_gen, d_tdesc, d_out);
     return MCT_OK;
 }

@@ -2070,12 +2070,15 @@ extern "C" int mct_track_update_default(mct_ctx* ctx, int n_obj, mct_pf* const* 
     }
     // arguments and descriptors travel only when they differ from what the device already holds (the kernel rewrites every
     // per-frame field of the descriptors itself)
+    bool fresh_args = false;
     if (ctx->gen_shadow_n != n_obj || memcmp(ctx->gen_shadow, g, sizeof(TrainGenDev) * n_obj) != 0) {
+        fresh_args = true;
         memcpy(ctx->gen_shadow, g, sizeof(TrainGenDev) * n_obj); ctx->gen_shadow_n = n_obj;
         MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_gen, ctx->gen_shadow, sizeof(TrainGenDev) * n_obj, cudaMemcpyHostToDevice, ctx->stream));
         MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));       // pageable source: rare (a changed hint or object set)
     }
     if (!ctx->tdesc_gen_valid || ctx->tdesc_shadow_n != n_obj || memcmp(ctx->tdesc_shadow, tds, sizeof(TrainDesc) * n_obj) != 0) {
+        fresh_args = true;
         if ((rc = train_descs_ready(ctx))) return rc;
         memcpy(ctx->tdesc_shadow, tds, sizeof(TrainDesc) * n_obj); ctx->tdesc_shadow_n = n_obj;
         memcpy(ctx->h_tdesc, tds, sizeof(TrainDesc) * n_obj);
@@ -2085,7 +2088,7 @@ extern "C" int mct_track_update_default(mct_ctx* ctx, int n_obj, mct_pf* const* 
     }
     for (int o = 0; o < n_obj; o++) { ctx->gen_clfs[o] = clfs[o]; clfs[o]->lastP = -1; clfs[o]->lastNn = -1; }
     ctx->gen_n = n_obj; ctx->gen_pending = 1; ctx->gen_seq++;
-    if ((rc = launch_train_gen_default(ctx, n_obj, ctx->d_gen, ctx->d_tdesc, ctx->h_gen_out_dev + (ctx->gen_seq & 1) * DESC_MAX_OBJ))) return rc;
+    if ((rc = launch_train_gen_default(ctx, n_obj, ctx->d_gen, ctx->d_tdesc, ctx->h_gen_out_dev + (ctx->gen_seq & 1) * DESC_MAX_OBJ, fresh_args))) return rc;
     if ((rc = launch_train_features(ctx, ctx->d_tdesc, tds, n_obj, &lb))) return rc;
     if ((rc = launch_ensemble_retain_batch(ctx, ctx->d_tdesc, tds, n_obj))) return rc;
     if ((rc = launch_weak_update_batch(ctx, ctx->d_tdesc, tds, n_obj))) return rc;

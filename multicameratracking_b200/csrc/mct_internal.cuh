@@ -304,6 +304,29 @@ void mct_prof_end_on(mct_ctx* ctx, cudaStream_t st);
         MCT_KERNEL_CHECK(ctx);                                                               \
     } while (0)
 
+// Programmatic dependent launch (sm_90+): a consumer launched with this attribute may become resident while its producer (the
+// previous kernel of the stream) is still running; it executes up to pdl_wait() -- which returns once the producer has completed
+// and its writes are visible -- and the producer allows it with pdl_trigger().  Takes ~1.7 us off a launch boundary
+// (tools/pdl_lab.cu).  Only used where the consumer cannot pile up in front of the producer (one CTA per SM, or a handful of CTAs);
+// a kernel that calls pdl_wait() without the attribute runs as before.  MCT_NO_PDL=1 launches everything the plain way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+static inline bool mct_pdl_enabled() { static int v = -1; if (v < 0) v = getenv("MCT_NO_PDL") ? 0 : 1; return v != 0; }
+#define MCT_LAUNCH_PDL(ctx, name, kern, grid, block, smem, ...)                               \
+    do {                                                                                     \
+        cudaLaunchConfig_t cfg__ = {};                                                       \
+        cfg__.gridDim = (grid); cfg__.blockDim = (block); cfg__.dynamicSmemBytes = (smem); cfg__.stream = (ctx)->stream; \
+        cudaLaunchAttribute at__[1];                                                         \
+        at__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                     \
+        at__[0].val.programmaticStreamSerializationAllowed = 1;                              \
+        cfg__.attrs = at__; cfg__.numAttrs = mct_pdl_enabled() ? 1 : 0;                      \
+        mct_prof_begin((ctx), (name));                                                       \
+        cudaError_t le__ = cudaLaunchKernelEx(&cfg__, kern, __VA_ARGS__);                    \
+        mct_prof_end(ctx);                                                                   \
+        if (le__ != cudaSuccess) { (void)cudaGetLastError(); return mct_fail((ctx), MCT_E_CUDA, "kernel launch failed: %s (line %d)", cudaGetErrorString(le__), __LINE__); } \
+        MCT_KERNEL_CHECK(ctx);                                                               \
+    } while (0)
+
 // Per-device launch state.  Function attributes (opt-in dynamic shared memory, non-portable cluster sizes) and __constant__
 // uploads belong to ONE device: every launcher keeps its high-water mark in a table indexed by ctx->device, so ctxs on several
 // GPUs of one process are independent (INTEGRATION.md "threads and devices").  The mutex makes check + set atomic for host
@@ -386,7 +409,7 @@ struct TrainGenDev {
     int mdch, cw0, ch0, dim;              // colour-histogram rows wanted; classifier blob size; nb^3
     int npx_b[2], tab_b, nch_b;           // what the launch was sized for (a plan beyond it takes the generic kernel)
 };
-int launch_train_gen_default(mct_ctx* ctx, int n_obj, const TrainGenDev* d_gen, TrainDesc* d_tdesc, mct_train_default_out* d_out);
+int launch_train_gen_default(mct_ctx* ctx, int n_obj, const TrainGenDev* d_gen, TrainDesc* d_tdesc, mct_train_default_out* d_out, bool fresh_args);
 int launch_weak_update_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj);
 int launch_mil_select_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj, const int* cluster_req);
 int launch_build_colormap_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj);
