@@ -159,6 +159,7 @@ int launch_pf_predict(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, int n_max,
 
 __global__ void __launch_bounds__(256) k_pf_testset(const ObjDesc* __restrict__ descs, int fw, int fh)
 {
+    pdl_trigger();                             // the classify kernel behind this one may become resident (it waits for these boxes)
     const ObjDesc& d = descs[blockIdx.y];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && d.nbig) *d.nbig = 0;                 // (the re-score variant starts here: no predict kernel in front)
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(256) k_pf_testset(const ObjDesc* __restrict__ 
 __global__ void __launch_bounds__(256) k_pf_predict_testset(const ObjDesc* __restrict__ descs, const StepArgs sa, int fw, int fh)
 {
     __shared__ ObjDesc s_desc;
+    pdl_trigger();                             // the classify kernel behind this one may become resident (it waits for these boxes)
     const ObjDesc& d = load_desc(descs + blockIdx.y, &s_desc);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
