@@ -159,10 +159,20 @@ weak_update_body(const float* __restrict__ feat, int ld, int F, int P, int Nn, i
         weak[6 * (size_t)F + f] = e0; weak[7 * (size_t)F + f] = e1;
         trained[f] = 1;
     }
-    // predictions (ClassifySetF) for positives then negatives
+    // predictions (ClassifySetF) for positives then negatives.  A feature row that holds one value for every sample -- most of
+    // the nb^3 joint colour bins are empty in every training box -- has one prediction: evaluated once instead of P + Nn times
+    // (the kernel is bound by instruction issue, and the f64 log of the response is most of a prediction's ~150 instructions)
     float* pr = pred + (size_t)f * ld;
-    for (int i = lane; i < P + Nn; i += 32)
-        pr[i] = weak_classify_q_dev(weak_type, xp[i], mu0, mu1, n0, n1, e0, e1);
+    const float x0 = xp[0];
+    bool same = true;
+    for (int i = lane; i < P + Nn; i += 32) same = same && (xp[i] == x0);
+    if (__all_sync(0xffffffffu, same)) {
+        const float v = weak_classify_q_dev(weak_type, x0, mu0, mu1, n0, n1, e0, e1);
+        for (int i = lane; i < P + Nn; i += 32) pr[i] = v;
+    } else {
+        for (int i = lane; i < P + Nn; i += 32)
+            pr[i] = weak_classify_q_dev(weak_type, xp[i], mu0, mu1, n0, n1, e0, e1);
+    }
 }
 
 __global__ void __launch_bounds__(256)
