@@ -750,8 +750,12 @@ int mct_feature_matrix_full(mct_clf* clf, const int* d_col, const int* d_row, co
 }
 
 // training features of all objects: Haar rows + MDCH rows, two launches for the whole camera
-int launch_train_features(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj, const TrainLaunchBounds* lb)
+int launch_train_features(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj, const TrainLaunchBounds* lb, bool weak_too)
 {
+    ctx->weak_split_done = 0;
+    // (MILEnsemble's retain step sits between the rows and the weak update and reads all rows: no split with such objects)
+    for (int o = 0; o < n_obj && weak_too; o++) if (h[o].strong_type == MCT_STRONG_MILENSEMBLE) weak_too = false;
+    if (getenv("MCT_NO_WEAK_SPLIT")) weak_too = false;
     int n_max = lb ? lb->n_max : 0, nh_max = 0, any_mdch = 0, dim_max = 0, nb = 0;
     for (int o = 0; o < n_obj; o++) {
         if (!lb) n_max = max(n_max, h[o].P + h[o].Nn);
@@ -820,9 +824,19 @@ int launch_train_features(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, 
             else MCT_LAUNCH(ctx, "k_mdch_batch", k_mdch_batch<<<g, MDCH_WARPS * 32, smem, ctx->stream>>>(d, ctx->binimg, ctx->W, ctx->H));
         }
     }
+    if (forked && weak_too) {
+        int rc;
+        if ((rc = launch_weak_update_part(ctx, d, h, n_obj, 1, ctx->train_stream))) return rc;      // Haar part behind the Haar rows, beside the colour kernels
+    }
     if (forked) {
         MCT_CUDA(ctx, cudaEventRecord(ctx->ev_tjoin, ctx->train_stream));
         MCT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_tjoin, 0));
+    }
+    if (forked && weak_too) {
+        // colour part behind the join: the generic colour kernel (objects whose plan left the launch bounds) rides on the side stream
+        int rc;
+        if ((rc = launch_weak_update_part(ctx, d, h, n_obj, 2, ctx->stream))) return rc;
+        ctx->weak_split_done = 1;
     }
     return MCT_OK;
 }

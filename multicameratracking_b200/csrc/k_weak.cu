@@ -67,11 +67,11 @@ __device__ __forceinline__ float norm_scale(const float* w, int n, int lane)
 __device__ __forceinline__ void
 weak_update_body(const float* __restrict__ feat, int ld, int F, int P, int Nn, int weak_type, float lr,
               const float* __restrict__ tw, float* __restrict__ weak, int* __restrict__ trained,
-              float* __restrict__ pred, const int* __restrict__ keep)
+              float* __restrict__ pred, const int* __restrict__ keep, int f_first = 0, int f_end = 0x7fffffff)
 {
     const int lane = threadIdx.x & 31;
-    const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (f >= F) return;
+    const int f = f_first + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (f >= F || f >= f_end) return;
     const float* xp = feat + (size_t)f * ld;
     const float* xn = xp + P;
     float mu0 = weak[0 * (size_t)F + f], mu1 = weak[1 * (size_t)F + f];
@@ -183,19 +183,29 @@ k_weak_update(const float* __restrict__ feat, int ld, int F, int P, int Nn, int 
     weak_update_body(feat, ld, F, P, Nn, weak_type, lr, tw, weak, trained, pred, keep);
 }
 // batched form: blockIdx.y = object
-__global__ void __launch_bounds__(256) k_weak_update_batch(const TrainDesc* __restrict__ descs)
+// part: 0 = every weak classifier, 1 = the Haar features' [0, n_haar), 2 = the colour features' [n_haar, F).  The two feature
+// families' training rows come from two streams (launch_train_features); the weak classifiers of a family only need their own
+// rows, so each part rides behind its rows and the Haar part (the expensive one: no constant rows) runs beside the colour kernels.
+__global__ void __launch_bounds__(256) k_weak_update_batch(const TrainDesc* __restrict__ descs, int part)
 {
     const TrainDesc& d = descs[blockIdx.y];
     if (d.P < 1 || d.Nn < 1) return;              // empty training set decided on the device (k_train_gen_default): classifier left as it is
-    weak_update_body(d.featT, d.ldT, d.F, d.P, d.Nn, d.weak_type, d.lr, d.tw, d.weak, d.trained, d.pred, d.keep);
+    const int f_first = part == 2 ? d.n_haar : 0, f_end = part == 1 ? d.n_haar : d.F;
+    weak_update_body(d.featT, d.ldT, d.F, d.P, d.Nn, d.weak_type, d.lr, d.tw, d.weak, d.trained, d.pred, d.keep, f_first, f_end);
+}
+int launch_weak_update_part(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj, int part, cudaStream_t st)
+{
+    int rows = 0;
+    for (int o = 0; o < n_obj; o++) rows = max(rows, part == 1 ? h[o].n_haar : (part == 2 ? h[o].F - h[o].n_haar : h[o].F));
+    if (rows <= 0) return MCT_OK;
+    dim3 g(ceil_div(rows, 8), n_obj);
+    MCT_LAUNCH_ON(ctx, st, "k_weak_update_batch", k_weak_update_batch<<<g, 256, 0, st>>>(d, part));
+    return MCT_OK;
 }
 int launch_weak_update_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj)
 {
-    int F_max = 0;
-    for (int o = 0; o < n_obj; o++) F_max = max(F_max, h[o].F);
-    dim3 g(ceil_div(F_max, 8), n_obj);
-    MCT_LAUNCH(ctx, "k_weak_update_batch", k_weak_update_batch<<<g, 256, 0, ctx->stream>>>(d));
-    return MCT_OK;
+    if (ctx->weak_split_done) { ctx->weak_split_done = 0; return MCT_OK; }     // already queued behind the feature rows, in two parts
+    return launch_weak_update_part(ctx, d, h, n_obj, 0, ctx->stream);
 }
 
 int launch_weak_update(mct_clf* clf, int P, int Nn, int has_weights)

@@ -1698,7 +1698,7 @@ static bool mdch_group_plan(MdchGroup* g, const mct_boxes* b, int first, int w0,
 // selection with one cluster per object, selected-classifier tables) instead of 8 copies + 5 launches per object.
 // stages the training boxes of all objects, fills the TrainDescs and launches the feature kernels: afterwards every classifier's
 // training matrix d_featT holds its rows [F][P + Nn] (stream-ordered, no synchronisation)
-static int train_stage_and_features(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, const mct_boxes* pos, const mct_boxes* neg, std::vector<int>& creq);
+static int train_stage_and_features(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, const mct_boxes* pos, const mct_boxes* neg, std::vector<int>& creq, bool weak_too = false);
 static int train_descs_ready(mct_ctx* ctx);
 
 extern "C" int mct_track_update(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, const mct_boxes* pos, const mct_boxes* neg)
@@ -1720,7 +1720,7 @@ extern "C" int mct_track_update(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, c
     }
     std::vector<int> creq;
     int rc;
-    if ((rc = train_stage_and_features(ctx, n_obj, clfs, pos, neg, creq))) return rc;
+    if ((rc = train_stage_and_features(ctx, n_obj, clfs, pos, neg, creq, true))) return rc;
     if ((rc = launch_ensemble_retain_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj))) return rc;
     if ((rc = launch_weak_update_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj))) return rc;
     if ((rc = launch_mil_select_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj, creq.data()))) return rc;
@@ -1758,7 +1758,7 @@ static int train_descs_ready(mct_ctx* ctx)
     return MCT_OK;
 }
 
-static int train_stage_and_features(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, const mct_boxes* pos, const mct_boxes* neg, std::vector<int>& creq_out)
+static int train_stage_and_features(mct_ctx* ctx, int n_obj, mct_clf* const* clfs, const mct_boxes* pos, const mct_boxes* neg, std::vector<int>& creq_out, bool weak_too)
 {
     size_t total = 0;
     for (int o = 0; o < n_obj; o++) total += (size_t)pos[o].n + (size_t)neg[o].n;
@@ -1839,7 +1839,7 @@ static int train_stage_and_features(mct_ctx* ctx, int n_obj, mct_clf* const* clf
     MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tdesc, ctx->h_tdesc, sizeof(TrainDesc) * n_obj, cudaMemcpyHostToDevice, ctx->stream));
     ctx->tdesc_gen_valid = 0;
     MCT_CUDA(ctx, cudaEventRecord(ctx->ev_train, ctx->stream));
-    if ((rc = launch_train_features(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj))) return rc;
+    if ((rc = launch_train_features(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj, nullptr, weak_too))) return rc;
     creq_out = creq;
     return MCT_OK;
 }
@@ -2089,7 +2089,7 @@ extern "C" int mct_track_update_default(mct_ctx* ctx, int n_obj, mct_pf* const* 
     for (int o = 0; o < n_obj; o++) { ctx->gen_clfs[o] = clfs[o]; clfs[o]->lastP = -1; clfs[o]->lastNn = -1; }
     ctx->gen_n = n_obj; ctx->gen_pending = 1; ctx->gen_seq++;
     if ((rc = launch_train_gen_default(ctx, n_obj, ctx->d_gen, ctx->d_tdesc, ctx->h_gen_out_dev + (ctx->gen_seq & 1) * DESC_MAX_OBJ, fresh_args))) return rc;
-    if ((rc = launch_train_features(ctx, ctx->d_tdesc, tds, n_obj, &lb))) return rc;
+    if ((rc = launch_train_features(ctx, ctx->d_tdesc, tds, n_obj, &lb, true))) return rc;
     if ((rc = launch_ensemble_retain_batch(ctx, ctx->d_tdesc, tds, n_obj))) return rc;
     if ((rc = launch_weak_update_batch(ctx, ctx->d_tdesc, tds, n_obj))) return rc;
     if ((rc = launch_mil_select_batch(ctx, ctx->d_tdesc, tds, n_obj, creq.data()))) return rc;

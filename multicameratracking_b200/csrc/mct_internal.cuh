@@ -112,6 +112,7 @@ struct mct_ctx {
     void* tdesc_shadow; int tdesc_shadow_n; int tdesc_gen_valid;
     mct_clf* gen_clfs[64]; int gen_n; int gen_pending;
     long long gen_seq, score_gen_seq, gen_checked_seq;   // read-outs alternate between two buffers (gen_seq & 1); see mct_track_collect
+    int weak_split_done;         // launch_train_features queued the weak-classifier update itself (one part per feature stream)
     cudaEvent_t ev_score[2]; int has_ev_score;      // behind the k_pf_update of the score call that wrote read-out slot 0 / 1
     long long score_issued, score_collected;        // fused score calls queued / collected: at most two in flight (slot = count & 1)
     long long score_gen_seq_slot[2];
@@ -395,7 +396,9 @@ int launch_ensemble_retain_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDe
 // launch bounds of the training-feature kernels when the set sizes and the colour-histogram plan are decided on the device
 // (mct_track_update_default): grids and shared memory from upper bounds, CTAs outside the actual plan leave at once
 struct TrainLaunchBounds { int n_max, nch, tab_words, chunk_words, npx_max, n_train_max; };
-int launch_train_features(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj, const TrainLaunchBounds* lb = nullptr);
+// weak_too: the caller runs the weak-classifier update next; with both feature families on their own streams it is then queued here,
+// split by family (ctx->weak_split_done tells launch_weak_update_batch)
+int launch_train_features(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj, const TrainLaunchBounds* lb = nullptr, bool weak_too = false);
 // per-object arguments of k_train_gen_default (device array, re-uploaded only when they change)
 struct TrainGenDev {
     PfTrk* trk; const PfDev* st;
@@ -411,6 +414,7 @@ struct TrainGenDev {
 };
 int launch_train_gen_default(mct_ctx* ctx, int n_obj, const TrainGenDev* d_gen, TrainDesc* d_tdesc, mct_train_default_out* d_out, bool fresh_args);
 int launch_weak_update_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj);
+int launch_weak_update_part(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj, int part, cudaStream_t st);
 int launch_mil_select_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj, const int* cluster_req);
 int launch_build_colormap_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h, int n_obj);
 int launch_foot_points(mct_ctx* ctx, const ObjDesc* d_desc, int n_obj, const float* d_h0, float* d_out);
