@@ -83,8 +83,12 @@ template <bool ROWS_SMEM>
 __device__ __forceinline__ void
 milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int Nn, int K,
                   const float* __restrict__ weak, int weak_type, int* __restrict__ sel, int* __restrict__ nsel,
-                  int FC, int PC)
+                  int FC, int PC, int RN)
 {
+    // RN negatives per pass (a multiple of 32, MIL_RN for the trackers' own classifiers): the appearance fuser's pooled sets hold
+    // the negatives of every camera (8 x 30), and with 32 per pass a round was eight barrier-separated passes over rows that
+    // come from L2 (29 us per round); the pass partition does not touch the order of the chains
+    const int RS = RN + MIL_PC + 4;
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
@@ -92,7 +96,7 @@ milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int N
     const int FL = (F + C - 1) / C;
     extern __shared__ __align__(16) unsigned char smraw[];
     float* scratch = (float*)smraw;                          // [FC][MIL_RS] terms of the current pass, one row per list entry
-    int* act = (int*)(scratch + (size_t)FC * MIL_RS);        // [2][FC] compacted candidate lists (slot | need_pos << 16)
+    int* act = (int*)(scratch + (size_t)FC * RS);        // [2][FC] compacted candidate lists (slot | need_pos << 16)
     float* Hs = (float*)(act + 2 * FC);                      // [M]
     float* rows = Hs + M;                                    // [FL][M] this CTA's candidate rows (ROWS_SMEM)
     unsigned char* selflag = (unsigned char*)(rows + (ROWS_SMEM ? (size_t)FL * M : 0));   // [F] 1 selected, 2 invalid
@@ -168,10 +172,10 @@ milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int N
                 // the first pass takes PC positives (most bags saturate inside it); a bag that did not saturate is unlikely to do so
                 // soon, so the later passes take MIL_PC at a time: fewer passes (barriers) when the classes do not separate
                 const int pcur = it == 0 ? PC : MIL_PC;
-                const int n0 = it * MIL_RN, p0 = it == 0 ? 0 : PC + (it - 1) * MIL_PC;
-                const int cntN = max(0, min(MIL_RN, Nn - n0)), cntP = max(0, min(pcur, P - p0));
+                const int n0 = it * RN, p0 = it == 0 ? 0 : PC + (it - 1) * MIL_PC;
+                const int cntN = max(0, min(RN, Nn - n0)), cntP = max(0, min(pcur, P - p0));
                 const int nbN = (cntN + 31) >> 5, nbP = (cntP + 31) >> 5, nblk = nbN + nbP;
-                const unsigned magic = 65536u / (unsigned)nblk + 1u;        // u / nblk exactly for u < 2^11, nblk <= 5
+                const unsigned magic = 65536u / (unsigned)nblk + 1u;        // u / nblk exactly for u < 65536 / nblk (u < 128 * 12 here)
                 const int* al = act + (g & 1) * FC;
                 // phase 1: terms, one warp per (list entry, 32 samples); a block's tail is filled with the chain's neutral
                 // element so that phase 2 runs whole blocks.  Three units per trip: their exp / reciprocal chains are
@@ -188,7 +192,7 @@ milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int N
                             const int e = al[a];
                             const int slot = e & 0xffff;
                             const float* pr = ROWS_SMEM ? rows + (fc + slot) * M : pred + (size_t)(rank + (fc + slot) * C) * ld;
-                            float* dst = scratch + a * MIL_RS;
+                            float* dst = scratch + a * RS;
                             if (bb < nbN) {
                                 const int r = bb * 32 + lane;
                                 kind[j] = (r < cntN) ? 1 : 3;                 // 3: tail of a negative block -> 0
@@ -197,7 +201,7 @@ milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int N
                             } else if (e >> 16) {
                                 const int r = (bb - nbN) * 32 + lane;
                                 kind[j] = (r < cntP) ? 2 : 4;                 // 4: tail of a positive block -> 1
-                                dp[j] = dst + MIL_RN + r;
+                                dp[j] = dst + RN + r;
                                 if (r < cntP) { const int i = p0 + r; xv[j] = __fadd_rn(Hs[i], pr[i]); }
                             }
                         }
@@ -224,8 +228,8 @@ milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int N
                 if (tid < ((nfc + 31) & ~31)) {
                     bool again = false, more_p = false;
                     if (active) {
-                        const float4* n4 = reinterpret_cast<const float4*>(scratch + col * MIL_RS);
-                        const float4* p4 = n4 + MIL_RN / 4;
+                        const float4* n4 = reinterpret_cast<const float4*>(scratch + col * RS);
+                        const float4* p4 = n4 + RN / 4;
                         const bool doP = !sat && nbP > 0;
                         if (nbN && doP) {
 #pragma unroll
@@ -249,6 +253,10 @@ milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int N
                                 like = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(like, y.x), y.y), y.z), y.w);
                             }
                         }
+                        for (int k = 8; k < nbN * 8; k++) {           // (more than 32 negatives in the pass)
+                            const float4 x = n4[k];
+                            sn = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sn, x.x), x.y), x.z), x.w);
+                        }
                         if (doP) {
                             for (int k = 8; k < nbP * 8; k++) {
                                 const float4 y = p4[k];
@@ -256,13 +264,18 @@ milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int N
                             }
                             sat = __fsub_rn(1.0f, like) == 1.0f;
                         }
-                        more_p = !sat && (p0 + pcur < P);
-                        again = (n0 + MIL_RN < Nn) || more_p;
+                        // A NaN in either chain stays a NaN to the end and makes the candidate's score a NaN whatever the remaining
+                        // terms are: the candidate is finished.  (The appearance fuser's global classifiers have learning rate 0: a
+                        // colour bin that is empty in a class has sigma = 0 and NaN responses.  Such a bag never saturates, and
+                        // every NaN candidate walked all ~2500 pooled positives in passes of 128, every round: 29 us per round.)
+                        const bool dead = (like != like) || (sn != sn);
+                        more_p = !sat && !dead && (p0 + pcur < P);
+                        again = !dead && ((n0 + RN < Nn) || more_p);
                         if (!again) {
                             active = false;
                             const int f = rank + (fc + tid) * C;
                             const float posl = sat ? posl_sat : (float)(-log((double)__fsub_rn(1.0f, like) + 1e-5));
-                            const float nll = __fadd_rn(__fdiv_rn(posl, fP), __fdiv_rn(sn, fN));
+                            const float nll = dead ? CUDART_NAN_F : __fadd_rn(__fdiv_rn(posl, fP), __fdiv_rn(sn, fN));
                             if (better_min(nll, f, bv, bf)) { bv = nll; bf = f; }
                         }
                     }
@@ -334,15 +347,15 @@ milboost_select_body(const float* __restrict__ pred, int ld, int F, int P, int N
 __global__ void __launch_bounds__(SEL_THREADS)
 k_milboost_select(const float* __restrict__ pred, int ld, int F, int P, int Nn, int K,
                   const float* __restrict__ weak, int weak_type, int* __restrict__ sel, int* __restrict__ nsel,
-                  int FC, int rows_in_smem, int PC)
+                  int FC, int rows_in_smem, int PC, int RN)
 {
-    if (rows_in_smem) milboost_select_body<true>(pred, ld, F, P, Nn, K, weak, weak_type, sel, nsel, FC, PC);
-    else milboost_select_body<false>(pred, ld, F, P, Nn, K, weak, weak_type, sel, nsel, FC, PC);
+    if (rows_in_smem) milboost_select_body<true>(pred, ld, F, P, Nn, K, weak, weak_type, sel, nsel, FC, PC, RN);
+    else milboost_select_body<false>(pred, ld, F, P, Nn, K, weak, weak_type, sel, nsel, FC, PC, RN);
 }
 // batched form: one cluster per object (blockIdx.y); objects of another strong-classifier type leave at once
 // (the whole cluster takes the same branch)
 __global__ void __launch_bounds__(SEL_THREADS)
-k_milboost_select_batch(const TrainDesc* __restrict__ descs, int FC, int FLmax, int Mmax, int PC)
+k_milboost_select_batch(const TrainDesc* __restrict__ descs, int FC, int FLmax, int Mmax, int PC, int RN)
 {
     const TrainDesc& d = descs[blockIdx.y];
     if (d.strong_type != MCT_STRONG_MILBOOST) return;
@@ -351,8 +364,8 @@ k_milboost_select_batch(const TrainDesc* __restrict__ descs, int FC, int FLmax, 
     const int FL = (d.F + (int)gridDim.x - 1) / (int)gridDim.x;
     const int rows_in_smem = FLmax > 0 && (size_t)FL * (d.P + d.Nn) <= (size_t)FLmax * Mmax && min(FC, FL) <= FC;
     const int fc = min(FC, max(FL, 1));
-    if (rows_in_smem) milboost_select_body<true>(d.pred, d.ldT, d.F, d.P, d.Nn, d.K, d.weak, d.weak_type, d.sel, d.nsel, fc, PC);
-    else milboost_select_body<false>(d.pred, d.ldT, d.F, d.P, d.Nn, d.K, d.weak, d.weak_type, d.sel, d.nsel, fc, PC);
+    if (rows_in_smem) milboost_select_body<true>(d.pred, d.ldT, d.F, d.P, d.Nn, d.K, d.weak, d.weak_type, d.sel, d.nsel, fc, PC, RN);
+    else milboost_select_body<false>(d.pred, d.ldT, d.F, d.P, d.Nn, d.K, d.weak, d.weak_type, d.sel, d.nsel, fc, PC, RN);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -586,11 +599,19 @@ static int mil_pc()
     if (!pc) { const char* e = getenv("MCT_MIL_PC"); pc = e ? atoi(e) : 32; if (pc < 1 || pc > MIL_PC) pc = 32; }
     return pc;
 }
-static size_t mil_smem_plan(int F, int M, int FL, int* FC_out, int* rows_out)
+// negatives per pass: one pass for sets of up to 256 negatives as long as the term rows of a candidate chunk stay under ~64 KB
+static int mil_rn(int Nn, int FL)
+{
+    const int FC = FL < MIL_FC ? (FL < 1 ? 1 : FL) : MIL_FC;
+    int RN = MIL_RN;
+    while (RN < 256 && RN < Nn && (size_t)FC * (2 * RN + MIL_PC + 4) * 4 <= 64 * 1024) RN *= 2;
+    return RN;
+}
+static size_t mil_smem_plan(int F, int M, int FL, int* FC_out, int* rows_out, int RN = MIL_RN)
 {
     int FC = FL < MIL_FC ? FL : MIL_FC;
     if (FC < 1) FC = 1;
-    size_t base = (size_t)M * 4 + (size_t)MIL_RS * FC * 4 + (size_t)2 * FC * 4 + (size_t)F;
+    size_t base = (size_t)M * 4 + (size_t)(RN + MIL_PC + 4) * FC * 4 + (size_t)2 * FC * 4 + (size_t)F;
     size_t rows = (size_t)FL * M * 4;
     int in_smem = base + rows <= (size_t)200 * 1024;
     *FC_out = FC; *rows_out = in_smem;
@@ -1019,7 +1040,8 @@ int launch_mil_select(mct_clf* clf, int P, int Nn)
     if (C > SEL_MAX_CLUSTER) C = SEL_MAX_CLUSTER;
     const int FL = ceil_div(F, C);
     int FC, rows_in_smem;
-    const size_t smem = mil_smem_plan(F, M, FL, &FC, &rows_in_smem);
+    const int RN = mil_rn(Nn, FL);
+    const size_t smem = mil_smem_plan(F, M, FL, &FC, &rows_in_smem, RN);
     if (smem > 220 * 1024) return mct_fail(ctx, MCT_E_UNSUPPORTED, "training set too large for the MIL selection kernel%s (M=%d)", "", M);
     static size_t s_attr[MCT_MAX_DEV];
     static int s_np[MCT_MAX_DEV];
@@ -1041,7 +1063,7 @@ int launch_mil_select(mct_clf* clf, int P, int Nn)
     int ld = clf->ldT, K = clf->K, wt = clf->p.weak_type;
     int* sel = clf->d_sel; int* nsel = clf->d_nsel;
     mct_prof_begin(ctx, "k_milboost_select");
-    MCT_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_milboost_select, pred, ld, F, P, Nn, K, weak, wt, sel, nsel, FC, rows_in_smem, mil_pc()));
+    MCT_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_milboost_select, pred, ld, F, P, Nn, K, weak, wt, sel, nsel, FC, rows_in_smem, mil_pc(), RN));
     mct_prof_end(ctx);
     MCT_KERNEL_CHECK(ctx);
     return MCT_OK;
@@ -1083,7 +1105,10 @@ int launch_mil_select_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h
         if (C > SEL_MAX_CLUSTER) C = SEL_MAX_CLUSTER;
         const int FL = ceil_div(F, C);
         int FC, rows_in_smem;
-        const size_t smem = mil_smem_plan(F, M, FL, &FC, &rows_in_smem);
+        int Nn_mil = 1;
+        for (int o = 0; o < n_obj; o++) if (h[o].strong_type == MCT_STRONG_MILBOOST) Nn_mil = max(Nn_mil, h[o].Nn);
+        const int RN = mil_rn(Nn_mil, FL);
+        const size_t smem = mil_smem_plan(F, M, FL, &FC, &rows_in_smem, RN);
         if (smem > 220 * 1024) return mct_fail(ctx, MCT_E_UNSUPPORTED, "training set too large for the MIL selection kernel%s (M=%d)", "", M);
         const int FLmax = rows_in_smem ? FL : 0, Mmax = M;
         static size_t s_attr[MCT_MAX_DEV];
@@ -1103,7 +1128,7 @@ int launch_mil_select_batch(mct_ctx* ctx, const TrainDesc* d, const TrainDesc* h
         attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         mct_prof_begin(ctx, "k_milboost_select_batch");
-        MCT_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_milboost_select_batch, d, FC, FLmax, Mmax, mil_pc()));
+        MCT_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_milboost_select_batch, d, FC, FLmax, Mmax, mil_pc(), RN));
         mct_prof_end(ctx);
         MCT_KERNEL_CHECK(ctx);
     }
