@@ -262,7 +262,8 @@ int mct_pf_get_summary_many(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, mct_pf_
  * likelihood map ((H-min)/range)^exponent (:541-566) -> UpdateAllParticlesWeight -> Normalize ->
  * ResampleIfRequired -> read-out.  noise: [n_obj][4][N] (host or dev); u01: [n_obj] host.  noise == NULL selects the
  * re-score variant (ParticleFilterTracker.cpp:1334-1482): the particles are scored where they are, without prediction.
- * summaries: [n_obj] host, valid after the call returns (the call synchronises the stream). */
+ * summaries: [n_obj] host, valid after the call returns (the call waits for the frame's read-outs).
+ * u01 == NULL: the draw of ResampleParticles comes from every object's device-resident stream (mct_pf_rng_set). */
 typedef struct {
     float w0, h0;           /* m_currentStateList[2], [3] */
     int   exponent;         /* 20 (:556); 1 for the re-score variant (:1407); 0 = the appearance fuser's map
@@ -279,8 +280,11 @@ int mct_track_score(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, mct_clf* const*
  * the same host pointer then finds it on the device instead of copying it in front of its first kernel.  The host block
  * must stay valid and unchanged until that call has been collected. */
 int mct_noise_prefetch(mct_ctx* ctx, const float* noise_host, size_t n_floats);
-/* asynchronous variant: no stream sync, summaries land in the ctx's pinned buffer; collect with
- * mct_track_collect (which synchronises). */
+/* asynchronous variant: no stream sync, summaries land in the ctx's pinned buffer; collect with mct_track_collect, which waits for
+ * the read-outs of the OLDEST call not collected yet (an event behind that call's last kernel; work queued later -- the frame's
+ * UpdateClassifier, the next frame -- keeps running).  Two calls may be in flight: the read-outs alternate between two slots;
+ * a third uncollected call retires the oldest.  With no call pending, mct_track_collect synchronises the stream and returns the
+ * latest read-outs again.  An empty training set met by the previous frame's mct_track_update_default is reported here. */
 int mct_track_score_async(mct_ctx* ctx, int n_obj, mct_pf* const* pfs, mct_clf* const* clfs,
                           const mct_track_params* params, const float* noise, int noise_is_device,
                           const float* u01);
