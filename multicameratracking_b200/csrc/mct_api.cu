@@ -830,6 +830,16 @@ __global__ void __launch_bounds__(256) k_gather_columns(const float* __restrict_
     const float* s = src + off[j];
     for (int f = blockIdx.y; f < F; f += gridDim.y) dst[(size_t)f * ld + j] = s[(size_t)f * row_stride];
 }
+// all classifiers of a camera in one launch (blockIdx.z = object; the object's column offsets hang off TrainDesc::col)
+__global__ void __launch_bounds__(256) k_gather_columns_batch(const TrainDesc* __restrict__ descs, const float* __restrict__ src, long long row_stride)
+{
+    const TrainDesc& d = descs[blockIdx.z];
+    const int n = d.P + d.Nn;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const float* s = src + d.col[j];
+    for (int f = blockIdx.y; f < d.F; f += gridDim.y) d.featT[(size_t)f * d.ldT + j] = s[(size_t)f * row_stride];
+}
 extern "C" int mct_classifier_update_from_gathered(mct_clf* c, const float* dev_rows, const int* col_offset_host, long long row_stride, int P, int Nn)
 {
     if (!c || !dev_rows || !col_offset_host || row_stride < 1) return MCT_E_ARG;
@@ -1894,27 +1904,49 @@ extern "C" int mct_track_update_from_gathered(mct_ctx* ctx, int n_obj, mct_clf* 
     int rc;
     if ((rc = train_descs_ready(ctx))) return rc;
     std::vector<int> creq(n_obj, 0);
-    size_t off = 0;
+    size_t total = 0;
+    int M_max = 0, F_max = 0;
     for (int o = 0; o < n_obj; o++) {
         mct_clf* c = clfs[o];
         if (!c || c->ctx != ctx) return mct_fail(ctx, MCT_E_ARG, "classifier handle belongs to another ctx%s");
         if (P[o] < 1 || Nn[o] < 1) return mct_fail(ctx, MCT_E_ARG, "Update needs at least one positive and one negative sample%s");
         const int M = P[o] + Nn[o];
         if (M > c->max_train) return mct_fail(ctx, MCT_E_ARG, "training set exceeds max_train%s (%d)", "", M);
-        MCT_CUDA(ctx, cudaMemcpyAsync(c->d_tcol, col_offsets_host + off, (size_t)M * 4, cudaMemcpyHostToDevice, ctx->stream));
-        MCT_LAUNCH(ctx, "k_gather_columns", k_gather_columns<<<dim3(ceil_div(M, 256), c->F < 64 ? c->F : 64), 256, 0, ctx->stream>>>(
-                       dev_rows, c->d_tcol, row_stride, M, c->F, c->d_featT, c->ldT));
+        total += (size_t)M; M_max = std::max(M_max, M); F_max = std::max(F_max, c->F);
+    }
+    // the column offsets of all objects travel with ONE copy through the pinned box staging buffer (one copy + one gather launch
+    // per object before: 16 small copies from pageable memory and 16 launches per camera-frame at configs[3])
+    const size_t need_boxes = (total + 3) / 4 + 1;
+    if (need_boxes > ctx->train_stage_cap && !ctx->h_train_stage) stage_take_parked(ctx, need_boxes);
+    if (need_boxes > ctx->train_stage_cap) {
+        MCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_train_stage) cudaFreeHost(ctx->h_train_stage);
+        if (ctx->d_train_stage) cudaFree(ctx->d_train_stage);
+        const size_t cap = need_boxes + 1024;
+        MCT_CUDA(ctx, cudaMallocHost(&ctx->h_train_stage, cap * 4 * sizeof(int)));
+        MCT_CUDA(ctx, cudaMalloc(&ctx->d_train_stage, cap * 4 * sizeof(int)));
+        ctx->train_stage_cap = cap;
+    }
+    memcpy(ctx->h_train_stage, col_offsets_host, total * sizeof(int));
+    size_t off = 0;
+    for (int o = 0; o < n_obj; o++) {
+        mct_clf* c = clfs[o];
+        const int M = P[o] + Nn[o];
         TrainDesc* t = &ctx->h_tdesc[o];
         fill_train_desc(t, c);
-        t->col = nullptr; t->row = nullptr; t->sx = nullptr; t->sy = nullptr; t->tw = nullptr;
+        t->col = ctx->d_train_stage + off; t->row = nullptr; t->sx = nullptr; t->sy = nullptr; t->tw = nullptr;
         t->P = P[o]; t->Nn = Nn[o]; t->mdch_fast = 0;
         c->lastP = P[o]; c->lastNn = Nn[o];
         creq[o] = c->cluster;
         off += (size_t)M;
     }
+    MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_train_stage, ctx->h_train_stage, total * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     MCT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tdesc, ctx->h_tdesc, sizeof(TrainDesc) * n_obj, cudaMemcpyHostToDevice, ctx->stream));
     ctx->tdesc_gen_valid = 0;
     MCT_CUDA(ctx, cudaEventRecord(ctx->ev_train, ctx->stream));
+    MCT_LAUNCH(ctx, "k_gather_columns", k_gather_columns_batch<<<dim3(ceil_div(M_max, 256), F_max < 64 ? F_max : 64, n_obj), 256, 0, ctx->stream>>>(
+                   ctx->d_tdesc, dev_rows, row_stride));
+    ctx->weak_split_done = 0;                          // (no feature streams here: the weak update below is the whole one)
     if ((rc = launch_ensemble_retain_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj))) return rc;
     if ((rc = launch_weak_update_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj))) return rc;
     if ((rc = launch_mil_select_batch(ctx, ctx->d_tdesc, ctx->h_tdesc, n_obj, creq.data()))) return rc;
