@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(256) k_mdch_train_finish(const TrainDesc* __re
     const float S0 = __fmul_rn((float)d.mtot[0], is0), S1 = __fmul_rn((float)d.mtot[1], is1);
     uint32_t* src = d.macc + (size_t)b * ld + i;                  // ld is a multiple of 4, the buffer 16-byte aligned
     const uint4 t = *reinterpret_cast<const uint4*>(src);
-    *reinterpret_cast<uint4*>(src) = make_uint4(0u, 0u, 0u, 0u);
+    if (t.x | t.y | t.z | t.w) *reinterpret_cast<uint4*>(src) = make_uint4(0u, 0u, 0u, 0u);     // (most bins are empty: nothing to clear)
     const unsigned tv[4] = {t.x, t.y, t.z, t.w};
     float* dst = d.featT + (size_t)(d.n_haar + b) * ld + i;
 #pragma unroll
