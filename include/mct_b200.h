@@ -433,6 +433,11 @@ int mct_track_update_default_collect(mct_ctx* ctx, int n_obj, mct_train_default_
 /* the boxes generated for object `obj` by the last mct_track_update_default (positives first; tests / diagnostics; synchronises) */
 int mct_track_update_default_boxes(mct_ctx* ctx, int obj, int cap, int* col, int* row, float* sx, float* sy, int* P, int* Nn);
 
+/* sizeof of the public structs in declaration order (mct_boxes, mct_clf_params, mct_haar_table, mct_pf_summary, mct_track_params,
+ * mct_ground_pdf_result, mct_train_gen, mct_train_gen_out, mct_sample_region, mct_sample_region_out, mct_train_default,
+ * mct_train_default_out): a binding in another language checks its own layouts against it.  Returns the number of entries. */
+int mct_abi_struct_sizes(int* out, int cap);
+
 #ifdef __cplusplus
 }
 #endif

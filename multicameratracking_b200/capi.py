@@ -41,7 +41,7 @@ SYMBOLS = [
     "mct_pf_get_summary_many", "mct_pf_rearrange_ground_many",
     # whole frame on the device
     "mct_pf_rng_set", "mct_pf_rng_get", "mct_track_update_default", "mct_track_update_default_collect",
-    "mct_track_update_default_boxes", "mct_frame_prefetch_flush",
+    "mct_track_update_default_boxes", "mct_frame_prefetch_flush", "mct_abi_struct_sizes",
 ]
 
 
@@ -550,6 +550,14 @@ def track_score(ctx, pfs, clfs, params, noise, u01, noise_device_ptr=None):
         rc = ctx.L.mct_track_score(ctx.h, n, pa, ca, tp, nz.ctypes.data_as(vp), 0, _fp(u), out)
     ctx.check(rc)
     return list(out)
+
+
+def abi_struct_layouts():
+    """(name, ctypes mirror) of every public struct in the order mct_abi_struct_sizes reports them"""
+    return [("mct_boxes", Boxes), ("mct_clf_params", ClfParams), ("mct_haar_table", HaarTable), ("mct_pf_summary", PfSummary),
+            ("mct_track_params", TrackParams), ("mct_ground_pdf_result", GroundPdfResult), ("mct_train_gen", TrainGen),
+            ("mct_train_gen_out", TrainGenOut), ("mct_sample_region", SampleRegion), ("mct_sample_region_out", SampleRegionOut),
+            ("mct_train_default", TrainDefault), ("mct_train_default_out", TrainDefaultOut)]
 
 
 def pf_rng_set(pf, state):

@@ -103,6 +103,18 @@ static StageCache g_stage_cache[MCT_MAX_DEV];
 static std::mutex g_stage_mu;
 
 extern "C" const char* mct_version(void) { return "mct-b200 0.1 (sm_100a)"; }
+// sizeof of every public struct, in the order of their declaration in mct_b200.h: lets a binding check its own layout
+// (tests/test_abi.py compares the ctypes mirrors in capi.py) without touching a device
+extern "C" int mct_abi_struct_sizes(int* out, int cap)
+{
+    const int v[] = {(int)sizeof(mct_boxes), (int)sizeof(mct_clf_params), (int)sizeof(mct_haar_table), (int)sizeof(mct_pf_summary),
+                     (int)sizeof(mct_track_params), (int)sizeof(mct_ground_pdf_result), (int)sizeof(mct_train_gen), (int)sizeof(mct_train_gen_out),
+                     (int)sizeof(mct_sample_region), (int)sizeof(mct_sample_region_out), (int)sizeof(mct_train_default),
+                     (int)sizeof(mct_train_default_out)};
+    const int n = (int)(sizeof(v) / sizeof(v[0]));
+    for (int i = 0; i < n && i < cap && out; i++) out[i] = v[i];
+    return n;
+}
 extern "C" const char* mct_last_error(mct_ctx* ctx) { return ctx ? ctx->err : g_mct_err; }
 extern "C" long long mct_launch_count(mct_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" void* mct_ctx_stream(mct_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }

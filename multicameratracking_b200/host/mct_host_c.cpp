@@ -395,6 +395,8 @@ int mcth_object_last_train(mcth_camera* c, int o, int which, int* col, int* row,
 }
 uint64_t mcth_object_rng_state(mcth_camera* c, int o) { return c->trackers[o]->Rng().state; }
 // whole frame on the device (default-strategy training sets from k_train_gen_default) on / off for this process
+// layout check for bindings (tests/test_abi.py: the ctypes mirror of mcth_object_params)
+int mcth_abi_object_params_size(void) { return (int)sizeof(mcth_object_params); }
 void mcth_set_device_training_sets(int on) { ParticleFilterTracker::SetDeviceTrainingSets(on != 0); }
 int mcth_get_device_training_sets(void) { return ParticleFilterTracker::DeviceTrainingSets() ? 1 : 0; }
 // m_states row of a frame (x, y, w, h as stored by StoreObjectState)

@@ -27,6 +27,27 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(lib, s), s
 
 
+def test_ctypes_mirrors_have_the_layout_of_the_c_structs():
+    """every Structure in capi.py is as large as the struct the library was compiled with (no device needed)"""
+    import ctypes as C
+    from multicameratracking_b200 import capi
+    L = capi.load()
+    L.mct_abi_struct_sizes.argtypes = [C.POINTER(C.c_int), C.c_int]
+    out = (C.c_int * 32)()
+    n = L.mct_abi_struct_sizes(out, 32)
+    layouts = capi.abi_struct_layouts()
+    assert n == len(layouts)
+    for k, (name, mirror) in enumerate(layouts):
+        assert C.sizeof(mirror) == out[k], (name, C.sizeof(mirror), out[k])
+
+
+def test_host_object_params_mirror_has_the_layout_of_the_c_struct():
+    import ctypes as C
+    from multicameratracking_b200 import host as mhost
+    L = mhost.load()
+    assert C.sizeof(mhost.ObjectParams) == L.mcth_abi_object_params_size()
+
+
 def test_library_is_sm100a_only():
     import subprocess
     from multicameratracking_b200 import capi
