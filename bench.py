@@ -12,7 +12,12 @@ Workload (BASELINE.json configs[1]): one camera per GPU, 8 objects, HaarAndColor
   e2e    = the same metric through the reference-facing C++ host API (ParticleFilterTracker::TrackCameraObjects)
            with HOST buffers: per step the H2D copy of the 4 frame planes + noise from pinned memory and the D2H
            read-out of the per-object summaries are inside the timed region.
-  extra  = tracked_frames_per_sec_per_camera: full frames (score path + UpdateClassifier) through the host API.
+  extra  = tracked_frames_per_sec_per_camera: full frames (score path + UpdateClassifier) through the host API; the
+           default-strategy training sets are generated on the device behind the frame's scoring kernels and the
+           trackers' RNG streams are device-resident meanwhile (MCT_HOST_TRAINING_SETS=1: host enumeration).
+  --config 0..4 = the other BASELINE configurations (0: 1 object, Haar only -- only the gray plane is handed over;
+           2 / 3: the camera network with the geometric / appearance fuser, one camera per rank under torchrun;
+           4: the Haar gather sweep).  MCT_E2E_STREAM=1: the streaming form of the per-frame call for the e2e leg.
 
 `--impl reference` times the CPU restatement of the reference (oracle/, all host threads via the reference's own
 omp pragmas) on the same config and metric.  Multi-GPU: one process per GPU (torchrun), one camera per rank,
